@@ -63,3 +63,109 @@ def cell_out(dump, icell, var):
     """[nrecs, nelem] array of one OUT_* variable for cell number `icell` of the dump."""
     col, ne = out_index(dump)[var]
     return dump["c%d/out" % icell][:, col:col + ne]
+
+
+# ---------------------------------------------------------------------------------------------
+# dump -> the input arrays of include/vicres.h (so the oracle port / the CUDA path can be handed
+# exactly the numbers the reference consumed) and -> the reference's outputs in VR_OUT_* order
+# ---------------------------------------------------------------------------------------------
+_SOIL_IDX = {n: i for i, n in enumerate(SOIL_SCALARS)}
+
+# VR_OUT_* name (vicres_b200/abi.py OUT_NAMES) -> (reference OUT_* name, element)
+REF_OUT = {
+    "PREC": ("OUT_PREC", 0), "EVAP": ("OUT_EVAP", 0), "RUNOFF": ("OUT_RUNOFF", 0),
+    "BASEFLOW": ("OUT_BASEFLOW", 0), "WDEW": ("OUT_WDEW", 0), "SOIL_LIQ0": ("OUT_SOIL_LIQ", 0),
+    "SOIL_LIQ1": ("OUT_SOIL_LIQ", 1), "SOIL_LIQ2": ("OUT_SOIL_LIQ", 2), "NET_SHORT": ("OUT_NET_SHORT", 0),
+    "R_NET": ("OUT_R_NET", 0), "EVAP_CANOP": ("OUT_EVAP_CANOP", 0), "TRANSP_VEG": ("OUT_TRANSP_VEG", 0),
+    "EVAP_BARE": ("OUT_EVAP_BARE", 0), "SUB_CANOP": ("OUT_SUB_CANOP", 0), "SUB_SNOW": ("OUT_SUB_SNOW", 0),
+    "AERO_RESIST": ("OUT_AERO_RESIST", 0), "SURF_TEMP": ("OUT_SURF_TEMP", 0), "ALBEDO": ("OUT_ALBEDO", 0),
+    "REL_HUMID": ("OUT_REL_HUMID", 0), "IN_LONG": ("OUT_IN_LONG", 0), "AIR_TEMP": ("OUT_AIR_TEMP", 0),
+    "WIND": ("OUT_WIND", 0), "SWE": ("OUT_SWE", 0), "SNOW_DEPTH": ("OUT_SNOW_DEPTH", 0),
+    "SNOW_CANOPY": ("OUT_SNOW_CANOPY", 0), "SNOW_COVER": ("OUT_SNOW_COVER", 0),
+    "WATER_ERROR": ("OUT_WATER_ERROR", 0), "INFLOW": ("OUT_INFLOW", 0), "SNOW_MELT": ("OUT_SNOW_MELT", 0),
+    "RAINF": ("OUT_RAINF", 0), "SNOWF": ("OUT_SNOWF", 0), "NET_LONG": ("OUT_NET_LONG", 0),
+    "ASAT": ("OUT_ASAT", 0), "SOIL_WET": ("OUT_SOIL_WET", 0), "ROOTMOIST": ("OUT_ROOTMOIST", 0),
+    "GRND_FLUX": ("OUT_GRND_FLUX", 0), "DELTAH": ("OUT_DELTAH", 0), "AERO_COND": ("OUT_AERO_COND", 0),
+    "SHORTWAVE": ("OUT_SHORTWAVE", 0), "LONGWAVE": ("OUT_LONGWAVE", 0),
+    "DELSOILMOIST": ("OUT_DELSOILMOIST", 0), "DELSWE": ("OUT_DELSWE", 0),
+    "DELINTERCEPT": ("OUT_DELINTERCEPT", 0), "SNOW_SURF_TEMP": ("OUT_SNOW_SURF_TEMP", 0),
+    "SNOW_PACK_TEMP": ("OUT_SNOW_PACK_TEMP", 0), "SALBEDO": ("OUT_SALBEDO", 0),
+}
+
+
+def case_from_dump(d):
+    """Return dict(opt=..., lib=..., cells=..., month, doy, forcing [9,nrec,C], tair0 [C],
+    ntile_max) built from a ref_driver dump `d`."""
+    L, NB, nrec, C = int(d["Nlayer"][0]), int(d["Nbands"][0]), int(d["nrecs"][0]), int(d["ncells"][0])
+    ncl = int(d["Nveglib"][0])
+    vl = d["veglib"]
+    lib = {
+        "overstory": vl[:ncl, 0].astype(np.int32), "rarc": vl[:ncl, 1], "rmin": vl[:ncl, 2],
+        "wind_h": vl[:ncl, 3], "RGL": vl[:ncl, 4], "rad_atten": vl[:ncl, 5], "wind_atten": vl[:ncl, 6],
+        "trunk_ratio": d["veglib_trunk_ratio"][:ncl], "roughness": vl[:ncl, 31:43],
+        "displacement": vl[:ncl, 43:55],
+    }
+    sc = np.stack([d["c%d/soil_scalars" % c] for c in range(C)])          # [C, 18]
+    cells = {}
+    for api, ref in [("lat", "lat"), ("elevation", "elevation"), ("b_infilt", "b_infilt"), ("Ds", "Ds"),
+                     ("Dsmax", "Dsmax"), ("Ws", "Ws"), ("c_expt", "c"), ("avg_temp", "avg_temp"),
+                     ("dp", "dp"), ("rough", "rough"), ("snow_rough", "snow_rough")]:
+        cells[api] = sc[:, _SOIL_IDX[ref]].copy()
+    for k in ["expt", "Ksat", "depth", "max_moist", "Wcr", "Wpwp", "resid_moist", "init_moist",
+              "bulk_density", "soil_density", "bulk_dens_min", "soil_dens_min", "quartz", "organic",
+              "porosity"]:
+        cells[k] = np.stack([d["c%d/%s" % (c, k)] for c in range(C)], axis=1)      # [L, C]
+    for k in ["AreaFract", "Tfactor", "Pfactor"]:
+        cells[k] = np.stack([d["c%d/%s" % (c, k)] for c in range(C)], axis=1)      # [NB, C]
+    tile_ptr = [0]
+    t_class, t_cv, t_root, t_lai, t_alb, t_vc = [], [], [], [], [], []
+    ntile_max = 0
+    for c in range(C):
+        nveg = int(d["c%d/Nveg" % c][0])
+        cls, cv = d["c%d/veg_class" % c], d["c%d/Cv" % c]
+        nt = 0
+        for v in range(nveg + 1):
+            if v == nveg and not cv[v] > 0:
+                continue                      # no bare-soil tile for this cell
+            bare = v == nveg
+            t_class.append(ncl if bare else int(cls[v]))
+            t_cv.append(cv[v])
+            t_root.append(np.zeros(L) if bare else d["c%d/root" % c][v])
+            if bare:
+                t_lai.append(np.zeros(12)); t_alb.append(np.zeros(12)); t_vc.append(np.zeros(12))
+            else:
+                vm = d["c%d/veg_monthly" % c][v]
+                t_lai.append(vm[0]); t_alb.append(vm[1]); t_vc.append(vm[2])
+            nt += 1
+        ntile_max = max(ntile_max, nveg + 1)
+        tile_ptr.append(tile_ptr[-1] + nt)
+    cells["tile_ptr"] = np.array(tile_ptr, dtype=np.int64)
+    cells["tile_class"] = np.array(t_class, dtype=np.int32)
+    cells["tile_Cv"] = np.array(t_cv)
+    cells["tile_root"] = np.array(t_root).reshape(-1, L)
+    cells["tile_LAI"] = np.array(t_lai).reshape(-1, 12)
+    cells["tile_albedo"] = np.array(t_alb).reshape(-1, 12)
+    cells["tile_vegcover"] = np.array(t_vc).reshape(-1, 12)
+    forcing = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2)   # [nrec, 9, C]
+    forcing = np.ascontiguousarray(forcing.transpose(1, 0, 2))                    # [9, nrec, C]
+    dmy = d["dmy"]
+    return {
+        "nlayer": L, "nbands": NB, "nrec": nrec, "ncell": C, "dt": int(d["dt"][0]),
+        "snow_step": int(d["snow_step"][0]), "NF": int(d["NF"][0]),
+        "max_snow_temp": float(d["MAX_SNOW_TEMP"][0]), "min_rain_temp": float(d["MIN_RAIN_TEMP"][0]),
+        "wind_h": float(d["wind_h"][0]),
+        "lib": lib, "cells": cells, "month": dmy[:, 1].astype(np.int32), "doy": dmy[:, 4].astype(np.int32),
+        "forcing": forcing, "tair0": forcing[0, 0, :].copy(), "ntile_max": ntile_max,
+    }
+
+
+def ref_outputs(d, names):
+    """[len(names), nrec, C] reference outputs (put_data's out_data[].data after each step)."""
+    C = int(d["ncells"][0])
+    idx = out_index(d)
+    res = []
+    for nm in names:
+        rn, el = REF_OUT[nm]
+        col, ne = idx[rn]
+        res.append(np.stack([d["c%d/out" % c][:, col + el] for c in range(C)], axis=1))
+    return np.stack(res)
