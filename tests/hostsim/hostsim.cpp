@@ -1,0 +1,76 @@
+// hostsim.cpp -- TEST HARNESS ONLY.  Compiles the device physics headers (vic_physics.cuh,
+// vic_aggregate.cuh, vic_host_prep.h) for the HOST with g++ and runs the same per-unit step and
+// per-cell aggregation serially, so that the non-GPU test tier can check the kernel's arithmetic
+// against the oracle.  It is not linked into libvicres.so and is not a product code path: the
+// product library only launches CUDA kernels and fails without a device.
+#include <stdio.h>
+#include <vector>
+#include "../../vicres_b200/csrc/vic_host_prep.h"
+#include "../../vicres_b200/csrc/vic_aggregate.cuh"
+
+using namespace vr;
+
+extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cells *cells, const vr_forcing *f,
+                      const double *tair0, double *out /* [n_out][nrec][C] */)
+{
+  Prepared P;
+  if (!prepare(*opt, *lib, *cells, 128, P)) { fprintf(stderr, "hostsim: %s\n", P.error.c_str()); return -1; }
+  const int NL = P.NL, nrec = f->nrec;
+  const int64_t C = P.C, U = P.U;
+  std::vector<UnitS> S(U ? U : 1);
+  std::vector<UnitC> UC(U ? U : 1);
+  std::vector<double> sv((size_t)SV_N * C, 0.0);
+  for (int64_t u = 0; u < U; u++) {
+    int64_t c = P.u_cell[u];
+    UnitC &uc = UC[u];
+    uc.is_bare = P.u_flags[u] & 1; uc.overstory = (P.u_flags[u] >> 1) & 1; uc.root0_mask = P.u_flags[u] >> 8;
+    uc.area = P.u_cv[u] * P.u_af[u]; uc.Tfactor = P.u_Tfactor[u]; uc.Pfactor = P.u_Pfactor[u];
+    uc.rarc = P.u_rarc[u]; uc.rmin = P.u_rmin[u]; uc.RGL = P.u_RGL[u];
+    for (int l = 0; l < MAXL; l++) uc.root[l] = P.u_root[(size_t)l * U + u];
+    double im[MAXL], mm[MAXL];
+    for (int l = 0; l < NL; l++) { im[l] = cells->init_moist[(size_t)l * C + c]; mm[l] = cells->max_moist[(size_t)l * C + c]; }
+    unit_init(im, mm, NL, tair0[c], uc.Tfactor, S[u]);
+  }
+  double terms[NTERM], acc[NTERM], o[VR_NOUTVAR];
+  for (int64_t c = 0; c < C; c++) {
+    CellC cc;
+    load_cell_consts(P.cc.data(), C, c, NL, cc);
+    // put_data(rec = -nrecs)
+    {
+      for (int k = 0; k < NTERM; k++) acc[k] = 0;
+      double eb = 0, tv = 0;
+      UnitOut z;
+      memset(&z, 0, sizeof z);
+      for (int64_t u = P.cell_uptr[c]; u < P.cell_uptr[c + 1]; u++) {
+        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S[u], z, NL, terms, 1);
+        cell_accumulate_ordered(acc, &eb, &tv, terms, 1, NL);
+      }
+      Forc f0;
+      memset(&f0, 0, sizeof f0);
+      f0.vp = 1; f0.vpd = 1;
+      cell_finish(acc, eb, tv, f0, NL, true, &sv[(size_t)c * SV_N], o);
+    }
+    for (int rec = 0; rec < nrec; rec++) {
+      Forc fo;
+      size_t k = (size_t)rec * C + c;
+      fo.air_temp = f->field[VR_F_AIR_TEMP][k]; fo.prec = f->field[VR_F_PREC][k]; fo.wind = f->field[VR_F_WIND][k];
+      fo.vp = f->field[VR_F_VP][k]; fo.vpd = f->field[VR_F_VPD][k]; fo.pressure = f->field[VR_F_PRESSURE][k];
+      fo.density = f->field[VR_F_DENSITY][k]; fo.shortwave = f->field[VR_F_SHORTWAVE][k];
+      fo.longwave = f->field[VR_F_LONGWAVE][k];
+      fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
+      for (int q = 0; q < NTERM; q++) acc[q] = 0;
+      double eb = 0, tv = 0;
+      for (int64_t u = P.cell_uptr[c]; u < P.cell_uptr[c + 1]; u++) {
+        UnitOut uo;
+        const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
+        const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];
+        unit_step(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S[u], uo);
+        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S[u], uo, NL, terms, 1);
+        cell_accumulate_ordered(acc, &eb, &tv, terms, 1, NL);
+      }
+      cell_finish(acc, eb, tv, fo, NL, false, &sv[(size_t)c * SV_N], o);
+      for (int v = 0; v < opt->n_out; v++) out[((size_t)v * nrec + rec) * C + c] = o[opt->out_vars[v]];
+    }
+  }
+  return 0;
+}

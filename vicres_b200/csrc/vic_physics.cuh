@@ -1,0 +1,1554 @@
+// vic_physics.cuh -- device physics of the B200-native VIC-Res water-balance cell step.
+//
+// One call of unit_step() advances ONE tile x band pair ("unit") of one grid cell through ONE
+// model record: the work the reference does in surface_fluxes() + runoff() for that pair
+// (runoff/model/surface_fluxes.c:11-1168, runoff.c:7-576) in frozen-soil-free water-balance mode
+// with SNOW_STEP == TIME_STEP.  It is a re-design, not a transcription:
+//   * state is a flat register struct (26 live words), not the reference's ~2 kB AoS structs;
+//     the reference's iter_/step_/snow_/soil_ struct copies collapse to scalars;
+//   * everything that depends only on parameters is hoisted to the host at vr_set_cells():
+//     aerodynamic-resistance coefficients per (class, soil roughness, month) -- the reference runs
+//     7 CalcAerodynamic per tile-step (full_energy.c:329-369) --, soil thermal constants, the
+//     QUICK_FLUX exponentials, ARNO exponents, baseflow coefficients, monthly canopy terms;
+//   * the Penman-Monteith air-state terms (2 exp) are computed once per unit-step and shared by
+//     the up-to-5 penman() evaluations of canopy_evap/transpiration/arno_evap;
+//   * the 6 PET reference evaporations and compute_zwt are not computed (they feed only
+//     OUT_PET_* / OUT_ZWT*).
+// Operation order inside each formula follows the reference so results stay within 1e-9 relative.
+//
+// The functions are __host__ __device__ so that tests/hostsim can compile this header with g++ and
+// check the arithmetic against the oracle without a GPU; the product library (vicres_capi.cu)
+// only ever launches them from CUDA kernels.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VR_HD __host__ __device__ __forceinline__
+#define VR_HDN __host__ __device__ __noinline__
+#else
+#define VR_HD inline
+#define VR_HDN inline
+#endif
+
+#ifndef VR_POW
+#define VR_POW(x, y) pow((x), (y))
+#endif
+
+namespace vr {
+
+// ---- constants (runoff/model/vicNl_def.h:160-440, snow.h:40-90) ----
+constexpr double HUGE_RESIST = 1.e20;
+constexpr double SMALLV = 1.e-12;
+constexpr double MISSINGV = -99999.;
+constexpr double VERR = -999.;
+constexpr double BARE_SOIL_ALBEDO = 0.2;
+constexpr double SEC_PER_DAY = 86400.;
+constexpr double ICE_DENSITY = 917.;
+constexpr double KELVIN = 273.15;
+constexpr double STEFAN_B = 5.6696e-8;
+constexpr double Lf = 3.337e5;
+constexpr double RHO_W = 999.842594;
+constexpr double Cp = 1013.0;
+constexpr double CH_ICE = 2100.0e3;
+constexpr double CH_WATER = 4186.8e3;
+constexpr double K_SNOW = 2.9302e-6;
+constexpr double EPS = 0.62196351;
+constexpr double G_GRAV = 9.81;
+constexpr double JOULESPCAL = 4.1868;
+constexpr double GRAMSPKG = 1000.;
+constexpr double A_SVP = 0.61078, B_SVP = 17.269, C_SVP = 237.3;
+constexpr double CLOSURE = 4000, RSMAX = 5000, VPDMINFACTOR = 0.1, RARC_SOIL = 100.0;
+constexpr double CP_PM = 1013, PS_PM = 101300;
+constexpr double SNOW_DT = 5.0;
+constexpr double LIQUID_WATER_CAPACITY = 0.035;
+constexpr double LAI_SNOW_MULTIPLIER = 0.0005;
+constexpr double MIN_INTERCEPTION_STORAGE = 0.005;
+constexpr double MAX_SURFACE_SWE = 0.125;
+constexpr double NEW_SNOW_DENSITY = 50.;
+constexpr double SNDENS_ETA0 = 3.6e6, SNDENS_C5 = 0.08, SNDENS_C6 = 0.021;
+constexpr double MIN_SWQ_EB_THRES = 0.0010;
+constexpr double NEW_SNOW_ALB = 0.85;
+constexpr double SNOW_ALB_ACCUM_A = 0.94, SNOW_ALB_ACCUM_B = 0.58, SNOW_ALB_THAW_A = 0.82, SNOW_ALB_THAW_B = 0.46;
+constexpr double TraceSnow = 0.03;
+constexpr int MAXL = 3;
+
+// ---- per-cell constants, precomputed on the host (vicres_capi.cu: build_cell_consts) ----
+enum {  // index into the per-cell constant block  cc[k*C + c]
+  CC_LAT = 0, CC_ELEV, CC_HALF_ELEV_LAPSE, CC_B, CC_INV_B, CC_INV_B1, CC_ONE_PLUS_B, CC_EX, CC_TOP_MAX,
+  CC_TOP_MAX_INFIL, CC_ARNO_MAXM, CC_ARNO_MAX_INFIL, CC_DSMAX24, CC_BF_FRAC, CC_BF_NL, CC_WS, CC_ONE_M_WS,
+  CC_C, CC_AVG_T, CC_DP, CC_D1, CC_EXP_M, CC_EXP_P, CC_KB_BARE,
+  CC_LAYER0,   // then per layer l: CC_LAYER0 + l*CL_N + field
+  CL_EXPT = 0, CL_KSAT24, CL_MAX_MOIST, CL_RESID, CL_QDEN, CL_WCR, CL_WPWP, CL_WCR_M_WPWP, CL_WET_DEN,
+  CL_DEPTH, CL_KDRY, CL_KSAT_M_KDRY, CL_POROS, CL_SOILFR, CL_CS_SOLID, CL_N
+};
+#define VR_CC_N(nlayer) (::vr::CC_LAYER0 + (nlayer) * ::vr::CL_N)
+
+struct CellC {   // the constants above, unpacked for one cell
+  double lat, elev, half_elev_lapse, b, inv_b, inv_b1, one_plus_b, ex, top_max, top_max_infil, arno_maxm,
+         arno_max_infil, dsmax24, bf_frac, bf_nl, Ws, one_m_Ws, c, avg_T, dp, D1, exp_m, exp_p, kb_bare;
+  double expt[MAXL], ksat24[MAXL], max_moist[MAXL], resid[MAXL], qden[MAXL], Wcr[MAXL], Wpwp[MAXL],
+         wcr_m_wpwp[MAXL], wet_den[MAXL], depth[MAXL], kdry[2], ksat_m_kdry[2], poros[2], soilfr[2], cs_solid[2];
+};
+
+// per-unit constants (tile x band)
+struct UnitC {
+  int is_bare, overstory, root0_mask;
+  double area, Tfactor, Pfactor, rarc, rmin, RGL;
+  float root[MAXL];
+};
+
+// per (tile, month) canopy terms (full_energy.c:210-227,306-308) -- tm[(t*12+mon)*TM_N + k]
+enum { TM_VEGCOVER = 0, TM_ALBEDO, TM_LAI, TM_WDMAX, TM_SURF_ATTEN, TM_N };
+// per (aero key, month) CalcAerodynamic coefficients: Ra = RA/wind, U = UC*wind
+enum { AE_RA0 = 0, AE_RA1, AE_RA2, AE_U0, AE_U1, AE_U2, AE_REF0, AE_REF1, AE_REF2, AE_ROUGH0, AE_ROUGH1,
+       AE_ROUGH2, AE_DISP0, AE_DISP1, AE_DISP2, AE_N };
+
+struct Forc { double air_temp, prec, wind, vp, vpd, pressure, density, shortwave, longwave; int mon, doy; };
+
+// carried state of one unit (what write_model_state.c keeps, plus LongUnderOut/Tfoliage)
+struct UnitS {
+  double moist[MAXL], Wdew, T0, T1, LongUnderOut, Tfoliage;
+  double swq, surf_temp, pack_temp, surf_water, pack_water, density, depth, albedo, coldcontent, coverage,
+         snow_canopy, tmp_int_storage;
+  int last_snow, MELTING, fb_snow, fb_fol;
+};
+enum { ST_MOIST0 = 0, ST_MOIST1, ST_MOIST2, ST_WDEW, ST_T0, ST_T1, ST_LONGUNDEROUT, ST_TFOLIAGE, ST_SWQ,
+       ST_SURF_TEMP, ST_PACK_TEMP, ST_SURF_WATER, ST_PACK_WATER, ST_DENSITY, ST_DEPTH, ST_ALBEDO,
+       ST_COLDCONTENT, ST_COVERAGE, ST_SNOW_CANOPY, ST_TMP_INT, ST_LAST_SNOW, ST_MELTING, ST_FB_SNOW,
+       ST_FB_FOL, ST_N };
+
+// what one unit hands to the per-cell aggregation (collect_wb_terms / collect_eb_terms inputs)
+struct UnitOut {
+  double evap[MAXL], bef[MAXL], vapor_flux, canopy_vapor_flux, canopyevap, asat, runoff, baseflow, inflow,
+         aero_resist[2], wetness, rootmoist, melt, Tsurf, NetShortAtmos, NetLongAtmos, in_long, albedo,
+         grnd_flux, deltaH, out_prec, out_rain, out_snow;
+  int snow_flag;
+};
+
+// unpack the constants of cell c from the SoA block cc[k*C + c]
+VR_HD void load_cell_consts(const double *cc, int64_t C, int64_t c, int NL, CellC &x)
+{
+#define G_(k) cc[(size_t)(k) * C + c]
+  x.lat = G_(CC_LAT); x.elev = G_(CC_ELEV); x.half_elev_lapse = G_(CC_HALF_ELEV_LAPSE); x.b = G_(CC_B);
+  x.inv_b = G_(CC_INV_B); x.inv_b1 = G_(CC_INV_B1); x.one_plus_b = G_(CC_ONE_PLUS_B); x.ex = G_(CC_EX);
+  x.top_max = G_(CC_TOP_MAX); x.top_max_infil = G_(CC_TOP_MAX_INFIL); x.arno_maxm = G_(CC_ARNO_MAXM);
+  x.arno_max_infil = G_(CC_ARNO_MAX_INFIL); x.dsmax24 = G_(CC_DSMAX24); x.bf_frac = G_(CC_BF_FRAC);
+  x.bf_nl = G_(CC_BF_NL); x.Ws = G_(CC_WS); x.one_m_Ws = G_(CC_ONE_M_WS); x.c = G_(CC_C); x.avg_T = G_(CC_AVG_T);
+  x.dp = G_(CC_DP); x.D1 = G_(CC_D1); x.exp_m = G_(CC_EXP_M); x.exp_p = G_(CC_EXP_P); x.kb_bare = G_(CC_KB_BARE);
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) {
+    if (l < NL) {
+      const int b = CC_LAYER0 + l * CL_N;
+      x.expt[l] = G_(b + CL_EXPT); x.ksat24[l] = G_(b + CL_KSAT24); x.max_moist[l] = G_(b + CL_MAX_MOIST);
+      x.resid[l] = G_(b + CL_RESID); x.qden[l] = G_(b + CL_QDEN); x.Wcr[l] = G_(b + CL_WCR);
+      x.Wpwp[l] = G_(b + CL_WPWP); x.wcr_m_wpwp[l] = G_(b + CL_WCR_M_WPWP); x.wet_den[l] = G_(b + CL_WET_DEN);
+      x.depth[l] = G_(b + CL_DEPTH);
+      if (l < 2) {
+        x.kdry[l] = G_(b + CL_KDRY); x.ksat_m_kdry[l] = G_(b + CL_KSAT_M_KDRY); x.poros[l] = G_(b + CL_POROS);
+        x.soilfr[l] = G_(b + CL_SOILFR); x.cs_solid[l] = G_(b + CL_CS_SOLID);
+      }
+    }
+  }
+#undef G_
+}
+
+// initialize_model_state.c:321-350,733-760 + initialize_snow/soil/veg: the state before record 0
+VR_HD void unit_init(const double *init_moist, const double *max_moist, int NL, double tair0, double Tfactor, UnitS &s)
+{
+  double surf_temp = tair0;
+  if (surf_temp < -1.) surf_temp = -1.;
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) {
+    s.moist[l] = 0;
+    if (l < NL) {
+      s.moist[l] = init_moist[l];
+      if (s.moist[l] > max_moist[l]) s.moist[l] = max_moist[l];
+    }
+  }
+  s.Wdew = 0; s.T0 = surf_temp; s.T1 = surf_temp;
+  double tmp = s.T0 + KELVIN;
+  s.LongUnderOut = STEFAN_B * tmp * tmp * tmp * tmp;
+  s.Tfoliage = tair0 + Tfactor;
+  s.swq = 0; s.surf_temp = 0; s.pack_temp = 0; s.surf_water = 0; s.pack_water = 0; s.density = 0; s.depth = 0;
+  s.albedo = 0; s.coldcontent = 0; s.coverage = 0; s.snow_canopy = 0; s.tmp_int_storage = 0;
+  s.last_snow = (int)MISSINGV; s.MELTING = 0; s.fb_snow = 0; s.fb_fol = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// L0 math
+// ---------------------------------------------------------------------------------------
+VR_HD double svp(double temp)   // svp.c:7-24
+{
+  double SVP = A_SVP * exp((B_SVP * temp) / (C_SVP + temp));
+  if (temp < 0) SVP *= 1.0 + .00972 * temp + .000042 * temp * temp;
+  return SVP * 1000.;
+}
+
+// Penman-Monteith (penman.c:201-249) split into its air-state part (once per unit-step) and the
+// per-surface evaluation.
+struct PenmanAir { double slope, lv, gamma, r_air_cp; };
+VR_HD PenmanAir penman_air(double tair, double half_elev_lapse, double elevation)
+{
+  PenmanAir p;
+  p.slope = (B_SVP * C_SVP) / ((C_SVP + tair) * (C_SVP + tair)) * svp(tair);
+  double h = 287 / 9.81 * ((tair + 273.15) + half_elev_lapse);
+  double pz = PS_PM * exp(-elevation / h);
+  p.lv = 2501000 - 2361 * tair;
+  p.gamma = 1628.6 * pz / p.lv;
+  double r_air = 0.003486 * pz / (275 + tair);
+  p.r_air_cp = r_air * CP_PM;
+  return p;
+}
+VR_HD double penman(const PenmanAir &p, double rad, double vpd, double ra, double rc, double rarc)
+{
+  double evap = (p.slope * rad + p.r_air_cp * vpd / ra) / (p.lv * (p.slope + p.gamma * (1 + (rc + rarc) / ra))) *
+                SEC_PER_DAY;
+  if (vpd >= 0.0 && evap < 0.0) evap = 0.0;
+  return evap;
+}
+
+VR_HD double calc_rc(double rs, double net_short, double RGL, double tair, double vpd, double lai, double gsm_inv)
+{   // penman.c:44-91, Jarvis branch
+  double rc;
+  if (rs == 0) rc = 0;
+  else if (lai == 0) rc = RSMAX;
+  else {
+    double DAYfactor;
+    if (rs > 0.) {
+      double f = net_short / RGL;
+      DAYfactor = (1. + f) / (f + rs / RSMAX);
+    }
+    else DAYfactor = 1.;
+    double Tfactor = .08 * tair - 0.0016 * tair * tair;
+    Tfactor = (Tfactor <= 0.0) ? 1e-10 : Tfactor;
+    double vpdfactor = 1 - vpd / CLOSURE;
+    vpdfactor = (vpdfactor < VPDMINFACTOR) ? VPDMINFACTOR : vpdfactor;
+    rc = rs / (lai * gsm_inv * Tfactor * vpdfactor) * DAYfactor;
+    rc = (rc > RSMAX) ? RSMAX : rc;
+  }
+  return rc;
+}
+
+VR_HD double stability_correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0)
+{   // StabilityCorrection.c:44-81
+  double Correction = 1.0;
+  if (TSurf != Tair) {
+    double Ri = G_GRAV * (Tair - TSurf) * (Z - d) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * Wind * Wind);
+    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (log((Z - d) / Z0) + 5));
+    if (Ri > RiLimit) Ri = RiLimit;
+    if (Ri > 0.0) Correction = (1 - Ri / 0.2) * (1 - Ri / 0.2);
+    else {
+      if (Ri < -0.5) Ri = -0.5;
+      Correction = sqrt(1 - 16 * Ri);
+    }
+  }
+  return Correction;
+}
+
+// root_brent.c:105-367 for a functor that never returns the reference's ERROR sentinel by design
+// (the two callers' functions are total on this path); bracket expansion and Brent iteration are
+// kept iteration-for-iteration.  Returns VERR when no bracket / no convergence.
+template <class F>
+VR_HD double root_brent(double a, double b, F &f)
+{
+  double c = 0, d = 0, e = 0, fa, fb, fc, m, p, q, r, s, tol;
+  fa = f(a);
+  fb = f(b);
+  int j = 0;
+  while ((fa * fb) >= 0 && j < 5) {
+    a -= 10; b += 10;
+    fa = f(a);
+    fb = f(b);
+    j++;
+  }
+  if ((fa * fb) >= 0) return VERR;
+  fc = fb;
+  for (int i = 0; i < 1000; i++) {
+    if (fb * fc > 0) { c = a; fc = fa; d = b - a; e = d; }
+    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    tol = 2 * 3e-8 * fabs(b) + 1e-7;
+    m = 0.5 * (c - b);
+    if (fabs(m) <= tol || fb == 0) return b;
+    if (fabs(e) < tol || fabs(fa) <= fabs(fb)) { d = m; e = d; }
+    else {
+      s = fb / fa;
+      if (a == c) { p = 2 * m * s; q = 1 - s; }
+      else {
+        q = fa / fc; r = fb / fc;
+        p = s * (2 * m * q * (q - r) - (b - a) * (r - 1));
+        q = (q - 1) * (r - 1) * (s - 1);
+      }
+      if (p > 0) q = -q; else p = -p;
+      s = e; e = d;
+      if ((2 * p) < (3 * m * q - fabs(tol * q)) && p < fabs(0.5 * s * q)) d = p / q;
+      else { d = m; e = d; }
+    }
+    a = b; fa = fb;
+    b += (fabs(d) > tol) ? d : ((m > 0) ? tol : -tol);
+    fb = f(b);
+  }
+  return VERR;
+}
+
+// ---------------------------------------------------------------------------------------
+// snow pack (snow_melt.c:119-579, SnowPackEnergyBalance.c:88-328, latent_heat_from_snow.c)
+// ---------------------------------------------------------------------------------------
+struct SnowPackEB {
+  // inputs
+  double Dt, Ra, Z, Z0_2, AirDens, EactAir, LongSnowIn, Lv, Press, Rain, NetShortUnder, Vpd, Wind, OldTSurf,
+         SnowDepth, SnowDensity, SurfaceLiquidWater, SweSurfaceLayer, Tair, TGrnd;
+  // outputs of the last evaluation
+  double Ra_used0, AdvectedEnergy, DeltaColdContent, GroundFlux, LatentHeat, LatentHeatSub, NetLongUnder,
+         RefreezeEnergy, SensibleHeat, vapor_flux, surface_flux;
+  VR_HD double operator()(double TSurf)
+  {
+    double TMean = TSurf;
+    if (Wind > 0.0) Ra_used0 = Ra / stability_correction(Z, 0., TMean, Tair, Wind, Z0_2);
+    else Ra_used0 = HUGE_RESIST;
+    double Tmp = TMean + KELVIN;
+    NetLongUnder = LongSnowIn - STEFAN_B * Tmp * Tmp * Tmp * Tmp;
+    double NetRad = NetShortUnder + NetLongUnder;
+    SensibleHeat = AirDens * Cp * (Tair - TMean) / Ra_used0;
+    // latent_heat_from_snow (BlowingMassFlux == 0: BLOWING FALSE)
+    double EsSnow = svp(TMean);
+    double SurfaceMassFlux = AirDens * (EPS / Press) * (EactAir - EsSnow) / Ra_used0;
+    if (Vpd == 0.0 && SurfaceMassFlux < 0.0) SurfaceMassFlux = 0.0;
+    double VaporMassFlux = SurfaceMassFlux + 0.;
+    if (TMean >= 0.0) {
+      LatentHeat = Lv * VaporMassFlux;
+      LatentHeatSub = 0;
+    }
+    else {
+      double Ls = (677. - 0.07 * TMean) * JOULESPCAL * GRAMSPKG;
+      LatentHeatSub = Ls * VaporMassFlux;
+      LatentHeat = 0;
+    }
+    vapor_flux = VaporMassFlux * Dt / RHO_W;
+    surface_flux = SurfaceMassFlux * Dt / RHO_W;
+    if (TMean == 0) AdvectedEnergy = (CH_WATER * (Tair)*Rain) / (Dt);
+    else AdvectedEnergy = 0.;
+    DeltaColdContent = CH_ICE * SweSurfaceLayer * (TSurf - OldTSurf) / (Dt);
+    if (SnowDepth > 0.) GroundFlux = 2.9302e-6 * SnowDensity * SnowDensity * (TGrnd - TMean) / SnowDepth / (Dt);
+    else GroundFlux = 0;
+    DeltaColdContent -= GroundFlux;
+    double RestTerm = NetRad + SensibleHeat + LatentHeat + LatentHeatSub + AdvectedEnergy + GroundFlux -
+                      DeltaColdContent + 0.;
+    RefreezeEnergy = (SurfaceLiquidWater * Lf * RHO_W) / (Dt);
+    if (TSurf == 0.0 && RestTerm > -(RefreezeEnergy)) {
+      RefreezeEnergy = -RestTerm;
+      RestTerm = 0.0;
+    }
+    else RestTerm += RefreezeEnergy;
+    return RestTerm;
+  }
+};
+
+struct SnowMeltOut {
+  double melt, NetLongSnow, OldTSurf, advection, deltaCC, latent, latent_sub, refreeze_energy, sensible,
+         vapor_flux, aero_used0;
+};
+
+// s: snow state (swq, surf_temp, pack_temp, surf_water, pack_water, depth, density, coldcontent updated)
+VR_HDN void snow_melt(UnitS &s, double Le, double NetShortSnow, double Tcanopy, double Tgrnd, double Z0_2,
+                      double aero_resist, double air_temp, double delta_t, double density, double LongSnowIn,
+                      double pressure, double rainfall, double snowfall, double vp, double vpd, double wind,
+                      double z2, SnowMeltOut &o)
+{
+  double SnowFall = snowfall / 1000., RainFall = rainfall / 1000.;
+  o.OldTSurf = s.surf_temp;
+  double Ice = s.swq - s.pack_water - s.surf_water;
+  double SurfaceSwq = (Ice > MAX_SURFACE_SWE) ? MAX_SURFACE_SWE : Ice;
+  double PackSwq = Ice - SurfaceSwq;
+  double SurfaceCC = CH_ICE * SurfaceSwq * s.surf_temp;
+  double PackCC = CH_ICE * PackSwq * s.pack_temp;
+  double SnowFallCC = (air_temp > 0.0) ? 0.0 : CH_ICE * SnowFall * air_temp;
+  if (SnowFall > (MAX_SURFACE_SWE - SurfaceSwq) && (MAX_SURFACE_SWE - SurfaceSwq) > SMALLV) {
+    double DeltaPackSwq = SurfaceSwq + SnowFall - MAX_SURFACE_SWE, DeltaPackCC;
+    if (DeltaPackSwq > SurfaceSwq) DeltaPackCC = SurfaceCC + (SnowFall - MAX_SURFACE_SWE) / SnowFall * SnowFallCC;
+    else DeltaPackCC = DeltaPackSwq / SurfaceSwq * SurfaceCC;
+    SurfaceSwq = MAX_SURFACE_SWE;
+    SurfaceCC += SnowFallCC - DeltaPackCC;
+    PackSwq += DeltaPackSwq;
+    PackCC += DeltaPackCC;
+  }
+  else {
+    SurfaceSwq += SnowFall;
+    SurfaceCC += SnowFallCC;
+  }
+  s.surf_temp = (SurfaceSwq > 0.0) ? SurfaceCC / (CH_ICE * SurfaceSwq) : 0.0;
+  s.pack_temp = (PackSwq > 0.0) ? PackCC / (CH_ICE * PackSwq) : 0.0;
+  Ice += SnowFall;
+  s.surf_water += RainFall;
+
+  SnowPackEB x;
+  x.Dt = delta_t; x.Ra = aero_resist; x.Z = z2; x.Z0_2 = Z0_2; x.AirDens = density; x.EactAir = vp;
+  x.LongSnowIn = LongSnowIn; x.Lv = Le; x.Press = pressure; x.Rain = RainFall; x.NetShortUnder = NetShortSnow;
+  x.Vpd = vpd; x.Wind = wind; x.OldTSurf = o.OldTSurf; x.SnowDepth = s.depth; x.SnowDensity = s.density;
+  x.SurfaceLiquidWater = s.surf_water; x.SweSurfaceLayer = SurfaceSwq; x.Tair = Tcanopy; x.TGrnd = Tgrnd;
+
+  double Qnet = x(0.0);
+  double vapor_flux = x.vapor_flux;
+  double RefreezeEnergy = x.RefreezeEnergy;
+  if (Qnet == 0.0) {
+    double SnowMelt;
+    s.surf_temp = 0.0;
+    if (RefreezeEnergy >= 0.0) {
+      double RefrozenWater = RefreezeEnergy / (Lf * RHO_W) * delta_t;
+      if (RefrozenWater > s.surf_water) {
+        RefrozenWater = s.surf_water;
+        RefreezeEnergy = RefrozenWater * Lf * RHO_W / (delta_t);
+      }
+      SurfaceSwq += RefrozenWater;
+      Ice += RefrozenWater;
+      s.surf_water -= RefrozenWater;
+      if (s.surf_water < 0.0) s.surf_water = 0.0;
+      SnowMelt = 0.0;
+    }
+    else SnowMelt = fabs(RefreezeEnergy) / (Lf * RHO_W) * delta_t;
+    if (s.surf_water < -(vapor_flux)) {
+      vapor_flux = -(s.surf_water);
+      s.surf_water = 0.0;
+    }
+    else s.surf_water += vapor_flux;
+    if (SnowMelt < Ice) {
+      if (SnowMelt <= PackSwq) {
+        s.surf_water += SnowMelt;
+        PackSwq -= SnowMelt;
+        Ice -= SnowMelt;
+      }
+      else {
+        s.surf_water += SnowMelt + s.pack_water;
+        s.pack_water = 0.0;
+        PackSwq = 0.0;
+        Ice -= SnowMelt;
+        SurfaceSwq = Ice;
+      }
+    }
+    else {
+      SnowMelt = Ice;
+      s.surf_water += Ice;
+      SurfaceSwq = 0.0;
+      s.surf_temp = 0.0;
+      PackSwq = 0.0;
+      s.pack_temp = 0.0;
+      Ice = 0.0;
+      RefreezeEnergy = RefreezeEnergy / fabs(RefreezeEnergy) * SnowMelt * Lf * RHO_W / (delta_t);
+    }
+  }
+  else {
+    if (SurfaceSwq > MIN_SWQ_EB_THRES) {
+      s.surf_temp = root_brent(s.surf_temp - SNOW_DT, s.surf_temp + SNOW_DT, x);
+      if (s.surf_temp <= -998) {    // TFALLBACK (snow_melt.c:361-366)
+        s.surf_temp = o.OldTSurf;
+        s.fb_snow++;
+      }
+    }
+    else s.surf_temp = 999;
+    if (s.surf_temp > -998 && s.surf_temp < 999) {
+      Qnet = x(s.surf_temp);
+      vapor_flux = x.vapor_flux;
+      RefreezeEnergy = x.RefreezeEnergy;
+      SurfaceSwq += s.surf_water;
+      Ice += s.surf_water;
+      s.surf_water = 0.0;
+      if (SurfaceSwq < -(vapor_flux)) {
+        vapor_flux = -SurfaceSwq;
+        SurfaceSwq = 0.0;
+        Ice = PackSwq;
+      }
+      else {
+        SurfaceSwq += vapor_flux;
+        Ice += vapor_flux;
+      }
+    }
+    else {
+      vapor_flux = x.vapor_flux;
+      RefreezeEnergy = x.RefreezeEnergy;
+    }
+  }
+  double melt;
+  double MaxLiquidWater = LIQUID_WATER_CAPACITY * SurfaceSwq;
+  if (s.surf_water > MaxLiquidWater) {
+    melt = s.surf_water - MaxLiquidWater;
+    s.surf_water = MaxLiquidWater;
+  }
+  else melt = 0.0;
+  s.pack_water += melt;
+  double PackRefreezeEnergy = s.pack_water * Lf * RHO_W;
+  if (PackCC < -PackRefreezeEnergy) {
+    PackSwq += s.pack_water;
+    Ice += s.pack_water;
+    s.pack_water = 0.0;
+    if (PackSwq > 0.0) {
+      PackCC = PackSwq * CH_ICE * s.pack_temp + PackRefreezeEnergy;
+      s.pack_temp = PackCC / (CH_ICE * PackSwq);
+      if (s.pack_temp > 0.) s.pack_temp = 0.;
+    }
+    else s.pack_temp = 0.0;
+  }
+  else {
+    s.pack_temp = 0.0;
+    double DeltaPackSwq = -PackCC / (Lf * RHO_W);
+    s.pack_water -= DeltaPackSwq;
+    PackSwq += DeltaPackSwq;
+    Ice += DeltaPackSwq;
+  }
+  MaxLiquidWater = LIQUID_WATER_CAPACITY * PackSwq;
+  if (s.pack_water > MaxLiquidWater) {
+    melt = s.pack_water - MaxLiquidWater;
+    s.pack_water = MaxLiquidWater;
+  }
+  else melt = 0.0;
+  Ice = PackSwq + SurfaceSwq;
+  if (Ice > MAX_SURFACE_SWE) {
+    SurfaceCC = CH_ICE * s.surf_temp * SurfaceSwq;
+    PackCC = CH_ICE * s.pack_temp * PackSwq;
+    if (SurfaceSwq > MAX_SURFACE_SWE) {
+      PackCC += SurfaceCC * (SurfaceSwq - MAX_SURFACE_SWE) / SurfaceSwq;
+      SurfaceCC -= SurfaceCC * (SurfaceSwq - MAX_SURFACE_SWE) / SurfaceSwq;
+      PackSwq += SurfaceSwq - MAX_SURFACE_SWE;
+      SurfaceSwq -= SurfaceSwq - MAX_SURFACE_SWE;
+    }
+    else if (SurfaceSwq < MAX_SURFACE_SWE) {
+      PackCC -= PackCC * (MAX_SURFACE_SWE - SurfaceSwq) / PackSwq;
+      SurfaceCC += PackCC * (MAX_SURFACE_SWE - SurfaceSwq) / PackSwq;
+      PackSwq -= MAX_SURFACE_SWE - SurfaceSwq;
+      SurfaceSwq += MAX_SURFACE_SWE - SurfaceSwq;
+    }
+    s.pack_temp = PackCC / (CH_ICE * PackSwq);
+    s.surf_temp = SurfaceCC / (CH_ICE * SurfaceSwq);
+  }
+  else s.pack_temp = 0.0;
+  s.swq = Ice + s.pack_water + s.surf_water;
+  if (s.swq == 0.0) {
+    s.surf_temp = 0.0;
+    s.pack_temp = 0.0;
+  }
+  o.melt = melt * 1000.;
+  s.coldcontent = SurfaceCC;
+  o.vapor_flux = vapor_flux * -1.;
+  o.advection = x.AdvectedEnergy;
+  o.deltaCC = x.DeltaColdContent;
+  o.latent = x.LatentHeat;
+  o.latent_sub = x.LatentHeatSub;
+  o.sensible = x.SensibleHeat;
+  o.refreeze_energy = RefreezeEnergy;
+  o.NetLongSnow = x.NetLongUnder;
+  o.aero_used0 = x.Ra_used0;
+}
+
+VR_HD double new_snow_density(double air_temp)   // snow_utility.c, DENS_BRAS
+{
+  air_temp = air_temp * 9. / 5. + 32.;
+  if (air_temp > 0) return NEW_SNOW_DENSITY + 1000. * (air_temp / 100.) * (air_temp / 100.);
+  return NEW_SNOW_DENSITY;
+}
+
+VR_HD double snow_density(double surf_temp, double depth_in, double new_snow, double sswq, double Tair, double dt)
+{   // snow_utility.c snow_density, DENS_BRAS
+  double density_new = (new_snow > 0.) ? new_snow_density(Tair) : 0.0;
+  double Tavg = surf_temp + KELVIN, depth = depth_in, swq = sswq, density;
+  if (new_snow > 0) {
+    if (depth > 0.) {
+      double delta_depth = (((new_snow / 25.4) * (depth / 0.0254)) / (swq / 0.0254) *
+                            VR_POW((depth / 0.0254) / 10., 0.35)) * 0.0254;
+      if (delta_depth > 0.9 * depth) delta_depth = 0.9 * depth;
+      double depth_new = new_snow / density_new;
+      depth = depth - delta_depth + depth_new;
+      swq += new_snow / 1000.;
+      density = 1000. * swq / depth;
+    }
+    else {
+      density = density_new;
+      swq += new_snow / 1000.;
+      depth = 1000. * swq / density;
+    }
+  }
+  else density = 1000. * swq / depth_in;
+  if (depth > 0.) {
+    double overburden = 0.5 * G_GRAV * RHO_W * swq;
+    double viscosity = SNDENS_ETA0 * exp(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density);
+    double delta_depth = overburden / viscosity * depth * dt * 3600;
+    if (delta_depth > 0.9 * depth) delta_depth = 0.9 * depth;
+    depth -= delta_depth;
+    density = 1000. * swq / depth;
+  }
+  return density;
+}
+
+VR_HD double snow_albedo(double new_snow, double swq, double albedo, double cold_content, double dt,
+                         int last_snow, int MELTING)
+{   // snow_utility.c snow_albedo
+  if (new_snow > TraceSnow && cold_content < 0.0) albedo = NEW_SNOW_ALB;
+  else if (swq > 0.0) {
+    if (cold_content < 0.0 && !MELTING)
+      albedo = NEW_SNOW_ALB * VR_POW(SNOW_ALB_ACCUM_A, VR_POW((double)last_snow * dt / 24., SNOW_ALB_ACCUM_B));
+    else
+      albedo = NEW_SNOW_ALB * VR_POW(SNOW_ALB_THAW_A, VR_POW((double)last_snow * dt / 24., SNOW_ALB_THAW_B));
+  }
+  else albedo = 0;
+  return albedo;
+}
+
+// ---------------------------------------------------------------------------------------
+// evaporation (canopy_evap.c:46-529, arno_evap.c:62-203)
+// ---------------------------------------------------------------------------------------
+struct VegV { double Wdew, canopyevap, throughfall, LAI, Wdmax, vegcover; };
+
+VR_HD void transpiration(const double *moist, const VegV &v, const UnitC &uc, const CellC &cc, int NL,
+                         const PenmanAir &pa, double rad, double vpd, double net_short, double air_temp,
+                         double ra, double dryFrac, double delta_t, double *layerevap)
+{
+  double avail[MAXL], moist1 = 0.0, Wcr1 = 0.0, moist2;
+  for (int i = 0; i < NL - 1; i++) {
+    if (uc.root[i] > 0.) {
+      avail[i] = 0. + ((moist[i] - 0.) * 1.);
+      moist1 += avail[i];
+      Wcr1 += cc.Wcr[i];
+    }
+    else avail[i] = 0.;
+  }
+  int il = NL - 1;
+  moist2 = 0. + ((moist[il] - 0.) * 1.);
+  avail[il] = moist2;
+  if ((moist1 >= Wcr1 && moist2 >= cc.Wcr[il] && Wcr1 > 0.) || (moist1 >= Wcr1 && (1 - uc.root[il]) >= 0.5) ||
+      (moist2 >= cc.Wcr[il] && uc.root[il] >= 0.5)) {
+    double rc = calc_rc(uc.rmin, net_short, uc.RGL, air_temp, vpd, v.LAI, 1.0);
+    double evap = penman(pa, rad, vpd, ra, rc, uc.rarc) * delta_t / SEC_PER_DAY * dryFrac;
+    double root_sum = 1.0, spare_evap = 0.0;
+    for (int i = 0; i < NL; i++) {
+      if (avail[i] >= cc.Wcr[i]) layerevap[i] = evap * (double)uc.root[i];
+      else {
+        double gsm_inv = (avail[i] >= cc.Wpwp[i]) ? (avail[i] - cc.Wpwp[i]) / cc.wcr_m_wpwp[i] : 0.0;
+        layerevap[i] = evap * gsm_inv * (double)uc.root[i];
+        root_sum -= uc.root[i];
+        spare_evap = evap * (double)uc.root[i] * (1.0 - gsm_inv);
+      }
+    }
+    if (spare_evap > 0.0)
+      for (int i = 0; i < NL; i++)
+        if (avail[i] >= cc.Wcr[i]) layerevap[i] += (double)uc.root[i] * spare_evap / root_sum;
+  }
+  else {
+    for (int i = 0; i < NL; i++) {
+      double gsm_inv;
+      if (avail[i] >= cc.Wcr[i]) gsm_inv = 1.0;
+      else if (avail[i] >= cc.Wpwp[i] && avail[i] < cc.Wcr[i]) gsm_inv = (avail[i] - cc.Wpwp[i]) / cc.wcr_m_wpwp[i];
+      else gsm_inv = 0.0;
+      if (gsm_inv > 0.0) {
+        double rc = calc_rc(uc.rmin, net_short, uc.RGL, air_temp, vpd, v.LAI, gsm_inv);
+        layerevap[i] = penman(pa, rad, vpd, ra, rc, uc.rarc) * delta_t / SEC_PER_DAY * dryFrac * (double)uc.root[i];
+      }
+      else layerevap[i] = 0.0;
+    }
+  }
+  for (int i = 0; i < NL; i++) {
+    if (layerevap[i] > moist[i] - cc.Wpwp[i]) layerevap[i] = moist[i] - cc.Wpwp[i];
+    if (layerevap[i] < 0.0) layerevap[i] = 0.0;
+  }
+}
+
+// returns Evap (m/s); writes v.canopyevap, v.throughfall, v.Wdew and layerevap[]
+VR_HD double canopy_evap(const double *moist, VegV &v, bool CALC_EVAP, const UnitC &uc, const CellC &cc, int NL,
+                         const PenmanAir &pa, double Wdew_in, double delta_t, double rad, double vpd,
+                         double net_short, double air_temp, double ra, double ppt, double *layerevap)
+{
+  double throughfall = 0, tmp_Wdew = Wdew_in, canopyevap, f, wet23 = 0;
+  for (int i = 0; i < NL; i++) layerevap[i] = 0;
+  if (tmp_Wdew > v.Wdmax) {
+    throughfall = tmp_Wdew - v.Wdmax;
+    tmp_Wdew = v.Wdmax;
+  }
+  if (v.LAI > 0) {
+    wet23 = VR_POW((tmp_Wdew / v.Wdmax), (2.0 / 3.0));
+    // calc_rc(rs = 0) == 0
+    canopyevap = 240 * wet23 * penman(pa, rad, vpd, ra, 0., uc.rarc) * delta_t / SEC_PER_DAY;
+  }
+  else canopyevap = 0;
+  if (canopyevap > 0.0 && delta_t == SEC_PER_DAY)
+    f = (1.0 < ((tmp_Wdew + ppt) / canopyevap)) ? 1.0 : ((tmp_Wdew + ppt) / canopyevap);
+  else if (canopyevap > 0.0) f = (1.0 < ((tmp_Wdew) / canopyevap)) ? 1.0 : ((tmp_Wdew) / canopyevap);
+  else f = 1.0;
+  canopyevap *= f;
+  double dryFrac;
+  if (v.Wdmax > 0) {
+    if (!(v.LAI > 0)) wet23 = VR_POW((tmp_Wdew / v.Wdmax), (2.0 / 3.0));
+    dryFrac = 1.0 - f * wet23;
+  }
+  else dryFrac = 0;
+  tmp_Wdew += ppt - canopyevap;
+  if (tmp_Wdew < 0.0) tmp_Wdew = 0.0;
+  if (tmp_Wdew > v.Wdmax) {
+    throughfall += tmp_Wdew - v.Wdmax;
+    tmp_Wdew = v.Wdmax;
+  }
+  if (CALC_EVAP)
+    transpiration(moist, v, uc, cc, NL, pa, rad, vpd, net_short, air_temp, ra, dryFrac, delta_t, layerevap);
+  v.canopyevap = canopyevap;
+  v.throughfall = throughfall;
+  v.Wdew = tmp_Wdew;
+  double tmp_Evap = canopyevap;
+  for (int i = 0; i < NL; i++) tmp_Evap += layerevap[i];
+  return 0. + tmp_Evap / (1000. * delta_t);
+}
+
+// returns Evap (m/s); writes *evap0 (mm) = layer[0].evap
+VR_HD double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, double rad, double vpd, double ra,
+                       double delta_t, double *evap0)
+{
+  double moist = 0. + (moist0 - 0.) * 1., evap, tmp, ratio;
+  if (moist > cc.arno_maxm) moist = cc.arno_maxm;
+  double Epot = 240 * penman(pa, rad, vpd, ra, 0.0, RARC_SOIL) * delta_t / SEC_PER_DAY;
+  if (cc.b == -1.0) tmp = cc.arno_max_infil;
+  else {
+    ratio = 1.0 - (moist) / (cc.arno_maxm);
+    if (ratio > 1.0 || ratio < 0.0) return VERR;
+    ratio = VR_POW(ratio, cc.inv_b1);
+    tmp = cc.arno_max_infil * (1.0 - ratio);
+  }
+  if (tmp >= cc.arno_max_infil) evap = Epot;
+  else {
+    ratio = tmp / cc.arno_max_infil;
+    ratio = 1.0 - ratio;
+    if (ratio > 1.0 || ratio < 0.0) return VERR;
+    if (ratio != 0.0) ratio = VR_POW(ratio, cc.b);
+    double as = 1 - ratio;
+    ratio = VR_POW(ratio, cc.inv_b);
+    double dummy = 1.0, tmpsum = 1.0;
+    for (int n = 1; n <= 30; n++) {       // arno_evap.c:168-173; the inner product is a running power
+      tmpsum = (n == 1) ? ratio : tmpsum * ratio;
+      dummy += cc.b * tmpsum / (cc.b + n);
+    }
+    double beta_asp = as + (1.0 - as) * (1.0 - ratio) * dummy;
+    evap = 240 * Epot * beta_asp;
+  }
+  if (evap > 0.0) {
+    if (moist > cc.resid[0]) {
+      if (evap > moist - cc.resid[0]) evap = moist - cc.resid[0];
+    }
+    else evap = 0.0;
+  }
+  *evap0 = evap;
+  return 0. + evap / 1000. / delta_t;
+}
+
+// ---------------------------------------------------------------------------------------
+// canopy snow interception (snow_intercept.c:8-560, func_canopy_energy_bal.c:29-290, massrelease.c)
+// ---------------------------------------------------------------------------------------
+VR_HD void mass_release(double &IntSnow, double &TempInt, double &Released, double &Drip)
+{   // massrelease.c:35-93: the tail recursion written as a loop
+  for (;;) {
+    if (IntSnow > MIN_INTERCEPTION_STORAGE) {
+      double Threshold = 0.10 * IntSnow, MaxRelease = 0.17 * IntSnow;
+      if (TempInt >= Threshold) {
+        Drip += Threshold;
+        IntSnow -= Threshold;
+        TempInt -= Threshold;
+        double rel;
+        if (IntSnow < MIN_INTERCEPTION_STORAGE) rel = 0.0;
+        else rel = ((IntSnow - MIN_INTERCEPTION_STORAGE) < MaxRelease) ? (IntSnow - MIN_INTERCEPTION_STORAGE) : MaxRelease;
+        Released += rel;
+        IntSnow -= rel;
+        continue;
+      }
+      double TempDrip = (TempInt < IntSnow) ? TempInt : IntSnow;
+      Drip += TempDrip;
+      IntSnow -= TempDrip;
+      return;
+    }
+    double TempDrip = (TempInt < IntSnow) ? TempInt : IntSnow;
+    Drip += TempDrip;
+    IntSnow -= TempDrip;
+    TempInt = 0.0;
+    return;
+  }
+}
+
+struct CanopyEB {
+  // inputs
+  double delta_t, AirDens, EactAir, Press, Le, Tcanopy, Vpd, Ra0, Ra1, Rainfall, IntRainOrg, IntSnow,
+         LongOverIn, LongUnderOut, NetShortOver;
+  const double *moist; VegV *v; const UnitC *uc; const CellC *cc; const PenmanAir *pa; int NL;
+  // outputs of the last evaluation
+  double Ra_used0, Ra_used1, IntRain, AdvectedEnergy, LatentHeat, LatentHeatSub, LongOverOut, NetLongOver,
+         RefreezeEnergy, SensibleHeat, VaporMassFlux;
+  VR_HD double operator()(double Tfoliage)
+  {
+    double Tmp = Tfoliage + KELVIN;
+    LongOverOut = STEFAN_B * (Tmp * Tmp * Tmp * Tmp);
+    double NetRadiation = NetShortOver + LongOverIn + LongUnderOut - 2 * (LongOverOut);
+    NetLongOver = LongOverIn - (LongOverOut);
+    if (IntSnow > 0) {
+      Ra_used0 = Ra0;
+      Ra_used1 = Ra1;
+      Ra_used1 *= 10.;                      // AR_406_FULL (func_canopy_energy_bal.c:195-196)
+      double EsSnow = svp(Tfoliage);
+      VaporMassFlux = AirDens * (EPS / Press) * (EactAir - EsSnow) / Ra_used1 / RHO_W;
+      if (Vpd == 0.0 && VaporMassFlux < 0.0) VaporMassFlux = 0.0;
+      double Ls = (677. - 0.07 * Tfoliage) * JOULESPCAL * GRAMSPKG;
+      LatentHeatSub = Ls * VaporMassFlux * RHO_W;
+      LatentHeat = 0;
+      v->throughfall = 0;
+    }
+    else {
+      Ra_used0 = Ra0;
+      Ra_used1 = Ra1;
+      double le[MAXL];
+      double Evap = canopy_evap(moist, *v, false, *uc, *cc, NL, *pa, IntRainOrg * 1000., delta_t, NetRadiation,
+                                Vpd, NetShortOver, Tcanopy, Ra_used1, Rainfall * 1000, le);
+      IntRain = v->Wdew / 1000.;    // *Wdew aliases *IntRain in the reference call (snow_intercept.c:399-416)
+      LatentHeat = Le * Evap * RHO_W;
+      LatentHeatSub = 0;
+    }
+    SensibleHeat = AirDens * Cp * (Tcanopy - Tfoliage) / Ra_used1;
+    AdvectedEnergy = (CH_WATER * Tcanopy * Rainfall) / (delta_t);
+    double RestTerm = SensibleHeat + LatentHeat + LatentHeatSub + NetRadiation + AdvectedEnergy;
+    if (IntSnow > 0) {
+      RefreezeEnergy = (IntRainOrg * Lf * RHO_W) / (delta_t);
+      if (Tfoliage == 0.0 && RestTerm > -(RefreezeEnergy)) {
+        RefreezeEnergy = -RestTerm;
+        RestTerm = 0.0;
+      }
+      else RestTerm += RefreezeEnergy;
+    }
+    else RefreezeEnergy = 0;
+    return RestTerm;
+  }
+};
+
+struct InterceptOut {
+  double AlbedoOver, canopy_refreeze, NetLongOver, NetShortOver, LongOverOut, canopy_vapor_flux, Ra_used0,
+         Ra_used1;
+  bool ra_written;
+};
+
+// Dt seconds; F == 1.  Updates s.snow_canopy, s.tmp_int_storage, s.Tfoliage, v.Wdew (IntRain, mm),
+// rainfall/snowfall (mm, in: above canopy, out: below canopy).
+VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, int NL, const PenmanAir &pa,
+                           const Forc &f, double Dt, double Le, double LongOverIn, double ShortOverIn,
+                           double Tcanopy, double bare_albedo, double Ra0, double Ra1, double wind1,
+                           double &RainFall, double &SnowFall, InterceptOut &o)
+{
+  double IntRain = v.Wdew, IntSnow = s.snow_canopy, MaxInt = v.Wdmax, LAI = v.LAI;
+  RainFall /= 1000.;
+  SnowFall /= 1000.;
+  IntRain /= 1000.;
+  MaxInt /= 1000.;
+  double IntRainOrg = IntRain;
+  IntSnow /= 1.;
+  IntRain /= 1.;
+  double InitialSnowInt = IntSnow, Drip = 0.0, ReleasedMass = 0.0, OldTfoliage = s.Tfoliage;
+  double Imax1 = 4.0 * LAI_SNOW_MULTIPLIER * LAI, MaxSnowInt, DeltaSnowInt;
+  if (s.Tfoliage < -1.0 && s.Tfoliage > -3.0) MaxSnowInt = (s.Tfoliage * 3.0 / 2.0) + (11.0 / 2.0);
+  else if (s.Tfoliage > -1.0) MaxSnowInt = 4.0;
+  else MaxSnowInt = 1.0;
+  MaxSnowInt *= LAI_SNOW_MULTIPLIER * LAI;
+  if (MaxSnowInt > 0) {
+    DeltaSnowInt = (1 - IntSnow / MaxSnowInt) * SnowFall;
+    if (DeltaSnowInt + IntSnow > MaxSnowInt) DeltaSnowInt = MaxSnowInt - IntSnow;
+    if (DeltaSnowInt < 0.0) DeltaSnowInt = 0.0;
+  }
+  else DeltaSnowInt = 0.0;
+  if (s.Tfoliage < -3.0 && DeltaSnowInt > 0.0 && wind1 > 1.0) {
+    double BlownSnow = (0.2 * wind1 - 0.2) * DeltaSnowInt;
+    if (BlownSnow >= DeltaSnowInt) BlownSnow = DeltaSnowInt;
+    DeltaSnowInt -= BlownSnow;
+  }
+  if (IntSnow + DeltaSnowInt > Imax1) DeltaSnowInt = 0.0;
+  double SnowThroughFall = (SnowFall - DeltaSnowInt) * 1. + (SnowFall) * (1 - 1.);
+  if (SnowFall == 0 && IntSnow < MIN_SWQ_EB_THRES) {
+    SnowThroughFall += IntSnow;
+    DeltaSnowInt -= IntSnow;
+  }
+  IntSnow += DeltaSnowInt;
+  if (IntSnow < SMALLV) IntSnow = 0.0;
+  double MaxWaterInt = LIQUID_WATER_CAPACITY * (IntSnow) + MaxInt, RainThroughFall;
+  if ((IntRain + RainFall) <= MaxWaterInt) {
+    IntRain += RainFall;
+    RainThroughFall = RainFall * (1 - 1.);
+  }
+  else {
+    RainThroughFall = (IntRain + RainFall - MaxWaterInt) * 1. + (RainFall * (1 - 1.));
+    IntRain = MaxWaterInt;
+  }
+  if (RainFall == 0 && IntRain < MIN_SWQ_EB_THRES) {
+    RainThroughFall += IntRain;
+    IntRain = 0.0;
+  }
+  if (IntRain + IntSnow > Imax1) {
+    double Overload = (IntSnow + IntRain) - Imax1;
+    double IntRainFract = IntRain / (IntRain + IntSnow);
+    double IntSnowFract = IntSnow / (IntRain + IntSnow);
+    IntRain = IntRain - Overload * IntRainFract;
+    IntSnow = IntSnow - Overload * IntSnowFract;
+    RainThroughFall = RainThroughFall + (Overload * IntRainFract) * 1.;
+    SnowThroughFall = SnowThroughFall + (Overload * IntSnowFract) * 1.;
+  }
+  if (IntRain + IntSnow < SMALLV) s.Tfoliage = Tcanopy;
+
+  CanopyEB x;
+  x.delta_t = Dt; x.AirDens = f.density; x.EactAir = f.vp; x.Press = f.pressure; x.Le = Le; x.Tcanopy = Tcanopy;
+  x.Vpd = f.vpd; x.Ra0 = Ra0; x.Ra1 = Ra1; x.Rainfall = RainFall; x.IntRainOrg = IntRainOrg; x.IntSnow = IntSnow;
+  x.LongOverIn = LongOverIn; x.LongUnderOut = s.LongUnderOut; x.moist = s.moist; x.v = &v; x.uc = &uc; x.cc = &cc;
+  x.pa = &pa; x.NL = NL; x.IntRain = IntRain; x.RefreezeEnergy = 0; x.VaporMassFlux = 0;
+  x.Ra_used0 = Ra0; x.Ra_used1 = Ra1;
+  o.ra_written = false;
+
+  double Tupper = MISSINGV, Tlower = MISSINGV, Qnet;
+  if (IntSnow > 0 || SnowFall > 0) {
+    o.AlbedoOver = NEW_SNOW_ALB;
+    o.NetShortOver = (1. - o.AlbedoOver) * ShortOverIn;
+    x.NetShortOver = o.NetShortOver;
+    Qnet = x(0.);
+    o.ra_written = true;
+    if (Qnet != 0) {
+      Tupper = 0;
+      if (s.Tfoliage <= 0.) Tlower = s.Tfoliage - SNOW_DT;
+      else Tlower = -SNOW_DT;
+    }
+    else s.Tfoliage = 0.;
+  }
+  else {
+    o.AlbedoOver = bare_albedo;
+    o.NetShortOver = (1. - o.AlbedoOver) * ShortOverIn;
+    x.NetShortOver = o.NetShortOver;
+    Tupper = s.Tfoliage + SNOW_DT;
+    Tlower = s.Tfoliage - SNOW_DT;
+  }
+  if (Tupper != MISSINGV && Tlower != MISSINGV) {
+    s.Tfoliage = root_brent(Tlower, Tupper, x);
+    if (s.Tfoliage <= -998) {     // TFALLBACK (snow_intercept.c:418-423)
+      s.Tfoliage = OldTfoliage;
+      s.fb_fol++;
+    }
+    Qnet = x(s.Tfoliage);
+    o.ra_written = true;
+  }
+  IntRain = x.IntRain;
+  double RefreezeEnergy = x.RefreezeEnergy, VaporMassFlux = x.VaporMassFlux;
+  if (IntSnow <= 0) RainThroughFall = v.throughfall / 1000.;
+  RefreezeEnergy *= Dt;
+  MaxWaterInt = LIQUID_WATER_CAPACITY * (IntSnow) + MaxInt;
+  VaporMassFlux *= Dt;
+  if (s.Tfoliage == 0) {
+    if (-(VaporMassFlux) > IntRain) {
+      VaporMassFlux = -(IntRain);
+      IntRain = 0.;
+    }
+    else IntRain += VaporMassFlux;
+    double PotSnowMelt;
+    if (RefreezeEnergy < 0)
+      PotSnowMelt = ((-RefreezeEnergy / Lf / RHO_W) < IntSnow) ? (-RefreezeEnergy / Lf / RHO_W) : IntSnow;
+    else PotSnowMelt = 0;
+    if ((IntRain + PotSnowMelt) <= MaxWaterInt) {
+      IntSnow -= PotSnowMelt;
+      IntRain += PotSnowMelt;
+    }
+    else {
+      double ExcessSnowMelt = PotSnowMelt + IntRain - MaxWaterInt;
+      IntSnow -= MaxWaterInt - (IntRain);
+      IntRain = MaxWaterInt;
+      if (IntSnow < 0.0) IntSnow = 0.0;
+      if (SnowThroughFall > 0.0 && InitialSnowInt <= MIN_INTERCEPTION_STORAGE) {
+        Drip += ExcessSnowMelt;
+        IntSnow -= ExcessSnowMelt;
+        if (IntSnow < 0.0) IntSnow = 0.0;
+      }
+      else s.tmp_int_storage += ExcessSnowMelt;
+      mass_release(IntSnow, s.tmp_int_storage, ReleasedMass, Drip);
+    }
+    MaxWaterInt = LIQUID_WATER_CAPACITY * (IntSnow) + MaxInt;
+    if (IntRain > MaxWaterInt) {
+      Drip += IntRain - MaxWaterInt;
+      IntRain = MaxWaterInt;
+    }
+  }
+  else {
+    s.tmp_int_storage = 0.0;
+    if (-RefreezeEnergy > -(IntRain)*Lf) {
+      IntSnow += fabs(RefreezeEnergy) / Lf;
+      IntRain -= fabs(RefreezeEnergy) / Lf;
+      RefreezeEnergy = 0.0;
+    }
+    else {
+      IntSnow += IntRain;
+      IntRain = 0.0;
+    }
+    if (-(VaporMassFlux) > IntSnow) {
+      VaporMassFlux = -(IntSnow);
+      IntSnow = 0.0;
+    }
+    else IntSnow += VaporMassFlux;
+  }
+  if (IntSnow == 0 && IntRain > MaxInt) {
+    RainThroughFall += IntRain - MaxInt;
+    IntRain = MaxInt;
+  }
+  RainFall = RainThroughFall + Drip;
+  SnowFall = SnowThroughFall + ReleasedMass;
+  VaporMassFlux *= -1.;
+  RainFall *= 1000.;
+  SnowFall *= 1000.;
+  IntRain *= 1000.;
+  s.snow_canopy = IntSnow;
+  v.Wdew = IntRain;
+  o.canopy_refreeze = RefreezeEnergy / Dt;
+  o.NetLongOver = x.NetLongOver;
+  o.LongOverOut = x.LongOverOut;
+  o.canopy_vapor_flux = VaporMassFlux;
+  o.Ra_used0 = x.Ra_used0;
+  o.Ra_used1 = x.Ra_used1;
+  (void)Qnet;
+}
+
+// ---------------------------------------------------------------------------------------
+// runoff.c:7-576 (Nfrost == 1, no ice): infiltration, hourly drainage, ARNO baseflow
+// ---------------------------------------------------------------------------------------
+VR_HD void runoff_and_asat(const CellC &cc, const double *moist, int NL, double inflow, double *A, double *runoff)
+{
+  double top_moist = 0.;
+  for (int l = 0; l < NL - 1; l++) top_moist += moist[l];
+  if (top_moist > cc.top_max) top_moist = cc.top_max;
+  *A = 1.0 - VR_POW((1.0 - top_moist / cc.top_max), cc.ex);
+  if (inflow == 0.0) { *runoff = 0.0; return; }
+  double i_0 = cc.top_max_infil * (1.0 - VR_POW((1.0 - *A), cc.inv_b));
+  if (cc.top_max_infil == 0.0) *runoff = inflow;
+  else if ((i_0 + inflow) > cc.top_max_infil) *runoff = inflow - cc.top_max + top_moist;
+  else {
+    double basis = 1.0 - (i_0 + inflow) / cc.top_max_infil;
+    *runoff = (inflow - cc.top_max + top_moist + cc.top_max * VR_POW(basis, cc.one_plus_b));
+  }
+  if (*runoff < 0.) *runoff = 0.;
+}
+
+// moist[]: in/out (mm); evap_l[]: in layer evaporation for the step (mm), evap_l[NL-1] may be reduced
+VR_HD void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moist, double *evap_l, double *asat,
+                       double *runoff_out, double *baseflow_out)
+{
+  double liq[MAXL], evap[MAXL], Q12[MAXL - 1], A, runoff_, baseflow = 0;
+  for (int l = 0; l < NL; l++) {
+    evap[l] = evap_l[l] / (double)dt;
+    liq[l] = moist[l];
+    if (evap[l] > 0) {
+      double avail_liq = (moist[l] - 0. - cc.resid[l]);
+      if (avail_liq < 0) avail_liq = 0;
+      double sum_liq = 0. + avail_liq * 1.;
+      double evap_fraction = (sum_liq > 0) ? evap[l] / sum_liq : 1.0;
+      evap[l] = avail_liq * evap_fraction;
+    }
+  }
+  runoff_and_asat(cc, liq, NL, ppt, &A, &runoff_);
+  double tmp_dt_runoff = runoff_ / (double)dt, dt_inflow = ppt / (double)dt;
+  for (int ts = 0; ts < dt; ts++) {
+    double inflow = dt_inflow;
+    for (int l = 0; l < NL - 1; l++) {
+      double tmp_liq = liq[l] - evap[l];
+      if (tmp_liq < cc.resid[l]) tmp_liq = cc.resid[l];
+      if (liq[l] > cc.resid[l]) Q12[l] = cc.ksat24[l] * VR_POW(((tmp_liq - cc.resid[l]) / cc.qden[l]), cc.expt[l]);
+      else Q12[l] = 0.;
+    }
+    for (int l = 0; l < NL - 1; l++) {
+      double dt_runoff = (l == 0) ? tmp_dt_runoff : 0, tmp_inflow = 0.;
+      liq[l] = liq[l] + (inflow - dt_runoff) - (Q12[l] + evap[l]);
+      if ((liq[l] + 0.) > cc.max_moist[l]) {
+        tmp_inflow = (liq[l] + 0.) - cc.max_moist[l];
+        liq[l] = cc.max_moist[l] - 0.;
+        if (l == 0) {
+          Q12[l] += tmp_inflow;
+          tmp_inflow = 0;
+        }
+        else {
+          int tl = l;
+          while (tmp_inflow > 0) {
+            tl--;
+            if (tl < 0) {
+              runoff_ += tmp_inflow;
+              tmp_inflow = 0;
+            }
+            else {
+              liq[tl] += tmp_inflow;
+              if ((liq[tl] + 0.) > cc.max_moist[tl]) {
+                tmp_inflow = ((liq[tl] + 0.) - cc.max_moist[tl]);
+                liq[tl] = cc.max_moist[tl] - 0.;
+              }
+              else tmp_inflow = 0;
+            }
+          }
+        }
+      }
+      if (liq[l] < 0) {
+        Q12[l] += liq[l];
+        liq[l] = 0;
+      }
+      if ((liq[l] + 0.) < cc.resid[l]) {
+        Q12[l] += (liq[l] + 0.) - cc.resid[l];
+        liq[l] = cc.resid[l] - 0.;
+      }
+      inflow = (Q12[l] + tmp_inflow);
+      Q12[l] += tmp_inflow;
+    }
+    int l = NL - 1;
+    double rel_moist = (liq[l] - cc.resid[l]) / cc.qden[l];
+    double dt_baseflow = cc.bf_frac * rel_moist;
+    if (rel_moist > cc.Ws) {
+      double frac = (rel_moist - cc.Ws) / cc.one_m_Ws;
+      dt_baseflow += cc.bf_nl * VR_POW(frac, cc.c);
+    }
+    if (dt_baseflow < 0) dt_baseflow = 0;
+    liq[l] += Q12[l - 1] - (evap[l] + dt_baseflow);
+    if ((liq[l] + 0.) < cc.resid[l]) {
+      dt_baseflow += (liq[l] + 0.) - cc.resid[l];
+      liq[l] = cc.resid[l] - 0.;
+    }
+    if ((liq[l] + 0.) > cc.max_moist[l]) {
+      double tmp_moist = ((liq[l] + 0.) - cc.max_moist[l]);
+      liq[l] = cc.max_moist[l] - 0.;
+      int tl = l;
+      while (tmp_moist > 0) {
+        tl--;
+        if (tl < 0) {
+          runoff_ += tmp_moist;
+          tmp_moist = 0;
+        }
+        else {
+          liq[tl] += tmp_moist;
+          if ((liq[tl] + 0.) > cc.max_moist[tl]) {
+            tmp_moist = ((liq[tl] + 0.) - cc.max_moist[tl]);
+            liq[tl] = cc.max_moist[tl] - 0.;
+          }
+          else tmp_moist = 0;
+        }
+      }
+    }
+    baseflow += dt_baseflow;
+  }
+  if (baseflow < 0) {
+    evap_l[NL - 1] += baseflow;
+    baseflow = 0;
+  }
+  double dummy;
+  runoff_and_asat(cc, liq, NL, 0., &A, &dummy);
+  for (int l = 0; l < NL; l++) moist[l] = 0. + ((liq[l] + 0.) * 1.);
+  *asat = 0. + A * 1.;
+  *runoff_out = 0. + runoff_ * 1.;
+  *baseflow_out = 0. + baseflow * 1.;
+}
+
+// ---------------------------------------------------------------------------------------
+// one unit, one record
+// ---------------------------------------------------------------------------------------
+// tm: this tile's TM_* terms for the month; ae: this tile's AE_* coefficients for the month
+VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
+                     int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o)
+{
+  const double delta_t = (double)dt_hours * 3600.;
+  const bool is_veg = !uc.is_bare;
+  const bool overstory = uc.overstory != 0;
+  VegV v;
+  double BareAlbedo, surf_atten;
+  // ---- full_energy.c:210-227,306-316: canopy terms of the month ----
+  if (is_veg) {
+    v.vegcover = tm[TM_VEGCOVER];
+    v.LAI = tm[TM_LAI];
+    v.Wdmax = tm[TM_WDMAX];
+    s.Wdew /= v.vegcover;
+    s.snow_canopy /= v.vegcover;
+    BareAlbedo = tm[TM_ALBEDO];
+    surf_atten = tm[TM_SURF_ATTEN];
+  }
+  else {
+    v.vegcover = 0; v.LAI = 0; v.Wdmax = 0;
+    BareAlbedo = BARE_SOIL_ALBEDO;
+    surf_atten = 1.;
+  }
+  v.Wdew = s.Wdew; v.canopyevap = 0; v.throughfall = 0;
+
+  // ---- prepare_full_energy.c:55-110 -> soil_conduction.c:5-61: kappa, Cs of layers 0 and 1 from the
+  //      pre-step moisture; Kdry, Ksat and the solid heat capacity are per-cell constants ----
+  double kappa[2], Cs[2];
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    double mv = s.moist[l] / cc.depth[l] / 1000;
+    double K;
+    if (mv > 0.) {
+      double Sr = mv / cc.poros[l];
+      double Ke = 0.7 * log10(Sr) + 1.0;
+      K = cc.ksat_m_kdry[l] * Ke + cc.kdry[l];
+      if (K < cc.kdry[l]) K = cc.kdry[l];
+    }
+    else K = cc.kdry[l];
+    kappa[l] = K;
+    double c = cc.cs_solid[l];
+    c += 4.2e6 * mv;
+    c += 1.3e3 * (1. - (cc.soilfr[l] + mv + 0.));
+    Cs[l] = c;
+  }
+
+  // ---- aerodynamics of the current cover: Ra = RA/wind, U = UC*wind (CalcAerodynamic.c:232-257) ----
+  double Ra[3], U[3];
+  if (f.wind > 0.) {
+    Ra[0] = ae[AE_RA0] / f.wind; Ra[1] = ae[AE_RA1] / f.wind; Ra[2] = ae[AE_RA2] / f.wind;
+  }
+  else { Ra[0] = HUGE_RESIST; Ra[1] = HUGE_RESIST; Ra[2] = HUGE_RESIST; }
+  U[0] = ae[AE_U0] * f.wind; U[1] = ae[AE_U1] * f.wind; U[2] = ae[AE_U2] * f.wind;
+  double ra_used0 = Ra[0], ra_used1 = Ra[1];
+
+  // ---- surface_fluxes.c:480-560 ----
+  const double Tair = f.air_temp + uc.Tfactor;
+  const double step_prec = f.prec * uc.Pfactor;
+  const double Tgrnd = s.T0, Tcanopy = Tair;
+  double coverage = s.coverage;
+  const double step_depth_old = s.depth, step_surf_temp_old = s.surf_temp;
+  const PenmanAir pa = penman_air(Tair, cc.half_elev_lapse, cc.elev);
+
+  // ---- solve_snow.c:7-577 ----
+  double rainonly = 0.;
+  if (Tair < max_snow_temp && Tair > min_rain_temp) rainonly = (Tair - min_rain_temp) / (max_snow_temp - min_rain_temp) * step_prec;
+  else if (Tair >= max_snow_temp) rainonly = step_prec;
+  double snowfall = 1. * (step_prec - rainonly), rainfall = 1. * rainonly;
+  if (snowfall < 1e-5) snowfall = 0.;
+  const double out_prec = snowfall + rainfall, out_rain = rainfall, out_snow = snowfall, store_snowfall = snowfall;
+  const double Le = (2.501e6 - 0.002361e6 * Tair);
+  int UnderStory = (s.swq > 0 || snowfall > 0) ? 2 : 0;
+  double ShortUnderIn = f.shortwave, LongUnderIn = f.longwave;
+  double melt = 0., ppt = 0., melt_energy = 0., NetLongSnow = 0., NetShortSnow = 0., NetShortGrnd = 0.,
+         delta_coverage = 0., AlbedoUnder, OldTSurf = 0., vapor_flux = 0., canopy_vapor_flux = 0.;
+  double es_latent = 0., es_latent_sub = 0., es_sensible = 0., es_advection = 0., es_deltaCC = 0., es_refreeze = 0.;
+  double AlbedoOver = 0., NetLongOver = 0., NetShortOver = 0., LongOverIn = 0.;
+  int snow_flag;
+  if (s.swq > 0 || snowfall > 0. || (s.snow_canopy > 0. && overstory)) {
+    snow_flag = 1;
+    if (!overstory) surf_atten = 1.;
+    const double old_coverage = s.coverage;
+    if (is_veg) {
+      if (overstory) {
+        ShortUnderIn *= surf_atten;
+        double ShortOverIn = (1. - surf_atten) * f.shortwave;
+        ShortOverIn /= v.vegcover;
+        InterceptOut io;
+        snow_intercept(s, v, uc, cc, NL, pa, f, (double)dt_hours * 3600, Le, f.longwave, ShortOverIn, Tcanopy,
+                       BareAlbedo, Ra[0], Ra[1], U[1], rainfall, snowfall, io);
+        LongUnderIn = io.LongOverOut;
+        AlbedoOver = io.AlbedoOver; NetLongOver = io.NetLongOver; NetShortOver = io.NetShortOver;
+        canopy_vapor_flux = io.canopy_vapor_flux;
+        ra_used0 = io.Ra_used0; ra_used1 = io.Ra_used1;
+        v.throughfall = rainfall + snowfall;
+        LongOverIn = f.longwave;
+      }
+      else if (snowfall > 0. && v.Wdew > 0.) {
+        rainfall += v.Wdew;
+        v.throughfall = rainfall + snowfall;
+        v.Wdew = 0.;
+        s.Tfoliage = Tair;
+      }
+      else {
+        v.throughfall = rainfall + snowfall;
+        s.Tfoliage = Tair;
+      }
+      v.throughfall = (1 - v.vegcover) * (out_prec) + v.vegcover * v.throughfall;
+      rainfall = (1 - v.vegcover) * (out_rain) + v.vegcover * (rainfall);
+      snowfall = (1 - v.vegcover) * (out_snow) + v.vegcover * (snowfall);
+      canopy_vapor_flux *= v.vegcover;
+      s.snow_canopy *= v.vegcover;
+      v.Wdew *= v.vegcover;
+      v.canopyevap *= v.vegcover;
+      NetShortOver *= v.vegcover;
+      NetLongOver *= v.vegcover;
+    }
+    if (s.swq > 0.0 || snowfall > 0) {
+      const double old_swq = s.swq;
+      UnderStory = 2;
+      if (s.swq > 0 && store_snowfall == 0) {
+        s.last_snow++;
+        s.albedo = snow_albedo(snowfall, s.swq, s.albedo, s.coldcontent, (double)dt_hours, s.last_snow, s.MELTING);
+        AlbedoUnder = (coverage * s.albedo + (1. - coverage) * BareAlbedo);
+      }
+      else {
+        s.last_snow = 0;
+        s.albedo = NEW_SNOW_ALB;
+        AlbedoUnder = s.albedo;
+      }
+      NetShortSnow = (1.0 - AlbedoUnder) * (ShortUnderIn);
+      SnowMeltOut mo;
+      snow_melt(s, Le, NetShortSnow, Tcanopy, Tgrnd, ae[AE_ROUGH2], Ra[2], Tair, (double)dt_hours * 3600, f.density,
+                LongUnderIn, f.pressure, rainfall, snowfall, f.vp, f.vpd, U[2], ae[AE_REF2], mo);
+      ra_used0 = mo.aero_used0;
+      vapor_flux = mo.vapor_flux; NetLongSnow = mo.NetLongSnow; OldTSurf = mo.OldTSurf;
+      es_advection = mo.advection; es_deltaCC = mo.deltaCC; es_latent = mo.latent; es_latent_sub = mo.latent_sub;
+      es_refreeze = mo.refreeze_energy; es_sensible = mo.sensible;
+      melt = mo.melt;
+      ppt += melt;
+      if (s.swq > 0.) {
+        if (s.surf_temp <= 0) s.density = snow_density(s.surf_temp, s.depth, snowfall, old_swq, Tair, (double)dt_hours);
+        else if (s.last_snow == 0) s.density = new_snow_density(Tair);
+        s.depth = 1000. * s.swq / s.density;
+        if (s.coldcontent >= 0 && ((cc.lat >= 0 && (f.doy > 60 && f.doy < 273)) || (cc.lat < 0 && (f.doy < 60 || f.doy > 273))))
+          s.MELTING = 1;
+        else if (s.MELTING && snowfall > TraceSnow) s.MELTING = 0;
+        s.coverage = 1.;
+      }
+      else s.coverage = 0.;
+      delta_coverage = old_coverage - s.coverage;
+      if (delta_coverage != 0) {
+        if (old_coverage > s.coverage) {
+          coverage = (old_coverage);
+          AlbedoUnder = (coverage - s.coverage) / (1. - s.coverage) * s.albedo;
+          AlbedoUnder += (1. - coverage) / (1. - s.coverage) * BareAlbedo;
+          melt_energy = (delta_coverage) * (es_advection - es_deltaCC + es_latent + es_latent_sub + es_sensible + es_refreeze + 0.);
+        }
+        else {
+          coverage = s.coverage;
+          delta_coverage = 0;
+        }
+      }
+      else if (old_coverage == 0 && s.coverage == 0) {
+        delta_coverage = 1.;
+        coverage = 0.;
+        melt_energy = (es_advection - es_deltaCC + es_latent + es_latent_sub + es_sensible + es_refreeze + 0.);
+      }
+      NetLongSnow *= (s.coverage);
+      NetShortSnow *= (s.coverage);
+      NetShortGrnd *= (s.coverage);
+      es_latent *= (s.coverage + delta_coverage);
+      es_latent_sub *= (s.coverage + delta_coverage);
+      es_sensible *= (s.coverage + delta_coverage);
+      if (s.swq == 0) {
+        s.density = 0.; s.depth = 0.; s.surf_water = 0; s.pack_water = 0; s.surf_temp = 0; s.pack_temp = 0;
+        s.coverage = 0; s.MELTING = 0;
+      }
+      snowfall = 0;
+      rainfall = 0;
+    }
+    else {
+      ppt += rainfall;
+      AlbedoOver = 0.;
+      AlbedoUnder = BareAlbedo;
+      s.last_snow = (int)MISSINGV;
+      s.MELTING = 0;
+    }
+  }
+  else {
+    UnderStory = 0;
+    snow_flag = 0;
+    AlbedoUnder = BareAlbedo;
+    s.Tfoliage = Tcanopy;
+    s.MELTING = 0;
+    s.last_snow = (int)MISSINGV;
+    s.albedo = NEW_SNOW_ALB;
+  }
+  (void)AlbedoUnder; (void)coverage;
+
+  // ---- surface_fluxes.c:680-695: thin pack -> solved together with the ground ----
+  bool INCLUDE_SNOW = false;
+  double eo_advection = 0.;
+  if (s.surf_temp == 999 && s.swq > 0) {
+    INCLUDE_SNOW = true;
+    eo_advection = es_advection;
+    s.surf_temp = step_surf_temp_old;
+    melt_energy = 0;
+  }
+
+  // ---- calc_surf_energy_bal.c (FULL_ENERGY FALSE: Tsurf = Tair) + func_surf_energy_bal.c ----
+  const bool VEG = is_veg && v.vegcover > 0.0;
+  const double T2 = cc.avg_T, Ts_old = s.T0, T1_old = s.T1, D1 = cc.D1, D2 = cc.D1;
+  const double kappa1 = kappa[0], kappa2 = kappa[1], Cs1 = Cs[0], Cs2 = Cs[1];
+  double Tsnow_surf = s.surf_temp;
+  const double Wdew_in = v.Wdew;
+  const double snow_coverage = s.coverage, SnowAlbedo = s.albedo;
+  const double snow_depth = (step_depth_old + s.depth) / 2.;
+  const double kappa_snow = (s.depth > 0.) ? K_SNOW * (s.density) * (s.density) / snow_depth : 0;
+  (void)kappa_snow;
+  const double NetShortBare = (ShortUnderIn * (1. - (snow_coverage + delta_coverage)) * (1. - BareAlbedo) +
+                               ShortUnderIn * (delta_coverage) * (1. - SnowAlbedo));
+  const double LongBareIn = (1. - snow_coverage) * LongUnderIn;
+  double TmpNetLongSnow, TmpNetShortSnow, LongSnowIn;
+  if (INCLUDE_SNOW || s.swq == 0) {
+    TmpNetLongSnow = NetLongSnow;
+    TmpNetShortSnow = NetShortSnow;
+    LongSnowIn = snow_coverage * LongUnderIn;
+  }
+  else { TmpNetShortSnow = 0.; TmpNetLongSnow = 0.; LongSnowIn = 0.; }
+  const double Tsurf = Tcanopy, TMean = Tsurf;
+  const double Tmp = TMean + KELVIN;
+  if (INCLUDE_SNOW) Tsnow_surf = TMean;
+  // estimate_T1.c:8-47 with exp(-D1/dp), exp(D1/dp) hoisted
+  double T1;
+  {
+    double C1 = Cs2 * cc.dp / D2 * (1. - cc.exp_m);
+    double C2 = -(1. - cc.exp_p) * cc.exp_m;
+    double C3 = kappa1 / D1 - kappa2 / D1 + kappa2 / D1 * cc.exp_m;
+    T1 = (kappa1 / 2. / D1 / D2 * (TMean) + C1 / delta_t * T1_old + (2. * C2 - 1. + cc.exp_m) * kappa2 / 2. / D1 / D2 * T2) /
+         (C1 / delta_t + kappa2 / D1 / D2 * C2 + C3 / 2. / D2);
+  }
+  const double grnd_flux = (snow_coverage + (1. - snow_coverage) * surf_atten) *
+                           (kappa1 / D1 * ((T1)-TMean) + (kappa2 / D2 * (1. - cc.exp_m) * (T2 - (T1)))) / 2.;
+  const double deltaH = (Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1 / delta_t / 2.);
+  double eo_deltaCC = 0., eo_refreeze = 0.;
+  if (INCLUDE_SNOW) {
+    if (TMean > 0) eo_deltaCC = CH_ICE * (s.swq - s.surf_water) * (0 - OldTSurf) / delta_t;
+    else eo_deltaCC = CH_ICE * (s.swq - s.surf_water) * (TMean - OldTSurf) / delta_t;
+    eo_refreeze = (s.surf_water * Lf * s.density) / delta_t;
+    eo_deltaCC *= snow_coverage;
+    eo_refreeze *= snow_coverage;
+  }
+  const double LongBareOut = STEFAN_B * Tmp * Tmp * Tmp * Tmp;
+  if (INCLUDE_SNOW) TmpNetLongSnow = (LongSnowIn - snow_coverage * LongBareOut);
+  const double NetLongBare = (LongBareIn - (1. - snow_coverage) * LongBareOut);
+  const double NetBareRad = (NetShortBare + (NetLongBare) + grnd_flux + deltaH + 0.);
+  // Ra_used[0]: StabilityCorrection(TSurf == Tair) == 1 (func_surf_energy_bal.c:684-693)
+  if (U[UnderStory] > 0.0) ra_used0 = Ra[UnderStory] / 1.0;
+  else ra_used0 = HUGE_RESIST;
+  if (v.vegcover < 1) {      // bare-gap blend, func_surf_energy_bal.c:712-749 (always for the bare tile)
+    if (ra_used0 > 0) {
+      double ga_veg = 1 / ra_used0;
+      double Ra_bare0 = (U[0] > 0.) ? cc.kb_bare / U[0] : HUGE_RESIST;
+      Ra_bare0 /= 1.0;
+      if (Ra_bare0 > 0) {
+        double ga_bare = 1 / Ra_bare0;
+        double ga_average = v.vegcover * ga_veg + (1 - v.vegcover) * ga_bare;
+        ra_used0 = 1 / ga_average;
+      }
+      else ra_used0 = 0;
+    }
+    else ra_used0 = 0;
+  }
+  double evap[MAXL], bef[MAXL], Evap;
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) { evap[l] = 0; bef[l] = 0; }
+  if (VEG && !snow_flag && v.vegcover > 0) {
+    Evap = canopy_evap(s.moist, v, true, uc, cc, NL, pa, Wdew_in, delta_t, NetBareRad, f.vpd, NetShortBare, Tcanopy,
+                       ra_used1, rainfall, evap);
+    if (v.vegcover < 1) {
+      double transp[MAXL];
+      for (int i = 0; i < NL; i++) { transp[i] = evap[i]; evap[i] = 0; }
+      Evap *= v.vegcover;
+      Evap += (1 - v.vegcover) * arno_evap(s.moist[0], cc, pa, surf_atten * NetBareRad, f.vpd, ra_used0, delta_t, &evap[0]);
+      for (int i = 0; i < NL; i++) {
+        evap[i] = v.vegcover * transp[i] + (1 - v.vegcover) * evap[i];
+        if (evap[i] > 0) bef[i] = 1 - (v.vegcover * transp[i]) / evap[i];
+        else bef[i] = 0;
+      }
+      v.throughfall = (1 - v.vegcover) * rainfall + v.vegcover * v.throughfall;
+      v.canopyevap *= v.vegcover;
+      v.Wdew *= v.vegcover;
+    }
+  }
+  else if (!snow_flag) {
+    Evap = arno_evap(s.moist[0], cc, pa, NetBareRad, f.vpd, ra_used0, delta_t, &evap[0]);
+    for (int i = 0; i < NL; i++) bef[i] = 1;
+  }
+  else Evap = 0.;
+  if (INCLUDE_SNOW) {
+    double latent_heat = -RHO_W * Le * Evap, latent_heat_sub;
+    // latent_heat_from_snow with the ground-surface resistance
+    double EsSnow = svp(TMean);
+    double SurfaceMassFlux = f.density * (EPS / f.pressure) * (f.vp - EsSnow) / ra_used0;
+    if (f.vpd == 0.0 && SurfaceMassFlux < 0.0) SurfaceMassFlux = 0.0;
+    double VaporMassFlux = SurfaceMassFlux + 0.;
+    double tl, tls;
+    if (TMean >= 0.0) { tl = Le * VaporMassFlux; tls = 0; }
+    else { tls = ((677. - 0.07 * TMean) * JOULESPCAL * GRAMSPKG) * VaporMassFlux; tl = 0; }
+    latent_heat += tl * snow_coverage;
+    latent_heat_sub = tls * snow_coverage;
+    vapor_flux = VaporMassFlux * delta_t / ICE_DENSITY;
+    double sensible_heat = f.density * Cp * (Tcanopy - (TMean)) / ra_used0;
+    double error = (NetBareRad + NetShortGrnd + TmpNetShortSnow + 1. * (TmpNetLongSnow)) + sensible_heat +
+                   (latent_heat + latent_heat_sub) + 0. * snow_coverage + melt_energy + eo_advection - eo_deltaCC;
+    if (Tsnow_surf == 0.0 && error > -(eo_refreeze)) eo_refreeze = -error;
+  }
+  // ---- calc_surf_energy_bal.c:584-731 ----
+  s.T0 = Tsurf;
+  s.T1 = T1;
+  if (!snow_flag && !INCLUDE_SNOW) ppt = is_veg ? v.throughfall : rainfall;
+  double NetLongUnder, NetShortUnder;
+  if (INCLUDE_SNOW) {
+    NetLongUnder = NetLongBare + TmpNetLongSnow;
+    NetShortUnder = NetShortBare + TmpNetShortSnow + NetShortGrnd;
+  }
+  else {
+    NetLongUnder = NetLongBare + NetLongSnow;
+    NetShortUnder = NetShortBare + NetShortSnow + NetShortGrnd;
+  }
+  s.LongUnderOut = LongUnderIn - NetLongUnder;
+  const double AlbedoUnderOut = ((1. - (snow_coverage + delta_coverage)) * BareAlbedo + (snow_coverage + delta_coverage) * SnowAlbedo);
+  o.Tsurf = (s.coverage * s.surf_temp + (1. - s.coverage) * Tsurf);
+  if (INCLUDE_SNOW) {
+    if (-(vapor_flux) > s.swq) vapor_flux = -(s.swq);
+    s.swq += vapor_flux;
+    s.surf_water += vapor_flux;
+    s.surf_water = (s.surf_water < 0) ? 0. : s.surf_water;
+    if (eo_refreeze >= 0.0) {
+      double refrozen_water = eo_refreeze / (Lf * RHO_W) * delta_t;
+      if (refrozen_water > s.surf_water) refrozen_water = s.surf_water;
+      s.surf_water -= refrozen_water;
+      if (s.surf_water < 0.0) s.surf_water = 0.0;
+      melt = 0.0;
+    }
+    else {
+      melt = fabs(eo_refreeze) / (Lf * RHO_W) * delta_t;
+      s.swq -= melt;
+      if (s.swq < 0) {
+        melt += s.swq;
+        s.swq = 0;
+      }
+    }
+    if (s.swq > 0) {
+      s.surf_temp = (Tsurf > 0) ? 0 : Tsurf;
+      s.coldcontent = CH_ICE * s.surf_temp * s.swq;
+      s.depth = 1000. * s.swq / s.density;
+      s.coverage = 1.;
+    }
+    else {
+      s.density = 0.; s.depth = 0.; s.surf_water = 0; s.pack_water = 0; s.surf_temp = 0; s.pack_temp = 0;
+      s.coverage = 0;
+    }
+    vapor_flux *= -1;
+    ppt += melt;
+  }
+  // ---- calc_atmos_energy_bal.c (CLOSE_ENERGY FALSE) / surface_fluxes.c:726-760 ----
+  if (snow_flag && overstory) {
+    o.NetLongAtmos = (1. * NetLongOver + (1. - 1.) * NetLongUnder);
+    o.NetShortAtmos = (NetShortOver + NetShortUnder);
+    o.in_long = LongOverIn;
+    o.albedo = AlbedoOver;
+  }
+  else {
+    o.NetLongAtmos = NetLongUnder;
+    o.NetShortAtmos = NetShortUnder;
+    o.in_long = LongUnderIn;
+    o.albedo = AlbedoUnderOut;
+  }
+  // ---- surface_fluxes.c:1110-1123: resistance -> conductance -> resistance over N_steps == 1 ----
+  {
+    double c0 = (ra_used0 > 0) ? 0. + 1 / ra_used0 : 0. + HUGE_RESIST;
+    double c1 = (ra_used1 > 0) ? 0. + 1 / ra_used1 : 0. + HUGE_RESIST;
+    o.aero_resist[0] = (c0 > 0 && c0 < HUGE_RESIST) ? 1 / (c0 / 1.) : ((c0 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
+    o.aero_resist[1] = (c1 > 0 && c1 < HUGE_RESIST) ? 1 / (c1 / 1.) : ((c1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
+  }
+  if (is_veg) s.Wdew = v.Wdew;
+  // ---- runoff.c ----
+  o.inflow = ppt;
+  runoff_step(cc, NL, dt_hours, ppt, s.moist, evap, &o.asat, &o.runoff, &o.baseflow);
+  // ---- full_energy.c:445-453 ----
+  double wet = 0, rootm = 0;
+  for (int l = 0; l < NL; l++) {
+    if ((uc.root0_mask >> l) & 1) rootm += s.moist[l];
+    wet += (s.moist[l] - cc.Wpwp[l]) / cc.wet_den[l];
+  }
+  wet /= NL;
+  o.wetness = wet;
+  o.rootmoist = rootm;
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) { o.evap[l] = evap[l]; o.bef[l] = bef[l]; }
+  o.vapor_flux = vapor_flux;
+  o.canopy_vapor_flux = is_veg ? canopy_vapor_flux : 0.;
+  o.canopyevap = is_veg ? v.canopyevap : 0.;
+  o.melt = melt;
+  o.grnd_flux = grnd_flux;
+  o.deltaH = deltaH;
+  o.out_prec = out_prec; o.out_rain = out_rain; o.out_snow = out_snow;
+  o.snow_flag = snow_flag;
+}
+
+}  // namespace vr
