@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- cell-timesteps/s of the water-balance cell step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref)
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic 100k-cell grid per GPU, 3 soil
+layers, water-balance mode, daily step; one "step" of the benchmark is one simulated YEAR (365
+records) of every cell, so the default K=10 timed steps are the 10 years the config names.
+  value   whole-job cell-timesteps/s with forcing and outputs resident in HBM (CUDA events)
+  e2e     the same through the C-ABI host call vr_step_block(): pinned host forcing in, host outputs
+          out, H2D + D2H copies inside the timed region
+  roofline.achieved = 280 algorithmic bytes per cell-timestep (9 forcing + 26 output fp64 words,
+          SURVEY.md 8d) x cell-timesteps per launch / mean k_step duration (CUDA events on the
+          launching stream)
+  cpu_baseline  the compiled reference (vic_ref_driver, step loop only) on a bounded sample on all
+          host cores (kind "reference"), else the oracle port on threads (kind "port")
+Multi-GPU: cells shard across ranks (no data-path collective) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-timesteps/sec (water-balance, 3 layers)"
+UNIT = "cell-timesteps/s"
+B_ALG = 8 * (9 + 26)          # bytes per cell-timestep, SURVEY.md section 8(d)
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "vic_ref_driver")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _make_ref_cases(tmp, cores, cells_per_core, ndays):
+    from vicres_b200 import synth
+    cases = []
+    for k in range(cores):
+        g = synth.make_case(os.path.join(tmp, "p%d" % k), ncells=cells_per_core, nlayer=3, nbands=1, ndays=ndays,
+                            seed=20261019 + k, skip_output=True)
+        cases.append(g)
+    return cases
+
+
+def _run_ref_once(cases):
+    """one process per core, each over its own cells (cells are independent: vicNl.c:197-356);
+    returns (cell_steps, max step-loop seconds, wall seconds)"""
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([REF_DRIVER, "-g", g, "-t"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for g in cases]
+    steps, loop = 0, 0.0
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("reference driver failed")
+        j = json.loads(out.strip().splitlines()[-1])
+        steps += j["cell_steps"]
+        loop = max(loop, j["step_loop_s"])
+    return steps, loop, time.perf_counter() - t0
+
+
+def _port_throughput(cores, cells_per_core, nrec):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle_lib
+    from vicres_b200 import abi, synth_soa
+    C = cores * cells_per_core
+    lib, cells = synth_soa.make_cells(C, nbands=1, seed=20261019)
+    f, month, doy = synth_soa.make_forcing(cells, nrec, seed=7)
+    opt = abi.default_options(3, 1, 24)
+    o = oracle_lib.Oracle(opt, lib, cells)
+    o.init_state(f[0, 0])
+    out = np.zeros((opt.n_out, nrec, C))
+    th = [threading.Thread(target=o.step_range, args=(month, doy, f, out, k * cells_per_core, (k + 1) * cells_per_core))
+          for k in range(cores)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    o.close()
+    return C * nrec / dt
+
+
+def cpu_baseline(cells_per_core=24, ndays=3653):
+    cores = host_cores()
+    if os.path.exists(REF_DRIVER):
+        with tempfile.TemporaryDirectory() as tmp:
+            cases = _make_ref_cases(tmp, cores, cells_per_core, ndays)
+            steps, loop, wall = _run_ref_once(cases)
+        return {"value": steps / loop, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": "%d cells x %d daily records (%d per core, one vic_ref_driver process per core, "
+                          "full_energy+put_data loop only; whole run incl. forcing disaggregation %.1f s)"
+                          % (cores * cells_per_core, ndays, cells_per_core, wall)}
+    v = _port_throughput(cores, 64, 730)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d cells x 730 daily records, oracle port on %d threads" % (cores * 64, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    cells_per_core, ndays = 8, 3653
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "gpu_launches": 0}
+    if os.path.exists(REF_DRIVER):
+        with tempfile.TemporaryDirectory() as tmp:
+            cases = _make_ref_cases(tmp, cores, cells_per_core, ndays)
+            for _ in range(args.warmup):
+                _run_ref_once(cases)
+            steps = loop = wall = 0.0
+            for _ in range(args.steps):
+                s, l, w = _run_ref_once(cases)
+                steps += s; loop += l; wall += w
+        value = steps / loop
+        kind = "reference"
+        sample = ("each step = %d cells x %d daily records, one vic_ref_driver process per core (%d), "
+                  "full_energy+put_data loop timed (max over processes); whole processes incl. forcing "
+                  "disaggregation and parsing: %.3e cell-timesteps/s" % (cores * cells_per_core, ndays, cores, steps / wall))
+        ms = 1e3 * loop / args.steps
+    else:
+        value = _port_throughput(cores, 64, 730)
+        kind, sample, ms = "port", "oracle port, %d threads, %d cells x 730 records" % (cores, cores * 64), None
+    line.update({"value": value, "ms_per_step": ms,
+                 "config": {"workload": "synthetic 100k-cell-grid parameter/forcing distribution, 3 soil layers, "
+                                        "water-balance mode, daily step, 10 years; bounded sample on host cores"},
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.p, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in out.splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, power) if p >= 0.5 * max(power)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vicres_b200 import abi, build, model, synth_soa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    C, R, K, W = args.cells, args.block, args.steps, max(args.warmup, 0)
+    lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=1, seed=20261019 + rank)
+    f_host, month, doy = synth_soa.make_forcing(cells, R, seed=7 + rank)
+    opt = abi.default_options(3, 1, 24)
+    n_out = opt.n_out
+    m = model.VicRes(opt, lib, cells, device=local)
+    m.init_state(f_host[0, 0])
+    dev = torch.device("cuda", local)
+
+    # ---- value: inputs/outputs resident in HBM ----
+    f_dev = torch.from_numpy(f_host).to(dev)
+    out_dev = torch.empty((n_out, R, C), dtype=torch.float64, device=dev)
+    ptrs = [f_dev[i].data_ptr() for i in range(abi.VR_NFORCING)]
+    stream = torch.cuda.current_stream(dev)
+
+    def one_step():
+        m.step_device(month, doy, ptrs, out_dev.data_ptr(), stream=stream.cuda_stream)
+
+    for _ in range(W):
+        one_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = m.num_launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    torch.cuda.synchronize(dev)
+    ev[0].record(stream)
+    for k in range(K):
+        one_step()
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    total_ms = ev[0].elapsed_time(ev[K])
+    launches = m.num_launches - l0
+    kernel_ms = sum(step_ms) / K       # one k_step launch per step, events bracket it on its stream
+    finite = bool(torch.isfinite(out_dev).all().item())
+    werr = float(out_dev.new_zeros(()).item())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * C * R * K / (total_ms_max * 1e-3)
+
+    # ---- e2e: host buffers through vr_step_block (H2D + D2H inside the timed region) ----
+    f_pin = torch.from_numpy(f_host).pin_memory()
+    out_pin = torch.empty((n_out, R, C), dtype=torch.float64).pin_memory()
+    f_np, out_np = f_pin.numpy(), out_pin.numpy()
+    Ke = max(1, min(K, args.e2e_steps))
+    for _ in range(min(W, 1)):
+        m.step(month, doy, f_np, out=out_np)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    l1 = m.num_launches
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        m.step(month, doy, f_np, out=out_np)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    launches += m.num_launches - l1
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * C * R * Ke / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    finite = finite and bool(np.isfinite(out_np).all())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, which = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = B_ALG * C * R / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_cell_step", 0) * C * R or None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 100k-cell grid, 3 soil layers, water-balance mode, daily step, "
+                                   "10 years (one step = one simulated year of every cell)",
+                       "cells_per_gpu": C, "records_per_step": R, "active_tile_band_units_per_gpu": m.num_units,
+                       "parallelism": "cells sharded over %d GPU(s), no data-path collective" % world,
+                       "l2": "inputs larger than L2: %.2f GB forcing + %.2f GB outputs per step" %
+                             (f_host.nbytes / 1e9, out_np.nbytes / 1e9),
+                       "outputs_finite": finite},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(f_host.nbytes),
+                    "d2h_bytes_per_step": int(out_np.nbytes), "steps": Ke},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": which, "kernel": "k_step", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_cell_step": B_ALG,
+                         "note": "the step is FP64-instruction-bound (about 2e4 fp64 instructions per tile-step), "
+                                 "not HBM-bound; see DESIGN.md section 6"},
+        }
+        if args.cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as e:      # the baseline is a reported number; never lose the GPU line over it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "error", "sample": str(e)}
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=100000)
+    ap.add_argument("--block", type=int, default=365, help="records per step (one simulated year)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,13 @@ void vr_default_options(vr_options *opt, int nlayer);  /* reference defaults + d
 int  vr_set_veglib(vr_handle *h, const vr_veglib *lib);
 int  vr_set_cells(vr_handle *h, const vr_cells *cells);
 
+/* Optional ensemble axis (toolbox calibration / eFAST / EET): cell c reads forcing
+ * column col[c] of forcing arrays that have ncol columns, so P parameter sets x N basin cells are
+ * P*N "cells" here that share N forcing columns (the reference re-reads the same forcing file in
+ * every vicNl run, toolbox/calibration/basin_calibration_eNSGAII.py:608-641). col == NULL restores
+ * the identity map. tair0 of vr_init_state is then indexed by forcing column as well. */
+int  vr_set_forcing_map(vr_handle *h, const int64_t *col /* [C] host */, int64_t ncol);
+
 /* initialize_model_state(): surf_temp = atmos[0].air_temp[NR] per cell (vicNl.c:260-264) and the
  * put_data(rec = -nrecs) storage initialisation (vicNl.c:287) */
 int  vr_init_state(vr_handle *h, const double *tair0 /* [C] host */);
@@ -175,6 +182,9 @@ int  vr_set_state(vr_handle *h, const void *blob_host);
 int64_t vr_num_units(const vr_handle *h);      /* active tile x band pairs */
 int64_t vr_num_launches(const vr_handle *h);   /* kernels launched by this handle so far */
 int  vr_last_kernel_ms(vr_handle *h, float *ms); /* CUDA-event time of the last step kernel */
+/* TFALLBACK counters summed over all units, as put_data.c:658-664 prints them:
+ * counts[0] = Tsnowsurf (snow_melt.c:361-366), counts[1] = Tfoliage (snow_intercept.c:418-423) */
+int  vr_fallback_counts(vr_handle *h, int64_t counts[2]);
 
 #ifdef __cplusplus
 }

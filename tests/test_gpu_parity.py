@@ -1,0 +1,176 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI of libvicres.so, against the golden
+fixtures (outputs of the reference itself) and against the oracle on seeded inputs; plus
+size-independent properties at larger sizes.  Tolerance: 1e-9 relative per cell-timestep
+(BASELINE.json north_star), see tests/common.py."""
+import numpy as np
+import pytest
+import oracle_lib
+from vicres_b200 import abi, build, synth_soa
+from common import FIXTURES, RTOL, check_outputs, load_fixture, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def VicRes():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    build.build()
+    from vicres_b200 import model
+    return model.VicRes
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_cuda_matches_reference_golden(VicRes, name):
+    fx = load_fixture(name)
+    m = VicRes(fx["opt"], fx["lib"], fx["cells"])
+    m.init_state(fx["tair0"])
+    out, status = m.step(fx["month"], fx["doy"], fx["forcing"])
+    assert not status.any()
+    check_outputs(out, fx["ref"], fx["names"], what="%s CUDA vs reference" % name)
+    assert m.num_launches >= 2
+    m.close()
+
+
+def test_block_split_is_bit_identical(VicRes):
+    fx = load_fixture("daily_snow_bands")
+    m = VicRes(fx["opt"], fx["lib"], fx["cells"])
+    m.init_state(fx["tair0"])
+    whole, _ = m.step(fx["month"], fx["doy"], fx["forcing"])
+    m.init_state(fx["tair0"])
+    parts = []
+    for a, b in [(0, 1), (1, 130), (130, 500)]:
+        o, _ = m.step(fx["month"][a:b], fx["doy"][a:b], np.ascontiguousarray(fx["forcing"][:, a:b]))
+        parts.append(o)
+    assert np.array_equal(whole, np.concatenate(parts, axis=1))
+    m.close()
+
+
+def test_state_roundtrip(VicRes):
+    fx = load_fixture("sub3h_snow")
+    m = VicRes(fx["opt"], fx["lib"], fx["cells"])
+    m.init_state(fx["tair0"])
+    h = 400
+    m.step(fx["month"][:h], fx["doy"][:h], np.ascontiguousarray(fx["forcing"][:, :h]))
+    blob = m.get_state()
+    rest, _ = m.step(fx["month"][h:], fx["doy"][h:], np.ascontiguousarray(fx["forcing"][:, h:]))
+    m2 = VicRes(fx["opt"], fx["lib"], fx["cells"])
+    m2.set_state(blob)
+    rest2, _ = m2.step(fx["month"][h:], fx["doy"][h:], np.ascontiguousarray(fx["forcing"][:, h:]))
+    assert np.array_equal(rest, rest2)
+    check_outputs(rest, fx["ref"][:, h:], fx["names"], what="restart")
+    m.close(); m2.close()
+
+
+def _tile(cells, rep):
+    """replicate every cell `rep` times (cell-major: copies of cell c are adjacent)"""
+    out = {}
+    C = len(cells["lat"])
+    idx = np.repeat(np.arange(C), rep)
+    for k in abi.CELL_SCALARS:
+        out[k] = cells[k][idx]
+    for k in abi.CELL_LAYER + abi.CELL_BAND:
+        out[k] = cells[k][:, idx]
+    tp = cells["tile_ptr"]
+    tiles = np.concatenate([np.arange(tp[c], tp[c + 1]) for c in idx])
+    nt = (tp[1:] - tp[:-1])[idx]
+    out["tile_ptr"] = np.concatenate([[0], np.cumsum(nt)]).astype(np.int64)
+    for k in ["tile_class", "tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]:
+        out[k] = cells[k][tiles]
+    return out, idx
+
+
+def test_parameter_set_axis_shares_forcing(VicRes):
+    """Ensemble layout (BASELINE config 4): P parameter sets x N cells with a forcing-column map."""
+    fx = load_fixture("daily_warm")
+    rep = 3
+    cells, idx = _tile(fx["cells"], rep)
+    rng = np.random.default_rng(1)
+    cells["b_infilt"] = cells["b_infilt"] * rng.uniform(0.5, 1.5, len(idx))
+    cells["Ds"] = np.clip(cells["Ds"] * rng.uniform(0.5, 1.5, len(idx)), 1e-3, 0.95)
+    names = fx["names"]
+    m = VicRes(fx["opt"], fx["lib"], cells, forcing_map=idx, n_forcing_cols=len(fx["tair0"]))
+    m.init_state(fx["tair0"])
+    out, _ = m.step(fx["month"], fx["doy"], fx["forcing"])
+    # same thing with the forcing physically replicated
+    m2 = VicRes(fx["opt"], fx["lib"], cells)
+    m2.init_state(fx["tair0"][idx])
+    out2, _ = m2.step(fx["month"], fx["doy"], np.ascontiguousarray(fx["forcing"][:, :, idx]))
+    assert np.array_equal(out, out2)
+    o = oracle_lib.Oracle(fx["opt"], fx["lib"], cells)
+    o.init_state(fx["tair0"][idx])
+    _, ref, _ = o.step(fx["month"], fx["doy"], np.ascontiguousarray(fx["forcing"][:, :, idx]))
+    check_outputs(out, ref, names, what="ensemble vs oracle")
+    m.close(); m2.close(); o.close()
+
+
+@pytest.mark.parametrize("nbands,dt,cold", [(1, 24, 0.0), (5, 24, 12.0), (2, 3, 15.0)])
+def test_cuda_matches_oracle_on_seeded_grid(VicRes, nbands, dt, cold):
+    C, nrec = 600, (400 if dt == 24 else 480)
+    lib, cells = synth_soa.make_cells(C, nbands=nbands, seed=11 + nbands, lat_range=(20.0, 65.0), overstory_frac=0.5)
+    f, month, doy = synth_soa.make_forcing(cells, nrec, dt_hours=dt, seed=5, cold=cold)
+    opt = abi.default_options(3, nbands, dt, out=abi.OUT_NAMES)
+    o = oracle_lib.Oracle(opt, lib, cells)
+    o.init_state(f[0, 0])
+    rc, ref, _ = o.step(month, doy, f)
+    assert rc == 0
+    m = VicRes(opt, lib, cells)
+    m.init_state(f[0, 0])
+    out, status = m.step(month, doy, f)
+    assert not status.any()
+    check_outputs(out, ref, abi.OUT_NAMES, what="seeded grid nb=%d dt=%d" % (nbands, dt))
+    assert np.array_equal(m.fallback_counts(), o.fallback_counts())
+    assert ref[abi.OUT["SWE"]].max() > (10.0 if cold else -1)
+    m.close(); o.close()
+
+
+def test_closure_and_sampled_parity_at_scale(VicRes):
+    """50k cells x 1 year: water-balance closure no worse than the reference's bar (1.35e-13 mm on
+    the bundled cell scales with storage; we hold 5e-12 mm), all outputs finite, and a random sample
+    of cells reproduces the oracle."""
+    C, nrec = 50000, 365
+    lib, cells = synth_soa.make_cells(C, nbands=1, seed=20261019)
+    f, month, doy = synth_soa.make_forcing(cells, nrec, seed=7)
+    names = abi.default_out_vars(3) + ["WATER_ERROR"]
+    opt = abi.default_options(3, 1, 24, out=names)
+    m = VicRes(opt, lib, cells)
+    m.init_state(f[0, 0])
+    out, status = m.step(month, doy, f)
+    assert not status.any() and np.isfinite(out).all()
+    assert np.abs(out[names.index("WATER_ERROR")]).max() < 5e-12
+    # mass conservation over the year, cell by cell: sum(P - E - R - B) == change in storage
+    i = {n: names.index(n) for n in names}
+    stor = out[i["SOIL_LIQ0"]] + out[i["SOIL_LIQ1"]] + out[i["SOIL_LIQ2"]] + out[i["SWE"]] + out[i["SNOW_CANOPY"]] + out[i["WDEW"]]
+    flux = (out[i["PREC"]] - out[i["EVAP"]] - out[i["RUNOFF"]] - out[i["BASEFLOW"]])[1:].sum(0)
+    assert np.abs(flux - (stor[-1] - stor[0])).max() < 1e-8
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(C, 40, replace=False))
+    sub, _ = _tile(cells, 1)
+    sub = {k: v for k, v in sub.items()}
+    # build the sub-grid of picked cells
+    sel = {}
+    for k in abi.CELL_SCALARS:
+        sel[k] = cells[k][pick]
+    for k in abi.CELL_LAYER + abi.CELL_BAND:
+        sel[k] = cells[k][:, pick]
+    tp = cells["tile_ptr"]
+    tiles = np.concatenate([np.arange(tp[c], tp[c + 1]) for c in pick])
+    sel["tile_ptr"] = np.concatenate([[0], np.cumsum((tp[1:] - tp[:-1])[pick])]).astype(np.int64)
+    for k in ["tile_class", "tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]:
+        sel[k] = cells[k][tiles]
+    o = oracle_lib.Oracle(opt, lib, sel)
+    fs = np.ascontiguousarray(f[:, :, pick])
+    o.init_state(fs[0, 0])
+    _, ref, _ = o.step(month, doy, fs)
+    check_outputs(out[:, :, pick], ref, names, what="sampled cells at 50k")
+    m.close(); o.close()
+
+
+def test_errors_are_reported_not_fatal(VicRes):
+    fx = load_fixture("daily_warm")
+    m = VicRes(fx["opt"], fx["lib"], fx["cells"])
+    from vicres_b200.model import VicResError
+    with pytest.raises(VicResError) as e:
+        m.step(fx["month"][:5], fx["doy"][:5], np.ascontiguousarray(fx["forcing"][:, :5]))   # before init_state
+    assert e.value.code == abi.VR_ERR_STATE
+    m.close()

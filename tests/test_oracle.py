@@ -1,0 +1,70 @@
+"""CPU tier: the oracle port against (1) the committed golden fixtures (outputs of the reference
+itself, tools/make_golden.py) and (2), when it was built here, the compiled reference run live."""
+import os
+import subprocess
+import numpy as np
+import pytest
+import oracle_lib
+import refdump
+from vicres_b200 import abi, synth
+from common import FIXTURES, ROOT, load_fixture
+
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "vic_ref_driver")
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_matches_golden_bit_exact(name):
+    fx = load_fixture(name)
+    o = oracle_lib.Oracle(fx["opt"], fx["lib"], fx["cells"])
+    assert o.init_state(fx["tair0"]) == 0
+    rc, out, _ = o.step(fx["month"], fx["doy"], fx["forcing"])
+    assert rc == 0
+    # same libm (glibc), same operation order, -ffp-contract=off on both sides -> identical bits
+    for i, n in enumerate(fx["names"]):
+        assert np.array_equal(out[i], fx["ref"][i]), "%s differs from the reference (%s)" % (n, name)
+    o.close()
+
+
+def test_oracle_block_split_is_identical():
+    fx = load_fixture("daily_snow_bands")
+    o = oracle_lib.Oracle(fx["opt"], fx["lib"], fx["cells"])
+    o.init_state(fx["tair0"])
+    outs = []
+    for a, b in [(0, 77), (77, 300), (300, 500)]:
+        rc, out, _ = o.step(fx["month"][a:b], fx["doy"][a:b], np.ascontiguousarray(fx["forcing"][:, a:b]))
+        assert rc == 0
+        outs.append(out)
+    out = np.concatenate(outs, axis=1)
+    assert np.array_equal(out, fx["ref"])
+    o.close()
+
+
+def test_closure_error_no_worse_than_reference():
+    for name in FIXTURES:
+        fx = load_fixture(name)
+        i = fx["names"].index("WATER_ERROR")
+        o = oracle_lib.Oracle(fx["opt"], fx["lib"], fx["cells"])
+        o.init_state(fx["tair0"])
+        _, out, _ = o.step(fx["month"], fx["doy"], fx["forcing"])
+        assert np.abs(out[i]).max() <= np.abs(fx["ref"][i]).max() + 1e-15
+        o.close()
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="compiled reference (oracle/_ref) not built here")
+def test_oracle_matches_live_reference(tmp_path):
+    g = synth.make_case(str(tmp_path / "case"), ncells=3, nlayer=3, nbands=2, ndays=200, cold=12.0,
+                        lat_range=(35, 60), overstory_frac=0.6, seed=4242)
+    dump = str(tmp_path / "dump.bin")
+    subprocess.run([DRIVER, "-g", g, "-d", dump], check=True, capture_output=True)
+    d = refdump.read_dump(dump)
+    cs = refdump.case_from_dump(d)
+    names = abi.OUT_NAMES
+    opt = abi.default_options(cs["nlayer"], cs["nbands"], cs["dt"], out=names,
+                              max_snow_temp=cs["max_snow_temp"], min_rain_temp=cs["min_rain_temp"])
+    o = oracle_lib.Oracle(opt, cs["lib"], cs["cells"])
+    o.init_state(cs["tair0"])
+    rc, out, _ = o.step(cs["month"], cs["doy"], cs["forcing"])
+    assert rc == 0
+    ref = refdump.ref_outputs(d, names)
+    assert np.array_equal(out, ref)
+    o.close()

@@ -1,0 +1,563 @@
+// vicres_capi.cu -- C ABI (include/vicres.h) and CUDA kernels of the B200-native VIC-Res cell step.
+//
+// Mapping: one THREAD owns one active tile x band unit and keeps its 24 state
+// words in registers across a whole block of records; the units of a cell sit in adjacent lanes, a
+// thread block holds whole consecutive cells (<= 128 units).  Per record every unit thread runs
+// vr::unit_step(), drops its 40 area-weighted terms into shared memory, and the cell's first lane
+// adds them in reference order (put_data.c) and writes the requested outputs, coalesced over cells.
+// Forcing is read as [field][rec][cell] (coalesced over cells, broadcast over a cell's units).
+// There is NO CPU fallback: every entry point needs a CUDA device and reports VR_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/vicres.h"
+#include "vic_physics.cuh"
+#include "vic_aggregate.cuh"
+#include "vic_host_prep.h"
+
+#ifndef VR_CTA
+#define VR_CTA 128
+#endif
+
+using namespace vr;
+
+namespace {
+
+struct DevModel {
+  int NL, NB, dt_hours, n_out;
+  double max_snow_temp, min_rain_temp;
+  int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
+  const double *cc;
+  const int64_t *cell_uptr, *cta_cell, *fcol;
+  const int32_t *u_cell, *u_tile, *u_flags, *u_aero, *cell_fail;
+  const double *u_cv, *u_af, *u_Tfactor, *u_Pfactor, *u_rarc, *u_rmin, *u_RGL, *tm, *ae, *init_moist;
+  const float *u_root;
+  double *state;                    // [ST_N][U]
+  double *sv;                       // [SV_N][C]
+  int32_t *cell_status;             // [C]
+  int32_t out_vars[VR_MAX_OUT];
+};
+
+struct DevForcing {
+  int nrec;
+  const int32_t *month, *doy;       // device
+  const double *field[VR_NFORCING]; // device, [nrec][FC]
+};
+
+__device__ __forceinline__ void load_unit_consts(const DevModel &M, int64_t u, UnitC &uc, double &cv, double &af)
+{
+  const int fl = M.u_flags[u];
+  uc.is_bare = fl & 1; uc.overstory = (fl >> 1) & 1; uc.root0_mask = fl >> 8;
+  cv = M.u_cv[u]; af = M.u_af[u];
+  uc.area = cv * af; uc.Tfactor = M.u_Tfactor[u]; uc.Pfactor = M.u_Pfactor[u];
+  uc.rarc = M.u_rarc[u]; uc.rmin = M.u_rmin[u]; uc.RGL = M.u_RGL[u];
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) uc.root[l] = M.u_root[(size_t)l * M.U + u];
+}
+
+__device__ __forceinline__ void load_state(const DevModel &M, int64_t u, UnitS &s)
+{
+#define L_(k) M.state[(size_t)(k) * M.U + u]
+  s.moist[0] = L_(ST_MOIST0); s.moist[1] = L_(ST_MOIST1); s.moist[2] = L_(ST_MOIST2); s.Wdew = L_(ST_WDEW);
+  s.T0 = L_(ST_T0); s.T1 = L_(ST_T1); s.LongUnderOut = L_(ST_LONGUNDEROUT); s.Tfoliage = L_(ST_TFOLIAGE);
+  s.swq = L_(ST_SWQ); s.surf_temp = L_(ST_SURF_TEMP); s.pack_temp = L_(ST_PACK_TEMP);
+  s.surf_water = L_(ST_SURF_WATER); s.pack_water = L_(ST_PACK_WATER); s.density = L_(ST_DENSITY);
+  s.depth = L_(ST_DEPTH); s.albedo = L_(ST_ALBEDO); s.coldcontent = L_(ST_COLDCONTENT);
+  s.coverage = L_(ST_COVERAGE); s.snow_canopy = L_(ST_SNOW_CANOPY); s.tmp_int_storage = L_(ST_TMP_INT);
+  s.last_snow = (int)L_(ST_LAST_SNOW); s.MELTING = (int)L_(ST_MELTING); s.fb_snow = (int)L_(ST_FB_SNOW);
+  s.fb_fol = (int)L_(ST_FB_FOL);
+#undef L_
+}
+
+__device__ __forceinline__ void store_state(const DevModel &M, int64_t u, const UnitS &s)
+{
+#define S_(k) M.state[(size_t)(k) * M.U + u]
+  S_(ST_MOIST0) = s.moist[0]; S_(ST_MOIST1) = s.moist[1]; S_(ST_MOIST2) = s.moist[2]; S_(ST_WDEW) = s.Wdew;
+  S_(ST_T0) = s.T0; S_(ST_T1) = s.T1; S_(ST_LONGUNDEROUT) = s.LongUnderOut; S_(ST_TFOLIAGE) = s.Tfoliage;
+  S_(ST_SWQ) = s.swq; S_(ST_SURF_TEMP) = s.surf_temp; S_(ST_PACK_TEMP) = s.pack_temp;
+  S_(ST_SURF_WATER) = s.surf_water; S_(ST_PACK_WATER) = s.pack_water; S_(ST_DENSITY) = s.density;
+  S_(ST_DEPTH) = s.depth; S_(ST_ALBEDO) = s.albedo; S_(ST_COLDCONTENT) = s.coldcontent;
+  S_(ST_COVERAGE) = s.coverage; S_(ST_SNOW_CANOPY) = s.snow_canopy; S_(ST_TMP_INT) = s.tmp_int_storage;
+  S_(ST_LAST_SNOW) = (double)s.last_snow; S_(ST_MELTING) = (double)s.MELTING; S_(ST_FB_SNOW) = (double)s.fb_snow;
+  S_(ST_FB_FOL) = (double)s.fb_fol;
+#undef S_
+}
+
+// initialize_model_state() + put_data(rec = -nrecs): one thread per unit, leaders fill save_data
+__global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0 /* [FC] */)
+{
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int64_t c0 = M.cta_cell[blockIdx.x], c1 = M.cta_cell[blockIdx.x + 1];
+  const int64_t u0 = M.cell_uptr[c0], u1 = M.cell_uptr[c1], u = u0 + tid;
+  const bool active = u < u1;
+  int64_t c = 0;
+  bool leader = false;
+  int nu = 0;
+  if (active) {
+    c = M.u_cell[u];
+    leader = (u == M.cell_uptr[c]);
+    nu = (int)(M.cell_uptr[c + 1] - M.cell_uptr[c]);
+    UnitC uc; UnitS s; UnitOut z;
+    double cv, af, im[MAXL], mm[MAXL];
+    load_unit_consts(M, u, uc, cv, af);
+    for (int l = 0; l < M.NL; l++) {
+      im[l] = M.init_moist[(size_t)l * M.C + c];
+      mm[l] = M.cc[(size_t)(CC_LAYER0 + l * CL_N + CL_MAX_MOIST) * M.C + c];
+    }
+    const int64_t fc = M.fcol ? M.fcol[c] : c;
+    unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
+    store_state(M, u, s);
+    memset(&z, 0, sizeof z);
+    unit_terms(uc, cv, af, s, z, M.NL, &sm[tid], VR_CTA);
+  }
+  __syncthreads();
+  if (leader) {
+    double acc[NTERM], eb = 0, tv = 0, sv[SV_N] = {0, 0, 0, 0}, o[VR_NOUTVAR];
+    for (int k = 0; k < NTERM; k++) acc[k] = 0;
+    for (int j = 0; j < nu; j++) cell_accumulate_ordered(acc, &eb, &tv, &sm[tid + j], VR_CTA, M.NL);
+    Forc f0;
+    memset(&f0, 0, sizeof f0);
+    f0.vp = 1; f0.vpd = 1;
+    cell_finish(acc, eb, tv, f0, M.NL, true, sv, o);
+    for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+    M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
+  }
+}
+
+// full_energy() + put_data() for F.nrec consecutive records of every cell
+__global__ void __launch_bounds__(VR_CTA) k_step(DevModel M, DevForcing F, double *__restrict__ out)
+{
+  extern __shared__ double sm[];     // [NTERM][VR_CTA]
+  const int tid = threadIdx.x;
+  const int64_t c0 = M.cta_cell[blockIdx.x], c1 = M.cta_cell[blockIdx.x + 1];
+  const int64_t u0 = M.cell_uptr[c0], u1 = M.cell_uptr[c1], u = u0 + tid;
+  const bool active = u < u1;
+  UnitC uc; CellC cc; UnitS s;
+  double cv = 0, af = 0, sv[SV_N] = {0, 0, 0, 0};
+  int64_t c = 0, fc = 0;
+  bool leader = false, failed = false;
+  int nu = 0;
+  const double *tm = nullptr, *ae = nullptr;
+  if (active) {
+    c = M.u_cell[u];
+    fc = M.fcol ? M.fcol[c] : c;
+    leader = (u == M.cell_uptr[c]);
+    nu = (int)(M.cell_uptr[c + 1] - M.cell_uptr[c]);
+    failed = M.cell_fail[c] != 0;
+    load_unit_consts(M, u, uc, cv, af);
+    load_cell_consts(M.cc, M.C, c, M.NL, cc);
+    load_state(M, u, s);
+    tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
+    ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
+    if (leader)
+      for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + c];
+  }
+  const int nrec = F.nrec, NL = M.NL;
+  for (int rec = 0; rec < nrec; rec++) {
+    Forc f;
+    if (active) {
+      const size_t k = (size_t)rec * M.FC + fc;
+      f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + k); f.prec = __ldg(F.field[VR_F_PREC] + k);
+      f.wind = __ldg(F.field[VR_F_WIND] + k); f.vp = __ldg(F.field[VR_F_VP] + k);
+      f.vpd = __ldg(F.field[VR_F_VPD] + k); f.pressure = __ldg(F.field[VR_F_PRESSURE] + k);
+      f.density = __ldg(F.field[VR_F_DENSITY] + k); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k);
+      f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
+      f.mon = __ldg(F.month + rec) - 1; f.doy = __ldg(F.doy + rec);
+      if (!failed) {
+        UnitOut uo;
+        unit_step(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp,
+                  M.min_rain_temp, s, uo);
+        unit_terms(uc, cv, af, s, uo, NL, &sm[tid], VR_CTA);
+      }
+    }
+    __syncthreads();
+    if (leader) {
+      double o[VR_NOUTVAR];
+      if (!failed) {
+        double acc[NTERM], eb = 0, tv = 0;
+#pragma unroll
+        for (int k = 0; k < NTERM; k++) acc[k] = 0;
+        for (int j = 0; j < nu; j++) cell_accumulate_ordered(acc, &eb, &tv, &sm[tid + j], VR_CTA, NL);
+        cell_finish(acc, eb, tv, f, NL, false, sv, o);
+      }
+      else {
+        for (int k = 0; k < VR_NOUTVAR; k++) o[k] = 0;
+      }
+      for (int v = 0; v < M.n_out; v++) out[((size_t)v * nrec + rec) * M.C + c] = o[M.out_vars[v]];
+    }
+    __syncthreads();
+  }
+  if (active && !failed) {
+    store_state(M, u, s);
+    if (leader)
+      for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+  }
+}
+
+template <class T>
+struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t upload(const std::vector<T> &v)
+  {
+    cudaError_t e = reserve(v.size());
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  cudaError_t reserve(size_t count)
+  {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct vr_handle {
+  vr_options opt;
+  int device = 0;
+  std::string err;
+  bool have_lib = false, have_cells = false, initialised = false;
+  // veglib copy
+  std::vector<int32_t> lib_overstory;
+  std::vector<double> lib_rarc, lib_rmin, lib_wind_h, lib_RGL, lib_rad_atten, lib_wind_atten, lib_trunk, lib_rough, lib_disp;
+  Prepared P;
+  DevModel M;
+  DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
+      d_forc, d_out, d_tair0;
+  DBuf<float> d_u_root;
+  DBuf<int64_t> d_cell_uptr, d_cta_cell, d_fcol;
+  DBuf<int32_t> d_u_cell, d_u_tile, d_u_flags, d_u_aero, d_cell_fail, d_cell_status, d_month, d_doy;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  bool timed = false;
+};
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                   \
+      return VR_ERR_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+
+extern "C" {
+
+void vr_default_options(vr_options *opt, int nlayer)
+{
+  memset(opt, 0, sizeof *opt);
+  opt->nlayer = nlayer; opt->nbands = 1; opt->dt_hours = 24; opt->snow_step_hours = 24;
+  opt->max_snow_temp = 0.5; opt->min_rain_temp = -0.5; opt->wind_h = 10.0;
+  int n = 0;
+  const int head[] = {VR_OUT_PREC, VR_OUT_EVAP, VR_OUT_RUNOFF, VR_OUT_BASEFLOW, VR_OUT_WDEW};
+  for (int v : head) opt->out_vars[n++] = v;
+  for (int l = 0; l < nlayer; l++) opt->out_vars[n++] = VR_OUT_SOIL_LIQ0 + l;
+  const int tail[] = {VR_OUT_NET_SHORT, VR_OUT_R_NET, VR_OUT_EVAP_CANOP, VR_OUT_TRANSP_VEG, VR_OUT_EVAP_BARE,
+                      VR_OUT_SUB_CANOP, VR_OUT_SUB_SNOW, VR_OUT_AERO_RESIST, VR_OUT_SURF_TEMP, VR_OUT_ALBEDO,
+                      VR_OUT_REL_HUMID, VR_OUT_IN_LONG, VR_OUT_AIR_TEMP, VR_OUT_WIND, VR_OUT_SWE,
+                      VR_OUT_SNOW_DEPTH, VR_OUT_SNOW_CANOPY, VR_OUT_SNOW_COVER};
+  for (int v : tail) opt->out_vars[n++] = v;
+  opt->n_out = n;
+}
+
+int vr_create(const vr_options *opt, int device, vr_handle **out)
+{
+  if (!opt || !out) { g_create_error = "null argument"; return VR_ERR_ARG; }
+  *out = nullptr;
+  if (opt->nlayer < 2 || opt->nlayer > VR_MAX_LAYERS || opt->nbands < 1 || opt->nbands > VR_MAX_BANDS ||
+      opt->n_out < 1 || opt->n_out > VR_MAX_OUT || opt->dt_hours < 1 || opt->dt_hours > 24 || 24 % opt->dt_hours) {
+    g_create_error = "vr_options out of range (nlayer 2..3, nbands 1..10, dt_hours divides 24, 1 <= n_out <= 64)";
+    return VR_ERR_ARG;
+  }
+  if (opt->snow_step_hours != opt->dt_hours) {
+    g_create_error = "SNOW_STEP != TIME_STEP (sub-stepped snow, NF > 1) is outside the supported water-balance path";
+    return VR_ERR_UNSUPPORTED;
+  }
+  if (!(opt->max_snow_temp > opt->min_rain_temp)) {
+    g_create_error = "MAX_SNOW_TEMP must be greater than MIN_RAIN_TEMP (calc_rainonly.c)";
+    return VR_ERR_ARG;
+  }
+  for (int v = 0; v < opt->n_out; v++)
+    if (opt->out_vars[v] < 0 || opt->out_vars[v] >= VR_NOUTVAR) { g_create_error = "unknown output variable id"; return VR_ERR_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+    return VR_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return VR_ERR_ARG; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return VR_ERR_CUDA; }
+  vr_handle *h = new vr_handle();
+  h->opt = *opt;
+  h->device = device;
+  memset(&h->M, 0, sizeof h->M);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete h;
+    return VR_ERR_CUDA;
+  }
+  cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTERM * VR_CTA * sizeof(double)));
+  cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTERM * VR_CTA * sizeof(double)));
+  *out = h;
+  return VR_OK;
+}
+
+void vr_destroy(vr_handle *h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->d_cc.release(); h->d_u_cv.release(); h->d_u_af.release(); h->d_u_Tf.release(); h->d_u_Pf.release();
+  h->d_u_rarc.release(); h->d_u_rmin.release(); h->d_u_RGL.release(); h->d_tm.release(); h->d_ae.release();
+  h->d_init_moist.release(); h->d_state.release(); h->d_sv.release(); h->d_forc.release(); h->d_out.release();
+  h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_cta_cell.release(); h->d_fcol.release();
+  h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
+  h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *vr_last_error(const vr_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vr_set_veglib(vr_handle *h, const vr_veglib *lib)
+{
+  if (!h || !lib || lib->nclass < 0) return VR_ERR_ARG;
+  const int n = lib->nclass;
+  h->lib_overstory.assign(lib->overstory, lib->overstory + n);
+  h->lib_rarc.assign(lib->rarc, lib->rarc + n); h->lib_rmin.assign(lib->rmin, lib->rmin + n);
+  h->lib_wind_h.assign(lib->wind_h, lib->wind_h + n); h->lib_RGL.assign(lib->RGL, lib->RGL + n);
+  h->lib_rad_atten.assign(lib->rad_atten, lib->rad_atten + n);
+  h->lib_wind_atten.assign(lib->wind_atten, lib->wind_atten + n);
+  h->lib_trunk.assign(lib->trunk_ratio, lib->trunk_ratio + n);
+  h->lib_rough.assign(lib->roughness, lib->roughness + (size_t)n * 12);
+  h->lib_disp.assign(lib->displacement, lib->displacement + (size_t)n * 12);
+  h->have_lib = true;
+  h->have_cells = false;
+  h->initialised = false;
+  return VR_OK;
+}
+
+int vr_set_cells(vr_handle *h, const vr_cells *cells)
+{
+  if (!h || !cells) return VR_ERR_ARG;
+  if (!h->have_lib) { h->err = "vr_set_veglib must be called before vr_set_cells"; return VR_ERR_STATE; }
+  if (cells->ncell <= 0) { h->err = "ncell must be positive"; return VR_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  vr_veglib lib;
+  lib.nclass = (int)h->lib_overstory.size();
+  lib.overstory = h->lib_overstory.data(); lib.rarc = h->lib_rarc.data(); lib.rmin = h->lib_rmin.data();
+  lib.wind_h = h->lib_wind_h.data(); lib.RGL = h->lib_RGL.data(); lib.rad_atten = h->lib_rad_atten.data();
+  lib.wind_atten = h->lib_wind_atten.data(); lib.trunk_ratio = h->lib_trunk.data();
+  lib.roughness = h->lib_rough.data(); lib.displacement = h->lib_disp.data();
+  h->P = Prepared();
+  if (!prepare(h->opt, lib, *cells, VR_CTA, h->P)) { h->err = h->P.error; return VR_ERR_ARG; }
+  Prepared &P = h->P;
+  const int64_t C = P.C, U = P.U;
+  std::vector<double> im((size_t)P.NL * C);
+  for (size_t i = 0; i < im.size(); i++) im[i] = cells->init_moist[i];
+  CK(h->d_cc.upload(P.cc)); CK(h->d_cell_uptr.upload(P.cell_uptr)); CK(h->d_cta_cell.upload(P.cta_cell));
+  CK(h->d_u_cell.upload(P.u_cell)); CK(h->d_u_tile.upload(P.u_tile)); CK(h->d_u_flags.upload(P.u_flags));
+  CK(h->d_u_aero.upload(P.u_aero)); CK(h->d_cell_fail.upload(P.cell_fail)); CK(h->d_u_cv.upload(P.u_cv));
+  CK(h->d_u_af.upload(P.u_af)); CK(h->d_u_Tf.upload(P.u_Tfactor)); CK(h->d_u_Pf.upload(P.u_Pfactor));
+  CK(h->d_u_rarc.upload(P.u_rarc)); CK(h->d_u_rmin.upload(P.u_rmin)); CK(h->d_u_RGL.upload(P.u_RGL));
+  CK(h->d_u_root.upload(P.u_root)); CK(h->d_tm.upload(P.tm)); CK(h->d_ae.upload(P.ae));
+  CK(h->d_init_moist.upload(im));
+  CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
+  CK(h->d_sv.reserve((size_t)SV_N * C));
+  CK(h->d_cell_status.reserve(C));
+  CK(cudaMemset(h->d_state.p, 0, (size_t)ST_N * (U ? U : 1) * sizeof(double)));
+  CK(cudaMemset(h->d_cell_status.p, 0, C * sizeof(int32_t)));
+  DevModel &M = h->M;
+  memset(&M, 0, sizeof M);
+  M.NL = P.NL; M.NB = P.NB; M.dt_hours = h->opt.dt_hours; M.n_out = h->opt.n_out;
+  M.max_snow_temp = h->opt.max_snow_temp; M.min_rain_temp = h->opt.min_rain_temp;
+  M.C = C; M.U = U; M.FC = C;
+  M.cc = h->d_cc.p; M.cell_uptr = h->d_cell_uptr.p; M.cta_cell = h->d_cta_cell.p; M.fcol = nullptr;
+  M.u_cell = h->d_u_cell.p; M.u_tile = h->d_u_tile.p; M.u_flags = h->d_u_flags.p; M.u_aero = h->d_u_aero.p;
+  M.cell_fail = h->d_cell_fail.p; M.u_cv = h->d_u_cv.p; M.u_af = h->d_u_af.p; M.u_Tfactor = h->d_u_Tf.p;
+  M.u_Pfactor = h->d_u_Pf.p; M.u_rarc = h->d_u_rarc.p; M.u_rmin = h->d_u_rmin.p; M.u_RGL = h->d_u_RGL.p;
+  M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
+  M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
+  for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
+  h->have_cells = true;
+  h->initialised = false;
+  return VR_OK;
+}
+
+int vr_set_forcing_map(vr_handle *h, const int64_t *col, int64_t ncol)
+{
+  if (!h) return VR_ERR_ARG;
+  if (!h->have_cells) { h->err = "vr_set_cells must be called before vr_set_forcing_map"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  if (!col) { h->M.fcol = nullptr; h->M.FC = h->M.C; return VR_OK; }
+  if (ncol <= 0) return VR_ERR_ARG;
+  std::vector<int64_t> v(col, col + h->M.C);
+  for (int64_t x : v)
+    if (x < 0 || x >= ncol) { h->err = "forcing map entry out of range"; return VR_ERR_ARG; }
+  CK(h->d_fcol.upload(v));
+  h->M.fcol = h->d_fcol.p;
+  h->M.FC = ncol;
+  return VR_OK;
+}
+
+int vr_init_state(vr_handle *h, const double *tair0)
+{
+  if (!h || !tair0) return VR_ERR_ARG;
+  if (!h->have_cells) { h->err = "vr_set_cells must be called before vr_init_state"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(h->d_tair0.reserve(h->M.FC));
+  CK(cudaMemcpyAsync(h->d_tair0.p, tair0, h->M.FC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  k_init<<<(unsigned)h->P.nCTA, VR_CTA, NTERM * VR_CTA * sizeof(double), h->stream>>>(h->M, h->d_tair0.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->initialised = true;
+  return VR_OK;
+}
+
+static int launch_step(vr_handle *h, const DevForcing &F, double *out_dev, cudaStream_t st)
+{
+  cudaEventRecord(h->ev0, st);
+  k_step<<<(unsigned)h->P.nCTA, VR_CTA, NTERM * VR_CTA * sizeof(double), st>>>(h->M, F, out_dev);
+  cudaEventRecord(h->ev1, st);
+  h->timed = true;
+  h->launches++;
+  CK(cudaGetLastError());
+  return VR_OK;
+}
+
+int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, void *cuda_stream)
+{
+  if (!h || !f || !out_dev || f->nrec <= 0) return VR_ERR_ARG;
+  if (!h->initialised) { h->err = "vr_init_state (or vr_set_state) must precede vr_step_block"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  CK(h->d_month.reserve(f->nrec)); CK(h->d_doy.reserve(f->nrec));
+  CK(cudaMemcpyAsync(h->d_month.p, f->month, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  DevForcing F;
+  F.nrec = f->nrec; F.month = h->d_month.p; F.doy = h->d_doy.p;
+  for (int i = 0; i < VR_NFORCING; i++) {
+    if (!f->field[i]) { h->err = "null forcing field"; return VR_ERR_ARG; }
+    F.field[i] = f->field[i];
+  }
+  return launch_step(h, F, out_dev, st);
+}
+
+int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *cell_status_host)
+{
+  if (!h || !f || !out_host || f->nrec <= 0) return VR_ERR_ARG;
+  if (!h->initialised) { h->err = "vr_init_state (or vr_set_state) must precede vr_step_block"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  const size_t n_in = (size_t)f->nrec * h->M.FC, n_out = (size_t)f->nrec * h->M.C;
+  CK(h->d_forc.reserve(n_in * VR_NFORCING));
+  CK(h->d_out.reserve(n_out * h->opt.n_out));
+  CK(h->d_month.reserve(f->nrec)); CK(h->d_doy.reserve(f->nrec));
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->d_month.p, f->month, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  DevForcing F;
+  F.nrec = f->nrec; F.month = h->d_month.p; F.doy = h->d_doy.p;
+  for (int i = 0; i < VR_NFORCING; i++) {
+    if (!f->field[i]) { h->err = "null forcing field"; return VR_ERR_ARG; }
+    CK(cudaMemcpyAsync(h->d_forc.p + i * n_in, f->field[i], n_in * sizeof(double), cudaMemcpyHostToDevice, st));
+    F.field[i] = h->d_forc.p + i * n_in;
+  }
+  int rc = launch_step(h, F, h->d_out.p, st);
+  if (rc != VR_OK) return rc;
+  CK(cudaMemcpyAsync(out_host, h->d_out.p, n_out * h->opt.n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (cell_status_host)
+    CK(cudaMemcpyAsync(cell_status_host, h->d_cell_status.p, h->M.C * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (cell_status_host)
+    for (int64_t c = 0; c < h->M.C; c++)
+      if (cell_status_host[c]) return VR_ERR_CELL;
+  return VR_OK;
+}
+
+int vr_synchronize(vr_handle *h)
+{
+  if (!h) return VR_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return VR_OK;
+}
+
+int64_t vr_state_size(const vr_handle *h)
+{
+  if (!h || !h->have_cells) return 0;
+  return (int64_t)(((size_t)ST_N * h->M.U + (size_t)SV_N * h->M.C) * sizeof(double));
+}
+
+int vr_get_state(vr_handle *h, void *blob)
+{
+  if (!h || !blob) return VR_ERR_ARG;
+  if (!h->initialised) { h->err = "no state yet"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  char *b = (char *)blob;
+  const size_t ns = (size_t)ST_N * h->M.U * sizeof(double), nv = (size_t)SV_N * h->M.C * sizeof(double);
+  CK(cudaMemcpy(b, h->d_state.p, ns, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b + ns, h->d_sv.p, nv, cudaMemcpyDeviceToHost));
+  return VR_OK;
+}
+
+int vr_set_state(vr_handle *h, const void *blob)
+{
+  if (!h || !blob) return VR_ERR_ARG;
+  if (!h->have_cells) { h->err = "vr_set_cells must be called before vr_set_state"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const char *b = (const char *)blob;
+  const size_t ns = (size_t)ST_N * h->M.U * sizeof(double), nv = (size_t)SV_N * h->M.C * sizeof(double);
+  CK(cudaMemcpy(h->d_state.p, b, ns, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_sv.p, b + ns, nv, cudaMemcpyHostToDevice));
+  h->initialised = true;
+  return VR_OK;
+}
+
+int64_t vr_num_units(const vr_handle *h) { return (h && h->have_cells) ? h->M.U : 0; }
+int64_t vr_num_launches(const vr_handle *h) { return h ? h->launches : 0; }
+
+int vr_last_kernel_ms(vr_handle *h, float *ms)
+{
+  if (!h || !ms) return VR_ERR_ARG;
+  if (!h->timed) { h->err = "no step launched yet"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return VR_OK;
+}
+
+int vr_fallback_counts(vr_handle *h, int64_t counts[2])
+{
+  if (!h || !counts) return VR_ERR_ARG;
+  if (!h->initialised) { h->err = "no state yet"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const int64_t U = h->M.U;
+  std::vector<double> a(U), b(U);
+  CK(cudaMemcpy(a.data(), h->d_state.p + (size_t)ST_FB_SNOW * U, U * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), h->d_state.p + (size_t)ST_FB_FOL * U, U * sizeof(double), cudaMemcpyDeviceToHost));
+  counts[0] = counts[1] = 0;
+  for (int64_t u = 0; u < U; u++) { counts[0] += (int64_t)a[u]; counts[1] += (int64_t)b[u]; }
+  return VR_OK;
+}
+
+}  // extern "C"

@@ -219,7 +219,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
     else:
         g += ["SNOW_BAND 1"]
     g += ["COMPUTE_TREELINE FALSE", "RESULT_DIR %s/" % result_dir, "OUT_STEP 0",
-          "SKIPYEAR %d" % (10000 if skip_output else 0),
+          "SKIPYEAR %d" % ((nrec * dt // 24) // 366 if skip_output else 0),   # make_dmy.c:163-169 indexes dmy[] per skipped year
           "COMPRESS FALSE", "BINARY_OUTPUT FALSE", "ALMA_OUTPUT FALSE", "MOISTFRACT FALSE",
           "PRT_HEADER FALSE", "PRT_SNOW_BAND FALSE"]
     if extra_global:
