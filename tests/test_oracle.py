@@ -68,3 +68,33 @@ def test_oracle_matches_live_reference(tmp_path):
     ref = refdump.ref_outputs(d, names)
     assert np.array_equal(out, ref)
     o.close()
+
+
+def test_reference_algorithm_is_ill_conditioned(tmp_path):
+    """Evidence for the parity policy in tests/common.py: the SAME restatement (bit-exact against the
+    reference when built like the reference) differs from the reference by far more than 1e-9 on a
+    few steps as soon as the compiler may contract a*b+c into FMA.  Skipped on hosts without FMA."""
+    import ctypes as C
+    so = str(tmp_path / "liborc_fma.so")
+    r = subprocess.run(["gcc", "-O3", "-mfma", "-ffp-contract=fast", "-fPIC", "-shared", "-o", so,
+                        os.path.join(ROOT, "oracle", "vic_oracle.c"), "-lm"], capture_output=True)
+    if r.returncode != 0 or "fma" not in open("/proc/cpuinfo").read():
+        pytest.skip("no FMA on this host")
+    fx = load_fixture("bundled_basin_cell")
+    L = C.CDLL(so)
+    L.vo_create.restype = C.c_void_p
+    L.vo_create.argtypes = [C.c_void_p] * 3
+    L.vo_init_state.argtypes = [C.c_void_p] * 2
+    L.vo_step_block.argtypes = [C.c_void_p] * 4 + [C.c_int]
+    lib, cells = abi.pack_veglib(fx["lib"]), abi.pack_cells(fx["cells"])
+    f = abi.pack_forcing(fx["month"], fx["doy"], fx["forcing"])
+    h = L.vo_create(C.byref(fx["opt"]), lib.ref(), cells.ref())
+    t0 = np.ascontiguousarray(fx["tair0"])
+    L.vo_init_state(h, t0.ctypes.data)
+    out = np.zeros_like(fx["ref"])
+    assert L.vo_step_block(h, f.ref(), out.ctypes.data, None, 0) == 0
+    from common import relerr
+    e = relerr(out, fx["ref"])
+    print("FMA-contracted reference algorithm vs reference: max rel %.2e, %.2e of values beyond 1e-9" % (e.max(), (e > 1e-9).mean()))
+    assert e.max() > 1e-9          # the reference is not reproducible to 1e-9 across compilers
+    assert (e > 1e-9).mean() < 0.05
