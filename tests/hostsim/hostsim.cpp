@@ -32,7 +32,8 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
     unit_init(im, mm, NL, tair0[c], uc.Tfactor, S[u]);
   }
   double terms[NTERM], acc[NTERM], o[VR_NOUTVAR];
-  for (int64_t c = 0; c < C; c++) {
+  for (int64_t cs = 0; cs < C; cs++) {
+    const int64_t c = P.order[cs];
     CellC cc;
     load_cell_consts(P.cc.data(), C, c, NL, cc);
     // put_data(rec = -nrecs)
@@ -41,7 +42,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
       double eb = 0, tv = 0;
       UnitOut z;
       memset(&z, 0, sizeof z);
-      for (int64_t u = P.cell_uptr[c]; u < P.cell_uptr[c + 1]; u++) {
+      for (int64_t u = P.cell_uptr[cs]; u < P.cell_uptr[cs + 1]; u++) {
         unit_terms(UC[u], P.u_cv[u], P.u_af[u], S[u], z, NL, terms, 1);
         cell_accumulate_ordered(acc, &eb, &tv, terms, 1, NL);
       }
@@ -60,7 +61,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
       fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
       for (int q = 0; q < NTERM; q++) acc[q] = 0;
       double eb = 0, tv = 0;
-      for (int64_t u = P.cell_uptr[c]; u < P.cell_uptr[c + 1]; u++) {
+      for (int64_t u = P.cell_uptr[cs]; u < P.cell_uptr[cs + 1]; u++) {
         UnitOut uo;
         const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
         const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];

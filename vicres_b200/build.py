@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libvicres.so")
 SOURCES = ["vicres_capi.cu"]
 DEPS = ["vicres_capi.cu", "vic_physics.cuh", "vic_aggregate.cuh", "vic_host_prep.h", "../../include/vicres.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-DVR_PHASE_BARRIERS"]
 
 
 def stale():

@@ -23,7 +23,7 @@ enum {
 enum { SV_SOIL = 0, SV_SWE, SV_WDEW, SV_STORAGE, SV_N };
 
 // terms[k * stride] for k in [0, NTERM)
-VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
+VR_HDN void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
                       double *terms, int stride)
 {
   const double AF = cv * af * 1. * 1.;
@@ -114,7 +114,7 @@ VR_HD void cell_accumulate_ordered(double *acc, double *eb, double *tv, const do
 }
 
 // finish one cell-record: o[VR_NOUTVAR]
-VR_HD void cell_finish(const double *acc, double eb, double tv, const Forc &f, int NL, bool init, double *sv, double *o)
+VR_HDN void cell_finish(const double *acc, double eb, double tv, const Forc &f, int NL, bool init, double *sv, double *o)
 {
 #pragma unroll
   for (int k = 0; k < VR_NOUTVAR; k++) o[k] = 0;

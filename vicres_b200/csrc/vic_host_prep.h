@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <tuple>
@@ -26,14 +27,17 @@ struct Prepared {
   int NL = 0, NB = 0, cta_threads = 128;
   int64_t C = 0, T = 0, U = 0, K = 0, nCTA = 0;
   std::vector<double> cc;            // [CC_N][C]
-  std::vector<int64_t> cell_uptr;    // [C+1]
-  std::vector<int32_t> u_cell, u_tile, u_flags, u_aero;   // [U]; flags: bit0 bare, bit1 overstory, bits 8.. root0 mask
+  std::vector<int64_t> order;        // [C] sorted position -> caller's cell index (climate-sorted, see prepare())
+  std::vector<int64_t> cell_uptr;    // [C+1] over SORTED positions
+  std::vector<int32_t> u_cell, u_tile, u_flags, u_aero;   // [U]; u_cell = caller's cell index; flags: bit0 bare, bit1 overstory, bits 8.. root0 mask
+  std::vector<int32_t> u_slot;       // [U] thread index inside its block that runs unit u
+  std::vector<int64_t> t_unit;       // [U] unit run by thread (u0_of_block + t)
   std::vector<double> u_cv, u_af, u_Tfactor, u_Pfactor, u_rarc, u_rmin, u_RGL;   // [U]
   std::vector<float> u_root;         // [MAXL][U]
   std::vector<double> tm;            // [T][12][TM_N]
   std::vector<double> ae;            // [K][12][AE_N]
   std::vector<int32_t> cell_fail;    // [C] 1 = CalcAerodynamic rejects a tile of this cell (full_energy returns ERROR)
-  std::vector<int64_t> cta_cell;     // [nCTA+1]
+  std::vector<int64_t> cta_cell;     // [nCTA+1] sorted positions
   std::string error;
 };
 
@@ -254,7 +258,17 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       }
     }
   }
-  for (int64_t c = 0; c < C; c++) {
+  // Cells are processed in an internal order sorted by mean annual air temperature (soil_con.avg_temp,
+  // the QUICK_FLUX lower boundary), then latitude: neighbouring lanes/warps then share the snow /
+  // no-snow branch on most days.  Results are written back at the caller's cell index.
+  P.order.resize(C);
+  for (int64_t c = 0; c < C; c++) P.order[c] = c;
+  std::stable_sort(P.order.begin(), P.order.end(), [&](int64_t a, int64_t b) {
+    if (cells.avg_temp[a] != cells.avg_temp[b]) return cells.avg_temp[a] < cells.avg_temp[b];
+    return cells.lat[a] > cells.lat[b];
+  });
+  for (int64_t cs = 0; cs < C; cs++) {
+    const int64_t c = P.order[cs];
     int64_t n = 0;
     for (int64_t t = cells.tile_ptr[c]; t < cells.tile_ptr[c + 1]; t++) {
       if (!(cells.tile_Cv[t] > 0.0)) continue;
@@ -283,7 +297,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       }
     }
     if (n > cta_threads) { P.error = "a cell has more active tile x band units than one thread block holds"; return false; }
-    P.cell_uptr[c + 1] = P.cell_uptr[c] + n;
+    P.cell_uptr[cs + 1] = P.cell_uptr[cs] + n;
   }
   P.U = P.cell_uptr[C];
   P.u_root.assign((size_t)MAXL * (P.U ? P.U : 1), 0.f);
@@ -292,7 +306,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     bool bare = P.u_flags[u] & 1;
     for (int l = 0; l < NL; l++) P.u_root[(size_t)l * P.U + u] = bare ? 0.f : (float)cells.tile_root[t * NL + l];
   }
-  // ---- CTA packing: whole consecutive cells, <= cta_threads units ----
+  // ---- CTA packing: whole consecutive (sorted) cells, <= cta_threads units ----
   P.cta_cell.clear();
   P.cta_cell.push_back(0);
   int64_t used = 0;
@@ -306,6 +320,23 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
   }
   if (C > 0) P.cta_cell.push_back(C);
   P.nCTA = (int64_t)P.cta_cell.size() - 1;
+  // ---- thread assignment inside a block: units grouped by kind (overstory, other vegetation, bare
+  //      soil) so that a warp mostly runs one evaporation / interception path ----
+  P.u_slot.assign(P.U ? P.U : 1, 0);
+  P.t_unit.assign(P.U ? P.U : 1, 0);
+  for (int64_t b = 0; b < P.nCTA; b++) {
+    const int64_t u0 = P.cell_uptr[P.cta_cell[b]], u1 = P.cell_uptr[P.cta_cell[b + 1]];
+    int64_t t = 0;
+    for (int kind = 0; kind < 3; kind++)
+      for (int64_t u = u0; u < u1; u++) {
+        const int fl = P.u_flags[u];
+        const int k = (fl & 2) ? 0 : ((fl & 1) ? 2 : 1);
+        if (k != kind) continue;
+        P.u_slot[u] = (int32_t)t;
+        P.t_unit[u0 + t] = u;
+        t++;
+      }
+  }
   return true;
 }
 

@@ -31,11 +31,91 @@
 #define VR_HDN inline
 #endif
 
+// One out-of-line copy of each transcendental: CUDA inlines pow/exp/log at every call site (60-250
+// SASS instructions each, ~35 sites), which made k_step 30k instructions / 480 KB and stalled the
+// warps on instruction fetch (profiles/r1_k_step_v1.md).  Out of line the whole step fits the
+// instruction cache.
 #ifndef VR_POW
-#define VR_POW(x, y) pow((x), (y))
+#define VR_POW(x, y) ::vr::m_pow((x), (y))
 #endif
+// Phase barrier: keeps the warps of a thread block at the same place in the (large) step code so
+// that one instruction-cache fill serves all of them (k_step is instruction-fetch bound, see
+// profiles/).  Every thread of the block must run unit_step() for this to be legal.
+#if defined(__CUDA_ARCH__) && defined(VR_PHASE_BARRIERS)
+#define VR_PHASE_SYNC() __syncthreads()
+#else
+#define VR_PHASE_SYNC()
+#endif
+#if defined(__CUDA_ARCH__) && defined(VR_LOOP_BARRIERS)
+#define VR_LOOP_SYNC() __syncthreads()
+#else
+#define VR_LOOP_SYNC()
+#endif
+#define VR_EXP(x) ::vr::m_exp(x)
+#define VR_LOG(x) ::vr::m_log(x)
+#define VR_LOG10(x) ::vr::m_log10(x)
 
 namespace vr {
+
+// x^y for the step's power laws (Brooks-Corey drainage, ARNO curves, albedo decay ...): 72 of the
+// ~85 pow() per tile-day sit in the hourly drainage loop (runoff.c:320-479) and CUDA's pow() costs
+// ~250 instructions (double-double log), which made it 80 % of k_step.  On the device
+// x^y = 2^(y*log2 x) is evaluated directly: log2 of the mantissa by the atanh series (|f| <= 0.172,
+// 10 terms, ~1 ulp), the exponent part y*e kept separate so it is added exactly, 2^r by a
+// degree-13 polynomial.  Relative error <= ~2e-16 * (2 + |y*log2 x|), i.e. < 1e-13 for every
+// argument range of the model -- four orders below the 1e-9 parity bar.  Zero, negative, subnormal,
+// non-finite or extreme arguments take CUDA's pow().  With -DVR_EXACT_LIBM (and always on the host)
+// plain pow() is used, which is what makes the host build bit-identical to the reference.
+VR_HDN double m_pow(double x, double y)
+{
+#if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM)
+  if (x == 1.0 || y == 0.0) return 1.0;
+  if (!(x >= 2.2250738585072014e-308) || !(x <= 1e300) || !(fabs(y) <= 1e5)) return pow(x, y);
+  const long long ix = __double_as_longlong(x);
+  int e = (int)((ix >> 52) & 0x7ff) - 1023;
+  double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double f = (m - 1.0) / (m + 1.0);
+  const double f2 = f * f;
+  // 2*atanh(f)/f = 2*(1 + f2/3 + f2^2/5 + ...), truncated after f2^10 (|f2| <= 0.0295 -> 1e-17)
+  double q = 2.0 / 21.0;
+  q = fma(q, f2, 2.0 / 19.0);
+  q = fma(q, f2, 2.0 / 17.0);
+  q = fma(q, f2, 2.0 / 15.0);
+  q = fma(q, f2, 2.0 / 13.0);
+  q = fma(q, f2, 2.0 / 11.0);
+  q = fma(q, f2, 2.0 / 9.0);
+  q = fma(q, f2, 2.0 / 7.0);
+  q = fma(q, f2, 2.0 / 5.0);
+  q = fma(q, f2, 2.0 / 3.0);
+  const double lnm = fma(q * f2, f, 2.0 * f);               // ln(m)
+  const double l2m = lnm * 1.4426950408889634;              // log2(m), |l2m| <= 0.5
+  const double t = fma(y, l2m, y * (double)e);              // y*log2(x)
+  if (!(fabs(t) < 1000.0)) return pow(x, y);
+  const double n = rint(t);
+  const double z = (t - n) * 0.6931471805599453;            // |z| <= 0.3466
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, z, 1.0 / 479001600.0);
+  p = fma(p, z, 1.0 / 39916800.0);
+  p = fma(p, z, 1.0 / 3628800.0);
+  p = fma(p, z, 1.0 / 362880.0);
+  p = fma(p, z, 1.0 / 40320.0);
+  p = fma(p, z, 1.0 / 5040.0);
+  p = fma(p, z, 1.0 / 720.0);
+  p = fma(p, z, 1.0 / 120.0);
+  p = fma(p, z, 1.0 / 24.0);
+  p = fma(p, z, 1.0 / 6.0);
+  p = fma(p, z, 0.5);
+  p = fma(p, z, 1.0);
+  p = fma(p, z, 1.0);
+  return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+#else
+  return pow(x, y);
+#endif
+}
+VR_HDN double m_exp(double x) { return exp(x); }
+VR_HDN double m_log(double x) { return log(x); }
+VR_HDN double m_log10(double x) { return log10(x); }
 
 // ---- constants (runoff/model/vicNl_def.h:160-440, snow.h:40-90) ----
 constexpr double HUGE_RESIST = 1.e20;
@@ -178,9 +258,9 @@ VR_HD void unit_init(const double *init_moist, const double *max_moist, int NL, 
 // ---------------------------------------------------------------------------------------
 // L0 math
 // ---------------------------------------------------------------------------------------
-VR_HD double svp(double temp)   // svp.c:7-24
+VR_HDN double svp(double temp)   // svp.c:7-24
 {
-  double SVP = A_SVP * exp((B_SVP * temp) / (C_SVP + temp));
+  double SVP = A_SVP * VR_EXP((B_SVP * temp) / (C_SVP + temp));
   if (temp < 0) SVP *= 1.0 + .00972 * temp + .000042 * temp * temp;
   return SVP * 1000.;
 }
@@ -188,19 +268,19 @@ VR_HD double svp(double temp)   // svp.c:7-24
 // Penman-Monteith (penman.c:201-249) split into its air-state part (once per unit-step) and the
 // per-surface evaluation.
 struct PenmanAir { double slope, lv, gamma, r_air_cp; };
-VR_HD PenmanAir penman_air(double tair, double half_elev_lapse, double elevation)
+VR_HDN PenmanAir penman_air(double tair, double half_elev_lapse, double elevation)
 {
   PenmanAir p;
   p.slope = (B_SVP * C_SVP) / ((C_SVP + tair) * (C_SVP + tair)) * svp(tair);
   double h = 287 / 9.81 * ((tair + 273.15) + half_elev_lapse);
-  double pz = PS_PM * exp(-elevation / h);
+  double pz = PS_PM * VR_EXP(-elevation / h);
   p.lv = 2501000 - 2361 * tair;
   p.gamma = 1628.6 * pz / p.lv;
   double r_air = 0.003486 * pz / (275 + tair);
   p.r_air_cp = r_air * CP_PM;
   return p;
 }
-VR_HD double penman(const PenmanAir &p, double rad, double vpd, double ra, double rc, double rarc)
+VR_HDN double penman(const PenmanAir &p, double rad, double vpd, double ra, double rc, double rarc)
 {
   double evap = (p.slope * rad + p.r_air_cp * vpd / ra) / (p.lv * (p.slope + p.gamma * (1 + (rc + rarc) / ra))) *
                 SEC_PER_DAY;
@@ -208,7 +288,7 @@ VR_HD double penman(const PenmanAir &p, double rad, double vpd, double ra, doubl
   return evap;
 }
 
-VR_HD double calc_rc(double rs, double net_short, double RGL, double tair, double vpd, double lai, double gsm_inv)
+VR_HDN double calc_rc(double rs, double net_short, double RGL, double tair, double vpd, double lai, double gsm_inv)
 {   // penman.c:44-91, Jarvis branch
   double rc;
   if (rs == 0) rc = 0;
@@ -230,12 +310,12 @@ VR_HD double calc_rc(double rs, double net_short, double RGL, double tair, doubl
   return rc;
 }
 
-VR_HD double stability_correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0)
+VR_HDN double stability_correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0)
 {   // StabilityCorrection.c:44-81
   double Correction = 1.0;
   if (TSurf != Tair) {
     double Ri = G_GRAV * (Tair - TSurf) * (Z - d) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * Wind * Wind);
-    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (log((Z - d) / Z0) + 5));
+    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (VR_LOG((Z - d) / Z0) + 5));
     if (Ri > RiLimit) Ri = RiLimit;
     if (Ri > 0.0) Correction = (1 - Ri / 0.2) * (1 - Ri / 0.2);
     else {
@@ -301,7 +381,7 @@ struct SnowPackEB {
   // outputs of the last evaluation
   double Ra_used0, AdvectedEnergy, DeltaColdContent, GroundFlux, LatentHeat, LatentHeatSub, NetLongUnder,
          RefreezeEnergy, SensibleHeat, vapor_flux, surface_flux;
-  VR_HD double operator()(double TSurf)
+  VR_HDN double operator()(double TSurf)
   {
     double TMean = TSurf;
     if (Wind > 0.0) Ra_used0 = Ra / stability_correction(Z, 0., TMean, Tair, Wind, Z0_2);
@@ -545,7 +625,7 @@ VR_HD double new_snow_density(double air_temp)   // snow_utility.c, DENS_BRAS
   return NEW_SNOW_DENSITY;
 }
 
-VR_HD double snow_density(double surf_temp, double depth_in, double new_snow, double sswq, double Tair, double dt)
+VR_HDN double snow_density(double surf_temp, double depth_in, double new_snow, double sswq, double Tair, double dt)
 {   // snow_utility.c snow_density, DENS_BRAS
   double density_new = (new_snow > 0.) ? new_snow_density(Tair) : 0.0;
   double Tavg = surf_temp + KELVIN, depth = depth_in, swq = sswq, density;
@@ -568,7 +648,7 @@ VR_HD double snow_density(double surf_temp, double depth_in, double new_snow, do
   else density = 1000. * swq / depth_in;
   if (depth > 0.) {
     double overburden = 0.5 * G_GRAV * RHO_W * swq;
-    double viscosity = SNDENS_ETA0 * exp(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density);
+    double viscosity = SNDENS_ETA0 * VR_EXP(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density);
     double delta_depth = overburden / viscosity * depth * dt * 3600;
     if (delta_depth > 0.9 * depth) delta_depth = 0.9 * depth;
     depth -= delta_depth;
@@ -577,7 +657,7 @@ VR_HD double snow_density(double surf_temp, double depth_in, double new_snow, do
   return density;
 }
 
-VR_HD double snow_albedo(double new_snow, double swq, double albedo, double cold_content, double dt,
+VR_HDN double snow_albedo(double new_snow, double swq, double albedo, double cold_content, double dt,
                          int last_snow, int MELTING)
 {   // snow_utility.c snow_albedo
   if (new_snow > TraceSnow && cold_content < 0.0) albedo = NEW_SNOW_ALB;
@@ -596,7 +676,7 @@ VR_HD double snow_albedo(double new_snow, double swq, double albedo, double cold
 // ---------------------------------------------------------------------------------------
 struct VegV { double Wdew, canopyevap, throughfall, LAI, Wdmax, vegcover; };
 
-VR_HD void transpiration(const double *moist, const VegV &v, const UnitC &uc, const CellC &cc, int NL,
+VR_HDN void transpiration(const double *moist, const VegV &v, const UnitC &uc, const CellC &cc, int NL,
                          const PenmanAir &pa, double rad, double vpd, double net_short, double air_temp,
                          double ra, double dryFrac, double delta_t, double *layerevap)
 {
@@ -631,6 +711,7 @@ VR_HD void transpiration(const double *moist, const VegV &v, const UnitC &uc, co
         if (avail[i] >= cc.Wcr[i]) layerevap[i] += (double)uc.root[i] * spare_evap / root_sum;
   }
   else {
+#pragma unroll 1
     for (int i = 0; i < NL; i++) {
       double gsm_inv;
       if (avail[i] >= cc.Wcr[i]) gsm_inv = 1.0;
@@ -650,7 +731,7 @@ VR_HD void transpiration(const double *moist, const VegV &v, const UnitC &uc, co
 }
 
 // returns Evap (m/s); writes v.canopyevap, v.throughfall, v.Wdew and layerevap[]
-VR_HD double canopy_evap(const double *moist, VegV &v, bool CALC_EVAP, const UnitC &uc, const CellC &cc, int NL,
+VR_HDN double canopy_evap(const double *moist, VegV &v, bool CALC_EVAP, const UnitC &uc, const CellC &cc, int NL,
                          const PenmanAir &pa, double Wdew_in, double delta_t, double rad, double vpd,
                          double net_short, double air_temp, double ra, double ppt, double *layerevap)
 {
@@ -694,7 +775,7 @@ VR_HD double canopy_evap(const double *moist, VegV &v, bool CALC_EVAP, const Uni
 }
 
 // returns Evap (m/s); writes *evap0 (mm) = layer[0].evap
-VR_HD double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, double rad, double vpd, double ra,
+VR_HDN double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, double rad, double vpd, double ra,
                        double delta_t, double *evap0)
 {
   double moist = 0. + (moist0 - 0.) * 1., evap, tmp, ratio;
@@ -716,6 +797,7 @@ VR_HD double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, doub
     double as = 1 - ratio;
     ratio = VR_POW(ratio, cc.inv_b);
     double dummy = 1.0, tmpsum = 1.0;
+#pragma unroll 1
     for (int n = 1; n <= 30; n++) {       // arno_evap.c:168-173; the inner product is a running power
       tmpsum = (n == 1) ? ratio : tmpsum * ratio;
       dummy += cc.b * tmpsum / (cc.b + n);
@@ -773,7 +855,7 @@ struct CanopyEB {
   // outputs of the last evaluation
   double Ra_used0, Ra_used1, IntRain, AdvectedEnergy, LatentHeat, LatentHeatSub, LongOverOut, NetLongOver,
          RefreezeEnergy, SensibleHeat, VaporMassFlux;
-  VR_HD double operator()(double Tfoliage)
+  VR_HDN double operator()(double Tfoliage)
   {
     double Tmp = Tfoliage + KELVIN;
     LongOverOut = STEFAN_B * (Tmp * Tmp * Tmp * Tmp);
@@ -1005,7 +1087,7 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
 // ---------------------------------------------------------------------------------------
 // runoff.c:7-576 (Nfrost == 1, no ice): infiltration, hourly drainage, ARNO baseflow
 // ---------------------------------------------------------------------------------------
-VR_HD void runoff_and_asat(const CellC &cc, const double *moist, int NL, double inflow, double *A, double *runoff)
+VR_HDN void runoff_and_asat(const CellC &cc, const double *moist, int NL, double inflow, double *A, double *runoff)
 {
   double top_moist = 0.;
   for (int l = 0; l < NL - 1; l++) top_moist += moist[l];
@@ -1023,7 +1105,7 @@ VR_HD void runoff_and_asat(const CellC &cc, const double *moist, int NL, double 
 }
 
 // moist[]: in/out (mm); evap_l[]: in layer evaporation for the step (mm), evap_l[NL-1] may be reduced
-VR_HD void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moist, double *evap_l, double *asat,
+VR_HDN void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moist, double *evap_l, double *asat,
                        double *runoff_out, double *baseflow_out)
 {
   double liq[MAXL], evap[MAXL], Q12[MAXL - 1], A, runoff_, baseflow = 0;
@@ -1040,7 +1122,9 @@ VR_HD void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *mois
   }
   runoff_and_asat(cc, liq, NL, ppt, &A, &runoff_);
   double tmp_dt_runoff = runoff_ / (double)dt, dt_inflow = ppt / (double)dt;
+#pragma unroll 1
   for (int ts = 0; ts < dt; ts++) {
+    VR_LOOP_SYNC();
     double inflow = dt_inflow;
     for (int l = 0; l < NL - 1; l++) {
       double tmp_liq = liq[l] - evap[l];
@@ -1093,7 +1177,7 @@ VR_HD void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *mois
     double dt_baseflow = cc.bf_frac * rel_moist;
     if (rel_moist > cc.Ws) {
       double frac = (rel_moist - cc.Ws) / cc.one_m_Ws;
-      dt_baseflow += cc.bf_nl * VR_POW(frac, cc.c);
+      dt_baseflow += cc.bf_nl * ((cc.c == 2.0) ? frac * frac : VR_POW(frac, cc.c));   // pow(x,2) == x*x
     }
     if (dt_baseflow < 0) dt_baseflow = 0;
     liq[l] += Q12[l - 1] - (evap[l] + dt_baseflow);
@@ -1139,7 +1223,7 @@ VR_HD void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *mois
 // one unit, one record
 // ---------------------------------------------------------------------------------------
 // tm: this tile's TM_* terms for the month; ae: this tile's AE_* coefficients for the month
-VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
+VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
                      int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o)
 {
   const double delta_t = (double)dt_hours * 3600.;
@@ -1173,7 +1257,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     double K;
     if (mv > 0.) {
       double Sr = mv / cc.poros[l];
-      double Ke = 0.7 * log10(Sr) + 1.0;
+      double Ke = 0.7 * VR_LOG10(Sr) + 1.0;
       K = cc.ksat_m_kdry[l] * Ke + cc.kdry[l];
       if (K < cc.kdry[l]) K = cc.kdry[l];
     }
@@ -1202,6 +1286,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   const double step_depth_old = s.depth, step_surf_temp_old = s.surf_temp;
   const PenmanAir pa = penman_air(Tair, cc.half_elev_lapse, cc.elev);
 
+  VR_PHASE_SYNC();
   // ---- solve_snow.c:7-577 ----
   double rainonly = 0.;
   if (Tair < max_snow_temp && Tair > min_rain_temp) rainonly = (Tair - min_rain_temp) / (max_snow_temp - min_rain_temp) * step_prec;
@@ -1339,6 +1424,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   }
   (void)AlbedoUnder; (void)coverage;
 
+  VR_PHASE_SYNC();
   // ---- surface_fluxes.c:680-695: thin pack -> solved together with the ground ----
   bool INCLUDE_SNOW = false;
   double eo_advection = 0.;
@@ -1372,7 +1458,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   const double Tsurf = Tcanopy, TMean = Tsurf;
   const double Tmp = TMean + KELVIN;
   if (INCLUDE_SNOW) Tsnow_surf = TMean;
-  // estimate_T1.c:8-47 with exp(-D1/dp), exp(D1/dp) hoisted
+  // estimate_T1.c:8-47 with VR_EXP(-D1/dp), VR_EXP(D1/dp) hoisted
   double T1;
   {
     double C1 = Cs2 * cc.dp / D2 * (1. - cc.exp_m);
@@ -1416,6 +1502,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   double evap[MAXL], bef[MAXL], Evap;
 #pragma unroll
   for (int l = 0; l < MAXL; l++) { evap[l] = 0; bef[l] = 0; }
+  VR_PHASE_SYNC();
   if (VEG && !snow_flag && v.vegcover > 0) {
     Evap = canopy_evap(s.moist, v, true, uc, cc, NL, pa, Wdew_in, delta_t, NetBareRad, f.vpd, NetShortBare, Tcanopy,
                        ra_used1, rainfall, evap);
@@ -1527,6 +1614,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     o.aero_resist[1] = (c1 > 0 && c1 < HUGE_RESIST) ? 1 / (c1 / 1.) : ((c1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
   }
   if (is_veg) s.Wdew = v.Wdew;
+  VR_PHASE_SYNC();
   // ---- runoff.c ----
   o.inflow = ppt;
   runoff_step(cc, NL, dt_hours, ppt, s.moist, evap, &o.asat, &o.runoff, &o.baseflow);

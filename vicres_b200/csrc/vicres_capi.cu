@@ -18,8 +18,14 @@
 #include "vic_aggregate.cuh"
 #include "vic_host_prep.h"
 
+// One 512-thread block per SM (128 registers per thread): k_step is instruction-fetch bound, and 16
+// warps that move through the step together (phase barriers in unit_step) share every instruction-
+// cache fill; measured 1.9x faster than 128-thread blocks (profiles/r1_tuning.md).
 #ifndef VR_CTA
-#define VR_CTA 128
+#define VR_CTA 512
+#endif
+#ifndef VR_MINB
+#define VR_MINB 1      // thread blocks per SM the register allocation must allow
 #endif
 
 using namespace vr;
@@ -31,8 +37,8 @@ struct DevModel {
   double max_snow_temp, min_rain_temp;
   int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
   const double *cc;
-  const int64_t *cell_uptr, *cta_cell, *fcol;
-  const int32_t *u_cell, *u_tile, *u_flags, *u_aero, *cell_fail;
+  const int64_t *cell_uptr, *cta_cell, *fcol, *order, *t_unit;
+  const int32_t *u_cell, *u_tile, *u_flags, *u_aero, *u_slot, *cell_fail;
   const double *u_cv, *u_af, *u_Tfactor, *u_Pfactor, *u_rarc, *u_rmin, *u_RGL, *tm, *ae, *init_moist;
   const float *u_root;
   double *state;                    // [ST_N][U]
@@ -86,21 +92,22 @@ __device__ __forceinline__ void store_state(const DevModel &M, int64_t u, const 
 #undef S_
 }
 
-// initialize_model_state() + put_data(rec = -nrecs): one thread per unit, leaders fill save_data
+// Thread roles inside a block that holds the sorted cells [cs0, cs1) with units [u0, u1):
+//   unit role      thread t < u1-u0 runs unit t_unit[u0+t] (grouped by kind); idle threads shadow the
+//                  block's last unit so that every thread runs the step and its phase barriers
+//   finisher role  thread t < cs1-cs0 aggregates sorted cell cs0+t: adds the terms of the cell's units in
+//                  reference order (slots u_slot[u]) and writes the cell's outputs
+
+// initialize_model_state() + put_data(rec = -nrecs)
 __global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0 /* [FC] */)
 {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  const int64_t c0 = M.cta_cell[blockIdx.x], c1 = M.cta_cell[blockIdx.x + 1];
-  const int64_t u0 = M.cell_uptr[c0], u1 = M.cell_uptr[c1], u = u0 + tid;
-  const bool active = u < u1;
-  int64_t c = 0;
-  bool leader = false;
-  int nu = 0;
-  if (active) {
-    c = M.u_cell[u];
-    leader = (u == M.cell_uptr[c]);
-    nu = (int)(M.cell_uptr[c + 1] - M.cell_uptr[c]);
+  const int64_t cs0 = M.cta_cell[blockIdx.x], cs1 = M.cta_cell[blockIdx.x + 1];
+  const int64_t u0 = M.cell_uptr[cs0], u1 = M.cell_uptr[cs1];
+  if (u0 + tid < u1) {
+    const int64_t u = M.t_unit[u0 + tid];
+    const int64_t c = M.u_cell[u];
     UnitC uc; UnitS s; UnitOut z;
     double cv, af, im[MAXL], mm[MAXL];
     load_unit_consts(M, u, uc, cv, af);
@@ -115,10 +122,12 @@ __global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0
     unit_terms(uc, cv, af, s, z, M.NL, &sm[tid], VR_CTA);
   }
   __syncthreads();
-  if (leader) {
+  if (cs0 + tid < cs1) {
+    const int64_t cs = cs0 + tid, c = M.order[cs];
     double acc[NTERM], eb = 0, tv = 0, sv[SV_N] = {0, 0, 0, 0}, o[VR_NOUTVAR];
     for (int k = 0; k < NTERM; k++) acc[k] = 0;
-    for (int j = 0; j < nu; j++) cell_accumulate_ordered(acc, &eb, &tv, &sm[tid + j], VR_CTA, M.NL);
+    for (int64_t u = M.cell_uptr[cs]; u < M.cell_uptr[cs + 1]; u++)
+      cell_accumulate_ordered(acc, &eb, &tv, &sm[M.u_slot[u]], VR_CTA, M.NL);
     Forc f0;
     memset(&f0, 0, sizeof f0);
     f0.vp = 1; f0.vpd = 1;
@@ -129,73 +138,80 @@ __global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0
 }
 
 // full_energy() + put_data() for F.nrec consecutive records of every cell
-__global__ void __launch_bounds__(VR_CTA) k_step(DevModel M, DevForcing F, double *__restrict__ out)
+__global__ void __launch_bounds__(VR_CTA, VR_MINB) k_step(DevModel M, DevForcing F, double *__restrict__ out)
 {
   extern __shared__ double sm[];     // [NTERM][VR_CTA]
   const int tid = threadIdx.x;
-  const int64_t c0 = M.cta_cell[blockIdx.x], c1 = M.cta_cell[blockIdx.x + 1];
-  const int64_t u0 = M.cell_uptr[c0], u1 = M.cell_uptr[c1], u = u0 + tid;
-  const bool active = u < u1;
+  const int64_t cs0 = M.cta_cell[blockIdx.x], cs1 = M.cta_cell[blockIdx.x + 1];
+  const int64_t u0 = M.cell_uptr[cs0], u1 = M.cell_uptr[cs1];
+  if (u1 <= u0) return;              // (uniform) a block without active units
+  const bool active = u0 + tid < u1;
+  const int64_t u = M.t_unit[active ? u0 + tid : u1 - 1];
+  // ---- unit role ----
   UnitC uc; CellC cc; UnitS s;
-  double cv = 0, af = 0, sv[SV_N] = {0, 0, 0, 0};
-  int64_t c = 0, fc = 0;
-  bool leader = false, failed = false;
-  int nu = 0;
-  const double *tm = nullptr, *ae = nullptr;
-  if (active) {
-    c = M.u_cell[u];
-    fc = M.fcol ? M.fcol[c] : c;
-    leader = (u == M.cell_uptr[c]);
-    nu = (int)(M.cell_uptr[c + 1] - M.cell_uptr[c]);
-    failed = M.cell_fail[c] != 0;
-    load_unit_consts(M, u, uc, cv, af);
-    load_cell_consts(M.cc, M.C, c, M.NL, cc);
-    load_state(M, u, s);
-    tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
-    ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
-    if (leader)
-      for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + c];
-  }
+  double cv, af;
+  const int64_t c = M.u_cell[u];
+  const int64_t fc = M.fcol ? M.fcol[c] : c;
+  const bool failed = M.cell_fail[c] != 0;
+  load_unit_consts(M, u, uc, cv, af);
+  load_cell_consts(M.cc, M.C, c, M.NL, cc);
+  load_state(M, u, s);
+  const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
+  const double *ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
+  // ---- finisher role ----
+  const bool finisher = cs0 + tid < cs1;
+  const int64_t fcs = finisher ? cs0 + tid : cs0;
+  const int64_t fcell = M.order[fcs];
+  const int64_t ffc = M.fcol ? M.fcol[fcell] : fcell;
+  const int64_t fu0 = M.cell_uptr[fcs], fu1 = M.cell_uptr[fcs + 1];
+  const bool ffailed = M.cell_fail[fcell] != 0;
+  double sv[SV_N] = {0, 0, 0, 0};
+  if (finisher)
+    for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + fcell];
+
   const int nrec = F.nrec, NL = M.NL;
   for (int rec = 0; rec < nrec; rec++) {
-    Forc f;
-    if (active) {
+    const int mon = __ldg(F.month + rec) - 1, doy = __ldg(F.doy + rec);
+    {
+      Forc f;
       const size_t k = (size_t)rec * M.FC + fc;
       f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + k); f.prec = __ldg(F.field[VR_F_PREC] + k);
       f.wind = __ldg(F.field[VR_F_WIND] + k); f.vp = __ldg(F.field[VR_F_VP] + k);
       f.vpd = __ldg(F.field[VR_F_VPD] + k); f.pressure = __ldg(F.field[VR_F_PRESSURE] + k);
       f.density = __ldg(F.field[VR_F_DENSITY] + k); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k);
       f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
-      f.mon = __ldg(F.month + rec) - 1; f.doy = __ldg(F.doy + rec);
-      if (!failed) {
-        UnitOut uo;
-        unit_step(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp,
-                  M.min_rain_temp, s, uo);
-        unit_terms(uc, cv, af, s, uo, NL, &sm[tid], VR_CTA);
-      }
+      f.mon = mon; f.doy = doy;
+      UnitOut uo;
+      unit_step(cc, uc, tm + mon * TM_N, ae + mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s, uo);
+      if (active) unit_terms(uc, cv, af, s, uo, NL, &sm[tid], VR_CTA);
     }
     __syncthreads();
-    if (leader) {
+    if (finisher) {
       double o[VR_NOUTVAR];
-      if (!failed) {
+      if (!ffailed) {
         double acc[NTERM], eb = 0, tv = 0;
 #pragma unroll
         for (int k = 0; k < NTERM; k++) acc[k] = 0;
-        for (int j = 0; j < nu; j++) cell_accumulate_ordered(acc, &eb, &tv, &sm[tid + j], VR_CTA, NL);
+        for (int64_t uu = fu0; uu < fu1; uu++)
+          cell_accumulate_ordered(acc, &eb, &tv, &sm[__ldg(M.u_slot + uu)], VR_CTA, NL);
+        Forc f;
+        const size_t k = (size_t)rec * M.FC + ffc;
+        f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + k); f.wind = __ldg(F.field[VR_F_WIND] + k);
+        f.vp = __ldg(F.field[VR_F_VP] + k); f.vpd = __ldg(F.field[VR_F_VPD] + k);
+        f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
+        f.prec = 0; f.pressure = 0; f.density = 0; f.mon = mon; f.doy = doy;
         cell_finish(acc, eb, tv, f, NL, false, sv, o);
       }
       else {
         for (int k = 0; k < VR_NOUTVAR; k++) o[k] = 0;
       }
-      for (int v = 0; v < M.n_out; v++) out[((size_t)v * nrec + rec) * M.C + c] = o[M.out_vars[v]];
+      for (int v = 0; v < M.n_out; v++) out[((size_t)v * nrec + rec) * M.C + fcell] = o[M.out_vars[v]];
     }
     __syncthreads();
   }
-  if (active && !failed) {
-    store_state(M, u, s);
-    if (leader)
-      for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
-  }
+  if (active && !failed) store_state(M, u, s);
+  if (finisher && !ffailed)
+    for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + fcell] = sv[k];
 }
 
 template <class T>
@@ -236,8 +252,8 @@ struct vr_handle {
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
       d_forc, d_out, d_tair0;
   DBuf<float> d_u_root;
-  DBuf<int64_t> d_cell_uptr, d_cta_cell, d_fcol;
-  DBuf<int32_t> d_u_cell, d_u_tile, d_u_flags, d_u_aero, d_cell_fail, d_cell_status, d_month, d_doy;
+  DBuf<int64_t> d_cell_uptr, d_cta_cell, d_fcol, d_order, d_t_unit;
+  DBuf<int32_t> d_u_cell, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
@@ -327,6 +343,7 @@ void vr_destroy(vr_handle *h)
   h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_cta_cell.release(); h->d_fcol.release();
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
+  h->d_order.release(); h->d_t_unit.release(); h->d_u_slot.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -378,6 +395,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   CK(h->d_u_rarc.upload(P.u_rarc)); CK(h->d_u_rmin.upload(P.u_rmin)); CK(h->d_u_RGL.upload(P.u_RGL));
   CK(h->d_u_root.upload(P.u_root)); CK(h->d_tm.upload(P.tm)); CK(h->d_ae.upload(P.ae));
   CK(h->d_init_moist.upload(im));
+  CK(h->d_order.upload(P.order)); CK(h->d_t_unit.upload(P.t_unit)); CK(h->d_u_slot.upload(P.u_slot));
   CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
   CK(h->d_sv.reserve((size_t)SV_N * C));
   CK(h->d_cell_status.reserve(C));
@@ -394,6 +412,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.u_Pfactor = h->d_u_Pf.p; M.u_rarc = h->d_u_rarc.p; M.u_rmin = h->d_u_rmin.p; M.u_RGL = h->d_u_RGL.p;
   M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
+  M.order = h->d_order.p; M.t_unit = h->d_t_unit.p; M.u_slot = h->d_u_slot.p;
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   h->have_cells = true;
   h->initialised = false;

@@ -45,7 +45,8 @@ def make_cells(ncell, nlayer=3, nbands=1, seed=20261019, lat_range=(-40.0, 60.0)
     cells["Dsmax"] = rng.uniform(1.0, 30.0, C)
     cells["Ws"] = rng.uniform(0.3, 0.95, C)
     cells["c_expt"] = np.full(C, 2.0)
-    cells["avg_temp"] = rng.uniform(5.0, 27.0, C)
+    # soil_con.avg_temp is the mean annual air temperature: keep it consistent with the forcing climate
+    cells["avg_temp"] = 27.0 - 0.45 * np.abs(cells["lat"]) - 0.0065 * cells["elevation"] + rng.normal(0.0, 1.0, C)
     cells["dp"] = np.full(C, 4.0)
     cells["rough"] = np.full(C, 0.001)
     cells["snow_rough"] = np.full(C, 0.0005)
