@@ -91,7 +91,7 @@ typedef struct vr_options {
   double  wind_h;           /* global_param.wind_h (WIND_H)                             */
   int32_t n_out;            /* number of output variables requested                     */
   int32_t out_vars[VR_MAX_OUT]; /* VR_OUT_* ids, in output order                        */
-  int32_t cells_per_block_hint; /* 0 = library default                                  */
+  int32_t cells_per_block_hint; /* records per pipelined H2D/compute/D2H chunk of vr_step_block; 0 = default (16) */
   int32_t reserved[7];
 } vr_options;
 

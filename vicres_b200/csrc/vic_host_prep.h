@@ -142,6 +142,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     CC(CC_BF_NL, c) = Dsmax24 * (1 - cells.Ds[c] / cells.Ws[c]);
     CC(CC_WS, c) = cells.Ws[c];
     CC(CC_ONE_M_WS, c) = (1 - cells.Ws[c]);
+    CC(CC_INV_ONE_M_WS, c) = 1.0 / (1 - cells.Ws[c]);
     CC(CC_C, c) = cells.c_expt[c];
     CC(CC_AVG_T, c) = cells.avg_temp[c];
     CC(CC_DP, c) = dp;
@@ -165,6 +166,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       CC(base + CL_MAX_MOIST, c) = cells.max_moist[k];
       CC(base + CL_RESID, c) = resid;
       CC(base + CL_QDEN, c) = cells.max_moist[k] - resid;
+      CC(base + CL_INV_QDEN, c) = 1.0 / (cells.max_moist[k] - resid);
       CC(base + CL_WCR, c) = cells.Wcr[k];
       CC(base + CL_WPWP, c) = cells.Wpwp[k];
       CC(base + CL_WCR_M_WPWP, c) = (cells.Wcr[k] - cells.Wpwp[k]);

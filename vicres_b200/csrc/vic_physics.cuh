@@ -70,45 +70,56 @@ VR_HDN double m_pow(double x, double y)
 {
 #if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM)
   if (x == 1.0 || y == 0.0) return 1.0;
-  if (!(x >= 2.2250738585072014e-308) || !(x <= 1e300) || !(fabs(y) <= 1e5)) return pow(x, y);
-  const long long ix = __double_as_longlong(x);
-  int e = (int)((ix >> 52) & 0x7ff) - 1023;
-  double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-  const double f = (m - 1.0) / (m + 1.0);
-  const double f2 = f * f;
-  // 2*atanh(f)/f = 2*(1 + f2/3 + f2^2/5 + ...), truncated after f2^10 (|f2| <= 0.0295 -> 1e-17)
-  double q = 2.0 / 21.0;
-  q = fma(q, f2, 2.0 / 19.0);
-  q = fma(q, f2, 2.0 / 17.0);
-  q = fma(q, f2, 2.0 / 15.0);
-  q = fma(q, f2, 2.0 / 13.0);
-  q = fma(q, f2, 2.0 / 11.0);
-  q = fma(q, f2, 2.0 / 9.0);
-  q = fma(q, f2, 2.0 / 7.0);
-  q = fma(q, f2, 2.0 / 5.0);
-  q = fma(q, f2, 2.0 / 3.0);
-  const double lnm = fma(q * f2, f, 2.0 * f);               // ln(m)
-  const double l2m = lnm * 1.4426950408889634;              // log2(m), |l2m| <= 0.5
-  const double t = fma(y, l2m, y * (double)e);              // y*log2(x)
-  if (!(fabs(t) < 1000.0)) return pow(x, y);
-  const double n = rint(t);
-  const double z = (t - n) * 0.6931471805599453;            // |z| <= 0.3466
-  double p = 1.0 / 6227020800.0;
-  p = fma(p, z, 1.0 / 479001600.0);
-  p = fma(p, z, 1.0 / 39916800.0);
-  p = fma(p, z, 1.0 / 3628800.0);
-  p = fma(p, z, 1.0 / 362880.0);
-  p = fma(p, z, 1.0 / 40320.0);
-  p = fma(p, z, 1.0 / 5040.0);
-  p = fma(p, z, 1.0 / 720.0);
-  p = fma(p, z, 1.0 / 120.0);
-  p = fma(p, z, 1.0 / 24.0);
-  p = fma(p, z, 1.0 / 6.0);
-  p = fma(p, z, 0.5);
-  p = fma(p, z, 1.0);
-  p = fma(p, z, 1.0);
-  return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+  if (x == 0.0 && y > 0.0) return 0.0;            // dry layer: Q12 = Ksat * 0^expt
+  if ((x >= 2.2250738585072014e-308) && (x <= 1e300) && (fabs(y) <= 1e5)) {
+    const long long ix = __double_as_longlong(x);
+    int e = (int)((ix >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    // f = (m-1)/(m+1) without the IEEE division sequence: approximate reciprocal + 2 Newton steps
+    const double d = m + 1.0, nm = m - 1.0;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    double f = nm * r;
+    f = fma(fma(-f, d, nm), r, f);
+    const double f2 = f * f;
+    // 2*atanh(f)/f = 2*(1 + f2/3 + f2^2/5 + ...), truncated after f2^10 (|f2| <= 0.0295 -> 1e-17)
+    double q = 2.0 / 21.0;
+    q = fma(q, f2, 2.0 / 19.0);
+    q = fma(q, f2, 2.0 / 17.0);
+    q = fma(q, f2, 2.0 / 15.0);
+    q = fma(q, f2, 2.0 / 13.0);
+    q = fma(q, f2, 2.0 / 11.0);
+    q = fma(q, f2, 2.0 / 9.0);
+    q = fma(q, f2, 2.0 / 7.0);
+    q = fma(q, f2, 2.0 / 5.0);
+    q = fma(q, f2, 2.0 / 3.0);
+    const double lnm = fma(q * f2, f, 2.0 * f);               // ln(m)
+    const double l2m = lnm * 1.4426950408889634;              // log2(m), |l2m| <= 0.5
+    const double t = fma(y, l2m, y * (double)e);              // y*log2(x)
+    if (fabs(t) < 1000.0) {
+      const double n = rint(t);
+      const double z = (t - n) * 0.6931471805599453;          // |z| <= 0.3466
+      double p = 1.0 / 6227020800.0;
+      p = fma(p, z, 1.0 / 479001600.0);
+      p = fma(p, z, 1.0 / 39916800.0);
+      p = fma(p, z, 1.0 / 3628800.0);
+      p = fma(p, z, 1.0 / 362880.0);
+      p = fma(p, z, 1.0 / 40320.0);
+      p = fma(p, z, 1.0 / 5040.0);
+      p = fma(p, z, 1.0 / 720.0);
+      p = fma(p, z, 1.0 / 120.0);
+      p = fma(p, z, 1.0 / 24.0);
+      p = fma(p, z, 1.0 / 6.0);
+      p = fma(p, z, 0.5);
+      p = fma(p, z, 1.0);
+      p = fma(p, z, 1.0);
+      return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+    }
+  }
+  return pow(x, y);
 #else
   return pow(x, y);
 #endif
@@ -157,18 +168,18 @@ constexpr int MAXL = 3;
 enum {  // index into the per-cell constant block  cc[k*C + c]
   CC_LAT = 0, CC_ELEV, CC_HALF_ELEV_LAPSE, CC_B, CC_INV_B, CC_INV_B1, CC_ONE_PLUS_B, CC_EX, CC_TOP_MAX,
   CC_TOP_MAX_INFIL, CC_ARNO_MAXM, CC_ARNO_MAX_INFIL, CC_DSMAX24, CC_BF_FRAC, CC_BF_NL, CC_WS, CC_ONE_M_WS,
-  CC_C, CC_AVG_T, CC_DP, CC_D1, CC_EXP_M, CC_EXP_P, CC_KB_BARE,
+  CC_C, CC_AVG_T, CC_DP, CC_D1, CC_EXP_M, CC_EXP_P, CC_KB_BARE, CC_INV_ONE_M_WS,
   CC_LAYER0,   // then per layer l: CC_LAYER0 + l*CL_N + field
   CL_EXPT = 0, CL_KSAT24, CL_MAX_MOIST, CL_RESID, CL_QDEN, CL_WCR, CL_WPWP, CL_WCR_M_WPWP, CL_WET_DEN,
-  CL_DEPTH, CL_KDRY, CL_KSAT_M_KDRY, CL_POROS, CL_SOILFR, CL_CS_SOLID, CL_N
+  CL_DEPTH, CL_INV_QDEN, CL_KDRY, CL_KSAT_M_KDRY, CL_POROS, CL_SOILFR, CL_CS_SOLID, CL_N
 };
 #define VR_CC_N(nlayer) (::vr::CC_LAYER0 + (nlayer) * ::vr::CL_N)
 
 struct CellC {   // the constants above, unpacked for one cell
   double lat, elev, half_elev_lapse, b, inv_b, inv_b1, one_plus_b, ex, top_max, top_max_infil, arno_maxm,
-         arno_max_infil, dsmax24, bf_frac, bf_nl, Ws, one_m_Ws, c, avg_T, dp, D1, exp_m, exp_p, kb_bare;
+         arno_max_infil, dsmax24, bf_frac, bf_nl, Ws, one_m_Ws, c, avg_T, dp, D1, exp_m, exp_p, kb_bare, inv_one_m_Ws;
   double expt[MAXL], ksat24[MAXL], max_moist[MAXL], resid[MAXL], qden[MAXL], Wcr[MAXL], Wpwp[MAXL],
-         wcr_m_wpwp[MAXL], wet_den[MAXL], depth[MAXL], kdry[2], ksat_m_kdry[2], poros[2], soilfr[2], cs_solid[2];
+         wcr_m_wpwp[MAXL], wet_den[MAXL], depth[MAXL], inv_qden[MAXL], kdry[2], ksat_m_kdry[2], poros[2], soilfr[2], cs_solid[2];
 };
 
 // per-unit constants (tile x band)
@@ -215,7 +226,7 @@ VR_HD void load_cell_consts(const double *cc, int64_t C, int64_t c, int NL, Cell
   x.top_max = G_(CC_TOP_MAX); x.top_max_infil = G_(CC_TOP_MAX_INFIL); x.arno_maxm = G_(CC_ARNO_MAXM);
   x.arno_max_infil = G_(CC_ARNO_MAX_INFIL); x.dsmax24 = G_(CC_DSMAX24); x.bf_frac = G_(CC_BF_FRAC);
   x.bf_nl = G_(CC_BF_NL); x.Ws = G_(CC_WS); x.one_m_Ws = G_(CC_ONE_M_WS); x.c = G_(CC_C); x.avg_T = G_(CC_AVG_T);
-  x.dp = G_(CC_DP); x.D1 = G_(CC_D1); x.exp_m = G_(CC_EXP_M); x.exp_p = G_(CC_EXP_P); x.kb_bare = G_(CC_KB_BARE);
+  x.dp = G_(CC_DP); x.D1 = G_(CC_D1); x.exp_m = G_(CC_EXP_M); x.exp_p = G_(CC_EXP_P); x.kb_bare = G_(CC_KB_BARE); x.inv_one_m_Ws = G_(CC_INV_ONE_M_WS);
 #pragma unroll
   for (int l = 0; l < MAXL; l++) {
     if (l < NL) {
@@ -223,7 +234,7 @@ VR_HD void load_cell_consts(const double *cc, int64_t C, int64_t c, int NL, Cell
       x.expt[l] = G_(b + CL_EXPT); x.ksat24[l] = G_(b + CL_KSAT24); x.max_moist[l] = G_(b + CL_MAX_MOIST);
       x.resid[l] = G_(b + CL_RESID); x.qden[l] = G_(b + CL_QDEN); x.Wcr[l] = G_(b + CL_WCR);
       x.Wpwp[l] = G_(b + CL_WPWP); x.wcr_m_wpwp[l] = G_(b + CL_WCR_M_WPWP); x.wet_den[l] = G_(b + CL_WET_DEN);
-      x.depth[l] = G_(b + CL_DEPTH);
+      x.depth[l] = G_(b + CL_DEPTH); x.inv_qden[l] = G_(b + CL_INV_QDEN);
       if (l < 2) {
         x.kdry[l] = G_(b + CL_KDRY); x.ksat_m_kdry[l] = G_(b + CL_KSAT_M_KDRY); x.poros[l] = G_(b + CL_POROS);
         x.soilfr[l] = G_(b + CL_SOILFR); x.cs_solid[l] = G_(b + CL_CS_SOLID);
@@ -1104,119 +1115,121 @@ VR_HDN void runoff_and_asat(const CellC &cc, const double *moist, int NL, double
   if (*runoff < 0.) *runoff = 0.;
 }
 
-// moist[]: in/out (mm); evap_l[]: in layer evaporation for the step (mm), evap_l[NL-1] may be reduced
-VR_HDN void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moist, double *evap_l, double *asat,
+// Division by a per-cell constant.  The device multiplies by the reciprocal prepared on the host
+// (1 ulp apart from the reference's x/d; the drainage loop alone has 96 such divisions per tile-day);
+// the host / VR_EXACT_LIBM build divides, which keeps tests/hostsim bit-identical to the reference.
+#if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM)
+#define VR_DIVC(x, d, inv_d) ((x) * (inv_d))
+#else
+#define VR_DIVC(x, d, inv_d) ((x) / (d))
+#endif
+
+// moist[]: in/out (mm); evap_l[]: in layer evaporation for the step (mm), evap_l[NL-1] may be reduced.
+// Layers are scalars (no dynamically indexed arrays -> no local memory in the hourly loop); the
+// reference's while-loops that push excess water upwards (runoff.c:362-391,448-475) are unrolled.
+template <int NL>
+VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, double *evap_l, double *asat,
                        double *runoff_out, double *baseflow_out)
 {
-  double liq[MAXL], evap[MAXL], Q12[MAXL - 1], A, runoff_, baseflow = 0;
+  constexpr int LB = NL - 1;                      // bottom layer
+  const double r0 = cc.resid[0], r1 = cc.resid[1], rB = cc.resid[LB];
+  const double m0 = cc.max_moist[0], m1 = cc.max_moist[1], mB = cc.max_moist[LB];
+  double liq0 = moist[0], liq1 = moist[1], liqB = moist[LB];
+  double ev[MAXL];
+#pragma unroll
   for (int l = 0; l < NL; l++) {
-    evap[l] = evap_l[l] / (double)dt;
-    liq[l] = moist[l];
-    if (evap[l] > 0) {
-      double avail_liq = (moist[l] - 0. - cc.resid[l]);
+    double e = evap_l[l] / (double)dt;
+    if (e > 0) {
+      double avail_liq = (moist[l] - cc.resid[l]);
       if (avail_liq < 0) avail_liq = 0;
-      double sum_liq = 0. + avail_liq * 1.;
-      double evap_fraction = (sum_liq > 0) ? evap[l] / sum_liq : 1.0;
-      evap[l] = avail_liq * evap_fraction;
+      double evap_fraction = (avail_liq > 0) ? e / avail_liq : 1.0;
+      e = avail_liq * evap_fraction;
     }
+    ev[l] = e;
   }
-  runoff_and_asat(cc, liq, NL, ppt, &A, &runoff_);
-  double tmp_dt_runoff = runoff_ / (double)dt, dt_inflow = ppt / (double)dt;
+  const double ev0 = ev[0], ev1 = ev[1], evB = ev[LB];
+  double A, runoff_, baseflow = 0;
+  {
+    double lq[MAXL] = {liq0, liq1, liqB};
+    runoff_and_asat(cc, lq, NL, ppt, &A, &runoff_);
+  }
+  const double tmp_dt_runoff = runoff_ / (double)dt, dt_inflow = ppt / (double)dt;
 #pragma unroll 1
   for (int ts = 0; ts < dt; ts++) {
-    VR_LOOP_SYNC();
-    double inflow = dt_inflow;
-    for (int l = 0; l < NL - 1; l++) {
-      double tmp_liq = liq[l] - evap[l];
-      if (tmp_liq < cc.resid[l]) tmp_liq = cc.resid[l];
-      if (liq[l] > cc.resid[l]) Q12[l] = cc.ksat24[l] * VR_POW(((tmp_liq - cc.resid[l]) / cc.qden[l]), cc.expt[l]);
-      else Q12[l] = 0.;
+    // Brooks-Corey drainage out of the upper layers (runoff.c:330-340)
+    double t0 = liq0 - ev0;
+    if (t0 < r0) t0 = r0;
+    double Q0 = (liq0 > r0) ? cc.ksat24[0] * VR_POW(VR_DIVC(t0 - r0, cc.qden[0], cc.inv_qden[0]), cc.expt[0]) : 0.;
+    double Q1 = 0.;
+    if (NL == 3) {
+      double t1 = liq1 - ev1;
+      if (t1 < r1) t1 = r1;
+      Q1 = (liq1 > r1) ? cc.ksat24[1] * VR_POW(VR_DIVC(t1 - r1, cc.qden[1], cc.inv_qden[1]), cc.expt[1]) : 0.;
     }
-    for (int l = 0; l < NL - 1; l++) {
-      double dt_runoff = (l == 0) ? tmp_dt_runoff : 0, tmp_inflow = 0.;
-      liq[l] = liq[l] + (inflow - dt_runoff) - (Q12[l] + evap[l]);
-      if ((liq[l] + 0.) > cc.max_moist[l]) {
-        tmp_inflow = (liq[l] + 0.) - cc.max_moist[l];
-        liq[l] = cc.max_moist[l] - 0.;
-        if (l == 0) {
-          Q12[l] += tmp_inflow;
-          tmp_inflow = 0;
-        }
-        else {
-          int tl = l;
-          while (tmp_inflow > 0) {
-            tl--;
-            if (tl < 0) {
-              runoff_ += tmp_inflow;
-              tmp_inflow = 0;
-            }
-            else {
-              liq[tl] += tmp_inflow;
-              if ((liq[tl] + 0.) > cc.max_moist[tl]) {
-                tmp_inflow = ((liq[tl] + 0.) - cc.max_moist[tl]);
-                liq[tl] = cc.max_moist[tl] - 0.;
-              }
-              else tmp_inflow = 0;
-            }
-          }
-        }
+    // top layer
+    liq0 = liq0 + (dt_inflow - tmp_dt_runoff) - (Q0 + ev0);
+    if (liq0 > m0) { Q0 += liq0 - m0; liq0 = m0; }
+    if (liq0 < 0) { Q0 += liq0; liq0 = 0; }
+    if (liq0 < r0) { Q0 += liq0 - r0; liq0 = r0; }
+    double Qin = Q0;                       // what reaches the layer below
+    if (NL == 3) {
+      liq1 = liq1 + Qin - (Q1 + ev1);
+      if (liq1 > m1) {
+        double ex = liq1 - m1;
+        liq1 = m1;
+        liq0 += ex;
+        if (liq0 > m0) { runoff_ += liq0 - m0; liq0 = m0; }
       }
-      if (liq[l] < 0) {
-        Q12[l] += liq[l];
-        liq[l] = 0;
-      }
-      if ((liq[l] + 0.) < cc.resid[l]) {
-        Q12[l] += (liq[l] + 0.) - cc.resid[l];
-        liq[l] = cc.resid[l] - 0.;
-      }
-      inflow = (Q12[l] + tmp_inflow);
-      Q12[l] += tmp_inflow;
+      if (liq1 < 0) { Q1 += liq1; liq1 = 0; }
+      if (liq1 < r1) { Q1 += liq1 - r1; liq1 = r1; }
+      Qin = Q1;
     }
-    int l = NL - 1;
-    double rel_moist = (liq[l] - cc.resid[l]) / cc.qden[l];
+    // bottom layer: ARNO baseflow (runoff.c:420-435)
+    const double rel_moist = VR_DIVC(liqB - rB, cc.qden[LB], cc.inv_qden[LB]);
     double dt_baseflow = cc.bf_frac * rel_moist;
     if (rel_moist > cc.Ws) {
-      double frac = (rel_moist - cc.Ws) / cc.one_m_Ws;
+      const double frac = VR_DIVC(rel_moist - cc.Ws, cc.one_m_Ws, cc.inv_one_m_Ws);
       dt_baseflow += cc.bf_nl * ((cc.c == 2.0) ? frac * frac : VR_POW(frac, cc.c));   // pow(x,2) == x*x
     }
     if (dt_baseflow < 0) dt_baseflow = 0;
-    liq[l] += Q12[l - 1] - (evap[l] + dt_baseflow);
-    if ((liq[l] + 0.) < cc.resid[l]) {
-      dt_baseflow += (liq[l] + 0.) - cc.resid[l];
-      liq[l] = cc.resid[l] - 0.;
-    }
-    if ((liq[l] + 0.) > cc.max_moist[l]) {
-      double tmp_moist = ((liq[l] + 0.) - cc.max_moist[l]);
-      liq[l] = cc.max_moist[l] - 0.;
-      int tl = l;
-      while (tmp_moist > 0) {
-        tl--;
-        if (tl < 0) {
-          runoff_ += tmp_moist;
-          tmp_moist = 0;
-        }
-        else {
-          liq[tl] += tmp_moist;
-          if ((liq[tl] + 0.) > cc.max_moist[tl]) {
-            tmp_moist = ((liq[tl] + 0.) - cc.max_moist[tl]);
-            liq[tl] = cc.max_moist[tl] - 0.;
-          }
-          else tmp_moist = 0;
-        }
+    liqB += Qin - (evB + dt_baseflow);
+    if (liqB < rB) { dt_baseflow += liqB - rB; liqB = rB; }
+    if (liqB > mB) {
+      double ex = liqB - mB;
+      liqB = mB;
+      if (NL == 3) {
+        liq1 += ex;
+        if (liq1 > m1) { ex = liq1 - m1; liq1 = m1; }
+        else ex = 0;
+      }
+      if (ex > 0) {
+        liq0 += ex;
+        if (liq0 > m0) { runoff_ += liq0 - m0; liq0 = m0; }
       }
     }
     baseflow += dt_baseflow;
+    if (NL == 2) liq1 = liqB;
   }
   if (baseflow < 0) {
-    evap_l[NL - 1] += baseflow;
+    evap_l[LB] += baseflow;
     baseflow = 0;
   }
   double dummy;
-  runoff_and_asat(cc, liq, NL, 0., &A, &dummy);
-  for (int l = 0; l < NL; l++) moist[l] = 0. + ((liq[l] + 0.) * 1.);
-  *asat = 0. + A * 1.;
-  *runoff_out = 0. + runoff_ * 1.;
-  *baseflow_out = 0. + baseflow * 1.;
+  double lq[MAXL] = {liq0, (NL == 3) ? liq1 : liqB, liqB};
+  runoff_and_asat(cc, lq, NL, 0., &A, &dummy);
+  moist[0] = liq0;
+  if (NL == 3) moist[1] = liq1;
+  moist[LB] = liqB;
+  *asat = A;
+  *runoff_out = runoff_;
+  *baseflow_out = baseflow;
+}
+
+VR_HDN void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moist, double *evap_l, double *asat,
+                        double *runoff_out, double *baseflow_out)
+{
+  if (NL == 3) runoff_core<3>(cc, dt, ppt, moist, evap_l, asat, runoff_out, baseflow_out);
+  else runoff_core<2>(cc, dt, ppt, moist, evap_l, asat, runoff_out, baseflow_out);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -254,8 +254,9 @@ struct vr_handle {
   DBuf<float> d_u_root;
   DBuf<int64_t> d_cell_uptr, d_cta_cell, d_fcol, d_order, d_t_unit;
   DBuf<int32_t> d_u_cell, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  int chunk = 16;                    // records per pipelined chunk of vr_step_block
   int64_t launches = 0;
   bool timed = false;
 };
@@ -321,14 +322,22 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
   h->opt = *opt;
   h->device = device;
   memset(&h->M, 0, sizeof h->M);
-  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+  bool ok = (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) == cudaSuccess &&
+            (e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) == cudaSuccess &&
+            (e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) == cudaSuccess &&
+            (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess;
+  for (int b = 0; ok && b < 2; b++)
+    ok = (e = cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming)) == cudaSuccess &&
+         (e = cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming)) == cudaSuccess &&
+         (e = cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming)) == cudaSuccess;
+  if (!ok) {
     g_create_error = cudaGetErrorString(e);
     delete h;
     return VR_ERR_CUDA;
   }
   cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTERM * VR_CTA * sizeof(double)));
   cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTERM * VR_CTA * sizeof(double)));
+  if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   *out = h;
   return VR_OK;
 }
@@ -346,7 +355,14 @@ void vr_destroy(vr_handle *h)
   h->d_order.release(); h->d_t_unit.release(); h->d_u_slot.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int b = 0; b < 2; b++) {
+    if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
+    if (h->ev_comp[b]) cudaEventDestroy(h->ev_comp[b]);
+    if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
 }
 
@@ -479,33 +495,58 @@ int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, voi
   return launch_step(h, F, out_dev, st);
 }
 
+// Host-buffer entry point.  The block of records is cut into chunks of h->chunk records that flow
+// through three streams -- H2D of chunk k+1, k_step of chunk k and D2H of chunk k-1 overlap (PCIe is
+// full duplex) -- with two device buffers per direction.  Forcing [field][rec][col] and outputs
+// [var][rec][cell] are record-major, so a chunk is one contiguous copy per field / variable.
 int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *cell_status_host)
 {
   if (!h || !f || !out_host || f->nrec <= 0) return VR_ERR_ARG;
   if (!h->initialised) { h->err = "vr_init_state (or vr_set_state) must precede vr_step_block"; return VR_ERR_STATE; }
-  CK(cudaSetDevice(h->device));
-  const size_t n_in = (size_t)f->nrec * h->M.FC, n_out = (size_t)f->nrec * h->M.C;
-  CK(h->d_forc.reserve(n_in * VR_NFORCING));
-  CK(h->d_out.reserve(n_out * h->opt.n_out));
-  CK(h->d_month.reserve(f->nrec)); CK(h->d_doy.reserve(f->nrec));
-  cudaStream_t st = h->stream;
-  CK(cudaMemcpyAsync(h->d_month.p, f->month, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  DevForcing F;
-  F.nrec = f->nrec; F.month = h->d_month.p; F.doy = h->d_doy.p;
-  for (int i = 0; i < VR_NFORCING; i++) {
+  for (int i = 0; i < VR_NFORCING; i++)
     if (!f->field[i]) { h->err = "null forcing field"; return VR_ERR_ARG; }
-    CK(cudaMemcpyAsync(h->d_forc.p + i * n_in, f->field[i], n_in * sizeof(double), cudaMemcpyHostToDevice, st));
-    F.field[i] = h->d_forc.p + i * n_in;
+  CK(cudaSetDevice(h->device));
+  const int nrec = f->nrec, n_out = h->opt.n_out, CH = h->chunk < nrec ? h->chunk : nrec;
+  const size_t FC = (size_t)h->M.FC, C = (size_t)h->M.C;
+  const size_t in_chunk = (size_t)CH * FC * VR_NFORCING, out_chunk = (size_t)CH * C * n_out;
+  CK(h->d_forc.reserve(2 * in_chunk));
+  CK(h->d_out.reserve(2 * out_chunk));
+  CK(h->d_month.reserve(nrec)); CK(h->d_doy.reserve(nrec));
+  CK(cudaMemcpyAsync(h->d_month.p, f->month, nrec * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
+  CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, nrec * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
+  int k = 0;
+  for (int r0 = 0; r0 < nrec; r0 += CH, k++) {
+    const int nr = (nrec - r0 < CH) ? nrec - r0 : CH, b = k & 1;
+    double *din = h->d_forc.p + (size_t)b * in_chunk, *dout = h->d_out.p + (size_t)b * out_chunk;
+    if (k >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));       // kernel of chunk k-2 has consumed din
+    DevForcing F;
+    F.nrec = nr; F.month = h->d_month.p + r0; F.doy = h->d_doy.p + r0;
+    for (int i = 0; i < VR_NFORCING; i++) {
+      CK(cudaMemcpyAsync(din + (size_t)i * nr * FC, f->field[i] + (size_t)r0 * FC, (size_t)nr * FC * sizeof(double),
+                         cudaMemcpyHostToDevice, h->s_in));
+      F.field[i] = din + (size_t)i * nr * FC;
+    }
+    CK(cudaEventRecord(h->ev_in[b], h->s_in));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+    if (k >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));      // D2H of chunk k-2 has drained dout
+    int rc = launch_step(h, F, dout, h->stream);
+    if (rc != VR_OK) return rc;
+    CK(cudaEventRecord(h->ev_comp[b], h->stream));
+    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
+    for (int v = 0; v < n_out; v++)
+      CK(cudaMemcpyAsync(out_host + ((size_t)v * nrec + r0) * C, dout + (size_t)v * nr * C, (size_t)nr * C * sizeof(double),
+                         cudaMemcpyDeviceToHost, h->s_out));
+    CK(cudaEventRecord(h->ev_out[b], h->s_out));
   }
-  int rc = launch_step(h, F, h->d_out.p, st);
-  if (rc != VR_OK) return rc;
-  CK(cudaMemcpyAsync(out_host, h->d_out.p, n_out * h->opt.n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (cell_status_host) {
+    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[(k - 1) & 1], 0));
+    CK(cudaMemcpyAsync(cell_status_host, h->d_cell_status.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out));
+  }
+  CK(cudaStreamSynchronize(h->s_in));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->s_out));
   if (cell_status_host)
-    CK(cudaMemcpyAsync(cell_status_host, h->d_cell_status.p, h->M.C * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (cell_status_host)
-    for (int64_t c = 0; c < h->M.C; c++)
+    for (size_t c = 0; c < C; c++)
       if (cell_status_host[c]) return VR_ERR_CELL;
   return VR_OK;
 }
