@@ -17,7 +17,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
   if (!prepare(*opt, *lib, *cells, 128, P)) { fprintf(stderr, "hostsim: %s\n", P.error.c_str()); return -1; }
   const int NL = P.NL, nrec = f->nrec;
   const int64_t C = P.C, U = P.U;
-  std::vector<UnitS> S(U ? U : 1);
+  std::vector<UnitS> S_(U ? U : 1);
   std::vector<UnitC> UC(U ? U : 1);
   std::vector<double> sv((size_t)SV_N * C, 0.0);
   for (int64_t u = 0; u < U; u++) {
@@ -29,27 +29,29 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
     for (int l = 0; l < MAXL; l++) uc.root[l] = P.u_root[(size_t)l * U + u];
     double im[MAXL], mm[MAXL];
     for (int l = 0; l < NL; l++) { im[l] = cells->init_moist[(size_t)l * C + c]; mm[l] = cells->max_moist[(size_t)l * C + c]; }
-    unit_init(im, mm, NL, tair0[c], uc.Tfactor, S[u]);
+    unit_init(im, mm, NL, tair0[c], uc.Tfactor, S_[u]);
   }
-  double terms[NTERM], acc[NTERM], o[VR_NOUTVAR];
+  TermMap tmap;
+  build_term_map(opt->out_vars, opt->n_out, tmap);
+  const int MAXU = 512;
+  std::vector<double> buf((size_t)NTERM * MAXU);
   for (int64_t cs = 0; cs < C; cs++) {
     const int64_t c = P.order[cs];
+    const int64_t fu0 = P.cell_uptr[cs];
+    const int nu = (int)(P.cell_uptr[cs + 1] - fu0);
     CellC cc;
     load_cell_consts(P.cc.data(), C, c, NL, cc);
-    // put_data(rec = -nrecs)
-    {
-      for (int k = 0; k < NTERM; k++) acc[k] = 0;
-      double eb = 0, tv = 0;
+    auto col_of = [&](int j) { return j; };
+    auto S = [&](int k) { return buf[(size_t)tmap.row[k] * MAXU + 0]; };
+    double *svc = &sv[(size_t)c * SV_N];
+    {   // put_data(rec = -nrecs)
       UnitOut z;
       memset(&z, 0, sizeof z);
-      for (int64_t u = P.cell_uptr[cs]; u < P.cell_uptr[cs + 1]; u++) {
-        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S[u], z, NL, terms, 1);
-        cell_accumulate_ordered(acc, &eb, &tv, terms, 1, NL);
+      for (int j = 0; j < nu; j++) unit_terms(UC[fu0 + j], P.u_cv[fu0 + j], P.u_af[fu0 + j], S_[fu0 + j], z, NL, tmap, &buf[j], MAXU);
+      if (nu > 0) {
+        cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);
+        cell_carry(S, NL, svc);
       }
-      Forc f0;
-      memset(&f0, 0, sizeof f0);
-      f0.vp = 1; f0.vpd = 1;
-      cell_finish(acc, eb, tv, f0, NL, true, &sv[(size_t)c * SV_N], o);
     }
     for (int rec = 0; rec < nrec; rec++) {
       Forc fo;
@@ -59,18 +61,20 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
       fo.density = f->field[VR_F_DENSITY][k]; fo.shortwave = f->field[VR_F_SHORTWAVE][k];
       fo.longwave = f->field[VR_F_LONGWAVE][k];
       fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
-      for (int q = 0; q < NTERM; q++) acc[q] = 0;
-      double eb = 0, tv = 0;
-      for (int64_t u = P.cell_uptr[cs]; u < P.cell_uptr[cs + 1]; u++) {
+      for (int j = 0; j < nu; j++) {
+        const int64_t u = fu0 + j;
         UnitOut uo;
         const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
         const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];
-        unit_step(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S[u], uo);
-        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S[u], uo, NL, terms, 1);
-        cell_accumulate_ordered(acc, &eb, &tv, terms, 1, NL);
+        unit_step(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u], uo);
+        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S_[u], uo, NL, tmap, &buf[j], MAXU);
       }
-      cell_finish(acc, eb, tv, fo, NL, false, &sv[(size_t)c * SV_N], o);
-      for (int v = 0; v < opt->n_out; v++) out[((size_t)v * nrec + rec) * C + c] = o[opt->out_vars[v]];
+      if (nu > 0) {
+        cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);
+        for (int v = 0; v < opt->n_out; v++)
+          out[((size_t)v * nrec + rec) * C + c] = cell_output(opt->out_vars[v], S, fo, NL, false, svc);
+        cell_carry(S, NL, svc);
+      }
     }
   }
   return 0;

@@ -22,172 +22,239 @@ enum {
 // per-cell carried words of save_data_struct / calc_water_balance_error (put_data.c:586-632)
 enum { SV_SOIL = 0, SV_SWE, SV_WDEW, SV_STORAGE, SV_N };
 
-// terms[k * stride] for k in [0, NTERM)
+// Which terms a set of requested outputs needs (the others are neither stored nor summed), and their
+// rows in the shared-memory term buffer.  LIQ*, SWE, SCANOPY and WDEW are always kept: they feed
+// the save_data words (storage deltas, closure error) that are carried from record to record.
+struct TermMap {
+  signed char row[NTERM];   // row in the term buffer, or -1
+  int n;                    // rows in use
+};
+
+inline void build_term_map(const int *out_vars, int n_out, TermMap &tmap)
+{
+  bool need[NTERM];
+  for (int k = 0; k < NTERM; k++) need[k] = false;
+  auto N = [&](int k) { need[k] = true; };
+  for (int k : {TE_LIQ0, TE_LIQ1, TE_LIQ2, TE_SWE, TE_SCANOPY, TE_WDEW}) N(k);
+  for (int i = 0; i < n_out; i++) {
+    switch (out_vars[i]) {
+      case VR_OUT_PREC: N(TE_PREC); break;
+      case VR_OUT_EVAP: N(TE_EVAP); break;
+      case VR_OUT_RUNOFF: N(TE_RUNOFF); break;
+      case VR_OUT_BASEFLOW: N(TE_BASEFLOW); break;
+      case VR_OUT_NET_SHORT: N(TE_NSHORT); break;
+      case VR_OUT_R_NET: N(TE_NSHORT); N(TE_NLONG); break;
+      case VR_OUT_EVAP_CANOP: N(TE_EVAP_CANOP); break;
+      case VR_OUT_TRANSP_VEG: N(TE_TV0); N(TE_TV1); N(TE_TV2); break;
+      case VR_OUT_EVAP_BARE: N(TE_EB0); N(TE_EB1); N(TE_EB2); break;
+      case VR_OUT_SUB_CANOP: N(TE_SUB_CANOP); break;
+      case VR_OUT_SUB_SNOW: N(TE_SUB_SNOW); break;
+      case VR_OUT_AERO_RESIST: case VR_OUT_AERO_COND: N(TE_COND); break;
+      case VR_OUT_SURF_TEMP: N(TE_SURFT); break;
+      case VR_OUT_ALBEDO: N(TE_ALBEDO); break;
+      case VR_OUT_IN_LONG: N(TE_INLONG); break;
+      case VR_OUT_SNOW_DEPTH: N(TE_SDEPTH); break;
+      case VR_OUT_SNOW_COVER: N(TE_SCOVER); break;
+      case VR_OUT_WATER_ERROR: N(TE_PREC); N(TE_EVAP); N(TE_RUNOFF); N(TE_BASEFLOW); break;
+      case VR_OUT_INFLOW: N(TE_INFLOW); break;
+      case VR_OUT_SNOW_MELT: N(TE_SMELT); break;
+      case VR_OUT_RAINF: N(TE_RAIN); break;
+      case VR_OUT_SNOWF: N(TE_SNOWF); break;
+      case VR_OUT_NET_LONG: N(TE_NLONG); break;
+      case VR_OUT_ASAT: N(TE_ASAT); break;
+      case VR_OUT_SOIL_WET: N(TE_WET); break;
+      case VR_OUT_ROOTMOIST: N(TE_ROOTM); break;
+      case VR_OUT_GRND_FLUX: N(TE_GFLUX); break;
+      case VR_OUT_DELTAH: N(TE_DH); break;
+      case VR_OUT_SNOW_SURF_TEMP: N(TE_SST); N(TE_CVSNOW); break;
+      case VR_OUT_SNOW_PACK_TEMP: N(TE_SPT); N(TE_CVSNOW); break;
+      case VR_OUT_SALBEDO: N(TE_SALB); N(TE_CVSNOW); break;
+      default: break;
+    }
+  }
+  tmap.n = 0;
+  for (int k = 0; k < NTERM; k++) tmap.row[k] = need[k] ? (signed char)(tmap.n++) : (signed char)-1;
+}
+
+// One unit's area-weighted terms -> term buffer column `col` (rows of `stride` doubles).
 VR_HDN void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
-                      double *terms, int stride)
+                       const TermMap &tmap, double *col, int stride)
 {
   const double AF = cv * af * 1. * 1.;
   const bool HasVeg = !uc.is_bare;
-#define T_(k) terms[(k) * stride]
+#define T_(k, expr) do { if (tmap.row[k] >= 0) col[tmap.row[k] * stride] = (expr); } while (0)
   double tmp_evap = 0.0;
 #pragma unroll
   for (int l = 0; l < MAXL; l++) {
     if (l < NL) {
       tmp_evap += o.evap[l];
       if (HasVeg) {
-        T_(TE_EB0 + l) = o.evap[l] * o.bef[l] * AF;
-        T_(TE_TV0 + l) = o.evap[l] * (1 - o.bef[l]) * AF;
+        T_(TE_EB0 + l, o.evap[l] * o.bef[l] * AF);
+        T_(TE_TV0 + l, o.evap[l] * (1 - o.bef[l]) * AF);
       }
       else {
-        T_(TE_EB0 + l) = o.evap[l] * AF;
-        T_(TE_TV0 + l) = 0.;
+        T_(TE_EB0 + l, o.evap[l] * AF);
+        T_(TE_TV0 + l, 0.);
       }
-      T_(TE_LIQ0 + l) = s.moist[l] * AF;
+      T_(TE_LIQ0 + l, s.moist[l] * AF);
     }
-    else { T_(TE_EB0 + l) = 0.; T_(TE_TV0 + l) = 0.; T_(TE_LIQ0 + l) = 0.; }
+    else { T_(TE_EB0 + l, 0.); T_(TE_TV0 + l, 0.); T_(TE_LIQ0 + l, 0.); }
   }
   tmp_evap += o.vapor_flux * 1000.;
-  T_(TE_SUB_SNOW) = o.vapor_flux * 1000. * AF;
+  T_(TE_SUB_SNOW, o.vapor_flux * 1000. * AF);
   if (HasVeg) {
     tmp_evap += o.canopy_vapor_flux * 1000.;
-    T_(TE_SUB_CANOP) = o.canopy_vapor_flux * 1000. * AF;
+    T_(TE_SUB_CANOP, o.canopy_vapor_flux * 1000. * AF);
     tmp_evap += o.canopyevap;
-    T_(TE_EVAP_CANOP) = o.canopyevap * AF;
-    T_(TE_WDEW) = s.Wdew * AF;
-    T_(TE_SCANOPY) = (s.snow_canopy) * AF * 1000.;
+    T_(TE_EVAP_CANOP, o.canopyevap * AF);
+    T_(TE_WDEW, s.Wdew * AF);
+    T_(TE_SCANOPY, (s.snow_canopy) * AF * 1000.);
   }
-  else { T_(TE_SUB_CANOP) = 0.; T_(TE_EVAP_CANOP) = 0.; T_(TE_WDEW) = 0.; T_(TE_SCANOPY) = 0.; }
-  T_(TE_EVAP) = tmp_evap * AF;
-  T_(TE_ASAT) = o.asat * AF;
-  T_(TE_RUNOFF) = o.runoff * AF;
-  T_(TE_BASEFLOW) = o.baseflow * AF;
-  T_(TE_INFLOW) = (o.inflow) * AF;
+  else { T_(TE_SUB_CANOP, 0.); T_(TE_EVAP_CANOP, 0.); T_(TE_WDEW, 0.); T_(TE_SCANOPY, 0.); }
+  T_(TE_EVAP, tmp_evap * AF);
+  T_(TE_ASAT, o.asat * AF);
+  T_(TE_RUNOFF, o.runoff * AF);
+  T_(TE_BASEFLOW, o.baseflow * AF);
+  T_(TE_INFLOW, (o.inflow) * AF);
   {
     const double ar = uc.overstory ? o.aero_resist[1] : o.aero_resist[0];
-    T_(TE_COND) = (ar > SMALLV) ? (1 / ar) * AF : HUGE_RESIST;
+    T_(TE_COND, (ar > SMALLV) ? (1 / ar) * AF : HUGE_RESIST);
   }
-  T_(TE_WET) = o.wetness * AF;
-  T_(TE_ROOTM) = o.rootmoist * AF;
-  T_(TE_SWE) = s.swq * AF * 1000.;
-  T_(TE_SDEPTH) = s.depth * AF * 100.;
+  T_(TE_WET, o.wetness * AF);
+  T_(TE_ROOTM, o.rootmoist * AF);
+  T_(TE_SWE, s.swq * AF * 1000.);
+  T_(TE_SDEPTH, s.depth * AF * 100.);
   if (s.swq > 0.0) {
-    T_(TE_SALB) = s.albedo * AF;
-    T_(TE_SST) = s.surf_temp * AF;
-    T_(TE_SPT) = s.pack_temp * AF;
-    T_(TE_CVSNOW) = cv * af * 1.;
+    T_(TE_SALB, s.albedo * AF);
+    T_(TE_SST, s.surf_temp * AF);
+    T_(TE_SPT, s.pack_temp * AF);
+    T_(TE_CVSNOW, cv * af * 1.);
   }
-  else { T_(TE_SALB) = 0.; T_(TE_SST) = 0.; T_(TE_SPT) = 0.; T_(TE_CVSNOW) = 0.; }
-  T_(TE_SMELT) = o.melt * AF;
-  T_(TE_SCOVER) = s.coverage * AF;
-  T_(TE_SURFT) = o.Tsurf * AF;
-  T_(TE_NSHORT) = o.NetShortAtmos * AF;
-  T_(TE_NLONG) = o.NetLongAtmos * AF;
-  T_(TE_INLONG) = o.in_long * AF;
-  T_(TE_ALBEDO) = o.albedo * AF;
-  T_(TE_GFLUX) = o.grnd_flux * AF;
-  T_(TE_DH) = o.deltaH * AF;
-  T_(TE_PREC) = o.out_prec * cv * af;
-  T_(TE_RAIN) = o.out_rain * cv * af;
-  T_(TE_SNOWF) = o.out_snow * cv * af;
+  else { T_(TE_SALB, 0.); T_(TE_SST, 0.); T_(TE_SPT, 0.); T_(TE_CVSNOW, 0.); }
+  T_(TE_SMELT, o.melt * AF);
+  T_(TE_SCOVER, s.coverage * AF);
+  T_(TE_SURFT, o.Tsurf * AF);
+  T_(TE_NSHORT, o.NetShortAtmos * AF);
+  T_(TE_NLONG, o.NetLongAtmos * AF);
+  T_(TE_INLONG, o.in_long * AF);
+  T_(TE_ALBEDO, o.albedo * AF);
+  T_(TE_GFLUX, -(o.grnd_flux * AF));     // collect_eb_terms subtracts these two
+  T_(TE_DH, -(o.deltaH * AF));
+  T_(TE_PREC, o.out_prec * cv * af);
+  T_(TE_RAIN, o.out_rain * cv * af);
+  T_(TE_SNOWF, o.out_snow * cv * af);
 #undef T_
 }
 
-// acc[NTERM] zero-initialised; add one unit's terms (same rounding sequence as the reference loop)
-VR_HD void cell_accumulate(double *acc, const double *terms, int stride)
+// Sum the terms of one cell's units IN REFERENCE ORDER (tiles ascending, bands ascending) and leave
+// the sums in the column of the cell's first unit.  cols[j] = buffer column of the cell's j-th unit.
+// The three per-layer EVAP_BARE / TRANSP_VEG terms of a unit are added layer by layer into ONE
+// accumulator each, exactly as collect_wb_terms does; the sums land in rows EB0 / TV0.
+template <class ColOf>
+VR_HD void cell_accumulate_inplace(double *buf, int stride, const TermMap &tmap, int nu, ColOf col_of, int NL)
 {
-#pragma unroll
+  const int c0 = col_of(0);
+#pragma unroll 1
   for (int k = 0; k < NTERM; k++) {
-    if (k == TE_GFLUX || k == TE_DH) acc[k] -= terms[k * stride];
-    else acc[k] += terms[k * stride];
+    const int r = tmap.row[k];
+    if (r < 0 || (k >= TE_EB0 && k <= TE_TV2)) continue;
+    double a = 0. + buf[r * stride + c0];
+    for (int j = 1; j < nu; j++) a += buf[r * stride + col_of(j)];
+    buf[r * stride + c0] = a;
+  }
+  if (tmap.row[TE_EB0] >= 0) {
+    double eb = 0;
+    for (int j = 0; j < nu; j++)
+      for (int l = 0; l < NL; l++) eb += buf[tmap.row[TE_EB0 + l] * stride + col_of(j)];
+    buf[tmap.row[TE_EB0] * stride + c0] = eb;
+  }
+  if (tmap.row[TE_TV0] >= 0) {
+    double tv = 0;
+    for (int j = 0; j < nu; j++)
+      for (int l = 0; l < NL; l++) tv += buf[tmap.row[TE_TV0 + l] * stride + col_of(j)];
+    buf[tmap.row[TE_TV0] * stride + c0] = tv;
   }
 }
 
-// the per-unit order of the three per-layer EVAP_BARE / TRANSP_VEG adds is layer-major inside a unit
-// (collect_wb_terms), which cell_accumulate cannot express with one slot per layer -> fold them here
-VR_HD void cell_accumulate_ordered(double *acc, double *eb, double *tv, const double *terms, int stride, int NL)
+// One output variable of a cell-record from the summed terms (put_data.c:540-632).  S(k) reads sum k.
+// water_error / deltas use the carried save_data words sv[] BEFORE cell_carry() updates them.
+template <class Sum>
+VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const double *sv)
 {
-  for (int l = 0; l < NL; l++) {
-    *eb += terms[(TE_EB0 + l) * stride];
-    *tv += terms[(TE_TV0 + l) * stride];
+  switch (var) {
+    case VR_OUT_AIR_TEMP: return f.air_temp;
+    case VR_OUT_LONGWAVE: return f.longwave;
+    case VR_OUT_SHORTWAVE: return f.shortwave;
+    case VR_OUT_WIND: return f.wind;
+    case VR_OUT_REL_HUMID: return 100. * f.vp / (f.vp + f.vpd);
+    case VR_OUT_PREC: return S(TE_PREC);
+    case VR_OUT_RAINF: return S(TE_RAIN);
+    case VR_OUT_SNOWF: return S(TE_SNOWF);
+    case VR_OUT_EVAP_BARE: return S(TE_EB0);
+    case VR_OUT_TRANSP_VEG: return S(TE_TV0);
+    case VR_OUT_EVAP: return S(TE_EVAP);
+    case VR_OUT_SUB_SNOW: return S(TE_SUB_SNOW);
+    case VR_OUT_SUB_CANOP: return S(TE_SUB_CANOP);
+    case VR_OUT_EVAP_CANOP: return S(TE_EVAP_CANOP);
+    case VR_OUT_ASAT: return S(TE_ASAT);
+    case VR_OUT_RUNOFF: return S(TE_RUNOFF);
+    case VR_OUT_BASEFLOW: return S(TE_BASEFLOW);
+    case VR_OUT_INFLOW: return S(TE_INFLOW);
+    case VR_OUT_WDEW: return S(TE_WDEW);
+    case VR_OUT_SOIL_LIQ0: return S(TE_LIQ0);
+    case VR_OUT_SOIL_LIQ1: return S(TE_LIQ1);
+    case VR_OUT_SOIL_LIQ2: return (NL > 2) ? S(TE_LIQ2) : 0.;
+    case VR_OUT_SOIL_WET: return S(TE_WET);
+    case VR_OUT_ROOTMOIST: return S(TE_ROOTM);
+    case VR_OUT_SWE: return S(TE_SWE);
+    case VR_OUT_SNOW_DEPTH: return S(TE_SDEPTH);
+    case VR_OUT_SNOW_CANOPY: return S(TE_SCANOPY);
+    case VR_OUT_SNOW_MELT: return S(TE_SMELT);
+    case VR_OUT_SNOW_COVER: return S(TE_SCOVER);
+    case VR_OUT_SURF_TEMP: return S(TE_SURFT);
+    case VR_OUT_NET_SHORT: return S(TE_NSHORT);
+    case VR_OUT_NET_LONG: return S(TE_NLONG);
+    case VR_OUT_R_NET: return S(TE_NSHORT) + S(TE_NLONG);
+    case VR_OUT_IN_LONG: return S(TE_INLONG);
+    case VR_OUT_ALBEDO: return S(TE_ALBEDO);
+    case VR_OUT_GRND_FLUX: return S(TE_GFLUX);
+    case VR_OUT_DELTAH: return S(TE_DH);
+    case VR_OUT_SALBEDO: { double c = S(TE_CVSNOW), v = S(TE_SALB); return (c > 0) ? v / c : v; }
+    case VR_OUT_SNOW_SURF_TEMP: { double c = S(TE_CVSNOW), v = S(TE_SST); return (c > 0) ? v / c : v; }
+    case VR_OUT_SNOW_PACK_TEMP: { double c = S(TE_CVSNOW), v = S(TE_SPT); return (c > 0) ? v / c : v; }
+    case VR_OUT_AERO_COND: return S(TE_COND);
+    case VR_OUT_AERO_RESIST: return (S(TE_COND) > SMALLV) ? 1 / S(TE_COND) : HUGE_RESIST;
+    case VR_OUT_DELSOILMOIST: {
+      double d = 0;
+      for (int l = 0; l < NL; l++) d += S(TE_LIQ0 + l) + 0.;
+      return init ? d : d - sv[SV_SOIL];
+    }
+    case VR_OUT_DELSWE: return init ? 0. : S(TE_SWE) + S(TE_SCANOPY) - sv[SV_SWE];
+    case VR_OUT_DELINTERCEPT: return init ? 0. : S(TE_WDEW) - sv[SV_WDEW];
+    case VR_OUT_WATER_ERROR: {
+      if (init) return 0.0;
+      const double inflow = S(TE_PREC) + 0.;
+      const double outflow = S(TE_EVAP) + S(TE_RUNOFF) + S(TE_BASEFLOW);
+      double storage = 0.;
+      for (int l = 0; l < NL; l++) storage += S(TE_LIQ0 + l) + 0.;
+      storage += S(TE_SWE) + S(TE_SCANOPY) + S(TE_WDEW) + 0.;
+      return inflow - outflow - (storage - sv[SV_STORAGE]);
+    }
+    default: return 0.;
   }
-  cell_accumulate(acc, terms, stride);
 }
 
-// finish one cell-record: o[VR_NOUTVAR]
-VR_HDN void cell_finish(const double *acc, double eb, double tv, const Forc &f, int NL, bool init, double *sv, double *o)
+// carry the save_data words to the next record (put_data.c:612-620, calc_water_balance_error)
+template <class Sum>
+VR_HD void cell_carry(Sum S, int NL, double *sv)
 {
-#pragma unroll
-  for (int k = 0; k < VR_NOUTVAR; k++) o[k] = 0;
-  o[VR_OUT_AIR_TEMP] = f.air_temp;
-  o[VR_OUT_LONGWAVE] = f.longwave;
-  o[VR_OUT_PREC] = acc[TE_PREC];
-  o[VR_OUT_RAINF] = acc[TE_RAIN];
-  o[VR_OUT_REL_HUMID] = 100. * f.vp / (f.vp + f.vpd);
-  o[VR_OUT_SHORTWAVE] = f.shortwave;
-  o[VR_OUT_SNOWF] = acc[TE_SNOWF];
-  o[VR_OUT_WIND] = f.wind;
-  o[VR_OUT_EVAP_BARE] = eb;
-  o[VR_OUT_TRANSP_VEG] = tv;
-  o[VR_OUT_EVAP] = acc[TE_EVAP];
-  o[VR_OUT_SUB_SNOW] = acc[TE_SUB_SNOW];
-  o[VR_OUT_SUB_CANOP] = acc[TE_SUB_CANOP];
-  o[VR_OUT_EVAP_CANOP] = acc[TE_EVAP_CANOP];
-  o[VR_OUT_ASAT] = acc[TE_ASAT];
-  o[VR_OUT_RUNOFF] = acc[TE_RUNOFF];
-  o[VR_OUT_BASEFLOW] = acc[TE_BASEFLOW];
-  o[VR_OUT_INFLOW] = acc[TE_INFLOW];
-  o[VR_OUT_WDEW] = acc[TE_WDEW];
-  o[VR_OUT_SOIL_LIQ0] = acc[TE_LIQ0];
-  o[VR_OUT_SOIL_LIQ1] = acc[TE_LIQ1];
-  o[VR_OUT_SOIL_LIQ2] = acc[TE_LIQ2];
-  o[VR_OUT_SOIL_WET] = acc[TE_WET];
-  o[VR_OUT_ROOTMOIST] = acc[TE_ROOTM];
-  o[VR_OUT_SWE] = acc[TE_SWE];
-  o[VR_OUT_SNOW_DEPTH] = acc[TE_SDEPTH];
-  o[VR_OUT_SNOW_CANOPY] = acc[TE_SCANOPY];
-  o[VR_OUT_SNOW_MELT] = acc[TE_SMELT];
-  o[VR_OUT_SNOW_COVER] = acc[TE_SCOVER];
-  o[VR_OUT_SURF_TEMP] = acc[TE_SURFT];
-  o[VR_OUT_NET_SHORT] = acc[TE_NSHORT];
-  o[VR_OUT_NET_LONG] = acc[TE_NLONG];
-  o[VR_OUT_IN_LONG] = acc[TE_INLONG];
-  o[VR_OUT_ALBEDO] = acc[TE_ALBEDO];
-  o[VR_OUT_GRND_FLUX] = acc[TE_GFLUX];
-  o[VR_OUT_DELTAH] = acc[TE_DH];
-  const double cv_snow = acc[TE_CVSNOW];
-  o[VR_OUT_SALBEDO] = acc[TE_SALB];
-  o[VR_OUT_SNOW_SURF_TEMP] = acc[TE_SST];
-  o[VR_OUT_SNOW_PACK_TEMP] = acc[TE_SPT];
-  if (cv_snow > 0) {
-    o[VR_OUT_SALBEDO] /= cv_snow;
-    o[VR_OUT_SNOW_SURF_TEMP] /= cv_snow;
-    o[VR_OUT_SNOW_PACK_TEMP] /= cv_snow;
-  }
-  o[VR_OUT_AERO_COND] = acc[TE_COND];
-  o[VR_OUT_AERO_RESIST] = (acc[TE_COND] > SMALLV) ? 1 / acc[TE_COND] : HUGE_RESIST;
-  double soil_tot = 0, dsm = 0;
-  for (int l = 0; l < NL; l++) {
-    double sm = o[VR_OUT_SOIL_LIQ0 + l] + 0.;
-    dsm += sm;
-    soil_tot += sm;
-  }
-  o[VR_OUT_DELSOILMOIST] = dsm;
-  if (!init) {
-    o[VR_OUT_DELSOILMOIST] -= sv[SV_SOIL];
-    o[VR_OUT_DELSWE] = o[VR_OUT_SWE] + o[VR_OUT_SNOW_CANOPY] - sv[SV_SWE];
-    o[VR_OUT_DELINTERCEPT] = o[VR_OUT_WDEW] - sv[SV_WDEW];
-  }
-  o[VR_OUT_R_NET] = o[VR_OUT_NET_SHORT] + o[VR_OUT_NET_LONG];
+  double soil_tot = 0, storage = 0.;
+  for (int l = 0; l < NL; l++) soil_tot += S(TE_LIQ0 + l) + 0.;
+  for (int l = 0; l < NL; l++) storage += S(TE_LIQ0 + l) + 0.;
+  storage += S(TE_SWE) + S(TE_SCANOPY) + S(TE_WDEW) + 0.;
   sv[SV_SOIL] = soil_tot;
-  sv[SV_SWE] = o[VR_OUT_SWE] + o[VR_OUT_SNOW_CANOPY];
-  sv[SV_WDEW] = o[VR_OUT_WDEW];
-  const double inflow = o[VR_OUT_PREC] + 0.;
-  const double outflow = o[VR_OUT_EVAP] + o[VR_OUT_RUNOFF] + o[VR_OUT_BASEFLOW];
-  double storage = 0.;
-  for (int l = 0; l < NL; l++) storage += o[VR_OUT_SOIL_LIQ0 + l] + 0.;
-  storage += o[VR_OUT_SWE] + o[VR_OUT_SNOW_CANOPY] + o[VR_OUT_WDEW] + 0.;
-  if (init) o[VR_OUT_WATER_ERROR] = 0.0;
-  else o[VR_OUT_WATER_ERROR] = inflow - outflow - (storage - sv[SV_STORAGE]);
+  sv[SV_SWE] = S(TE_SWE) + S(TE_SCANOPY);
+  sv[SV_WDEW] = S(TE_WDEW);
   sv[SV_STORAGE] = storage;
 }
 

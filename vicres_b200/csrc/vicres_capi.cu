@@ -45,6 +45,7 @@ struct DevModel {
   double *sv;                       // [SV_N][C]
   int32_t *cell_status;             // [C]
   int32_t out_vars[VR_MAX_OUT];
+  TermMap tmap;                     // rows of the shared-memory term buffer the requested outputs need
 };
 
 struct DevForcing {
@@ -119,19 +120,21 @@ __global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0
     unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
     store_state(M, u, s);
     memset(&z, 0, sizeof z);
-    unit_terms(uc, cv, af, s, z, M.NL, &sm[tid], VR_CTA);
+    unit_terms(uc, cv, af, s, z, M.NL, M.tmap, &sm[tid], VR_CTA);
   }
   __syncthreads();
   if (cs0 + tid < cs1) {
     const int64_t cs = cs0 + tid, c = M.order[cs];
-    double acc[NTERM], eb = 0, tv = 0, sv[SV_N] = {0, 0, 0, 0}, o[VR_NOUTVAR];
-    for (int k = 0; k < NTERM; k++) acc[k] = 0;
-    for (int64_t u = M.cell_uptr[cs]; u < M.cell_uptr[cs + 1]; u++)
-      cell_accumulate_ordered(acc, &eb, &tv, &sm[M.u_slot[u]], VR_CTA, M.NL);
-    Forc f0;
-    memset(&f0, 0, sizeof f0);
-    f0.vp = 1; f0.vpd = 1;
-    cell_finish(acc, eb, tv, f0, M.NL, true, sv, o);
+    const int64_t fu0 = M.cell_uptr[cs];
+    const int nu = (int)(M.cell_uptr[cs + 1] - fu0);
+    double sv[SV_N] = {0, 0, 0, 0};
+    if (nu > 0) {
+      auto col_of = [&](int j) { return (int)M.u_slot[fu0 + j]; };
+      cell_accumulate_inplace(sm, VR_CTA, M.tmap, nu, col_of, M.NL);
+      const int c0 = col_of(0);
+      auto S = [&](int k) { return sm[M.tmap.row[k] * VR_CTA + c0]; };
+      cell_carry(S, M.NL, sv);
+    }
     for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
     M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
   }
@@ -183,29 +186,30 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_step(DevModel M, DevForcing
       f.mon = mon; f.doy = doy;
       UnitOut uo;
       unit_step(cc, uc, tm + mon * TM_N, ae + mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s, uo);
-      if (active) unit_terms(uc, cv, af, s, uo, NL, &sm[tid], VR_CTA);
+      if (active) unit_terms(uc, cv, af, s, uo, NL, M.tmap, &sm[tid], VR_CTA);
     }
     __syncthreads();
     if (finisher) {
-      double o[VR_NOUTVAR];
-      if (!ffailed) {
-        double acc[NTERM], eb = 0, tv = 0;
-#pragma unroll
-        for (int k = 0; k < NTERM; k++) acc[k] = 0;
-        for (int64_t uu = fu0; uu < fu1; uu++)
-          cell_accumulate_ordered(acc, &eb, &tv, &sm[__ldg(M.u_slot + uu)], VR_CTA, NL);
+      const int nu = (int)(fu1 - fu0);
+      if (!ffailed && nu > 0) {
+        auto col_of = [&](int j) { return (int)__ldg(M.u_slot + fu0 + j); };
+        cell_accumulate_inplace(sm, VR_CTA, M.tmap, nu, col_of, NL);
+        const int c0 = col_of(0);
+        auto S = [&](int k) { return sm[M.tmap.row[k] * VR_CTA + c0]; };
         Forc f;
         const size_t k = (size_t)rec * M.FC + ffc;
         f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + k); f.wind = __ldg(F.field[VR_F_WIND] + k);
         f.vp = __ldg(F.field[VR_F_VP] + k); f.vpd = __ldg(F.field[VR_F_VPD] + k);
         f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
         f.prec = 0; f.pressure = 0; f.density = 0; f.mon = mon; f.doy = doy;
-        cell_finish(acc, eb, tv, f, NL, false, sv, o);
+#pragma unroll 1
+        for (int v = 0; v < M.n_out; v++)
+          out[((size_t)v * nrec + rec) * M.C + fcell] = cell_output(M.out_vars[v], S, f, NL, false, sv);
+        cell_carry(S, NL, sv);
       }
       else {
-        for (int k = 0; k < VR_NOUTVAR; k++) o[k] = 0;
+        for (int v = 0; v < M.n_out; v++) out[((size_t)v * nrec + rec) * M.C + fcell] = 0.;
       }
-      for (int v = 0; v < M.n_out; v++) out[((size_t)v * nrec + rec) * M.C + fcell] = o[M.out_vars[v]];
     }
     __syncthreads();
   }
@@ -335,8 +339,8 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     delete h;
     return VR_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTERM * VR_CTA * sizeof(double)));
-  cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTERM * VR_CTA * sizeof(double)));
+  cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NTERM * VR_CTA * sizeof(double)));
+  cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NTERM * VR_CTA * sizeof(double)));
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   *out = h;
   return VR_OK;
@@ -430,6 +434,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
   M.order = h->d_order.p; M.t_unit = h->d_t_unit.p; M.u_slot = h->d_u_slot.p;
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
+  build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
   h->have_cells = true;
   h->initialised = false;
   return VR_OK;
@@ -458,7 +463,7 @@ int vr_init_state(vr_handle *h, const double *tair0)
   CK(cudaSetDevice(h->device));
   CK(h->d_tair0.reserve(h->M.FC));
   CK(cudaMemcpyAsync(h->d_tair0.p, tair0, h->M.FC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  k_init<<<(unsigned)h->P.nCTA, VR_CTA, NTERM * VR_CTA * sizeof(double), h->stream>>>(h->M, h->d_tair0.p);
+  k_init<<<(unsigned)h->P.nCTA, VR_CTA, (size_t)h->M.tmap.n * VR_CTA * sizeof(double), h->stream>>>(h->M, h->d_tair0.p);
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -469,7 +474,7 @@ int vr_init_state(vr_handle *h, const double *tair0)
 static int launch_step(vr_handle *h, const DevForcing &F, double *out_dev, cudaStream_t st)
 {
   cudaEventRecord(h->ev0, st);
-  k_step<<<(unsigned)h->P.nCTA, VR_CTA, NTERM * VR_CTA * sizeof(double), st>>>(h->M, F, out_dev);
+  k_step<<<(unsigned)h->P.nCTA, VR_CTA, (size_t)h->M.tmap.n * VR_CTA * sizeof(double), st>>>(h->M, F, out_dev);
   cudaEventRecord(h->ev1, st);
   h->timed = true;
   h->launches++;
