@@ -40,7 +40,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
     const int64_t fu0 = P.cell_uptr[cs];
     const int nu = (int)(P.cell_uptr[cs + 1] - fu0);
     CellC cc;
-    load_cell_consts(P.cc.data(), C, c, NL, cc);
+    load_cell_consts(P.cc.data(), C, cs, NL, cc);
     auto col_of = [&](int j) { return j; };
     auto S = [&](int k) { return buf[(size_t)tmap.row[k] * MAXU + 0]; };
     double *svc = &sv[(size_t)c * SV_N];
@@ -63,11 +63,10 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
       fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
       for (int j = 0; j < nu; j++) {
         const int64_t u = fu0 + j;
-        UnitOut uo;
         const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
         const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];
-        unit_step(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u], uo);
-        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S_[u], uo, NL, tmap, &buf[j], MAXU);
+        unit_step_terms(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u],
+                        P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true);
       }
       if (nu > 0) {
         cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);

@@ -77,7 +77,7 @@ inline void build_term_map(const int *out_vars, int n_out, TermMap &tmap)
 }
 
 // One unit's area-weighted terms -> term buffer column `col` (rows of `stride` doubles).
-VR_HDN void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
+VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
                        const TermMap &tmap, double *col, int stride)
 {
   const double AF = cv * af * 1. * 1.;
@@ -144,6 +144,18 @@ VR_HDN void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, co
   T_(TE_RAIN, o.out_rain * cv * af);
   T_(TE_SNOWF, o.out_snow * cv * af);
 #undef T_
+}
+
+// One unit, one record, and its terms: the single out-of-line body the kernel calls per record.  Keeping
+// unit_step() and unit_terms() in one function lets the ~30 per-unit results travel in registers
+// instead of a UnitOut struct in local memory.
+VR_HDN void unit_step_terms(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
+                            int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, double cv, double af,
+                            const TermMap &tmap, double *col, int stride, bool write)
+{
+  UnitOut uo;
+  unit_step(cc, uc, tm, ae, f, NL, dt_hours, max_snow_temp, min_rain_temp, s, uo);
+  if (write) unit_terms(uc, cv, af, s, uo, NL, tmap, col, stride);
 }
 
 // Sum the terms of one cell's units IN REFERENCE ORDER (tiles ascending, bands ascending) and leave

@@ -30,6 +30,7 @@ struct Prepared {
   std::vector<int64_t> order;        // [C] sorted position -> caller's cell index (climate-sorted, see prepare())
   std::vector<int64_t> cell_uptr;    // [C+1] over SORTED positions
   std::vector<int32_t> u_cell, u_tile, u_flags, u_aero;   // [U]; u_cell = caller's cell index; flags: bit0 bare, bit1 overstory, bits 8.. root0 mask
+  std::vector<int32_t> u_pos;        // [U] sorted position of the unit's cell
   std::vector<int32_t> u_slot;       // [U] thread index inside its block that runs unit u
   std::vector<int64_t> t_unit;       // [U] unit run by thread (u0_of_block + t)
   std::vector<double> u_cv, u_af, u_Tfactor, u_Pfactor, u_rarc, u_rmin, u_RGL;   // [U]
@@ -114,10 +115,21 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
   const int64_t C = cells.ncell, T = cells.tile_ptr[C];
   P.NL = NL; P.NB = NB; P.C = C; P.T = T; P.cta_threads = cta_threads;
   if (NL < 2 || NL > VR_MAX_LAYERS || NB < 1 || NB > VR_MAX_BANDS) { P.error = "nlayer must be 2..3 and nbands 1..10"; return false; }
+  // Cells are processed in an internal order sorted by mean annual air temperature (soil_con.avg_temp,
+  // the QUICK_FLUX lower boundary), then latitude: neighbouring lanes/warps then share the snow /
+  // no-snow branch on most days.  Results are written back at the caller's cell index.
+  P.order.resize(C);
+  for (int64_t c = 0; c < C; c++) P.order[c] = c;
+  std::stable_sort(P.order.begin(), P.order.end(), [&](int64_t a, int64_t b) {
+    if (cells.avg_temp[a] != cells.avg_temp[b]) return cells.avg_temp[a] < cells.avg_temp[b];
+    return cells.lat[a] > cells.lat[b];
+  });
+  // per-cell constants, stored BY SORTED POSITION so that neighbouring lanes read neighbouring words
   const int CCN = VR_CC_N(NL);
   P.cc.assign((size_t)CCN * C, 0.0);
-  auto CC = [&](int k, int64_t c) -> double & { return P.cc[(size_t)k * C + c]; };
-  for (int64_t c = 0; c < C; c++) {
+  for (int64_t pos = 0; pos < C; pos++) {
+    const int64_t c = P.order[pos];
+    auto CC = [&](int k, int64_t) -> double & { return P.cc[(size_t)k * C + pos]; };
     const double b = cells.b_infilt[c], elev = cells.elevation[c], dp = cells.dp[c];
     CC(CC_LAT, c) = cells.lat[c];
     CC(CC_ELEV, c) = elev;
@@ -260,15 +272,6 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       }
     }
   }
-  // Cells are processed in an internal order sorted by mean annual air temperature (soil_con.avg_temp,
-  // the QUICK_FLUX lower boundary), then latitude: neighbouring lanes/warps then share the snow /
-  // no-snow branch on most days.  Results are written back at the caller's cell index.
-  P.order.resize(C);
-  for (int64_t c = 0; c < C; c++) P.order[c] = c;
-  std::stable_sort(P.order.begin(), P.order.end(), [&](int64_t a, int64_t b) {
-    if (cells.avg_temp[a] != cells.avg_temp[b]) return cells.avg_temp[a] < cells.avg_temp[b];
-    return cells.lat[a] > cells.lat[b];
-  });
   for (int64_t cs = 0; cs < C; cs++) {
     const int64_t c = P.order[cs];
     int64_t n = 0;
@@ -285,6 +288,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       for (int b = 0; b < NB; b++) {
         if (!(cells.AreaFract[(size_t)b * C + c] > 0)) continue;
         P.u_cell.push_back((int32_t)c);
+        P.u_pos.push_back((int32_t)cs);
         P.u_tile.push_back((int32_t)t);
         P.u_flags.push_back((bare ? 1 : 0) | ((!bare && lib.overstory[cls]) ? 2 : 0) | (mask << 8));
         P.u_aero.push_back(t_key[t]);

@@ -175,11 +175,55 @@ enum {  // index into the per-cell constant block  cc[k*C + c]
 };
 #define VR_CC_N(nlayer) (::vr::CC_LAYER0 + (nlayer) * ::vr::CL_N)
 
-struct CellC {   // the constants above, unpacked for one cell
-  double lat, elev, half_elev_lapse, b, inv_b, inv_b1, one_plus_b, ex, top_max, top_max_infil, arno_maxm,
-         arno_max_infil, dsmax24, bf_frac, bf_nl, Ws, one_m_Ws, c, avg_T, dp, D1, exp_m, exp_p, kb_bare, inv_one_m_Ws;
-  double expt[MAXL], ksat24[MAXL], max_moist[MAXL], resid[MAXL], qden[MAXL], Wcr[MAXL], Wpwp[MAXL],
-         wcr_m_wpwp[MAXL], wet_den[MAXL], depth[MAXL], inv_qden[MAXL], kdry[2], ksat_m_kdry[2], poros[2], soilfr[2], cs_solid[2];
+struct CellC {   // read-only view of one cell's constants in the block cc[k*C + pos] (pos = sorted position)
+  const double *p;   // &cc[pos]
+  int64_t C;
+#if defined(__CUDA_ARCH__)
+  VR_HD double g(int k) const { return __ldg(p + (size_t)k * C); }
+#else
+  VR_HD double g(int k) const { return p[(size_t)k * C]; }
+#endif
+  VR_HD double lat() const { return g(CC_LAT); }
+  VR_HD double elev() const { return g(CC_ELEV); }
+  VR_HD double half_elev_lapse() const { return g(CC_HALF_ELEV_LAPSE); }
+  VR_HD double b() const { return g(CC_B); }
+  VR_HD double inv_b() const { return g(CC_INV_B); }
+  VR_HD double inv_b1() const { return g(CC_INV_B1); }
+  VR_HD double one_plus_b() const { return g(CC_ONE_PLUS_B); }
+  VR_HD double ex() const { return g(CC_EX); }
+  VR_HD double top_max() const { return g(CC_TOP_MAX); }
+  VR_HD double top_max_infil() const { return g(CC_TOP_MAX_INFIL); }
+  VR_HD double arno_maxm() const { return g(CC_ARNO_MAXM); }
+  VR_HD double arno_max_infil() const { return g(CC_ARNO_MAX_INFIL); }
+  VR_HD double dsmax24() const { return g(CC_DSMAX24); }
+  VR_HD double bf_frac() const { return g(CC_BF_FRAC); }
+  VR_HD double bf_nl() const { return g(CC_BF_NL); }
+  VR_HD double Ws() const { return g(CC_WS); }
+  VR_HD double one_m_Ws() const { return g(CC_ONE_M_WS); }
+  VR_HD double c() const { return g(CC_C); }
+  VR_HD double avg_T() const { return g(CC_AVG_T); }
+  VR_HD double dp() const { return g(CC_DP); }
+  VR_HD double D1() const { return g(CC_D1); }
+  VR_HD double exp_m() const { return g(CC_EXP_M); }
+  VR_HD double exp_p() const { return g(CC_EXP_P); }
+  VR_HD double kb_bare() const { return g(CC_KB_BARE); }
+  VR_HD double inv_one_m_Ws() const { return g(CC_INV_ONE_M_WS); }
+  VR_HD double expt(int l) const { return g(CC_LAYER0 + l * CL_N + CL_EXPT); }
+  VR_HD double ksat24(int l) const { return g(CC_LAYER0 + l * CL_N + CL_KSAT24); }
+  VR_HD double max_moist(int l) const { return g(CC_LAYER0 + l * CL_N + CL_MAX_MOIST); }
+  VR_HD double resid(int l) const { return g(CC_LAYER0 + l * CL_N + CL_RESID); }
+  VR_HD double qden(int l) const { return g(CC_LAYER0 + l * CL_N + CL_QDEN); }
+  VR_HD double Wcr(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WCR); }
+  VR_HD double Wpwp(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WPWP); }
+  VR_HD double wcr_m_wpwp(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WCR_M_WPWP); }
+  VR_HD double wet_den(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WET_DEN); }
+  VR_HD double depth(int l) const { return g(CC_LAYER0 + l * CL_N + CL_DEPTH); }
+  VR_HD double inv_qden(int l) const { return g(CC_LAYER0 + l * CL_N + CL_INV_QDEN); }
+  VR_HD double kdry(int l) const { return g(CC_LAYER0 + l * CL_N + CL_KDRY); }
+  VR_HD double ksat_m_kdry(int l) const { return g(CC_LAYER0 + l * CL_N + CL_KSAT_M_KDRY); }
+  VR_HD double poros(int l) const { return g(CC_LAYER0 + l * CL_N + CL_POROS); }
+  VR_HD double soilfr(int l) const { return g(CC_LAYER0 + l * CL_N + CL_SOILFR); }
+  VR_HD double cs_solid(int l) const { return g(CC_LAYER0 + l * CL_N + CL_CS_SOLID); }
 };
 
 // per-unit constants (tile x band)
@@ -217,31 +261,12 @@ struct UnitOut {
   int snow_flag;
 };
 
-// unpack the constants of cell c from the SoA block cc[k*C + c]
-VR_HD void load_cell_consts(const double *cc, int64_t C, int64_t c, int NL, CellC &x)
+// view of the constants of the cell at sorted position pos
+VR_HD void load_cell_consts(const double *cc, int64_t C, int64_t pos, int NL, CellC &x)
 {
-#define G_(k) cc[(size_t)(k) * C + c]
-  x.lat = G_(CC_LAT); x.elev = G_(CC_ELEV); x.half_elev_lapse = G_(CC_HALF_ELEV_LAPSE); x.b = G_(CC_B);
-  x.inv_b = G_(CC_INV_B); x.inv_b1 = G_(CC_INV_B1); x.one_plus_b = G_(CC_ONE_PLUS_B); x.ex = G_(CC_EX);
-  x.top_max = G_(CC_TOP_MAX); x.top_max_infil = G_(CC_TOP_MAX_INFIL); x.arno_maxm = G_(CC_ARNO_MAXM);
-  x.arno_max_infil = G_(CC_ARNO_MAX_INFIL); x.dsmax24 = G_(CC_DSMAX24); x.bf_frac = G_(CC_BF_FRAC);
-  x.bf_nl = G_(CC_BF_NL); x.Ws = G_(CC_WS); x.one_m_Ws = G_(CC_ONE_M_WS); x.c = G_(CC_C); x.avg_T = G_(CC_AVG_T);
-  x.dp = G_(CC_DP); x.D1 = G_(CC_D1); x.exp_m = G_(CC_EXP_M); x.exp_p = G_(CC_EXP_P); x.kb_bare = G_(CC_KB_BARE); x.inv_one_m_Ws = G_(CC_INV_ONE_M_WS);
-#pragma unroll
-  for (int l = 0; l < MAXL; l++) {
-    if (l < NL) {
-      const int b = CC_LAYER0 + l * CL_N;
-      x.expt[l] = G_(b + CL_EXPT); x.ksat24[l] = G_(b + CL_KSAT24); x.max_moist[l] = G_(b + CL_MAX_MOIST);
-      x.resid[l] = G_(b + CL_RESID); x.qden[l] = G_(b + CL_QDEN); x.Wcr[l] = G_(b + CL_WCR);
-      x.Wpwp[l] = G_(b + CL_WPWP); x.wcr_m_wpwp[l] = G_(b + CL_WCR_M_WPWP); x.wet_den[l] = G_(b + CL_WET_DEN);
-      x.depth[l] = G_(b + CL_DEPTH); x.inv_qden[l] = G_(b + CL_INV_QDEN);
-      if (l < 2) {
-        x.kdry[l] = G_(b + CL_KDRY); x.ksat_m_kdry[l] = G_(b + CL_KSAT_M_KDRY); x.poros[l] = G_(b + CL_POROS);
-        x.soilfr[l] = G_(b + CL_SOILFR); x.cs_solid[l] = G_(b + CL_CS_SOLID);
-      }
-    }
-  }
-#undef G_
+  (void)NL;
+  x.p = cc + pos;
+  x.C = C;
 }
 
 // initialize_model_state.c:321-350,733-760 + initialize_snow/soil/veg: the state before record 0
@@ -696,22 +721,22 @@ VR_HDN void transpiration(const double *moist, const VegV &v, const UnitC &uc, c
     if (uc.root[i] > 0.) {
       avail[i] = 0. + ((moist[i] - 0.) * 1.);
       moist1 += avail[i];
-      Wcr1 += cc.Wcr[i];
+      Wcr1 += cc.Wcr(i);
     }
     else avail[i] = 0.;
   }
   int il = NL - 1;
   moist2 = 0. + ((moist[il] - 0.) * 1.);
   avail[il] = moist2;
-  if ((moist1 >= Wcr1 && moist2 >= cc.Wcr[il] && Wcr1 > 0.) || (moist1 >= Wcr1 && (1 - uc.root[il]) >= 0.5) ||
-      (moist2 >= cc.Wcr[il] && uc.root[il] >= 0.5)) {
+  if ((moist1 >= Wcr1 && moist2 >= cc.Wcr(il) && Wcr1 > 0.) || (moist1 >= Wcr1 && (1 - uc.root[il]) >= 0.5) ||
+      (moist2 >= cc.Wcr(il) && uc.root[il] >= 0.5)) {
     double rc = calc_rc(uc.rmin, net_short, uc.RGL, air_temp, vpd, v.LAI, 1.0);
     double evap = penman(pa, rad, vpd, ra, rc, uc.rarc) * delta_t / SEC_PER_DAY * dryFrac;
     double root_sum = 1.0, spare_evap = 0.0;
     for (int i = 0; i < NL; i++) {
-      if (avail[i] >= cc.Wcr[i]) layerevap[i] = evap * (double)uc.root[i];
+      if (avail[i] >= cc.Wcr(i)) layerevap[i] = evap * (double)uc.root[i];
       else {
-        double gsm_inv = (avail[i] >= cc.Wpwp[i]) ? (avail[i] - cc.Wpwp[i]) / cc.wcr_m_wpwp[i] : 0.0;
+        double gsm_inv = (avail[i] >= cc.Wpwp(i)) ? (avail[i] - cc.Wpwp(i)) / cc.wcr_m_wpwp(i) : 0.0;
         layerevap[i] = evap * gsm_inv * (double)uc.root[i];
         root_sum -= uc.root[i];
         spare_evap = evap * (double)uc.root[i] * (1.0 - gsm_inv);
@@ -719,14 +744,14 @@ VR_HDN void transpiration(const double *moist, const VegV &v, const UnitC &uc, c
     }
     if (spare_evap > 0.0)
       for (int i = 0; i < NL; i++)
-        if (avail[i] >= cc.Wcr[i]) layerevap[i] += (double)uc.root[i] * spare_evap / root_sum;
+        if (avail[i] >= cc.Wcr(i)) layerevap[i] += (double)uc.root[i] * spare_evap / root_sum;
   }
   else {
 #pragma unroll 1
     for (int i = 0; i < NL; i++) {
       double gsm_inv;
-      if (avail[i] >= cc.Wcr[i]) gsm_inv = 1.0;
-      else if (avail[i] >= cc.Wpwp[i] && avail[i] < cc.Wcr[i]) gsm_inv = (avail[i] - cc.Wpwp[i]) / cc.wcr_m_wpwp[i];
+      if (avail[i] >= cc.Wcr(i)) gsm_inv = 1.0;
+      else if (avail[i] >= cc.Wpwp(i) && avail[i] < cc.Wcr(i)) gsm_inv = (avail[i] - cc.Wpwp(i)) / cc.wcr_m_wpwp(i);
       else gsm_inv = 0.0;
       if (gsm_inv > 0.0) {
         double rc = calc_rc(uc.rmin, net_short, uc.RGL, air_temp, vpd, v.LAI, gsm_inv);
@@ -736,7 +761,7 @@ VR_HDN void transpiration(const double *moist, const VegV &v, const UnitC &uc, c
     }
   }
   for (int i = 0; i < NL; i++) {
-    if (layerevap[i] > moist[i] - cc.Wpwp[i]) layerevap[i] = moist[i] - cc.Wpwp[i];
+    if (layerevap[i] > moist[i] - cc.Wpwp(i)) layerevap[i] = moist[i] - cc.Wpwp(i);
     if (layerevap[i] < 0.0) layerevap[i] = 0.0;
   }
 }
@@ -790,35 +815,35 @@ VR_HDN double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, dou
                        double delta_t, double *evap0)
 {
   double moist = 0. + (moist0 - 0.) * 1., evap, tmp, ratio;
-  if (moist > cc.arno_maxm) moist = cc.arno_maxm;
+  if (moist > cc.arno_maxm()) moist = cc.arno_maxm();
   double Epot = 240 * penman(pa, rad, vpd, ra, 0.0, RARC_SOIL) * delta_t / SEC_PER_DAY;
-  if (cc.b == -1.0) tmp = cc.arno_max_infil;
+  if (cc.b() == -1.0) tmp = cc.arno_max_infil();
   else {
-    ratio = 1.0 - (moist) / (cc.arno_maxm);
+    ratio = 1.0 - (moist) / (cc.arno_maxm());
     if (ratio > 1.0 || ratio < 0.0) return VERR;
-    ratio = VR_POW(ratio, cc.inv_b1);
-    tmp = cc.arno_max_infil * (1.0 - ratio);
+    ratio = VR_POW(ratio, cc.inv_b1());
+    tmp = cc.arno_max_infil() * (1.0 - ratio);
   }
-  if (tmp >= cc.arno_max_infil) evap = Epot;
+  if (tmp >= cc.arno_max_infil()) evap = Epot;
   else {
-    ratio = tmp / cc.arno_max_infil;
+    ratio = tmp / cc.arno_max_infil();
     ratio = 1.0 - ratio;
     if (ratio > 1.0 || ratio < 0.0) return VERR;
-    if (ratio != 0.0) ratio = VR_POW(ratio, cc.b);
+    if (ratio != 0.0) ratio = VR_POW(ratio, cc.b());
     double as = 1 - ratio;
-    ratio = VR_POW(ratio, cc.inv_b);
+    ratio = VR_POW(ratio, cc.inv_b());
     double dummy = 1.0, tmpsum = 1.0;
 #pragma unroll 1
     for (int n = 1; n <= 30; n++) {       // arno_evap.c:168-173; the inner product is a running power
       tmpsum = (n == 1) ? ratio : tmpsum * ratio;
-      dummy += cc.b * tmpsum / (cc.b + n);
+      dummy += cc.b() * tmpsum / (cc.b() + n);
     }
     double beta_asp = as + (1.0 - as) * (1.0 - ratio) * dummy;
     evap = 240 * Epot * beta_asp;
   }
   if (evap > 0.0) {
-    if (moist > cc.resid[0]) {
-      if (evap > moist - cc.resid[0]) evap = moist - cc.resid[0];
+    if (moist > cc.resid(0)) {
+      if (evap > moist - cc.resid(0)) evap = moist - cc.resid(0);
     }
     else evap = 0.0;
   }
@@ -1102,15 +1127,15 @@ VR_HDN void runoff_and_asat(const CellC &cc, const double *moist, int NL, double
 {
   double top_moist = 0.;
   for (int l = 0; l < NL - 1; l++) top_moist += moist[l];
-  if (top_moist > cc.top_max) top_moist = cc.top_max;
-  *A = 1.0 - VR_POW((1.0 - top_moist / cc.top_max), cc.ex);
+  if (top_moist > cc.top_max()) top_moist = cc.top_max();
+  *A = 1.0 - VR_POW((1.0 - top_moist / cc.top_max()), cc.ex());
   if (inflow == 0.0) { *runoff = 0.0; return; }
-  double i_0 = cc.top_max_infil * (1.0 - VR_POW((1.0 - *A), cc.inv_b));
-  if (cc.top_max_infil == 0.0) *runoff = inflow;
-  else if ((i_0 + inflow) > cc.top_max_infil) *runoff = inflow - cc.top_max + top_moist;
+  double i_0 = cc.top_max_infil() * (1.0 - VR_POW((1.0 - *A), cc.inv_b()));
+  if (cc.top_max_infil() == 0.0) *runoff = inflow;
+  else if ((i_0 + inflow) > cc.top_max_infil()) *runoff = inflow - cc.top_max() + top_moist;
   else {
-    double basis = 1.0 - (i_0 + inflow) / cc.top_max_infil;
-    *runoff = (inflow - cc.top_max + top_moist + cc.top_max * VR_POW(basis, cc.one_plus_b));
+    double basis = 1.0 - (i_0 + inflow) / cc.top_max_infil();
+    *runoff = (inflow - cc.top_max() + top_moist + cc.top_max() * VR_POW(basis, cc.one_plus_b()));
   }
   if (*runoff < 0.) *runoff = 0.;
 }
@@ -1132,15 +1157,21 @@ VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, doubl
                        double *runoff_out, double *baseflow_out)
 {
   constexpr int LB = NL - 1;                      // bottom layer
-  const double r0 = cc.resid[0], r1 = cc.resid[1], rB = cc.resid[LB];
-  const double m0 = cc.max_moist[0], m1 = cc.max_moist[1], mB = cc.max_moist[LB];
+  const double r0 = cc.resid(0), r1 = cc.resid(1), rB = cc.resid(LB);
+  const double m0 = cc.max_moist(0), m1 = cc.max_moist(1), mB = cc.max_moist(LB);
+  const double ks0 = cc.ksat24(0), ks1 = cc.ksat24(1), ex0 = cc.expt(0), ex1 = cc.expt(1);
+  const double qd0 = cc.qden(0), qd1 = cc.qden(1), qdB = cc.qden(LB);
+  const double iq0 = cc.inv_qden(0), iq1 = cc.inv_qden(1), iqB = cc.inv_qden(LB);
+  const double bf_frac = cc.bf_frac(), bf_nl = cc.bf_nl(), Ws = cc.Ws(), one_m_Ws = cc.one_m_Ws(),
+               inv_one_m_Ws = cc.inv_one_m_Ws(), cexp = cc.c();
+  (void)qd0; (void)qd1; (void)qdB; (void)iq0; (void)iq1; (void)iqB; (void)one_m_Ws; (void)inv_one_m_Ws;
   double liq0 = moist[0], liq1 = moist[1], liqB = moist[LB];
   double ev[MAXL];
 #pragma unroll
   for (int l = 0; l < NL; l++) {
     double e = evap_l[l] / (double)dt;
     if (e > 0) {
-      double avail_liq = (moist[l] - cc.resid[l]);
+      double avail_liq = (moist[l] - cc.resid(l));
       if (avail_liq < 0) avail_liq = 0;
       double evap_fraction = (avail_liq > 0) ? e / avail_liq : 1.0;
       e = avail_liq * evap_fraction;
@@ -1159,12 +1190,12 @@ VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, doubl
     // Brooks-Corey drainage out of the upper layers (runoff.c:330-340)
     double t0 = liq0 - ev0;
     if (t0 < r0) t0 = r0;
-    double Q0 = (liq0 > r0) ? cc.ksat24[0] * VR_POW(VR_DIVC(t0 - r0, cc.qden[0], cc.inv_qden[0]), cc.expt[0]) : 0.;
+    double Q0 = (liq0 > r0) ? ks0 * VR_POW(VR_DIVC(t0 - r0, qd0, iq0), ex0) : 0.;
     double Q1 = 0.;
     if (NL == 3) {
       double t1 = liq1 - ev1;
       if (t1 < r1) t1 = r1;
-      Q1 = (liq1 > r1) ? cc.ksat24[1] * VR_POW(VR_DIVC(t1 - r1, cc.qden[1], cc.inv_qden[1]), cc.expt[1]) : 0.;
+      Q1 = (liq1 > r1) ? ks1 * VR_POW(VR_DIVC(t1 - r1, qd1, iq1), ex1) : 0.;
     }
     // top layer
     liq0 = liq0 + (dt_inflow - tmp_dt_runoff) - (Q0 + ev0);
@@ -1185,11 +1216,11 @@ VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, doubl
       Qin = Q1;
     }
     // bottom layer: ARNO baseflow (runoff.c:420-435)
-    const double rel_moist = VR_DIVC(liqB - rB, cc.qden[LB], cc.inv_qden[LB]);
-    double dt_baseflow = cc.bf_frac * rel_moist;
-    if (rel_moist > cc.Ws) {
-      const double frac = VR_DIVC(rel_moist - cc.Ws, cc.one_m_Ws, cc.inv_one_m_Ws);
-      dt_baseflow += cc.bf_nl * ((cc.c == 2.0) ? frac * frac : VR_POW(frac, cc.c));   // pow(x,2) == x*x
+    const double rel_moist = VR_DIVC(liqB - rB, qdB, iqB);
+    double dt_baseflow = bf_frac * rel_moist;
+    if (rel_moist > Ws) {
+      const double frac = VR_DIVC(rel_moist - Ws, one_m_Ws, inv_one_m_Ws);
+      dt_baseflow += bf_nl * ((cexp == 2.0) ? frac * frac : VR_POW(frac, cexp));   // pow(x,2) == x*x
     }
     if (dt_baseflow < 0) dt_baseflow = 0;
     liqB += Qin - (evB + dt_baseflow);
@@ -1236,7 +1267,7 @@ VR_HDN void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moi
 // one unit, one record
 // ---------------------------------------------------------------------------------------
 // tm: this tile's TM_* terms for the month; ae: this tile's AE_* coefficients for the month
-VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
+VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
                      int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o)
 {
   const double delta_t = (double)dt_hours * 3600.;
@@ -1266,19 +1297,19 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
   double kappa[2], Cs[2];
 #pragma unroll
   for (int l = 0; l < 2; l++) {
-    double mv = s.moist[l] / cc.depth[l] / 1000;
+    double mv = s.moist[l] / cc.depth(l) / 1000;
     double K;
     if (mv > 0.) {
-      double Sr = mv / cc.poros[l];
+      double Sr = mv / cc.poros(l);
       double Ke = 0.7 * VR_LOG10(Sr) + 1.0;
-      K = cc.ksat_m_kdry[l] * Ke + cc.kdry[l];
-      if (K < cc.kdry[l]) K = cc.kdry[l];
+      K = cc.ksat_m_kdry(l) * Ke + cc.kdry(l);
+      if (K < cc.kdry(l)) K = cc.kdry(l);
     }
-    else K = cc.kdry[l];
+    else K = cc.kdry(l);
     kappa[l] = K;
-    double c = cc.cs_solid[l];
+    double c = cc.cs_solid(l);
     c += 4.2e6 * mv;
-    c += 1.3e3 * (1. - (cc.soilfr[l] + mv + 0.));
+    c += 1.3e3 * (1. - (cc.soilfr(l) + mv + 0.));
     Cs[l] = c;
   }
 
@@ -1297,7 +1328,7 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
   const double Tgrnd = s.T0, Tcanopy = Tair;
   double coverage = s.coverage;
   const double step_depth_old = s.depth, step_surf_temp_old = s.surf_temp;
-  const PenmanAir pa = penman_air(Tair, cc.half_elev_lapse, cc.elev);
+  const PenmanAir pa = penman_air(Tair, cc.half_elev_lapse(), cc.elev());
 
   VR_PHASE_SYNC();
   // ---- solve_snow.c:7-577 ----
@@ -1381,7 +1412,7 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
         if (s.surf_temp <= 0) s.density = snow_density(s.surf_temp, s.depth, snowfall, old_swq, Tair, (double)dt_hours);
         else if (s.last_snow == 0) s.density = new_snow_density(Tair);
         s.depth = 1000. * s.swq / s.density;
-        if (s.coldcontent >= 0 && ((cc.lat >= 0 && (f.doy > 60 && f.doy < 273)) || (cc.lat < 0 && (f.doy < 60 || f.doy > 273))))
+        if (s.coldcontent >= 0 && ((cc.lat() >= 0 && (f.doy > 60 && f.doy < 273)) || (cc.lat() < 0 && (f.doy < 60 || f.doy > 273))))
           s.MELTING = 1;
         else if (s.MELTING && snowfall > TraceSnow) s.MELTING = 0;
         s.coverage = 1.;
@@ -1450,7 +1481,7 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
 
   // ---- calc_surf_energy_bal.c (FULL_ENERGY FALSE: Tsurf = Tair) + func_surf_energy_bal.c ----
   const bool VEG = is_veg && v.vegcover > 0.0;
-  const double T2 = cc.avg_T, Ts_old = s.T0, T1_old = s.T1, D1 = cc.D1, D2 = cc.D1;
+  const double T2 = cc.avg_T(), Ts_old = s.T0, T1_old = s.T1, D1 = cc.D1(), D2 = cc.D1();
   const double kappa1 = kappa[0], kappa2 = kappa[1], Cs1 = Cs[0], Cs2 = Cs[1];
   double Tsnow_surf = s.surf_temp;
   const double Wdew_in = v.Wdew;
@@ -1474,14 +1505,14 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
   // estimate_T1.c:8-47 with VR_EXP(-D1/dp), VR_EXP(D1/dp) hoisted
   double T1;
   {
-    double C1 = Cs2 * cc.dp / D2 * (1. - cc.exp_m);
-    double C2 = -(1. - cc.exp_p) * cc.exp_m;
-    double C3 = kappa1 / D1 - kappa2 / D1 + kappa2 / D1 * cc.exp_m;
-    T1 = (kappa1 / 2. / D1 / D2 * (TMean) + C1 / delta_t * T1_old + (2. * C2 - 1. + cc.exp_m) * kappa2 / 2. / D1 / D2 * T2) /
+    double C1 = Cs2 * cc.dp() / D2 * (1. - cc.exp_m());
+    double C2 = -(1. - cc.exp_p()) * cc.exp_m();
+    double C3 = kappa1 / D1 - kappa2 / D1 + kappa2 / D1 * cc.exp_m();
+    T1 = (kappa1 / 2. / D1 / D2 * (TMean) + C1 / delta_t * T1_old + (2. * C2 - 1. + cc.exp_m()) * kappa2 / 2. / D1 / D2 * T2) /
          (C1 / delta_t + kappa2 / D1 / D2 * C2 + C3 / 2. / D2);
   }
   const double grnd_flux = (snow_coverage + (1. - snow_coverage) * surf_atten) *
-                           (kappa1 / D1 * ((T1)-TMean) + (kappa2 / D2 * (1. - cc.exp_m) * (T2 - (T1)))) / 2.;
+                           (kappa1 / D1 * ((T1)-TMean) + (kappa2 / D2 * (1. - cc.exp_m()) * (T2 - (T1)))) / 2.;
   const double deltaH = (Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1 / delta_t / 2.);
   double eo_deltaCC = 0., eo_refreeze = 0.;
   if (INCLUDE_SNOW) {
@@ -1501,7 +1532,7 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
   if (v.vegcover < 1) {      // bare-gap blend, func_surf_energy_bal.c:712-749 (always for the bare tile)
     if (ra_used0 > 0) {
       double ga_veg = 1 / ra_used0;
-      double Ra_bare0 = (U[0] > 0.) ? cc.kb_bare / U[0] : HUGE_RESIST;
+      double Ra_bare0 = (U[0] > 0.) ? cc.kb_bare() / U[0] : HUGE_RESIST;
       Ra_bare0 /= 1.0;
       if (Ra_bare0 > 0) {
         double ga_bare = 1 / Ra_bare0;
@@ -1635,7 +1666,7 @@ VR_HDN void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const 
   double wet = 0, rootm = 0;
   for (int l = 0; l < NL; l++) {
     if ((uc.root0_mask >> l) & 1) rootm += s.moist[l];
-    wet += (s.moist[l] - cc.Wpwp[l]) / cc.wet_den[l];
+    wet += (s.moist[l] - cc.Wpwp(l)) / cc.wet_den(l);
   }
   wet /= NL;
   o.wetness = wet;

@@ -38,7 +38,7 @@ struct DevModel {
   int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
   const double *cc;
   const int64_t *cell_uptr, *cta_cell, *fcol, *order, *t_unit;
-  const int32_t *u_cell, *u_tile, *u_flags, *u_aero, *u_slot, *cell_fail;
+  const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *cell_fail;
   const double *u_cv, *u_af, *u_Tfactor, *u_Pfactor, *u_rarc, *u_rmin, *u_RGL, *tm, *ae, *init_moist;
   const float *u_root;
   double *state;                    // [ST_N][U]
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0
     load_unit_consts(M, u, uc, cv, af);
     for (int l = 0; l < M.NL; l++) {
       im[l] = M.init_moist[(size_t)l * M.C + c];
-      mm[l] = M.cc[(size_t)(CC_LAYER0 + l * CL_N + CL_MAX_MOIST) * M.C + c];
+      mm[l] = M.cc[(size_t)(CC_LAYER0 + l * CL_N + CL_MAX_MOIST) * M.C + M.u_pos[u]];
     }
     const int64_t fc = M.fcol ? M.fcol[c] : c;
     unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_step(DevModel M, DevForcing
   const int64_t fc = M.fcol ? M.fcol[c] : c;
   const bool failed = M.cell_fail[c] != 0;
   load_unit_consts(M, u, uc, cv, af);
-  load_cell_consts(M.cc, M.C, c, M.NL, cc);
+  load_cell_consts(M.cc, M.C, M.u_pos[u], M.NL, cc);
   load_state(M, u, s);
   const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
   const double *ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
@@ -184,9 +184,8 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_step(DevModel M, DevForcing
       f.density = __ldg(F.field[VR_F_DENSITY] + k); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k);
       f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
       f.mon = mon; f.doy = doy;
-      UnitOut uo;
-      unit_step(cc, uc, tm + mon * TM_N, ae + mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s, uo);
-      if (active) unit_terms(uc, cv, af, s, uo, NL, M.tmap, &sm[tid], VR_CTA);
+      unit_step_terms(cc, uc, tm + mon * TM_N, ae + mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
+                      cv, af, M.tmap, &sm[tid], VR_CTA, active);
     }
     __syncthreads();
     if (finisher) {
@@ -257,7 +256,7 @@ struct vr_handle {
       d_forc, d_out, d_tair0;
   DBuf<float> d_u_root;
   DBuf<int64_t> d_cell_uptr, d_cta_cell, d_fcol, d_order, d_t_unit;
-  DBuf<int32_t> d_u_cell, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
+  DBuf<int32_t> d_u_cell, d_u_pos, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
   cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int chunk = 16;                    // records per pipelined chunk of vr_step_block
@@ -356,7 +355,7 @@ void vr_destroy(vr_handle *h)
   h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_cta_cell.release(); h->d_fcol.release();
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
-  h->d_order.release(); h->d_t_unit.release(); h->d_u_slot.release();
+  h->d_order.release(); h->d_t_unit.release(); h->d_u_slot.release(); h->d_u_pos.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int b = 0; b < 2; b++) {
@@ -409,7 +408,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   std::vector<double> im((size_t)P.NL * C);
   for (size_t i = 0; i < im.size(); i++) im[i] = cells->init_moist[i];
   CK(h->d_cc.upload(P.cc)); CK(h->d_cell_uptr.upload(P.cell_uptr)); CK(h->d_cta_cell.upload(P.cta_cell));
-  CK(h->d_u_cell.upload(P.u_cell)); CK(h->d_u_tile.upload(P.u_tile)); CK(h->d_u_flags.upload(P.u_flags));
+  CK(h->d_u_cell.upload(P.u_cell)); CK(h->d_u_pos.upload(P.u_pos)); CK(h->d_u_tile.upload(P.u_tile)); CK(h->d_u_flags.upload(P.u_flags));
   CK(h->d_u_aero.upload(P.u_aero)); CK(h->d_cell_fail.upload(P.cell_fail)); CK(h->d_u_cv.upload(P.u_cv));
   CK(h->d_u_af.upload(P.u_af)); CK(h->d_u_Tf.upload(P.u_Tfactor)); CK(h->d_u_Pf.upload(P.u_Pfactor));
   CK(h->d_u_rarc.upload(P.u_rarc)); CK(h->d_u_rmin.upload(P.u_rmin)); CK(h->d_u_RGL.upload(P.u_RGL));
@@ -427,7 +426,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.max_snow_temp = h->opt.max_snow_temp; M.min_rain_temp = h->opt.min_rain_temp;
   M.C = C; M.U = U; M.FC = C;
   M.cc = h->d_cc.p; M.cell_uptr = h->d_cell_uptr.p; M.cta_cell = h->d_cta_cell.p; M.fcol = nullptr;
-  M.u_cell = h->d_u_cell.p; M.u_tile = h->d_u_tile.p; M.u_flags = h->d_u_flags.p; M.u_aero = h->d_u_aero.p;
+  M.u_cell = h->d_u_cell.p; M.u_pos = h->d_u_pos.p; M.u_tile = h->d_u_tile.p; M.u_flags = h->d_u_flags.p; M.u_aero = h->d_u_aero.p;
   M.cell_fail = h->d_cell_fail.p; M.u_cv = h->d_u_cv.p; M.u_af = h->d_u_af.p; M.u_Tfactor = h->d_u_Tf.p;
   M.u_Pfactor = h->d_u_Pf.p; M.u_rarc = h->d_u_rarc.p; M.u_rmin = h->d_u_rmin.p; M.u_RGL = h->d_u_RGL.p;
   M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
