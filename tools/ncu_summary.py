@@ -1,0 +1,104 @@
+"""Summarise an `ncu --set full --import-source on` capture of k_step into markdown + JSON.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep "<label>" <cells> <records> [--traffic-json profiles/k_step_traffic.json]
+
+Prints the key counters, the stall mix and a per-device-function table (share of executed warp
+instructions, lane utilisation, share of stall samples), mapping SASS addresses to the out-of-line
+device functions through the symbol table of vicres_b200/libvicres.so.
+"""
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "dram__bytes_read.sum",
+        "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"]
+
+
+def ncu_csv(rep, page):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+
+def main():
+    rep, label, cells, recs = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    rows = ncu_csv(rep, "raw")
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+    print("## %s\n" % label)
+    print("capture: `%s`, %d cells x %d records in the profiled launch\n" % (os.path.basename(rep), cells, recs))
+    print("| counter | value |\n|---|---|")
+    for k in KEYS:
+        if k in m:
+            print("| `%s` | %s %s |" % (k, m[k][0], m[k][1]))
+    stalls = sorted(((float(v[0].replace(",", "")), h) for h, v in m.items()
+                     if "average_warps_issue_stalled" in h and "not_issued" not in h and v[0]), reverse=True)
+    print("\nstall mix (warps per issue-active cycle): " +
+          ", ".join("%s %.2f" % (h.split("issue_stalled_")[1].split("_per_")[0], x) for x, h in stalls[:8]))
+    dram = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
+    per = dram / (cells * recs)
+    print("\nDRAM traffic: %.3f GB = **%.0f B per cell-timestep** (algorithmic 280 B)\n" % (dram / 1e9, per))
+    if "--traffic-json" in sys.argv:
+        path = sys.argv[sys.argv.index("--traffic-json") + 1]
+        json.dump({"dram_bytes_per_cell_step": per, "source": os.path.basename(rep), "cells": cells, "records": recs,
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch / (cells x records)"},
+                  open(path, "w"), indent=1)
+    if "--no-functions" in sys.argv:     # the symbol table of the current libvicres.so does not match an old capture
+        return
+    # per-function table
+    so = os.path.join(ROOT, "vicres_b200", "libvicres.so")
+    elf = subprocess.run(["cuobjdump", "-elf", so], capture_output=True, text=True).stdout
+    syms = []
+    for l in elf.splitlines():
+        p = l.split()
+        if len(p) < 7 or "k_step" not in l:
+            continue
+        try:
+            val, sz = int(p[1], 16), int(p[2], 16)
+        except ValueError:
+            continue
+        if sz == 0:
+            continue
+        name = re.sub(r"\$?_ZN\d+_GLOBAL__N__[0-9a-f_]*vicres_capi_cu_[0-9a-f]*6k_stepENS_8DevModelENS_10DevForcingEPd", "", p[-1])
+        syms.append((val, sz, name))
+    subs = sorted(s for s in syms if s[2].startswith("$"))
+    src = ncu_csv(rep, "source")
+    h = src[1]
+    ia, ii, it, isamp = h.index("Address"), h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("# Samples")
+    base = int(src[2][ia], 16)
+    agg = {}
+    for r in src[2:]:
+        off = int(r[ia], 16) - base
+        name = "k_step (kernel body: loads, finisher, barriers)"
+        for v, sz, n in subs:
+            if v <= off < v + sz:
+                name = n
+                break
+        a = agg.setdefault(name, [0, 0, 0, 0])
+        a[0] += int(r[ii]); a[1] += int(r[it]); a[2] += int(r[isamp]); a[3] += 1
+    tot, tots = sum(a[0] for a in agg.values()), sum(a[2] for a in agg.values())
+    demangle = lambda n: re.sub(r"^\$_ZN2vr\d+", "vr::", n).split("E")[0] if n.startswith("$_ZN2vr") else n
+    print("| device function | SASS instrs | share of executed warp-instrs | lanes active | share of stall samples |\n|---|---|---|---|---|")
+    for n, a in sorted(agg.items(), key=lambda x: -x[1][2])[:16]:
+        print("| %s | %d | %.1f %% | %.1f / 32 | %.1f %% |" % (demangle(n), a[3], 100 * a[0] / tot, a[1] / max(a[0], 1), 100 * a[2] / tots))
+    print("\ntotal executed warp instructions %.3e; thread instructions per cell-timestep %.0f\n" %
+          (tot, sum(a[1] for a in agg.values()) / max(1, cells * recs)))
+
+
+if __name__ == "__main__":
+    main()
