@@ -1,0 +1,65 @@
+/* vicres_route.h -- C ABI of the B200-native VIC-Res routing pass (unit hydrographs + convolution).
+ *
+ * Replaces, for one station, the reference's
+ *   MAKE_UHM            routing/model/unit_hyd_routines.f:7-50     per-cell 48-tap Green's function
+ *   SEARCH_WHOLECATCHMENT / SEARCH_CATCHMENTRS   init_routines.f:103-168, reservoir.f:578-763
+ *                       catchment cell lists of the station and of every reservoir above it
+ *   MAKE_GRID_UH        unit_hyd_routines.f:55-178                per-cell UH_S(107) to its node
+ *   MAKE_CONVOLUTION    reservoir.f:216-526                       node inflow = sum over cells of UH_S * (runoff+baseflow)
+ * (the reference drives them from rout.f:318-478 and reservoir.f:769-1140).  All arithmetic is fp32,
+ * as in the Fortran (REAL), with the reference's accumulation order: cells in catchment-list order,
+ * taps ascending.  Reservoir operating rules (MAKE_CONVOLUTIONRS day loop) and open-water evaporation
+ * on reservoir-surface cells (RESER == 9999) are not part of this round; grids that contain 9999
+ * cells inside a catchment are rejected with VR_ERR_UNSUPPORTED.
+ *
+ * Grid arrays are in FILE order: index r*ncol + c where r = 0 is the FIRST data line of the ESRI
+ * ASCII file (northern-most row) and c = 0 its first value.  Station col/row are the numbers of
+ * stations.txt (rout.f:333-341).
+ */
+#ifndef VICRES_ROUTE_H
+#define VICRES_ROUTE_H
+#include <stdint.h>
+#include "vicres.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VR_UH_LE 48        /* LE, hourly taps of the cell impulse response (rout.f:31-40) */
+#define VR_UH_DAY 96       /* UH_DAY */
+#define VR_UH_KE 12        /* KE, taps of UH_BOX (UH.all) */
+#define VR_UH_NS (VR_UH_KE + VR_UH_DAY - 1)   /* 107 daily taps of UH_S */
+
+typedef struct vr_route_grid {
+  int32_t ncol, nrow;
+  const int32_t *dir;     /* D8 codes 0..8 (READ_DIREC, reservoir.f:149-211) */
+  const int32_t *reser;   /* reservoirlocation.txt: 0, reservoir id, 9999 = reservoir surface; may be NULL */
+  const float *velo, *diff, *xmask;   /* per cell (a constant in configuration.txt is a filled grid) */
+} vr_route_grid;
+
+typedef struct vr_route vr_route;
+
+int  vr_route_create(const vr_route_grid *g, int32_t station_col, int32_t station_row,
+                     const float *uh_box /* [VR_UH_KE] */, int device, vr_route **out);
+void vr_route_destroy(vr_route *h);
+const char *vr_route_last_error(const vr_route *h);
+
+/* nodes: the reservoirs found above the station, in the reference's discovery order, then the station */
+int32_t vr_route_num_nodes(const vr_route *h);
+int  vr_route_node_info(const vr_route *h, int32_t node, int32_t *res_id, int64_t *ncells);
+/* catchment cells of a node in the reference's list order, as file-order grid indices r*ncol+c */
+int  vr_route_node_cells(const vr_route *h, int32_t node, int32_t *grid_index);
+/* UH_S of a node: [ncells][VR_UH_NS] (what the reference writes to <name>.uh_s) */
+int  vr_route_get_uh(vr_route *h, int32_t node, float *uh_s);
+
+/* flows[node*ndays + i] (m3/s): runoff, baseflow are [nrow*ncol][ndays] mm/day by file-order grid
+ * cell (cells without data hold zeros, as the reference inserts for missing flux files); `scale` is
+ * the mm/day -> m3/s factor (the reference hard-codes 0.18308, reservoir.f:479-480). Host pointers. */
+int  vr_route_convolve(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,
+                       float *flows);
+int  vr_route_last_kernel_ms(vr_route *h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
