@@ -57,6 +57,17 @@ int  vr_route_get_uh(vr_route *h, int32_t node, float *uh_s);
  * the mm/day -> m3/s factor (the reference hard-codes 0.18308, reservoir.f:479-480). Host pointers. */
 int  vr_route_convolve(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,
                        float *flows);
+/* Full form of MAKE_CONVOLUTION's per-cell handling:
+ *   cell_scale[ncell]   per-cell mm/day -> m3/s factor instead of `scale` (the shipped prebuilt binary used
+ *                       FACTOR*0.028 with FACTOR = FRACTION*35.315*AREA/86400000, reservoir.f:357-364)
+ *   ev_vege, ev_soil, tr_vege [ncell][ndays] + cell_factor[ncell]: the reference's correction on days whose VIC
+ *                       evaporation components sum below zero (reservoir.f:496-499)
+ *   present[ncell]      0 = flux file missing: zeros are routed and the correction sees the PREVIOUS cell's
+ *                       evaporation series (the reference resets only runoff/baseflow, reservoir.f:398-409)
+ * Any of them may be NULL. */
+int  vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,
+                          const float *cell_scale, const float *ev_vege, const float *ev_soil, const float *tr_vege,
+                          const float *cell_factor, const unsigned char *present, float *flows);
 int  vr_route_last_kernel_ms(vr_route *h, float *ms);
 
 #ifdef __cplusplus

@@ -16,8 +16,8 @@ def lib():
     return model.load_library()
 
 
-def declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "vicres.h")).read()
+def declared_symbols(header="vicres.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(vr_[a-z_0-9]+)\s*\(", txt)))
 
@@ -28,6 +28,14 @@ def test_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), "libvicres.so does not export %s" % s
     assert sorted(model.EXPORTS) == syms
+
+
+def test_exports_every_declared_routing_symbol(lib):
+    from vicres_b200 import route
+    syms = declared_symbols("vicres_route.h")
+    for s in syms:
+        assert hasattr(lib, s), "libvicres.so does not export %s" % s
+    assert sorted(route.ROUTE_EXPORTS) == syms
 
 
 def test_struct_layout_matches_c(tmp_path):

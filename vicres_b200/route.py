@@ -1,0 +1,83 @@
+"""Host-side mirror of the routing pass over the C ABI of include/vicres_route.h (ctypes only).
+
+    r = Route(grid, station_col, station_row, uh_box)     # catchments + unit hydrographs (GPU)
+    rid, cells, uh_s = r.node(n)                           # what the reference writes to <name>.uh_s
+    flows = r.convolve(runoff, baseflow)                   # [nnodes, ndays] node inflows (m3/s)
+"""
+import ctypes as C
+import numpy as np
+from . import model, route_abi
+
+ROUTE_EXPORTS = ["vr_route_create", "vr_route_destroy", "vr_route_last_error", "vr_route_num_nodes",
+                 "vr_route_node_info", "vr_route_node_cells", "vr_route_get_uh", "vr_route_convolve",
+                 "vr_route_convolve_ex", "vr_route_last_kernel_ms"]
+
+
+def _lib():
+    L = model.load_library()
+    if not getattr(L, "_route_ready", False):
+        vp = C.c_void_p
+        L.vr_route_create.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int, C.POINTER(vp)]
+        L.vr_route_destroy.argtypes = [vp]
+        L.vr_route_destroy.restype = None
+        L.vr_route_last_error.argtypes = [vp]
+        L.vr_route_last_error.restype = C.c_char_p
+        L.vr_route_num_nodes.argtypes = [vp]
+        L.vr_route_node_info.argtypes = [vp, C.c_int32, vp, vp]
+        L.vr_route_node_cells.argtypes = [vp, C.c_int32, vp]
+        L.vr_route_get_uh.argtypes = [vp, C.c_int32, vp]
+        L.vr_route_convolve.argtypes = [vp, C.c_int32, vp, vp, C.c_float, vp]
+        L.vr_route_convolve_ex.argtypes = [vp, C.c_int32, vp, vp, C.c_float] + [vp] * 7
+        L.vr_route_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L._route_ready = True
+    return L
+
+
+class Route:
+    def __init__(self, grid, station_col, station_row, uh_box, device=0):
+        self.L = _lib()
+        self.g = route_abi.pack_grid(grid)
+        self.box = np.ascontiguousarray(uh_box, dtype=np.float32)
+        assert self.box.size == route_abi.KE
+        self.h = C.c_void_p()
+        rc = self.L.vr_route_create(self.g.ref(), station_col, station_row, self.box.ctypes.data, device, C.byref(self.h))
+        if rc != 0:
+            raise model.VicResError(rc, self.L.vr_route_last_error(None).decode())
+        self.nnodes = int(self.L.vr_route_num_nodes(self.h))
+        self.ncell = int(self.g.struct.ncol) * int(self.g.struct.nrow)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise model.VicResError(rc, self.L.vr_route_last_error(self.h).decode())
+
+    def node(self, n):
+        rid, nc = C.c_int32(), C.c_int64()
+        self._check(self.L.vr_route_node_info(self.h, n, C.byref(rid), C.byref(nc)))
+        cells = np.zeros(nc.value, dtype=np.int32)
+        uh = np.zeros((nc.value, route_abi.NS), dtype=np.float32)
+        self._check(self.L.vr_route_node_cells(self.h, n, cells.ctypes.data))
+        self._check(self.L.vr_route_get_uh(self.h, n, uh.ctypes.data))
+        return int(rid.value), cells, uh
+
+    def convolve(self, runoff, baseflow, scale=0.18308, cell_scale=None, evap=None, cell_factor=None, present=None):
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        runoff, baseflow, cell_scale, cell_factor = f32(runoff), f32(baseflow), f32(cell_scale), f32(cell_factor)
+        assert runoff.shape == baseflow.shape and runoff.shape[0] == self.ncell
+        ev = [f32(a) for a in evap] if evap is not None else [None, None, None]
+        pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+        ndays = runoff.shape[1]
+        flows = np.zeros((self.nnodes, ndays), dtype=np.float32)
+        p = lambda a: None if a is None else a.ctypes.data
+        self._check(self.L.vr_route_convolve_ex(self.h, ndays, p(runoff), p(baseflow), C.c_float(scale), p(cell_scale),
+                                                p(ev[0]), p(ev[1]), p(ev[2]), p(cell_factor), p(pres), p(flows)))
+        return flows
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self.L.vr_route_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if self.h:
+            self.L.vr_route_destroy(self.h)
+            self.h = C.c_void_p()
