@@ -1,0 +1,54 @@
+/* vicres_files.h -- host-side readers/writers for the reference's own file formats, so that the B200
+ * path is a drop-in for vicNl's parameter hand-off and flux output:
+ *   soil parameter file     runoff/model/read_soilparam.c:8-640   (one row per cell; derived max_moist, Wcr,
+ *                           Wpwp, porosity ..., depths rounded to mm through a float, :342)
+ *   vegetation library      runoff/model/read_veglib.c:8-190
+ *   vegetation parameters   runoff/model/read_vegparam.c:8-340 + calc_root_fraction.c:8-150
+ *   snow band file          runoff/model/read_snowband.c:8-125
+ *   flux output             runoff/model/write_data.c ASCII branch ("%04i\t%02i\t%02i\t" + "%.4f" columns)
+ * The readers produce exactly the numbers the reference holds after ITS readers (checked bit for
+ * bit against a dump of the reference's structs, tests/test_files.py).  Plain C ABI; host only.
+ */
+#ifndef VICRES_FILES_H
+#define VICRES_FILES_H
+#include "vicres.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vr_param_files {
+  int32_t nlayer;            /* NLAYER */
+  int32_t nbands;            /* SNOW_BAND */
+  int32_t root_zones;        /* ROOT_ZONES */
+  int32_t vegparam_lai;      /* VEGPARAM_LAI TRUE: every tile line is followed by 12 monthly LAI values */
+  int32_t lai_from_vegparam; /* LAI_SRC FROM_VEGPARAM */
+  const char *soil, *veglib, *vegparam;
+  const char *snowband;      /* may be NULL when nbands == 1 */
+} vr_param_files;
+
+typedef struct vr_params vr_params;          /* owns every array the structs below point to */
+
+int  vr_params_read(const vr_param_files *f, vr_params **out);
+void vr_params_free(vr_params *p);
+const char *vr_params_last_error(void);
+const vr_cells  *vr_params_cells(const vr_params *p);     /* cells flagged "run" (first column) in file order */
+const vr_veglib *vr_params_veglib(const vr_params *p);
+const int32_t *vr_params_gridcel(const vr_params *p);     /* [C] cell numbers            */
+const float   *vr_params_lat(const vr_params *p);         /* [C] as stored (float)       */
+const float   *vr_params_lng(const vr_params *p);
+
+/* The reference's ASCII result files (write_data.c:196-226, names from make_in_and_outfiles.c:46-86):
+ * one file "<result_dir>/<prefix>_<lat>_<lng>" per cell (lat/lng printed with grid_decimal places),
+ * one row per record: "%04i\t%02i\t%02i\t" (plus "%02i\t" hour when hour != NULL, i.e. dt < 24) and
+ * the selected columns in "%.4f" separated by "\t ".  The default lists (set_output_defaults.c:66-93)
+ * are prefix "fluxes" = the first 20+nlayer-1 default outputs and prefix "snow" = the last 4.
+ * out: [n_total][nrec][C] as vr_step_block returns it; cols: [n_cols] rows of `out` to print. */
+int  vr_write_results(const char *result_dir, const char *prefix, int32_t grid_decimal, int64_t ncell,
+                      const float *lat, const float *lng, int32_t nrec, const int32_t *year, const int32_t *month,
+                      const int32_t *day, const int32_t *hour, int32_t n_cols, const int32_t *cols,
+                      const double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -30,6 +30,15 @@ def test_exports_every_declared_symbol(lib):
     assert sorted(model.EXPORTS) == syms
 
 
+def test_exports_every_declared_file_symbol(lib):
+    from vicres_b200 import files
+    syms = declared_symbols("vicres_files.h")
+    assert len(syms) == 9
+    for s in syms:
+        assert hasattr(lib, s), "libvicres.so does not export %s" % s
+    assert sorted(files.FILES_EXPORTS) == syms
+
+
 def test_exports_every_declared_routing_symbol(lib):
     from vicres_b200 import route
     syms = declared_symbols("vicres_route.h")

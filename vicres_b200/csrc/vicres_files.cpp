@@ -1,0 +1,425 @@
+// vicres_files.cpp -- readers for the reference's parameter files and the ASCII flux writer
+// (include/vicres_files.h).  Host C++ only; no CUDA here.  Each reader follows the conversions of
+// the reference reader it replaces (sscanf %f -> strtof, %lf -> strtod, float fields kept float).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/vicres_files.h"
+
+namespace {
+
+std::string g_err;
+
+struct VegClass {
+  int id = 0, overstory = 0;
+  double rarc = 0, rmin = 0, LAI[12], albedo[12], roughness[12], displacement[12], wind_h = 0, rad_atten = 0,
+         wind_atten = 0, trunk_ratio = 0;
+  float RGL = 0;
+};
+
+std::vector<std::string> tokens(const std::string &line)
+{
+  std::vector<std::string> t;
+  size_t i = 0, n = line.size();
+  while (i < n) {
+    while (i < n && (line[i] == ' ' || line[i] == '\t' || line[i] == '\r' || line[i] == '\n')) i++;
+    size_t j = i;
+    while (j < n && !(line[j] == ' ' || line[j] == '\t' || line[j] == '\r' || line[j] == '\n')) j++;
+    if (j > i) t.push_back(line.substr(i, j - i));
+    i = j;
+  }
+  return t;
+}
+
+bool read_line(FILE *f, std::string &s)
+{
+  s.clear();
+  int c;
+  bool any = false;
+  while ((c = fgetc(f)) != EOF) {
+    any = true;
+    if (c == '\n') break;
+    s.push_back((char)c);
+  }
+  return any;
+}
+
+double linear_interp(double x, double lx, double ux, double ly, double uy) { return ((x - lx) / (ux - lx) * (uy - ly) + ly); }
+
+}  // namespace
+
+struct vr_params {
+  int L = 0, NB = 0;
+  std::vector<int32_t> gridcel;
+  std::vector<float> lat, lng;
+  // cells
+  std::vector<double> c_lat, elevation, b_infilt, Ds, Dsmax, Ws, c_expt, avg_temp, dp, rough, snow_rough;
+  std::vector<double> expt, Ksat, depth, max_moist, Wcr, Wpwp, resid_moist, init_moist, bulk_density, soil_density,
+      bulk_dens_min, soil_dens_min, quartz, organic, porosity;           // [L][C]
+  std::vector<double> AreaFract, Tfactor, Pfactor;                         // [NB][C]
+  std::vector<int64_t> tile_ptr;
+  std::vector<int32_t> tile_class;
+  std::vector<double> tile_Cv, tile_root, tile_LAI, tile_albedo, tile_vegcover;
+  // veglib
+  std::vector<int32_t> l_over;
+  std::vector<double> l_rarc, l_rmin, l_wind_h, l_RGL, l_rad, l_watt, l_trunk, l_rough, l_disp;
+  vr_cells cells;
+  vr_veglib lib;
+};
+
+extern "C" {
+
+const char *vr_params_last_error(void) { return g_err.c_str(); }
+void vr_params_free(vr_params *p) { delete p; }
+const vr_cells *vr_params_cells(const vr_params *p) { return p ? &p->cells : nullptr; }
+const vr_veglib *vr_params_veglib(const vr_params *p) { return p ? &p->lib : nullptr; }
+const int32_t *vr_params_gridcel(const vr_params *p) { return p ? p->gridcel.data() : nullptr; }
+const float *vr_params_lat(const vr_params *p) { return p ? p->lat.data() : nullptr; }
+const float *vr_params_lng(const vr_params *p) { return p ? p->lng.data() : nullptr; }
+
+int vr_params_read(const vr_param_files *fo, vr_params **out)
+{
+  if (!fo || !out || !fo->soil || !fo->veglib || !fo->vegparam) { g_err = "null argument"; return VR_ERR_ARG; }
+  *out = nullptr;
+  const int L = fo->nlayer, NB = fo->nbands, RZ = fo->root_zones;
+  if (L < 2 || L > VR_MAX_LAYERS || NB < 1 || NB > VR_MAX_BANDS || RZ < 1 || RZ > 16) { g_err = "nlayer/nbands/root_zones out of range"; return VR_ERR_ARG; }
+  if (NB > 1 && !fo->snowband) { g_err = "SNOW_BAND > 1 needs a snow band file"; return VR_ERR_ARG; }
+
+  // ---- vegetation library (read_veglib.c): class lines start with a digit ----
+  std::vector<VegClass> lib;
+  {
+    FILE *f = fopen(fo->veglib, "r");
+    if (!f) { g_err = std::string("cannot open ") + fo->veglib; return VR_ERR_ARG; }
+    std::string line;
+    while (read_line(f, line)) {
+      size_t i = 0;
+      while (i < line.size() && (line[i] == ' ' || line[i] == '\t')) i++;
+      if (i >= line.size() || line[i] < '0' || line[i] > '9') continue;
+      std::vector<std::string> t = tokens(line);
+      const size_t need = 4 + 12 * 4 + 5;
+      if (t.size() < need) { fclose(f); g_err = "vegetation library line has too few columns"; return VR_ERR_ARG; }
+      VegClass v;
+      size_t k = 0;
+      v.id = atoi(t[k++].c_str());
+      v.overstory = atoi(t[k++].c_str());
+      v.rarc = strtod(t[k++].c_str(), nullptr);
+      v.rmin = strtod(t[k++].c_str(), nullptr);
+      for (int j = 0; j < 12; j++) v.LAI[j] = strtod(t[k++].c_str(), nullptr);
+      for (int j = 0; j < 12; j++) v.albedo[j] = strtod(t[k++].c_str(), nullptr);
+      for (int j = 0; j < 12; j++) v.roughness[j] = strtod(t[k++].c_str(), nullptr);
+      for (int j = 0; j < 12; j++) v.displacement[j] = strtod(t[k++].c_str(), nullptr);
+      v.wind_h = strtod(t[k++].c_str(), nullptr);
+      v.RGL = strtof(t[k++].c_str(), nullptr);
+      v.rad_atten = strtod(t[k++].c_str(), nullptr);
+      v.wind_atten = strtod(t[k++].c_str(), nullptr);
+      v.trunk_ratio = strtod(t[k++].c_str(), nullptr);
+      lib.push_back(v);
+    }
+    fclose(f);
+    if (lib.empty()) { g_err = "no classes in the vegetation library"; return VR_ERR_ARG; }
+  }
+
+  vr_params *P = new vr_params();
+  P->L = L; P->NB = NB;
+  struct Soil {
+    int gridcel; float lat, lng, elevation;
+    double b, Ds, Dsmax, Ws, c, avg_temp, dp, rough, snow_rough;
+    double expt[3], Ksat[3], init_moist[3], depth[3], quartz[3], bdm[3], sdm[3], wcr_fr[3], wpwp_fr[3], resid[3];
+  };
+  std::vector<Soil> soils;
+  {
+    FILE *f = fopen(fo->soil, "r");
+    if (!f) { delete P; g_err = std::string("cannot open ") + fo->soil; return VR_ERR_ARG; }
+    std::string line;
+    while (read_line(f, line)) {
+      std::vector<std::string> t = tokens(line);
+      if (t.empty()) continue;
+      if (atoi(t[0].c_str()) == 0) continue;                  // RUN_MODEL flag
+      const size_t need = 9 + 4 * L + 1 + L + 2 + 4 * L + 1 + 2 * L + 3 + L + 1;
+      if (t.size() < need) { fclose(f); delete P; g_err = "soil file row has too few columns for NLAYER"; return VR_ERR_ARG; }
+      Soil s;
+      size_t k = 1;
+      s.gridcel = atoi(t[k++].c_str());
+      s.lat = strtof(t[k++].c_str(), nullptr);
+      s.lng = strtof(t[k++].c_str(), nullptr);
+      s.b = strtod(t[k++].c_str(), nullptr);
+      s.Ds = strtod(t[k++].c_str(), nullptr);
+      s.Dsmax = strtod(t[k++].c_str(), nullptr);
+      s.Ws = strtod(t[k++].c_str(), nullptr);
+      s.c = strtod(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) s.expt[l] = strtod(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) s.Ksat[l] = strtod(t[k++].c_str(), nullptr);
+      k += L;                                                  // phi_s
+      for (int l = 0; l < L; l++) s.init_moist[l] = strtod(t[k++].c_str(), nullptr);
+      s.elevation = strtof(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) {
+        double d = strtod(t[k++].c_str(), nullptr);
+        s.depth[l] = (float)(int)(d * 1000 + 0.5) / 1000;     // read_soilparam.c:342: float / int
+      }
+      s.avg_temp = strtod(t[k++].c_str(), nullptr);
+      s.dp = strtod(t[k++].c_str(), nullptr);
+      k += L;                                                  // bubble
+      for (int l = 0; l < L; l++) s.quartz[l] = strtod(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) s.bdm[l] = strtod(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) s.sdm[l] = strtod(t[k++].c_str(), nullptr);
+      k += 1;                                                  // off_gmt
+      for (int l = 0; l < L; l++) s.wcr_fr[l] = strtod(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) s.wpwp_fr[l] = strtod(t[k++].c_str(), nullptr);
+      s.rough = strtod(t[k++].c_str(), nullptr);
+      s.snow_rough = strtod(t[k++].c_str(), nullptr);
+      k += 1;                                                  // annual_prec
+      for (int l = 0; l < L; l++) s.resid[l] = strtod(t[k++].c_str(), nullptr);
+      if (s.b <= 0) { fclose(f); delete P; g_err = "b_infilt must be positive"; return VR_ERR_ARG; }
+      soils.push_back(s);
+    }
+    fclose(f);
+  }
+  const int64_t C = (int64_t)soils.size();
+  if (C == 0) { delete P; g_err = "no cells flagged to run in the soil file"; return VR_ERR_ARG; }
+  auto LC = [&](std::vector<double> &v) { v.assign((size_t)L * C, 0.0); };
+  P->c_lat.resize(C); P->elevation.resize(C); P->b_infilt.resize(C); P->Ds.resize(C); P->Dsmax.resize(C); P->Ws.resize(C);
+  P->c_expt.resize(C); P->avg_temp.resize(C); P->dp.resize(C); P->rough.resize(C); P->snow_rough.resize(C);
+  LC(P->expt); LC(P->Ksat); LC(P->depth); LC(P->max_moist); LC(P->Wcr); LC(P->Wpwp); LC(P->resid_moist); LC(P->init_moist);
+  LC(P->bulk_density); LC(P->soil_density); LC(P->bulk_dens_min); LC(P->soil_dens_min); LC(P->quartz); LC(P->organic); LC(P->porosity);
+  P->AreaFract.assign((size_t)NB * C, 0.0); P->Tfactor.assign((size_t)NB * C, 0.0); P->Pfactor.assign((size_t)NB * C, 1.0);
+  P->gridcel.resize(C); P->lat.resize(C); P->lng.resize(C);
+  std::vector<float> elev_f(C);
+  for (int64_t c = 0; c < C; c++) {
+    const Soil &s = soils[c];
+    P->gridcel[c] = s.gridcel; P->lat[c] = s.lat; P->lng[c] = s.lng; elev_f[c] = s.elevation;
+    P->c_lat[c] = s.lat; P->b_infilt[c] = s.b; P->Ds[c] = s.Ds; P->Dsmax[c] = s.Dsmax; P->Ws[c] = s.Ws; P->c_expt[c] = s.c;
+    P->avg_temp[c] = s.avg_temp; P->dp[c] = s.dp; P->rough[c] = s.rough; P->snow_rough[c] = s.snow_rough;
+    for (int l = 0; l < L; l++) {
+      const size_t k = (size_t)l * C + c;
+      const double organic = 0.0, bdo = -9999, sdo = -9999;     // ORGANIC_FRACT FALSE (read_soilparam.c:268-274)
+      const double bulk = (1 - organic) * s.bdm[l] + organic * bdo, sdens = (1 - organic) * s.sdm[l] + organic * sdo;
+      const double poros = 1.0 - bulk / sdens, mm = s.depth[l] * poros * 1000.;
+      P->expt[k] = s.expt[l]; P->Ksat[k] = s.Ksat[l]; P->depth[k] = s.depth[l]; P->max_moist[k] = mm;
+      P->Wcr[k] = s.wcr_fr[l] * mm; P->Wpwp[k] = s.wpwp_fr[l] * mm;
+      P->resid_moist[k] = (s.resid[l] == -99999.) ? 0.0 : s.resid[l];
+      P->init_moist[k] = s.init_moist[l]; P->bulk_density[k] = bulk; P->soil_density[k] = sdens;
+      P->bulk_dens_min[k] = s.bdm[l]; P->soil_dens_min[k] = s.sdm[l]; P->quartz[k] = s.quartz[l]; P->organic[k] = organic;
+      P->porosity[k] = poros;
+    }
+    P->AreaFract[c] = 1.;                                       // band 0 (read_soilparam.c:478-486)
+  }
+
+  // ---- snow bands (read_snowband.c) ----
+  if (NB > 1) {
+    FILE *f = fopen(fo->snowband, "r");
+    if (!f) { delete P; g_err = std::string("cannot open ") + fo->snowband; return VR_ERR_ARG; }
+    std::map<int, std::vector<std::string>> rows;
+    std::string line;
+    while (read_line(f, line)) {
+      std::vector<std::string> t = tokens(line);
+      if (t.size() >= (size_t)(1 + 3 * NB)) rows[atoi(t[0].c_str())] = t;
+    }
+    fclose(f);
+    for (int64_t c = 0; c < C; c++) {
+      auto it = rows.find(P->gridcel[c]);
+      if (it == rows.end()) continue;                            // the reference warns and keeps one band
+      const std::vector<std::string> &t = it->second;
+      double total = 0., af[VR_MAX_BANDS], pf[VR_MAX_BANDS];
+      float be[VR_MAX_BANDS], avg_elev = 0;
+      for (int b = 0; b < NB; b++) { af[b] = strtod(t[1 + b].c_str(), nullptr); total += af[b]; }
+      if (total != 1.) for (int b = 0; b < NB; b++) af[b] /= total;
+      for (int b = 0; b < NB; b++) { be[b] = strtof(t[1 + NB + b].c_str(), nullptr); avg_elev += be[b] * af[b]; }
+      if (fabs(avg_elev - elev_f[c]) > 1.0) elev_f[c] = (float)avg_elev;
+      total = 0.;
+      for (int b = 0; b < NB; b++) { pf[b] = strtod(t[1 + 2 * NB + b].c_str(), nullptr); total += pf[b]; }
+      if (total != 1.) for (int b = 0; b < NB; b++) pf[b] /= total;
+      for (int b = 0; b < NB; b++) {
+        const size_t k = (size_t)b * C + c;
+        P->AreaFract[k] = af[b];
+        P->Tfactor[k] = (elev_f[c] - be[b]) * -1 * (-0.0065);
+        P->Pfactor[k] = (af[b] > 0) ? pf[b] / af[b] : 0.;
+      }
+    }
+  }
+  for (int64_t c = 0; c < C; c++) P->elevation[c] = elev_f[c];
+
+  // ---- vegetation parameters (read_vegparam.c) + root fractions (calc_root_fraction.c) ----
+  {
+    FILE *f = fopen(fo->vegparam, "r");
+    if (!f) { delete P; g_err = std::string("cannot open ") + fo->vegparam; return VR_ERR_ARG; }
+    struct Tile { int cls; double Cv; std::vector<float> zd, zf; double LAI[12]; bool has_lai; };
+    std::map<int, std::vector<Tile>> blocks;
+    std::string line;
+    const int per_tile = 1 + (fo->vegparam_lai ? 1 : 0);
+    while (read_line(f, line)) {
+      std::vector<std::string> t = tokens(line);
+      if (t.size() < 2) continue;
+      const int cell = atoi(t[0].c_str()), nveg = atoi(t[1].c_str());
+      std::vector<Tile> tiles;
+      for (int i = 0; i < nveg; i++) {
+        Tile tl;
+        tl.has_lai = false;
+        if (!read_line(f, line)) break;
+        std::vector<std::string> v = tokens(line);
+        if ((int)v.size() != 2 + 2 * RZ) { fclose(f); delete P; g_err = "vegetation parameter tile line: wrong number of fields for ROOT_ZONES"; return VR_ERR_ARG; }
+        tl.cls = atoi(v[0].c_str());
+        tl.Cv = atof(v[1].c_str());
+        float sum = 0.f;
+        for (int j = 0; j < RZ; j++) {
+          tl.zd.push_back((float)atof(v[2 + 2 * j].c_str()));
+          tl.zf.push_back((float)atof(v[3 + 2 * j].c_str()));
+          sum += tl.zf.back();
+        }
+        if (sum != 1.f) for (int j = 0; j < RZ; j++) tl.zf[j] /= sum;
+        if (per_tile == 2) {
+          if (!read_line(f, line)) break;
+          std::vector<std::string> m = tokens(line);
+          if (m.size() != 12) { fclose(f); delete P; g_err = "vegetation parameter LAI line needs 12 values"; return VR_ERR_ARG; }
+          for (int j = 0; j < 12; j++) tl.LAI[j] = atof(m[j].c_str());
+          tl.has_lai = true;
+        }
+        tiles.push_back(tl);
+      }
+      blocks[cell] = tiles;
+    }
+    fclose(f);
+    P->tile_ptr.assign(C + 1, 0);
+    for (int64_t c = 0; c < C; c++) {
+      auto it = blocks.find(P->gridcel[c]);
+      if (it == blocks.end()) { delete P; g_err = "grid cell missing from the vegetation parameter file"; return VR_ERR_ARG; }
+      std::vector<Tile> &tiles = it->second;
+      const int Nveg = (int)tiles.size();
+      double Cv_sum = 0;
+      for (const Tile &tl : tiles) Cv_sum += tl.Cv;
+      if (Cv_sum > 1.0 || (Cv_sum > 0.99 && Cv_sum < 1.0)) {
+        for (Tile &tl : tiles) tl.Cv = tl.Cv / Cv_sum;
+        Cv_sum = 1.;
+      }
+      for (int i = 0; i < Nveg; i++) {
+        const Tile &tl = tiles[i];
+        int cls = -1;
+        for (size_t j = 0; j < lib.size(); j++) if (lib[j].id == tl.cls) cls = (int)j;
+        if (cls < 0) { delete P; g_err = "vegetation class not in the library"; return VR_ERR_ARG; }
+        // calc_root_fractions
+        float root[VR_MAX_LAYERS] = {0, 0, 0}, sum_fract = 0, dum;
+        int layer = 0, zone = 0;
+        double Lstep = P->depth[(size_t)0 * C + c], Lsum = Lstep, Zsum = 0, Zstep, Zmin_fract, Zmin_depth, Zmax;
+        while (zone < RZ) {
+          Zstep = (double)tl.zd[zone];
+          if ((Zsum + Zstep) <= Lsum && Zsum >= Lsum - Lstep) sum_fract += tl.zf[zone];
+          else {
+            if (Zsum < Lsum - Lstep) {
+              Zmin_depth = Lsum - Lstep;
+              Zmin_fract = linear_interp(Zmin_depth, Zsum, Zsum + Zstep, 0, tl.zf[zone]);
+            }
+            else { Zmin_depth = Zsum; Zmin_fract = 0.; }
+            if (Zsum + Zstep <= Lsum) Zmax = Zsum + Zstep;
+            else Zmax = Lsum;
+            sum_fract += linear_interp(Zmax, Zsum, Zsum + Zstep, 0, tl.zf[zone]) - Zmin_fract;
+            (void)Zmin_depth;
+          }
+          if (Zsum + Zstep < Lsum) { Zsum += Zstep; zone++; }
+          else if (Zsum + Zstep == Lsum) {
+            Zsum += Zstep; zone++;
+            if (layer < L) { root[layer] = sum_fract; sum_fract = 0.; }
+            layer++;
+            if (layer < L) { Lstep = P->depth[(size_t)layer * C + c]; Lsum += Lstep; }
+            else if (layer == L && zone < RZ) {
+              Zstep = (double)tl.zd[zone];
+              Lstep = Zsum + Zstep - Lsum;
+              if (zone < RZ - 1) for (int i2 = zone + 1; i2 < RZ; i2++) Lstep += tl.zd[i2];
+              Lsum += Lstep;
+            }
+          }
+          else if (Zsum + Zstep > Lsum) {
+            if (layer < L) { root[layer] = sum_fract; sum_fract = 0.; }
+            layer++;
+            if (layer < L) { Lstep = P->depth[(size_t)layer * C + c]; Lsum += Lstep; }
+            else if (layer == L) {
+              Lstep = Zsum + Zstep - Lsum;
+              if (zone < RZ - 1) for (int i2 = zone + 1; i2 < RZ; i2++) Lstep += tl.zd[i2];
+              Lsum += Lstep;
+            }
+          }
+        }
+        if (sum_fract > 0 && layer >= L) root[L - 1] += sum_fract;
+        else if (sum_fract > 0) root[layer] += sum_fract;
+        dum = 0.;
+        for (int l = 0; l < L; l++) { if (root[l] < 1.e-4) root[l] = 0.; dum += root[l]; }
+        if (dum == 0.0) { delete P; g_err = "root fractions sum to zero"; return VR_ERR_ARG; }
+        for (int l = 0; l < L; l++) root[l] /= dum;
+        P->tile_class.push_back(cls);
+        P->tile_Cv.push_back(tl.Cv);
+        for (int l = 0; l < L; l++) P->tile_root.push_back(root[l]);
+        for (int j = 0; j < 12; j++) {
+          double lai = lib[cls].LAI[j];
+          if (tl.has_lai && fo->lai_from_vegparam && tl.LAI[j] != -1) lai = tl.LAI[j];    // NODATA_VH
+          P->tile_LAI.push_back(lai);
+          P->tile_albedo.push_back(lib[cls].albedo[j]);
+          P->tile_vegcover.push_back(1.00);                      // VEGLIB_VEGCOVER FALSE
+        }
+      }
+      if (Cv_sum < 1.) {                                         // bare-soil tile (read_vegparam.c:318-322)
+        P->tile_class.push_back((int32_t)lib.size());
+        P->tile_Cv.push_back(1.0 - Cv_sum);
+        for (int l = 0; l < L; l++) P->tile_root.push_back(0.);
+        for (int j = 0; j < 12; j++) { P->tile_LAI.push_back(0.); P->tile_albedo.push_back(0.); P->tile_vegcover.push_back(0.); }
+      }
+      P->tile_ptr[c + 1] = (int64_t)P->tile_class.size();
+    }
+  }
+
+  // ---- veglib arrays ----
+  for (const VegClass &v : lib) {
+    P->l_over.push_back(v.overstory); P->l_rarc.push_back(v.rarc); P->l_rmin.push_back(v.rmin); P->l_wind_h.push_back(v.wind_h);
+    P->l_RGL.push_back((double)v.RGL); P->l_rad.push_back(v.rad_atten); P->l_watt.push_back(v.wind_atten); P->l_trunk.push_back(v.trunk_ratio);
+    for (int j = 0; j < 12; j++) { P->l_rough.push_back(v.roughness[j]); P->l_disp.push_back(v.displacement[j]); }
+  }
+  vr_veglib &lb = P->lib;
+  lb.nclass = (int32_t)lib.size(); lb.overstory = P->l_over.data(); lb.rarc = P->l_rarc.data(); lb.rmin = P->l_rmin.data();
+  lb.wind_h = P->l_wind_h.data(); lb.RGL = P->l_RGL.data(); lb.rad_atten = P->l_rad.data(); lb.wind_atten = P->l_watt.data();
+  lb.trunk_ratio = P->l_trunk.data(); lb.roughness = P->l_rough.data(); lb.displacement = P->l_disp.data();
+  vr_cells &cl = P->cells;
+  cl.ncell = C; cl.lat = P->c_lat.data(); cl.elevation = P->elevation.data(); cl.b_infilt = P->b_infilt.data(); cl.Ds = P->Ds.data();
+  cl.Dsmax = P->Dsmax.data(); cl.Ws = P->Ws.data(); cl.c_expt = P->c_expt.data(); cl.avg_temp = P->avg_temp.data(); cl.dp = P->dp.data();
+  cl.rough = P->rough.data(); cl.snow_rough = P->snow_rough.data(); cl.expt = P->expt.data(); cl.Ksat = P->Ksat.data();
+  cl.depth = P->depth.data(); cl.max_moist = P->max_moist.data(); cl.Wcr = P->Wcr.data(); cl.Wpwp = P->Wpwp.data();
+  cl.resid_moist = P->resid_moist.data(); cl.init_moist = P->init_moist.data(); cl.bulk_density = P->bulk_density.data();
+  cl.soil_density = P->soil_density.data(); cl.bulk_dens_min = P->bulk_dens_min.data(); cl.soil_dens_min = P->soil_dens_min.data();
+  cl.quartz = P->quartz.data(); cl.organic = P->organic.data(); cl.porosity = P->porosity.data();
+  cl.AreaFract = P->AreaFract.data(); cl.Tfactor = P->Tfactor.data(); cl.Pfactor = P->Pfactor.data();
+  cl.tile_ptr = P->tile_ptr.data(); cl.tile_class = P->tile_class.data(); cl.tile_Cv = P->tile_Cv.data();
+  cl.tile_root = P->tile_root.data(); cl.tile_LAI = P->tile_LAI.data(); cl.tile_albedo = P->tile_albedo.data();
+  cl.tile_vegcover = P->tile_vegcover.data();
+  *out = P;
+  return VR_OK;
+}
+
+int vr_write_results(const char *result_dir, const char *prefix, int32_t grid_decimal, int64_t ncell, const float *lat,
+                     const float *lng, int32_t nrec, const int32_t *year, const int32_t *month, const int32_t *day,
+                     const int32_t *hour, int32_t n_cols, const int32_t *cols, const double *out)
+{
+  if (!result_dir || !prefix || !lat || !lng || !year || !month || !day || !out || !cols || ncell < 1 || nrec < 1 || n_cols < 1) {
+    g_err = "null or empty argument";
+    return VR_ERR_ARG;
+  }
+  char fmt[64], name[4096];
+  snprintf(fmt, sizeof fmt, "%%s/%%s_%%.%df_%%.%df", grid_decimal, grid_decimal);      // make_in_and_outfiles.c:46-86
+  for (int64_t c = 0; c < ncell; c++) {
+    snprintf(name, sizeof name, fmt, result_dir, prefix, lat[c], lng[c]);
+    FILE *f = fopen(name, "w");
+    if (!f) { g_err = std::string("cannot create ") + name; return VR_ERR_ARG; }
+    for (int r = 0; r < nrec; r++) {
+      if (hour) fprintf(f, "%04i\t%02i\t%02i\t%02i\t", year[r], month[r], day[r], hour[r]);
+      else fprintf(f, "%04i\t%02i\t%02i\t", year[r], month[r], day[r]);
+      for (int v = 0; v < n_cols; v++) {
+        if (v) fprintf(f, "\t ");
+        fprintf(f, "%.4f", out[((size_t)cols[v] * nrec + r) * ncell + c]);
+      }
+      fprintf(f, "\n");
+    }
+    if (fclose(f) != 0) { g_err = std::string("write failed: ") + name; return VR_ERR_ARG; }
+  }
+  return VR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""ctypes binding of include/vicres_files.h: the reference's parameter files -> the struct-of-arrays
+hand-off of include/vicres.h, and the ASCII flux writer.  Host only (no GPU needed).
+
+Mirrors read_soilparam / read_veglib / read_vegparam / read_snowband (runoff/model/*.c) and
+write_data.c's ASCII branch; the parsing itself is in csrc/vicres_files.cpp.
+"""
+import ctypes as C
+import numpy as np
+from . import abi
+from .model import load_library, VicResError
+
+
+class ParamFilesC(C.Structure):
+    _fields_ = [("nlayer", C.c_int32), ("nbands", C.c_int32), ("root_zones", C.c_int32),
+                ("vegparam_lai", C.c_int32), ("lai_from_vegparam", C.c_int32),
+                ("soil", C.c_char_p), ("veglib", C.c_char_p), ("vegparam", C.c_char_p),
+                ("snowband", C.c_char_p)]
+
+
+FILES_EXPORTS = ["vr_params_read", "vr_params_free", "vr_params_last_error", "vr_params_cells",
+                 "vr_params_veglib", "vr_params_gridcel", "vr_params_lat", "vr_params_lng", "vr_write_results"]
+
+
+def _bind(lib):
+    lib.vr_params_read.argtypes = [C.POINTER(ParamFilesC), C.POINTER(C.c_void_p)]
+    lib.vr_params_read.restype = C.c_int
+    lib.vr_params_free.argtypes = [C.c_void_p]
+    lib.vr_params_free.restype = None
+    lib.vr_params_last_error.restype = C.c_char_p
+    lib.vr_params_cells.argtypes = [C.c_void_p]
+    lib.vr_params_cells.restype = C.POINTER(abi.vr_cells)
+    lib.vr_params_veglib.argtypes = [C.c_void_p]
+    lib.vr_params_veglib.restype = C.POINTER(abi.vr_veglib)
+    for n, t in [("vr_params_gridcel", C.c_int32), ("vr_params_lat", C.c_float), ("vr_params_lng", C.c_float)]:
+        getattr(lib, n).argtypes = [C.c_void_p]
+        getattr(lib, n).restype = C.POINTER(t)
+    lib.vr_write_results.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_double)]
+    lib.vr_write_results.restype = C.c_int
+    return lib
+
+
+def _arr(ptr, n, dtype):
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True) if n else np.zeros(0, dtype)
+
+
+def read_params(soil, veglib, vegparam, snowband=None, nlayer=3, nbands=1, root_zones=3,
+                vegparam_lai=False, lai_from_vegparam=False, lib=None):
+    """Parse the four parameter files; returns (lib_dict, cells_dict, meta) in the layout
+    abi.pack_veglib / abi.pack_cells take.  meta: gridcel, lat, lng (float32 as the reference stores)."""
+    so = _bind(lib or load_library())
+    pf = ParamFilesC(nlayer, nbands, root_zones, int(vegparam_lai), int(lai_from_vegparam),
+                     soil.encode(), veglib.encode(), vegparam.encode(), snowband.encode() if snowband else None)
+    h = C.c_void_p()
+    rc = so.vr_params_read(C.byref(pf), C.byref(h))
+    if rc != 0:
+        raise VicResError(rc, "vr_params_read: %s" % so.vr_params_last_error().decode())
+    try:
+        cs, vl = so.vr_params_cells(h).contents, so.vr_params_veglib(h).contents
+        Cn, L, NB, ncl = int(cs.ncell), nlayer, nbands, int(vl.nclass)
+        cells = {k: _arr(getattr(cs, k), Cn, np.float64) for k in abi.CELL_SCALARS}
+        for k in abi.CELL_LAYER:
+            cells[k] = _arr(getattr(cs, k), L * Cn, np.float64).reshape(L, Cn)
+        for k in abi.CELL_BAND:
+            cells[k] = _arr(getattr(cs, k), NB * Cn, np.float64).reshape(NB, Cn)
+        cells["tile_ptr"] = _arr(cs.tile_ptr, Cn + 1, np.int64)
+        T = int(cells["tile_ptr"][-1])
+        cells["tile_class"] = _arr(cs.tile_class, T, np.int32)
+        cells["tile_Cv"] = _arr(cs.tile_Cv, T, np.float64)
+        cells["tile_root"] = _arr(cs.tile_root, T * L, np.float64).reshape(T, L)
+        for k in ["tile_LAI", "tile_albedo", "tile_vegcover"]:
+            cells[k] = _arr(getattr(cs, k), T * 12, np.float64).reshape(T, 12)
+        libd = {"overstory": _arr(vl.overstory, ncl, np.int32)}
+        for k in ["rarc", "rmin", "wind_h", "RGL", "rad_atten", "wind_atten", "trunk_ratio"]:
+            libd[k] = _arr(getattr(vl, k), ncl, np.float64)
+        for k in ["roughness", "displacement"]:
+            libd[k] = _arr(getattr(vl, k), ncl * 12, np.float64).reshape(ncl, 12)
+        meta = {"gridcel": _arr(so.vr_params_gridcel(h), Cn, np.int32),
+                "lat": _arr(so.vr_params_lat(h), Cn, np.float32), "lng": _arr(so.vr_params_lng(h), Cn, np.float32)}
+    finally:
+        so.vr_params_free(h)
+    return libd, cells, meta
+
+
+def write_results(result_dir, prefix, lat, lng, year, month, day, out, cols=None, hour=None, grid_decimal=4,
+                  lib=None):
+    """out: [n_out, nrec, C] float64 as VicRes.step returns; one `<prefix>_<lat>_<lng>` file per cell
+    holding the rows `cols` of out (default all).  hour: per record when dt < 24, else None."""
+    so = _bind(lib or load_library())
+    out = np.ascontiguousarray(out, np.float64)
+    n_out, nrec, Cn = out.shape
+    cols = np.arange(n_out, dtype=np.int32) if cols is None else np.ascontiguousarray(cols, np.int32)
+    lat, lng = np.ascontiguousarray(lat, np.float32), np.ascontiguousarray(lng, np.float32)
+    y, m, d = (np.ascontiguousarray(a, np.int32) for a in (year, month, day))
+    f32, i32 = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    hp = None
+    if hour is not None:
+        hour = np.ascontiguousarray(hour, np.int32)
+        hp = hour.ctypes.data_as(i32)
+    rc = so.vr_write_results(result_dir.encode(), prefix.encode(), grid_decimal, Cn, lat.ctypes.data_as(f32),
+                             lng.ctypes.data_as(f32), nrec, y.ctypes.data_as(i32), m.ctypes.data_as(i32),
+                             d.ctypes.data_as(i32), hp, len(cols), cols.ctypes.data_as(i32),
+                             out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise VicResError(rc, "vr_write_results: %s" % so.vr_params_last_error().decode())
