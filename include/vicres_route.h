@@ -8,9 +8,12 @@
  *   MAKE_CONVOLUTION    reservoir.f:216-526                       node inflow = sum over cells of UH_S * (runoff+baseflow)
  * (the reference drives them from rout.f:318-478 and reservoir.f:769-1140).  All arithmetic is fp32,
  * as in the Fortran (REAL), with the reference's accumulation order: cells in catchment-list order,
- * taps ascending.  Reservoir operating rules (MAKE_CONVOLUTIONRS day loop) and open-water evaporation
- * on reservoir-surface cells (RESER == 9999) are not part of this round; grids that contain 9999
- * cells inside a catchment are rejected with VR_ERR_UNSUPPORTED.
+ * taps ascending.
+ *   MAKE_RESERVOIR_UH   unit_hyd_routines.f:218-346               UH_R(107) reservoir -> next reservoir / station
+ *   MAKE_CONVOLUTIONRS  reservoir.f:1142-1684                     the reservoir day loop (rules 0-6, spill,
+ *                       environmental flow, irrigation, seepage, head, energy, release routing through UH_R)
+ * Open-water evaporation on reservoir-surface cells (RESER == 9999, reservoir.f:410-475) is not part
+ * of this round; grids that contain 9999 cells inside a catchment are rejected with VR_ERR_UNSUPPORTED.
  *
  * Grid arrays are in FILE order: index r*ncol + c where r = 0 is the FIRST data line of the ESRI
  * ASCII file (northern-most row) and c = 0 its first value.  Station col/row are the numbers of
@@ -69,6 +72,64 @@ int  vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const
                           const float *cell_scale, const float *ev_vege, const float *ev_soil, const float *tr_vege,
                           const float *cell_factor, const unsigned char *present, float *flows);
 int  vr_route_last_kernel_ms(vr_route *h, float *ms);
+
+/* ---- reservoirs (MAKE_CONVOLUTIONRS) -------------------------------------------------------------- */
+
+/* One resN.txt (reservoir.f:1021-1131), units as in the file (volumes 1000 m3, flows m3/s, levels m). */
+typedef struct vr_reservoir {
+  float hresermax, hresermin;          /* HRESERMAX, HRESERMIN                                     */
+  float v_live, v_dead;                /* VRESERTHAT, VDEAD                                        */
+  float head, q_design;                /* HYDRAUHEAD, QRESERTHAT                                   */
+  int32_t ope_year;                    /* OPEYEAR                                                  */
+  float v_initial;                     /* VINITIAL                                                 */
+  float seepage, infiltration;
+  int32_t hydropower_type;             /* 0 run-of-river, 1 storage                                */
+  int32_t hydropower_generator;        /* 1 generators on                                          */
+  float env_flow;                      /* fraction of q_design                                     */
+  int32_t rule;                        /* 0..6                                                     */
+  float hmax, hmin, op1[2];            /* rule 1: levels and the day numbers T1, T2                */
+  float reslv[12];                     /* rule 2: monthly target level                             */
+  float demand, x1, x2, x3, x4;        /* rule 3 (x1, x4 in radians)                               */
+  float demand5[12], op5x1[12], op5x2[12], op5x3[12], op5x4[12];   /* rule 5                       */
+  int32_t bathymetry;                  /* BTHMET_ACTIVE                                            */
+  float bth[4];                        /* BTHMET_A..D                                              */
+  const float *series;                 /* rule 4 release / rule 6 storage series [ndays], already aligned to the
+                                          first simulated day (the reference's STARTDAY offset); else NULL */
+  const float *irrigation;             /* [ndays] withdrawals (WITHIRRIGATION = 1) or NULL         */
+} vr_reservoir;
+
+typedef struct vr_res_options {
+  int32_t start_year, start_month;     /* START_YEAR, START_MO (CURRENTYEAR / CRTDATE, reservoir.f:1154,1172) */
+  int32_t legacy_rule_curve;           /* 0: today's reservoir.f (80 % lower/upper bands, :1222-1265);
+                                          1: the zone logic the shipped prebuilt `rout` still runs (kept as
+                                          comments in reservoir.f:1268-1302) -- the variant parity is pinned on */
+  int32_t reserved[5];
+} vr_res_options;
+
+/* Per-day series of every reservoir; each pointer may be NULL. Layout [set][reservoir][ndays (+1)]. */
+typedef struct vr_res_series {
+  float *vol;        /* [nsets][nres][ndays+1]  VOL(J,1..NDAY+1)           */
+  float *hho;        /* [nsets][nres][ndays+1]  HHO                        */
+  float *flowin;     /* [nsets][nres][ndays]    FLOWIN                     */
+  float *flowout;    /* [nsets][nres][ndays]    FLOWOUT                    */
+  float *turbine;    /* [nsets][nres][ndays]    FLOWOUT_TURB               */
+  float *energy;     /* [nsets][nres][ndays]    ENERGYPRO                  */
+  float *htk;        /* [nsets][nres][ndays]    HTK (target level)         */
+} vr_res_series;
+
+/* node -> RES_DIRECT(:,2) (id of the next reservoir downstream, 0 = none) and the node its release is routed
+ * to (reservoir.f:1529-1567: the next reservoir when it lies above this station, else the station) */
+int  vr_route_res_info(const vr_route *h, int32_t node, int32_t *downstream_id, int32_t *target_node);
+/* UH_R of a reservoir node: [VR_UH_NS] (what the reference writes to RES<i>_<to>.uh_r) */
+int  vr_route_get_uh_r(vr_route *h, int32_t node, float *uh_r);
+/* replace it with a user-supplied one, as the reference does when it reads an existing .uh_r file
+ * (reservoir.f:1544-1554) */
+int  vr_route_set_uh_r(vr_route *h, int32_t node, const float *uh_r);
+/* The day loop for nsets independent parameter sets (toolbox/optimization evaluates many rule sets on the
+ * same naturalised inflows).  natural: [nnodes][ndays] from vr_route_convolve; res: [nsets][nnodes-1] in node
+ * order; flow: [nsets][ndays] regulated station discharge.  Host pointers. */
+int  vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *natural, const vr_reservoir *res,
+                         const vr_res_options *opt, float *flow, const vr_res_series *out);
 
 #ifdef __cplusplus
 }

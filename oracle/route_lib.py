@@ -24,6 +24,9 @@ def lib():
         L.ro_node_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ro_get_uh.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ro_convolve.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        L.ro_res_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ro_get_uh_r.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ro_reservoirs.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
         _lib = L
     return _lib
 
@@ -56,6 +59,26 @@ class RouteOracle:
         lib().ro_convolve(self.h, ndays, p(runoff), p(baseflow), p(cell_scale), p(ev[0]), p(ev[1]), p(ev[2]),
                           p(cell_factor), p(pres), p(flows))
         return flows
+
+    def res_info(self, n):
+        ds, tg = C.c_int(), C.c_int()
+        lib().ro_res_info(self.h, n, C.byref(ds), C.byref(tg))
+        uh = np.zeros(route_abi.NS, dtype=np.float32)
+        lib().ro_get_uh_r(self.h, n, uh.ctypes.data)
+        return ds.value, tg.value, uh
+
+    def reservoirs(self, natural, res, start_year, start_month, legacy=False):
+        """natural [nnodes, ndays]; res: list of route_abi.reservoir dicts (node order) -> dict of series"""
+        natural = np.ascontiguousarray(natural, dtype=np.float32)
+        ndays, nres = natural.shape[1], self.nnodes - 1
+        arr, keep = route_abi.pack_reservoirs([res])
+        opt = route_abi.vr_res_options(start_year, start_month, int(legacy))
+        out = {"flow": np.zeros(ndays, dtype=np.float32)}
+        for k, ext in route_abi.RES_SERIES:
+            out[k] = np.zeros((nres, ndays + ext), dtype=np.float32)
+        lib().ro_reservoirs(self.h, ndays, natural.ctypes.data, C.cast(arr, C.c_void_p), C.cast(C.pointer(opt), C.c_void_p),
+                            out["flow"].ctypes.data, *[out[k].ctypes.data for k, _ in route_abi.RES_SERIES])
+        return out
 
     def close(self):
         if self.h:

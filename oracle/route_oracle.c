@@ -7,6 +7,8 @@
  *   MAKE_UHM                routing/model/unit_hyd_routines.f:7-50
  *   MAKE_GRID_UH            routing/model/unit_hyd_routines.f:55-178
  *   MAKE_CONVOLUTION        routing/model/reservoir.f:216-526   (without open-water evaporation)
+ *   MAKE_RESERVOIR_UH       routing/model/unit_hyd_routines.f:218-346
+ *   MAKE_CONVOLUTIONRS      routing/model/reservoir.f:1142-1684 (day loop; STEPBYSTEP = .FALSE.)
  * The Fortran cannot be compiled here (no Fortran compiler); this restatement is pinned against the
  * reference's shipped prebuilt `rout` binary run as a black box (tests/golden/route_*.npz made by
  * tools/make_route_golden.py: its .uh_s files and naturalised node inflows).  That binary predates
@@ -76,7 +78,7 @@ static int reaches(const fgrid *f, int I, int J, int PI, int PJ, int mode)
   }
 }
 
-typedef struct { int res_id, ncells, PI, PJ; int *ci, *cj; } onode;
+typedef struct { int res_id, ncells, PI, PJ; int *ci, *cj; int ds_id, target; float uh_r[VR_UH_NS]; } onode;
 
 /* MAKE_UHM for one cell */
 static void make_uhm_cell(float velo, float diff, float xmask, float *uh)
@@ -187,6 +189,27 @@ ro_model *ro_create(const vr_route_grid *g, int station_col, int station_row, co
     for (k = 0; k < nd->ncells; k++)
       grid_uh_cell(&m->f, m->uhm, nd->ci[k], nd->cj[k], nd->PI, nd->PJ, uh_box, m->uh_s[n] + (size_t)k * VR_UH_NS);
   }
+  /* RES_DIRECT(:,2): walk downstream from each reservoir cell (reservoir.f:733-759); UH_R to the next
+   * reservoir when it is one of this station's nodes, else to the station (unit_hyd_routines.f:246-270) */
+  for (n = 0; n < m->nnodes - 1; n++) {
+    onode *nd = &m->node[n];
+    int II = nd->PI, JJ = nd->PJ, guard = 0, DI = PI, DJ = PJ;
+    nd->ds_id = 0;
+    for (;;) {
+      int r, a, b;
+      if (II > g->ncol || II < 1 || JJ > g->nrow || JJ < 1) { nd->ds_id = 0; break; }
+      r = m->f.reser[IX(&m->f, II, JJ)];
+      if (r > 0 && r != 9999 && (II != nd->PI || JJ != nd->PJ)) { nd->ds_id = r; break; }
+      a = m->f.d1[IX(&m->f, II, JJ)]; b = m->f.d2[IX(&m->f, II, JJ)];
+      if (a != 0 && b != 0) { II = a; JJ = b; } else break;
+      if (++guard > ncell + 4) break;
+    }
+    nd->target = m->nnodes - 1;
+    for (k = 0; k < m->nnodes - 1; k++)
+      if (nd->ds_id > 0 && m->node[k].res_id == nd->ds_id) { nd->target = k; DI = m->node[k].PI; DJ = m->node[k].PJ; break; }
+    grid_uh_cell(&m->f, m->uhm, nd->PI, nd->PJ, DI, DJ, uh_box, nd->uh_r);
+  }
+  m->node[m->nnodes - 1].ds_id = 0; m->node[m->nnodes - 1].target = -1;
   return m;
 }
 
@@ -260,5 +283,269 @@ int ro_convolve(const ro_model *m, int ndays, const float *runoff, const float *
     }
   }
   free(RUNO); free(BASE);
+  return 0;
+}
+
+int ro_res_info(const ro_model *m, int node, int *ds_id, int *target)
+{
+  *ds_id = m->node[node].ds_id; *target = m->node[node].target; return 0;
+}
+int ro_get_uh_r(const ro_model *m, int node, float *uh_r)
+{
+  memcpy(uh_r, m->node[node].uh_r, sizeof(float) * VR_UH_NS); return 0;
+}
+
+static int cal_month(int CRTDATE)      /* reservoir.f:1688-1716 */
+{
+  static const int lim[11] = {31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+  int k;
+  for (k = 0; k < 11; k++) if (CRTDATE <= lim[k]) return k + 1;
+  return 12;
+}
+
+#define A2(a, J, I) (a)[(size_t)(J) * (ndays + 2) + (I)]     /* (reservoir J 0-based, day I 1-based) */
+
+/* MAKE_CONVOLUTIONRS steps 3-6 for one station and one parameter set (reservoir.f:1007-1600, STEPBYSTEP
+ * false so II == I).  natural: [nnodes][ndays]; res: [nnodes-1]; every local Fortran array starts at zero
+ * (static storage).  Outputs as in include/vicres_route.h (any pointer may be NULL). */
+int ro_reservoirs(const ro_model *m, int ndays, const float *natural, const vr_reservoir *res, const vr_res_options *opt,
+                  float *flow, float *o_vol, float *o_hho, float *o_flowin, float *o_flowout, float *o_turb,
+                  float *o_energy, float *o_htk)
+{
+  const int NORES = m->nnodes, NR = NORES - 1;
+  const size_t W = (size_t)ndays + 2;
+  float *RESFLOWS = calloc((size_t)NORES * W, sizeof(float)), *VOL = calloc((size_t)(NR + 1) * W, sizeof(float));
+  float *FLOWIN = calloc((size_t)(NR + 1) * W, sizeof(float)), *FLOWOUT = calloc((size_t)(NR + 1) * W, sizeof(float));
+  float *TURB = calloc((size_t)(NR + 1) * W, sizeof(float)), *HHO = calloc((size_t)(NR + 1) * W, sizeof(float));
+  float *ENERGY = calloc((size_t)(NR + 1) * W, sizeof(float)), *HTK = calloc((size_t)(NR + 1) * W, sizeof(float));
+  float *H0 = calloc(NR + 1, sizeof(float));
+  int I, J, KK;
+  for (J = 0; J < NORES; J++) for (I = 1; I <= ndays; I++) A2(RESFLOWS, J, I) = natural[(size_t)J * ndays + (I - 1)];
+  for (J = 0; J < NR; J++) {
+    const vr_reservoir *r = &res[J];
+    if (r->bathymetry == 1) H0[J] = r->bth[0] / (1 + r->bth[3]);
+    else {
+      float KFACTOR = sqrtf(r->v_dead / r->v_live);
+      H0[J] = (KFACTOR * r->hresermax - r->hresermin) / (KFACTOR - 1);
+    }
+    if (opt->start_year >= r->ope_year) A2(VOL, J, 1) = r->v_initial;
+    else A2(VOL, J, 1) = 0.001f;
+  }
+  for (I = 1; I <= ndays; I++) {
+    for (J = 0; J < NR; J++) {
+      const vr_reservoir *r = &res[J];
+      float HMAX = r->hmax, HMIN = r->hmin, VRESER = 0, REALHEAD = 0, QRESER = 0, Qmin = 0;
+      int CURRENTYEAR = opt->start_year + (int)(I / 365), CRTDATE, operating;
+      if (r->rule == 1 && HMAX < HMIN) { float t = HMAX; HMAX = HMIN; HMIN = t; }
+      operating = CURRENTYEAR >= r->ope_year;
+      if (operating) {
+        float X1 = r->x1, X2 = r->x2, X3 = r->x3, X4 = r->x4, Demand = r->demand;
+        VRESER = r->v_live + r->v_dead; REALHEAD = r->head; QRESER = r->q_design;
+        A2(FLOWIN, J, I) = A2(RESFLOWS, J, I);
+        Qmin = r->env_flow * r->q_design;
+        CRTDATE = (int)(1.0f * (I % 365) + (opt->start_month - 1) * 30);
+        if (r->rule == 1 || r->rule == 2) {
+          float DESIGNWL, CURRENTWL;
+          const float *OP1 = r->op1;
+          if (r->rule == 1) {
+            if (OP1[0] > OP1[1]) {
+              if (CRTDATE > OP1[1] && CRTDATE < OP1[0]) DESIGNWL = (CRTDATE - OP1[1]) / (OP1[0] - OP1[1]) * (HMAX - HMIN);
+              else if (CRTDATE >= OP1[0]) DESIGNWL = (HMAX - HMIN) - (CRTDATE - OP1[0]) / (365 - OP1[0] + OP1[1]) * (HMAX - HMIN);
+              else DESIGNWL = (HMAX - HMIN) - (CRTDATE + 365 - OP1[0]) / (365 - OP1[0] + OP1[1]) * (HMAX - HMIN);
+            }
+            else {
+              if (CRTDATE > OP1[0] && CRTDATE < OP1[1]) DESIGNWL = (HMAX - HMIN) - (CRTDATE - OP1[0]) / (OP1[1] - OP1[0]) * (HMAX - HMIN);
+              else if (CRTDATE >= OP1[1]) DESIGNWL = (HMAX - HMIN) / (365 - OP1[1] + OP1[0]) * (CRTDATE - OP1[1]);
+              else DESIGNWL = (HMAX - HMIN) / (365 - OP1[1] + OP1[0]) * (CRTDATE - OP1[0]) + (HMAX - HMIN);
+            }
+            DESIGNWL = DESIGNWL + (HMIN - H0[J]);
+          }
+          else {
+            DESIGNWL = r->reslv[cal_month(CRTDATE) - 1];
+            DESIGNWL = DESIGNWL - H0[J];
+          }
+          A2(HTK, J, I) = DESIGNWL + H0[J];
+          if (r->bathymetry == 1)
+            CURRENTWL = r->bth[0] / (expf(-1 * A2(VOL, J, I) / 1000 * r->bth[1]) + A2(VOL, J, I) / 1000 * r->bth[2] + r->bth[3]);
+          else CURRENTWL = A2(VOL, J, I) * (r->hresermax - H0[J]) / VRESER;
+          if (!opt->legacy_rule_curve) {
+            float LRC_WL = HMIN + 0.80f * (A2(HTK, J, I) - HMIN), URC_WL = HMAX - 0.80f * (HMAX - A2(HTK, J, I));
+            float LRC_VOL = (LRC_WL - H0[J]) * VRESER / (r->hresermax - H0[J]);
+            float URC_VOL = (URC_WL - H0[J]) * VRESER / (r->hresermax - H0[J]);
+            if (A2(VOL, J, I) > URC_VOL) {
+              A2(VOL, J, I + 1) = URC_VOL;
+              A2(FLOWOUT, J, I) = (A2(VOL, J, I) + A2(FLOWIN, J, I) * 24 * 3.6f - URC_VOL) / 24 / 3.6f;
+              A2(TURB, J, I) = fminf(fmaxf(A2(FLOWOUT, J, I), Qmin), QRESER);
+            }
+            else if (A2(VOL, J, I) < LRC_VOL) {
+              A2(FLOWOUT, J, I) = Qmin;
+              A2(TURB, J, I) = Qmin;
+              A2(VOL, J, I + 1) = A2(VOL, J, I) + (A2(FLOWIN, J, I) - A2(TURB, J, I)) * 24 * 3.6f;
+            }
+            else {
+              float RC_SLOPE = (VRESER - r->v_dead) / (OP1[0] - OP1[1]);
+              if (CRTDATE > OP1[1] && CRTDATE < OP1[0]) A2(VOL, J, I + 1) = A2(VOL, J, I) + RC_SLOPE;
+              else A2(VOL, J, I + 1) = A2(VOL, J, I) - RC_SLOPE;
+              A2(FLOWOUT, J, I) = (A2(VOL, J, I) - A2(VOL, J, I + 1)) / 24 / 3.6f + A2(FLOWIN, J, I);
+              A2(TURB, J, I) = fminf(fmaxf(A2(FLOWOUT, J, I), Qmin), QRESER);
+            }
+          }
+          else {       /* zone logic of the shipped binary (reservoir.f:1268-1302, commented out today) */
+            float TARGET = (DESIGNWL * VRESER) / (r->hresermax - H0[J]);
+            if (CURRENTWL >= DESIGNWL) {
+              if ((A2(VOL, J, I) + A2(FLOWIN, J, I) * 24 * 3.6f - QRESER * 24 * 3.6f) > TARGET) {
+                A2(VOL, J, I + 1) = A2(VOL, J, I) + A2(FLOWIN, J, I) * 24 * 3.6f - QRESER * 24 * 3.6f;
+                A2(FLOWOUT, J, I) = QRESER;
+                A2(TURB, J, I) = A2(FLOWOUT, J, I);
+              }
+              else {
+                A2(VOL, J, I + 1) = TARGET;
+                A2(FLOWOUT, J, I) = (A2(VOL, J, I) - A2(VOL, J, I + 1)) / 24 / 3.6f + A2(FLOWIN, J, I);
+                A2(TURB, J, I) = A2(FLOWOUT, J, I);
+              }
+            }
+            else {
+              if ((A2(VOL, J, I) + A2(FLOWIN, J, I) * 24 * 3.6f) > TARGET) {
+                A2(VOL, J, I + 1) = TARGET;
+                A2(FLOWOUT, J, I) = A2(FLOWIN, J, I) - (A2(VOL, J, I + 1) - A2(VOL, J, I)) / 24 / 3.6f;
+                A2(TURB, J, I) = A2(FLOWOUT, J, I);
+                if (A2(TURB, J, I) > QRESER) {       /* the binary still stores the excess (:1289, commented out today) */
+                  A2(VOL, J, I + 1) = A2(VOL, J, I + 1) + (A2(TURB, J, I) - QRESER) * 24 * 3.6f;
+                  A2(TURB, J, I) = QRESER;
+                }
+              }
+              else {
+                A2(VOL, J, I + 1) = A2(VOL, J, I) + A2(FLOWIN, J, I) * 24 * 3.6f;
+                A2(FLOWOUT, J, I) = Qmin;
+                A2(TURB, J, I) = A2(FLOWOUT, J, I);
+              }
+            }
+          }
+        }
+        else if (r->rule == 3 || r->rule == 5) {
+          float V = A2(VOL, J, I), FIN = A2(FLOWIN, J, I), FO;
+          if (r->rule == 5) {
+            int mth = cal_month(CRTDATE) - 1;
+            X1 = r->op5x1[mth]; X2 = r->op5x2[mth]; X3 = r->op5x3[mth]; X4 = r->op5x4[mth]; Demand = r->demand5[mth];
+          }
+          if (V < r->v_dead) FO = 0;
+          else if (V <= X2) {
+            if ((V - r->v_dead + FIN * 24 * 3.6f) <= (Demand + (V - X2) * tanf(X1) * 24 * 3.6f)) FO = (V - r->v_dead) / 24 / 3.6f + FIN;
+            else FO = Demand + (V - X2) * tanf(X1);
+          }
+          else if (V >= X3) {
+            if ((Demand + (V - X3) * tanf(X4)) * 24 * 3.6f > (V) - r->v_dead) FO = (V - r->v_dead) / 24 / 3.6f;
+            else if ((Demand + (V - X3) * tanf(X4)) > QRESER) FO = QRESER;
+            else FO = Demand + (V - X3) * tanf(X4);
+          }
+          else {
+            if (Demand * 24 * 3.6f > (V - r->v_dead)) FO = (V - r->v_dead) / 24 / 3.6f;
+            else FO = Demand;
+          }
+          A2(FLOWOUT, J, I) = FO;
+          A2(TURB, J, I) = FO;
+          if (A2(TURB, J, I) > QRESER) A2(TURB, J, I) = QRESER;
+          A2(VOL, J, I + 1) = V + (FIN - FO) * 24 * 3.6f;
+        }
+        else if (r->rule == 4) {
+          float OP4 = r->series ? r->series[I - 1] : 0.0f;
+          if (OP4 > QRESER && A2(VOL, J, I) < VRESER) OP4 = QRESER;
+          if (OP4 * 24 * 3.6f > ((A2(VOL, J, I) - r->v_dead)) + A2(FLOWIN, J, I) * 24 * 3.6f)
+            A2(TURB, J, I) = (A2(VOL, J, I) - r->v_dead) / 24 / 3.6f + A2(FLOWIN, J, I);
+          else A2(TURB, J, I) = OP4;
+          if (A2(TURB, J, I) < 0) A2(TURB, J, I) = 0;
+          A2(VOL, J, I + 1) = A2(VOL, J, I) + (A2(FLOWIN, J, I) - A2(TURB, J, I)) * 24 * 3.6f;
+          if (A2(TURB, J, I) > QRESER) A2(TURB, J, I) = QRESER;
+        }
+        else if (r->rule == 6) {
+          float OP6 = r->series ? r->series[I - 1] : 0.0f;
+          if (A2(FLOWIN, J, I) - (OP6 - A2(VOL, J, I)) / 24 / 3.6f > 0) {
+            A2(VOL, J, I + 1) = OP6;
+            A2(FLOWOUT, J, I) = A2(FLOWIN, J, I) - (A2(VOL, J, I + 1) - A2(VOL, J, I)) / 24 / 3.6f;
+          }
+          else {
+            A2(FLOWOUT, J, I) = Qmin;
+            A2(VOL, J, I + 1) = A2(VOL, J, I) + (A2(FLOWIN, J, I) - A2(FLOWOUT, J, I)) * 24 * 3.6f;
+          }
+          A2(TURB, J, I) = A2(FLOWOUT, J, I);
+          if (A2(TURB, J, I) > QRESER) A2(TURB, J, I) = QRESER;
+        }
+        /* STEP 5-7 (reservoir.f:1422-1508) */
+        if (A2(ENERGY, J, I) < 0) A2(ENERGY, J, I) = 0;
+        if (A2(VOL, J, I + 1) > VRESER) {
+          if (opt->legacy_rule_curve) {     /* the binary spills the excess; today's source clamps first and adds 0 */
+            A2(FLOWOUT, J, I) = A2(TURB, J, I) + (A2(VOL, J, I + 1) - VRESER) / 24 / 3.6f;
+            A2(VOL, J, I + 1) = VRESER;
+          }
+          else {
+            A2(VOL, J, I + 1) = VRESER;
+            A2(FLOWOUT, J, I) = A2(TURB, J, I) + (A2(VOL, J, I + 1) - VRESER) / 24 / 3.6f;
+          }
+        }
+        else A2(FLOWOUT, J, I) = A2(TURB, J, I);
+        if (A2(VOL, J, I) < 0) A2(VOL, J, I) = 0;
+        if (A2(FLOWOUT, J, I) < Qmin) A2(FLOWOUT, J, I) = Qmin;
+        if (r->hydropower_generator == 0) A2(TURB, J, I) = 0.0f;
+        {
+          float IRR = r->irrigation ? r->irrigation[I - 1] : 0.0f;
+          if (A2(FLOWOUT, J, I) >= IRR) A2(FLOWOUT, J, I) = A2(FLOWOUT, J, I) - IRR;
+          else A2(FLOWOUT, J, I) = Qmin;
+        }
+        if (A2(VOL, J, I + 1) - (r->seepage + r->infiltration) * 24 * 3.6f > 0) {
+          A2(VOL, J, I + 1) = A2(VOL, J, I + 1) - (r->seepage + r->infiltration) * 24 * 3.6f;
+          A2(FLOWOUT, J, I) = A2(FLOWOUT, J, I) + r->seepage;
+        }
+        else A2(VOL, J, I + 1) = 0;
+        A2(HHO, J, I) = A2(VOL, J, I) / VRESER * (r->hresermax - H0[J]) + H0[J];
+        A2(HHO, J, I + 1) = A2(VOL, J, I + 1) / VRESER * (r->hresermax - H0[J]) + H0[J];
+        A2(ENERGY, J, I) = 0.9f * 9.81f * A2(TURB, J, I) * ((A2(HHO, J, I) + A2(HHO, J, I + 1)) / 2 - (r->hresermax - REALHEAD)) / 1000;
+        if (r->rule == 0) {
+          A2(FLOWOUT, J, I) = A2(FLOWIN, J, I);
+          if (A2(FLOWOUT, J, I) <= Qmin) A2(FLOWOUT, J, I) = Qmin;
+          if (r->hydropower_generator == 1) A2(TURB, J, I) = A2(FLOWOUT, J, I);
+          else A2(TURB, J, I) = 0.0f;
+          if (A2(TURB, J, I) > QRESER) A2(TURB, J, I) = QRESER;
+        }
+        if (r->rule == 0 || r->hydropower_type == 0) {
+          A2(VOL, J, I + 1) = VRESER;
+          A2(ENERGY, J, I) = 0.9f * 9.81f * A2(TURB, J, I);
+          A2(ENERGY, J, I) = A2(ENERGY, J, I) * (REALHEAD) / 1000;
+          A2(HTK, J, I) = REALHEAD;
+          A2(HHO, J, I) = r->hresermax;
+          A2(HHO, J, I + 1) = r->hresermax;
+        }
+      }
+      else {      /* label 125: not yet commissioned (reservoir.f:1514-1525) */
+        A2(FLOWIN, J, I) = A2(RESFLOWS, J, I);
+        A2(FLOWOUT, J, I) = A2(FLOWIN, J, I);
+        A2(VOL, J, I) = 0; A2(ENERGY, J, I) = 0; A2(HTK, J, I) = 0; A2(HHO, J, I) = 0; A2(TURB, J, I) = 0.0f;
+      }
+      /* STEP 6: release through UH_R into the target node's inflow of day I+1 (reservoir.f:1569-1575) */
+      {
+        const int T = m->node[J].target;
+        const float *UH_RR = m->node[J].uh_r;
+        for (KK = 1; KK <= VR_UH_NS; KK++)
+          if ((I - KK + 1) >= 1)
+            A2(RESFLOWS, T, I + 1) = A2(RESFLOWS, T, I + 1) + UH_RR[KK - 1] * A2(FLOWOUT, J, I - KK + 1);
+      }
+    }
+    if (A2(RESFLOWS, NORES - 1, I) < 0) A2(RESFLOWS, NORES - 1, I) = 0;
+    flow[I - 1] = A2(RESFLOWS, NORES - 1, I);
+  }
+  for (J = 0; J < NR; J++) {
+    for (I = 1; I <= ndays + 1; I++) {
+      if (o_vol) o_vol[(size_t)J * (ndays + 1) + I - 1] = A2(VOL, J, I);
+      if (o_hho) o_hho[(size_t)J * (ndays + 1) + I - 1] = A2(HHO, J, I);
+    }
+    for (I = 1; I <= ndays; I++) {
+      size_t q = (size_t)J * ndays + I - 1;
+      if (o_flowin) o_flowin[q] = A2(FLOWIN, J, I);
+      if (o_flowout) o_flowout[q] = A2(FLOWOUT, J, I);
+      if (o_turb) o_turb[q] = A2(TURB, J, I);
+      if (o_energy) o_energy[q] = A2(ENERGY, J, I);
+      if (o_htk) o_htk[q] = A2(HTK, J, I);
+    }
+  }
+  free(RESFLOWS); free(VOL); free(FLOWIN); free(FLOWOUT); free(TURB); free(HHO); free(ENERGY); free(HTK); free(H0);
   return 0;
 }

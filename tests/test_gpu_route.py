@@ -77,3 +77,108 @@ def test_cuda_route_large_network_vs_oracle(Route):
     # mass: with normalised UH_S the routed volume equals the generated volume once the tail has drained
     print("routed cells %d, nodes %d, convolve kernel %.3f ms" % (tot, r.nnodes, r.last_kernel_ms()))
     r.close(); o.close()
+
+
+def random_reservoir(rng, rule, ndays):
+    """parameters spread so that every branch of the rule is visited over a few hundred days"""
+    vlive = float(rng.uniform(3000, 30000)); vdead = float(vlive * rng.uniform(0.1, 0.3))
+    hmax = float(rng.uniform(110, 160)); hmin = float(hmax - rng.uniform(15, 40))
+    q = float(rng.uniform(5, 60))
+    d = route_abi.reservoir(hresermax=hmax, hresermin=hmin, v_live=vlive, v_dead=vdead, head=float(0.6 * (hmax - hmin) + 20),
+                            q_design=q, ope_year=int(rng.choice([1999, 1999, 2001])), v_initial=float(vdead + rng.uniform(0.1, 0.9) * vlive),
+                            seepage=float(rng.choice([0.0, 0.05])), infiltration=float(rng.choice([0.0, 0.02])),
+                            hydropower_type=int(rng.choice([0, 1, 1, 1])), hydropower_generator=int(rng.choice([0, 1, 1])),
+                            env_flow=float(rng.choice([0.05, 0.1])), rule=rule, bathymetry=0)
+    if rule == 1:
+        t = sorted(int(x) for x in rng.choice(np.arange(20, 340), 2, replace=False))
+        d.update(hmax=hmax - 1, hmin=hmin + 2, op1=[t[1], t[0]] if rng.uniform() < 0.5 else [t[0], t[1]])
+    elif rule == 2:
+        d.update(reslv=[float(x) for x in rng.uniform(hmin, hmax, 12)])
+    elif rule == 3:
+        d.update(demand=float(q * 0.3), x1=float(rng.uniform(0.1, 1.2)), x2=float(vdead + 0.3 * vlive), x3=float(vdead + 0.8 * vlive),
+                 x4=float(rng.uniform(0.1, 1.4)))
+    elif rule == 5:
+        d.update(demand5=[float(q * rng.uniform(0.1, 0.5)) for _ in range(12)], op5x1=[float(rng.uniform(0.1, 1.2)) for _ in range(12)],
+                 op5x2=[float(vdead + rng.uniform(0.2, 0.4) * vlive) for _ in range(12)],
+                 op5x3=[float(vdead + rng.uniform(0.7, 0.9) * vlive) for _ in range(12)],
+                 op5x4=[float(rng.uniform(0.1, 1.4)) for _ in range(12)])
+    elif rule == 4:
+        d.update(series=rng.uniform(0, 1.5 * q, ndays).astype(np.float32))
+    elif rule == 6:
+        d.update(series=rng.uniform(vdead, vdead + vlive, ndays).astype(np.float32))
+    if rng.uniform() < 0.3:
+        d.update(irrigation=rng.uniform(0, 0.2 * q, ndays).astype(np.float32))
+    return d
+
+
+@pytest.mark.parametrize("legacy", [False, True])
+def test_cuda_reservoir_day_loop_bit_exact_vs_oracle(Route, legacy):
+    """all seven rules, chained reservoirs, 8 parameter sets in one launch; with the oracle's UH_R injected
+    (the reference's read-an-existing-.uh_r path) every series must equal the serial restatement bit for bit"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_route_golden import random_tree
+    rng = np.random.default_rng(17)
+    nrow, ncol, ndays = 30, 40, 900
+    d, out = random_tree(nrow, ncol, rng, fill=0.75)
+    active = np.argwhere(d > 0)
+    reser = np.zeros_like(d)
+    for i, k in enumerate(rng.choice(len(active), 40, replace=False)):
+        reser[tuple(active[k])] = i + 1
+    grid = dict(dir=d, reser=reser, velo=rng.uniform(0.8, 2.5, (nrow, ncol)).astype(np.float32),
+                diff=rng.uniform(400, 1500, (nrow, ncol)).astype(np.float32),
+                xmask=rng.uniform(15000, 30000, (nrow, ncol)).astype(np.float32))
+    box = rng.dirichlet(np.ones(12)).astype(np.float32)
+    col, row = int(out[1]) + 1, int(nrow - out[0])
+    r = Route(grid, col, row, box)
+    o = route_lib.RouteOracle(grid, col, row, box)
+    nres = r.nnodes - 1
+    assert nres >= 10
+    chained = 0
+    for n in range(nres):
+        ds, tg, uh = r.res_info(n)
+        ods, otg, ouh = o.res_info(n)
+        assert (ds, tg) == (ods, otg)
+        assert np.allclose(uh, ouh, rtol=2e-6, atol=1e-12)
+        chained += tg < nres
+        r.set_uh_r(n, ouh)
+    assert chained >= 2
+    natural = (rng.gamma(0.6, 30.0, (r.nnodes, ndays)) * (rng.uniform(size=(r.nnodes, ndays)) < 0.7)).astype(np.float32)
+    natural[:, 200:230] -= 5.0                      # negative naturalised inflow (evaporation larger than runoff)
+    nsets = 8
+    sets = [[random_reservoir(rng, int((n + s) % 7), ndays) for n in range(nres)] for s in range(nsets)]
+    out_gpu = r.reservoirs(natural, sets, 2000, 3, legacy=legacy)
+    for s in range(nsets):
+        ref = o.reservoirs(natural, sets[s], 2000, 3, legacy=legacy)
+        assert np.array_equal(out_gpu["flow"][s], ref["flow"], equal_nan=True), "station flow, set %d" % s
+        for k, _ in route_abi.RES_SERIES:
+            assert np.array_equal(out_gpu[k][s], ref[k], equal_nan=True), "%s, set %d: %d values differ" % (
+                k, s, (out_gpu[k][s] != ref[k]).sum())
+    assert r.last_kernel_ms() > 0
+    r.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["toy", "rand20x16"])
+def test_cuda_reservoirs_match_prebuilt_binary(Route, name, tmp_path):
+    """end to end on the device (its own UH_S, UH_R and convolution) against the binary's reservoir files:
+    the unit hydrographs differ from glibc's in the last bit, so 2e-5 relative instead of bit equality"""
+    from test_route_oracle import binary_columns, fixture_reservoirs
+    z, grid, (col, row), fac = load_route_fixture(name)
+    r = Route(grid, col, row, z["uh_box"])
+    ids = [r.node(n)[0] for n in range(r.nnodes - 1)]
+    ndays = int(z["ndays"])
+    flows = r.convolve(z["runoff"], z["baseflow"], cell_scale=fac * np.float32(0.028),
+                       evap=(z["ev_vege"], z["ev_soil"], z["tr_vege"]), cell_factor=fac, present=z["present"])
+    res = fixture_reservoirs(z, ids, tmp_path, ndays)
+    out = r.reservoirs(flows, [res], 2000, 1, legacy=True)
+    one = {k: v[0] for k, v in out.items()}
+    for j, rid in enumerate(ids):
+        ref = z["resday_%d" % rid]
+        mine = binary_columns(one, j, res[j])
+        mine[:, [0, 3, 5, 8]] = np.maximum(mine[:, [0, 3, 5, 8]], 0)
+        mine[:, 7] = np.where(mine[:, 2] > 0, np.minimum(mine[:, 6], np.float32(res[j]["q_design"])), mine[:, 7])
+        err = np.abs(mine - ref) / np.maximum(np.abs(ref), 1e-2)
+        assert err.max() < 2e-5, "reservoir %d: %.3e" % (rid, err.max())
+    err = np.abs(one["flow"] - z["station_flow"]) / np.maximum(np.abs(z["station_flow"]), 1e-2)
+    assert err.max() < 2e-5
+    r.close()

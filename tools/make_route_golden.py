@@ -66,7 +66,34 @@ def random_tree(nrow, ncol, rng, fill=0.8):
     return d, out
 
 
-def write_case(work, d, reser, station_rc, hdr, velo, diff, xmask, box, flux, ndays):
+def res_text(rng, rid):
+    """A resN.txt in the layout the prebuilt binary reads (one HYDROPOWER value; today's reservoir.f reads two).
+    Only what the binary provably shares with today's source is exercised: rules 1 and 2 and reservoirs that
+    are commissioned after the simulated period (tests/test_route_oracle.py)."""
+    hmax = float(np.round(rng.uniform(110, 160), 1))
+    hmin = float(np.round(hmax - rng.uniform(15, 40), 1))
+    vlive = float(np.round(rng.uniform(2000, 60000), 0))
+    vdead = float(np.round(vlive * rng.uniform(0.1, 0.3), 0))
+    q = float(np.round(rng.uniform(3, 40), 1))
+    kind = rid % 4
+    year = 2003 if kind == 3 else 1999
+    vini = float(np.round(vdead + rng.uniform(0.2, 0.9) * vlive, 0))
+    if kind == 2:
+        rule, body = 2, " ".join("%.1f" % x for x in np.sort(rng.uniform(hmin, hmax, 12)))
+    else:
+        t1, t2 = sorted(int(x) for x in rng.choice(np.arange(20, 340), 2, replace=False))
+        if rid % 2:
+            t1, t2 = t2, t1
+        rule, body = 1, "%.1f %.1f %d %d" % (hmax - 1.0, hmin + 2.0, t1, t2)
+    return ("Hmax(M)\tHmin(M)\tSlive(1000M3)\tSdead(1000M3)\tHturbine(M)\tQdesign (M3/s)\tYear\tSinitial(1000M3)\tName\n"
+            "%g\t%g\t%g\t%g\t%g\t%g\t%d\t%g\tR%d\nSEEPAGE\tINFILTRATION\n%.4f\t%.4f\nIRRIGATION\n0\nDUMMY\nHYDROPOWER\n1\n"
+            "ENVIRONMENTAL FLOW\n%.2f\nOPERATION STRATEGY\n%d\n%s\nBATHYMETRY PARAMETERS\n0\n135.186458\t0.033764077\t-0.00041473\t1.11114436\n"
+            % (hmax, hmin, vlive, vdead, float(np.round(0.6 * (hmax - hmin) + 20, 1)), q, year, vini, rid,
+               rng.uniform(0, 0.05) if rid % 3 == 0 else 0.0, rng.uniform(0, 0.03) if rid % 3 == 0 else 0.0,
+               rng.choice([0.05, 0.1]), rule, body))
+
+
+def write_case(work, d, reser, station_rc, hdr, velo, diff, xmask, box, flux, ndays, res_rng=None):
     nrow, ncol = d.shape
     par = os.path.join(work, "parameters")
     for sub in ("", "unit_hydrograph", "reservoirs/res_par", "naturalized_flow/search_catchment"):
@@ -98,7 +125,8 @@ def write_case(work, d, reser, station_rc, hdr, velo, diff, xmask, box, flux, nd
     res_txt = open(os.path.join(REF, "parameters", "reservoirs", "res_par", "res1.txt")).read()
     for rid in sorted(set(int(x) for x in reser.ravel() if 0 < x < 9999)):
         with open(os.path.join(par, "reservoirs", "res_par", "res%d.txt" % rid), "w") as f:
-            f.write(res_txt)
+            f.write(res_text(res_rng, rid) if res_rng is not None else
+                    open(os.path.join(REF, "parameters", "reservoirs", "res_par", "res%d.txt" % min(rid, 2))).read())
     for (rr, cc), a in flux.items():
         lat, lon = route_abi.cell_latlon(hdr, nrow, ncol, rr, cc)
         with open(os.path.join(work, "input", "fluxes_%.4f_%.4f" % (lat, lon)), "w") as f:
@@ -159,6 +187,13 @@ def collect(work, name, d, reser, station_rc, hdr, velo, diff, xmask, box, flux,
     arrays.update(runoff=runoff, baseflow=base, ev_vege=evv, tr_vege=trv, ev_soil=evs, present=present)
     for k, v in uh.items():
         arrays["uh_" + k] = v
+    # reservoir pass: UH_R files, the resN.txt texts, the binary's reservoir_<id>_<station>.day and station flow
+    for f in glob.glob(os.path.join(work, "parameters", "unit_hydrograph", "*.uh_r")):
+        arrays["uhr_" + os.path.basename(f)[:-5]] = np.loadtxt(f).astype(np.float32)
+    for rid in arrays["res_order"][:-1]:
+        arrays["restxt_%d" % rid] = np.array(open(os.path.join(work, "parameters", "reservoirs", "res_par", "res%d.txt" % rid)).read())
+        arrays["resday_%d" % rid] = np.loadtxt(os.path.join(work, "output", "reservoir_%d_OUTLT.day" % rid), skiprows=1)[:, 3:].astype(np.float32)
+    arrays["station_flow"] = np.loadtxt(os.path.join(work, "output", "OUTLT.day"))[:, 3].astype(np.float32)
     out = os.path.join(ROOT, "tests", "golden", "route_%s.npz" % name)
     np.savez_compressed(out, **arrays)
     print("%-12s grid %dx%d nodes %d  uh files %s  %.0f kB" % (name, nrow, ncol, nf.shape[0], sorted(uh), os.path.getsize(out) / 1e3))
@@ -210,7 +245,7 @@ def random_case(tmp, env, name, nrow, ncol, seed, nres):
             evv, trv, evs = rng.uniform(0, 1, ndays), rng.uniform(0, 2, ndays), rng.uniform(0, 1, ndays)
             trv[0] = -rng.uniform(5, 60)         # the first-day negative evaporation quirk
             flux[(r, c)] = np.stack([ro, ba, evv, trv, evs], axis=1)
-    write_case(work, d, reser, out, hdr, velo, diff, xmask, box, flux, ndays)
+    write_case(work, d, reser, out, hdr, velo, diff, xmask, box, flux, ndays, res_rng=rng)
     run_binary(work, env)
     collect(work, name, d, reser, out, hdr, np.round(velo, 4), np.round(diff, 2), np.round(xmask, 1), box, flux, ndays)
 

@@ -10,6 +10,13 @@
 //   k_convolve   one thread per (node, day): adds the cells of the node's catchment in list order,
 //                taps ascending, i.e. exactly the accumulation order of reservoir.f:483-491, which is
 //                what makes the fp32 result independent of the parallelisation
+//   k_reservoirs one thread block per parameter set, one thread per reservoir: the MAKE_CONVOLUTIONRS day
+//                loop (reservoir.f:1142-1600).  Days are sequential; inside a day the reservoirs are
+//                independent (a release reaches the next node on day I+1), so phase A = every reservoir
+//                operates, barrier, phase B = every node adds its upstream releases through UH_R in
+//                reservoir order, taps ascending (the order of reservoir.f:1569-1575), barrier.
+//                Transcendentals (tan of the hedging angles, sqrt in H0) are evaluated on the host so
+//                the device does only IEEE + - * / and compares: results equal the serial loop bit for bit
 // Everything is fp32 like the Fortran REALs and compiled with -fmad=false.  No CPU fallback.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -66,7 +73,7 @@ bool reaches(const Graph &g, int k, int target, int mode)
   return false;
 }
 
-struct Node { int res_id = 0, cell = -1; std::vector<int> cells; };
+struct Node { int res_id = 0, cell = -1, ds_id = 0, target = -1; std::vector<int> cells; };
 
 void list_cells(const Graph &g, int target, int mode, std::vector<int> &out)
 {
@@ -189,6 +196,247 @@ __global__ void __launch_bounds__(128) k_convolve(ConvArgs a)
   a.flows[(size_t)node * a.ndays + i] = flow;
 }
 
+// ---- reservoirs ------------------------------------------------------------------------------------
+struct ResC {            // one reservoir of one parameter set, host-prepared
+  float hresermax, vreser, v_dead, head, q_design, qmin, vol1, seepage, loss, H0, span;   // span = HRESERMAX - H0
+  float hmax, hmin, op1a, op1b, reslv[12];
+  float demand, x2, x3, tan1, tan4;
+  float demand5[12], x2_5[12], x3_5[12], tan1_5[12], tan4_5[12];
+  float bth[4];
+  int ope_year, rule, hp_type, hp_gen, bathymetry;
+  long long series, irrigation;        // offsets into the series pool, -1 = none
+};
+
+struct ResArgs {
+  int nnodes, ndays, start_year, start_month, legacy;
+  const ResC *res;                     // [nsets][nres]
+  const float *pool;                   // rule 4/6 and irrigation series
+  const float *natural;                // [nnodes][ndays]
+  const float *uh_r;                   // [nres][NS]
+  const int *target;                   // [nres]
+  const int *up_ptr, *up_idx;          // CSR: upstream reservoirs of every node, ascending
+  float *resflows;                     // [nsets][nnodes][ndays+2]   (index = day, 1-based)
+  float *vol, *hho;                    // [nsets][nres][ndays+1]
+  float *flowin, *flowout, *turb, *energy, *htk;   // [nsets][nres][ndays]
+  float *flow;                         // [nsets][ndays]
+};
+
+__device__ __forceinline__ int cal_month(int d)     // reservoir.f:1688-1716
+{
+  const int lim[11] = {31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+  int m = 12;
+#pragma unroll
+  for (int k = 10; k >= 0; k--) if (d <= lim[k]) m = k + 1;
+  return m;
+}
+
+__global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
+{
+  const int set = blockIdx.x, nres = a.nnodes - 1, nd = a.ndays;
+  const size_t W = (size_t)nd + 2;
+  float *RF = a.resflows + (size_t)set * a.nnodes * W;
+  for (size_t q = threadIdx.x; q < (size_t)a.nnodes * W; q += blockDim.x) {
+    const int n = (int)(q / W), I = (int)(q % W);
+    RF[q] = (I >= 1 && I <= nd) ? a.natural[(size_t)n * nd + I - 1] : 0.0f;
+  }
+  __syncthreads();
+  for (int I = 1; I <= nd; I++) {
+    // ---- phase A: operate every reservoir on day I ----
+    for (int J = threadIdx.x; J < nres; J += blockDim.x) {
+      const ResC &r = a.res[(size_t)set * nres + J];
+      const size_t b1 = ((size_t)set * nres + J) * (nd + 1), b0 = ((size_t)set * nres + J) * nd;
+      float vol = (I == 1) ? r.vol1 : a.vol[b1 + I - 1];
+      float vnext = 0.0f, flowin, flowout = 0.0f, turb = 0.0f, energy = 0.0f, htk = 0.0f, hho0 = 0.0f, hho1 = 0.0f;
+      const int year = a.start_year + I / 365;
+      bool write_h1 = false;
+      if (year >= r.ope_year) {
+        const float VRESER = r.vreser, QRESER = r.q_design, Qmin = r.qmin;
+        flowin = RF[(size_t)J * W + I];
+        const int CRTDATE = (int)(1.0f * (float)(I % 365) + (float)((a.start_month - 1) * 30));
+        if (r.rule == 1 || r.rule == 2) {
+          float DESIGNWL;
+          const float fd = (float)CRTDATE, dH = r.hmax - r.hmin;
+          if (r.rule == 1) {
+            if (r.op1a > r.op1b) {
+              if (fd > r.op1b && fd < r.op1a) DESIGNWL = (fd - r.op1b) / (r.op1a - r.op1b) * dH;
+              else if (fd >= r.op1a) DESIGNWL = dH - (fd - r.op1a) / (365.0f - r.op1a + r.op1b) * dH;
+              else DESIGNWL = dH - ((float)(CRTDATE + 365) - r.op1a) / (365.0f - r.op1a + r.op1b) * dH;
+            }
+            else {
+              if (fd > r.op1a && fd < r.op1b) DESIGNWL = dH - (fd - r.op1a) / (r.op1b - r.op1a) * dH;
+              else if (fd >= r.op1b) DESIGNWL = dH / (365.0f - r.op1b + r.op1a) * (fd - r.op1b);
+              else DESIGNWL = dH / (365.0f - r.op1b + r.op1a) * (fd - r.op1a) + dH;
+            }
+            DESIGNWL = DESIGNWL + (r.hmin - r.H0);
+          }
+          else DESIGNWL = r.reslv[cal_month(CRTDATE) - 1] - r.H0;
+          htk = DESIGNWL + r.H0;
+          if (!a.legacy) {
+            const float LRC_WL = r.hmin + 0.80f * (htk - r.hmin), URC_WL = r.hmax - 0.80f * (r.hmax - htk);
+            const float LRC_VOL = (LRC_WL - r.H0) * VRESER / r.span, URC_VOL = (URC_WL - r.H0) * VRESER / r.span;
+            if (vol > URC_VOL) {
+              vnext = URC_VOL;
+              flowout = (vol + flowin * 24.0f * 3.6f - URC_VOL) / 24.0f / 3.6f;
+              turb = fminf(fmaxf(flowout, Qmin), QRESER);
+            }
+            else if (vol < LRC_VOL) {
+              flowout = Qmin; turb = Qmin;
+              vnext = vol + (flowin - turb) * 24.0f * 3.6f;
+            }
+            else {
+              const float RC_SLOPE = (VRESER - r.v_dead) / (r.op1a - r.op1b);
+              vnext = (fd > r.op1b && fd < r.op1a) ? vol + RC_SLOPE : vol - RC_SLOPE;
+              flowout = (vol - vnext) / 24.0f / 3.6f + flowin;
+              turb = fminf(fmaxf(flowout, Qmin), QRESER);
+            }
+          }
+          else {
+            float CURRENTWL;
+            if (r.bathymetry == 1) CURRENTWL = r.bth[0] / (expf(-1.0f * vol / 1000.0f * r.bth[1]) + vol / 1000.0f * r.bth[2] + r.bth[3]);
+            else CURRENTWL = vol * r.span / VRESER;
+            const float TARGET = (DESIGNWL * VRESER) / r.span;
+            if (CURRENTWL >= DESIGNWL) {
+              if ((vol + flowin * 24.0f * 3.6f - QRESER * 24.0f * 3.6f) > TARGET) {
+                vnext = vol + flowin * 24.0f * 3.6f - QRESER * 24.0f * 3.6f;
+                flowout = QRESER; turb = flowout;
+              }
+              else {
+                vnext = TARGET;
+                flowout = (vol - vnext) / 24.0f / 3.6f + flowin; turb = flowout;
+              }
+            }
+            else {
+              if ((vol + flowin * 24.0f * 3.6f) > TARGET) {
+                vnext = TARGET;
+                flowout = flowin - (vnext - vol) / 24.0f / 3.6f; turb = flowout;
+                if (turb > QRESER) { vnext = vnext + (turb - QRESER) * 24.0f * 3.6f; turb = QRESER; }
+              }
+              else {
+                vnext = vol + flowin * 24.0f * 3.6f;
+                flowout = Qmin; turb = flowout;
+              }
+            }
+          }
+        }
+        else if (r.rule == 3 || r.rule == 5) {
+          float X2 = r.x2, X3 = r.x3, T1 = r.tan1, T4 = r.tan4, Demand = r.demand;
+          if (r.rule == 5) {
+            const int m = cal_month(CRTDATE) - 1;
+            X2 = r.x2_5[m]; X3 = r.x3_5[m]; T1 = r.tan1_5[m]; T4 = r.tan4_5[m]; Demand = r.demand5[m];
+          }
+          if (vol < r.v_dead) flowout = 0.0f;
+          else if (vol <= X2) {
+            if ((vol - r.v_dead + flowin * 24.0f * 3.6f) <= (Demand + (vol - X2) * T1 * 24.0f * 3.6f)) flowout = (vol - r.v_dead) / 24.0f / 3.6f + flowin;
+            else flowout = Demand + (vol - X2) * T1;
+          }
+          else if (vol >= X3) {
+            if ((Demand + (vol - X3) * T4) * 24.0f * 3.6f > vol - r.v_dead) flowout = (vol - r.v_dead) / 24.0f / 3.6f;
+            else if ((Demand + (vol - X3) * T4) > QRESER) flowout = QRESER;
+            else flowout = Demand + (vol - X3) * T4;
+          }
+          else {
+            if (Demand * 24.0f * 3.6f > (vol - r.v_dead)) flowout = (vol - r.v_dead) / 24.0f / 3.6f;
+            else flowout = Demand;
+          }
+          turb = flowout;
+          if (turb > QRESER) turb = QRESER;
+          vnext = vol + (flowin - flowout) * 24.0f * 3.6f;
+        }
+        else if (r.rule == 4) {
+          float OP4 = r.series >= 0 ? a.pool[r.series + I - 1] : 0.0f;
+          if (OP4 > QRESER && vol < VRESER) OP4 = QRESER;
+          if (OP4 * 24.0f * 3.6f > (vol - r.v_dead) + flowin * 24.0f * 3.6f) turb = (vol - r.v_dead) / 24.0f / 3.6f + flowin;
+          else turb = OP4;
+          if (turb < 0.0f) turb = 0.0f;
+          vnext = vol + (flowin - turb) * 24.0f * 3.6f;
+          if (turb > QRESER) turb = QRESER;
+        }
+        else if (r.rule == 6) {
+          const float OP6 = r.series >= 0 ? a.pool[r.series + I - 1] : 0.0f;
+          if (flowin - (OP6 - vol) / 24.0f / 3.6f > 0.0f) {
+            vnext = OP6;
+            flowout = flowin - (vnext - vol) / 24.0f / 3.6f;
+          }
+          else {
+            flowout = Qmin;
+            vnext = vol + (flowin - flowout) * 24.0f * 3.6f;
+          }
+          turb = flowout;
+          if (turb > QRESER) turb = QRESER;
+        }
+        // step 5-7: spill, environmental flow, irrigation, seepage, head, energy (reservoir.f:1422-1508)
+        if (vnext > VRESER) {
+          if (a.legacy) { flowout = turb + (vnext - VRESER) / 24.0f / 3.6f; vnext = VRESER; }
+          else { vnext = VRESER; flowout = turb + (vnext - VRESER) / 24.0f / 3.6f; }
+        }
+        else flowout = turb;
+        if (vol < 0.0f) vol = 0.0f;
+        if (flowout < Qmin) flowout = Qmin;
+        if (r.hp_gen == 0) turb = 0.0f;
+        {
+          const float IRR = r.irrigation >= 0 ? a.pool[r.irrigation + I - 1] : 0.0f;
+          if (flowout >= IRR) flowout = flowout - IRR;
+          else flowout = Qmin;
+        }
+        if (vnext - r.loss * 24.0f * 3.6f > 0.0f) {
+          vnext = vnext - r.loss * 24.0f * 3.6f;
+          flowout = flowout + r.seepage;
+        }
+        else vnext = 0.0f;
+        hho0 = vol / VRESER * r.span + r.H0;
+        hho1 = vnext / VRESER * r.span + r.H0;
+        energy = 0.9f * 9.81f * turb * ((hho0 + hho1) / 2.0f - (r.hresermax - r.head)) / 1000.0f;
+        if (r.rule == 0) {
+          flowout = flowin;
+          if (flowout <= Qmin) flowout = Qmin;
+          turb = (r.hp_gen == 1) ? flowout : 0.0f;
+          if (turb > QRESER) turb = QRESER;
+        }
+        if (r.rule == 0 || r.hp_type == 0) {
+          vnext = VRESER;
+          energy = 0.9f * 9.81f * turb;
+          energy = energy * r.head / 1000.0f;
+          htk = r.head;
+          hho0 = r.hresermax; hho1 = r.hresermax;
+        }
+        write_h1 = true;
+      }
+      else {                                            // label 125: not commissioned yet
+        flowin = RF[(size_t)J * W + I];
+        flowout = flowin;
+        vol = 0.0f;
+      }
+      a.vol[b1 + I - 1] = vol;
+      a.vol[b1 + I] = vnext;
+      a.hho[b1 + I - 1] = hho0;
+      if (write_h1 || I == nd) a.hho[b1 + I] = write_h1 ? hho1 : 0.0f;
+      a.flowin[b0 + I - 1] = flowin; a.flowout[b0 + I - 1] = flowout; a.turb[b0 + I - 1] = turb;
+      a.energy[b0 + I - 1] = energy; a.htk[b0 + I - 1] = htk;
+    }
+    if (threadIdx.x == blockDim.x - 1) {                // station: RESFLOWS(NORES, I) is complete since day I-1
+      float f = RF[(size_t)nres * W + I];
+      if (f < 0.0f) f = 0.0f;
+      a.flow[(size_t)set * nd + I - 1] = f;
+    }
+    __syncthreads();
+    // ---- phase B: releases of day <= I reach the next node on day I+1 through UH_R ----
+    for (int k = threadIdx.x; k < a.nnodes; k += blockDim.x) {
+      const int u0 = a.up_ptr[k], u1 = a.up_ptr[k + 1];
+      if (u0 == u1) continue;
+      float acc = RF[(size_t)k * W + I + 1];
+      for (int u = u0; u < u1; u++) {
+        const int J = a.up_idx[u];
+        const float *uh = a.uh_r + (size_t)J * NS;
+        const float *fo = a.flowout + ((size_t)set * nres + J) * nd;
+        const int kmax = I < NS ? I : NS;
+        for (int KK = 1; KK <= kmax; KK++) acc = acc + uh[KK - 1] * fo[I - KK];
+      }
+      RF[(size_t)k * W + I + 1] = acc;
+    }
+    __syncthreads();
+  }
+}
+
 template <class T>
 struct DB {
   T *p = nullptr; size_t n = 0;
@@ -223,6 +471,10 @@ struct vr_route {
   DB<int64_t> d_node_ptr;
   DB<float> d_velo, d_diff, d_xmask, d_uhm, d_box, d_uh_s, d_ro, d_ba, d_evv, d_evs, d_trv, d_scale, d_factor, d_flows;
   DB<unsigned char> d_present;
+  std::vector<float> uh_r;             // [nres][NS]
+  DB<float> d_uh_r, d_pool, d_natural, d_resflows, d_vol, d_hho, d_flowin, d_flowout, d_turb, d_energy, d_htk, d_flow;
+  DB<int> d_target, d_up_ptr, d_up_idx;
+  DB<ResC> d_res;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
@@ -249,6 +501,9 @@ void vr_route_destroy(vr_route *h)
   h->d_next.rel(); h->d_cells.rel(); h->d_node_ptr.rel(); h->d_velo.rel(); h->d_diff.rel(); h->d_xmask.rel();
   h->d_uhm.rel(); h->d_box.rel(); h->d_uh_s.rel(); h->d_ro.rel(); h->d_ba.rel(); h->d_evv.rel(); h->d_evs.rel();
   h->d_trv.rel(); h->d_scale.rel(); h->d_factor.rel(); h->d_flows.rel(); h->d_present.rel();
+  h->d_uh_r.rel(); h->d_pool.rel(); h->d_natural.rel(); h->d_resflows.rel(); h->d_vol.rel(); h->d_hho.rel();
+  h->d_flowin.rel(); h->d_flowout.rel(); h->d_turb.rel(); h->d_energy.rel(); h->d_htk.rel(); h->d_flow.rel();
+  h->d_target.rel(); h->d_up_ptr.rel(); h->d_up_idx.rel(); h->d_res.rel();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -272,6 +527,31 @@ static int route_build(vr_route *h, const vr_route_grid *g, const float *uh_box)
     k_grid_uh<<<(unsigned)cnt, 256>>>(h->d_cells.p + e0, h->nodes[n].cell, h->d_next.p, h->d_uhm.p, h->d_box.p,
                                       h->d_uh_s.p + (size_t)e0 * NS);
     RK(cudaGetLastError());
+  }
+  // MAKE_RESERVOIR_UH: the same path convolution from the reservoir cell to its target node's cell
+  const int nres = (int)h->nodes.size() - 1;
+  if (nres > 0) {
+    std::vector<int> start(nres), target(nres), up_ptr(h->nodes.size() + 1, 0), up_idx;
+    for (int j = 0; j < nres; j++) { start[j] = h->nodes[j].cell; target[j] = h->nodes[j].target; }
+    for (size_t k = 0; k < h->nodes.size(); k++) {
+      for (int j = 0; j < nres; j++) if (target[j] == (int)k) up_idx.push_back(j);
+      up_ptr[k + 1] = (int)up_idx.size();
+    }
+    DB<int> d_start;
+    RK(d_start.put(start.data(), nres));
+    RK(h->d_uh_r.res((size_t)nres * NS));
+    for (int j = 0; j < nres; j++) {
+      k_grid_uh<<<1, 256>>>(d_start.p + j, h->nodes[target[j]].cell, h->d_next.p, h->d_uhm.p, h->d_box.p,
+                            h->d_uh_r.p + (size_t)j * NS);
+      RK(cudaGetLastError());
+    }
+    RK(cudaDeviceSynchronize());
+    d_start.rel();
+    h->uh_r.resize((size_t)nres * NS);
+    RK(cudaMemcpy(h->uh_r.data(), h->d_uh_r.p, h->uh_r.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    RK(h->d_target.put(target.data(), nres));
+    RK(h->d_up_ptr.put(up_ptr.data(), up_ptr.size()));
+    RK(h->d_up_idx.put(up_idx.data(), up_idx.size()));
   }
   RK(cudaDeviceSynchronize());
   return VR_OK;
@@ -318,6 +598,21 @@ int vr_route_create(const vr_route_grid *g, int32_t station_col, int32_t station
     nd.res_id = 0; nd.cell = station;
     list_cells(h->g, station, 2, nd.cells);
     h->nodes.push_back(std::move(nd));
+  }
+  // RES_DIRECT(:,2): the next reservoir met walking downstream (reservoir.f:733-759); its release is routed to
+  // that reservoir when it is one of this station's nodes, else to the station (reservoir.f:1529-1567)
+  for (size_t n = 0; n + 1 < h->nodes.size(); n++) {
+    Node &nd = h->nodes[n];
+    int k = h->g.next[nd.cell];
+    nd.ds_id = 0;
+    for (int guard = 0; k >= 0 && guard <= g->ncol * g->nrow + 4; guard++) {
+      const int r = h->g.reser[k];
+      if (r > 0 && r != 9999) { nd.ds_id = r; break; }
+      k = h->g.next[k];
+    }
+    nd.target = (int)h->nodes.size() - 1;
+    for (size_t m = 0; m + 1 < h->nodes.size(); m++)
+      if (nd.ds_id > 0 && h->nodes[m].res_id == nd.ds_id) { nd.target = (int)m; break; }
   }
   h->node_ptr.assign(1, 0);
   for (const Node &nd : h->nodes) {
@@ -409,6 +704,108 @@ int vr_route_last_kernel_ms(vr_route *h, float *ms)
   RK(cudaSetDevice(h->device));
   RK(cudaEventSynchronize(h->ev1));
   RK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return VR_OK;
+}
+
+int vr_route_res_info(const vr_route *h, int32_t node, int32_t *downstream_id, int32_t *target_node)
+{
+  if (!h || node < 0 || node >= (int32_t)h->nodes.size()) return VR_ERR_ARG;
+  if (downstream_id) *downstream_id = h->nodes[node].ds_id;
+  if (target_node) *target_node = h->nodes[node].target;
+  return VR_OK;
+}
+
+int vr_route_get_uh_r(vr_route *h, int32_t node, float *uh_r)
+{
+  if (!h || !uh_r || node < 0 || node + 1 >= (int32_t)h->nodes.size()) return VR_ERR_ARG;
+  memcpy(uh_r, h->uh_r.data() + (size_t)node * NS, NS * sizeof(float));
+  return VR_OK;
+}
+
+int vr_route_set_uh_r(vr_route *h, int32_t node, const float *uh_r)
+{
+  if (!h || !uh_r || node < 0 || node + 1 >= (int32_t)h->nodes.size()) return VR_ERR_ARG;
+  RK(cudaSetDevice(h->device));
+  memcpy(h->uh_r.data() + (size_t)node * NS, uh_r, NS * sizeof(float));
+  RK(cudaMemcpy(h->d_uh_r.p + (size_t)node * NS, uh_r, NS * sizeof(float), cudaMemcpyHostToDevice));
+  return VR_OK;
+}
+
+int vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *natural, const vr_reservoir *res,
+                        const vr_res_options *opt, float *flow, const vr_res_series *out)
+{
+  if (!h || !natural || !opt || !flow || ndays < 1 || nsets < 1) return VR_ERR_ARG;
+  const int nnodes = (int)h->nodes.size(), nres = nnodes - 1;
+  if (nres > 0 && !res) return VR_ERR_ARG;
+  RK(cudaSetDevice(h->device));
+  // host preparation: everything that needs libm (tan, sqrt) or is constant over the days
+  std::vector<ResC> rc((size_t)nsets * nres);
+  std::vector<float> pool;
+  for (size_t q = 0; q < rc.size(); q++) {
+    const vr_reservoir &r = res[q];
+    ResC &c = rc[q];
+    memset(&c, 0, sizeof c);
+    if (r.rule < 0 || r.rule > 6) { h->err = "reservoir rule must be 0..6"; return VR_ERR_ARG; }
+    c.hresermax = r.hresermax; c.vreser = r.v_live + r.v_dead; c.v_dead = r.v_dead; c.head = r.head; c.q_design = r.q_design;
+    c.qmin = r.env_flow * r.q_design;
+    c.vol1 = (opt->start_year >= r.ope_year) ? r.v_initial : 0.001f;
+    c.seepage = r.seepage; c.loss = r.seepage + r.infiltration;
+    if (r.bathymetry == 1) c.H0 = r.bth[0] / (1 + r.bth[3]);
+    else {
+      const float KFACTOR = sqrtf(r.v_dead / r.v_live);
+      c.H0 = (KFACTOR * r.hresermax - r.hresermin) / (KFACTOR - 1);
+    }
+    c.span = r.hresermax - c.H0;
+    c.hmax = r.hmax; c.hmin = r.hmin;
+    if (r.rule == 1 && c.hmax < c.hmin) { const float t = c.hmax; c.hmax = c.hmin; c.hmin = t; }
+    c.op1a = r.op1[0]; c.op1b = r.op1[1];
+    c.demand = r.demand; c.x2 = r.x2; c.x3 = r.x3; c.tan1 = tanf(r.x1); c.tan4 = tanf(r.x4);
+    for (int m = 0; m < 12; m++) {
+      c.reslv[m] = r.reslv[m]; c.demand5[m] = r.demand5[m]; c.x2_5[m] = r.op5x2[m]; c.x3_5[m] = r.op5x3[m];
+      c.tan1_5[m] = tanf(r.op5x1[m]); c.tan4_5[m] = tanf(r.op5x4[m]);
+    }
+    for (int m = 0; m < 4; m++) c.bth[m] = r.bth[m];
+    c.ope_year = r.ope_year; c.rule = r.rule; c.hp_type = r.hydropower_type; c.hp_gen = r.hydropower_generator;
+    c.bathymetry = r.bathymetry;
+    c.series = -1; c.irrigation = -1;
+    if ((r.rule == 4 || r.rule == 6) && r.series) { c.series = (long long)pool.size(); pool.insert(pool.end(), r.series, r.series + ndays); }
+    if (r.irrigation) { c.irrigation = (long long)pool.size(); pool.insert(pool.end(), r.irrigation, r.irrigation + ndays); }
+  }
+  const size_t S = (size_t)nsets, R = (size_t)(nres > 0 ? nres : 1), D = (size_t)ndays;
+  RK(h->d_res.put(rc.data(), rc.size()));
+  RK(h->d_pool.put(pool.data(), pool.size()));
+  RK(h->d_natural.put(natural, (size_t)nnodes * D));
+  RK(h->d_resflows.res(S * nnodes * (D + 2)));
+  RK(h->d_vol.res(S * R * (D + 1))); RK(h->d_hho.res(S * R * (D + 1)));
+  RK(h->d_flowin.res(S * R * D)); RK(h->d_flowout.res(S * R * D)); RK(h->d_turb.res(S * R * D));
+  RK(h->d_energy.res(S * R * D)); RK(h->d_htk.res(S * R * D)); RK(h->d_flow.res(S * D));
+  RK(cudaMemset(h->d_hho.p, 0, S * R * (D + 1) * sizeof(float)));
+  std::vector<int> up0(nnodes + 1, 0);
+  if (nres == 0) RK(h->d_up_ptr.put(up0.data(), up0.size()));
+  ResArgs a;
+  a.nnodes = nnodes; a.ndays = ndays; a.start_year = opt->start_year; a.start_month = opt->start_month;
+  a.legacy = opt->legacy_rule_curve; a.res = h->d_res.p; a.pool = h->d_pool.p; a.natural = h->d_natural.p;
+  a.uh_r = h->d_uh_r.p; a.target = h->d_target.p; a.up_ptr = h->d_up_ptr.p; a.up_idx = h->d_up_idx.p;
+  a.resflows = h->d_resflows.p; a.vol = h->d_vol.p; a.hho = h->d_hho.p; a.flowin = h->d_flowin.p;
+  a.flowout = h->d_flowout.p; a.turb = h->d_turb.p; a.energy = h->d_energy.p; a.htk = h->d_htk.p; a.flow = h->d_flow.p;
+  int threads = ((nnodes + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  cudaEventRecord(h->ev0);
+  k_reservoirs<<<nsets, threads>>>(a);
+  cudaEventRecord(h->ev1);
+  h->timed = true;
+  RK(cudaGetLastError());
+  RK(cudaMemcpy(flow, h->d_flow.p, S * D * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out && nres > 0) {
+    const size_t n1 = S * R * (D + 1) * sizeof(float), n0 = S * R * D * sizeof(float);
+    if (out->vol) RK(cudaMemcpy(out->vol, h->d_vol.p, n1, cudaMemcpyDeviceToHost));
+    if (out->hho) RK(cudaMemcpy(out->hho, h->d_hho.p, n1, cudaMemcpyDeviceToHost));
+    if (out->flowin) RK(cudaMemcpy(out->flowin, h->d_flowin.p, n0, cudaMemcpyDeviceToHost));
+    if (out->flowout) RK(cudaMemcpy(out->flowout, h->d_flowout.p, n0, cudaMemcpyDeviceToHost));
+    if (out->turbine) RK(cudaMemcpy(out->turbine, h->d_turb.p, n0, cudaMemcpyDeviceToHost));
+    if (out->energy) RK(cudaMemcpy(out->energy, h->d_energy.p, n0, cudaMemcpyDeviceToHost));
+    if (out->htk) RK(cudaMemcpy(out->htk, h->d_htk.p, n0, cudaMemcpyDeviceToHost));
+  }
   return VR_OK;
 }
 

@@ -3,6 +3,7 @@
     r = Route(grid, station_col, station_row, uh_box)     # catchments + unit hydrographs (GPU)
     rid, cells, uh_s = r.node(n)                           # what the reference writes to <name>.uh_s
     flows = r.convolve(runoff, baseflow)                   # [nnodes, ndays] node inflows (m3/s)
+    out = r.reservoirs(flows, [res_list], 2000, 1)         # reservoir day loop for one or many rule sets
 """
 import ctypes as C
 import numpy as np
@@ -10,7 +11,8 @@ from . import model, route_abi
 
 ROUTE_EXPORTS = ["vr_route_create", "vr_route_destroy", "vr_route_last_error", "vr_route_num_nodes",
                  "vr_route_node_info", "vr_route_node_cells", "vr_route_get_uh", "vr_route_convolve",
-                 "vr_route_convolve_ex", "vr_route_last_kernel_ms"]
+                 "vr_route_convolve_ex", "vr_route_last_kernel_ms", "vr_route_res_info", "vr_route_get_uh_r",
+                 "vr_route_set_uh_r", "vr_route_reservoirs"]
 
 
 def _lib():
@@ -29,6 +31,10 @@ def _lib():
         L.vr_route_convolve.argtypes = [vp, C.c_int32, vp, vp, C.c_float, vp]
         L.vr_route_convolve_ex.argtypes = [vp, C.c_int32, vp, vp, C.c_float] + [vp] * 7
         L.vr_route_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.vr_route_res_info.argtypes = [vp, C.c_int32, vp, vp]
+        L.vr_route_get_uh_r.argtypes = [vp, C.c_int32, vp]
+        L.vr_route_set_uh_r.argtypes = [vp, C.c_int32, vp]
+        L.vr_route_reservoirs.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L._route_ready = True
     return L
 
@@ -71,6 +77,38 @@ class Route:
         self._check(self.L.vr_route_convolve_ex(self.h, ndays, p(runoff), p(baseflow), C.c_float(scale), p(cell_scale),
                                                 p(ev[0]), p(ev[1]), p(ev[2]), p(cell_factor), p(pres), p(flows)))
         return flows
+
+    def res_info(self, n):
+        """(downstream reservoir id, node the release is routed to, UH_R[107]) of reservoir node n"""
+        ds, tg = C.c_int32(), C.c_int32()
+        self._check(self.L.vr_route_res_info(self.h, n, C.byref(ds), C.byref(tg)))
+        uh = np.zeros(route_abi.NS, dtype=np.float32)
+        self._check(self.L.vr_route_get_uh_r(self.h, n, uh.ctypes.data))
+        return int(ds.value), int(tg.value), uh
+
+    def set_uh_r(self, n, uh_r):
+        uh_r = np.ascontiguousarray(uh_r, dtype=np.float32)
+        assert uh_r.size == route_abi.NS
+        self._check(self.L.vr_route_set_uh_r(self.h, n, uh_r.ctypes.data))
+
+    def reservoirs(self, natural, sets, start_year, start_month, legacy=False):
+        """MAKE_CONVOLUTIONRS for len(sets) parameter sets at once.  natural: [nnodes, ndays] from convolve();
+        sets: list of lists of route_abi.reservoir dicts (node order).  Returns dict: flow [nsets, ndays] and
+        vol/hho [nsets, nres, ndays+1], flowin/flowout/turbine/energy/htk [nsets, nres, ndays]."""
+        natural = np.ascontiguousarray(natural, dtype=np.float32)
+        assert natural.shape[0] == self.nnodes
+        ndays, nres, nsets = natural.shape[1], self.nnodes - 1, len(sets)
+        arr, keep = route_abi.pack_reservoirs(sets) if nres else (None, None)
+        opt = route_abi.vr_res_options(start_year, start_month, int(legacy))
+        out = {"flow": np.zeros((nsets, ndays), dtype=np.float32)}
+        ser = route_abi.vr_res_series()
+        for k, ext in route_abi.RES_SERIES:
+            out[k] = np.zeros((nsets, nres, ndays + ext), dtype=np.float32)
+            setattr(ser, k, out[k].ctypes.data_as(C.POINTER(C.c_float)))
+        self._check(self.L.vr_route_reservoirs(self.h, ndays, nsets, natural.ctypes.data,
+                                               C.cast(arr, C.c_void_p) if nres else None, C.cast(C.pointer(opt), C.c_void_p),
+                                               out["flow"].ctypes.data, C.cast(C.pointer(ser), C.c_void_p)))
+        return out
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -72,3 +72,139 @@ def cell_factors(hdr, nrow, ncol, fraction=1.0):
                                                                np.sin((jloc + size / f32(2.0)) * PI / f32(180)))
             out[r * ncol + c] = frac[r, c] * f32(35.315) * f32(area) / (f32(86400.0) * f32(1000.0))
     return out
+
+
+# ---- reservoirs (MAKE_CONVOLUTIONRS) ---------------------------------------------------------------
+_pf = C.POINTER(C.c_float)
+
+
+class vr_reservoir(C.Structure):
+    _fields_ = [("hresermax", C.c_float), ("hresermin", C.c_float), ("v_live", C.c_float), ("v_dead", C.c_float),
+                ("head", C.c_float), ("q_design", C.c_float), ("ope_year", C.c_int32), ("v_initial", C.c_float),
+                ("seepage", C.c_float), ("infiltration", C.c_float), ("hydropower_type", C.c_int32),
+                ("hydropower_generator", C.c_int32), ("env_flow", C.c_float), ("rule", C.c_int32),
+                ("hmax", C.c_float), ("hmin", C.c_float), ("op1", C.c_float * 2), ("reslv", C.c_float * 12),
+                ("demand", C.c_float), ("x1", C.c_float), ("x2", C.c_float), ("x3", C.c_float), ("x4", C.c_float),
+                ("demand5", C.c_float * 12), ("op5x1", C.c_float * 12), ("op5x2", C.c_float * 12),
+                ("op5x3", C.c_float * 12), ("op5x4", C.c_float * 12), ("bathymetry", C.c_int32),
+                ("bth", C.c_float * 4), ("series", _pf), ("irrigation", _pf)]
+
+
+class vr_res_options(C.Structure):
+    _fields_ = [("start_year", C.c_int32), ("start_month", C.c_int32), ("legacy_rule_curve", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+class vr_res_series(C.Structure):
+    _fields_ = [(n, _pf) for n in ("vol", "hho", "flowin", "flowout", "turbine", "energy", "htk")]
+
+
+RES_SERIES = [("vol", 1), ("hho", 1), ("flowin", 0), ("flowout", 0), ("turbine", 0), ("energy", 0), ("htk", 0)]
+
+
+def reservoir(**kw):
+    """A parameter dict with the reference's defaults for everything not given (zeros: the Fortran arrays
+    live in static storage).  Keys are the vr_reservoir field names; series/irrigation are arrays."""
+    d = dict(hresermax=0.0, hresermin=0.0, v_live=0.0, v_dead=0.0, head=0.0, q_design=0.0, ope_year=0, v_initial=0.0,
+             seepage=0.0, infiltration=0.0, hydropower_type=1, hydropower_generator=1, env_flow=0.0, rule=0,
+             hmax=0.0, hmin=0.0, op1=[0.0, 0.0], reslv=[0.0] * 12, demand=0.0, x1=0.0, x2=0.0, x3=0.0, x4=0.0,
+             demand5=[0.0] * 12, op5x1=[0.0] * 12, op5x2=[0.0] * 12, op5x3=[0.0] * 12, op5x4=[0.0] * 12,
+             bathymetry=0, bth=[0.0] * 4, series=None, irrigation=None)
+    for k in kw:
+        if k not in d:
+            raise KeyError(k)
+    d.update(kw)
+    return d
+
+
+def pack_reservoirs(sets):
+    """sets: list (parameter sets) of lists (reservoirs in node order) of dicts -> (ctypes array, keepalive)"""
+    nsets, nres = len(sets), len(sets[0])
+    arr = (vr_reservoir * (nsets * nres))()
+    keep = []
+    for s, rs in enumerate(sets):
+        assert len(rs) == nres
+        for j, d in enumerate(rs):
+            r = arr[s * nres + j]
+            for name, ty in vr_reservoir._fields_:
+                v = d[name]
+                if name in ("series", "irrigation"):
+                    if v is not None:
+                        a = np.ascontiguousarray(v, dtype=np.float32)
+                        keep.append(a)
+                        setattr(r, name, a.ctypes.data_as(_pf))
+                elif hasattr(ty, "_length_"):
+                    setattr(r, name, ty(*[float(x) for x in v]))
+                else:
+                    setattr(r, name, v)
+    return arr, keep
+
+
+def read_reservoir_file(path, start_year=None, start_month=None, ndays=None):
+    """resN.txt as MAKE_CONVOLUTIONRS reads it (reservoir.f:1021-1131).  Accepts today's layout (HYDROPOWER
+    type + generator lines) and the older one the shipped res_par/*.txt use (a single HYDROPOWER value =
+    generator switch).  Series files of rules 4/6 and irrigation are aligned to (start_year, start_month, 1)."""
+    L = [ln.rstrip("\n") for ln in open(path)]
+    it = iter(L)
+    nxt = lambda: next(it)
+    nxt()
+    f = nxt().split()
+    d = reservoir(hresermax=float(f[0]), hresermin=float(f[1]), v_live=float(f[2]), v_dead=float(f[3]), head=float(f[4]),
+                  q_design=float(f[5]), ope_year=int(float(f[6])), v_initial=float(f[7]))
+    nxt()
+    f = nxt().split()
+    d["seepage"], d["infiltration"] = float(f[0]), float(f[1])
+    nxt()
+    with_irr = int(nxt().split()[0])
+    ipath = nxt().strip()
+    nxt()                                   # HYDROPOWER header
+    a = nxt().split()[0]
+    b = nxt().strip()
+    try:                                    # today's layout: type, generator, header, env flow
+        d["hydropower_type"], d["hydropower_generator"] = int(a), int(b.split()[0])
+        nxt()
+    except (ValueError, IndexError):        # older layout: one value, b was the ENVIRONMENTAL FLOW header
+        d["hydropower_type"], d["hydropower_generator"] = 1, int(a)
+    d["env_flow"] = float(nxt().split()[0])
+    nxt()
+    d["rule"] = int(nxt().split()[0])
+
+    def series(fn):
+        rows = [r.split() for r in open(fn).read().splitlines()[1:] if r.strip()]
+        vals = np.array([float(r[3]) for r in rows], dtype=np.float32)
+        start = 0
+        for k, r in enumerate(rows):
+            if (int(r[0]), int(r[1]), int(r[2])) == (start_year, start_month, 1):
+                start = k                    # STARTDAY = L-1 (reservoir.f:1087-1089)
+        out = np.zeros(ndays, dtype=np.float32)
+        n = max(0, min(ndays, len(vals) - start))
+        out[:n] = vals[start:start + n]
+        return out
+    if d["rule"] == 0:
+        nxt()
+    elif d["rule"] == 1:
+        f = [float(x) for x in nxt().split()[:4]]
+        d["hmax"], d["hmin"], d["op1"] = f[0], f[1], [f[2], f[3]]
+    elif d["rule"] == 2:
+        d["reslv"] = [float(x) for x in nxt().split()[:12]]
+    elif d["rule"] == 3:
+        f = [float(x) for x in nxt().split()[:5]]
+        d["demand"], d["x1"], d["x2"], d["x3"], d["x4"] = f
+    elif d["rule"] in (4, 6):
+        d["series"] = series(nxt().strip())
+    elif d["rule"] == 5:
+        for m in range(12):
+            f = [float(x) for x in nxt().split()[:5]]
+            d["demand5"][m], d["op5x1"][m], d["op5x2"][m], d["op5x3"][m], d["op5x4"][m] = f
+    nxt()
+    d["bathymetry"] = int(nxt().split()[0])
+    if d["bathymetry"] == 1:
+        d["bth"] = [float(x) for x in nxt().split()[:4]]
+    if with_irr == 1:
+        rows = open(ipath).read().splitlines()
+        n = int(rows[1].split()[0])
+        irr = np.zeros(ndays, dtype=np.float32)
+        v = np.array([float(r.split()[0]) for r in rows[3:3 + n]], dtype=np.float32)
+        irr[:min(ndays, n)] = v[:ndays]
+        d["irrigation"] = irr
+    return d
