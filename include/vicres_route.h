@@ -12,8 +12,9 @@
  *   MAKE_RESERVOIR_UH   unit_hyd_routines.f:218-346               UH_R(107) reservoir -> next reservoir / station
  *   MAKE_CONVOLUTIONRS  reservoir.f:1142-1684                     the reservoir day loop (rules 0-6, spill,
  *                       environmental flow, irrigation, seepage, head, energy, release routing through UH_R)
- * Open-water evaporation on reservoir-surface cells (RESER == 9999, reservoir.f:410-475) is not part
- * of this round; grids that contain 9999 cells inside a catchment are rejected with VR_ERR_UNSUPPORTED.
+ * Open-water (Penman 1948, table driven) evaporation on reservoir-surface cells (RESER == 9999,
+ * reservoir.f:410-475,496-503) is part of vr_route_convolve_in; the two shorter convolve calls reject grids
+ * with 9999 cells inside a catchment with VR_ERR_UNSUPPORTED because they lack the meteorology it needs.
  *
  * Grid arrays are in FILE order: index r*ncol + c where r = 0 is the FIRST data line of the ESRI
  * ASCII file (northern-most row) and c = 0 its first value.  Station col/row are the numbers of
@@ -71,6 +72,23 @@ int  vr_route_convolve(vr_route *h, int32_t ndays, const float *runoff, const fl
 int  vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,
                           const float *cell_scale, const float *ev_vege, const float *ev_soil, const float *tr_vege,
                           const float *cell_factor, const unsigned char *present, float *flows);
+/* Everything MAKE_CONVOLUTION reads, including the columns of the flux files that drive the open-water
+ * evaporation of reservoir-surface cells.  Unused pointers may be NULL (then as vr_route_convolve_ex). */
+typedef struct vr_route_inputs {
+  const float *runoff, *baseflow;          /* [ncell][ndays] mm/day                                        */
+  float scale;                             /* mm/day -> m3/s when cell_scale == NULL                       */
+  const float *cell_scale;                 /* [ncell]                                                      */
+  const float *ev_vege, *ev_soil, *tr_vege;/* [ncell][ndays]                                               */
+  const float *cell_factor;                /* [ncell] FACTOR                                               */
+  const unsigned char *present;            /* [ncell] flux file found                                      */
+  const float *rh, *tair, *wind;           /* [ncell][ndays] RHD (%), AIRTEMP (C), WINDS (m/s)             */
+  const float *cell_lat, *cell_lon;        /* [ncell] JLOC, ILOC (reservoir.f:353-356)                     */
+  const int32_t *node_ope_year;            /* [nnodes] OPEYEAR of the node's reservoir (reservoir.f:318-325); station 0 */
+  int32_t start_year, start_month;         /* START_YEAR, START_MO                                         */
+  int32_t reserved[4];
+} vr_route_inputs;
+/* res_evaporation: [nnodes][ndays] RES_EVAPORATION (sum of 0.9*E0 over the node's surface cells) or NULL */
+int  vr_route_convolve_in(vr_route *h, int32_t ndays, const vr_route_inputs *in, float *flows, float *res_evaporation);
 int  vr_route_last_kernel_ms(vr_route *h, float *ms);
 
 /* ---- reservoirs (MAKE_CONVOLUTIONRS) -------------------------------------------------------------- */

@@ -24,6 +24,7 @@ def lib():
         L.ro_node_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ro_get_uh.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ro_convolve.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        L.ro_convolve_in.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ro_res_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ro_get_uh_r.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ro_reservoirs.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
@@ -59,6 +60,14 @@ class RouteOracle:
         lib().ro_convolve(self.h, ndays, p(runoff), p(baseflow), p(cell_scale), p(ev[0]), p(ev[1]), p(ev[2]),
                           p(cell_factor), p(pres), p(flows))
         return flows
+
+    def convolve_in(self, **kw):
+        """MAKE_CONVOLUTION in full; keywords of route_abi.pack_route_inputs -> (flows, res_evaporation)"""
+        s, keep, ndays = route_abi.pack_route_inputs(**kw)
+        flows = np.zeros((self.nnodes, ndays), dtype=np.float32)
+        resev = np.zeros((self.nnodes, ndays), dtype=np.float32)
+        lib().ro_convolve_in(self.h, ndays, C.cast(C.pointer(s), C.c_void_p), flows.ctypes.data, resev.ctypes.data)
+        return flows, resev
 
     def res_info(self, n):
         ds, tg = C.c_int(), C.c_int()

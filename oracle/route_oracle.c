@@ -286,6 +286,127 @@ int ro_convolve(const ro_model *m, int ndays, const float *runoff, const float *
   return 0;
 }
 
+
+/* Penman (1948) tables of MAKE_CONVOLUTION (reservoir.f:271-301): extraterrestrial radiation Ra (mm/day) by
+ * month (rows) and 10-degree latitude band 60N..60S (13 columns), delta/gamma and saturation vapour
+ * pressure by half degree 0..22 C, sigma*Ta^4 by degree -1..21 C */
+static const float RA_TAB[13][12] = {
+  {1.4f, 3.6f, 7.0f, 11.1f, 14.6f, 16.4f, 15.6f, 12.6f, 8.5f, 4.7f, 2.0f, 0.9f},
+  {3.7f, 6.0f, 9.2f, 12.7f, 15.5f, 16.6f, 16.1f, 13.7f, 10.4f, 7.1f, 4.4f, 3.1f},
+  {6.2f, 8.4f, 11.1f, 13.8f, 15.9f, 16.7f, 16.3f, 14.7f, 12.1f, 9.3f, 6.8f, 5.6f},
+  {8.1f, 10.5f, 12.8f, 14.7f, 16.1f, 16.5f, 16.2f, 15.2f, 13.5f, 11.2f, 9.1f, 7.9f},
+  {10.8f, 12.4f, 14.0f, 15.2f, 15.7f, 15.8f, 15.8f, 15.4f, 14.4f, 12.9f, 11.3f, 10.4f},
+  {12.8f, 13.9f, 14.8f, 15.2f, 15.0f, 14.8f, 14.9f, 15.0f, 14.8f, 14.2f, 13.1f, 12.5f},
+  {14.6f, 15.0f, 15.2f, 14.7f, 13.9f, 13.4f, 13.6f, 14.3f, 14.9f, 15.0f, 14.6f, 14.3f},
+  {15.9f, 15.7f, 15.1f, 13.9f, 12.5f, 11.7f, 12.0f, 13.1f, 14.4f, 15.4f, 15.7f, 15.8f},
+  {16.8f, 16.0f, 14.5f, 12.5f, 10.7f, 9.7f, 10.1f, 11.6f, 13.6f, 15.3f, 16.4f, 16.9f},
+  {17.2f, 15.8f, 13.5f, 10.9f, 8.6f, 7.5f, 7.9f, 9.7f, 12.3f, 14.8f, 16.7f, 17.5f},
+  {17.3f, 15.1f, 12.2f, 8.9f, 6.4f, 5.2f, 5.6f, 7.6f, 10.7f, 13.8f, 16.5f, 17.8f},
+  {16.9f, 14.1f, 10.4f, 6.7f, 4.1f, 2.9f, 3.4f, 5.4f, 8.7f, 12.5f, 16.0f, 17.6f},
+  {16.5f, 12.6f, 8.3f, 4.3f, 1.8f, 0.9f, 1.3f, 3.1f, 6.5f, 10.8f, 15.1f, 17.5f}};
+static const float DG_TAB[45] = {0.69f, 0.71f, 0.73f, 0.76f, 0.78f, 0.80f, 0.83f, 0.85f, 0.88f, 0.91f, 0.94f, 0.97f, 1.00f, 1.03f, 1.06f,
+  1.09f, 1.13f, 1.16f, 1.19f, 1.23f, 1.26f, 1.30f, 1.34f, 1.38f, 1.42f, 1.47f, 1.51f, 1.56f, 1.60f, 1.65f, 1.69f, 1.74f, 1.79f, 1.84f,
+  1.89f, 1.94f, 1.99f, 2.04f, 2.11f, 2.17f, 2.23f, 2.28f, 2.35f, 2.41f, 2.48f};
+static const float EA_TAB[45] = {4.58f, 4.75f, 4.93f, 5.11f, 5.30f, 5.49f, 5.69f, 5.89f, 6.10f, 6.32f, 6.54f, 6.77f, 7.02f, 7.26f, 7.52f,
+  7.79f, 8.05f, 8.33f, 8.62f, 8.91f, 9.21f, 9.52f, 9.84f, 10.18f, 10.52f, 10.87f, 11.23f, 11.61f, 11.99f, 12.38f, 12.79f, 13.13f, 13.63f,
+  14.08f, 14.53f, 15.00f, 15.49f, 15.97f, 16.47f, 17.53f, 18.68f, 19.80f, 21.10f, 0.0f, 0.0f};
+static const float T4_TAB[23] = {11.0f, 11.2f, 11.4f, 11.5f, 11.7f, 11.9f, 12.0f, 12.2f, 12.3f, 12.5f, 12.7f, 12.9f, 13.1f, 13.3f, 13.5f,
+  13.7f, 13.9f, 14.0f, 14.2f, 14.4f, 14.6f, 14.8f, 15.0f};
+
+/* E0 (mm/day) of one reservoir-surface cell and day (reservoir.f:425-468).  The saturation-pressure table has
+ * 43 entries but the Fortran indexes it up to 45 for 21.5 <= T <= 22 C (out of bounds).  The shipped binary
+ * behaves there as if the two missing elements were 0 (that value reproduces its NF1.txt on the evaporation
+ * fixture, tests/golden/route_evap14x16.npz), so the table is padded with two zeros. */
+static float open_water_e0(float temp, float winds, float rhd, float Ra)
+{
+  const float nN = 0.6f;
+  float wind = winds * 24 * 3600 / 1609, deltagamma, ea, deltaTa4, ed;
+  if (temp < 0) deltagamma = 0.69f; else if (temp > 22) deltagamma = 2.48f; else deltagamma = DG_TAB[(int)(temp * 2)];
+  if (temp < 0) ea = 4.4f; else if (temp > 22) ea = 21.1f;
+  else ea = EA_TAB[(int)(temp * 2)];
+  if (temp < -1) deltaTa4 = 11.0f; else if (temp > 21) deltaTa4 = 15.0f; else deltaTa4 = T4_TAB[(int)(temp) + 1];
+  ed = ea * rhd / 100;
+  return (deltagamma * (0.95f * (0.18f + 0.55f * nN) * Ra - deltaTa4 * (0.56f - 0.09f * sqrtf(ed)) * (0.10f + 0.90f * nN))
+          + 0.35f * (0.5f + wind / 100) * (ea - ed)) / (deltagamma + 1);
+}
+/* column of Ra for the cell's latitude/longitude (reservoir.f:427-435), 0-based */
+static int ra_column(float jloc, float iloc)
+{
+  const int b = (int)(jloc / 10);
+  int c;
+  if (b > 60) c = 1;
+  else if (b <= 60 && (int)(iloc / 10) >= 0) c = 7 - b;
+  else if (b < -60) c = 13;
+  else c = 7 - b;
+  if (c < 1) c = 1;
+  if (c > 13) c = 13;
+  return c - 1;
+}
+
+/* MAKE_CONVOLUTION in full (reservoir.f:216-526): as ro_convolve plus the open-water evaporation of
+ * reservoir-surface cells.  potentialevapo(day) lives across the cells of one node: a surface cell met before
+ * the node's commissioning test passes keeps the previous cell's values (the Fortran array is only reset for
+ * non-surface cells and missing files). */
+int ro_convolve_in(const ro_model *m, int ndays, const vr_route_inputs *in, float *flows, float *res_evap)
+{
+  int n, k, I, J;
+  long long last;
+  float *RUNO = malloc(sizeof(float) * ndays), *BASE = malloc(sizeof(float) * ndays), *pe = malloc(sizeof(float) * ndays);
+  const int has_ev = in->ev_vege && in->ev_soil && in->tr_vege && in->cell_factor;
+  const int has_met = in->rh && in->tair && in->wind && in->cell_lat && in->cell_lon;
+  int MONTH_OF_YEAR = (int)((ndays % 365) / 30) + in->start_month;
+  const int CURRENTYEAR = in->start_year + (int)(ndays % 365);
+  if (MONTH_OF_YEAR > 12) MONTH_OF_YEAR = 12;
+  for (n = 0; n < m->nnodes; n++) {
+    const onode *nd = &m->node[n];
+    float *FLOW = flows + (size_t)n * ndays;
+    const int OPEYEAR = in->node_ope_year ? in->node_ope_year[n] : 0;
+    float EVA_FACTOR = 0.0f;
+    for (I = 0; I < ndays; I++) { FLOW[I] = 0.0f; pe[I] = 0.0f; if (res_evap) res_evap[(size_t)n * ndays + I] = 0.0f; }
+    last = -1;
+    for (k = 0; k < nd->ncells; k++) {
+      int gi = (m->f.nrow - nd->cj[k]) * m->f.ncol + (m->f.ncol - nd->ci[k]);
+      const float *us = m->uh_s[n] + (size_t)k * VR_UH_NS;
+      const float sc = in->cell_scale ? in->cell_scale[gi] : in->scale;
+      const int here = !in->present || in->present[gi];
+      if (here) last = gi;
+      else for (I = 0; I < ndays; I++) pe[I] = 0.0f;
+      for (I = 0; I < ndays; I++) {
+        RUNO[I] = here ? in->runoff[(size_t)gi * ndays + I] * sc : 0.0f * sc;
+        BASE[I] = here ? in->baseflow[(size_t)gi * ndays + I] * sc : 0.0f * sc;
+      }
+      if (m->f.reser[IX(&m->f, nd->ci[k], nd->cj[k])] == 9999 && has_met) {
+        for (I = 0; I < ndays; I++) {
+          if (CURRENTYEAR >= OPEYEAR) {
+            const float Ra = RA_TAB[ra_column(in->cell_lat[gi], in->cell_lon[gi])][MONTH_OF_YEAR - 1];
+            /* a missing file leaves AIRTEMP/WINDS/RHD holding the previous cell's series (zeros at first) */
+            const float temp = last >= 0 ? in->tair[(size_t)last * ndays + I] : 0.0f;
+            const float wnd = last >= 0 ? in->wind[(size_t)last * ndays + I] : 0.0f;
+            const float rhd = last >= 0 ? in->rh[(size_t)last * ndays + I] : 0.0f;
+            pe[I] = open_water_e0(temp, wnd, rhd, Ra);
+            EVA_FACTOR = 0.9f;
+            if (res_evap) res_evap[(size_t)n * ndays + I] = res_evap[(size_t)n * ndays + I] + pe[I] * EVA_FACTOR;
+          }
+        }
+      }
+      else for (I = 0; I < ndays; I++) pe[I] = 0.0f;
+      for (I = 1; I <= ndays; I++) {
+        for (J = 1; J <= VR_UH_NS; J++)
+          if ((I - J + 1) >= 1) FLOW[I - 1] = FLOW[I - 1] + us[J - 1] * (BASE[I - J] + RUNO[I - J]);
+        if (has_ev) {
+          float evv = 0.0f, evs = 0.0f, trv = 0.0f, FACTOR = in->cell_factor[gi];
+          if (last >= 0) { size_t q = (size_t)last * ndays + (I - 1); evv = in->ev_vege[q]; evs = in->ev_soil[q]; trv = in->tr_vege[q]; }
+          if (pe[I - 1] * EVA_FACTOR > (evv + evs + trv))
+            FLOW[I - 1] = FLOW[I - 1] - pe[I - 1] * FACTOR * 0.028f / 1000 * EVA_FACTOR + (evs + evv + trv) * FACTOR * 0.028f / 1000;
+        }
+        if (pe[I - 1] < 0.0001f) pe[I - 1] = 0;
+      }
+    }
+  }
+  free(RUNO); free(BASE); free(pe);
+  return 0;
+}
+
 int ro_res_info(const ro_model *m, int node, int *ds_id, int *target)
 {
   *ds_id = m->node[node].ds_id; *target = m->node[node].target; return 0;

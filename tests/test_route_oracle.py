@@ -41,6 +41,9 @@ def test_route_oracle_matches_prebuilt_binary(name):
         # the binary prints 9 significant digits: equal after the same rounding
         assert np.allclose(uh, ref, rtol=2e-7, atol=1e-30), "UH_S of node %d" % n
     assert res_ids[:-1] == [int(x) for x in z["res_order"][:-1]] and res_ids[-1] == 0
+    if (z["reser"] == 9999).any():                 # needs the evaporation inputs: see the open-water test below
+        o.close()
+        return
     # the shipped binary scales by FACTOR*0.028; today's source hard-codes 0.18308 (reservoir.f:479-480)
     flows = o.convolve(z["runoff"], z["baseflow"], cell_scale=fac * np.float32(0.028),
                        evap=(z["ev_vege"], z["ev_soil"], z["tr_vege"]), cell_factor=fac, present=z["present"])
@@ -119,4 +122,35 @@ def test_current_rule_curve_differs_from_binary_only_where_documented(tmp_path):
     assert np.isfinite(new["flow"]).all() and (new["flow"] >= 0).all()
     # quirk kept: today's source clamps VOL before adding the spill, so FLOWOUT never exceeds the turbine flow
     assert np.array_equal(new["flowout"], new["turbine"])
+    o.close()
+
+
+def evap_inputs(z, grid, fac, nodes_res_ids, tmp_path):
+    nrow, ncol = z["dir"].shape
+    hdr = {"xllcorner": str(z["hdr"][0]), "yllcorner": str(z["hdr"][1]), "cellsize": str(z["hdr"][2])}
+    lat, lon = route_abi.cell_coords(hdr, nrow, ncol)
+    res = fixture_reservoirs(z, nodes_res_ids, tmp_path, int(z["ndays"]))
+    return dict(runoff=z["runoff"], baseflow=z["baseflow"], cell_scale=fac * np.float32(0.028),
+                evap=(z["ev_vege"], z["ev_soil"], z["tr_vege"]), cell_factor=fac, present=z["present"],
+                met=(z["rh"], z["tair"], z["wind"]), cell_lat=lat, cell_lon=lon,
+                node_ope_year=[r["ope_year"] for r in res] + [0], start_year=2000, start_month=1)
+
+
+def test_open_water_evaporation_matches_prebuilt_binary(tmp_path):
+    """reservoir-surface cells (9999): Penman table evaporation subtracted in MAKE_CONVOLUTION
+    (reservoir.f:410-475,496-499) against the binary's NF1.txt; without it the node is 3 % off"""
+    z, grid, (col, row), fac = load_route_fixture("evap14x16")
+    o = route_lib.RouteOracle(grid, col, row, z["uh_box"])
+    ids = [o.node(n)[0] for n in range(o.nnodes - 1)]
+    n9 = [int((z["reser"].ravel()[o.node(n)[1]] == 9999).sum()) for n in range(o.nnodes)]
+    assert sum(n9) >= 2
+    kw = evap_inputs(z, grid, fac, ids, tmp_path)
+    flows, resev = o.convolve_in(**kw)
+    err = np.abs(flows - z["nf"]) / np.maximum(np.abs(z["nf"]), 1e-3)
+    assert err.max() < 5e-6, "node inflow vs binary: %.3e" % err.max()
+    kw.pop("met")
+    dry, _ = o.convolve_in(**kw)
+    err0 = np.abs(dry - z["nf"]) / np.maximum(np.abs(z["nf"]), 1e-3)
+    assert err0.max() > 1e-3                       # the fixture does exercise the evaporation
+    assert (resev[np.array(n9) > 0] > 0).any() and (resev[np.array(n9) == 0] == 0).all()
     o.close()

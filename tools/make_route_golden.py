@@ -133,9 +133,10 @@ def write_case(work, d, reser, station_rc, hdr, velo, diff, xmask, box, flux, nd
             day = 0
             for mo, nd in zip(range(1, 6), (31, 29, 31, 30, 31)):
                 for dd in range(1, nd + 1):
-                    ro, ba, evv, trv, evs = a[day]
+                    ro, ba, evv, trv, evs = a[day][:5]
+                    rh, ta, wi = a[day][5:8] if a.shape[1] >= 8 else (49.0, 15.0, 3.0)
                     cols = [0.0, evv + trv + evs, ro, ba, 0.0, 10.0, 50.0, 55.0, -26.0, evv, trv, evs, 0.0, 0.0, 5.7, 15.0,
-                            0.12, 49.0, 309.0, 15.0, 3.0]
+                            0.12, rh, 309.0, ta, wi]
                     f.write("2000\t%d\t%d\t" % (mo, dd) + "\t".join("%.4f" % x for x in cols) + "\n")
                     day += 1
     cfg = ["# Routing main file", "# NAME OF FLOW DIRECTION FILE", "../parameters/flowdirection.txt",
@@ -175,12 +176,16 @@ def collect(work, name, d, reser, station_rc, hdr, velo, diff, xmask, box, flux,
               "hdr": np.array([float(hdr["xllcorner"]), float(hdr["yllcorner"]), float(hdr["cellsize"])]),
               "nf": nf, "res_order": resdir[:, 0].astype(np.int32), "ndays": np.array(ndays)}
     runoff = np.zeros((nrow * ncol, ndays), dtype=np.float32)
-    base, evv, trv, evs = (np.zeros_like(runoff) for _ in range(4))
+    base, evv, trv, evs, rh, tair, wind = (np.zeros_like(runoff) for _ in range(7))
+    rh[:], tair[:], wind[:] = 49.0, 15.0, 3.0
     for (rr, cc), a in flux.items():
         k = rr * ncol + cc
         # what the binary reads back from the %.4f text
         a4 = np.array([[float("%.4f" % x) for x in row] for row in a], dtype=np.float32)
-        runoff[k], base[k], evv[k], trv[k], evs[k] = a4.T
+        runoff[k], base[k], evv[k], trv[k], evs[k] = a4.T[:5]
+        if a4.shape[1] >= 8:
+            rh[k], tair[k], wind[k] = a4.T[5:8]
+    arrays.update(rh=rh, tair=tair, wind=wind)
     present = np.zeros(nrow * ncol, dtype=np.uint8)
     for (rr, cc) in flux:
         present[rr * ncol + cc] = 1
@@ -250,12 +255,44 @@ def random_case(tmp, env, name, nrow, ncol, seed, nres):
     collect(work, name, d, reser, out, hdr, np.round(velo, 4), np.round(diff, 2), np.round(xmask, 1), box, flux, ndays)
 
 
+def evap_case(tmp, env, name="evap14x16", nrow=14, ncol=16, seed=31):
+    """reservoir-surface cells (RESER == 9999) with varying RH / air temperature / wind: exercises the
+    open-water evaporation of MAKE_CONVOLUTION (reservoir.f:410-475), incl. the 21.5-22 C table overrun"""
+    rng = np.random.default_rng(seed)
+    work = os.path.join(tmp, name)
+    d, out = random_tree(nrow, ncol, rng)
+    hdr = {"xllcorner": "100.0", "yllcorner": "10.0", "cellsize": "0.25"}
+    active = np.argwhere(d > 0)
+    reser = np.zeros_like(d)
+    pick = rng.choice(len(active), size=10, replace=False)
+    for i, k in enumerate(pick[:4]):
+        reser[tuple(active[k])] = i + 1
+    for k in pick[4:]:
+        reser[tuple(active[k])] = 9999
+    velo = rng.uniform(0.8, 2.5, (nrow, ncol))
+    diff = rng.uniform(400.0, 1500.0, (nrow, ncol))
+    xmask = rng.uniform(15000.0, 30000.0, (nrow, ncol))
+    box = np.round(rng.dirichlet(np.ones(12) * 0.6), 4)
+    ndays = 152
+    flux = {}
+    for (r, c) in [tuple(x) for x in active] + [out]:
+        if rng.uniform() < 0.85:
+            ro = rng.gamma(0.5, 4.0, ndays) * (rng.uniform(size=ndays) < 0.4)
+            ba = np.abs(rng.normal(1.0, 0.5, ndays))
+            flux[(r, c)] = np.stack([ro, ba, rng.uniform(0, 1, ndays), rng.uniform(0, 2, ndays), rng.uniform(0, 1, ndays),
+                                     rng.uniform(20, 95, ndays), rng.uniform(-4, 27, ndays), rng.uniform(0, 8, ndays)], axis=1)
+    write_case(work, d, reser, out, hdr, velo, diff, xmask, box, flux, ndays, res_rng=rng)
+    run_binary(work, env)
+    collect(work, name, d, reser, out, hdr, np.round(velo, 4), np.round(diff, 2), np.round(xmask, 1), box, flux, ndays)
+
+
 def main():
     with tempfile.TemporaryDirectory() as tmp:
         env = gfortran_env(tmp)
         toy_case(tmp, env)
         random_case(tmp, env, "rand12x10", 10, 12, 7, 3)
         random_case(tmp, env, "rand20x16", 16, 20, 11, 4)
+        evap_case(tmp, env)
 
 
 if __name__ == "__main__":

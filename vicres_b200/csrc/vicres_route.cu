@@ -156,6 +156,63 @@ __global__ void __launch_bounds__(256) k_grid_uh(const int *__restrict__ cells, 
   if (tid < NS) uh_s[(size_t)blockIdx.x * NS + tid] = us[tid] / total;
 }
 
+/* Penman (1948) tables of MAKE_CONVOLUTION (reservoir.f:271-301): extraterrestrial radiation Ra (mm/day) by
+ * month (rows) and 10-degree latitude band 60N..60S (13 columns), delta/gamma and saturation vapour
+ * pressure by half degree 0..22 C, sigma*Ta^4 by degree -1..21 C */
+__constant__ float RA_TAB[13][12] = {
+  {1.4f, 3.6f, 7.0f, 11.1f, 14.6f, 16.4f, 15.6f, 12.6f, 8.5f, 4.7f, 2.0f, 0.9f},
+  {3.7f, 6.0f, 9.2f, 12.7f, 15.5f, 16.6f, 16.1f, 13.7f, 10.4f, 7.1f, 4.4f, 3.1f},
+  {6.2f, 8.4f, 11.1f, 13.8f, 15.9f, 16.7f, 16.3f, 14.7f, 12.1f, 9.3f, 6.8f, 5.6f},
+  {8.1f, 10.5f, 12.8f, 14.7f, 16.1f, 16.5f, 16.2f, 15.2f, 13.5f, 11.2f, 9.1f, 7.9f},
+  {10.8f, 12.4f, 14.0f, 15.2f, 15.7f, 15.8f, 15.8f, 15.4f, 14.4f, 12.9f, 11.3f, 10.4f},
+  {12.8f, 13.9f, 14.8f, 15.2f, 15.0f, 14.8f, 14.9f, 15.0f, 14.8f, 14.2f, 13.1f, 12.5f},
+  {14.6f, 15.0f, 15.2f, 14.7f, 13.9f, 13.4f, 13.6f, 14.3f, 14.9f, 15.0f, 14.6f, 14.3f},
+  {15.9f, 15.7f, 15.1f, 13.9f, 12.5f, 11.7f, 12.0f, 13.1f, 14.4f, 15.4f, 15.7f, 15.8f},
+  {16.8f, 16.0f, 14.5f, 12.5f, 10.7f, 9.7f, 10.1f, 11.6f, 13.6f, 15.3f, 16.4f, 16.9f},
+  {17.2f, 15.8f, 13.5f, 10.9f, 8.6f, 7.5f, 7.9f, 9.7f, 12.3f, 14.8f, 16.7f, 17.5f},
+  {17.3f, 15.1f, 12.2f, 8.9f, 6.4f, 5.2f, 5.6f, 7.6f, 10.7f, 13.8f, 16.5f, 17.8f},
+  {16.9f, 14.1f, 10.4f, 6.7f, 4.1f, 2.9f, 3.4f, 5.4f, 8.7f, 12.5f, 16.0f, 17.6f},
+  {16.5f, 12.6f, 8.3f, 4.3f, 1.8f, 0.9f, 1.3f, 3.1f, 6.5f, 10.8f, 15.1f, 17.5f}};
+__constant__ float DG_TAB[45] = {0.69f, 0.71f, 0.73f, 0.76f, 0.78f, 0.80f, 0.83f, 0.85f, 0.88f, 0.91f, 0.94f, 0.97f, 1.00f, 1.03f, 1.06f,
+  1.09f, 1.13f, 1.16f, 1.19f, 1.23f, 1.26f, 1.30f, 1.34f, 1.38f, 1.42f, 1.47f, 1.51f, 1.56f, 1.60f, 1.65f, 1.69f, 1.74f, 1.79f, 1.84f,
+  1.89f, 1.94f, 1.99f, 2.04f, 2.11f, 2.17f, 2.23f, 2.28f, 2.35f, 2.41f, 2.48f};
+__constant__ float EA_TAB[45] = {4.58f, 4.75f, 4.93f, 5.11f, 5.30f, 5.49f, 5.69f, 5.89f, 6.10f, 6.32f, 6.54f, 6.77f, 7.02f, 7.26f, 7.52f,
+  7.79f, 8.05f, 8.33f, 8.62f, 8.91f, 9.21f, 9.52f, 9.84f, 10.18f, 10.52f, 10.87f, 11.23f, 11.61f, 11.99f, 12.38f, 12.79f, 13.13f, 13.63f,
+  14.08f, 14.53f, 15.00f, 15.49f, 15.97f, 16.47f, 17.53f, 18.68f, 19.80f, 21.10f, 0.0f, 0.0f};
+__constant__ float T4_TAB[23] = {11.0f, 11.2f, 11.4f, 11.5f, 11.7f, 11.9f, 12.0f, 12.2f, 12.3f, 12.5f, 12.7f, 12.9f, 13.1f, 13.3f, 13.5f,
+  13.7f, 13.9f, 14.0f, 14.2f, 14.4f, 14.6f, 14.8f, 15.0f};
+
+/* E0 (mm/day) of one reservoir-surface cell and day (reservoir.f:425-468).  The saturation-pressure table has
+ * 43 entries but the Fortran indexes it up to 45 for 21.5 <= T <= 22 C (out of bounds).  The shipped binary
+ * behaves there as if the two missing elements were 0 (that value reproduces its NF1.txt on the evaporation
+ * fixture, tests/golden/route_evap14x16.npz), so the table is padded with two zeros.  sqrtf is IEEE on the device. */
+__device__ float open_water_e0(float temp, float winds, float rhd, float Ra)
+{
+  const float nN = 0.6f;
+  float wind = winds * 24 * 3600 / 1609, deltagamma, ea, deltaTa4, ed;
+  if (temp < 0) deltagamma = 0.69f; else if (temp > 22) deltagamma = 2.48f; else deltagamma = DG_TAB[(int)(temp * 2)];
+  if (temp < 0) ea = 4.4f; else if (temp > 22) ea = 21.1f;
+  else ea = EA_TAB[(int)(temp * 2)];
+  if (temp < -1) deltaTa4 = 11.0f; else if (temp > 21) deltaTa4 = 15.0f; else deltaTa4 = T4_TAB[(int)(temp) + 1];
+  ed = ea * rhd / 100;
+  return (deltagamma * (0.95f * (0.18f + 0.55f * nN) * Ra - deltaTa4 * (0.56f - 0.09f * sqrtf(ed)) * (0.10f + 0.90f * nN))
+          + 0.35f * (0.5f + wind / 100) * (ea - ed)) / (deltagamma + 1);
+}
+/* column of Ra for the cell's latitude/longitude (reservoir.f:427-435), 0-based */
+__device__ int ra_column(float jloc, float iloc)
+{
+  const int b = (int)(jloc / 10);
+  int c;
+  if (b > 60) c = 1;
+  else if (b <= 60 && (int)(iloc / 10) >= 0) c = 7 - b;
+  else if (b < -60) c = 13;
+  else c = 7 - b;
+  if (c < 1) c = 1;
+  if (c > 13) c = 13;
+  return c - 1;
+}
+
+
 struct ConvArgs {
   int nnodes, ndays;
   const int64_t *node_ptr;      // [nnodes+1] into cells / uh rows
@@ -166,15 +223,23 @@ struct ConvArgs {
   const unsigned char *present;                                   // [ncell] or null
   float scale;
   float *flows;                 // [nnodes][ndays]
+  // open-water evaporation of reservoir-surface cells (null rh: none)
+  const float *rh, *tair, *wind, *cell_lat, *cell_lon;
+  const int *reser, *node_ope_year;
+  int month_of_year, current_year;
+  float *res_evap;              // [nnodes][ndays] or null
 };
 
+// One thread per (node, day): cells in list order, taps ascending.  potentialevapo(day), EVA_FACTOR and the
+// "arrays still hold the previous cell's file" state of the Fortran are per-day scalars here.
 __global__ void __launch_bounds__(128) k_convolve(ConvArgs a)
 {
   const int node = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;   // i = day - 1
   if (i >= a.ndays) return;
-  float flow = 0.0f;
+  float flow = 0.0f, pe = 0.0f, eva_factor = 0.0f, resev = 0.0f;
   long long last = -1;
   const bool evap = a.ev_vege && a.ev_soil && a.tr_vege && a.cell_factor;
+  const int ope = a.node_ope_year ? a.node_ope_year[node] : 0;
   for (int64_t e = a.node_ptr[node]; e < a.node_ptr[node + 1]; e++) {
     const int gi = a.cells[e];
     const bool here = !a.present || a.present[gi];
@@ -186,14 +251,29 @@ __global__ void __launch_bounds__(128) k_convolve(ConvArgs a)
       const int jmax = (i + 1 < NS) ? i + 1 : NS;
       for (int J = 1; J <= jmax; J++) flow = flow + us[J - 1] * (ba[i - J + 1] * sc + ro[i - J + 1] * sc);
     }
+    else pe = 0.0f;
     // a missing cell contributes UH*(0*sc + 0*sc) = +0 to every day: nothing to add
-    if (evap && last >= 0) {
-      const size_t q = (size_t)last * a.ndays + i;
-      if (0.0f > (a.ev_vege[q] + a.ev_soil[q] + a.tr_vege[q]))
-        flow = flow - 0.0f + (a.ev_soil[q] + a.ev_vege[q] + a.tr_vege[q]) * a.cell_factor[gi] * 0.028f / 1000;
+    if (a.rh && a.reser[gi] == 9999) {
+      if (a.current_year >= ope) {
+        const size_t q = (size_t)(last >= 0 ? last : 0) * a.ndays + i;
+        const float temp = last >= 0 ? a.tair[q] : 0.0f, wnd = last >= 0 ? a.wind[q] : 0.0f, rhd = last >= 0 ? a.rh[q] : 0.0f;
+        pe = open_water_e0(temp, wnd, rhd, RA_TAB[ra_column(a.cell_lat[gi], a.cell_lon[gi])][a.month_of_year - 1]);
+        eva_factor = 0.9f;
+        resev = resev + pe * eva_factor;
+      }
     }
+    else pe = 0.0f;
+    if (evap) {
+      float evv = 0.0f, evs = 0.0f, trv = 0.0f;
+      if (last >= 0) { const size_t q = (size_t)last * a.ndays + i; evv = a.ev_vege[q]; evs = a.ev_soil[q]; trv = a.tr_vege[q]; }
+      const float FACTOR = a.cell_factor[gi];
+      if (pe * eva_factor > (evv + evs + trv))
+        flow = flow - pe * FACTOR * 0.028f / 1000 * eva_factor + (evs + evv + trv) * FACTOR * 0.028f / 1000;
+    }
+    if (pe < 0.0001f) pe = 0.0f;
   }
   a.flows[(size_t)node * a.ndays + i] = flow;
+  if (a.res_evap) a.res_evap[(size_t)node * a.ndays + i] = resev;
 }
 
 // ---- reservoirs ------------------------------------------------------------------------------------
@@ -471,6 +551,9 @@ struct vr_route {
   DB<int64_t> d_node_ptr;
   DB<float> d_velo, d_diff, d_xmask, d_uhm, d_box, d_uh_s, d_ro, d_ba, d_evv, d_evs, d_trv, d_scale, d_factor, d_flows;
   DB<unsigned char> d_present;
+  bool has_surface = false;            // reservoir-surface cells (9999) inside a catchment
+  DB<float> d_rh, d_tair, d_wind, d_lat, d_lon, d_resev;
+  DB<int> d_reser, d_ope;
   std::vector<float> uh_r;             // [nres][NS]
   DB<float> d_uh_r, d_pool, d_natural, d_resflows, d_vol, d_hho, d_flowin, d_flowout, d_turb, d_energy, d_htk, d_flow;
   DB<int> d_target, d_up_ptr, d_up_idx;
@@ -501,6 +584,7 @@ void vr_route_destroy(vr_route *h)
   h->d_next.rel(); h->d_cells.rel(); h->d_node_ptr.rel(); h->d_velo.rel(); h->d_diff.rel(); h->d_xmask.rel();
   h->d_uhm.rel(); h->d_box.rel(); h->d_uh_s.rel(); h->d_ro.rel(); h->d_ba.rel(); h->d_evv.rel(); h->d_evs.rel();
   h->d_trv.rel(); h->d_scale.rel(); h->d_factor.rel(); h->d_flows.rel(); h->d_present.rel();
+  h->d_rh.rel(); h->d_tair.rel(); h->d_wind.rel(); h->d_lat.rel(); h->d_lon.rel(); h->d_resev.rel(); h->d_reser.rel(); h->d_ope.rel();
   h->d_uh_r.rel(); h->d_pool.rel(); h->d_natural.rel(); h->d_resflows.rel(); h->d_vol.rel(); h->d_hho.rel();
   h->d_flowin.rel(); h->d_flowout.rel(); h->d_turb.rel(); h->d_energy.rel(); h->d_htk.rel(); h->d_flow.rel();
   h->d_target.rel(); h->d_up_ptr.rel(); h->d_up_idx.rel(); h->d_res.rel();
@@ -617,12 +701,7 @@ int vr_route_create(const vr_route_grid *g, int32_t station_col, int32_t station
   h->node_ptr.assign(1, 0);
   for (const Node &nd : h->nodes) {
     for (int k : nd.cells) {
-      if (h->g.reser[k] == 9999) {
-        g_route_error = "reservoir-surface cells (9999) inside a catchment need the open-water evaporation of "
-                        "reservoir.f:410-475, which is not part of this round";
-        delete h;
-        return VR_ERR_UNSUPPORTED;
-      }
+      if (h->g.reser[k] == 9999) h->has_surface = true;
       h->cells.push_back(k);
     }
     h->node_ptr.push_back((int64_t)h->cells.size());
@@ -661,25 +740,43 @@ int vr_route_get_uh(vr_route *h, int32_t node, float *uh_s)
   return VR_OK;
 }
 
-int vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,
-                         const float *cell_scale, const float *ev_vege, const float *ev_soil, const float *tr_vege,
-                         const float *cell_factor, const unsigned char *present, float *flows)
+int vr_route_convolve_in(vr_route *h, int32_t ndays, const vr_route_inputs *in, float *flows, float *res_evaporation)
 {
-  if (!h || !runoff || !baseflow || !flows || ndays < 1) return VR_ERR_ARG;
+  if (!h || !in || !in->runoff || !in->baseflow || !flows || ndays < 1) return VR_ERR_ARG;
   RK(cudaSetDevice(h->device));
+  const bool met = in->rh && in->tair && in->wind && in->cell_lat && in->cell_lon;
+  if (h->has_surface && !met) {
+    h->err = "reservoir-surface cells (9999) inside a catchment: MAKE_CONVOLUTION needs rh/tair/wind and the cell "
+             "coordinates for their open-water evaporation (vr_route_convolve_in)";
+    return VR_ERR_UNSUPPORTED;
+  }
   const size_t ncell = (size_t)h->g.ncol * h->g.nrow, n = ncell * ndays;
-  RK(h->d_ro.put(runoff, n)); RK(h->d_ba.put(baseflow, n));
+  RK(h->d_ro.put(in->runoff, n)); RK(h->d_ba.put(in->baseflow, n));
   ConvArgs a;
   memset(&a, 0, sizeof a);
   a.nnodes = (int)h->nodes.size(); a.ndays = ndays; a.node_ptr = h->d_node_ptr.p; a.cells = h->d_cells.p;
-  a.uh_s = h->d_uh_s.p; a.runoff = h->d_ro.p; a.baseflow = h->d_ba.p; a.scale = scale;
-  if (cell_scale) { RK(h->d_scale.put(cell_scale, ncell)); a.cell_scale = h->d_scale.p; }
-  if (ev_vege && ev_soil && tr_vege && cell_factor) {
-    RK(h->d_evv.put(ev_vege, n)); RK(h->d_evs.put(ev_soil, n)); RK(h->d_trv.put(tr_vege, n));
-    RK(h->d_factor.put(cell_factor, ncell));
+  a.uh_s = h->d_uh_s.p; a.runoff = h->d_ro.p; a.baseflow = h->d_ba.p; a.scale = in->scale;
+  if (in->cell_scale) { RK(h->d_scale.put(in->cell_scale, ncell)); a.cell_scale = h->d_scale.p; }
+  if (in->ev_vege && in->ev_soil && in->tr_vege && in->cell_factor) {
+    RK(h->d_evv.put(in->ev_vege, n)); RK(h->d_evs.put(in->ev_soil, n)); RK(h->d_trv.put(in->tr_vege, n));
+    RK(h->d_factor.put(in->cell_factor, ncell));
     a.ev_vege = h->d_evv.p; a.ev_soil = h->d_evs.p; a.tr_vege = h->d_trv.p; a.cell_factor = h->d_factor.p;
   }
-  if (present) { RK(h->d_present.put(present, ncell)); a.present = h->d_present.p; }
+  if (in->present) { RK(h->d_present.put(in->present, ncell)); a.present = h->d_present.p; }
+  if (met) {
+    RK(h->d_rh.put(in->rh, n)); RK(h->d_tair.put(in->tair, n)); RK(h->d_wind.put(in->wind, n));
+    RK(h->d_lat.put(in->cell_lat, ncell)); RK(h->d_lon.put(in->cell_lon, ncell));
+    RK(h->d_reser.put(h->g.reser.data(), ncell));
+    a.rh = h->d_rh.p; a.tair = h->d_tair.p; a.wind = h->d_wind.p; a.cell_lat = h->d_lat.p; a.cell_lon = h->d_lon.p;
+    a.reser = h->d_reser.p;
+    if (in->node_ope_year) { RK(h->d_ope.put(in->node_ope_year, a.nnodes)); a.node_ope_year = h->d_ope.p; }
+    // both are computed from NDAY, not from the day (reservoir.f:420-421)
+    a.month_of_year = (ndays % 365) / 30 + in->start_month;
+    if (a.month_of_year > 12) a.month_of_year = 12;
+    if (a.month_of_year < 1) { h->err = "start_month must be 1..12"; return VR_ERR_ARG; }
+    a.current_year = in->start_year + ndays % 365;
+    if (res_evaporation) { RK(h->d_resev.res((size_t)a.nnodes * ndays)); a.res_evap = h->d_resev.p; }
+  }
   RK(h->d_flows.res((size_t)a.nnodes * ndays));
   a.flows = h->d_flows.p;
   dim3 grid((ndays + 127) / 128, a.nnodes);
@@ -689,7 +786,22 @@ int vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const 
   h->timed = true;
   RK(cudaGetLastError());
   RK(cudaMemcpy(flows, h->d_flows.p, (size_t)a.nnodes * ndays * sizeof(float), cudaMemcpyDeviceToHost));
+  if (res_evaporation) {
+    if (a.res_evap) RK(cudaMemcpy(res_evaporation, h->d_resev.p, (size_t)a.nnodes * ndays * sizeof(float), cudaMemcpyDeviceToHost));
+    else memset(res_evaporation, 0, (size_t)a.nnodes * ndays * sizeof(float));
+  }
   return VR_OK;
+}
+
+int vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,
+                         const float *cell_scale, const float *ev_vege, const float *ev_soil, const float *tr_vege,
+                         const float *cell_factor, const unsigned char *present, float *flows)
+{
+  vr_route_inputs in;
+  memset(&in, 0, sizeof in);
+  in.runoff = runoff; in.baseflow = baseflow; in.scale = scale; in.cell_scale = cell_scale; in.ev_vege = ev_vege;
+  in.ev_soil = ev_soil; in.tr_vege = tr_vege; in.cell_factor = cell_factor; in.present = present;
+  return vr_route_convolve_in(h, ndays, &in, flows, nullptr);
 }
 
 int vr_route_convolve(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale, float *flows)

@@ -11,7 +11,7 @@ from . import model, route_abi
 
 ROUTE_EXPORTS = ["vr_route_create", "vr_route_destroy", "vr_route_last_error", "vr_route_num_nodes",
                  "vr_route_node_info", "vr_route_node_cells", "vr_route_get_uh", "vr_route_convolve",
-                 "vr_route_convolve_ex", "vr_route_last_kernel_ms", "vr_route_res_info", "vr_route_get_uh_r",
+                 "vr_route_convolve_ex", "vr_route_convolve_in", "vr_route_last_kernel_ms", "vr_route_res_info", "vr_route_get_uh_r",
                  "vr_route_set_uh_r", "vr_route_reservoirs"]
 
 
@@ -30,6 +30,7 @@ def _lib():
         L.vr_route_get_uh.argtypes = [vp, C.c_int32, vp]
         L.vr_route_convolve.argtypes = [vp, C.c_int32, vp, vp, C.c_float, vp]
         L.vr_route_convolve_ex.argtypes = [vp, C.c_int32, vp, vp, C.c_float] + [vp] * 7
+        L.vr_route_convolve_in.argtypes = [vp, C.c_int32, vp, vp, vp]
         L.vr_route_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.vr_route_res_info.argtypes = [vp, C.c_int32, vp, vp]
         L.vr_route_get_uh_r.argtypes = [vp, C.c_int32, vp]
@@ -77,6 +78,16 @@ class Route:
         self._check(self.L.vr_route_convolve_ex(self.h, ndays, p(runoff), p(baseflow), C.c_float(scale), p(cell_scale),
                                                 p(ev[0]), p(ev[1]), p(ev[2]), p(cell_factor), p(pres), p(flows)))
         return flows
+
+    def convolve_in(self, **kw):
+        """MAKE_CONVOLUTION in full (open-water evaporation of reservoir-surface cells included); keywords of
+        route_abi.pack_route_inputs -> (flows [nnodes, ndays], res_evaporation [nnodes, ndays])"""
+        s, keep, ndays = route_abi.pack_route_inputs(**kw)
+        flows = np.zeros((self.nnodes, ndays), dtype=np.float32)
+        resev = np.zeros((self.nnodes, ndays), dtype=np.float32)
+        self._check(self.L.vr_route_convolve_in(self.h, ndays, C.cast(C.pointer(s), C.c_void_p), flows.ctypes.data,
+                                                resev.ctypes.data))
+        return flows, resev
 
     def res_info(self, n):
         """(downstream reservoir id, node the release is routed to, UH_R[107]) of reservoir node n"""

@@ -208,3 +208,57 @@ def read_reservoir_file(path, start_year=None, start_month=None, ndays=None):
         irr[:min(ndays, n)] = v[:ndays]
         d["irrigation"] = irr
     return d
+
+
+class vr_route_inputs(C.Structure):
+    _fields_ = [("runoff", _pf), ("baseflow", _pf), ("scale", C.c_float), ("cell_scale", _pf), ("ev_vege", _pf),
+                ("ev_soil", _pf), ("tr_vege", _pf), ("cell_factor", _pf), ("present", C.POINTER(C.c_ubyte)),
+                ("rh", _pf), ("tair", _pf), ("wind", _pf), ("cell_lat", _pf), ("cell_lon", _pf),
+                ("node_ope_year", C.POINTER(C.c_int32)), ("start_year", C.c_int32), ("start_month", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+def pack_route_inputs(runoff, baseflow, scale=0.18308, cell_scale=None, evap=None, cell_factor=None, present=None,
+                      met=None, cell_lat=None, cell_lon=None, node_ope_year=None, start_year=0, start_month=1):
+    """-> (vr_route_inputs, keepalive, ndays).  evap = (ev_vege, ev_soil, tr_vege); met = (rh, tair, wind)"""
+    s = vr_route_inputs()
+    keep = []
+
+    def f32(a):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a)
+        return a.ctypes.data_as(_pf)
+    runoff = np.ascontiguousarray(runoff, dtype=np.float32)
+    s.runoff, s.baseflow, s.scale, s.cell_scale = f32(runoff), f32(baseflow), scale, f32(cell_scale)
+    if evap is not None:
+        s.ev_vege, s.ev_soil, s.tr_vege = f32(evap[0]), f32(evap[1]), f32(evap[2])
+    s.cell_factor = f32(cell_factor)
+    if present is not None:
+        p = np.ascontiguousarray(present, dtype=np.uint8)
+        keep.append(p)
+        s.present = p.ctypes.data_as(C.POINTER(C.c_ubyte))
+    if met is not None:
+        s.rh, s.tair, s.wind = f32(met[0]), f32(met[1]), f32(met[2])
+    s.cell_lat, s.cell_lon = f32(cell_lat), f32(cell_lon)
+    if node_ope_year is not None:
+        y = np.ascontiguousarray(node_ope_year, dtype=np.int32)
+        keep.append(y)
+        s.node_ope_year = y.ctypes.data_as(C.POINTER(C.c_int32))
+    s.start_year, s.start_month = start_year, start_month
+    return s, keep, runoff.shape[1]
+
+
+def cell_coords(hdr, nrow, ncol):
+    """JLOC, ILOC of every file-order cell in REAL arithmetic (reservoir.f:353-356)"""
+    f32 = np.float32
+    xc, yc, size = f32(float(hdr["xllcorner"])), f32(float(hdr["yllcorner"])), f32(float(hdr["cellsize"]))
+    lat = np.zeros(nrow * ncol, dtype=np.float32)
+    lon = np.zeros(nrow * ncol, dtype=np.float32)
+    for r in range(nrow):
+        for c in range(ncol):
+            I, J = ncol - c, nrow - r
+            lon[r * ncol + c] = xc + f32(ncol - I) * size + size / f32(2.0)
+            lat[r * ncol + c] = yc + f32(J) * size - size / f32(2.0)
+    return lat, lon
