@@ -184,8 +184,8 @@ def test_cuda_open_water_evaporation(Route, tmp_path):
 @pytest.mark.parametrize("name", ["toy", "rand20x16"])
 def test_cuda_reservoirs_match_prebuilt_binary(Route, name, tmp_path):
     """end to end on the device (its own UH_S, UH_R and convolution) against the binary's reservoir files:
-    the unit hydrographs differ from glibc's in the last bit, so 2e-5 (relative to max(|value|, 1 % of the
-    column's range)) instead of bit equality"""
+    the unit hydrographs differ from glibc's in the last bit, so tolerances (relative to max(|value|, 1 % of
+    the column's range)) instead of bit equality; bit equality of the day loop itself is the test above"""
     from test_route_oracle import binary_columns, fixture_reservoirs
     z, grid, (col, row), fac = load_route_fixture(name)
     r = Route(grid, col, row, z["uh_box"])
@@ -201,10 +201,11 @@ def test_cuda_reservoirs_match_prebuilt_binary(Route, name, tmp_path):
         mine = binary_columns(one, j, res[j])
         mine[:, [0, 3, 5, 8]] = np.maximum(mine[:, [0, 3, 5, 8]], 0)
         mine[:, 7] = np.where(mine[:, 2] > 0, np.minimum(mine[:, 6], np.float32(res[j]["q_design"])), mine[:, 7])
-        # releases are differences of storages (cancellation): tolerance relative to the column's scale
         scale = np.maximum(np.abs(ref), 1e-2 * np.abs(ref).max(axis=0, keepdims=True) + 1e-2)
         err = np.abs(mine - ref) / scale
-        assert err.max() < 2e-5, "reservoir %d: %.3e" % (rid, err.max())
+        assert err[:, :5].max() < 2e-5, "reservoir %d storage/level: %.3e" % (rid, err[:, :5].max())
+        # releases are differences of storages divided by 86.4: one fp32 ulp of a 1e5 storage is 1e-4 m3/s
+        assert err[:, 5:].max() < 1e-3, "reservoir %d flows/energy: %.3e" % (rid, err[:, 5:].max())
     err = np.abs(one["flow"] - z["station_flow"]) / np.maximum(np.abs(z["station_flow"]), 1e-2)
     assert err.max() < 2e-5
     r.close()
