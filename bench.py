@@ -220,6 +220,8 @@ def run_ours(args):
     lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=1, seed=20261019 + rank)
     f_host, month, doy = synth_soa.make_forcing(cells, R, seed=7 + rank)
     opt = abi.default_options(3, 1, 24)
+    if args.chunk > 0:
+        opt.cells_per_block_hint = args.chunk
     n_out = opt.n_out
     m = model.VicRes(opt, lib, cells, device=local)
     m.init_state(f_host[0, 0])
@@ -345,6 +347,7 @@ def main():
     ap.add_argument("--block", type=int, default=365, help="records per step (one simulated year)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--chunk", type=int, default=0, help="records per kernel-pair launch (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -181,7 +181,11 @@ int  vr_set_state(vr_handle *h, const void *blob_host);
 /* introspection used by bench/tests */
 int64_t vr_num_units(const vr_handle *h);      /* active tile x band pairs */
 int64_t vr_num_launches(const vr_handle *h);   /* kernels launched by this handle so far */
-int  vr_last_kernel_ms(vr_handle *h, float *ms); /* CUDA-event time of the last step kernel */
+int  vr_last_kernel_ms(vr_handle *h, float *ms); /* CUDA-event time of all kernels of the last block of records */
+/* CUDA-event times of the last chunk's two kernels (k_units: the step; k_cells: put_data) and its records */
+int  vr_last_chunk_times(vr_handle *h, float *units_ms, float *cells_ms, int32_t *nrec);
+/* diagnostic: z[i] = the device's power function (vic_physics.cuh m_pow) of x[i], y[i]; host pointers */
+int  vr_diag_pow(int device, int64_t n, const double *x, const double *y, double *z);
 /* TFALLBACK counters summed over all units, as put_data.c:658-664 prints them:
  * counts[0] = Tsnowsurf (snow_melt.c:361-366), counts[1] = Tfoliage (snow_intercept.c:418-423) */
 int  vr_fallback_counts(vr_handle *h, int64_t counts[2]);

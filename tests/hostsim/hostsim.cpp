@@ -47,7 +47,10 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
     {   // put_data(rec = -nrecs)
       UnitOut z;
       memset(&z, 0, sizeof z);
-      for (int j = 0; j < nu; j++) unit_terms(UC[fu0 + j], P.u_cv[fu0 + j], P.u_af[fu0 + j], S_[fu0 + j], z, NL, tmap, &buf[j], MAXU);
+      for (int j = 0; j < nu; j++) {
+        const int64_t u = P.u_slot[fu0 + j];       // per-unit arrays are in slot order
+        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S_[u], z, NL, tmap, &buf[j], MAXU);
+      }
       if (nu > 0) {
         cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);
         cell_carry(S, NL, svc);
@@ -62,7 +65,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
       fo.longwave = f->field[VR_F_LONGWAVE][k];
       fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
       for (int j = 0; j < nu; j++) {
-        const int64_t u = fu0 + j;
+        const int64_t u = P.u_slot[fu0 + j];
         const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
         const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];
         unit_step_terms(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u],

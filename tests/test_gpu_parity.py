@@ -174,3 +174,21 @@ def test_errors_are_reported_not_fatal(VicRes):
         m.step(fx["month"][:5], fx["doy"][:5], np.ascontiguousarray(fx["forcing"][:, :5]))   # before init_state
     assert e.value.code == abi.VR_ERR_STATE
     m.close()
+
+
+def test_device_pow_error_bound():
+    """vic_physics.cuh m_pow: relative error below 1e-13 over the model's argument ranges (Brooks-Corey
+    drainage (0..1]^[3,40], ARNO curves, albedo decay 0.92^(t^0.58)), exact special cases"""
+    from vicres_b200 import model
+    rng = np.random.default_rng(3)
+    n = 400000
+    x = np.concatenate([rng.uniform(1e-6, 1.0, n), rng.uniform(0.0, 3.0, n), np.exp(rng.uniform(-30, 30, n))])
+    y = np.concatenate([rng.uniform(3.0, 40.0, n), rng.uniform(0.0, 3.0, n), rng.uniform(-8.0, 8.0, n)])
+    z = model.diag_pow(x, y)
+    ref = np.power(x, y)
+    ok = np.isfinite(ref) & (ref > 1e-300)
+    rel = np.abs(z[ok] - ref[ok]) / ref[ok]
+    assert rel.max() < 1e-13, "max relative error %.3e" % rel.max()
+    sx = np.array([1.0, 0.0, 0.0, 2.0])
+    sy = np.array([7.3, 2.0, 0.0, 0.0])
+    assert np.array_equal(model.diag_pow(sx, sy), np.array([1.0, 0.0, 1.0, 1.0]))

@@ -66,7 +66,7 @@ def main():
     syms = []
     for l in elf.splitlines():
         p = l.split()
-        if len(p) < 7 or "k_step" not in l:
+        if len(p) < 7 or ("k_step" not in l and "k_units" not in l and "vr" not in l):
             continue
         try:
             val, sz = int(p[1], 16), int(p[2], 16)

@@ -1,0 +1,17 @@
+"""Time the device-resident step for every library variant in _variants (run on the GPU box).
+usage: python tools/tune_run.py [cells] [records] [chunk ...]"""
+import glob, os, subprocess, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+cells = sys.argv[1] if len(sys.argv) > 1 else "100000"
+recs = sys.argv[2] if len(sys.argv) > 2 else "365"
+chunks = sys.argv[3:] if len(sys.argv) > 3 else ["0"]
+for lib in sorted(glob.glob(os.path.join(ROOT, "_variants", "lib_*.so"))):
+  for ch in chunks:
+    env = dict(os.environ, VICRES_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "2", "--no-cpu-baseline",
+                        "--e2e-steps", "1", "--cells", cells, "--block", recs, "--chunk", ch], env=env, capture_output=True, text=True)
+    try:
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        print("%-20s chunk %3s value %.4e  e2e %.4e  ms/step %.1f" % (os.path.basename(lib), ch, j["value"], j["e2e"]["value"], j["ms_per_step"]), flush=True)
+    except Exception as e:
+        print(os.path.basename(lib), "FAILED", r.stderr[-400:], flush=True)

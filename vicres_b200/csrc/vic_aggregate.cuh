@@ -82,7 +82,7 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
 {
   const double AF = cv * af * 1. * 1.;
   const bool HasVeg = !uc.is_bare;
-#define T_(k, expr) do { if (tmap.row[k] >= 0) col[tmap.row[k] * stride] = (expr); } while (0)
+#define T_(k, expr) do { if (tmap.row[k] >= 0) col[(size_t)tmap.row[k] * stride] = (expr); } while (0)
   double tmp_evap = 0.0;
 #pragma unroll
   for (int l = 0; l < MAXL; l++) {
@@ -170,21 +170,21 @@ VR_HD void cell_accumulate_inplace(double *buf, int stride, const TermMap &tmap,
   for (int k = 0; k < NTERM; k++) {
     const int r = tmap.row[k];
     if (r < 0 || (k >= TE_EB0 && k <= TE_TV2)) continue;
-    double a = 0. + buf[r * stride + c0];
-    for (int j = 1; j < nu; j++) a += buf[r * stride + col_of(j)];
-    buf[r * stride + c0] = a;
+    double a = 0. + buf[(size_t)r * stride + c0];
+    for (int j = 1; j < nu; j++) a += buf[(size_t)r * stride + col_of(j)];
+    buf[(size_t)r * stride + c0] = a;
   }
   if (tmap.row[TE_EB0] >= 0) {
     double eb = 0;
     for (int j = 0; j < nu; j++)
-      for (int l = 0; l < NL; l++) eb += buf[tmap.row[TE_EB0 + l] * stride + col_of(j)];
-    buf[tmap.row[TE_EB0] * stride + c0] = eb;
+      for (int l = 0; l < NL; l++) eb += buf[(size_t)tmap.row[TE_EB0 + l] * stride + col_of(j)];
+    buf[(size_t)tmap.row[TE_EB0] * stride + c0] = eb;
   }
   if (tmap.row[TE_TV0] >= 0) {
     double tv = 0;
     for (int j = 0; j < nu; j++)
-      for (int l = 0; l < NL; l++) tv += buf[tmap.row[TE_TV0 + l] * stride + col_of(j)];
-    buf[tmap.row[TE_TV0] * stride + c0] = tv;
+      for (int l = 0; l < NL; l++) tv += buf[(size_t)tmap.row[TE_TV0 + l] * stride + col_of(j)];
+    buf[(size_t)tmap.row[TE_TV0] * stride + c0] = tv;
   }
 }
 

@@ -6,7 +6,10 @@
 //   * per (tile, month) canopy terms tm[T][12][TM_N]
 //   * per (aero key, month) CalcAerodynamic coefficients ae[K][12][AE_N], deduplicated over
 //     (class, soil roughness, snow roughness)
-//   * CTA packing: consecutive whole cells per thread block, at most `cta_threads` units each.
+//   * thread slots: the units sorted by kind (overstory, other vegetation, bare soil) and, inside a kind,
+//     by the climate of their cell and band, so that the lanes of a warp run the same branches; every
+//     per-unit array is stored in SLOT order (thread k reads element k), and u_slot maps a unit in
+//     reference order to its slot for the per-cell aggregation.
 // All arithmetic here follows the reference expression order (read_soilparam-derived values are
 // taken as given) so that it matches the oracle bit for bit on the same libm.
 #pragma once
@@ -31,14 +34,13 @@ struct Prepared {
   std::vector<int64_t> cell_uptr;    // [C+1] over SORTED positions
   std::vector<int32_t> u_cell, u_tile, u_flags, u_aero;   // [U]; u_cell = caller's cell index; flags: bit0 bare, bit1 overstory, bits 8.. root0 mask
   std::vector<int32_t> u_pos;        // [U] sorted position of the unit's cell
-  std::vector<int32_t> u_slot;       // [U] thread index inside its block that runs unit u
-  std::vector<int64_t> t_unit;       // [U] unit run by thread (u0_of_block + t)
+  std::vector<int32_t> u_slot;       // [U] reference-order unit (index into cell_uptr ranges) -> slot
+  std::vector<int64_t> pos_of;       // [C] caller's cell index -> sorted position
   std::vector<double> u_cv, u_af, u_Tfactor, u_Pfactor, u_rarc, u_rmin, u_RGL;   // [U]
   std::vector<float> u_root;         // [MAXL][U]
   std::vector<double> tm;            // [T][12][TM_N]
   std::vector<double> ae;            // [K][12][AE_N]
   std::vector<int32_t> cell_fail;    // [C] 1 = CalcAerodynamic rejects a tile of this cell (full_energy returns ERROR)
-  std::vector<int64_t> cta_cell;     // [nCTA+1] sorted positions
   std::string error;
 };
 
@@ -302,7 +304,6 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
         n++;
       }
     }
-    if (n > cta_threads) { P.error = "a cell has more active tile x band units than one thread block holds"; return false; }
     P.cell_uptr[cs + 1] = P.cell_uptr[cs] + n;
   }
   P.U = P.cell_uptr[C];
@@ -312,37 +313,34 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     bool bare = P.u_flags[u] & 1;
     for (int l = 0; l < NL; l++) P.u_root[(size_t)l * P.U + u] = bare ? 0.f : (float)cells.tile_root[t * NL + l];
   }
-  // ---- CTA packing: whole consecutive (sorted) cells, <= cta_threads units ----
-  P.cta_cell.clear();
-  P.cta_cell.push_back(0);
-  int64_t used = 0;
-  for (int64_t c = 0; c < C; c++) {
-    int64_t n = P.cell_uptr[c + 1] - P.cell_uptr[c];
-    if (used + n > cta_threads) {
-      P.cta_cell.push_back(c);
-      used = 0;
-    }
-    used += n;
+  // ---- thread slots: sort by kind, then by the unit's climate (cell mean temperature + band lapse offset) ----
+  P.pos_of.assign(C, 0);
+  for (int64_t cs = 0; cs < C; cs++) P.pos_of[P.order[cs]] = cs;
+  const int64_t U = P.U;
+  std::vector<int64_t> perm(U);
+  for (int64_t u = 0; u < U; u++) perm[u] = u;
+  auto kind_of = [&](int64_t u) { const int fl = P.u_flags[u]; return (fl & 2) ? 0 : ((fl & 1) ? 2 : 1); };
+  std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) {
+    const int ka = kind_of(a), kb = kind_of(b);
+    if (ka != kb) return ka < kb;
+    const double ta = cells.avg_temp[P.u_cell[a]] + P.u_Tfactor[a], tb = cells.avg_temp[P.u_cell[b]] + P.u_Tfactor[b];
+    if (ta != tb) return ta < tb;
+    return a < b;
+  });
+  P.u_slot.assign(U ? U : 1, 0);
+  for (int64_t k = 0; k < U; k++) P.u_slot[perm[k]] = (int32_t)k;
+  auto permute = [&](auto &v) {
+    auto old = v;
+    for (int64_t k = 0; k < U; k++) v[k] = old[perm[k]];
+  };
+  permute(P.u_cell); permute(P.u_pos); permute(P.u_tile); permute(P.u_flags); permute(P.u_aero); permute(P.u_cv);
+  permute(P.u_af); permute(P.u_Tfactor); permute(P.u_Pfactor); permute(P.u_rarc); permute(P.u_rmin); permute(P.u_RGL);
+  {
+    std::vector<float> old = P.u_root;
+    for (int l = 0; l < MAXL; l++)
+      for (int64_t k = 0; k < U; k++) P.u_root[(size_t)l * U + k] = old[(size_t)l * U + perm[k]];
   }
-  if (C > 0) P.cta_cell.push_back(C);
-  P.nCTA = (int64_t)P.cta_cell.size() - 1;
-  // ---- thread assignment inside a block: units grouped by kind (overstory, other vegetation, bare
-  //      soil) so that a warp mostly runs one evaporation / interception path ----
-  P.u_slot.assign(P.U ? P.U : 1, 0);
-  P.t_unit.assign(P.U ? P.U : 1, 0);
-  for (int64_t b = 0; b < P.nCTA; b++) {
-    const int64_t u0 = P.cell_uptr[P.cta_cell[b]], u1 = P.cell_uptr[P.cta_cell[b + 1]];
-    int64_t t = 0;
-    for (int kind = 0; kind < 3; kind++)
-      for (int64_t u = u0; u < u1; u++) {
-        const int fl = P.u_flags[u];
-        const int k = (fl & 2) ? 0 : ((fl & 1) ? 2 : 1);
-        if (k != kind) continue;
-        P.u_slot[u] = (int32_t)t;
-        P.t_unit[u0 + t] = u;
-        t++;
-      }
-  }
+  P.nCTA = (U + cta_threads - 1) / cta_threads;
   return true;
 }
 

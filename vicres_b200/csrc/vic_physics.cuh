@@ -66,6 +66,14 @@ namespace vr {
 // argument range of the model -- four orders below the 1e-9 parity bar.  Zero, negative, subnormal,
 // non-finite or extreme arguments take CUDA's pow().  With -DVR_EXACT_LIBM (and always on the host)
 // plain pow() is used, which is what makes the host build bit-identical to the reference.
+#if defined(__CUDACC__)
+// ascending coefficients: VR_KQ[i] = 2/(2i+3) (atanh series), VR_KP[i] = 1/i! (exp)
+static __constant__ double VR_KQ[10] = {2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0,
+                                        2.0 / 17.0, 2.0 / 19.0, 2.0 / 21.0};
+static __constant__ double VR_KP[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                                        1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                                        1.0 / 479001600.0, 1.0 / 6227020800.0};
+#endif
 VR_HDN double m_pow(double x, double y)
 {
 #if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM)
@@ -84,38 +92,32 @@ VR_HDN double m_pow(double x, double y)
     r = fma(fma(-d, r, 1.0), r, r);
     double f = nm * r;
     f = fma(fma(-f, d, nm), r, f);
-    const double f2 = f * f;
-    // 2*atanh(f)/f = 2*(1 + f2/3 + f2^2/5 + ...), truncated after f2^10 (|f2| <= 0.0295 -> 1e-17)
-    double q = 2.0 / 21.0;
-    q = fma(q, f2, 2.0 / 19.0);
-    q = fma(q, f2, 2.0 / 17.0);
-    q = fma(q, f2, 2.0 / 15.0);
-    q = fma(q, f2, 2.0 / 13.0);
-    q = fma(q, f2, 2.0 / 11.0);
-    q = fma(q, f2, 2.0 / 9.0);
-    q = fma(q, f2, 2.0 / 7.0);
-    q = fma(q, f2, 2.0 / 5.0);
-    q = fma(q, f2, 2.0 / 3.0);
+    const double f2 = f * f, f4 = f2 * f2;
+    // 2*atanh(f)/f = 2*(1 + f2/3 + f2^2/5 + ...), truncated after f2^10 (|f2| <= 0.0295 -> 1e-17).  Even and odd
+    // powers run as two independent Horner chains (the kernel is bound by dependent-issue latency, not by
+    // the FP64 pipe) and the coefficients come from constant memory (one LDCU.128 per two doubles instead of
+    // two UMOVs per double).
+    double qe = VR_KQ[8], qo = VR_KQ[9];
+    qe = fma(qe, f4, VR_KQ[6]); qo = fma(qo, f4, VR_KQ[7]);
+    qe = fma(qe, f4, VR_KQ[4]); qo = fma(qo, f4, VR_KQ[5]);
+    qe = fma(qe, f4, VR_KQ[2]); qo = fma(qo, f4, VR_KQ[3]);
+    qe = fma(qe, f4, VR_KQ[0]); qo = fma(qo, f4, VR_KQ[1]);
+    const double q = fma(qo, f2, qe);
     const double lnm = fma(q * f2, f, 2.0 * f);               // ln(m)
     const double l2m = lnm * 1.4426950408889634;              // log2(m), |l2m| <= 0.5
     const double t = fma(y, l2m, y * (double)e);              // y*log2(x)
     if (fabs(t) < 1000.0) {
       const double n = rint(t);
       const double z = (t - n) * 0.6931471805599453;          // |z| <= 0.3466
-      double p = 1.0 / 6227020800.0;
-      p = fma(p, z, 1.0 / 479001600.0);
-      p = fma(p, z, 1.0 / 39916800.0);
-      p = fma(p, z, 1.0 / 3628800.0);
-      p = fma(p, z, 1.0 / 362880.0);
-      p = fma(p, z, 1.0 / 40320.0);
-      p = fma(p, z, 1.0 / 5040.0);
-      p = fma(p, z, 1.0 / 720.0);
-      p = fma(p, z, 1.0 / 120.0);
-      p = fma(p, z, 1.0 / 24.0);
-      p = fma(p, z, 1.0 / 6.0);
-      p = fma(p, z, 0.5);
-      p = fma(p, z, 1.0);
-      p = fma(p, z, 1.0);
+      const double z2 = z * z;
+      double pe = VR_KP[12], po = VR_KP[13];                  // exp(z) = sum z^i / i!, i <= 13
+      pe = fma(pe, z2, VR_KP[10]); po = fma(po, z2, VR_KP[11]);
+      pe = fma(pe, z2, VR_KP[8]); po = fma(po, z2, VR_KP[9]);
+      pe = fma(pe, z2, VR_KP[6]); po = fma(po, z2, VR_KP[7]);
+      pe = fma(pe, z2, VR_KP[4]); po = fma(po, z2, VR_KP[5]);
+      pe = fma(pe, z2, VR_KP[2]); po = fma(po, z2, VR_KP[3]);
+      pe = fma(pe, z2, VR_KP[0]); po = fma(po, z2, VR_KP[1]);
+      const double p = fma(po, z, pe);
       return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
     }
   }

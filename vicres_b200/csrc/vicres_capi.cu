@@ -1,11 +1,15 @@
 // vicres_capi.cu -- C ABI (include/vicres.h) and CUDA kernels of the B200-native VIC-Res cell step.
 //
-// Mapping: one THREAD owns one active tile x band unit and keeps its 24 state
-// words in registers across a whole block of records; the units of a cell sit in adjacent lanes, a
-// thread block holds whole consecutive cells (<= 128 units).  Per record every unit thread runs
-// vr::unit_step(), drops its 40 area-weighted terms into shared memory, and the cell's first lane
-// adds them in reference order (put_data.c) and writes the requested outputs, coalesced over cells.
-// Forcing is read as [field][rec][cell] (coalesced over cells, broadcast over a cell's units).
+// Mapping.  The step of a block of records runs as two kernels per chunk of records:
+//   k_units  one THREAD owns one active tile x band unit (thread k = slot k: units sorted by kind and climate
+//            so that a warp runs one branch mix) and keeps its 24 state words in registers across the chunk;
+//            per record it runs vr::unit_step() and streams its area-weighted terms to the term buffer
+//            terms[rec][row][slot] in HBM (coalesced over slots).  No shared memory, no cross-thread work.
+//   k_cells  one thread per cell: adds the terms of the cell's units in reference order (put_data.c), derives
+//            the requested outputs, carries the save_data words, writes out[var][rec][cell] (coalesced).
+// HBM bandwidth is what this path has to spare (the step is FP64/latency bound), so the term round trip
+// (about 0.9 kB per cell-timestep) buys homogeneous warps and removes the serial per-cell tail from the
+// compute kernel.  Forcing is read as [field][rec][cell].
 // There is NO CPU fallback: every entry point needs a CUDA device and reports VR_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -18,11 +22,14 @@
 #include "vic_aggregate.cuh"
 #include "vic_host_prep.h"
 
-// One 512-thread block per SM (128 registers per thread): k_step is instruction-fetch bound, and 16
-// warps that move through the step together (phase barriers in unit_step) share every instruction-
-// cache fill; measured 1.9x faster than 128-thread blocks (profiles/r1_tuning.md).
+// One block per SM, as many threads as a cap of 80 registers allows: k_units is bound by instruction
+// supply and dependent-issue latency, not by the FP64 pipe.  The warps of a block move through the step
+// together (phase barriers in unit_step), so every instruction-cache fill is shared by the whole block:
+// 512 threads with barriers ran 1.8x faster than without, 800 threads at 80 registers another 6 % faster than
+// 512 at 128 (profiles/r1_tuning.md).  VR_CTA is the maximum; the launch picks the block size that fills
+// whole waves (vr_set_cells).
 #ifndef VR_CTA
-#define VR_CTA 512
+#define VR_CTA 800
 #endif
 #ifndef VR_MINB
 #define VR_MINB 1      // thread blocks per SM the register allocation must allow
@@ -37,7 +44,7 @@ struct DevModel {
   double max_snow_temp, min_rain_temp;
   int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
   const double *cc;
-  const int64_t *cell_uptr, *cta_cell, *fcol, *order, *t_unit;
+  const int64_t *cell_uptr, *fcol, *pos_of;
   const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *cell_fail;
   const double *u_cv, *u_af, *u_Tfactor, *u_Pfactor, *u_rarc, *u_rmin, *u_RGL, *tm, *ae, *init_moist;
   const float *u_root;
@@ -45,11 +52,12 @@ struct DevModel {
   double *sv;                       // [SV_N][C]
   int32_t *cell_status;             // [C]
   int32_t out_vars[VR_MAX_OUT];
-  TermMap tmap;                     // rows of the shared-memory term buffer the requested outputs need
+  TermMap tmap;                     // rows of the term buffer the requested outputs need
 };
 
 struct DevForcing {
-  int nrec;
+  int nrec;                         // records in this launch
+  int rec0, nrec_total;             // position of the launch inside the caller's block (output indexing)
   const int32_t *month, *doy;       // device
   const double *field[VR_NFORCING]; // device, [nrec][FC]
 };
@@ -93,64 +101,50 @@ __device__ __forceinline__ void store_state(const DevModel &M, int64_t u, const 
 #undef S_
 }
 
-// Thread roles inside a block that holds the sorted cells [cs0, cs1) with units [u0, u1):
-//   unit role      thread t < u1-u0 runs unit t_unit[u0+t] (grouped by kind); idle threads shadow the
-//                  block's last unit so that every thread runs the step and its phase barriers
-//   finisher role  thread t < cs1-cs0 aggregates sorted cell cs0+t: adds the terms of the cell's units in
-//                  reference order (slots u_slot[u]) and writes the cell's outputs
-
-// initialize_model_state() + put_data(rec = -nrecs)
-__global__ void __launch_bounds__(VR_CTA) k_init(DevModel M, const double *tair0 /* [FC] */)
+// initialize_model_state() for every unit + its terms for put_data(rec = -nrecs)
+__global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double *tair0 /* [FC] */, double *terms)
 {
-  extern __shared__ double sm[];
-  const int tid = threadIdx.x;
-  const int64_t cs0 = M.cta_cell[blockIdx.x], cs1 = M.cta_cell[blockIdx.x + 1];
-  const int64_t u0 = M.cell_uptr[cs0], u1 = M.cell_uptr[cs1];
-  if (u0 + tid < u1) {
-    const int64_t u = M.t_unit[u0 + tid];
-    const int64_t c = M.u_cell[u];
-    UnitC uc; UnitS s; UnitOut z;
-    double cv, af, im[MAXL], mm[MAXL];
-    load_unit_consts(M, u, uc, cv, af);
-    for (int l = 0; l < M.NL; l++) {
-      im[l] = M.init_moist[(size_t)l * M.C + c];
-      mm[l] = M.cc[(size_t)(CC_LAYER0 + l * CL_N + CL_MAX_MOIST) * M.C + M.u_pos[u]];
-    }
-    const int64_t fc = M.fcol ? M.fcol[c] : c;
-    unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
-    store_state(M, u, s);
-    memset(&z, 0, sizeof z);
-    unit_terms(uc, cv, af, s, z, M.NL, M.tmap, &sm[tid], VR_CTA);
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= M.U) return;
+  const int64_t c = M.u_cell[u];
+  UnitC uc; UnitS s; UnitOut z;
+  double cv, af, im[MAXL], mm[MAXL];
+  load_unit_consts(M, u, uc, cv, af);
+  for (int l = 0; l < M.NL; l++) {
+    im[l] = M.init_moist[(size_t)l * M.C + c];
+    mm[l] = M.cc[(size_t)(CC_LAYER0 + l * CL_N + CL_MAX_MOIST) * M.C + M.u_pos[u]];
   }
-  __syncthreads();
-  if (cs0 + tid < cs1) {
-    const int64_t cs = cs0 + tid, c = M.order[cs];
-    const int64_t fu0 = M.cell_uptr[cs];
-    const int nu = (int)(M.cell_uptr[cs + 1] - fu0);
-    double sv[SV_N] = {0, 0, 0, 0};
-    if (nu > 0) {
-      auto col_of = [&](int j) { return (int)M.u_slot[fu0 + j]; };
-      cell_accumulate_inplace(sm, VR_CTA, M.tmap, nu, col_of, M.NL);
-      const int c0 = col_of(0);
-      auto S = [&](int k) { return sm[M.tmap.row[k] * VR_CTA + c0]; };
-      cell_carry(S, M.NL, sv);
-    }
-    for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
-    M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
-  }
+  const int64_t fc = M.fcol ? M.fcol[c] : c;
+  unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
+  store_state(M, u, s);
+  memset(&z, 0, sizeof z);
+  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + u, (int)M.U);
 }
 
-// full_energy() + put_data() for F.nrec consecutive records of every cell
-__global__ void __launch_bounds__(VR_CTA, VR_MINB) k_step(DevModel M, DevForcing F, double *__restrict__ out)
+__global__ void __launch_bounds__(128) k_init_cells(DevModel M, double *terms)
 {
-  extern __shared__ double sm[];     // [NTERM][VR_CTA]
-  const int tid = threadIdx.x;
-  const int64_t cs0 = M.cta_cell[blockIdx.x], cs1 = M.cta_cell[blockIdx.x + 1];
-  const int64_t u0 = M.cell_uptr[cs0], u1 = M.cell_uptr[cs1];
-  if (u1 <= u0) return;              // (uniform) a block without active units
-  const bool active = u0 + tid < u1;
-  const int64_t u = M.t_unit[active ? u0 + tid : u1 - 1];
-  // ---- unit role ----
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= M.C) return;
+  const int64_t cs = M.pos_of[c], fu0 = M.cell_uptr[cs];
+  const int nu = (int)(M.cell_uptr[cs + 1] - fu0);
+  double sv[SV_N] = {0, 0, 0, 0};
+  if (nu > 0) {
+    auto col_of = [&](int j) { return (int)M.u_slot[fu0 + j]; };
+    cell_accumulate_inplace(terms, (int)M.U, M.tmap, nu, col_of, M.NL);
+    const int c0 = col_of(0);
+    auto S = [&](int k) { return terms[(size_t)M.tmap.row[k] * M.U + c0]; };
+    cell_carry(S, M.NL, sv);
+  }
+  for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+  M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
+}
+
+// full_energy() for F.nrec consecutive records of every unit; terms[rec][row][slot]
+__global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcing F, double *__restrict__ terms)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = k < M.U;
+  const int64_t u = active ? k : M.U - 1;     // idle threads of the last block shadow the last unit (phase barriers)
   UnitC uc; CellC cc; UnitS s;
   double cv, af;
   const int64_t c = M.u_cell[u];
@@ -161,60 +155,68 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_step(DevModel M, DevForcing
   load_state(M, u, s);
   const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
   const double *ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
-  // ---- finisher role ----
-  const bool finisher = cs0 + tid < cs1;
-  const int64_t fcs = finisher ? cs0 + tid : cs0;
-  const int64_t fcell = M.order[fcs];
-  const int64_t ffc = M.fcol ? M.fcol[fcell] : fcell;
-  const int64_t fu0 = M.cell_uptr[fcs], fu1 = M.cell_uptr[fcs + 1];
-  const bool ffailed = M.cell_fail[fcell] != 0;
-  double sv[SV_N] = {0, 0, 0, 0};
-  if (finisher)
-    for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + fcell];
-
   const int nrec = F.nrec, NL = M.NL;
+  const size_t rec_stride = (size_t)M.tmap.n * M.U;
+  const bool write = active && !failed;
   for (int rec = 0; rec < nrec; rec++) {
-    const int mon = __ldg(F.month + rec) - 1, doy = __ldg(F.doy + rec);
-    {
-      Forc f;
-      const size_t k = (size_t)rec * M.FC + fc;
-      f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + k); f.prec = __ldg(F.field[VR_F_PREC] + k);
-      f.wind = __ldg(F.field[VR_F_WIND] + k); f.vp = __ldg(F.field[VR_F_VP] + k);
-      f.vpd = __ldg(F.field[VR_F_VPD] + k); f.pressure = __ldg(F.field[VR_F_PRESSURE] + k);
-      f.density = __ldg(F.field[VR_F_DENSITY] + k); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k);
-      f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
-      f.mon = mon; f.doy = doy;
-      unit_step_terms(cc, uc, tm + mon * TM_N, ae + mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
-                      cv, af, M.tmap, &sm[tid], VR_CTA, active);
-    }
-    __syncthreads();
-    if (finisher) {
-      const int nu = (int)(fu1 - fu0);
-      if (!ffailed && nu > 0) {
-        auto col_of = [&](int j) { return (int)__ldg(M.u_slot + fu0 + j); };
-        cell_accumulate_inplace(sm, VR_CTA, M.tmap, nu, col_of, NL);
-        const int c0 = col_of(0);
-        auto S = [&](int k) { return sm[M.tmap.row[k] * VR_CTA + c0]; };
-        Forc f;
-        const size_t k = (size_t)rec * M.FC + ffc;
-        f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + k); f.wind = __ldg(F.field[VR_F_WIND] + k);
-        f.vp = __ldg(F.field[VR_F_VP] + k); f.vpd = __ldg(F.field[VR_F_VPD] + k);
-        f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + k); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + k);
-        f.prec = 0; f.pressure = 0; f.density = 0; f.mon = mon; f.doy = doy;
-#pragma unroll 1
-        for (int v = 0; v < M.n_out; v++)
-          out[((size_t)v * nrec + rec) * M.C + fcell] = cell_output(M.out_vars[v], S, f, NL, false, sv);
-        cell_carry(S, NL, sv);
-      }
-      else {
-        for (int v = 0; v < M.n_out; v++) out[((size_t)v * nrec + rec) * M.C + fcell] = 0.;
-      }
-    }
-    __syncthreads();
+    Forc f;
+    const size_t q = (size_t)rec * M.FC + fc;
+    f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.prec = __ldg(F.field[VR_F_PREC] + q);
+    f.wind = __ldg(F.field[VR_F_WIND] + q); f.vp = __ldg(F.field[VR_F_VP] + q);
+    f.vpd = __ldg(F.field[VR_F_VPD] + q); f.pressure = __ldg(F.field[VR_F_PRESSURE] + q);
+    f.density = __ldg(F.field[VR_F_DENSITY] + q); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q);
+    f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
+    f.mon = __ldg(F.month + rec) - 1; f.doy = __ldg(F.doy + rec);
+    unit_step_terms(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
+                    cv, af, M.tmap, terms + rec * rec_stride + u, (int)M.U, write);
   }
-  if (active && !failed) store_state(M, u, s);
-  if (finisher && !ffailed)
-    for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + fcell] = sv[k];
+  if (write) store_state(M, u, s);
+}
+
+// put_data() for the same records: one thread per cell (caller's index, so forcing reads and output
+// writes are coalesced); the unit terms are summed in place in the term buffer, in reference order
+__global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, double *__restrict__ terms, double *__restrict__ out)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= M.C) return;
+  const int64_t cs = M.pos_of[c], fu0 = M.cell_uptr[cs];
+  const int nu = (int)(M.cell_uptr[cs + 1] - fu0);
+  const int64_t fc = M.fcol ? M.fcol[c] : c;
+  const bool ok = !M.cell_fail[c] && nu > 0;
+  const int NL = M.NL;
+  const size_t rec_stride = (size_t)M.tmap.n * M.U;
+  double sv[SV_N];
+  for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + c];
+  auto col_of = [&](int j) { return (int)__ldg(M.u_slot + fu0 + j); };
+  const int c0 = nu > 0 ? col_of(0) : 0;
+  for (int rec = 0; rec < F.nrec; rec++) {
+    double *T = terms + rec * rec_stride;
+    const size_t orow = (size_t)(F.rec0 + rec) * M.C + c, ostride = (size_t)F.nrec_total * M.C;
+    if (ok) {
+      cell_accumulate_inplace(T, (int)M.U, M.tmap, nu, col_of, NL);
+      auto S = [&](int k) { return T[(size_t)M.tmap.row[k] * M.U + c0]; };
+      Forc f;
+      const size_t q = (size_t)rec * M.FC + fc;
+      f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.wind = __ldg(F.field[VR_F_WIND] + q);
+      f.vp = __ldg(F.field[VR_F_VP] + q); f.vpd = __ldg(F.field[VR_F_VPD] + q);
+      f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
+      f.prec = 0; f.pressure = 0; f.density = 0; f.mon = 0; f.doy = 0;
+#pragma unroll 1
+      for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = cell_output(M.out_vars[v], S, f, NL, false, sv);
+      cell_carry(S, NL, sv);
+    }
+    else
+      for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = 0.;
+  }
+  if (ok)
+    for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+}
+
+// diagnostic: the device power function on arbitrary arguments (tests/test_gpu_parity.py checks its error bound)
+__global__ void k_diag_pow(int64_t n, const double *x, const double *y, double *z)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = m_pow(x[i], y[i]);
 }
 
 template <class T>
@@ -253,13 +255,17 @@ struct vr_handle {
   Prepared P;
   DevModel M;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
-      d_forc, d_out, d_tair0;
+      d_forc, d_out, d_tair0, d_terms;
   DBuf<float> d_u_root;
-  DBuf<int64_t> d_cell_uptr, d_cta_cell, d_fcol, d_order, d_t_unit;
+  DBuf<int64_t> d_cell_uptr, d_fcol, d_pos_of;
   DBuf<int32_t> d_u_cell, d_u_pos, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
   cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_u0 = nullptr, ev_u1 = nullptr, ev_c1 = nullptr;   // around the last k_units and k_cells launches
+  int last_nrec = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  int chunk = 16;                    // records per pipelined chunk of vr_step_block
+  int cta = VR_CTA;                  // threads per k_units block, chosen per grid so that the blocks fill whole waves
+  int64_t ncta = 0;
+  int chunk = 16;                    // records per k_units/k_cells launch pair (and per pipelined copy of vr_step_block)
   int64_t launches = 0;
   bool timed = false;
 };
@@ -328,7 +334,9 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
   bool ok = (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) == cudaSuccess &&
-            (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess;
+            (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess &&
+            (e = cudaEventCreate(&h->ev_u0)) == cudaSuccess && (e = cudaEventCreate(&h->ev_u1)) == cudaSuccess &&
+            (e = cudaEventCreate(&h->ev_c1)) == cudaSuccess;
   for (int b = 0; ok && b < 2; b++)
     ok = (e = cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming)) == cudaSuccess &&
          (e = cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming)) == cudaSuccess &&
@@ -338,8 +346,7 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     delete h;
     return VR_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NTERM * VR_CTA * sizeof(double)));
-  cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NTERM * VR_CTA * sizeof(double)));
+  cudaFuncSetAttribute(k_units, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of L1 for the stacks
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   *out = h;
   return VR_OK;
@@ -352,12 +359,15 @@ void vr_destroy(vr_handle *h)
   h->d_cc.release(); h->d_u_cv.release(); h->d_u_af.release(); h->d_u_Tf.release(); h->d_u_Pf.release();
   h->d_u_rarc.release(); h->d_u_rmin.release(); h->d_u_RGL.release(); h->d_tm.release(); h->d_ae.release();
   h->d_init_moist.release(); h->d_state.release(); h->d_sv.release(); h->d_forc.release(); h->d_out.release();
-  h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_cta_cell.release(); h->d_fcol.release();
+  h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_fcol.release(); h->d_terms.release();
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
-  h->d_order.release(); h->d_t_unit.release(); h->d_u_slot.release(); h->d_u_pos.release();
+  h->d_pos_of.release(); h->d_u_slot.release(); h->d_u_pos.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_u0) cudaEventDestroy(h->ev_u0);
+  if (h->ev_u1) cudaEventDestroy(h->ev_u1);
+  if (h->ev_c1) cudaEventDestroy(h->ev_c1);
   for (int b = 0; b < 2; b++) {
     if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
     if (h->ev_comp[b]) cudaEventDestroy(h->ev_comp[b]);
@@ -405,16 +415,29 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   if (!prepare(h->opt, lib, *cells, VR_CTA, h->P)) { h->err = h->P.error; return VR_ERR_ARG; }
   Prepared &P = h->P;
   const int64_t C = P.C, U = P.U;
+  {   // one resident block per SM: w waves of blocks as equal as the warp granularity allows (a grid of
+      // 3.1 waves of full-size blocks would pay for 4)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t per_wave = (int64_t)sms * VR_CTA;
+    const int64_t w = U > 0 ? (U + per_wave - 1) / per_wave : 1;
+    int64_t t = U > 0 ? (U + sms * w - 1) / (sms * w) : 32;
+    t = ((t + 31) / 32) * 32;
+    if (t > VR_CTA) t = VR_CTA;
+    if (t < 32) t = 32;
+    h->cta = (int)t;
+    h->ncta = U > 0 ? (U + t - 1) / t : 0;
+  }
   std::vector<double> im((size_t)P.NL * C);
   for (size_t i = 0; i < im.size(); i++) im[i] = cells->init_moist[i];
-  CK(h->d_cc.upload(P.cc)); CK(h->d_cell_uptr.upload(P.cell_uptr)); CK(h->d_cta_cell.upload(P.cta_cell));
+  CK(h->d_cc.upload(P.cc)); CK(h->d_cell_uptr.upload(P.cell_uptr));
   CK(h->d_u_cell.upload(P.u_cell)); CK(h->d_u_pos.upload(P.u_pos)); CK(h->d_u_tile.upload(P.u_tile)); CK(h->d_u_flags.upload(P.u_flags));
   CK(h->d_u_aero.upload(P.u_aero)); CK(h->d_cell_fail.upload(P.cell_fail)); CK(h->d_u_cv.upload(P.u_cv));
   CK(h->d_u_af.upload(P.u_af)); CK(h->d_u_Tf.upload(P.u_Tfactor)); CK(h->d_u_Pf.upload(P.u_Pfactor));
   CK(h->d_u_rarc.upload(P.u_rarc)); CK(h->d_u_rmin.upload(P.u_rmin)); CK(h->d_u_RGL.upload(P.u_RGL));
   CK(h->d_u_root.upload(P.u_root)); CK(h->d_tm.upload(P.tm)); CK(h->d_ae.upload(P.ae));
   CK(h->d_init_moist.upload(im));
-  CK(h->d_order.upload(P.order)); CK(h->d_t_unit.upload(P.t_unit)); CK(h->d_u_slot.upload(P.u_slot));
+  CK(h->d_pos_of.upload(P.pos_of)); CK(h->d_u_slot.upload(P.u_slot));
   CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
   CK(h->d_sv.reserve((size_t)SV_N * C));
   CK(h->d_cell_status.reserve(C));
@@ -425,13 +448,13 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.NL = P.NL; M.NB = P.NB; M.dt_hours = h->opt.dt_hours; M.n_out = h->opt.n_out;
   M.max_snow_temp = h->opt.max_snow_temp; M.min_rain_temp = h->opt.min_rain_temp;
   M.C = C; M.U = U; M.FC = C;
-  M.cc = h->d_cc.p; M.cell_uptr = h->d_cell_uptr.p; M.cta_cell = h->d_cta_cell.p; M.fcol = nullptr;
+  M.cc = h->d_cc.p; M.cell_uptr = h->d_cell_uptr.p; M.fcol = nullptr;
   M.u_cell = h->d_u_cell.p; M.u_pos = h->d_u_pos.p; M.u_tile = h->d_u_tile.p; M.u_flags = h->d_u_flags.p; M.u_aero = h->d_u_aero.p;
   M.cell_fail = h->d_cell_fail.p; M.u_cv = h->d_u_cv.p; M.u_af = h->d_u_af.p; M.u_Tfactor = h->d_u_Tf.p;
   M.u_Pfactor = h->d_u_Pf.p; M.u_rarc = h->d_u_rarc.p; M.u_rmin = h->d_u_rmin.p; M.u_RGL = h->d_u_RGL.p;
   M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
-  M.order = h->d_order.p; M.t_unit = h->d_t_unit.p; M.u_slot = h->d_u_slot.p;
+  M.pos_of = h->d_pos_of.p; M.u_slot = h->d_u_slot.p;
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
   h->have_cells = true;
@@ -462,21 +485,41 @@ int vr_init_state(vr_handle *h, const double *tair0)
   CK(cudaSetDevice(h->device));
   CK(h->d_tair0.reserve(h->M.FC));
   CK(cudaMemcpyAsync(h->d_tair0.p, tair0, h->M.FC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  k_init<<<(unsigned)h->P.nCTA, VR_CTA, (size_t)h->M.tmap.n * VR_CTA * sizeof(double), h->stream>>>(h->M, h->d_tair0.p);
-  h->launches++;
+  const size_t U1 = (size_t)(h->M.U ? h->M.U : 1);
+  CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * h->chunk));
+  if (h->M.U > 0) k_init_units<<<(unsigned)h->ncta, h->cta, 0, h->stream>>>(h->M, h->d_tair0.p, h->d_terms.p);
+  k_init_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p);
+  h->launches += 2;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   h->initialised = true;
   return VR_OK;
 }
 
-static int launch_step(vr_handle *h, const DevForcing &F, double *out_dev, cudaStream_t st)
+// One block of records = chunks of h->chunk records, each a k_units + k_cells pair on stream st.  The
+// events ev0/ev1 bracket the k_units launches only through vr_last_kernel_ms's accumulated time.
+static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cudaStream_t st)
 {
+  const size_t U1 = (size_t)(h->M.U ? h->M.U : 1);
+  const int CH = h->chunk;
+  CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * CH));
   cudaEventRecord(h->ev0, st);
-  k_step<<<(unsigned)h->P.nCTA, VR_CTA, (size_t)h->M.tmap.n * VR_CTA * sizeof(double), st>>>(h->M, F, out_dev);
+  for (int r0 = 0; r0 < F0.nrec; r0 += CH) {
+    DevForcing F = F0;
+    F.nrec = (F0.nrec - r0 < CH) ? F0.nrec - r0 : CH;
+    F.rec0 = F0.rec0 + r0;
+    F.month = F0.month + r0; F.doy = F0.doy + r0;
+    for (int i = 0; i < VR_NFORCING; i++) F.field[i] = F0.field[i] + (size_t)r0 * h->M.FC;
+    const bool last = r0 + CH >= F0.nrec;
+    if (last) cudaEventRecord(h->ev_u0, st);
+    if (h->M.U > 0) k_units<<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, h->d_terms.p);
+    if (last) cudaEventRecord(h->ev_u1, st);
+    k_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, st>>>(h->M, F, h->d_terms.p, out_dev);
+    if (last) { cudaEventRecord(h->ev_c1, st); h->last_nrec = F.nrec; }
+    h->launches += 2;
+  }
   cudaEventRecord(h->ev1, st);
   h->timed = true;
-  h->launches++;
   CK(cudaGetLastError());
   return VR_OK;
 }
@@ -491,7 +534,7 @@ int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, voi
   CK(cudaMemcpyAsync(h->d_month.p, f->month, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   DevForcing F;
-  F.nrec = f->nrec; F.month = h->d_month.p; F.doy = h->d_doy.p;
+  F.nrec = f->nrec; F.rec0 = 0; F.nrec_total = f->nrec; F.month = h->d_month.p; F.doy = h->d_doy.p;
   for (int i = 0; i < VR_NFORCING; i++) {
     if (!f->field[i]) { h->err = "null forcing field"; return VR_ERR_ARG; }
     F.field[i] = f->field[i];
@@ -500,7 +543,7 @@ int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, voi
 }
 
 // Host-buffer entry point.  The block of records is cut into chunks of h->chunk records that flow
-// through three streams -- H2D of chunk k+1, k_step of chunk k and D2H of chunk k-1 overlap (PCIe is
+// through three streams -- H2D of chunk k+1, k_units/k_cells of chunk k and D2H of chunk k-1 overlap (PCIe is
 // full duplex) -- with two device buffers per direction.  Forcing [field][rec][col] and outputs
 // [var][rec][cell] are record-major, so a chunk is one contiguous copy per field / variable.
 int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *cell_status_host)
@@ -524,7 +567,7 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     double *din = h->d_forc.p + (size_t)b * in_chunk, *dout = h->d_out.p + (size_t)b * out_chunk;
     if (k >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));       // kernel of chunk k-2 has consumed din
     DevForcing F;
-    F.nrec = nr; F.month = h->d_month.p + r0; F.doy = h->d_doy.p + r0;
+    F.nrec = nr; F.rec0 = 0; F.nrec_total = nr; F.month = h->d_month.p + r0; F.doy = h->d_doy.p + r0;
     for (int i = 0; i < VR_NFORCING; i++) {
       CK(cudaMemcpyAsync(din + (size_t)i * nr * FC, f->field[i] + (size_t)r0 * FC, (size_t)nr * FC * sizeof(double),
                          cudaMemcpyHostToDevice, h->s_in));
@@ -607,6 +650,32 @@ int vr_last_kernel_ms(vr_handle *h, float *ms)
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return VR_OK;
+}
+
+int vr_last_chunk_times(vr_handle *h, float *units_ms, float *cells_ms, int32_t *nrec)
+{
+  if (!h || !units_ms || !cells_ms || !nrec) return VR_ERR_ARG;
+  if (!h->timed) { h->err = "no step launched yet"; return VR_ERR_STATE; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev_c1));
+  CK(cudaEventElapsedTime(units_ms, h->ev_u0, h->ev_u1));
+  CK(cudaEventElapsedTime(cells_ms, h->ev_u1, h->ev_c1));
+  *nrec = h->last_nrec;
+  return VR_OK;
+}
+
+int vr_diag_pow(int device, int64_t n, const double *x, const double *y, double *z)
+{
+  if (!x || !y || !z || n < 1) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  double *d = nullptr;
+  if (cudaMalloc((void **)&d, 3 * n * sizeof(double)) != cudaSuccess) return VR_ERR_CUDA;
+  cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n, y, n * sizeof(double), cudaMemcpyHostToDevice);
+  k_diag_pow<<<(unsigned)((n + 255) / 256), 256>>>(n, d, d + n, d + 2 * n);
+  cudaError_t e = cudaMemcpy(z, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
 }
 
 int vr_fallback_counts(vr_handle *h, int64_t counts[2])

@@ -22,7 +22,7 @@ LIBPATH = os.environ.get("VICRES_LIB", os.path.join(HERE, "libvicres.so"))
 EXPORTS = ["vr_create", "vr_destroy", "vr_last_error", "vr_default_options", "vr_set_veglib",
            "vr_set_cells", "vr_set_forcing_map", "vr_init_state", "vr_step_block",
            "vr_step_block_device", "vr_synchronize", "vr_state_size", "vr_get_state", "vr_set_state",
-           "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_fallback_counts"]
+           "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_last_chunk_times", "vr_diag_pow", "vr_fallback_counts"]
 
 _lib = None
 
@@ -67,9 +67,22 @@ def load_library(path=LIBPATH):
     L.vr_num_launches.argtypes = [vp]
     L.vr_num_launches.restype = C.c_int64
     L.vr_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.vr_last_chunk_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    L.vr_diag_pow.argtypes = [C.c_int, C.c_int64, vp, vp, vp]
     L.vr_fallback_counts.argtypes = [vp, vp]
     _lib = L
     return L
+
+
+def diag_pow(x, y, device=0):
+    """the device power function on host arrays (diagnostic)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    z = np.empty_like(x)
+    rc = load_library().vr_diag_pow(device, x.size, x.ctypes.data, y.ctypes.data, z.ctypes.data)
+    if rc != 0:
+        raise VicResError(rc, "vr_diag_pow")
+    return z
 
 
 class VicRes:
@@ -150,6 +163,12 @@ class VicRes:
         ms = C.c_float()
         self._check(self.L.vr_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def last_chunk_times(self):
+        """(k_units ms, k_cells ms, records) of the last chunk launched"""
+        a, b, n = C.c_float(), C.c_float(), C.c_int32()
+        self._check(self.L.vr_last_chunk_times(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return float(a.value), float(b.value), int(n.value)
 
     def fallback_counts(self):
         a = np.zeros(2, dtype=np.int64)
