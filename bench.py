@@ -11,8 +11,10 @@ records) of every cell, so the default K=10 timed steps are the 10 years the con
   e2e     the same through the C-ABI host call vr_step_block(): pinned host forcing in, host outputs
           out, H2D + D2H copies inside the timed region
   roofline.achieved = 280 algorithmic bytes per cell-timestep (9 forcing + 26 output fp64 words,
-          SURVEY.md 8d) x cell-timesteps per launch / mean k_step duration (CUDA events on the
-          launching stream)
+          SURVEY.md 8d) x cell-timesteps per launch / mean duration of the dominant kernel k_units
+          (CUDA events recorded by the library around every launch on the launching stream)
+  fp64    the same launches against the FP64 pipe: FP64 thread-instructions per cell-timestep (from
+          the committed ncu capture, profiles/k_step_traffic.json) x rate / DFMA peak measured live
   cpu_baseline  the compiled reference (vic_ref_driver, step loop only) on a bounded sample on all
           host cores (kind "reference"), else the oracle port on threads (kind "port")
 Multi-GPU: cells shard across ranks (no data-path collective) -> weak scaling.
@@ -246,6 +248,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = m.num_launches
+    m.kernel_times()                     # reset the library's per-launch event sums
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     torch.cuda.synchronize(dev)
     ev[0].record(stream)
@@ -258,7 +261,9 @@ def run_ours(args):
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
     total_ms = ev[0].elapsed_time(ev[K])
     launches = m.num_launches - l0
-    kernel_ms = sum(step_ms) / K       # one k_step launch per step, events bracket it on its own stream
+    units_ms, cells_ms, pairs, krecs = m.kernel_times()      # every k_units / k_cells launch of the timed region
+    kernel_ms = units_ms / max(pairs, 1)                     # mean k_units launch
+    recs_per_launch = krecs / max(pairs, 1)
     finite = bool(torch.isfinite(out_dev).all().item())
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -297,12 +302,19 @@ def run_ours(args):
             peak, which = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = B_ALG * C * R / (kernel_ms * 1e-3) / 1e9
+        achieved = B_ALG * C * recs_per_launch / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k_step_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_cell_step", 0) * C * R or None
+            traffic = tj.get("dram_bytes_per_cell_step", 0) * C * recs_per_launch or None
+            fp64_per = tj.get("fp64_thread_inst_per_cell_step")
+        else:
+            fp64_per = None
+        try:
+            dfma_peak = model.diag_fp64_peak(local)
+        except Exception:
+            dfma_peak = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -320,10 +332,18 @@ def run_ours(args):
                     "kernel_ms_in_last_step": e2e_kernel_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel": "k_step", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "peak_source": which, "kernel": "k_units", "kernel_ms": kernel_ms,
+                         "launches_timed": pairs, "records_per_launch": recs_per_launch,
+                         "kernel_share_of_step": units_ms / max(sum(step_ms), 1e-9),
+                         "k_cells_share_of_step": cells_ms / max(sum(step_ms), 1e-9),
                          "algorithmic_bytes_per_cell_step": B_ALG,
-                         "note": "the step is FP64-instruction-bound (about 2e4 fp64 instructions per tile-step), "
-                                 "not HBM-bound; see DESIGN.md section 6"},
+                         "note": "the step is FP64 / dependent-issue bound, not HBM-bound (SURVEY.md 8d): see the "
+                                 "fp64 object and DESIGN.md section 6"},
+            "fp64": None if not (fp64_per and dfma_peak) else {
+                "fp64_thread_inst_per_cell_step": fp64_per,
+                "achieved_inst_per_s": fp64_per * C * recs_per_launch / (kernel_ms * 1e-3),
+                "peak_dfma_per_s": dfma_peak, "peak_source": "measured live (vr_diag_fp64_peak: independent DFMA chains, all SMs)",
+                "frac": fp64_per * C * recs_per_launch / (kernel_ms * 1e-3) / dfma_peak},
         }
         if args.cpu_baseline:
             try:

@@ -182,8 +182,13 @@ int  vr_set_state(vr_handle *h, const void *blob_host);
 int64_t vr_num_units(const vr_handle *h);      /* active tile x band pairs */
 int64_t vr_num_launches(const vr_handle *h);   /* kernels launched by this handle so far */
 int  vr_last_kernel_ms(vr_handle *h, float *ms); /* CUDA-event time of all kernels of the last block of records */
-/* CUDA-event times of the last chunk's two kernels (k_units: the step; k_cells: put_data) and its records */
-int  vr_last_chunk_times(vr_handle *h, float *units_ms, float *cells_ms, int32_t *nrec);
+/* CUDA-event times, summed over every kernel pair launched since the previous call of this function (at most
+ * 8192 pairs are kept): k_units = the step of all units, k_cells = put_data of all cells; launch_pairs and the
+ * records they covered.  Synchronises with the launches; resets the sums. */
+int  vr_kernel_times(vr_handle *h, double *units_ms, double *cells_ms, int64_t *launch_pairs, int64_t *records);
+/* diagnostic: measured FP64 fused-multiply-add thread-instructions per second of the device (independent
+ * chains on every SM), the denominator of bench.py's FP64 roofline */
+int  vr_diag_fp64_peak(int device, double *dfma_per_s);
 /* diagnostic: z[i] = the device's power function (vic_physics.cuh m_pow) of x[i], y[i]; host pointers */
 int  vr_diag_pow(int device, int64_t n, const double *x, const double *y, double *z);
 /* TFALLBACK counters summed over all units, as put_data.c:658-664 prints them:

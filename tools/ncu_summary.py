@@ -21,8 +21,10 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__share
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "sass__inst_executed_local_loads", "sass__inst_executed_local_stores", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
-        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"]
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed", "smsp__cycles_elapsed.avg",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]
 
 
 def ncu_csv(rep, page):
@@ -55,8 +57,14 @@ def main():
     print("\nDRAM traffic: %.3f GB = **%.0f B per cell-timestep** (algorithmic 280 B)\n" % (dram / 1e9, per))
     if "--traffic-json" in sys.argv:
         path = sys.argv[sys.argv.index("--traffic-json") + 1]
-        json.dump({"dram_bytes_per_cell_step": per, "source": os.path.basename(rep), "cells": cells, "records": recs,
-                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch / (cells x records)"},
+        def cnt(k):
+            return float(m[k][0].replace(",", "")) if k in m else 0.0
+        # thread-level FP64 arithmetic instructions of the launch: (sum over SMSPs per elapsed cycle) x cycles
+        fp64 = sum(cnt("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % o)
+                   for o in ("dfma", "dmul", "dadd")) * cnt("smsp__cycles_elapsed.avg")
+        json.dump({"dram_bytes_per_cell_step": per, "fp64_thread_inst_per_cell_step": fp64 / (cells * recs),
+                   "source": os.path.basename(rep), "cells": cells, "records": recs,
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum, and DFMA+DMUL+DADD thread instructions, of one k_units launch / (cells x records)"},
                   open(path, "w"), indent=1)
     if "--no-functions" in sys.argv:     # the symbol table of the current libvicres.so does not match an old capture
         return

@@ -219,6 +219,19 @@ __global__ void k_diag_pow(int64_t n, const double *x, const double *y, double *
   if (i < n) z[i] = m_pow(x[i], y[i]);
 }
 
+// diagnostic: FP64 FMA issue peak of the device -- 8 independent DFMA chains per thread, all SMs
+__global__ void __launch_bounds__(256) k_diag_dfma(int iters, double seed, double *sink)
+{
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678) sink[0] = r;
+}
+
 template <class T>
 struct DBuf {
   T *p = nullptr;
@@ -260,8 +273,9 @@ struct vr_handle {
   DBuf<int64_t> d_cell_uptr, d_fcol, d_pos_of;
   DBuf<int32_t> d_u_cell, d_u_pos, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
   cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_u0 = nullptr, ev_u1 = nullptr, ev_c1 = nullptr;   // around the last k_units and k_cells launches
-  int last_nrec = 0;
+  struct EvTriple { cudaEvent_t u0, u1, c1; int nrec; };
+  std::vector<EvTriple> evs;         // around every k_units / k_cells launch since the last vr_kernel_times()
+  size_t evs_used = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int cta = VR_CTA;                  // threads per k_units block, chosen per grid so that the blocks fill whole waves
   int64_t ncta = 0;
@@ -334,9 +348,7 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
   bool ok = (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) == cudaSuccess &&
-            (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess &&
-            (e = cudaEventCreate(&h->ev_u0)) == cudaSuccess && (e = cudaEventCreate(&h->ev_u1)) == cudaSuccess &&
-            (e = cudaEventCreate(&h->ev_c1)) == cudaSuccess;
+            (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess;
   for (int b = 0; ok && b < 2; b++)
     ok = (e = cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming)) == cudaSuccess &&
          (e = cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming)) == cudaSuccess &&
@@ -365,9 +377,7 @@ void vr_destroy(vr_handle *h)
   h->d_pos_of.release(); h->d_u_slot.release(); h->d_u_pos.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->ev_u0) cudaEventDestroy(h->ev_u0);
-  if (h->ev_u1) cudaEventDestroy(h->ev_u1);
-  if (h->ev_c1) cudaEventDestroy(h->ev_c1);
+  for (auto &t : h->evs) { cudaEventDestroy(t.u0); cudaEventDestroy(t.u1); cudaEventDestroy(t.c1); }
   for (int b = 0; b < 2; b++) {
     if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
     if (h->ev_comp[b]) cudaEventDestroy(h->ev_comp[b]);
@@ -510,12 +520,22 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     F.rec0 = F0.rec0 + r0;
     F.month = F0.month + r0; F.doy = F0.doy + r0;
     for (int i = 0; i < VR_NFORCING; i++) F.field[i] = F0.field[i] + (size_t)r0 * h->M.FC;
-    const bool last = r0 + CH >= F0.nrec;
-    if (last) cudaEventRecord(h->ev_u0, st);
+    vr_handle::EvTriple *t = nullptr;
+    if (h->evs_used < 8192) {                      // beyond that the oldest launches simply go untimed
+      if (h->evs_used == h->evs.size()) {
+        vr_handle::EvTriple n;
+        cudaEventCreate(&n.u0); cudaEventCreate(&n.u1); cudaEventCreate(&n.c1);
+        n.nrec = 0;
+        h->evs.push_back(n);
+      }
+      t = &h->evs[h->evs_used++];
+      t->nrec = F.nrec;
+    }
+    if (t) cudaEventRecord(t->u0, st);
     if (h->M.U > 0) k_units<<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, h->d_terms.p);
-    if (last) cudaEventRecord(h->ev_u1, st);
+    if (t) cudaEventRecord(t->u1, st);
     k_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, st>>>(h->M, F, h->d_terms.p, out_dev);
-    if (last) { cudaEventRecord(h->ev_c1, st); h->last_nrec = F.nrec; }
+    if (t) cudaEventRecord(t->c1, st);
     h->launches += 2;
   }
   cudaEventRecord(h->ev1, st);
@@ -652,15 +672,44 @@ int vr_last_kernel_ms(vr_handle *h, float *ms)
   return VR_OK;
 }
 
-int vr_last_chunk_times(vr_handle *h, float *units_ms, float *cells_ms, int32_t *nrec)
+int vr_kernel_times(vr_handle *h, double *units_ms, double *cells_ms, int64_t *launch_pairs, int64_t *records)
 {
-  if (!h || !units_ms || !cells_ms || !nrec) return VR_ERR_ARG;
-  if (!h->timed) { h->err = "no step launched yet"; return VR_ERR_STATE; }
+  if (!h || !units_ms || !cells_ms || !launch_pairs || !records) return VR_ERR_ARG;
   CK(cudaSetDevice(h->device));
-  CK(cudaEventSynchronize(h->ev_c1));
-  CK(cudaEventElapsedTime(units_ms, h->ev_u0, h->ev_u1));
-  CK(cudaEventElapsedTime(cells_ms, h->ev_u1, h->ev_c1));
-  *nrec = h->last_nrec;
+  *units_ms = 0; *cells_ms = 0; *launch_pairs = 0; *records = 0;
+  for (size_t i = 0; i < h->evs_used; i++) {
+    vr_handle::EvTriple &t = h->evs[i];
+    float a = 0, b = 0;
+    CK(cudaEventSynchronize(t.c1));
+    CK(cudaEventElapsedTime(&a, t.u0, t.u1));
+    CK(cudaEventElapsedTime(&b, t.u1, t.c1));
+    *units_ms += a; *cells_ms += b; *launch_pairs += 1; *records += t.nrec;
+  }
+  h->evs_used = 0;
+  return VR_OK;
+}
+
+int vr_diag_fp64_peak(int device, double *dfma_per_s)
+{
+  if (!dfma_per_s) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  double *sink = nullptr;
+  if (cudaMalloc((void **)&sink, 8) != cudaSuccess) return VR_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = sms * 8, iters = 200000;
+  k_diag_dfma<<<blocks, 256>>>(1000, 1.0, sink);               // warm-up
+  cudaEventRecord(e0);
+  k_diag_dfma<<<blocks, 256>>>(iters, 1.0, sink);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  if (e != cudaSuccess || ms <= 0) return VR_ERR_CUDA;
+  *dfma_per_s = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
   return VR_OK;
 }
 

@@ -22,7 +22,7 @@ LIBPATH = os.environ.get("VICRES_LIB", os.path.join(HERE, "libvicres.so"))
 EXPORTS = ["vr_create", "vr_destroy", "vr_last_error", "vr_default_options", "vr_set_veglib",
            "vr_set_cells", "vr_set_forcing_map", "vr_init_state", "vr_step_block",
            "vr_step_block_device", "vr_synchronize", "vr_state_size", "vr_get_state", "vr_set_state",
-           "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_last_chunk_times", "vr_diag_pow", "vr_fallback_counts"]
+           "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts"]
 
 _lib = None
 
@@ -67,11 +67,21 @@ def load_library(path=LIBPATH):
     L.vr_num_launches.argtypes = [vp]
     L.vr_num_launches.restype = C.c_int64
     L.vr_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
-    L.vr_last_chunk_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    L.vr_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.vr_diag_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.vr_diag_pow.argtypes = [C.c_int, C.c_int64, vp, vp, vp]
     L.vr_fallback_counts.argtypes = [vp, vp]
     _lib = L
     return L
+
+
+def diag_fp64_peak(device=0):
+    """measured DFMA thread-instructions per second of the device"""
+    v = C.c_double()
+    rc = load_library().vr_diag_fp64_peak(device, C.byref(v))
+    if rc != 0:
+        raise VicResError(rc, "vr_diag_fp64_peak")
+    return float(v.value)
 
 
 def diag_pow(x, y, device=0):
@@ -164,11 +174,11 @@ class VicRes:
         self._check(self.L.vr_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
 
-    def last_chunk_times(self):
-        """(k_units ms, k_cells ms, records) of the last chunk launched"""
-        a, b, n = C.c_float(), C.c_float(), C.c_int32()
-        self._check(self.L.vr_last_chunk_times(self.h, C.byref(a), C.byref(b), C.byref(n)))
-        return float(a.value), float(b.value), int(n.value)
+    def kernel_times(self):
+        """(k_units ms, k_cells ms, launch pairs, records) summed since the previous call; synchronises"""
+        a, b, n, r = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+        self._check(self.L.vr_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(r)))
+        return float(a.value), float(b.value), int(n.value), int(r.value)
 
     def fallback_counts(self):
         a = np.zeros(2, dtype=np.int64)
