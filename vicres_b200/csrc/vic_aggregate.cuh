@@ -188,6 +188,44 @@ VR_HD void cell_accumulate_inplace(double *buf, int stride, const TermMap &tmap,
   }
 }
 
+// The same ordered sums, from a read-only term buffer whose columns u0 .. u0+nu-1 are the cell's units in
+// reference order, into column `dcol` of a separate sum buffer (rows of `dstride` doubles).
+VR_HD void cell_accumulate_to(const double *src, size_t sstride, int64_t u0, int nu, const TermMap &tmap, int NL,
+                              double *dst, size_t dstride, int64_t dcol)
+{
+#pragma unroll 1
+  for (int k = 0; k < NTERM; k++) {
+    const int r = tmap.row[k];
+    if (r < 0 || (k >= TE_EB0 && k <= TE_TV2)) continue;
+    const double *p = src + (size_t)r * sstride + u0;
+    double a = 0. + p[0];
+    for (int j = 1; j < nu; j++) a += p[j];
+    dst[(size_t)r * dstride + dcol] = a;
+  }
+  if (tmap.row[TE_EB0] >= 0) {
+    double eb = 0;
+    for (int j = 0; j < nu; j++)
+      for (int l = 0; l < NL; l++) eb += src[(size_t)tmap.row[TE_EB0 + l] * sstride + u0 + j];
+    dst[(size_t)tmap.row[TE_EB0] * dstride + dcol] = eb;
+  }
+  if (tmap.row[TE_TV0] >= 0) {
+    double tv = 0;
+    for (int j = 0; j < nu; j++)
+      for (int l = 0; l < NL; l++) tv += src[(size_t)tmap.row[TE_TV0 + l] * sstride + u0 + j];
+    dst[(size_t)tmap.row[TE_TV0] * dstride + dcol] = tv;
+  }
+}
+
+// ordered sum of one term over the cell's units (the save_data words of the PREVIOUS record are rebuilt
+// from these when the records of a chunk are aggregated in parallel)
+VR_HD double cell_term_sum(const double *src, size_t sstride, int64_t u0, int nu, int row)
+{
+  const double *p = src + (size_t)row * sstride + u0;
+  double a = 0. + p[0];
+  for (int j = 1; j < nu; j++) a += p[j];
+  return a;
+}
+
 // One output variable of a cell-record from the summed terms (put_data.c:540-632).  S(k) reads sum k.
 // water_error / deltas use the carried save_data words sv[] BEFORE cell_carry() updates them.
 template <class Sum>

@@ -35,6 +35,7 @@ struct Prepared {
   std::vector<int32_t> u_cell, u_tile, u_flags, u_aero;   // [U]; u_cell = caller's cell index; flags: bit0 bare, bit1 overstory, bits 8.. root0 mask
   std::vector<int32_t> u_pos;        // [U] sorted position of the unit's cell
   std::vector<int32_t> u_slot;       // [U] reference-order unit (index into cell_uptr ranges) -> slot
+  std::vector<int32_t> u_logical;    // [U] slot -> reference-order unit (column of the term buffer)
   std::vector<int64_t> pos_of;       // [C] caller's cell index -> sorted position
   std::vector<double> u_cv, u_af, u_Tfactor, u_Pfactor, u_rarc, u_rmin, u_RGL;   // [U]
   std::vector<float> u_root;         // [MAXL][U]
@@ -328,7 +329,8 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     return a < b;
   });
   P.u_slot.assign(U ? U : 1, 0);
-  for (int64_t k = 0; k < U; k++) P.u_slot[perm[k]] = (int32_t)k;
+  P.u_logical.assign(U ? U : 1, 0);
+  for (int64_t k = 0; k < U; k++) { P.u_slot[perm[k]] = (int32_t)k; P.u_logical[k] = (int32_t)perm[k]; }
   auto permute = [&](auto &v) {
     auto old = v;
     for (int64_t k = 0; k < U; k++) v[k] = old[perm[k]];

@@ -44,8 +44,9 @@ struct DevModel {
   double max_snow_temp, min_rain_temp;
   int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
   const double *cc;
-  const int64_t *cell_uptr, *fcol, *pos_of;
-  const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *cell_fail;
+  const int64_t *cell_uptr, *fcol;
+  const int64_t *order;             // sorted position -> caller's cell index
+  const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *u_logical, *cell_fail;
   const double *u_cv, *u_af, *u_Tfactor, *u_Pfactor, *u_rarc, *u_rmin, *u_RGL, *tm, *ae, *init_moist;
   const float *u_root;
   double *state;                    // [ST_N][U]
@@ -118,28 +119,27 @@ __global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double 
   unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
   store_state(M, u, s);
   memset(&z, 0, sizeof z);
-  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + u, (int)M.U);
+  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U);
 }
 
-__global__ void __launch_bounds__(128) k_init_cells(DevModel M, double *terms)
+__global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *terms, double *sums)
 {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= M.C) return;
-  const int64_t cs = M.pos_of[c], fu0 = M.cell_uptr[cs];
+  const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // sorted position
+  if (cs >= M.C) return;
+  const int64_t c = M.order[cs], fu0 = M.cell_uptr[cs];
   const int nu = (int)(M.cell_uptr[cs + 1] - fu0);
   double sv[SV_N] = {0, 0, 0, 0};
   if (nu > 0) {
-    auto col_of = [&](int j) { return (int)M.u_slot[fu0 + j]; };
-    cell_accumulate_inplace(terms, (int)M.U, M.tmap, nu, col_of, M.NL);
-    const int c0 = col_of(0);
-    auto S = [&](int k) { return terms[(size_t)M.tmap.row[k] * M.U + c0]; };
+    cell_accumulate_to(terms, (size_t)M.U, fu0, nu, M.tmap, M.NL, sums, (size_t)M.C, cs);
+    auto S = [&](int k) { return sums[(size_t)M.tmap.row[k] * M.C + cs]; };
     cell_carry(S, M.NL, sv);
   }
   for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
   M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
 }
 
-// full_energy() for F.nrec consecutive records of every unit; terms[rec][row][slot]
+// full_energy() for F.nrec consecutive records of every unit; terms[rec][row][unit in reference order]: the
+// stores scatter (fire and forget) so that k_cells reads each cell's units contiguously
 __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcing F, double *__restrict__ terms)
 {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcin
   const int nrec = F.nrec, NL = M.NL;
   const size_t rec_stride = (size_t)M.tmap.n * M.U;
   const bool write = active && !failed;
+  const int64_t col = M.u_logical[u];
   for (int rec = 0; rec < nrec; rec++) {
     Forc f;
     const size_t q = (size_t)rec * M.FC + fc;
@@ -168,48 +169,57 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcin
     f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
     f.mon = __ldg(F.month + rec) - 1; f.doy = __ldg(F.doy + rec);
     unit_step_terms(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
-                    cv, af, M.tmap, terms + rec * rec_stride + u, (int)M.U, write);
+                    cv, af, M.tmap, terms + rec * rec_stride + col, (int)M.U, write);
   }
   if (write) store_state(M, u, s);
 }
 
-// put_data() for the same records: one thread per cell (caller's index, so forcing reads and output
-// writes are coalesced); the unit terms are summed in place in the term buffer, in reference order
-__global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, double *__restrict__ terms, double *__restrict__ out)
+// put_data() for the same records: one thread per (cell in sorted order, record).  A cell's units are
+// contiguous columns of the term buffer, consecutive threads own consecutive cells, so the term reads are
+// coalesced; the ordered sums go to sums[rec][row][cell] and the outputs to the caller's cell index.  The
+// save_data words a record needs from its predecessor (storage deltas, closure error) are rebuilt from the
+// predecessor's terms, which makes the records of a chunk independent; record 0 uses the carried M.sv.
+__global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const double *__restrict__ terms,
+                                               double *__restrict__ sums, double *__restrict__ out)
 {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= M.C) return;
-  const int64_t cs = M.pos_of[c], fu0 = M.cell_uptr[cs];
+  const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rec = blockIdx.y;
+  if (cs >= M.C) return;
+  const int64_t c = M.order[cs], fu0 = M.cell_uptr[cs];
   const int nu = (int)(M.cell_uptr[cs + 1] - fu0);
   const int64_t fc = M.fcol ? M.fcol[c] : c;
   const bool ok = !M.cell_fail[c] && nu > 0;
   const int NL = M.NL;
-  const size_t rec_stride = (size_t)M.tmap.n * M.U;
-  double sv[SV_N];
-  for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + c];
-  auto col_of = [&](int j) { return (int)__ldg(M.u_slot + fu0 + j); };
-  const int c0 = nu > 0 ? col_of(0) : 0;
-  for (int rec = 0; rec < F.nrec; rec++) {
-    double *T = terms + rec * rec_stride;
-    const size_t orow = (size_t)(F.rec0 + rec) * M.C + c, ostride = (size_t)F.nrec_total * M.C;
-    if (ok) {
-      cell_accumulate_inplace(T, (int)M.U, M.tmap, nu, col_of, NL);
-      auto S = [&](int k) { return T[(size_t)M.tmap.row[k] * M.U + c0]; };
-      Forc f;
-      const size_t q = (size_t)rec * M.FC + fc;
-      f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.wind = __ldg(F.field[VR_F_WIND] + q);
-      f.vp = __ldg(F.field[VR_F_VP] + q); f.vpd = __ldg(F.field[VR_F_VPD] + q);
-      f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
-      f.prec = 0; f.pressure = 0; f.density = 0; f.mon = 0; f.doy = 0;
-#pragma unroll 1
-      for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = cell_output(M.out_vars[v], S, f, NL, false, sv);
-      cell_carry(S, NL, sv);
-    }
-    else
-      for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = 0.;
+  const size_t rec_stride = (size_t)M.tmap.n * M.U, sum_stride = (size_t)M.tmap.n * M.C;
+  const size_t orow = (size_t)(F.rec0 + rec) * M.C + c, ostride = (size_t)F.nrec_total * M.C;
+  if (!ok) {
+    for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = 0.;
+    return;
   }
-  if (ok)
+  double sv[SV_N];
+  if (rec == 0)
+    for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + c];
+  else {
+    const double *P = terms + (rec - 1) * rec_stride;
+    auto SP = [&](int k) { return cell_term_sum(P, (size_t)M.U, fu0, nu, M.tmap.row[k]); };
+    cell_carry(SP, NL, sv);
+  }
+  const double *T = terms + rec * rec_stride;
+  double *Sm = sums + rec * sum_stride;
+  cell_accumulate_to(T, (size_t)M.U, fu0, nu, M.tmap, NL, Sm, (size_t)M.C, cs);
+  auto S = [&](int k) { return Sm[(size_t)M.tmap.row[k] * M.C + cs]; };
+  Forc f;
+  const size_t q = (size_t)rec * M.FC + fc;
+  f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.wind = __ldg(F.field[VR_F_WIND] + q);
+  f.vp = __ldg(F.field[VR_F_VP] + q); f.vpd = __ldg(F.field[VR_F_VPD] + q);
+  f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
+  f.prec = 0; f.pressure = 0; f.density = 0; f.mon = 0; f.doy = 0;
+#pragma unroll 1
+  for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = cell_output(M.out_vars[v], S, f, NL, false, sv);
+  if (rec == F.nrec - 1) {
+    cell_carry(S, NL, sv);
     for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+  }
 }
 
 // diagnostic: the device power function on arbitrary arguments (tests/test_gpu_parity.py checks its error bound)
@@ -268,10 +278,10 @@ struct vr_handle {
   Prepared P;
   DevModel M;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
-      d_forc, d_out, d_tair0, d_terms;
+      d_forc, d_out, d_tair0, d_terms, d_sums;
   DBuf<float> d_u_root;
-  DBuf<int64_t> d_cell_uptr, d_fcol, d_pos_of;
-  DBuf<int32_t> d_u_cell, d_u_pos, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
+  DBuf<int64_t> d_cell_uptr, d_fcol, d_order;
+  DBuf<int32_t> d_u_logical, d_u_cell, d_u_pos, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
   cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
   struct EvTriple { cudaEvent_t u0, u1, c1; int nrec; };
   std::vector<EvTriple> evs;         // around every k_units / k_cells launch since the last vr_kernel_times()
@@ -371,10 +381,10 @@ void vr_destroy(vr_handle *h)
   h->d_cc.release(); h->d_u_cv.release(); h->d_u_af.release(); h->d_u_Tf.release(); h->d_u_Pf.release();
   h->d_u_rarc.release(); h->d_u_rmin.release(); h->d_u_RGL.release(); h->d_tm.release(); h->d_ae.release();
   h->d_init_moist.release(); h->d_state.release(); h->d_sv.release(); h->d_forc.release(); h->d_out.release();
-  h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_fcol.release(); h->d_terms.release();
+  h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_fcol.release(); h->d_terms.release(); h->d_sums.release(); h->d_u_logical.release();
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
-  h->d_pos_of.release(); h->d_u_slot.release(); h->d_u_pos.release();
+  h->d_order.release(); h->d_u_slot.release(); h->d_u_pos.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto &t : h->evs) { cudaEventDestroy(t.u0); cudaEventDestroy(t.u1); cudaEventDestroy(t.c1); }
@@ -447,7 +457,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   CK(h->d_u_rarc.upload(P.u_rarc)); CK(h->d_u_rmin.upload(P.u_rmin)); CK(h->d_u_RGL.upload(P.u_RGL));
   CK(h->d_u_root.upload(P.u_root)); CK(h->d_tm.upload(P.tm)); CK(h->d_ae.upload(P.ae));
   CK(h->d_init_moist.upload(im));
-  CK(h->d_pos_of.upload(P.pos_of)); CK(h->d_u_slot.upload(P.u_slot));
+  CK(h->d_order.upload(P.order)); CK(h->d_u_slot.upload(P.u_slot)); CK(h->d_u_logical.upload(P.u_logical));
   CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
   CK(h->d_sv.reserve((size_t)SV_N * C));
   CK(h->d_cell_status.reserve(C));
@@ -464,7 +474,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.u_Pfactor = h->d_u_Pf.p; M.u_rarc = h->d_u_rarc.p; M.u_rmin = h->d_u_rmin.p; M.u_RGL = h->d_u_RGL.p;
   M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
-  M.pos_of = h->d_pos_of.p; M.u_slot = h->d_u_slot.p;
+  M.order = h->d_order.p; M.u_slot = h->d_u_slot.p; M.u_logical = h->d_u_logical.p;
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
   h->have_cells = true;
@@ -497,8 +507,9 @@ int vr_init_state(vr_handle *h, const double *tair0)
   CK(cudaMemcpyAsync(h->d_tair0.p, tair0, h->M.FC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const size_t U1 = (size_t)(h->M.U ? h->M.U : 1);
   CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * h->chunk));
+  CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * h->chunk));
   if (h->M.U > 0) k_init_units<<<(unsigned)h->ncta, h->cta, 0, h->stream>>>(h->M, h->d_tair0.p, h->d_terms.p);
-  k_init_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p);
+  k_init_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p, h->d_sums.p);
   h->launches += 2;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -513,6 +524,7 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
   const size_t U1 = (size_t)(h->M.U ? h->M.U : 1);
   const int CH = h->chunk;
   CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * CH));
+  CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * CH));
   cudaEventRecord(h->ev0, st);
   for (int r0 = 0; r0 < F0.nrec; r0 += CH) {
     DevForcing F = F0;
@@ -534,7 +546,7 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     if (t) cudaEventRecord(t->u0, st);
     if (h->M.U > 0) k_units<<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, h->d_terms.p);
     if (t) cudaEventRecord(t->u1, st);
-    k_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, st>>>(h->M, F, h->d_terms.p, out_dev);
+    k_cells<<<dim3((unsigned)((h->M.C + 127) / 128), (unsigned)F.nrec), 128, 0, st>>>(h->M, F, h->d_terms.p, h->d_sums.p, out_dev);
     if (t) cudaEventRecord(t->c1, st);
     h->launches += 2;
   }
