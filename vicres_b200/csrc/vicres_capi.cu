@@ -289,7 +289,8 @@ struct vr_handle {
   struct EvTriple { cudaEvent_t u0, u1, c0, c1; int nrec; };
   std::vector<EvTriple> evs;         // around every k_units / k_cells launch since the last vr_kernel_times()
   size_t evs_used = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  static constexpr int NBUF = 4;     // copy buffers per direction of the host pipeline
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[NBUF] = {}, ev_comp[NBUF] = {}, ev_out[NBUF] = {};
   int cta = VR_CTA;                  // threads per k_units block, chosen per grid so that the blocks fill whole waves
   int64_t ncta = 0;
   int chunk = 16;                    // records per k_units/k_cells launch pair (and per pipelined copy of vr_step_block)
@@ -364,11 +365,12 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
             (e = cudaStreamCreateWithFlags(&h->s_cells, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) == cudaSuccess &&
             (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess;
-  for (int b = 0; ok && b < 2; b++)
+  for (int b = 0; ok && b < vr_handle::NBUF; b++)
     ok = (e = cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming)) == cudaSuccess &&
          (e = cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming)) == cudaSuccess &&
-         (e = cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming)) == cudaSuccess &&
-         (e = cudaEventCreateWithFlags(&h->ev_units[b], cudaEventDisableTiming)) == cudaSuccess &&
+         (e = cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming)) == cudaSuccess;
+  for (int b = 0; ok && b < 2; b++)
+    ok = (e = cudaEventCreateWithFlags(&h->ev_units[b], cudaEventDisableTiming)) == cudaSuccess &&
          (e = cudaEventCreateWithFlags(&h->ev_cells[b], cudaEventDisableTiming)) == cudaSuccess;
   if (!ok) {
     g_create_error = cudaGetErrorString(e);
@@ -401,7 +403,7 @@ void vr_destroy(vr_handle *h)
     if (h->ev_units[b]) cudaEventDestroy(h->ev_units[b]);
     if (h->ev_cells[b]) cudaEventDestroy(h->ev_cells[b]);
   }
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < vr_handle::NBUF; b++) {
     if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
     if (h->ev_comp[b]) cudaEventDestroy(h->ev_comp[b]);
     if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
@@ -604,8 +606,9 @@ int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, voi
 }
 
 // Host-buffer entry point.  The block of records is cut into chunks of h->chunk records that flow
-// through three streams -- H2D of chunk k+1, k_units/k_cells of chunk k and D2H of chunk k-1 overlap (PCIe is
-// full duplex) -- with two device buffers per direction.  Forcing [field][rec][col] and outputs
+// through four streams (copies in, k_units, k_cells, copies out): H2D of later chunks, the kernels of chunk k
+// and D2H of earlier chunks overlap (PCIe is full duplex), with NBUF device buffers per direction.  Forcing
+// [field][rec][col] and outputs
 // [var][rec][cell] are record-major, so a chunk is one contiguous copy per field / variable.
 int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *cell_status_host)
 {
@@ -617,16 +620,17 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
   const int nrec = f->nrec, n_out = h->opt.n_out, CH = h->chunk < nrec ? h->chunk : nrec;
   const size_t FC = (size_t)h->M.FC, C = (size_t)h->M.C;
   const size_t in_chunk = (size_t)CH * FC * VR_NFORCING, out_chunk = (size_t)CH * C * n_out;
-  CK(h->d_forc.reserve(2 * in_chunk));
-  CK(h->d_out.reserve(2 * out_chunk));
+  const int NB = vr_handle::NBUF;
+  CK(h->d_forc.reserve(NB * in_chunk));
+  CK(h->d_out.reserve(NB * out_chunk));
   CK(h->d_month.reserve(nrec)); CK(h->d_doy.reserve(nrec));
   CK(cudaMemcpyAsync(h->d_month.p, f->month, nrec * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
   CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, nrec * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
   int k = 0;
   for (int r0 = 0; r0 < nrec; r0 += CH, k++) {
-    const int nr = (nrec - r0 < CH) ? nrec - r0 : CH, b = k & 1;
+    const int nr = (nrec - r0 < CH) ? nrec - r0 : CH, b = k % NB;
     double *din = h->d_forc.p + (size_t)b * in_chunk, *dout = h->d_out.p + (size_t)b * out_chunk;
-    if (k >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));       // kernel of chunk k-2 has consumed din
+    if (k >= NB) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));      // the kernels of chunk k-NB have consumed din
     DevForcing F;
     F.nrec = nr; F.rec0 = 0; F.nrec_total = nr; F.month = h->d_month.p + r0; F.doy = h->d_doy.p + r0;
     for (int i = 0; i < VR_NFORCING; i++) {
@@ -636,13 +640,12 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     }
     CK(cudaEventRecord(h->ev_in[b], h->s_in));
     CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
-    if (k >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));      // D2H of chunk k-2 has drained dout
-    // joined: here the outputs of chunk k must leave as early as possible (D2H of chunk k overlaps the step of
-    // chunk k+1); letting k_cells(k) trail behind k_units(k+1) would stall the two-buffer copy pipeline
-    // (measured: 1.42e8 unjoined vs 1.81e8 joined cell-steps/s end to end)
-    int rc = launch_step(h, F, dout, h->stream, true);
+    if (k >= NB) CK(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));     // D2H of chunk k-NB has drained dout
+    // not joined: k_cells(k) trails behind k_units(k+1) on its own stream; four copy buffers per direction
+    // keep H2D / kernels / D2H flowing although the outputs of a chunk leave one kernel later
+    int rc = launch_step(h, F, dout, h->stream, false);
     if (rc != VR_OK) return rc;
-    CK(cudaEventRecord(h->ev_comp[b], h->stream));                        // forcing consumed and outputs written
+    CK(cudaEventRecord(h->ev_comp[b], h->s_cells));                       // forcing consumed and outputs written
     CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
     for (int v = 0; v < n_out; v++)
       CK(cudaMemcpyAsync(out_host + ((size_t)v * nrec + r0) * C, dout + (size_t)v * nr * C, (size_t)nr * C * sizeof(double),
@@ -650,7 +653,7 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     CK(cudaEventRecord(h->ev_out[b], h->s_out));
   }
   if (cell_status_host) {
-    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[(k - 1) & 1], 0));
+    CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[(k - 1) % NB], 0));
     CK(cudaMemcpyAsync(cell_status_host, h->d_cell_status.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out));
   }
   CK(cudaStreamSynchronize(h->s_in));
