@@ -324,6 +324,12 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
   std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) {
     const int ka = kind_of(a), kb = kind_of(b);
     if (ka != kb) return ka < kb;
+#ifndef VR_SORT_NO_HEMISPHERE
+    // the two hemispheres have opposite snow seasons: keep them in different warps
+    const bool na = cells.lat[P.u_cell[a]] >= 0, nb = cells.lat[P.u_cell[b]] >= 0;
+    if (na != nb) return na;
+#endif
+    // (a latitude-dependent seasonal-amplitude term in the key was tried and is slower: profiles/r1_tuning.md)
     const double ta = cells.avg_temp[P.u_cell[a]] + P.u_Tfactor[a], tb = cells.avg_temp[P.u_cell[b]] + P.u_Tfactor[b];
     if (ta != tb) return ta < tb;
     return a < b;
