@@ -48,6 +48,11 @@ int  vr_write_results(const char *result_dir, const char *prefix, int32_t grid_d
                       const int32_t *day, const int32_t *hour, int32_t n_cols, const int32_t *cols,
                       const double *out);
 
+/* out[i] = the value in[i] has after a round trip through a "%.<decimals>f" text column (the reference's flux
+ * files are the hand-off between vicNl and rout): lets the step's outputs go to the routing pass in memory and
+ * still equal what rout would have read. */
+int  vr_round_decimals(int64_t n, const double *in, double *out, int32_t decimals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,13 @@ def test_files_to_cuda_to_writer(tmp_path):
         nbad += int((a != b).sum())
         ntot += a.size
     assert nbad <= 0.01 * ntot
+
+
+def test_round_decimals_equals_text_round_trip():
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.normal(0, 50, 200000), rng.uniform(-1, 1, 100000) * 1e-3,
+                        np.round(rng.normal(0, 5, 100000), 4) + 0.00005,          # decimal ties and near-ties
+                        np.array([0.0, -0.0, 0.00005, 0.00015, 0.00025, 1e-9, 123456.78905, -2.5e-5])])
+    want = np.array([float("%.4f" % v) for v in x])
+    got = files.round_decimals(x, 4)
+    assert np.array_equal(got, want)

@@ -422,4 +422,26 @@ int vr_write_results(const char *result_dir, const char *prefix, int32_t grid_de
   return VR_OK;
 }
 
+// What a value becomes on its way through a "%.<d>f" text file and back (printf rounds the exact binary value
+// to d decimals, ties to even; strtod returns the double nearest to that decimal): the exact product x*10^d
+// is rebuilt as t + r with an fma, so borderline cases round like printf does, without formatting a string.
+int vr_round_decimals(int64_t n, const double *in, double *out, int32_t decimals)
+{
+  if (!in || !out || n < 0 || decimals < 0 || decimals > 9) { g_err = "bad argument"; return VR_ERR_ARG; }
+  double p = 1.0;
+  for (int i = 0; i < decimals; i++) p *= 10.0;
+  for (int64_t i = 0; i < n; i++) {
+    const double x = in[i];
+    if (!(fabs(x) < 1e11)) { out[i] = x; continue; }          // beyond 2^53 / 10^d the product is no longer exact enough
+    const double t = x * p, r = fma(x, p, -t);                 // x*p == t + r exactly
+    double k = nearbyint(t);                                  // ties to even on the ROUNDED product
+    const double d0 = t - k;                                   // exact, a multiple of ulp(t) in [-0.5, 0.5]
+    if (d0 == 0.5) { if (r > 0.0) k += 1.0; }                  // exact product above the tie -> up
+    else if (d0 == -0.5) { if (r < 0.0) k -= 1.0; }            // below the tie -> down
+    // |d0| < 0.5: |r| <= ulp(t)/2 cannot carry the exact product across a tie
+    out[i] = k / p;
+  }
+  return VR_OK;
+}
+
 }  // extern "C"

@@ -18,7 +18,7 @@ class ParamFilesC(C.Structure):
 
 
 FILES_EXPORTS = ["vr_params_read", "vr_params_free", "vr_params_last_error", "vr_params_cells",
-                 "vr_params_veglib", "vr_params_gridcel", "vr_params_lat", "vr_params_lng", "vr_write_results"]
+                 "vr_params_veglib", "vr_params_gridcel", "vr_params_lat", "vr_params_lng", "vr_write_results", "vr_round_decimals"]
 
 
 def _bind(lib):
@@ -39,6 +39,8 @@ def _bind(lib):
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_double)]
     lib.vr_write_results.restype = C.c_int
+    lib.vr_round_decimals.argtypes = [C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]
+    lib.vr_round_decimals.restype = C.c_int
     return lib
 
 
@@ -105,3 +107,15 @@ def write_results(result_dir, prefix, lat, lng, year, month, day, out, cols=None
                              out.ctypes.data_as(C.POINTER(C.c_double)))
     if rc != 0:
         raise VicResError(rc, "vr_write_results: %s" % so.vr_params_last_error().decode())
+
+
+def round_decimals(a, decimals=4, lib=None):
+    """values as they come back from a "%.<decimals>f" text column (printf rounding + strtod), without text"""
+    so = _bind(lib or load_library())
+    a = np.ascontiguousarray(a, np.float64)
+    out = np.empty_like(a)
+    pd = C.POINTER(C.c_double)
+    rc = so.vr_round_decimals(a.size, a.ctypes.data_as(pd), out.ctypes.data_as(pd), decimals)
+    if rc != 0:
+        raise VicResError(rc, "vr_round_decimals")
+    return out

@@ -56,7 +56,7 @@ def _fmt(x, nd=6):
 def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261019,
               startyear=1981, lat_range=(-40.0, 60.0), cold=0.0, overstory_frac=0.3,
               max_veg=3, extra_global="", result_dir=None, skip_output=False, snow_step=None,
-              wind_zero_frac=0.0):
+              wind_zero_frac=0.0, coords=None):
     """Write a complete reference-format case under `outdir`; return the global file path.
 
     dt == 24: daily PREC/TMAX/TMIN/WIND forcing (as the bundled basin); dt < 24: sub-daily
@@ -82,6 +82,8 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         cellid = c + 1
         lat = round(float(rng.uniform(*lat_range)), 4)
         lng = round(float(rng.uniform(-120.0, 120.0)), 4)
+        if coords is not None:                   # cells placed on given points (e.g. routing grid cell centres)
+            lat, lng = round(float(coords[c][0]), 4), round(float(coords[c][1]), 4)
         elev = float(np.round(rng.uniform(0.0, 2000.0), 1))
         b_inf = rng.uniform(0.001, 0.4)
         Ds = rng.uniform(0.001, 0.9)
