@@ -149,6 +149,12 @@ int  vr_route_set_uh_r(vr_route *h, int32_t node, const float *uh_r);
 int  vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *natural, const vr_reservoir *res,
                          const vr_res_options *opt, float *flow, const vr_res_series *out);
 
+/* ---- calibration objectives (toolbox/calibration/basin_calibration_eNSGAII.py:86-175) ---------------------
+ * out[set][4] = NSE, TRMSE (Box-Cox 0.3), MSDE, ROCE of sim[set][ndays] (station discharge of every parameter
+ * set, e.g. the `flow` of vr_route_reservoirs) against obs[ndays]; handle_negatives = the toolbox's abs(). */
+int  vr_objectives(int device, int32_t nsets, int32_t ndays, const float *sim, const double *obs,
+                   int32_t handle_negatives, double *out);
+
 #ifdef __cplusplus
 }
 #endif

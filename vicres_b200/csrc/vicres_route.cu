@@ -517,6 +517,54 @@ __global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
   }
 }
 
+// ---- calibration objectives (toolbox/calibration/basin_calibration_eNSGAII.py:86-175) ----------------
+// One block per parameter set; fp64 tree reductions over the days.  out[set][4] = NSE, TRMSE, MSDE, ROCE.
+__device__ double block_sum(double v, double *sh)
+{
+  const int t = threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (t < s) sh[t] += sh[t + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_objectives(int ndays, const float *__restrict__ sim, const double *__restrict__ obs,
+                                                    int handle_neg, double *__restrict__ out)
+{
+  __shared__ double sh[256];
+  const float *x = sim + (size_t)blockIdx.x * ndays;
+  double so = 0;
+  for (int i = threadIdx.x; i < ndays; i += blockDim.x) so += obs[i];
+  const double sum_obs = block_sum(so, sh), obs_mean = sum_obs / ndays;
+  double num = 0, den = 0, tr = 0, ms = 0, ss = 0;
+  for (int i = threadIdx.x; i < ndays; i += blockDim.x) {
+    const double o = obs[i], v = handle_neg ? fabs((double)x[i]) : (double)x[i], oa = handle_neg ? fabs(o) : o;
+    num += (v - o) * (v - o);
+    den += (o - obs_mean) * (o - obs_mean);
+    const double zs = (pow(v + 1, 0.3) - 1) / 0.3, zo = (pow(oa + 1, 0.3) - 1) / 0.3;
+    tr += (zs - zo) * (zs - zo);
+    ss += v;
+    if (i + 1 < ndays) {
+      const double v1 = handle_neg ? fabs((double)x[i + 1]) : (double)x[i + 1];
+      const double dd = (obs[i + 1] - o) - (v1 - v);
+      ms += dd * dd;
+    }
+  }
+  num = block_sum(num, sh); den = block_sum(den, sh); tr = block_sum(tr, sh); ms = block_sum(ms, sh); ss = block_sum(ss, sh);
+  if (threadIdx.x == 0) {
+    double *r = out + (size_t)blockIdx.x * 4;
+    r[0] = 1 - num / den;
+    r[1] = sqrt(tr / ndays);
+    r[2] = (ndays > 1) ? ms / (ndays - 1) : nan("");
+    r[3] = (sum_obs == 0) ? ((ss != 0) ? INFINITY : nan("")) : fabs(ss - sum_obs) / sum_obs;
+  }
+}
+
 template <class T>
 struct DB {
   T *p = nullptr; size_t n = 0;
@@ -816,6 +864,26 @@ int vr_route_last_kernel_ms(vr_route *h, float *ms)
   RK(cudaSetDevice(h->device));
   RK(cudaEventSynchronize(h->ev1));
   RK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return VR_OK;
+}
+
+int vr_objectives(int device, int32_t nsets, int32_t ndays, const float *sim, const double *obs, int32_t handle_negatives,
+                  double *out)
+{
+  if (!sim || !obs || !out || nsets < 1 || ndays < 1) { g_route_error = "null or empty argument"; return VR_ERR_ARG; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_route_error = "no such CUDA device (this library has no CPU path)"; return VR_ERR_CUDA; }
+  float *d_sim = nullptr; double *d_obs = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_sim, (size_t)nsets * ndays * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_obs, (size_t)ndays * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (size_t)nsets * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d_sim, sim, (size_t)nsets * ndays * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_obs, obs, (size_t)ndays * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_objectives<<<nsets, 256>>>(ndays, d_sim, d_obs, handle_negatives, d_out);
+    e = cudaMemcpy(out, d_out, (size_t)nsets * 4 * sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_sim); cudaFree(d_obs); cudaFree(d_out);
+  if (e != cudaSuccess) { g_route_error = cudaGetErrorString(e); return VR_ERR_CUDA; }
   return VR_OK;
 }
 

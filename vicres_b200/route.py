@@ -12,7 +12,7 @@ from . import model, route_abi
 ROUTE_EXPORTS = ["vr_route_create", "vr_route_destroy", "vr_route_last_error", "vr_route_num_nodes",
                  "vr_route_node_info", "vr_route_node_cells", "vr_route_get_uh", "vr_route_convolve",
                  "vr_route_convolve_ex", "vr_route_convolve_in", "vr_route_last_kernel_ms", "vr_route_res_info", "vr_route_get_uh_r",
-                 "vr_route_set_uh_r", "vr_route_reservoirs"]
+                 "vr_route_set_uh_r", "vr_route_reservoirs", "vr_objectives"]
 
 
 def _lib():
@@ -36,6 +36,7 @@ def _lib():
         L.vr_route_get_uh_r.argtypes = [vp, C.c_int32, vp]
         L.vr_route_set_uh_r.argtypes = [vp, C.c_int32, vp]
         L.vr_route_reservoirs.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+        L.vr_objectives.argtypes = [C.c_int, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]
         L._route_ready = True
     return L
 
@@ -130,3 +131,17 @@ class Route:
         if self.h:
             self.L.vr_route_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def objectives(sim, obs, handle_negatives=True, device=0):
+    """[nsets, 4] = NSE, TRMSE, MSDE, ROCE of sim [nsets, ndays] (float32 flows) against obs [ndays]"""
+    L = _lib()
+    sim = np.ascontiguousarray(sim, dtype=np.float32)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    assert sim.ndim == 2 and sim.shape[1] == obs.size
+    out = np.zeros((sim.shape[0], 4), dtype=np.float64)
+    rc = L.vr_objectives(device, sim.shape[0], sim.shape[1], sim.ctypes.data, obs.ctypes.data, int(handle_negatives),
+                         out.ctypes.data)
+    if rc != 0:
+        raise model.VicResError(rc, L.vr_route_last_error(None).decode())
+    return out
