@@ -36,6 +36,7 @@ extern "C" {
 
 #define VR_MAX_LAYERS 3   /* MAX_LAYERS, vicNl_def.h:171 */
 #define VR_MAX_BANDS 10   /* MAX_BANDS,  vicNl_def.h:173 */
+#define VR_ZWT_NPOINTS 11      /* MAX_ZWTVMOIST, vicNl_def.h */
 #define VR_MAX_OUT 64
 
 typedef enum vr_status {
@@ -76,6 +77,10 @@ enum {
   VR_OUT_DELTAH, VR_OUT_AERO_COND, VR_OUT_SHORTWAVE, VR_OUT_LONGWAVE,
   VR_OUT_DELSOILMOIST, VR_OUT_DELSWE, VR_OUT_DELINTERCEPT, VR_OUT_SNOW_SURF_TEMP,
   VR_OUT_SNOW_PACK_TEMP, VR_OUT_SALBEDO,
+  /* potential evaporation of the six reference covers (compute_pot_evap.c; needs vr_veglib.LAI/albedo) */
+  VR_OUT_PET_SATSOIL, VR_OUT_PET_H2OSURF, VR_OUT_PET_SHORT, VR_OUT_PET_TALL, VR_OUT_PET_NATVEG, VR_OUT_PET_VEGNOCR,
+  /* water table position, cm (compute_zwt.c; needs vr_cells.zwt_zwt/zwt_moist) */
+  VR_OUT_ZWT, VR_OUT_ZWT_LUMPED,
   VR_NOUTVAR
 };
 
@@ -109,6 +114,8 @@ typedef struct vr_veglib {
   const double  *trunk_ratio;    /* [nclass] */
   const double  *roughness;      /* [nclass*12] */
   const double  *displacement;   /* [nclass*12] */
+  const double  *LAI;            /* [nclass*12] veg_lib.LAI    -- read only for VR_OUT_PET_NATVEG / _VEGNOCR; else may be NULL */
+  const double  *albedo;         /* [nclass*12] veg_lib.albedo -- the same                                                     */
 } vr_veglib;
 
 /* Cells: soil_con_struct + veg_con_struct[] restated as SoA (vicNl_def.h:937-1031). All values
@@ -133,6 +140,10 @@ typedef struct vr_cells {
   const double  *tile_LAI;       /* [T*12] veg_con.LAI   (monthly climatology)     */
   const double  *tile_albedo;    /* [T*12] veg_con.albedo                           */
   const double  *tile_vegcover;  /* [T*12] veg_con.vegcover                         */
+  /* soil moisture v water table curves, soil_con.zwtvmoist_zwt / _moist (read_soilparam.c:822-921): curve k =
+   * layer k for k < nlayer, nlayer = top layers lumped, nlayer+1 = whole column; VR_ZWT_NPOINTS points each;
+   * value of point i of curve k of cell c at ((k*VR_ZWT_NPOINTS + i)*C + c).  Read only for VR_OUT_ZWT*; else NULL. */
+  const double  *zwt_zwt, *zwt_moist;
 } vr_cells;
 
 /* One block of records for all cells. Pointers are HOST memory for vr_step_block and DEVICE

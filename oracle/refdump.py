@@ -90,6 +90,9 @@ REF_OUT = {
     "DELSOILMOIST": ("OUT_DELSOILMOIST", 0), "DELSWE": ("OUT_DELSWE", 0),
     "DELINTERCEPT": ("OUT_DELINTERCEPT", 0), "SNOW_SURF_TEMP": ("OUT_SNOW_SURF_TEMP", 0),
     "SNOW_PACK_TEMP": ("OUT_SNOW_PACK_TEMP", 0), "SALBEDO": ("OUT_SALBEDO", 0),
+    "PET_SATSOIL": ("OUT_PET_SATSOIL", 0), "PET_H2OSURF": ("OUT_PET_H2OSURF", 0), "PET_SHORT": ("OUT_PET_SHORT", 0),
+    "PET_TALL": ("OUT_PET_TALL", 0), "PET_NATVEG": ("OUT_PET_NATVEG", 0), "PET_VEGNOCR": ("OUT_PET_VEGNOCR", 0),
+    "ZWT": ("OUT_ZWT", 0), "ZWT_LUMPED": ("OUT_ZWT_LUMPED", 0),
 }
 
 
@@ -103,7 +106,7 @@ def case_from_dump(d):
         "overstory": vl[:ncl, 0].astype(np.int32), "rarc": vl[:ncl, 1], "rmin": vl[:ncl, 2],
         "wind_h": vl[:ncl, 3], "RGL": vl[:ncl, 4], "rad_atten": vl[:ncl, 5], "wind_atten": vl[:ncl, 6],
         "trunk_ratio": d["veglib_trunk_ratio"][:ncl], "roughness": vl[:ncl, 31:43],
-        "displacement": vl[:ncl, 43:55],
+        "displacement": vl[:ncl, 43:55], "LAI": vl[:ncl, 7:19], "albedo": vl[:ncl, 19:31],
     }
     sc = np.stack([d["c%d/soil_scalars" % c] for c in range(C)])          # [C, 18]
     cells = {}
@@ -117,6 +120,9 @@ def case_from_dump(d):
         cells[k] = np.stack([d["c%d/%s" % (c, k)] for c in range(C)], axis=1)      # [L, C]
     for k in ["AreaFract", "Tfactor", "Pfactor"]:
         cells[k] = np.stack([d["c%d/%s" % (c, k)] for c in range(C)], axis=1)      # [NB, C]
+    # zwtvmoist curves: the dump holds [MAX_LAYERS+2, 11] per cell, curve k of the model is row k
+    for k, nm in [("zwt_zwt", "zwtvmoist_zwt"), ("zwt_moist", "zwtvmoist_moist")]:
+        cells[k] = np.stack([d["c%d/%s" % (c, nm)][:L + 2] for c in range(C)], axis=2)  # [L+2, 11, C]
     tile_ptr = [0]
     t_class, t_cv, t_root, t_lai, t_alb, t_vc = [], [], [], [], [], []
     ntile_max = 0

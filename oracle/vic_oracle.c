@@ -80,6 +80,7 @@ typedef struct { double moist, evap, bare_evap_frac, kappa, Cs, T; } olayer;
 typedef struct {
   olayer layer[MAXL];
   double runoff, baseflow, asat, inflow, aero_resist[2], rootmoist, wetness;
+  double pot_evap[6], zwt, zwt_lumped, layer_zwt[MAXL];
 } ocell;
 typedef struct { double Wdew, canopyevap, throughfall, LAI, Wdmax, vegcover, albedo, rc; } ovegvar;
 typedef struct {
@@ -103,6 +104,7 @@ typedef struct { ocell cell; ovegvar veg; osnow snow; oenergy energy; } ounit;
 typedef struct {
   int overstory;
   double rarc, rmin, wind_h, RGL, rad_atten, wind_atten, trunk_ratio, roughness[12], displacement[12];
+  double LAI[12], albedo[12];      /* library values: read by compute_pot_evap only */
 } oveglib;
 
 typedef struct {   /* soil_con_struct subset (vicNl_def.h:937-1008) for one cell */
@@ -111,6 +113,8 @@ typedef struct {   /* soil_con_struct subset (vicNl_def.h:937-1008) for one cell
          resid_moist[MAXL], init_moist[MAXL], bulk_density[MAXL], soil_density[MAXL],
          bulk_dens_min[MAXL], soil_dens_min[MAXL], quartz[MAXL], organic[MAXL], porosity[MAXL];
   double AreaFract[VR_MAX_BANDS], Tfactor[VR_MAX_BANDS], Pfactor[VR_MAX_BANDS];
+  int have_zwt;
+  double zwtvmoist_zwt[MAXL + 2][VR_ZWT_NPOINTS], zwtvmoist_moist[MAXL + 2][VR_ZWT_NPOINTS];
 } osoil;
 
 typedef struct {   /* one record of atmos_data_struct, index [NR] == [0] (vicNl_def.h:1090-1113) */
@@ -131,6 +135,7 @@ struct vo_model {
   /* save_data_struct + calc_water_balance_error statics, per cell (put_data.c:586-632) */
   double *save_soil, *save_swe, *save_wdew, *last_storage;
   int initialised;
+  int want_pet;              /* an OUT_PET_* variable is requested: run the reference-cover passes */
 };
 
 static int NLAYER;   /* options.Nlayer; set per call from the model (single model per process use) */
@@ -1888,6 +1893,83 @@ static double calc_surf_energy_bal(double Le, double LongUnderIn, double NetLong
 /* ======================================================================================
  * runoff.c:7-576 (Nfrost == 1, ice == 0)
  * ====================================================================================== */
+/* compute_zwt.c:7-45 */
+static double compute_zwt(const osoil *soil_con, int lindex, double moist)
+{
+  int i;
+  double zwt = -99999.;
+  i = VR_ZWT_NPOINTS - 1;
+  while (i >= 1 && moist > soil_con->zwtvmoist_moist[lindex][i]) i--;
+  if (i == VR_ZWT_NPOINTS - 1) {
+    if (moist < soil_con->zwtvmoist_moist[lindex][i]) zwt = 999;
+    else if (moist == soil_con->zwtvmoist_moist[lindex][i]) zwt = soil_con->zwtvmoist_zwt[lindex][i];
+  }
+  else
+    zwt = soil_con->zwtvmoist_zwt[lindex][i + 1] +
+          (soil_con->zwtvmoist_zwt[lindex][i] - soil_con->zwtvmoist_zwt[lindex][i + 1]) *
+              (moist - soil_con->zwtvmoist_moist[lindex][i + 1]) /
+              (soil_con->zwtvmoist_moist[lindex][i] - soil_con->zwtvmoist_moist[lindex][i + 1]);
+  return zwt;
+}
+
+/* compute_zwt.c:48-113 */
+static void wrap_compute_zwt(const osoil *soil_con, ocell *cell)
+{
+  int lindex;
+  double total_depth = 0, tmp_depth, tmp_moist;
+  for (lindex = 0; lindex < NLAYER; lindex++) total_depth += soil_con->depth[lindex];
+  for (lindex = 0; lindex < NLAYER; lindex++) cell->layer_zwt[lindex] = compute_zwt(soil_con, lindex, cell->layer[lindex].moist);
+  if (cell->layer_zwt[NLAYER - 1] == 999) cell->layer_zwt[NLAYER - 1] = -total_depth * 100;
+  lindex = NLAYER - 1;
+  tmp_depth = total_depth;
+  while (lindex >= 0 && soil_con->max_moist[lindex] - cell->layer[lindex].moist <= SMALL) {
+    tmp_depth -= soil_con->depth[lindex];
+    lindex--;
+  }
+  if (lindex < 0) cell->zwt = 0;
+  else if (lindex < NLAYER - 1) {
+    if (cell->layer_zwt[lindex] != 999) cell->zwt = cell->layer_zwt[lindex];
+    else cell->zwt = -tmp_depth * 100;
+  }
+  else cell->zwt = cell->layer_zwt[lindex];
+  tmp_moist = 0;
+  for (lindex = 0; lindex < NLAYER; lindex++) tmp_moist += cell->layer[lindex].moist;
+  cell->zwt_lumped = compute_zwt(soil_con, NLAYER + 1, tmp_moist);
+  if (cell->zwt_lumped == 999) cell->zwt_lumped = -total_depth * 100;
+}
+
+/* compute_pot_evap.c:8-80.  lib: the model's library incl. the 4 reference classes at [nclass .. nclass+3]; the
+ * bare tile's class IS entry nclass.  net_short is read by calc_rc() before it is assigned for cover i (the
+ * reference's order); it starts as 0 here, and only NATVEG (after TALL) can depend on it. */
+static void compute_pot_evap(const oveglib *lib, int nclass, int veg_class, int mon, int dt, double shortwave,
+                             double net_longwave, double tair, double vpd, double elevation,
+                             double aero_resist[6][2], double *pot_evap)
+{
+  static const char ref_crop[6] = {0, 0, 1, 1, 0, 0};
+  int i;
+  double albedo, net_short = 0., net_rad, rs, rarc, RGL, lai, rc, ra;
+  for (i = 0; i < 6; i++) {
+    if (i < 4) {
+      rs = lib[nclass + i].rmin; rarc = lib[nclass + i].rarc; RGL = lib[nclass + i].RGL;
+      lai = lib[nclass + i].LAI[mon]; albedo = lib[nclass + i].albedo[mon];
+    }
+    else {
+      rs = lib[veg_class].rmin;
+      if (i == 5) rs = 0;
+      rarc = lib[veg_class].rarc; RGL = lib[veg_class].RGL; lai = lib[veg_class].LAI[mon]; albedo = lib[veg_class].albedo[mon];
+    }
+    if (rs == 0) rc = 0;
+    else if (lai == 0) rc = RSMAX;
+    else if (ref_crop[i]) { rc = rs / (lai * 0.5); rc = (rc > RSMAX) ? RSMAX : rc; }
+    else rc = calc_rc(rs, net_short, (float)RGL, tair, vpd, lai, 1.0);
+    if (i < 4 || !lib[veg_class].overstory) ra = aero_resist[i][0];
+    else ra = aero_resist[i][1];
+    net_short = (1.0 - albedo) * shortwave;
+    net_rad = net_short + net_longwave;
+    pot_evap[i] = penman(tair, elevation, net_rad, vpd, ra, rc, rarc) * dt / 24.0;
+  }
+}
+
 static void compute_runoff_and_asat(const osoil *soil_con, const double *moist, double inflow, double *A,
                                     double *runoff)
 {
@@ -2058,6 +2140,7 @@ static int runoff(ocell *cell, const osoil *soil_con, double ppt, int dt)
   cell->asat += A * 1.;
   cell->runoff += runoff_ * 1.;
   cell->baseflow += baseflow * 1.;
+  if (soil_con->have_zwt) wrap_compute_zwt(soil_con, cell);      /* runoff.c:503 */
   return 0;
 }
 
@@ -2070,7 +2153,8 @@ static int surface_fluxes(const vr_options *opt, int overstory, double BareAlbed
                           double *ref_height, double *roughness, double *wind, const float *root, int Nveg,
                           int band, double dp, int iveg, const oveglib *vl, const oatmos *atmos,
                           oenergy *energy, ocell *cell, osnow *snow, const osoil *soil_con,
-                          ovegvar *veg_var, double *out_prec, double *out_rain, double *out_snow)
+                          ovegvar *veg_var, double *out_prec, double *out_rain, double *out_snow,
+                          const oveglib *lib, int nclass, int veg_class, double pet_aero[7][3] /* NULL: PET not wanted */)
 {
   int INCLUDE_SNOW = 0, UNSTABLE_SNOW = 0, UnderStory, lidx, N_steps = 1, step_dt = opt->dt_hours;
   double Le, LongUnderIn, LongUnderOut, NetLongSnow, NetShortSnow, NetShortGrnd, OldTSurf, ShortUnderIn,
@@ -2205,6 +2289,26 @@ static int surface_fluxes(const vr_options *opt, int overstory, double BareAlbed
     }
     step_Wdew = soil_veg_var.Wdew;
   }
+  /* potential evaporation of the six reference covers (surface_fluxes.c:868-897, 1019, 1123) */
+  if (pet_aero) {
+    double stability_factor[2], step_aero_resist[6][2];
+    int p;
+    if (iter_aero_resist_used[0] == HUGE_RESIST) stability_factor[0] = HUGE_RESIST;
+    else stability_factor[0] = iter_aero_resist_used[0] / pet_aero[6][UnderStory];
+    if (iter_aero_resist_used[1] == iter_aero_resist_used[0]) stability_factor[1] = stability_factor[0];
+    else {
+      if (iter_aero_resist_used[1] == HUGE_RESIST) stability_factor[1] = HUGE_RESIST;
+      else stability_factor[1] = iter_aero_resist_used[1] / pet_aero[6][1];
+    }
+    for (p = 0; p < 6; p++) {
+      if (stability_factor[0] == HUGE_RESIST) step_aero_resist[p][0] = HUGE_RESIST;
+      else step_aero_resist[p][0] = pet_aero[p][UnderStory] * stability_factor[0];
+      if (stability_factor[1] == HUGE_RESIST) step_aero_resist[p][1] = HUGE_RESIST;
+      else step_aero_resist[p][1] = pet_aero[p][1] * stability_factor[1];
+    }
+    compute_pot_evap(lib, nclass, veg_class, atmos->month - 1, opt->dt_hours, atmos->shortwave, iter_soil_energy.NetLongAtmos,
+                     Tair, VPDcanopy, soil_con->elevation, step_aero_resist, cell->pot_evap);
+  }
   for (lidx = 0; lidx < NLAYER; lidx++) store_layerevap[lidx] = 0. + step_layer[lidx].evap;
   if (iter_aero_resist_used[0] > 0) store_aero_cond_used[0] = 0. + 1 / iter_aero_resist_used[0];
   else store_aero_cond_used[0] = 0. + HUGE_RESIST;
@@ -2331,7 +2435,7 @@ static int full_energy(vo_model *m, int64_t c, const oatmos *atmos, double *out_
   }
   for (iveg = 0; iveg < ntile; iveg++) {
     double Cv, wind_h, surf_atten, bare_albedo, height, displacement[3], roughness[3], ref_height[3],
-           tmp_wind[3], aero_resist[3];
+           tmp_wind[3], aero_resist[3], pet_aero[7][3];
     int overstory, veg_class, is_bare;
     oveglib vl;
     t = t0 + iveg;
@@ -2385,6 +2489,26 @@ static int full_energy(vo_model *m, int64_t c, const oatmos *atmos, double *out_
     if (CalcAerodynamic(overstory, height, vl.trunk_ratio, soil_con->snow_rough, soil_con->rough, vl.wind_atten,
                         aero_resist, tmp_wind, displacement, ref_height, roughness) == VERROR)
       return VERROR;
+    /* the p < N_PET_TYPES passes (full_energy.c:329-369): the reference covers, then twice the current one */
+    if (m->want_pet) {
+      int p;
+      for (p = 0; p < 7; p++) {
+        oveglib pv = (p < 4) ? m->lib[m->nclass + p] : vl;
+        double pd[3], pr[3], ph[3], pw[3];
+        if (p == 0) {       /* SATSOIL is the bare-soil entry read_soilparam.c:551-554 overwrote for this cell */
+          pv.roughness[mon] = soil_con->rough;
+          pv.displacement[mon] = soil_con->rough * 0.667 / 0.123;
+        }
+        pw[0] = atmos->wind; pw[1] = VERROR; pw[2] = VERROR;
+        pd[0] = pv.displacement[mon]; pr[0] = pv.roughness[mon];
+        if (p >= 4 && pr[0] == 0) pr[0] = soil_con->rough;
+        if (pd[0] < wind_h) ph[0] = wind_h;
+        else ph[0] = pd[0] + wind_h + pr[0];
+        if (CalcAerodynamic(pv.overstory, pd[0] / RATIO_DH_HEIGHT_VEG, pv.trunk_ratio, soil_con->snow_rough, soil_con->rough,
+                            pv.wind_atten, pet_aero[p], pw, pd, ph, pr) == VERROR)
+          return VERROR;
+      }
+    }
     for (lidx = 0; lidx < NLAYER; lidx++) rootv[lidx] = is_bare ? 0.f : (float)m->tile_root[t * NLAYER + lidx];
     for (band = 0; band < NB; band++) {
       if (soil_con->AreaFract[band] > 0) {
@@ -2398,7 +2522,7 @@ static int full_energy(vo_model *m, int64_t c, const oatmos *atmos, double *out_
         err = surface_fluxes(opt, overstory, bare_albedo, surf_atten, ar3, d3, rh3, ro3, w3, rootv,
                              is_bare ? iveg : -1 /* Nveg: iveg == Nveg only for the bare tile */, band,
                              soil_con->dp, iveg, &vl, atmos, &u->energy, &u->cell, &u->snow, soil_con, &u->veg,
-                             &out_prec, &out_rain, &out_snow);
+                             &out_prec, &out_rain, &out_snow, m->lib, m->nclass, veg_class, m->want_pet ? pet_aero : NULL);
         if (err == VERROR) return VERROR;
         *out_prec_sum += out_prec * Cv * soil_con->AreaFract[band];
         *out_rain_sum += out_rain * Cv * soil_con->AreaFract[band];
@@ -2498,6 +2622,9 @@ static void put_data(vo_model *m, int64_t c, const oatmos *atmos, double out_pre
       }
       o[VR_OUT_SOIL_WET] += u->cell.wetness * AreaFactor;
       o[VR_OUT_ROOTMOIST] += u->cell.rootmoist * AreaFactor;
+      for (index = 0; index < 6; index++) o[VR_OUT_PET_SATSOIL + index] += u->cell.pot_evap[index] * AreaFactor;   /* put_data.c:846-851 */
+      o[VR_OUT_ZWT] += u->cell.zwt * AreaFactor;                                                                   /* :917-918 */
+      o[VR_OUT_ZWT_LUMPED] += u->cell.zwt_lumped * AreaFactor;
       o[VR_OUT_SWE] += u->snow.swq * AreaFactor * 1000.;
       o[VR_OUT_SNOW_DEPTH] += u->snow.depth * AreaFactor * 100.;
       if (u->snow.swq > 0.0) {
@@ -2578,19 +2705,35 @@ vo_model *vo_create(const vr_options *opt, const vr_veglib *lib, const vr_cells 
   int i, j, l, b, L = opt->nlayer, NB = opt->nbands;
   m->opt = *opt;
   m->nclass = lib->nclass;
-  m->lib = (oveglib *)calloc(lib->nclass + 1, sizeof(oveglib));
+  for (i = 0; i < opt->n_out; i++)
+    if (opt->out_vars[i] >= VR_OUT_PET_SATSOIL && opt->out_vars[i] <= VR_OUT_PET_VEGNOCR) m->want_pet = 1;
+  m->lib = (oveglib *)calloc(lib->nclass + 4, sizeof(oveglib));      /* + the 4 PET reference classes (read_veglib.c:168-187) */
   for (i = 0; i < lib->nclass; i++) {
     oveglib *v = &m->lib[i];
     v->overstory = lib->overstory[i]; v->rarc = lib->rarc[i]; v->rmin = lib->rmin[i];
     v->wind_h = lib->wind_h[i]; v->RGL = lib->RGL[i]; v->rad_atten = lib->rad_atten[i];
     v->wind_atten = lib->wind_atten[i]; v->trunk_ratio = lib->trunk_ratio[i];
     for (j = 0; j < 12; j++) { v->roughness[j] = lib->roughness[i * 12 + j]; v->displacement[j] = lib->displacement[i * 12 + j]; }
+    for (j = 0; j < 12; j++) { v->LAI[j] = lib->LAI ? lib->LAI[i * 12 + j] : 0.0; v->albedo[j] = lib->albedo ? lib->albedo[i * 12 + j] : 0.0; }
   }
   { /* bare-soil pseudo class == PET_SATSOIL reference entry (global.h:9-21, read_veglib.c:136-153) */
     oveglib *v = &m->lib[lib->nclass];
     v->overstory = 0; v->rarc = 0.0; v->rmin = 0.0; v->wind_h = 10.0; v->RGL = 0.0; v->rad_atten = 0.0;
     v->wind_atten = 0.0; v->trunk_ratio = 0.0;
     for (j = 0; j < 12; j++) { v->roughness[j] = 0.001; v->displacement[j] = 0.0054; }
+  }
+  { /* global.h:53-65 */
+    static const double ref_rarc[4] = {0.0, 0.0, 25, 25}, ref_rmin[4] = {0.0, 0.0, 100, 100}, ref_lai[4] = {1.0, 1.0, 2.88, 4.45},
+                        ref_alb[4] = {BARE_SOIL_ALBEDO, 0.08, 0.23, 0.23}, ref_rough[4] = {0.001, 0.001, 0.0148, 0.0615},
+                        ref_displ[4] = {0.0054, 0.0054, 0.08, 0.3333}, ref_RGL[4] = {0.0, 0.0, 100, 100};
+    for (i = 0; i < 4; i++) {
+      oveglib *v = &m->lib[lib->nclass + i];
+      v->overstory = 0; v->rarc = ref_rarc[i]; v->rmin = ref_rmin[i]; v->wind_h = 10.0; v->RGL = ref_RGL[i];
+      v->rad_atten = 0.0; v->wind_atten = 0.0; v->trunk_ratio = 0.0;
+      for (j = 0; j < 12; j++) {
+        v->roughness[j] = ref_rough[i]; v->displacement[j] = ref_displ[i]; v->LAI[j] = ref_lai[i]; v->albedo[j] = ref_alb[i];
+      }
+    }
   }
   m->C = C; m->T = T;
   m->soil = (osoil *)calloc(C ? C : 1, sizeof(osoil));
@@ -2613,6 +2756,13 @@ vo_model *vo_create(const vr_options *opt, const vr_veglib *lib, const vr_cells 
       size_t k = (size_t)b * C + c;
       s->AreaFract[b] = cells->AreaFract[k]; s->Tfactor[b] = cells->Tfactor[k]; s->Pfactor[b] = cells->Pfactor[k];
     }
+    s->have_zwt = (cells->zwt_zwt && cells->zwt_moist);
+    if (s->have_zwt)
+      for (l = 0; l < L + 2; l++)
+        for (i = 0; i < VR_ZWT_NPOINTS; i++) {
+          size_t k = ((size_t)l * VR_ZWT_NPOINTS + i) * C + c;
+          s->zwtvmoist_zwt[l][i] = cells->zwt_zwt[k]; s->zwtvmoist_moist[l][i] = cells->zwt_moist[k];
+        }
   }
   m->tile_ptr = (int64_t *)malloc(sizeof(int64_t) * (C + 1));
   memcpy(m->tile_ptr, cells->tile_ptr, sizeof(int64_t) * (C + 1));

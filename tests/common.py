@@ -7,7 +7,7 @@ from vicres_b200 import abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith("route_"))
+                  if not os.path.basename(p).startswith(("route_", "objectives")))
 
 # Parity tolerance of BASELINE.json's north_star: fp64 fluxes and states within 1e-9 relative per
 # cell-timestep.  Values are compared as |a-b| <= RTOL * max(|a|,|b|,ABS_FLOOR); the floor stops

@@ -24,6 +24,7 @@ OUT_NAMES = [
     "WATER_ERROR", "INFLOW", "SNOW_MELT", "RAINF", "SNOWF", "NET_LONG", "ASAT", "SOIL_WET",
     "ROOTMOIST", "GRND_FLUX", "DELTAH", "AERO_COND", "SHORTWAVE", "LONGWAVE", "DELSOILMOIST",
     "DELSWE", "DELINTERCEPT", "SNOW_SURF_TEMP", "SNOW_PACK_TEMP", "SALBEDO",
+    "PET_SATSOIL", "PET_H2OSURF", "PET_SHORT", "PET_TALL", "PET_NATVEG", "PET_VEGNOCR", "ZWT", "ZWT_LUMPED",
 ]
 OUT = {n: i for i, n in enumerate(OUT_NAMES)}
 VR_NOUTVAR = len(OUT_NAMES)
@@ -44,7 +45,7 @@ class vr_options(C.Structure):
 class vr_veglib(C.Structure):
     _fields_ = [("nclass", C.c_int32), ("overstory", _pi32), ("rarc", _pd), ("rmin", _pd),
                 ("wind_h", _pd), ("RGL", _pd), ("rad_atten", _pd), ("wind_atten", _pd),
-                ("trunk_ratio", _pd), ("roughness", _pd), ("displacement", _pd)]
+                ("trunk_ratio", _pd), ("roughness", _pd), ("displacement", _pd), ("LAI", _pd), ("albedo", _pd)]
 
 
 CELL_SCALARS = ["lat", "elevation", "b_infilt", "Ds", "Dsmax", "Ws", "c_expt", "avg_temp", "dp",
@@ -59,7 +60,8 @@ TILE_F64 = ["tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]
 class vr_cells(C.Structure):
     _fields_ = ([("ncell", C.c_int64)] + [(n, _pd) for n in CELL_SCALARS] +
                 [(n, _pd) for n in CELL_LAYER] + [(n, _pd) for n in CELL_BAND] +
-                [("tile_ptr", _pi64), ("tile_class", _pi32)] + [(n, _pd) for n in TILE_F64])
+                [("tile_ptr", _pi64), ("tile_class", _pi32)] + [(n, _pd) for n in TILE_F64] +
+                [("zwt_zwt", _pd), ("zwt_moist", _pd)])
 
 
 class vr_forcing(C.Structure):
@@ -121,6 +123,10 @@ def pack_veglib(lib):
               "displacement"]:
         keep[k] = _f64(lib[k]).reshape(-1)
         setattr(s, k, _ptr(keep[k], _pd))
+    for k in ["LAI", "albedo"]:                      # optional: only the PET outputs of the tile's own class read them
+        if lib.get(k) is not None:
+            keep[k] = _f64(lib[k]).reshape(-1)
+            setattr(s, k, _ptr(keep[k], _pd))
     return Packed(s, keep)
 
 
@@ -138,6 +144,10 @@ def pack_cells(cells):
     keep["tile_class"] = np.ascontiguousarray(cells["tile_class"], dtype=np.int32)
     s.tile_ptr = _ptr(keep["tile_ptr"], _pi64)
     s.tile_class = _ptr(keep["tile_class"], _pi32)
+    for k in ["zwt_zwt", "zwt_moist"]:               # optional [(L+2), 11, C] curves: only the ZWT outputs read them
+        if cells.get(k) is not None:
+            keep[k] = _f64(cells[k]).reshape(-1)
+            setattr(s, k, _ptr(keep[k], _pd))
     return Packed(s, keep)
 
 

@@ -16,7 +16,8 @@ enum {
   TE_EB0 = 0, TE_EB1, TE_EB2, TE_TV0, TE_TV1, TE_TV2, TE_EVAP, TE_SUB_SNOW, TE_SUB_CANOP, TE_EVAP_CANOP,
   TE_ASAT, TE_RUNOFF, TE_BASEFLOW, TE_INFLOW, TE_WDEW, TE_COND, TE_LIQ0, TE_LIQ1, TE_LIQ2, TE_WET, TE_ROOTM,
   TE_SWE, TE_SDEPTH, TE_SALB, TE_SST, TE_SPT, TE_CVSNOW, TE_SCANOPY, TE_SMELT, TE_SCOVER, TE_SURFT,
-  TE_NSHORT, TE_NLONG, TE_INLONG, TE_ALBEDO, TE_GFLUX, TE_DH, TE_PREC, TE_RAIN, TE_SNOWF, NTERM
+  TE_NSHORT, TE_NLONG, TE_INLONG, TE_ALBEDO, TE_GFLUX, TE_DH, TE_PREC, TE_RAIN, TE_SNOWF,
+  TE_PET0, TE_PET1, TE_PET2, TE_PET3, TE_PET4, TE_PET5, TE_ZWT, TE_ZWTL, NTERM
 };
 
 // per-cell carried words of save_data_struct / calc_water_balance_error (put_data.c:586-632)
@@ -69,6 +70,10 @@ inline void build_term_map(const int *out_vars, int n_out, TermMap &tmap)
       case VR_OUT_SNOW_SURF_TEMP: N(TE_SST); N(TE_CVSNOW); break;
       case VR_OUT_SNOW_PACK_TEMP: N(TE_SPT); N(TE_CVSNOW); break;
       case VR_OUT_SALBEDO: N(TE_SALB); N(TE_CVSNOW); break;
+      case VR_OUT_PET_SATSOIL: case VR_OUT_PET_H2OSURF: case VR_OUT_PET_SHORT: case VR_OUT_PET_TALL:
+      case VR_OUT_PET_NATVEG: case VR_OUT_PET_VEGNOCR: N(TE_PET0 + (out_vars[i] - VR_OUT_PET_SATSOIL)); break;
+      case VR_OUT_ZWT: N(TE_ZWT); break;
+      case VR_OUT_ZWT_LUMPED: N(TE_ZWTL); break;
       default: break;
     }
   }
@@ -143,6 +148,10 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
   T_(TE_PREC, o.out_prec * cv * af);
   T_(TE_RAIN, o.out_rain * cv * af);
   T_(TE_SNOWF, o.out_snow * cv * af);
+#pragma unroll
+  for (int i = 0; i < 6; i++) T_(TE_PET0 + i, o.pot_evap[i] * AF);      // put_data.c:846-851
+  T_(TE_ZWT, o.zwt * AF);                                                // put_data.c:917-918
+  T_(TE_ZWTL, o.zwt_lumped * AF);
 #undef T_
 }
 
@@ -154,7 +163,10 @@ VR_HDN void unit_step_terms(const CellC &cc, const UnitC &uc, const double *tm, 
                             const TermMap &tmap, double *col, int stride, bool write)
 {
   UnitOut uo;
-  unit_step(cc, uc, tm, ae, f, NL, dt_hours, max_snow_temp, min_rain_temp, s, uo);
+  int extras = 0;
+  for (int i = 0; i < 6; i++) if (tmap.row[TE_PET0 + i] >= 0) extras |= EX_PET;
+  if (tmap.row[TE_ZWT] >= 0 || tmap.row[TE_ZWTL] >= 0) extras |= EX_ZWT;
+  unit_step(cc, uc, tm, ae, f, NL, dt_hours, max_snow_temp, min_rain_temp, s, uo, extras);
   if (write) unit_terms(uc, cv, af, s, uo, NL, tmap, col, stride);
 }
 
@@ -272,6 +284,14 @@ VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const
     case VR_OUT_SALBEDO: { double c = S(TE_CVSNOW), v = S(TE_SALB); return (c > 0) ? v / c : v; }
     case VR_OUT_SNOW_SURF_TEMP: { double c = S(TE_CVSNOW), v = S(TE_SST); return (c > 0) ? v / c : v; }
     case VR_OUT_SNOW_PACK_TEMP: { double c = S(TE_CVSNOW), v = S(TE_SPT); return (c > 0) ? v / c : v; }
+    case VR_OUT_PET_SATSOIL: return S(TE_PET0);
+    case VR_OUT_PET_H2OSURF: return S(TE_PET1);
+    case VR_OUT_PET_SHORT: return S(TE_PET2);
+    case VR_OUT_PET_TALL: return S(TE_PET3);
+    case VR_OUT_PET_NATVEG: return S(TE_PET4);
+    case VR_OUT_PET_VEGNOCR: return S(TE_PET5);
+    case VR_OUT_ZWT: return S(TE_ZWT);
+    case VR_OUT_ZWT_LUMPED: return S(TE_ZWTL);
     case VR_OUT_AERO_COND: return S(TE_COND);
     case VR_OUT_AERO_RESIST: return (S(TE_COND) > SMALLV) ? 1 / S(TE_COND) : HUGE_RESIST;
     case VR_OUT_DELSOILMOIST: {

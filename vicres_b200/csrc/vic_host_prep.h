@@ -28,6 +28,7 @@ namespace vr {
 
 struct Prepared {
   int NL = 0, NB = 0, cta_threads = 128;
+  int ccn = 0;                       // rows of cc (VR_CC_N + the optional zwtvmoist tail)
   int64_t C = 0, T = 0, U = 0, K = 0, nCTA = 0;
   std::vector<double> cc;            // [CC_N][C]
   std::vector<int64_t> order;        // [C] sorted position -> caller's cell index (climate-sorted, see prepare())
@@ -128,7 +129,15 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     return cells.lat[a] > cells.lat[b];
   });
   // per-cell constants, stored BY SORTED POSITION so that neighbouring lanes read neighbouring words
-  const int CCN = VR_CC_N(NL);
+  bool want_pet_nat = false, want_zwt = false;
+  for (int v = 0; v < opt.n_out; v++) {
+    if (opt.out_vars[v] == VR_OUT_PET_NATVEG || opt.out_vars[v] == VR_OUT_PET_VEGNOCR) want_pet_nat = true;
+    if (opt.out_vars[v] == VR_OUT_ZWT || opt.out_vars[v] == VR_OUT_ZWT_LUMPED) want_zwt = true;
+  }
+  if (want_pet_nat && (!lib.LAI || !lib.albedo)) { P.error = "OUT_PET_NATVEG / OUT_PET_VEGNOCR need vr_veglib.LAI and .albedo"; return false; }
+  if (want_zwt && (!cells.zwt_zwt || !cells.zwt_moist)) { P.error = "OUT_ZWT / OUT_ZWT_LUMPED need vr_cells.zwt_zwt and .zwt_moist"; return false; }
+  const int CCN = VR_CC_N(NL) + (want_zwt ? VR_CC_ZWT_N(NL) : 0);
+  P.ccn = CCN;
   P.cc.assign((size_t)CCN * C, 0.0);
   for (int64_t pos = 0; pos < C; pos++) {
     const int64_t c = P.order[pos];
@@ -207,6 +216,13 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
         CC(base + CL_CS_SOLID, c) = cs;
       }
     }
+    if (want_zwt)
+      for (int k = 0; k < NL + 2; k++)
+        for (int i = 0; i < ZWT_NP; i++) {
+          const size_t q = ((size_t)k * ZWT_NP + i) * C + c;
+          CC(VR_CC_N(NL) + k * ZWT_NP + i, c) = cells.zwt_zwt[q];
+          CC(VR_CC_N(NL) + (NL + 2 + k) * ZWT_NP + i, c) = cells.zwt_moist[q];
+        }
   }
 
   // ---- tile x month canopy terms ----
@@ -214,9 +230,18 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
   for (int64_t t = 0; t < T; t++) {
     int cls = cells.tile_class[t];
     if (cls < 0 || cls > lib.nclass) { P.error = "tile_class out of range"; return false; }
-    if (cls == lib.nclass) continue;
+    if (cls == lib.nclass) {          // bare tile: its "library class" is the SATSOIL reference entry (global.h:56-57)
+      for (int m = 0; m < 12; m++) {
+        double *q = &P.tm[((size_t)t * 12 + m) * TM_N];
+        q[TM_LIB_LAI] = 1.0;
+        q[TM_LIB_ALB] = BARE_SOIL_ALBEDO;
+      }
+      continue;
+    }
     for (int m = 0; m < 12; m++) {
       double *q = &P.tm[((size_t)t * 12 + m) * TM_N];
+      q[TM_LIB_LAI] = lib.LAI ? lib.LAI[cls * 12 + m] : 0.0;
+      q[TM_LIB_ALB] = lib.albedo ? lib.albedo[cls * 12 + m] : 0.0;
       double vegcover = cells.tile_vegcover[t * 12 + m];
       if (vegcover < 0.0001) vegcover = 0.0001;          // MIN_VEGCOVER, full_energy.c:214-215
       double LAI = cells.tile_LAI[t * 12 + m];
@@ -272,6 +297,19 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       for (int i = 0; i < 3; i++) {
         q[AE_RA0 + i] = Ra[i]; q[AE_U0 + i] = U[i]; q[AE_REF0 + i] = rfh[i]; q[AE_ROUGH0 + i] = rgh[i];
         q[AE_DISP0 + i] = dsp[i];
+      }
+      // the four PET reference covers seen from this tile (full_energy.c:329-369): their own displacement and
+      // roughness (global.h:59-60; SATSOIL's were overwritten with the cell's soil values, read_soilparam.c:551-554),
+      // no overstory, but the reference height test uses the TILE's wind_h
+      for (int p = 0; p < 4; p++) {
+        const double ref_rough[4] = {0.001, 0.001, 0.0148, 0.0615}, ref_displ[4] = {0.0054, 0.0054, 0.08, 0.3333};
+        double d3[3] = {0, 0, 0}, r3[3] = {0, 0, 0}, h3[3] = {0, 0, 0}, Rp[3] = {0, 0, 0}, Up[3] = {0, 0, 0};
+        d3[0] = (p == 0) ? rough * 0.667 / 0.123 : ref_displ[p];
+        r3[0] = (p == 0) ? rough : ref_rough[p];
+        if (d3[0] < wind_h) h3[0] = wind_h;
+        else h3[0] = d3[0] + wind_h + r3[0];
+        if (aero_coeffs(0, d3[0] / 0.67, 0.0, snow_rough, rough, 0.0, Rp, Up, d3, h3, r3) != 0) key_fail[k] = 1;
+        for (int i = 0; i < 3; i++) q[AE_PET + 3 * p + i] = Rp[i];
       }
     }
   }

@@ -176,6 +176,9 @@ enum {  // index into the per-cell constant block  cc[k*C + c]
   CL_DEPTH, CL_INV_QDEN, CL_KDRY, CL_KSAT_M_KDRY, CL_POROS, CL_SOILFR, CL_CS_SOLID, CL_N
 };
 #define VR_CC_N(nlayer) (::vr::CC_LAYER0 + (nlayer) * ::vr::CL_N)
+// optional tail of the block: the zwtvmoist curves, (nlayer+2) curves x ZWT_NP points, zwt then moist
+constexpr int ZWT_NP = 11;      // MAX_ZWTVMOIST
+#define VR_CC_ZWT_N(nlayer) (2 * ((nlayer) + 2) * ::vr::ZWT_NP)
 
 struct CellC {   // read-only view of one cell's constants in the block cc[k*C + pos] (pos = sorted position)
   const double *p;   // &cc[pos]
@@ -226,6 +229,9 @@ struct CellC {   // read-only view of one cell's constants in the block cc[k*C +
   VR_HD double poros(int l) const { return g(CC_LAYER0 + l * CL_N + CL_POROS); }
   VR_HD double soilfr(int l) const { return g(CC_LAYER0 + l * CL_N + CL_SOILFR); }
   VR_HD double cs_solid(int l) const { return g(CC_LAYER0 + l * CL_N + CL_CS_SOLID); }
+  // zwtvmoist curve k, point i (only valid when the block carries the optional tail)
+  VR_HD double zwt_z(int NL, int k, int i) const { return g(VR_CC_N(NL) + k * ZWT_NP + i); }
+  VR_HD double zwt_m(int NL, int k, int i) const { return g(VR_CC_N(NL) + (NL + 2 + k) * ZWT_NP + i); }
 };
 
 // per-unit constants (tile x band)
@@ -236,10 +242,13 @@ struct UnitC {
 };
 
 // per (tile, month) canopy terms (full_energy.c:210-227,306-308) -- tm[(t*12+mon)*TM_N + k]
-enum { TM_VEGCOVER = 0, TM_ALBEDO, TM_LAI, TM_WDMAX, TM_SURF_ATTEN, TM_N };
+// TM_LIB_*: the LIBRARY's LAI / albedo of the tile's class (the SATSOIL reference entry for the bare tile), which
+// compute_pot_evap reads for the NATVEG / VEGNOCR potential evaporation
+enum { TM_VEGCOVER = 0, TM_ALBEDO, TM_LAI, TM_WDMAX, TM_SURF_ATTEN, TM_LIB_LAI, TM_LIB_ALB, TM_N };
 // per (aero key, month) CalcAerodynamic coefficients: Ra = RA/wind, U = UC*wind
+// AE_PET + 3*p + i: RA coefficient i of PET reference cover p (SATSOIL, H2OSURF, SHORT, TALL; full_energy.c:329-369)
 enum { AE_RA0 = 0, AE_RA1, AE_RA2, AE_U0, AE_U1, AE_U2, AE_REF0, AE_REF1, AE_REF2, AE_ROUGH0, AE_ROUGH1,
-       AE_ROUGH2, AE_DISP0, AE_DISP1, AE_DISP2, AE_N };
+       AE_ROUGH2, AE_DISP0, AE_DISP1, AE_DISP2, AE_PET, AE_N = AE_PET + 12 };
 
 struct Forc { double air_temp, prec, wind, vp, vpd, pressure, density, shortwave, longwave; int mon, doy; };
 
@@ -260,6 +269,7 @@ struct UnitOut {
   double evap[MAXL], bef[MAXL], vapor_flux, canopy_vapor_flux, canopyevap, asat, runoff, baseflow, inflow,
          aero_resist[2], wetness, rootmoist, melt, Tsurf, NetShortAtmos, NetLongAtmos, in_long, albedo,
          grnd_flux, deltaH, out_prec, out_rain, out_snow;
+  double pot_evap[6], zwt, zwt_lumped;      // only filled when requested (unit_step's `extras`)
   int snow_flag;
 };
 
@@ -1269,8 +1279,89 @@ VR_HDN void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moi
 // one unit, one record
 // ---------------------------------------------------------------------------------------
 // tm: this tile's TM_* terms for the month; ae: this tile's AE_* coefficients for the month
+// bits of unit_step's `extras`
+enum { EX_PET = 1, EX_ZWT = 2 };
+
+// compute_pot_evap.c:8-80 with the reference-cover parameters of global.h:53-67.  ra0/ra1/raU: the unit's raw
+// aerodynamic resistances [0], [1], [UnderStory]; used0/used1: the ones the iteration ended with
+// (surface_fluxes.c:868-894 rebuilds a stability factor from them and applies it to every reference cover).
+// calc_rc() of cover i sees the net_short of cover i-1 (the reference assigns it afterwards); only NATVEG
+// depends on it, and it gets TALL's.
+VR_HDN void pot_evap6(const UnitC &uc, const double *tm, const double *ae, const PenmanAir &pa, int UnderStory, double wind,
+                      double raU, double ra1, double used0, double used1, double shortwave, double net_longwave,
+                      double tair, double vpd, int dt_hours, double *pot)
+{
+  double sf0, sf1;
+  if (used0 == HUGE_RESIST) sf0 = HUGE_RESIST; else sf0 = used0 / raU;
+  if (used1 == used0) sf1 = sf0;
+  else if (used1 == HUGE_RESIST) sf1 = HUGE_RESIST;
+  else sf1 = used1 / ra1;
+  const double ref_rmin[4] = {0.0, 0.0, 100, 100}, ref_rarc[4] = {0.0, 0.0, 25, 25}, ref_lai[4] = {1.0, 1.0, 2.88, 4.45};
+  const double ref_alb[4] = {BARE_SOIL_ALBEDO, 0.08, 0.23, 0.23};
+  double net_short = 0.;
+  for (int i = 0; i < 6; i++) {
+    double rs, rarc, RGL, lai, albedo, a0, a1;
+    if (i < 4) {
+      rs = ref_rmin[i]; rarc = ref_rarc[i]; RGL = (i < 2) ? 0.0 : 100; lai = ref_lai[i]; albedo = ref_alb[i];
+      const double *q = ae + AE_PET + 3 * i;
+      if (wind > 0.) { a0 = q[UnderStory] / wind; a1 = q[1] / wind; }
+      else { a0 = HUGE_RESIST; a1 = HUGE_RESIST; }
+    }
+    else {
+      rs = (i == 5) ? 0 : uc.rmin; rarc = uc.rarc; RGL = uc.RGL; lai = tm[TM_LIB_LAI]; albedo = tm[TM_LIB_ALB];
+      a0 = raU; a1 = ra1;
+    }
+    double rc;
+    if (rs == 0) rc = 0;
+    else if (lai == 0) rc = RSMAX;
+    else if (i == 2 || i == 3) { rc = rs / (lai * 0.5); rc = (rc > RSMAX) ? RSMAX : rc; }
+    else rc = calc_rc(rs, net_short, RGL, tair, vpd, lai, 1.0);
+    const double s0 = (sf0 == HUGE_RESIST) ? HUGE_RESIST : a0 * sf0, s1 = (sf1 == HUGE_RESIST) ? HUGE_RESIST : a1 * sf1;
+    const double ra = (i < 4 || !uc.overstory) ? s0 : s1;
+    net_short = (1.0 - albedo) * shortwave;
+    const double net_rad = net_short + net_longwave;
+    pot[i] = penman(pa, net_rad, vpd, ra, rc, rarc) * dt_hours / 24.0;
+  }
+}
+
+// compute_zwt.c:7-45
+VR_HD double zwt_curve(const CellC &cc, int NL, int k, double moist)
+{
+  double zwt = MISSINGV;
+  int i = ZWT_NP - 1;
+  while (i >= 1 && moist > cc.zwt_m(NL, k, i)) i--;
+  if (i == ZWT_NP - 1) {
+    if (moist < cc.zwt_m(NL, k, i)) zwt = 999;
+    else if (moist == cc.zwt_m(NL, k, i)) zwt = cc.zwt_z(NL, k, i);
+  }
+  else
+    zwt = cc.zwt_z(NL, k, i + 1) + (cc.zwt_z(NL, k, i) - cc.zwt_z(NL, k, i + 1)) * (moist - cc.zwt_m(NL, k, i + 1)) /
+                                       (cc.zwt_m(NL, k, i) - cc.zwt_m(NL, k, i + 1));
+  return zwt;
+}
+
+// wrap_compute_zwt (compute_zwt.c:48-113), called at the end of runoff() (runoff.c:503)
+VR_HDN void water_table(const CellC &cc, int NL, const double *moist, double *zwt_out, double *lumped_out)
+{
+  double total_depth = 0, lz[MAXL];
+  for (int l = 0; l < NL; l++) total_depth += cc.depth(l);
+  for (int l = 0; l < NL; l++) lz[l] = zwt_curve(cc, NL, l, moist[l]);
+  if (lz[NL - 1] == 999) lz[NL - 1] = -total_depth * 100;
+  int l = NL - 1;
+  double tmp_depth = total_depth, zwt;
+  while (l >= 0 && cc.max_moist(l) - moist[l] <= SMALLV) { tmp_depth -= cc.depth(l); l--; }
+  if (l < 0) zwt = 0;
+  else if (l < NL - 1) zwt = (lz[l] != 999) ? lz[l] : -tmp_depth * 100;
+  else zwt = lz[l];
+  double tmp_moist = 0;
+  for (int k = 0; k < NL; k++) tmp_moist += moist[k];
+  double zl = zwt_curve(cc, NL, NL + 1, tmp_moist);
+  if (zl == 999) zl = -total_depth * 100;
+  *zwt_out = zwt; *lumped_out = zl;
+}
+
 VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
-                     int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o)
+                     int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o, int extras = 0)
 {
   const double delta_t = (double)dt_hours * 3600.;
   const bool is_veg = !uc.is_bare;
@@ -1659,11 +1750,15 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     o.aero_resist[0] = (c0 > 0 && c0 < HUGE_RESIST) ? 1 / (c0 / 1.) : ((c0 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
     o.aero_resist[1] = (c1 > 0 && c1 < HUGE_RESIST) ? 1 / (c1 / 1.) : ((c1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
   }
+  if (extras & EX_PET)
+    pot_evap6(uc, tm, ae, pa, UnderStory, f.wind, Ra[UnderStory], Ra[1], ra_used0, ra_used1, f.shortwave, o.NetLongAtmos, Tair,
+              f.vpd, dt_hours, o.pot_evap);
   if (is_veg) s.Wdew = v.Wdew;
   VR_PHASE_SYNC();
   // ---- runoff.c ----
   o.inflow = ppt;
   runoff_step(cc, NL, dt_hours, ppt, s.moist, evap, &o.asat, &o.runoff, &o.baseflow);
+  if (extras & EX_ZWT) water_table(cc, NL, s.moist, &o.zwt, &o.zwt_lumped);
   // ---- full_energy.c:445-453 ----
   double wet = 0, rootm = 0;
   for (int l = 0; l < NL; l++) {

@@ -274,7 +274,8 @@ struct vr_handle {
   bool have_lib = false, have_cells = false, initialised = false;
   // veglib copy
   std::vector<int32_t> lib_overstory;
-  std::vector<double> lib_rarc, lib_rmin, lib_wind_h, lib_RGL, lib_rad_atten, lib_wind_atten, lib_trunk, lib_rough, lib_disp;
+  std::vector<double> lib_rarc, lib_rmin, lib_wind_h, lib_RGL, lib_rad_atten, lib_wind_atten, lib_trunk, lib_rough, lib_disp,
+      lib_LAI, lib_albedo;
   Prepared P;
   DevModel M;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
@@ -428,6 +429,11 @@ int vr_set_veglib(vr_handle *h, const vr_veglib *lib)
   h->lib_trunk.assign(lib->trunk_ratio, lib->trunk_ratio + n);
   h->lib_rough.assign(lib->roughness, lib->roughness + (size_t)n * 12);
   h->lib_disp.assign(lib->displacement, lib->displacement + (size_t)n * 12);
+  h->lib_LAI.clear(); h->lib_albedo.clear();
+  if (lib->LAI && lib->albedo) {
+    h->lib_LAI.assign(lib->LAI, lib->LAI + (size_t)n * 12);
+    h->lib_albedo.assign(lib->albedo, lib->albedo + (size_t)n * 12);
+  }
   h->have_lib = true;
   h->have_cells = false;
   h->initialised = false;
@@ -446,6 +452,8 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   lib.wind_h = h->lib_wind_h.data(); lib.RGL = h->lib_RGL.data(); lib.rad_atten = h->lib_rad_atten.data();
   lib.wind_atten = h->lib_wind_atten.data(); lib.trunk_ratio = h->lib_trunk.data();
   lib.roughness = h->lib_rough.data(); lib.displacement = h->lib_disp.data();
+  lib.LAI = h->lib_LAI.empty() ? nullptr : h->lib_LAI.data();
+  lib.albedo = h->lib_albedo.empty() ? nullptr : h->lib_albedo.data();
   h->P = Prepared();
   if (!prepare(h->opt, lib, *cells, VR_CTA, h->P)) { h->err = h->P.error; return VR_ERR_ARG; }
   Prepared &P = h->P;

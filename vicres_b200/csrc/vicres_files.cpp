@@ -66,7 +66,8 @@ struct vr_params {
   std::vector<double> tile_Cv, tile_root, tile_LAI, tile_albedo, tile_vegcover;
   // veglib
   std::vector<int32_t> l_over;
-  std::vector<double> l_rarc, l_rmin, l_wind_h, l_RGL, l_rad, l_watt, l_trunk, l_rough, l_disp;
+  std::vector<double> l_rarc, l_rmin, l_wind_h, l_RGL, l_rad, l_watt, l_trunk, l_rough, l_disp, l_LAI, l_alb;
+  std::vector<double> zwt_zwt, zwt_moist;                                  // [(L+2)][11][C]
   vr_cells cells;
   vr_veglib lib;
 };
@@ -128,7 +129,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
   struct Soil {
     int gridcel; float lat, lng, elevation;
     double b, Ds, Dsmax, Ws, c, avg_temp, dp, rough, snow_rough;
-    double expt[3], Ksat[3], init_moist[3], depth[3], quartz[3], bdm[3], sdm[3], wcr_fr[3], wpwp_fr[3], resid[3];
+    double expt[3], Ksat[3], init_moist[3], depth[3], quartz[3], bdm[3], sdm[3], wcr_fr[3], wpwp_fr[3], resid[3], bubble[3];
   };
   std::vector<Soil> soils;
   {
@@ -162,7 +163,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
       }
       s.avg_temp = strtod(t[k++].c_str(), nullptr);
       s.dp = strtod(t[k++].c_str(), nullptr);
-      k += L;                                                  // bubble
+      for (int l = 0; l < L; l++) s.bubble[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.quartz[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.bdm[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.sdm[l] = strtod(t[k++].c_str(), nullptr);
@@ -206,6 +207,100 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
       P->porosity[k] = poros;
     }
     P->AreaFract[c] = 1.;                                       // band 0 (read_soilparam.c:478-486)
+  }
+  // ---- soil moisture v water table curves (read_soilparam.c:822-921; arithmetic order kept) ----
+  {
+    const int NP = VR_ZWT_NPOINTS;
+    P->zwt_zwt.assign((size_t)(L + 2) * NP * C, 0.0);
+    P->zwt_moist.assign((size_t)(L + 2) * NP * C, 0.0);
+    for (int64_t c = 0; c < C; c++) {
+      const Soil &s = soils[c];
+      double depth[3], max_moist[3], resid[3];
+      for (int l = 0; l < L; l++) {
+        depth[l] = s.depth[l]; max_moist[l] = P->max_moist[(size_t)l * C + c]; resid[l] = P->resid_moist[(size_t)l * C + c];
+      }
+      auto Z = [&](int k, int i) -> double & { return P->zwt_zwt[((size_t)k * NP + i) * C + c]; };
+      auto M = [&](int k, int i) -> double & { return P->zwt_moist[((size_t)k * NP + i) * C + c]; };
+      double tmp_depth = 0, b, bubble, tmp_resid_moist, zwt_prime, w_avg, tmp_max_moist, tmp_moist, tmp_depth2, b_save,
+             bub_save, tmp_depth2_save, zwt_prime_eff;
+      for (int layer = 0; layer < L; layer++) {
+        b = 0.5 * (s.expt[layer] - 3);
+        bubble = s.bubble[layer];
+        tmp_resid_moist = resid[layer] * depth[layer] * 1000;
+        zwt_prime = 0;
+        for (int i = 0; i < NP; i++) {
+          Z(layer, i) = -tmp_depth * 100 - zwt_prime;
+          w_avg = (depth[layer] * 100 - zwt_prime - (b / (b - 1)) * bubble * (1 - pow((zwt_prime + bubble) / bubble, (b - 1) / b))) /
+                  (depth[layer] * 100);
+          if (w_avg < 0) w_avg = 0;
+          if (w_avg > 1) w_avg = 1;
+          M(layer, i) = w_avg * (max_moist[layer] - tmp_resid_moist) + tmp_resid_moist;
+          zwt_prime += depth[layer] * 100 / (NP - 1);
+        }
+        tmp_depth += depth[layer];
+      }
+      tmp_depth = 0; b = 0; bubble = 0; tmp_max_moist = 0; tmp_resid_moist = 0;
+      for (int layer = 0; layer < L - 1; layer++) {
+        b += 0.5 * (s.expt[layer] - 3) * depth[layer];
+        bubble += s.bubble[layer] * depth[layer];
+        tmp_max_moist += max_moist[layer];
+        tmp_resid_moist += resid[layer] * depth[layer] * 1000;
+        tmp_depth += depth[layer];
+      }
+      b /= tmp_depth;
+      bubble /= tmp_depth;
+      zwt_prime = 0;
+      for (int i = 0; i < NP; i++) {
+        Z(L, i) = -zwt_prime;
+        w_avg = (tmp_depth * 100 - zwt_prime - (b / (b - 1)) * bubble * (1 - pow((zwt_prime + bubble) / bubble, (b - 1) / b))) /
+                (tmp_depth * 100);
+        if (w_avg < 0) w_avg = 0;
+        if (w_avg > 1) w_avg = 1;
+        M(L, i) = w_avg * (tmp_max_moist - tmp_resid_moist) + tmp_resid_moist;
+        zwt_prime += tmp_depth * 100 / (NP - 1);
+      }
+      tmp_depth = 0;
+      for (int layer = 0; layer < L; layer++) tmp_depth += depth[layer];
+      zwt_prime = 0;
+      for (int i = 0; i < NP; i++) {
+        Z(L + 1, i) = -zwt_prime;
+        if (zwt_prime == 0) {
+          tmp_moist = 0;
+          for (int layer = 0; layer < L; layer++) tmp_moist += max_moist[layer];
+          M(L + 1, i) = tmp_moist;
+        }
+        else {
+          tmp_moist = 0;
+          int layer = L - 1;
+          tmp_depth2 = tmp_depth - depth[layer];
+          while (layer > 0 && zwt_prime <= tmp_depth2 * 100) {
+            tmp_moist += max_moist[layer];
+            layer--;
+            tmp_depth2 -= depth[layer];
+          }
+          w_avg = (tmp_depth2 * 100 + depth[layer] * 100 - zwt_prime) / (depth[layer] * 100);
+          b = 0.5 * (s.expt[layer] - 3);
+          bubble = s.bubble[layer];
+          tmp_resid_moist = resid[layer] * depth[layer] * 1000;
+          w_avg += -(b / (b - 1)) * bubble * (1 - pow((zwt_prime + bubble - tmp_depth2 * 100) / bubble, (b - 1) / b)) / (depth[layer] * 100);
+          tmp_moist += w_avg * (max_moist[layer] - tmp_resid_moist) + tmp_resid_moist;
+          b_save = b; bub_save = bubble; tmp_depth2_save = tmp_depth2;
+          while (layer > 0) {
+            layer--;
+            tmp_depth2 -= depth[layer];
+            b = 0.5 * (s.expt[layer] - 3);
+            bubble = s.bubble[layer];
+            tmp_resid_moist = resid[layer] * depth[layer] * 1000;
+            zwt_prime_eff = tmp_depth2_save * 100 - bubble + bubble * pow((zwt_prime + bub_save - tmp_depth2_save * 100) / bub_save, b / b_save);
+            w_avg = -(b / (b - 1)) * bubble * (1 - pow((zwt_prime_eff + bubble - tmp_depth2 * 100) / bubble, (b - 1) / b)) / (depth[layer] * 100);
+            tmp_moist += w_avg * (max_moist[layer] - tmp_resid_moist) + tmp_resid_moist;
+            b_save = b; bub_save = bubble; tmp_depth2_save = tmp_depth2;
+          }
+          M(L + 1, i) = tmp_moist;
+        }
+        zwt_prime += tmp_depth * 100 / (NP - 1);
+      }
+    }
   }
 
   // ---- snow bands (read_snowband.c) ----
@@ -372,12 +467,16 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
   for (const VegClass &v : lib) {
     P->l_over.push_back(v.overstory); P->l_rarc.push_back(v.rarc); P->l_rmin.push_back(v.rmin); P->l_wind_h.push_back(v.wind_h);
     P->l_RGL.push_back((double)v.RGL); P->l_rad.push_back(v.rad_atten); P->l_watt.push_back(v.wind_atten); P->l_trunk.push_back(v.trunk_ratio);
-    for (int j = 0; j < 12; j++) { P->l_rough.push_back(v.roughness[j]); P->l_disp.push_back(v.displacement[j]); }
+    for (int j = 0; j < 12; j++) {
+      P->l_rough.push_back(v.roughness[j]); P->l_disp.push_back(v.displacement[j]);
+      P->l_LAI.push_back(v.LAI[j]); P->l_alb.push_back(v.albedo[j]);
+    }
   }
   vr_veglib &lb = P->lib;
   lb.nclass = (int32_t)lib.size(); lb.overstory = P->l_over.data(); lb.rarc = P->l_rarc.data(); lb.rmin = P->l_rmin.data();
   lb.wind_h = P->l_wind_h.data(); lb.RGL = P->l_RGL.data(); lb.rad_atten = P->l_rad.data(); lb.wind_atten = P->l_watt.data();
   lb.trunk_ratio = P->l_trunk.data(); lb.roughness = P->l_rough.data(); lb.displacement = P->l_disp.data();
+  lb.LAI = P->l_LAI.data(); lb.albedo = P->l_alb.data();
   vr_cells &cl = P->cells;
   cl.ncell = C; cl.lat = P->c_lat.data(); cl.elevation = P->elevation.data(); cl.b_infilt = P->b_infilt.data(); cl.Ds = P->Ds.data();
   cl.Dsmax = P->Dsmax.data(); cl.Ws = P->Ws.data(); cl.c_expt = P->c_expt.data(); cl.avg_temp = P->avg_temp.data(); cl.dp = P->dp.data();
@@ -390,6 +489,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
   cl.tile_ptr = P->tile_ptr.data(); cl.tile_class = P->tile_class.data(); cl.tile_Cv = P->tile_Cv.data();
   cl.tile_root = P->tile_root.data(); cl.tile_LAI = P->tile_LAI.data(); cl.tile_albedo = P->tile_albedo.data();
   cl.tile_vegcover = P->tile_vegcover.data();
+  cl.zwt_zwt = P->zwt_zwt.data(); cl.zwt_moist = P->zwt_moist.data();
   *out = P;
   return VR_OK;
 }

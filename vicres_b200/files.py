@@ -74,10 +74,12 @@ def read_params(soil, veglib, vegparam, snowband=None, nlayer=3, nbands=1, root_
         cells["tile_root"] = _arr(cs.tile_root, T * L, np.float64).reshape(T, L)
         for k in ["tile_LAI", "tile_albedo", "tile_vegcover"]:
             cells[k] = _arr(getattr(cs, k), T * 12, np.float64).reshape(T, 12)
+        for k in ["zwt_zwt", "zwt_moist"]:
+            cells[k] = _arr(getattr(cs, k), (L + 2) * 11 * Cn, np.float64).reshape(L + 2, 11, Cn)
         libd = {"overstory": _arr(vl.overstory, ncl, np.int32)}
         for k in ["rarc", "rmin", "wind_h", "RGL", "rad_atten", "wind_atten", "trunk_ratio"]:
             libd[k] = _arr(getattr(vl, k), ncl, np.float64)
-        for k in ["roughness", "displacement"]:
+        for k in ["roughness", "displacement", "LAI", "albedo"]:
             libd[k] = _arr(getattr(vl, k), ncl * 12, np.float64).reshape(ncl, 12)
         meta = {"gridcel": _arr(so.vr_params_gridcel(h), Cn, np.int32),
                 "lat": _arr(so.vr_params_lat(h), Cn, np.float32), "lng": _arr(so.vr_params_lng(h), Cn, np.float32)}

@@ -120,6 +120,23 @@ def make_cells(ncell, nlayer=3, nbands=1, seed=20261019, lat_range=(-40.0, 60.0)
     vc[is_bare] = 0.0
     cells.update(tile_ptr=tile_ptr, tile_class=cls, tile_Cv=cv, tile_root=root, tile_LAI=lai,
                  tile_albedo=alb, tile_vegcover=vc)
+    # library LAI / albedo (read by the NATVEG / VEGNOCR potential evaporation) and soil moisture v water table
+    # curves (read by OUT_ZWT*).  The curves here are synthetic monotone tables of the right shape -- the real
+    # ones (read_soilparam.c:822-921) are exercised by the golden fixtures and by csrc/vicres_files.cpp.
+    lib["LAI"], lib["albedo"] = lib_lai, lib_alb
+    frac = (np.arange(11) / 10.0)[None, :, None]                              # [1, 11, 1]
+    zz = np.zeros((L + 2, 11, C))
+    zm = np.zeros((L + 2, 11, C))
+    top = np.zeros(C)
+    for l in range(L):
+        zz[l] = -(top[None, :] + depth[l][None, :] * frac[0]) * 100.0
+        zm[l] = mm[l][None, :] * (1.0 - 0.4 * frac[0] ** 1.5)
+        top = top + depth[l]
+    zz[L] = -(depth[:L - 1].sum(0)[None, :] * frac[0]) * 100.0
+    zm[L] = mm[:L - 1].sum(0)[None, :] * (1.0 - 0.4 * frac[0] ** 1.5)
+    zz[L + 1] = -(depth.sum(0)[None, :] * frac[0]) * 100.0
+    zm[L + 1] = mm.sum(0)[None, :] * (1.0 - 0.4 * frac[0] ** 1.5)
+    cells["zwt_zwt"], cells["zwt_moist"] = zz, zm
     return lib, cells
 
 
