@@ -68,8 +68,17 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
         const int64_t u = P.u_slot[fu0 + j];
         const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
         const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];
-        unit_step_terms(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u],
-                        P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true);
+        const double *tl = P.tl.size() > 1 ? &P.tl[((size_t)P.u_tile[u] * 12 + fo.mon) * TL_N] : nullptr;
+        const double *ap = P.ap.size() > 1 ? &P.ap[((size_t)P.u_aero[u] * 12 + fo.mon) * AP_N] : nullptr;
+#define HS_STEP(EX) unit_step_terms<EX>(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u], \
+                                        P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap)
+        switch (term_extras(tmap)) {
+          case 0: HS_STEP(0); break;
+          case EX_PET: HS_STEP(EX_PET); break;
+          case EX_ZWT: HS_STEP(EX_ZWT); break;
+          default: HS_STEP(EX_PET | EX_ZWT); break;
+        }
+#undef HS_STEP
       }
       if (nu > 0) {
         cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);

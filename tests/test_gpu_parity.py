@@ -77,6 +77,9 @@ def _tile(cells, rep):
     out["tile_ptr"] = np.concatenate([[0], np.cumsum(nt)]).astype(np.int64)
     for k in ["tile_class", "tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]:
         out[k] = cells[k][tiles]
+    for k in ["zwt_zwt", "zwt_moist"]:
+        if cells.get(k) is not None:
+            out[k] = np.ascontiguousarray(cells[k][:, :, idx])
     return out, idx
 
 

@@ -82,8 +82,9 @@ inline void build_term_map(const int *out_vars, int n_out, TermMap &tmap)
 }
 
 // One unit's area-weighted terms -> term buffer column `col` (rows of `stride` doubles).
+template <int extras = EX_PET | EX_ZWT>
 VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
-                       const TermMap &tmap, double *col, int stride)
+                       const TermMap &tmap, double *col, int stride, const UnitExtra *x = nullptr)
 {
   const double AF = cv * af * 1. * 1.;
   const bool HasVeg = !uc.is_bare;
@@ -148,26 +149,39 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
   T_(TE_PREC, o.out_prec * cv * af);
   T_(TE_RAIN, o.out_rain * cv * af);
   T_(TE_SNOWF, o.out_snow * cv * af);
+  if (extras & EX_PET) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) T_(TE_PET0 + i, o.pot_evap[i] * AF);      // put_data.c:846-851
-  T_(TE_ZWT, o.zwt * AF);                                                // put_data.c:917-918
-  T_(TE_ZWTL, o.zwt_lumped * AF);
+    for (int i = 0; i < 6; i++) T_(TE_PET0 + i, (x ? x->pot_evap[i] : 0.) * AF);    // put_data.c:846-851
+  }
+  if (extras & EX_ZWT) {
+    T_(TE_ZWT, (x ? x->zwt : 0.) * AF);                                  // put_data.c:917-918
+    T_(TE_ZWTL, (x ? x->zwt_lumped : 0.) * AF);
+  }
 #undef T_
 }
 
 // One unit, one record, and its terms: the single out-of-line body the kernel calls per record.  Keeping
 // unit_step() and unit_terms() in one function lets the ~30 per-unit results travel in registers
 // instead of a UnitOut struct in local memory.
+template <int extras>
 VR_HDN void unit_step_terms(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
                             int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, double cv, double af,
-                            const TermMap &tmap, double *col, int stride, bool write)
+                            const TermMap &tmap, double *col, int stride, bool write, const double *tl = nullptr,
+                            const double *ap = nullptr)
 {
   UnitOut uo;
+  UnitExtra ux;
+  unit_step<extras>(cc, uc, tm, ae, f, NL, dt_hours, max_snow_temp, min_rain_temp, s, uo, ux, tl, ap);
+  if (write) unit_terms<extras>(uc, cv, af, s, uo, NL, tmap, col, stride, &ux);
+}
+
+// which optional results the requested outputs need
+inline int term_extras(const TermMap &tmap)
+{
   int extras = 0;
   for (int i = 0; i < 6; i++) if (tmap.row[TE_PET0 + i] >= 0) extras |= EX_PET;
   if (tmap.row[TE_ZWT] >= 0 || tmap.row[TE_ZWTL] >= 0) extras |= EX_ZWT;
-  unit_step(cc, uc, tm, ae, f, NL, dt_hours, max_snow_temp, min_rain_temp, s, uo, extras);
-  if (write) unit_terms(uc, cv, af, s, uo, NL, tmap, col, stride);
+  return extras;
 }
 
 // Sum the terms of one cell's units IN REFERENCE ORDER (tiles ascending, bands ascending) and leave

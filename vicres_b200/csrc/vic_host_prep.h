@@ -42,6 +42,8 @@ struct Prepared {
   std::vector<float> u_root;         // [MAXL][U]
   std::vector<double> tm;            // [T][12][TM_N]
   std::vector<double> ae;            // [K][12][AE_N]
+  std::vector<double> tl;            // [T][12][TL_N]  potential-evaporation tables, filled when an OUT_PET_* is requested
+  std::vector<double> ap;            // [K][12][AP_N]
   std::vector<int32_t> cell_fail;    // [C] 1 = CalcAerodynamic rejects a tile of this cell (full_energy returns ERROR)
   std::string error;
 };
@@ -129,8 +131,9 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     return cells.lat[a] > cells.lat[b];
   });
   // per-cell constants, stored BY SORTED POSITION so that neighbouring lanes read neighbouring words
-  bool want_pet_nat = false, want_zwt = false;
+  bool want_pet_nat = false, want_zwt = false, want_pet = false;
   for (int v = 0; v < opt.n_out; v++) {
+    if (opt.out_vars[v] >= VR_OUT_PET_SATSOIL && opt.out_vars[v] <= VR_OUT_PET_VEGNOCR) want_pet = true;
     if (opt.out_vars[v] == VR_OUT_PET_NATVEG || opt.out_vars[v] == VR_OUT_PET_VEGNOCR) want_pet_nat = true;
     if (opt.out_vars[v] == VR_OUT_ZWT || opt.out_vars[v] == VR_OUT_ZWT_LUMPED) want_zwt = true;
   }
@@ -227,21 +230,18 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
 
   // ---- tile x month canopy terms ----
   P.tm.assign((size_t)T * 12 * TM_N, 0.0);
+  P.tl.assign(want_pet ? (size_t)T * 12 * TL_N : 1, 0.0);
   for (int64_t t = 0; t < T; t++) {
     int cls = cells.tile_class[t];
     if (cls < 0 || cls > lib.nclass) { P.error = "tile_class out of range"; return false; }
-    if (cls == lib.nclass) {          // bare tile: its "library class" is the SATSOIL reference entry (global.h:56-57)
-      for (int m = 0; m < 12; m++) {
-        double *q = &P.tm[((size_t)t * 12 + m) * TM_N];
-        q[TM_LIB_LAI] = 1.0;
-        q[TM_LIB_ALB] = BARE_SOIL_ALBEDO;
-      }
-      continue;
+    for (int m = 0; m < 12 && want_pet; m++) {
+      double *q = &P.tl[((size_t)t * 12 + m) * TL_N];
+      if (cls == lib.nclass) { q[TL_LAI] = 1.0; q[TL_ALB] = BARE_SOIL_ALBEDO; }   // SATSOIL reference entry (global.h:56-57)
+      else { q[TL_LAI] = lib.LAI ? lib.LAI[cls * 12 + m] : 0.0; q[TL_ALB] = lib.albedo ? lib.albedo[cls * 12 + m] : 0.0; }
     }
+    if (cls == lib.nclass) continue;
     for (int m = 0; m < 12; m++) {
       double *q = &P.tm[((size_t)t * 12 + m) * TM_N];
-      q[TM_LIB_LAI] = lib.LAI ? lib.LAI[cls * 12 + m] : 0.0;
-      q[TM_LIB_ALB] = lib.albedo ? lib.albedo[cls * 12 + m] : 0.0;
       double vegcover = cells.tile_vegcover[t * 12 + m];
       if (vegcover < 0.0001) vegcover = 0.0001;          // MIN_VEGCOVER, full_energy.c:214-215
       double LAI = cells.tile_LAI[t * 12 + m];
@@ -275,6 +275,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
   }
   P.K = (int64_t)keylist.size();
   P.ae.assign((size_t)(P.K ? P.K : 1) * 12 * AE_N, 0.0);
+  P.ap.assign(want_pet ? (size_t)(P.K ? P.K : 1) * 12 * AP_N : 1, 0.0);
   std::vector<char> key_fail(P.K ? P.K : 1, 0);
   for (int64_t k = 0; k < P.K; k++) {
     int cls = std::get<0>(keylist[k]);
@@ -301,7 +302,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
       // the four PET reference covers seen from this tile (full_energy.c:329-369): their own displacement and
       // roughness (global.h:59-60; SATSOIL's were overwritten with the cell's soil values, read_soilparam.c:551-554),
       // no overstory, but the reference height test uses the TILE's wind_h
-      for (int p = 0; p < 4; p++) {
+      for (int p = 0; p < 4 && want_pet; p++) {
         const double ref_rough[4] = {0.001, 0.001, 0.0148, 0.0615}, ref_displ[4] = {0.0054, 0.0054, 0.08, 0.3333};
         double d3[3] = {0, 0, 0}, r3[3] = {0, 0, 0}, h3[3] = {0, 0, 0}, Rp[3] = {0, 0, 0}, Up[3] = {0, 0, 0};
         d3[0] = (p == 0) ? rough * 0.667 / 0.123 : ref_displ[p];
@@ -309,7 +310,7 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
         if (d3[0] < wind_h) h3[0] = wind_h;
         else h3[0] = d3[0] + wind_h + r3[0];
         if (aero_coeffs(0, d3[0] / 0.67, 0.0, snow_rough, rough, 0.0, Rp, Up, d3, h3, r3) != 0) key_fail[k] = 1;
-        for (int i = 0; i < 3; i++) q[AE_PET + 3 * p + i] = Rp[i];
+        for (int i = 0; i < 3; i++) P.ap[((size_t)k * 12 + m) * AP_N + 3 * p + i] = Rp[i];
       }
     }
   }

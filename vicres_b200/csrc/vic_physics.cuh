@@ -12,8 +12,8 @@
 //     QUICK_FLUX exponentials, ARNO exponents, baseflow coefficients, monthly canopy terms;
 //   * the Penman-Monteith air-state terms (2 exp) are computed once per unit-step and shared by
 //     the up-to-5 penman() evaluations of canopy_evap/transpiration/arno_evap;
-//   * the 6 PET reference evaporations and compute_zwt are not computed (they feed only
-//     OUT_PET_* / OUT_ZWT*).
+//   * the 6 PET reference evaporations (compute_pot_evap.c) and compute_zwt are compile-time options of
+//     unit_step (template argument `extras`): they feed only OUT_PET_* / OUT_ZWT*.
 // Operation order inside each formula follows the reference so results stay within 1e-9 relative.
 //
 // The functions are __host__ __device__ so that tests/hostsim can compile this header with g++ and
@@ -242,13 +242,16 @@ struct UnitC {
 };
 
 // per (tile, month) canopy terms (full_energy.c:210-227,306-308) -- tm[(t*12+mon)*TM_N + k]
-// TM_LIB_*: the LIBRARY's LAI / albedo of the tile's class (the SATSOIL reference entry for the bare tile), which
-// compute_pot_evap reads for the NATVEG / VEGNOCR potential evaporation
-enum { TM_VEGCOVER = 0, TM_ALBEDO, TM_LAI, TM_WDMAX, TM_SURF_ATTEN, TM_LIB_LAI, TM_LIB_ALB, TM_N };
+enum { TM_VEGCOVER = 0, TM_ALBEDO, TM_LAI, TM_WDMAX, TM_SURF_ATTEN, TM_N };
+// separate per (tile, month) table read only by the potential evaporation: the LIBRARY's LAI / albedo of the
+// tile's class (the SATSOIL reference entry for the bare tile), compute_pot_evap.c:62-66
+enum { TL_LAI = 0, TL_ALB, TL_N };
 // per (aero key, month) CalcAerodynamic coefficients: Ra = RA/wind, U = UC*wind
-// AE_PET + 3*p + i: RA coefficient i of PET reference cover p (SATSOIL, H2OSURF, SHORT, TALL; full_energy.c:329-369)
 enum { AE_RA0 = 0, AE_RA1, AE_RA2, AE_U0, AE_U1, AE_U2, AE_REF0, AE_REF1, AE_REF2, AE_ROUGH0, AE_ROUGH1,
-       AE_ROUGH2, AE_DISP0, AE_DISP1, AE_DISP2, AE_PET, AE_N = AE_PET + 12 };
+       AE_ROUGH2, AE_DISP0, AE_DISP1, AE_DISP2, AE_N };
+// separate per (aero key, month) table read only by the potential evaporation: entry 3*p + i = RA coefficient i
+// of PET reference cover p (SATSOIL, H2OSURF, SHORT, TALL; full_energy.c:329-369)
+enum { AP_N = 12 };
 
 struct Forc { double air_temp, prec, wind, vp, vpd, pressure, density, shortwave, longwave; int mon, doy; };
 
@@ -269,9 +272,11 @@ struct UnitOut {
   double evap[MAXL], bef[MAXL], vapor_flux, canopy_vapor_flux, canopyevap, asat, runoff, baseflow, inflow,
          aero_resist[2], wetness, rootmoist, melt, Tsurf, NetShortAtmos, NetLongAtmos, in_long, albedo,
          grnd_flux, deltaH, out_prec, out_rain, out_snow;
-  double pot_evap[6], zwt, zwt_lumped;      // only filled when requested (unit_step's `extras`)
   int snow_flag;
 };
+
+// optional results (unit_step's `extras`); a separate struct so that the default kernel instance carries none of it
+struct UnitExtra { double pot_evap[6], zwt, zwt_lumped; };
 
 // view of the constants of the cell at sorted position pos
 VR_HD void load_cell_consts(const double *cc, int64_t C, int64_t pos, int NL, CellC &x)
@@ -1287,7 +1292,7 @@ enum { EX_PET = 1, EX_ZWT = 2 };
 // (surface_fluxes.c:868-894 rebuilds a stability factor from them and applies it to every reference cover).
 // calc_rc() of cover i sees the net_short of cover i-1 (the reference assigns it afterwards); only NATVEG
 // depends on it, and it gets TALL's.
-VR_HDN void pot_evap6(const UnitC &uc, const double *tm, const double *ae, const PenmanAir &pa, int UnderStory, double wind,
+VR_HDN void pot_evap6(const UnitC &uc, const double *tl, const double *ap, const PenmanAir &pa, int UnderStory, double wind,
                       double raU, double ra1, double used0, double used1, double shortwave, double net_longwave,
                       double tair, double vpd, int dt_hours, double *pot)
 {
@@ -1303,12 +1308,12 @@ VR_HDN void pot_evap6(const UnitC &uc, const double *tm, const double *ae, const
     double rs, rarc, RGL, lai, albedo, a0, a1;
     if (i < 4) {
       rs = ref_rmin[i]; rarc = ref_rarc[i]; RGL = (i < 2) ? 0.0 : 100; lai = ref_lai[i]; albedo = ref_alb[i];
-      const double *q = ae + AE_PET + 3 * i;
+      const double *q = ap + 3 * i;
       if (wind > 0.) { a0 = q[UnderStory] / wind; a1 = q[1] / wind; }
       else { a0 = HUGE_RESIST; a1 = HUGE_RESIST; }
     }
     else {
-      rs = (i == 5) ? 0 : uc.rmin; rarc = uc.rarc; RGL = uc.RGL; lai = tm[TM_LIB_LAI]; albedo = tm[TM_LIB_ALB];
+      rs = (i == 5) ? 0 : uc.rmin; rarc = uc.rarc; RGL = uc.RGL; lai = tl[TL_LAI]; albedo = tl[TL_ALB];
       a0 = raU; a1 = ra1;
     }
     double rc;
@@ -1360,8 +1365,13 @@ VR_HDN void water_table(const CellC &cc, int NL, const double *moist, double *zw
   *zwt_out = zwt; *lumped_out = zl;
 }
 
+// extras: compile-time set of optional results (EX_PET, EX_ZWT) -- the kernel without them carries none of their
+// code or registers (their mere presence behind a run-time flag cost 4 % of the default configuration)
+// tl, ap: the potential-evaporation tables of the tile and aero key for the month (read only with EX_PET)
+template <int extras>
 VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
-                     int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o, int extras = 0)
+                     int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o, UnitExtra &x,
+                     const double *tl = nullptr, const double *ap = nullptr)
 {
   const double delta_t = (double)dt_hours * 3600.;
   const bool is_veg = !uc.is_bare;
@@ -1751,14 +1761,14 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     o.aero_resist[1] = (c1 > 0 && c1 < HUGE_RESIST) ? 1 / (c1 / 1.) : ((c1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
   }
   if (extras & EX_PET)
-    pot_evap6(uc, tm, ae, pa, UnderStory, f.wind, Ra[UnderStory], Ra[1], ra_used0, ra_used1, f.shortwave, o.NetLongAtmos, Tair,
-              f.vpd, dt_hours, o.pot_evap);
+    pot_evap6(uc, tl, ap, pa, UnderStory, f.wind, Ra[UnderStory], Ra[1], ra_used0, ra_used1, f.shortwave, o.NetLongAtmos, Tair,
+              f.vpd, dt_hours, x.pot_evap);
   if (is_veg) s.Wdew = v.Wdew;
   VR_PHASE_SYNC();
   // ---- runoff.c ----
   o.inflow = ppt;
   runoff_step(cc, NL, dt_hours, ppt, s.moist, evap, &o.asat, &o.runoff, &o.baseflow);
-  if (extras & EX_ZWT) water_table(cc, NL, s.moist, &o.zwt, &o.zwt_lumped);
+  if (extras & EX_ZWT) water_table(cc, NL, s.moist, &x.zwt, &x.zwt_lumped);
   // ---- full_energy.c:445-453 ----
   double wet = 0, rootm = 0;
   for (int l = 0; l < NL; l++) {

@@ -48,6 +48,7 @@ struct DevModel {
   const int64_t *order;             // sorted position -> caller's cell index
   const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *u_logical, *cell_fail;
   const double *u_cv, *u_af, *u_Tfactor, *u_Pfactor, *u_rarc, *u_rmin, *u_RGL, *tm, *ae, *init_moist;
+  const double *tl, *ap;            // potential-evaporation tables (valid when an OUT_PET_* is requested)
   const float *u_root;
   double *state;                    // [ST_N][U]
   double *sv;                       // [SV_N][C]
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *te
 
 // full_energy() for F.nrec consecutive records of every unit; terms[rec][row][unit in reference order]: the
 // stores scatter (fire and forget) so that k_cells reads each cell's units contiguously
+template <int EXTRAS>
 __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcing F, double *__restrict__ terms)
 {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcin
   load_state(M, u, s);
   const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
   const double *ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
+  const double *tl = (EXTRAS & EX_PET) ? M.tl + (size_t)M.u_tile[u] * 12 * TL_N : nullptr;
+  const double *ap = (EXTRAS & EX_PET) ? M.ap + (size_t)M.u_aero[u] * 12 * AP_N : nullptr;
   const int nrec = F.nrec, NL = M.NL;
   const size_t rec_stride = (size_t)M.tmap.n * M.U;
   const bool write = active && !failed;
@@ -168,8 +172,9 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcin
     f.density = __ldg(F.field[VR_F_DENSITY] + q); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q);
     f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
     f.mon = __ldg(F.month + rec) - 1; f.doy = __ldg(F.doy + rec);
-    unit_step_terms(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
-                    cv, af, M.tmap, terms + rec * rec_stride + col, (int)M.U, write);
+    unit_step_terms<EXTRAS>(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
+                    cv, af, M.tmap, terms + rec * rec_stride + col, (int)M.U, write,
+                    (EXTRAS & EX_PET) ? tl + f.mon * TL_N : nullptr, (EXTRAS & EX_PET) ? ap + f.mon * AP_N : nullptr);
   }
   if (write) store_state(M, u, s);
 }
@@ -278,6 +283,7 @@ struct vr_handle {
       lib_LAI, lib_albedo;
   Prepared P;
   DevModel M;
+  DBuf<double> d_tl, d_ap;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
       d_forc, d_out, d_tair0, d_terms, d_sums;
   DBuf<float> d_u_root;
@@ -292,6 +298,7 @@ struct vr_handle {
   size_t evs_used = 0;
   static constexpr int NBUF = 4;     // copy buffers per direction of the host pipeline
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[NBUF] = {}, ev_comp[NBUF] = {}, ev_out[NBUF] = {};
+  int extras = 0;                    // EX_PET | EX_ZWT when such outputs are requested: selects the k_units instance
   int cta = VR_CTA;                  // threads per k_units block, chosen per grid so that the blocks fill whole waves
   int64_t ncta = 0;
   int chunk = 16;                    // records per k_units/k_cells launch pair (and per pipelined copy of vr_step_block)
@@ -378,7 +385,10 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     delete h;
     return VR_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_units, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of L1 for the stacks
+  cudaFuncSetAttribute(k_units<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of L1 for the stacks
+  cudaFuncSetAttribute(k_units<EX_PET>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_ZWT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_PET | EX_ZWT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   *out = h;
   return VR_OK;
@@ -391,6 +401,7 @@ void vr_destroy(vr_handle *h)
   h->d_cc.release(); h->d_u_cv.release(); h->d_u_af.release(); h->d_u_Tf.release(); h->d_u_Pf.release();
   h->d_u_rarc.release(); h->d_u_rmin.release(); h->d_u_RGL.release(); h->d_tm.release(); h->d_ae.release();
   h->d_init_moist.release(); h->d_state.release(); h->d_sv.release(); h->d_forc.release(); h->d_out.release();
+  h->d_tl.release(); h->d_ap.release();
   h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_fcol.release(); h->d_terms.release(); h->d_sums.release(); h->d_u_logical.release();
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
@@ -479,6 +490,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   CK(h->d_u_af.upload(P.u_af)); CK(h->d_u_Tf.upload(P.u_Tfactor)); CK(h->d_u_Pf.upload(P.u_Pfactor));
   CK(h->d_u_rarc.upload(P.u_rarc)); CK(h->d_u_rmin.upload(P.u_rmin)); CK(h->d_u_RGL.upload(P.u_RGL));
   CK(h->d_u_root.upload(P.u_root)); CK(h->d_tm.upload(P.tm)); CK(h->d_ae.upload(P.ae));
+  CK(h->d_tl.upload(P.tl)); CK(h->d_ap.upload(P.ap));
   CK(h->d_init_moist.upload(im));
   CK(h->d_order.upload(P.order)); CK(h->d_u_slot.upload(P.u_slot)); CK(h->d_u_logical.upload(P.u_logical));
   CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
@@ -495,11 +507,13 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.u_cell = h->d_u_cell.p; M.u_pos = h->d_u_pos.p; M.u_tile = h->d_u_tile.p; M.u_flags = h->d_u_flags.p; M.u_aero = h->d_u_aero.p;
   M.cell_fail = h->d_cell_fail.p; M.u_cv = h->d_u_cv.p; M.u_af = h->d_u_af.p; M.u_Tfactor = h->d_u_Tf.p;
   M.u_Pfactor = h->d_u_Pf.p; M.u_rarc = h->d_u_rarc.p; M.u_rmin = h->d_u_rmin.p; M.u_RGL = h->d_u_RGL.p;
+  M.tl = h->d_tl.p; M.ap = h->d_ap.p;
   M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
   M.order = h->d_order.p; M.u_slot = h->d_u_slot.p; M.u_logical = h->d_u_logical.p;
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
+  h->extras = term_extras(M.tmap);
   h->have_cells = true;
   h->initialised = false;
   return VR_OK;
@@ -577,7 +591,14 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     }
     if (h->pair_seq >= 2) cudaStreamWaitEvent(st, h->ev_cells[b], 0);     // pair i-2 has been aggregated out of terms[b]
     if (t) cudaEventRecord(t->u0, st);
-    if (h->M.U > 0) k_units<<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms);
+    if (h->M.U > 0) {
+      switch (h->extras) {       // one kernel instance per set of optional results
+        case 0: k_units<0><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        case EX_PET: k_units<EX_PET><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        case EX_ZWT: k_units<EX_ZWT><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        default: k_units<EX_PET | EX_ZWT><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+      }
+    }
     if (t) cudaEventRecord(t->u1, st);
     cudaEventRecord(h->ev_units[b], st);
     cudaStreamWaitEvent(h->s_cells, h->ev_units[b], 0);

@@ -25,4 +25,7 @@ def slice_cells(cells, c0, c1):
     out["tile_ptr"] = (tp[c0:c1 + 1] - t0).astype(np.int64)
     for k in ["tile_class", "tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]:
         out[k] = np.ascontiguousarray(np.asarray(cells[k])[t0:t1])
+    for k in ["zwt_zwt", "zwt_moist"]:                 # optional [(L+2), 11, C] curves
+        if cells.get(k) is not None:
+            out[k] = np.ascontiguousarray(np.asarray(cells[k])[:, :, c0:c1])
     return out
