@@ -219,9 +219,10 @@ def run_ours(args):
         dist.barrier()
 
     C, R, K, W = args.cells, args.block, args.steps, max(args.warmup, 0)
-    lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=1, seed=20261019 + rank)
-    f_host, month, doy = synth_soa.make_forcing(cells, R, seed=7 + rank)
-    opt = abi.default_options(3, 1, 24)
+    lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=args.bands, seed=20261019 + rank,
+                                      **({"lat_range": (35.0, 65.0), "overstory_frac": 0.3} if args.bands > 1 else {}))
+    f_host, month, doy = synth_soa.make_forcing(cells, R, dt_hours=args.dt, seed=7 + rank, cold=args.cold)
+    opt = abi.default_options(3, args.bands, args.dt)
     if args.chunk > 0:
         opt.cells_per_block_hint = args.chunk
     n_out = opt.n_out
@@ -319,8 +320,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 100k-cell grid, 3 soil layers, water-balance mode, daily step, "
-                                   "10 years (one step = one simulated year of every cell)",
+            "config": {"workload": ("synthetic 100k-cell grid, 3 soil layers, water-balance mode, daily step, "
+                                    "10 years (one step = one simulated year of every cell)") if
+                                   (C == 100000 and R == 365 and args.bands == 1 and args.dt == 24) else
+                                   ("synthetic %d-cell grid, 3 soil layers, %d snow band(s), %d-hourly step, "
+                                    "%d records per step" % (C, args.bands, args.dt, R)),
                        "cells_per_gpu": C, "records_per_step": R, "active_tile_band_units_per_gpu": m.num_units,
                        "parallelism": "cells sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "inputs larger than L2: %.2f GB forcing + %.2f GB outputs per step" %
@@ -369,6 +373,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--chunk", type=int, default=0, help="records per kernel-pair launch (0 = library default)")
+    ap.add_argument("--bands", type=int, default=1, help="snow bands (BASELINE config 3 uses 5)")
+    ap.add_argument("--dt", type=int, default=24, help="model step in hours (config 3: 3)")
+    ap.add_argument("--cold", type=float, default=0.0, help="lower all temperatures (deg C) to force snow")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -514,6 +514,13 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
   h->extras = term_extras(M.tmap);
+  {   // records per launch pair: the caller's hint or 16, capped so that the two term buffers stay below 24 GB
+      // (a 1M-cell, 5-band grid has 1.2e7 units: 16 records would need 80 GB of terms)
+    h->chunk = h->opt.cells_per_block_hint > 0 ? h->opt.cells_per_block_hint : 16;
+    const double per_rec = 2.0 * M.tmap.n * (double)(U ? U : 1) * sizeof(double);
+    const int cap = (int)(24e9 / per_rec);
+    if (h->chunk > cap) h->chunk = cap < 1 ? 1 : cap;
+  }
   h->have_cells = true;
   h->initialised = false;
   return VR_OK;

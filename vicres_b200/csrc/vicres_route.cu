@@ -14,7 +14,8 @@
 //                loop (reservoir.f:1142-1600).  Days are sequential; inside a day the reservoirs are
 //                independent (a release reaches the next node on day I+1), so phase A = every reservoir
 //                operates, barrier, phase B = every node adds its upstream releases through UH_R in
-//                reservoir order, taps ascending (the order of reservoir.f:1569-1575), barrier.
+//                reservoir order, taps ascending (the order of reservoir.f:1569-1575), barrier; the station's
+//                inflow, which feeds nothing back, is summed after the loop with one thread per day.
 //                Transcendentals (tan of the hedging angles, sqrt in H0) are evaluated on the host so
 //                the device does only IEEE + - * / and compares: results equal the serial loop bit for bit
 // Everything is fp32 like the Fortran REALs and compiled with -fmad=false.  No CPU fallback.
@@ -493,27 +494,67 @@ __global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
       a.flowin[b0 + I - 1] = flowin; a.flowout[b0 + I - 1] = flowout; a.turb[b0 + I - 1] = turb;
       a.energy[b0 + I - 1] = energy; a.htk[b0 + I - 1] = htk;
     }
-    if (threadIdx.x == blockDim.x - 1) {                // station: RESFLOWS(NORES, I) is complete since day I-1
-      float f = RF[(size_t)nres * W + I];
-      if (f < 0.0f) f = 0.0f;
-      a.flow[(size_t)set * nd + I - 1] = f;
-    }
     __syncthreads();
-    // ---- phase B: releases of day <= I reach the next node on day I+1 through UH_R ----
-    for (int k = threadIdx.x; k < a.nnodes; k += blockDim.x) {
-      const int u0 = a.up_ptr[k], u1 = a.up_ptr[k + 1];
-      if (u0 == u1) continue;
-      float acc = RF[(size_t)k * W + I + 1];
-      for (int u = u0; u < u1; u++) {
-        const int J = a.up_idx[u];
-        const float *uh = a.uh_r + (size_t)J * NS;
-        const float *fo = a.flowout + ((size_t)set * nres + J) * nd;
-        const int kmax = I < NS ? I : NS;
-        for (int KK = 1; KK <= kmax; KK++) acc = acc + uh[KK - 1] * fo[I - KK];
+    // ---- phase B: releases of day <= I reach the next RESERVOIR on day I+1 through UH_R (the station's
+    //      inflow feeds nothing back, so it is summed after the day loop, all days in parallel) ----
+#ifndef VR_RES_SKIP_B
+    // One WARP per target: the lanes fetch and multiply 32 terms at a time, then every lane replays the serial
+    // chain acc = acc + t_i through shuffles (same order, same roundings as the one-thread loop; the loads and
+    // multiplies leave the dependent path).
+    {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+      const int kmax = I < NS ? I : NS;
+      for (int k = warp; k < nres; k += nwarps) {
+        const int u0 = a.up_ptr[k], u1 = a.up_ptr[k + 1];
+        if (u0 == u1) continue;
+        float acc = RF[(size_t)k * W + I + 1];
+        const int n = (u1 - u0) * kmax;
+        // this lane's position in the chain, (upstream reservoir ju, tap kk), advanced by 32 terms per group
+        int ju = lane / kmax, kk = lane % kmax + 1;
+        auto term = [&]() -> float {
+          float v = 0.0f;
+          if (u0 + ju < u1) {
+            const int J = a.up_idx[u0 + ju];
+            v = a.uh_r[(size_t)J * NS + kk - 1] * a.flowout[((size_t)set * nres + J) * nd + I - kk];
+          }
+          kk += 32;
+          while (kk > kmax) { kk -= kmax; ju++; }
+          return v;
+        };
+        float t = term();
+        for (int base = 0; base < n; base += 32) {
+          const float tn = term();                   // next group's loads fly while this group's adds run
+          float tv[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) tv[i] = __shfl_sync(0xffffffffu, t, i);     // 32 independent shuffles first
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc = acc + tv[i];   // then the dependent chain of adds; past the end of the
+          t = tn;                                            // chain the terms are +0.0f, which adds exactly nothing
+        }
+        if (lane == 0) RF[(size_t)k * W + I + 1] = acc;
       }
-      RF[(size_t)k * W + I + 1] = acc;
     }
+#endif
     __syncthreads();
+  }
+  // ---- station: RESFLOWS(NORES, I) = naturalised inflow + the releases routed to it during day I-1, added in the
+  //      reference's order (reservoirs ascending, taps ascending: reservoir.f:1569-1575), then clamped (:1589-1593).
+  //      One thread per day: the serial chain of up to (reservoirs x 107) fp32 adds runs for all days at once.
+  {
+    const int k = nres, u0 = a.up_ptr[k], u1 = a.up_ptr[k + 1];
+    for (int I = 1 + threadIdx.x; I <= nd; I += blockDim.x) {
+      float acc = RF[(size_t)k * W + I];
+      if (I >= 2)
+        for (int u = u0; u < u1; u++) {
+          const int J = a.up_idx[u];
+          const float *uh = a.uh_r + (size_t)J * NS;
+          const float *fo = a.flowout + ((size_t)set * nres + J) * nd;
+          const int kmax = (I - 1) < NS ? (I - 1) : NS;
+          for (int KK = 1; KK <= kmax; KK++) acc = acc + uh[KK - 1] * fo[I - 1 - KK];
+        }
+      if (acc < 0.0f) acc = 0.0f;
+      a.flow[(size_t)set * nd + I - 1] = acc;
+    }
   }
 }
 
@@ -969,6 +1010,7 @@ int vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *
   a.resflows = h->d_resflows.p; a.vol = h->d_vol.p; a.hho = h->d_hho.p; a.flowin = h->d_flowin.p;
   a.flowout = h->d_flowout.p; a.turb = h->d_turb.p; a.energy = h->d_energy.p; a.htk = h->d_htk.p; a.flow = h->d_flow.p;
   int threads = ((nnodes + 31) / 32) * 32;
+  if (threads < 512) threads = 512;              // the day-parallel station pass wants threads, the day loop does not mind
   if (threads > 1024) threads = 1024;
   cudaEventRecord(h->ev0);
   k_reservoirs<<<nsets, threads>>>(a);
