@@ -202,7 +202,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from vicres_b200 import abi, build, model, synth_soa
+    from vicres_b200 import abi, build, model, shard, synth_soa
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,11 +222,32 @@ def run_ours(args):
     lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=args.bands, seed=20261019 + rank,
                                       **({"lat_range": (35.0, 65.0), "overstory_frac": 0.3} if args.bands > 1 else {}))
     f_host, month, doy = synth_soa.make_forcing(cells, R, dt_hours=args.dt, seed=7 + rank, cold=args.cold)
-    opt = abi.default_options(3, args.bands, args.dt)
+    opt = abi.default_options(3, args.bands, args.dt, out=["RUNOFF", "BASEFLOW"] if args.ensemble else None)
     if args.chunk > 0:
         opt.cells_per_block_hint = args.chunk
     n_out = opt.n_out
-    m = model.VicRes(opt, lib, cells, device=local)
+    fmap = None
+    if args.ensemble:       # P copies of the basin's cells with perturbed calibration parameters, one forcing column per basin cell
+        P, N = args.ensemble, C
+        rng = np.random.default_rng(99 + rank)
+        idx = np.tile(np.arange(N), P)
+        ens = shard.slice_cells(cells, 0, N)            # (copy)
+        tp = np.asarray(cells["tile_ptr"]); nt = tp[1:] - tp[:-1]
+        tiles = np.concatenate([np.arange(tp[c], tp[c + 1]) for c in range(N)])
+        for k in abi.CELL_SCALARS:
+            ens[k] = np.tile(cells[k], P)
+        for k in abi.CELL_LAYER + abi.CELL_BAND:
+            ens[k] = np.tile(cells[k], (1, P))
+        for k in ["zwt_zwt", "zwt_moist"]:
+            ens[k] = np.tile(cells[k], (1, 1, P))
+        ens["tile_ptr"] = np.concatenate([[0], np.cumsum(np.tile(nt, P))]).astype(np.int64)
+        for k in ["tile_class", "tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]:
+            ens[k] = np.concatenate([np.asarray(cells[k])[tiles]] * P)
+        ens["b_infilt"] = rng.uniform(0.001, 0.9, P * N); ens["Ds"] = rng.uniform(0.001, 0.9, P * N)
+        ens["Dsmax"] = rng.uniform(1.0, 30.0, P * N); ens["Ws"] = rng.uniform(0.3, 0.9, P * N)
+        ens["c_expt"] = rng.uniform(1.0, 3.0, P * N)
+        cells, fmap, C = ens, idx, P * N
+    m = model.VicRes(opt, lib, cells, device=local, forcing_map=fmap, n_forcing_cols=f_host.shape[2] if fmap is not None else None)
     m.init_state(f_host[0, 0])
     dev = torch.device("cuda", local)
 
@@ -323,7 +344,9 @@ def run_ours(args):
             "config": {"workload": ("synthetic 100k-cell grid, 3 soil layers, water-balance mode, daily step, "
                                     "10 years (one step = one simulated year of every cell)") if
                                    (C == 100000 and R == 365 and args.bands == 1 and args.dt == 24) else
-                                   ("synthetic %d-cell grid, 3 soil layers, %d snow band(s), %d-hourly step, "
+                                   (("ensemble of %d parameter sets x %d basin cells sharing %d forcing columns, outputs RUNOFF+BASEFLOW, "
+                                     % (args.ensemble, C // max(args.ensemble, 1), C // max(args.ensemble, 1)) if args.ensemble else "") +
+                                    "synthetic %d-cell grid, 3 soil layers, %d snow band(s), %d-hourly step, "
                                     "%d records per step" % (C, args.bands, args.dt, R)),
                        "cells_per_gpu": C, "records_per_step": R, "active_tile_band_units_per_gpu": m.num_units,
                        "parallelism": "cells sharded over %d GPU(s), no data-path collective" % world,
@@ -376,6 +399,9 @@ def main():
     ap.add_argument("--bands", type=int, default=1, help="snow bands (BASELINE config 3 uses 5)")
     ap.add_argument("--dt", type=int, default=24, help="model step in hours (config 3: 3)")
     ap.add_argument("--cold", type=float, default=0.0, help="lower all temperatures (deg C) to force snow")
+    ap.add_argument("--ensemble", type=int, default=0,
+                    help="BASELINE config 4: P parameter sets x --cells basin cells sharing the basin's forcing columns "
+                         "(outputs RUNOFF and BASEFLOW only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
