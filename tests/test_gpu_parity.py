@@ -195,3 +195,36 @@ def test_device_pow_error_bound():
     sx = np.array([1.0, 0.0, 0.0, 2.0])
     sy = np.array([7.3, 2.0, 0.0, 0.0])
     assert np.array_equal(model.diag_pow(sx, sy), np.array([1.0, 0.0, 1.0, 1.0]))
+
+
+def test_edge_shapes(VicRes):
+    """one cell x one record; a grid whose last block is nearly empty; a cell without any tile (outputs 0,
+    neighbours unaffected); a single output variable"""
+    lib, cells = synth_soa.make_cells(1, nbands=1, seed=2)
+    f, month, doy = synth_soa.make_forcing(cells, 1, seed=3)
+    opt = abi.default_options(3, 1, 24)
+    m = VicRes(opt, lib, cells)
+    m.init_state(f[0, 0])
+    out, status = m.step(month, doy, f)
+    o = oracle_lib.Oracle(opt, lib, cells)
+    o.init_state(f[0, 0])
+    _, ref, _ = o.step(month, doy, f)
+    assert out.shape == (opt.n_out, 1, 1) and relerr(out, ref).max() < RTOL
+    m.close(); o.close()
+    # 33 cells, cell 7 stripped of its tiles
+    lib, cells = synth_soa.make_cells(33, nbands=2, seed=4)
+    tp = cells["tile_ptr"].copy()
+    a, b = int(tp[7]), int(tp[8])
+    keep = np.r_[0:a, b:int(tp[-1])]
+    for k in ["tile_class", "tile_Cv", "tile_root", "tile_LAI", "tile_albedo", "tile_vegcover"]:
+        cells[k] = cells[k][keep]
+    tp[8:] -= (b - a)
+    cells["tile_ptr"] = tp
+    f, month, doy = synth_soa.make_forcing(cells, 37, seed=6)
+    opt1 = abi.default_options(3, 2, 24, out=["RUNOFF"])
+    m = VicRes(opt1, lib, cells)
+    m.init_state(f[0, 0])
+    out, status = m.step(month, doy, f)
+    assert out.shape == (1, 37, 33) and np.isfinite(out).all() and not status.any()
+    assert (out[0, :, 7] == 0).all() and out[0].sum() > 0
+    m.close()

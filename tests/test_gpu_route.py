@@ -182,3 +182,17 @@ def test_cuda_reservoirs_match_prebuilt_binary(Route, name, tmp_path):
     err = np.abs(one["flow"] - z["station_flow"]) / np.maximum(np.abs(z["station_flow"]), 1e-2)
     assert err.max() < 2e-5
     r.close()
+
+
+def test_cuda_station_without_reservoirs(Route):
+    """a catchment with no reservoir above the station: one node, the reservoir pass is the clamp of the
+    naturalised flow (reservoir.f:1589-1593)"""
+    z, grid, (col, row), fac = load_route_fixture("rand12x10")
+    r = Route(grid, col, row, z["uh_box"])
+    assert r.nnodes == 1
+    nat = r.convolve(z["runoff"], z["baseflow"])
+    nat[0, 5] = -3.0
+    out = r.reservoirs(nat, [[]], 2000, 1)
+    assert out["flow"].shape == (1, nat.shape[1]) and out["flow"][0, 5] == 0
+    assert np.array_equal(np.maximum(nat[0], 0), out["flow"][0])
+    r.close()
