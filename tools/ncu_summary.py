@@ -1,4 +1,4 @@
-"""Summarise an `ncu --set full --import-source on` capture of k_step into markdown + JSON.
+"""Summarise an `ncu --set full --import-source on` capture of the step kernel (k_units) into markdown + JSON.
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep "<label>" <cells> <records> [--traffic-json profiles/k_step_traffic.json]
 
@@ -92,7 +92,7 @@ def main():
     agg = {}
     for r in src[2:]:
         off = int(r[ia], 16) - base
-        name = "k_step (kernel body: loads, finisher, barriers)"
+        name = "k_units (kernel body: loads, stores, record loop)"
         for v, sz, n in subs:
             if v <= off < v + sz:
                 name = n

@@ -32,14 +32,14 @@
 #endif
 
 // One out-of-line copy of each transcendental: CUDA inlines pow/exp/log at every call site (60-250
-// SASS instructions each, ~35 sites), which made k_step 30k instructions / 480 KB and stalled the
-// warps on instruction fetch (profiles/r1_k_step_v1.md).  Out of line the whole step fits the
+// SASS instructions each, ~35 sites), which made the step kernel 30k instructions / 480 KB and stalled the
+// warps on instruction fetch (profiles/r1_k_step_ncu.md, v1).  Out of line the whole step fits the
 // instruction cache.
 #ifndef VR_POW
 #define VR_POW(x, y) ::vr::m_pow((x), (y))
 #endif
 // Phase barrier: keeps the warps of a thread block at the same place in the (large) step code so
-// that one instruction-cache fill serves all of them (k_step is instruction-fetch bound, see
+// that one instruction-cache fill serves all of them (the step kernel is instruction-supply bound, see
 // profiles/).  Every thread of the block must run unit_step() for this to be legal.
 #if defined(__CUDA_ARCH__) && defined(VR_PHASE_BARRIERS)
 #define VR_PHASE_SYNC() __syncthreads()
@@ -59,7 +59,7 @@ namespace vr {
 
 // x^y for the step's power laws (Brooks-Corey drainage, ARNO curves, albedo decay ...): 72 of the
 // ~85 pow() per tile-day sit in the hourly drainage loop (runoff.c:320-479) and CUDA's pow() costs
-// ~250 instructions (double-double log), which made it 80 % of k_step.  On the device
+// ~250 instructions (double-double log), which made it 80 % of the step kernel.  On the device
 // x^y = 2^(y*log2 x) is evaluated directly: log2 of the mantissa by the atanh series (|f| <= 0.172,
 // 10 terms, ~1 ulp), the exponent part y*e kept separate so it is added exactly, 2^r by a
 // degree-13 polynomial.  Relative error <= ~2e-16 * (2 + |y*log2 x|), i.e. < 1e-13 for every

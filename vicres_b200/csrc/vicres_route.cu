@@ -497,7 +497,6 @@ __global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
     __syncthreads();
     // ---- phase B: releases of day <= I reach the next RESERVOIR on day I+1 through UH_R (the station's
     //      inflow feeds nothing back, so it is summed after the day loop, all days in parallel) ----
-#ifndef VR_RES_SKIP_B
     // One WARP per target: the lanes fetch and multiply 32 terms at a time, then every lane replays the serial
     // chain acc = acc + t_i through shuffles (same order, same roundings as the one-thread loop; the loads and
     // multiplies leave the dependent path).
@@ -534,7 +533,6 @@ __global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
         if (lane == 0) RF[(size_t)k * W + I + 1] = acc;
       }
     }
-#endif
     __syncthreads();
   }
   // ---- station: RESFLOWS(NORES, I) = naturalised inflow + the releases routed to it during day I-1, added in the
