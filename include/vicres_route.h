@@ -85,7 +85,10 @@ typedef struct vr_route_inputs {
   const float *cell_lat, *cell_lon;        /* [ncell] JLOC, ILOC (reservoir.f:353-356)                     */
   const int32_t *node_ope_year;            /* [nnodes] OPEYEAR of the node's reservoir (reservoir.f:318-325); station 0 */
   int32_t start_year, start_month;         /* START_YEAR, START_MO                                         */
-  int32_t reserved[4];
+  int32_t node_begin, node_end;            /* only nodes [node_begin, node_end) are computed (the other rows of `flows` are left
+                                              untouched); 0, 0 = all.  Nodes are independent in MAKE_CONVOLUTION, so ranks of a
+                                              multi-GPU run take node ranges and all-gather the rows: no change of summation order */
+  int32_t reserved[2];
 } vr_route_inputs;
 /* res_evaporation: [nnodes][ndays] RES_EVAPORATION (sum of 0.9*E0 over the node's surface cells) or NULL */
 int  vr_route_convolve_in(vr_route *h, int32_t ndays, const vr_route_inputs *in, float *flows, float *res_evaporation);

@@ -76,6 +76,11 @@ class RouteOracle:
         lib().ro_get_uh_r(self.h, n, uh.ctypes.data)
         return ds.value, tg.value, uh
 
+    def reservoirs_sets(self, natural, sets, start_year, start_month, legacy=False):
+        """the Route.reservoirs surface: a list of parameter sets -> dict with a leading set axis"""
+        outs = [self.reservoirs(natural, s, start_year, start_month, legacy=legacy) for s in sets]
+        return {k: np.stack([o[k] for o in outs]) for k in outs[0]} if outs else {"flow": np.zeros((0, natural.shape[1]), np.float32)}
+
     def reservoirs(self, natural, res, start_year, start_month, legacy=False):
         """natural [nnodes, ndays]; res: list of route_abi.reservoir dicts (node order) -> dict of series"""
         natural = np.ascontiguousarray(natural, dtype=np.float32)

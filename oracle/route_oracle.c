@@ -357,7 +357,7 @@ int ro_convolve_in(const ro_model *m, int ndays, const vr_route_inputs *in, floa
   int MONTH_OF_YEAR = (int)((ndays % 365) / 30) + in->start_month;
   const int CURRENTYEAR = in->start_year + (int)(ndays % 365);
   if (MONTH_OF_YEAR > 12) MONTH_OF_YEAR = 12;
-  for (n = 0; n < m->nnodes; n++) {
+  for (n = (in->node_end > 0 ? in->node_begin : 0); n < (in->node_end > 0 ? in->node_end : m->nnodes); n++) {
     const onode *nd = &m->node[n];
     float *FLOW = flows + (size_t)n * ndays;
     const int OPEYEAR = in->node_ope_year ? in->node_ope_year[n] : 0;

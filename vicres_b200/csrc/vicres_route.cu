@@ -228,6 +228,7 @@ struct ConvArgs {
   const float *rh, *tair, *wind, *cell_lat, *cell_lon;
   const int *reser, *node_ope_year;
   int month_of_year, current_year;
+  int node_begin;               // first node of this launch (grid.y counts from it)
   float *res_evap;              // [nnodes][ndays] or null
 };
 
@@ -235,7 +236,7 @@ struct ConvArgs {
 // "arrays still hold the previous cell's file" state of the Fortran are per-day scalars here.
 __global__ void __launch_bounds__(128) k_convolve(ConvArgs a)
 {
-  const int node = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;   // i = day - 1
+  const int node = a.node_begin + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;   // i = day - 1
   if (i >= a.ndays) return;
   float flow = 0.0f, pe = 0.0f, eva_factor = 0.0f, resev = 0.0f;
   long long last = -1;
@@ -866,16 +867,23 @@ int vr_route_convolve_in(vr_route *h, int32_t ndays, const vr_route_inputs *in, 
   }
   RK(h->d_flows.res((size_t)a.nnodes * ndays));
   a.flows = h->d_flows.p;
-  dim3 grid((ndays + 127) / 128, a.nnodes);
+  int n0 = 0, n1 = a.nnodes;
+  if (in->node_end > 0) {
+    n0 = in->node_begin; n1 = in->node_end;
+    if (n0 < 0 || n1 > a.nnodes || n0 >= n1) { h->err = "node range outside [0, nnodes)"; return VR_ERR_ARG; }
+  }
+  a.node_begin = n0;
+  dim3 grid((ndays + 127) / 128, n1 - n0);
   cudaEventRecord(h->ev0);
   k_convolve<<<grid, 128>>>(a);
   cudaEventRecord(h->ev1);
   h->timed = true;
   RK(cudaGetLastError());
-  RK(cudaMemcpy(flows, h->d_flows.p, (size_t)a.nnodes * ndays * sizeof(float), cudaMemcpyDeviceToHost));
+  const size_t off = (size_t)n0 * ndays, cnt = (size_t)(n1 - n0) * ndays;
+  RK(cudaMemcpy(flows + off, h->d_flows.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost));
   if (res_evaporation) {
-    if (a.res_evap) RK(cudaMemcpy(res_evaporation, h->d_resev.p, (size_t)a.nnodes * ndays * sizeof(float), cudaMemcpyDeviceToHost));
-    else memset(res_evaporation, 0, (size_t)a.nnodes * ndays * sizeof(float));
+    if (a.res_evap) RK(cudaMemcpy(res_evaporation + off, h->d_resev.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    else memset(res_evaporation + off, 0, cnt * sizeof(float));
   }
   return VR_OK;
 }

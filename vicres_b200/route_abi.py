@@ -215,11 +215,12 @@ class vr_route_inputs(C.Structure):
                 ("ev_soil", _pf), ("tr_vege", _pf), ("cell_factor", _pf), ("present", C.POINTER(C.c_ubyte)),
                 ("rh", _pf), ("tair", _pf), ("wind", _pf), ("cell_lat", _pf), ("cell_lon", _pf),
                 ("node_ope_year", C.POINTER(C.c_int32)), ("start_year", C.c_int32), ("start_month", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("node_begin", C.c_int32), ("node_end", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 def pack_route_inputs(runoff, baseflow, scale=0.18308, cell_scale=None, evap=None, cell_factor=None, present=None,
-                      met=None, cell_lat=None, cell_lon=None, node_ope_year=None, start_year=0, start_month=1):
+                      met=None, cell_lat=None, cell_lon=None, node_ope_year=None, start_year=0, start_month=1,
+                      nodes=None):
     """-> (vr_route_inputs, keepalive, ndays).  evap = (ev_vege, ev_soil, tr_vege); met = (rh, tair, wind)"""
     s = vr_route_inputs()
     keep = []
@@ -247,6 +248,8 @@ def pack_route_inputs(runoff, baseflow, scale=0.18308, cell_scale=None, evap=Non
         keep.append(y)
         s.node_ope_year = y.ctypes.data_as(C.POINTER(C.c_int32))
     s.start_year, s.start_month = start_year, start_month
+    if nodes is not None:
+        s.node_begin, s.node_end = int(nodes[0]), int(nodes[1])
     return s, keep, runoff.shape[1]
 
 
