@@ -48,6 +48,44 @@ int  vr_write_results(const char *result_dir, const char *prefix, int32_t grid_d
                       const int32_t *day, const int32_t *hour, int32_t n_cols, const int32_t *cols,
                       const double *out);
 
+/* ---- global parameter file (get_global_param.c:210-727) and calendar (make_dmy.c) ---------------------- */
+#define VR_MAX_FORCE_TYPES 16
+typedef struct vr_global {
+  /* what vr_options needs */
+  int32_t nlayer, time_step, snow_step;            /* NLAYER, TIME_STEP, SNOW_STEP                              */
+  double  max_snow_temp, min_rain_temp, wind_h;    /* MAX_SNOW_TEMP, MIN_RAIN_TEMP, WIND_H                      */
+  double  min_wind_speed, measure_h;               /* MIN_WIND_SPEED, MEASURE_H (used by the forcing preparation) */
+  /* simulated period: nrecs is computed from the END* date when NRECS is absent (make_dmy.c:52-90) */
+  int32_t startyear, startmonth, startday, starthour, nrecs, skipyear;
+  /* parameter files, as vr_param_files wants them */
+  int32_t snow_band, root_zones, vegparam_lai, lai_from_vegparam, grid_decimal;
+  char soil[512], veglib[512], vegparam[512], snowband[512], result_dir[512];
+  /* forcing description of FORCING1 (first file type only) */
+  char forcing1[512];
+  int32_t force_ascii, force_little_endian, force_dt, n_force_types;
+  int32_t forceyear, forcemonth, forceday, forcehour;
+  char force_type[VR_MAX_FORCE_TYPES][16];         /* FORCE_TYPE names in column order (SKIP included)         */
+  int32_t force_signed[VR_MAX_FORCE_TYPES];        /* binary files: SIGNED / UNSIGNED                           */
+  double  force_multiplier[VR_MAX_FORCE_TYPES];    /* binary files: value = short / multiplier                  */
+  int32_t binary_output, out_step, compress;
+  /* options this library does not implement are not an error to PARSE; vr_global_unsupported() names them */
+  int32_t full_energy, frozen_soil, lakes, carbon, blowing, corrprec, compute_treeline, dist_prcp, organic_fract,
+          july_tavg_supplied, alma_input, init_state;
+} vr_global;
+
+int  vr_global_read(const char *path, vr_global *out);
+/* NULL when the water-balance path of this library covers the file's options, else a text naming the first
+ * option it does not (FULL_ENERGY TRUE, FROZEN_SOIL TRUE, SNOW_STEP != TIME_STEP, ...) */
+const char *vr_global_unsupported(const vr_global *g);
+/* calendar of the nrecs model records (make_dmy.c:92-120); each array [g->nrecs] */
+int  vr_make_dmy(const vr_global *g, int32_t *year, int32_t *month, int32_t *day, int32_t *hour, int32_t *day_in_year);
+/* records to skip at the head of the forcing file (make_dmy.c:122-150) */
+int32_t vr_force_skip(const vr_global *g);
+/* one cell's forcing file "<forcing1><lat>_<lng>" (read_atmos_data.c:120-235): columns in FORCE_TYPE order, ASCII or
+ * 2-byte scaled binary (with or without the 0xFFFF header); data: [n_force_types][nrec_forcing] (SKIP columns are
+ * read and kept), nrec_forcing = nrecs * time_step / force_dt.  Returns the records read or a negative status. */
+int64_t vr_read_forcing_file(const vr_global *g, const char *path, int64_t nrec_forcing, double *data);
+
 /* out[i] = the value in[i] has after a round trip through a "%.<decimals>f" text column (the reference's flux
  * files are the hand-off between vicNl and rout): lets the step's outputs go to the routing pass in memory and
  * still equal what rout would have read. */

@@ -199,3 +199,85 @@ def test_round_decimals_equals_text_round_trip():
     want = np.array([float("%.4f" % v) for v in x])
     got = files.round_decimals(x, 4)
     assert np.array_equal(got, want)
+
+
+def test_global_file_calendar_and_forcing_reader(tmp_path):
+    """get_global_param / make_dmy / read_atmos_data on a written case: END* date -> NRECS across a leap year,
+    option flags, ASCII and 2-byte binary forcing columns"""
+    g = tmp_path / "global.txt"
+    forc = tmp_path / "forc_"
+    g.write_text("\n".join([
+        "# comment", "NLAYER 2", "TIME_STEP 24", "SNOW_STEP 24", "STARTYEAR 1999", "STARTMONTH 12", "STARTDAY 30", "STARTHOUR 0",
+        "ENDYEAR 2000", "ENDMONTH 3", "ENDDAY 1", "FULL_ENERGY FALSE", "FROZEN_SOIL FALSE", "MIN_WIND_SPEED 0.1",
+        "MAX_SNOW_TEMP 0.7", "MIN_RAIN_TEMP -0.3", "FORCING1 %s" % forc, "FORCE_FORMAT ASCII", "N_TYPES 4", "FORCE_TYPE PREC",
+        "FORCE_TYPE TMAX", "FORCE_TYPE TMIN", "FORCE_TYPE WIND", "FORCE_DT 24", "FORCEYEAR 1999", "FORCEMONTH 12",
+        "FORCEDAY 28", "FORCEHOUR 0", "GRID_DECIMAL 4", "WIND_H 10.0", "SOIL a/soil.txt", "VEGLIB a/veglib.txt",
+        "VEGPARAM a/veg.txt", "ROOT_ZONES 3", "VEGPARAM_LAI TRUE", "LAI_SRC FROM_VEGPARAM", "SNOW_BAND 5 a/bands.txt",
+        "RESULT_DIR out/", "SKIPYEAR 0"]) + "\n")
+    G = files.Global(str(g))
+    assert (G.nlayer, G.time_step, G.snow_step, G.snow_band, G.root_zones) == (2, 24, 24, 5, 3)
+    assert G.nrecs == 2 + 31 + 29 + 1 and G.unsupported is None            # 30 Dec 1999 .. 1 Mar 2000, leap February
+    assert (G.max_snow_temp, G.min_rain_temp) == (0.7, -0.3) and G.snowband == "a/bands.txt"
+    assert G.param_files()["lai_from_vegparam"] and G.force_types == ["PREC", "TMAX", "TMIN", "WIND"]
+    dmy = G.dmy()
+    assert dmy[0].tolist() == [1999, 12, 30, 0, 364] and dmy[2].tolist() == [2000, 1, 1, 0, 1]
+    assert dmy[-1].tolist() == [2000, 3, 1, 0, 61]
+    rng = np.random.default_rng(0)
+    n = G.nrecs + 2
+    vals = np.round(np.stack([rng.gamma(1, 5, n), rng.normal(20, 5, n), rng.normal(8, 5, n), rng.uniform(0, 9, n)], 1), 2)
+    (tmp_path / "forc_12.3400_-56.7800").write_text("\n".join(" ".join("%.2f" % x for x in r) for r in vals) + "\n")
+    cols, got = G.read_forcing(12.34, -56.78)
+    assert got == G.nrecs
+    for i, k in enumerate(G.force_types):                                  # two records skipped (FORCEDAY 28 -> STARTDAY 30)
+        assert np.array_equal(cols[k], vals[2:, i])
+    # the same data as 2-byte scaled binary with the VIC header
+    g2 = tmp_path / "global_bin.txt"
+    g2.write_text(g.read_text().replace("FORCE_FORMAT ASCII", "FORCE_FORMAT BINARY\nFORCE_ENDIAN LITTLE")
+                  .replace("FORCE_TYPE PREC", "FORCE_TYPE PREC UNSIGNED 40").replace("FORCE_TYPE TMAX", "FORCE_TYPE TMAX SIGNED 100")
+                  .replace("FORCE_TYPE TMIN", "FORCE_TYPE TMIN SIGNED 100").replace("FORCE_TYPE WIND", "FORCE_TYPE WIND SIGNED 100")
+                  .replace(str(forc), str(tmp_path / "bin_")))
+    mult = np.array([40, 100, 100, 100])
+    raw = np.round(vals * mult).astype(np.int64)
+    hdr = np.array([0xFFFF] * 4 + [10], dtype="<u2").tobytes()
+    body = b"".join(np.array([r[0]], dtype="<u2").tobytes() + np.array(r[1:], dtype="<i2").tobytes() for r in raw)
+    (tmp_path / "bin_12.3400_-56.7800").write_bytes(hdr + body)
+    G2 = files.Global(str(g2))
+    cols2, got2 = G2.read_forcing(12.34, -56.78)
+    assert got2 == G.nrecs
+    for i, k in enumerate(G2.force_types):
+        assert np.array_equal(cols2[k], raw[2:, i] / mult[i])
+    bad = tmp_path / "fe.txt"
+    bad.write_text(g.read_text().replace("FULL_ENERGY FALSE", "FULL_ENERGY TRUE"))
+    assert files.Global(str(bad)).unsupported == "FULL_ENERGY TRUE"
+    sub = tmp_path / "sub.txt"
+    sub.write_text(g.read_text().replace("SNOW_STEP 24", "SNOW_STEP 3"))
+    assert files.Global(str(sub)).unsupported == "SNOW_STEP != TIME_STEP"
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="compiled reference (oracle/_ref) not built here")
+def test_global_file_against_live_reference(tmp_path):
+    """the calendar and record count the reference derives from the same global file (dump of vic_ref_driver),
+    and its raw forcing columns"""
+    work = str(tmp_path / "case")
+    g = synth.make_case(work, ncells=2, nlayer=3, nbands=2, ndays=430, startyear=1983, seed=12)
+    dump = os.path.join(work, "dump.bin")
+    subprocess.run([DRIVER, "-g", g, "-d", dump], check=True, capture_output=True)
+    d = refdump.read_dump(dump)
+    G = files.Global(g)
+    assert G.unsupported is None and G.nrecs == int(d["nrecs"][0])
+    assert np.array_equal(G.dmy(), np.asarray(d["dmy"]))
+    lib, cells, meta = files.read_params(**G.param_files())
+    cs = refdump.case_from_dump(d)
+    _same(cells, cs["cells"], "cells via the global file")
+    cols, got = G.read_forcing(float(meta["lat"][0]), float(meta["lng"][0]))
+    assert got == G.nrecs and set(cols) == {"PREC", "TMAX", "TMIN", "WIND"}
+    # the reference's step sees prec unchanged in daily mode (initialize_atmos only disaggregates sub-daily)
+    assert np.allclose(cols["PREC"], cs["forcing"][1, :, 0], rtol=0, atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "parameters", "globalparam.txt")), reason="reference tree not present")
+def test_bundled_global_file():
+    G = files.Global(os.path.join(REF, "parameters", "globalparam.txt"))
+    assert G.unsupported is None and (G.nlayer, G.time_step, G.root_zones) == (2, 24, 3)
+    assert G.nrecs == 15340                                  # SURVEY appendix A.2: 1981-01-01 .. 2022-12-31
+    assert G.force_types == ["PREC", "TMAX", "TMIN", "WIND"] and G.vegparam_lai == 1 and G.lai_from_vegparam == 1

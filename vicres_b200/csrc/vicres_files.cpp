@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -520,6 +521,229 @@ int vr_write_results(const char *result_dir, const char *prefix, int32_t grid_de
     if (fclose(f) != 0) { g_err = std::string("write failed: ") + name; return VR_ERR_ARG; }
   }
   return VR_OK;
+}
+
+// ---- global parameter file (get_global_param.c) ----
+static bool leapyr(int y) { return ((y % 4 == 0) && (y % 100 != 0)) || (y % 400 == 0); }
+static void next_step(int &year, int &month, int &day, int &hr, int &jday, int dt)     // make_dmy.c:175-205
+{
+  int days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  hr += dt;
+  if (hr >= 24) {
+    hr = 0; day += 1; jday += 1;
+    days[1] = leapyr(year) ? 29 : 28;
+    if (day > days[month - 1]) {
+      day = 1; month += 1;
+      if (month == 13) { month = 1; jday = 1; year += 1; }
+    }
+  }
+}
+
+int vr_global_read(const char *path, vr_global *g)
+{
+  if (!path || !g) { g_err = "null argument"; return VR_ERR_ARG; }
+  FILE *f = fopen(path, "r");
+  if (!f) { g_err = std::string("cannot open ") + path; return VR_ERR_ARG; }
+  memset(g, 0, sizeof *g);
+  // initialize_global.c:146-211
+  g->nlayer = 3; g->time_step = -99999; g->snow_step = 1; g->max_snow_temp = 0.5; g->min_rain_temp = -0.5; g->wind_h = 10.0;
+  g->min_wind_speed = 0.1; g->measure_h = 2.0; g->snow_band = 1; g->root_zones = -99999; g->grid_decimal = 2;
+  g->starthour = 0; g->nrecs = -99999; g->force_dt = -99999; g->force_ascii = 0; g->force_little_endian = 1;
+  int endyear = -99999, endmonth = -99999, endday = -99999, file_num = -1, field = -1;
+  auto flag = [](const std::vector<std::string> &t) { return t.size() > 1 && strcasecmp(t[1].c_str(), "TRUE") == 0; };
+  auto copy = [](char *dst, const std::string &v) { snprintf(dst, 512, "%s", v.c_str()); };
+  std::string line;
+  while (read_line(f, line)) {
+    std::vector<std::string> t = tokens(line);
+    if (t.empty() || t[0][0] == '#') continue;
+    const char *k = t[0].c_str();
+    auto I = [&](int d = 0) { return t.size() > 1 ? atoi(t[1].c_str()) : d; };
+    auto D = [&](double d = 0) { return t.size() > 1 ? strtod(t[1].c_str(), nullptr) : d; };
+    if (!strcasecmp(k, "NLAYER")) g->nlayer = I();
+    else if (!strcasecmp(k, "TIME_STEP")) g->time_step = I();
+    else if (!strcasecmp(k, "SNOW_STEP")) g->snow_step = I();
+    else if (!strcasecmp(k, "STARTYEAR")) g->startyear = I();
+    else if (!strcasecmp(k, "STARTMONTH")) g->startmonth = I();
+    else if (!strcasecmp(k, "STARTDAY")) g->startday = I();
+    else if (!strcasecmp(k, "STARTHOUR")) g->starthour = I();
+    else if (!strcasecmp(k, "NRECS")) g->nrecs = I();
+    else if (!strcasecmp(k, "ENDYEAR")) endyear = I();
+    else if (!strcasecmp(k, "ENDMONTH")) endmonth = I();
+    else if (!strcasecmp(k, "ENDDAY")) endday = I();
+    else if (!strcasecmp(k, "FULL_ENERGY")) g->full_energy = flag(t);
+    else if (!strcasecmp(k, "FROZEN_SOIL")) g->frozen_soil = flag(t);
+    else if (!strcasecmp(k, "BLOWING")) g->blowing = flag(t);
+    else if (!strcasecmp(k, "CORRPREC")) g->corrprec = flag(t);
+    else if (!strcasecmp(k, "DIST_PRCP")) g->dist_prcp = flag(t);
+    else if (!strcasecmp(k, "CARBON")) g->carbon = flag(t);
+    else if (!strcasecmp(k, "LAKES")) g->lakes = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0);
+    else if (!strcasecmp(k, "COMPUTE_TREELINE")) g->compute_treeline = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0);
+    else if (!strcasecmp(k, "ORGANIC_FRACT")) g->organic_fract = flag(t);
+    else if (!strcasecmp(k, "JULY_TAVG_SUPPLIED")) g->july_tavg_supplied = flag(t);
+    else if (!strcasecmp(k, "ALMA_INPUT")) g->alma_input = flag(t);
+    else if (!strcasecmp(k, "INIT_STATE")) g->init_state = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0);
+    else if (!strcasecmp(k, "MIN_WIND_SPEED")) g->min_wind_speed = (double)strtof(t.size() > 1 ? t[1].c_str() : "0", nullptr);
+    else if (!strcasecmp(k, "MIN_RAIN_TEMP")) g->min_rain_temp = D();
+    else if (!strcasecmp(k, "MAX_SNOW_TEMP")) g->max_snow_temp = D();
+    else if (!strcasecmp(k, "WIND_H")) g->wind_h = D();
+    else if (!strcasecmp(k, "MEASURE_H")) g->measure_h = D();
+    else if (!strcasecmp(k, "GRID_DECIMAL")) g->grid_decimal = I();
+    else if (!strcasecmp(k, "SOIL") && t.size() > 1) copy(g->soil, t[1]);
+    else if (!strcasecmp(k, "VEGLIB") && t.size() > 1) copy(g->veglib, t[1]);
+    else if (!strcasecmp(k, "VEGPARAM") && t.size() > 1) copy(g->vegparam, t[1]);
+    else if (!strcasecmp(k, "ROOT_ZONES")) g->root_zones = I();
+    else if (!strcasecmp(k, "VEGPARAM_LAI")) g->vegparam_lai = flag(t);
+    else if (!strcasecmp(k, "LAI_SRC") || !strcasecmp(k, "GLOBAL_LAI"))
+      g->lai_from_vegparam = (t.size() > 1 && (!strcasecmp(t[1].c_str(), "FROM_VEGPARAM") || !strcasecmp(t[1].c_str(), "LAI_FROM_VEGPARAM") ||
+                                               (!strcasecmp(k, "GLOBAL_LAI") && flag(t))));
+    else if (!strcasecmp(k, "SNOW_BAND")) { g->snow_band = I(1); if (t.size() > 2) copy(g->snowband, t[2]); }
+    else if (!strcasecmp(k, "RESULT_DIR") && t.size() > 1) copy(g->result_dir, t[1]);
+    else if (!strcasecmp(k, "SKIPYEAR")) g->skipyear = I();
+    else if (!strcasecmp(k, "OUT_STEP")) g->out_step = I();
+    else if (!strcasecmp(k, "BINARY_OUTPUT")) g->binary_output = flag(t);
+    else if (!strcasecmp(k, "COMPRESS")) g->compress = flag(t);
+    else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }
+    else if (!strcasecmp(k, "FORCING2")) { file_num = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0) ? 1 : -1; field = -1; }
+    else if (file_num == 0) {          // description of FORCING1 (get_force_type.c)
+      if (!strcasecmp(k, "FORCE_FORMAT")) g->force_ascii = (t.size() > 1 && !strcasecmp(t[1].c_str(), "ASCII"));
+      else if (!strcasecmp(k, "FORCE_ENDIAN")) g->force_little_endian = !(t.size() > 1 && !strcasecmp(t[1].c_str(), "BIG"));
+      else if (!strcasecmp(k, "N_TYPES")) g->n_force_types = I();
+      else if (!strcasecmp(k, "FORCE_DT")) g->force_dt = I();
+      else if (!strcasecmp(k, "FORCEYEAR")) g->forceyear = I();
+      else if (!strcasecmp(k, "FORCEMONTH")) g->forcemonth = I();
+      else if (!strcasecmp(k, "FORCEDAY")) g->forceday = I();
+      else if (!strcasecmp(k, "FORCEHOUR")) g->forcehour = I();
+      else if (!strcasecmp(k, "FORCE_TYPE") && t.size() > 1) {
+        field++;
+        if (field >= VR_MAX_FORCE_TYPES) { fclose(f); g_err = "too many FORCE_TYPE lines"; return VR_ERR_ARG; }
+        snprintf(g->force_type[field], 16, "%s", t[1].c_str());
+        g->force_signed[field] = 1; g->force_multiplier[field] = 1.0;
+        if (t.size() > 3) {             // binary: FORCE_TYPE <name> SIGNED|UNSIGNED <multiplier>
+          g->force_signed[field] = strcasecmp(t[2].c_str(), "UNSIGNED") != 0;
+          g->force_multiplier[field] = strtod(t[3].c_str(), nullptr);
+        }
+      }
+    }
+  }
+  fclose(f);
+  if (g->time_step == -99999) { g_err = "TIME_STEP missing from the global parameter file"; return VR_ERR_ARG; }
+  if (g->snow_step == 1 && g->time_step != 1) { /* SNOW_STEP default 1 only matters in full-energy runs; keep what the file says */ }
+  if (g->startyear <= 0 || g->startmonth < 1 || g->startmonth > 12 || g->startday < 1) { g_err = "simulation start date missing or invalid"; return VR_ERR_ARG; }
+  if (g->nrecs == -99999) {            // make_dmy.c:52-90: count the steps up to the day after the end date
+    if (endyear == -99999 || endmonth == -99999 || endday == -99999) { g_err = "neither NRECS nor ENDYEAR/ENDMONTH/ENDDAY given"; return VR_ERR_ARG; }
+    int days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    days[1] = leapyr(endyear) ? 29 : 28;
+    if (endday < days[endmonth - 1]) endday++;
+    else { endday = 1; endmonth++; if (endmonth > 12) { endmonth = 1; endyear++; } }
+    int y = g->startyear, mo = g->startmonth, d = g->startday, h = g->starthour, j = 0, n = 0;
+    for (;;) {
+      next_step(y, mo, d, h, j, g->time_step);
+      n++;
+      if (y == endyear && mo == endmonth && d == endday) break;
+      if (n > 100000000) { g_err = "end date is not after the start date"; return VR_ERR_ARG; }
+    }
+    g->nrecs = n;
+  }
+  if (g->n_force_types != 0 && field + 1 != g->n_force_types) { g_err = "N_TYPES does not match the number of FORCE_TYPE lines"; return VR_ERR_ARG; }
+  g->n_force_types = field + 1;
+  return VR_OK;
+}
+
+const char *vr_global_unsupported(const vr_global *g)
+{
+  if (!g) return "null";
+  if (g->full_energy) return "FULL_ENERGY TRUE";
+  if (g->frozen_soil) return "FROZEN_SOIL TRUE";
+  if (g->lakes) return "LAKES";
+  if (g->carbon) return "CARBON TRUE";
+  if (g->blowing) return "BLOWING TRUE";
+  if (g->corrprec) return "CORRPREC TRUE";
+  if (g->compute_treeline) return "COMPUTE_TREELINE";
+  if (g->dist_prcp) return "DIST_PRCP TRUE";
+  if (g->organic_fract) return "ORGANIC_FRACT TRUE";
+  if (g->init_state) return "INIT_STATE";
+  if (g->snow_step != g->time_step) return "SNOW_STEP != TIME_STEP";
+  if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
+  return nullptr;
+}
+
+int vr_make_dmy(const vr_global *g, int32_t *year, int32_t *month, int32_t *day, int32_t *hour, int32_t *day_in_year)
+{
+  if (!g || !year || !month || !day || !hour || !day_in_year || g->nrecs < 1) { g_err = "null argument"; return VR_ERR_ARG; }
+  int days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  int y = g->startyear, mo = g->startmonth, d = g->startday, h = g->starthour, j = d;
+  days[1] = leapyr(y) ? 29 : 28;
+  for (int i = 0; i < mo - 1; i++) j += days[i];
+  for (int i = 0; i < g->nrecs; i++) {
+    hour[i] = h; day[i] = d; month[i] = mo; year[i] = y; day_in_year[i] = j;
+    next_step(y, mo, d, h, j, g->time_step);
+  }
+  return VR_OK;
+}
+
+int32_t vr_force_skip(const vr_global *g)
+{
+  if (!g || g->forceyear <= 0) return 0;
+  int days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  int y = g->forceyear, mo = g->forcemonth, d = g->forceday, h = g->forcehour, j = d, skip = 0;
+  days[1] = leapyr(y) ? 29 : 28;
+  for (int i = 0; i < mo - 1; i++) j += days[i];
+  int sj = g->startday;
+  days[1] = leapyr(g->startyear) ? 29 : 28;
+  for (int i = 0; i < g->startmonth - 1; i++) sj += days[i];
+  while (y < g->startyear || (y == g->startyear && j < sj) || (y == g->startyear && j == sj && h < g->starthour)) {
+    next_step(y, mo, d, h, j, g->time_step);          // the reference steps with the MODEL dt here (make_dmy.c:139-146)
+    skip++;
+  }
+  return skip;
+}
+
+int64_t vr_read_forcing_file(const vr_global *g, const char *path, int64_t nrec, double *data)
+{
+  if (!g || !path || !data || nrec < 1 || g->n_force_types < 1) { g_err = "null or empty argument"; return VR_ERR_ARG; }
+  const int nf = g->n_force_types;
+  const int64_t skip = vr_force_skip(g);
+  int64_t rec = 0;
+  if (g->force_ascii) {
+    FILE *f = fopen(path, "r");
+    if (!f) { g_err = std::string("cannot open ") + path; return VR_ERR_ARG; }
+    std::string line;
+    for (int64_t i = 0; i < skip; i++)
+      if (!read_line(f, line)) { fclose(f); g_err = "no data for the specified period in the forcing file"; return VR_ERR_ARG; }
+    while (rec < nrec) {
+      bool ok = true;
+      for (int i = 0; i < nf && ok; i++) ok = fscanf(f, "%lf", &data[(size_t)i * nrec + rec]) == 1;
+      if (!ok) break;
+      rec++;
+    }
+    fclose(f);
+  }
+  else {
+    FILE *f = fopen(path, "rb");
+    if (!f) { g_err = std::string("cannot open ") + path; return VR_ERR_ARG; }
+    auto rd = [&](unsigned short &v) {
+      if (fread(&v, 2, 1, f) != 1) return false;
+      if (!g->force_little_endian) v = (unsigned short)(((v & 0xFF) << 8) | ((v >> 8) & 0xFF));   // host is little endian
+      return true;
+    };
+    unsigned short id[4] = {0, 0, 0, 0}, nb = 0;
+    long nbytes = 0;
+    for (int i = 0; i < 4; i++) rd(id[i]);
+    if (id[0] == 0xFFFF && id[1] == 0xFFFF && id[2] == 0xFFFF && id[3] == 0xFFFF && rd(nb)) nbytes = nb;
+    fseek(f, nbytes + (long)(skip * nf * 2), SEEK_SET);
+    while (rec < nrec) {
+      bool ok = true;
+      for (int i = 0; i < nf && ok; i++) {
+        unsigned short u;
+        ok = rd(u);
+        if (ok) data[(size_t)i * nrec + rec] = (g->force_signed[i] ? (double)(short)u : (double)u) / g->force_multiplier[i];
+      }
+      if (!ok) break;
+      rec++;
+    }
+    fclose(f);
+  }
+  return rec;
 }
 
 // What a value becomes on its way through a "%.<d>f" text file and back (printf rounds the exact binary value

@@ -121,3 +121,87 @@ def round_decimals(a, decimals=4, lib=None):
     if rc != 0:
         raise VicResError(rc, "vr_round_decimals")
     return out
+
+
+# ---- global parameter file, calendar, forcing files ---------------------------------------------------------
+VR_MAX_FORCE_TYPES = 16
+
+
+class GlobalC(C.Structure):
+    _fields_ = ([("nlayer", C.c_int32), ("time_step", C.c_int32), ("snow_step", C.c_int32),
+                 ("max_snow_temp", C.c_double), ("min_rain_temp", C.c_double), ("wind_h", C.c_double),
+                 ("min_wind_speed", C.c_double), ("measure_h", C.c_double)] +
+                [(n, C.c_int32) for n in ("startyear", "startmonth", "startday", "starthour", "nrecs", "skipyear",
+                                          "snow_band", "root_zones", "vegparam_lai", "lai_from_vegparam", "grid_decimal")] +
+                [(n, C.c_char * 512) for n in ("soil", "veglib", "vegparam", "snowband", "result_dir", "forcing1")] +
+                [(n, C.c_int32) for n in ("force_ascii", "force_little_endian", "force_dt", "n_force_types", "forceyear",
+                                          "forcemonth", "forceday", "forcehour")] +
+                [("force_type", (C.c_char * 16) * VR_MAX_FORCE_TYPES), ("force_signed", C.c_int32 * VR_MAX_FORCE_TYPES),
+                 ("force_multiplier", C.c_double * VR_MAX_FORCE_TYPES)] +
+                [(n, C.c_int32) for n in ("binary_output", "out_step", "compress", "full_energy", "frozen_soil", "lakes",
+                                          "carbon", "blowing", "corrprec", "compute_treeline", "dist_prcp", "organic_fract",
+                                          "july_tavg_supplied", "alma_input", "init_state")])
+
+
+FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_read_forcing_file"]
+
+
+def _bind_global(so):
+    so.vr_global_read.argtypes = [C.c_char_p, C.POINTER(GlobalC)]
+    so.vr_global_unsupported.argtypes = [C.POINTER(GlobalC)]
+    so.vr_global_unsupported.restype = C.c_char_p
+    so.vr_make_dmy.argtypes = [C.POINTER(GlobalC)] + [C.POINTER(C.c_int32)] * 5
+    so.vr_force_skip.argtypes = [C.POINTER(GlobalC)]
+    so.vr_read_forcing_file.argtypes = [C.POINTER(GlobalC), C.c_char_p, C.c_int64, C.POINTER(C.c_double)]
+    so.vr_read_forcing_file.restype = C.c_int64
+    return so
+
+
+class Global:
+    """a parsed global parameter file (get_global_param.c) with its calendar (make_dmy.c)"""
+
+    def __init__(self, path, lib=None):
+        self.so = _bind_global(_bind(lib or load_library()))
+        self.c = GlobalC()
+        rc = self.so.vr_global_read(path.encode(), C.byref(self.c))
+        if rc != 0:
+            raise VicResError(rc, "vr_global_read: %s" % self.so.vr_params_last_error().decode())
+
+    def __getattr__(self, k):
+        v = getattr(self.c, k)
+        return v.decode() if isinstance(v, bytes) else v
+
+    @property
+    def unsupported(self):
+        r = self.so.vr_global_unsupported(C.byref(self.c))
+        return r.decode() if r else None
+
+    @property
+    def force_types(self):
+        return [self.c.force_type[i].value.decode() for i in range(self.c.n_force_types)]
+
+    def dmy(self):
+        """[nrecs, 5] year, month, day, hour, day_in_year"""
+        n = self.c.nrecs
+        a = [np.zeros(n, dtype=np.int32) for _ in range(5)]
+        p = C.POINTER(C.c_int32)
+        rc = self.so.vr_make_dmy(C.byref(self.c), *[x.ctypes.data_as(p) for x in a])
+        if rc != 0:
+            raise VicResError(rc, "vr_make_dmy")
+        return np.stack(a, axis=1)
+
+    def param_files(self):
+        """keyword arguments for read_params()"""
+        return dict(soil=self.soil, veglib=self.veglib, vegparam=self.vegparam, snowband=self.snowband or None,
+                    nlayer=self.nlayer, nbands=self.snow_band, root_zones=self.root_zones,
+                    vegparam_lai=bool(self.vegparam_lai), lai_from_vegparam=bool(self.lai_from_vegparam))
+
+    def read_forcing(self, lat, lng):
+        """the columns of the cell's forcing file, {FORCE_TYPE: [nrec_forcing]} (no disaggregation)"""
+        nrec = self.c.nrecs * self.c.time_step // self.c.force_dt
+        data = np.zeros((self.c.n_force_types, nrec), dtype=np.float64)
+        path = "%s%.*f_%.*f" % (self.forcing1, self.grid_decimal, lat, self.grid_decimal, lng)
+        got = self.so.vr_read_forcing_file(C.byref(self.c), path.encode(), nrec, data.ctypes.data_as(C.POINTER(C.c_double)))
+        if got < 0:
+            raise VicResError(int(got), "vr_read_forcing_file: %s" % self.so.vr_params_last_error().decode())
+        return {t: data[i, :got] for i, t in enumerate(self.force_types)}, int(got)
