@@ -74,7 +74,8 @@ def main():
     syms = []
     for l in elf.splitlines():
         p = l.split()
-        if len(p) < 7 or ("k_step" not in l and "k_units" not in l and "vr" not in l):
+        # the default kernel instance only (k_units<0>): its out-of-line device functions are "$<kernel>$<function>"
+        if len(p) < 7 or "k_unitsILi0E" not in l:
             continue
         try:
             val, sz = int(p[1], 16), int(p[2], 16)
@@ -82,7 +83,7 @@ def main():
             continue
         if sz == 0:
             continue
-        name = re.sub(r"\$?_ZN\d+_GLOBAL__N__[0-9a-f_]*vicres_capi_cu_[0-9a-f]*6k_stepENS_8DevModelENS_10DevForcingEPd", "", p[-1])
+        name = re.sub(r"\$?_ZN\d+_GLOBAL__N__[0-9a-f_]*vicres_capi_cu_[0-9a-f]*7k_unitsILi0EEEvNS_8DevModelENS_10DevForcingEPd", "", p[-1])
         syms.append((val, sz, name))
     subs = sorted(s for s in syms if s[2].startswith("$"))
     src = ncu_csv(rep, "source")
@@ -100,7 +101,12 @@ def main():
         a = agg.setdefault(name, [0, 0, 0, 0])
         a[0] += int(r[ii]); a[1] += int(r[it]); a[2] += int(r[isamp]); a[3] += 1
     tot, tots = sum(a[0] for a in agg.values()), sum(a[2] for a in agg.values())
-    demangle = lambda n: re.sub(r"^\$_ZN2vr\d+", "vr::", n).split("E")[0] if n.startswith("$_ZN2vr") else n
+    def demangle(n):
+        m = re.match(r"^\$_ZN2vr(\d+)", n)
+        if not m:
+            return n
+        k = int(m.group(1))
+        return "vr::" + n[m.end():m.end() + k]
     print("| device function | SASS instrs | share of executed warp-instrs | lanes active | share of stall samples |\n|---|---|---|---|---|")
     for n, a in sorted(agg.items(), key=lambda x: -x[1][2])[:16]:
         print("| %s | %d | %.1f %% | %.1f / 32 | %.1f %% |" % (demangle(n), a[3], 100 * a[0] / tot, a[1] / max(a[0], 1), 100 * a[2] / tots))
