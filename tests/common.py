@@ -9,6 +9,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
                   if not os.path.basename(p).startswith(("route_", "objectives")))
 
+ATMOS_FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "atmos_*.npz")))
+
 # Parity tolerance of BASELINE.json's north_star: fp64 fluxes and states within 1e-9 relative per
 # cell-timestep.  Values are compared as |a-b| <= RTOL * max(|a|,|b|,ABS_FLOOR); the floor stops
 # quantities that are ~0 by cancellation (closure error ~1e-13 mm, fluxes that are exactly 0 on one
@@ -90,3 +92,22 @@ def check_outputs(out, ref, names, rtol=RTOL, what="", mode="envelope"):
     if mode == "cells":
         assert st["bad_cell_frac"] <= MAX_BAD_CELLS, what + ": %.4f of cells diverge\n" % st["bad_cell_frac"] + "\n".join(worst)
     return st
+
+
+def load_atmos_fixture(name):
+    """tests/golden/atmos_*.npz (tools/make_atmos_golden.py): raw forcing columns, site values, options and the
+    reference's own atmos[] fields."""
+    from vicres_b200 import atmos
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dt, nrecs, sy, sm, sd, sh, layout, fdt = [int(x) for x in z["meta"]]
+    ov = {str(k): str(v) for k, v in zip(z["ov_keys"], z["ov_vals"]) if str(k)}
+    for k, v in list(ov.items()):
+        ov[k] = {"True": True, "False": False}.get(v, v)
+        if k == "sw_prec_thresh":
+            ov[k] = float(v)
+    opt = atmos.options(time_step=dt, nrecs=nrecs, startyear=sy, startmonth=sm, startday=sd, starthour=sh, layout=layout,
+                        force_dt=fdt, **ov)
+    raw = z["raw"]
+    site = {k[5:]: z[k] for k in z.files if k.startswith("site_")}
+    rawd = {"prec": raw[0], "t_a": raw[1], "t_b": raw[2] if layout == 0 else None, "wind": raw[3 if layout == 0 else 2]}
+    return {"opt": opt, "site": site, "raw": rawd, "ref": z["atmos"]}

@@ -1,0 +1,107 @@
+"""Generate tests/golden/atmos_*.npz by RUNNING THE REFERENCE's own initialize_atmos.
+
+Run in the build container (needs /root/reference and `make -C oracle ref`):
+
+    python tools/make_atmos_golden.py
+
+Each case is a set of reference-format files written by vicres_b200/synth.py (or the reference's bundled
+Mekong cell); oracle/_ref/vic_ref_driver (the unmodified reference objects behind oracle/ref_driver.c) runs
+initialize_atmos on every cell and dumps atmos[] in fp64.  A fixture keeps the raw forcing columns as the
+reference read them, the site values of soil_con, the options, and the reference's nine atmos fields.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import refdump  # noqa: E402
+from vicres_b200 import synth  # noqa: E402
+import make_golden  # noqa: E402
+
+DRIVER = make_golden.DRIVER
+
+# name: (synth kwargs, option overrides for vr_atmos_options)
+CASES = {
+    "atmos_daily": (dict(ncells=5, ndays=800, startyear=1983, lat_range=(-55, 64), seed=301), {}),
+    "atmos_daily_offset": (dict(ncells=6, ndays=450, startyear=1984, lat_range=(-40, 60), off_gmt=0, seed=302), {}),
+    "atmos_daily_cold_polar": (dict(ncells=4, ndays=420, startyear=1987, lat_range=(62, 82), cold=8.0, off_gmt=2, seed=303,
+                                    extra_global="MTCLIM_SWE_CORR TRUE\nLW_CLOUD LW_CLOUD_BRAS\nLW_TYPE LW_TVA"),
+                               dict(mtclim_swe_corr=True, lw_cloud="LW_CLOUD_BRAS", lw_type="LW_TVA")),
+    "atmos_sub3h": (dict(ncells=4, ndays=200, dt=3, startyear=1988, lat_range=(-50, 65), cold=6.0, seed=304), {}),
+    "atmos_sub6h_offset": (dict(ncells=4, ndays=120, dt=6, startyear=1990, lat_range=(20, 60), off_gmt=-3, seed=305), {}),
+    "atmos_daily_to_3h": (dict(ncells=3, ndays=150, dt=3, force_daily=True, startyear=1991, lat_range=(-30, 50), off_gmt=5,
+                               seed=306), {}),
+    "atmos_converge_noplapse": (dict(ncells=3, ndays=380, startyear=1992, seed=307,
+                                     extra_global="VP_ITER VP_ITER_CONVERGE\nPLAPSE FALSE\nLW_TYPE LW_BRUTSAERT"),
+                                dict(vp_iter="VP_ITER_CONVERGE", plapse=False, lw_type="LW_BRUTSAERT")),
+    # the reference's VP_ITER parser sets VP_INTERP to 1 for every value but VP_ITER_CONVERGE
+    # (get_global_param.c:405-412), so "VP_INTERP FALSE" must come after VP_ITER to stay FALSE
+    "atmos_annual_nointerp": (dict(ncells=3, ndays=300, startyear=1993, seed=308,
+                                   extra_global="VP_ITER VP_ITER_ANNUAL\nVP_INTERP FALSE\nLW_TYPE LW_IDSO\nSW_PREC_THRESH 0.1"),
+                              dict(vp_iter="VP_ITER_ANNUAL", vp_interp=False, lw_type="LW_IDSO", sw_prec_thresh=0.1)),
+    "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,
+                                extra_global="VP_ITER VP_ITER_NONE\nLW_TYPE LW_SATTERLUND"),
+                           dict(vp_iter="VP_ITER_NONE", lw_type="LW_SATTERLUND")),
+}
+
+
+def read_raw(gfile, lat, lng, ncol):
+    """The forcing columns as read_atmos_data parses them (ASCII), [ncol][nrec_f][C]."""
+    g = dict(ln.split(None, 1) for ln in open(gfile) if ln.split() and ln.split()[0] == "FORCING1")
+    pre = g["FORCING1"].strip()
+    cols = []
+    for la, lo in zip(lat, lng):
+        a = np.loadtxt("%s%.4f_%.4f" % (pre, la, lo), ndmin=2)
+        cols.append(a[:, :ncol])
+    return np.ascontiguousarray(np.stack(cols, axis=2).transpose(1, 0, 2))
+
+
+def save(name, gfile, dump, kw, ov, start=None):
+    d = refdump.read_dump(dump)
+    C = int(d["ncells"][0])
+    sc = np.stack([d["c%d/soil_scalars" % c] for c in range(C)])
+    site = {"lat": sc[:, 0], "lng": sc[:, 1], "elevation": sc[:, 2], "annual_prec": sc[:, 12], "time_zone_lng": sc[:, 17]}
+    atm = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2).transpose(1, 0, 2)   # [9, nrec, C]
+    dt = int(d["dt"][0])
+    daily = dt == 24 or kw.get("force_daily", False)
+    raw = read_raw(gfile, site["lat"], site["lng"], 4 if daily else 3)
+    nrecs = int(d["nrecs"][0])
+    nrf = nrecs * dt // (24 if daily else dt)
+    dmy = d["dmy"]
+    arrays = {"raw": raw[:, :nrf], "atmos": np.ascontiguousarray(atm),
+              "meta": np.array([dt, nrecs, dmy[0, 0], dmy[0, 1], dmy[0, 2], dmy[0, 3], 0 if daily else 1, 24 if daily else dt],
+                               dtype=np.int64),
+              "ov_keys": np.array(list(ov.keys()) or [""]), "ov_vals": np.array([str(v) for v in ov.values()] or [""])}
+    for k, v in site.items():
+        arrays["site_" + k] = v
+    out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(out, **arrays)
+    print("%-26s cells %d recs %d  %.1f kB" % (name, C, nrecs, os.path.getsize(out) / 1e3))
+
+
+def main():
+    if not os.path.exists(DRIVER):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (kw, ov) in CASES.items():
+            work = os.path.join(tmp, name)
+            g = synth.make_case(work, max_veg=1, **kw)
+            dump = os.path.join(work, "dump.bin")
+            make_golden.run_driver(g, dump)
+            save(name, g, dump, kw, ov)
+        work = os.path.join(tmp, "bundled")
+        os.makedirs(work)
+        g = make_golden.bundled_case(work)
+        dump = os.path.join(work, "dump.bin")
+        make_golden.run_driver(g, dump)
+        save("atmos_bundled_basin_cell", g, dump, {}, {})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+"""Host-side mirror of the reference's forcing preparation over the C ABI of include/vicres_atmos.h.
+
+The reference calls, once per cell, `initialize_atmos(atmos, dmy, filep.forcing, ...)`
+(runoff/model/vicNl.c:239-241); `prepare()` does that for all cells at once on the GPU:
+
+    o = atmos.options(time_step=24, nrecs=3653, startyear=1981)         # global-file values
+    f = atmos.prepare(o, site, raw)         # [9, nrecs, C]: what VicRes.step() takes as forcing
+
+ctypes declarations and marshalling only; every number is computed by the CUDA library
+(vicres_b200/csrc/vicres_atmos.cu).  There is no CPU path behind it.
+"""
+import ctypes as C
+import numpy as np
+from . import abi, model
+
+DAILY_TMAX_TMIN, SUBDAILY_AIR_TEMP = 0, 1
+VP_ITER = {"VP_ITER_NONE": 0, "VP_ITER_ALWAYS": 1, "VP_ITER_ANNUAL": 2, "VP_ITER_CONVERGE": 3}
+LW_TYPE = {"LW_TVA": 0, "LW_ANDERSON": 1, "LW_BRUTSAERT": 2, "LW_SATTERLUND": 3, "LW_IDSO": 4, "LW_PRATA": 5}
+LW_CLOUD = {"LW_CLOUD_BRAS": 0, "LW_CLOUD_DEARDORFF": 1}
+
+EXPORTS = ["vr_atmos_default_options", "vr_atmos_ndays", "vr_atmos_prepare", "vr_atmos_prepare_device",
+           "vr_atmos_last_times", "vr_atmos_last_error"]
+
+_pd = C.POINTER(C.c_double)
+
+
+class vr_atmos_options(C.Structure):
+    _fields_ = [("time_step", C.c_int32), ("nrecs", C.c_int32), ("startyear", C.c_int32), ("startmonth", C.c_int32),
+                ("startday", C.c_int32), ("starthour", C.c_int32), ("layout", C.c_int32), ("force_dt", C.c_int32),
+                ("has_wind", C.c_int32), ("vp_interp", C.c_int32), ("vp_iter", C.c_int32),
+                ("mtclim_swe_corr", C.c_int32), ("lw_type", C.c_int32), ("lw_cloud", C.c_int32), ("plapse", C.c_int32),
+                ("reserved0", C.c_int32), ("min_wind_speed", C.c_double), ("sw_prec_thresh", C.c_double),
+                ("reserved", C.c_int32 * 8)]
+
+
+SITE_FIELDS = ["lat", "lng", "time_zone_lng", "elevation", "annual_prec", "slope", "aspect", "ehoriz", "whoriz"]
+
+
+class vr_atmos_cells(C.Structure):
+    _fields_ = [("ncell", C.c_int64)] + [(n, _pd) for n in SITE_FIELDS]
+
+
+class vr_atmos_raw(C.Structure):
+    _fields_ = [("nrec_forcing", C.c_int64), ("prec", _pd), ("t_a", _pd), ("t_b", _pd), ("wind", _pd)]
+
+
+def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, starthour=0, layout=None, force_dt=None,
+            has_wind=True, vp_interp=True, vp_iter="VP_ITER_ALWAYS", mtclim_swe_corr=False, lw_type="LW_PRATA",
+            lw_cloud="LW_CLOUD_DEARDORFF", plapse=True, min_wind_speed=0.1, sw_prec_thresh=0.0):
+    """vr_atmos_options with the reference's defaults (initialize_global.c:146-211)."""
+    o = vr_atmos_options()
+    if force_dt is None:
+        force_dt = 24 if layout in (None, DAILY_TMAX_TMIN) else time_step
+    if layout is None:
+        layout = DAILY_TMAX_TMIN if force_dt == 24 else SUBDAILY_AIR_TEMP
+    o.time_step, o.nrecs, o.startyear, o.startmonth, o.startday, o.starthour = time_step, nrecs, startyear, startmonth, startday, starthour
+    o.layout, o.force_dt, o.has_wind = layout, force_dt, int(has_wind)
+    o.vp_interp, o.vp_iter, o.mtclim_swe_corr = int(vp_interp), VP_ITER.get(vp_iter, vp_iter), int(mtclim_swe_corr)
+    o.lw_type, o.lw_cloud, o.plapse = LW_TYPE.get(lw_type, lw_type), LW_CLOUD.get(lw_cloud, lw_cloud), int(plapse)
+    o.min_wind_speed, o.sw_prec_thresh = min_wind_speed, sw_prec_thresh
+    return o
+
+
+class Packed:
+    def __init__(self, struct, keep):
+        self.struct, self._keep = struct, keep
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def pack_site(site):
+    """site: dict of [C] arrays lat, lng, time_zone_lng, elevation, annual_prec (+ optional slope ...)."""
+    s, keep = vr_atmos_cells(), []
+    s.ncell = len(site["lat"])
+    for n in SITE_FIELDS:
+        if site.get(n) is not None:
+            a = np.ascontiguousarray(site[n], dtype=np.float64)
+            keep.append(a)
+            setattr(s, n, a.ctypes.data_as(_pd))
+    return Packed(s, keep)
+
+
+def pack_raw(raw):
+    """raw: dict prec, t_a, t_b (or None), wind (or None), each [nrec_forcing, C]."""
+    s, keep = vr_atmos_raw(), []
+    s.nrec_forcing = raw["prec"].shape[0]
+    for n in ("prec", "t_a", "t_b", "wind"):
+        if raw.get(n) is not None:
+            a = np.ascontiguousarray(raw[n], dtype=np.float64)
+            keep.append(a)
+            setattr(s, n, a.ctypes.data_as(_pd))
+    return Packed(s, keep)
+
+
+def _lib():
+    L = model.load_library()
+    if not getattr(L, "_atmos_declared", False):
+        vp = C.c_void_p
+        L.vr_atmos_default_options.argtypes = [vp]
+        L.vr_atmos_default_options.restype = None
+        L.vr_atmos_ndays.argtypes = [vp]
+        L.vr_atmos_prepare.argtypes = [C.c_int, vp, vp, vp, vp]
+        L.vr_atmos_prepare_device.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+        L.vr_atmos_last_times.argtypes = [vp, vp]
+        L.vr_atmos_last_error.restype = C.c_char_p
+        L._atmos_declared = True
+    return L
+
+
+def _check(L, rc):
+    if rc != 0:
+        raise model.VicResError(rc, (L.vr_atmos_last_error() or b"").decode())
+
+
+def prepare(opt, site, raw, device=0):
+    """initialize_atmos for all cells: returns the nine atmos fields [9, nrecs, C] (host arrays)."""
+    L = _lib()
+    ps, pr = pack_site(site), pack_raw(raw)
+    Cn = ps.struct.ncell
+    out = np.zeros((abi.VR_NFORCING, opt.nrecs, Cn))
+    ptrs = (_pd * abi.VR_NFORCING)(*[out[f].ctypes.data_as(_pd) for f in range(abi.VR_NFORCING)])
+    _check(L, L.vr_atmos_prepare(device, C.byref(opt), ps.ref(), pr.ref(), ptrs))
+    return out
+
+
+def prepare_device(opt, site_dev, raw_dev, out_dev, ncell, nrec_forcing, device=0, stream=None):
+    """Device-resident variant: site_dev / raw_dev map names to device pointers (ints), out_dev is a list of
+    nine device pointers, each [nrecs*C] doubles."""
+    L = _lib()
+    s = vr_atmos_cells()
+    s.ncell = ncell
+    for n in SITE_FIELDS:
+        if site_dev.get(n):
+            setattr(s, n, C.cast(site_dev[n], _pd))
+    r = vr_atmos_raw()
+    r.nrec_forcing = nrec_forcing
+    for n in ("prec", "t_a", "t_b", "wind"):
+        if raw_dev.get(n):
+            setattr(r, n, C.cast(raw_dev[n], _pd))
+    ptrs = (_pd * abi.VR_NFORCING)(*[C.cast(p, _pd) for p in out_dev])
+    _check(L, L.vr_atmos_prepare_device(device, C.byref(opt), C.byref(s), C.byref(r), ptrs, stream))
+
+
+def last_times():
+    """(solar-table ms, MTCLIM daily ms, disaggregation ms, launches) of the last prepare call."""
+    L = _lib()
+    ms = (C.c_double * 3)()
+    n = C.c_int64()
+    L.vr_atmos_last_times(ms, C.byref(n))
+    return ms[0], ms[1], ms[2], n.value
+
+
+def options_from_global(g):
+    """vr_atmos_options from a parsed global file (vicres_b200.files.read_global dict)."""
+    types = [t for t in g["force_type"] if t != "SKIP"]
+    layout = SUBDAILY_AIR_TEMP if "AIR_TEMP" in types else DAILY_TMAX_TMIN
+    return options(time_step=g["time_step"], nrecs=g["nrecs"], startyear=g["startyear"], startmonth=g["startmonth"],
+                   startday=g["startday"], starthour=g["starthour"], layout=layout, force_dt=g["force_dt"],
+                   has_wind="WIND" in types, min_wind_speed=g["min_wind_speed"],
+                   vp_interp=g.get("vp_interp", 1), vp_iter=g.get("vp_iter", 1), mtclim_swe_corr=g.get("mtclim_swe_corr", 0),
+                   lw_type=g.get("lw_type", 5), lw_cloud=g.get("lw_cloud", 1), plapse=g.get("plapse", 1),
+                   sw_prec_thresh=g.get("sw_prec_thresh", 0.0))

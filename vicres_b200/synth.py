@@ -56,12 +56,14 @@ def _fmt(x, nd=6):
 def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261019,
               startyear=1981, lat_range=(-40.0, 60.0), cold=0.0, overstory_frac=0.3,
               max_veg=3, extra_global="", result_dir=None, skip_output=False, snow_step=None,
-              wind_zero_frac=0.0, coords=None):
+              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False):
     """Write a complete reference-format case under `outdir`; return the global file path.
 
     dt == 24: daily PREC/TMAX/TMIN/WIND forcing (as the bundled basin); dt < 24: sub-daily
     PREC/AIR_TEMP/WIND records at the model step.  `cold` lowers all temperatures (deg C) to
-    force snow.  All randomness comes from `seed`.
+    force snow.  All randomness comes from `seed`.  `off_gmt` (hours) replaces the cells' own time zone
+    (round(lng/15)), so that local time differs from the forcing's time; `force_daily` writes the daily
+    four-column file even when dt < 24 (FORCE_DT 24 with a sub-daily TIME_STEP).
     """
     rng = np.random.default_rng(seed)
     os.makedirs(outdir, exist_ok=True)
@@ -106,7 +108,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         dp = 4.0
         bubble = rng.uniform(5.0, 40.0, L)
         quartz = rng.uniform(0.1, 0.8, L)
-        off_gmt = round(lng / 15.0)
+        off_gmt_c = round(lng / 15.0) if off_gmt is None else off_gmt
         wcr_fr = rng.uniform(0.55, 0.75, L)
         wpwp_fr = rng.uniform(0.2, 0.5, L)
         rough, snow_rough = 0.001, 0.0005
@@ -117,7 +119,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         cols += [_fmt(x, 4) for x in expt] + [_fmt(x, 3) for x in Ksat] + ["%.0f" % x for x in phi_s]
         cols += [_fmt(x, 4) for x in init_moist] + ["%.1f" % elev] + [_fmt(x, 4) for x in depth]
         cols += [_fmt(avg_T, 3), _fmt(dp, 1)] + [_fmt(x, 3) for x in bubble] + [_fmt(x, 4) for x in quartz]
-        cols += [_fmt(x, 2) for x in bulk] + [_fmt(x, 2) for x in sdens] + ["%d" % off_gmt]
+        cols += [_fmt(x, 2) for x in bulk] + [_fmt(x, 2) for x in sdens] + ["%g" % off_gmt_c]
         cols += [_fmt(x, 4) for x in wcr_fr] + [_fmt(x, 4) for x in wpwp_fr]
         cols += [_fmt(rough, 4), _fmt(snow_rough, 4), _fmt(annual_prec, 1)] + [_fmt(x, 4) for x in resid] + ["0"]
         soil_lines.append("\t".join(cols))
@@ -181,7 +183,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
             wind = np.where(rng.uniform(size=ndays) < wind_zero_frac, 0.0, wind)
         fn = os.path.join(forc_dir, "data_%.4f_%.4f" % (lat, lng))
         with open(fn, "w") as f:
-            if dt == 24:
+            if dt == 24 or force_daily:
                 for i in range(ndays):
                     f.write("%.4f %.4f %.4f %.4f\n" % (prec[i], tmax[i], tmin[i], wind[i]))
             else:
@@ -206,7 +208,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
           "FULL_ENERGY FALSE", "FROZEN_SOIL FALSE", "NO_FLUX FALSE", "CORRPREC FALSE",
           "MIN_WIND_SPEED 0.1", "MAX_SNOW_TEMP 0.5", "MIN_RAIN_TEMP -0.5",
           "FORCING1 %s/data_" % forc_dir, "FORCE_FORMAT ASCII", "FORCE_ENDIAN LITTLE"]
-    if dt == 24:
+    if dt == 24 or force_daily:
         g += ["N_TYPES 4", "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN", "FORCE_TYPE WIND",
               "FORCE_DT 24"]
     else:
