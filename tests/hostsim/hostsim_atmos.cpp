@@ -1,0 +1,46 @@
+// hostsim_atmos.cpp -- TEST HARNESS ONLY.  Compiles the device header of the forcing preparation
+// (vicres_b200/csrc/vic_atmos.cuh) for the HOST with g++ and runs the bodies serially in the order the
+// kernels of vicres_atmos.cu run them, so that the non-GPU test tier can check the restructured
+// arithmetic (hourly radiation fractions without the tiny_radfract array, per-day radiation chains,
+// array-free Hermite spline) against the reference's own atmos[] records.  Not linked into
+// libvicres.so, not a product code path.
+#include <vector>
+#include "../../vicres_b200/csrc/vic_atmos.cuh"
+
+extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw, double *const out[VR_NFORCING])
+{
+  if (va::unsupported(*o)) return -2;
+  va::Ctx x{};
+  va::fill_options(*o, x);
+  const int64_t C = cells->ncell;
+  const int nd = x.Ndays + 1;
+  std::vector<int16_t> cal(x.Ndays + 2);
+  va::build_calendar(*o, x.Ndays, cal.data());
+  x.cal = cal.data();
+  x.C = C; x.c0 = 0; x.CB = C; x.nrf = raw->nrec_forcing;
+  x.lat = cells->lat; x.lng = cells->lng; x.tz = cells->time_zone_lng; x.elev = cells->elevation;
+  x.slope = cells->slope; x.aspect = cells->aspect; x.ehoriz = cells->ehoriz; x.whoriz = cells->whoriz;
+  x.r_prec = raw->prec; x.r_ta = raw->t_a; x.r_tb = raw->t_b; x.r_wind = raw->wind;
+  std::vector<double> tab((size_t)va::NYD * 28 * C), dly((size_t)nd * 7 * C), tcon(2 * C);
+  std::vector<int8_t> hrs((size_t)nd * 2 * C);
+  x.ttmax0 = tab.data(); x.flat = x.ttmax0 + va::NYD * C; x.slp = x.flat + va::NYD * C; x.dayl = x.slp + va::NYD * C;
+  x.hf = x.dayl + va::NYD * C;
+  double *d = dly.data();
+  x.prec_d = d; x.swe = d + (size_t)nd * C; x.srad = d + (size_t)2 * nd * C; x.pva = d + (size_t)3 * nd * C;
+  x.tskc = d + (size_t)4 * nd * C; x.tdew = d + (size_t)5 * nd * C; x.parr = d + (size_t)6 * nd * C;
+  x.tcon = tcon.data();
+  x.tminh = hrs.data(); x.tmaxh = hrs.data() + (size_t)nd * C;
+  for (int f = 0; f < VR_NFORCING; f++) x.out[f] = out[f];
+  for (int64_t c = 0; c < C; c++)
+    for (int yd = 0; yd < va::NYD; yd++) va::solar_day(x, c, yd);
+  for (int64_t c = 0; c < C; c++) va::daily_prep(x, c);
+  for (int64_t c = 0; c < C; c++)
+    for (int day = 0; day < nd; day++) va::daily_rad(x, c, day);
+  if (x.vp_iter == VR_VP_ITER_CONVERGE)
+    for (int64_t c = 0; c < C; c++) va::converge(x, c);
+  for (int64_t c = 0; c < C; c++)
+    for (int day = 0; day < nd; day++) va::minmax_hour(x, c, day);
+  for (int64_t c = 0; c < C; c++)
+    for (int rec = 0; rec < x.nrecs; rec++) va::record(x, c, rec);
+  return 0;
+}

@@ -2,6 +2,7 @@
 ctypes struct mirrors have the C layout, and the library refuses to run without a CUDA device (no
 CPU fallback).  No compute calls."""
 import ctypes as C
+import numpy as np
 import os
 import re
 import subprocess
@@ -45,6 +46,52 @@ def test_exports_every_declared_routing_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), "libvicres.so does not export %s" % s
     assert sorted(route.ROUTE_EXPORTS) == syms
+
+
+def test_exports_every_declared_atmos_symbol(lib):
+    from vicres_b200 import atmos
+    syms = declared_symbols("vicres_atmos.h")
+    assert len(syms) == 6
+    for s in syms:
+        assert hasattr(lib, s), "libvicres.so does not export %s" % s
+    assert sorted(atmos.EXPORTS) == syms
+
+
+def test_atmos_struct_layout_and_defaults(lib, tmp_path):
+    from vicres_b200 import atmos
+    src = tmp_path / "sza.c"
+    src.write_text('#include <stdio.h>\n#include "vicres_atmos.h"\nint main(){printf("%zu %zu %zu\\n",'
+                   "sizeof(vr_atmos_options),sizeof(vr_atmos_cells),sizeof(vr_atmos_raw));return 0;}\n")
+    exe = tmp_path / "sza"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(atmos.vr_atmos_options), C.sizeof(atmos.vr_atmos_cells), C.sizeof(atmos.vr_atmos_raw)]
+    o = atmos.vr_atmos_options()
+    atmos._lib().vr_atmos_default_options(C.byref(o))
+    mine = atmos.options(nrecs=0)
+    for name, _ in atmos.vr_atmos_options._fields_:
+        if not name.startswith("reserved"):
+            assert getattr(o, name) == getattr(mine, name), name
+
+
+def test_atmos_has_no_cpu_fallback_and_validates_without_a_device(lib):
+    import torch
+    from vicres_b200 import atmos
+    L = atmos._lib()
+    o = atmos.options(nrecs=10, layout=atmos.DAILY_TMAX_TMIN, force_dt=12)
+    assert L.vr_atmos_prepare(0, C.byref(o), None, None, None) == abi.VR_ERR_ARG
+    z = np.zeros(10)
+    site = atmos.pack_site({"lat": z[:1], "lng": z[:1], "time_zone_lng": z[:1], "elevation": z[:1], "annual_prec": z[:1]})
+    raw = atmos.pack_raw({"prec": z[:, None], "t_a": z[:, None], "t_b": z[:, None], "wind": z[:, None]})
+    out = np.zeros((abi.VR_NFORCING, 10, 1))
+    pd = C.POINTER(C.c_double)
+    ptrs = (pd * abi.VR_NFORCING)(*[out[f].ctypes.data_as(pd) for f in range(abi.VR_NFORCING)])
+    assert L.vr_atmos_prepare(0, C.byref(o), site.ref(), raw.ref(), ptrs) == abi.VR_ERR_UNSUPPORTED
+    assert b"FORCE_DT" in L.vr_atmos_last_error()
+    if not torch.cuda.is_available():
+        o = atmos.options(nrecs=10)
+        assert L.vr_atmos_prepare(0, C.byref(o), site.ref(), raw.ref(), ptrs) == abi.VR_ERR_CUDA
+        assert b"no CPU path" in L.vr_atmos_last_error()
 
 
 def test_struct_layout_matches_c(tmp_path):

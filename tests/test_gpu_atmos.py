@@ -1,0 +1,113 @@
+"""GPU tier (-m gpu): the CUDA forcing preparation (vr_atmos_prepare, vicres_b200/csrc/vicres_atmos.cu) through the
+C ABI against the reference's own atmos[] records and against the oracle restatement on seeded grids.
+
+Tolerance: 1e-9 relative (BASELINE.json north_star).  What can exceed it, and why: the
+reference decides the hour of sunrise by `hourlyrad > 0`, and the first 30-second slot after sunrise holds
+cos(zenith) evaluated AT the sunrise hour angle -- a rounding residual of either sign.  When that slot is the last
+one of its clock hour, CUDA's cos/acos and glibc's (1 ulp apart) can disagree on whether the hour has sun, which moves
+Tmin/Tmax hours of that day by one.  So the assertions are: finite; >= 99 % of all values within 1e-9; precipitation,
+wind and shortwave (which do not depend on those hours) within 1e-9 everywhere; the rest within the physical bound of
+a one-hour shift of the diurnal cycle."""
+import numpy as np
+import pytest
+import atmos_lib
+from vicres_b200 import abi, atmos, build, synth_soa
+from common import ATMOS_FIXTURES, RTOL, load_atmos_fixture, relerr
+
+pytestmark = pytest.mark.gpu
+F = {n: i for i, n in enumerate(abi.FORCING_FIELDS)}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    build.build()
+    return atmos
+
+
+def check(out, ref, what):
+    assert np.isfinite(out).all(), what + ": non-finite output"
+    e = relerr(out, ref)
+    frac = float((e <= RTOL).mean())
+    days = float((e <= RTOL).all(axis=0).mean())
+    print("ATMOS PARITY %s: %.6f of %d values within 1e-9 (%.6f of (record, cell) pairs entirely); max rel %.3e" %
+          (what, frac, e.size, days, e.max()))
+    for n in ("prec", "wind", "shortwave"):
+        assert e[F[n]].max() <= RTOL, "%s: %s off by %.3e" % (what, n, e[F[n]].max())
+    assert frac >= 0.99, "%s: only %.4f within 1e-9" % (what, frac)
+    assert np.abs(out[F["air_temp"]] - ref[F["air_temp"]]).max() < 2.0, what + ": air temperature beyond a one-hour shift"
+    assert e[F["pressure"]].max() < 1e-3 and e[F["longwave"]].max() < 5e-2
+    return frac
+
+
+@pytest.mark.parametrize("name", ATMOS_FIXTURES)
+def test_cuda_matches_reference_atmos(gpu, name):
+    fx = load_atmos_fixture(name)
+    out = gpu.prepare(fx["opt"], fx["site"], fx["raw"])
+    check(out, fx["ref"], "%s CUDA vs reference" % name)
+    ms = gpu.last_times()
+    assert ms[3] >= 5 and ms[0] > 0
+
+
+def test_seeded_grid_matches_oracle_and_batches_are_bit_identical(gpu):
+    """4 000 cells x 400 days: a sample of cells against the oracle; the whole grid again in batches of 1 024 cells."""
+    C, nd = 4000, 400
+    site = synth_soa.make_site(C, seed=21, lat_range=(-55.0, 66.0), own_time_zone=False)
+    raw = synth_soa.make_raw_forcing(site["lat"], site["elevation"], nd, seed=22, cold=5.0)
+    opt = atmos.options(time_step=24, nrecs=nd, startyear=1983)
+    out = gpu.prepare(opt, site, raw)
+    sample = np.arange(0, C, 97)
+    ssite = {k: v[sample] for k, v in site.items()}
+    sraw = {k: (np.ascontiguousarray(v[:, sample]) if v is not None else None) for k, v in raw.items()}
+    ref = atmos_lib.prepare(opt, ssite, sraw)
+    check(out[:, :, sample], ref, "seeded 4000 x 400 (sample of %d cells) CUDA vs oracle" % len(sample))
+    opt.reserved[0] = 1024
+    out2 = gpu.prepare(opt, site, raw)
+    assert np.array_equal(out, out2)
+
+
+def test_subdaily_grid_matches_oracle(gpu):
+    C, nd = 600, 120
+    site = synth_soa.make_site(C, seed=31, lat_range=(35.0, 65.0))
+    raw = synth_soa.make_raw_forcing(site["lat"], site["elevation"], nd, dt_hours=3, seed=32, cold=8.0)
+    opt = atmos.options(time_step=3, nrecs=nd * 8, startyear=1990, layout=atmos.SUBDAILY_AIR_TEMP, force_dt=3)
+    out = gpu.prepare(opt, site, raw)
+    sample = np.arange(0, C, 13)
+    ref = atmos_lib.prepare(opt, {k: v[sample] for k, v in site.items()},
+                            {k: (np.ascontiguousarray(v[:, sample]) if v is not None else None) for k, v in raw.items()})
+    check(out[:, :, sample], ref, "sub-daily 600 x 120 d CUDA vs oracle")
+
+
+def test_physical_properties_at_scale(gpu):
+    """50 000 cells x 365 days (no oracle): daily precipitation is handed through unchanged, VPD >= 0 and VP <= svp(T),
+    shortwave is 0 for no cell more than the polar night allows, pressure falls with elevation."""
+    C, nd = 50000, 365
+    site = synth_soa.make_site(C, seed=41)
+    raw = synth_soa.make_raw_forcing(site["lat"], site["elevation"], nd, seed=42)
+    opt = atmos.options(time_step=24, nrecs=nd, startyear=1981)
+    out = gpu.prepare(opt, site, raw)
+    assert np.isfinite(out).all()
+    assert np.array_equal(out[F["prec"]], raw["prec"])          # hour offset 0: local days are the forcing's days
+    assert np.array_equal(out[F["wind"]], raw["wind"])
+    assert (out[F["vpd"]] >= 0).all()
+    assert (out[F["shortwave"]] > 0).all() and out[F["shortwave"]].max() < 500.0
+    tmean = out[F["air_temp"]]
+    assert (tmean <= raw["t_a"] + 1e-9).all() and (tmean >= raw["t_b"] - 1e-9).all()
+    hi, lo = site["elevation"] > 1500, site["elevation"] < 300
+    assert out[F["pressure"]][:, hi].mean() < out[F["pressure"]][:, lo].mean() - 1e4
+
+
+def test_unsupported_and_argument_errors(gpu):
+    from vicres_b200 import model
+    fx = load_atmos_fixture("atmos_short_record")
+    o = fx["opt"]
+    o.force_dt = 12
+    with pytest.raises(model.VicResError) as e:
+        gpu.prepare(o, fx["site"], fx["raw"])
+    assert e.value.code == abi.VR_ERR_UNSUPPORTED
+    o.force_dt = 24
+    bad = dict(fx["raw"]); bad["t_b"] = None
+    with pytest.raises(model.VicResError) as e:
+        gpu.prepare(o, fx["site"], bad)
+    assert e.value.code == abi.VR_ERR_ARG

@@ -1,0 +1,228 @@
+// vicres_atmos.cu -- kernels and C ABI of the forcing preparation (include/vicres_atmos.h).
+//
+// Five kernels over one batch of cells at a time (scratch tables of a batch: 82 kB per cell for the solar
+// geometry + 5 doubles and 2 bytes per cell-day), each a thin launch of a body of vic_atmos.cuh:
+//   k_solar   one thread per (cell, yearday)   -- the 30-second hour-angle walk, >99 % of the arithmetic
+//   k_prep    one thread per cell              -- recurrences over days (MTCLIM snowpack), daily totals
+//   k_rad     one thread per (cell, local day) -- radiation / humidity chain of the day
+//   k_conv    one thread per cell              -- VP_ITER_CONVERGE only
+//   k_hours   one thread per (cell, local day) -- hours of Tmin / Tmax
+//   k_rec     one thread per (cell, record)    -- the nine atmos fields of the record
+// Threads of a warp are 32 consecutive cells of the same row, so every scratch and output access is a
+// coalesced 256-byte line.  No CPU path: without a device the entry points return VR_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "vic_atmos.cuh"
+
+namespace {
+
+constexpr int TPB = 128;
+thread_local std::string g_err;
+struct Timing { std::vector<cudaEvent_t> ev; int64_t launches = 0; cudaStream_t stream = nullptr; int device = 0; };
+thread_local Timing g_t;
+
+int fail(int code, const std::string &m) { g_err = m; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(VR_ERR_CUDA, std::string(#call ": ") + cudaGetErrorString(e_)); } while (0)
+
+// row = blockIdx.x / nbc, cells of the block = (blockIdx.x % nbc) * TPB ...
+__device__ __forceinline__ bool locate(const va::Ctx &x, int64_t cb, int &row, int64_t &c)
+{
+  const int64_t nbc = (cb + TPB - 1) / TPB;
+  row = (int)(blockIdx.x / nbc);
+  const int64_t lc = (blockIdx.x % nbc) * TPB + threadIdx.x;
+  c = x.c0 + lc;
+  return lc < cb;
+}
+__global__ void __launch_bounds__(TPB) k_solar(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int yd; int64_t c;
+  if (locate(x, cb, yd, c)) va::solar_day(x, c, yd);
+}
+__global__ void __launch_bounds__(TPB) k_prep(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int r; int64_t c;
+  if (locate(x, cb, r, c)) va::daily_prep(x, c);
+}
+__global__ void __launch_bounds__(TPB) k_rad(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int day; int64_t c;
+  if (locate(x, cb, day, c)) va::daily_rad(x, c, day);
+}
+__global__ void __launch_bounds__(TPB) k_conv(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int r; int64_t c;
+  if (locate(x, cb, r, c)) va::converge(x, c);
+}
+__global__ void __launch_bounds__(TPB) k_hours(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int day; int64_t c;
+  if (locate(x, cb, day, c)) va::minmax_hour(x, c, day);
+}
+__global__ void __launch_bounds__(TPB) k_rec(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int rec; int64_t c;
+  if (locate(x, cb, rec, c)) va::record(x, c, rec);
+}
+
+void drop_events()
+{
+  for (cudaEvent_t e : g_t.ev) cudaEventDestroy(e);
+  g_t.ev.clear();
+  g_t.launches = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vr_atmos_default_options(vr_atmos_options *o)
+{
+  if (!o) return;
+  *o = vr_atmos_options{};
+  o->time_step = 24; o->startyear = 1981; o->startmonth = 1; o->startday = 1;
+  o->layout = VR_ATMOS_DAILY_TMAX_TMIN; o->force_dt = 24; o->has_wind = 1;
+  o->vp_interp = 1; o->vp_iter = VR_VP_ITER_ALWAYS; o->mtclim_swe_corr = 0; o->lw_type = VR_LW_PRATA;
+  o->lw_cloud = VR_LW_CLOUD_DEARDORFF; o->plapse = 1; o->min_wind_speed = 0.1; o->sw_prec_thresh = 0.;
+}
+
+int32_t vr_atmos_ndays(const vr_atmos_options *o) { return o ? va::ndays_of(*o) : 0; }
+const char *vr_atmos_last_error(void) { return g_err.c_str(); }
+
+int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
+                            double *const out[VR_NFORCING], void *cuda_stream)
+{
+  if (!o || !cells || !raw || !out) return fail(VR_ERR_ARG, "null argument");
+  if (const char *why = va::unsupported(*o)) return fail(VR_ERR_UNSUPPORTED, why);
+  if (cells->ncell < 1 || !cells->lat || !cells->lng || !cells->time_zone_lng || !cells->elevation)
+    return fail(VR_ERR_ARG, "cells: lat, lng, time_zone_lng and elevation are required");
+  if (!raw->prec || !raw->t_a || (o->layout == VR_ATMOS_DAILY_TMAX_TMIN && !raw->t_b) || (o->has_wind && !raw->wind))
+    return fail(VR_ERR_ARG, "raw: a forcing column of the declared layout is missing");
+  if (raw->nrec_forcing < 1) return fail(VR_ERR_ARG, "raw: nrec_forcing < 1");
+  for (int f = 0; f < VR_NFORCING; f++) if (!out[f]) return fail(VR_ERR_ARG, "out: null field");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev)
+    return fail(VR_ERR_CUDA, "no CUDA device: the forcing preparation has no CPU path");
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  drop_events();
+  g_t.stream = st; g_t.device = device;
+
+  va::Ctx x{};
+  va::fill_options(*o, x);
+  const int64_t C = cells->ncell;
+  const int nd = x.Ndays + 1;                       // local days of a cell whose local time is not the forcing's
+  int64_t CB = o->reserved[0] > 0 ? o->reserved[0] : 32768;
+  if (CB > C) CB = C;
+  x.C = C; x.CB = CB; x.nrf = raw->nrec_forcing;
+  x.lat = cells->lat; x.lng = cells->lng; x.tz = cells->time_zone_lng; x.elev = cells->elevation;
+  x.slope = cells->slope; x.aspect = cells->aspect; x.ehoriz = cells->ehoriz; x.whoriz = cells->whoriz;
+  x.r_prec = raw->prec; x.r_ta = raw->t_a; x.r_tb = raw->t_b; x.r_wind = raw->wind;
+  for (int f = 0; f < VR_NFORCING; f++) x.out[f] = out[f];
+
+  // scratch of one batch, one stream-ordered allocation
+  const bool conv = o->vp_iter == VR_VP_ITER_CONVERGE;
+  const int ndaily = 4 + (o->mtclim_swe_corr ? 1 : 0) + (conv ? 2 : 0);
+  const size_t n_tab = (size_t)va::NYD * 28 * CB, n_day = (size_t)nd * CB;
+  const size_t bytes = (n_tab + n_day * ndaily + 2 * (size_t)CB) * sizeof(double) + 2 * n_day + (size_t)(x.Ndays + 2) * sizeof(int16_t) + 64;
+  char *base = nullptr;
+  CK(cudaMallocAsync((void **)&base, bytes, st));
+  double *d = (double *)base;
+  x.ttmax0 = d; x.flat = d + (size_t)va::NYD * CB; x.slp = d + (size_t)2 * va::NYD * CB; x.dayl = d + (size_t)3 * va::NYD * CB;
+  x.hf = d + (size_t)4 * va::NYD * CB;
+  d += n_tab;
+  x.prec_d = d; d += n_day;
+  x.srad = d; d += n_day;
+  x.pva = d; d += n_day;
+  x.tskc = d; d += n_day;
+  if (o->mtclim_swe_corr) { x.swe = d; d += n_day; }
+  if (conv) { x.tdew = d; d += n_day; x.parr = d; d += n_day; }
+  x.tcon = d; d += 2 * CB;
+  x.tminh = (int8_t *)d;
+  x.tmaxh = x.tminh + n_day;
+  int16_t *cal_dev = (int16_t *)(((uintptr_t)(x.tmaxh + n_day) + 15) & ~(uintptr_t)15);
+  std::vector<int16_t> cal(x.Ndays + 2);
+  va::build_calendar(*o, x.Ndays, cal.data());
+  CK(cudaMemcpyAsync(cal_dev, cal.data(), cal.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));                      // `cal` is pageable host memory that dies with this call
+  x.cal = cal_dev;
+
+  auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_t.ev.push_back(e); };
+  for (int64_t c0 = 0; c0 < C; c0 += CB) {
+    const int64_t cb = (C - c0 < CB) ? C - c0 : CB;
+    const int64_t nbc = (cb + TPB - 1) / TPB;
+    x.c0 = c0;
+    mark();
+    k_solar<<<(unsigned)(nbc * va::NYD), TPB, 0, st>>>(x, cb);
+    mark();
+    k_prep<<<(unsigned)nbc, TPB, 0, st>>>(x, cb);
+    k_rad<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb);
+    g_t.launches += 3;
+    if (conv) { k_conv<<<(unsigned)nbc, TPB, 0, st>>>(x, cb); g_t.launches++; }
+    mark();
+    k_hours<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb);
+    k_rec<<<(unsigned)(nbc * x.nrecs), TPB, 0, st>>>(x, cb);
+    g_t.launches += 2;
+    mark();
+  }
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(base, st));
+  return VR_OK;
+}
+
+int vr_atmos_prepare(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
+                     double *const out[VR_NFORCING])
+{
+  if (!o || !cells || !raw || !out) return fail(VR_ERR_ARG, "null argument");
+  if (const char *why = va::unsupported(*o)) return fail(VR_ERR_UNSUPPORTED, why);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev)
+    return fail(VR_ERR_CUDA, "no CUDA device: the forcing preparation has no CPU path");
+  CK(cudaSetDevice(device));
+  const int64_t C = cells->ncell, nrf = raw->nrec_forcing;
+  if (C < 1 || nrf < 1) return fail(VR_ERR_ARG, "empty input");
+  const double *site_h[9] = {cells->lat, cells->lng, cells->time_zone_lng, cells->elevation, cells->annual_prec,
+                             cells->slope, cells->aspect, cells->ehoriz, cells->whoriz};
+  const double *raw_h[4] = {raw->prec, raw->t_a, raw->t_b, raw->wind};
+  const size_t n_out = (size_t)o->nrecs * C;
+  double *dev = nullptr;
+  CK(cudaMalloc((void **)&dev, ((size_t)9 * C + (size_t)4 * nrf * C + VR_NFORCING * n_out) * sizeof(double)));
+  const double *site_d[9] = {}, *raw_d[4] = {};
+  double *p = dev;
+  int rc = VR_OK;
+  for (int i = 0; i < 9 && rc == VR_OK; i++, p += C)
+    if (site_h[i]) { site_d[i] = p; if (cudaMemcpy(p, site_h[i], C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
+  for (int i = 0; i < 4 && rc == VR_OK; i++, p += (size_t)nrf * C)
+    if (raw_h[i]) { raw_d[i] = p; if (cudaMemcpy(p, raw_h[i], (size_t)nrf * C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
+  if (rc != VR_OK) { cudaFree(dev); return fail(rc, "host to device copy failed"); }
+  vr_atmos_cells cd{C, site_d[0], site_d[1], site_d[2], site_d[3], site_d[4], site_d[5], site_d[6], site_d[7], site_d[8]};
+  vr_atmos_raw rd{nrf, raw_d[0], raw_d[1], raw_d[2], raw_d[3]};
+  double *out_d[VR_NFORCING];
+  for (int f = 0; f < VR_NFORCING; f++) out_d[f] = p + (size_t)f * n_out;
+  rc = vr_atmos_prepare_device(device, o, &cd, &rd, out_d, nullptr);
+  if (rc == VR_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(VR_ERR_CUDA, std::string("kernel: ") + cudaGetErrorString(cudaGetLastError()));
+  for (int f = 0; f < VR_NFORCING && rc == VR_OK; f++)
+    if (cudaMemcpy(out[f], out_d[f], n_out * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(VR_ERR_CUDA, "device to host copy failed");
+  cudaFree(dev);
+  return rc;
+}
+
+int vr_atmos_last_times(double ms[3], int64_t *launches)
+{
+  if (!ms) return fail(VR_ERR_ARG, "null argument");
+  ms[0] = ms[1] = ms[2] = 0.;
+  if (launches) *launches = g_t.launches;
+  if (g_t.ev.empty()) return VR_OK;
+  CK(cudaSetDevice(g_t.device));
+  CK(cudaEventSynchronize(g_t.ev.back()));
+  for (size_t b = 0; b + 3 < g_t.ev.size(); b += 4)
+    for (int k = 0; k < 3; k++) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, g_t.ev[b + k], g_t.ev[b + k + 1]));
+      ms[k] += t;
+    }
+  return VR_OK;
+}
+
+}  // extern "C"

@@ -184,3 +184,44 @@ def make_forcing(cells, nrec, dt_hours=24, seed=7, start_doy=1, cold=0.0, xp=np,
     longwave = (0.72 + 0.15 * wet) * 5.6696e-8 * (tair + 273.15) ** 4
     f = np.stack([tair, prec, wind, vp, vpd, pressure, density, shortwave, longwave]).astype(np.float64)
     return np.ascontiguousarray(f), month, doy.astype(np.int32)
+
+
+def make_raw_forcing(lat, elevation, ndays, dt_hours=24, seed=11, cold=0.0, start_doy=1, decimals=4):
+    """Seeded raw forcing COLUMNS (what the reference's forcing files hold): daily
+    PREC/TMAX/TMIN/WIND for dt_hours == 24, else PREC/AIR_TEMP/WIND records of dt_hours.  Returns the dict
+    vicres_b200.atmos.prepare takes; values rounded like a "%.4f" text column."""
+    rng = np.random.default_rng(seed)
+    C = len(lat)
+    doy = ((np.arange(ndays) + start_doy - 1) % 365 + 1)[:, None]
+    north = (lat >= 0)[None, :]
+    phase = np.where(north, 2.0 * np.pi * (doy - 200.0) / 365.0, 2.0 * np.pi * (doy - 17.0) / 365.0)
+    tmean = (27.0 - 0.45 * np.abs(lat) - 0.0065 * elevation - cold)[None, :] + (2.0 + 0.30 * np.abs(lat))[None, :] * np.cos(phase)
+    tmean = tmean + rng.normal(0.0, 3.0, (ndays, C))
+    dtr = rng.uniform(5.0, 14.0, (ndays, C))
+    u = rng.uniform(size=(ndays, C))
+    wet = np.zeros((ndays, C), bool)
+    w = np.zeros(C, bool)
+    for i in range(ndays):
+        w = u[i] < np.where(w, 0.6, 0.22)
+        wet[i] = w
+    prec = np.where(wet, rng.gamma(0.8, 8.0, (ndays, C)), 0.0)
+    wind = np.maximum(np.exp(rng.normal(1.0, 0.5, (ndays, C))), 0.1)
+    r = lambda a: np.ascontiguousarray(np.round(a, decimals))
+    if dt_hours == 24:
+        return {"prec": r(prec), "t_a": r(tmean + 0.5 * dtr), "t_b": r(tmean - 0.5 * dtr), "wind": r(wind)}
+    spd = 24 // dt_hours
+    hrs = (np.arange(spd) + 0.5) * dt_hours
+    ta = tmean[:, None, :] + 0.5 * dtr[:, None, :] * np.cos(2.0 * np.pi * (hrs - 15.0) / 24.0)[None, :, None]
+    return {"prec": r(np.repeat(prec / spd, spd, axis=0)), "t_a": r(ta.reshape(ndays * spd, C)), "t_b": None,
+            "wind": r(np.repeat(wind, spd, axis=0))}
+
+
+def make_site(ncell, seed=3, lat_range=(-40.0, 60.0), own_time_zone=True):
+    """Seeded site values as soil_con holds them (floats widened to double)."""
+    rng = np.random.default_rng(seed)
+    lat = np.float32(rng.uniform(lat_range[0], lat_range[1], ncell)).astype(np.float64)
+    lng = np.float32(rng.uniform(-120.0, 120.0, ncell)).astype(np.float64)
+    off_gmt = np.rint(lng / 15.0) if own_time_zone else np.zeros(ncell)
+    return {"lat": lat, "lng": lng, "time_zone_lng": np.float32(off_gmt * 360.0 / 24.0).astype(np.float64),
+            "elevation": np.float32(rng.uniform(0.0, 2000.0, ncell)).astype(np.float64),
+            "annual_prec": np.full(ncell, 1000.0)}
