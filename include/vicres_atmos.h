@@ -87,6 +87,8 @@ int  vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atm
  * [1] MTCLIM daily pass, [2] sub-daily disaggregation; launches = kernels launched */
 int  vr_atmos_last_times(double ms[3], int64_t *launches);
 const char *vr_atmos_last_error(void);
+/* diagnostic: the device's correctly rounded acos(x[i]) and cos(y[i]), y in [0, pi] (vic_cr_trig.cuh); host pointers */
+int  vr_atmos_diag_cr(int device, int64_t n, const double *x, double *acos_out, const double *y, double *cos_out);
 
 #ifdef __cplusplus
 }

@@ -44,3 +44,10 @@ extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, 
     for (int rec = 0; rec < x.nrecs; rec++) va::record(x, c, rec);
   return 0;
 }
+
+#include "../../vicres_b200/csrc/vic_cr_trig.cuh"
+// correctly rounded acos / cos of vic_cr_trig.cuh, for the test against mpmath
+extern "C" void hs_cr(int64_t n, const double *x, double *acos_out, const double *y, double *cos_out)
+{
+  for (int64_t i = 0; i < n; i++) { acos_out[i] = vcr::acos_cr(x[i]); cos_out[i] = vcr::cos_cr(y[i]); }
+}

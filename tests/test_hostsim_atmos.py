@@ -38,3 +38,25 @@ def test_device_arithmetic_on_host_is_bit_identical(hostsim, name):
         bad = np.argwhere(out[f] != fx["ref"][f])
         assert bad.size == 0, "%s: %s differs at %d values, first (rec, cell) %s: %r vs %r" % (
             name, fname, len(bad), bad[0], out[f][tuple(bad[0])], fx["ref"][f][tuple(bad[0])])
+
+
+def test_correctly_rounded_acos_cos_against_mpmath(hostsim):
+    """vic_cr_trig.cuh (host build) gives the correctly rounded acos and cos; glibc's own differ from that in
+    about 0.1 % of arguments, which bounds how often the device can still take another sunrise branch."""
+    mp = pytest.importorskip("mpmath")
+    rng = np.random.default_rng(1)
+    n = 5000
+    x, y = rng.uniform(-0.9999, 0.9999, n), rng.uniform(0.0, np.pi, n)
+    a, c = np.zeros(n), np.zeros(n)
+    hostsim.hs_cr.argtypes = [C.c_int64] + [C.c_void_p] * 4
+    hostsim.hs_cr(n, x.ctypes.data, a.ctypes.data, y.ctypes.data, c.ctypes.data)
+    mp.mp.dps = 60
+    ra = np.array([float(mp.acos(mp.mpf(float(v)))) for v in x])
+    rc = np.array([float(mp.cos(mp.mpf(float(v)))) for v in y])
+    assert np.array_equal(a, ra) and np.array_equal(c, rc)
+    libm = C.CDLL("libm.so.6")
+    libm.acos.restype = libm.cos.restype = C.c_double
+    libm.acos.argtypes = libm.cos.argtypes = [C.c_double]
+    ga = np.array([libm.acos(float(v)) for v in x])
+    gc = np.array([libm.cos(float(v)) for v in y])
+    assert (ga != ra).mean() < 0.01 and (gc != rc).mean() < 0.01

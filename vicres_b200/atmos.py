@@ -19,7 +19,7 @@ LW_TYPE = {"LW_TVA": 0, "LW_ANDERSON": 1, "LW_BRUTSAERT": 2, "LW_SATTERLUND": 3,
 LW_CLOUD = {"LW_CLOUD_BRAS": 0, "LW_CLOUD_DEARDORFF": 1}
 
 EXPORTS = ["vr_atmos_default_options", "vr_atmos_ndays", "vr_atmos_prepare", "vr_atmos_prepare_device",
-           "vr_atmos_last_times", "vr_atmos_last_error"]
+           "vr_atmos_last_times", "vr_atmos_last_error", "vr_atmos_diag_cr"]
 
 _pd = C.POINTER(C.c_double)
 
@@ -104,6 +104,7 @@ def _lib():
         L.vr_atmos_prepare_device.argtypes = [C.c_int, vp, vp, vp, vp, vp]
         L.vr_atmos_last_times.argtypes = [vp, vp]
         L.vr_atmos_last_error.restype = C.c_char_p
+        L.vr_atmos_diag_cr.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp]
         L._atmos_declared = True
     return L
 
@@ -161,3 +162,12 @@ def options_from_global(g):
                    vp_interp=g.get("vp_interp", 1), vp_iter=g.get("vp_iter", 1), mtclim_swe_corr=g.get("mtclim_swe_corr", 0),
                    lw_type=g.get("lw_type", 5), lw_cloud=g.get("lw_cloud", 1), plapse=g.get("plapse", 1),
                    sw_prec_thresh=g.get("sw_prec_thresh", 0.0))
+
+
+def diag_cr(x, y, device=0):
+    """The device's correctly rounded acos(x), cos(y) (diagnostic for the tests)."""
+    L = _lib()
+    x, y = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+    a, c = np.zeros_like(x), np.zeros_like(y)
+    _check(L, L.vr_atmos_diag_cr(device, len(x), x.ctypes.data, a.ctypes.data, y.ctypes.data, c.ctypes.data))
+    return a, c

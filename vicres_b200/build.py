@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvicres.so")
 SOURCES = ["vicres_capi.cu", "vicres_route.cu", "vicres_atmos.cu", "vicres_files.cpp"]
-DEPS = ["vicres_capi.cu", "vicres_route.cu", "vicres_files.cpp", "vicres_atmos.cu", "vic_atmos.cuh", "../../include/vicres_atmos.h", "../../include/vicres_files.h", "vic_physics.cuh", "vic_aggregate.cuh", "vic_host_prep.h",
+DEPS = ["vicres_capi.cu", "vicres_route.cu", "vicres_files.cpp", "vicres_atmos.cu", "vic_atmos.cuh", "vic_cr_trig.cuh", "../../include/vicres_atmos.h", "../../include/vicres_files.h", "vic_physics.cuh", "vic_aggregate.cuh", "vic_host_prep.h",
         "../../include/vicres.h", "../../include/vicres_route.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-DVR_PHASE_BARRIERS"]

@@ -18,14 +18,16 @@
 //                                    aggregation to the model step, pressure, density, VPD, longwave
 //
 // Every formula keeps the reference's operation order (-fmad=false), every sum its term order.  The header also
-// compiles for the host (tests/hostsim, test harness only), where VA_POW is libm's pow: that build is bit-identical
+// compiles for the host (tests/hostsim, test harness only) with libm throughout: that build is bit-identical
 // to the reference.  On the device pow(trans1, am) is exp(am * log(trans1)) with the logarithm taken once per
-// (cell, yearday), pow(x, 1.5) is x*sqrt(x) and pow(x, 0.5) is sqrt(x): differences of a few ulp.
+// (cell, yearday), pow(x, 1.5) is x*sqrt(x) and pow(x, 0.5) is sqrt(x): differences of a few ulp; the two
+// evaluations a discrete decision hangs on (the sunrise hour angle and its cosine) are correctly rounded.
 #ifndef VIC_ATMOS_CUH
 #define VIC_ATMOS_CUH
 #include <math.h>
 #include <stdint.h>
 #include "../../include/vicres_atmos.h"
+#include "vic_cr_trig.cuh"
 
 #if defined(__CUDACC__)
 #define VA_HD __host__ __device__ __forceinline__
@@ -222,7 +224,16 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   double coshss = -(sinegeom) / cosegeom;
   if (coshss < -1.0) coshss = -1.0;
   if (coshss > 1.0) coshss = 1.0;
+  // On the device the sunrise hour angle and the cosine of the walk's first step are evaluated correctly rounded
+  // (vic_cr_trig.cuh): the sign of cos(zenith) at that step, zero up to rounding, decides the hour of sunrise.
+#if defined(__CUDA_ARCH__)
+  const double hss = vcr::acos_cr(coshss);
+  const double cos_h0 = vcr::cos_cr(hss);
+#define VA_COS_STEP(h) ((h) == -hss ? cos_h0 : cos(h))
+#else
   const double hss = acos(coshss);
+#define VA_COS_STEP(h) cos(h)
+#endif
   double daylength = 2.0 * hss * SECPERRAD;
   if (daylength > 86400) daylength = 86400;
   double sc = 1368.0 + 45.5 * sin((2.0 * MT_PI * (double)yd / 365.25) + 1.7);
@@ -234,6 +245,7 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
     double sinh_, cosh_;
 #if defined(__CUDA_ARCH__)
     sincos(h, &sinh_, &cosh_);
+    if (h == -hss) cosh_ = cos_h0;
 #else
     cosh_ = cos(h); sinh_ = sin(h);
 #endif
@@ -287,7 +299,7 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
     acc += norm ? v / sum_flat : v;
   };
   for (double h = -hss; h < hss; h += dh) {
-    double cza = cosegeom * cos(h) + sinegeom;
+    double cza = cosegeom * VA_COS_STEP(h) + sinegeom;
     double v = 0.0;
     if (cza > 0.0) { double dft = dir_beam_topa * cza; if (dft > 0) v = dft; }
     int ts = tiny_slot(h);
@@ -305,7 +317,7 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
         prev = ts;
         if (ts >= E) { prev = -1; break; }
       }
-      double cza = cosegeom * cos(h) + sinegeom;
+      double cza = cosegeom * VA_COS_STEP(h) + sinegeom;
       double v = 0.0;
       if (cza > 0.0) { double dft = dir_beam_topa * cza; if (dft > 0) v = dft; }
       pend = v;
@@ -313,6 +325,7 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
     if (prev >= 0 && prev < E) acc += norm ? pend / sum_flat : pend;
   }
   if (cur_j >= 0) hf[(int64_t)cur_j * CB] = acc;
+#undef VA_COS_STEP
 }
 
 // ---------------------------------------------------------------------------------------------------------------

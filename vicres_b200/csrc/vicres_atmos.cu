@@ -66,6 +66,12 @@ __global__ void __launch_bounds__(TPB) k_rec(const __grid_constant__ va::Ctx x, 
   if (locate(x, cb, rec, c)) va::record(x, c, rec);
 }
 
+__global__ void k_diag_cr(int64_t n, const double *x, double *a, const double *y, double *c)
+{
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = vcr::acos_cr(x[i]); c[i] = vcr::cos_cr(y[i]); }
+}
+
 void drop_events()
 {
   for (cudaEvent_t e : g_t.ev) cudaEventDestroy(e);
@@ -127,6 +133,12 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
   const size_t n_tab = (size_t)va::NYD * 28 * CB, n_day = (size_t)nd * CB;
   const size_t bytes = (n_tab + n_day * ndaily + 2 * (size_t)CB) * sizeof(double) + 2 * n_day + (size_t)(x.Ndays + 2) * sizeof(int16_t) + 64;
   char *base = nullptr;
+  {   // keep the scratch in the device's default pool between calls (the default threshold returns it at every sync)
+    cudaMemPool_t pool;
+    uint64_t keep = UINT64_MAX;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CK(cudaMallocAsync((void **)&base, bytes, st));
   double *d = (double *)base;
   x.ttmax0 = d; x.flat = d + (size_t)va::NYD * CB; x.slp = d + (size_t)2 * va::NYD * CB; x.dayl = d + (size_t)3 * va::NYD * CB;
@@ -206,6 +218,26 @@ int vr_atmos_prepare(int device, const vr_atmos_options *o, const vr_atmos_cells
     if (cudaMemcpy(out[f], out_d[f], n_out * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(VR_ERR_CUDA, "device to host copy failed");
   cudaFree(dev);
   return rc;
+}
+
+int vr_atmos_diag_cr(int device, int64_t n, const double *x, double *acos_out, const double *y, double *cos_out)
+{
+  if (n < 1 || !x || !acos_out || !y || !cos_out) return fail(VR_ERR_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev)
+    return fail(VR_ERR_CUDA, "no CUDA device: the forcing preparation has no CPU path");
+  CK(cudaSetDevice(device));
+  double *d = nullptr;
+  CK(cudaMalloc((void **)&d, 4 * n * sizeof(double)));
+  cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(d + 2 * n, y, n * sizeof(double), cudaMemcpyHostToDevice);
+  k_diag_cr<<<(unsigned)((n + 255) / 256), 256>>>(n, d, d + n, d + 2 * n, d + 3 * n);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(acos_out, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaMemcpy(cos_out, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(VR_ERR_CUDA, cudaGetErrorString(e));
+  return VR_OK;
 }
 
 int vr_atmos_last_times(double ms[3], int64_t *launches)
