@@ -90,6 +90,12 @@ const char *vr_atmos_last_error(void);
 /* diagnostic: the device's correctly rounded acos(x[i]) and cos(y[i]), y in [0, pi] (vic_cr_trig.cuh); host pointers */
 int  vr_atmos_diag_cr(int device, int64_t n, const double *x, double *acos_out, const double *y, double *cos_out);
 
+/* diagnostic: the solar-geometry tables of n cells (lng = time_zone_lng, i.e. no sub-hour offset, unless given):
+ * tab[(row*n + c)], rows 0..364 ttmax0, 365..729 flat potential radiation, 730..1094 slope potential radiation,
+ * 1095..1459 daylength, then 365*24 rows of hourly radiation fractions (yearday-major); host pointers */
+int  vr_atmos_diag_solar(int device, int64_t n, const double *lat, const double *elevation, const double *lng,
+                         const double *time_zone_lng, double *tab);
+
 #ifdef __cplusplus
 }
 #endif

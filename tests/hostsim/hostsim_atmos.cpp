@@ -51,3 +51,20 @@ extern "C" void hs_cr(int64_t n, const double *x, double *acos_out, const double
 {
   for (int64_t i = 0; i < n; i++) { acos_out[i] = vcr::acos_cr(x[i]); cos_out[i] = vcr::cos_cr(y[i]); }
 }
+extern "C" void hs_cr_sin(int64_t n, const double *y, double *sin_out)
+{
+  for (int64_t i = 0; i < n; i++) sin_out[i] = vcr::sin_cr(y[i]);
+}
+
+// solar-geometry tables of n cells, layout of vr_atmos_diag_solar
+extern "C" void hs_solar(int64_t n, const double *lat, const double *elev, const double *lng, const double *tz, double *tab)
+{
+  std::vector<double> zero(n, 0.0);
+  va::Ctx x{};
+  x.C = n; x.CB = n; x.c0 = 0;
+  x.lat = lat; x.elev = elev; x.lng = lng ? lng : zero.data(); x.tz = tz ? tz : zero.data();
+  x.ttmax0 = tab; x.flat = tab + (size_t)va::NYD * n; x.slp = tab + (size_t)2 * va::NYD * n; x.dayl = tab + (size_t)3 * va::NYD * n;
+  x.hf = tab + (size_t)4 * va::NYD * n;
+  for (int64_t c = 0; c < n; c++)
+    for (int yd = 0; yd < va::NYD; yd++) va::solar_day(x, c, yd);
+}

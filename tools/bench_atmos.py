@@ -49,7 +49,7 @@ def main():
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         k = atmos.last_times()
-        if r > 0:
+        if r > 0 or a.reps == 0:
             ms_all.append((wall, k[0], k[1], k[2], k[3]))
     ms = np.array(ms_all).mean(axis=0)
     finite = bool(torch.isfinite(out).all().item())

@@ -19,7 +19,7 @@ LW_TYPE = {"LW_TVA": 0, "LW_ANDERSON": 1, "LW_BRUTSAERT": 2, "LW_SATTERLUND": 3,
 LW_CLOUD = {"LW_CLOUD_BRAS": 0, "LW_CLOUD_DEARDORFF": 1}
 
 EXPORTS = ["vr_atmos_default_options", "vr_atmos_ndays", "vr_atmos_prepare", "vr_atmos_prepare_device",
-           "vr_atmos_last_times", "vr_atmos_last_error", "vr_atmos_diag_cr"]
+           "vr_atmos_last_times", "vr_atmos_last_error", "vr_atmos_diag_cr", "vr_atmos_diag_solar"]
 
 _pd = C.POINTER(C.c_double)
 
@@ -105,6 +105,7 @@ def _lib():
         L.vr_atmos_last_times.argtypes = [vp, vp]
         L.vr_atmos_last_error.restype = C.c_char_p
         L.vr_atmos_diag_cr.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp]
+        L.vr_atmos_diag_solar.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         L._atmos_declared = True
     return L
 
@@ -171,3 +172,16 @@ def diag_cr(x, y, device=0):
     a, c = np.zeros_like(x), np.zeros_like(y)
     _check(L, L.vr_atmos_diag_cr(device, len(x), x.ctypes.data, a.ctypes.data, y.ctypes.data, c.ctypes.data))
     return a, c
+
+
+def diag_solar(lat, elevation, lng=None, time_zone_lng=None, device=0):
+    """The device's solar-geometry tables of n cells: dict ttmax0/flat/slope/daylength [365, n], hf [365, 24, n]."""
+    L = _lib()
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    lat, elevation, lng, time_zone_lng = f(lat), f(elevation), f(lng), f(time_zone_lng)
+    n = len(lat)
+    tab = np.zeros((365 * 28, n))
+    p = lambda a: None if a is None else a.ctypes.data
+    _check(L, L.vr_atmos_diag_solar(device, n, p(lat), p(elevation), p(lng), p(time_zone_lng), tab.ctypes.data))
+    return {"ttmax0": tab[0:365], "flat": tab[365:730], "slope": tab[730:1095], "daylength": tab[1095:1460],
+            "hf": tab[1460:].reshape(365, 24, n)}

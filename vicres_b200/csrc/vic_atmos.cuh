@@ -206,7 +206,19 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   lat *= RADPERDEG;
   if (lat > 1.5707) lat = 1.5707;
   if (lat < -1.5707) lat = -1.5707;
-  const double coslat = cos(lat), sinlat = sin(lat);
+  // On the device every trigonometric value the sunrise hour angle is built from, the angle itself and the cosine
+  // of the walk's first step are evaluated correctly rounded (vic_cr_trig.cuh): cos(zenith) at that first step is
+  // zero up to rounding and its sign decides the hour of sunrise, so the device has to round like glibc does.
+#if defined(__CUDA_ARCH__) || defined(VA_FORCE_CR)
+#define VA_COS(x) vcr::cos_cr(x)
+#define VA_SIN(x) vcr::sin_cr(x)
+#define VA_ACOS(x) vcr::acos_cr(x)
+#else
+#define VA_COS(x) cos(x)
+#define VA_SIN(x) sin(x)
+#define VA_ACOS(x) acos(x)
+#endif
+  const double coslat = VA_COS(lat), sinlat = VA_SIN(lat);
   const double cosslp = cos(site_slp * RADPERDEG), sinslp = sin(site_slp * RADPERDEG);
   const double cosasp = cos(site_asp * RADPERDEG), sinasp = sin(site_asp * RADPERDEG);
   const double coszeh = cos(1.570796 - (site_eh * RADPERDEG)), coszwh = cos(1.570796 - (site_wh * RADPERDEG));
@@ -215,8 +227,8 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   const double ln_trans1 = log(trans1);
 #endif
   // :791-822
-  double decl = MINDECL * cos(((double)yd + DAYSOFF) * RADPERDAY);
-  double cosdecl = cos(decl), sindecl = sin(decl);
+  double decl = MINDECL * VA_COS(((double)yd + DAYSOFF) * RADPERDAY);
+  double cosdecl = VA_COS(decl), sindecl = VA_SIN(decl);
   double bsg1 = -sinslp * sinasp * cosdecl;
   double bsg2 = (-cosasp * sinslp * sinlat + cosslp * coslat) * cosdecl;
   double bsg3 = (cosasp * sinslp * coslat + cosslp * sinlat) * sindecl;
@@ -224,16 +236,9 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   double coshss = -(sinegeom) / cosegeom;
   if (coshss < -1.0) coshss = -1.0;
   if (coshss > 1.0) coshss = 1.0;
-  // On the device the sunrise hour angle and the cosine of the walk's first step are evaluated correctly rounded
-  // (vic_cr_trig.cuh): the sign of cos(zenith) at that step, zero up to rounding, decides the hour of sunrise.
-#if defined(__CUDA_ARCH__)
-  const double hss = vcr::acos_cr(coshss);
-  const double cos_h0 = vcr::cos_cr(hss);
+  const double hss = VA_ACOS(coshss);
+  const double cos_h0 = VA_COS(hss);
 #define VA_COS_STEP(h) ((h) == -hss ? cos_h0 : cos(h))
-#else
-  const double hss = acos(coshss);
-#define VA_COS_STEP(h) cos(h)
-#endif
   double daylength = 2.0 * hss * SECPERRAD;
   if (daylength > 86400) daylength = 86400;
   double sc = 1368.0 + 45.5 * sin((2.0 * MT_PI * (double)yd / 365.25) + 1.7);
@@ -247,7 +252,7 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
     sincos(h, &sinh_, &cosh_);
     if (h == -hss) cosh_ = cos_h0;
 #else
-    cosh_ = cos(h); sinh_ = sin(h);
+    cosh_ = VA_COS_STEP(h); sinh_ = sin(h);
 #endif
     double cza = cosegeom * cosh_ + sinegeom;
     double cbsa = sinh_ * bsg1 + cosh_ * bsg2 + bsg3;
@@ -326,6 +331,9 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   }
   if (cur_j >= 0) hf[(int64_t)cur_j * CB] = acc;
 #undef VA_COS_STEP
+#undef VA_COS
+#undef VA_SIN
+#undef VA_ACOS
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ VC_HD dd add(dd x, dd y) { dd s = two_sum(x.hi, y.hi); return quick_two_sum(s.hi
 VC_HD dd mul(dd x, dd y) { dd p = two_prod(x.hi, y.hi); return quick_two_sum(p.hi, p.lo + (x.hi * y.lo + x.lo * y.hi)); }
 VC_HD dd neg(dd x) { return {-x.hi, -x.lo}; }
 
-// cos and sin of y in [0, pi] to ~2^-100
+// cos and sin of y in [0, 6.8] to ~2^-100
 VC_HDN void sincos_dd(double y, dd &c, dd &s)
 {
   const double PI16_H = 0x1.921fb54442d18p-3, PI16_M = 0x1.1a62633145c07p-57, PI16_L = -0x1.f1976b7ed8fbcp-113;
@@ -63,7 +63,7 @@ VC_HDN void sincos_dd(double y, dd &c, dd &s)
     {0x1.6827863b97d97p-53, 0x1.eec01221a8b0bp-107}, {0x1.2f49b46814157p-57, 0x1.2650f61dbdcb4p-112}};
   int k = (int)(y * (16.0 / 3.14159265358979323846) + 0.5);
   if (k < 0) k = 0;
-  if (k > 16) k = 16;
+  if (k > 35) k = 35;
   // t = y - k*pi/16
   dd p = two_prod((double)k, PI16_H);
   dd t = two_sum(y - p.hi, -(p.lo + ((double)k * PI16_M + (double)k * PI16_L)));
@@ -74,16 +74,26 @@ VC_HDN void sincos_dd(double y, dd &c, dd &s)
     pc = add(dd{F[2 * m][0], F[2 * m][1]}, neg(mul(u, pc)));
   }
   dd st = mul(t, ps), ct = pc;
-  dd ck = {T[k][0], T[k][1]}, sk = {T[k][2], T[k][3]};
+  int kk = k & 31;                                      // period 2 pi; the table holds the first half turn
+  const double sgn = kk > 16 ? -1.0 : 1.0;
+  if (kk > 16) kk = 32 - kk;
+  dd ck = {T[kk][0], T[kk][1]}, sk = {sgn * T[kk][2], sgn * T[kk][3]};
   c = add(mul(ck, ct), neg(mul(sk, st)));
   s = add(mul(sk, ct), mul(ck, st));
 }
 
-VC_HD double cos_cr(double y)            // y in [0, pi]
+VC_HD double cos_cr(double y)            // |y| <= 6.8
 {
   dd c, s;
-  sincos_dd(y, c, s);
+  sincos_dd(fabs(y), c, s);
   return c.hi + c.lo;
+}
+VC_HD double sin_cr(double y)            // |y| <= 6.8
+{
+  dd c, s;
+  sincos_dd(fabs(y), c, s);
+  double r = s.hi + s.lo;
+  return y < 0 ? -r : r;
 }
 
 VC_HD double acos_cr(double x)

@@ -240,6 +240,36 @@ int vr_atmos_diag_cr(int device, int64_t n, const double *x, double *acos_out, c
   return VR_OK;
 }
 
+int vr_atmos_diag_solar(int device, int64_t n, const double *lat, const double *elevation, const double *lng,
+                        const double *time_zone_lng, double *tab)
+{
+  if (n < 1 || !lat || !elevation || !tab) return fail(VR_ERR_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev)
+    return fail(VR_ERR_CUDA, "no CUDA device: the forcing preparation has no CPU path");
+  CK(cudaSetDevice(device));
+  const size_t n_tab = (size_t)va::NYD * 28 * n;
+  double *d = nullptr;
+  CK(cudaMalloc((void **)&d, (n_tab + 4 * n) * sizeof(double)));
+  CK(cudaMemset(d, 0, (n_tab + 4 * n) * sizeof(double)));
+  double *site = d + n_tab;
+  cudaMemcpy(site, lat, n * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(site + n, elevation, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (lng) cudaMemcpy(site + 2 * n, lng, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (time_zone_lng) cudaMemcpy(site + 3 * n, time_zone_lng, n * sizeof(double), cudaMemcpyHostToDevice);
+  va::Ctx x{};
+  x.C = n; x.CB = n; x.c0 = 0;
+  x.lat = site; x.elev = site + n; x.lng = site + 2 * n; x.tz = site + 3 * n;
+  x.ttmax0 = d; x.flat = d + (size_t)va::NYD * n; x.slp = d + (size_t)2 * va::NYD * n; x.dayl = d + (size_t)3 * va::NYD * n;
+  x.hf = d + (size_t)4 * va::NYD * n;
+  k_solar<<<(unsigned)(((n + TPB - 1) / TPB) * va::NYD), TPB>>>(x, n);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaMemcpy(tab, d, n_tab * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(VR_ERR_CUDA, cudaGetErrorString(e));
+  return VR_OK;
+}
+
 int vr_atmos_last_times(double ms[3], int64_t *launches)
 {
   if (!ms) return fail(VR_ERR_ARG, "null argument");
