@@ -373,6 +373,18 @@ def run_ours(args):
                 "peak_dfma_per_s": dfma_peak, "peak_source": "measured live (vr_diag_fp64_peak: independent DFMA chains, all SMs)",
                 "frac": fp64_per * C * recs_per_launch / (kernel_ms * 1e-3) / dfma_peak},
         }
+        if args.forcing_prep and world == 1 and not args.ensemble:
+            # raw forcing columns -> the nine atmos fields, for the whole 10-year period of this grid
+            # (outside the timed step; reported beside it)
+            try:
+                del f_dev, out_dev
+                torch.cuda.empty_cache()
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_atmos
+                line["forcing_prep"] = bench_atmos.measure(cells=args.cells, days=3653 if args.dt == 24 else 365, dt=args.dt,
+                                                           reps=2, cpu_cells=8 if args.cpu_baseline else 0, device=local)
+            except Exception as e:
+                line["forcing_prep"] = {"error": str(e)}
         if args.cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
@@ -395,6 +407,8 @@ def main():
     ap.add_argument("--block", type=int, default=365, help="records per step (one simulated year)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-forcing-prep", dest="forcing_prep", action="store_false",
+                    help="skip the forcing-preparation measurement (vr_atmos_prepare_device) appended to the line")
     ap.add_argument("--chunk", type=int, default=0, help="records per kernel-pair launch (0 = library default)")
     ap.add_argument("--bands", type=int, default=1, help="snow bands (BASELINE config 3 uses 5)")
     ap.add_argument("--dt", type=int, default=24, help="model step in hours (config 3: 3)")

@@ -92,9 +92,11 @@ int  vr_atmos_diag_cr(int device, int64_t n, const double *x, double *acos_out, 
 
 /* diagnostic: the solar-geometry tables of n cells (lng = time_zone_lng, i.e. no sub-hour offset, unless given):
  * tab[(row*n + c)], rows 0..364 ttmax0, 365..729 flat potential radiation, 730..1094 slope potential radiation,
- * 1095..1459 daylength, then 365*24 rows of hourly radiation fractions (yearday-major); host pointers */
+ * 1095..1459 daylength, then 365*24 rows of hourly radiation fractions (yearday-major); host pointers.
+ * exact_walk != 0 runs the hour-angle walk with the reference's libm call per step instead of the production
+ * kernel's rotation / table form (vic_atmos.cuh, solar_day_t) */
 int  vr_atmos_diag_solar(int device, int64_t n, const double *lat, const double *elevation, const double *lng,
-                         const double *time_zone_lng, double *tab);
+                         const double *time_zone_lng, double *tab, int32_t exact_walk);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ def check(out, ref, what):
           (what, frac, e.size, days, e.max()))
     for n in ("prec", "wind", "shortwave"):
         assert e[F[n]].max() <= RTOL, "%s: %s off by %.3e" % (what, n, e[F[n]].max())
-    assert frac >= 0.99, "%s: only %.4f within 1e-9" % (what, frac)
+    assert frac >= 0.999, "%s: only %.5f within 1e-9" % (what, frac)
     assert np.abs(out[F["air_temp"]] - ref[F["air_temp"]]).max() < 2.0, what + ": air temperature beyond a one-hour shift"
     assert e[F["pressure"]].max() < 1e-3 and e[F["longwave"]].max() < 5e-2
     return frac
@@ -134,7 +134,8 @@ def test_sunrise_pattern_matches_the_host_build(gpu):
     compiled for the host with glibc (bit-identical to the reference): 2 000 cells x 365 yeardays.  The device rounds
     the geometry like glibc does (vic_cr_trig.cuh), so at most a few pairs in 10^5 may differ (glibc's own acos/cos
     are not correctly rounded for ~0.1 % of arguments, and a difference shows only when the sunrise slot is the last
-    of its hour); the continuous tables agree to 1e-12."""
+    of its hour); the continuous tables agree to 1e-10 (1e-14 except on
+    polar winter days a few steps long)."""
     import ctypes as C
     import os
     import subprocess
@@ -158,7 +159,13 @@ def test_sunrise_pattern_matches_the_host_build(gpu):
           (int(pairs.sum()), pairs.size, same_dayl))
     assert pairs.mean() < 1e-4 and same_dayl > 0.99
     ok = host["flat"] > 0
-    for k in ("ttmax0", "flat"):
-        assert np.abs(dev[k][ok] / host[k][ok] - 1).max() < 1e-12, k
+    for k in ("ttmax0", "flat"):         # worst case: polar winter days of a few steps with cos(zenith) ~ 1e-3
+        assert np.abs(dev[k][ok] / host[k][ok] - 1).max() < 1e-10, k
     big = host["hf"] > 1e-6
     assert np.abs(dev["hf"][big] / host["hf"][big] - 1).max() < 1e-11
+    # the production kernel (rotation / table form of the walk) against the walk with a libm call per step
+    ex = gpu.diag_solar(lat, elev, exact_walk=True)
+    assert np.array_equal(dev["hf"] > 0, ex["hf"] > 0) and np.array_equal(dev["daylength"], ex["daylength"])
+    for k in ("ttmax0", "flat"):
+        assert np.abs(dev[k][ok] / ex[k][ok] - 1).max() < 1e-10, k
+    assert np.abs(dev["hf"][big] / ex["hf"][big] - 1).max() < 1e-11

@@ -105,7 +105,7 @@ def _lib():
         L.vr_atmos_last_times.argtypes = [vp, vp]
         L.vr_atmos_last_error.restype = C.c_char_p
         L.vr_atmos_diag_cr.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp]
-        L.vr_atmos_diag_solar.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
+        L.vr_atmos_diag_solar.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp, C.c_int32]
         L._atmos_declared = True
     return L
 
@@ -174,7 +174,7 @@ def diag_cr(x, y, device=0):
     return a, c
 
 
-def diag_solar(lat, elevation, lng=None, time_zone_lng=None, device=0):
+def diag_solar(lat, elevation, lng=None, time_zone_lng=None, device=0, exact_walk=False):
     """The device's solar-geometry tables of n cells: dict ttmax0/flat/slope/daylength [365, n], hf [365, 24, n]."""
     L = _lib()
     f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
@@ -182,6 +182,6 @@ def diag_solar(lat, elevation, lng=None, time_zone_lng=None, device=0):
     n = len(lat)
     tab = np.zeros((365 * 28, n))
     p = lambda a: None if a is None else a.ctypes.data
-    _check(L, L.vr_atmos_diag_solar(device, n, p(lat), p(elevation), p(lng), p(time_zone_lng), tab.ctypes.data))
+    _check(L, L.vr_atmos_diag_solar(device, n, p(lat), p(elevation), p(lng), p(time_zone_lng), tab.ctypes.data, int(exact_walk)))
     return {"ttmax0": tab[0:365], "flat": tab[365:730], "slope": tab[730:1095], "daylength": tab[1095:1460],
             "hf": tab[1460:].reshape(365, 24, n)}

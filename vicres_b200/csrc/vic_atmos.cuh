@@ -181,6 +181,19 @@ VA_HD double longwave(const Ctx &x, double tskc, double air_temp, double vp)   /
 struct SolarGeom {
   double cosegeom, sinegeom, bsg1, bsg2, bsg3, hss, dir_beam_topa, dh, coszeh, coszwh;
 };
+#if defined(__CUDA_ARCH__)
+// the same integer from a multiplication, falling back to the division when the quotient is within 1e-9 of an integer
+__device__ __forceinline__ int tiny_slot_fast(double h)
+{
+  const double num = 12L * 3600L + h * SECPERRAD;
+  double q = num * (1.0 / SRADDT);
+  if (fabs(q - rint(q)) < 1e-9) q = num / SRADDT;
+  int t = (int)q;
+  if (t < 0) t = 0;
+  if (t > TINY - 1) t = TINY - 1;
+  return t;
+}
+#endif
 VA_HD int tiny_slot(double h)
 {
   int t = (int)((12L * 3600L + h * SECPERRAD) / SRADDT);
@@ -189,7 +202,23 @@ VA_HD int tiny_slot(double h)
   return t;
 }
 
-VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
+// cos((70+k) * RADPERDEG), k = 0..19: the zenith angles at which the optical air mass table (mtclim_vic.c:851-859)
+// steps to its next entry
+#define VA_ZENITH_STEPS {0.34202030908371178, 0.32556832362552834, 0.30901716693075376, 0.29237188064059616, \
+  0.27563753506904187, 0.25881922765838938, 0.24192208142651928, 0.22495124340637382, 0.20791188307812145, \
+  0.19080919079448339, 0.17364837619970241, 0.1564346666426352, 0.13917330558445171, 0.12186955100142652, \
+  0.10452867378330888, 0.087155956127758991, 0.069756689931339946, 0.052336175177555268, 0.03489971832242298, \
+  0.017452630678078236}
+
+// FAST (device only): same walk with three changes that stay far inside the 1e-9 bar and touch no decision --
+//  * cos/sin of the hour angle by rotation through the constant step, re-anchored with sincos every 16 steps
+//    (error < 1e-14) instead of two libm calls per step;
+//  * the air-mass table entry from comparisons of cos(zenith) with the 20 table angles instead of acos per step,
+//    and the transmittance of the 21 table entries from a per-thread table (`t21`, stride `ts21`) instead of pow;
+//  * the slot values multiplied by 1/total instead of divided.
+// ck: the 20 zenith steps (shared memory).
+template <bool FAST>
+VA_HDN void solar_day_t(const Ctx &x, int64_t c, int yd, const double *ck, double *t21, int ts21)
 {
   const double optam[21] = {2.90, 3.05, 3.21, 3.39, 3.69, 3.82, 4.07, 4.37, 4.72, 5.12, 5.60,
                             6.18, 6.88, 7.77, 8.90, 10.39, 12.44, 15.36, 19.79, 26.96, 30.00};
@@ -246,34 +275,56 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   double sum_trans = 0.0, sum_flat = 0.0, sum_slope = 0.0;
 
   // first walk, :828-899 without the tiny_radfract stores
-  for (double h = -hss; h < hss; h += dh) {
-    double sinh_, cosh_;
 #if defined(__CUDA_ARCH__)
-    sincos(h, &sinh_, &cosh_);
-    if (h == -hss) cosh_ = cos_h0;
+  const double cd = cos(dh), sd = sin(dh);
+  if (FAST) for (int k = 0; k < 21; k++) t21[k * ts21] = exp(optam[k] * ln_trans1);
+#define VA_STEP_TRIG(n, h, cs, sn)                                                          \
+  if (!FAST || ((n) & 15) == 0) { sincos((h), &sn, &cs); if ((n) == 0) cs = cos_h0; }        \
+  else { double c2_ = __fma_rn(cs, cd, -(sn * sd)); sn = __fma_rn(sn, cd, cs * sd); cs = c2_; }
 #else
-    cosh_ = VA_COS_STEP(h); sinh_ = sin(h);
+#define VA_STEP_TRIG(n, h, cs, sn) { cs = VA_COS_STEP(h); sn = sin(h); }
 #endif
-    double cza = cosegeom * cosh_ + sinegeom;
-    double cbsa = sinh_ * bsg1 + cosh_ * bsg2 + bsg3;
-    if (cza > 0.0) {
-      double dir_flat_topa = dir_beam_topa * cza;
-      double am = 1.0 / (cza + 0.0000001);
-      if (am > 2.9) {
-        int ami = (int)(acos(cza) / RADPERDEG) - 69;
-        if (ami < 0) ami = 0;
-        if (ami > 20) ami = 20;
-        am = optam[ami];
+  {
+    double sinh_ = 0., cosh_ = 1.;
+    int n = 0, ami = 0;
+    for (double h = -hss; h < hss; h += dh, n++) {
+      VA_STEP_TRIG(n, h, cosh_, sinh_)
+      double cza = cosegeom * cosh_ + sinegeom;
+      double cbsa = sinh_ * bsg1 + cosh_ * bsg2 + bsg3;
+      if (cza > 0.0) {
+        double dir_flat_topa = dir_beam_topa * cza;
+        double trans2;
+#if defined(__CUDA_ARCH__)
+        if (FAST) {
+          const double t = cza + 0.0000001;
+          if (t * 2.9 < 1.0) {                             // am > 2.9; both branches give trans1^2.9 at the seam
+            while (ami > 0 && cza > ck[ami - 1]) ami--;
+            while (ami < 20 && cza <= ck[ami]) ami++;
+            trans2 = t21[ami * ts21];
+          }
+          else trans2 = exp((1.0 / t) * ln_trans1);
+        }
+        else
+#endif
+        {
+          double am = 1.0 / (cza + 0.0000001);
+          if (am > 2.9) {
+            int ai = (int)(acos(cza) / RADPERDEG) - 69;
+            if (ai < 0) ai = 0;
+            if (ai > 20) ai = 20;
+            am = optam[ai];
+          }
+#if defined(__CUDA_ARCH__)
+          trans2 = exp(am * ln_trans1);
+#else
+          trans2 = pow(trans1, am);
+#endif
+        }
+        sum_trans += trans2 * dir_flat_topa;
+        sum_flat += dir_flat_topa;
+        if ((h < 0.0 && cza > coszeh && cbsa > 0.0) || (h >= 0.0 && cza > coszwh && cbsa > 0.0))
+          sum_slope += dir_beam_topa * cbsa;
       }
-#if defined(__CUDA_ARCH__)
-      double trans2 = exp(am * ln_trans1);
-#else
-      double trans2 = pow(trans1, am);
-#endif
-      sum_trans += trans2 * dir_flat_topa;
-      sum_flat += dir_flat_topa;
-      if ((h < 0.0 && cza > coszeh && cbsa > 0.0) || (h >= 0.0 && cza > coszwh && cbsa > 0.0))
-        sum_slope += dir_beam_topa * cbsa;
     }
   }
   if (daylength) {                                        // :910-919
@@ -291,50 +342,68 @@ VA_HDN void solar_day(const Ctx &x, int64_t c, int yd)
   const int jw = off > 0 ? 0 : 23;
   double *hf = x.hf + (int64_t)yd * 24 * CB + lc;
   for (int j = 0; j < 24; j++) hf[(int64_t)j * CB] = 0.0;
-  int prev = -1, cur_j = -1;
+  int prev = -1, cur_j = -1, hour_end = -1;             // hour_end: first slot after the current clock hour
   double pend = 0.0, acc = 0.0;
+#if defined(__CUDA_ARCH__)
+  const double inv_flat = 1.0 / sum_flat;
+  auto share = [&](double v) { return norm ? (FAST ? v * inv_flat : v / sum_flat) : v; };
+#else
+  auto share = [&](double v) { return norm ? v / sum_flat : v; };
+#endif
   auto commit = [&](int ts, double v) {
     if (ts < E) return;
-    int j = ((ts + off) % TINY + TINY) % TINY / TINY_HOUR;
-    if (j != cur_j) {
+    if (ts >= hour_end) {
+      const int w = ((ts + off) % TINY + TINY) % TINY;    // position in the clock day
+      const int j = w / TINY_HOUR;
       if (cur_j >= 0) hf[(int64_t)cur_j * CB] = acc;
       cur_j = j;
       acc = 0.0;
+      hour_end = ts + (TINY_HOUR - (w - j * TINY_HOUR));
     }
-    acc += norm ? v / sum_flat : v;
+    acc += share(v);
   };
-  for (double h = -hss; h < hss; h += dh) {
-    double cza = cosegeom * VA_COS_STEP(h) + sinegeom;
+  double sinh_ = 0., cosh_ = 1.;
+  int n = 0;
+  for (double h = -hss; h < hss; h += dh, n++) {
+    VA_STEP_TRIG(n, h, cosh_, sinh_)
+    double cza = cosegeom * cosh_ + sinegeom;
     double v = 0.0;
     if (cza > 0.0) { double dft = dir_beam_topa * cza; if (dft > 0) v = dft; }
+#if defined(__CUDA_ARCH__)
+    int ts = FAST ? tiny_slot_fast(h) : tiny_slot(h);
+#else
     int ts = tiny_slot(h);
+#endif
     if (ts != prev) { if (prev >= 0) commit(prev, pend); prev = ts; }
     pend = v;
   }
   if (prev >= 0) commit(prev, pend);
   if (E > 0) {
     if (cur_j != jw) { if (cur_j >= 0) hf[(int64_t)cur_j * CB] = acc; cur_j = jw; acc = 0.0; }
-    prev = -1; pend = 0.0;
-    for (double h = -hss; h < hss; h += dh) {
+    prev = -1; pend = 0.0; n = 0;
+    for (double h = -hss; h < hss; h += dh, n++) {
       int ts = tiny_slot(h);
       if (ts != prev) {
-        if (prev >= 0) acc += norm ? pend / sum_flat : pend;
+        if (prev >= 0) acc += share(pend);
         prev = ts;
         if (ts >= E) { prev = -1; break; }
       }
-      double cza = cosegeom * VA_COS_STEP(h) + sinegeom;
+      VA_STEP_TRIG(n, h, cosh_, sinh_)
+      double cza = cosegeom * cosh_ + sinegeom;
       double v = 0.0;
       if (cza > 0.0) { double dft = dir_beam_topa * cza; if (dft > 0) v = dft; }
       pend = v;
     }
-    if (prev >= 0 && prev < E) acc += norm ? pend / sum_flat : pend;
+    if (prev >= 0 && prev < E) acc += share(pend);
   }
   if (cur_j >= 0) hf[(int64_t)cur_j * CB] = acc;
+#undef VA_STEP_TRIG
 #undef VA_COS_STEP
 #undef VA_COS
 #undef VA_SIN
 #undef VA_ACOS
 }
+VA_HD void solar_day(const Ctx &x, int64_t c, int yd) { solar_day_t<false>(x, c, yd, nullptr, nullptr, 0); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // daily_prep: per cell, sequential over the local days.
@@ -605,12 +674,14 @@ VA_HD double hourly_tair(const Ctx &x, const Geo &g, int64_t c, int hour)
   const int64_t lc = c - x.c0;
   const int ndays = g.ndl, n = 2 * ndays + 2;
   const double xbar = hour;
-  int klo = 0, khi = n - 1;
-  while (khi - klo > 1) {
-    int k = (khi + klo) >> 1;
-    if (node_x(x, lc, ndays, k) > xbar) khi = k;
-    else klo = k;
-  }
+  // hermint's bisection (calc_air_temperature.c:51-56) ends at the last node k <= n-2 with x[k] <= xbar.  The nodes
+  // increase strictly (two per day, the later one before hour 23, the earlier one not before hour -1 of its day), so
+  // that node is the last node of the day before unless one of this day's two nodes is already reached.
+  const int d = hour / 24;
+  int klo = 2 * d;
+  if (node_x(x, lc, ndays, 2 * d + 1) <= xbar) klo = 2 * d + 1;
+  if (node_x(x, lc, ndays, 2 * d + 2) <= xbar) klo = 2 * d + 2;
+  if (klo > n - 2) klo = n - 2;
   const double x0 = node_x(x, lc, ndays, klo), x1 = node_x(x, lc, ndays, klo + 1);
   const double y0 = node_y(x, g, c, ndays, klo), y1 = node_y(x, g, c, ndays, klo + 1);
   double dx = x1 - x0;

@@ -37,8 +37,19 @@ __device__ __forceinline__ bool locate(const va::Ctx &x, int64_t cb, int &row, i
 }
 __global__ void __launch_bounds__(TPB) k_solar(const __grid_constant__ va::Ctx x, int64_t cb)
 {
+  __shared__ double s_ck[20];
+  __shared__ double s_t21[21 * TPB];            // transmittance of the 21 air-mass table entries, per thread
+  const double ck[20] = VA_ZENITH_STEPS;
+  if (threadIdx.x < 20) s_ck[threadIdx.x] = ck[threadIdx.x];
+  __syncthreads();
   int yd; int64_t c;
-  if (locate(x, cb, yd, c)) va::solar_day(x, c, yd);
+  if (locate(x, cb, yd, c)) va::solar_day_t<true>(x, c, yd, s_ck, s_t21 + threadIdx.x, TPB);
+}
+// the walk exactly as the reference writes it (libm call per step): diagnostic twin of k_solar
+__global__ void __launch_bounds__(TPB) k_solar_exact(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int yd; int64_t c;
+  if (locate(x, cb, yd, c)) va::solar_day_t<false>(x, c, yd, nullptr, nullptr, 0);
 }
 __global__ void __launch_bounds__(TPB) k_prep(const __grid_constant__ va::Ctx x, int64_t cb)
 {
@@ -241,7 +252,7 @@ int vr_atmos_diag_cr(int device, int64_t n, const double *x, double *acos_out, c
 }
 
 int vr_atmos_diag_solar(int device, int64_t n, const double *lat, const double *elevation, const double *lng,
-                        const double *time_zone_lng, double *tab)
+                        const double *time_zone_lng, double *tab, int32_t exact_walk)
 {
   if (n < 1 || !lat || !elevation || !tab) return fail(VR_ERR_ARG, "null argument");
   int ndev = 0;
@@ -262,7 +273,8 @@ int vr_atmos_diag_solar(int device, int64_t n, const double *lat, const double *
   x.lat = site; x.elev = site + n; x.lng = site + 2 * n; x.tz = site + 3 * n;
   x.ttmax0 = d; x.flat = d + (size_t)va::NYD * n; x.slp = d + (size_t)2 * va::NYD * n; x.dayl = d + (size_t)3 * va::NYD * n;
   x.hf = d + (size_t)4 * va::NYD * n;
-  k_solar<<<(unsigned)(((n + TPB - 1) / TPB) * va::NYD), TPB>>>(x, n);
+  if (exact_walk) k_solar_exact<<<(unsigned)(((n + TPB - 1) / TPB) * va::NYD), TPB>>>(x, n);
+  else k_solar<<<(unsigned)(((n + TPB - 1) / TPB) * va::NYD), TPB>>>(x, n);
   cudaError_t e = cudaDeviceSynchronize();
   cudaMemcpy(tab, d, n_tab * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d);
