@@ -7,7 +7,7 @@ from vicres_b200 import abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith(("route_", "objectives")))
+                  if not os.path.basename(p).startswith(("route_", "objectives", "atmos_")))
 
 ATMOS_FIXTURES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "atmos_*.npz")))
 
