@@ -36,6 +36,9 @@ const vr_veglib *vr_params_veglib(const vr_params *p);
 const int32_t *vr_params_gridcel(const vr_params *p);     /* [C] cell numbers            */
 const float   *vr_params_lat(const vr_params *p);         /* [C] as stored (float)       */
 const float   *vr_params_lng(const vr_params *p);
+/* [C] site values initialize_atmos reads, as soil_con holds them (floats widened): which = 0 lat, 1 lng,
+ * 2 time_zone_lng (off_gmt*360/24, read_soilparam.c:934), 3 elevation, 4 annual_prec -> vr_atmos_cells */
+const double  *vr_params_site(const vr_params *p, int32_t which);
 
 /* The reference's ASCII result files (write_data.c:196-226, names from make_in_and_outfiles.c:46-86):
  * one file "<result_dir>/<prefix>_<lat>_<lng>" per cell (lat/lng printed with grid_decimal places),
@@ -71,6 +74,9 @@ typedef struct vr_global {
   /* options this library does not implement are not an error to PARSE; vr_global_unsupported() names them */
   int32_t full_energy, frozen_soil, lakes, carbon, blowing, corrprec, compute_treeline, dist_prcp, organic_fract,
           july_tavg_supplied, alma_input, init_state;
+  /* options of the forcing preparation (include/vicres_atmos.h); values as vicNl_def.h:208-223 */
+  int32_t vp_interp, vp_iter, mtclim_swe_corr, lw_type, lw_cloud, plapse;
+  double  sw_prec_thresh;
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -1,0 +1,63 @@
+"""The whole `vicNl -g <global file>` command line on the GPU (vicres_b200/vicnl.py: global file -> parameter files
+-> forcing files -> forcing preparation -> cell step -> result files) against the files the UNMODIFIED reference
+wrote for the same case (tests/golden/vicnl_case, tools/make_vicnl_golden.py)."""
+import os
+import shutil
+import numpy as np
+import pytest
+from common import GOLDEN
+from vicres_b200 import files
+
+CASES = os.path.join(GOLDEN, "vicnl_case")
+
+
+def _stage(name, tmp_path):
+    """copy the inputs, point the global file at the copy, drop the reference's results"""
+    dst = tmp_path / name
+    shutil.copytree(os.path.join(CASES, name), dst)
+    ref = tmp_path / (name + "_ref")
+    shutil.move(str(dst / "results"), ref)
+    os.makedirs(dst / "results")
+    g = dst / "global.txt"
+    g.write_text(g.read_text().replace("@DIR@", str(dst)))
+    return str(g), str(dst / "results"), str(ref)
+
+
+@pytest.mark.parametrize("name", ["daily", "sub3h"])
+def test_global_file_and_forcing_files_parse(name, tmp_path):
+    """CPU tier: the host side of the driver up to the device hand-off."""
+    from vicres_b200 import atmos
+    gpath, _, ref = _stage(name, tmp_path)
+    g = files.Global(gpath)
+    assert g.unsupported is None
+    lib, cells, meta = files.read_params(**g.param_files())
+    ao = atmos.options_from_global(g)
+    assert ao.layout == (atmos.DAILY_TMAX_TMIN if name == "daily" else atmos.SUBDAILY_AIR_TEMP)
+    assert (ao.vp_interp, ao.vp_iter, ao.lw_type, ao.lw_cloud, ao.plapse) == (1, 1, 5, 1, 1)
+    d, got = g.read_forcing(float(meta["lat"][0]), float(meta["lng"][0]))
+    assert got == g.nrecs * g.time_step // g.force_dt and set(d) >= {"PREC", "WIND"}
+    site = meta["site"]
+    assert np.array_equal(site["lat"], meta["lat"].astype(np.float64)) and np.array_equal(site["lng"], meta["lng"].astype(np.float64))
+    if name == "daily":
+        assert np.all(site["time_zone_lng"] == 15.0) and np.all(site["annual_prec"] == 1000.0)
+    assert len(os.listdir(ref)) == 2 * len(meta["gridcel"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["daily", "sub3h"])
+def test_vicnl_command_line_reproduces_the_reference_result_files(name, tmp_path):
+    from vicres_b200 import vicnl
+    gpath, res, ref = _stage(name, tmp_path)
+    assert vicnl.main(["-g", gpath]) == 0
+    assert sorted(os.listdir(res)) == sorted(os.listdir(ref))
+    nbad = ntot = 0
+    for n in sorted(os.listdir(ref)):
+        a, b = np.loadtxt(os.path.join(res, n)), np.loadtxt(os.path.join(ref, n))
+        assert a.shape == b.shape, n
+        ncal = 3 if name == "daily" else 4
+        assert np.array_equal(a[:, :ncal], b[:, :ncal]), n
+        assert np.all(np.abs(a - b) <= 1.0001e-4 + 1e-5 * np.abs(b)), n     # one unit in the 4th decimal
+        nbad += int((a != b).sum())
+        ntot += a.size
+    print("VICNL %s: %d of %d printed values differ from the reference's files (by one unit of the last digit)" % (name, nbad, ntot))
+    assert nbad <= 0.01 * ntot

@@ -154,15 +154,23 @@ def last_times():
 
 
 def options_from_global(g):
-    """vr_atmos_options from a parsed global file (vicres_b200.files.read_global dict)."""
-    types = [t for t in g["force_type"] if t != "SKIP"]
+    """vr_atmos_options from a parsed global file (vicres_b200.files.Global)."""
+    types = [t for t in g.force_types if t != "SKIP"]
+    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND")]
+    if extra:
+        raise model.VicResError(abi.VR_ERR_UNSUPPORTED, "forcing column(s) %s are outside the supported layouts" % ", ".join(extra))
     layout = SUBDAILY_AIR_TEMP if "AIR_TEMP" in types else DAILY_TMAX_TMIN
-    return options(time_step=g["time_step"], nrecs=g["nrecs"], startyear=g["startyear"], startmonth=g["startmonth"],
-                   startday=g["startday"], starthour=g["starthour"], layout=layout, force_dt=g["force_dt"],
-                   has_wind="WIND" in types, min_wind_speed=g["min_wind_speed"],
-                   vp_interp=g.get("vp_interp", 1), vp_iter=g.get("vp_iter", 1), mtclim_swe_corr=g.get("mtclim_swe_corr", 0),
-                   lw_type=g.get("lw_type", 5), lw_cloud=g.get("lw_cloud", 1), plapse=g.get("plapse", 1),
-                   sw_prec_thresh=g.get("sw_prec_thresh", 0.0))
+    return options(time_step=g.time_step, nrecs=g.nrecs, startyear=g.startyear, startmonth=g.startmonth,
+                   startday=g.startday, starthour=g.starthour, layout=layout, force_dt=g.force_dt,
+                   has_wind="WIND" in types, min_wind_speed=g.min_wind_speed, vp_interp=g.vp_interp, vp_iter=g.vp_iter,
+                   mtclim_swe_corr=g.mtclim_swe_corr, lw_type=g.lw_type, lw_cloud=g.lw_cloud, plapse=g.plapse,
+                   sw_prec_thresh=g.sw_prec_thresh)
+
+
+def raw_from_columns(cols, layout):
+    """{FORCE_TYPE: [nrec, C]} -> the dict prepare() takes."""
+    return {"prec": cols["PREC"], "t_a": cols["TMAX" if layout == DAILY_TMAX_TMIN else "AIR_TEMP"],
+            "t_b": cols.get("TMIN") if layout == DAILY_TMAX_TMIN else None, "wind": cols.get("WIND")}
 
 
 def diag_cr(x, y, device=0):

@@ -57,6 +57,7 @@ struct vr_params {
   int L = 0, NB = 0;
   std::vector<int32_t> gridcel;
   std::vector<float> lat, lng;
+  std::vector<double> site_lng, site_tz, site_annual_prec;   // what initialize_atmos reads from soil_con
   // cells
   std::vector<double> c_lat, elevation, b_infilt, Ds, Dsmax, Ws, c_expt, avg_temp, dp, rough, snow_rough;
   std::vector<double> expt, Ksat, depth, max_moist, Wcr, Wpwp, resid_moist, init_moist, bulk_density, soil_density,
@@ -82,6 +83,18 @@ const vr_veglib *vr_params_veglib(const vr_params *p) { return p ? &p->lib : nul
 const int32_t *vr_params_gridcel(const vr_params *p) { return p ? p->gridcel.data() : nullptr; }
 const float *vr_params_lat(const vr_params *p) { return p ? p->lat.data() : nullptr; }
 const float *vr_params_lng(const vr_params *p) { return p ? p->lng.data() : nullptr; }
+const double *vr_params_site(const vr_params *p, int32_t which)
+{
+  if (!p) return nullptr;
+  switch (which) {
+    case 0: return p->cells.lat;
+    case 1: return p->site_lng.data();
+    case 2: return p->site_tz.data();
+    case 3: return p->cells.elevation;
+    case 4: return p->site_annual_prec.data();
+    default: return nullptr;
+  }
+}
 
 int vr_params_read(const vr_param_files *fo, vr_params **out)
 {
@@ -128,7 +141,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
   vr_params *P = new vr_params();
   P->L = L; P->NB = NB;
   struct Soil {
-    int gridcel; float lat, lng, elevation;
+    int gridcel; float lat, lng, elevation; double off_gmt, annual_prec;
     double b, Ds, Dsmax, Ws, c, avg_temp, dp, rough, snow_rough;
     double expt[3], Ksat[3], init_moist[3], depth[3], quartz[3], bdm[3], sdm[3], wcr_fr[3], wpwp_fr[3], resid[3], bubble[3];
   };
@@ -168,12 +181,12 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
       for (int l = 0; l < L; l++) s.quartz[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.bdm[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.sdm[l] = strtod(t[k++].c_str(), nullptr);
-      k += 1;                                                  // off_gmt
+      s.off_gmt = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.wcr_fr[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.wpwp_fr[l] = strtod(t[k++].c_str(), nullptr);
       s.rough = strtod(t[k++].c_str(), nullptr);
       s.snow_rough = strtod(t[k++].c_str(), nullptr);
-      k += 1;                                                  // annual_prec
+      s.annual_prec = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.resid[l] = strtod(t[k++].c_str(), nullptr);
       if (s.b <= 0) { fclose(f); delete P; g_err = "b_infilt must be positive"; return VR_ERR_ARG; }
       soils.push_back(s);
@@ -189,10 +202,12 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
   LC(P->bulk_density); LC(P->soil_density); LC(P->bulk_dens_min); LC(P->soil_dens_min); LC(P->quartz); LC(P->organic); LC(P->porosity);
   P->AreaFract.assign((size_t)NB * C, 0.0); P->Tfactor.assign((size_t)NB * C, 0.0); P->Pfactor.assign((size_t)NB * C, 1.0);
   P->gridcel.resize(C); P->lat.resize(C); P->lng.resize(C);
+  P->site_lng.resize(C); P->site_tz.resize(C); P->site_annual_prec.resize(C);
   std::vector<float> elev_f(C);
   for (int64_t c = 0; c < C; c++) {
     const Soil &s = soils[c];
     P->gridcel[c] = s.gridcel; P->lat[c] = s.lat; P->lng[c] = s.lng; elev_f[c] = s.elevation;
+    P->site_lng[c] = s.lng; P->site_tz[c] = (float)(s.off_gmt * 360. / 24.); P->site_annual_prec[c] = s.annual_prec;   // read_soilparam.c:934
     P->c_lat[c] = s.lat; P->b_infilt[c] = s.b; P->Ds[c] = s.Ds; P->Dsmax[c] = s.Dsmax; P->Ws[c] = s.Ws; P->c_expt[c] = s.c;
     P->avg_temp[c] = s.avg_temp; P->dp[c] = s.dp; P->rough[c] = s.rough; P->snow_rough[c] = s.snow_rough;
     for (int l = 0; l < L; l++) {
@@ -548,6 +563,7 @@ int vr_global_read(const char *path, vr_global *g)
   // initialize_global.c:146-211
   g->nlayer = 3; g->time_step = -99999; g->snow_step = 1; g->max_snow_temp = 0.5; g->min_rain_temp = -0.5; g->wind_h = 10.0;
   g->min_wind_speed = 0.1; g->measure_h = 2.0; g->snow_band = 1; g->root_zones = -99999; g->grid_decimal = 2;
+  g->vp_interp = 1; g->vp_iter = 1; g->mtclim_swe_corr = 0; g->lw_type = 5; g->lw_cloud = 1; g->plapse = 1; g->sw_prec_thresh = 0.;
   g->starthour = 0; g->nrecs = -99999; g->force_dt = -99999; g->force_ascii = 0; g->force_little_endian = 1;
   int endyear = -99999, endmonth = -99999, endday = -99999, file_num = -1, field = -1;
   auto flag = [](const std::vector<std::string> &t) { return t.size() > 1 && strcasecmp(t[1].c_str(), "TRUE") == 0; };
@@ -583,6 +599,24 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "ALMA_INPUT")) g->alma_input = flag(t);
     else if (!strcasecmp(k, "INIT_STATE")) g->init_state = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0);
     else if (!strcasecmp(k, "MIN_WIND_SPEED")) g->min_wind_speed = (double)strtof(t.size() > 1 ? t[1].c_str() : "0", nullptr);
+    else if (!strcasecmp(k, "VP_INTERP")) g->vp_interp = flag(t);
+    else if (!strcasecmp(k, "VP_ITER")) {
+      // get_global_param.c:405-412: four ifs and one else -- every value but VP_ITER_CONVERGE also sets VP_INTERP to 1
+      const char *v = t.size() > 1 ? t[1].c_str() : "";
+      if (!strcasecmp(v, "VP_ITER_NONE")) g->vp_iter = 0;
+      if (!strcasecmp(v, "VP_ITER_ALWAYS")) g->vp_iter = 1;
+      if (!strcasecmp(v, "VP_ITER_ANNUAL")) g->vp_iter = 2;
+      if (!strcasecmp(v, "VP_ITER_CONVERGE")) g->vp_iter = 3;
+      else g->vp_interp = 1;
+    }
+    else if (!strcasecmp(k, "MTCLIM_SWE_CORR")) g->mtclim_swe_corr = flag(t);
+    else if (!strcasecmp(k, "PLAPSE")) g->plapse = !(t.size() > 1 && !strcasecmp(t[1].c_str(), "FALSE"));
+    else if (!strcasecmp(k, "SW_PREC_THRESH")) g->sw_prec_thresh = t.size() > 1 ? atof(t[1].c_str()) : 0.;
+    else if (!strcasecmp(k, "LW_CLOUD")) g->lw_cloud = (t.size() > 1 && !strcasecmp(t[1].c_str(), "LW_CLOUD_DEARDORFF")) ? 1 : 0;
+    else if (!strcasecmp(k, "LW_TYPE")) {
+      static const char *names[6] = {"LW_TVA", "LW_ANDERSON", "LW_BRUTSAERT", "LW_SATTERLUND", "LW_IDSO", "LW_PRATA"};
+      for (int i = 0; i < 6; i++) if (t.size() > 1 && !strcasecmp(t[1].c_str(), names[i])) g->lw_type = i;
+    }
     else if (!strcasecmp(k, "MIN_RAIN_TEMP")) g->min_rain_temp = D();
     else if (!strcasecmp(k, "MAX_SNOW_TEMP")) g->max_snow_temp = D();
     else if (!strcasecmp(k, "WIND_H")) g->wind_h = D();

@@ -18,7 +18,7 @@ class ParamFilesC(C.Structure):
 
 
 FILES_EXPORTS = ["vr_params_read", "vr_params_free", "vr_params_last_error", "vr_params_cells",
-                 "vr_params_veglib", "vr_params_gridcel", "vr_params_lat", "vr_params_lng", "vr_write_results", "vr_round_decimals"]
+                 "vr_params_veglib", "vr_params_gridcel", "vr_params_lat", "vr_params_lng", "vr_params_site", "vr_write_results", "vr_round_decimals"]
 
 
 def _bind(lib):
@@ -34,6 +34,8 @@ def _bind(lib):
     for n, t in [("vr_params_gridcel", C.c_int32), ("vr_params_lat", C.c_float), ("vr_params_lng", C.c_float)]:
         getattr(lib, n).argtypes = [C.c_void_p]
         getattr(lib, n).restype = C.POINTER(t)
+    lib.vr_params_site.argtypes = [C.c_void_p, C.c_int32]
+    lib.vr_params_site.restype = C.POINTER(C.c_double)
     lib.vr_write_results.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.POINTER(C.c_float),
                                      C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
@@ -82,7 +84,10 @@ def read_params(soil, veglib, vegparam, snowband=None, nlayer=3, nbands=1, root_
         for k in ["roughness", "displacement", "LAI", "albedo"]:
             libd[k] = _arr(getattr(vl, k), ncl * 12, np.float64).reshape(ncl, 12)
         meta = {"gridcel": _arr(so.vr_params_gridcel(h), Cn, np.int32),
-                "lat": _arr(so.vr_params_lat(h), Cn, np.float32), "lng": _arr(so.vr_params_lng(h), Cn, np.float32)}
+                "lat": _arr(so.vr_params_lat(h), Cn, np.float32), "lng": _arr(so.vr_params_lng(h), Cn, np.float32),
+                # what initialize_atmos reads of soil_con: the vr_atmos_cells hand-off (vicres_b200/atmos.py)
+                "site": {n: _arr(so.vr_params_site(h, i), Cn, np.float64)
+                         for i, n in enumerate(["lat", "lng", "time_zone_lng", "elevation", "annual_prec"])}}
     finally:
         so.vr_params_free(h)
     return libd, cells, meta
@@ -140,7 +145,9 @@ class GlobalC(C.Structure):
                  ("force_multiplier", C.c_double * VR_MAX_FORCE_TYPES)] +
                 [(n, C.c_int32) for n in ("binary_output", "out_step", "compress", "full_energy", "frozen_soil", "lakes",
                                           "carbon", "blowing", "corrprec", "compute_treeline", "dist_prcp", "organic_fract",
-                                          "july_tavg_supplied", "alma_input", "init_state")])
+                                          "july_tavg_supplied", "alma_input", "init_state",
+                                          "vp_interp", "vp_iter", "mtclim_swe_corr", "lw_type", "lw_cloud", "plapse")] +
+                [("sw_prec_thresh", C.c_double)])
 
 
 FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_read_forcing_file"]

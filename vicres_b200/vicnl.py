@@ -1,0 +1,87 @@
+"""`vicNl -g <global parameter file>` on the GPU: the reference's command line (runoff/model/vicNl.c:11-380,
+cmd_proc.c) over the C ABI of libvicres.so.
+
+    python -m vicres_b200.vicnl -g globalparam.txt [--device 0]
+
+What the reference does per cell -- read_soilparam / read_vegparam / read_snowband, initialize_atmos (forcing file ->
+atmos[]), initialize_model_state, the record loop of full_energy + put_data, write_data -- is done here for all cells
+of the soil file at once:
+
+    vr_global_read -> vr_params_read -> vr_read_forcing_file (per cell) -> vr_atmos_prepare_device
+    -> vr_create / vr_set_cells / vr_init_state -> vr_step_block_device -> vr_write_results
+
+and leaves the same `fluxes_<lat>_<lng>` / `snow_<lat>_<lng>` files in RESULT_DIR.  Marshalling only: every number
+comes from the CUDA library; a global file with options outside the library's path is refused with the reason
+(vr_global_unsupported), never run differently.
+"""
+import argparse
+import sys
+import numpy as np
+from . import abi, atmos, files, model
+
+
+def run(global_path, device=0, write=True, records_per_block=0):
+    """Returns (out [n_out, nrecs, C], meta, dmy); writes the result files when `write`."""
+    import torch
+    g = files.Global(global_path)
+    why = g.unsupported
+    if why:
+        raise model.VicResError(abi.VR_ERR_UNSUPPORTED, why)
+    lib, cells, meta = files.read_params(**g.param_files())
+    Cn = len(meta["gridcel"])
+    ao = atmos.options_from_global(g)
+    # forcing files -> [type][record][cell] columns
+    cols = None
+    for c in range(Cn):
+        d, got = g.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))
+        if cols is None:
+            cols = {t: np.zeros((len(v), Cn)) for t, v in d.items() if t != "SKIP"}
+        for t in cols:
+            cols[t][:got, c] = d[t][:got]
+    raw = atmos.raw_from_columns(cols, ao.layout)
+    dev = torch.device("cuda", device)
+    nrecs = g.nrecs
+    site_t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in meta["site"].items()}
+    raw_t = {k: (torch.from_numpy(np.ascontiguousarray(v)).to(dev) if v is not None else None) for k, v in raw.items()}
+    f_dev = torch.empty((abi.VR_NFORCING, nrecs, Cn), dtype=torch.float64, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else 0
+    atmos.prepare_device(ao, {k: ptr(v) for k, v in site_t.items()}, {k: ptr(v) for k, v in raw_t.items()},
+                         [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["prec"].shape[0], device=device)
+    torch.cuda.synchronize(dev)
+    opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, max_snow_temp=g.max_snow_temp,
+                              min_rain_temp=g.min_rain_temp, wind_h=g.wind_h)
+    m = model.VicRes(opt, lib, cells, device=device)
+    m.init_state(f_dev[abi.FORCING_FIELDS.index("air_temp"), 0].cpu().numpy())
+    dmy = g.dmy()
+    out_dev = torch.empty((opt.n_out, nrecs, Cn), dtype=torch.float64, device=dev)
+    B = records_per_block or nrecs
+    for r0 in range(0, nrecs, B):
+        r1 = min(nrecs, r0 + B)
+        blk = torch.empty((opt.n_out, r1 - r0, Cn), dtype=torch.float64, device=dev)
+        fb = f_dev[:, r0:r1].contiguous()
+        m.step_device(dmy[r0:r1, 1], dmy[r0:r1, 4], [fb[f].data_ptr() for f in range(abi.VR_NFORCING)], blk.data_ptr())
+        m.synchronize()
+        out_dev[:, r0:r1] = blk
+    out = out_dev.cpu().numpy()
+    m.close()
+    if write:
+        nflux = 20 + g.nlayer - 1               # set_output_defaults.c:66-93: fluxes = the first 20+L-1, snow = the last 4
+        hour = dmy[:, 3] if g.time_step < 24 else None
+        for prefix, sel in (("fluxes", np.arange(nflux)), ("snow", np.arange(nflux, nflux + 4))):
+            files.write_results(g.result_dir, prefix, meta["lat"], meta["lng"], dmy[:, 0], dmy[:, 1], dmy[:, 2], out,
+                                cols=sel, hour=hour, grid_decimal=g.grid_decimal)
+    return out, meta, dmy
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="vicres_b200.vicnl", description="vicNl -g on the GPU (water-balance mode)")
+    ap.add_argument("-g", dest="global_file", required=True, help="global parameter file (get_global_param.c format)")
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args(argv)
+    out, meta, dmy = run(a.global_file, a.device)
+    print("vicres_b200.vicnl: %d cells x %d records written" % (out.shape[2], out.shape[1]), file=sys.stderr)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
