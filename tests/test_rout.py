@@ -1,0 +1,127 @@
+"""The `rout <configuration file>` command line on the GPU (vicres_b200/rout.py) against the reference's shipped
+prebuilt binary: the case files are written from the golden fixtures (which hold the binary's inputs and outputs,
+tools/make_route_golden.py), in today's configuration layout and in the binary's older one."""
+import os
+import numpy as np
+import pytest
+from common import GOLDEN
+from vicres_b200 import rout, route_abi
+
+
+def write_case(work, z, layout):
+    nrow, ncol = z["dir"].shape
+    hdr = {"xllcorner": repr(float(z["hdr"][0])), "yllcorner": repr(float(z["hdr"][1])), "cellsize": repr(float(z["hdr"][2]))}
+    par = os.path.join(work, "parameters")
+    for sub in ("", "unit_hydrograph", "reservoirs/res_par", "naturalized_flow"):
+        os.makedirs(os.path.join(par, sub), exist_ok=True)
+    for sub in ("input", "output", "model"):
+        os.makedirs(os.path.join(work, sub), exist_ok=True)
+
+    def esri(path, a, fmt, header=True):
+        with open(path, "w") as f:
+            if header:
+                f.write("ncols %d\nnrows %d\nxllcorner %s\nyllcorner %s\ncellsize %s\nNODATA_value 0\n" %
+                        (ncol, nrow, hdr["xllcorner"], hdr["yllcorner"], hdr["cellsize"]))
+            for r in range(nrow):
+                f.write(" ".join(fmt % x for x in a[r]) + "\n")
+    esri(os.path.join(par, "flowdirection.txt"), z["dir"], "%d")
+    esri(os.path.join(par, "reservoirlocation.txt"), z["reser"], "%d", header=False)
+    esri(os.path.join(par, "velocity.txt"), z["velo"], "%.9g")
+    esri(os.path.join(par, "diffusion.txt"), z["diff"], "%.9g")
+    esri(os.path.join(par, "xmask.txt"), z["xmask"], "%.9g")
+    r, c = [int(x) for x in z["station_rc"]]
+    with open(os.path.join(par, "stations.txt"), "w") as f:
+        f.write("1 OUTLT %d %d -9999\nNONE\n" % (c + 1, nrow - r))
+    with open(os.path.join(par, "unit_hydrograph", "UH.all"), "w") as f:
+        for k in range(12):
+            f.write("%d %.9g\n" % (k, z["uh_box"][k]))
+    for k in z.files:
+        if k.startswith("restxt_"):
+            with open(os.path.join(par, "reservoirs", "res_par", "res%s.txt" % k[7:]), "w") as f:
+                f.write(str(z[k]))
+    ndays = int(z["ndays"])
+    dates = [(2000, mo, dd) for mo, nd in zip(range(1, 6), (31, 29, 31, 30, 31)) for dd in range(1, nd + 1)][:ndays]
+    for g in np.flatnonzero(z["present"]):
+        rr, cc = divmod(int(g), ncol)
+        lat, lon = route_abi.cell_latlon(hdr, nrow, ncol, rr, cc)
+        with open(os.path.join(work, "input", "fluxes_%.4f_%.4f" % (lat, lon)), "w") as f:
+            for day, (y, mo, dd) in enumerate(dates):
+                ro, ba, evv, trv, evs = (z[k][g, day] for k in ("runoff", "baseflow", "ev_vege", "tr_vege", "ev_soil"))
+                cols = [0.0, evv + trv + evs, ro, ba, 0.0, 10.0, 50.0, 55.0, -26.0, evv, trv, evs, 0.0, 0.0, 5.7, 15.0, 0.12,
+                        z["rh"][g, day], 309.0, z["tair"][g, day], z["wind"][g, day]]
+                f.write("%d\t%d\t%d\t" % (y, mo, dd) + "\t".join("%.4f" % x for x in cols) + "\n")
+    cfg = ["# Routing main file", "# NAME OF FLOW DIRECTION FILE", "../parameters/flowdirection.txt",
+           "# NAME OF VELOCITY FILE", ".true.", "../parameters/velocity.txt", "# NAME OF DIFF FILE", ".true.",
+           "../parameters/diffusion.txt", "# NAME OF XMASK FILE", ".true.", "../parameters/xmask.txt",
+           "# NAME OF FRACTION FILE", ".false.", "1.0", "# NAME OF STATION FILE", "../parameters/stations.txt"]
+    if layout == "current":
+        cfg += ["# NAME OF GRID LOCATION FILE", ".false.", "0.0", "0.0"]
+    cfg += ["# PATH OF INPUT FILES AND PRECISION", "../input/fluxes_", "4"]
+    if layout == "current":
+        cfg += ["classic"]
+    cfg += ["# PATH OF OUTPUT FILES", "../output/", "# RESERVOIR LOCATION", "../parameters/reservoirlocation.txt",
+            "# RESERVOIR PARAMETERS", "../parameters/reservoirs/res_par/", "# NATURALIZED FLOW", ".false. ",
+            "../parameters/naturalized_flow/ ", "# YEAR AND MONTH OF MODEL OUTPUT TO ROUTE & ROUTED OUTPUT TO WRITE         ",
+            "2000 1 2000 5 ", "2000 1 2000 5 ", "# NAME OF UNIT HYDROGRAPH FILE         ", "../parameters/unit_hydrograph/",
+            "# Simulation Mode: True: Run Step-by-Step Mode; False: Run all Steps", ".false.",
+            "# Start Day and Current Simulation Day (for STEPBYSTEP Version)", "2000 1 1 2000 5 31", "# Coupler Iteration", "1",
+            "# Write Outputs", ".true."]
+    path = os.path.join(par, "configuration.txt")
+    with open(path, "w") as f:
+        f.write("\n".join(cfg) + "\n")
+    return path
+
+
+@pytest.mark.parametrize("layout", ["current", "binary"])
+def test_configuration_file_parses_in_both_layouts(layout, tmp_path):
+    z = np.load(os.path.join(GOLDEN, "route_toy.npz"))
+    cfg = rout.read_configuration(write_case(str(tmp_path), z, layout))
+    assert cfg["layout"] == layout and cfg["flowdirection"] == "../parameters/flowdirection.txt"
+    assert cfg["velocity"] == "../parameters/velocity.txt" and cfg["fraction"] == 1.0 and cfg["dprec"] == 4
+    assert (cfg["start_year"], cfg["start_month"], cfg["stop_year"], cfg["stop_month"]) == (2000, 1, 2000, 5)
+    assert cfg["uh_path"] == "../parameters/unit_hydrograph/" and not cfg["stepbystep"] and not cfg["nf_exist"]
+    assert rout.period(cfg)[0] == 152
+    st = rout.read_stations(os.path.join(str(tmp_path), "parameters", "stations.txt"))
+    assert len(st) == 1 and st[0]["name"] == "OUTLT"
+
+
+def test_reference_bundled_configuration_parses():
+    """the configuration.txt the reference ships (today's layout)"""
+    p = "/root/reference/routing/parameters/configuration.txt"
+    if not os.path.exists(p):
+        pytest.skip("reference tree not present")
+    cfg = rout.read_configuration(p)
+    assert cfg["layout"] == "current" and cfg["vicdriver"] == "classic" and cfg["velocity"] == 1.2 and cfg["diffusion"] == 800.0
+    assert cfg["grid_location"] == ("../parameters/grid_lat.txt", "../parameters/grid_lon.txt")
+    assert cfg["inpath"] == "../input/fluxes_" and cfg["outpath"] == "../output/"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["route_toy", "route_rand12x10"])
+def test_rout_command_line_reproduces_the_binary_outputs(name, tmp_path):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfgp = write_case(str(tmp_path), z, "current")
+    model_dir = os.path.join(str(tmp_path), "model")
+    cwd = os.getcwd()
+    os.chdir(model_dir)                       # the reference resolves the configuration's paths from the model directory
+    try:
+        assert rout.main(["../parameters/configuration.txt", "--legacy"]) == 0
+    finally:
+        os.chdir(cwd)
+    out = os.path.join(str(tmp_path), "output")
+    flow = np.loadtxt(os.path.join(out, "OUTLT.day"))
+    assert flow.shape == (int(z["ndays"]), 4) and tuple(flow[0, :3]) == (2000, 1, 1) and tuple(flow[-1, :3]) == (2000, 5, 31)
+    ref = z["station_flow"]
+    err = np.abs(flow[:, 3] - ref) / np.maximum(np.abs(ref), 1e-2 * np.abs(ref).max())
+    assert err.max() < 1e-4, "station discharge vs the binary: %.3e" % err.max()
+    nres = 0
+    for k in z.files:
+        if not k.startswith("resday_"):
+            continue
+        a = np.loadtxt(os.path.join(out, "reservoir_%s_OUTLT.day" % k[7:]), skiprows=1)[:, 3:]
+        b = z[k]
+        assert a.shape == b.shape
+        scale = np.maximum(np.abs(b), 1e-2 * np.abs(b).max(axis=0) + 1e-3)
+        assert (np.abs(a - b) / scale).max() < 2e-4, "reservoir %s file vs the binary" % k[7:]
+        nres += 1
+    print("ROUT %s: station discharge max rel %.2e vs the binary, %d reservoir files" % (name, err.max(), nres))
