@@ -8,14 +8,20 @@ from common import GOLDEN
 from vicres_b200 import abi, ensemble, files
 
 CASE = os.path.join(GOLDEN, "files_case")
+_L, _NB, _DT = [int(x) for x in np.load(os.path.join(CASE, "expected.npz"))["meta"]]
 KW = dict(soil=os.path.join(CASE, "soil.txt"), veglib=os.path.join(CASE, "veglib.txt"), vegparam=os.path.join(CASE, "veg.txt"),
-          snowband=os.path.join(CASE, "snowband.txt"), nlayer=3, nbands=2, root_zones=3)
+          snowband=os.path.join(CASE, "snowband.txt"), nlayer=_L, nbands=_NB, root_zones=3)
 NAMES = ["b_infilt", "Ds", "Dsmax", "Ws", "c", "d1", "d2", "d3"]
 
 
 def _sets(P, seed=3):
+    """unit samples scaled the toolbox's way; Ds is kept below Ws (above it the ARNO curve has a negative nonlinear
+    branch, runoff.c:497-507, and the reference itself runs into NaN)"""
     rng = np.random.default_rng(seed)
-    return ensemble.scale_samples(rng.uniform(0.02, 0.98, (P, len(NAMES))), NAMES)
+    X = rng.uniform(0.02, 0.98, (P, len(NAMES)))
+    X[:, NAMES.index("Ds")] *= 0.4
+    X[:, NAMES.index("Ws")] = 0.5 + 0.5 * X[:, NAMES.index("Ws")]
+    return ensemble.scale_samples(X, NAMES)
 
 
 def _toolbox_rewrite(soil_in, soil_out, values):

@@ -97,7 +97,7 @@ def test_reference_bundled_configuration_parses():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["route_toy", "route_rand12x10"])
+@pytest.mark.parametrize("name", ["route_toy", "route_rand12x10", "route_rand20x16"])
 def test_rout_command_line_reproduces_the_binary_outputs(name, tmp_path):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfgp = write_case(str(tmp_path), z, "current")
@@ -121,7 +121,10 @@ def test_rout_command_line_reproduces_the_binary_outputs(name, tmp_path):
         a = np.loadtxt(os.path.join(out, "reservoir_%s_OUTLT.day" % k[7:]), skiprows=1)[:, 3:]
         b = z[k]
         assert a.shape == b.shape
-        scale = np.maximum(np.abs(b), 1e-2 * np.abs(b).max(axis=0) + 1e-3)
-        assert (np.abs(a - b) / scale).max() < 2e-4, "reservoir %s file vs the binary" % k[7:]
+        scale = np.maximum(np.abs(b), 1e-2 * np.abs(b).max(axis=0, keepdims=True) + 1e-2)
+        err = np.abs(a - b) / scale
+        assert err[:, :5].max() < 2e-5, "reservoir %s storage/level columns vs the binary: %.3e" % (k[7:], err[:, :5].max())
+        # releases are differences of storages divided by 86.4: one fp32 ulp of a 1e5 storage is 1e-4 m3/s
+        assert err[:, 5:].max() < 1e-3, "reservoir %s flow/energy columns vs the binary: %.3e" % (k[7:], err[:, 5:].max())
         nres += 1
     print("ROUT %s: station discharge max rel %.2e vs the binary, %d reservoir files" % (name, err.max(), nres))

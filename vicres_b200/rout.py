@@ -111,6 +111,22 @@ def read_stations(path):
     return out
 
 
+def reservoir_day_columns(series, j, res, start_year, legacy=False):
+    """The nine value columns of reservoir_<id>_<station>.day (write_routines.f:172-200) of reservoir j: storage at
+    the start and end of the day, full supply volume (0 until the year of commissioning, reservoir.f:1154-1161), level
+    at the start and end, inflow, release, turbine flow, energy.  legacy: as the shipped prebuilt binary prints them
+    (negative storages / levels / inflows / energy as 0; the turbine column is the release capped at Qdesign)."""
+    n = series["flowin"].shape[1]
+    full = np.full(n, np.float32(res["v_live"]) + np.float32(res["v_dead"]), dtype=np.float32)
+    full[start_year + np.arange(1, n + 1) // 365 < res["ope_year"]] = 0
+    c = np.stack([series["vol"][j][:-1], series["vol"][j][1:], full, series["hho"][j][:-1], series["hho"][j][1:],
+                  series["flowin"][j], series["flowout"][j], series["turbine"][j], series["energy"][j]], axis=1)
+    if legacy:
+        c[:, [0, 3, 5, 8]] = np.maximum(c[:, [0, 3, 5, 8]], 0)
+        c[:, 7] = np.where(c[:, 2] > 0, np.minimum(c[:, 6], np.float32(res["q_design"])), c[:, 7])
+    return c
+
+
 def run(config_path, device=0, legacy=False, cwd=None, write=True):
     """legacy: the arithmetic variant of the shipped prebuilt binary (area-based runoff scale, older rule-curve code;
     DESIGN.md section 9) instead of today's reservoir.f.  Returns {station: {"flow", "dates", "reservoirs"}}."""
@@ -152,14 +168,11 @@ def run(config_path, device=0, legacy=False, cwd=None, write=True):
                     f.write("%12d%12d%12d   %.9g\n" % (y, m, dd, q))
             r = results[st["name"]]["reservoirs"]
             for j, rid in enumerate(ids):
-                vfull = np.float32(res[j]["v_live"]) + np.float32(res[j]["v_dead"])         # VRESER, reservoir.f:1156
+                cols = reservoir_day_columns(r, j, res[j], cfg["start_year"], legacy)
                 with open(P(os.path.join(cfg["outpath"], "reservoir_%d_%s.day" % (rid, st["name"]))), "w") as f:
                     f.write(" Year Month Day Volume_1000cm Volume_t+1_1000cm FullSupplyVolume WaterLevel_m WaterLevel_t+1_m Qinflow_cms \n")
                     for k, (y, m, dd) in enumerate(dates):
-                        open_ = cfg["start_year"] + k // 365 >= res[j]["ope_year"]           # reservoir.f:1154-1161
-                        vals = [r["vol"][j][k], r["vol"][j][k + 1], vfull if open_ else np.float32(0), r["hho"][j][k], r["hho"][j][k + 1], r["flowin"][j][k],
-                                r["flowout"][j][k], r["turbine"][j][k], r["energy"][j][k]]
-                        f.write("%12d%12d%12d" % (y, m, dd) + "".join("   %.9g" % v for v in vals) + "\n")
+                        f.write("%12d%12d%12d" % (y, m, dd) + "".join("   %.9g" % v for v in cols[k]) + "\n")
     return results
 
 
