@@ -9,6 +9,8 @@ from vicres_b200 import rout, route_abi
 
 
 def write_case(work, z, layout):
+    files_ = list(z.files)
+    z = {k: z[k] for k in files_}              # an NpzFile decompresses an array on every access
     nrow, ncol = z["dir"].shape
     hdr = {"xllcorner": repr(float(z["hdr"][0])), "yllcorner": repr(float(z["hdr"][1])), "cellsize": repr(float(z["hdr"][2]))}
     par = os.path.join(work, "parameters")
@@ -35,7 +37,7 @@ def write_case(work, z, layout):
     with open(os.path.join(par, "unit_hydrograph", "UH.all"), "w") as f:
         for k in range(12):
             f.write("%d %.9g\n" % (k, z["uh_box"][k]))
-    for k in z.files:
+    for k in files_:
         if k.startswith("restxt_"):
             with open(os.path.join(par, "reservoirs", "res_par", "res%s.txt" % k[7:]), "w") as f:
                 f.write(str(z[k]))
