@@ -65,6 +65,9 @@ def test_seeded_grid_matches_oracle_and_batches_are_bit_identical(gpu):
     opt.reserved[0] = 1024
     out2 = gpu.prepare(opt, site, raw)
     assert np.array_equal(out, out2)
+    opt.reserved[0], opt.reserved[1] = 0, 1          # the daily radiation kernel without its shared-memory tile
+    out3 = gpu.prepare(opt, site, raw)
+    assert np.array_equal(out, out3)
 
 
 def test_subdaily_grid_matches_oracle(gpu):

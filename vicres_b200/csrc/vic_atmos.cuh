@@ -521,11 +521,21 @@ VA_HD double day_dtr(const Ctx &x, const Geo &g, int64_t c, int day)   // :649-6
 //   VP_ITER_NONE, VP_ITER_ANNUAL: one pass.  (ANNUAL either keeps the first pass or -- PET/P >= 2.5 -- resets the
 //     humidity to its initial value and repeats that same pass, :1018-1057: the results are those of one pass.)
 //   VP_ITER_ALWAYS: two passes.   VP_ITER_CONVERGE: one pass here, the rest in converge().
-VA_HDN void daily_rad(const Ctx &x, int64_t c, int day)
+// window[k] of the 90-day precipitation window (:716-725) as an index into the daily series
+VA_HD int prcp_window_src(int k, int ndays, int isloop) { return k < 90 ? (isloop ? ndays - 90 + k : k) : k - 90; }
+VA_HD int prcp_isloop(const Ctx &x, const Geo &g)          // :706-713
+{
+  const int start_yday = yday_of(x, g, 0), end_yday = yday_of(x, g, g.ndl - 1);
+  if (start_yday != 1) return (end_yday == start_yday - 1) ? 1 : 0;
+  return (end_yday == 365 || end_yday == 366) ? 1 : 0;
+}
+
+// dtr_of(d): diurnal range of local day d; win_of(k): entry k of the precipitation window (cm).  The host build and
+// k_rad read them from the inputs; k_rad_tiled reads them from the shared-memory tile of its 32 cells x 32 days.
+template <class DTR, class WIN>
+VA_HD void daily_rad_t(const Ctx &x, int64_t c, int day, const Geo &g, DTR dtr_of, WIN win_of)
 {
   const int64_t lc = c - x.c0, CB = x.CB;
-  const Geo g = cell_geo(x, c);
-  if (day >= g.ndl) return;
   const int ndays = g.ndl;
   // 30-day pulled boxcar of the diurnal range (:658-669, pulled_boxcar :1338-1394)
   const int w = ndays >= 30 ? 30 : ndays;
@@ -533,9 +543,9 @@ VA_HDN void daily_rad(const Ctx &x, int64_t c, int day)
   for (int i = 0; i < w; i++) sum_wt += 1.0;
   const int e = day < w - 1 ? w - 1 : day;
   double total = 0.0;
-  for (int j = 0; j < w; j++) total += day_dtr(x, g, c, e - w + j + 1) * 1.0;
+  for (int j = 0; j < w; j++) total += dtr_of(e - w + j + 1) * 1.0;
   const double sm_dtr = total / sum_wt;
-  const double dtr = day_dtr(x, g, c, day);
+  const double dtr = dtr_of(day);
   // effective annual precipitation (:684-741)
   double parray;
   if (ndays < 90) {
@@ -545,16 +555,8 @@ VA_HDN void daily_rad(const Ctx &x, int64_t c, int day)
     if (parray < 8.0) parray = 8.0;
   }
   else {
-    const int start_yday = yday_of(x, g, 0), end_yday = yday_of(x, g, ndays - 1);
-    int isloop;
-    if (start_yday != 1) isloop = (end_yday == start_yday - 1) ? 1 : 0;
-    else isloop = (end_yday == 365 || end_yday == 366) ? 1 : 0;
     double s = 0.0;
-    for (int j = 0; j < 90; j++) {
-      int k = day + j;                                   // window[k]
-      int src = k < 90 ? (isloop ? ndays - 90 + k : k) : k - 90;
-      s += mt_prcp(x, lc, src) * 1.0;
-    }
+    for (int j = 0; j < 90; j++) s += win_of(day + j) * 1.0;
     s = (s / 90.0) * 365.25;
     parray = (s < 8.0) ? 8.0 : s;
   }
@@ -579,6 +581,48 @@ VA_HDN void daily_rad(const Ctx &x, int64_t c, int day)
   x.tskc[k] = tfmax;                                      // cloud transmittance; converted to tskc where it is read
   if (x.vp_iter == VR_VP_ITER_CONVERGE) { x.tdew[k] = r.tdew; x.parr[k] = parray; }
 }
+
+VA_HDN void daily_rad(const Ctx &x, int64_t c, int day)
+{
+  const int64_t lc = c - x.c0;
+  const Geo g = cell_geo(x, c);
+  if (day >= g.ndl) return;
+  const int isloop = g.ndl >= 90 ? prcp_isloop(x, g) : 0;
+  daily_rad_t(x, c, day, g, [&](int d) { return day_dtr(x, g, c, d); },
+              [&](int k) { return mt_prcp(x, lc, prcp_window_src(k, g.ndl, isloop)); });
+}
+
+#if defined(__CUDACC__)
+// One block = RT_C cells x RT_D consecutive local days.  Every thread needs the 90 window entries and the 30 ranges
+// that end at its day; neighbouring days share all but one of them, so the block stages the RT_D+89 window entries and
+// RT_D+29 ranges of each of its cells in shared memory once (global reads per thread 150 -> 8) and every thread adds
+// its terms from there in the reference's order.
+constexpr int RT_C = 32, RT_D = 32;
+__device__ __forceinline__ void daily_rad_tile(const Ctx &x, int64_t cb, int64_t tile_c, int tile_d)
+{
+  __shared__ double s_win[RT_D + 89][RT_C];
+  __shared__ double s_dtr[RT_D + 29][RT_C];
+  const int tx = threadIdx.x % RT_C, ty = threadIdx.x / RT_C;
+  const int64_t lc = tile_c * RT_C + tx;
+  const bool valid = lc < cb;
+  const int64_t c = x.c0 + (valid ? lc : 0);
+  const Geo g = cell_geo(x, c);
+  const int D0 = tile_d * RT_D, ndl = g.ndl;
+  const int isloop = (valid && ndl >= 90) ? prcp_isloop(x, g) : 0;
+  for (int kk = ty; kk < RT_D + 89; kk += RT_D) {
+    const int src = prcp_window_src(D0 + kk, ndl, isloop);
+    s_win[kk][tx] = (valid && ndl >= 90 && src >= 0 && src < ndl) ? mt_prcp(x, c - x.c0, src) : 0.0;
+  }
+  for (int rr = ty; rr < RT_D + 29; rr += RT_D) {
+    const int r = D0 - 29 + rr;
+    s_dtr[rr][tx] = (valid && r >= 0 && r < ndl) ? day_dtr(x, g, c, r) : 0.0;
+  }
+  __syncthreads();
+  const int day = D0 + ty;
+  if (!valid || day >= ndl) return;
+  daily_rad_t(x, c, day, g, [&](int d) { return s_dtr[d - (D0 - 29)][tx]; }, [&](int k) { return s_win[k - D0][tx]; });
+}
+#endif
 
 // VP_ITER_CONVERGE: :1041-1057 after the first pass; one cell, all days per pass, rmse in day order.
 VA_HDN void converge(const Ctx &x, int64_t c)

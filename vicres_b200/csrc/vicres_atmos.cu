@@ -4,7 +4,8 @@
 // geometry + 5 doubles and 2 bytes per cell-day), each a thin launch of a body of vic_atmos.cuh:
 //   k_solar   one thread per (cell, yearday)   -- the 30-second hour-angle walk, >99 % of the arithmetic
 //   k_prep    one thread per cell              -- recurrences over days (MTCLIM snowpack), daily totals
-//   k_rad     one thread per (cell, local day) -- radiation / humidity chain of the day
+//   k_rad_tiled  one thread per (cell, local day), blocks of 32 cells x 32 days with the windows staged in shared
+//                memory -- radiation / humidity chain of the day (k_rad: the same without the tile)
 //   k_conv    one thread per cell              -- VP_ITER_CONVERGE only
 //   k_hours   one thread per (cell, local day) -- hours of Tmin / Tmax
 //   k_rec     one thread per (cell, record)    -- the nine atmos fields of the record
@@ -60,6 +61,11 @@ __global__ void __launch_bounds__(TPB) k_rad(const __grid_constant__ va::Ctx x, 
 {
   int day; int64_t c;
   if (locate(x, cb, day, c)) va::daily_rad(x, c, day);
+}
+__global__ void __launch_bounds__(va::RT_C * va::RT_D) k_rad_tiled(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  const int64_t ntc = (cb + va::RT_C - 1) / va::RT_C;
+  va::daily_rad_tile(x, cb, blockIdx.x % ntc, (int)(blockIdx.x / ntc));
 }
 __global__ void __launch_bounds__(TPB) k_conv(const __grid_constant__ va::Ctx x, int64_t cb)
 {
@@ -180,7 +186,8 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
     k_solar<<<(unsigned)(nbc * va::NYD), TPB, 0, st>>>(x, cb);
     mark();
     k_prep<<<(unsigned)nbc, TPB, 0, st>>>(x, cb);
-    k_rad<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb);
+    if (o->reserved[1] == 1) k_rad<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb);     // untiled twin, for the tests
+    else k_rad_tiled<<<(unsigned)(((cb + va::RT_C - 1) / va::RT_C) * ((nd + va::RT_D - 1) / va::RT_D)), va::RT_C * va::RT_D, 0, st>>>(x, cb);
     g_t.launches += 3;
     if (conv) { k_conv<<<(unsigned)nbc, TPB, 0, st>>>(x, cb); g_t.launches++; }
     mark();
