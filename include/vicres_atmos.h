@@ -52,7 +52,8 @@ typedef struct vr_atmos_options {
   int32_t reserved0;
   double  min_wind_speed;   /* MIN_WIND_SPEED   default 0.1                                      */
   double  sw_prec_thresh;   /* SW_PREC_THRESH   default 0 (mm; compared with MTCLIM's cm value as the reference does) */
-  int32_t reserved[8];      /* [0] cells per batch (0 = 32768); [1] = 1: untiled daily-radiation kernel (tests) */
+  int32_t reserved[8];      /* [0] cells per batch (0 = 32768); [1] = 1: untiled daily-radiation kernel,
+                             * [2] = 1: solar kernel in the caller's cell order instead of latitude order (tests) */
 } vr_atmos_options;
 
 void vr_atmos_default_options(vr_atmos_options *o);

@@ -68,6 +68,9 @@ def test_seeded_grid_matches_oracle_and_batches_are_bit_identical(gpu):
     opt.reserved[0], opt.reserved[1] = 0, 1          # the daily radiation kernel without its shared-memory tile
     out3 = gpu.prepare(opt, site, raw)
     assert np.array_equal(out, out3)
+    opt.reserved[1], opt.reserved[2] = 0, 1          # the solar kernel in the caller's cell order
+    out4 = gpu.prepare(opt, site, raw)
+    assert np.array_equal(out, out4)
 
 
 def test_subdaily_grid_matches_oracle(gpu):

@@ -68,6 +68,7 @@ struct Ctx {
   double *prec_d, *swe, *srad, *pva, *tskc, *tdew, *parr;
   double *tcon;                // [2][CB] Tmax, Tmin of the sub-daily layout
   int8_t *tminh, *tmaxh;       // [ndl][CB]
+  const int32_t *perm;         // [CB] k_solar only: batch-local cell indices ordered by latitude (or null)
   double *out[VR_NFORCING];
 };
 

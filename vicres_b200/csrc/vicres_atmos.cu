@@ -36,6 +36,32 @@ __device__ __forceinline__ bool locate(const va::Ctx &x, int64_t cb, int &row, i
   c = x.c0 + lc;
   return lc < cb;
 }
+// The trip count of the hour-angle walk is the daylength, a monotonic function of latitude on a given yearday: the
+// threads of a warp take cells that are neighbours in latitude (x.perm), not in the caller's order, so that they leave
+// the walk together.  Only this kernel uses the order; it writes its tables at the cell's own position.
+constexpr int LAT_BUCKETS = 1440;               // 1/8 degree
+__global__ void k_lat_hist(const __grid_constant__ va::Ctx x, int64_t cb, int32_t *hist)
+{
+  const int64_t lc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= cb) return;
+  int b = (int)((x.lat[x.c0 + lc] + 90.0) * 8.0);
+  b = b < 0 ? 0 : (b >= LAT_BUCKETS ? LAT_BUCKETS - 1 : b);
+  atomicAdd(&hist[b], 1);
+}
+__global__ void k_lat_scan(int32_t *hist)        // one thread: 1440 additions
+{
+  int32_t run = 0;
+  for (int b = 0; b < LAT_BUCKETS; b++) { const int32_t n = hist[b]; hist[b] = run; run += n; }
+}
+__global__ void k_lat_scatter(const __grid_constant__ va::Ctx x, int64_t cb, int32_t *hist, int32_t *perm)
+{
+  const int64_t lc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= cb) return;
+  int b = (int)((x.lat[x.c0 + lc] + 90.0) * 8.0);
+  b = b < 0 ? 0 : (b >= LAT_BUCKETS ? LAT_BUCKETS - 1 : b);
+  perm[atomicAdd(&hist[b], 1)] = (int32_t)lc;
+}
+
 __global__ void __launch_bounds__(TPB) k_solar(const __grid_constant__ va::Ctx x, int64_t cb)
 {
   __shared__ double s_ck[20];
@@ -44,7 +70,9 @@ __global__ void __launch_bounds__(TPB) k_solar(const __grid_constant__ va::Ctx x
   if (threadIdx.x < 20) s_ck[threadIdx.x] = ck[threadIdx.x];
   __syncthreads();
   int yd; int64_t c;
-  if (locate(x, cb, yd, c)) va::solar_day_t<true>(x, c, yd, s_ck, s_t21 + threadIdx.x, TPB);
+  if (!locate(x, cb, yd, c)) return;
+  if (x.perm) c = x.c0 + x.perm[c - x.c0];
+  va::solar_day_t<true>(x, c, yd, s_ck, s_t21 + threadIdx.x, TPB);
 }
 // the walk exactly as the reference writes it (libm call per step): diagnostic twin of k_solar
 __global__ void __launch_bounds__(TPB) k_solar_exact(const __grid_constant__ va::Ctx x, int64_t cb)
@@ -148,7 +176,8 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
   const bool conv = o->vp_iter == VR_VP_ITER_CONVERGE;
   const int ndaily = 4 + (o->mtclim_swe_corr ? 1 : 0) + (conv ? 2 : 0);
   const size_t n_tab = (size_t)va::NYD * 28 * CB, n_day = (size_t)nd * CB;
-  const size_t bytes = (n_tab + n_day * ndaily + 2 * (size_t)CB) * sizeof(double) + 2 * n_day + (size_t)(x.Ndays + 2) * sizeof(int16_t) + 64;
+  const size_t bytes = (n_tab + n_day * ndaily + 2 * (size_t)CB) * sizeof(double) + 2 * n_day + (size_t)(x.Ndays + 2) * sizeof(int16_t) + 64 +
+                       ((size_t)CB + LAT_BUCKETS) * sizeof(int32_t) + 16;
   char *base = nullptr;
   {   // keep the scratch in the device's default pool between calls (the default threshold returns it at every sync)
     cudaMemPool_t pool;
@@ -171,6 +200,8 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
   x.tminh = (int8_t *)d;
   x.tmaxh = x.tminh + n_day;
   int16_t *cal_dev = (int16_t *)(((uintptr_t)(x.tmaxh + n_day) + 15) & ~(uintptr_t)15);
+  int32_t *perm_dev = (int32_t *)(((uintptr_t)(cal_dev + x.Ndays + 2) + 15) & ~(uintptr_t)15);
+  int32_t *hist_dev = perm_dev + CB;
   std::vector<int16_t> cal(x.Ndays + 2);
   va::build_calendar(*o, x.Ndays, cal.data());
   CK(cudaMemcpyAsync(cal_dev, cal.data(), cal.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
@@ -183,7 +214,16 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
     const int64_t nbc = (cb + TPB - 1) / TPB;
     x.c0 = c0;
     mark();
+    if (o->reserved[2] != 1) {                       // latitude order of the batch (reserved[2] == 1: caller's order)
+      CK(cudaMemsetAsync(hist_dev, 0, LAT_BUCKETS * sizeof(int32_t), st));
+      k_lat_hist<<<(unsigned)((cb + 255) / 256), 256, 0, st>>>(x, cb, hist_dev);
+      k_lat_scan<<<1, 1, 0, st>>>(hist_dev);
+      k_lat_scatter<<<(unsigned)((cb + 255) / 256), 256, 0, st>>>(x, cb, hist_dev, perm_dev);
+      x.perm = perm_dev;
+      g_t.launches += 3;
+    }
     k_solar<<<(unsigned)(nbc * va::NYD), TPB, 0, st>>>(x, cb);
+    x.perm = nullptr;
     mark();
     k_prep<<<(unsigned)nbc, TPB, 0, st>>>(x, cb);
     if (o->reserved[1] == 1) k_rad<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb);     // untiled twin, for the tests
