@@ -109,5 +109,6 @@ def load_atmos_fixture(name):
                         force_dt=fdt, **ov)
     raw = z["raw"]
     site = {k[5:]: z[k] for k in z.files if k.startswith("site_")}
-    rawd = {"prec": raw[0], "t_a": raw[1], "t_b": raw[2] if layout == 0 else None, "wind": raw[3 if layout == 0 else 2]}
+    iw = 3 if layout == 0 else 2
+    rawd = {"prec": raw[0], "t_a": raw[1], "t_b": raw[2] if layout == 0 else None, "wind": raw[iw] if raw.shape[0] > iw else None}
     return {"opt": opt, "site": site, "raw": rawd, "ref": z["atmos"]}

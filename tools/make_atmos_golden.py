@@ -45,6 +45,8 @@ CASES = {
     "atmos_annual_nointerp": (dict(ncells=3, ndays=300, startyear=1993, seed=308,
                                    extra_global="VP_ITER VP_ITER_ANNUAL\nVP_INTERP FALSE\nLW_TYPE LW_IDSO\nSW_PREC_THRESH 0.1"),
                               dict(vp_iter="VP_ITER_ANNUAL", vp_interp=False, lw_type="LW_IDSO", sw_prec_thresh=0.1)),
+    "atmos_daily_no_wind": (dict(ncells=3, ndays=120, startyear=1996, lat_range=(-35, 55), off_gmt=-2, no_wind=True, seed=310),
+                            dict(has_wind=False)),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,
                                 extra_global="VP_ITER VP_ITER_NONE\nLW_TYPE LW_SATTERLUND"),
                            dict(vp_iter="VP_ITER_NONE", lw_type="LW_SATTERLUND")),
@@ -70,7 +72,8 @@ def save(name, gfile, dump, kw, ov, start=None):
     atm = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2).transpose(1, 0, 2)   # [9, nrec, C]
     dt = int(d["dt"][0])
     daily = dt == 24 or kw.get("force_daily", False)
-    raw = read_raw(gfile, site["lat"], site["lng"], 4 if daily else 3)
+    ncol = (4 if daily else 3) - (1 if kw.get("no_wind") else 0)
+    raw = read_raw(gfile, site["lat"], site["lng"], ncol)
     nrecs = int(d["nrecs"][0])
     nrf = nrecs * dt // (24 if daily else dt)
     dmy = d["dmy"]

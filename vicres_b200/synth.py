@@ -56,14 +56,15 @@ def _fmt(x, nd=6):
 def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261019,
               startyear=1981, lat_range=(-40.0, 60.0), cold=0.0, overstory_frac=0.3,
               max_veg=3, extra_global="", result_dir=None, skip_output=False, snow_step=None,
-              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False):
+              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False):
     """Write a complete reference-format case under `outdir`; return the global file path.
 
     dt == 24: daily PREC/TMAX/TMIN/WIND forcing (as the bundled basin); dt < 24: sub-daily
     PREC/AIR_TEMP/WIND records at the model step.  `cold` lowers all temperatures (deg C) to
     force snow.  All randomness comes from `seed`.  `off_gmt` (hours) replaces the cells' own time zone
     (round(lng/15)), so that local time differs from the forcing's time; `force_daily` writes the daily
-    four-column file even when dt < 24 (FORCE_DT 24 with a sub-daily TIME_STEP).
+    four-column file even when dt < 24 (FORCE_DT 24 with a sub-daily TIME_STEP); `no_wind` leaves the
+    WIND column out (the reference then uses DEFAULT_WIND_SPEED).
     """
     rng = np.random.default_rng(seed)
     os.makedirs(outdir, exist_ok=True)
@@ -185,7 +186,10 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         with open(fn, "w") as f:
             if dt == 24 or force_daily:
                 for i in range(ndays):
-                    f.write("%.4f %.4f %.4f %.4f\n" % (prec[i], tmax[i], tmin[i], wind[i]))
+                    if no_wind:
+                        f.write("%.4f %.4f %.4f\n" % (prec[i], tmax[i], tmin[i]))
+                    else:
+                        f.write("%.4f %.4f %.4f %.4f\n" % (prec[i], tmax[i], tmin[i], wind[i]))
             else:
                 hrs = (np.arange(steps_per_day) + 0.5) * dt
                 for i in range(ndays):
@@ -209,8 +213,8 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
           "MIN_WIND_SPEED 0.1", "MAX_SNOW_TEMP 0.5", "MIN_RAIN_TEMP -0.5",
           "FORCING1 %s/data_" % forc_dir, "FORCE_FORMAT ASCII", "FORCE_ENDIAN LITTLE"]
     if dt == 24 or force_daily:
-        g += ["N_TYPES 4", "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN", "FORCE_TYPE WIND",
-              "FORCE_DT 24"]
+        g += (["N_TYPES 3", "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN"] if no_wind else
+              ["N_TYPES 4", "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN", "FORCE_TYPE WIND"]) + ["FORCE_DT 24"]
     else:
         g += ["N_TYPES 3", "FORCE_TYPE PREC", "FORCE_TYPE AIR_TEMP", "FORCE_TYPE WIND", "FORCE_DT %d" % dt]
     g += ["FORCEYEAR %d" % startyear, "FORCEMONTH 1", "FORCEDAY 1", "FORCEHOUR 0", "GRID_DECIMAL 4",
