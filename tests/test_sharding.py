@@ -74,3 +74,39 @@ def test_two_rank_sharded_run_equals_single_process(tmp_path):
     o.init_state(f[0, 0])
     _, ref, _ = o.step(month, doy, f)
     assert np.array_equal(full, ref)
+
+
+def _atmos_worker(rank, world, port, path):
+    import atmos_lib
+    from vicres_b200 import atmos
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C, nd = 9, 150
+    site = synth_soa.make_site(C, seed=5, lat_range=(-45.0, 62.0), own_time_zone=False)
+    raw = synth_soa.make_raw_forcing(site["lat"], site["elevation"], nd, seed=6, cold=4.0)
+    opt = atmos.options(time_step=24, nrecs=nd, startyear=1988)
+    c0, c1 = shard.cell_block(C, rank, world)
+    s, r = shard.slice_atmos_inputs(site, raw, c0, c1)
+    part = atmos_lib.prepare(opt, s, r)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (c0, c1, part))
+    if rank == 0:
+        full = np.zeros((abi.VR_NFORCING, nd, C))
+        for a, b, p_ in gathered:
+            full[:, :, a:b] = p_
+        np.save(path, full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_forcing_preparation_equals_single_process(tmp_path):
+    """the forcing preparation shards like the step: per-rank cell blocks (ragged: 9 cells over 2 ranks), no collective"""
+    import atmos_lib
+    from vicres_b200 import atmos
+    path = str(tmp_path / "atmos.npy")
+    mp.spawn(_atmos_worker, args=(2, _free_port(), path), nprocs=2, join=True)
+    C, nd = 9, 150
+    site = synth_soa.make_site(C, seed=5, lat_range=(-45.0, 62.0), own_time_zone=False)
+    raw = synth_soa.make_raw_forcing(site["lat"], site["elevation"], nd, seed=6, cold=4.0)
+    ref = atmos_lib.prepare(atmos.options(time_step=24, nrecs=nd, startyear=1988), site, raw)
+    assert np.array_equal(np.load(path), ref)

@@ -29,3 +29,11 @@ def slice_cells(cells, c0, c1):
         if cells.get(k) is not None:
             out[k] = np.ascontiguousarray(np.asarray(cells[k])[:, :, c0:c1])
     return out
+
+
+def slice_atmos_inputs(site, raw, c0, c1):
+    """The forcing-preparation inputs (vicres_b200/atmos.py: site values and raw forcing columns [nrec, C]) of cells
+    [c0, c1): initialize_atmos is per cell too, so the ranks prepare their own blocks with no collective."""
+    s = {k: np.ascontiguousarray(np.asarray(v)[c0:c1]) for k, v in site.items() if v is not None}
+    r = {k: (np.ascontiguousarray(np.asarray(v)[:, c0:c1]) if v is not None else None) for k, v in raw.items()}
+    return s, r
