@@ -189,6 +189,17 @@ int64_t vr_state_size(const vr_handle *h);                 /* bytes */
 int  vr_get_state(vr_handle *h, void *blob_host);
 int  vr_set_state(vr_handle *h, const void *blob_host);
 
+/* The reference's own state file (write_model_state.c:100-300 with the header of open_state_file.c; ASCII "%f"
+ * columns or BINARY_STATE_FILE): per cell `cellnum Nveg Nbands dz_node[3] Zsum_node[3]`, then per vegetation tile
+ * (the bare-soil tile last) x snow band `veg band moist[L] ice[L] [Wdew] last_snow MELTING coverage swq surf_temp
+ * surf_water pack_temp pack_water density coldcontent snow_canopy T[3]`.  gridcel: [C] the cells' numbers.
+ * vr_read_state_file is read_initial_model_state + the state branch of initialize_model_state (:233-330, 590-633):
+ * moisture capped at max_moist, snow pack terms made consistent, depth from swq / density, LongUnderOut from T[0],
+ * Tfoliage from tair0 (atmos[0].air_temp of the restarted run), then the put_data(rec = -nrecs) storages. */
+int  vr_write_state_file(vr_handle *h, const char *path, int32_t year, int32_t month, int32_t day, int32_t binary,
+                         const int32_t *gridcel);
+int  vr_read_state_file(vr_handle *h, const char *path, int32_t binary, const double *tair0, const int32_t *gridcel);
+
 /* introspection used by bench/tests */
 int64_t vr_num_units(const vr_handle *h);      /* active tile x band pairs */
 int64_t vr_num_launches(const vr_handle *h);   /* kernels launched by this handle so far */

@@ -77,6 +77,10 @@ typedef struct vr_global {
   /* options of the forcing preparation (include/vicres_atmos.h); values as vicNl_def.h:208-223 */
   int32_t vp_interp, vp_iter, mtclim_swe_corr, lw_type, lw_cloud, plapse;
   double  sw_prec_thresh;
+  /* state files (INIT_STATE <file>; STATENAME <prefix> + STATEYEAR/STATEMONTH/STATEDAY: the file written at the end of
+   * that day is "<prefix>_YYYYMMDD", get_global_param.c:961-964; BINARY_STATE_FILE) -> vr_read/write_state_file */
+  char    init_state_file[512], statename[512];
+  int32_t stateyear, statemonth, stateday, binary_state_file;
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -123,6 +123,19 @@ __global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double 
   unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U);
 }
 
+// the terms of a state that is already in place (restart from a state file) for put_data(rec = -nrecs)
+__global__ void __launch_bounds__(VR_CTA) k_restored_units(DevModel M, double *terms)
+{
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= M.U) return;
+  UnitC uc; UnitS s; UnitOut z;
+  double cv, af;
+  load_unit_consts(M, u, uc, cv, af);
+  load_state(M, u, s);
+  memset(&z, 0, sizeof z);
+  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U);
+}
+
 __global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *terms, double *sums)
 {
   const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // sorted position
@@ -282,6 +295,14 @@ struct vr_handle {
   std::vector<double> lib_rarc, lib_rmin, lib_wind_h, lib_RGL, lib_rad_atten, lib_wind_atten, lib_trunk, lib_rough, lib_disp,
       lib_LAI, lib_albedo;
   Prepared P;
+  // what the reference's state file needs of the cells (write_model_state.c / read_initial_model_state.c)
+  struct CellKeep {
+    std::vector<int64_t> tile_ptr;
+    std::vector<int32_t> tile_class;
+    std::vector<double> tile_Cv, AreaFract, Tfactor, init_moist, max_moist, depth0, dp, avg_temp;
+    int nclass = 0;
+  } keep;
+  std::vector<double> tair0_host;
   DevModel M;
   DBuf<double> d_tl, d_ap;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
@@ -469,6 +490,22 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   if (!prepare(h->opt, lib, *cells, VR_CTA, h->P)) { h->err = h->P.error; return VR_ERR_ARG; }
   Prepared &P = h->P;
   const int64_t C = P.C, U = P.U;
+  {
+    auto &k = h->keep;
+    const int NL = h->opt.nlayer, NB = h->opt.nbands;
+    const int64_t T = cells->tile_ptr[C];
+    k.nclass = lib.nclass;
+    k.tile_ptr.assign(cells->tile_ptr, cells->tile_ptr + C + 1);
+    k.tile_class.assign(cells->tile_class, cells->tile_class + T);
+    k.tile_Cv.assign(cells->tile_Cv, cells->tile_Cv + T);
+    k.AreaFract.assign(cells->AreaFract, cells->AreaFract + (size_t)NB * C);
+    k.Tfactor.assign(cells->Tfactor, cells->Tfactor + (size_t)NB * C);
+    k.init_moist.assign(cells->init_moist, cells->init_moist + (size_t)NL * C);
+    k.max_moist.assign(cells->max_moist, cells->max_moist + (size_t)NL * C);
+    k.depth0.assign(cells->depth, cells->depth + C);
+    k.dp.assign(cells->dp, cells->dp + C);
+    k.avg_temp.assign(cells->avg_temp, cells->avg_temp + C);
+  }
   {   // one resident block per SM: w waves of blocks as equal as the warp granularity allows (a grid of
       // 3.1 waves of full-size blocks would pay for 4)
     int sms = 148;
@@ -549,6 +586,7 @@ int vr_init_state(vr_handle *h, const double *tair0)
   CK(cudaSetDevice(h->device));
   CK(h->d_tair0.reserve(h->M.FC));
   CK(cudaMemcpyAsync(h->d_tair0.p, tair0, h->M.FC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->tair0_host.assign(tair0, tair0 + h->M.FC);
   const size_t U1 = (size_t)(h->M.U ? h->M.U : 1);
   CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * h->chunk));
   CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * h->chunk));
@@ -742,6 +780,230 @@ int vr_set_state(vr_handle *h, const void *blob)
   const size_t ns = (size_t)ST_N * h->M.U * sizeof(double), nv = (size_t)SV_N * h->M.C * sizeof(double);
   CK(cudaMemcpy(h->d_state.p, b, ns, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_sv.p, b + ns, nv, cudaMemcpyHostToDevice));
+  h->initialised = true;
+  return VR_OK;
+}
+
+// ---- the reference's state file (write_model_state.c:100-300, open_state_file.c, read_initial_model_state.c,
+// initialize_model_state.c:233-330, 590-633) ------------------------------------------------------------------
+namespace {
+// slot of unit (cell c, tile t, band b), or -1: the construction order of prepare() (sorted cells, tiles with Cv > 0,
+// bands with AreaFract > 0) gives the unit's index in reference order, P.u_slot its thread slot
+std::vector<int64_t> unit_slots(const vr_handle *h)
+{
+  const Prepared &P = h->P;
+  const auto &k = h->keep;
+  const int64_t C = P.C;
+  const int NB = h->opt.nbands;
+  const int64_t T = k.tile_ptr[C];
+  std::vector<int64_t> slot((size_t)T * NB, -1);
+  int64_t u = 0;
+  for (int64_t cs = 0; cs < C; cs++) {
+    const int64_t c = P.order[cs];
+    for (int64_t t = k.tile_ptr[c]; t < k.tile_ptr[c + 1]; t++) {
+      if (!(k.tile_Cv[t] > 0.0)) continue;
+      for (int b = 0; b < NB; b++) {
+        if (!(k.AreaFract[(size_t)b * C + c] > 0)) continue;
+        slot[(size_t)t * NB + b] = P.u_slot[u++];
+      }
+    }
+  }
+  return slot;
+}
+}  // namespace
+
+int vr_write_state_file(vr_handle *h, const char *path, int32_t year, int32_t month, int32_t day, int32_t binary,
+                        const int32_t *gridcel)
+{
+  if (!h || !path || !gridcel) return VR_ERR_ARG;
+  if (!h->initialised) { h->err = "no state yet"; return VR_ERR_STATE; }
+  const int64_t C = h->M.C, U = h->M.U;
+  const int NL = h->opt.nlayer, NB = h->opt.nbands, NN = 3, ncls = h->keep.nclass;
+  std::vector<double> st((size_t)ST_N * (U ? U : 1) + (size_t)SV_N * C);
+  int rc = vr_get_state(h, st.data());
+  if (rc != VR_OK) return rc;
+  FILE *f = fopen(path, binary ? "wb" : "w");
+  if (!f) { h->err = std::string("cannot open ") + path; return VR_ERR_ARG; }
+  const std::vector<int64_t> slot = unit_slots(h);
+  const auto &k = h->keep;
+  auto S = [&](int w, int64_t sl) { return st[(size_t)w * U + sl]; };
+  auto wi = [&](int v) { fwrite(&v, sizeof(int), 1, f); };
+  auto wd = [&](double v) { fwrite(&v, sizeof(double), 1, f); };
+  if (binary) { wi(year); wi(month); wi(day); wi(NL); wi(NN); }
+  else fprintf(f, "%i %i %i\n%i %i\n", year, month, day, NL, NN);
+  for (int64_t c = 0; c < C; c++) {
+    const int64_t t0 = k.tile_ptr[c], t1 = k.tile_ptr[c + 1];
+    const bool has_bare = t1 > t0 && k.tile_class[t1 - 1] == ncls;
+    const int Nveg = (int)(t1 - t0) - (has_bare ? 1 : 0);
+    // QUICK_FLUX node layout, initialize_model_state.c:311-317
+    const double dz[3] = {k.depth0[c], k.depth0[c], 2. * (k.dp[c] - 1.5 * k.depth0[c])}, zs[3] = {0., k.depth0[c], k.dp[c]};
+    if (binary) {
+      wi(gridcel[c]); wi(Nveg); wi(NB);
+      const int nbytes = NN * 8 * 2 + (Nveg + 1) * NB * 2 * 4 + (Nveg + 1) * NB * NL * 8 * 2 + Nveg * NB * 8 +
+                         (Nveg + 1) * NB * (4 + 1 + 9 * 8) + (Nveg + 1) * NB * NN * 8;       // write_model_state.c:120-135
+      wi(nbytes);
+      for (int i = 0; i < NN; i++) wd(dz[i]);
+      for (int i = 0; i < NN; i++) wd(zs[i]);
+    }
+    else {
+      fprintf(f, "%i %i %i", gridcel[c], Nveg, NB);
+      for (int i = 0; i < NN; i++) fprintf(f, " %f ", dz[i]);
+      for (int i = 0; i < NN; i++) fprintf(f, " %f ", zs[i]);
+      fprintf(f, "\n");
+    }
+    double surf = h->tair0_host.empty() ? 0. : h->tair0_host[h->P.C == (int64_t)h->tair0_host.size() ? c : 0];
+    if (surf < -1.) surf = -1.;
+    for (int veg = 0; veg <= Nveg; veg++) {
+      const int64_t t = veg < Nveg ? t0 + veg : (has_bare ? t1 - 1 : -1);
+      for (int b = 0; b < NB; b++) {
+        const int64_t sl = t >= 0 ? slot[(size_t)t * NB + b] : -1;
+        double moist[MAXL], wdew = 0., sn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, T[3] = {surf, surf, k.avg_temp[c]};
+        int last_snow = (int)MISSINGV, melting = 0;
+        for (int l = 0; l < NL; l++) {        // tiles / bands without area keep what initialize_model_state gave them
+          moist[l] = t >= 0 ? k.init_moist[(size_t)l * C + c] : 0.;
+          if (moist[l] > k.max_moist[(size_t)l * C + c]) moist[l] = k.max_moist[(size_t)l * C + c];
+        }
+        if (sl >= 0) {
+          for (int l = 0; l < NL; l++) moist[l] = S(ST_MOIST0 + l, sl);
+          wdew = S(ST_WDEW, sl);
+          last_snow = (int)S(ST_LAST_SNOW, sl); melting = (int)S(ST_MELTING, sl);
+          const int w[9] = {ST_COVERAGE, ST_SWQ, ST_SURF_TEMP, ST_SURF_WATER, ST_PACK_TEMP, ST_PACK_WATER, ST_DENSITY, ST_COLDCONTENT,
+                            ST_SNOW_CANOPY};
+          for (int i = 0; i < 9; i++) sn[i] = S(w[i], sl);
+          T[0] = S(ST_T0, sl); T[1] = S(ST_T1, sl);
+          T[2] = k.avg_temp[c] + k.Tfactor[(size_t)b * C + c];
+        }
+        if (binary) {
+          wi(veg); wi(b);
+          for (int l = 0; l < NL; l++) wd(moist[l]);
+          for (int l = 0; l < NL; l++) wd(0.);
+          if (veg < Nveg) wd(wdew);
+          wi(last_snow);
+          char m = (char)melting; fwrite(&m, 1, 1, f);
+          for (int i = 0; i < 9; i++) wd(sn[i]);
+          for (int i = 0; i < NN; i++) wd(T[i]);
+        }
+        else {
+          fprintf(f, "%i %i", veg, b);
+          for (int l = 0; l < NL; l++) fprintf(f, " %f", moist[l]);
+          for (int l = 0; l < NL; l++) fprintf(f, " %f", 0.);
+          if (veg < Nveg) fprintf(f, " %f", wdew);
+          fprintf(f, " %i %i %f %f %f %f %f %f %f %f %f", last_snow, melting, sn[0], sn[1], sn[2], sn[3], sn[4], sn[5], sn[6], sn[7], sn[8]);
+          for (int i = 0; i < NN; i++) fprintf(f, " %f", T[i]);
+          fprintf(f, "\n");
+        }
+      }
+    }
+  }
+  fclose(f);
+  return VR_OK;
+}
+
+int vr_read_state_file(vr_handle *h, const char *path, int32_t binary, const double *tair0, const int32_t *gridcel)
+{
+  if (!h || !path || !tair0 || !gridcel) return VR_ERR_ARG;
+  if (!h->have_cells) { h->err = "vr_set_cells must be called before vr_read_state_file"; return VR_ERR_STATE; }
+  if (h->M.fcol) { h->err = "state files and a forcing map (parameter-set axis) are not combined"; return VR_ERR_UNSUPPORTED; }
+  FILE *f = fopen(path, binary ? "rb" : "r");
+  if (!f) { h->err = std::string("cannot open ") + path; return VR_ERR_ARG; }
+  const int64_t C = h->M.C, U = h->M.U;
+  const int NL = h->opt.nlayer, NB = h->opt.nbands, ncls = h->keep.nclass;
+  const auto &k = h->keep;
+  const std::vector<int64_t> slot = unit_slots(h);
+  std::vector<double> st((size_t)ST_N * (U ? U : 1) + (size_t)SV_N * C, 0.0);
+  auto S = [&](int w, int64_t sl) -> double & { return st[(size_t)w * U + sl]; };
+  bool ok = true;
+  auto ri = [&]() { int v = 0; if (binary) ok = ok && fread(&v, sizeof(int), 1, f) == 1; else ok = ok && fscanf(f, "%d", &v) == 1; return v; };
+  auto rd = [&]() { double v = 0; if (binary) ok = ok && fread(&v, sizeof(double), 1, f) == 1; else ok = ok && fscanf(f, "%lf", &v) == 1; return v; };
+  ri(); ri(); ri();                                        // date of the state (check_state_file.c:60-70)
+  const int fl = ri(), fn = ri();
+  if (!ok || fl != NL) { fclose(f); h->err = "state file: number of soil layers does not match"; return VR_ERR_ARG; }
+  if (fn != 3) { fclose(f); h->err = "state file: number of soil thermal nodes is not 3 (QUICK_FLUX)"; return VR_ERR_UNSUPPORTED; }
+  std::vector<char> seen(C, 0);
+  std::vector<int64_t> of_cell;                            // gridcel -> cell index (cells come in any order)
+  {
+    int32_t mx = 0;
+    for (int64_t c = 0; c < C; c++) if (gridcel[c] > mx) mx = gridcel[c];
+    of_cell.assign((size_t)mx + 1, -1);
+    for (int64_t c = 0; c < C; c++) if (gridcel[c] >= 0) of_cell[gridcel[c]] = c;
+  }
+  for (;;) {
+    const int cellnum = ri();
+    if (!ok) break;                                        // end of file
+    const int fveg = ri(), fband = ri();
+    if (binary) ri();                                      // Nbytes
+    for (int i = 0; i < 6; i++) rd();                      // dz_node, Zsum_node: recomputed from depth and dp
+    const int64_t c = (cellnum >= 0 && cellnum < (int)of_cell.size()) ? of_cell[cellnum] : -1;
+    int Nveg = -1;
+    int64_t t0 = 0, t1 = 0;
+    bool has_bare = false;
+    if (c >= 0) {
+      t0 = k.tile_ptr[c]; t1 = k.tile_ptr[c + 1];
+      has_bare = t1 > t0 && k.tile_class[t1 - 1] == ncls;
+      Nveg = (int)(t1 - t0) - (has_bare ? 1 : 0);
+      if (fveg != Nveg || fband != NB) {
+        fclose(f);
+        h->err = "state file: vegetation tiles or snow bands of cell " + std::to_string(cellnum) + " do not match the parameter files";
+        return VR_ERR_ARG;
+      }
+      seen[c] = 1;
+    }
+    for (int veg = 0; veg <= fveg && ok; veg++)
+      for (int b = 0; b < fband && ok; b++) {
+        ri(); ri();
+        double moist[MAXL] = {0, 0, 0}, wdew = 0., sn[9], T[3];
+        for (int l = 0; l < fl; l++) moist[l] = rd();
+        for (int l = 0; l < fl; l++) rd();                 // ice (Nfrost == 1)
+        if (veg < fveg) wdew = rd();
+        const int last_snow = ri();
+        int melting;
+        if (binary) { char m = 0; ok = ok && fread(&m, 1, 1, f) == 1; melting = m; } else melting = ri();
+        for (int i = 0; i < 9; i++) sn[i] = rd();
+        for (int i = 0; i < 3; i++) T[i] = rd();
+        if (c < 0 || !ok) continue;
+        const int64_t t = veg < Nveg ? t0 + veg : (has_bare ? t1 - 1 : -1);
+        const int64_t sl = t >= 0 ? slot[(size_t)t * NB + b] : -1;
+        if (sl < 0) continue;
+        for (int l = 0; l < NL; l++) {                     // initialize_model_state.c:240-250
+          const double mm = k.max_moist[(size_t)l * C + c];
+          S(ST_MOIST0 + l, sl) = moist[l] > mm ? mm : moist[l];
+        }
+        S(ST_WDEW, sl) = wdew;
+        double coverage = sn[0], swq = sn[1], surf_temp = sn[2], surf_water = sn[3], pack_temp = sn[4], pack_water = sn[5],
+               density = sn[6], coldcontent = sn[7], snow_canopy = sn[8];
+        const double depth = density > 0. ? 1000. * swq / density : 0.;     // read_initial_model_state.c:341-343
+        double pack_swq, surf_swq;                          // initialize_model_state.c:288-305
+        if (swq > 0.125) { pack_swq = swq - 0.125; surf_swq = 0.125; }
+        else { pack_swq = 0; surf_swq = swq; pack_temp = 0; }
+        if (surf_water > 0.035 * surf_swq) { pack_water += surf_water - (0.035 * surf_swq); surf_water = 0.035 * surf_swq; }
+        if (pack_water > 0.035 * pack_swq) pack_water = 0.035 * pack_swq;
+        S(ST_SWQ, sl) = swq; S(ST_SURF_TEMP, sl) = surf_temp; S(ST_PACK_TEMP, sl) = pack_temp; S(ST_SURF_WATER, sl) = surf_water;
+        S(ST_PACK_WATER, sl) = pack_water; S(ST_DENSITY, sl) = density; S(ST_DEPTH, sl) = depth; S(ST_ALBEDO, sl) = 0.;
+        S(ST_COLDCONTENT, sl) = coldcontent; S(ST_COVERAGE, sl) = coverage; S(ST_SNOW_CANOPY, sl) = snow_canopy;
+        S(ST_TMP_INT, sl) = 0.; S(ST_LAST_SNOW, sl) = (double)last_snow; S(ST_MELTING, sl) = (double)melting;
+        S(ST_T0, sl) = T[0]; S(ST_T1, sl) = T[1];
+        const double tk = T[0] + KELVIN;                    // initialize_model_state.c:623-626
+        S(ST_LONGUNDEROUT, sl) = STEFAN_B * tk * tk * tk * tk;
+        S(ST_TFOLIAGE, sl) = tair0[c] + k.Tfactor[(size_t)b * C + c];
+        S(ST_FB_SNOW, sl) = 0.; S(ST_FB_FOL, sl) = 0.;
+      }
+  }
+  fclose(f);
+  for (int64_t c = 0; c < C; c++)
+    if (!seen[c]) { h->err = "state file: cell " + std::to_string(gridcel[c]) + " not found"; return VR_ERR_ARG; }
+  CK(cudaSetDevice(h->device));
+  int rc = vr_set_state(h, st.data());
+  if (rc != VR_OK) return rc;
+  h->tair0_host.assign(tair0, tair0 + C);
+  // put_data(rec = -nrecs): the storage terms of the restored state (vicNl.c:287)
+  const size_t U1 = (size_t)(U ? U : 1);
+  CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * h->chunk));
+  CK(h->d_sums.reserve((size_t)h->M.tmap.n * C * h->chunk));
+  if (U > 0) k_restored_units<<<(unsigned)h->ncta, h->cta, 0, h->stream>>>(h->M, h->d_terms.p);
+  k_init_cells<<<(unsigned)((C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p, h->d_sums.p);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
   h->initialised = true;
   return VR_OK;
 }

@@ -597,7 +597,15 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "ORGANIC_FRACT")) g->organic_fract = flag(t);
     else if (!strcasecmp(k, "JULY_TAVG_SUPPLIED")) g->july_tavg_supplied = flag(t);
     else if (!strcasecmp(k, "ALMA_INPUT")) g->alma_input = flag(t);
-    else if (!strcasecmp(k, "INIT_STATE")) g->init_state = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0);
+    else if (!strcasecmp(k, "INIT_STATE")) {
+      g->init_state = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0);
+      if (g->init_state) copy(g->init_state_file, t[1]);
+    }
+    else if (!strcasecmp(k, "STATENAME") && t.size() > 1) copy(g->statename, t[1]);
+    else if (!strcasecmp(k, "STATEYEAR")) g->stateyear = I();
+    else if (!strcasecmp(k, "STATEMONTH")) g->statemonth = I();
+    else if (!strcasecmp(k, "STATEDAY")) g->stateday = I();
+    else if (!strcasecmp(k, "BINARY_STATE_FILE")) g->binary_state_file = !(t.size() > 1 && !strcasecmp(t[1].c_str(), "FALSE"));
     else if (!strcasecmp(k, "MIN_WIND_SPEED")) g->min_wind_speed = (double)strtof(t.size() > 1 ? t[1].c_str() : "0", nullptr);
     else if (!strcasecmp(k, "VP_INTERP")) g->vp_interp = flag(t);
     else if (!strcasecmp(k, "VP_ITER")) {
@@ -695,7 +703,6 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->compute_treeline) return "COMPUTE_TREELINE";
   if (g->dist_prcp) return "DIST_PRCP TRUE";
   if (g->organic_fract) return "ORGANIC_FRACT TRUE";
-  if (g->init_state) return "INIT_STATE";
   if (g->snow_step != g->time_step) return "SNOW_STEP != TIME_STEP";
   if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
   return nullptr;

@@ -22,7 +22,7 @@ LIBPATH = os.environ.get("VICRES_LIB", os.path.join(HERE, "libvicres.so"))
 EXPORTS = ["vr_create", "vr_destroy", "vr_last_error", "vr_default_options", "vr_set_veglib",
            "vr_set_cells", "vr_set_forcing_map", "vr_init_state", "vr_step_block",
            "vr_step_block_device", "vr_synchronize", "vr_state_size", "vr_get_state", "vr_set_state",
-           "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts"]
+           "vr_write_state_file", "vr_read_state_file", "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts"]
 
 _lib = None
 
@@ -58,6 +58,8 @@ def load_library(path=LIBPATH):
     L.vr_step_block.argtypes = [vp, vp, vp, vp]
     L.vr_step_block_device.argtypes = [vp, vp, vp, vp]
     L.vr_synchronize.argtypes = [vp]
+    L.vr_write_state_file.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.vr_read_state_file.argtypes = [vp, C.c_char_p, C.c_int32, vp, vp]
     L.vr_state_size.argtypes = [vp]
     L.vr_state_size.restype = C.c_int64
     L.vr_get_state.argtypes = [vp, vp]
@@ -165,6 +167,17 @@ class VicRes:
         self._keep = (mon, dy, s)
         self._check(self.L.vr_step_block_device(self.h, C.byref(s), C.c_void_p(int(out_ptr)),
                                                 C.c_void_p(int(stream)) if stream else None))
+
+    def write_state_file(self, path, year, month, day, gridcel, binary=False):
+        """the reference's state file (write_model_state.c) of the current state"""
+        g = np.ascontiguousarray(gridcel, dtype=np.int32)
+        self._check(self.L.vr_write_state_file(self.h, path.encode(), year, month, day, int(binary), g.ctypes.data))
+
+    def read_state_file(self, path, tair0, gridcel, binary=False):
+        """restart from a state file of the reference (read_initial_model_state.c); replaces init_state()"""
+        g = np.ascontiguousarray(gridcel, dtype=np.int32)
+        t = np.ascontiguousarray(tair0, dtype=np.float64)
+        self._check(self.L.vr_read_state_file(self.h, path.encode(), int(binary), t.ctypes.data, g.ctypes.data))
 
     def synchronize(self):
         self._check(self.L.vr_synchronize(self.h))

@@ -51,17 +51,29 @@ def run(global_path, device=0, write=True, records_per_block=0):
     opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, max_snow_temp=g.max_snow_temp,
                               min_rain_temp=g.min_rain_temp, wind_h=g.wind_h)
     m = model.VicRes(opt, lib, cells, device=device)
-    m.init_state(f_dev[abi.FORCING_FIELDS.index("air_temp"), 0].cpu().numpy())
+    tair0 = f_dev[abi.FORCING_FIELDS.index("air_temp"), 0].cpu().numpy()
+    if g.init_state:                     # INIT_STATE <file>: read_initial_model_state instead of the cold start
+        m.read_state_file(g.init_state_file, tair0, meta["gridcel"], binary=bool(g.binary_state_file))
+    else:
+        m.init_state(tair0)
     dmy = g.dmy()
     out_dev = torch.empty((opt.n_out, nrecs, Cn), dtype=torch.float64, device=dev)
+    # STATENAME + STATEYEAR/MONTH/DAY: the state after the last record of that day (vicNl.c:311-318)
+    save_after = -1
+    if g.statename:
+        hit = np.flatnonzero((dmy[:, 0] == g.stateyear) & (dmy[:, 1] == g.statemonth) & (dmy[:, 2] == g.stateday))
+        save_after = int(hit[-1]) if len(hit) else -1
     B = records_per_block or nrecs
-    for r0 in range(0, nrecs, B):
-        r1 = min(nrecs, r0 + B)
+    cuts = sorted(set(list(range(0, nrecs, B)) + ([save_after + 1] if 0 <= save_after < nrecs - 1 else []) + [nrecs]))
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
         blk = torch.empty((opt.n_out, r1 - r0, Cn), dtype=torch.float64, device=dev)
         fb = f_dev[:, r0:r1].contiguous()
         m.step_device(dmy[r0:r1, 1], dmy[r0:r1, 4], [fb[f].data_ptr() for f in range(abi.VR_NFORCING)], blk.data_ptr())
         m.synchronize()
         out_dev[:, r0:r1] = blk
+        if r1 - 1 == save_after:
+            m.write_state_file("%s_%04d%02d%02d" % (g.statename, g.stateyear, g.statemonth, g.stateday), g.stateyear, g.statemonth,
+                               g.stateday, meta["gridcel"], binary=bool(g.binary_state_file))
     out = out_dev.cpu().numpy()
     m.close()
     if write:
