@@ -53,7 +53,8 @@ def main():
         shutil.copytree(work, dst)
         for g in ("global.txt", "global_restart.txt"):
             p = os.path.join(dst, g)
-            open(p, "w").write(open(p).read().replace(work, "@DIR@"))
+            txt_g = open(p).read().replace(work, "@DIR@")
+            open(p, "w").write(txt_g)
     sz = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(dst) for f in fs)
     print("state_case: %.0f kB" % (sz / 1e3))
     print(open(os.path.join(dst, "state_19840429")).read()[:900])
