@@ -15,7 +15,7 @@ CASE = os.path.join(GOLDEN, "state_case")
 def _stage(tmp_path):
     dst = tmp_path / "case"
     shutil.copytree(CASE, dst)
-    for g in ("global.txt", "global_restart.txt"):
+    for g in ("global.txt", "global_restart.txt", "global_bin.txt", "global_restart_bin.txt"):
         p = dst / g
         p.write_text(p.read_text().replace("@DIR@", str(dst)))
     shutil.rmtree(dst / "results", ignore_errors=True)
@@ -92,3 +92,49 @@ def test_restart_from_a_state_file_reproduces_the_reference_restart(tmp_path, so
     nb, nt = _compare_results(str(dst / "results"), os.path.join(CASE, "results_restart"))
     print("RESTART (%s state file): %d of %d printed values differ from the reference's restarted run" % (source, nb, nt))
     assert nb <= 0.01 * nt
+
+
+@pytest.mark.gpu
+def test_binary_state_file_restart_and_layout(tmp_path):
+    """BINARY_STATE_FILE TRUE: restart on the GPU from the reference's binary state file against vicNl restarted from it;
+    and the binary file the GPU run writes has the reference's byte layout (same size, same integers, doubles to 1e-9)"""
+    from vicres_b200 import vicnl
+    dst = _stage(tmp_path)
+    assert vicnl.main(["-g", str(dst / "global_restart_bin.txt")]) == 0
+    nb, nt = _compare_results(str(dst / "results"), os.path.join(CASE, "results_restart_bin"))
+    print("RESTART (reference binary state file): %d of %d printed values differ" % (nb, nt))
+    assert nb <= 0.01 * nt
+    ref = open(os.path.join(CASE, "statebin_19840429"), "rb").read()
+    os.remove(dst / "statebin_19840429")
+    shutil.rmtree(dst / "results")
+    os.makedirs(dst / "results")
+    assert vicnl.main(["-g", str(dst / "global_bin.txt")]) == 0
+    mine = open(dst / "statebin_19840429", "rb").read()
+    assert len(mine) == len(ref)
+    # walk the reference's layout: header 5 ints; per cell 4 ints + 6 doubles; per (veg, band) 2 ints, 2L doubles,
+    # [Wdew], int, char, 9 doubles, 3 doubles
+    import struct
+    off, L = 20, 3
+    assert mine[:20] == ref[:20]
+    ndbl = nbad = 0
+    while off < len(ref):
+        cell, nveg, nband, nbytes = struct.unpack_from("<4i", ref, off)
+        assert struct.unpack_from("<4i", mine, off) == (cell, nveg, nband, nbytes)
+        off += 16
+        spans = [(off, 6)]
+        off += 48
+        for veg in range(nveg + 1):
+            for b in range(nband):
+                assert mine[off:off + 8] == ref[off:off + 8]
+                off += 8
+                n = 2 * L + (1 if veg < nveg else 0)
+                spans.append((off, n)); off += 8 * n
+                assert mine[off:off + 5] == ref[off:off + 5]          # last_snow, MELTING
+                off += 5
+                spans.append((off, 12)); off += 96
+        for o, n in spans:
+            a, r = np.frombuffer(mine, "<f8", n, o), np.frombuffer(ref, "<f8", n, o)
+            ndbl += n
+            nbad += int((np.abs(a - r) > 1e-9 * np.maximum(np.abs(r), 1e-3)).sum())
+    print("BINARY STATE FILE: %d of %d doubles beyond 1e-9 of the reference's" % (nbad, ndbl))
+    assert nbad <= 0.01 * ndbl

@@ -50,8 +50,21 @@ def main():
         r = subprocess.run([VICNL, "-g", g2], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
         shutil.move(os.path.join(work, "results"), os.path.join(work, "results_restart"))
+        # the same pair with BINARY_STATE_FILE TRUE (exact doubles instead of "%f" columns)
+        g1b = os.path.join(work, "global_bin.txt")
+        open(g1b, "w").write(txt.replace("BINARY_STATE_FILE FALSE", "BINARY_STATE_FILE TRUE").replace("%s/state\n" % work, "%s/statebin\n" % work))
+        os.makedirs(os.path.join(work, "results"))
+        r = subprocess.run([VICNL, "-g", g1b], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        shutil.rmtree(os.path.join(work, "results"))
+        os.makedirs(os.path.join(work, "results"))
+        g2b = os.path.join(work, "global_restart_bin.txt")
+        open(g2b, "w").write("\n".join(txt2[:-1] + ["BINARY_STATE_FILE TRUE", "INIT_STATE %s/statebin_19840429" % work]) + "\n")
+        r = subprocess.run([VICNL, "-g", g2b], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        shutil.move(os.path.join(work, "results"), os.path.join(work, "results_restart_bin"))
         shutil.copytree(work, dst)
-        for g in ("global.txt", "global_restart.txt"):
+        for g in ("global.txt", "global_restart.txt", "global_bin.txt", "global_restart_bin.txt"):
             p = os.path.join(dst, g)
             txt_g = open(p).read().replace(work, "@DIR@")
             open(p, "w").write(txt_g)

@@ -857,10 +857,13 @@ int vr_write_state_file(vr_handle *h, const char *path, int32_t year, int32_t mo
       const int64_t t = veg < Nveg ? t0 + veg : (has_bare ? t1 - 1 : -1);
       for (int b = 0; b < NB; b++) {
         const int64_t sl = t >= 0 ? slot[(size_t)t * NB + b] : -1;
+        // tiles / bands without area keep what initialize_model_state gave them: the initial moisture everywhere,
+        // node temperatures only for tiles with Cv > 0 (:336-445)
         double moist[MAXL], wdew = 0., sn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, T[3] = {surf, surf, k.avg_temp[c]};
+        if (t < 0) T[0] = T[1] = T[2] = 0.;
         int last_snow = (int)MISSINGV, melting = 0;
-        for (int l = 0; l < NL; l++) {        // tiles / bands without area keep what initialize_model_state gave them
-          moist[l] = t >= 0 ? k.init_moist[(size_t)l * C + c] : 0.;
+        for (int l = 0; l < NL; l++) {
+          moist[l] = k.init_moist[(size_t)l * C + c];
           if (moist[l] > k.max_moist[(size_t)l * C + c]) moist[l] = k.max_moist[(size_t)l * C + c];
         }
         if (sl >= 0) {
@@ -871,7 +874,8 @@ int vr_write_state_file(vr_handle *h, const char *path, int32_t year, int32_t mo
                             ST_SNOW_CANOPY};
           for (int i = 0; i < 9; i++) sn[i] = S(w[i], sl);
           T[0] = S(ST_T0, sl); T[1] = S(ST_T1, sl);
-          T[2] = k.avg_temp[c] + k.Tfactor[(size_t)b * C + c];
+          // the third node is diagnosed from T1 each step (calc_surf_energy_bal.c:588, Zsum_node[2] = dp)
+          T[2] = k.avg_temp[c] + (T[1] - k.avg_temp[c]) * exp(-(k.dp[c] - k.depth0[c]) / k.dp[c]);
         }
         if (binary) {
           wi(veg); wi(b);
