@@ -738,6 +738,33 @@ VA_HD double hourly_tair(const Ctx &x, const Geo &g, int64_t c, int hour)
   return y0 + dx * (0. + dx * (yc3 + dx * yc4));
 }
 
+// The same value with the interval's coefficients kept while consecutive hours stay in it (a record's hours change
+// interval at most three times): identical arithmetic, evaluated once per interval instead of once per hour.
+struct SplineSeg { int klo = -1; double x0 = 0., y0 = 0., yc3 = 0., yc4 = 0.; };
+VA_HD double hourly_tair_cached(const Ctx &x, const Geo &g, int64_t c, int hour, SplineSeg &sg)
+{
+  const int64_t lc = c - x.c0;
+  const int ndays = g.ndl, n = 2 * ndays + 2;
+  const double xbar = hour;
+  const int d = hour / 24;
+  int klo = 2 * d;
+  if (node_x(x, lc, ndays, 2 * d + 1) <= xbar) klo = 2 * d + 1;
+  if (node_x(x, lc, ndays, 2 * d + 2) <= xbar) klo = 2 * d + 2;
+  if (klo > n - 2) klo = n - 2;
+  if (klo != sg.klo) {
+    const double x0 = node_x(x, lc, ndays, klo), x1 = node_x(x, lc, ndays, klo + 1);
+    const double y0 = node_y(x, g, c, ndays, klo), y1 = node_y(x, g, c, ndays, klo + 1);
+    const double dx = x1 - x0;
+    const double divdf1 = (y1 - y0) / dx;
+    const double divdf3 = 0. + 0. - 2 * divdf1;
+    sg.klo = klo; sg.x0 = x0; sg.y0 = y0;
+    sg.yc3 = (divdf1 - 0. - divdf3) / dx;
+    sg.yc4 = divdf3 / (dx * dx);
+  }
+  const double dx = xbar - sg.x0;
+  return sg.y0 + dx * (0. + dx * (sg.yc3 + dx * sg.yc4));
+}
+
 // local VP of one hour, initialize_atmos.c:1229-1275
 VA_HD double hourly_vp(const Ctx &x, const Geo &g, int64_t lc, int idx)
 {
@@ -777,7 +804,8 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
     // the MIN_WIND_SPEED clamp at :654-657 addresses wind[NF], one past the record's value: no effect
     wind = x.has_wind ? local_daily(x.r_wind, x, g, c, dayi) : 3.0;
     double s = 0;                                          // :1005-1019
-    for (int idx = hour; idx < hour + dt; idx++) s += hourly_tair(x, g, c, idx);
+    SplineSeg sg;
+    for (int idx = hour; idx < hour + dt; idx++) s += hourly_tair_cached(x, g, c, idx, sg);
     ta = s / dt;
   }
   else {                                                   // :616-628, :662-678, :737-752
@@ -798,9 +826,16 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
     ta = s / dt;
   }
   double sw = 0, vp = 0;                                   // :974-987, :1278-1291
+  int rad_day = -1, rad_ydi = 0;
+  double tmp_rad = 0.;
   for (int idx = hour; idx < hour + dt; idx++) {
     const int d = idx / 24;
-    sw += hourly_rad(x, g, lc, d, idx - d * 24);
+    if (d != rad_day) {                                    // hourly_rad()'s per-day factor, once per day
+      rad_day = d;
+      rad_ydi = ydi_of(x, g, d);
+      tmp_rad = x.srad[(int64_t)d * x.CB + lc] * x.dayl[(int64_t)rad_ydi * x.CB + lc] / 3600.;
+    }
+    sw += x.hf[((int64_t)rad_ydi * 24 + (idx - d * 24)) * x.CB + lc] * tmp_rad;
     vp += hourly_vp(x, g, lc, idx);
   }
   sw /= dt;
