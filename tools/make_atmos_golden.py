@@ -45,6 +45,10 @@ CASES = {
     "atmos_annual_nointerp": (dict(ncells=3, ndays=300, startyear=1993, seed=308,
                                    extra_global="VP_ITER VP_ITER_ANNUAL\nVP_INTERP FALSE\nLW_TYPE LW_IDSO\nSW_PREC_THRESH 0.1"),
                               dict(vp_iter="VP_ITER_ANNUAL", vp_interp=False, lw_type="LW_IDSO", sw_prec_thresh=0.1)),
+    # Not a fixture: STARTHOUR != 0 with sub-daily forcing.  The reference then indexes its forcing array up to
+    # (Ndays_local*24 - starthour + hour_offset_int)/FORCE_DT - fstepspday, past the nrecs records it allocated
+    # (initialize_atmos.c:511-513), so its last local day -- and through the precipitation totals all of MTCLIM's humidity --
+    # depends on whatever follows the array in memory.  The library reads zeros there (what calloc gives inside the array).
     "atmos_daily_no_wind": (dict(ncells=3, ndays=120, startyear=1996, lat_range=(-35, 55), off_gmt=-2, no_wind=True, seed=310),
                             dict(has_wind=False)),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,
@@ -77,7 +81,8 @@ def save(name, gfile, dump, kw, ov, start=None):
     nrecs = int(d["nrecs"][0])
     nrf = nrecs * dt // (24 if daily else dt)
     dmy = d["dmy"]
-    arrays = {"raw": raw[:, :nrf], "atmos": np.ascontiguousarray(atm),
+    skip = 0 if daily else int(dmy[0, 3]) // dt            # forcing records before the model's first hour (FORCEHOUR 0)
+    arrays = {"raw": raw[:, skip:skip + nrf], "atmos": np.ascontiguousarray(atm),
               "meta": np.array([dt, nrecs, dmy[0, 0], dmy[0, 1], dmy[0, 2], dmy[0, 3], 0 if daily else 1, 24 if daily else dt],
                                dtype=np.int64),
               "ov_keys": np.array(list(ov.keys()) or [""]), "ov_vals": np.array([str(v) for v in ov.values()] or [""])}
