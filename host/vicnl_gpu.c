@@ -1,0 +1,161 @@
+/* vicnl_gpu.c -- `vicNl -g <global parameter file>` as a plain C host program over the C ABI of libvicres.so.
+ *
+ * What the reference's main() (runoff/model/vicNl.c:11-380) does cell by cell -- read_soilparam / read_vegparam /
+ * read_snowband, initialize_atmos, initialize_model_state (or INIT_STATE), the record loop of full_energy + put_data,
+ * write_data, write_model_state -- this program does for all cells of the soil file with the batched calls of
+ * include/vicres.h, vicres_files.h and vicres_atmos.h:
+ *
+ *   vr_global_read -> vr_params_read -> vr_read_forcing_file (per cell) -> vr_atmos_prepare
+ *   -> vr_create / vr_set_veglib / vr_set_cells / vr_init_state | vr_read_state_file
+ *   -> vr_step_block (in blocks of records; the state stays on the GPU) [-> vr_write_state_file]
+ *   -> vr_write_results ("fluxes_<lat>_<lng>", "snow_<lat>_<lng>")
+ *
+ * Build:  gcc -O2 -Iinclude -o host/vicnl_gpu host/vicnl_gpu.c -Lvicres_b200 -lvicres -Wl,-rpath,$PWD/vicres_b200
+ * No numerics here: every number comes from the library, which has no CPU path.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "vicres.h"
+#include "vicres_files.h"
+#include "vicres_atmos.h"
+
+static void die(const char *what, const char *why)
+{
+  fprintf(stderr, "vicnl_gpu: %s: %s\n", what, why ? why : "");
+  exit(1);
+}
+
+int main(int argc, char **argv)
+{
+  const char *gfile = NULL;
+  int device = 0, block = 365, i;
+  for (i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "-g") && i + 1 < argc) gfile = argv[++i];
+    else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--block") && i + 1 < argc) block = atoi(argv[++i]);
+  }
+  if (!gfile) die("usage", "vicnl_gpu -g <global parameter file> [--device N] [--block records]");
+
+  static vr_global g;
+  if (vr_global_read(gfile, &g) != VR_OK) die("global file", vr_params_last_error());
+  if (vr_global_unsupported(&g)) die("option outside the water-balance path of this library", vr_global_unsupported(&g));
+
+  /* parameter files */
+  vr_param_files pf;
+  memset(&pf, 0, sizeof pf);
+  pf.nlayer = g.nlayer; pf.nbands = g.snow_band; pf.root_zones = g.root_zones; pf.vegparam_lai = g.vegparam_lai;
+  pf.lai_from_vegparam = g.lai_from_vegparam; pf.soil = g.soil; pf.veglib = g.veglib; pf.vegparam = g.vegparam;
+  pf.snowband = g.snowband[0] ? g.snowband : NULL;
+  vr_params *par = NULL;
+  if (vr_params_read(&pf, &par) != VR_OK) die("parameter files", vr_params_last_error());
+  const vr_cells *cells = vr_params_cells(par);
+  const int64_t C = cells->ncell;
+  const float *lat = vr_params_lat(par), *lng = vr_params_lng(par);
+  const int32_t *gridcel = vr_params_gridcel(par);
+
+  /* calendar */
+  const int nrecs = g.nrecs;
+  int32_t *year = malloc(sizeof(int32_t) * nrecs), *month = malloc(sizeof(int32_t) * nrecs), *day = malloc(sizeof(int32_t) * nrecs),
+          *hour = malloc(sizeof(int32_t) * nrecs), *doy = malloc(sizeof(int32_t) * nrecs);
+  if (vr_make_dmy(&g, year, month, day, hour, doy) != VR_OK) die("calendar", vr_params_last_error());
+
+  /* forcing files -> raw columns [type][record][cell] */
+  const int64_t nrf = (int64_t)nrecs * g.time_step / g.force_dt;
+  const int nt = g.n_force_types;
+  double *one = malloc(sizeof(double) * nt * nrf), *raw = calloc((size_t)nt * nrf * C, sizeof(double));
+  int64_t c, r;
+  int t, col_prec = -1, col_ta = -1, col_tb = -1, col_wind = -1, subdaily = 0;
+  for (t = 0; t < nt; t++) {
+    if (!strcmp(g.force_type[t], "PREC")) col_prec = t;
+    else if (!strcmp(g.force_type[t], "TMAX")) col_ta = t;
+    else if (!strcmp(g.force_type[t], "TMIN")) col_tb = t;
+    else if (!strcmp(g.force_type[t], "AIR_TEMP")) { col_ta = t; subdaily = 1; }
+    else if (!strcmp(g.force_type[t], "WIND")) col_wind = t;
+    else if (strcmp(g.force_type[t], "SKIP")) die("forcing column outside the supported layouts", g.force_type[t]);
+  }
+  if (col_prec < 0 || col_ta < 0 || (!subdaily && col_tb < 0)) die("forcing file", "needs PREC and TMAX+TMIN or AIR_TEMP");
+  for (c = 0; c < C; c++) {
+    char path[1200];
+    snprintf(path, sizeof path, "%s%.*f_%.*f", g.forcing1, g.grid_decimal, lat[c], g.grid_decimal, lng[c]);
+    int64_t got = vr_read_forcing_file(&g, path, nrf, one);
+    if (got < 0) die(path, vr_params_last_error());
+    for (t = 0; t < nt; t++)
+      for (r = 0; r < got; r++) raw[((size_t)t * nrf + r) * C + c] = one[(size_t)t * nrf + r];
+  }
+
+  /* initialize_atmos for all cells */
+  vr_atmos_options ao;
+  vr_atmos_default_options(&ao);
+  ao.time_step = g.time_step; ao.nrecs = nrecs; ao.startyear = g.startyear; ao.startmonth = g.startmonth;
+  ao.startday = g.startday; ao.starthour = g.starthour; ao.force_dt = g.force_dt;
+  ao.layout = subdaily ? VR_ATMOS_SUBDAILY_AIR_TEMP : VR_ATMOS_DAILY_TMAX_TMIN;
+  ao.has_wind = col_wind >= 0; ao.min_wind_speed = g.min_wind_speed; ao.vp_interp = g.vp_interp; ao.vp_iter = g.vp_iter;
+  ao.mtclim_swe_corr = g.mtclim_swe_corr; ao.lw_type = g.lw_type; ao.lw_cloud = g.lw_cloud; ao.plapse = g.plapse;
+  ao.sw_prec_thresh = g.sw_prec_thresh;
+  vr_atmos_cells site;
+  memset(&site, 0, sizeof site);
+  site.ncell = C; site.lat = vr_params_site(par, 0); site.lng = vr_params_site(par, 1);
+  site.time_zone_lng = vr_params_site(par, 2); site.elevation = vr_params_site(par, 3); site.annual_prec = vr_params_site(par, 4);
+  vr_atmos_raw rw;
+  rw.nrec_forcing = nrf; rw.prec = raw + (size_t)col_prec * nrf * C; rw.t_a = raw + (size_t)col_ta * nrf * C;
+  rw.t_b = col_tb >= 0 ? raw + (size_t)col_tb * nrf * C : NULL; rw.wind = col_wind >= 0 ? raw + (size_t)col_wind * nrf * C : NULL;
+  double *field[VR_NFORCING];
+  for (i = 0; i < VR_NFORCING; i++) field[i] = malloc(sizeof(double) * (size_t)nrecs * C);
+  if (vr_atmos_prepare(device, &ao, &site, &rw, field) != VR_OK) die("forcing preparation", vr_atmos_last_error());
+
+  /* the model */
+  vr_options opt;
+  vr_default_options(&opt, g.nlayer);
+  opt.nbands = g.snow_band; opt.dt_hours = g.time_step; opt.snow_step_hours = g.snow_step;
+  opt.max_snow_temp = g.max_snow_temp; opt.min_rain_temp = g.min_rain_temp; opt.wind_h = g.wind_h;
+  vr_handle *h = NULL;
+  if (vr_create(&opt, device, &h) != VR_OK) die("vr_create", vr_last_error(NULL));
+  if (vr_set_veglib(h, vr_params_veglib(par)) != VR_OK || vr_set_cells(h, cells) != VR_OK) die("parameters", vr_last_error(h));
+  const double *tair0 = field[VR_F_AIR_TEMP];                 /* atmos[0].air_temp of every cell */
+  if (g.init_state) {
+    if (vr_read_state_file(h, g.init_state_file, g.binary_state_file, tair0, gridcel) != VR_OK) die("INIT_STATE", vr_last_error(h));
+  }
+  else if (vr_init_state(h, tair0) != VR_OK) die("vr_init_state", vr_last_error(h));
+
+  /* record loop in blocks; a block ends at the day whose state is to be saved (vicNl.c:311-318) */
+  const int n_out = opt.n_out;
+  double *out = malloc(sizeof(double) * (size_t)n_out * nrecs * C), *blk = malloc(sizeof(double) * (size_t)n_out * block * C);
+  int32_t *status = calloc(C, sizeof(int32_t));
+  int save_after = -1, r0;
+  if (g.statename[0])
+    for (i = 0; i < nrecs; i++)
+      if (year[i] == g.stateyear && month[i] == g.statemonth && day[i] == g.stateday) save_after = i;
+  for (r0 = 0; r0 < nrecs;) {
+    int nr = nrecs - r0 < block ? nrecs - r0 : block, v;
+    if (save_after >= r0 && save_after < r0 + nr) nr = save_after - r0 + 1;
+    vr_forcing f;
+    f.nrec = nr; f.month = month + r0; f.day_in_year = doy + r0;
+    for (i = 0; i < VR_NFORCING; i++) f.field[i] = field[i] + (size_t)r0 * C;
+    int rc = vr_step_block(h, &f, blk, status);
+    if (rc != VR_OK && rc != VR_ERR_CELL) die("vr_step_block", vr_last_error(h));
+    for (v = 0; v < n_out; v++)
+      memcpy(out + ((size_t)v * nrecs + r0) * C, blk + (size_t)v * nr * C, sizeof(double) * (size_t)nr * C);
+    if (r0 + nr - 1 == save_after) {
+      char path[1200];
+      snprintf(path, sizeof path, "%s_%04d%02d%02d", g.statename, g.stateyear, g.statemonth, g.stateday);
+      if (vr_write_state_file(h, path, g.stateyear, g.statemonth, g.stateday, g.binary_state_file, gridcel) != VR_OK)
+        die("state file", vr_last_error(h));
+    }
+    r0 += nr;
+  }
+
+  /* write_data: the default fluxes / snow files (set_output_defaults.c:66-93) */
+  const int nflux = 20 + g.nlayer - 1;
+  int32_t cols[VR_MAX_OUT];
+  for (i = 0; i < nflux; i++) cols[i] = i;
+  if (vr_write_results(g.result_dir, "fluxes", g.grid_decimal, C, lat, lng, nrecs, year, month, day, g.time_step < 24 ? hour : NULL,
+                       nflux, cols, out) != VR_OK) die("fluxes files", vr_params_last_error());
+  for (i = 0; i < 4; i++) cols[i] = nflux + i;
+  if (vr_write_results(g.result_dir, "snow", g.grid_decimal, C, lat, lng, nrecs, year, month, day, g.time_step < 24 ? hour : NULL,
+                       4, cols, out) != VR_OK) die("snow files", vr_params_last_error());
+  fprintf(stderr, "vicnl_gpu: %lld cells x %d records written to %s\n", (long long)C, nrecs, g.result_dir);
+  vr_destroy(h);
+  vr_params_free(par);
+  return 0;
+}

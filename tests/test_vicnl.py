@@ -61,3 +61,50 @@ def test_vicnl_command_line_reproduces_the_reference_result_files(name, tmp_path
         ntot += a.size
     print("VICNL %s: %d of %d printed values differ from the reference's files (by one unit of the last digit)" % (name, nbad, ntot))
     assert nbad <= 0.01 * ntot
+
+
+def _build_c_driver(tmp_path):
+    import subprocess
+    from common import ROOT
+    from vicres_b200 import build
+    build.build()
+    exe = str(tmp_path / "vicnl_gpu")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "host", "vicnl_gpu.c"), "-L", os.path.join(ROOT, "vicres_b200"), "-lvicres",
+                    "-Wl,-rpath," + os.path.join(ROOT, "vicres_b200")], check=True)
+    return exe
+
+
+def test_c_host_driver_compiles_against_the_headers(tmp_path):
+    """CPU tier: host/vicnl_gpu.c is plain C over include/*.h and links against libvicres.so; without a GPU it stops
+    at the first device call with the library's message (no CPU path)."""
+    import subprocess
+    import torch
+    exe = _build_c_driver(tmp_path)
+    gpath, _, _ = _stage("daily", tmp_path)
+    r = subprocess.run([exe, "-g", gpath], capture_output=True, text=True)
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "no CPU path" in r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["daily", "sub3h"])
+def test_c_host_driver_reproduces_the_reference_result_files(name, tmp_path):
+    """the same command line from the plain C host program (host/vicnl_gpu.c), records in blocks of 50"""
+    import subprocess
+    exe = _build_c_driver(tmp_path)
+    gpath, res, ref = _stage(name, tmp_path)
+    r = subprocess.run([exe, "-g", gpath, "--block", "50"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert sorted(os.listdir(res)) == sorted(os.listdir(ref))
+    nbad = ntot = 0
+    for n in sorted(os.listdir(ref)):
+        a, b = np.loadtxt(os.path.join(res, n)), np.loadtxt(os.path.join(ref, n))
+        assert a.shape == b.shape, n
+        assert np.all(np.abs(a - b) <= 1.0001e-4 + 1e-5 * np.abs(b)), n
+        nbad += int((a != b).sum())
+        ntot += a.size
+    print("VICNL_GPU (C host) %s: %d of %d printed values differ from the reference's files" % (name, nbad, ntot))
+    assert nbad <= 0.01 * ntot
