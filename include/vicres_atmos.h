@@ -17,8 +17,8 @@
  * Supported forcing files (everything else -> VR_ERR_UNSUPPORTED, nothing is silently ignored):
  *   VR_ATMOS_DAILY_TMAX_TMIN    FORCE_DT 24, columns PREC TMAX TMIN [WIND]   (the bundled basin's format)
  *   VR_ATMOS_SUBDAILY_AIR_TEMP  FORCE_DT < 24, columns PREC AIR_TEMP [WIND]
- * with SNOW_STEP == TIME_STEP (NF == 1), ALMA_INPUT FALSE, no observed SHORTWAVE/LONGWAVE/VP/PRESSURE/DENSITY
- * columns.  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
+ * each optionally with observed SHORTWAVE, LONGWAVE and VP columns at the same FORCE_DT; SNOW_STEP == TIME_STEP
+ * (NF == 1), ALMA_INPUT FALSE, no QAIR / REL_HUMID / PRESSURE / DENSITY columns.  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
  */
 #ifndef VICRES_ATMOS_H
 #define VICRES_ATMOS_H
@@ -72,6 +72,10 @@ typedef struct vr_atmos_cells {
 typedef struct vr_atmos_raw {
   int64_t nrec_forcing;
   const double *prec, *t_a, *t_b, *wind;
+  /* optional observed columns at the file's FORCE_DT, NULL when absent: SHORTWAVE (W/m2), LONGWAVE (W/m2), VP (kPa as in
+   * the file; converted to Pa like initialize_atmos.c:404-414).  With them MTCLIM runs in its "observed" modes
+   * (ctrl.insw / ctrl.invp, mtclim_vic.c:982-995, 1173-1185). */
+  const double *shortwave, *longwave, *vp;
 } vr_atmos_raw;
 
 /* Number of local days MTCLIM runs over for a cell with this integer hour offset (Ndays or Ndays+1). */

@@ -178,7 +178,7 @@ static void hourly_t(int ndays, const int *tmaxhour, const double *tmax, const i
 }
 
 typedef struct mt_data {
-  int ndays;
+  int ndays, insw, invp;
   int *yday;
   double *tmax, *tmin, *prcp, *s_tmax, *s_tmin, *s_tday, *s_prcp, *s_hum, *s_srad, *s_dayl, *s_swe, *s_fdir, *s_tskc,
          *s_tfmax;
@@ -208,7 +208,15 @@ static void srad_humidity_onetime(const vr_atmos_options *o, mt_data *d, double 
       if (sc > 100.0) sc = 100.0;
     }
     else sc = 0.0;
-    d->s_srad[i] = srad1 + srad2 + sc;
+    if (d->insw) {                                     /* :1173-1182 */
+      double potrad = (srad1 + srad2 + sc) * daylength[yday] / t_final / 86400;
+      if (potrad > 0 && d->s_srad[i] > 0 && daylength[yday] > 0) {
+        d->s_tfmax[i] = (d->s_srad[i]) / (potrad * t_tmax);
+        if (d->s_tfmax[i] > 1.0) d->s_tfmax[i] = 1.0;
+      }
+      else d->s_tfmax[i] = 1.0;
+    }
+    else d->s_srad[i] = srad1 + srad2 + sc;
     if (o->lw_cloud == VR_LW_CLOUD_DEARDORFF) d->s_tskc[i] = (1. - d->s_tfmax[i]);
     else d->s_tskc[i] = sqrt((1. - d->s_tfmax[i]) / 0.65);
     d->s_fdir[i] = pdir;
@@ -364,7 +372,7 @@ static void srad_humidity_iterative(const vr_atmos_options *o, mt_data *d, doubl
     if (d->prcp[i] > o->sw_prec_thresh) t_fmax *= RAIN_SCALAR;
     d->s_tfmax[i] = t_fmax;
   }
-  for (i = 0; i < ndays; i++) { tdew[i] = d->s_tmin[i]; pva[i] = svp(tdew[i]); }   /* :976-996 */
+  for (i = 0; i < ndays; i++) { tdew[i] = d->s_tmin[i]; pva[i] = d->invp ? d->s_hum[i] : svp(tdew[i]); }   /* :976-996 */
   pa = atm_pres(site_elev);                         /* :999-1005 */
   for (i = 0; i < ndays; i++) {
     d->s_dayl[i] = daylength[d->yday[i] - 1];
@@ -375,7 +383,7 @@ static void srad_humidity_iterative(const vr_atmos_options *o, mt_data *d, doubl
   sum_pet = 0.0;                                    /* :1011-1015 */
   for (i = 0; i < ndays; i++) sum_pet += pet[i];
   ann_pet = (sum_pet / (double)ndays) * 365.25;
-  if (o->vp_iter == VR_VP_ITER_ANNUAL && ann_pet / ann_prcp >= 2.5)   /* :1018-1023 */
+  if (d->invp || (o->vp_iter == VR_VP_ITER_ANNUAL && ann_pet / ann_prcp >= 2.5))   /* :1018-1023 */
     for (i = 0; i < ndays; i++) { tdew[i] = tdew_save[i]; pva[i] = pva_save[i]; }
   if (o->vp_iter == VR_VP_ITER_ALWAYS || (o->vp_iter == VR_VP_ITER_ANNUAL && ann_pet / ann_prcp >= 2.5) ||
       o->vp_iter == VR_VP_ITER_CONVERGE)            /* :1026-1038 */
@@ -391,7 +399,7 @@ static void srad_humidity_iterative(const vr_atmos_options *o, mt_data *d, doubl
     rmse_tdew = pow(rmse_tdew, 0.5);
     iter++;
   }
-  for (i = 0; i < ndays; i++) d->s_hum[i] = pva[i]; /* :1060-1066 */
+  if (!d->invp) for (i = 0; i < ndays; i++) d->s_hum[i] = pva[i]; /* :1060-1066 */
   free(dtr); free(sm_dtr); free(parray); free(window); free(tdew); free(pet); free(pva); free(tdew_save); free(pva_save);
 }
 
@@ -411,8 +419,8 @@ int32_t ao_ndays(const vr_atmos_options *o)
  * dbg (optional, [6][Ndays_local]): daily s_srad, s_dayl, tskc, vp, tminhour, tmaxhour. */
 int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_lng, double elevation, double annual_prec,
             double slope, double aspect, double ehoriz, double whoriz, int64_t stride, int64_t nrec_forcing,
-            const double *c_prec, const double *c_ta, const double *c_tb, const double *c_wind, double *const out[VR_NFORCING],
-            double *dbg)
+            const double *c_prec, const double *c_ta, const double *c_tb, const double *c_wind, const double *c_sw,
+            const double *c_lw, const double *c_vp, double *const out[VR_NFORCING], double *dbg)
 {
   static const int month_days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
   const int dt = o->time_step, nrecs = o->nrecs, fdt = o->force_dt, daily = (o->layout == VR_ATMOS_DAILY_TMAX_TMIN);
@@ -422,6 +430,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   int Ndays = ao_ndays(o), Ndays_local, local_starthour, local_startday, local_startmonth, local_startyear;
   int day_in_year, year, month, day, rec, hour, idx, i, j, k, shift;
   int *yday, *tmaxhour, *tminhour;
+  double *l_sw, *l_lw;
   double *l_prec, *l_ta, *l_tb, *l_wind, *l_vp, *hourlyrad, *prec, *tmax, *tmin, *tair, *tskc, *daily_vp, *radfract;
   mt_data d;
   hour_offset -= hour_offset_int;
@@ -463,6 +472,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   l_prec = calloc(Ndays_local * 24, sizeof(double)); l_ta = calloc(Ndays_local * 24, sizeof(double));
   l_tb = calloc(Ndays_local * 24, sizeof(double)); l_wind = calloc(Ndays_local * 24, sizeof(double));
   l_vp = calloc(Ndays_local * 24, sizeof(double)); hourlyrad = calloc(Ndays_local * 24, sizeof(double));
+  l_sw = calloc(Ndays_local * 24, sizeof(double)); l_lw = calloc(Ndays_local * 24, sizeof(double));
   tair = calloc(Ndays_local * 24, sizeof(double));
   prec = calloc(Ndays_local, sizeof(double)); tmax = calloc(Ndays_local, sizeof(double));
   tmin = calloc(Ndays_local, sizeof(double)); tskc = calloc(Ndays_local, sizeof(double));
@@ -481,6 +491,8 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i);
       l_tb[idx] = fetch(c_tb, stride, nrec_forcing, i);
       l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
+      l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
+      l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * 1000.;       /* kPa2Pa, :404-414 */
     }
   }
   else {
@@ -492,6 +504,8 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i) / fdt;
       l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i);
       l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
+      l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
+      l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * 1000.;
     }
   }
   shift = (o->starthour - hour_offset_int < 0) ? 24 : 0;
@@ -535,8 +549,24 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     }
   }
 
+  /* vapour pressure, part 1 (:869-915) and shortwave, part 1 (:925-940) */
+  if (c_vp) {
+    for (day = 0; day < Ndays_local; day++) {
+      if (fdt == 24) daily_vp[day] = l_vp[day];
+      else {
+        daily_vp[day] = 0;
+        for (hour = 0; hour < 24; hour++) daily_vp[day] += l_vp[day * 24 + hour];
+        daily_vp[day] /= 24;
+      }
+    }
+  }
+  if (c_sw)
+    for (day = 0; day < Ndays_local; day++)
+      for (hour = 0; hour < 24; hour++) hourlyrad[day * 24 + hour] = (fdt == 24) ? l_sw[day] : l_sw[day * 24 + hour];
+
   /* mtclim_wrapper.c:84-218: init, calc_tair (mtclim_vic.c:405-433), calc_prcp (:437-469), snowpack (:474-530) */
   d.ndays = Ndays_local;
+  d.insw = c_sw != NULL; d.invp = c_vp != NULL;
   d.yday = yday;
   d.tmax = tmax; d.tmin = tmin;
   d.prcp = calloc(Ndays_local, sizeof(double)); d.s_tmax = calloc(Ndays_local, sizeof(double));
@@ -549,6 +579,14 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     double isoh = annual_prec / 10., ratio, dz = (elevation - elevation) / 1000.0, lr = -1 * T_LAPSE * 1000., snowpack, sum;
     int count, start_yday, prev_yday;
     for (i = 0; i < Ndays_local; i++) d.prcp[i] = prec[i] / 10.;
+    for (i = 0; i < Ndays_local; i++) {               /* mtclim_wrapper.c:196-204 */
+      if (d.insw) {
+        d.s_srad[i] = 0;
+        for (j = 0; j < 24; j++) d.s_srad[i] += hourlyrad[i * 24 + j];
+        d.s_srad[i] /= 24;
+      }
+      if (d.invp) d.s_hum[i] = daily_vp[i];
+    }
     for (i = 0; i < Ndays_local; i++) {
       double tx, tn, tmean;
       d.s_tmax[i] = tx = d.tmax[i] + (dz * lr);
@@ -592,7 +630,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     int tinystepsphour = 3600 / SRADDT;
     int tiny_offset = (int)((float)tinystepsphour * hour_offset);
     for (i = 0; i < Ndays_local; i++) {
-      double tmp_rad = d.s_srad[i] * d.s_dayl[i] / 3600.;
+      double tmp_rad = d.insw ? d.s_srad[i] * 24. : d.s_srad[i] * d.s_dayl[i] / 3600.;
       for (j = 0; j < 24; j++) {
         double s = 0;
         for (k = 0; k < tinystepsphour; k++) {
@@ -608,6 +646,8 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     }
   }
 
+  if (c_sw && fdt < 24)                             /* :966-972: sub-daily observations replace MTCLIM's hours */
+    for (i = 0; i < Ndays_local * 24; i++) hourlyrad[i] = l_sw[i];
   /* shortwave :974-987 */
   for (rec = 0; rec < nrecs; rec++) {
     double s = 0;
@@ -634,8 +674,9 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     if (o->plapse) out[VR_F_DENSITY][rec * stride] = p / (RD * (KELVIN + ta));
     else out[VR_F_DENSITY][rec * stride] = 0.003486 * p / (275.0 + ta);
   }
-  /* vapour pressure :1220-1291 */
-  if (o->vp_interp) {
+  /* vapour pressure :1220-1291 (skipped when sub-daily VP was supplied: l_vp holds the observations) */
+  if (c_vp && fdt < 24) { }
+  else if (o->vp_interp) {
     for (day = 0; day < Ndays_local; day++) {
       double delta_t_minus, delta_t_plus;
       if (day == 0 && Ndays_local == 1) { delta_t_minus = 24; delta_t_plus = 24; }
@@ -668,7 +709,15 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     if (vpd < 0) { vpd = 0; vp = svp(ta); }
     out[VR_F_VP][rec * stride] = vp;
     out[VR_F_VPD][rec * stride] = vpd;
-    out[VR_F_LONGWAVE][rec * stride] = calc_longwave(o, tskc[DAY_OF(hour)], ta, vp);   /* :1361-1388 */
+    if (c_lw) {                                        /* :1389-1420 */
+      if (fdt == 24) out[VR_F_LONGWAVE][rec * stride] = l_lw[DAY_OF(hour)];
+      else {
+        double sl = 0;
+        for (idx = hour; idx < hour + dt; idx++) sl += l_lw[idx];
+        out[VR_F_LONGWAVE][rec * stride] = sl / dt;
+      }
+    }
+    else out[VR_F_LONGWAVE][rec * stride] = calc_longwave(o, tskc[DAY_OF(hour)], ta, vp);   /* :1361-1388 */
   }
   if (dbg) {
     for (i = 0; i < Ndays_local; i++) {
@@ -677,6 +726,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       dbg[4 * Ndays_local + i] = tminhour[i]; dbg[5 * Ndays_local + i] = tmaxhour[i];
     }
   }
+  free(l_sw); free(l_lw);
   free(yday); free(l_prec); free(l_ta); free(l_tb); free(l_wind); free(l_vp); free(hourlyrad); free(tair);
   free(prec); free(tmax); free(tmin); free(tskc); free(daily_vp); free(tmaxhour); free(tminhour); free(radfract);
   free(d.prcp); free(d.s_tmax); free(d.s_tmin); free(d.s_tday); free(d.s_prcp); free(d.s_hum); free(d.s_srad);
@@ -696,7 +746,9 @@ int ao_prepare(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_
     rc = ao_cell(o, cells->lat[c], cells->lng[c], cells->time_zone_lng[c], cells->elevation[c], cells->annual_prec[c],
                  cells->slope ? cells->slope[c] : 0., cells->aspect ? cells->aspect[c] : 0.,
                  cells->ehoriz ? cells->ehoriz[c] : 0., cells->whoriz ? cells->whoriz[c] : 0., C, raw->nrec_forcing,
-                 raw->prec + c, raw->t_a + c, raw->t_b ? raw->t_b + c : NULL, raw->wind ? raw->wind + c : NULL, oc, NULL);
+                 raw->prec + c, raw->t_a + c, raw->t_b ? raw->t_b + c : NULL, raw->wind ? raw->wind + c : NULL,
+                 raw->shortwave ? raw->shortwave + c : NULL, raw->longwave ? raw->longwave + c : NULL, raw->vp ? raw->vp + c : NULL,
+                 oc, NULL);
     if (rc) return rc;
   }
   return 0;

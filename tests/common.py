@@ -109,6 +109,10 @@ def load_atmos_fixture(name):
                         force_dt=fdt, **ov)
     raw = z["raw"]
     site = {k[5:]: z[k] for k in z.files if k.startswith("site_")}
+    extra = [str(x) for x in z["extra_cols"] if str(x)] if "extra_cols" in z.files else []
     iw = 3 if layout == 0 else 2
-    rawd = {"prec": raw[0], "t_a": raw[1], "t_b": raw[2] if layout == 0 else None, "wind": raw[iw] if raw.shape[0] > iw else None}
+    has_wind = raw.shape[0] - len(extra) > iw
+    rawd = {"prec": raw[0], "t_a": raw[1], "t_b": raw[2] if layout == 0 else None, "wind": raw[iw] if has_wind else None}
+    for j, name in enumerate(extra):
+        rawd[name.lower()] = raw[raw.shape[0] - len(extra) + j]
     return {"opt": opt, "site": site, "raw": rawd, "ref": z["atmos"]}

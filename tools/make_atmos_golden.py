@@ -49,6 +49,14 @@ CASES = {
     # (Ndays_local*24 - starthour + hour_offset_int)/FORCE_DT - fstepspday, past the nrecs records it allocated
     # (initialize_atmos.c:511-513), so its last local day -- and through the precipitation totals all of MTCLIM's humidity --
     # depends on whatever follows the array in memory.  The library reads zeros there (what calloc gives inside the array).
+    # observed columns: MTCLIM in its insw / invp modes, supplied longwave
+    "atmos_daily_obs_sw_lw_vp": (dict(ncells=3, ndays=200, startyear=1997, lat_range=(-30, 58), off_gmt=1, cold=3.0, seed=312,
+                                      extra_cols=("SHORTWAVE", "LONGWAVE", "VP")), {}),
+    "atmos_sub3h_obs_sw_lw_vp": (dict(ncells=3, ndays=90, dt=3, startyear=1998, lat_range=(30, 60), cold=4.0, seed=313,
+                                      extra_cols=("SHORTWAVE", "LONGWAVE", "VP")), {}),
+    "atmos_daily_obs_sw": (dict(ncells=2, ndays=150, startyear=1999, lat_range=(10, 50), seed=314, extra_cols=("SHORTWAVE",)), {}),
+    "atmos_sub3h_obs_vp": (dict(ncells=2, ndays=60, dt=3, startyear=1999, lat_range=(35, 55), off_gmt=-1, seed=315,
+                                extra_cols=("VP",)), {}),
     "atmos_daily_no_wind": (dict(ncells=3, ndays=120, startyear=1996, lat_range=(-35, 55), off_gmt=-2, no_wind=True, seed=310),
                             dict(has_wind=False)),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,
@@ -76,7 +84,8 @@ def save(name, gfile, dump, kw, ov, start=None):
     atm = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2).transpose(1, 0, 2)   # [9, nrec, C]
     dt = int(d["dt"][0])
     daily = dt == 24 or kw.get("force_daily", False)
-    ncol = (4 if daily else 3) - (1 if kw.get("no_wind") else 0)
+    extra = list(kw.get("extra_cols", ()))
+    ncol = (4 if daily else 3) - (1 if kw.get("no_wind") else 0) + len(extra)
     raw = read_raw(gfile, site["lat"], site["lng"], ncol)
     nrecs = int(d["nrecs"][0])
     nrf = nrecs * dt // (24 if daily else dt)
@@ -85,7 +94,8 @@ def save(name, gfile, dump, kw, ov, start=None):
     arrays = {"raw": raw[:, skip:skip + nrf], "atmos": np.ascontiguousarray(atm),
               "meta": np.array([dt, nrecs, dmy[0, 0], dmy[0, 1], dmy[0, 2], dmy[0, 3], 0 if daily else 1, 24 if daily else dt],
                                dtype=np.int64),
-              "ov_keys": np.array(list(ov.keys()) or [""]), "ov_vals": np.array([str(v) for v in ov.values()] or [""])}
+              "ov_keys": np.array(list(ov.keys()) or [""]), "ov_vals": np.array([str(v) for v in ov.values()] or [""]),
+              "extra_cols": np.array(extra or [""])}
     for k, v in site.items():
         arrays["site_" + k] = v
     out = os.path.join(ROOT, "tests", "golden", name + ".npz")

@@ -41,7 +41,11 @@ class vr_atmos_cells(C.Structure):
 
 
 class vr_atmos_raw(C.Structure):
-    _fields_ = [("nrec_forcing", C.c_int64), ("prec", _pd), ("t_a", _pd), ("t_b", _pd), ("wind", _pd)]
+    _fields_ = [("nrec_forcing", C.c_int64), ("prec", _pd), ("t_a", _pd), ("t_b", _pd), ("wind", _pd),
+                ("shortwave", _pd), ("longwave", _pd), ("vp", _pd)]
+
+
+RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp")
 
 
 def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, starthour=0, layout=None, force_dt=None,
@@ -82,10 +86,10 @@ def pack_site(site):
 
 
 def pack_raw(raw):
-    """raw: dict prec, t_a, t_b (or None), wind (or None), each [nrec_forcing, C]."""
+    """raw: dict prec, t_a, t_b (or None), wind (or None) and optionally shortwave, longwave, vp (kPa), each [nrec_forcing, C]."""
     s, keep = vr_atmos_raw(), []
     s.nrec_forcing = raw["prec"].shape[0]
-    for n in ("prec", "t_a", "t_b", "wind"):
+    for n in RAW_FIELDS:
         if raw.get(n) is not None:
             a = np.ascontiguousarray(raw[n], dtype=np.float64)
             keep.append(a)
@@ -137,7 +141,7 @@ def prepare_device(opt, site_dev, raw_dev, out_dev, ncell, nrec_forcing, device=
             setattr(s, n, C.cast(site_dev[n], _pd))
     r = vr_atmos_raw()
     r.nrec_forcing = nrec_forcing
-    for n in ("prec", "t_a", "t_b", "wind"):
+    for n in RAW_FIELDS:
         if raw_dev.get(n):
             setattr(r, n, C.cast(raw_dev[n], _pd))
     ptrs = (_pd * abi.VR_NFORCING)(*[C.cast(p, _pd) for p in out_dev])
@@ -156,7 +160,7 @@ def last_times():
 def options_from_global(g):
     """vr_atmos_options from a parsed global file (vicres_b200.files.Global)."""
     types = [t for t in g.force_types if t != "SKIP"]
-    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND")]
+    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND", "SHORTWAVE", "LONGWAVE", "VP")]
     if extra:
         raise model.VicResError(abi.VR_ERR_UNSUPPORTED, "forcing column(s) %s are outside the supported layouts" % ", ".join(extra))
     layout = SUBDAILY_AIR_TEMP if "AIR_TEMP" in types else DAILY_TMAX_TMIN
@@ -170,7 +174,8 @@ def options_from_global(g):
 def raw_from_columns(cols, layout):
     """{FORCE_TYPE: [nrec, C]} -> the dict prepare() takes."""
     return {"prec": cols["PREC"], "t_a": cols["TMAX" if layout == DAILY_TMAX_TMIN else "AIR_TEMP"],
-            "t_b": cols.get("TMIN") if layout == DAILY_TMAX_TMIN else None, "wind": cols.get("WIND")}
+            "t_b": cols.get("TMIN") if layout == DAILY_TMAX_TMIN else None, "wind": cols.get("WIND"),
+            "shortwave": cols.get("SHORTWAVE"), "longwave": cols.get("LONGWAVE"), "vp": cols.get("VP")}
 
 
 def diag_cr(x, y, device=0):

@@ -62,6 +62,7 @@ struct Ctx {
   int64_t C, c0, CB, nrf;
   const double *lat, *lng, *tz, *elev, *slope, *aspect, *ehoriz, *whoriz;
   const double *r_prec, *r_ta, *r_tb, *r_wind;
+  const double *r_sw, *r_lw, *r_vp;   // optional observed SHORTWAVE, LONGWAVE, VP (kPa) columns, or null
   // scratch: solar tables [365][CB] and hourly fractions [365*24][CB]
   double *ttmax0, *flat, *slp, *dayl, *hf;
   // scratch: daily series [ndl][CB]
@@ -121,6 +122,13 @@ VA_HD double day_tmin(const Ctx &x, const Geo &g, int64_t c, int day)
 {
   return x.fdt == 24 ? local_daily(x.r_tb, x, g, c, day) : x.tcon[x.CB + c - x.c0];
 }
+
+// observed columns in local time: hour idx of the local hourly axis (initialize_atmos.c:488-539; VP in Pa, :404-414)
+VA_HD double obs_hour(const double *col, const Ctx &x, const Geo &g, int64_t c, int idx)
+{
+  return x.fdt == 24 ? local_daily(col, x, g, c, idx / 24) : local_hourly(col, x, g, c, idx);
+}
+VA_HD double obs_vp_hour(const Ctx &x, const Geo &g, int64_t c, int idx) { return obs_hour(x.r_vp, x, g, c, idx) * 1000.; }
 
 #if defined(__CUDA_ARCH__)
 #define VA_POW15(x) ((x) * sqrt(x))
@@ -435,6 +443,23 @@ VA_HDN void daily_prep(const Ctx &x, int64_t c)
     }
     x.prec_d[(int64_t)day * CB + lc] = p;
   }
+  if (x.r_sw)                                             // mtclim_wrapper.c:196-202: 24-hour mean of the observations
+    for (int day = 0; day < g.ndl; day++) {
+      double s = 0;
+      for (int j = 0; j < 24; j++) s += obs_hour(x.r_sw, x, g, c, day * 24 + j);
+      x.srad[(int64_t)day * CB + lc] = s / 24;
+    }
+  if (x.r_vp)                                             // initialize_atmos.c:873-898
+    for (int day = 0; day < g.ndl; day++) {
+      double v;
+      if (x.fdt == 24) v = obs_vp_hour(x, g, c, day * 24);
+      else {
+        v = 0;
+        for (int j = 0; j < 24; j++) v += obs_vp_hour(x, g, c, day * 24 + j);
+        v /= 24;
+      }
+      x.pva[(int64_t)day * CB + lc] = v;
+    }
   if (!x.swe_corr) return;
   // snowpack(), mtclim_vic.c:474-530; s_prcp = prcp * 1 (calc_prcp with site_isoh == base_isoh)
   double snowpack = 0.0, sum = 0.0;
@@ -460,9 +485,10 @@ VA_HDN void daily_prep(const Ctx &x, int64_t c)
 
 // ---------------------------------------------------------------------------------------------------------------
 // compute_srad_humidity_onetime for one day, mtclim_vic.c:1117-1219
-struct DayRad { double srad, tdew, pva; };
+struct DayRad { double srad, tdew, pva, tfmax; };
+// srad_obs: the observed 24-hour mean when SHORTWAVE is supplied (ctrl->insw), else unused
 VA_HD DayRad rad_pass(const Ctx &x, int64_t lc, int ydi, double pva_in, double tfmax, double swe, double sky_prop,
-                      double stmin, double stday, double parray, double pa, double dtr)
+                      double stmin, double stday, double parray, double pa, double dtr, double srad_obs = 0.)
 {
   const int64_t k = (int64_t)ydi * x.CB + lc;
   const double daylength = x.dayl[k];
@@ -484,7 +510,17 @@ VA_HD DayRad rad_pass(const Ctx &x, int64_t lc, int ydi, double pva_in, double t
   }
   else sc = 0.0;
   DayRad r;
-  r.srad = srad1 + srad2 + sc;
+  r.tfmax = tfmax;
+  if (x.r_sw) {                                           // :1173-1182: cloud transmittance from the observation
+    double potrad = (srad1 + srad2 + sc) * daylength / t_final / 86400;
+    if (potrad > 0 && srad_obs > 0 && daylength > 0) {
+      r.tfmax = (srad_obs) / (potrad * t_tmax);
+      if (r.tfmax > 1.0) r.tfmax = 1.0;
+    }
+    else r.tfmax = 1.0;
+    r.srad = srad_obs;
+  }
+  else r.srad = srad1 + srad2 + sc;
   double tmink = stmin + KELVIN;
   double pet = calc_pet(r.srad, stday, pa, daylength);
   double ratio = pet / parray;
@@ -574,12 +610,16 @@ VA_HD void daily_rad_t(const Ctx &x, int64_t c, int day, const Geo &g, DTR dtr_o
   const double sky_prop = sky_proportion(x, c);
   const double swe = x.swe_corr ? x.swe[(int64_t)day * CB + lc] : 0.0;
   const int ydi = ydi_of(x, g, day);
-  DayRad r = rad_pass(x, lc, ydi, svp(stmin), tfmax, swe, sky_prop, stmin, stday, parray, pa, dtr);
-  if (x.vp_iter == VR_VP_ITER_ALWAYS) r = rad_pass(x, lc, ydi, r.pva, tfmax, swe, sky_prop, stmin, stday, parray, pa, dtr);
   const int64_t k = (int64_t)day * CB + lc;
+  const double srad_obs = x.r_sw ? x.srad[k] : 0., vp_obs = x.r_vp ? x.pva[k] : 0.;   // written by daily_prep
+  DayRad r = rad_pass(x, lc, ydi, x.r_vp ? vp_obs : svp(stmin), tfmax, swe, sky_prop, stmin, stday, parray, pa, dtr, srad_obs);
+  // observed humidity is restored after the first pass (:1018-1023); the second pass sees the transmittance the first
+  // one derived from observed radiation
+  if (x.vp_iter == VR_VP_ITER_ALWAYS)
+    r = rad_pass(x, lc, ydi, x.r_vp ? vp_obs : r.pva, r.tfmax, swe, sky_prop, stmin, stday, parray, pa, dtr, srad_obs);
   x.srad[k] = r.srad;
-  x.pva[k] = r.pva;
-  x.tskc[k] = tfmax;                                      // cloud transmittance; converted to tskc where it is read
+  x.pva[k] = x.r_vp ? vp_obs : r.pva;                     // :1060-1066
+  x.tskc[k] = r.tfmax;                                    // cloud transmittance; converted to tskc where it is read
   if (x.vp_iter == VR_VP_ITER_CONVERGE) { x.tdew[k] = r.tdew; x.parr[k] = parray; }
 }
 
@@ -659,8 +699,10 @@ VA_HDN void converge(const Ctx &x, int64_t c)
 // hourlyrad[day*24 + j], mtclim_wrapper.c:252-269 (MTCLIM-estimated radiation: daylight average x daylength)
 VA_HD double hourly_rad(const Ctx &x, const Geo &g, int64_t lc, int day, int j)
 {
+  if (x.r_sw && x.fdt < 24) return local_hourly(x.r_sw, x, g, x.c0 + lc, day * 24 + j);   // initialize_atmos.c:966-972
   const int ydi = ydi_of(x, g, day);
-  double tmp_rad = x.srad[(int64_t)day * x.CB + lc] * x.dayl[(int64_t)ydi * x.CB + lc] / 3600.;
+  const double srad = x.srad[(int64_t)day * x.CB + lc];
+  double tmp_rad = x.r_sw ? srad * 24. : srad * x.dayl[(int64_t)ydi * x.CB + lc] / 3600.;   // mtclim_wrapper.c:252-257
   return x.hf[((int64_t)ydi * 24 + j) * x.CB + lc] * tmp_rad;
 }
 
@@ -768,6 +810,7 @@ VA_HD double hourly_tair_cached(const Ctx &x, const Geo &g, int64_t c, int hour,
 // local VP of one hour, initialize_atmos.c:1229-1275
 VA_HD double hourly_vp(const Ctx &x, const Geo &g, int64_t lc, int idx)
 {
+  if (x.r_vp && x.fdt < 24) return obs_vp_hour(x, g, x.c0 + lc, idx);    // sub-daily observations, :891-913
   const int day = idx / 24, hour = idx - day * 24, nd = g.ndl;
   const int64_t CB = x.CB;
   const double v = x.pva[(int64_t)day * CB + lc];
@@ -830,12 +873,15 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
   double tmp_rad = 0.;
   for (int idx = hour; idx < hour + dt; idx++) {
     const int d = idx / 24;
-    if (d != rad_day) {                                    // hourly_rad()'s per-day factor, once per day
-      rad_day = d;
-      rad_ydi = ydi_of(x, g, d);
-      tmp_rad = x.srad[(int64_t)d * x.CB + lc] * x.dayl[(int64_t)rad_ydi * x.CB + lc] / 3600.;
+    if (x.r_sw) sw += hourly_rad(x, g, lc, d, idx - d * 24);
+    else {
+      if (d != rad_day) {                                  // hourly_rad()'s per-day factor, once per day
+        rad_day = d;
+        rad_ydi = ydi_of(x, g, d);
+        tmp_rad = x.srad[(int64_t)d * x.CB + lc] * x.dayl[(int64_t)rad_ydi * x.CB + lc] / 3600.;
+      }
+      sw += x.hf[((int64_t)rad_ydi * 24 + (idx - d * 24)) * x.CB + lc] * tmp_rad;
     }
-    sw += x.hf[((int64_t)rad_ydi * 24 + (idx - d * 24)) * x.CB + lc] * tmp_rad;
     vp += hourly_vp(x, g, lc, idx);
   }
   sw /= dt;
@@ -862,7 +908,17 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
   x.out[VR_F_PRESSURE][o] = p;
   x.out[VR_F_DENSITY][o] = dens;
   x.out[VR_F_SHORTWAVE][o] = sw;
-  x.out[VR_F_LONGWAVE][o] = longwave(x, tskc, ta, vp);
+  double lw;
+  if (x.r_lw) {                                            // :1389-1420
+    if (x.fdt == 24) lw = local_daily(x.r_lw, x, g, c, dayi);
+    else {
+      double s = 0;
+      for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_lw, x, g, c, idx);
+      lw = s / dt;
+    }
+  }
+  else lw = longwave(x, tskc, ta, vp);
+  x.out[VR_F_LONGWAVE][o] = lw;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -900,6 +956,11 @@ inline void build_calendar(const vr_atmos_options &o, int ndays, int16_t *cal /*
       if (month > 12) { diy = 1; month = 1; year++; }
     }
   }
+}
+inline const char *unsupported_raw(const vr_atmos_options &o, const vr_atmos_raw &r)
+{
+  if (o.vp_iter == VR_VP_ITER_CONVERGE && (r.shortwave || r.vp)) return "VP_ITER_CONVERGE with observed SHORTWAVE or VP columns";
+  return nullptr;
 }
 inline const char *unsupported(const vr_atmos_options &o)
 {

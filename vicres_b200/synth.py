@@ -56,7 +56,7 @@ def _fmt(x, nd=6):
 def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261019,
               startyear=1981, lat_range=(-40.0, 60.0), cold=0.0, overstory_frac=0.3,
               max_veg=3, extra_global="", result_dir=None, skip_output=False, snow_step=None,
-              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False):
+              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False, extra_cols=()):
     """Write a complete reference-format case under `outdir`; return the global file path.
 
     dt == 24: daily PREC/TMAX/TMIN/WIND forcing (as the bundled basin); dt < 24: sub-daily
@@ -64,7 +64,8 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
     force snow.  All randomness comes from `seed`.  `off_gmt` (hours) replaces the cells' own time zone
     (round(lng/15)), so that local time differs from the forcing's time; `force_daily` writes the daily
     four-column file even when dt < 24 (FORCE_DT 24 with a sub-daily TIME_STEP); `no_wind` leaves the
-    WIND column out (the reference then uses DEFAULT_WIND_SPEED).
+    WIND column out (the reference then uses DEFAULT_WIND_SPEED); `extra_cols` appends observed SHORTWAVE (W/m2),
+    LONGWAVE (W/m2) and / or VP (kPa) columns.
     """
     rng = np.random.default_rng(seed)
     os.makedirs(outdir, exist_ok=True)
@@ -182,20 +183,41 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         wind = np.maximum(np.exp(rng.normal(1.0, 0.5, ndays)), 0.1)
         if wind_zero_frac > 0:
             wind = np.where(rng.uniform(size=ndays) < wind_zero_frac, 0.0, wind)
+        # optional observed columns (values only need to be plausible)
+        if extra_cols:                  # drawn only when asked for: the random stream of the other cases stays as it was
+            sw_day = np.clip(180.0 + 120.0 * np.cos(phase) * (1 if lat >= 0 else -1) + rng.normal(0, 40, ndays), 5.0, 420.0)
+            lw_day = np.clip(300.0 + 2.5 * tmean + rng.normal(0, 15, ndays), 120.0, 480.0)
+            vp_day = np.clip(0.6108 * np.exp(17.27 * tmin / (237.3 + tmin)) * rng.uniform(0.7, 1.0, ndays), 0.02, 4.0)
+
+        def extras(i, k=None):
+            out = []
+            for name in extra_cols:
+                if name == "SHORTWAVE":
+                    if k is None:
+                        out.append(sw_day[i])
+                    else:               # a daylight bell over the sub-daily records, zero at night, same daily mean
+                        w = np.maximum(np.cos(2.0 * np.pi * (hrs - 12.0) / 24.0), 0.0)
+                        out.append(sw_day[i] * w[k] * steps_per_day / max(w.sum(), 1e-9))
+                elif name == "LONGWAVE":
+                    out.append(lw_day[i] + (0.0 if k is None else 10.0 * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)))
+                elif name == "VP":
+                    out.append(vp_day[i] * (1.0 if k is None else 1.0 + 0.05 * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)))
+            return "".join(" %.4f" % x for x in out)
+        hrs = (np.arange(steps_per_day) + 0.5) * dt if dt < 24 else None
         fn = os.path.join(forc_dir, "data_%.4f_%.4f" % (lat, lng))
         with open(fn, "w") as f:
             if dt == 24 or force_daily:
                 for i in range(ndays):
                     if no_wind:
-                        f.write("%.4f %.4f %.4f\n" % (prec[i], tmax[i], tmin[i]))
+                        f.write("%.4f %.4f %.4f%s\n" % (prec[i], tmax[i], tmin[i], extras(i)))
                     else:
-                        f.write("%.4f %.4f %.4f %.4f\n" % (prec[i], tmax[i], tmin[i], wind[i]))
+                        f.write("%.4f %.4f %.4f %.4f%s\n" % (prec[i], tmax[i], tmin[i], wind[i], extras(i)))
             else:
                 hrs = (np.arange(steps_per_day) + 0.5) * dt
                 for i in range(ndays):
                     for k in range(steps_per_day):
                         ta = tmean[i] + 0.5 * dtr[i] * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)
-                        f.write("%.4f %.4f %.4f\n" % (prec[i] / steps_per_day, ta, wind[i]))
+                        f.write("%.4f %.4f %.4f%s\n" % (prec[i] / steps_per_day, ta, wind[i], extras(i, k)))
 
     with open(os.path.join(outdir, "soil.txt"), "w") as f:
         f.write("\n".join(soil_lines) + "\n")
@@ -213,10 +235,11 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
           "MIN_WIND_SPEED 0.1", "MAX_SNOW_TEMP 0.5", "MIN_RAIN_TEMP -0.5",
           "FORCING1 %s/data_" % forc_dir, "FORCE_FORMAT ASCII", "FORCE_ENDIAN LITTLE"]
     if dt == 24 or force_daily:
-        g += (["N_TYPES 3", "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN"] if no_wind else
-              ["N_TYPES 4", "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN", "FORCE_TYPE WIND"]) + ["FORCE_DT 24"]
+        types = ["PREC", "TMAX", "TMIN"] + ([] if no_wind else ["WIND"]) + list(extra_cols)
+        g += ["N_TYPES %d" % len(types)] + ["FORCE_TYPE %s" % t for t in types] + ["FORCE_DT 24"]
     else:
-        g += ["N_TYPES 3", "FORCE_TYPE PREC", "FORCE_TYPE AIR_TEMP", "FORCE_TYPE WIND", "FORCE_DT %d" % dt]
+        types = ["PREC", "AIR_TEMP", "WIND"] + list(extra_cols)
+        g += ["N_TYPES %d" % len(types)] + ["FORCE_TYPE %s" % t for t in types] + ["FORCE_DT %d" % dt]
     g += ["FORCEYEAR %d" % startyear, "FORCEMONTH 1", "FORCEDAY 1", "FORCEHOUR 0", "GRID_DECIMAL 4",
           "WIND_H 10.0", "MEASURE_H 2.0", "ALMA_INPUT FALSE",
           "SOIL %s/soil.txt" % outdir, "BASEFLOW ARNO", "JULY_TAVG_SUPPLIED FALSE", "ORGANIC_FRACT FALSE",
