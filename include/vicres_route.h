@@ -90,6 +90,14 @@ typedef struct vr_route_inputs {
                                               multi-GPU run take node ranges and all-gather the rows: no change of summation order */
   int32_t reserved[2];
 } vr_route_inputs;
+/* The flux hand-off between the two passes on the device: rows `rows[v]` of the cell step's output block
+ * out_dev [.][ndays][ncell] (device, as vr_step_block_device leaves it) -> the routing pass's columns dst_dev[v]
+ * [ngrid][ndays] float (device), cell c going to grid cell grid_of_cell[c] (host array; -1 = not on the routing grid), every
+ * value through the "%.4f" text round trip of the flux files (write_data.c -> READ(20,*), reservoir.f:373-389) exactly as
+ * vr_round_decimals + the conversion to REAL do on the host.  present_dev [ngrid] (device, may be NULL) is set for the grid
+ * cells that received a VIC cell.  The input arrays of vr_route_inputs / vr_route_convolve_ex may be host OR device memory. */
+int  vr_route_fluxes_from_step(int device, const double *out_dev, int64_t ncell, int32_t ndays, int32_t nvar, const int32_t *rows,
+                               const int64_t *grid_of_cell, int64_t ngrid, float *const dst_dev[], unsigned char *present_dev);
 /* res_evaporation: [nnodes][ndays] RES_EVAPORATION (sum of 0.9*E0 over the node's surface cells) or NULL */
 int  vr_route_convolve_in(vr_route *h, int32_t ndays, const vr_route_inputs *in, float *flows, float *res_evaporation);
 int  vr_route_last_kernel_ms(vr_route *h, float *ms);

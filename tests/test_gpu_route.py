@@ -196,3 +196,54 @@ def test_cuda_station_without_reservoirs(Route):
     assert out["flow"].shape == (1, nat.shape[1]) and out["flow"][0, 5] == 0
     assert np.array_equal(np.maximum(nat[0], 0), out["flow"][0])
     r.close()
+
+
+def test_device_flux_handoff_equals_the_text_round_trip(Route):
+    """vr_route_fluxes_from_step (device) against the host path vr_round_decimals + conversion to float32: random values,
+    exact decimal ties and their neighbours, values around zero; then the convolution fed from device memory against
+    the one fed from the host arrays."""
+    import torch
+    from vicres_b200 import couple, files, route
+    rng = np.random.default_rng(3)
+    C, nd = 700, 130
+    names = list(couple.ROUTE_VARS) + ["SWE"]
+    x = rng.normal(0, 30, (len(names), nd, C))
+    k = rng.integers(-200000, 200000, (nd, C))
+    x[0] = (k + 0.5) / 1e4                                   # decimals that tie in the fifth place (as doubles: just off the tie)
+    x[1] = np.nextafter((k + 0.5) / 1e4, np.inf)
+    x[2] = np.nextafter((k + 0.5) / 1e4, -np.inf)
+    x[3] = rng.uniform(-1, 1, (nd, C)) * 1e-4
+    x[4] = k / 8.0 + 0.03125                                 # exactly representable binary fractions: true ties of the exact value
+    dev = torch.device("cuda", 0)
+    out_dev = torch.from_numpy(x).to(dev)
+    ngrid = 900
+    gmap = rng.permutation(ngrid)[:C].astype(np.int64)
+    gmap[::50] = -1
+    cols, present = route.fluxes_from_step_device(out_dev, names, gmap, ngrid)
+    want = files.round_decimals(x[:8], 4).astype(np.float32)          # [8, nd, C]
+    on = gmap >= 0
+    for j, key in enumerate(couple.KEYS):
+        got = cols[key].cpu().numpy()                        # [ngrid, nd]
+        assert np.array_equal(got[gmap[on]], want[j][:, on].T), key
+        off = np.ones(ngrid, bool); off[gmap[on]] = False
+        assert not got[off].any()
+    p = present.cpu().numpy()
+    assert p.sum() == on.sum() and p[gmap[on]].all()
+
+
+def test_convolution_from_device_columns(Route):
+    import torch
+    from vicres_b200 import route
+    z, grid, (col, row), fac = load_route_fixture("rand20x16")
+    r = Route(grid, col, row, z["uh_box"])
+    ndays = int(z["ndays"])
+    host = r.convolve_in(runoff=z["runoff"], baseflow=z["baseflow"], evap=(z["ev_vege"], z["ev_soil"], z["tr_vege"]),
+                         cell_factor=fac, cell_scale=fac * np.float32(0.028), present=z["present"])[0]
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(z[k], dtype=np.float32)).to(dev) for k in ("runoff", "baseflow", "ev_vege", "ev_soil", "tr_vege")}
+    pres = torch.from_numpy(np.ascontiguousarray(z["present"], dtype=np.uint8)).to(dev)
+    ptrs = {k: v.data_ptr() for k, v in t.items()}
+    ptrs["present"] = pres.data_ptr()
+    got = r.convolve_in_device(ndays, ptrs, cell_factor=fac, cell_scale=fac * np.float32(0.028))
+    assert np.array_equal(got, host)
+    r.close()

@@ -612,7 +612,7 @@ struct DB {
   {
     cudaError_t e = res(count);
     if (e != cudaSuccess || !count) return e;
-    return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyDefault);     // host or device source (unified addressing)
   }
   cudaError_t res(size_t count)
   {
@@ -886,6 +886,80 @@ int vr_route_convolve_in(vr_route *h, int32_t ndays, const vr_route_inputs *in, 
     else memset(res_evaporation + off, 0, cnt * sizeof(float));
   }
   return VR_OK;
+}
+
+// ---- flux hand-off on the device -------------------------------------------------------------------------------
+// A value as rout reads it back from vicNl's "%.4f" column (write_data.c -> READ(20,*), reservoir.f:373-389): the decimal
+// with four places nearest to the binary double (ties of the exact value to even, like printf), converted to REAL.
+// x*10^4 is split into its rounded product and the exact residual (fma), so the nearest integer is taken of the exact
+// value; n/10^4 is the correctly rounded double of that decimal (what strtod returns), then one rounding to float --
+// the same two steps as the host path (vr_round_decimals, then the float conversion).
+__device__ __forceinline__ float through_text4(double x)
+{
+  const double p = x * 1e4, e = fma(x, 1e4, -p);
+  double n = rint(p);
+  const double r = (p - n) + e;
+  if (r > 0.5) n += 1.0;
+  else if (r < -0.5) n -= 1.0;
+  return (float)(n / 1e4);
+}
+
+// tile of 32 records x 32 cells: coalesced reads along the cells, coalesced writes along the days of each grid cell
+__global__ void __launch_bounds__(1024) k_fluxes_from_step(const double *__restrict__ out, int64_t C, int ndays, int nvar,
+                                                           const int32_t *__restrict__ rows, const int64_t *__restrict__ grid_of_cell,
+                                                           float *const *__restrict__ dst)
+{
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * 32;
+  const int d0 = blockIdx.y * 32;
+  for (int v = 0; v < nvar; v++) {
+    const double *src = out + (size_t)rows[v] * ndays * C;
+    const int64_t c = c0 + tx;
+    const int d = d0 + ty;
+    tile[ty][tx] = (c < C && d < ndays) ? through_text4(src[(size_t)d * C + c]) : 0.f;
+    __syncthreads();
+    const int64_t cw = c0 + ty;                       // this warp writes the days of cell cw
+    const int dw = d0 + tx;
+    if (cw < C && dw < ndays) {
+      const int64_t g = grid_of_cell[cw];
+      if (g >= 0) dst[v][(size_t)g * ndays + dw] = tile[tx][ty];
+    }
+    __syncthreads();
+  }
+}
+
+int vr_route_fluxes_from_step(int device, const double *out_dev, int64_t ncell, int32_t ndays, int32_t nvar, const int32_t *rows,
+                              const int64_t *grid_of_cell, int64_t ngrid, float *const dst_dev[], unsigned char *present_dev)
+{
+  if (!out_dev || ncell < 1 || ndays < 1 || nvar < 1 || nvar > 16 || !rows || !grid_of_cell || !dst_dev || ngrid < 1) return VR_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return VR_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  for (int64_t c = 0; c < ncell; c++)
+    if (grid_of_cell[c] >= ngrid) return VR_ERR_ARG;
+  DB<int32_t> d_rows;
+  DB<int64_t> d_map;
+  DB<float *> d_dst;
+  std::vector<float *> dst(dst_dev, dst_dev + nvar);
+  cudaError_t e = d_rows.put(rows, nvar);
+  if (e == cudaSuccess) e = d_map.put(grid_of_cell, ncell);
+  if (e == cudaSuccess) e = d_dst.put(dst.data(), nvar);
+  for (int v = 0; v < nvar && e == cudaSuccess; v++) e = cudaMemset(dst_dev[v], 0, (size_t)ngrid * ndays * sizeof(float));
+  if (e == cudaSuccess && present_dev) {
+    std::vector<unsigned char> pres(ngrid, 0);
+    for (int64_t c = 0; c < ncell; c++) if (grid_of_cell[c] >= 0) pres[grid_of_cell[c]] = 1;
+    e = cudaMemcpy(present_dev, pres.data(), ngrid, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    dim3 grid((unsigned)((ncell + 31) / 32), (unsigned)((ndays + 31) / 32));
+    k_fluxes_from_step<<<grid, 1024>>>(out_dev, ncell, ndays, nvar, d_rows.p, d_map.p, d_dst.p);
+    e = cudaDeviceSynchronize();
+  }
+  if (d_rows.p) cudaFree(d_rows.p);
+  if (d_map.p) cudaFree(d_map.p);
+  if (d_dst.p) cudaFree(d_dst.p);
+  return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
 }
 
 int vr_route_convolve_ex(vr_route *h, int32_t ndays, const float *runoff, const float *baseflow, float scale,

@@ -12,7 +12,7 @@ from . import model, route_abi
 ROUTE_EXPORTS = ["vr_route_create", "vr_route_destroy", "vr_route_last_error", "vr_route_num_nodes",
                  "vr_route_node_info", "vr_route_node_cells", "vr_route_get_uh", "vr_route_convolve",
                  "vr_route_convolve_ex", "vr_route_convolve_in", "vr_route_last_kernel_ms", "vr_route_res_info", "vr_route_get_uh_r",
-                 "vr_route_set_uh_r", "vr_route_reservoirs", "vr_objectives"]
+                 "vr_route_set_uh_r", "vr_route_reservoirs", "vr_objectives", "vr_route_fluxes_from_step"]
 
 
 def _lib():
@@ -37,6 +37,7 @@ def _lib():
         L.vr_route_set_uh_r.argtypes = [vp, C.c_int32, vp]
         L.vr_route_reservoirs.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L.vr_objectives.argtypes = [C.c_int, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]
+        L.vr_route_fluxes_from_step.argtypes = [C.c_int, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, C.c_int64, vp, vp]
         L._route_ready = True
     return L
 
@@ -89,6 +90,27 @@ class Route:
         self._check(self.L.vr_route_convolve_in(self.h, ndays, C.cast(C.pointer(s), C.c_void_p), flows.ctypes.data,
                                                 resev.ctypes.data))
         return flows, resev
+
+    def convolve_in_device(self, ndays, ptrs, cell_factor=None, cell_scale=None, scale=0.18308):
+        """vr_route_convolve_in on columns that are already in DEVICE memory (fluxes_from_step_device): ptrs maps
+        runoff, baseflow, ev_vege, ev_soil, tr_vege (and optionally present) to device pointers of [ncell][ndays] float32."""
+        s = route_abi.vr_route_inputs()
+        pf = C.POINTER(C.c_float)
+        keep = []
+        for k in ("runoff", "baseflow", "ev_vege", "ev_soil", "tr_vege"):
+            if ptrs.get(k):
+                setattr(s, k, C.cast(ptrs[k], pf))
+        if ptrs.get("present"):
+            s.present = C.cast(ptrs["present"], C.POINTER(C.c_ubyte))
+        s.scale = scale
+        for name, a in (("cell_factor", cell_factor), ("cell_scale", cell_scale)):
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                keep.append(a)
+                setattr(s, name, a.ctypes.data_as(pf))
+        flows = np.zeros((self.nnodes, ndays), dtype=np.float32)
+        self._check(self.L.vr_route_convolve_in(self.h, ndays, C.cast(C.pointer(s), C.c_void_p), flows.ctypes.data, None))
+        return flows
 
     def res_info(self, n):
         """(downstream reservoir id, node the release is routed to, UH_R[107]) of reservoir node n"""
@@ -145,3 +167,23 @@ def objectives(sim, obs, handle_negatives=True, device=0):
     if rc != 0:
         raise model.VicResError(rc, L.vr_route_last_error(None).decode())
     return out
+
+
+def fluxes_from_step_device(out_dev, names, grid_of_cell, ngrid, device=0):
+    """The flux hand-off on the device.  out_dev: torch float64 CUDA tensor [n_out, ndays, C] (the step's output block),
+    names: its VR_OUT names; grid_of_cell [C] (-1 = not on the routing grid).  Returns ({key: torch float32 CUDA tensor
+    [ngrid, ndays]} for couple.KEYS, present uint8 CUDA tensor [ngrid]): what Route.convolve_in_device takes."""
+    import torch
+    from . import couple
+    L = _lib()
+    n_out, ndays, Cn = out_dev.shape
+    rows = np.array([names.index(v) for v in couple.ROUTE_VARS], dtype=np.int32)
+    gmap = np.ascontiguousarray(grid_of_cell, dtype=np.int64)
+    dst = [torch.empty((ngrid, ndays), dtype=torch.float32, device=out_dev.device) for _ in couple.KEYS]
+    present = torch.empty(ngrid, dtype=torch.uint8, device=out_dev.device)
+    ptrs = (C.c_void_p * len(dst))(*[t.data_ptr() for t in dst])
+    rc = L.vr_route_fluxes_from_step(device, out_dev.data_ptr(), Cn, ndays, len(dst), rows.ctypes.data, gmap.ctypes.data, ngrid,
+                                     ptrs, present.data_ptr())
+    if rc != 0:
+        raise model.VicResError(rc, "vr_route_fluxes_from_step")
+    return dict(zip(couple.KEYS, dst)), present
