@@ -83,13 +83,11 @@ def main():
     T["step_s"] = time.perf_counter() - t0
     T["step_cell_steps_per_s"] = C * nd / T["step_s"]
 
-    # 3. hand-off: the eight routing columns, through the "%.4f" round trip the flux files impose, [cell][day] float32
+    # 3. hand-off on the device: the eight routing columns through the "%.4f" round trip the flux files impose,
+    #    transposed to [cell][day] float32 (vr_route_fluxes_from_step); one VIC cell per grid node, same order
     t0 = time.perf_counter()
-    sel = [names.index(v) for v in couple.ROUTE_VARS]
-    block = out_dev[sel].cpu().numpy()                     # [8, nd, C]
-    block = files.round_decimals(block, 4)
-    inp = {k: np.ascontiguousarray(block[j].T.astype(np.float32)) for j, k in enumerate(couple.KEYS)}
-    present = np.ones(C, dtype=np.uint8)
+    cols, present_dev = route.fluxes_from_step_device(out_dev, names, np.arange(C, dtype=np.int64), C)
+    torch.cuda.synchronize(dev)
     T["handoff_s"] = time.perf_counter() - t0
     m.close()
 
@@ -99,8 +97,9 @@ def main():
     T["uh_build_s"] = time.perf_counter() - t0
     fac = route_abi.cell_factors(hdr, nrow, ncol)
     t0 = time.perf_counter()
-    nat = r.convolve_in(runoff=inp["runoff"], baseflow=inp["baseflow"], evap=(inp["ev_vege"], inp["ev_soil"], inp["tr_vege"]),
-                        cell_factor=fac, present=present)[0]
+    ptrs = {k: cols[k].data_ptr() for k in ("runoff", "baseflow", "ev_vege", "ev_soil", "tr_vege")}
+    ptrs["present"] = present_dev.data_ptr()
+    nat = r.convolve_in_device(nd, ptrs, cell_factor=fac)
     T["convolve_s"] = time.perf_counter() - t0
     T["convolve_kernel_ms"] = r.last_kernel_ms()
     nres = r.nnodes - 1

@@ -898,9 +898,11 @@ __device__ __forceinline__ float through_text4(double x)
 {
   const double p = x * 1e4, e = fma(x, 1e4, -p);
   double n = rint(p);
-  const double r = (p - n) + e;
-  if (r > 0.5) n += 1.0;
-  else if (r < -0.5) n -= 1.0;
+  // p - n is exact and, unless it is +-0.5, at least one ulp of p away from +-0.5 while |e| is at most half an ulp:
+  // only a product that rounds onto a half decides by the sign of the residual (an exact tie keeps rint's even choice)
+  const double d = p - n;
+  if (d == 0.5 && e > 0.0) n += 1.0;
+  else if (d == -0.5 && e < 0.0) n -= 1.0;
   return (float)(n / 1e4);
 }
 
