@@ -76,6 +76,43 @@ bool reaches(const Graph &g, int k, int target, int mode)
 
 struct Node { int res_id = 0, cell = -1, ds_id = 0, target = -1; std::vector<int> cells; };
 
+// The three searches of reaches() for every cell at once, one downstream walk per cell with memoisation (the
+// reference walks the path of every cell again for every node: SEARCH_WHOLECATCHMENT / SEARCH_CATCHMENTRS,
+// reservoir.f:578-763):
+//   whole[k]    mode 0: the path from k reaches the station
+//   first_res[k] mode 1: the first real reservoir cell (reser > 0, != 9999) on the path from k, k included, or -1 --
+//               k is in the list of the reservoir at cell T exactly when first_res[k] == T
+//   direct[k]   mode 2: the path reaches the station before any cell with reser > 0 (k included; the station cell itself
+//               counts as reached)
+// A path that runs into a cycle or off the grid reaches nothing, like the guard of reaches().
+struct CatchmentMaps { std::vector<char> whole, direct; std::vector<int> first_res; };
+void catchment_maps(const Graph &g, int station, CatchmentMaps &m)
+{
+  const int n = g.ncol * g.nrow;
+  m.whole.assign(n, 0); m.direct.assign(n, 0); m.first_res.assign(n, -1);
+  std::vector<char> state(n, 0);                     // 0 new, 1 on the current path, 2 done
+  std::vector<int> path;
+  for (int s = 0; s < n; s++) {
+    if (state[s]) continue;
+    path.clear();
+    int k = s;
+    while (k >= 0 && state[k] == 0) { state[k] = 1; path.push_back(k); k = g.next[k]; }
+    // k: off the grid (-1), a finished cell, or a cell of the current path (cycle): the values below it
+    char w = 0, d = 0;
+    int fr = -1;
+    if (k >= 0 && state[k] == 2) { w = m.whole[k]; d = m.direct[k]; fr = m.first_res[k]; }
+    for (size_t i = path.size(); i-- > 0;) {
+      const int c = path[i];
+      const bool real = g.reser[c] > 0 && g.reser[c] != 9999;
+      if (c == station) { w = 1; d = 1; }
+      else if (g.reser[c] > 0) d = 0;
+      if (real) fr = c;
+      m.whole[c] = w; m.direct[c] = d; m.first_res[c] = fr;
+      state[c] = 2;
+    }
+  }
+}
+
 void list_cells(const Graph &g, int target, int mode, std::vector<int> &out)
 {
   out.clear();
@@ -754,22 +791,30 @@ int vr_route_create(const vr_route_grid *g, int32_t station_col, int32_t station
   build_graph(g, h->g);
   // station cell: PI = ICOL + 1 - col (rout.f:341), PJ = row
   const int PI = g->ncol + 1 - station_col, PJ = station_row, station = gidx(h->g, PI, PJ);
-  std::vector<int> whole;
-  list_cells(h->g, station, 0, whole);
-  for (int k : whole) {                               // reservoirs in the reference's discovery (scan) order
-    const int r = h->g.reser[k];
-    if (r > 0 && r != 9999) {
-      Node nd;
-      nd.res_id = r; nd.cell = k;
-      list_cells(h->g, k, 1, nd.cells);
-      h->nodes.push_back(std::move(nd));
-    }
-  }
   {
-    Node nd;
-    nd.res_id = 0; nd.cell = station;
-    list_cells(h->g, station, 2, nd.cells);
-    h->nodes.push_back(std::move(nd));
+    CatchmentMaps cm;
+    catchment_maps(h->g, station, cm);
+    std::vector<int> node_of(g->ncol * g->nrow, -1);
+    for (int I = 1; I <= g->ncol; I++)                // the reference scans I outer, J inner
+      for (int J = 1; J <= g->nrow; J++) {            // reservoirs in the reference's discovery (scan) order
+        const int k = gidx(h->g, I, J), r = h->g.reser[k];
+        if (cm.whole[k] && r > 0 && r != 9999) {
+          Node nd;
+          nd.res_id = r; nd.cell = k;
+          node_of[k] = (int)h->nodes.size();
+          h->nodes.push_back(std::move(nd));
+        }
+      }
+    Node st;
+    st.res_id = 0; st.cell = station;
+    for (int I = 1; I <= g->ncol; I++)
+      for (int J = 1; J <= g->nrow; J++) {
+        const int k = gidx(h->g, I, J);
+        const int fr = cm.first_res[k];
+        if (fr >= 0 && node_of[fr] >= 0) h->nodes[node_of[fr]].cells.push_back(k);
+        if (cm.direct[k]) st.cells.push_back(k);
+      }
+    h->nodes.push_back(std::move(st));
   }
   // RES_DIRECT(:,2): the next reservoir met walking downstream (reservoir.f:733-759); its release is routed to
   // that reservoir when it is one of this station's nodes, else to the station (reservoir.f:1529-1567)
