@@ -154,3 +154,19 @@ def test_open_water_evaporation_matches_prebuilt_binary(tmp_path):
     assert err0.max() > 1e-3                       # the fixture does exercise the evaporation
     assert (resev[np.array(n9) > 0] > 0).any() and (resev[np.array(n9) == 0] == 0).all()
     o.close()
+
+
+def test_memoised_catchment_search_equals_the_path_by_path_search(tmp_path):
+    """host part of vr_route_create: one downstream walk per cell with memoisation gives the same cell lists, in the
+    same order, as walking every cell's path again for every node (tests/hostsim/route_graph_check.cu; random
+    direction grids incl. cycles)"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "route_graph_check")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim", "route_graph_check.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O2", "-w", "-o", exe, src], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 of" in r.stdout, r.stdout[-500:]

@@ -97,19 +97,29 @@ void catchment_maps(const Graph &g, int station, CatchmentMaps &m)
     path.clear();
     int k = s;
     while (k >= 0 && state[k] == 0) { state[k] = 1; path.push_back(k); k = g.next[k]; }
-    // k: off the grid (-1), a finished cell, or a cell of the current path (cycle): the values below it
+    // k: off the grid (< 0), a finished cell, or a cell of the current path (the walk closed a cycle)
     char w = 0, d = 0;
     int fr = -1;
     if (k >= 0 && state[k] == 2) { w = m.whole[k]; d = m.direct[k]; fr = m.first_res[k]; }
-    for (size_t i = path.size(); i-- > 0;) {
-      const int c = path[i];
+    auto visit = [&](int c) {
       const bool real = g.reser[c] > 0 && g.reser[c] != 9999;
       if (c == station) { w = 1; d = 1; }
       else if (g.reser[c] > 0) d = 0;
       if (real) fr = c;
       m.whole[c] = w; m.direct[c] = d; m.first_res[c] = fr;
       state[c] = 2;
+    };
+    size_t tail = path.size();
+    if (k >= 0 && state[k] == 1) {
+      // a walk from a cell of a cycle goes round it until it meets its target (reaches() allows more steps than there are
+      // cells): every cycle cell sees the nearest event ahead of it, wrapped -- two backward sweeps over the cycle
+      size_t j = 0;
+      while (path[j] != k) j++;
+      for (int sweep = 0; sweep < 2; sweep++)
+        for (size_t i = path.size(); i-- > j;) visit(path[i]);
+      tail = j;
     }
+    for (size_t i = tail; i-- > 0;) visit(path[i]);
   }
 }
 
