@@ -188,6 +188,7 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   CK(cudaMallocAsync((void **)&base, bytes, st));
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaFreeAsync(base, st); return fail(VR_ERR_CUDA, std::string(#call ": ") + cudaGetErrorString(e_)); } } while (0)
   double *d = (double *)base;
   x.ttmax0 = d; x.flat = d + (size_t)va::NYD * CB; x.slp = d + (size_t)2 * va::NYD * CB; x.dayl = d + (size_t)3 * va::NYD * CB;
   x.hf = d + (size_t)4 * va::NYD * CB;
@@ -206,8 +207,8 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
   int32_t *hist_dev = perm_dev + CB;
   std::vector<int16_t> cal(x.Ndays + 2);
   va::build_calendar(*o, x.Ndays, cal.data());
-  CK(cudaMemcpyAsync(cal_dev, cal.data(), cal.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));                      // `cal` is pageable host memory that dies with this call
+  CKF(cudaMemcpyAsync(cal_dev, cal.data(), cal.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  CKF(cudaStreamSynchronize(st));                      // `cal` is pageable host memory that dies with this call
   x.cal = cal_dev;
 
   auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_t.ev.push_back(e); };
@@ -217,7 +218,7 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
     x.c0 = c0;
     mark();
     if (o->reserved[2] != 1) {                       // latitude order of the batch (reserved[2] == 1: caller's order)
-      CK(cudaMemsetAsync(hist_dev, 0, LAT_BUCKETS * sizeof(int32_t), st));
+      CKF(cudaMemsetAsync(hist_dev, 0, LAT_BUCKETS * sizeof(int32_t), st));
       k_lat_hist<<<(unsigned)((cb + 255) / 256), 256, 0, st>>>(x, cb, hist_dev);
       k_lat_scan<<<1, 1, 0, st>>>(hist_dev);
       k_lat_scatter<<<(unsigned)((cb + 255) / 256), 256, 0, st>>>(x, cb, hist_dev, perm_dev);
@@ -238,7 +239,8 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
     g_t.launches += 2;
     mark();
   }
-  CK(cudaGetLastError());
+  CKF(cudaGetLastError());
+#undef CKF
   CK(cudaFreeAsync(base, st));
   return VR_OK;
 }
