@@ -65,7 +65,7 @@ int main(int argc, char **argv)
   const int nt = g.n_force_types;
   double *one = malloc(sizeof(double) * nt * nrf), *raw = calloc((size_t)nt * nrf * C, sizeof(double));
   int64_t c, r;
-  int t, col_prec = -1, col_ta = -1, col_tb = -1, col_wind = -1, col_sw = -1, col_lw = -1, col_vp = -1, subdaily = 0;
+  int t, col_prec = -1, col_ta = -1, col_tb = -1, col_wind = -1, col_sw = -1, col_lw = -1, col_vp = -1, col_pr = -1, col_de = -1, subdaily = 0;
   for (t = 0; t < nt; t++) {
     if (!strcmp(g.force_type[t], "PREC")) col_prec = t;
     else if (!strcmp(g.force_type[t], "TMAX")) col_ta = t;
@@ -75,6 +75,8 @@ int main(int argc, char **argv)
     else if (!strcmp(g.force_type[t], "SHORTWAVE")) col_sw = t;
     else if (!strcmp(g.force_type[t], "LONGWAVE")) col_lw = t;
     else if (!strcmp(g.force_type[t], "VP")) col_vp = t;
+    else if (!strcmp(g.force_type[t], "PRESSURE")) col_pr = t;
+    else if (!strcmp(g.force_type[t], "DENSITY")) col_de = t;
     else if (strcmp(g.force_type[t], "SKIP")) die("forcing column outside the supported layouts", g.force_type[t]);
   }
   if (col_prec < 0 || col_ta < 0 || (!subdaily && col_tb < 0)) die("forcing file", "needs PREC and TMAX+TMIN or AIR_TEMP");
@@ -105,6 +107,7 @@ int main(int argc, char **argv)
   rw.t_b = col_tb >= 0 ? raw + (size_t)col_tb * nrf * C : NULL; rw.wind = col_wind >= 0 ? raw + (size_t)col_wind * nrf * C : NULL;
   rw.shortwave = col_sw >= 0 ? raw + (size_t)col_sw * nrf * C : NULL; rw.longwave = col_lw >= 0 ? raw + (size_t)col_lw * nrf * C : NULL;
   rw.vp = col_vp >= 0 ? raw + (size_t)col_vp * nrf * C : NULL;
+  rw.pressure = col_pr >= 0 ? raw + (size_t)col_pr * nrf * C : NULL; rw.density = col_de >= 0 ? raw + (size_t)col_de * nrf * C : NULL;
   double *field[VR_NFORCING];
   for (i = 0; i < VR_NFORCING; i++) field[i] = malloc(sizeof(double) * (size_t)nrecs * C);
   if (vr_atmos_prepare(device, &ao, &site, &rw, field) != VR_OK) die("forcing preparation", vr_atmos_last_error());

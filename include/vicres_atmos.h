@@ -17,8 +17,8 @@
  * Supported forcing files (everything else -> VR_ERR_UNSUPPORTED, nothing is silently ignored):
  *   VR_ATMOS_DAILY_TMAX_TMIN    FORCE_DT 24, columns PREC TMAX TMIN [WIND]   (the bundled basin's format)
  *   VR_ATMOS_SUBDAILY_AIR_TEMP  FORCE_DT < 24, columns PREC AIR_TEMP [WIND]
- * each optionally with observed SHORTWAVE, LONGWAVE and VP columns at the same FORCE_DT; SNOW_STEP == TIME_STEP
- * (NF == 1), ALMA_INPUT FALSE, no QAIR / REL_HUMID / PRESSURE / DENSITY columns.  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
+ * each optionally with observed SHORTWAVE, LONGWAVE, VP, PRESSURE and DENSITY columns at the same FORCE_DT; SNOW_STEP == TIME_STEP
+ * (NF == 1), ALMA_INPUT FALSE, no QAIR / REL_HUMID columns.  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
  */
 #ifndef VICRES_ATMOS_H
 #define VICRES_ATMOS_H
@@ -76,6 +76,9 @@ typedef struct vr_atmos_raw {
    * the file; converted to Pa like initialize_atmos.c:404-414).  With them MTCLIM runs in its "observed" modes
    * (ctrl.insw / ctrl.invp, mtclim_vic.c:982-995, 1173-1185). */
   const double *shortwave, *longwave, *vp;
+  /* optional observed PRESSURE (kPa as in the file) and DENSITY (kg/m3) columns (initialize_atmos.c:1032-1170): the one
+   * that is missing is derived from the other and the air temperature, both missing = the PLAPSE estimate */
+  const double *pressure, *density;
 } vr_atmos_raw;
 
 /* Number of local days MTCLIM runs over for a cell with this integer hour offset (Ndays or Ndays+1). */

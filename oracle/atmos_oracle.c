@@ -420,7 +420,7 @@ int32_t ao_ndays(const vr_atmos_options *o)
 int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_lng, double elevation, double annual_prec,
             double slope, double aspect, double ehoriz, double whoriz, int64_t stride, int64_t nrec_forcing,
             const double *c_prec, const double *c_ta, const double *c_tb, const double *c_wind, const double *c_sw,
-            const double *c_lw, const double *c_vp, double *const out[VR_NFORCING], double *dbg)
+            const double *c_lw, const double *c_vp, const double *c_pr, const double *c_de, double *const out[VR_NFORCING], double *dbg)
 {
   static const int month_days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
   const int dt = o->time_step, nrecs = o->nrecs, fdt = o->force_dt, daily = (o->layout == VR_ATMOS_DAILY_TMAX_TMIN);
@@ -430,7 +430,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   int Ndays = ao_ndays(o), Ndays_local, local_starthour, local_startday, local_startmonth, local_startyear;
   int day_in_year, year, month, day, rec, hour, idx, i, j, k, shift;
   int *yday, *tmaxhour, *tminhour;
-  double *l_sw, *l_lw;
+  double *l_sw, *l_lw, *l_pr, *l_de;
   double *l_prec, *l_ta, *l_tb, *l_wind, *l_vp, *hourlyrad, *prec, *tmax, *tmin, *tair, *tskc, *daily_vp, *radfract;
   mt_data d;
   hour_offset -= hour_offset_int;
@@ -473,6 +473,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   l_tb = calloc(Ndays_local * 24, sizeof(double)); l_wind = calloc(Ndays_local * 24, sizeof(double));
   l_vp = calloc(Ndays_local * 24, sizeof(double)); hourlyrad = calloc(Ndays_local * 24, sizeof(double));
   l_sw = calloc(Ndays_local * 24, sizeof(double)); l_lw = calloc(Ndays_local * 24, sizeof(double));
+  l_pr = calloc(Ndays_local * 24, sizeof(double)); l_de = calloc(Ndays_local * 24, sizeof(double));
   tair = calloc(Ndays_local * 24, sizeof(double));
   prec = calloc(Ndays_local, sizeof(double)); tmax = calloc(Ndays_local, sizeof(double));
   tmin = calloc(Ndays_local, sizeof(double)); tskc = calloc(Ndays_local, sizeof(double));
@@ -493,6 +494,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
       l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
       l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * 1000.;       /* kPa2Pa, :404-414 */
+      l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * 1000.; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
     }
   }
   else {
@@ -506,6 +508,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
       l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
       l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * 1000.;
+      l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * 1000.; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
     }
   }
   shift = (o->starthour - hour_offset_int < 0) ? 24 : 0;
@@ -665,13 +668,24 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       out[VR_F_AIR_TEMP][rec * stride] = s / dt;
     }
   }
-  /* pressure :1070-1092, density :1152-1170 */
+  /* density :1032-1064, pressure :1070-1146, density from pressure :1152-1170 */
   for (rec = 0; rec < nrecs; rec++) {
-    double ta = out[VR_F_AIR_TEMP][rec * stride], p;
-    if (o->plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
+    double ta = out[VR_F_AIR_TEMP][rec * stride], p, de = 0.;
+    hour = REC_HOUR(rec);
+    if (c_de) {
+      if (fdt == 24) de = l_de[DAY_OF(hour)];
+      else { double s2 = 0; for (idx = hour; idx < hour + dt; idx++) s2 += l_de[idx]; de = s2 / dt; }
+    }
+    if (c_pr) {
+      if (fdt == 24) p = l_pr[DAY_OF(hour)];
+      else { double s2 = 0; for (idx = hour; idx < hour + dt; idx++) s2 += l_pr[idx]; p = s2 / dt; }
+    }
+    else if (c_de) p = o->plapse ? (KELVIN + ta) * de * RD : (275.0 + ta) * de / 0.003486;
+    else if (o->plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
     else p = 95500.;
     out[VR_F_PRESSURE][rec * stride] = p;
-    if (o->plapse) out[VR_F_DENSITY][rec * stride] = p / (RD * (KELVIN + ta));
+    if (c_de) out[VR_F_DENSITY][rec * stride] = de;
+    else if (o->plapse) out[VR_F_DENSITY][rec * stride] = p / (RD * (KELVIN + ta));
     else out[VR_F_DENSITY][rec * stride] = 0.003486 * p / (275.0 + ta);
   }
   /* vapour pressure :1220-1291 (skipped when sub-daily VP was supplied: l_vp holds the observations) */
@@ -726,7 +740,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       dbg[4 * Ndays_local + i] = tminhour[i]; dbg[5 * Ndays_local + i] = tmaxhour[i];
     }
   }
-  free(l_sw); free(l_lw);
+  free(l_sw); free(l_lw); free(l_pr); free(l_de);
   free(yday); free(l_prec); free(l_ta); free(l_tb); free(l_wind); free(l_vp); free(hourlyrad); free(tair);
   free(prec); free(tmax); free(tmin); free(tskc); free(daily_vp); free(tmaxhour); free(tminhour); free(radfract);
   free(d.prcp); free(d.s_tmax); free(d.s_tmin); free(d.s_tday); free(d.s_prcp); free(d.s_hum); free(d.s_srad);
@@ -748,7 +762,7 @@ int ao_prepare(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_
                  cells->ehoriz ? cells->ehoriz[c] : 0., cells->whoriz ? cells->whoriz[c] : 0., C, raw->nrec_forcing,
                  raw->prec + c, raw->t_a + c, raw->t_b ? raw->t_b + c : NULL, raw->wind ? raw->wind + c : NULL,
                  raw->shortwave ? raw->shortwave + c : NULL, raw->longwave ? raw->longwave + c : NULL, raw->vp ? raw->vp + c : NULL,
-                 oc, NULL);
+                 raw->pressure ? raw->pressure + c : NULL, raw->density ? raw->density + c : NULL, oc, NULL);
     if (rc) return rc;
   }
   return 0;

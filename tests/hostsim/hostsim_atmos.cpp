@@ -21,7 +21,7 @@ extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, 
   x.lat = cells->lat; x.lng = cells->lng; x.tz = cells->time_zone_lng; x.elev = cells->elevation;
   x.slope = cells->slope; x.aspect = cells->aspect; x.ehoriz = cells->ehoriz; x.whoriz = cells->whoriz;
   x.r_prec = raw->prec; x.r_ta = raw->t_a; x.r_tb = raw->t_b; x.r_wind = raw->wind;
-  x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp;
+  x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp; x.r_pr = raw->pressure; x.r_de = raw->density;
   if (va::unsupported_raw(*o, *raw)) return -2;
   std::vector<double> tab((size_t)va::NYD * 28 * C), dly((size_t)nd * 7 * C), tcon(2 * C);
   std::vector<int8_t> hrs((size_t)nd * 2 * C);

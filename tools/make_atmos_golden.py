@@ -57,6 +57,11 @@ CASES = {
     "atmos_daily_obs_sw": (dict(ncells=2, ndays=150, startyear=1999, lat_range=(10, 50), seed=314, extra_cols=("SHORTWAVE",)), {}),
     "atmos_sub3h_obs_vp": (dict(ncells=2, ndays=60, dt=3, startyear=1999, lat_range=(35, 55), off_gmt=-1, seed=315,
                                 extra_cols=("VP",)), {}),
+    "atmos_sub3h_obs_all": (dict(ncells=2, ndays=60, dt=3, startyear=2000, lat_range=(30, 55), seed=316,
+                                 extra_cols=("SHORTWAVE", "LONGWAVE", "VP", "PRESSURE", "DENSITY")), {}),
+    "atmos_daily_obs_pressure": (dict(ncells=2, ndays=100, startyear=2001, lat_range=(0, 45), off_gmt=3, seed=317,
+                                      extra_cols=("PRESSURE",), extra_global="PLAPSE FALSE"), dict(plapse=False)),
+    "atmos_daily_obs_density": (dict(ncells=2, ndays=100, startyear=2001, lat_range=(0, 45), seed=318, extra_cols=("DENSITY",)), {}),
     "atmos_daily_no_wind": (dict(ncells=3, ndays=120, startyear=1996, lat_range=(-35, 55), off_gmt=-2, no_wind=True, seed=310),
                             dict(has_wind=False)),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,

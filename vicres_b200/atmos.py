@@ -42,10 +42,10 @@ class vr_atmos_cells(C.Structure):
 
 class vr_atmos_raw(C.Structure):
     _fields_ = [("nrec_forcing", C.c_int64), ("prec", _pd), ("t_a", _pd), ("t_b", _pd), ("wind", _pd),
-                ("shortwave", _pd), ("longwave", _pd), ("vp", _pd)]
+                ("shortwave", _pd), ("longwave", _pd), ("vp", _pd), ("pressure", _pd), ("density", _pd)]
 
 
-RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp")
+RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp", "pressure", "density")
 
 
 def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, starthour=0, layout=None, force_dt=None,
@@ -160,7 +160,7 @@ def last_times():
 def options_from_global(g):
     """vr_atmos_options from a parsed global file (vicres_b200.files.Global)."""
     types = [t for t in g.force_types if t != "SKIP"]
-    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND", "SHORTWAVE", "LONGWAVE", "VP")]
+    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND", "SHORTWAVE", "LONGWAVE", "VP", "PRESSURE", "DENSITY")]
     if extra:
         raise model.VicResError(abi.VR_ERR_UNSUPPORTED, "forcing column(s) %s are outside the supported layouts" % ", ".join(extra))
     layout = SUBDAILY_AIR_TEMP if "AIR_TEMP" in types else DAILY_TMAX_TMIN
@@ -175,7 +175,8 @@ def raw_from_columns(cols, layout):
     """{FORCE_TYPE: [nrec, C]} -> the dict prepare() takes."""
     return {"prec": cols["PREC"], "t_a": cols["TMAX" if layout == DAILY_TMAX_TMIN else "AIR_TEMP"],
             "t_b": cols.get("TMIN") if layout == DAILY_TMAX_TMIN else None, "wind": cols.get("WIND"),
-            "shortwave": cols.get("SHORTWAVE"), "longwave": cols.get("LONGWAVE"), "vp": cols.get("VP")}
+            "shortwave": cols.get("SHORTWAVE"), "longwave": cols.get("LONGWAVE"), "vp": cols.get("VP"),
+            "pressure": cols.get("PRESSURE"), "density": cols.get("DENSITY")}
 
 
 def diag_cr(x, y, device=0):

@@ -63,6 +63,7 @@ struct Ctx {
   const double *lat, *lng, *tz, *elev, *slope, *aspect, *ehoriz, *whoriz;
   const double *r_prec, *r_ta, *r_tb, *r_wind;
   const double *r_sw, *r_lw, *r_vp;   // optional observed SHORTWAVE, LONGWAVE, VP (kPa) columns, or null
+  const double *r_pr, *r_de;          // optional observed PRESSURE (kPa), DENSITY columns, or null
   // scratch: solar tables [365][CB] and hourly fractions [365*24][CB]
   double *ttmax0, *flat, *slp, *dayl, *hf;
   // scratch: daily series [ndl][CB]
@@ -887,15 +888,19 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
   sw /= dt;
   vp /= dt;
   const double elevation = x.elev[c];
-  double p, dens;                                          // :1070-1092, :1152-1170
-  if (x.plapse) {
-    p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
-    dens = p / (RD * (KELVIN + ta));
+  double p, dens = 0.;                                     // :1032-1170
+  if (x.r_de) {
+    if (x.fdt == 24) dens = local_daily(x.r_de, x, g, c, dayi);
+    else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_de, x, g, c, idx); dens = s / dt; }
   }
-  else {
-    p = 95500.;
-    dens = 0.003486 * p / (275.0 + ta);
+  if (x.r_pr) {
+    if (x.fdt == 24) p = local_daily(x.r_pr, x, g, c, dayi) * 1000.;
+    else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_pr, x, g, c, idx) * 1000.; p = s / dt; }
   }
+  else if (x.r_de) p = x.plapse ? (KELVIN + ta) * dens * RD : (275.0 + ta) * dens / 0.003486;
+  else if (x.plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
+  else p = 95500.;
+  if (!x.r_de) dens = x.plapse ? p / (RD * (KELVIN + ta)) : 0.003486 * p / (275.0 + ta);
   double vpd = svp(ta) - vp;                               // :1336-1355
   if (vpd < 0) { vpd = 0; vp = svp(ta); }
   const double tf = x.tskc[(int64_t)dayi * x.CB + lc];      // :1188-1193, :1361-1388

@@ -171,7 +171,7 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
   x.lat = cells->lat; x.lng = cells->lng; x.tz = cells->time_zone_lng; x.elev = cells->elevation;
   x.slope = cells->slope; x.aspect = cells->aspect; x.ehoriz = cells->ehoriz; x.whoriz = cells->whoriz;
   x.r_prec = raw->prec; x.r_ta = raw->t_a; x.r_tb = raw->t_b; x.r_wind = raw->wind;
-  x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp;
+  x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp; x.r_pr = raw->pressure; x.r_de = raw->density;
   for (int f = 0; f < VR_NFORCING; f++) x.out[f] = out[f];
 
   // scratch of one batch, one stream-ordered allocation
@@ -258,20 +258,21 @@ int vr_atmos_prepare(int device, const vr_atmos_options *o, const vr_atmos_cells
   if (C < 1 || nrf < 1) return fail(VR_ERR_ARG, "empty input");
   const double *site_h[9] = {cells->lat, cells->lng, cells->time_zone_lng, cells->elevation, cells->annual_prec,
                              cells->slope, cells->aspect, cells->ehoriz, cells->whoriz};
-  const double *raw_h[7] = {raw->prec, raw->t_a, raw->t_b, raw->wind, raw->shortwave, raw->longwave, raw->vp};
+  const double *raw_h[9] = {raw->prec, raw->t_a, raw->t_b, raw->wind, raw->shortwave, raw->longwave, raw->vp, raw->pressure,
+                            raw->density};
   const size_t n_out = (size_t)o->nrecs * C;
   double *dev = nullptr;
-  CK(cudaMalloc((void **)&dev, ((size_t)9 * C + (size_t)7 * nrf * C + VR_NFORCING * n_out) * sizeof(double)));
-  const double *site_d[9] = {}, *raw_d[7] = {};
+  CK(cudaMalloc((void **)&dev, ((size_t)9 * C + (size_t)9 * nrf * C + VR_NFORCING * n_out) * sizeof(double)));
+  const double *site_d[9] = {}, *raw_d[9] = {};
   double *p = dev;
   int rc = VR_OK;
   for (int i = 0; i < 9 && rc == VR_OK; i++, p += C)
     if (site_h[i]) { site_d[i] = p; if (cudaMemcpy(p, site_h[i], C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
-  for (int i = 0; i < 7 && rc == VR_OK; i++, p += (size_t)nrf * C)
+  for (int i = 0; i < 9 && rc == VR_OK; i++, p += (size_t)nrf * C)
     if (raw_h[i]) { raw_d[i] = p; if (cudaMemcpy(p, raw_h[i], (size_t)nrf * C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
   if (rc != VR_OK) { cudaFree(dev); return fail(rc, "host to device copy failed"); }
   vr_atmos_cells cd{C, site_d[0], site_d[1], site_d[2], site_d[3], site_d[4], site_d[5], site_d[6], site_d[7], site_d[8]};
-  vr_atmos_raw rd{nrf, raw_d[0], raw_d[1], raw_d[2], raw_d[3], raw_d[4], raw_d[5], raw_d[6]};
+  vr_atmos_raw rd{nrf, raw_d[0], raw_d[1], raw_d[2], raw_d[3], raw_d[4], raw_d[5], raw_d[6], raw_d[7], raw_d[8]};
   double *out_d[VR_NFORCING];
   for (int f = 0; f < VR_NFORCING; f++) out_d[f] = p + (size_t)f * n_out;
   rc = vr_atmos_prepare_device(device, o, &cd, &rd, out_d, nullptr);

@@ -200,6 +200,10 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
                         out.append(sw_day[i] * w[k] * steps_per_day / max(w.sum(), 1e-9))
                 elif name == "LONGWAVE":
                     out.append(lw_day[i] + (0.0 if k is None else 10.0 * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)))
+                elif name == "PRESSURE":            # kPa
+                    out.append(101.3 * np.exp(-elev / 8400.0) + 0.4 * np.sin(0.3 * i + (0 if k is None else 0.2 * k)))
+                elif name == "DENSITY":
+                    out.append(1.25 * np.exp(-elev / 9000.0) - 0.003 * tmean[i] + (0.0 if k is None else 0.004 * np.cos(hrs[k] / 3.8)))
                 elif name == "VP":
                     out.append(vp_day[i] * (1.0 if k is None else 1.0 + 0.05 * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)))
             return "".join(" %.4f" % x for x in out)
