@@ -97,7 +97,7 @@ int main(int argc, char **argv)
   ao.layout = subdaily ? VR_ATMOS_SUBDAILY_AIR_TEMP : VR_ATMOS_DAILY_TMAX_TMIN;
   ao.has_wind = col_wind >= 0; ao.min_wind_speed = g.min_wind_speed; ao.vp_interp = g.vp_interp; ao.vp_iter = g.vp_iter;
   ao.mtclim_swe_corr = g.mtclim_swe_corr; ao.lw_type = g.lw_type; ao.lw_cloud = g.lw_cloud; ao.plapse = g.plapse;
-  ao.sw_prec_thresh = g.sw_prec_thresh;
+  ao.sw_prec_thresh = g.sw_prec_thresh; ao.alma_input = g.alma_input;
   vr_atmos_cells site;
   memset(&site, 0, sizeof site);
   site.ncell = C; site.lat = vr_params_site(par, 0); site.lng = vr_params_site(par, 1);

@@ -18,7 +18,7 @@
  *   VR_ATMOS_DAILY_TMAX_TMIN    FORCE_DT 24, columns PREC TMAX TMIN [WIND]   (the bundled basin's format)
  *   VR_ATMOS_SUBDAILY_AIR_TEMP  FORCE_DT < 24, columns PREC AIR_TEMP [WIND]
  * each optionally with observed SHORTWAVE, LONGWAVE, VP, PRESSURE and DENSITY columns at the same FORCE_DT; SNOW_STEP == TIME_STEP
- * (NF == 1), ALMA_INPUT FALSE, no QAIR / REL_HUMID columns.  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
+ * (NF == 1), no QAIR / REL_HUMID columns (nor the ALMA-only RAINF / SNOWF / WIND_E / WIND_N splits).  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
  */
 #ifndef VICRES_ATMOS_H
 #define VICRES_ATMOS_H
@@ -49,7 +49,8 @@ typedef struct vr_atmos_options {
   int32_t lw_type;          /* LW_TYPE          default VR_LW_PRATA                              */
   int32_t lw_cloud;         /* LW_CLOUD         default VR_LW_CLOUD_DEARDORFF                    */
   int32_t plapse;           /* PLAPSE           default TRUE                                     */
-  int32_t reserved0;
+  int32_t alma_input;       /* ALMA_INPUT       default FALSE; TRUE: PREC is a rate (mm/s), temperatures are K, VP and
+                             * PRESSURE are Pa (initialize_atmos.c:374-402)                      */
   double  min_wind_speed;   /* MIN_WIND_SPEED   default 0.1                                      */
   double  sw_prec_thresh;   /* SW_PREC_THRESH   default 0 (mm; compared with MTCLIM's cm value as the reference does) */
   int32_t reserved[8];      /* [0] cells per batch (0 = 32768); [1] = 1: untiled daily-radiation kernel,

@@ -481,6 +481,9 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   tmaxhour = calloc(Ndays_local, sizeof(int)); tminhour = calloc(Ndays_local, sizeof(int));
   radfract = malloc(sizeof(double) * 366 * TINYSTEPS);
 
+  /* unit conversion, :374-416: ALMA rates -> amounts per forcing step and K -> C, else kPa -> Pa */
+  const double pscale = o->alma_input ? (double)(fdt * 3600) : 1.0, tshift = o->alma_input ? KELVIN : 0.0,
+               kpa = o->alma_input ? 1.0 : 1000.;
   /* forcing arrays referenced to local time, :469-540 */
   if (fdt == 24) {
     for (idx = 0; idx < Ndays_local; idx++) {
@@ -488,13 +491,13 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       if (hour_offset_int > 0) i--;
       if (i < 0) i = 0;
       if (i >= Ndays) i = Ndays - 1;
-      l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i);
-      l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i);
-      l_tb[idx] = fetch(c_tb, stride, nrec_forcing, i);
+      l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i) * pscale;
+      l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i) - tshift;
+      l_tb[idx] = fetch(c_tb, stride, nrec_forcing, i) - tshift;
       l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
       l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
-      l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * 1000.;       /* kPa2Pa, :404-414 */
-      l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * 1000.; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
+      l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * kpa;         /* kPa2Pa, :404-414 */
+      l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * kpa; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
     }
   }
   else {
@@ -503,12 +506,12 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       i = (idx - o->starthour + hour_offset_int) / fdt;
       if (i < 0) i += fstepspday;
       if (i >= Ndays * fstepspday) i -= fstepspday;
-      l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i) / fdt;
-      l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i);
+      l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i) * pscale / fdt;
+      l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i) - tshift;
       l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
       l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
-      l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * 1000.;
-      l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * 1000.; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
+      l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * kpa;
+      l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * kpa; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
     }
   }
   shift = (o->starthour - hour_offset_int < 0) ? 24 : 0;

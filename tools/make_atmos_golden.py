@@ -62,6 +62,10 @@ CASES = {
     "atmos_daily_obs_pressure": (dict(ncells=2, ndays=100, startyear=2001, lat_range=(0, 45), off_gmt=3, seed=317,
                                       extra_cols=("PRESSURE",), extra_global="PLAPSE FALSE"), dict(plapse=False)),
     "atmos_daily_obs_density": (dict(ncells=2, ndays=100, startyear=2001, lat_range=(0, 45), seed=318, extra_cols=("DENSITY",)), {}),
+    "atmos_daily_alma": (dict(ncells=2, ndays=120, startyear=2002, lat_range=(5, 50), off_gmt=-4, seed=319, alma=True,
+                              extra_cols=("VP", "PRESSURE")), dict(alma_input=True)),
+    "atmos_sub3h_alma": (dict(ncells=2, ndays=50, dt=3, startyear=2003, lat_range=(35, 60), seed=320, alma=True,
+                              extra_cols=("SHORTWAVE", "LONGWAVE")), dict(alma_input=True)),
     "atmos_daily_no_wind": (dict(ncells=3, ndays=120, startyear=1996, lat_range=(-35, 55), off_gmt=-2, no_wind=True, seed=310),
                             dict(has_wind=False)),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,

@@ -29,7 +29,7 @@ class vr_atmos_options(C.Structure):
                 ("startday", C.c_int32), ("starthour", C.c_int32), ("layout", C.c_int32), ("force_dt", C.c_int32),
                 ("has_wind", C.c_int32), ("vp_interp", C.c_int32), ("vp_iter", C.c_int32),
                 ("mtclim_swe_corr", C.c_int32), ("lw_type", C.c_int32), ("lw_cloud", C.c_int32), ("plapse", C.c_int32),
-                ("reserved0", C.c_int32), ("min_wind_speed", C.c_double), ("sw_prec_thresh", C.c_double),
+                ("alma_input", C.c_int32), ("min_wind_speed", C.c_double), ("sw_prec_thresh", C.c_double),
                 ("reserved", C.c_int32 * 8)]
 
 
@@ -50,7 +50,7 @@ RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp", "pres
 
 def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, starthour=0, layout=None, force_dt=None,
             has_wind=True, vp_interp=True, vp_iter="VP_ITER_ALWAYS", mtclim_swe_corr=False, lw_type="LW_PRATA",
-            lw_cloud="LW_CLOUD_DEARDORFF", plapse=True, min_wind_speed=0.1, sw_prec_thresh=0.0):
+            lw_cloud="LW_CLOUD_DEARDORFF", plapse=True, min_wind_speed=0.1, sw_prec_thresh=0.0, alma_input=False):
     """vr_atmos_options with the reference's defaults (initialize_global.c:146-211)."""
     o = vr_atmos_options()
     if force_dt is None:
@@ -62,6 +62,7 @@ def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, sta
     o.vp_interp, o.vp_iter, o.mtclim_swe_corr = int(vp_interp), VP_ITER.get(vp_iter, vp_iter), int(mtclim_swe_corr)
     o.lw_type, o.lw_cloud, o.plapse = LW_TYPE.get(lw_type, lw_type), LW_CLOUD.get(lw_cloud, lw_cloud), int(plapse)
     o.min_wind_speed, o.sw_prec_thresh = min_wind_speed, sw_prec_thresh
+    o.alma_input = int(alma_input)
     return o
 
 
@@ -168,7 +169,7 @@ def options_from_global(g):
                    startday=g.startday, starthour=g.starthour, layout=layout, force_dt=g.force_dt,
                    has_wind="WIND" in types, min_wind_speed=g.min_wind_speed, vp_interp=g.vp_interp, vp_iter=g.vp_iter,
                    mtclim_swe_corr=g.mtclim_swe_corr, lw_type=g.lw_type, lw_cloud=g.lw_cloud, plapse=g.plapse,
-                   sw_prec_thresh=g.sw_prec_thresh)
+                   sw_prec_thresh=g.sw_prec_thresh, alma_input=g.alma_input)
 
 
 def raw_from_columns(cols, layout):

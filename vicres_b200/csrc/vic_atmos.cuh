@@ -54,7 +54,7 @@ constexpr int TINY = 2880, TINY_HOUR = 120, NYD = 365;
 // scratch arrays hold one batch of cells and are indexed [row*CB + (c - c0)].
 struct Ctx {
   // options
-  int dt, nrecs, starthour, layout, fdt, has_wind, vp_interp, vp_iter, swe_corr, lw_type, lw_cloud, plapse;
+  int dt, nrecs, starthour, layout, fdt, has_wind, vp_interp, vp_iter, swe_corr, lw_type, lw_cloud, plapse, alma;
   double min_wind, sw_thresh;
   int Ndays, fsteps;
   const int16_t *cal;          // [Ndays+2] day_in_year of the days from one day BEFORE the start date on
@@ -115,13 +115,19 @@ VA_HD double local_hourly(const double *col, const Ctx &x, const Geo &g, int64_t
   if (i >= x.Ndays * x.fsteps) i -= x.fsteps;
   return fetch(col, x, c, i);
 }
+// unit conversion of the columns as read (initialize_atmos.c:374-416): ALMA rates -> amounts per forcing step and K -> C,
+// else kPa -> Pa.  (x * 1.0 and x - 0.0 are exact, so the traditional units go through unchanged.)
+VA_HD double u_prec(const Ctx &x, double v) { return v * (x.alma ? (double)(x.fdt * 3600) : 1.0); }
+VA_HD double u_temp(const Ctx &x, double v) { return v - (x.alma ? KELVIN : 0.0); }
+VA_HD double u_kpa(const Ctx &x, double v) { return v * (x.alma ? 1.0 : 1000.); }
+
 VA_HD double day_tmax(const Ctx &x, const Geo &g, int64_t c, int day)
 {
-  return x.fdt == 24 ? local_daily(x.r_ta, x, g, c, day) : x.tcon[c - x.c0];
+  return x.fdt == 24 ? u_temp(x, local_daily(x.r_ta, x, g, c, day)) : x.tcon[c - x.c0];
 }
 VA_HD double day_tmin(const Ctx &x, const Geo &g, int64_t c, int day)
 {
-  return x.fdt == 24 ? local_daily(x.r_tb, x, g, c, day) : x.tcon[x.CB + c - x.c0];
+  return x.fdt == 24 ? u_temp(x, local_daily(x.r_tb, x, g, c, day)) : x.tcon[x.CB + c - x.c0];
 }
 
 // observed columns in local time: hour idx of the local hourly axis (initialize_atmos.c:488-539; VP in Pa, :404-414)
@@ -129,7 +135,7 @@ VA_HD double obs_hour(const double *col, const Ctx &x, const Geo &g, int64_t c, 
 {
   return x.fdt == 24 ? local_daily(col, x, g, c, idx / 24) : local_hourly(col, x, g, c, idx);
 }
-VA_HD double obs_vp_hour(const Ctx &x, const Geo &g, int64_t c, int idx) { return obs_hour(x.r_vp, x, g, c, idx) * 1000.; }
+VA_HD double obs_vp_hour(const Ctx &x, const Geo &g, int64_t c, int idx) { return u_kpa(x, obs_hour(x.r_vp, x, g, c, idx)); }
 
 #if defined(__CUDA_ARCH__)
 #define VA_POW15(x) ((x) * sqrt(x))
@@ -429,7 +435,7 @@ VA_HDN void daily_prep(const Ctx &x, int64_t c)
     // initialize_atmos.c:758-766 -- the reference reads the FIRST local day's hours for every day
     double tmax = -9999, tmin = -9999;
     for (int hour = 0; hour < 24; hour++) {
-      double t = local_hourly(x.r_ta, x, g, c, hour);
+      double t = u_temp(x, local_hourly(x.r_ta, x, g, c, hour));
       if (hour >= 9 && (tmax == -9999 || t > tmax)) tmax = t;
       if (hour < 12 && (tmin == -9999 || t < tmin)) tmin = t;
     }
@@ -437,10 +443,10 @@ VA_HDN void daily_prep(const Ctx &x, int64_t c)
   }
   for (int day = 0; day < g.ndl; day++) {                  // :597-635
     double p;
-    if (x.fdt == 24) p = local_daily(x.r_prec, x, g, c, day);
+    if (x.fdt == 24) p = u_prec(x, local_daily(x.r_prec, x, g, c, day));
     else {
       p = 0;
-      for (int hour = 0; hour < 24; hour++) p += local_hourly(x.r_prec, x, g, c, day * 24 + hour) / x.fdt;
+      for (int hour = 0; hour < 24; hour++) p += u_prec(x, local_hourly(x.r_prec, x, g, c, day * 24 + hour)) / x.fdt;
     }
     x.prec_d[(int64_t)day * CB + lc] = p;
   }
@@ -844,7 +850,7 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
   const int dayi = (int)((float)hour / 24.0);
   double prec, wind, ta;
   if (x.fdt == 24) {                                       // :597-613, :641-659
-    prec = local_daily(x.r_prec, x, g, c, dayi) / (float)(1 * stepspday);
+    prec = u_prec(x, local_daily(x.r_prec, x, g, c, dayi)) / (float)(1 * stepspday);
     // the MIN_WIND_SPEED clamp at :654-657 addresses wind[NF], one past the record's value: no effect
     wind = x.has_wind ? local_daily(x.r_wind, x, g, c, dayi) : 3.0;
     double s = 0;                                          // :1005-1019
@@ -854,7 +860,7 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
   }
   else {                                                   // :616-628, :662-678, :737-752
     double s = 0;
-    for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_prec, x, g, c, idx) / x.fdt;
+    for (int idx = hour; idx < hour + dt; idx++) s += u_prec(x, local_hourly(x.r_prec, x, g, c, idx)) / x.fdt;
     prec = s;
     if (x.has_wind) {
       s = 0;
@@ -866,7 +872,7 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
     }
     else wind = 3.0;
     s = 0;
-    for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_ta, x, g, c, idx);
+    for (int idx = hour; idx < hour + dt; idx++) s += u_temp(x, local_hourly(x.r_ta, x, g, c, idx));
     ta = s / dt;
   }
   double sw = 0, vp = 0;                                   // :974-987, :1278-1291
@@ -894,8 +900,8 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
     else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_de, x, g, c, idx); dens = s / dt; }
   }
   if (x.r_pr) {
-    if (x.fdt == 24) p = local_daily(x.r_pr, x, g, c, dayi) * 1000.;
-    else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_pr, x, g, c, idx) * 1000.; p = s / dt; }
+    if (x.fdt == 24) p = u_kpa(x, local_daily(x.r_pr, x, g, c, dayi));
+    else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += u_kpa(x, local_hourly(x.r_pr, x, g, c, idx)); p = s / dt; }
   }
   else if (x.r_de) p = x.plapse ? (KELVIN + ta) * dens * RD : (275.0 + ta) * dens / 0.003486;
   else if (x.plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
@@ -983,7 +989,7 @@ inline void fill_options(const vr_atmos_options &o, Ctx &x)
 {
   x.dt = o.time_step; x.nrecs = o.nrecs; x.starthour = o.starthour; x.layout = o.layout; x.fdt = o.force_dt;
   x.has_wind = o.has_wind; x.vp_interp = o.vp_interp; x.vp_iter = o.vp_iter; x.swe_corr = o.mtclim_swe_corr;
-  x.lw_type = o.lw_type; x.lw_cloud = o.lw_cloud; x.plapse = o.plapse; x.min_wind = o.min_wind_speed;
+  x.lw_type = o.lw_type; x.lw_cloud = o.lw_cloud; x.plapse = o.plapse; x.alma = o.alma_input; x.min_wind = o.min_wind_speed;
   x.sw_thresh = o.sw_prec_thresh; x.Ndays = ndays_of(o); x.fsteps = 24 / o.force_dt;
 }
 

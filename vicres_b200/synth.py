@@ -56,7 +56,7 @@ def _fmt(x, nd=6):
 def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261019,
               startyear=1981, lat_range=(-40.0, 60.0), cold=0.0, overstory_frac=0.3,
               max_veg=3, extra_global="", result_dir=None, skip_output=False, snow_step=None,
-              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False, extra_cols=()):
+              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False, extra_cols=(), alma=False):
     """Write a complete reference-format case under `outdir`; return the global file path.
 
     dt == 24: daily PREC/TMAX/TMIN/WIND forcing (as the bundled basin); dt < 24: sub-daily
@@ -65,7 +65,8 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
     (round(lng/15)), so that local time differs from the forcing's time; `force_daily` writes the daily
     four-column file even when dt < 24 (FORCE_DT 24 with a sub-daily TIME_STEP); `no_wind` leaves the
     WIND column out (the reference then uses DEFAULT_WIND_SPEED); `extra_cols` appends observed SHORTWAVE (W/m2),
-    LONGWAVE (W/m2) and / or VP (kPa) columns.
+    LONGWAVE (W/m2) and / or VP (kPa) columns; `alma` writes the file in ALMA units (PREC as a rate in mm/s,
+    temperatures in K, VP and PRESSURE in Pa) with ALMA_INPUT TRUE.
     """
     rng = np.random.default_rng(seed)
     os.makedirs(outdir, exist_ok=True)
@@ -206,13 +207,17 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
                     out.append(1.25 * np.exp(-elev / 9000.0) - 0.003 * tmean[i] + (0.0 if k is None else 0.004 * np.cos(hrs[k] / 3.8)))
                 elif name == "VP":
                     out.append(vp_day[i] * (1.0 if k is None else 1.0 + 0.05 * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)))
+            if alma:
+                out = [x * 1000.0 if name in ("VP", "PRESSURE") else x for x, name in zip(out, extra_cols)]
             return "".join(" %.4f" % x for x in out)
         hrs = (np.arange(steps_per_day) + 0.5) * dt if dt < 24 else None
         fn = os.path.join(forc_dir, "data_%.4f_%.4f" % (lat, lng))
         with open(fn, "w") as f:
             if dt == 24 or force_daily:
                 for i in range(ndays):
-                    if no_wind:
+                    if alma:
+                        f.write("%.8e %.4f %.4f %.4f%s\n" % (prec[i] / 86400.0, tmax[i] + 273.15, tmin[i] + 273.15, wind[i], extras(i)))
+                    elif no_wind:
                         f.write("%.4f %.4f %.4f%s\n" % (prec[i], tmax[i], tmin[i], extras(i)))
                     else:
                         f.write("%.4f %.4f %.4f %.4f%s\n" % (prec[i], tmax[i], tmin[i], wind[i], extras(i)))
@@ -221,7 +226,10 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
                 for i in range(ndays):
                     for k in range(steps_per_day):
                         ta = tmean[i] + 0.5 * dtr[i] * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)
-                        f.write("%.4f %.4f %.4f%s\n" % (prec[i] / steps_per_day, ta, wind[i], extras(i, k)))
+                        if alma:
+                            f.write("%.8e %.4f %.4f%s\n" % (prec[i] / 86400.0, ta + 273.15, wind[i], extras(i, k)))
+                        else:
+                            f.write("%.4f %.4f %.4f%s\n" % (prec[i] / steps_per_day, ta, wind[i], extras(i, k)))
 
     with open(os.path.join(outdir, "soil.txt"), "w") as f:
         f.write("\n".join(soil_lines) + "\n")
@@ -245,7 +253,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         types = ["PREC", "AIR_TEMP", "WIND"] + list(extra_cols)
         g += ["N_TYPES %d" % len(types)] + ["FORCE_TYPE %s" % t for t in types] + ["FORCE_DT %d" % dt]
     g += ["FORCEYEAR %d" % startyear, "FORCEMONTH 1", "FORCEDAY 1", "FORCEHOUR 0", "GRID_DECIMAL 4",
-          "WIND_H 10.0", "MEASURE_H 2.0", "ALMA_INPUT FALSE",
+          "WIND_H 10.0", "MEASURE_H 2.0", "ALMA_INPUT %s" % ("TRUE" if alma else "FALSE"),
           "SOIL %s/soil.txt" % outdir, "BASEFLOW ARNO", "JULY_TAVG_SUPPLIED FALSE", "ORGANIC_FRACT FALSE",
           "VEGLIB %s/veglib.txt" % outdir, "VEGPARAM %s/veg.txt" % outdir, "ROOT_ZONES 3",
           "VEGPARAM_LAI FALSE", "LAI_SRC FROM_VEGLIB"]
