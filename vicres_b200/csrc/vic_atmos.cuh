@@ -841,7 +841,7 @@ VA_HD double hourly_vp(const Ctx &x, const Geo &g, int64_t lc, int idx)
   return v;
 }
 
-VA_HDN void record(const Ctx &x, int64_t c, int rec)
+VA_HD void record_inl(const Ctx &x, int64_t c, int rec)
 {
   const int64_t lc = c - x.c0, o = (int64_t)rec * x.C + c;
   const Geo g = cell_geo(x, c);
@@ -931,6 +931,8 @@ VA_HDN void record(const Ctx &x, int64_t c, int rec)
   else lw = longwave(x, tskc, ta, vp);
   x.out[VR_F_LONGWAVE][o] = lw;
 }
+
+VA_HDN void record(const Ctx &x, int64_t c, int rec) { record_inl(x, c, rec); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host helpers shared by the library and the test harness

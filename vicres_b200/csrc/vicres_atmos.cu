@@ -108,7 +108,15 @@ __global__ void __launch_bounds__(TPB) k_hours(const __grid_constant__ va::Ctx x
 __global__ void __launch_bounds__(TPB) k_rec(const __grid_constant__ va::Ctx x, int64_t cb)
 {
   int rec; int64_t c;
-  if (locate(x, cb, rec, c)) va::record(x, c, rec);
+  if (!locate(x, cb, rec, c)) return;
+  // the plain four-column layout in traditional units gets a copy of the body in which the observed-column branches
+  // and the unit factors are compile-time dead (the fields are constants of the local copy)
+  if (!x.r_sw && !x.r_lw && !x.r_vp && !x.r_pr && !x.r_de && !x.alma) {
+    va::Ctx y = x;
+    y.r_sw = nullptr; y.r_lw = nullptr; y.r_vp = nullptr; y.r_pr = nullptr; y.r_de = nullptr; y.alma = 0;
+    va::record_inl(y, c, rec);
+  }
+  else va::record_inl(x, c, rec);
 }
 
 __global__ void k_diag_cr(int64_t n, const double *x, double *a, const double *y, double *c)
