@@ -85,6 +85,7 @@ int main(int argc, char **argv)
     snprintf(path, sizeof path, "%s%.*f_%.*f", g.forcing1, g.grid_decimal, lat[c], g.grid_decimal, lng[c]);
     int64_t got = vr_read_forcing_file(&g, path, nrf, one);
     if (got < 0) die(path, vr_params_last_error());
+    if (got < nrf) die(path, "Not enough records in the forcing file");      /* read_atmos_data.c:178-182 */
     for (t = 0; t < nt; t++)
       for (r = 0; r < got; r++) raw[((size_t)t * nrf + r) * C + c] = one[(size_t)t * nrf + r];
   }

@@ -90,7 +90,8 @@ typedef struct vr_options {
   int32_t nlayer;           /* options.Nlayer, 2 or 3                                   */
   int32_t nbands;           /* options.SNOW_BAND, 1..10                                 */
   int32_t dt_hours;         /* global_param.dt (TIME_STEP), 1..24                       */
-  int32_t snow_step_hours;  /* options.SNOW_STEP; must equal dt_hours here (NF == 1)    */
+  int32_t snow_step_hours;  /* options.SNOW_STEP, a divisor of dt_hours: NF = dt_hours / snow_step_hours passes of the
+                               snow model per record (surface_fluxes.c:385-396, get_global_param.c:761-770)         */
   double  max_snow_temp;    /* global_param.MAX_SNOW_TEMP                               */
   double  min_rain_temp;    /* global_param.MIN_RAIN_TEMP                               */
   double  wind_h;           /* global_param.wind_h (WIND_H)                             */
@@ -152,7 +153,10 @@ typedef struct vr_forcing {
   int32_t nrec;
   const int32_t *month;        /* [nrec] dmy.month 1..12            (host memory in both calls) */
   const int32_t *day_in_year;  /* [nrec] dmy.day_in_year 1..366     (host memory in both calls) */
-  const double  *field[VR_NFORCING];   /* each [nrec*C] */
+  const double  *field[VR_NFORCING];   /* each [nrec*C]; with NF > 1 each [nrec*(NF+1)*C]: per record the NF
+                                          sub-step values, then the record's own (atmos-><field>[0..NF-1], [NR]) */
+  const int32_t *snowflag;     /* [nrec*C] atmos->snowflag[NR], or NULL; read only when NF > 1 (same memory space
+                                  as field[])                                                                  */
 } vr_forcing;
 
 typedef struct vr_handle vr_handle;

@@ -81,6 +81,9 @@ typedef struct vr_global {
    * that day is "<prefix>_YYYYMMDD", get_global_param.c:961-964; BINARY_STATE_FILE) -> vr_read/write_state_file */
   char    init_state_file[512], statename[512];
   int32_t stateyear, statemonth, stateday, binary_state_file;
+  /* a second forcing file (FORCING2 <prefix>) and a custom output selection (N_OUTFILES / OUTFILE / OUTVAR lines,
+   * parse_output_info.c:62-118; counted here, parsed by vr_outsel_read) */
+  int32_t forcing2, n_outfile_lines, n_outvar_lines;
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -152,8 +152,17 @@ def case_from_dump(d):
     cells["tile_LAI"] = np.array(t_lai).reshape(-1, 12)
     cells["tile_albedo"] = np.array(t_alb).reshape(-1, 12)
     cells["tile_vegcover"] = np.array(t_vc).reshape(-1, 12)
-    forcing = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2)   # [nrec, 9, C]
-    forcing = np.ascontiguousarray(forcing.transpose(1, 0, 2))                    # [9, nrec, C]
+    NF = int(d["NF"][0])
+    if NF == 1:
+        forcing = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2)   # [nrec, 9, C]
+        forcing = np.ascontiguousarray(forcing.transpose(1, 0, 2))                    # [9, nrec, C]
+        snowflag = None
+    else:
+        # sub-stepped snow model: per record the NF sub-step values, then the record's own (index NR == NF):
+        # [nrec, 9, NF+1] per cell -> [9, nrec * (NF+1), C], the layout of vr_forcing.field[]
+        a = np.stack([d["c%d/atmos" % c] for c in range(C)], axis=3)                  # [nrec, 9, NF+1, C]
+        forcing = np.ascontiguousarray(a.transpose(1, 0, 2, 3).reshape(9, nrec * (NF + 1), C))
+        snowflag = np.ascontiguousarray(np.stack([d["c%d/snowflag" % c][:, NF] for c in range(C)], axis=1).astype(np.int32))
     dmy = d["dmy"]
     return {
         "nlayer": L, "nbands": NB, "nrec": nrec, "ncell": C, "dt": int(d["dt"][0]),
@@ -161,7 +170,9 @@ def case_from_dump(d):
         "max_snow_temp": float(d["MAX_SNOW_TEMP"][0]), "min_rain_temp": float(d["MIN_RAIN_TEMP"][0]),
         "wind_h": float(d["wind_h"][0]),
         "lib": lib, "cells": cells, "month": dmy[:, 1].astype(np.int32), "doy": dmy[:, 4].astype(np.int32),
-        "forcing": forcing, "tair0": forcing[0, 0, :].copy(), "ntile_max": ntile_max,
+        "forcing": forcing, "snowflag": snowflag,
+        "tair0": forcing[0, NF if NF > 1 else 0, :].copy(),       # atmos[0].air_temp[NR]
+        "ntile_max": ntile_max,
     }
 
 

@@ -25,15 +25,18 @@ def relerr(a, b, floor=ABS_FLOOR):
 
 def load_fixture(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    nlayer, nbands, dt = [int(x) for x in z["meta"]]
+    nlayer, nbands, dt = [int(x) for x in z["meta"][:3]]
+    snow_step = int(z["meta"][3]) if len(z["meta"]) > 3 else dt
     mst, mrt, wind_h = [float(x) for x in z["meta_f"]]
     names = [str(x) for x in z["out_names"]]
     lib = {k[4:]: z[k] for k in z.files if k.startswith("lib_")}
     cells = {k[6:]: z[k] for k in z.files if k.startswith("cells_")}
-    opt = abi.default_options(nlayer, nbands, dt, out=names, max_snow_temp=mst, min_rain_temp=mrt, wind_h=wind_h)
+    opt = abi.default_options(nlayer, nbands, dt, out=names, max_snow_temp=mst, min_rain_temp=mrt, wind_h=wind_h,
+                              snow_step_hours=snow_step)
     return {"opt": opt, "lib": lib, "cells": cells, "month": z["month"], "doy": z["doy"],
-            "forcing": z["forcing"], "tair0": z["tair0"], "names": names, "ref": z["ref_out"],
-            "nlayer": nlayer, "nbands": nbands, "dt": dt}
+            "forcing": z["forcing"], "snowflag": z["snowflag"] if "snowflag" in z.files else None,
+            "tair0": z["tair0"], "names": names, "ref": z["ref_out"],
+            "nlayer": nlayer, "nbands": nbands, "dt": dt, "snow_step": snow_step}
 
 
 # Parity policy.  The reference algorithm is ill-conditioned on a small share of steps:

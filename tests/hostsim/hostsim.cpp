@@ -10,6 +10,29 @@
 
 using namespace vr;
 
+// the unit's snow words for unit_record(): here simply the UnitS of the harness
+struct HostSnowIO {
+  UnitS *s;
+  SnowS load() const
+  {
+    SnowS x;
+    x.swq = s->swq; x.surf_temp = s->surf_temp; x.pack_temp = s->pack_temp; x.surf_water = s->surf_water;
+    x.pack_water = s->pack_water; x.density = s->density; x.depth = s->depth; x.albedo = s->albedo;
+    x.coldcontent = s->coldcontent; x.coverage = s->coverage; x.snow_canopy = s->snow_canopy;
+    x.tmp_int_storage = s->tmp_int_storage; x.last_snow = s->last_snow; x.MELTING = s->MELTING;
+    return x;
+  }
+  void store(const SnowS &x) const
+  {
+    s->swq = x.swq; s->surf_temp = x.surf_temp; s->pack_temp = x.pack_temp; s->surf_water = x.surf_water;
+    s->pack_water = x.pack_water; s->density = x.density; s->depth = x.depth; s->albedo = x.albedo;
+    s->coldcontent = x.coldcontent; s->coverage = x.coverage; s->snow_canopy = x.snow_canopy;
+    s->tmp_int_storage = x.tmp_int_storage; s->last_snow = x.last_snow; s->MELTING = x.MELTING;
+  }
+  void store_none() const { s->albedo = NEW_SNOW_ALB; s->last_snow = (int)MISSINGV; s->MELTING = 0; }
+  void fallback(int kind) const { if (kind) s->fb_fol++; else s->fb_snow++; }
+};
+
 extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cells *cells, const vr_forcing *f,
                       const double *tair0, double *out /* [n_out][nrec][C] */)
 {
@@ -56,22 +79,36 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
         cell_carry(S, NL, svc);
       }
     }
+    const int NF = opt->dt_hours / opt->snow_step_hours, NS = NF > 1 ? NF + 1 : 1;
     for (int rec = 0; rec < nrec; rec++) {
-      Forc fo;
-      size_t k = (size_t)rec * C + c;
-      fo.air_temp = f->field[VR_F_AIR_TEMP][k]; fo.prec = f->field[VR_F_PREC][k]; fo.wind = f->field[VR_F_WIND][k];
-      fo.vp = f->field[VR_F_VP][k]; fo.vpd = f->field[VR_F_VPD][k]; fo.pressure = f->field[VR_F_PRESSURE][k];
-      fo.density = f->field[VR_F_DENSITY][k]; fo.shortwave = f->field[VR_F_SHORTWAVE][k];
-      fo.longwave = f->field[VR_F_LONGWAVE][k];
-      fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
+      // sub-record kk of this record ([field][rec * NS + kk][cell]; kk == NS - 1 is the record itself)
+      auto forc = [&](int kk) {
+        Forc fo;
+        size_t k = ((size_t)rec * NS + kk) * C + c;
+        fo.air_temp = f->field[VR_F_AIR_TEMP][k]; fo.prec = f->field[VR_F_PREC][k]; fo.wind = f->field[VR_F_WIND][k];
+        fo.vp = f->field[VR_F_VP][k]; fo.vpd = f->field[VR_F_VPD][k]; fo.pressure = f->field[VR_F_PRESSURE][k];
+        fo.density = f->field[VR_F_DENSITY][k]; fo.shortwave = f->field[VR_F_SHORTWAVE][k];
+        fo.longwave = f->field[VR_F_LONGWAVE][k];
+        fo.mon = f->month[rec] - 1; fo.doy = f->day_in_year[rec];
+        fo.snowflag = (NF > 1 && f->snowflag) ? f->snowflag[(size_t)rec * C + c] : 0;
+        return fo;
+      };
+      const Forc fo = forc(NS - 1);
       for (int j = 0; j < nu; j++) {
         const int64_t u = P.u_slot[fu0 + j];
         const double *tm = &P.tm[((size_t)P.u_tile[u] * 12 + fo.mon) * TM_N];
         const double *ae = &P.ae[((size_t)P.u_aero[u] * 12 + fo.mon) * AE_N];
         const double *tl = P.tl.size() > 1 ? &P.tl[((size_t)P.u_tile[u] * 12 + fo.mon) * TL_N] : nullptr;
         const double *ap = P.ap.size() > 1 ? &P.ap[((size_t)P.u_aero[u] * 12 + fo.mon) * AP_N] : nullptr;
-#define HS_STEP(EX) unit_step_terms<EX>(cc, UC[u], tm, ae, fo, NL, opt->dt_hours, opt->max_snow_temp, opt->min_rain_temp, S_[u], \
-                                        P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap)
+        HostSnowIO sio{&S_[u]};
+        UnitS &s = S_[u];
+        HotS h;
+        for (int l = 0; l < MAXL; l++) h.moist.v[l] = s.moist[l];
+        h.Wdew = s.Wdew; h.T0 = s.T0; h.T1 = s.T1; h.LongUnderOut = s.LongUnderOut; h.Tfoliage = s.Tfoliage;
+        bool snowy = s.swq > 0 || s.snow_canopy > 0 || s.coverage != 0;
+        bool tidy = !snowy && (s.last_snow != (int)MISSINGV || s.MELTING != 0 || s.albedo != NEW_SNOW_ALB);
+#define HS_STEP(EX) unit_record<EX>(cc, UC[u], tm, ae, forc, NF, NL, opt->dt_hours, opt->snow_step_hours, opt->max_snow_temp, \
+                                    opt->min_rain_temp, h, snowy, tidy, sio, P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap)
         switch (term_extras(tmap)) {
           case 0: HS_STEP(0); break;
           case EX_PET: HS_STEP(EX_PET); break;
@@ -79,6 +116,9 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
           default: HS_STEP(EX_PET | EX_ZWT); break;
         }
 #undef HS_STEP
+        if (tidy) sio.store_none();     // the harness keeps no flags between records
+        for (int l = 0; l < MAXL; l++) s.moist[l] = h.moist.v[l];
+        s.Wdew = h.Wdew; s.T0 = h.T0; s.T1 = h.T1; s.LongUnderOut = h.LongUnderOut; s.Tfoliage = h.Tfoliage;
       }
       if (nu > 0) {
         cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);

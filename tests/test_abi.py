@@ -117,8 +117,8 @@ def test_default_options_match_reference_default_output_list(lib):
 def test_argument_validation_needs_no_device(lib):
     h = C.c_void_p()
     bad = abi.default_options(3)
-    bad.snow_step_hours = 1                     # NF > 1: outside the supported path
-    assert lib.vr_create(C.byref(bad), 0, C.byref(h)) == abi.VR_ERR_UNSUPPORTED
+    bad.snow_step_hours = 5                     # SNOW_STEP must divide TIME_STEP (get_global_param.c:761-770)
+    assert lib.vr_create(C.byref(bad), 0, C.byref(h)) == abi.VR_ERR_ARG
     bad = abi.default_options(3)
     bad.nlayer = 5
     assert lib.vr_create(C.byref(bad), 0, C.byref(h)) == abi.VR_ERR_ARG

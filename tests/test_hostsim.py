@@ -30,9 +30,21 @@ def hostsim():
 def test_device_physics_on_host_matches_golden(hostsim, name):
     fx = load_fixture(name)
     lib, cells = abi.pack_veglib(fx["lib"]), abi.pack_cells(fx["cells"])
-    f = abi.pack_forcing(fx["month"], fx["doy"], fx["forcing"])
+    f = abi.pack_forcing(fx["month"], fx["doy"], fx["forcing"], fx["snowflag"])
     out = np.zeros_like(fx["ref"])
     t0 = np.ascontiguousarray(fx["tair0"])
     assert hostsim.hs_run(C.byref(fx["opt"]), lib.ref(), cells.ref(), f.ref(), t0.ctypes.data, out.ctypes.data) == 0
     for i, n in enumerate(fx["names"]):
         assert np.array_equal(out[i], fx["ref"][i]), "%s differs from the reference (%s)" % (n, name)
+
+
+def test_pow_table_error_bound(tmp_path):
+    """The arithmetic of the device power function (vr::pow_table_eval: table-driven log2 / exp2) compiled for the
+    host, against powl() on 2e6 seeded arguments of the model's ranges: relative error <= 2e-16 * (2 + |y log2 x|),
+    which is < 1e-13 for every argument the step produces."""
+    exe = str(tmp_path / "pow_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", exe,
+                    os.path.join(HS_DIR, "pow_table_check.cpp"), "-lm"], check=True)
+    n, norm, rel, unhandled = subprocess.run([exe, "2000000"], check=True, capture_output=True, text=True).stdout.split()
+    assert int(unhandled) == 0
+    assert float(norm) <= 2e-16 and float(rel) < 1e-13

@@ -35,6 +35,12 @@ CASES = {
     "sub3h_snow": dict(ncells=4, nlayer=3, nbands=2, ndays=100, dt=3, cold=16.0, lat_range=(35, 65),
                        overstory_frac=0.5, seed=103),
     "zero_wind_l2": dict(ncells=4, nlayer=2, nbands=1, ndays=300, cold=10.0, wind_zero_frac=0.1, seed=104),
+    # SNOW_STEP < TIME_STEP: the snow model sub-stepped (NF = 8 and NF = 24 passes per daily record; the reference
+    # allows it only with a daily model step, get_global_param.c:771-774)
+    "daily_snowstep3": dict(ncells=6, nlayer=3, nbands=2, ndays=400, cold=12.0, lat_range=(30, 62), overstory_frac=0.5,
+                            snow_step=3, seed=105),
+    "daily_snowstep1": dict(ncells=4, nlayer=3, nbands=1, ndays=200, cold=10.0, lat_range=(35, 60), overstory_frac=0.5,
+                            snow_step=1, seed=106),
 }
 
 
@@ -86,8 +92,10 @@ def save_fixture(name, dump):
     ref = refdump.ref_outputs(d, names)
     arrays = {"out_names": np.array(names), "ref_out": ref, "forcing": cs["forcing"], "month": cs["month"],
               "doy": cs["doy"], "tair0": cs["tair0"],
-              "meta": np.array([cs["nlayer"], cs["nbands"], cs["dt"]], dtype=np.int64),
+              "meta": np.array([cs["nlayer"], cs["nbands"], cs["dt"], cs["snow_step"]], dtype=np.int64),
               "meta_f": np.array([cs["max_snow_temp"], cs["min_rain_temp"], cs["wind_h"]])}
+    if cs["snowflag"] is not None:
+        arrays["snowflag"] = cs["snowflag"]
     for k, v in cs["lib"].items():
         arrays["lib_" + k] = np.asarray(v)
     for k, v in cs["cells"].items():
@@ -101,13 +109,18 @@ def save_fixture(name, dump):
 def main():
     if not os.path.exists(DRIVER):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    only = sys.argv[1:]
     with tempfile.TemporaryDirectory() as tmp:
         for name, kw in CASES.items():
+            if only and name not in only:
+                continue
             work = os.path.join(tmp, name)
             g = synth.make_case(work, **kw)
             dump = os.path.join(work, "dump.bin")
             run_driver(g, dump)
             save_fixture(name, dump)
+        if only and "bundled_basin_cell" not in only:
+            return
         work = os.path.join(tmp, "bundled")
         os.makedirs(work)
         g = bundled_case(work)

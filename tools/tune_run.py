@@ -9,9 +9,9 @@ for lib in sorted(glob.glob(os.path.join(ROOT, "_variants", "lib_*.so"))):
   for ch in chunks:
     env = dict(os.environ, VICRES_LIB=lib)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "2", "--no-cpu-baseline",
-                        "--e2e-steps", "1", "--cells", cells, "--block", recs, "--chunk", ch], env=env, capture_output=True, text=True)
+                        "--e2e-steps", "1", "--no-forcing-prep", "--cells", cells, "--block", recs, "--chunk", ch], env=env, capture_output=True, text=True)
     try:
         j = json.loads(r.stdout.strip().splitlines()[-1])
-        print("%-20s chunk %3s value %.4e  e2e %.4e  ms/step %.1f" % (os.path.basename(lib), ch, j["value"], j["e2e"]["value"], j["ms_per_step"]), flush=True)
+        print("%-24s chunk %3s value %.4e  e2e %.4e  ms/step %.1f  k_units %.3f ms  sm %s MHz" % (os.path.basename(lib), ch, j["value"], j["e2e"]["value"], j["ms_per_step"], j["roofline"]["kernel_ms"], j["clocks"]["sm_mhz"]), flush=True)
     except Exception as e:
         print(os.path.basename(lib), "FAILED", r.stderr[-400:], flush=True)

@@ -66,7 +66,7 @@ class vr_cells(C.Structure):
 
 class vr_forcing(C.Structure):
     _fields_ = [("nrec", C.c_int32), ("month", _pi32), ("day_in_year", _pi32),
-                ("field", _pd * VR_NFORCING)]
+                ("field", _pd * VR_NFORCING), ("snowflag", _pi32)]
 
 
 def _f64(a):
@@ -78,11 +78,11 @@ def _ptr(a, ty):
 
 
 def default_options(nlayer=3, nbands=1, dt_hours=24, out=None, max_snow_temp=0.5, min_rain_temp=-0.5,
-                    wind_h=10.0):
+                    wind_h=10.0, snow_step_hours=None):
     """Reference defaults (initialize_global.c:146-211) and the default fluxes+snow output set
     (set_output_defaults.c:78-162): 19 + nlayer flux columns, 4 snow columns."""
     o = vr_options()
-    o.nlayer, o.nbands, o.dt_hours, o.snow_step_hours = nlayer, nbands, dt_hours, dt_hours
+    o.nlayer, o.nbands, o.dt_hours, o.snow_step_hours = nlayer, nbands, dt_hours, snow_step_hours or dt_hours
     o.max_snow_temp, o.min_rain_temp, o.wind_h = max_snow_temp, min_rain_temp, wind_h
     if out is None:
         out = default_out_vars(nlayer)
@@ -151,8 +151,9 @@ def pack_cells(cells):
     return Packed(s, keep)
 
 
-def pack_forcing(month, day_in_year, fields):
-    """fields: [9, nrec, C] float64 (or list of 9 [nrec, C] arrays) in FORCING_FIELDS order."""
+def pack_forcing(month, day_in_year, fields, snowflag=None):
+    """fields: [9, nrec, C] float64 (or list of 9 [nrec, C] arrays) in FORCING_FIELDS order; with a sub-stepped snow
+    model (NF > 1) [9, nrec * (NF + 1), C] and snowflag [nrec, C] int32."""
     s = vr_forcing()
     keep = {"month": np.ascontiguousarray(month, dtype=np.int32),
             "doy": np.ascontiguousarray(day_in_year, dtype=np.int32)}
@@ -162,4 +163,7 @@ def pack_forcing(month, day_in_year, fields):
     for i in range(VR_NFORCING):
         keep["f%d" % i] = _f64(fields[i])
         s.field[i] = _ptr(keep["f%d" % i], _pd)
+    if snowflag is not None:
+        keep["snowflag"] = np.ascontiguousarray(snowflag, dtype=np.int32)
+        s.snowflag = _ptr(keep["snowflag"], _pi32)
     return Packed(s, keep)

@@ -10,6 +10,18 @@
 #include "../../include/vicres.h"
 #include "vic_physics.cuh"
 
+// The term buffer is written once by k_units and read once by k_cells, 50 MB per record of a 100k-cell grid.  With
+// -DVR_STREAM_HINTS its stores and loads carry the evict-first hint; measured 2.6 % SLOWER on the 100k-cell benchmark
+// (the L2 no longer merges the scattered 8-byte stores into full sectors before they leave; profiles/r2_tuning.md),
+// so the hint is off by default.
+#if defined(__CUDA_ARCH__) && defined(VR_STREAM_HINTS)
+#define VR_STREAM_ST(p, v) __stcs((p), (v))
+#define VR_STREAM_LD(p) __ldcs(p)
+#else
+#define VR_STREAM_ST(p, v) (*(p) = (v))
+#define VR_STREAM_LD(p) (*(p))
+#endif
+
 namespace vr {
 
 enum {
@@ -88,7 +100,7 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
 {
   const double AF = cv * af * 1. * 1.;
   const bool HasVeg = !uc.is_bare;
-#define T_(k, expr) do { if (tmap.row[k] >= 0) col[(size_t)tmap.row[k] * stride] = (expr); } while (0)
+#define T_(k, expr) do { if (tmap.row[k] >= 0) VR_STREAM_ST(col + (size_t)tmap.row[k] * stride, (expr)); } while (0)
   double tmp_evap = 0.0;
 #pragma unroll
   for (int l = 0; l < MAXL; l++) {
@@ -160,19 +172,206 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
 #undef T_
 }
 
-// One unit, one record, and its terms: the single out-of-line body the kernel calls per record.  Keeping
-// unit_step() and unit_terms() in one function lets the ~30 per-unit results travel in registers
-// instead of a UnitOut struct in local memory.
-template <int extras>
-VR_HDN void unit_step_terms(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
-                            int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, double cv, double af,
-                            const TermMap &tmap, double *col, int stride, bool write, const double *tl = nullptr,
-                            const double *ap = nullptr)
+// One unit, one record, and its terms: full_energy.c:210-470 for one tile x band pair -- the canopy terms of the
+// month, the passes of surface_fluxes' sub-step loop (one, or NF = TIME_STEP / SNOW_STEP when the snow model is
+// sub-stepped and the unit has snow or the record has snowfall: surface_fluxes.c:385-396), their sums and averages
+// (:1030-1123), runoff() once per record (:1130-1150), and the unit's area-weighted terms.
+//   forc(k)  -> Forc of sub-step k = 0..NF-1, or of the record itself for k == NF (k == 0 when NF == 1)
+//   sio      -> the unit's snow words: load() / store(SnowS) / fallback(kind); only touched on the snow path
+//   h, snowy -> the hot state and "some snow word is non-zero", which the caller keeps in registers between records
+//   tidy     -> the stored MELTING / last_snow / albedo are not yet what the reference's no-snow branch leaves behind
+//               (solve_snow.c:565-577); the first record without snow stores them (sio.store_none())
+// Terms that do not depend on runoff() are stored before it is called, so that nothing but the evaporation and the
+// moisture stays live across the hourly drainage loop.  Returns 1 when the reference would have returned ERROR
+// (arno_evap.c:112-151).
+template <int extras, class ForcOf, class SnowIO>
+VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
+                      int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
+                      bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride, bool write,
+                      const double *tl = nullptr, const double *ap = nullptr)
 {
-  UnitOut uo;
-  UnitExtra ux;
-  unit_step<extras>(cc, uc, tm, ae, f, NL, dt_hours, max_snow_temp, min_rain_temp, s, uo, ux, tl, ap);
-  if (write) unit_terms<extras>(uc, cv, af, s, uo, NL, tmap, col, stride, &ux);
+  const bool is_veg = !uc.is_bare, overstory = uc.overstory != 0;
+  VegP vp;
+  vp.rarc = uc.rarc; vp.rmin = uc.rmin; vp.RGL = uc.RGL;
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) vp.root[l] = uc.root[l];
+  CanopyM cm;
+  cm.vegcover = 0; cm.LAI = 0; cm.Wdmax = 0; cm.albedo = BARE_SOIL_ALBEDO; cm.surf_atten = 1.;
+  if (is_veg) {
+    cm.vegcover = tm[TM_VEGCOVER]; cm.LAI = tm[TM_LAI]; cm.Wdmax = tm[TM_WDMAX]; cm.albedo = tm[TM_ALBEDO];
+    cm.surf_atten = tm[TM_SURF_ATTEN];
+  }
+  const Forc fr = forc(NF > 1 ? NF : 0);
+  // which instance of the pass: the one with the snow model when the unit carries snow, the record has snowfall
+  // anywhere in the cell (sub-stepping follows) or in this band
+  bool general = snowy || (NF > 1 && fr.snowflag);
+  if (!general) {
+    double rf, sf;
+    rain_snow_split(fr.air_temp + uc.Tfactor, fr.prec * uc.Pfactor, max_snow_temp, min_rain_temp, rf, sf);
+    general = sf > 0.;
+  }
+#if defined(__CUDA_ARCH__)
+  general = __any_sync(0xffffffffu, general);     // per warp: a warp never runs both instances
+#endif
+  SnowS sn = snow_none();
+  if (general) sn = sio.load();
+  else if (tidy) { sio.store_none(); tidy = false; }
+  // full_energy.c:221-224: storages per unit of vegetated area
+  if (is_veg) {
+    h.Wdew /= cm.vegcover;
+    if (general) sn.snow_canopy /= cm.vegcover;
+  }
+  const bool substep = NF > 1 && (sn.swq > 0 || sn.snow_canopy > 0 || fr.snowflag);     // surface_fluxes.c:385-396
+  const int npass = substep ? NF : 1, pdt = substep ? snow_step_hours : dt_hours;
+  const double Tgrnd = h.T0;
+  double coverage = sn.coverage, surf_atten = cm.surf_atten;
+  // sums over the passes (surface_fluxes.c:935-1025)
+  double st_ppt = 0, st_canopyevap = 0, st_throughfall = 0, st_vapor = 0, st_cvapor = 0, st_melt = 0, st_prec = 0,
+         st_rain = 0, st_snow = 0, st_nshort = 0, st_nlong = 0, st_lover = 0, st_lunder = 0, st_aover = 0, st_aunder = 0,
+         st_gflux = 0, st_dh = 0, st_cond0 = 0, st_cond1 = 0, st_luo = 0, Tsurf = 0;
+  M3 st_evap, bef;
+  P6 st_pot;
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) { st_evap.v[l] = 0; bef.v[l] = 0; }
+#pragma unroll
+  for (int i = 0; i < 6; i++) st_pot.v[i] = 0;
+  int snow_flag = 0, err = 0;
+  const bool sync_ok = NF == 1;
+#pragma unroll 1
+  for (int p = 0; p < npass; p++) {
+    Forc f = fr;
+    if (substep) {
+      f = forc(p);
+      f.wind = fr.wind;           // the aerodynamic resistances of all passes come from wind[NR] (full_energy.c:332)
+    }
+    SurfOut r;
+    if (general)
+      r = surface_pass<extras, true>(cc, vp, is_veg, overstory, uc.Tfactor, uc.Pfactor, cm, ae, f, NL, pdt, max_snow_temp,
+                                     min_rain_temp, Tgrnd, h, sn, coverage, surf_atten, tl, ap, sync_ok, dt_hours);
+    else
+      r = surface_pass<extras, false>(cc, vp, is_veg, overstory, uc.Tfactor, uc.Pfactor, cm, ae, f, NL, pdt, max_snow_temp,
+                                      min_rain_temp, Tgrnd, h, sn, coverage, surf_atten, tl, ap, sync_ok, dt_hours);
+    if (is_veg) { st_throughfall += r.throughfall; st_canopyevap += r.canopyevap; st_cvapor += r.canopy_vapor_flux; }
+#pragma unroll
+    for (int l = 0; l < MAXL; l++) {
+      if (l < NL) st_evap.v[l] += r.evap.v[l];
+      bef.v[l] = r.bef.v[l];
+    }
+    st_ppt += r.ppt;
+    st_cond0 += (r.ra_used0 > 0) ? 1 / r.ra_used0 : HUGE_RESIST;
+    st_cond1 += (r.ra_used1 > 0) ? 1 / r.ra_used1 : HUGE_RESIST;
+    st_melt += r.melt; st_vapor += r.vapor_flux;
+    st_prec += r.out_prec; st_rain += r.out_rain; st_snow += r.out_snow;
+    st_aover += r.AlbedoOver; st_aunder += r.AlbedoUnder; st_lover += r.LongOverIn; st_lunder += r.LongUnderIn;
+    st_nlong += r.NetLongAtmos; st_nshort += r.NetShortAtmos; st_dh += r.deltaH; st_gflux += r.grnd_flux;
+    st_luo += h.LongUnderOut;
+    if (extras & EX_PET) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) st_pot.v[i] += r.pot.v[i];
+    }
+    Tsurf = r.Tsurf;
+    snow_flag = r.snow_flag;
+    err |= r.err;
+    if (r.fb_snow) sio.fallback(0);
+    if (r.fb_fol) sio.fallback(1);
+  }
+  if (general) {
+    sio.store(sn);
+    snowy = sn.swq > 0 || sn.snow_canopy > 0 || sn.coverage != 0;
+    tidy = !snowy && (sn.last_snow != (int)MISSINGV || sn.MELTING != 0 || sn.albedo != NEW_SNOW_ALB);
+  }
+  const double N = (double)npass;
+  h.LongUnderOut = st_luo / N;      // the record leaves the AVERAGE of its passes behind (surface_fluxes.c:1041), the other
+                                    // carried words (T[0], T[1], Tfoliage, snow, canopy storage) the last pass's values
+  // surface_fluxes.c:1110-1123: resistance -> conductance -> resistance over the passes
+  const double ar0 = (st_cond0 > 0 && st_cond0 < HUGE_RESIST) ? 1 / (st_cond0 / N) : ((st_cond0 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
+  const double ar1 = (st_cond1 > 0 && st_cond1 < HUGE_RESIST) ? 1 / (st_cond1 / N) : ((st_cond1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
+  const double AF = cv * af * 1. * 1.;
+#define T_(k, expr) do { if (write && tmap.row[k] >= 0) VR_STREAM_ST(col + (size_t)tmap.row[k] * stride, (expr)); } while (0)
+  // ---- terms that are final before runoff() (collect_wb_terms / collect_eb_terms, put_data.c:298-632) ----
+  T_(TE_SUB_SNOW, st_vapor * 1000. * AF);
+  if (is_veg) {
+    T_(TE_SUB_CANOP, st_cvapor * 1000. * AF);
+    T_(TE_EVAP_CANOP, st_canopyevap * AF);
+    T_(TE_WDEW, h.Wdew * AF);
+    T_(TE_SCANOPY, (sn.snow_canopy) * AF * 1000.);
+  }
+  else { T_(TE_SUB_CANOP, 0.); T_(TE_EVAP_CANOP, 0.); T_(TE_WDEW, 0.); T_(TE_SCANOPY, 0.); }
+  T_(TE_INFLOW, (st_ppt) * AF);
+  {
+    const double ar = overstory ? ar1 : ar0;
+    T_(TE_COND, (ar > SMALLV) ? (1 / ar) * AF : HUGE_RESIST);
+  }
+  T_(TE_SWE, sn.swq * AF * 1000.);
+  T_(TE_SDEPTH, sn.depth * AF * 100.);
+  if (sn.swq > 0.0) {
+    T_(TE_SALB, sn.albedo * AF);
+    T_(TE_SST, sn.surf_temp * AF);
+    T_(TE_SPT, sn.pack_temp * AF);
+    T_(TE_CVSNOW, cv * af * 1.);
+  }
+  else { T_(TE_SALB, 0.); T_(TE_SST, 0.); T_(TE_SPT, 0.); T_(TE_CVSNOW, 0.); }
+  T_(TE_SMELT, st_melt * AF);
+  T_(TE_SCOVER, sn.coverage * AF);
+  T_(TE_SURFT, Tsurf * AF);
+  T_(TE_NSHORT, (st_nshort / N) * AF);
+  T_(TE_NLONG, (st_nlong / N) * AF);
+  T_(TE_INLONG, ((snow_flag && overstory) ? st_lover / N : st_lunder / N) * AF);
+  T_(TE_ALBEDO, ((snow_flag && overstory) ? st_aover / N : st_aunder / N) * AF);
+  T_(TE_GFLUX, -((st_gflux / N) * AF));     // collect_eb_terms subtracts these two
+  T_(TE_DH, -((st_dh / N) * AF));
+  T_(TE_PREC, st_prec * cv * af);
+  T_(TE_RAIN, st_rain * cv * af);
+  T_(TE_SNOWF, st_snow * cv * af);
+  if (extras & EX_PET) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) T_(TE_PET0 + i, (st_pot.v[i] / N) * AF);    // put_data.c:846-851
+  }
+  VR_PHASE_SYNC(3, true);
+  // ---- runoff.c ----
+  const RunoffOut ro = runoff_step(cc, NL, dt_hours, st_ppt, h.moist, st_evap);
+  h.moist = ro.moist;
+  if (NL == 3) st_evap.v[2] = ro.evap_bottom; else st_evap.v[1] = ro.evap_bottom;
+  // ---- full_energy.c:445-453 ----
+  double wet = 0, rootm = 0, tmp_evap = 0.0;
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) {
+    if (l < NL) {
+      if ((uc.root0_mask >> l) & 1) rootm += h.moist.v[l];
+      wet += (h.moist.v[l] - cc.Wpwp(l)) / cc.wet_den(l);
+      tmp_evap += st_evap.v[l];
+      if (is_veg) {
+        T_(TE_EB0 + l, st_evap.v[l] * bef.v[l] * AF);
+        T_(TE_TV0 + l, st_evap.v[l] * (1 - bef.v[l]) * AF);
+      }
+      else {
+        T_(TE_EB0 + l, st_evap.v[l] * AF);
+        T_(TE_TV0 + l, 0.);
+      }
+      T_(TE_LIQ0 + l, h.moist.v[l] * AF);
+    }
+    else { T_(TE_EB0 + l, 0.); T_(TE_TV0 + l, 0.); T_(TE_LIQ0 + l, 0.); }
+  }
+  wet /= NL;
+  tmp_evap += st_vapor * 1000.;
+  if (is_veg) {
+    tmp_evap += st_cvapor * 1000.;
+    tmp_evap += st_canopyevap;
+  }
+  T_(TE_EVAP, tmp_evap * AF);
+  T_(TE_ASAT, ro.asat * AF);
+  T_(TE_RUNOFF, ro.runoff * AF);
+  T_(TE_BASEFLOW, ro.baseflow * AF);
+  T_(TE_WET, wet * AF);
+  T_(TE_ROOTM, rootm * AF);
+  if (extras & EX_ZWT) {
+    const ZwtOut z = water_table(cc, NL, h.moist);
+    T_(TE_ZWT, z.zwt * AF);                                  // put_data.c:917-918
+    T_(TE_ZWTL, z.lumped * AF);
+  }
+#undef T_
+  (void)st_throughfall;
+  return err;
 }
 
 // which optional results the requested outputs need
@@ -224,20 +423,20 @@ VR_HD void cell_accumulate_to(const double *src, size_t sstride, int64_t u0, int
     const int r = tmap.row[k];
     if (r < 0 || (k >= TE_EB0 && k <= TE_TV2)) continue;
     const double *p = src + (size_t)r * sstride + u0;
-    double a = 0. + p[0];
-    for (int j = 1; j < nu; j++) a += p[j];
+    double a = 0. + VR_STREAM_LD(p);
+    for (int j = 1; j < nu; j++) a += VR_STREAM_LD(p + j);
     dst[(size_t)r * dstride + dcol] = a;
   }
   if (tmap.row[TE_EB0] >= 0) {
     double eb = 0;
     for (int j = 0; j < nu; j++)
-      for (int l = 0; l < NL; l++) eb += src[(size_t)tmap.row[TE_EB0 + l] * sstride + u0 + j];
+      for (int l = 0; l < NL; l++) eb += VR_STREAM_LD(src + (size_t)tmap.row[TE_EB0 + l] * sstride + u0 + j);
     dst[(size_t)tmap.row[TE_EB0] * dstride + dcol] = eb;
   }
   if (tmap.row[TE_TV0] >= 0) {
     double tv = 0;
     for (int j = 0; j < nu; j++)
-      for (int l = 0; l < NL; l++) tv += src[(size_t)tmap.row[TE_TV0 + l] * sstride + u0 + j];
+      for (int l = 0; l < NL; l++) tv += VR_STREAM_LD(src + (size_t)tmap.row[TE_TV0 + l] * sstride + u0 + j);
     dst[(size_t)tmap.row[TE_TV0] * dstride + dcol] = tv;
   }
 }
@@ -247,8 +446,8 @@ VR_HD void cell_accumulate_to(const double *src, size_t sstride, int64_t u0, int
 VR_HD double cell_term_sum(const double *src, size_t sstride, int64_t u0, int nu, int row)
 {
   const double *p = src + (size_t)row * sstride + u0;
-  double a = 0. + p[0];
-  for (int j = 1; j < nu; j++) a += p[j];
+  double a = 0. + VR_STREAM_LD(p);
+  for (int j = 1; j < nu; j++) a += VR_STREAM_LD(p + j);
   return a;
 }
 

@@ -22,6 +22,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define VR_HD __host__ __device__ __forceinline__
@@ -41,10 +42,13 @@
 // Phase barrier: keeps the warps of a thread block at the same place in the (large) step code so
 // that one instruction-cache fill serves all of them (the step kernel is instruction-supply bound, see
 // profiles/).  Every thread of the block must run unit_step() for this to be legal.
+#ifndef VR_BAR_MASK
+#define VR_BAR_MASK 15      // which of the four phase barriers of unit_step are compiled in (tuning knob)
+#endif
 #if defined(__CUDA_ARCH__) && defined(VR_PHASE_BARRIERS)
-#define VR_PHASE_SYNC() __syncthreads()
+#define VR_PHASE_SYNC(i, ok) do { if (((VR_BAR_MASK >> (i)) & 1) && (ok)) __syncthreads(); } while (0)
 #else
-#define VR_PHASE_SYNC()
+#define VR_PHASE_SYNC(i, ok)
 #endif
 #if defined(__CUDA_ARCH__) && defined(VR_LOOP_BARRIERS)
 #define VR_LOOP_SYNC() __syncthreads()
@@ -59,68 +63,96 @@ namespace vr {
 
 // x^y for the step's power laws (Brooks-Corey drainage, ARNO curves, albedo decay ...): 72 of the
 // ~85 pow() per tile-day sit in the hourly drainage loop (runoff.c:320-479) and CUDA's pow() costs
-// ~250 instructions (double-double log), which made it 80 % of the step kernel.  On the device
-// x^y = 2^(y*log2 x) is evaluated directly: log2 of the mantissa by the atanh series (|f| <= 0.172,
-// 10 terms, ~1 ulp), the exponent part y*e kept separate so it is added exactly, 2^r by a
-// degree-13 polynomial.  Relative error <= ~2e-16 * (2 + |y*log2 x|), i.e. < 1e-13 for every
-// argument range of the model -- four orders below the 1e-9 parity bar.  Zero, negative, subnormal,
-// non-finite or extreme arguments take CUDA's pow().  With -DVR_EXACT_LIBM (and always on the host)
-// plain pow() is used, which is what makes the host build bit-identical to the reference.
+// ~250 instructions (double-double log), which made it 80 % of the first step kernel.  On the device
+// x^y = 2^(y*log2 x) is evaluated directly with two small tables in shared memory (tools/make_pow_tables.py):
+//   log2 x = e + l2c[i] + log2(1 + r),  i = round((m - 1) * 128),  r = m * inv_c[i] - 1 (one exact fma, |r| <= 2^-8),
+//            log2(1 + r) = r * (degree-6 Taylor polynomial); entries with c >= sqrt(2) belong to the binade above so
+//            that x -> 1 from either side has no cancellation; the exponent part y*e is kept separate (added exactly);
+//   2^t    = 2^n * 2^(j/64) * 2^g,  t = n + j/64 + g,  |g| <= 1/128,  2^g - 1 = g * (degree-4 Taylor polynomial).
+// Relative error <= ~2e-16 * (2 + |y*log2 x|), i.e. < 1e-13 for every argument range of the model -- four orders
+// below the 1e-9 parity bar (tests: test_device_pow_error_bound on the GPU, test_pow_table_error_bound on the host).
+// About 60 SASS instructions (the atanh-series version of round 1: 179).  Zero, negative, subnormal, non-finite or
+// extreme arguments take CUDA's pow().  With -DVR_EXACT_LIBM (and always in host builds of the step) plain pow() is
+// used, which is what makes the host build bit-identical to the reference.
+#include "vic_pow_tables.h"
+struct PowTables { double logtab[2 * 129]; double exptab[64]; };
+VR_HD double pow_table_eval(double x, double y, const double *logtab, const double *exptab, bool *handled)
+{
+  constexpr double L[7] = VR_POW_L_INIT;
+  constexpr double E[5] = VR_POW_E_INIT;
+  *handled = false;
+  if (!((x >= 2.2250738585072014e-308) && (x <= 1e300) && (fabs(y) <= 1e5))) return 0.;
+#if defined(__CUDA_ARCH__)
+  const int hi = __double2hiint(x);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+#else
+  long long ix;
+  memcpy(&ix, &x, 8);
+  const int hi = (int)(ix >> 32);
+  const long long im = (ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+  double m;
+  memcpy(&m, &im, 8);
+#endif
+  const int i = ((hi & 0x000fffff) + 0x1000) >> 13;                    // 0..128
+  const int e = (hi >> 20) - 1023 + (i >= VR_POW_SPLIT ? 1 : 0);
+  const double r = fma(m, logtab[2 * i], -1.0);
+  const double r2 = r * r;
+  const double p01 = fma(L[1], r, L[0]), p23 = fma(L[3], r, L[2]), p45 = fma(L[5], r, L[4]);
+  const double q = fma(p23, r2, p01), u = fma(L[6], r2, p45);
+  const double pl = fma(u, r2 * r2, q);
+  const double l2m = fma(r, pl, logtab[2 * i + 1]);                     // log2(m) relative to the entry's binade
+  const double t = fma(y, l2m, y * (double)e);                         // y * log2(x)
+  if (!(fabs(t) < 1000.0)) return 0.;
+  const double kd0 = fma(t, 64.0, 6755399441055744.0);                 // 1.5 * 2^52: the integer lands in the low word
+#if defined(__CUDA_ARCH__)
+  const int k = __double2loint(kd0);
+#else
+  long long ik;
+  memcpy(&ik, &kd0, 8);
+  const int k = (int)(ik & 0xffffffffLL);
+#endif
+  const double kd = kd0 - 6755399441055744.0;
+  const double g = fma(kd, -0.015625, t);                              // exact
+  double pe = fma(E[4], g, E[3]);
+  pe = fma(pe, g, E[2]); pe = fma(pe, g, E[1]); pe = fma(pe, g, E[0]);
+  const double T = exptab[k & 63];
+  const double res = fma(T * g, pe, T);
+  const int n = k >> 6;
+  *handled = true;
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
+#else
+  long long ir;
+  memcpy(&ir, &res, 8);
+  ir += (long long)n << 52;
+  double out;
+  memcpy(&out, &ir, 8);
+  return out;
+#endif
+}
+
 #if defined(__CUDACC__)
-// ascending coefficients: VR_KQ[i] = 2/(2i+3) (atanh series), VR_KP[i] = 1/i! (exp)
-static __constant__ double VR_KQ[10] = {2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0,
-                                        2.0 / 17.0, 2.0 / 19.0, 2.0 / 21.0};
-static __constant__ double VR_KP[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
-                                        1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
-                                        1.0 / 479001600.0, 1.0 / 6227020800.0};
+static __device__ const double VR_POW_LOGTAB_G[2 * 129] = VR_POW_LOGTAB_INIT;
+static __device__ const double VR_POW_EXPTAB_G[64] = VR_POW_EXPTAB_INIT;
+__shared__ PowTables vr_pow_tables;
+// every kernel that reaches m_pow() calls this first (all threads of the block)
+__device__ __forceinline__ void pow_tables_init()
+{
+#if !defined(VR_EXACT_LIBM)
+  for (int i = threadIdx.x; i < 2 * 129; i += blockDim.x) vr_pow_tables.logtab[i] = VR_POW_LOGTAB_G[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) vr_pow_tables.exptab[i] = VR_POW_EXPTAB_G[i];
+  __syncthreads();
+#endif
+}
 #endif
 VR_HDN double m_pow(double x, double y)
 {
 #if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM)
   if (x == 1.0 || y == 0.0) return 1.0;
   if (x == 0.0 && y > 0.0) return 0.0;            // dry layer: Q12 = Ksat * 0^expt
-  if ((x >= 2.2250738585072014e-308) && (x <= 1e300) && (fabs(y) <= 1e5)) {
-    const long long ix = __double_as_longlong(x);
-    int e = (int)((ix >> 52) & 0x7ff) - 1023;
-    double m = __longlong_as_double((ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-    // f = (m-1)/(m+1) without the IEEE division sequence: approximate reciprocal + 2 Newton steps
-    const double d = m + 1.0, nm = m - 1.0;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    r = fma(fma(-d, r, 1.0), r, r);
-    r = fma(fma(-d, r, 1.0), r, r);
-    double f = nm * r;
-    f = fma(fma(-f, d, nm), r, f);
-    const double f2 = f * f, f4 = f2 * f2;
-    // 2*atanh(f)/f = 2*(1 + f2/3 + f2^2/5 + ...), truncated after f2^10 (|f2| <= 0.0295 -> 1e-17).  Even and odd
-    // powers run as two independent Horner chains (the kernel is bound by dependent-issue latency, not by
-    // the FP64 pipe) and the coefficients come from constant memory (one LDCU.128 per two doubles instead of
-    // two UMOVs per double).
-    double qe = VR_KQ[8], qo = VR_KQ[9];
-    qe = fma(qe, f4, VR_KQ[6]); qo = fma(qo, f4, VR_KQ[7]);
-    qe = fma(qe, f4, VR_KQ[4]); qo = fma(qo, f4, VR_KQ[5]);
-    qe = fma(qe, f4, VR_KQ[2]); qo = fma(qo, f4, VR_KQ[3]);
-    qe = fma(qe, f4, VR_KQ[0]); qo = fma(qo, f4, VR_KQ[1]);
-    const double q = fma(qo, f2, qe);
-    const double lnm = fma(q * f2, f, 2.0 * f);               // ln(m)
-    const double l2m = lnm * 1.4426950408889634;              // log2(m), |l2m| <= 0.5
-    const double t = fma(y, l2m, y * (double)e);              // y*log2(x)
-    if (fabs(t) < 1000.0) {
-      const double n = rint(t);
-      const double z = (t - n) * 0.6931471805599453;          // |z| <= 0.3466
-      const double z2 = z * z;
-      double pe = VR_KP[12], po = VR_KP[13];                  // exp(z) = sum z^i / i!, i <= 13
-      pe = fma(pe, z2, VR_KP[10]); po = fma(po, z2, VR_KP[11]);
-      pe = fma(pe, z2, VR_KP[8]); po = fma(po, z2, VR_KP[9]);
-      pe = fma(pe, z2, VR_KP[6]); po = fma(po, z2, VR_KP[7]);
-      pe = fma(pe, z2, VR_KP[4]); po = fma(po, z2, VR_KP[5]);
-      pe = fma(pe, z2, VR_KP[2]); po = fma(po, z2, VR_KP[3]);
-      pe = fma(pe, z2, VR_KP[0]); po = fma(po, z2, VR_KP[1]);
-      const double p = fma(po, z, pe);
-      return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
-    }
-  }
+  bool handled;
+  const double v = pow_table_eval(x, y, vr_pow_tables.logtab, vr_pow_tables.exptab, &handled);
+  if (handled) return v;
   return pow(x, y);
 #else
   return pow(x, y);
@@ -253,7 +285,9 @@ enum { AE_RA0 = 0, AE_RA1, AE_RA2, AE_U0, AE_U1, AE_U2, AE_REF0, AE_REF1, AE_REF
 // of PET reference cover p (SATSOIL, H2OSURF, SHORT, TALL; full_energy.c:329-369)
 enum { AP_N = 12 };
 
-struct Forc { double air_temp, prec, wind, vp, vpd, pressure, density, shortwave, longwave; int mon, doy; };
+// atmos fields of one record or sub-step; snowflag: atmos->snowflag[NR] of the record (initialize_atmos.c:1390-1400),
+// read only when the snow model is sub-stepped (SNOW_STEP < TIME_STEP)
+struct Forc { double air_temp, prec, wind, vp, vpd, pressure, density, shortwave, longwave; int mon, doy, snowflag; };
 
 // carried state of one unit (what write_model_state.c keeps, plus LongUnderOut/Tfoliage)
 struct UnitS {
@@ -333,7 +367,7 @@ VR_HDN PenmanAir penman_air(double tair, double half_elev_lapse, double elevatio
   p.r_air_cp = r_air * CP_PM;
   return p;
 }
-VR_HDN double penman(const PenmanAir &p, double rad, double vpd, double ra, double rc, double rarc)
+VR_HDN double penman(PenmanAir p, double rad, double vpd, double ra, double rc, double rarc)
 {
   double evap = (p.slope * rad + p.r_air_cp * vpd / ra) / (p.lv * (p.slope + p.gamma * (1 + (rc + rarc) / ra))) *
                 SEC_PER_DAY;
@@ -379,30 +413,46 @@ VR_HDN double stability_correction(double Z, double d, double TSurf, double Tair
   return Correction;
 }
 
-// root_brent.c:105-367 for a functor that never returns the reference's ERROR sentinel by design
-// (the two callers' functions are total on this path); bracket expansion and Brent iteration are
-// kept iteration-for-iteration.  Returns VERR when no bracket / no convergence.
-template <class F>
-VR_HD double root_brent(double a, double b, F &f)
-{
-  double c = 0, d = 0, e = 0, fa, fb, fc, m, p, q, r, s, tol;
-  fa = f(a);
-  fb = f(b);
-  int j = 0;
-  while ((fa * fb) >= 0 && j < 5) {
-    a -= 10; b += 10;
-    fa = f(a);
-    fb = f(b);
-    j++;
+// small by-value aggregates: the CUDA ABI passes and returns these in registers, so the out-of-line leaves below have
+// no object in local memory (round 1 passed UnitS / VegV / PenmanAir / layer arrays by reference: a 2.4 kB frame whose
+// misses in L1 were the largest stall class of the step kernel, profiles/r2_k_units_ncu.md)
+struct M3 { double v[MAXL]; };
+
+// root_brent.c:105-367 as a resumable state machine, so that a caller has ONE evaluation site of its energy balance
+// (the reference calls the function at 5 places inside root_brent and at 2 more around it); bracket expansion and
+// Brent iteration are kept evaluation for evaluation.  start(a, b), then feed(f(x)) until it returns true: result is the
+// root, or VERR when there is no bracket / no convergence.
+struct Brent {
+  double a, b, c, d, e, fa, fb, fc, x, result;
+  int stage, j, i;
+  VR_HD void start(double a_, double b_)
+  {
+    a = a_; b = b_; c = 0; d = 0; e = 0; fa = 0; fb = 0; fc = 0; x = a_; result = VERR; stage = 0; j = 0; i = 0;
   }
-  if ((fa * fb) >= 0) return VERR;
-  fc = fb;
-  for (int i = 0; i < 1000; i++) {
+  VR_HD bool feed(double fx)
+  {
+    if (stage == 0) { fa = fx; x = b; stage = 1; return false; }
+    if (stage == 1) {
+      fb = fx;
+      if ((fa * fb) >= 0) {
+        if (j < 5) { a -= 10; b += 10; j++; x = a; stage = 0; return false; }
+        result = VERR;
+        return true;
+      }
+      fc = fb;
+      stage = 2;
+    }
+    else {
+      fb = fx;
+      i++;
+      if (i >= 1000) { result = VERR; return true; }
+    }
+    double m, p, q, r, s, tol;
     if (fb * fc > 0) { c = a; fc = fa; d = b - a; e = d; }
     if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
     tol = 2 * 3e-8 * fabs(b) + 1e-7;
     m = 0.5 * (c - b);
-    if (fabs(m) <= tol || fb == 0) return b;
+    if (fabs(m) <= tol || fb == 0) { result = b; return true; }
     if (fabs(e) < tol || fabs(fa) <= fabs(fb)) { d = m; e = d; }
     else {
       s = fb / fa;
@@ -419,10 +469,10 @@ VR_HD double root_brent(double a, double b, F &f)
     }
     a = b; fa = fb;
     b += (fabs(d) > tol) ? d : ((m > 0) ? tol : -tol);
-    fb = f(b);
+    x = b;
+    return false;
   }
-  return VERR;
-}
+};
 
 // ---------------------------------------------------------------------------------------
 // snow pack (snow_melt.c:119-579, SnowPackEnergyBalance.c:88-328, latent_heat_from_snow.c)
@@ -434,7 +484,7 @@ struct SnowPackEB {
   // outputs of the last evaluation
   double Ra_used0, AdvectedEnergy, DeltaColdContent, GroundFlux, LatentHeat, LatentHeatSub, NetLongUnder,
          RefreezeEnergy, SensibleHeat, vapor_flux, surface_flux;
-  VR_HDN double operator()(double TSurf)
+  VR_HD double operator()(double TSurf)
   {
     double TMean = TSurf;
     if (Wind > 0.0) Ra_used0 = Ra / stability_correction(Z, 0., TMean, Tair, Wind, Z0_2);
@@ -477,17 +527,22 @@ struct SnowPackEB {
   }
 };
 
+// the pack words snow_melt reads and writes
+struct PackS { double swq, surf_temp, pack_temp, surf_water, pack_water, depth, density, coldcontent; };
 struct SnowMeltOut {
+  PackS s;
   double melt, NetLongSnow, OldTSurf, advection, deltaCC, latent, latent_sub, refreeze_energy, sensible,
          vapor_flux, aero_used0;
+  int fallback;      // 1 when TFALLBACK kept the old surface temperature (snow_melt.c:361-366)
 };
 
-// s: snow state (swq, surf_temp, pack_temp, surf_water, pack_water, depth, density, coldcontent updated)
-VR_HDN void snow_melt(UnitS &s, double Le, double NetShortSnow, double Tcanopy, double Tgrnd, double Z0_2,
-                      double aero_resist, double air_temp, double delta_t, double density, double LongSnowIn,
-                      double pressure, double rainfall, double snowfall, double vp, double vpd, double wind,
-                      double z2, SnowMeltOut &o)
+VR_HDN SnowMeltOut snow_melt(PackS s, double Le, double NetShortSnow, double Tcanopy, double Tgrnd, double Z0_2,
+                             double aero_resist, double air_temp, double delta_t, double density, double LongSnowIn,
+                             double pressure, double rainfall, double snowfall, double vp, double vpd, double wind,
+                             double z2)
 {
+  SnowMeltOut o;
+  o.fallback = 0;
   double SnowFall = snowfall / 1000., RainFall = rainfall / 1000.;
   o.OldTSurf = s.surf_temp;
   double Ice = s.swq - s.pack_water - s.surf_water;
@@ -520,10 +575,45 @@ VR_HDN void snow_melt(UnitS &s, double Le, double NetShortSnow, double Tcanopy, 
   x.Vpd = vpd; x.Wind = wind; x.OldTSurf = o.OldTSurf; x.SnowDepth = s.depth; x.SnowDensity = s.density;
   x.SurfaceLiquidWater = s.surf_water; x.SweSurfaceLayer = SurfaceSwq; x.Tair = Tcanopy; x.TGrnd = Tgrnd;
 
-  double Qnet = x(0.0);
-  double vapor_flux = x.vapor_flux;
-  double RefreezeEnergy = x.RefreezeEnergy;
-  if (Qnet == 0.0) {
+  // ONE evaluation site of the pack's energy balance: stage 0 = at 0 C (snow_melt.c:316), stage 1 = the evaluations
+  // of root_brent (:349-357), stage 2 = at the root (:381)
+  double Qnet, vapor_flux = 0, RefreezeEnergy = 0, T = 0.0;
+  int stage = 0;
+  bool melting = false, solved = false;
+  Brent br;
+  for (;;) {
+    Qnet = x(T);
+    if (stage == 0) {
+      vapor_flux = x.vapor_flux;
+      RefreezeEnergy = x.RefreezeEnergy;
+      if (Qnet == 0.0) { melting = true; break; }
+      if (SurfaceSwq > MIN_SWQ_EB_THRES) {
+        br.start(s.surf_temp - SNOW_DT, s.surf_temp + SNOW_DT);
+        T = br.x;
+        stage = 1;
+        continue;
+      }
+      s.surf_temp = 999;
+      break;
+    }
+    if (stage == 1) {
+      if (!br.feed(Qnet)) { T = br.x; continue; }
+      s.surf_temp = br.result;
+      if (s.surf_temp <= -998) {    // TFALLBACK (snow_melt.c:361-366)
+        s.surf_temp = o.OldTSurf;
+        o.fallback = 1;
+      }
+      if (s.surf_temp > -998 && s.surf_temp < 999) { T = s.surf_temp; stage = 2; continue; }
+      vapor_flux = x.vapor_flux;
+      RefreezeEnergy = x.RefreezeEnergy;
+      break;
+    }
+    vapor_flux = x.vapor_flux;
+    RefreezeEnergy = x.RefreezeEnergy;
+    solved = true;
+    break;
+  }
+  if (melting) {
     double SnowMelt;
     s.surf_temp = 0.0;
     if (RefreezeEnergy >= 0.0) {
@@ -569,35 +659,18 @@ VR_HDN void snow_melt(UnitS &s, double Le, double NetShortSnow, double Tcanopy, 
       RefreezeEnergy = RefreezeEnergy / fabs(RefreezeEnergy) * SnowMelt * Lf * RHO_W / (delta_t);
     }
   }
-  else {
-    if (SurfaceSwq > MIN_SWQ_EB_THRES) {
-      s.surf_temp = root_brent(s.surf_temp - SNOW_DT, s.surf_temp + SNOW_DT, x);
-      if (s.surf_temp <= -998) {    // TFALLBACK (snow_melt.c:361-366)
-        s.surf_temp = o.OldTSurf;
-        s.fb_snow++;
-      }
-    }
-    else s.surf_temp = 999;
-    if (s.surf_temp > -998 && s.surf_temp < 999) {
-      Qnet = x(s.surf_temp);
-      vapor_flux = x.vapor_flux;
-      RefreezeEnergy = x.RefreezeEnergy;
-      SurfaceSwq += s.surf_water;
-      Ice += s.surf_water;
-      s.surf_water = 0.0;
-      if (SurfaceSwq < -(vapor_flux)) {
-        vapor_flux = -SurfaceSwq;
-        SurfaceSwq = 0.0;
-        Ice = PackSwq;
-      }
-      else {
-        SurfaceSwq += vapor_flux;
-        Ice += vapor_flux;
-      }
+  else if (solved) {
+    SurfaceSwq += s.surf_water;
+    Ice += s.surf_water;
+    s.surf_water = 0.0;
+    if (SurfaceSwq < -(vapor_flux)) {
+      vapor_flux = -SurfaceSwq;
+      SurfaceSwq = 0.0;
+      Ice = PackSwq;
     }
     else {
-      vapor_flux = x.vapor_flux;
-      RefreezeEnergy = x.RefreezeEnergy;
+      SurfaceSwq += vapor_flux;
+      Ice += vapor_flux;
     }
   }
   double melt;
@@ -669,6 +742,8 @@ VR_HDN void snow_melt(UnitS &s, double Le, double NetShortSnow, double Tcanopy, 
   o.refreeze_energy = RefreezeEnergy;
   o.NetLongSnow = x.NetLongUnder;
   o.aero_used0 = x.Ra_used0;
+  o.s = s;
+  return o;
 }
 
 VR_HD double new_snow_density(double air_temp)   // snow_utility.c, DENS_BRAS
@@ -727,77 +802,103 @@ VR_HDN double snow_albedo(double new_snow, double swq, double albedo, double col
 // ---------------------------------------------------------------------------------------
 // evaporation (canopy_evap.c:46-529, arno_evap.c:62-203)
 // ---------------------------------------------------------------------------------------
-struct VegV { double Wdew, canopyevap, throughfall, LAI, Wdmax, vegcover; };
+// what the evaporation leaves need of a vegetation tile (veg_lib / veg_con): by value, 9 registers
+struct VegP { double rarc, rmin, RGL; float root[MAXL]; };
 
-VR_HDN void transpiration(const double *moist, const VegV &v, const UnitC &uc, const CellC &cc, int NL,
-                         const PenmanAir &pa, double rad, double vpd, double net_short, double air_temp,
-                         double ra, double dryFrac, double delta_t, double *layerevap)
+// canopy_evap.c:332-529 (transpiration); returns the layer evaporation of the step (mm)
+VR_HDN M3 transpiration(M3 moist, double LAI, VegP vp, CellC cc, int NL, PenmanAir pa, double rad, double vpd,
+                        double net_short, double air_temp, double ra, double dryFrac, double delta_t)
 {
+  M3 le;
   double avail[MAXL], moist1 = 0.0, Wcr1 = 0.0, moist2;
-  for (int i = 0; i < NL - 1; i++) {
-    if (uc.root[i] > 0.) {
-      avail[i] = 0. + ((moist[i] - 0.) * 1.);
-      moist1 += avail[i];
-      Wcr1 += cc.Wcr(i);
-    }
-    else avail[i] = 0.;
-  }
-  int il = NL - 1;
-  moist2 = 0. + ((moist[il] - 0.) * 1.);
-  avail[il] = moist2;
-  if ((moist1 >= Wcr1 && moist2 >= cc.Wcr(il) && Wcr1 > 0.) || (moist1 >= Wcr1 && (1 - uc.root[il]) >= 0.5) ||
-      (moist2 >= cc.Wcr(il) && uc.root[il] >= 0.5)) {
-    double rc = calc_rc(uc.rmin, net_short, uc.RGL, air_temp, vpd, v.LAI, 1.0);
-    double evap = penman(pa, rad, vpd, ra, rc, uc.rarc) * delta_t / SEC_PER_DAY * dryFrac;
-    double root_sum = 1.0, spare_evap = 0.0;
-    for (int i = 0; i < NL; i++) {
-      if (avail[i] >= cc.Wcr(i)) layerevap[i] = evap * (double)uc.root[i];
-      else {
-        double gsm_inv = (avail[i] >= cc.Wpwp(i)) ? (avail[i] - cc.Wpwp(i)) / cc.wcr_m_wpwp(i) : 0.0;
-        layerevap[i] = evap * gsm_inv * (double)uc.root[i];
-        root_sum -= uc.root[i];
-        spare_evap = evap * (double)uc.root[i] * (1.0 - gsm_inv);
+  const int il = NL - 1;
+#pragma unroll
+  for (int i = 0; i < MAXL; i++) {
+    le.v[i] = 0.;
+    avail[i] = 0.;
+    if (i < il) {
+      if (vp.root[i] > 0.) {
+        avail[i] = 0. + ((moist.v[i] - 0.) * 1.);
+        moist1 += avail[i];
+        Wcr1 += cc.Wcr(i);
       }
     }
-    if (spare_evap > 0.0)
-      for (int i = 0; i < NL; i++)
-        if (avail[i] >= cc.Wcr(i)) layerevap[i] += (double)uc.root[i] * spare_evap / root_sum;
+  }
+  const double moist_il = (il == 2) ? moist.v[2] : moist.v[1];
+  const double Wcr_il = (il == 2) ? cc.Wcr(2) : cc.Wcr(1);
+  const double root_il = (il == 2) ? (double)vp.root[2] : (double)vp.root[1];
+  const float rootf_il = (il == 2) ? vp.root[2] : vp.root[1];
+  moist2 = 0. + ((moist_il - 0.) * 1.);
+  if (il == 2) avail[2] = moist2; else avail[1] = moist2;
+  (void)root_il;
+  if ((moist1 >= Wcr1 && moist2 >= Wcr_il && Wcr1 > 0.) || (moist1 >= Wcr1 && (1 - rootf_il) >= 0.5) ||
+      (moist2 >= Wcr_il && rootf_il >= 0.5)) {
+    double rc = calc_rc(vp.rmin, net_short, vp.RGL, air_temp, vpd, LAI, 1.0);
+    double evap = penman(pa, rad, vpd, ra, rc, vp.rarc) * delta_t / SEC_PER_DAY * dryFrac;
+    double root_sum = 1.0, spare_evap = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAXL; i++) {
+      if (i < NL) {
+        if (avail[i] >= cc.Wcr(i)) le.v[i] = evap * (double)vp.root[i];
+        else {
+          double gsm_inv = (avail[i] >= cc.Wpwp(i)) ? (avail[i] - cc.Wpwp(i)) / cc.wcr_m_wpwp(i) : 0.0;
+          le.v[i] = evap * gsm_inv * (double)vp.root[i];
+          root_sum -= vp.root[i];
+          spare_evap = evap * (double)vp.root[i] * (1.0 - gsm_inv);
+        }
+      }
+    }
+    if (spare_evap > 0.0) {
+#pragma unroll
+      for (int i = 0; i < MAXL; i++)
+        if (i < NL && avail[i] >= cc.Wcr(i)) le.v[i] += (double)vp.root[i] * spare_evap / root_sum;
+    }
   }
   else {
-#pragma unroll 1
-    for (int i = 0; i < NL; i++) {
-      double gsm_inv;
-      if (avail[i] >= cc.Wcr(i)) gsm_inv = 1.0;
-      else if (avail[i] >= cc.Wpwp(i) && avail[i] < cc.Wcr(i)) gsm_inv = (avail[i] - cc.Wpwp(i)) / cc.wcr_m_wpwp(i);
-      else gsm_inv = 0.0;
-      if (gsm_inv > 0.0) {
-        double rc = calc_rc(uc.rmin, net_short, uc.RGL, air_temp, vpd, v.LAI, gsm_inv);
-        layerevap[i] = penman(pa, rad, vpd, ra, rc, uc.rarc) * delta_t / SEC_PER_DAY * dryFrac * (double)uc.root[i];
+#pragma unroll
+    for (int i = 0; i < MAXL; i++) {
+      if (i < NL) {
+        double gsm_inv;
+        if (avail[i] >= cc.Wcr(i)) gsm_inv = 1.0;
+        else if (avail[i] >= cc.Wpwp(i) && avail[i] < cc.Wcr(i)) gsm_inv = (avail[i] - cc.Wpwp(i)) / cc.wcr_m_wpwp(i);
+        else gsm_inv = 0.0;
+        if (gsm_inv > 0.0) {
+          double rc = calc_rc(vp.rmin, net_short, vp.RGL, air_temp, vpd, LAI, gsm_inv);
+          le.v[i] = penman(pa, rad, vpd, ra, rc, vp.rarc) * delta_t / SEC_PER_DAY * dryFrac * (double)vp.root[i];
+        }
+        else le.v[i] = 0.0;
       }
-      else layerevap[i] = 0.0;
     }
   }
-  for (int i = 0; i < NL; i++) {
-    if (layerevap[i] > moist[i] - cc.Wpwp(i)) layerevap[i] = moist[i] - cc.Wpwp(i);
-    if (layerevap[i] < 0.0) layerevap[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < MAXL; i++) {
+    if (i < NL) {
+      if (le.v[i] > moist.v[i] - cc.Wpwp(i)) le.v[i] = moist.v[i] - cc.Wpwp(i);
+      if (le.v[i] < 0.0) le.v[i] = 0.0;
+    }
   }
+  return le;
 }
 
-// returns Evap (m/s); writes v.canopyevap, v.throughfall, v.Wdew and layerevap[]
-VR_HDN double canopy_evap(const double *moist, VegV &v, bool CALC_EVAP, const UnitC &uc, const CellC &cc, int NL,
-                         const PenmanAir &pa, double Wdew_in, double delta_t, double rad, double vpd,
-                         double net_short, double air_temp, double ra, double ppt, double *layerevap)
+// canopy_evap.c:46-330.  Returns Evap (m/s), the canopy evaporation, throughfall and new canopy storage (mm) and
+// the layer evaporation.
+struct CanopyOut { double Evap, canopyevap, throughfall, Wdew; M3 le; };
+VR_HDN CanopyOut canopy_evap(M3 moist, double LAI, double Wdmax, bool CALC_EVAP, VegP vp, CellC cc, int NL,
+                             PenmanAir pa, double Wdew_in, double delta_t, double rad, double vpd, double net_short,
+                             double air_temp, double ra, double ppt)
 {
+  CanopyOut o;
   double throughfall = 0, tmp_Wdew = Wdew_in, canopyevap, f, wet23 = 0;
-  for (int i = 0; i < NL; i++) layerevap[i] = 0;
-  if (tmp_Wdew > v.Wdmax) {
-    throughfall = tmp_Wdew - v.Wdmax;
-    tmp_Wdew = v.Wdmax;
+#pragma unroll
+  for (int i = 0; i < MAXL; i++) o.le.v[i] = 0;
+  if (tmp_Wdew > Wdmax) {
+    throughfall = tmp_Wdew - Wdmax;
+    tmp_Wdew = Wdmax;
   }
-  if (v.LAI > 0) {
-    wet23 = VR_POW((tmp_Wdew / v.Wdmax), (2.0 / 3.0));
+  if (LAI > 0) {
+    wet23 = VR_POW((tmp_Wdew / Wdmax), (2.0 / 3.0));
     // calc_rc(rs = 0) == 0
-    canopyevap = 240 * wet23 * penman(pa, rad, vpd, ra, 0., uc.rarc) * delta_t / SEC_PER_DAY;
+    canopyevap = 240 * wet23 * penman(pa, rad, vpd, ra, 0., vp.rarc) * delta_t / SEC_PER_DAY;
   }
   else canopyevap = 0;
   if (canopyevap > 0.0 && delta_t == SEC_PER_DAY)
@@ -806,38 +907,42 @@ VR_HDN double canopy_evap(const double *moist, VegV &v, bool CALC_EVAP, const Un
   else f = 1.0;
   canopyevap *= f;
   double dryFrac;
-  if (v.Wdmax > 0) {
-    if (!(v.LAI > 0)) wet23 = VR_POW((tmp_Wdew / v.Wdmax), (2.0 / 3.0));
+  if (Wdmax > 0) {
+    if (!(LAI > 0)) wet23 = VR_POW((tmp_Wdew / Wdmax), (2.0 / 3.0));
     dryFrac = 1.0 - f * wet23;
   }
   else dryFrac = 0;
   tmp_Wdew += ppt - canopyevap;
   if (tmp_Wdew < 0.0) tmp_Wdew = 0.0;
-  if (tmp_Wdew > v.Wdmax) {
-    throughfall += tmp_Wdew - v.Wdmax;
-    tmp_Wdew = v.Wdmax;
+  if (tmp_Wdew > Wdmax) {
+    throughfall += tmp_Wdew - Wdmax;
+    tmp_Wdew = Wdmax;
   }
-  if (CALC_EVAP)
-    transpiration(moist, v, uc, cc, NL, pa, rad, vpd, net_short, air_temp, ra, dryFrac, delta_t, layerevap);
-  v.canopyevap = canopyevap;
-  v.throughfall = throughfall;
-  v.Wdew = tmp_Wdew;
+  if (CALC_EVAP) o.le = transpiration(moist, LAI, vp, cc, NL, pa, rad, vpd, net_short, air_temp, ra, dryFrac, delta_t);
+  o.canopyevap = canopyevap;
+  o.throughfall = throughfall;
+  o.Wdew = tmp_Wdew;
   double tmp_Evap = canopyevap;
-  for (int i = 0; i < NL; i++) tmp_Evap += layerevap[i];
-  return 0. + tmp_Evap / (1000. * delta_t);
+#pragma unroll
+  for (int i = 0; i < MAXL; i++)
+    if (i < NL) tmp_Evap += o.le.v[i];
+  o.Evap = 0. + tmp_Evap / (1000. * delta_t);
+  return o;
 }
 
-// returns Evap (m/s); writes *evap0 (mm) = layer[0].evap
-VR_HDN double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, double rad, double vpd, double ra,
-                       double delta_t, double *evap0)
+// arno_evap.c:62-203.  Evap (m/s; VERR on the reference's ERROR returns) and layer[0].evap (mm)
+struct ArnoOut { double Evap, evap0; };
+VR_HDN ArnoOut arno_evap(double moist0, CellC cc, PenmanAir pa, double rad, double vpd, double ra, double delta_t)
 {
+  ArnoOut o;
+  o.evap0 = 0.;
   double moist = 0. + (moist0 - 0.) * 1., evap, tmp, ratio;
   if (moist > cc.arno_maxm()) moist = cc.arno_maxm();
   double Epot = 240 * penman(pa, rad, vpd, ra, 0.0, RARC_SOIL) * delta_t / SEC_PER_DAY;
   if (cc.b() == -1.0) tmp = cc.arno_max_infil();
   else {
     ratio = 1.0 - (moist) / (cc.arno_maxm());
-    if (ratio > 1.0 || ratio < 0.0) return VERR;
+    if (ratio > 1.0 || ratio < 0.0) { o.Evap = VERR; return o; }
     ratio = VR_POW(ratio, cc.inv_b1());
     tmp = cc.arno_max_infil() * (1.0 - ratio);
   }
@@ -845,15 +950,16 @@ VR_HDN double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, dou
   else {
     ratio = tmp / cc.arno_max_infil();
     ratio = 1.0 - ratio;
-    if (ratio > 1.0 || ratio < 0.0) return VERR;
+    if (ratio > 1.0 || ratio < 0.0) { o.Evap = VERR; return o; }
     if (ratio != 0.0) ratio = VR_POW(ratio, cc.b());
     double as = 1 - ratio;
     ratio = VR_POW(ratio, cc.inv_b());
     double dummy = 1.0, tmpsum = 1.0;
+    const double b = cc.b();
 #pragma unroll 1
     for (int n = 1; n <= 30; n++) {       // arno_evap.c:168-173; the inner product is a running power
       tmpsum = (n == 1) ? ratio : tmpsum * ratio;
-      dummy += cc.b() * tmpsum / (cc.b() + n);
+      dummy += b * tmpsum / (b + n);
     }
     double beta_asp = as + (1.0 - as) * (1.0 - ratio) * dummy;
     evap = 240 * Epot * beta_asp;
@@ -864,8 +970,9 @@ VR_HDN double arno_evap(double moist0, const CellC &cc, const PenmanAir &pa, dou
     }
     else evap = 0.0;
   }
-  *evap0 = evap;
-  return 0. + evap / 1000. / delta_t;
+  o.evap0 = evap;
+  o.Evap = 0. + evap / 1000. / delta_t;
+  return o;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -903,12 +1010,14 @@ VR_HD void mass_release(double &IntSnow, double &TempInt, double &Released, doub
 struct CanopyEB {
   // inputs
   double delta_t, AirDens, EactAir, Press, Le, Tcanopy, Vpd, Ra0, Ra1, Rainfall, IntRainOrg, IntSnow,
-         LongOverIn, LongUnderOut, NetShortOver;
-  const double *moist; VegV *v; const UnitC *uc; const CellC *cc; const PenmanAir *pa; int NL;
+         LongOverIn, LongUnderOut, NetShortOver, LAI, Wdmax;
+  M3 moist; VegP vp; CellC cc; PenmanAir pa; int NL;
+  // the vegetation words canopy_evap updates through the reference's pointers (veg_var->Wdew, canopyevap, throughfall)
+  double v_Wdew, v_canopyevap, v_throughfall;
   // outputs of the last evaluation
   double Ra_used0, Ra_used1, IntRain, AdvectedEnergy, LatentHeat, LatentHeatSub, LongOverOut, NetLongOver,
          RefreezeEnergy, SensibleHeat, VaporMassFlux;
-  VR_HDN double operator()(double Tfoliage)
+  VR_HD double operator()(double Tfoliage)
   {
     double Tmp = Tfoliage + KELVIN;
     LongOverOut = STEFAN_B * (Tmp * Tmp * Tmp * Tmp);
@@ -924,16 +1033,16 @@ struct CanopyEB {
       double Ls = (677. - 0.07 * Tfoliage) * JOULESPCAL * GRAMSPKG;
       LatentHeatSub = Ls * VaporMassFlux * RHO_W;
       LatentHeat = 0;
-      v->throughfall = 0;
+      v_throughfall = 0;
     }
     else {
       Ra_used0 = Ra0;
       Ra_used1 = Ra1;
-      double le[MAXL];
-      double Evap = canopy_evap(moist, *v, false, *uc, *cc, NL, *pa, IntRainOrg * 1000., delta_t, NetRadiation,
-                                Vpd, NetShortOver, Tcanopy, Ra_used1, Rainfall * 1000, le);
-      IntRain = v->Wdew / 1000.;    // *Wdew aliases *IntRain in the reference call (snow_intercept.c:399-416)
-      LatentHeat = Le * Evap * RHO_W;
+      const CanopyOut ce = canopy_evap(moist, LAI, Wdmax, false, vp, cc, NL, pa, IntRainOrg * 1000., delta_t, NetRadiation,
+                                       Vpd, NetShortOver, Tcanopy, Ra_used1, Rainfall * 1000);
+      v_Wdew = ce.Wdew; v_canopyevap = ce.canopyevap; v_throughfall = ce.throughfall;
+      IntRain = v_Wdew / 1000.;    // *Wdew aliases *IntRain in the reference call (snow_intercept.c:399-416)
+      LatentHeat = Le * ce.Evap * RHO_W;
       LatentHeatSub = 0;
     }
     SensibleHeat = AirDens * Cp * (Tcanopy - Tfoliage) / Ra_used1;
@@ -952,20 +1061,26 @@ struct CanopyEB {
   }
 };
 
+struct InterceptIn {
+  double Tfoliage, LongUnderOut, snow_canopy, tmp_int_storage, Wdew, Wdmax, LAI, canopyevap, throughfall;
+  double density, vp, pressure, vpd;          // atmos fields of the (sub-)step
+  double Dt, Le, LongOverIn, ShortOverIn, Tcanopy, bare_albedo, Ra0, Ra1, wind1, RainFall, SnowFall;
+};
 struct InterceptOut {
-  double AlbedoOver, canopy_refreeze, NetLongOver, NetShortOver, LongOverOut, canopy_vapor_flux, Ra_used0,
-         Ra_used1;
-  bool ra_written;
+  double Tfoliage, snow_canopy, tmp_int_storage, Wdew, canopyevap, throughfall, RainFall, SnowFall;
+  double AlbedoOver, canopy_refreeze, NetLongOver, NetShortOver, LongOverOut, canopy_vapor_flux, Ra_used0, Ra_used1;
+  int fallback;
 };
 
-// Dt seconds; F == 1.  Updates s.snow_canopy, s.tmp_int_storage, s.Tfoliage, v.Wdew (IntRain, mm),
-// rainfall/snowfall (mm, in: above canopy, out: below canopy).
-VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, int NL, const PenmanAir &pa,
-                           const Forc &f, double Dt, double Le, double LongOverIn, double ShortOverIn,
-                           double Tcanopy, double bare_albedo, double Ra0, double Ra1, double wind1,
-                           double &RainFall, double &SnowFall, InterceptOut &o)
+// Dt seconds; F == 1.  RainFall / SnowFall in mm: in above the canopy, out below it.
+VR_HDN InterceptOut snow_intercept(InterceptIn in, M3 moist, VegP vp, CellC cc, int NL, PenmanAir pa)
 {
-  double IntRain = v.Wdew, IntSnow = s.snow_canopy, MaxInt = v.Wdmax, LAI = v.LAI;
+  InterceptOut o;
+  o.fallback = 0;
+  double Tfoliage = in.Tfoliage, tmp_int_storage = in.tmp_int_storage;
+  double IntRain = in.Wdew, IntSnow = in.snow_canopy, MaxInt = in.Wdmax, LAI = in.LAI;
+  double RainFall = in.RainFall, SnowFall = in.SnowFall;
+  const double Dt = in.Dt, Tcanopy = in.Tcanopy, wind1 = in.wind1;
   RainFall /= 1000.;
   SnowFall /= 1000.;
   IntRain /= 1000.;
@@ -973,10 +1088,10 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
   double IntRainOrg = IntRain;
   IntSnow /= 1.;
   IntRain /= 1.;
-  double InitialSnowInt = IntSnow, Drip = 0.0, ReleasedMass = 0.0, OldTfoliage = s.Tfoliage;
+  double InitialSnowInt = IntSnow, Drip = 0.0, ReleasedMass = 0.0, OldTfoliage = Tfoliage;
   double Imax1 = 4.0 * LAI_SNOW_MULTIPLIER * LAI, MaxSnowInt, DeltaSnowInt;
-  if (s.Tfoliage < -1.0 && s.Tfoliage > -3.0) MaxSnowInt = (s.Tfoliage * 3.0 / 2.0) + (11.0 / 2.0);
-  else if (s.Tfoliage > -1.0) MaxSnowInt = 4.0;
+  if (Tfoliage < -1.0 && Tfoliage > -3.0) MaxSnowInt = (Tfoliage * 3.0 / 2.0) + (11.0 / 2.0);
+  else if (Tfoliage > -1.0) MaxSnowInt = 4.0;
   else MaxSnowInt = 1.0;
   MaxSnowInt *= LAI_SNOW_MULTIPLIER * LAI;
   if (MaxSnowInt > 0) {
@@ -985,7 +1100,7 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
     if (DeltaSnowInt < 0.0) DeltaSnowInt = 0.0;
   }
   else DeltaSnowInt = 0.0;
-  if (s.Tfoliage < -3.0 && DeltaSnowInt > 0.0 && wind1 > 1.0) {
+  if (Tfoliage < -3.0 && DeltaSnowInt > 0.0 && wind1 > 1.0) {
     double BlownSnow = (0.2 * wind1 - 0.2) * DeltaSnowInt;
     if (BlownSnow >= DeltaSnowInt) BlownSnow = DeltaSnowInt;
     DeltaSnowInt -= BlownSnow;
@@ -1020,53 +1135,71 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
     RainThroughFall = RainThroughFall + (Overload * IntRainFract) * 1.;
     SnowThroughFall = SnowThroughFall + (Overload * IntSnowFract) * 1.;
   }
-  if (IntRain + IntSnow < SMALLV) s.Tfoliage = Tcanopy;
+  if (IntRain + IntSnow < SMALLV) Tfoliage = Tcanopy;
 
   CanopyEB x;
-  x.delta_t = Dt; x.AirDens = f.density; x.EactAir = f.vp; x.Press = f.pressure; x.Le = Le; x.Tcanopy = Tcanopy;
-  x.Vpd = f.vpd; x.Ra0 = Ra0; x.Ra1 = Ra1; x.Rainfall = RainFall; x.IntRainOrg = IntRainOrg; x.IntSnow = IntSnow;
-  x.LongOverIn = LongOverIn; x.LongUnderOut = s.LongUnderOut; x.moist = s.moist; x.v = &v; x.uc = &uc; x.cc = &cc;
-  x.pa = &pa; x.NL = NL; x.IntRain = IntRain; x.RefreezeEnergy = 0; x.VaporMassFlux = 0;
-  x.Ra_used0 = Ra0; x.Ra_used1 = Ra1;
-  o.ra_written = false;
+  x.delta_t = Dt; x.AirDens = in.density; x.EactAir = in.vp; x.Press = in.pressure; x.Le = in.Le; x.Tcanopy = Tcanopy;
+  x.Vpd = in.vpd; x.Ra0 = in.Ra0; x.Ra1 = in.Ra1; x.Rainfall = RainFall; x.IntRainOrg = IntRainOrg; x.IntSnow = IntSnow;
+  x.LongOverIn = in.LongOverIn; x.LongUnderOut = in.LongUnderOut; x.LAI = LAI; x.Wdmax = in.Wdmax;
+  x.moist = moist; x.vp = vp; x.cc = cc; x.pa = pa; x.NL = NL;
+  x.v_Wdew = in.Wdew; x.v_canopyevap = in.canopyevap; x.v_throughfall = in.throughfall;
+  x.IntRain = IntRain; x.RefreezeEnergy = 0; x.VaporMassFlux = 0;
+  x.Ra_used0 = in.Ra0; x.Ra_used1 = in.Ra1;
+  x.NetLongOver = 0; x.LongOverOut = 0;
 
-  double Tupper = MISSINGV, Tlower = MISSINGV, Qnet;
+  // ONE evaluation site of the canopy energy balance: stage 0 = at 0 C (snow_intercept.c:358-372), stage 1 = the
+  // evaluations of root_brent (:399-416), stage 2 = at the root (:425-440)
+  double Qnet, T;
+  int stage;
+  Brent br;
   if (IntSnow > 0 || SnowFall > 0) {
     o.AlbedoOver = NEW_SNOW_ALB;
-    o.NetShortOver = (1. - o.AlbedoOver) * ShortOverIn;
+    o.NetShortOver = (1. - o.AlbedoOver) * in.ShortOverIn;
     x.NetShortOver = o.NetShortOver;
-    Qnet = x(0.);
-    o.ra_written = true;
-    if (Qnet != 0) {
-      Tupper = 0;
-      if (s.Tfoliage <= 0.) Tlower = s.Tfoliage - SNOW_DT;
-      else Tlower = -SNOW_DT;
-    }
-    else s.Tfoliage = 0.;
+    T = 0.;
+    stage = 0;
   }
   else {
-    o.AlbedoOver = bare_albedo;
-    o.NetShortOver = (1. - o.AlbedoOver) * ShortOverIn;
+    o.AlbedoOver = in.bare_albedo;
+    o.NetShortOver = (1. - o.AlbedoOver) * in.ShortOverIn;
     x.NetShortOver = o.NetShortOver;
-    Tupper = s.Tfoliage + SNOW_DT;
-    Tlower = s.Tfoliage - SNOW_DT;
+    br.start(Tfoliage - SNOW_DT, Tfoliage + SNOW_DT);
+    T = br.x;
+    stage = 1;
   }
-  if (Tupper != MISSINGV && Tlower != MISSINGV) {
-    s.Tfoliage = root_brent(Tlower, Tupper, x);
-    if (s.Tfoliage <= -998) {     // TFALLBACK (snow_intercept.c:418-423)
-      s.Tfoliage = OldTfoliage;
-      s.fb_fol++;
+  for (;;) {
+    Qnet = x(T);
+    if (stage == 0) {
+      if (Qnet != 0) {
+        const double Tlower = (Tfoliage <= 0.) ? Tfoliage - SNOW_DT : -SNOW_DT;
+        br.start(Tlower, 0.);
+        T = br.x;
+        stage = 1;
+        continue;
+      }
+      Tfoliage = 0.;
+      break;
     }
-    Qnet = x(s.Tfoliage);
-    o.ra_written = true;
+    if (stage == 1) {
+      if (!br.feed(Qnet)) { T = br.x; continue; }
+      Tfoliage = br.result;
+      if (Tfoliage <= -998) {     // TFALLBACK (snow_intercept.c:418-423)
+        Tfoliage = OldTfoliage;
+        o.fallback = 1;
+      }
+      T = Tfoliage;
+      stage = 2;
+      continue;
+    }
+    break;
   }
   IntRain = x.IntRain;
   double RefreezeEnergy = x.RefreezeEnergy, VaporMassFlux = x.VaporMassFlux;
-  if (IntSnow <= 0) RainThroughFall = v.throughfall / 1000.;
+  if (IntSnow <= 0) RainThroughFall = x.v_throughfall / 1000.;
   RefreezeEnergy *= Dt;
   MaxWaterInt = LIQUID_WATER_CAPACITY * (IntSnow) + MaxInt;
   VaporMassFlux *= Dt;
-  if (s.Tfoliage == 0) {
+  if (Tfoliage == 0) {
     if (-(VaporMassFlux) > IntRain) {
       VaporMassFlux = -(IntRain);
       IntRain = 0.;
@@ -1090,8 +1223,8 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
         IntSnow -= ExcessSnowMelt;
         if (IntSnow < 0.0) IntSnow = 0.0;
       }
-      else s.tmp_int_storage += ExcessSnowMelt;
-      mass_release(IntSnow, s.tmp_int_storage, ReleasedMass, Drip);
+      else tmp_int_storage += ExcessSnowMelt;
+      mass_release(IntSnow, tmp_int_storage, ReleasedMass, Drip);
     }
     MaxWaterInt = LIQUID_WATER_CAPACITY * (IntSnow) + MaxInt;
     if (IntRain > MaxWaterInt) {
@@ -1100,7 +1233,7 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
     }
   }
   else {
-    s.tmp_int_storage = 0.0;
+    tmp_int_storage = 0.0;
     if (-RefreezeEnergy > -(IntRain)*Lf) {
       IntSnow += fabs(RefreezeEnergy) / Lf;
       IntRain -= fabs(RefreezeEnergy) / Lf;
@@ -1126,8 +1259,9 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
   RainFall *= 1000.;
   SnowFall *= 1000.;
   IntRain *= 1000.;
-  s.snow_canopy = IntSnow;
-  v.Wdew = IntRain;
+  o.Tfoliage = Tfoliage; o.snow_canopy = IntSnow; o.tmp_int_storage = tmp_int_storage;
+  o.Wdew = IntRain; o.canopyevap = x.v_canopyevap; o.throughfall = x.v_throughfall;
+  o.RainFall = RainFall; o.SnowFall = SnowFall;
   o.canopy_refreeze = RefreezeEnergy / Dt;
   o.NetLongOver = x.NetLongOver;
   o.LongOverOut = x.LongOverOut;
@@ -1135,26 +1269,28 @@ VR_HDN void snow_intercept(UnitS &s, VegV &v, const UnitC &uc, const CellC &cc, 
   o.Ra_used0 = x.Ra_used0;
   o.Ra_used1 = x.Ra_used1;
   (void)Qnet;
+  return o;
 }
 
 // ---------------------------------------------------------------------------------------
 // runoff.c:7-576 (Nfrost == 1, no ice): infiltration, hourly drainage, ARNO baseflow
 // ---------------------------------------------------------------------------------------
-VR_HDN void runoff_and_asat(const CellC &cc, const double *moist, int NL, double inflow, double *A, double *runoff)
+struct AsatOut { double A, runoff; };
+VR_HDN AsatOut runoff_and_asat(CellC cc, double top_moist, double inflow)
 {
-  double top_moist = 0.;
-  for (int l = 0; l < NL - 1; l++) top_moist += moist[l];
+  AsatOut o;
   if (top_moist > cc.top_max()) top_moist = cc.top_max();
-  *A = 1.0 - VR_POW((1.0 - top_moist / cc.top_max()), cc.ex());
-  if (inflow == 0.0) { *runoff = 0.0; return; }
-  double i_0 = cc.top_max_infil() * (1.0 - VR_POW((1.0 - *A), cc.inv_b()));
-  if (cc.top_max_infil() == 0.0) *runoff = inflow;
-  else if ((i_0 + inflow) > cc.top_max_infil()) *runoff = inflow - cc.top_max() + top_moist;
+  o.A = 1.0 - VR_POW((1.0 - top_moist / cc.top_max()), cc.ex());
+  if (inflow == 0.0) { o.runoff = 0.0; return o; }
+  double i_0 = cc.top_max_infil() * (1.0 - VR_POW((1.0 - o.A), cc.inv_b()));
+  if (cc.top_max_infil() == 0.0) o.runoff = inflow;
+  else if ((i_0 + inflow) > cc.top_max_infil()) o.runoff = inflow - cc.top_max() + top_moist;
   else {
     double basis = 1.0 - (i_0 + inflow) / cc.top_max_infil();
-    *runoff = (inflow - cc.top_max() + top_moist + cc.top_max() * VR_POW(basis, cc.one_plus_b()));
+    o.runoff = (inflow - cc.top_max() + top_moist + cc.top_max() * VR_POW(basis, cc.one_plus_b()));
   }
-  if (*runoff < 0.) *runoff = 0.;
+  if (o.runoff < 0.) o.runoff = 0.;
+  return o;
 }
 
 // Division by a per-cell constant.  The device multiplies by the reciprocal prepared on the host
@@ -1166,12 +1302,12 @@ VR_HDN void runoff_and_asat(const CellC &cc, const double *moist, int NL, double
 #define VR_DIVC(x, d, inv_d) ((x) / (d))
 #endif
 
-// moist[]: in/out (mm); evap_l[]: in layer evaporation for the step (mm), evap_l[NL-1] may be reduced.
+// moist: in/out (mm); evap: the layer evaporation of the step (mm), the bottom layer's may be reduced.
 // Layers are scalars (no dynamically indexed arrays -> no local memory in the hourly loop); the
 // reference's while-loops that push excess water upwards (runoff.c:362-391,448-475) are unrolled.
+struct RunoffOut { M3 moist; double evap_bottom, asat, runoff, baseflow; };
 template <int NL>
-VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, double *evap_l, double *asat,
-                       double *runoff_out, double *baseflow_out)
+VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
 {
   constexpr int LB = NL - 1;                      // bottom layer
   const double r0 = cc.resid(0), r1 = cc.resid(1), rB = cc.resid(LB);
@@ -1182,13 +1318,13 @@ VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, doubl
   const double bf_frac = cc.bf_frac(), bf_nl = cc.bf_nl(), Ws = cc.Ws(), one_m_Ws = cc.one_m_Ws(),
                inv_one_m_Ws = cc.inv_one_m_Ws(), cexp = cc.c();
   (void)qd0; (void)qd1; (void)qdB; (void)iq0; (void)iq1; (void)iqB; (void)one_m_Ws; (void)inv_one_m_Ws;
-  double liq0 = moist[0], liq1 = moist[1], liqB = moist[LB];
+  double liq0 = moist.v[0], liq1 = moist.v[1], liqB = moist.v[LB];
   double ev[MAXL];
 #pragma unroll
   for (int l = 0; l < NL; l++) {
-    double e = evap_l[l] / (double)dt;
+    double e = evap.v[l] / (double)dt;
     if (e > 0) {
-      double avail_liq = (moist[l] - cc.resid(l));
+      double avail_liq = (moist.v[l] - cc.resid(l));
       if (avail_liq < 0) avail_liq = 0;
       double evap_fraction = (avail_liq > 0) ? e / avail_liq : 1.0;
       e = avail_liq * evap_fraction;
@@ -1198,8 +1334,8 @@ VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, doubl
   const double ev0 = ev[0], ev1 = ev[1], evB = ev[LB];
   double A, runoff_, baseflow = 0;
   {
-    double lq[MAXL] = {liq0, liq1, liqB};
-    runoff_and_asat(cc, lq, NL, ppt, &A, &runoff_);
+    const AsatOut a = runoff_and_asat(cc, (NL == 3) ? (0. + liq0) + liq1 : 0. + liq0, ppt);
+    A = a.A; runoff_ = a.runoff;
   }
   const double tmp_dt_runoff = runoff_ / (double)dt, dt_inflow = ppt / (double)dt;
 #pragma unroll 1
@@ -1258,33 +1394,32 @@ VR_HD void runoff_core(const CellC &cc, int dt, double ppt, double *moist, doubl
     baseflow += dt_baseflow;
     if (NL == 2) liq1 = liqB;
   }
+  RunoffOut o;
+  o.evap_bottom = evap.v[LB];
   if (baseflow < 0) {
-    evap_l[LB] += baseflow;
+    o.evap_bottom += baseflow;
     baseflow = 0;
   }
-  double dummy;
-  double lq[MAXL] = {liq0, (NL == 3) ? liq1 : liqB, liqB};
-  runoff_and_asat(cc, lq, NL, 0., &A, &dummy);
-  moist[0] = liq0;
-  if (NL == 3) moist[1] = liq1;
-  moist[LB] = liqB;
-  *asat = A;
-  *runoff_out = runoff_;
-  *baseflow_out = baseflow;
+  const AsatOut a = runoff_and_asat(cc, (NL == 3) ? (0. + liq0) + liq1 : 0. + liq0, 0.);
+  o.moist.v[0] = liq0;
+  o.moist.v[1] = (NL == 3) ? liq1 : liqB;
+  o.moist.v[2] = (NL == 3) ? liqB : moist.v[2];
+  o.asat = a.A;
+  o.runoff = runoff_;
+  o.baseflow = baseflow;
+  return o;
 }
 
-VR_HDN void runoff_step(const CellC &cc, int NL, int dt, double ppt, double *moist, double *evap_l, double *asat,
-                        double *runoff_out, double *baseflow_out)
+VR_HDN RunoffOut runoff_step(CellC cc, int NL, int dt, double ppt, M3 moist, M3 evap)
 {
-  if (NL == 3) runoff_core<3>(cc, dt, ppt, moist, evap_l, asat, runoff_out, baseflow_out);
-  else runoff_core<2>(cc, dt, ppt, moist, evap_l, asat, runoff_out, baseflow_out);
+  if (NL == 3) return runoff_core<3>(cc, dt, ppt, moist, evap);
+  return runoff_core<2>(cc, dt, ppt, moist, evap);
 }
 
 // ---------------------------------------------------------------------------------------
 // one unit, one record
 // ---------------------------------------------------------------------------------------
-// tm: this tile's TM_* terms for the month; ae: this tile's AE_* coefficients for the month
-// bits of unit_step's `extras`
+// bits of the step's `extras`
 enum { EX_PET = 1, EX_ZWT = 2 };
 
 // compute_pot_evap.c:8-80 with the reference-cover parameters of global.h:53-67.  ra0/ra1/raU: the unit's raw
@@ -1292,28 +1427,32 @@ enum { EX_PET = 1, EX_ZWT = 2 };
 // (surface_fluxes.c:868-894 rebuilds a stability factor from them and applies it to every reference cover).
 // calc_rc() of cover i sees the net_short of cover i-1 (the reference assigns it afterwards); only NATVEG
 // depends on it, and it gets TALL's.
-VR_HDN void pot_evap6(const UnitC &uc, const double *tl, const double *ap, const PenmanAir &pa, int UnderStory, double wind,
-                      double raU, double ra1, double used0, double used1, double shortwave, double net_longwave,
-                      double tair, double vpd, int dt_hours, double *pot)
+struct P6 { double v[6]; };
+VR_HDN P6 pot_evap6(VegP vp, int overstory, const double *tl, const double *ap, PenmanAir pa, int UnderStory, double wind,
+                    double raU, double ra1, double used0, double used1, double shortwave, double net_longwave,
+                    double tair, double vpd, int dt_hours)
 {
+  P6 pot;
   double sf0, sf1;
   if (used0 == HUGE_RESIST) sf0 = HUGE_RESIST; else sf0 = used0 / raU;
   if (used1 == used0) sf1 = sf0;
   else if (used1 == HUGE_RESIST) sf1 = HUGE_RESIST;
   else sf1 = used1 / ra1;
-  const double ref_rmin[4] = {0.0, 0.0, 100, 100}, ref_rarc[4] = {0.0, 0.0, 25, 25}, ref_lai[4] = {1.0, 1.0, 2.88, 4.45};
-  const double ref_alb[4] = {BARE_SOIL_ALBEDO, 0.08, 0.23, 0.23};
   double net_short = 0.;
+#pragma unroll
   for (int i = 0; i < 6; i++) {
+    const double ref_rmin = (i < 2) ? 0.0 : 100, ref_rarc = (i < 2) ? 0.0 : 25;
+    const double ref_lai = (i < 2) ? 1.0 : ((i == 2) ? 2.88 : 4.45);
+    const double ref_alb = (i == 0) ? BARE_SOIL_ALBEDO : ((i == 1) ? 0.08 : 0.23);
     double rs, rarc, RGL, lai, albedo, a0, a1;
     if (i < 4) {
-      rs = ref_rmin[i]; rarc = ref_rarc[i]; RGL = (i < 2) ? 0.0 : 100; lai = ref_lai[i]; albedo = ref_alb[i];
+      rs = ref_rmin; rarc = ref_rarc; RGL = (i < 2) ? 0.0 : 100; lai = ref_lai; albedo = ref_alb;
       const double *q = ap + 3 * i;
-      if (wind > 0.) { a0 = q[UnderStory] / wind; a1 = q[1] / wind; }
+      if (wind > 0.) { a0 = ((UnderStory == 2) ? q[2] : q[0]) / wind; a1 = q[1] / wind; }
       else { a0 = HUGE_RESIST; a1 = HUGE_RESIST; }
     }
     else {
-      rs = (i == 5) ? 0 : uc.rmin; rarc = uc.rarc; RGL = uc.RGL; lai = tl[TL_LAI]; albedo = tl[TL_ALB];
+      rs = (i == 5) ? 0 : vp.rmin; rarc = vp.rarc; RGL = vp.RGL; lai = tl[TL_LAI]; albedo = tl[TL_ALB];
       a0 = raU; a1 = ra1;
     }
     double rc;
@@ -1322,15 +1461,16 @@ VR_HDN void pot_evap6(const UnitC &uc, const double *tl, const double *ap, const
     else if (i == 2 || i == 3) { rc = rs / (lai * 0.5); rc = (rc > RSMAX) ? RSMAX : rc; }
     else rc = calc_rc(rs, net_short, RGL, tair, vpd, lai, 1.0);
     const double s0 = (sf0 == HUGE_RESIST) ? HUGE_RESIST : a0 * sf0, s1 = (sf1 == HUGE_RESIST) ? HUGE_RESIST : a1 * sf1;
-    const double ra = (i < 4 || !uc.overstory) ? s0 : s1;
+    const double ra = (i < 4 || !overstory) ? s0 : s1;
     net_short = (1.0 - albedo) * shortwave;
     const double net_rad = net_short + net_longwave;
-    pot[i] = penman(pa, net_rad, vpd, ra, rc, rarc) * dt_hours / 24.0;
+    pot.v[i] = penman(pa, net_rad, vpd, ra, rc, rarc) * dt_hours / 24.0;
   }
+  return pot;
 }
 
 // compute_zwt.c:7-45
-VR_HD double zwt_curve(const CellC &cc, int NL, int k, double moist)
+VR_HD double zwt_curve(CellC cc, int NL, int k, double moist)
 {
   double zwt = MISSINGV;
   int i = ZWT_NP - 1;
@@ -1346,61 +1486,117 @@ VR_HD double zwt_curve(const CellC &cc, int NL, int k, double moist)
 }
 
 // wrap_compute_zwt (compute_zwt.c:48-113), called at the end of runoff() (runoff.c:503)
-VR_HDN void water_table(const CellC &cc, int NL, const double *moist, double *zwt_out, double *lumped_out)
+struct ZwtOut { double zwt, lumped; };
+VR_HDN ZwtOut water_table(CellC cc, int NL, M3 moist)
 {
   double total_depth = 0, lz[MAXL];
-  for (int l = 0; l < NL; l++) total_depth += cc.depth(l);
-  for (int l = 0; l < NL; l++) lz[l] = zwt_curve(cc, NL, l, moist[l]);
-  if (lz[NL - 1] == 999) lz[NL - 1] = -total_depth * 100;
-  int l = NL - 1;
-  double tmp_depth = total_depth, zwt;
-  while (l >= 0 && cc.max_moist(l) - moist[l] <= SMALLV) { tmp_depth -= cc.depth(l); l--; }
-  if (l < 0) zwt = 0;
-  else if (l < NL - 1) zwt = (lz[l] != 999) ? lz[l] : -tmp_depth * 100;
-  else zwt = lz[l];
+#pragma unroll
+  for (int l = 0; l < MAXL; l++) {
+    lz[l] = 0;
+    if (l < NL) total_depth += cc.depth(l);
+  }
+#pragma unroll
+  for (int l = 0; l < MAXL; l++)
+    if (l < NL) lz[l] = zwt_curve(cc, NL, l, moist.v[l]);
+  // bottom layer
+  if (NL == 3) { if (lz[2] == 999) lz[2] = -total_depth * 100; }
+  else { if (lz[1] == 999) lz[1] = -total_depth * 100; }
+  double tmp_depth = total_depth, zwt = 0;
+  bool found = false;
+#pragma unroll
+  for (int l = MAXL - 1; l >= 0; l--) {
+    if (l < NL && !found) {
+      if (cc.max_moist(l) - moist.v[l] <= SMALLV) tmp_depth -= cc.depth(l);
+      else {
+        found = true;
+        if (l < NL - 1) zwt = (lz[l] != 999) ? lz[l] : -tmp_depth * 100;
+        else zwt = lz[l];
+      }
+    }
+  }
+  if (!found) zwt = 0;
   double tmp_moist = 0;
-  for (int k = 0; k < NL; k++) tmp_moist += moist[k];
+#pragma unroll
+  for (int k = 0; k < MAXL; k++)
+    if (k < NL) tmp_moist += moist.v[k];
   double zl = zwt_curve(cc, NL, NL + 1, tmp_moist);
   if (zl == 999) zl = -total_depth * 100;
-  *zwt_out = zwt; *lumped_out = zl;
+  ZwtOut o;
+  o.zwt = zwt; o.lumped = zl;
+  return o;
 }
 
-// extras: compile-time set of optional results (EX_PET, EX_ZWT) -- the kernel without them carries none of their
-// code or registers (their mere presence behind a run-time flag cost 4 % of the default configuration)
-// tl, ap: the potential-evaporation tables of the tile and aero key for the month (read only with EX_PET)
-template <int extras>
-VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const double *ae, const Forc &f, int NL,
-                     int dt_hours, double max_snow_temp, double min_rain_temp, UnitS &s, UnitOut &o, UnitExtra &x,
-                     const double *tl = nullptr, const double *ap = nullptr)
+// carried state split by temperature: the words every record touches, and the snow words that only the snow path reads
+struct HotS { M3 moist; double Wdew, T0, T1, LongUnderOut, Tfoliage; };
+struct SnowS {
+  double swq, surf_temp, pack_temp, surf_water, pack_water, density, depth, albedo, coldcontent, coverage, snow_canopy,
+         tmp_int_storage;
+  int last_snow, MELTING;
+};
+// what the reference's else-branch of solve_snow leaves behind when there is no snow anywhere (solve_snow.c:540-577)
+VR_HD SnowS snow_none()
 {
+  SnowS z;
+  z.swq = 0; z.surf_temp = 0; z.pack_temp = 0; z.surf_water = 0; z.pack_water = 0; z.density = 0; z.depth = 0;
+  z.albedo = NEW_SNOW_ALB; z.coldcontent = 0; z.coverage = 0; z.snow_canopy = 0; z.tmp_int_storage = 0;
+  z.last_snow = (int)MISSINGV; z.MELTING = 0;
+  return z;
+}
+
+// calc_rainonly.c:8-58 + solve_snow.c:185-197: rain / snow partition of the (sub-)step's precipitation
+VR_HD void rain_snow_split(double Tair, double step_prec, double max_snow_temp, double min_rain_temp, double &rainfall,
+                           double &snowfall)
+{
+  double rainonly = 0.;
+  if (Tair < max_snow_temp && Tair > min_rain_temp) rainonly = (Tair - min_rain_temp) / (max_snow_temp - min_rain_temp) * step_prec;
+  else if (Tair >= max_snow_temp) rainonly = step_prec;
+  snowfall = 1. * (step_prec - rainonly);
+  rainfall = 1. * rainonly;
+  if (snowfall < 1e-5) snowfall = 0.;
+}
+
+// per (unit, month) canopy terms handed to the step (full_energy.c:210-227,306-316)
+struct CanopyM { double vegcover, LAI, Wdmax, albedo, surf_atten; };
+
+// results of ONE pass of surface_fluxes' sub-step loop (surface_fluxes.c:480-1025) that the caller sums / averages
+struct SurfOut {
+  double ppt, canopyevap, throughfall, vapor_flux, canopy_vapor_flux, melt, out_prec, out_rain, out_snow;
+  M3 evap, bef;
+  double Tsurf, NetShortAtmos, NetLongAtmos, LongOverIn, LongUnderIn, AlbedoOver, AlbedoUnder, grnd_flux, deltaH,
+         ra_used0, ra_used1;
+  P6 pot;
+  int snow_flag, fb_snow, fb_fol, err;
+};
+
+// One pass of the sub-step loop for one unit: solve_snow.c:7-577, then calc_surf_energy_bal.c / func_surf_energy_bal.c in
+// water-balance mode (FULL_ENERGY FALSE: Tsurf = Tair), canopy_evap / arno_evap.  SNOW == false is the instance for a
+// unit without any snow state and without snowfall in this pass: the snow words are the constants of snow_none() and none
+// of the snow code is compiled in; the caller picks the instance per WARP, so a warp never runs both.
+// h: hot state (moist is read only; Wdew, T0, T1, LongUnderOut, Tfoliage are advanced); sn: snow state (advanced);
+// coverage, surf_atten: surface_fluxes' variables of those names, which live across the passes of a record (a pass with
+// snow on a tile without overstory leaves surf_atten = 1 behind for the rest of the record, solve_snow.c:215); Tgrnd:
+// energy->T[0] at the start of the record; dt_hours: length of this pass.
+template <int extras, bool SNOW>
+VR_HD SurfOut surface_pass(CellC cc, VegP vp, bool is_veg, bool overstory, double Tfactor, double Pfactor, CanopyM cm,
+                           const double *ae, Forc f, int NL, int dt_hours, double max_snow_temp, double min_rain_temp,
+                           double Tgrnd, HotS &h, SnowS &sn, double &coverage, double &surf_atten, const double *tl,
+                           const double *ap, bool sync_ok, int rec_dt_hours)
+{
+  (void)sync_ok;
+  SurfOut o;
+  o.err = 0; o.fb_snow = 0; o.fb_fol = 0;
   const double delta_t = (double)dt_hours * 3600.;
-  const bool is_veg = !uc.is_bare;
-  const bool overstory = uc.overstory != 0;
-  VegV v;
-  double BareAlbedo, surf_atten;
-  // ---- full_energy.c:210-227,306-316: canopy terms of the month ----
-  if (is_veg) {
-    v.vegcover = tm[TM_VEGCOVER];
-    v.LAI = tm[TM_LAI];
-    v.Wdmax = tm[TM_WDMAX];
-    s.Wdew /= v.vegcover;
-    s.snow_canopy /= v.vegcover;
-    BareAlbedo = tm[TM_ALBEDO];
-    surf_atten = tm[TM_SURF_ATTEN];
-  }
-  else {
-    v.vegcover = 0; v.LAI = 0; v.Wdmax = 0;
-    BareAlbedo = BARE_SOIL_ALBEDO;
-    surf_atten = 1.;
-  }
-  v.Wdew = s.Wdew; v.canopyevap = 0; v.throughfall = 0;
+  double BareAlbedo, vegcover, LAI, Wdmax;
+  if (is_veg) { vegcover = cm.vegcover; LAI = cm.LAI; Wdmax = cm.Wdmax; BareAlbedo = cm.albedo; }
+  else { vegcover = 0; LAI = 0; Wdmax = 0; BareAlbedo = BARE_SOIL_ALBEDO; }
+  double v_Wdew = h.Wdew, v_canopyevap = 0, v_throughfall = 0;
 
   // ---- prepare_full_energy.c:55-110 -> soil_conduction.c:5-61: kappa, Cs of layers 0 and 1 from the
   //      pre-step moisture; Kdry, Ksat and the solid heat capacity are per-cell constants ----
   double kappa[2], Cs[2];
 #pragma unroll
   for (int l = 0; l < 2; l++) {
-    double mv = s.moist[l] / cc.depth(l) / 1000;
+    double mv = h.moist.v[l] / cc.depth(l) / 1000;
     double K;
     if (mv > 0.) {
       double Sr = mv / cc.poros(l);
@@ -1417,137 +1613,147 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   }
 
   // ---- aerodynamics of the current cover: Ra = RA/wind, U = UC*wind (CalcAerodynamic.c:232-257) ----
-  double Ra[3], U[3];
-  if (f.wind > 0.) {
-    Ra[0] = ae[AE_RA0] / f.wind; Ra[1] = ae[AE_RA1] / f.wind; Ra[2] = ae[AE_RA2] / f.wind;
-  }
-  else { Ra[0] = HUGE_RESIST; Ra[1] = HUGE_RESIST; Ra[2] = HUGE_RESIST; }
-  U[0] = ae[AE_U0] * f.wind; U[1] = ae[AE_U1] * f.wind; U[2] = ae[AE_U2] * f.wind;
-  double ra_used0 = Ra[0], ra_used1 = Ra[1];
+  double Ra0, Ra1, Ra2;
+  if (f.wind > 0.) { Ra0 = ae[AE_RA0] / f.wind; Ra1 = ae[AE_RA1] / f.wind; Ra2 = ae[AE_RA2] / f.wind; }
+  else { Ra0 = HUGE_RESIST; Ra1 = HUGE_RESIST; Ra2 = HUGE_RESIST; }
+  const double U0 = ae[AE_U0] * f.wind, U1 = ae[AE_U1] * f.wind, U2 = ae[AE_U2] * f.wind;
+  double ra_used0 = Ra0, ra_used1 = Ra1;
+  (void)U1; (void)U2; (void)Ra2;
 
   // ---- surface_fluxes.c:480-560 ----
-  const double Tair = f.air_temp + uc.Tfactor;
-  const double step_prec = f.prec * uc.Pfactor;
-  const double Tgrnd = s.T0, Tcanopy = Tair;
-  double coverage = s.coverage;
-  const double step_depth_old = s.depth, step_surf_temp_old = s.surf_temp;
+  const double Tair = f.air_temp + Tfactor;
+  const double step_prec = f.prec * Pfactor;
+  const double Tcanopy = Tair;
+  const double step_depth_old = sn.depth, step_surf_temp_old = sn.surf_temp;
   const PenmanAir pa = penman_air(Tair, cc.half_elev_lapse(), cc.elev());
 
-  VR_PHASE_SYNC();
   // ---- solve_snow.c:7-577 ----
-  double rainonly = 0.;
-  if (Tair < max_snow_temp && Tair > min_rain_temp) rainonly = (Tair - min_rain_temp) / (max_snow_temp - min_rain_temp) * step_prec;
-  else if (Tair >= max_snow_temp) rainonly = step_prec;
-  double snowfall = 1. * (step_prec - rainonly), rainfall = 1. * rainonly;
-  if (snowfall < 1e-5) snowfall = 0.;
+  double snowfall, rainfall;
+  rain_snow_split(Tair, step_prec, max_snow_temp, min_rain_temp, rainfall, snowfall);
   const double out_prec = snowfall + rainfall, out_rain = rainfall, out_snow = snowfall, store_snowfall = snowfall;
   const double Le = (2.501e6 - 0.002361e6 * Tair);
-  int UnderStory = (s.swq > 0 || snowfall > 0) ? 2 : 0;
+  int UnderStory = 0;
   double ShortUnderIn = f.shortwave, LongUnderIn = f.longwave;
   double melt = 0., ppt = 0., melt_energy = 0., NetLongSnow = 0., NetShortSnow = 0., NetShortGrnd = 0.,
          delta_coverage = 0., AlbedoUnder, OldTSurf = 0., vapor_flux = 0., canopy_vapor_flux = 0.;
   double es_latent = 0., es_latent_sub = 0., es_sensible = 0., es_advection = 0., es_deltaCC = 0., es_refreeze = 0.;
   double AlbedoOver = 0., NetLongOver = 0., NetShortOver = 0., LongOverIn = 0.;
-  int snow_flag;
-  if (s.swq > 0 || snowfall > 0. || (s.snow_canopy > 0. && overstory)) {
+  int snow_flag = 0;
+  if (SNOW && (sn.swq > 0 || snowfall > 0. || (sn.snow_canopy > 0. && overstory))) {
+    UnderStory = (sn.swq > 0 || snowfall > 0) ? 2 : 0;
     snow_flag = 1;
     if (!overstory) surf_atten = 1.;
-    const double old_coverage = s.coverage;
+    const double old_coverage = sn.coverage;
     if (is_veg) {
       if (overstory) {
         ShortUnderIn *= surf_atten;
         double ShortOverIn = (1. - surf_atten) * f.shortwave;
-        ShortOverIn /= v.vegcover;
-        InterceptOut io;
-        snow_intercept(s, v, uc, cc, NL, pa, f, (double)dt_hours * 3600, Le, f.longwave, ShortOverIn, Tcanopy,
-                       BareAlbedo, Ra[0], Ra[1], U[1], rainfall, snowfall, io);
+        ShortOverIn /= vegcover;
+        InterceptIn ii;
+        ii.Tfoliage = h.Tfoliage; ii.LongUnderOut = h.LongUnderOut; ii.snow_canopy = sn.snow_canopy;
+        ii.tmp_int_storage = sn.tmp_int_storage; ii.Wdew = v_Wdew; ii.Wdmax = Wdmax; ii.LAI = LAI;
+        ii.canopyevap = v_canopyevap; ii.throughfall = v_throughfall;
+        ii.density = f.density; ii.vp = f.vp; ii.pressure = f.pressure; ii.vpd = f.vpd;
+        ii.Dt = (double)dt_hours * 3600; ii.Le = Le; ii.LongOverIn = f.longwave; ii.ShortOverIn = ShortOverIn;
+        ii.Tcanopy = Tcanopy; ii.bare_albedo = BareAlbedo; ii.Ra0 = Ra0; ii.Ra1 = Ra1; ii.wind1 = U1;
+        ii.RainFall = rainfall; ii.SnowFall = snowfall;
+        const InterceptOut io = snow_intercept(ii, h.moist, vp, cc, NL, pa);
+        h.Tfoliage = io.Tfoliage; sn.snow_canopy = io.snow_canopy; sn.tmp_int_storage = io.tmp_int_storage;
+        v_Wdew = io.Wdew; v_canopyevap = io.canopyevap;
+        rainfall = io.RainFall; snowfall = io.SnowFall;
+        o.fb_fol = io.fallback;
         LongUnderIn = io.LongOverOut;
         AlbedoOver = io.AlbedoOver; NetLongOver = io.NetLongOver; NetShortOver = io.NetShortOver;
         canopy_vapor_flux = io.canopy_vapor_flux;
         ra_used0 = io.Ra_used0; ra_used1 = io.Ra_used1;
-        v.throughfall = rainfall + snowfall;
+        v_throughfall = rainfall + snowfall;
         LongOverIn = f.longwave;
       }
-      else if (snowfall > 0. && v.Wdew > 0.) {
-        rainfall += v.Wdew;
-        v.throughfall = rainfall + snowfall;
-        v.Wdew = 0.;
-        s.Tfoliage = Tair;
+      else if (snowfall > 0. && v_Wdew > 0.) {
+        rainfall += v_Wdew;
+        v_throughfall = rainfall + snowfall;
+        v_Wdew = 0.;
+        h.Tfoliage = Tair;
       }
       else {
-        v.throughfall = rainfall + snowfall;
-        s.Tfoliage = Tair;
+        v_throughfall = rainfall + snowfall;
+        h.Tfoliage = Tair;
       }
-      v.throughfall = (1 - v.vegcover) * (out_prec) + v.vegcover * v.throughfall;
-      rainfall = (1 - v.vegcover) * (out_rain) + v.vegcover * (rainfall);
-      snowfall = (1 - v.vegcover) * (out_snow) + v.vegcover * (snowfall);
-      canopy_vapor_flux *= v.vegcover;
-      s.snow_canopy *= v.vegcover;
-      v.Wdew *= v.vegcover;
-      v.canopyevap *= v.vegcover;
-      NetShortOver *= v.vegcover;
-      NetLongOver *= v.vegcover;
+      v_throughfall = (1 - vegcover) * (out_prec) + vegcover * v_throughfall;
+      rainfall = (1 - vegcover) * (out_rain) + vegcover * (rainfall);
+      snowfall = (1 - vegcover) * (out_snow) + vegcover * (snowfall);
+      canopy_vapor_flux *= vegcover;
+      sn.snow_canopy *= vegcover;
+      v_Wdew *= vegcover;
+      v_canopyevap *= vegcover;
+      NetShortOver *= vegcover;
+      NetLongOver *= vegcover;
     }
-    if (s.swq > 0.0 || snowfall > 0) {
-      const double old_swq = s.swq;
+    if (sn.swq > 0.0 || snowfall > 0) {
+      const double old_swq = sn.swq;
       UnderStory = 2;
-      if (s.swq > 0 && store_snowfall == 0) {
-        s.last_snow++;
-        s.albedo = snow_albedo(snowfall, s.swq, s.albedo, s.coldcontent, (double)dt_hours, s.last_snow, s.MELTING);
-        AlbedoUnder = (coverage * s.albedo + (1. - coverage) * BareAlbedo);
+      if (sn.swq > 0 && store_snowfall == 0) {
+        sn.last_snow++;
+        sn.albedo = snow_albedo(snowfall, sn.swq, sn.albedo, sn.coldcontent, (double)dt_hours, sn.last_snow, sn.MELTING);
+        AlbedoUnder = (coverage * sn.albedo + (1. - coverage) * BareAlbedo);
       }
       else {
-        s.last_snow = 0;
-        s.albedo = NEW_SNOW_ALB;
-        AlbedoUnder = s.albedo;
+        sn.last_snow = 0;
+        sn.albedo = NEW_SNOW_ALB;
+        AlbedoUnder = sn.albedo;
       }
       NetShortSnow = (1.0 - AlbedoUnder) * (ShortUnderIn);
-      SnowMeltOut mo;
-      snow_melt(s, Le, NetShortSnow, Tcanopy, Tgrnd, ae[AE_ROUGH2], Ra[2], Tair, (double)dt_hours * 3600, f.density,
-                LongUnderIn, f.pressure, rainfall, snowfall, f.vp, f.vpd, U[2], ae[AE_REF2], mo);
+      PackS pk;
+      pk.swq = sn.swq; pk.surf_temp = sn.surf_temp; pk.pack_temp = sn.pack_temp; pk.surf_water = sn.surf_water;
+      pk.pack_water = sn.pack_water; pk.depth = sn.depth; pk.density = sn.density; pk.coldcontent = sn.coldcontent;
+      const SnowMeltOut mo = snow_melt(pk, Le, NetShortSnow, Tcanopy, Tgrnd, ae[AE_ROUGH2], Ra2, Tair, (double)dt_hours * 3600,
+                                       f.density, LongUnderIn, f.pressure, rainfall, snowfall, f.vp, f.vpd, U2, ae[AE_REF2]);
+      sn.swq = mo.s.swq; sn.surf_temp = mo.s.surf_temp; sn.pack_temp = mo.s.pack_temp; sn.surf_water = mo.s.surf_water;
+      sn.pack_water = mo.s.pack_water; sn.depth = mo.s.depth; sn.density = mo.s.density; sn.coldcontent = mo.s.coldcontent;
+      o.fb_snow = mo.fallback;
       ra_used0 = mo.aero_used0;
       vapor_flux = mo.vapor_flux; NetLongSnow = mo.NetLongSnow; OldTSurf = mo.OldTSurf;
       es_advection = mo.advection; es_deltaCC = mo.deltaCC; es_latent = mo.latent; es_latent_sub = mo.latent_sub;
       es_refreeze = mo.refreeze_energy; es_sensible = mo.sensible;
       melt = mo.melt;
       ppt += melt;
-      if (s.swq > 0.) {
-        if (s.surf_temp <= 0) s.density = snow_density(s.surf_temp, s.depth, snowfall, old_swq, Tair, (double)dt_hours);
-        else if (s.last_snow == 0) s.density = new_snow_density(Tair);
-        s.depth = 1000. * s.swq / s.density;
-        if (s.coldcontent >= 0 && ((cc.lat() >= 0 && (f.doy > 60 && f.doy < 273)) || (cc.lat() < 0 && (f.doy < 60 || f.doy > 273))))
-          s.MELTING = 1;
-        else if (s.MELTING && snowfall > TraceSnow) s.MELTING = 0;
-        s.coverage = 1.;
+      if (sn.swq > 0.) {
+        if (sn.surf_temp <= 0) sn.density = snow_density(sn.surf_temp, sn.depth, snowfall, old_swq, Tair, (double)dt_hours);
+        else if (sn.last_snow == 0) sn.density = new_snow_density(Tair);
+        sn.depth = 1000. * sn.swq / sn.density;
+        if (sn.coldcontent >= 0 && ((cc.lat() >= 0 && (f.doy > 60 && f.doy < 273)) || (cc.lat() < 0 && (f.doy < 60 || f.doy > 273))))
+          sn.MELTING = 1;
+        else if (sn.MELTING && snowfall > TraceSnow) sn.MELTING = 0;
+        sn.coverage = 1.;
       }
-      else s.coverage = 0.;
-      delta_coverage = old_coverage - s.coverage;
+      else sn.coverage = 0.;
+      delta_coverage = old_coverage - sn.coverage;
       if (delta_coverage != 0) {
-        if (old_coverage > s.coverage) {
+        if (old_coverage > sn.coverage) {
           coverage = (old_coverage);
-          AlbedoUnder = (coverage - s.coverage) / (1. - s.coverage) * s.albedo;
-          AlbedoUnder += (1. - coverage) / (1. - s.coverage) * BareAlbedo;
+          AlbedoUnder = (coverage - sn.coverage) / (1. - sn.coverage) * sn.albedo;
+          AlbedoUnder += (1. - coverage) / (1. - sn.coverage) * BareAlbedo;
           melt_energy = (delta_coverage) * (es_advection - es_deltaCC + es_latent + es_latent_sub + es_sensible + es_refreeze + 0.);
         }
         else {
-          coverage = s.coverage;
+          coverage = sn.coverage;
           delta_coverage = 0;
         }
       }
-      else if (old_coverage == 0 && s.coverage == 0) {
+      else if (old_coverage == 0 && sn.coverage == 0) {
         delta_coverage = 1.;
         coverage = 0.;
         melt_energy = (es_advection - es_deltaCC + es_latent + es_latent_sub + es_sensible + es_refreeze + 0.);
       }
-      NetLongSnow *= (s.coverage);
-      NetShortSnow *= (s.coverage);
-      NetShortGrnd *= (s.coverage);
-      es_latent *= (s.coverage + delta_coverage);
-      es_latent_sub *= (s.coverage + delta_coverage);
-      es_sensible *= (s.coverage + delta_coverage);
-      if (s.swq == 0) {
-        s.density = 0.; s.depth = 0.; s.surf_water = 0; s.pack_water = 0; s.surf_temp = 0; s.pack_temp = 0;
-        s.coverage = 0; s.MELTING = 0;
+      NetLongSnow *= (sn.coverage);
+      NetShortSnow *= (sn.coverage);
+      NetShortGrnd *= (sn.coverage);
+      es_latent *= (sn.coverage + delta_coverage);
+      es_latent_sub *= (sn.coverage + delta_coverage);
+      es_sensible *= (sn.coverage + delta_coverage);
+      if (sn.swq == 0) {
+        sn.density = 0.; sn.depth = 0.; sn.surf_water = 0; sn.pack_water = 0; sn.surf_temp = 0; sn.pack_temp = 0;
+        sn.coverage = 0; sn.MELTING = 0;
       }
       snowfall = 0;
       rainfall = 0;
@@ -1556,47 +1762,46 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
       ppt += rainfall;
       AlbedoOver = 0.;
       AlbedoUnder = BareAlbedo;
-      s.last_snow = (int)MISSINGV;
-      s.MELTING = 0;
+      sn.last_snow = (int)MISSINGV;
+      sn.MELTING = 0;
     }
   }
   else {
     UnderStory = 0;
     snow_flag = 0;
     AlbedoUnder = BareAlbedo;
-    s.Tfoliage = Tcanopy;
-    s.MELTING = 0;
-    s.last_snow = (int)MISSINGV;
-    s.albedo = NEW_SNOW_ALB;
+    h.Tfoliage = Tcanopy;
+    sn.MELTING = 0;
+    sn.last_snow = (int)MISSINGV;
+    sn.albedo = NEW_SNOW_ALB;
   }
-  (void)AlbedoUnder; (void)coverage;
+  (void)AlbedoUnder;
 
-  VR_PHASE_SYNC();
+  VR_PHASE_SYNC(1, sync_ok);
   // ---- surface_fluxes.c:680-695: thin pack -> solved together with the ground ----
   bool INCLUDE_SNOW = false;
   double eo_advection = 0.;
-  if (s.surf_temp == 999 && s.swq > 0) {
+  if (SNOW && sn.surf_temp == 999 && sn.swq > 0) {
     INCLUDE_SNOW = true;
     eo_advection = es_advection;
-    s.surf_temp = step_surf_temp_old;
+    sn.surf_temp = step_surf_temp_old;
     melt_energy = 0;
   }
 
   // ---- calc_surf_energy_bal.c (FULL_ENERGY FALSE: Tsurf = Tair) + func_surf_energy_bal.c ----
-  const bool VEG = is_veg && v.vegcover > 0.0;
-  const double T2 = cc.avg_T(), Ts_old = s.T0, T1_old = s.T1, D1 = cc.D1(), D2 = cc.D1();
+  const bool VEG = is_veg && vegcover > 0.0;
+  const double T2 = cc.avg_T(), Ts_old = h.T0, T1_old = h.T1, D1 = cc.D1(), D2 = cc.D1();
   const double kappa1 = kappa[0], kappa2 = kappa[1], Cs1 = Cs[0], Cs2 = Cs[1];
-  double Tsnow_surf = s.surf_temp;
-  const double Wdew_in = v.Wdew;
-  const double snow_coverage = s.coverage, SnowAlbedo = s.albedo;
-  const double snow_depth = (step_depth_old + s.depth) / 2.;
-  const double kappa_snow = (s.depth > 0.) ? K_SNOW * (s.density) * (s.density) / snow_depth : 0;
-  (void)kappa_snow;
+  double Tsnow_surf = sn.surf_temp;
+  const double Wdew_in = v_Wdew;
+  const double snow_coverage = sn.coverage, SnowAlbedo = sn.albedo;
+  const double snow_depth = (step_depth_old + sn.depth) / 2.;
+  (void)snow_depth;
   const double NetShortBare = (ShortUnderIn * (1. - (snow_coverage + delta_coverage)) * (1. - BareAlbedo) +
                                ShortUnderIn * (delta_coverage) * (1. - SnowAlbedo));
   const double LongBareIn = (1. - snow_coverage) * LongUnderIn;
   double TmpNetLongSnow, TmpNetShortSnow, LongSnowIn;
-  if (INCLUDE_SNOW || s.swq == 0) {
+  if (INCLUDE_SNOW || sn.swq == 0) {
     TmpNetLongSnow = NetLongSnow;
     TmpNetShortSnow = NetShortSnow;
     LongSnowIn = snow_coverage * LongUnderIn;
@@ -1605,7 +1810,7 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   const double Tsurf = Tcanopy, TMean = Tsurf;
   const double Tmp = TMean + KELVIN;
   if (INCLUDE_SNOW) Tsnow_surf = TMean;
-  // estimate_T1.c:8-47 with VR_EXP(-D1/dp), VR_EXP(D1/dp) hoisted
+  // estimate_T1.c:8-47 with exp(-D1/dp), exp(D1/dp) hoisted
   double T1;
   {
     double C1 = Cs2 * cc.dp() / D2 * (1. - cc.exp_m());
@@ -1619,9 +1824,9 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   const double deltaH = (Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1 / delta_t / 2.);
   double eo_deltaCC = 0., eo_refreeze = 0.;
   if (INCLUDE_SNOW) {
-    if (TMean > 0) eo_deltaCC = CH_ICE * (s.swq - s.surf_water) * (0 - OldTSurf) / delta_t;
-    else eo_deltaCC = CH_ICE * (s.swq - s.surf_water) * (TMean - OldTSurf) / delta_t;
-    eo_refreeze = (s.surf_water * Lf * s.density) / delta_t;
+    if (TMean > 0) eo_deltaCC = CH_ICE * (sn.swq - sn.surf_water) * (0 - OldTSurf) / delta_t;
+    else eo_deltaCC = CH_ICE * (sn.swq - sn.surf_water) * (TMean - OldTSurf) / delta_t;
+    eo_refreeze = (sn.surf_water * Lf * sn.density) / delta_t;
     eo_deltaCC *= snow_coverage;
     eo_refreeze *= snow_coverage;
   }
@@ -1630,47 +1835,62 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   const double NetLongBare = (LongBareIn - (1. - snow_coverage) * LongBareOut);
   const double NetBareRad = (NetShortBare + (NetLongBare) + grnd_flux + deltaH + 0.);
   // Ra_used[0]: StabilityCorrection(TSurf == Tair) == 1 (func_surf_energy_bal.c:684-693)
-  if (U[UnderStory] > 0.0) ra_used0 = Ra[UnderStory] / 1.0;
+  const double U_us = (UnderStory == 2) ? U2 : U0, Ra_us = (UnderStory == 2) ? Ra2 : Ra0;
+  if (U_us > 0.0) ra_used0 = Ra_us / 1.0;
   else ra_used0 = HUGE_RESIST;
-  if (v.vegcover < 1) {      // bare-gap blend, func_surf_energy_bal.c:712-749 (always for the bare tile)
+  if (vegcover < 1) {      // bare-gap blend, func_surf_energy_bal.c:712-749 (always for the bare tile)
     if (ra_used0 > 0) {
       double ga_veg = 1 / ra_used0;
-      double Ra_bare0 = (U[0] > 0.) ? cc.kb_bare() / U[0] : HUGE_RESIST;
+      double Ra_bare0 = (U0 > 0.) ? cc.kb_bare() / U0 : HUGE_RESIST;
       Ra_bare0 /= 1.0;
       if (Ra_bare0 > 0) {
         double ga_bare = 1 / Ra_bare0;
-        double ga_average = v.vegcover * ga_veg + (1 - v.vegcover) * ga_bare;
+        double ga_average = vegcover * ga_veg + (1 - vegcover) * ga_bare;
         ra_used0 = 1 / ga_average;
       }
       else ra_used0 = 0;
     }
     else ra_used0 = 0;
   }
-  double evap[MAXL], bef[MAXL], Evap;
+  M3 evap, bef;
+  double Evap;
 #pragma unroll
-  for (int l = 0; l < MAXL; l++) { evap[l] = 0; bef[l] = 0; }
-  VR_PHASE_SYNC();
-  if (VEG && !snow_flag && v.vegcover > 0) {
-    Evap = canopy_evap(s.moist, v, true, uc, cc, NL, pa, Wdew_in, delta_t, NetBareRad, f.vpd, NetShortBare, Tcanopy,
-                       ra_used1, rainfall, evap);
-    if (v.vegcover < 1) {
-      double transp[MAXL];
-      for (int i = 0; i < NL; i++) { transp[i] = evap[i]; evap[i] = 0; }
-      Evap *= v.vegcover;
-      Evap += (1 - v.vegcover) * arno_evap(s.moist[0], cc, pa, surf_atten * NetBareRad, f.vpd, ra_used0, delta_t, &evap[0]);
-      for (int i = 0; i < NL; i++) {
-        evap[i] = v.vegcover * transp[i] + (1 - v.vegcover) * evap[i];
-        if (evap[i] > 0) bef[i] = 1 - (v.vegcover * transp[i]) / evap[i];
-        else bef[i] = 0;
+  for (int l = 0; l < MAXL; l++) { evap.v[l] = 0; bef.v[l] = 0; }
+  VR_PHASE_SYNC(2, sync_ok);
+  if (VEG && !snow_flag && vegcover > 0) {
+    const CanopyOut ce = canopy_evap(h.moist, LAI, Wdmax, true, vp, cc, NL, pa, Wdew_in, delta_t, NetBareRad, f.vpd, NetShortBare,
+                                     Tcanopy, ra_used1, rainfall);
+    Evap = ce.Evap; evap = ce.le;
+    v_canopyevap = ce.canopyevap; v_throughfall = ce.throughfall; v_Wdew = ce.Wdew;
+    if (vegcover < 1) {
+      M3 transp = evap;
+#pragma unroll
+      for (int i = 0; i < MAXL; i++) evap.v[i] = 0;
+      Evap *= vegcover;
+      const ArnoOut ao = arno_evap(h.moist.v[0], cc, pa, surf_atten * NetBareRad, f.vpd, ra_used0, delta_t);
+      if (ao.Evap == VERR) o.err = 1;
+      evap.v[0] = ao.evap0;
+      Evap += (1 - vegcover) * ao.Evap;
+#pragma unroll
+      for (int i = 0; i < MAXL; i++) {
+        if (i < NL) {
+          evap.v[i] = vegcover * transp.v[i] + (1 - vegcover) * evap.v[i];
+          if (evap.v[i] > 0) bef.v[i] = 1 - (vegcover * transp.v[i]) / evap.v[i];
+          else bef.v[i] = 0;
+        }
       }
-      v.throughfall = (1 - v.vegcover) * rainfall + v.vegcover * v.throughfall;
-      v.canopyevap *= v.vegcover;
-      v.Wdew *= v.vegcover;
+      v_throughfall = (1 - vegcover) * rainfall + vegcover * v_throughfall;
+      v_canopyevap *= vegcover;
+      v_Wdew *= vegcover;
     }
   }
   else if (!snow_flag) {
-    Evap = arno_evap(s.moist[0], cc, pa, NetBareRad, f.vpd, ra_used0, delta_t, &evap[0]);
-    for (int i = 0; i < NL; i++) bef[i] = 1;
+    const ArnoOut ao = arno_evap(h.moist.v[0], cc, pa, NetBareRad, f.vpd, ra_used0, delta_t);
+    if (ao.Evap == VERR) o.err = 1;
+    Evap = ao.Evap; evap.v[0] = ao.evap0;
+#pragma unroll
+    for (int i = 0; i < MAXL; i++)
+      if (i < NL) bef.v[i] = 1;
   }
   else Evap = 0.;
   if (INCLUDE_SNOW) {
@@ -1680,10 +1900,10 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     double SurfaceMassFlux = f.density * (EPS / f.pressure) * (f.vp - EsSnow) / ra_used0;
     if (f.vpd == 0.0 && SurfaceMassFlux < 0.0) SurfaceMassFlux = 0.0;
     double VaporMassFlux = SurfaceMassFlux + 0.;
-    double tl, tls;
-    if (TMean >= 0.0) { tl = Le * VaporMassFlux; tls = 0; }
-    else { tls = ((677. - 0.07 * TMean) * JOULESPCAL * GRAMSPKG) * VaporMassFlux; tl = 0; }
-    latent_heat += tl * snow_coverage;
+    double tlh, tls;
+    if (TMean >= 0.0) { tlh = Le * VaporMassFlux; tls = 0; }
+    else { tls = ((677. - 0.07 * TMean) * JOULESPCAL * GRAMSPKG) * VaporMassFlux; tlh = 0; }
+    latent_heat += tlh * snow_coverage;
     latent_heat_sub = tls * snow_coverage;
     vapor_flux = VaporMassFlux * delta_t / ICE_DENSITY;
     double sensible_heat = f.density * Cp * (Tcanopy - (TMean)) / ra_used0;
@@ -1692,9 +1912,9 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     if (Tsnow_surf == 0.0 && error > -(eo_refreeze)) eo_refreeze = -error;
   }
   // ---- calc_surf_energy_bal.c:584-731 ----
-  s.T0 = Tsurf;
-  s.T1 = T1;
-  if (!snow_flag && !INCLUDE_SNOW) ppt = is_veg ? v.throughfall : rainfall;
+  h.T0 = Tsurf;
+  h.T1 = T1;
+  if (!snow_flag && !INCLUDE_SNOW) ppt = is_veg ? v_throughfall : rainfall;
   double NetLongUnder, NetShortUnder;
   if (INCLUDE_SNOW) {
     NetLongUnder = NetLongBare + TmpNetLongSnow;
@@ -1704,38 +1924,38 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
     NetLongUnder = NetLongBare + NetLongSnow;
     NetShortUnder = NetShortBare + NetShortSnow + NetShortGrnd;
   }
-  s.LongUnderOut = LongUnderIn - NetLongUnder;
+  h.LongUnderOut = LongUnderIn - NetLongUnder;
   const double AlbedoUnderOut = ((1. - (snow_coverage + delta_coverage)) * BareAlbedo + (snow_coverage + delta_coverage) * SnowAlbedo);
-  o.Tsurf = (s.coverage * s.surf_temp + (1. - s.coverage) * Tsurf);
+  o.Tsurf = (sn.coverage * sn.surf_temp + (1. - sn.coverage) * Tsurf);
   if (INCLUDE_SNOW) {
-    if (-(vapor_flux) > s.swq) vapor_flux = -(s.swq);
-    s.swq += vapor_flux;
-    s.surf_water += vapor_flux;
-    s.surf_water = (s.surf_water < 0) ? 0. : s.surf_water;
+    if (-(vapor_flux) > sn.swq) vapor_flux = -(sn.swq);
+    sn.swq += vapor_flux;
+    sn.surf_water += vapor_flux;
+    sn.surf_water = (sn.surf_water < 0) ? 0. : sn.surf_water;
     if (eo_refreeze >= 0.0) {
       double refrozen_water = eo_refreeze / (Lf * RHO_W) * delta_t;
-      if (refrozen_water > s.surf_water) refrozen_water = s.surf_water;
-      s.surf_water -= refrozen_water;
-      if (s.surf_water < 0.0) s.surf_water = 0.0;
+      if (refrozen_water > sn.surf_water) refrozen_water = sn.surf_water;
+      sn.surf_water -= refrozen_water;
+      if (sn.surf_water < 0.0) sn.surf_water = 0.0;
       melt = 0.0;
     }
     else {
       melt = fabs(eo_refreeze) / (Lf * RHO_W) * delta_t;
-      s.swq -= melt;
-      if (s.swq < 0) {
-        melt += s.swq;
-        s.swq = 0;
+      sn.swq -= melt;
+      if (sn.swq < 0) {
+        melt += sn.swq;
+        sn.swq = 0;
       }
     }
-    if (s.swq > 0) {
-      s.surf_temp = (Tsurf > 0) ? 0 : Tsurf;
-      s.coldcontent = CH_ICE * s.surf_temp * s.swq;
-      s.depth = 1000. * s.swq / s.density;
-      s.coverage = 1.;
+    if (sn.swq > 0) {
+      sn.surf_temp = (Tsurf > 0) ? 0 : Tsurf;
+      sn.coldcontent = CH_ICE * sn.surf_temp * sn.swq;
+      sn.depth = 1000. * sn.swq / sn.density;
+      sn.coverage = 1.;
     }
     else {
-      s.density = 0.; s.depth = 0.; s.surf_water = 0; s.pack_water = 0; s.surf_temp = 0; s.pack_temp = 0;
-      s.coverage = 0;
+      sn.density = 0.; sn.depth = 0.; sn.surf_water = 0; sn.pack_water = 0; sn.surf_temp = 0; sn.pack_temp = 0;
+      sn.coverage = 0;
     }
     vapor_flux *= -1;
     ppt += melt;
@@ -1744,50 +1964,24 @@ VR_HD void unit_step(const CellC &cc, const UnitC &uc, const double *tm, const d
   if (snow_flag && overstory) {
     o.NetLongAtmos = (1. * NetLongOver + (1. - 1.) * NetLongUnder);
     o.NetShortAtmos = (NetShortOver + NetShortUnder);
-    o.in_long = LongOverIn;
-    o.albedo = AlbedoOver;
   }
   else {
     o.NetLongAtmos = NetLongUnder;
     o.NetShortAtmos = NetShortUnder;
-    o.in_long = LongUnderIn;
-    o.albedo = AlbedoUnderOut;
   }
-  // ---- surface_fluxes.c:1110-1123: resistance -> conductance -> resistance over N_steps == 1 ----
-  {
-    double c0 = (ra_used0 > 0) ? 0. + 1 / ra_used0 : 0. + HUGE_RESIST;
-    double c1 = (ra_used1 > 0) ? 0. + 1 / ra_used1 : 0. + HUGE_RESIST;
-    o.aero_resist[0] = (c0 > 0 && c0 < HUGE_RESIST) ? 1 / (c0 / 1.) : ((c0 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
-    o.aero_resist[1] = (c1 > 0 && c1 < HUGE_RESIST) ? 1 / (c1 / 1.) : ((c1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
-  }
+  // put_data.c:1094-1104 picks the over- or understory value with the record's final snow flag, after the averages
+  o.LongOverIn = LongOverIn; o.LongUnderIn = LongUnderIn; o.AlbedoOver = AlbedoOver; o.AlbedoUnder = AlbedoUnderOut;
   if (extras & EX_PET)
-    pot_evap6(uc, tl, ap, pa, UnderStory, f.wind, Ra[UnderStory], Ra[1], ra_used0, ra_used1, f.shortwave, o.NetLongAtmos, Tair,
-              f.vpd, dt_hours, x.pot_evap);
-  if (is_veg) s.Wdew = v.Wdew;
-  VR_PHASE_SYNC();
-  // ---- runoff.c ----
-  o.inflow = ppt;
-  runoff_step(cc, NL, dt_hours, ppt, s.moist, evap, &o.asat, &o.runoff, &o.baseflow);
-  if (extras & EX_ZWT) water_table(cc, NL, s.moist, &x.zwt, &x.zwt_lumped);
-  // ---- full_energy.c:445-453 ----
-  double wet = 0, rootm = 0;
-  for (int l = 0; l < NL; l++) {
-    if ((uc.root0_mask >> l) & 1) rootm += s.moist[l];
-    wet += (s.moist[l] - cc.Wpwp(l)) / cc.wet_den(l);
-  }
-  wet /= NL;
-  o.wetness = wet;
-  o.rootmoist = rootm;
-#pragma unroll
-  for (int l = 0; l < MAXL; l++) { o.evap[l] = evap[l]; o.bef[l] = bef[l]; }
-  o.vapor_flux = vapor_flux;
-  o.canopy_vapor_flux = is_veg ? canopy_vapor_flux : 0.;
-  o.canopyevap = is_veg ? v.canopyevap : 0.;
-  o.melt = melt;
-  o.grnd_flux = grnd_flux;
-  o.deltaH = deltaH;
+    o.pot = pot_evap6(vp, overstory ? 1 : 0, tl, ap, pa, UnderStory, f.wind, Ra_us, Ra1, ra_used0, ra_used1, f.shortwave,
+                      o.NetLongAtmos, Tair, f.vpd, rec_dt_hours);     // gp->dt, not step_dt (surface_fluxes.c:897)
+  h.Wdew = v_Wdew;
+  o.ppt = ppt; o.canopyevap = v_canopyevap; o.throughfall = v_throughfall;
+  o.vapor_flux = vapor_flux; o.canopy_vapor_flux = canopy_vapor_flux; o.melt = melt;
   o.out_prec = out_prec; o.out_rain = out_rain; o.out_snow = out_snow;
+  o.evap = evap; o.bef = bef;
+  o.grnd_flux = grnd_flux; o.deltaH = deltaH; o.ra_used0 = ra_used0; o.ra_used1 = ra_used1;
   o.snow_flag = snow_flag;
+  return o;
 }
 
 }  // namespace vr

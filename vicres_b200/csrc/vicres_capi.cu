@@ -37,13 +37,23 @@
 
 using namespace vr;
 
+// forcing is read once per unit and record (and once more by k_cells); -DVR_STREAM_HINTS marks it evict-first like the
+// term stream (measured: 2.6 % slower on the 100k-cell benchmark, profiles/r2_tuning.md, so off by default)
+#if defined(VR_STREAM_HINTS)
+#define VR_FORC_LD(p) __ldcs(p)
+#else
+#define VR_FORC_LD(p) __ldg(p)
+#endif
+
 namespace {
 
 struct DevModel {
-  int NL, NB, dt_hours, n_out;
+  int NL, NB, dt_hours, snow_step_hours, NF, n_out;   // NF = dt_hours / snow_step_hours passes of the snow model
   double max_snow_temp, min_rain_temp;
   int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
-  const double *cc;
+  const double *cc;                 // [ccn][C] per-cell constants by sorted position
+  const double *ccu;                // [ccn][U] the same per unit in slot order: what k_units reads (coalesced)
+  int ccn;
   const int64_t *cell_uptr, *fcol;
   const int64_t *order;             // sorted position -> caller's cell index
   const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *u_logical, *cell_fail;
@@ -62,6 +72,9 @@ struct DevForcing {
   int rec0, nrec_total;             // position of the launch inside the caller's block (output indexing)
   const int32_t *month, *doy;       // device
   const double *field[VR_NFORCING]; // device, [nrec][FC]
+  const double *slots;              // device, [nrec * NS][VR_NFORCING][U]: the same values per unit in slot order (k_forcing_slots)
+  const int32_t *snowflag;          // device, [nrec][FC] or null: atmos->snowflag[NR] (read only when NF > 1)
+  int rec_abs;                      // records the handle has stepped before this launch (cell_status = first failing record + 1)
 };
 
 __device__ __forceinline__ void load_unit_consts(const DevModel &M, int64_t u, UnitC &uc, double &cv, double &af)
@@ -103,6 +116,16 @@ __device__ __forceinline__ void store_state(const DevModel &M, int64_t u, const 
 #undef S_
 }
 
+// per-unit copy of the per-cell constants in slot order: a warp of k_units reads 32 consecutive doubles per constant
+// instead of gathering 32 sectors (the units of a cell sit in different slots: slots are sorted by kind and climate)
+__global__ void k_unit_consts(DevModel M, double *ccu)
+{
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= M.U) return;
+  const int64_t pos = M.u_pos[u];
+  for (int k = 0; k < M.ccn; k++) ccu[(size_t)k * M.U + u] = M.cc[(size_t)k * M.C + pos];
+}
+
 // initialize_model_state() for every unit + its terms for put_data(rec = -nrecs)
 __global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double *tair0 /* [FC] */, double *terms)
 {
@@ -136,7 +159,7 @@ __global__ void __launch_bounds__(VR_CTA) k_restored_units(DevModel M, double *t
   unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U);
 }
 
-__global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *terms, double *sums)
+__global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *terms, double *sums, int svb)
 {
   const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // sorted position
   if (cs >= M.C) return;
@@ -148,48 +171,133 @@ __global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *te
     auto S = [&](int k) { return sums[(size_t)M.tmap.row[k] * M.C + cs]; };
     cell_carry(S, M.NL, sv);
   }
-  for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+  for (int k = 0; k < SV_N; k++) M.sv[((size_t)svb * SV_N + k) * M.C + c] = sv[k];
   M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
 }
 
-// full_energy() for F.nrec consecutive records of every unit; terms[rec][row][unit in reference order]: the
-// stores scatter (fire and forget) so that k_cells reads each cell's units contiguously
+// Forcing of a chunk per unit in slot order: k_units then reads 32 consecutive doubles per field and warp (the units of
+// a cell sit in different slots, so reading [field][rec][cell] directly is a gather of 32 sectors per request).
+__global__ void __launch_bounds__(256) k_forcing_slots(DevModel M, DevForcing F, double *__restrict__ dst)
+{
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rec = blockIdx.y;             // sub-record: F.nrec * NS of them
+  if (u >= M.U) return;
+  const int64_t c = M.u_cell[u];
+  const size_t q = (size_t)rec * M.FC + (M.fcol ? M.fcol[c] : c);
+  double *d = dst + (size_t)rec * VR_NFORCING * M.U + u;
+#pragma unroll
+  for (int i = 0; i < VR_NFORCING; i++) d[(size_t)i * M.U] = VR_FORC_LD(F.field[i] + q);
+}
+
+// the snow words of unit u in the state block (slot order): read and written only on the snow path of a record
+struct SnowIO {
+  double *st;          // &state[u]
+  size_t U;
+  bool wr;             // false for the idle threads of the last block and for failed cells: they read, never write
+  __device__ __forceinline__ double &w(int k) const { return st[(size_t)k * U]; }
+  __device__ __forceinline__ SnowS load() const
+  {
+    SnowS s;
+    s.swq = w(ST_SWQ); s.surf_temp = w(ST_SURF_TEMP); s.pack_temp = w(ST_PACK_TEMP); s.surf_water = w(ST_SURF_WATER);
+    s.pack_water = w(ST_PACK_WATER); s.density = w(ST_DENSITY); s.depth = w(ST_DEPTH); s.albedo = w(ST_ALBEDO);
+    s.coldcontent = w(ST_COLDCONTENT); s.coverage = w(ST_COVERAGE); s.snow_canopy = w(ST_SNOW_CANOPY);
+    s.tmp_int_storage = w(ST_TMP_INT); s.last_snow = (int)w(ST_LAST_SNOW); s.MELTING = (int)w(ST_MELTING);
+    return s;
+  }
+  __device__ __forceinline__ void store(const SnowS &s) const
+  {
+    if (!wr) return;
+    w(ST_SWQ) = s.swq; w(ST_SURF_TEMP) = s.surf_temp; w(ST_PACK_TEMP) = s.pack_temp; w(ST_SURF_WATER) = s.surf_water;
+    w(ST_PACK_WATER) = s.pack_water; w(ST_DENSITY) = s.density; w(ST_DEPTH) = s.depth; w(ST_ALBEDO) = s.albedo;
+    w(ST_COLDCONTENT) = s.coldcontent; w(ST_COVERAGE) = s.coverage; w(ST_SNOW_CANOPY) = s.snow_canopy;
+    w(ST_TMP_INT) = s.tmp_int_storage; w(ST_LAST_SNOW) = (double)s.last_snow; w(ST_MELTING) = (double)s.MELTING;
+  }
+  __device__ __forceinline__ void store_none() const
+  {
+    if (!wr) return;
+    w(ST_ALBEDO) = NEW_SNOW_ALB; w(ST_LAST_SNOW) = (double)(int)MISSINGV; w(ST_MELTING) = 0.;
+  }
+  __device__ __forceinline__ void fallback(int kind) const
+  {
+    if (wr) w(kind ? ST_FB_FOL : ST_FB_SNOW) += 1.;
+  }
+};
+
+// full_energy() for F.nrec consecutive records of every unit.  One thread owns one unit (slot order) and carries the
+// unit's hot state (moisture, canopy storage, T0, T1, LongUnderOut, Tfoliage) in registers across the chunk; the snow
+// words stay in the state block and are read / written by the records that run the snow model.  Everything a thread
+// reads per record -- forcing (k_forcing_slots), constants (k_unit_consts), state -- is in slot order: 32 consecutive
+// doubles per warp and request.  terms[rec][row][unit in reference order]: the stores scatter (fire and forget) so
+// that k_cells reads each cell's units contiguously.
 template <int EXTRAS>
 __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcing F, double *__restrict__ terms)
 {
+  pow_tables_init();
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = k < M.U;
   const int64_t u = active ? k : M.U - 1;     // idle threads of the last block shadow the last unit (phase barriers)
-  UnitC uc; CellC cc; UnitS s;
+  UnitC uc; CellC cc;
   double cv, af;
   const int64_t c = M.u_cell[u];
-  const int64_t fc = M.fcol ? M.fcol[c] : c;
   const bool failed = M.cell_fail[c] != 0;
   load_unit_consts(M, u, uc, cv, af);
+#if defined(VR_CC_PER_CELL)
   load_cell_consts(M.cc, M.C, M.u_pos[u], M.NL, cc);
-  load_state(M, u, s);
+#else
+  load_cell_consts(M.ccu, M.U, u, M.NL, cc);
+#endif
+  const bool write = active && !failed;
+  SnowIO sio;
+  sio.st = M.state + u;
+  sio.U = (size_t)M.U;
+  sio.wr = write;
+  HotS h;
+  bool snowy, tidy;
+  {
+    const double *st = M.state + u;
+    const size_t U = (size_t)M.U;
+    h.moist.v[0] = st[ST_MOIST0 * U]; h.moist.v[1] = st[ST_MOIST1 * U]; h.moist.v[2] = st[ST_MOIST2 * U];
+    h.Wdew = st[ST_WDEW * U]; h.T0 = st[ST_T0 * U]; h.T1 = st[ST_T1 * U]; h.LongUnderOut = st[ST_LONGUNDEROUT * U];
+    h.Tfoliage = st[ST_TFOLIAGE * U];
+    snowy = st[ST_SWQ * U] > 0 || st[ST_SNOW_CANOPY * U] > 0 || st[ST_COVERAGE * U] != 0;
+    tidy = !snowy && ((int)st[ST_LAST_SNOW * U] != (int)MISSINGV || st[ST_MELTING * U] != 0. || st[ST_ALBEDO * U] != NEW_SNOW_ALB);
+  }
   const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
   const double *ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
   const double *tl = (EXTRAS & EX_PET) ? M.tl + (size_t)M.u_tile[u] * 12 * TL_N : nullptr;
   const double *ap = (EXTRAS & EX_PET) ? M.ap + (size_t)M.u_aero[u] * 12 * AP_N : nullptr;
-  const int nrec = F.nrec, NL = M.NL;
+  const int nrec = F.nrec, NL = M.NL, NF = M.NF, NS = M.NF > 1 ? M.NF + 1 : 1;
   const size_t rec_stride = (size_t)M.tmap.n * M.U;
-  const bool write = active && !failed;
   const int64_t col = M.u_logical[u];
+  int first_err = 0;
   for (int rec = 0; rec < nrec; rec++) {
-    Forc f;
-    const size_t q = (size_t)rec * M.FC + fc;
-    f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.prec = __ldg(F.field[VR_F_PREC] + q);
-    f.wind = __ldg(F.field[VR_F_WIND] + q); f.vp = __ldg(F.field[VR_F_VP] + q);
-    f.vpd = __ldg(F.field[VR_F_VPD] + q); f.pressure = __ldg(F.field[VR_F_PRESSURE] + q);
-    f.density = __ldg(F.field[VR_F_DENSITY] + q); f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q);
-    f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
-    f.mon = __ldg(F.month + rec) - 1; f.doy = __ldg(F.doy + rec);
-    unit_step_terms<EXTRAS>(cc, uc, tm + f.mon * TM_N, ae + f.mon * AE_N, f, NL, M.dt_hours, M.max_snow_temp, M.min_rain_temp, s,
-                    cv, af, M.tmap, terms + rec * rec_stride + col, (int)M.U, write,
-                    (EXTRAS & EX_PET) ? tl + f.mon * TL_N : nullptr, (EXTRAS & EX_PET) ? ap + f.mon * AP_N : nullptr);
+    const int mon = __ldg(F.month + rec) - 1, doy = __ldg(F.doy + rec);
+    // sub-record k of this record, per unit in slot order
+    auto forc = [&](int kk) {
+      Forc f;
+      const double *q = F.slots + ((size_t)rec * NS + kk) * VR_NFORCING * M.U + u;
+      const size_t st = (size_t)M.U;
+      f.air_temp = __ldg(q + VR_F_AIR_TEMP * st); f.prec = __ldg(q + VR_F_PREC * st); f.wind = __ldg(q + VR_F_WIND * st);
+      f.vp = __ldg(q + VR_F_VP * st); f.vpd = __ldg(q + VR_F_VPD * st); f.pressure = __ldg(q + VR_F_PRESSURE * st);
+      f.density = __ldg(q + VR_F_DENSITY * st); f.shortwave = __ldg(q + VR_F_SHORTWAVE * st); f.longwave = __ldg(q + VR_F_LONGWAVE * st);
+      f.mon = mon; f.doy = doy;
+      f.snowflag = (NF > 1 && F.snowflag) ? (int)__ldg(F.snowflag + (size_t)rec * M.FC + (M.fcol ? M.fcol[c] : c)) : 0;
+      return f;
+    };
+    const int e = unit_record<EXTRAS>(cc, uc, tm + mon * TM_N, ae + mon * AE_N, forc, NF, NL, M.dt_hours, M.snow_step_hours,
+                                      M.max_snow_temp, M.min_rain_temp, h, snowy, tidy, sio, cv, af, M.tmap,
+                                      terms + rec * rec_stride + col, (int)M.U, write,
+                                      (EXTRAS & EX_PET) ? tl + mon * TL_N : nullptr, (EXTRAS & EX_PET) ? ap + mon * AP_N : nullptr);
+    if (e && !first_err) first_err = F.rec_abs + rec + 1;
   }
-  if (write) store_state(M, u, s);
+  if (write) {
+    double *st = M.state + u;
+    const size_t U = (size_t)M.U;
+    st[ST_MOIST0 * U] = h.moist.v[0]; st[ST_MOIST1 * U] = h.moist.v[1]; st[ST_MOIST2 * U] = h.moist.v[2];
+    st[ST_WDEW * U] = h.Wdew; st[ST_T0 * U] = h.T0; st[ST_T1 * U] = h.T1; st[ST_LONGUNDEROUT * U] = h.LongUnderOut;
+    st[ST_TFOLIAGE * U] = h.Tfoliage;
+    if (first_err) atomicCAS(M.cell_status + c, 0, first_err);     // first failing record + 1 (arno_evap.c:112-151)
+  }
 }
 
 // put_data() for the same records: one thread per (cell in sorted order, record).  A cell's units are
@@ -197,8 +305,10 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcin
 // coalesced; the ordered sums go to sums[rec][row][cell] and the outputs to the caller's cell index.  The
 // save_data words a record needs from its predecessor (storage deltas, closure error) are rebuilt from the
 // predecessor's terms, which makes the records of a chunk independent; record 0 uses the carried M.sv.
+// M.sv is double-buffered: the blocks of record 0 read buffer svb while the blocks of the last record write buffer
+// svb ^ 1 (blocks of one grid have no order), the host flips svb per launch.
 __global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const double *__restrict__ terms,
-                                               double *__restrict__ sums, double *__restrict__ out)
+                                               double *__restrict__ sums, double *__restrict__ out, int svb)
 {
   const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rec = blockIdx.y;
@@ -216,7 +326,7 @@ __global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const d
   }
   double sv[SV_N];
   if (rec == 0)
-    for (int k = 0; k < SV_N; k++) sv[k] = M.sv[(size_t)k * M.C + c];
+    for (int k = 0; k < SV_N; k++) sv[k] = M.sv[((size_t)svb * SV_N + k) * M.C + c];
   else {
     const double *P = terms + (rec - 1) * rec_stride;
     auto SP = [&](int k) { return cell_term_sum(P, (size_t)M.U, fu0, nu, M.tmap.row[k]); };
@@ -227,22 +337,24 @@ __global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const d
   cell_accumulate_to(T, (size_t)M.U, fu0, nu, M.tmap, NL, Sm, (size_t)M.C, cs);
   auto S = [&](int k) { return Sm[(size_t)M.tmap.row[k] * M.C + cs]; };
   Forc f;
-  const size_t q = (size_t)rec * M.FC + fc;
+  const int NS = M.NF > 1 ? M.NF + 1 : 1;
+  const size_t q = ((size_t)rec * NS + (NS - 1)) * M.FC + fc;        // the record's own values (atmos-><field>[NR])
   f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.wind = __ldg(F.field[VR_F_WIND] + q);
   f.vp = __ldg(F.field[VR_F_VP] + q); f.vpd = __ldg(F.field[VR_F_VPD] + q);
   f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
-  f.prec = 0; f.pressure = 0; f.density = 0; f.mon = 0; f.doy = 0;
+  f.prec = 0; f.pressure = 0; f.density = 0; f.mon = 0; f.doy = 0; f.snowflag = 0;
 #pragma unroll 1
-  for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = cell_output(M.out_vars[v], S, f, NL, false, sv);
+  for (int v = 0; v < M.n_out; v++) VR_STREAM_ST(out + (size_t)v * ostride + orow, cell_output(M.out_vars[v], S, f, NL, false, sv));
   if (rec == F.nrec - 1) {
     cell_carry(S, NL, sv);
-    for (int k = 0; k < SV_N; k++) M.sv[(size_t)k * M.C + c] = sv[k];
+    for (int k = 0; k < SV_N; k++) M.sv[((size_t)(svb ^ 1) * SV_N + k) * M.C + c] = sv[k];
   }
 }
 
 // diagnostic: the device power function on arbitrary arguments (tests/test_gpu_parity.py checks its error bound)
 __global__ void k_diag_pow(int64_t n, const double *x, const double *y, double *z)
 {
+  pow_tables_init();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = m_pow(x[i], y[i]);
 }
@@ -304,7 +416,7 @@ struct vr_handle {
   } keep;
   std::vector<double> tair0_host;
   DevModel M;
-  DBuf<double> d_tl, d_ap;
+  DBuf<double> d_tl, d_ap, d_ccu, d_fslots;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
       d_forc, d_out, d_tair0, d_terms, d_sums;
   DBuf<float> d_u_root;
@@ -314,6 +426,9 @@ struct vr_handle {
   cudaStream_t s_cells = nullptr;    // k_cells of chunk k runs here, beside k_units of chunk k+1 on the step stream
   cudaEvent_t ev_fork = nullptr, ev_units[2] = {nullptr, nullptr}, ev_cells[2] = {nullptr, nullptr};
   int64_t pair_seq = 0;              // launch pairs so far: pair i uses term buffer i & 1
+  int svb = 0;                       // which half of d_sv holds the carried save_data words
+  int64_t rec_done = 0;              // records stepped since vr_init_state / vr_set_state (cell_status numbering)
+  DBuf<int32_t> d_snowflag;
   struct EvTriple { cudaEvent_t u0, u1, c0, c1; int nrec; };
   std::vector<EvTriple> evs;         // around every k_units / k_cells launch since the last vr_kernel_times()
   size_t evs_used = 0;
@@ -366,9 +481,14 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     g_create_error = "vr_options out of range (nlayer 2..3, nbands 1..10, dt_hours divides 24, 1 <= n_out <= 64)";
     return VR_ERR_ARG;
   }
-  if (opt->snow_step_hours != opt->dt_hours) {
-    g_create_error = "SNOW_STEP != TIME_STEP (sub-stepped snow, NF > 1) is outside the supported water-balance path";
-    return VR_ERR_UNSUPPORTED;
+  if (opt->snow_step_hours < 1 || opt->snow_step_hours > opt->dt_hours || opt->dt_hours % opt->snow_step_hours) {
+    g_create_error = "SNOW_STEP must divide TIME_STEP (get_global_param.c:761-770)";
+    return VR_ERR_ARG;
+  }
+  if (opt->dt_hours < 24 && opt->snow_step_hours != opt->dt_hours) {
+    g_create_error = "If the model step is smaller than daily, the snow model should run at the same time step as the rest "
+                     "of the model (get_global_param.c:762-763)";
+    return VR_ERR_ARG;
   }
   if (!(opt->max_snow_temp > opt->min_rain_temp)) {
     g_create_error = "MAX_SNOW_TEMP must be greater than MIN_RAIN_TEMP (calc_rainonly.c)";
@@ -422,7 +542,7 @@ void vr_destroy(vr_handle *h)
   h->d_cc.release(); h->d_u_cv.release(); h->d_u_af.release(); h->d_u_Tf.release(); h->d_u_Pf.release();
   h->d_u_rarc.release(); h->d_u_rmin.release(); h->d_u_RGL.release(); h->d_tm.release(); h->d_ae.release();
   h->d_init_moist.release(); h->d_state.release(); h->d_sv.release(); h->d_forc.release(); h->d_out.release();
-  h->d_tl.release(); h->d_ap.release();
+  h->d_tl.release(); h->d_ap.release(); h->d_ccu.release(); h->d_fslots.release(); h->d_snowflag.release();
   h->d_tair0.release(); h->d_u_root.release(); h->d_cell_uptr.release(); h->d_fcol.release(); h->d_terms.release(); h->d_sums.release(); h->d_u_logical.release();
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
@@ -531,13 +651,14 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   CK(h->d_init_moist.upload(im));
   CK(h->d_order.upload(P.order)); CK(h->d_u_slot.upload(P.u_slot)); CK(h->d_u_logical.upload(P.u_logical));
   CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
-  CK(h->d_sv.reserve((size_t)SV_N * C));
+  CK(h->d_sv.reserve((size_t)2 * SV_N * C));
   CK(h->d_cell_status.reserve(C));
   CK(cudaMemset(h->d_state.p, 0, (size_t)ST_N * (U ? U : 1) * sizeof(double)));
   CK(cudaMemset(h->d_cell_status.p, 0, C * sizeof(int32_t)));
   DevModel &M = h->M;
   memset(&M, 0, sizeof M);
   M.NL = P.NL; M.NB = P.NB; M.dt_hours = h->opt.dt_hours; M.n_out = h->opt.n_out;
+  M.snow_step_hours = h->opt.snow_step_hours; M.NF = h->opt.dt_hours / h->opt.snow_step_hours;
   M.max_snow_temp = h->opt.max_snow_temp; M.min_rain_temp = h->opt.min_rain_temp;
   M.C = C; M.U = U; M.FC = C;
   M.cc = h->d_cc.p; M.cell_uptr = h->d_cell_uptr.p; M.fcol = nullptr;
@@ -548,6 +669,14 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.tm = h->d_tm.p; M.ae = h->d_ae.p; M.init_moist = h->d_init_moist.p; M.u_root = h->d_u_root.p;
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
   M.order = h->d_order.p; M.u_slot = h->d_u_slot.p; M.u_logical = h->d_u_logical.p;
+  M.ccn = P.ccn;
+  CK(h->d_ccu.reserve((size_t)P.ccn * (U ? U : 1)));
+  M.ccu = h->d_ccu.p;
+  if (U > 0) {
+    k_unit_consts<<<(unsigned)((U + 255) / 256), 256, 0, h->stream>>>(M, h->d_ccu.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
   h->extras = term_extras(M.tmap);
@@ -591,12 +720,13 @@ int vr_init_state(vr_handle *h, const double *tair0)
   CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * h->chunk));
   CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * h->chunk));
   if (h->M.U > 0) k_init_units<<<(unsigned)h->ncta, h->cta, 0, h->stream>>>(h->M, h->d_tair0.p, h->d_terms.p);
-  k_init_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p, h->d_sums.p);
+  k_init_cells<<<(unsigned)((h->M.C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p, h->d_sums.p, h->svb);
   h->launches += 2;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->s_cells));
   h->initialised = true;
+  h->rec_done = 0;
   return VR_OK;
 }
 
@@ -611,6 +741,8 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
   const size_t tsize = (size_t)h->M.tmap.n * U1 * CH;
   CK(h->d_terms.reserve(2 * tsize));
   CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * CH));
+  const int NS = h->M.NF > 1 ? h->M.NF + 1 : 1;          // forcing sub-records per record (sub-steps + the record itself)
+  CK(h->d_fslots.reserve((size_t)CH * NS * VR_NFORCING * U1));
   cudaEventRecord(h->ev0, st);
   cudaEventRecord(h->ev_fork, st);                       // what the caller queued on st (forcing, free output buffer)
   cudaStreamWaitEvent(h->s_cells, h->ev_fork, 0);
@@ -620,7 +752,9 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     F.nrec = (F0.nrec - r0 < CH) ? F0.nrec - r0 : CH;
     F.rec0 = F0.rec0 + r0;
     F.month = F0.month + r0; F.doy = F0.doy + r0;
-    for (int i = 0; i < VR_NFORCING; i++) F.field[i] = F0.field[i] + (size_t)r0 * h->M.FC;
+    for (int i = 0; i < VR_NFORCING; i++) F.field[i] = F0.field[i] + (size_t)r0 * NS * h->M.FC;
+    F.snowflag = F0.snowflag ? F0.snowflag + (size_t)r0 * h->M.FC : nullptr;
+    F.rec_abs = F0.rec_abs + r0;
     b = (int)(h->pair_seq & 1);
     double *terms = h->d_terms.p + (size_t)b * tsize;
     vr_handle::EvTriple *t = nullptr;
@@ -637,6 +771,11 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     if (h->pair_seq >= 2) cudaStreamWaitEvent(st, h->ev_cells[b], 0);     // pair i-2 has been aggregated out of terms[b]
     if (t) cudaEventRecord(t->u0, st);
     if (h->M.U > 0) {
+      k_forcing_slots<<<dim3((unsigned)((h->M.U + 255) / 256), (unsigned)(F.nrec * NS)), 256, 0, st>>>(h->M, F, h->d_fslots.p);
+      F.slots = h->d_fslots.p;
+      h->launches += 1;
+    }
+    if (h->M.U > 0) {
       switch (h->extras) {       // one kernel instance per set of optional results
         case 0: k_units<0><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
         case EX_PET: k_units<EX_PET><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
@@ -648,7 +787,8 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     cudaEventRecord(h->ev_units[b], st);
     cudaStreamWaitEvent(h->s_cells, h->ev_units[b], 0);
     if (t) cudaEventRecord(t->c0, h->s_cells);
-    k_cells<<<dim3((unsigned)((h->M.C + 127) / 128), (unsigned)F.nrec), 128, 0, h->s_cells>>>(h->M, F, terms, h->d_sums.p, out_dev);
+    k_cells<<<dim3((unsigned)((h->M.C + 127) / 128), (unsigned)F.nrec), 128, 0, h->s_cells>>>(h->M, F, terms, h->d_sums.p, out_dev, h->svb);
+    h->svb ^= 1;
     if (t) cudaEventRecord(t->c1, h->s_cells);
     cudaEventRecord(h->ev_cells[b], h->s_cells);
     h->pair_seq++;
@@ -671,11 +811,14 @@ int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, voi
   CK(cudaMemcpyAsync(h->d_month.p, f->month, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, f->nrec * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   DevForcing F;
+  F.slots = nullptr;
+  F.snowflag = f->snowflag; F.rec_abs = (int)h->rec_done;
   F.nrec = f->nrec; F.rec0 = 0; F.nrec_total = f->nrec; F.month = h->d_month.p; F.doy = h->d_doy.p;
   for (int i = 0; i < VR_NFORCING; i++) {
     if (!f->field[i]) { h->err = "null forcing field"; return VR_ERR_ARG; }
     F.field[i] = f->field[i];
   }
+  h->rec_done += f->nrec;
   return launch_step(h, F, out_dev, st, true);
 }
 
@@ -693,8 +836,14 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
   CK(cudaSetDevice(h->device));
   const int nrec = f->nrec, n_out = h->opt.n_out, CH = h->chunk < nrec ? h->chunk : nrec;
   const size_t FC = (size_t)h->M.FC, C = (size_t)h->M.C;
-  const size_t in_chunk = (size_t)CH * FC * VR_NFORCING, out_chunk = (size_t)CH * C * n_out;
+  const size_t NS = h->M.NF > 1 ? h->M.NF + 1 : 1;               // forcing sub-records per record
+  const size_t in_chunk = (size_t)CH * NS * FC * VR_NFORCING, out_chunk = (size_t)CH * C * n_out;
   const int NB = vr_handle::NBUF;
+  const bool flags = NS > 1 && f->snowflag;
+  if (flags) {
+    CK(h->d_snowflag.reserve((size_t)nrec * FC));
+    CK(cudaMemcpyAsync(h->d_snowflag.p, f->snowflag, (size_t)nrec * FC * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
+  }
   CK(h->d_forc.reserve(NB * in_chunk));
   CK(h->d_out.reserve(NB * out_chunk));
   CK(h->d_month.reserve(nrec)); CK(h->d_doy.reserve(nrec));
@@ -706,11 +855,14 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     double *din = h->d_forc.p + (size_t)b * in_chunk, *dout = h->d_out.p + (size_t)b * out_chunk;
     if (k >= NB) CK(cudaStreamWaitEvent(h->s_in, h->ev_comp[b], 0));      // the kernels of chunk k-NB have consumed din
     DevForcing F;
+    F.slots = nullptr;
+    F.snowflag = flags ? h->d_snowflag.p + (size_t)r0 * FC : nullptr;
+    F.rec_abs = (int)h->rec_done + r0;
     F.nrec = nr; F.rec0 = 0; F.nrec_total = nr; F.month = h->d_month.p + r0; F.doy = h->d_doy.p + r0;
     for (int i = 0; i < VR_NFORCING; i++) {
-      CK(cudaMemcpyAsync(din + (size_t)i * nr * FC, f->field[i] + (size_t)r0 * FC, (size_t)nr * FC * sizeof(double),
+      CK(cudaMemcpyAsync(din + (size_t)i * nr * NS * FC, f->field[i] + (size_t)r0 * NS * FC, (size_t)nr * NS * FC * sizeof(double),
                          cudaMemcpyHostToDevice, h->s_in));
-      F.field[i] = din + (size_t)i * nr * FC;
+      F.field[i] = din + (size_t)i * nr * NS * FC;
     }
     CK(cudaEventRecord(h->ev_in[b], h->s_in));
     CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
@@ -730,6 +882,7 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[(k - 1) % NB], 0));
     CK(cudaMemcpyAsync(cell_status_host, h->d_cell_status.p, C * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out));
   }
+  h->rec_done += nrec;
   CK(cudaStreamSynchronize(h->s_in));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->s_cells));
@@ -765,7 +918,7 @@ int vr_get_state(vr_handle *h, void *blob)
   char *b = (char *)blob;
   const size_t ns = (size_t)ST_N * h->M.U * sizeof(double), nv = (size_t)SV_N * h->M.C * sizeof(double);
   CK(cudaMemcpy(b, h->d_state.p, ns, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(b + ns, h->d_sv.p, nv, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b + ns, h->d_sv.p + (size_t)h->svb * SV_N * h->M.C, nv, cudaMemcpyDeviceToHost));
   return VR_OK;
 }
 
@@ -779,7 +932,7 @@ int vr_set_state(vr_handle *h, const void *blob)
   const char *b = (const char *)blob;
   const size_t ns = (size_t)ST_N * h->M.U * sizeof(double), nv = (size_t)SV_N * h->M.C * sizeof(double);
   CK(cudaMemcpy(h->d_state.p, b, ns, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_sv.p, b + ns, nv, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_sv.p + (size_t)h->svb * SV_N * h->M.C, b + ns, nv, cudaMemcpyHostToDevice));
   h->initialised = true;
   return VR_OK;
 }
@@ -1004,7 +1157,7 @@ int vr_read_state_file(vr_handle *h, const char *path, int32_t binary, const dou
   CK(h->d_terms.reserve((size_t)h->M.tmap.n * U1 * h->chunk));
   CK(h->d_sums.reserve((size_t)h->M.tmap.n * C * h->chunk));
   if (U > 0) k_restored_units<<<(unsigned)h->ncta, h->cta, 0, h->stream>>>(h->M, h->d_terms.p);
-  k_init_cells<<<(unsigned)((C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p, h->d_sums.p);
+  k_init_cells<<<(unsigned)((C + 127) / 128), 128, 0, h->stream>>>(h->M, h->d_terms.p, h->d_sums.p, h->svb);
   h->launches += 2;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));

@@ -397,7 +397,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
     for (int64_t c = 0; c < C; c++) {
       auto it = blocks.find(P->gridcel[c]);
       if (it == blocks.end()) { delete P; g_err = "grid cell missing from the vegetation parameter file"; return VR_ERR_ARG; }
-      std::vector<Tile> &tiles = it->second;
+      std::vector<Tile> tiles = it->second;      // a copy: several soil rows may share a gridcel (parameter sets)
       const int Nveg = (int)tiles.size();
       double Cv_sum = 0;
       for (const Tile &tl : tiles) Cv_sum += tl.Cv;
@@ -644,8 +644,13 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "OUT_STEP")) g->out_step = I();
     else if (!strcasecmp(k, "BINARY_OUTPUT")) g->binary_output = flag(t);
     else if (!strcasecmp(k, "COMPRESS")) g->compress = flag(t);
+    else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
+    else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
     else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }
-    else if (!strcasecmp(k, "FORCING2")) { file_num = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0) ? 1 : -1; field = -1; }
+    else if (!strcasecmp(k, "FORCING2")) {     // a second forcing file is not read by this library (vr_global_unsupported names it)
+      file_num = 1;
+      g->forcing2 = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0 && strcasecmp(t[1].c_str(), "MISSING") != 0);
+    }
     else if (file_num == 0) {          // description of FORCING1 (get_force_type.c)
       if (!strcasecmp(k, "FORCE_FORMAT")) g->force_ascii = (t.size() > 1 && !strcasecmp(t[1].c_str(), "ASCII"));
       else if (!strcasecmp(k, "FORCE_ENDIAN")) g->force_little_endian = !(t.size() > 1 && !strcasecmp(t[1].c_str(), "BIG"));
@@ -705,6 +710,12 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->organic_fract) return "ORGANIC_FRACT TRUE";
   if (g->snow_step != g->time_step) return "SNOW_STEP != TIME_STEP";
   if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
+  if (g->forcing2) return "FORCING2 (a second forcing file)";
+  if (g->out_step != 0 && g->out_step != g->time_step) return "OUT_STEP != TIME_STEP (output aggregation)";
+  if (g->skipyear > 0) return "SKIPYEAR > 0";
+  if (g->binary_output) return "BINARY_OUTPUT TRUE";
+  if (g->compress) return "COMPRESS TRUE";
+  if (g->n_outfile_lines > 0 || g->n_outvar_lines > 0) return "OUTFILE / OUTVAR (custom output selection)";
   return nullptr;
 }
 
@@ -743,7 +754,14 @@ int64_t vr_read_forcing_file(const vr_global *g, const char *path, int64_t nrec,
 {
   if (!g || !path || !data || nrec < 1 || g->n_force_types < 1) { g_err = "null or empty argument"; return VR_ERR_ARG; }
   const int nf = g->n_force_types;
-  const int64_t skip = vr_force_skip(g);
+  // read_atmos_data.c:91-98: vr_force_skip() counts MODEL steps; the file holds one line per FORCE_DT hours
+  const int fdt = g->force_dt > 0 ? g->force_dt : g->time_step;
+  const int64_t mskip = vr_force_skip(g);
+  if ((g->time_step < 24 && ((int64_t)fdt * mskip) % g->time_step > 0) || (g->time_step == 24 && g->time_step % fdt > 0)) {
+    g_err = "Currently unable to handle a model starting date that does not correspond to a line in the forcing file.";
+    return VR_ERR_ARG;
+  }
+  const int64_t skip = (int64_t)((float)(g->time_step * mskip)) / fdt;
   int64_t rec = 0;
   if (g->force_ascii) {
     FILE *f = fopen(path, "r");

@@ -148,7 +148,8 @@ class GlobalC(C.Structure):
                                           "july_tavg_supplied", "alma_input", "init_state",
                                           "vp_interp", "vp_iter", "mtclim_swe_corr", "lw_type", "lw_cloud", "plapse")] +
                 [("sw_prec_thresh", C.c_double), ("init_state_file", C.c_char * 512), ("statename", C.c_char * 512)] +
-                [(n, C.c_int32) for n in ("stateyear", "statemonth", "stateday", "binary_state_file")])
+                [(n, C.c_int32) for n in ("stateyear", "statemonth", "stateday", "binary_state_file",
+                                          "forcing2", "n_outfile_lines", "n_outvar_lines")])
 
 
 FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_read_forcing_file"]

@@ -34,6 +34,10 @@ def run(global_path, device=0, write=True, records_per_block=0):
     cols = None
     for c in range(Cn):
         d, got = g.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))
+        need = g.nrecs * g.time_step // g.c.force_dt
+        if got < need:                   # read_atmos_data.c:178-182, 258-262: "Not enough records in the forcing file"
+            raise model.VicResError(abi.VR_ERR_ARG, "Not enough records in the forcing file of cell %d (%d < %d)"
+                                    % (int(meta["gridcel"][c]), got, need))
         if cols is None:
             cols = {t: np.zeros((len(v), Cn)) for t, v in d.items() if t != "SKIP"}
         for t in cols:
