@@ -51,8 +51,8 @@ class Oracle:
         t = np.ascontiguousarray(tair0, dtype=np.float64)
         return lib().vo_init_state(self.h, t.ctypes.data)
 
-    def step(self, month, doy, forcing, units_maxtile=0):
-        f = abi.pack_forcing(month, doy, forcing)
+    def step(self, month, doy, forcing, units_maxtile=0, snowflag=None):
+        f = abi.pack_forcing(month, doy, forcing, snowflag)
         nrec = len(month)
         out = np.zeros((self.opt.n_out, nrec, self.ncell))
         units = None
@@ -62,8 +62,8 @@ class Oracle:
                                  units.ctypes.data if units is not None else None, units_maxtile)
         return rc, out, units
 
-    def step_range(self, month, doy, forcing, out, c0, c1):
-        f = abi.pack_forcing(month, doy, forcing)
+    def step_range(self, month, doy, forcing, out, c0, c1, snowflag=None):
+        f = abi.pack_forcing(month, doy, forcing, snowflag)
         return lib().vo_step_block_range(self.h, f.ref(), out.ctypes.data, c0, c1)
 
     def fallback_counts(self):

@@ -117,9 +117,9 @@ typedef struct {   /* soil_con_struct subset (vicNl_def.h:937-1008) for one cell
   double zwtvmoist_zwt[MAXL + 2][VR_ZWT_NPOINTS], zwtvmoist_moist[MAXL + 2][VR_ZWT_NPOINTS];
 } osoil;
 
-typedef struct {   /* one record of atmos_data_struct, index [NR] == [0] (vicNl_def.h:1090-1113) */
+typedef struct {   /* one element of a record of atmos_data_struct: a sub-step [0..NF-1] or the record itself [NR] (vicNl_def.h:1090-1113) */
   double air_temp, prec, wind, vp, vpd, pressure, density, shortwave, longwave;
-  int month, day_in_year;
+  int month, day_in_year, snowflag;
 } oatmos;
 
 struct vo_model {
@@ -2145,18 +2145,28 @@ static int runoff(ocell *cell, const osoil *soil_con, double ppt, int dt)
 }
 
 /* ======================================================================================
- * surface_fluxes.c:11-1168 with NF == 1 (one sub-step, hidx == 0, N_steps == 1) and
- * CLOSE_ENERGY FALSE (MAX_ITER_GRND_CANOPY == 0: each do-while body runs exactly once)
+ * surface_fluxes.c:11-1168: the sub-step loop (NF = TIME_STEP / SNOW_STEP passes when the tile has snow or the
+ * record has snowfall, else one pass with the record's own forcing, :385-396) with
+ * CLOSE_ENERGY FALSE (MAX_ITER_GRND_CANOPY == 0: each inner do-while body runs exactly once)
  * ====================================================================================== */
 static int surface_fluxes(const vr_options *opt, int overstory, double BareAlbedo, double surf_atten,
                           double *aero_resist /* [3] of the current veg */, double *displacement,
                           double *ref_height, double *roughness, double *wind, const float *root, int Nveg,
-                          int band, double dp, int iveg, const oveglib *vl, const oatmos *atmos,
-                          oenergy *energy, ocell *cell, osnow *snow, const osoil *soil_con,
+                          int band, double dp, int iveg, const oveglib *vl, const oatmos *atm /* [NF + 1] or [1] */,
+                          int NF, int NR, oenergy *energy, ocell *cell, osnow *snow, const osoil *soil_con,
                           ovegvar *veg_var, double *out_prec, double *out_rain, double *out_snow,
                           const oveglib *lib, int nclass, int veg_class, double pet_aero[7][3] /* NULL: PET not wanted */)
 {
-  int INCLUDE_SNOW = 0, UNSTABLE_SNOW = 0, UnderStory, lidx, N_steps = 1, step_dt = opt->dt_hours;
+  int INCLUDE_SNOW = 0, UNSTABLE_SNOW = 0, UnderStory, lidx, N_steps = 1, step_dt = opt->dt_hours, hidx, endhidx;
+  double store_ppt = 0, store_melt = 0, store_vapor_flux = 0, store_surface_flux = 0, store_blowing_flux = 0,
+         store_pot_evap[6];
+  double store_AlbedoOver = 0, store_AlbedoUnder = 0, store_AtmosLatent = 0, store_AtmosLatentSub = 0,
+         store_AtmosSensible = 0, store_LongOverIn = 0, store_LongUnderIn = 0, store_LongUnderOut = 0,
+         store_NetLongAtmos = 0, store_NetLongOver = 0, store_NetLongUnder = 0, store_NetShortAtmos = 0,
+         store_NetShortGrnd = 0, store_NetShortOver = 0, store_NetShortUnder = 0, store_ShortOverIn = 0,
+         store_ShortUnderIn = 0, store_canopy_advection = 0, store_canopy_latent = 0, store_canopy_latent_sub = 0,
+         store_canopy_sensible = 0, store_canopy_refreeze = 0, store_deltaH = 0, store_fusion = 0, store_grnd_flux = 0,
+         store_latent = 0, store_latent_sub = 0, store_melt_energy = 0, store_sensible = 0;
   double Le, LongUnderIn, LongUnderOut, NetLongSnow, NetShortSnow, NetShortGrnd, OldTSurf, ShortUnderIn,
          Tair, Tcanopy, Tgrnd, Tsurf, VPDcanopy, VPcanopy, coverage, delta_coverage, ppt, rainfall,
          snowfall, snow_flux, snow_grnd_flux, step_melt, step_melt_energy, step_out_prec, step_out_rain,
@@ -2193,181 +2203,250 @@ static int surface_fluxes(const vr_options *opt, int overstory, double BareAlbed
   last_snow_coverage = snow->coverage;
   step_Wdew = veg_var->Wdew;
 
-  /* ---- the single sub-step (surface_fluxes.c:480-1025) ---- */
-  Tair = atmos->air_temp + soil_con->Tfactor[band];
-  step_prec = atmos->prec * soil_con->Pfactor[band];
-  Tgrnd = energy->T[0];
-  Tcanopy = Tair;
-  VPcanopy = atmos->vp;
-  VPDcanopy = atmos->vpd;
-  step_snow.blowing_flux = 0.0;      /* BLOWING FALSE */
-  UnderStory = 999;
-  snow_grnd_flux = -snow_flux;
-  iter_snow_energy = snow_energy;
-  iter_soil_energy = soil_energy;
-  iter_snow_veg_var = snow_veg_var;
-  iter_soil_veg_var = soil_veg_var;
-  iter_snow = step_snow;
-  for (lidx = 0; lidx < NLAYER; lidx++) iter_layer[lidx] = step_layer[lidx];
-  iter_snow_veg_var.Wdew = step_Wdew;
-  iter_soil_veg_var.Wdew = step_Wdew;
-  iter_snow_veg_var.canopyevap = 0;
-  iter_soil_veg_var.canopyevap = 0;
-  for (lidx = 0; lidx < NLAYER; lidx++) iter_layer[lidx].evap = 0;
-  iter_aero_resist[0] = aero_resist[0]; iter_aero_resist[1] = aero_resist[1]; iter_aero_resist[2] = aero_resist[2];
-  iter_aero_resist_used[0] = aero_resist_used[0];
-  iter_aero_resist_used[1] = aero_resist_used[1];
-  iter_snow.canopy_vapor_flux = 0;
-  iter_snow.vapor_flux = 0;
-  iter_snow.surface_flux = 0;
-  LongUnderOut = iter_soil_energy.LongUnderOut;
-  dryFrac = -1;
-  step_melt = solve_snow(overstory, BareAlbedo, LongUnderOut, opt->min_rain_temp, opt->max_snow_temp, Tcanopy,
-                         Tgrnd, Tair, step_prec, snow_grnd_flux, &energy->AlbedoUnder, &Le, &LongUnderIn,
-                         &NetLongSnow, &NetShortGrnd, &NetShortSnow, &ShortUnderIn, &OldTSurf,
-                         iter_aero_resist, iter_aero_resist_used, &coverage, &delta_coverage, displacement,
-                         &step_melt_energy, &step_out_prec, &step_out_rain, &step_out_snow, &step_ppt,
-                         &rainfall, ref_height, roughness, &snow_inflow, &snowfall, &surf_atten, wind, root,
-                         UNSTABLE_SNOW, Nveg, iveg, step_dt, vl, &UnderStory, &dryFrac, atmos,
-                         &iter_snow_energy, iter_layer, &iter_snow, soil_con, &iter_snow_veg_var);
-  if ((iter_snow.surf_temp == 999 || UNSTABLE_SNOW) && iter_snow.swq > 0) {
-    INCLUDE_SNOW = UnderStory + 1;
-    iter_soil_energy.advection = iter_snow_energy.advection;
-    iter_snow.surf_temp = step_snow.surf_temp;
-    step_melt_energy = 0;
-  }
-  else INCLUDE_SNOW = 0;
-  Tsurf = calc_surf_energy_bal(Le, LongUnderIn, NetLongSnow, NetShortGrnd, NetShortSnow, OldTSurf,
-                               ShortUnderIn, iter_snow.albedo, iter_snow_energy.latent,
-                               iter_snow_energy.latent_sub, iter_snow_energy.sensible, Tcanopy, VPDcanopy,
-                               VPcanopy, delta_coverage, dp, step_melt_energy, iter_snow.coverage,
-                               (step_snow.depth + iter_snow.depth) / 2., BareAlbedo, surf_atten,
-                               iter_aero_resist, iter_aero_resist_used, displacement, &step_melt, &step_ppt,
-                               rainfall, ref_height, roughness, wind, root, INCLUDE_SNOW, UnderStory, Nveg,
-                               step_dt, iveg, overstory, vl, &dryFrac, atmos, &iter_soil_energy, iter_layer,
-                               &iter_snow, soil_con, &iter_soil_veg_var);
-  if (INCLUDE_SNOW) step_ppt += step_melt;
-  if (iter_snow.snow && overstory) {
-    /* calc_atmos_energy_bal.c with CLOSE_ENERGY FALSE: Tcanopy = Tair; F = 1 */
-    double InOverSensible = iter_snow_energy.canopy_sensible, InUnderSensible = iter_soil_energy.sensible;
-    double F = 1;
-    iter_soil_energy.AtmosSensible = InOverSensible + InUnderSensible;
-    iter_soil_energy.NetLongAtmos = (F * iter_snow_energy.NetLongOver + (1. - F) * iter_soil_energy.NetLongUnder);
-    iter_soil_energy.NetShortAtmos = (iter_snow_energy.NetShortOver + iter_soil_energy.NetShortUnder);
-    iter_soil_energy.AtmosLatent = (iter_snow_energy.canopy_latent + iter_soil_energy.latent);
-    iter_soil_energy.AtmosLatentSub = (iter_snow_energy.canopy_latent_sub + iter_soil_energy.latent_sub);
-    Tcanopy = Tair;
-    /* func_atmos_energy_bal.c: SensibleHeat = density*Cp*(Tair-Tcanopy)/Ra */
-    iter_soil_energy.AtmosSensible = atmos->density * Cp * (Tair - Tcanopy) / iter_aero_resist_used[1];
+  /* ---- sub-step controls (surface_fluxes.c:385-396) ---- */
+  if (snow->swq > 0 || snow->snow_canopy > 0 || atm[NR].snowflag) {
+    hidx = 0; endhidx = hidx + NF; step_dt = opt->snow_step_hours;
   }
   else {
-    iter_soil_energy.AtmosLatent = iter_soil_energy.latent;
-    iter_soil_energy.AtmosLatentSub = iter_soil_energy.latent_sub;
-    iter_soil_energy.AtmosSensible = iter_soil_energy.sensible;
-    iter_soil_energy.NetLongAtmos = iter_soil_energy.NetLongUnder;
-    iter_soil_energy.NetShortAtmos = iter_soil_energy.NetShortUnder;
+    hidx = NR; endhidx = hidx + 1; step_dt = opt->dt_hours;
   }
-  iter_soil_energy.Tcanopy = Tcanopy;
-  iter_snow_energy.Tcanopy = Tcanopy;
+  N_steps = 0;
+  for (lidx = 0; lidx < MAXL; lidx++) store_layerevap[lidx] = 0;
+  store_aero_cond_used[0] = store_aero_cond_used[1] = 0;
+  for (lidx = 0; lidx < 6; lidx++) store_pot_evap[lidx] = 0;
 
-  snow_energy = iter_snow_energy;
-  soil_energy = iter_soil_energy;
-  snow_veg_var = iter_snow_veg_var;
-  soil_veg_var = iter_soil_veg_var;
-  step_snow = iter_snow;
-  for (lidx = 0; lidx < NLAYER; lidx++) step_layer[lidx] = iter_layer[lidx];
-  if (iveg != Nveg) {
-    if (step_snow.snow) {
-      store_throughfall += snow_veg_var.throughfall;
-      store_canopyevap += snow_veg_var.canopyevap;
-      soil_veg_var.Wdew = snow_veg_var.Wdew;
+  /* ---- the sub-steps (surface_fluxes.c:480-1025) ---- */
+  do {
+    const oatmos *atmos = &atm[hidx];
+    Tair = atmos->air_temp + soil_con->Tfactor[band];
+    step_prec = atmos->prec * soil_con->Pfactor[band];
+    Tgrnd = energy->T[0];
+    Tcanopy = Tair;
+    VPcanopy = atmos->vp;
+    VPDcanopy = atmos->vpd;
+    step_snow.blowing_flux = 0.0;      /* BLOWING FALSE */
+    UnderStory = 999;
+    snow_grnd_flux = -snow_flux;
+    iter_snow_energy = snow_energy;
+    iter_soil_energy = soil_energy;
+    iter_snow_veg_var = snow_veg_var;
+    iter_soil_veg_var = soil_veg_var;
+    iter_snow = step_snow;
+    for (lidx = 0; lidx < NLAYER; lidx++) iter_layer[lidx] = step_layer[lidx];
+    iter_snow_veg_var.Wdew = step_Wdew;
+    iter_soil_veg_var.Wdew = step_Wdew;
+    iter_snow_veg_var.canopyevap = 0;
+    iter_soil_veg_var.canopyevap = 0;
+    for (lidx = 0; lidx < NLAYER; lidx++) iter_layer[lidx].evap = 0;
+    iter_aero_resist[0] = aero_resist[0]; iter_aero_resist[1] = aero_resist[1]; iter_aero_resist[2] = aero_resist[2];
+    iter_aero_resist_used[0] = aero_resist_used[0];
+    iter_aero_resist_used[1] = aero_resist_used[1];
+    iter_snow.canopy_vapor_flux = 0;
+    iter_snow.vapor_flux = 0;
+    iter_snow.surface_flux = 0;
+    LongUnderOut = iter_soil_energy.LongUnderOut;
+    dryFrac = -1;
+    step_melt = solve_snow(overstory, BareAlbedo, LongUnderOut, opt->min_rain_temp, opt->max_snow_temp, Tcanopy,
+                           Tgrnd, Tair, step_prec, snow_grnd_flux, &energy->AlbedoUnder, &Le, &LongUnderIn,
+                           &NetLongSnow, &NetShortGrnd, &NetShortSnow, &ShortUnderIn, &OldTSurf,
+                           iter_aero_resist, iter_aero_resist_used, &coverage, &delta_coverage, displacement,
+                           &step_melt_energy, &step_out_prec, &step_out_rain, &step_out_snow, &step_ppt,
+                           &rainfall, ref_height, roughness, &snow_inflow, &snowfall, &surf_atten, wind, root,
+                           UNSTABLE_SNOW, Nveg, iveg, step_dt, vl, &UnderStory, &dryFrac, atmos,
+                           &iter_snow_energy, iter_layer, &iter_snow, soil_con, &iter_snow_veg_var);
+    if ((iter_snow.surf_temp == 999 || UNSTABLE_SNOW) && iter_snow.swq > 0) {
+      INCLUDE_SNOW = UnderStory + 1;
+      iter_soil_energy.advection = iter_snow_energy.advection;
+      iter_snow.surf_temp = step_snow.surf_temp;
+      step_melt_energy = 0;
+    }
+    else INCLUDE_SNOW = 0;
+    Tsurf = calc_surf_energy_bal(Le, LongUnderIn, NetLongSnow, NetShortGrnd, NetShortSnow, OldTSurf,
+                                 ShortUnderIn, iter_snow.albedo, iter_snow_energy.latent,
+                                 iter_snow_energy.latent_sub, iter_snow_energy.sensible, Tcanopy, VPDcanopy,
+                                 VPcanopy, delta_coverage, dp, step_melt_energy, iter_snow.coverage,
+                                 (step_snow.depth + iter_snow.depth) / 2., BareAlbedo, surf_atten,
+                                 iter_aero_resist, iter_aero_resist_used, displacement, &step_melt, &step_ppt,
+                                 rainfall, ref_height, roughness, wind, root, INCLUDE_SNOW, UnderStory, Nveg,
+                                 step_dt, iveg, overstory, vl, &dryFrac, atmos, &iter_soil_energy, iter_layer,
+                                 &iter_snow, soil_con, &iter_soil_veg_var);
+    if (INCLUDE_SNOW) step_ppt += step_melt;
+    if (iter_snow.snow && overstory) {
+      /* calc_atmos_energy_bal.c with CLOSE_ENERGY FALSE: Tcanopy = Tair; F = 1 */
+      double InOverSensible = iter_snow_energy.canopy_sensible, InUnderSensible = iter_soil_energy.sensible;
+      double F = 1;
+      iter_soil_energy.AtmosSensible = InOverSensible + InUnderSensible;
+      iter_soil_energy.NetLongAtmos = (F * iter_snow_energy.NetLongOver + (1. - F) * iter_soil_energy.NetLongUnder);
+      iter_soil_energy.NetShortAtmos = (iter_snow_energy.NetShortOver + iter_soil_energy.NetShortUnder);
+      iter_soil_energy.AtmosLatent = (iter_snow_energy.canopy_latent + iter_soil_energy.latent);
+      iter_soil_energy.AtmosLatentSub = (iter_snow_energy.canopy_latent_sub + iter_soil_energy.latent_sub);
+      Tcanopy = Tair;
+      /* func_atmos_energy_bal.c: SensibleHeat = density*Cp*(Tair-Tcanopy)/Ra */
+      iter_soil_energy.AtmosSensible = atmos->density * Cp * (Tair - Tcanopy) / iter_aero_resist_used[1];
     }
     else {
-      store_throughfall += soil_veg_var.throughfall;
-      store_canopyevap += soil_veg_var.canopyevap;
-      snow_veg_var.Wdew = soil_veg_var.Wdew;
+      iter_soil_energy.AtmosLatent = iter_soil_energy.latent;
+      iter_soil_energy.AtmosLatentSub = iter_soil_energy.latent_sub;
+      iter_soil_energy.AtmosSensible = iter_soil_energy.sensible;
+      iter_soil_energy.NetLongAtmos = iter_soil_energy.NetLongUnder;
+      iter_soil_energy.NetShortAtmos = iter_soil_energy.NetShortUnder;
     }
-    step_Wdew = soil_veg_var.Wdew;
-  }
-  /* potential evaporation of the six reference covers (surface_fluxes.c:868-897, 1019, 1123) */
-  if (pet_aero) {
-    double stability_factor[2], step_aero_resist[6][2];
-    int p;
-    if (iter_aero_resist_used[0] == HUGE_RESIST) stability_factor[0] = HUGE_RESIST;
-    else stability_factor[0] = iter_aero_resist_used[0] / pet_aero[6][UnderStory];
-    if (iter_aero_resist_used[1] == iter_aero_resist_used[0]) stability_factor[1] = stability_factor[0];
-    else {
-      if (iter_aero_resist_used[1] == HUGE_RESIST) stability_factor[1] = HUGE_RESIST;
-      else stability_factor[1] = iter_aero_resist_used[1] / pet_aero[6][1];
-    }
-    for (p = 0; p < 6; p++) {
-      if (stability_factor[0] == HUGE_RESIST) step_aero_resist[p][0] = HUGE_RESIST;
-      else step_aero_resist[p][0] = pet_aero[p][UnderStory] * stability_factor[0];
-      if (stability_factor[1] == HUGE_RESIST) step_aero_resist[p][1] = HUGE_RESIST;
-      else step_aero_resist[p][1] = pet_aero[p][1] * stability_factor[1];
-    }
-    compute_pot_evap(lib, nclass, veg_class, atmos->month - 1, opt->dt_hours, atmos->shortwave, iter_soil_energy.NetLongAtmos,
-                     Tair, VPDcanopy, soil_con->elevation, step_aero_resist, cell->pot_evap);
-  }
-  for (lidx = 0; lidx < NLAYER; lidx++) store_layerevap[lidx] = 0. + step_layer[lidx].evap;
-  if (iter_aero_resist_used[0] > 0) store_aero_cond_used[0] = 0. + 1 / iter_aero_resist_used[0];
-  else store_aero_cond_used[0] = 0. + HUGE_RESIST;
-  if (iter_aero_resist_used[1] > 0) store_aero_cond_used[1] = 0. + 1 / iter_aero_resist_used[1];
-  else store_aero_cond_used[1] = 0. + HUGE_RESIST;
-  if (iveg != Nveg) store_canopy_vapor_flux += step_snow.canopy_vapor_flux;
-  *out_prec += step_out_prec;
-  *out_rain += step_out_rain;
-  *out_snow += step_out_snow;
-  if (INCLUDE_SNOW) {
-    snow_energy.advected_sensible = soil_energy.advected_sensible;
-    snow_energy.advection = soil_energy.advection;
-    snow_energy.deltaCC = soil_energy.deltaCC;
-    snow_energy.latent = soil_energy.latent;
-    snow_energy.latent_sub = soil_energy.latent_sub;
-    snow_energy.refreeze_energy = soil_energy.refreeze_energy;
-    snow_energy.sensible = soil_energy.sensible;
-    snow_energy.snow_flux = soil_energy.snow_flux;
-  }
-  if (step_snow.swq == 0 && INCLUDE_SNOW) {
-    if (last_snow_coverage == 0 && step_prec > 0) last_snow_coverage = 1;
-    store_advected_sensible += snow_energy.advected_sensible * last_snow_coverage;
-    store_advection += snow_energy.advection * last_snow_coverage;
-    store_deltaCC += snow_energy.deltaCC * last_snow_coverage;
-    store_snow_flux += soil_energy.snow_flux * last_snow_coverage;
-    store_refreeze_energy += snow_energy.refreeze_energy * last_snow_coverage;
-  }
-  else if (step_snow.snow || INCLUDE_SNOW) {
-    store_advected_sensible += snow_energy.advected_sensible * (step_snow.coverage + delta_coverage);
-    store_advection += snow_energy.advection * (step_snow.coverage + delta_coverage);
-    store_deltaCC += snow_energy.deltaCC * (step_snow.coverage + delta_coverage);
-    store_snow_flux += soil_energy.snow_flux * (step_snow.coverage + delta_coverage);
-    store_refreeze_energy += snow_energy.refreeze_energy * (step_snow.coverage + delta_coverage);
-  }
+    iter_soil_energy.Tcanopy = Tcanopy;
+    iter_snow_energy.Tcanopy = Tcanopy;
 
-  /* ---- fold the sub-step back (surface_fluxes.c:1030-1160), N_steps == 1 ---- */
+    /* potential evaporation of the six reference covers (surface_fluxes.c:868-897, 1019, 1123) */
+    if (pet_aero) {
+      double stability_factor[2], step_aero_resist[6][2], iter_pot_evap[6];
+      int p;
+      if (iter_aero_resist_used[0] == HUGE_RESIST) stability_factor[0] = HUGE_RESIST;
+      else stability_factor[0] = iter_aero_resist_used[0] / pet_aero[6][UnderStory];
+      if (iter_aero_resist_used[1] == iter_aero_resist_used[0]) stability_factor[1] = stability_factor[0];
+      else {
+        if (iter_aero_resist_used[1] == HUGE_RESIST) stability_factor[1] = HUGE_RESIST;
+        else stability_factor[1] = iter_aero_resist_used[1] / pet_aero[6][1];
+      }
+      for (p = 0; p < 6; p++) {
+        if (stability_factor[0] == HUGE_RESIST) step_aero_resist[p][0] = HUGE_RESIST;
+        else step_aero_resist[p][0] = pet_aero[p][UnderStory] * stability_factor[0];
+        if (stability_factor[1] == HUGE_RESIST) step_aero_resist[p][1] = HUGE_RESIST;
+        else step_aero_resist[p][1] = pet_aero[p][1] * stability_factor[1];
+      }
+      compute_pot_evap(lib, nclass, veg_class, atmos->month - 1, opt->dt_hours, atmos->shortwave, iter_soil_energy.NetLongAtmos,
+                       Tair, VPDcanopy, soil_con->elevation, step_aero_resist, iter_pot_evap);
+      for (p = 0; p < 6; p++) store_pot_evap[p] += iter_pot_evap[p];
+    }
+
+    /* ---- store the sub-step (surface_fluxes.c:905-1025) ---- */
+    snow_energy = iter_snow_energy;
+    soil_energy = iter_soil_energy;
+    snow_veg_var = iter_snow_veg_var;
+    soil_veg_var = iter_soil_veg_var;
+    step_snow = iter_snow;
+    for (lidx = 0; lidx < NLAYER; lidx++) step_layer[lidx] = iter_layer[lidx];
+    if (iveg != Nveg) {
+      if (step_snow.snow) {
+        store_throughfall += snow_veg_var.throughfall;
+        store_canopyevap += snow_veg_var.canopyevap;
+        soil_veg_var.Wdew = snow_veg_var.Wdew;
+      }
+      else {
+        store_throughfall += soil_veg_var.throughfall;
+        store_canopyevap += soil_veg_var.canopyevap;
+        snow_veg_var.Wdew = soil_veg_var.Wdew;
+      }
+      step_Wdew = soil_veg_var.Wdew;
+    }
+    for (lidx = 0; lidx < NLAYER; lidx++) store_layerevap[lidx] += step_layer[lidx].evap;
+    store_ppt += step_ppt;
+    if (iter_aero_resist_used[0] > 0) store_aero_cond_used[0] += 1 / iter_aero_resist_used[0];
+    else store_aero_cond_used[0] += HUGE_RESIST;
+    if (iter_aero_resist_used[1] > 0) store_aero_cond_used[1] += 1 / iter_aero_resist_used[1];
+    else store_aero_cond_used[1] += HUGE_RESIST;
+    if (iveg != Nveg) store_canopy_vapor_flux += step_snow.canopy_vapor_flux;
+    store_melt += step_melt;
+    store_vapor_flux += step_snow.vapor_flux;
+    store_surface_flux += step_snow.surface_flux;
+    store_blowing_flux += step_snow.blowing_flux;
+    *out_prec += step_out_prec;
+    *out_rain += step_out_rain;
+    *out_snow += step_out_snow;
+    if (INCLUDE_SNOW) {
+      snow_energy.advected_sensible = soil_energy.advected_sensible;
+      snow_energy.advection = soil_energy.advection;
+      snow_energy.deltaCC = soil_energy.deltaCC;
+      snow_energy.latent = soil_energy.latent;
+      snow_energy.latent_sub = soil_energy.latent_sub;
+      snow_energy.refreeze_energy = soil_energy.refreeze_energy;
+      snow_energy.sensible = soil_energy.sensible;
+      snow_energy.snow_flux = soil_energy.snow_flux;
+    }
+    store_AlbedoOver += snow_energy.AlbedoOver;
+    store_AlbedoUnder += soil_energy.AlbedoUnder;
+    store_AtmosLatent += soil_energy.AtmosLatent;
+    store_AtmosLatentSub += soil_energy.AtmosLatentSub;
+    store_AtmosSensible += soil_energy.AtmosSensible;
+    store_LongOverIn += snow_energy.LongOverIn;
+    store_LongUnderIn += LongUnderIn;
+    store_LongUnderOut += soil_energy.LongUnderOut;
+    store_NetLongAtmos += soil_energy.NetLongAtmos;
+    store_NetLongOver += snow_energy.NetLongOver;
+    store_NetLongUnder += soil_energy.NetLongUnder;
+    store_NetShortAtmos += soil_energy.NetShortAtmos;
+    store_NetShortGrnd += NetShortGrnd;
+    store_NetShortOver += snow_energy.NetShortOver;
+    store_NetShortUnder += soil_energy.NetShortUnder;
+    store_ShortOverIn += snow_energy.ShortOverIn;
+    store_ShortUnderIn += soil_energy.ShortUnderIn;
+    store_canopy_advection += snow_energy.canopy_advection;
+    store_canopy_latent += snow_energy.canopy_latent;
+    store_canopy_latent_sub += snow_energy.canopy_latent_sub;
+    store_canopy_sensible += snow_energy.canopy_sensible;
+    store_canopy_refreeze += snow_energy.canopy_refreeze;
+    store_deltaH += soil_energy.deltaH;
+    store_fusion += soil_energy.fusion;
+    store_grnd_flux += soil_energy.grnd_flux;
+    store_latent += soil_energy.latent;
+    store_latent_sub += soil_energy.latent_sub;
+    store_melt_energy += step_melt_energy;
+    store_sensible += soil_energy.sensible;
+    if (step_snow.swq == 0 && INCLUDE_SNOW) {
+      if (last_snow_coverage == 0 && step_prec > 0) last_snow_coverage = 1;
+      store_advected_sensible += snow_energy.advected_sensible * last_snow_coverage;
+      store_advection += snow_energy.advection * last_snow_coverage;
+      store_deltaCC += snow_energy.deltaCC * last_snow_coverage;
+      store_snow_flux += soil_energy.snow_flux * last_snow_coverage;
+      store_refreeze_energy += snow_energy.refreeze_energy * last_snow_coverage;
+    }
+    else if (step_snow.snow || INCLUDE_SNOW) {
+      store_advected_sensible += snow_energy.advected_sensible * (step_snow.coverage + delta_coverage);
+      store_advection += snow_energy.advection * (step_snow.coverage + delta_coverage);
+      store_deltaCC += snow_energy.deltaCC * (step_snow.coverage + delta_coverage);
+      store_snow_flux += soil_energy.snow_flux * (step_snow.coverage + delta_coverage);
+      store_refreeze_energy += snow_energy.refreeze_energy * (step_snow.coverage + delta_coverage);
+    }
+    N_steps++;
+    hidx++;
+  } while (hidx < endhidx);
+
+  /* ---- fold the sub-steps back (surface_fluxes.c:1030-1160) ---- */
   (*snow) = step_snow;
-  snow->vapor_flux = 0. + step_snow.vapor_flux;
-  snow->blowing_flux = 0. + step_snow.blowing_flux;
-  snow->surface_flux = 0. + step_snow.surface_flux;
+  snow->vapor_flux = store_vapor_flux;
+  snow->blowing_flux = store_blowing_flux;
+  snow->surface_flux = store_surface_flux;
   snow->canopy_vapor_flux = store_canopy_vapor_flux;
-  snow->melt = 0. + step_melt;
-  ppt = 0. + step_ppt;
+  snow->melt = store_melt;
+  ppt = store_ppt;
   (*energy) = soil_energy;
-  energy->AlbedoOver = (0. + snow_energy.AlbedoOver) / (double)N_steps;
-  energy->AlbedoUnder = (0. + soil_energy.AlbedoUnder) / (double)N_steps;
-  energy->LongOverIn = (0. + snow_energy.LongOverIn) / (double)N_steps;
-  energy->LongUnderIn = (0. + LongUnderIn) / (double)N_steps;
-  energy->NetLongOver = (0. + snow_energy.NetLongOver) / (double)N_steps;
-  energy->NetShortGrnd = (0. + NetShortGrnd) / (double)N_steps;
-  energy->NetShortOver = (0. + snow_energy.NetShortOver) / (double)N_steps;
-  energy->ShortOverIn = (0. + snow_energy.ShortOverIn) / (double)N_steps;
+  energy->AlbedoOver = store_AlbedoOver / (double)N_steps;
+  energy->AlbedoUnder = store_AlbedoUnder / (double)N_steps;
+  energy->AtmosLatent = store_AtmosLatent / (double)N_steps;
+  energy->AtmosLatentSub = store_AtmosLatentSub / (double)N_steps;
+  energy->AtmosSensible = store_AtmosSensible / (double)N_steps;
+  energy->LongOverIn = store_LongOverIn / (double)N_steps;
+  energy->LongUnderIn = store_LongUnderIn / (double)N_steps;
+  energy->LongUnderOut = store_LongUnderOut / (double)N_steps;
+  energy->NetLongAtmos = store_NetLongAtmos / (double)N_steps;
+  energy->NetLongOver = store_NetLongOver / (double)N_steps;
+  energy->NetLongUnder = store_NetLongUnder / (double)N_steps;
+  energy->NetShortAtmos = store_NetShortAtmos / (double)N_steps;
+  energy->NetShortGrnd = store_NetShortGrnd / (double)N_steps;
+  energy->NetShortOver = store_NetShortOver / (double)N_steps;
+  energy->NetShortUnder = store_NetShortUnder / (double)N_steps;
+  energy->ShortOverIn = store_ShortOverIn / (double)N_steps;
+  energy->ShortUnderIn = store_ShortUnderIn / (double)N_steps;
   energy->advected_sensible = store_advected_sensible / (double)N_steps;
-  energy->canopy_advection = (0. + snow_energy.canopy_advection) / (double)N_steps;
-  energy->canopy_latent = (0. + snow_energy.canopy_latent) / (double)N_steps;
-  energy->canopy_latent_sub = (0. + snow_energy.canopy_latent_sub) / (double)N_steps;
-  energy->canopy_refreeze = (0. + snow_energy.canopy_refreeze) / (double)N_steps;
-  energy->canopy_sensible = (0. + snow_energy.canopy_sensible) / (double)N_steps;
-  energy->melt_energy = (0. + step_melt_energy) / (double)N_steps;
+  energy->canopy_advection = store_canopy_advection / (double)N_steps;
+  energy->canopy_latent = store_canopy_latent / (double)N_steps;
+  energy->canopy_latent_sub = store_canopy_latent_sub / (double)N_steps;
+  energy->canopy_refreeze = store_canopy_refreeze / (double)N_steps;
+  energy->canopy_sensible = store_canopy_sensible / (double)N_steps;
+  energy->deltaH = store_deltaH / (double)N_steps;
+  energy->fusion = store_fusion / (double)N_steps;
+  energy->grnd_flux = store_grnd_flux / (double)N_steps;
+  energy->latent = store_latent / (double)N_steps;
+  energy->latent_sub = store_latent_sub / (double)N_steps;
+  energy->melt_energy = store_melt_energy / (double)N_steps;
+  energy->sensible = store_sensible / (double)N_steps;
   if (snow->snow || INCLUDE_SNOW) {
     energy->advection = store_advection / (double)N_steps;
     energy->deltaCC = store_deltaCC / (double)N_steps;
@@ -2393,6 +2472,7 @@ static int surface_fluxes(const vr_options *opt, int overstory, double BareAlbed
     else if (store_aero_cond_used[lidx] >= HUGE_RESIST) aero_resist_used[lidx] = 0;
     else aero_resist_used[lidx] = HUGE_RESIST;
   }
+  if (pet_aero) for (lidx = 0; lidx < 6; lidx++) cell->pot_evap[lidx] = store_pot_evap[lidx] / (double)N_steps;
   cell->inflow = ppt;
   return runoff(cell, soil_con, ppt, opt->dt_hours);
 }
@@ -2400,9 +2480,11 @@ static int surface_fluxes(const vr_options *opt, int overstory, double BareAlbed
 /* ======================================================================================
  * full_energy.c:8-571 (one cell, one record) -- without lakes / carbon / PET reference covers
  * ====================================================================================== */
-static int full_energy(vo_model *m, int64_t c, const oatmos *atmos, double *out_prec_sum,
+static int full_energy(vo_model *m, int64_t c, const oatmos *atm /* [NF + 1], or [1] when NF == 1 */, double *out_prec_sum,
                        double *out_rain_sum, double *out_snow_sum)
 {
+  const int NF = m->opt.dt_hours / m->opt.snow_step_hours, NR = NF > 1 ? NF : 0;
+  const oatmos *atmos = &atm[NR];
   const vr_options *opt = &m->opt;
   const osoil *soil_con = &m->soil[c];
   int64_t t0 = m->tile_ptr[c], t1 = m->tile_ptr[c + 1], t;
@@ -2521,7 +2603,7 @@ static int full_energy(vo_model *m, int64_t c, const oatmos *atmos, double *out_
         out_prec = out_rain = out_snow = 0;
         err = surface_fluxes(opt, overstory, bare_albedo, surf_atten, ar3, d3, rh3, ro3, w3, rootv,
                              is_bare ? iveg : -1 /* Nveg: iveg == Nveg only for the bare tile */, band,
-                             soil_con->dp, iveg, &vl, atmos, &u->energy, &u->cell, &u->snow, soil_con, &u->veg,
+                             soil_con->dp, iveg, &vl, atm, NF, NR, &u->energy, &u->cell, &u->snow, soil_con, &u->veg,
                              &out_prec, &out_rain, &out_snow, m->lib, m->nclass, veg_class, m->want_pet ? pet_aero : NULL);
         if (err == VERROR) return VERROR;
         *out_prec_sum += out_prec * Cv * soil_con->AreaFract[band];
@@ -2859,15 +2941,22 @@ static int step_range(vo_model *m, const vr_forcing *f, double *out, double *uni
   if (!m->initialised) return VR_ERR_STATE;
   for (c = c0; c < c1; c++) {
     for (rec = 0; rec < nrec; rec++) {
-      oatmos a;
-      size_t k = (size_t)rec * C + c;
-      a.air_temp = f->field[VR_F_AIR_TEMP][k]; a.prec = f->field[VR_F_PREC][k];
-      a.wind = f->field[VR_F_WIND][k]; a.vp = f->field[VR_F_VP][k]; a.vpd = f->field[VR_F_VPD][k];
-      a.pressure = f->field[VR_F_PRESSURE][k]; a.density = f->field[VR_F_DENSITY][k];
-      a.shortwave = f->field[VR_F_SHORTWAVE][k]; a.longwave = f->field[VR_F_LONGWAVE][k];
-      a.month = f->month[rec]; a.day_in_year = f->day_in_year[rec];
-      if (full_energy(m, c, &a, &op, &orn, &osn) == VERROR) { rc = VR_ERR_CELL; break; }
-      put_data(m, c, &a, op, orn, osn, 0, o);
+      /* the record's sub-steps [0..NF-1] and the record itself [NR] (vr_forcing.field: [nrec * NS][C]) */
+      oatmos as[25];
+      const int NF = m->opt.dt_hours / m->opt.snow_step_hours, NS = NF > 1 ? NF + 1 : 1;
+      int j;
+      for (j = 0; j < NS; j++) {
+        oatmos *a = &as[j];
+        size_t k = ((size_t)rec * NS + j) * C + c;
+        a->air_temp = f->field[VR_F_AIR_TEMP][k]; a->prec = f->field[VR_F_PREC][k];
+        a->wind = f->field[VR_F_WIND][k]; a->vp = f->field[VR_F_VP][k]; a->vpd = f->field[VR_F_VPD][k];
+        a->pressure = f->field[VR_F_PRESSURE][k]; a->density = f->field[VR_F_DENSITY][k];
+        a->shortwave = f->field[VR_F_SHORTWAVE][k]; a->longwave = f->field[VR_F_LONGWAVE][k];
+        a->month = f->month[rec]; a->day_in_year = f->day_in_year[rec];
+        a->snowflag = (NF > 1 && f->snowflag) ? f->snowflag[(size_t)rec * C + c] : 0;
+      }
+      if (full_energy(m, c, as, &op, &orn, &osn) == VERROR) { rc = VR_ERR_CELL; break; }
+      put_data(m, c, &as[NS - 1], op, orn, osn, 0, o);
       for (v = 0; v < m->opt.n_out; v++) out[((size_t)v * nrec + rec) * C + c] = o[m->opt.out_vars[v]];
       if (units_dbg) {
         for (t = m->tile_ptr[c]; t < m->tile_ptr[c + 1]; t++) {

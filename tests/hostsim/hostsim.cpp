@@ -107,8 +107,10 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
         h.Wdew = s.Wdew; h.T0 = s.T0; h.T1 = s.T1; h.LongUnderOut = s.LongUnderOut; h.Tfoliage = s.Tfoliage;
         bool snowy = s.swq > 0 || s.snow_canopy > 0 || s.coverage != 0;
         bool tidy = !snowy && (s.last_snow != (int)MISSINGV || s.MELTING != 0 || s.albedo != NEW_SNOW_ALB);
-#define HS_STEP(EX) unit_record<EX>(cc, UC[u], tm, ae, forc, NF, NL, opt->dt_hours, opt->snow_step_hours, opt->max_snow_temp, \
-                                    opt->min_rain_temp, h, snowy, tidy, sio, P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap)
+#define HS_ARGS cc, UC[u], tm, ae, forc, NF, NL, opt->dt_hours, opt->snow_step_hours, opt->max_snow_temp, opt->min_rain_temp, h, snowy, \
+                tidy, sio, P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap
+        // the instance the kernel would launch: the one without sums / averages when NF == 1
+#define HS_STEP(EX) do { if (NF > 1) unit_record<EX, true>(HS_ARGS); else unit_record<EX, false>(HS_ARGS); } while (0)
         switch (term_extras(tmap)) {
           case 0: HS_STEP(0); break;
           case EX_PET: HS_STEP(EX_PET); break;
@@ -116,6 +118,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
           default: HS_STEP(EX_PET | EX_ZWT); break;
         }
 #undef HS_STEP
+#undef HS_ARGS
         if (tidy) sio.store_none();     // the harness keeps no flags between records
         for (int l = 0; l < MAXL; l++) s.moist[l] = h.moist.v[l];
         s.Wdew = h.Wdew; s.T0 = h.T0; s.T1 = h.T1; s.LongUnderOut = h.LongUnderOut; s.Tfoliage = h.Tfoliage;

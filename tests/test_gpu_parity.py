@@ -25,7 +25,7 @@ def test_cuda_matches_reference_golden(VicRes, name):
     fx = load_fixture(name)
     m = VicRes(fx["opt"], fx["lib"], fx["cells"])
     m.init_state(fx["tair0"])
-    out, status = m.step(fx["month"], fx["doy"], fx["forcing"])
+    out, status = m.step(fx["month"], fx["doy"], fx["forcing"], snowflag=fx["snowflag"])
     assert not status.any()
     check_outputs(out, fx["ref"], fx["names"], what="%s CUDA vs reference" % name)
     assert m.num_launches >= 2

@@ -17,7 +17,7 @@ def test_oracle_matches_golden_bit_exact(name):
     fx = load_fixture(name)
     o = oracle_lib.Oracle(fx["opt"], fx["lib"], fx["cells"])
     assert o.init_state(fx["tair0"]) == 0
-    rc, out, _ = o.step(fx["month"], fx["doy"], fx["forcing"])
+    rc, out, _ = o.step(fx["month"], fx["doy"], fx["forcing"], snowflag=fx["snowflag"])
     assert rc == 0
     # same libm (glibc), same operation order, -ffp-contract=off on both sides -> identical bits
     for i, n in enumerate(fx["names"]):
@@ -45,7 +45,7 @@ def test_closure_error_no_worse_than_reference():
         i = fx["names"].index("WATER_ERROR")
         o = oracle_lib.Oracle(fx["opt"], fx["lib"], fx["cells"])
         o.init_state(fx["tair0"])
-        _, out, _ = o.step(fx["month"], fx["doy"], fx["forcing"])
+        _, out, _ = o.step(fx["month"], fx["doy"], fx["forcing"], snowflag=fx["snowflag"])
         assert np.abs(out[i]).max() <= np.abs(fx["ref"][i]).max() + 1e-15
         o.close()
 

@@ -183,8 +183,10 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
 //               (solve_snow.c:565-577); the first record without snow stores them (sio.store_none())
 // Terms that do not depend on runoff() are stored before it is called, so that nothing but the evaporation and the
 // moisture stays live across the hourly drainage loop.  Returns 1 when the reference would have returned ERROR
-// (arno_evap.c:112-151).
-template <int extras, class ForcOf, class SnowIO>
+// (arno_evap.c:112-151).  SUB == false is the instance for SNOW_STEP == TIME_STEP (NF == 1): one pass, no sums or averages
+// (a sum over one pass and a division by 1.0 are exact, so the results are the same; the instance only sheds ~25
+// live accumulators and the divisions).
+template <int extras, bool SUB, class ForcOf, class SnowIO>
 VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
                       int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
                       bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride, bool write,
@@ -221,8 +223,10 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
     h.Wdew /= cm.vegcover;
     if (general) sn.snow_canopy /= cm.vegcover;
   }
-  const bool substep = NF > 1 && (sn.swq > 0 || sn.snow_canopy > 0 || fr.snowflag);     // surface_fluxes.c:385-396
+  const bool substep = SUB && NF > 1 && (sn.swq > 0 || sn.snow_canopy > 0 || fr.snowflag);     // surface_fluxes.c:385-396
   const int npass = substep ? NF : 1, pdt = substep ? snow_step_hours : dt_hours;
+#define ACC_(a, v) do { if (SUB) a += (v); else a = (v); } while (0)
+#define AVG_(x) (SUB ? (x) / N : (x))
   const double Tgrnd = h.T0;
   double coverage = sn.coverage, surf_atten = cm.surf_atten;
   // sums over the passes (surface_fluxes.c:935-1025)
@@ -251,23 +255,23 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
     else
       r = surface_pass<extras, false>(cc, vp, is_veg, overstory, uc.Tfactor, uc.Pfactor, cm, ae, f, NL, pdt, max_snow_temp,
                                       min_rain_temp, Tgrnd, h, sn, coverage, surf_atten, tl, ap, sync_ok, dt_hours);
-    if (is_veg) { st_throughfall += r.throughfall; st_canopyevap += r.canopyevap; st_cvapor += r.canopy_vapor_flux; }
+    if (is_veg) { ACC_(st_throughfall, r.throughfall); ACC_(st_canopyevap, r.canopyevap); ACC_(st_cvapor, r.canopy_vapor_flux); }
 #pragma unroll
     for (int l = 0; l < MAXL; l++) {
-      if (l < NL) st_evap.v[l] += r.evap.v[l];
+      if (l < NL) ACC_(st_evap.v[l], r.evap.v[l]);
       bef.v[l] = r.bef.v[l];
     }
-    st_ppt += r.ppt;
-    st_cond0 += (r.ra_used0 > 0) ? 1 / r.ra_used0 : HUGE_RESIST;
-    st_cond1 += (r.ra_used1 > 0) ? 1 / r.ra_used1 : HUGE_RESIST;
-    st_melt += r.melt; st_vapor += r.vapor_flux;
-    st_prec += r.out_prec; st_rain += r.out_rain; st_snow += r.out_snow;
-    st_aover += r.AlbedoOver; st_aunder += r.AlbedoUnder; st_lover += r.LongOverIn; st_lunder += r.LongUnderIn;
-    st_nlong += r.NetLongAtmos; st_nshort += r.NetShortAtmos; st_dh += r.deltaH; st_gflux += r.grnd_flux;
-    st_luo += h.LongUnderOut;
+    ACC_(st_ppt, r.ppt);
+    ACC_(st_cond0, (r.ra_used0 > 0) ? 1 / r.ra_used0 : HUGE_RESIST);
+    ACC_(st_cond1, (r.ra_used1 > 0) ? 1 / r.ra_used1 : HUGE_RESIST);
+    ACC_(st_melt, r.melt); ACC_(st_vapor, r.vapor_flux);
+    ACC_(st_prec, r.out_prec); ACC_(st_rain, r.out_rain); ACC_(st_snow, r.out_snow);
+    ACC_(st_aover, r.AlbedoOver); ACC_(st_aunder, r.AlbedoUnder); ACC_(st_lover, r.LongOverIn); ACC_(st_lunder, r.LongUnderIn);
+    ACC_(st_nlong, r.NetLongAtmos); ACC_(st_nshort, r.NetShortAtmos); ACC_(st_dh, r.deltaH); ACC_(st_gflux, r.grnd_flux);
+    ACC_(st_luo, h.LongUnderOut);
     if (extras & EX_PET) {
 #pragma unroll
-      for (int i = 0; i < 6; i++) st_pot.v[i] += r.pot.v[i];
+      for (int i = 0; i < 6; i++) ACC_(st_pot.v[i], r.pot.v[i]);
     }
     Tsurf = r.Tsurf;
     snow_flag = r.snow_flag;
@@ -281,11 +285,11 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
     tidy = !snowy && (sn.last_snow != (int)MISSINGV || sn.MELTING != 0 || sn.albedo != NEW_SNOW_ALB);
   }
   const double N = (double)npass;
-  h.LongUnderOut = st_luo / N;      // the record leaves the AVERAGE of its passes behind (surface_fluxes.c:1041), the other
+  h.LongUnderOut = AVG_(st_luo);     // the record leaves the AVERAGE of its passes behind (surface_fluxes.c:1041), the other
                                     // carried words (T[0], T[1], Tfoliage, snow, canopy storage) the last pass's values
   // surface_fluxes.c:1110-1123: resistance -> conductance -> resistance over the passes
-  const double ar0 = (st_cond0 > 0 && st_cond0 < HUGE_RESIST) ? 1 / (st_cond0 / N) : ((st_cond0 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
-  const double ar1 = (st_cond1 > 0 && st_cond1 < HUGE_RESIST) ? 1 / (st_cond1 / N) : ((st_cond1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
+  const double ar0 = (st_cond0 > 0 && st_cond0 < HUGE_RESIST) ? 1 / AVG_(st_cond0) : ((st_cond0 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
+  const double ar1 = (st_cond1 > 0 && st_cond1 < HUGE_RESIST) ? 1 / AVG_(st_cond1) : ((st_cond1 >= HUGE_RESIST) ? 0 : HUGE_RESIST);
   const double AF = cv * af * 1. * 1.;
 #define T_(k, expr) do { if (write && tmap.row[k] >= 0) VR_STREAM_ST(col + (size_t)tmap.row[k] * stride, (expr)); } while (0)
   // ---- terms that are final before runoff() (collect_wb_terms / collect_eb_terms, put_data.c:298-632) ----
@@ -314,18 +318,18 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
   T_(TE_SMELT, st_melt * AF);
   T_(TE_SCOVER, sn.coverage * AF);
   T_(TE_SURFT, Tsurf * AF);
-  T_(TE_NSHORT, (st_nshort / N) * AF);
-  T_(TE_NLONG, (st_nlong / N) * AF);
-  T_(TE_INLONG, ((snow_flag && overstory) ? st_lover / N : st_lunder / N) * AF);
-  T_(TE_ALBEDO, ((snow_flag && overstory) ? st_aover / N : st_aunder / N) * AF);
-  T_(TE_GFLUX, -((st_gflux / N) * AF));     // collect_eb_terms subtracts these two
-  T_(TE_DH, -((st_dh / N) * AF));
+  T_(TE_NSHORT, AVG_(st_nshort) * AF);
+  T_(TE_NLONG, AVG_(st_nlong) * AF);
+  T_(TE_INLONG, ((snow_flag && overstory) ? AVG_(st_lover) : AVG_(st_lunder)) * AF);
+  T_(TE_ALBEDO, ((snow_flag && overstory) ? AVG_(st_aover) : AVG_(st_aunder)) * AF);
+  T_(TE_GFLUX, -(AVG_(st_gflux) * AF));     // collect_eb_terms subtracts these two
+  T_(TE_DH, -(AVG_(st_dh) * AF));
   T_(TE_PREC, st_prec * cv * af);
   T_(TE_RAIN, st_rain * cv * af);
   T_(TE_SNOWF, st_snow * cv * af);
   if (extras & EX_PET) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) T_(TE_PET0 + i, (st_pot.v[i] / N) * AF);    // put_data.c:846-851
+    for (int i = 0; i < 6; i++) T_(TE_PET0 + i, AVG_(st_pot.v[i]) * AF);    // put_data.c:846-851
   }
   VR_PHASE_SYNC(3, true);
   // ---- runoff.c ----
@@ -370,7 +374,9 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
     T_(TE_ZWTL, z.lumped * AF);
   }
 #undef T_
-  (void)st_throughfall;
+#undef ACC_
+#undef AVG_
+  (void)st_throughfall; (void)N;
   return err;
 }
 

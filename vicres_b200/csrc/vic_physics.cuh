@@ -158,6 +158,21 @@ VR_HDN double m_pow(double x, double y)
   return pow(x, y);
 #endif
 }
+// the same, inlined: for the two Brooks-Corey powers of the hourly drainage loop, where the call (argument moves and the
+// caller's live constants kept out of the callee's registers) costs more than the second copy of the code
+VR_HD double m_pow_inl(double x, double y)
+{
+#if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM) && !defined(VR_POW_CALL_IN_LOOP)
+  if (x == 1.0 || y == 0.0) return 1.0;
+  if (x == 0.0 && y > 0.0) return 0.0;
+  bool handled;
+  const double v = pow_table_eval(x, y, vr_pow_tables.logtab, vr_pow_tables.exptab, &handled);
+  if (handled) return v;
+  return m_pow(x, y);
+#else
+  return m_pow(x, y);
+#endif
+}
 VR_HDN double m_exp(double x) { return exp(x); }
 VR_HDN double m_log(double x) { return log(x); }
 VR_HDN double m_log10(double x) { return log10(x); }
@@ -1343,12 +1358,12 @@ VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
     // Brooks-Corey drainage out of the upper layers (runoff.c:330-340)
     double t0 = liq0 - ev0;
     if (t0 < r0) t0 = r0;
-    double Q0 = (liq0 > r0) ? ks0 * VR_POW(VR_DIVC(t0 - r0, qd0, iq0), ex0) : 0.;
+    double Q0 = (liq0 > r0) ? ks0 * m_pow_inl(VR_DIVC(t0 - r0, qd0, iq0), ex0) : 0.;
     double Q1 = 0.;
     if (NL == 3) {
       double t1 = liq1 - ev1;
       if (t1 < r1) t1 = r1;
-      Q1 = (liq1 > r1) ? ks1 * VR_POW(VR_DIVC(t1 - r1, qd1, iq1), ex1) : 0.;
+      Q1 = (liq1 > r1) ? ks1 * m_pow_inl(VR_DIVC(t1 - r1, qd1, iq1), ex1) : 0.;
     }
     // top layer
     liq0 = liq0 + (dt_inflow - tmp_dt_runoff) - (Q0 + ev0);

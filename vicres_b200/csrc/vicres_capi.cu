@@ -229,7 +229,7 @@ struct SnowIO {
 // reads per record -- forcing (k_forcing_slots), constants (k_unit_consts), state -- is in slot order: 32 consecutive
 // doubles per warp and request.  terms[rec][row][unit in reference order]: the stores scatter (fire and forget) so
 // that k_cells reads each cell's units contiguously.
-template <int EXTRAS>
+template <int EXTRAS, bool SUB>
 __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcing F, double *__restrict__ terms)
 {
   pow_tables_init();
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcin
       f.snowflag = (NF > 1 && F.snowflag) ? (int)__ldg(F.snowflag + (size_t)rec * M.FC + (M.fcol ? M.fcol[c] : c)) : 0;
       return f;
     };
-    const int e = unit_record<EXTRAS>(cc, uc, tm + mon * TM_N, ae + mon * AE_N, forc, NF, NL, M.dt_hours, M.snow_step_hours,
+    const int e = unit_record<EXTRAS, SUB>(cc, uc, tm + mon * TM_N, ae + mon * AE_N, forc, NF, NL, M.dt_hours, M.snow_step_hours,
                                       M.max_snow_temp, M.min_rain_temp, h, snowy, tidy, sio, cv, af, M.tmap,
                                       terms + rec * rec_stride + col, (int)M.U, write,
                                       (EXTRAS & EX_PET) ? tl + mon * TL_N : nullptr, (EXTRAS & EX_PET) ? ap + mon * AP_N : nullptr);
@@ -526,10 +526,14 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     delete h;
     return VR_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_units<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of L1 for the stacks
-  cudaFuncSetAttribute(k_units<EX_PET>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_ZWT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_PET | EX_ZWT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of L1 for the stacks
+  cudaFuncSetAttribute(k_units<EX_PET, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_ZWT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_PET | EX_ZWT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_PET, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_ZWT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  cudaFuncSetAttribute(k_units<EX_PET | EX_ZWT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   *out = h;
   return VR_OK;
@@ -776,11 +780,18 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
       h->launches += 1;
     }
     if (h->M.U > 0) {
-      switch (h->extras) {       // one kernel instance per set of optional results
-        case 0: k_units<0><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        case EX_PET: k_units<EX_PET><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        case EX_ZWT: k_units<EX_ZWT><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        default: k_units<EX_PET | EX_ZWT><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+      // one kernel instance per set of optional results; a sub-stepped snow model (NF > 1) has two
+      if (h->M.NF > 1) switch (h->extras) {
+        case 0: k_units<0, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        case EX_PET: k_units<EX_PET, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        case EX_ZWT: k_units<EX_ZWT, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        default: k_units<EX_PET | EX_ZWT, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+      }
+      else switch (h->extras) {
+        case 0: k_units<0, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        case EX_PET: k_units<EX_PET, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        case EX_ZWT: k_units<EX_ZWT, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+        default: k_units<EX_PET | EX_ZWT, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
       }
     }
     if (t) cudaEventRecord(t->u1, st);

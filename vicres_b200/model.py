@@ -138,13 +138,16 @@ class VicRes:
         assert t.shape == (self.ncol,)
         self._check(self.L.vr_init_state(self.h, t.ctypes.data))
 
-    def step(self, month, doy, forcing, out=None):
+    def step(self, month, doy, forcing, out=None, snowflag=None):
         """forcing: [9, nrec, ncol] float64 host array (numpy, or a pinned CPU torch tensor's
-        .numpy()).  Returns (out [n_out, nrec, C], cell_status [C])."""
-        f = abi.pack_forcing(month, doy, forcing)
+        .numpy()); with a sub-stepped snow model (snow_step_hours < dt_hours, NF passes) [9, nrec * (NF + 1), ncol]
+        and snowflag [nrec, ncol] int32.  Returns (out [n_out, nrec, C], cell_status [C])."""
+        f = abi.pack_forcing(month, doy, forcing, snowflag)
         nrec = f.struct.nrec
+        nf = self.opt.dt_hours // self.opt.snow_step_hours
+        ns = nf + 1 if nf > 1 else 1
         for i in range(abi.VR_NFORCING):
-            assert f.keep["f%d" % i].size == nrec * self.ncol, "forcing field %d has the wrong size" % i
+            assert f.keep["f%d" % i].size == nrec * ns * self.ncol, "forcing field %d has the wrong size" % i
         if out is None:
             out = np.empty((self.n_out, nrec, self.ncell), dtype=np.float64)
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.n_out * nrec * self.ncell
