@@ -175,24 +175,44 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
 // One unit, one record, and its terms: full_energy.c:210-470 for one tile x band pair -- the canopy terms of the
 // month, the passes of surface_fluxes' sub-step loop (one, or NF = TIME_STEP / SNOW_STEP when the snow model is
 // sub-stepped and the unit has snow or the record has snowfall: surface_fluxes.c:385-396), their sums and averages
-// (:1030-1123), runoff() once per record (:1130-1150), and the unit's area-weighted terms.
+// (:1030-1123), runoff() once per record (:1130-1150), and the unit's area-weighted terms.  The record is cut at the call
+// of runoff() into unit_front() and unit_back(): the product runs them as separate kernels (vicres_capi.cu), the host
+// harness of the tests one after the other (unit_record()).
 //   forc(k)  -> Forc of sub-step k = 0..NF-1, or of the record itself for k == NF (k == 0 when NF == 1)
 //   sio      -> the unit's snow words: load() / store(SnowS) / fallback(kind); only touched on the snow path
-//   h, snowy -> the hot state and "some snow word is non-zero", which the caller keeps in registers between records
+//   h, snowy -> the hot state and "some snow word is non-zero"
 //   tidy     -> the stored MELTING / last_snow / albedo are not yet what the reference's no-snow branch leaves behind
 //               (solve_snow.c:565-577); the first record without snow stores them (sio.store_none())
-// Terms that do not depend on runoff() are stored before it is called, so that nothing but the evaporation and the
-// moisture stays live across the hourly drainage loop.  Returns 1 when the reference would have returned ERROR
-// (arno_evap.c:112-151).  SUB == false is the instance for SNOW_STEP == TIME_STEP (NF == 1): one pass, no sums or averages
-// (a sum over one pass and a division by 1.0 are exact, so the results are the same; the instance only sheds ~25
-// live accumulators and the divisions).
-template <int extras, bool SUB, class ForcOf, class SnowIO>
-VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
-                      int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
-                      bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride, bool write,
-                      const double *tl = nullptr, const double *ap = nullptr)
+// Terms that do not depend on runoff() are stored by unit_front(), the others by unit_back().  SUB == false is the instance
+// for SNOW_STEP == TIME_STEP (NF == 1): one pass, no sums or averages (a sum over one pass and a division by 1.0 are
+// exact, so the results are the same; the instance only sheds ~25 live accumulators and the divisions).
+
+// what unit_front() hands to unit_back(): the record's water reaching the soil, the layer evaporation and its bare-soil
+// fractions, and the three vapour sums that enter OUT_EVAP after the layer evaporation (put_data.c:318-350)
+struct FrontOut { double ppt, vapor, cvapor, canopyevap; M3 evap, bef; int err; };
+enum { FO_PPT = 0, FO_VAPOR, FO_CVAPOR, FO_CANOPYEVAP, FO_EVAP0, FO_EVAP1, FO_EVAP2, FO_BEF0, FO_BEF1, FO_BEF2, FO_N };
+
+// does this unit run the pass WITH the snow model in this record: it carries snow, the record has snowfall anywhere in
+// the cell (sub-stepping follows, surface_fluxes.c:385-396) or in this band
+VR_HD bool unit_needs_snow(const Forc &fr, double Tfactor, double Pfactor, int NF, double max_snow_temp, double min_rain_temp,
+                           bool snowy)
+{
+  if (snowy || (NF > 1 && fr.snowflag)) return true;
+  double rf, sf;
+  rain_snow_split(fr.air_temp + Tfactor, fr.prec * Pfactor, max_snow_temp, min_rain_temp, rf, sf);
+  return sf > 0.;
+}
+
+// GENERAL: the instance with the snow model (surface_pass<.., true>); the caller decides with unit_needs_snow() -- per
+// unit in the split kernels (the units that need it are compacted into their own launch), per warp in a fused loop.
+template <int extras, bool SUB, bool GENERAL, class ForcOf, class SnowIO>
+VR_HD FrontOut unit_front(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
+                          int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
+                          bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride,
+                          bool write, bool sync_ok, const double *tl = nullptr, const double *ap = nullptr)
 {
   const bool is_veg = !uc.is_bare, overstory = uc.overstory != 0;
+  constexpr bool general = GENERAL;
   VegP vp;
   vp.rarc = uc.rarc; vp.rmin = uc.rmin; vp.RGL = uc.RGL;
 #pragma unroll
@@ -204,17 +224,6 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
     cm.surf_atten = tm[TM_SURF_ATTEN];
   }
   const Forc fr = forc(NF > 1 ? NF : 0);
-  // which instance of the pass: the one with the snow model when the unit carries snow, the record has snowfall
-  // anywhere in the cell (sub-stepping follows) or in this band
-  bool general = snowy || (NF > 1 && fr.snowflag);
-  if (!general) {
-    double rf, sf;
-    rain_snow_split(fr.air_temp + uc.Tfactor, fr.prec * uc.Pfactor, max_snow_temp, min_rain_temp, rf, sf);
-    general = sf > 0.;
-  }
-#if defined(__CUDA_ARCH__)
-  general = __any_sync(0xffffffffu, general);     // per warp: a warp never runs both instances
-#endif
   SnowS sn = snow_none();
   if (general) sn = sio.load();
   else if (tidy) { sio.store_none(); tidy = false; }
@@ -223,7 +232,7 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
     h.Wdew /= cm.vegcover;
     if (general) sn.snow_canopy /= cm.vegcover;
   }
-  const bool substep = SUB && NF > 1 && (sn.swq > 0 || sn.snow_canopy > 0 || fr.snowflag);     // surface_fluxes.c:385-396
+  const bool substep = SUB && general && NF > 1 && (sn.swq > 0 || sn.snow_canopy > 0 || fr.snowflag);     // surface_fluxes.c:385-396
   const int npass = substep ? NF : 1, pdt = substep ? snow_step_hours : dt_hours;
 #define ACC_(a, v) do { if (SUB) a += (v); else a = (v); } while (0)
 #define AVG_(x) (SUB ? (x) / N : (x))
@@ -240,7 +249,6 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
 #pragma unroll
   for (int i = 0; i < 6; i++) st_pot.v[i] = 0;
   int snow_flag = 0, err = 0;
-  const bool sync_ok = NF == 1;
 #pragma unroll 1
   for (int p = 0; p < npass; p++) {
     Forc f = fr;
@@ -248,13 +256,9 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
       f = forc(p);
       f.wind = fr.wind;           // the aerodynamic resistances of all passes come from wind[NR] (full_energy.c:332)
     }
-    SurfOut r;
-    if (general)
-      r = surface_pass<extras, true>(cc, vp, is_veg, overstory, uc.Tfactor, uc.Pfactor, cm, ae, f, NL, pdt, max_snow_temp,
-                                     min_rain_temp, Tgrnd, h, sn, coverage, surf_atten, tl, ap, sync_ok, dt_hours);
-    else
-      r = surface_pass<extras, false>(cc, vp, is_veg, overstory, uc.Tfactor, uc.Pfactor, cm, ae, f, NL, pdt, max_snow_temp,
-                                      min_rain_temp, Tgrnd, h, sn, coverage, surf_atten, tl, ap, sync_ok, dt_hours);
+    const SurfOut r = surface_pass<extras, GENERAL>(cc, vp, is_veg, overstory, uc.Tfactor, uc.Pfactor, cm, ae, f, NL, pdt,
+                                                    max_snow_temp, min_rain_temp, Tgrnd, h, sn, coverage, surf_atten, tl, ap,
+                                                    sync_ok && NF == 1, dt_hours);
     if (is_veg) { ACC_(st_throughfall, r.throughfall); ACC_(st_canopyevap, r.canopyevap); ACC_(st_cvapor, r.canopy_vapor_flux); }
 #pragma unroll
     for (int l = 0; l < MAXL; l++) {
@@ -331,36 +335,53 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
 #pragma unroll
     for (int i = 0; i < 6; i++) T_(TE_PET0 + i, AVG_(st_pot.v[i]) * AF);    // put_data.c:846-851
   }
-  VR_PHASE_SYNC(3, true);
+#undef T_
+#undef ACC_
+#undef AVG_
+  (void)st_throughfall; (void)N;
+  FrontOut o;
+  o.ppt = st_ppt; o.vapor = st_vapor; o.cvapor = st_cvapor; o.canopyevap = st_canopyevap;
+  o.evap = st_evap; o.bef = bef; o.err = err;
+  return o;
+}
+
+// runoff() of the record (surface_fluxes.c:1130-1150), full_energy.c:445-453, and the terms that depend on them
+template <int extras>
+VR_HD void unit_back(CellC cc, bool is_veg, int root0_mask, int NL, int dt_hours, FrontOut fo, M3 &moist, double cv, double af,
+                     const TermMap &tmap, double *col, int stride, bool write)
+{
+  const double AF = cv * af * 1. * 1.;
+#define T_(k, expr) do { if (write && tmap.row[k] >= 0) VR_STREAM_ST(col + (size_t)tmap.row[k] * stride, (expr)); } while (0)
   // ---- runoff.c ----
-  const RunoffOut ro = runoff_step(cc, NL, dt_hours, st_ppt, h.moist, st_evap);
-  h.moist = ro.moist;
+  const RunoffOut ro = runoff_step(cc, NL, dt_hours, fo.ppt, moist, fo.evap);
+  moist = ro.moist;
+  M3 st_evap = fo.evap;
   if (NL == 3) st_evap.v[2] = ro.evap_bottom; else st_evap.v[1] = ro.evap_bottom;
   // ---- full_energy.c:445-453 ----
   double wet = 0, rootm = 0, tmp_evap = 0.0;
 #pragma unroll
   for (int l = 0; l < MAXL; l++) {
     if (l < NL) {
-      if ((uc.root0_mask >> l) & 1) rootm += h.moist.v[l];
-      wet += (h.moist.v[l] - cc.Wpwp(l)) / cc.wet_den(l);
+      if ((root0_mask >> l) & 1) rootm += moist.v[l];
+      wet += (moist.v[l] - cc.Wpwp(l)) / cc.wet_den(l);
       tmp_evap += st_evap.v[l];
       if (is_veg) {
-        T_(TE_EB0 + l, st_evap.v[l] * bef.v[l] * AF);
-        T_(TE_TV0 + l, st_evap.v[l] * (1 - bef.v[l]) * AF);
+        T_(TE_EB0 + l, st_evap.v[l] * fo.bef.v[l] * AF);
+        T_(TE_TV0 + l, st_evap.v[l] * (1 - fo.bef.v[l]) * AF);
       }
       else {
         T_(TE_EB0 + l, st_evap.v[l] * AF);
         T_(TE_TV0 + l, 0.);
       }
-      T_(TE_LIQ0 + l, h.moist.v[l] * AF);
+      T_(TE_LIQ0 + l, moist.v[l] * AF);
     }
     else { T_(TE_EB0 + l, 0.); T_(TE_TV0 + l, 0.); T_(TE_LIQ0 + l, 0.); }
   }
   wet /= NL;
-  tmp_evap += st_vapor * 1000.;
+  tmp_evap += fo.vapor * 1000.;
   if (is_veg) {
-    tmp_evap += st_cvapor * 1000.;
-    tmp_evap += st_canopyevap;
+    tmp_evap += fo.cvapor * 1000.;
+    tmp_evap += fo.canopyevap;
   }
   T_(TE_EVAP, tmp_evap * AF);
   T_(TE_ASAT, ro.asat * AF);
@@ -369,15 +390,32 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
   T_(TE_WET, wet * AF);
   T_(TE_ROOTM, rootm * AF);
   if (extras & EX_ZWT) {
-    const ZwtOut z = water_table(cc, NL, h.moist);
+    const ZwtOut z = water_table(cc, NL, moist);
     T_(TE_ZWT, z.zwt * AF);                                  // put_data.c:917-918
     T_(TE_ZWTL, z.lumped * AF);
   }
 #undef T_
-#undef ACC_
-#undef AVG_
-  (void)st_throughfall; (void)N;
-  return err;
+}
+
+// the two halves one after the other (host harness of the tests).  Returns 1 when the reference would have returned ERROR
+// (arno_evap.c:112-151).
+template <int extras, bool SUB, class ForcOf, class SnowIO>
+VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
+                      int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
+                      bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride, bool write,
+                      const double *tl = nullptr, const double *ap = nullptr)
+{
+  const Forc fr = forc(NF > 1 ? NF : 0);
+  const bool general = unit_needs_snow(fr, uc.Tfactor, uc.Pfactor, NF, max_snow_temp, min_rain_temp, snowy);
+  FrontOut fo;
+  if (general)
+    fo = unit_front<extras, SUB, true>(cc, uc, tm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp, h,
+                                       snowy, tidy, sio, cv, af, tmap, col, stride, write, false, tl, ap);
+  else
+    fo = unit_front<extras, false, false>(cc, uc, tm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp,
+                                          h, snowy, tidy, sio, cv, af, tmap, col, stride, write, false, tl, ap);
+  unit_back<extras>(cc, !uc.is_bare, uc.root0_mask, NL, dt_hours, fo, h.moist, cv, af, tmap, col, stride, write);
+  return fo.err;
 }
 
 // which optional results the requested outputs need

@@ -1,15 +1,21 @@
 // vicres_capi.cu -- C ABI (include/vicres.h) and CUDA kernels of the B200-native VIC-Res cell step.
 //
-// Mapping.  The step of a block of records runs as two kernels per chunk of records:
-//   k_units  one THREAD owns one active tile x band unit (thread k = slot k: units sorted by kind and climate
-//            so that a warp runs one branch mix) and keeps its 24 state words in registers across the chunk;
-//            per record it runs vr::unit_step() and streams its area-weighted terms to the term buffer
-//            terms[rec][row][slot] in HBM (coalesced over slots).  No shared memory, no cross-thread work.
-//   k_cells  one thread per cell: adds the terms of the cell's units in reference order (put_data.c), derives
-//            the requested outputs, carries the save_data words, writes out[var][rec][cell] (coalesced).
-// HBM bandwidth is what this path has to spare (the step is FP64/latency bound), so the term round trip
-// (about 0.9 kB per cell-timestep) buys homogeneous warps and removes the serial per-cell tail from the
-// compute kernel.  Forcing is read as [field][rec][cell].
+// Mapping (DESIGN.md sections 3 and 4).  One THREAD owns one active tile x band unit; the units are in slot order
+// (sorted by kind and climate) and everything a thread touches -- constants, forcing, state, hand-off words -- is a
+// struct-of-arrays column in slot order, so every request of a warp is 32 consecutive doubles.  A record of all units
+// runs as three small kernels (the cut is the call of runoff(), surface_fluxes.c:1130):
+//   k_front       surface_fluxes' pass WITHOUT the snow model for every unit that carries no snow and gets no snowfall
+//                 in this record; the others are appended to a list (warp ballot + one atomic per warp)
+//   k_front_snow  the pass WITH the snow model (solve_snow, Brent solves, sub-steps) for the listed units only: the
+//                 snow lanes are compacted into full warps instead of idling beside snow-free lanes
+//   k_back        runoff() -- the hourly drainage loop, 45 % of the step's instructions -- and the terms after it
+// and a chunk of records ends with
+//   k_cells       one thread per (cell, record): adds the terms of the cell's units in reference order (put_data.c),
+//                 derives the requested outputs, carries the save_data words, writes out[var][rec][cell].
+// Each kernel keeps only its own live values in registers (no spill stack shared across phases), is small enough for the
+// instruction cache without block-wide lock step, and runs at the occupancy its own register count allows.  HBM
+// bandwidth is what this path has to spare (the step is FP64 / latency bound), so the hand-off between the kernels
+// (10 words per unit) and the term round trip (about 0.9 kB per cell-timestep) are cheap.
 // There is NO CPU fallback: every entry point needs a CUDA device and reports VR_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -22,18 +28,27 @@
 #include "vic_aggregate.cuh"
 #include "vic_host_prep.h"
 
-// One block per SM, as many threads as a cap of 80 registers allows: k_units is bound by instruction
-// supply and dependent-issue latency, not by the FP64 pipe.  The warps of a block move through the step
-// together (phase barriers in unit_step), so every instruction-cache fill is shared by the whole block:
-// 512 threads with barriers ran 1.8x faster than without, 800 threads at 80 registers another 6 % faster than
-// 512 at 128 (profiles/r1_tuning.md).  VR_CTA is the maximum; the launch picks the block size that fills
-// whole waves (vr_set_cells).
-#ifndef VR_CTA
-#define VR_CTA 800
+// threads per block / blocks per SM the register allocation of each step kernel must allow (tuning knobs,
+// profiles/r2_tuning.md)
+#ifndef VR_FRONT_CTA
+#define VR_FRONT_CTA 256
 #endif
-#ifndef VR_MINB
-#define VR_MINB 1      // thread blocks per SM the register allocation must allow
+#ifndef VR_FRONT_MINB
+#define VR_FRONT_MINB 2
 #endif
+#ifndef VR_SNOW_CTA
+#define VR_SNOW_CTA 128
+#endif
+#ifndef VR_SNOW_MINB
+#define VR_SNOW_MINB 4
+#endif
+#ifndef VR_BACK_CTA
+#define VR_BACK_CTA 256
+#endif
+#ifndef VR_BACK_MINB
+#define VR_BACK_MINB 3
+#endif
+#define VR_CTA 256     // the set-up kernels
 
 using namespace vr;
 
@@ -61,6 +76,10 @@ struct DevModel {
   const double *tl, *ap;            // potential-evaporation tables (valid when an OUT_PET_* is requested)
   const float *u_root;
   double *state;                    // [ST_N][U]
+  double *fo;                       // [FO_N][U] what k_front / k_front_snow hand to k_back (FrontOut)
+  int32_t *uflag;                   // [U] bit 0: the unit carries snow, bit 1: its stored snow flags need tidying
+  int32_t *snow_list;               // [U] slots of the units that run k_front_snow in the current record
+  int32_t *snow_cnt;                // [records per chunk] their number, per record of the chunk
   double *sv;                       // [SV_N][C]
   int32_t *cell_status;             // [C]
   int32_t out_vars[VR_MAX_OUT];
@@ -223,81 +242,146 @@ struct SnowIO {
   }
 };
 
-// full_energy() for F.nrec consecutive records of every unit.  One thread owns one unit (slot order) and carries the
-// unit's hot state (moisture, canopy storage, T0, T1, LongUnderOut, Tfoliage) in registers across the chunk; the snow
-// words stay in the state block and are read / written by the records that run the snow model.  Everything a thread
-// reads per record -- forcing (k_forcing_slots), constants (k_unit_consts), state -- is in slot order: 32 consecutive
-// doubles per warp and request.  terms[rec][row][unit in reference order]: the stores scatter (fire and forget) so
-// that k_cells reads each cell's units contiguously.
-template <int EXTRAS, bool SUB>
-__global__ void __launch_bounds__(VR_CTA, VR_MINB) k_units(DevModel M, DevForcing F, double *__restrict__ terms)
+// bits of M.uflag
+enum { UF_SNOWY = 1, UF_TIDY = 2 };
+
+// uflag from the state block (after vr_init_state / vr_set_state / a state file)
+__global__ void k_unit_flags(DevModel M)
 {
-  pow_tables_init();
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = k < M.U;
-  const int64_t u = active ? k : M.U - 1;     // idle threads of the last block shadow the last unit (phase barriers)
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= M.U) return;
+  const double *st = M.state + u;
+  const size_t U = (size_t)M.U;
+  const bool snowy = st[ST_SWQ * U] > 0 || st[ST_SNOW_CANOPY * U] > 0 || st[ST_COVERAGE * U] != 0;
+  const bool tidy = !snowy && ((int)st[ST_LAST_SNOW * U] != (int)MISSINGV || st[ST_MELTING * U] != 0. || st[ST_ALBEDO * U] != NEW_SNOW_ALB);
+  M.uflag[u] = (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
+}
+
+// sub-record kk of record rec of the chunk for unit u, from the slot-ordered copy of k_forcing_slots
+__device__ __forceinline__ Forc load_forcing(const DevModel &M, const DevForcing &F, int rec, int kk, int NS, int64_t u, int64_t c,
+                                             int mon, int doy)
+{
+  Forc f;
+  const double *q = F.slots + ((size_t)rec * NS + kk) * VR_NFORCING * M.U + u;
+  const size_t st = (size_t)M.U;
+  f.air_temp = __ldg(q + VR_F_AIR_TEMP * st); f.prec = __ldg(q + VR_F_PREC * st); f.wind = __ldg(q + VR_F_WIND * st);
+  f.vp = __ldg(q + VR_F_VP * st); f.vpd = __ldg(q + VR_F_VPD * st); f.pressure = __ldg(q + VR_F_PRESSURE * st);
+  f.density = __ldg(q + VR_F_DENSITY * st); f.shortwave = __ldg(q + VR_F_SHORTWAVE * st); f.longwave = __ldg(q + VR_F_LONGWAVE * st);
+  f.mon = mon; f.doy = doy;
+  f.snowflag = (M.NF > 1 && F.snowflag) ? (int)__ldg(F.snowflag + (size_t)rec * M.FC + (M.fcol ? M.fcol[c] : c)) : 0;
+  return f;
+}
+
+// surface_fluxes' passes of record `rec` of the chunk for unit u (everything before runoff()): hot state in, hot state
+// and the hand-off words out, terms to the term buffer column of the unit
+template <int EXTRAS, bool SUB, bool SNOW>
+__device__ __forceinline__ void front_unit(const DevModel &M, const DevForcing &F, int rec, int64_t u, int64_t c, int flags,
+                                           double *__restrict__ terms)
+{
   UnitC uc; CellC cc;
   double cv, af;
-  const int64_t c = M.u_cell[u];
-  const bool failed = M.cell_fail[c] != 0;
   load_unit_consts(M, u, uc, cv, af);
-#if defined(VR_CC_PER_CELL)
-  load_cell_consts(M.cc, M.C, M.u_pos[u], M.NL, cc);
-#else
   load_cell_consts(M.ccu, M.U, u, M.NL, cc);
-#endif
-  const bool write = active && !failed;
   SnowIO sio;
   sio.st = M.state + u;
   sio.U = (size_t)M.U;
-  sio.wr = write;
+  sio.wr = true;
+  double *st = M.state + u;
+  const size_t U = (size_t)M.U;
   HotS h;
-  bool snowy, tidy;
-  {
-    const double *st = M.state + u;
-    const size_t U = (size_t)M.U;
-    h.moist.v[0] = st[ST_MOIST0 * U]; h.moist.v[1] = st[ST_MOIST1 * U]; h.moist.v[2] = st[ST_MOIST2 * U];
-    h.Wdew = st[ST_WDEW * U]; h.T0 = st[ST_T0 * U]; h.T1 = st[ST_T1 * U]; h.LongUnderOut = st[ST_LONGUNDEROUT * U];
-    h.Tfoliage = st[ST_TFOLIAGE * U];
-    snowy = st[ST_SWQ * U] > 0 || st[ST_SNOW_CANOPY * U] > 0 || st[ST_COVERAGE * U] != 0;
-    tidy = !snowy && ((int)st[ST_LAST_SNOW * U] != (int)MISSINGV || st[ST_MELTING * U] != 0. || st[ST_ALBEDO * U] != NEW_SNOW_ALB);
+  h.moist.v[0] = st[ST_MOIST0 * U]; h.moist.v[1] = st[ST_MOIST1 * U]; h.moist.v[2] = st[ST_MOIST2 * U];
+  h.Wdew = st[ST_WDEW * U]; h.T0 = st[ST_T0 * U]; h.T1 = st[ST_T1 * U]; h.LongUnderOut = st[ST_LONGUNDEROUT * U];
+  h.Tfoliage = st[ST_TFOLIAGE * U];
+  bool snowy = (flags & UF_SNOWY) != 0, tidy = (flags & UF_TIDY) != 0;
+  const int mon = __ldg(F.month + rec) - 1, doy = __ldg(F.doy + rec);
+  const int NS = M.NF > 1 ? M.NF + 1 : 1;
+  const double *tm = M.tm + ((size_t)M.u_tile[u] * 12 + mon) * TM_N;
+  const double *ae = M.ae + ((size_t)M.u_aero[u] * 12 + mon) * AE_N;
+  const double *tl = (EXTRAS & EX_PET) ? M.tl + ((size_t)M.u_tile[u] * 12 + mon) * TL_N : nullptr;
+  const double *ap = (EXTRAS & EX_PET) ? M.ap + ((size_t)M.u_aero[u] * 12 + mon) * AP_N : nullptr;
+  auto forc = [&](int kk) { return load_forcing(M, F, rec, kk, NS, u, c, mon, doy); };
+  const FrontOut fo = unit_front<EXTRAS, SUB, SNOW>(cc, uc, tm, ae, forc, M.NF, M.NL, M.dt_hours, M.snow_step_hours, M.max_snow_temp,
+                                                    M.min_rain_temp, h, snowy, tidy, sio, cv, af, M.tmap,
+                                                    terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true, false,
+                                                    tl, ap);
+  st[ST_WDEW * U] = h.Wdew; st[ST_T0 * U] = h.T0; st[ST_T1 * U] = h.T1; st[ST_LONGUNDEROUT * U] = h.LongUnderOut;
+  st[ST_TFOLIAGE * U] = h.Tfoliage;
+  double *o = M.fo + u;
+  o[FO_PPT * U] = fo.ppt; o[FO_VAPOR * U] = fo.vapor; o[FO_CVAPOR * U] = fo.cvapor; o[FO_CANOPYEVAP * U] = fo.canopyevap;
+  o[FO_EVAP0 * U] = fo.evap.v[0]; o[FO_EVAP1 * U] = fo.evap.v[1]; o[FO_EVAP2 * U] = fo.evap.v[2];
+  o[FO_BEF0 * U] = fo.bef.v[0]; o[FO_BEF1 * U] = fo.bef.v[1]; o[FO_BEF2 * U] = fo.bef.v[2];
+  const int nf = (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
+  if (nf != flags) M.uflag[u] = nf;
+  if (fo.err) atomicCAS(M.cell_status + c, 0, F.rec_abs + rec + 1);     // first failing record + 1 (arno_evap.c:112-151)
+}
+
+// Record `rec` of the chunk, units without snow: one thread per unit in slot order.  A unit that needs the snow model in
+// this record is appended to M.snow_list instead (one atomic per warp; the lanes keep their order, so neighbours in the
+// list are neighbours in kind and climate) and handled by k_front_snow.
+template <int EXTRAS>
+__global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
+{
+  pow_tables_init();
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t u = k < M.U ? k : M.U - 1;
+  const int64_t c = M.u_cell[u];
+  const bool valid = k < M.U && M.cell_fail[c] == 0;
+  const int flags = M.uflag[u];
+  bool general = false;
+  if (valid) {
+    const int NS = M.NF > 1 ? M.NF + 1 : 1;
+    const Forc fr = load_forcing(M, F, rec, NS - 1, NS, u, c, 0, 0);
+    general = unit_needs_snow(fr, M.u_Tfactor[u], M.u_Pfactor[u], M.NF, M.max_snow_temp, M.min_rain_temp, (flags & UF_SNOWY) != 0);
   }
-  const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
-  const double *ae = M.ae + (size_t)M.u_aero[u] * 12 * AE_N;
-  const double *tl = (EXTRAS & EX_PET) ? M.tl + (size_t)M.u_tile[u] * 12 * TL_N : nullptr;
-  const double *ap = (EXTRAS & EX_PET) ? M.ap + (size_t)M.u_aero[u] * 12 * AP_N : nullptr;
-  const int nrec = F.nrec, NL = M.NL, NF = M.NF, NS = M.NF > 1 ? M.NF + 1 : 1;
-  const size_t rec_stride = (size_t)M.tmap.n * M.U;
-  const int64_t col = M.u_logical[u];
-  int first_err = 0;
-  for (int rec = 0; rec < nrec; rec++) {
-    const int mon = __ldg(F.month + rec) - 1, doy = __ldg(F.doy + rec);
-    // sub-record k of this record, per unit in slot order
-    auto forc = [&](int kk) {
-      Forc f;
-      const double *q = F.slots + ((size_t)rec * NS + kk) * VR_NFORCING * M.U + u;
-      const size_t st = (size_t)M.U;
-      f.air_temp = __ldg(q + VR_F_AIR_TEMP * st); f.prec = __ldg(q + VR_F_PREC * st); f.wind = __ldg(q + VR_F_WIND * st);
-      f.vp = __ldg(q + VR_F_VP * st); f.vpd = __ldg(q + VR_F_VPD * st); f.pressure = __ldg(q + VR_F_PRESSURE * st);
-      f.density = __ldg(q + VR_F_DENSITY * st); f.shortwave = __ldg(q + VR_F_SHORTWAVE * st); f.longwave = __ldg(q + VR_F_LONGWAVE * st);
-      f.mon = mon; f.doy = doy;
-      f.snowflag = (NF > 1 && F.snowflag) ? (int)__ldg(F.snowflag + (size_t)rec * M.FC + (M.fcol ? M.fcol[c] : c)) : 0;
-      return f;
-    };
-    const int e = unit_record<EXTRAS, SUB>(cc, uc, tm + mon * TM_N, ae + mon * AE_N, forc, NF, NL, M.dt_hours, M.snow_step_hours,
-                                      M.max_snow_temp, M.min_rain_temp, h, snowy, tidy, sio, cv, af, M.tmap,
-                                      terms + rec * rec_stride + col, (int)M.U, write,
-                                      (EXTRAS & EX_PET) ? tl + mon * TL_N : nullptr, (EXTRAS & EX_PET) ? ap + mon * AP_N : nullptr);
-    if (e && !first_err) first_err = F.rec_abs + rec + 1;
+  const unsigned ballot = __ballot_sync(0xffffffffu, general);
+  if (ballot) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(M.snow_cnt + rec, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (general) M.snow_list[base + __popc(ballot & ((1u << lane) - 1u))] = (int32_t)u;
   }
-  if (write) {
-    double *st = M.state + u;
-    const size_t U = (size_t)M.U;
-    st[ST_MOIST0 * U] = h.moist.v[0]; st[ST_MOIST1 * U] = h.moist.v[1]; st[ST_MOIST2 * U] = h.moist.v[2];
-    st[ST_WDEW * U] = h.Wdew; st[ST_T0 * U] = h.T0; st[ST_T1 * U] = h.T1; st[ST_LONGUNDEROUT * U] = h.LongUnderOut;
-    st[ST_TFOLIAGE * U] = h.Tfoliage;
-    if (first_err) atomicCAS(M.cell_status + c, 0, first_err);     // first failing record + 1 (arno_evap.c:112-151)
+  if (!valid || general) return;
+  front_unit<EXTRAS, false, false>(M, F, rec, u, c, flags, terms);
+}
+
+// Record `rec` of the chunk, the listed units: solve_snow() and the rest of the pass, sub-stepped when SNOW_STEP <
+// TIME_STEP (SUB).  Grid-stride over the list (its length is only known on the device).
+template <int EXTRAS, bool SUB>
+__global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_front_snow(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
+{
+  pow_tables_init();
+  const int n = M.snow_cnt[rec];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = M.snow_list[i];
+    front_unit<EXTRAS, SUB, true>(M, F, rec, u, M.u_cell[u], M.uflag[u], terms);
   }
+}
+
+// Record `rec` of the chunk: runoff() and what follows it, one thread per unit in slot order.
+template <int EXTRAS>
+__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, int rec, double *__restrict__ terms)
+{
+  pow_tables_init();
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= M.U) return;
+  if (M.cell_fail[M.u_cell[u]] != 0) return;
+  const size_t U = (size_t)M.U;
+  CellC cc;
+  load_cell_consts(M.ccu, M.U, u, M.NL, cc);
+  const double *o = M.fo + u;
+  FrontOut fo;
+  fo.ppt = o[FO_PPT * U]; fo.vapor = o[FO_VAPOR * U]; fo.cvapor = o[FO_CVAPOR * U]; fo.canopyevap = o[FO_CANOPYEVAP * U];
+  fo.evap.v[0] = o[FO_EVAP0 * U]; fo.evap.v[1] = o[FO_EVAP1 * U]; fo.evap.v[2] = o[FO_EVAP2 * U];
+  fo.bef.v[0] = o[FO_BEF0 * U]; fo.bef.v[1] = o[FO_BEF1 * U]; fo.bef.v[2] = o[FO_BEF2 * U];
+  fo.err = 0;
+  double *st = M.state + u;
+  M3 moist;
+  moist.v[0] = st[ST_MOIST0 * U]; moist.v[1] = st[ST_MOIST1 * U]; moist.v[2] = st[ST_MOIST2 * U];
+  const int fl = M.u_flags[u];
+  unit_back<EXTRAS>(cc, (fl & 1) == 0, fl >> 8, M.NL, M.dt_hours, fo, moist, M.u_cv[u], M.u_af[u], M.tmap,
+                    terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true);
+  st[ST_MOIST0 * U] = moist.v[0]; st[ST_MOIST1 * U] = moist.v[1]; st[ST_MOIST2 * U] = moist.v[2];
 }
 
 // put_data() for the same records: one thread per (cell in sorted order, record).  A cell's units are
@@ -434,10 +518,14 @@ struct vr_handle {
   size_t evs_used = 0;
   static constexpr int NBUF = 4;     // copy buffers per direction of the host pipeline
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[NBUF] = {}, ev_comp[NBUF] = {}, ev_out[NBUF] = {};
-  int extras = 0;                    // EX_PET | EX_ZWT when such outputs are requested: selects the k_units instance
-  int cta = VR_CTA;                  // threads per k_units block, chosen per grid so that the blocks fill whole waves
+  int extras = 0;                    // EX_PET | EX_ZWT when such outputs are requested: selects the kernel instances
+  int cta = VR_CTA;                  // threads per block of the set-up kernels
   int64_t ncta = 0;
-  int chunk = 16;                    // records per k_units/k_cells launch pair (and per pipelined copy of vr_step_block)
+  int sms = 148;
+  bool flags_dirty = true;           // M.uflag must be rebuilt from the state block before the next step
+  DBuf<double> d_fo;
+  DBuf<int32_t> d_uflag, d_snow_list, d_snow_cnt;
+  int chunk = 16;                    // records per launch of k_cells (and per pipelined copy of vr_step_block)
   int64_t launches = 0;
   bool timed = false;
 };
@@ -452,6 +540,20 @@ static std::string g_create_error;
       return VR_ERR_CUDA;                                                                            \
     }                                                                                                \
   } while (0)
+
+template <int EX>
+static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *terms, cudaStream_t st)
+{
+  const int64_t U = h->M.U;
+  const unsigned gf = (unsigned)((U + VR_FRONT_CTA - 1) / VR_FRONT_CTA), gb = (unsigned)((U + VR_BACK_CTA - 1) / VR_BACK_CTA);
+  int64_t gs = (U + VR_SNOW_CTA - 1) / VR_SNOW_CTA;
+  const int64_t gs_max = (int64_t)h->sms * VR_SNOW_MINB * 4;     // grid-stride: a few waves at most
+  if (gs > gs_max) gs = gs_max;
+  k_front<EX><<<gf, VR_FRONT_CTA, 0, st>>>(h->M, F, rec, terms);
+  if (h->M.NF > 1) k_front_snow<EX, true><<<(unsigned)gs, VR_SNOW_CTA, 0, st>>>(h->M, F, rec, terms);
+  else k_front_snow<EX, false><<<(unsigned)gs, VR_SNOW_CTA, 0, st>>>(h->M, F, rec, terms);
+  k_back<EX & EX_ZWT><<<gb, VR_BACK_CTA, 0, st>>>(h->M, rec, terms);
+}
 
 extern "C" {
 
@@ -526,14 +628,6 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     delete h;
     return VR_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_units<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of L1 for the stacks
-  cudaFuncSetAttribute(k_units<EX_PET, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_ZWT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_PET | EX_ZWT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_PET, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_ZWT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  cudaFuncSetAttribute(k_units<EX_PET | EX_ZWT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   *out = h;
   return VR_OK;
@@ -551,6 +645,7 @@ void vr_destroy(vr_handle *h)
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
   h->d_order.release(); h->d_u_slot.release(); h->d_u_pos.release();
+  h->d_fo.release(); h->d_uflag.release(); h->d_snow_list.release(); h->d_snow_cnt.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto &t : h->evs) { cudaEventDestroy(t.u0); cudaEventDestroy(t.u1); cudaEventDestroy(t.c0); cudaEventDestroy(t.c1); }
@@ -630,19 +725,9 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
     k.dp.assign(cells->dp, cells->dp + C);
     k.avg_temp.assign(cells->avg_temp, cells->avg_temp + C);
   }
-  {   // one resident block per SM: w waves of blocks as equal as the warp granularity allows (a grid of
-      // 3.1 waves of full-size blocks would pay for 4)
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int64_t per_wave = (int64_t)sms * VR_CTA;
-    const int64_t w = U > 0 ? (U + per_wave - 1) / per_wave : 1;
-    int64_t t = U > 0 ? (U + sms * w - 1) / (sms * w) : 32;
-    t = ((t + 31) / 32) * 32;
-    if (t > VR_CTA) t = VR_CTA;
-    if (t < 32) t = 32;
-    h->cta = (int)t;
-    h->ncta = U > 0 ? (U + t - 1) / t : 0;
-  }
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device);
+  h->cta = VR_CTA;
+  h->ncta = U > 0 ? (U + VR_CTA - 1) / VR_CTA : 0;
   std::vector<double> im((size_t)P.NL * C);
   for (size_t i = 0; i < im.size(); i++) im[i] = cells->init_moist[i];
   CK(h->d_cc.upload(P.cc)); CK(h->d_cell_uptr.upload(P.cell_uptr));
@@ -676,6 +761,11 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.ccn = P.ccn;
   CK(h->d_ccu.reserve((size_t)P.ccn * (U ? U : 1)));
   M.ccu = h->d_ccu.p;
+  CK(h->d_fo.reserve((size_t)FO_N * (U ? U : 1)));
+  CK(h->d_uflag.reserve(U ? U : 1));
+  CK(h->d_snow_list.reserve(U ? U : 1));
+  M.fo = h->d_fo.p; M.uflag = h->d_uflag.p; M.snow_list = h->d_snow_list.p;
+  h->flags_dirty = true;
   if (U > 0) {
     k_unit_consts<<<(unsigned)((U + 255) / 256), 256, 0, h->stream>>>(M, h->d_ccu.p);
     CK(cudaGetLastError());
@@ -730,14 +820,15 @@ int vr_init_state(vr_handle *h, const double *tair0)
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->s_cells));
   h->initialised = true;
+  h->flags_dirty = true;
   h->rec_done = 0;
   return VR_OK;
 }
 
-// One block of records = chunks of h->chunk records, each a k_units + k_cells pair.  k_units runs on the
-// step stream st, k_cells on h->s_cells: the aggregation of chunk k overlaps the step of chunk k+1 (two term
-// buffers).  With join the step stream waits for the last aggregation, so the caller sees ordinary stream
-// semantics; the host pipeline of vr_step_block orders its copies on the events instead.
+// One block of records = chunks of h->chunk records.  Per record of a chunk the step stream st runs k_front,
+// k_front_snow and k_back for all units; the chunk ends with k_cells on h->s_cells, so that the aggregation of chunk k
+// overlaps the step of chunk k+1 (two term buffers).  With join the step stream waits for the last aggregation, so
+// the caller sees ordinary stream semantics; the host pipeline of vr_step_block orders its copies on the events instead.
 static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cudaStream_t st, bool join)
 {
   const size_t U1 = (size_t)(h->M.U ? h->M.U : 1);
@@ -747,9 +838,16 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
   CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * CH));
   const int NS = h->M.NF > 1 ? h->M.NF + 1 : 1;          // forcing sub-records per record (sub-steps + the record itself)
   CK(h->d_fslots.reserve((size_t)CH * NS * VR_NFORCING * U1));
+  CK(h->d_snow_cnt.reserve(CH));
+  h->M.snow_cnt = h->d_snow_cnt.p;
   cudaEventRecord(h->ev0, st);
   cudaEventRecord(h->ev_fork, st);                       // what the caller queued on st (forcing, free output buffer)
   cudaStreamWaitEvent(h->s_cells, h->ev_fork, 0);
+  if (h->flags_dirty && h->M.U > 0) {
+    k_unit_flags<<<(unsigned)((h->M.U + 255) / 256), 256, 0, st>>>(h->M);
+    h->launches += 1;
+    h->flags_dirty = false;
+  }
   int b = 0;
   for (int r0 = 0; r0 < F0.nrec; r0 += CH) {
     DevForcing F = F0;
@@ -772,26 +870,21 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
       t = &h->evs[h->evs_used++];
       t->nrec = F.nrec;
     }
-    if (h->pair_seq >= 2) cudaStreamWaitEvent(st, h->ev_cells[b], 0);     // pair i-2 has been aggregated out of terms[b]
+    if (h->pair_seq >= 2) cudaStreamWaitEvent(st, h->ev_cells[b], 0);     // chunk i-2 has been aggregated out of terms[b]
     if (t) cudaEventRecord(t->u0, st);
     if (h->M.U > 0) {
+      cudaMemsetAsync(h->d_snow_cnt.p, 0, (size_t)CH * sizeof(int32_t), st);
       k_forcing_slots<<<dim3((unsigned)((h->M.U + 255) / 256), (unsigned)(F.nrec * NS)), 256, 0, st>>>(h->M, F, h->d_fslots.p);
       F.slots = h->d_fslots.p;
       h->launches += 1;
-    }
-    if (h->M.U > 0) {
-      // one kernel instance per set of optional results; a sub-stepped snow model (NF > 1) has two
-      if (h->M.NF > 1) switch (h->extras) {
-        case 0: k_units<0, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        case EX_PET: k_units<EX_PET, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        case EX_ZWT: k_units<EX_ZWT, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        default: k_units<EX_PET | EX_ZWT, true><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-      }
-      else switch (h->extras) {
-        case 0: k_units<0, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        case EX_PET: k_units<EX_PET, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        case EX_ZWT: k_units<EX_ZWT, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
-        default: k_units<EX_PET | EX_ZWT, false><<<(unsigned)h->ncta, h->cta, 0, st>>>(h->M, F, terms); break;
+      for (int rec = 0; rec < F.nrec; rec++) {
+        switch (h->extras) {      // one set of kernel instances per set of optional results
+          case 0: launch_record<0>(h, F, rec, terms, st); break;
+          case EX_PET: launch_record<EX_PET>(h, F, rec, terms, st); break;
+          case EX_ZWT: launch_record<EX_ZWT>(h, F, rec, terms, st); break;
+          default: launch_record<EX_PET | EX_ZWT>(h, F, rec, terms, st); break;
+        }
+        h->launches += 3;
       }
     }
     if (t) cudaEventRecord(t->u1, st);
@@ -803,7 +896,7 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     if (t) cudaEventRecord(t->c1, h->s_cells);
     cudaEventRecord(h->ev_cells[b], h->s_cells);
     h->pair_seq++;
-    h->launches += 2;
+    h->launches += 1;
   }
   if (join) cudaStreamWaitEvent(st, h->ev_cells[b], 0);
   cudaEventRecord(h->ev1, st);
@@ -945,6 +1038,7 @@ int vr_set_state(vr_handle *h, const void *blob)
   CK(cudaMemcpy(h->d_state.p, b, ns, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_sv.p + (size_t)h->svb * SV_N * h->M.C, b + ns, nv, cudaMemcpyHostToDevice));
   h->initialised = true;
+  h->flags_dirty = true;
   return VR_OK;
 }
 
@@ -1173,6 +1267,7 @@ int vr_read_state_file(vr_handle *h, const char *path, int32_t binary, const dou
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   h->initialised = true;
+  h->flags_dirty = true;
   return VR_OK;
 }
 
