@@ -276,6 +276,7 @@ def run_ours(args):
         sampler.start()
     l0 = m.num_launches
     m.kernel_times()                     # reset the library's per-launch event sums
+    m.step_diag()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     torch.cuda.synchronize(dev)
     ev[0].record(stream)
@@ -288,7 +289,8 @@ def run_ours(args):
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
     total_ms = ev[0].elapsed_time(ev[K])
     launches = m.num_launches - l0
-    units_ms, cells_ms, pairs, krecs = m.kernel_times()      # every k_units / k_cells launch of the timed region
+    units_ms, cells_ms, pairs, krecs = m.kernel_times()      # every chunk of step kernels / k_cells launch of the timed region
+    diag = m.step_diag()
     kernel_ms = units_ms / max(pairs, 1)                     # mean k_units launch
     recs_per_launch = krecs / max(pairs, 1)
     finite = bool(torch.isfinite(out_dev).all().item())
@@ -372,6 +374,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_cell_step": B_ALG,
                          "note": "the step is FP64 / dependent-issue bound, not HBM-bound (SURVEY.md 8d): see the "
                                  "fp64 object and DESIGN.md section 6"},
+            "step_kernels": {"snow_unit_record_share": diag["snow_unit_records"] / max(diag["unit_records"], 1),
+                             "us_per_record": None if not diag["records_timed"] else
+                             {k: 1e3 * diag[k + "_ms"] / diag["records_timed"] for k in ("front", "snow", "back")}},
             "fp64": None if not (fp64_per and dfma_peak) else {
                 "fp64_thread_inst_per_cell_step": fp64_per,
                 "achieved_inst_per_s": fp64_per * C * recs_per_launch / (kernel_ms * 1e-3),

@@ -31,6 +31,24 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    # several captured launches: keep the file sections whose "Function Name" contains --kernel (default: the first one)
+    want = sys.argv[sys.argv.index("--kernel") + 1] if "--kernel" in sys.argv else None
+    keep, func, cur_file, chosen = [], None, None, None
+    for r in rows:
+        if len(r) == 2 and r[0] == "File Path":
+            cur_file = r
+            continue
+        if len(r) == 2 and r[0] == "Function Name":
+            func = r[1]
+            if chosen is None and (want is None or (want + "<") in func or (want + "(") in func):
+                chosen = func
+            if func == chosen:
+                keep.append(cur_file)
+            continue
+        if func == chosen and chosen is not None:
+            keep.append(r)
+    print("kernel: %s" % chosen)
+    rows = keep
     fname, hdr = None, None
     lines = {}          # (file, line) -> dict
     seen_addr = set()

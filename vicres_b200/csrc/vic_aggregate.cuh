@@ -206,7 +206,7 @@ VR_HD bool unit_needs_snow(const Forc &fr, double Tfactor, double Pfactor, int N
 // GENERAL: the instance with the snow model (surface_pass<.., true>); the caller decides with unit_needs_snow() -- per
 // unit in the split kernels (the units that need it are compacted into their own launch), per warp in a fused loop.
 template <int extras, bool SUB, bool GENERAL, class ForcOf, class SnowIO>
-VR_HD FrontOut unit_front(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
+VR_HD FrontOut unit_front(CellC cc, const UnitC &uc, CanopyM cm, const double *ae, ForcOf forc, int NF, int NL,
                           int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
                           bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride,
                           bool write, bool sync_ok, const double *tl = nullptr, const double *ap = nullptr)
@@ -217,12 +217,7 @@ VR_HD FrontOut unit_front(CellC cc, const UnitC &uc, const double *tm, const dou
   vp.rarc = uc.rarc; vp.rmin = uc.rmin; vp.RGL = uc.RGL;
 #pragma unroll
   for (int l = 0; l < MAXL; l++) vp.root[l] = uc.root[l];
-  CanopyM cm;
-  cm.vegcover = 0; cm.LAI = 0; cm.Wdmax = 0; cm.albedo = BARE_SOIL_ALBEDO; cm.surf_atten = 1.;
-  if (is_veg) {
-    cm.vegcover = tm[TM_VEGCOVER]; cm.LAI = tm[TM_LAI]; cm.Wdmax = tm[TM_WDMAX]; cm.albedo = tm[TM_ALBEDO];
-    cm.surf_atten = tm[TM_SURF_ATTEN];
-  }
+  if (!is_veg) { cm.vegcover = 0; cm.LAI = 0; cm.Wdmax = 0; cm.albedo = BARE_SOIL_ALBEDO; cm.surf_atten = 1.; }
   const Forc fr = forc(NF > 1 ? NF : 0);
   SnowS sn = snow_none();
   if (general) sn = sio.load();
@@ -407,12 +402,15 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
 {
   const Forc fr = forc(NF > 1 ? NF : 0);
   const bool general = unit_needs_snow(fr, uc.Tfactor, uc.Pfactor, NF, max_snow_temp, min_rain_temp, snowy);
+  CanopyM cm;      // the month's canopy terms of the tile (full_energy.c:210-227,306-316)
+  cm.vegcover = tm[TM_VEGCOVER]; cm.LAI = tm[TM_LAI]; cm.Wdmax = tm[TM_WDMAX]; cm.albedo = tm[TM_ALBEDO];
+  cm.surf_atten = tm[TM_SURF_ATTEN];
   FrontOut fo;
   if (general)
-    fo = unit_front<extras, SUB, true>(cc, uc, tm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp, h,
+    fo = unit_front<extras, SUB, true>(cc, uc, cm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp, h,
                                        snowy, tidy, sio, cv, af, tmap, col, stride, write, false, tl, ap);
   else
-    fo = unit_front<extras, false, false>(cc, uc, tm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp,
+    fo = unit_front<extras, false, false>(cc, uc, cm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp,
                                           h, snowy, tidy, sio, cv, af, tmap, col, stride, write, false, tl, ap);
   unit_back<extras>(cc, !uc.is_bare, uc.root0_mask, NL, dt_hours, fo, h.moist, cv, af, tmap, col, stride, write);
   return fo.err;

@@ -186,19 +186,19 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
     }
     for (int l = 0; l < NL; l++) {
       const size_t k = (size_t)l * C + c;
-      const int base = CC_LAYER0 + l * CL_N;
+      const int fb = CC_FL0 + l * CLF_N, bb = CC_BL0 + l * CLB_N;
       const double depth = cells.depth[k], resid = cells.resid_moist[k] * depth * 1000.;
-      CC(base + CL_EXPT, c) = cells.expt[k];
-      CC(base + CL_KSAT24, c) = cells.Ksat[k] / 24.;
-      CC(base + CL_MAX_MOIST, c) = cells.max_moist[k];
-      CC(base + CL_RESID, c) = resid;
-      CC(base + CL_QDEN, c) = cells.max_moist[k] - resid;
-      CC(base + CL_INV_QDEN, c) = 1.0 / (cells.max_moist[k] - resid);
-      CC(base + CL_WCR, c) = cells.Wcr[k];
-      CC(base + CL_WPWP, c) = cells.Wpwp[k];
-      CC(base + CL_WCR_M_WPWP, c) = (cells.Wcr[k] - cells.Wpwp[k]);
-      CC(base + CL_WET_DEN, c) = (cells.porosity[k] * depth * 1000 - cells.Wpwp[k]);
-      CC(base + CL_DEPTH, c) = depth;
+      CC(bb + CLB_EXPT, c) = cells.expt[k];
+      CC(bb + CLB_KSAT24, c) = cells.Ksat[k] / 24.;
+      CC(bb + CLB_MAX_MOIST, c) = cells.max_moist[k];
+      CC(fb + CLF_RESID, c) = resid;
+      CC(bb + CLB_QDEN, c) = cells.max_moist[k] - resid;
+      CC(bb + CLB_INV_QDEN, c) = 1.0 / (cells.max_moist[k] - resid);
+      CC(fb + CLF_WCR, c) = cells.Wcr[k];
+      CC(fb + CLF_WPWP, c) = cells.Wpwp[k];
+      CC(fb + CLF_WCR_M_WPWP, c) = (cells.Wcr[k] - cells.Wpwp[k]);
+      CC(bb + CLB_WET_DEN, c) = (cells.porosity[k] * depth * 1000 - cells.Wpwp[k]);
+      CC(fb + CLF_DEPTH, c) = depth;
       {   // soil_conduction.c:5-49 constants (ice-free: Wu == moist)
         const double organic = cells.organic[k], quartz = cells.quartz[k];
         const double Kdry_min = (0.135 * cells.bulk_dens_min[k] + 64.7) / (cells.soil_dens_min[k] - 0.947 * cells.bulk_dens_min[k]);
@@ -212,11 +212,11 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
         const double soilfr = cells.bulk_density[k] / cells.soil_density[k];
         double cs = 2.0e6 * soilfr * (1 - organic);
         cs += 2.7e6 * soilfr * organic;
-        CC(base + CL_KDRY, c) = Kdry;
-        CC(base + CL_KSAT_M_KDRY, c) = (Ksat - Kdry);
-        CC(base + CL_POROS, c) = porosity;
-        CC(base + CL_SOILFR, c) = soilfr;
-        CC(base + CL_CS_SOLID, c) = cs;
+        CC(fb + CLF_KDRY, c) = Kdry;
+        CC(fb + CLF_KSAT_M_KDRY, c) = (Ksat - Kdry);
+        CC(fb + CLF_POROS, c) = porosity;
+        CC(fb + CLF_SOILFR, c) = soilfr;
+        CC(fb + CLF_CS_SOLID, c) = cs;
       }
     }
     if (want_zwt)

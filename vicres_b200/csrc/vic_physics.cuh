@@ -102,6 +102,7 @@ VR_HD double pow_table_eval(double x, double y, const double *logtab, const doub
   const double pl = fma(u, r2 * r2, q);
   const double l2m = fma(r, pl, logtab[2 * i + 1]);                     // log2(m) relative to the entry's binade
   const double t = fma(y, l2m, y * (double)e);                         // y * log2(x)
+  if (t < -1100.0) { *handled = true; return 0.; }                     // x^y underflows to +0 (ARNO curves with 1/b up to 1000)
   if (!(fabs(t) < 1000.0)) return 0.;
   const double kd0 = fma(t, 64.0, 6755399441055744.0);                 // 1.5 * 2^52: the integer lands in the low word
 #if defined(__CUDA_ARCH__)
@@ -173,6 +174,45 @@ VR_HD double m_pow_inl(double x, double y)
   return m_pow(x, y);
 #endif
 }
+#if defined(__CUDACC__)
+// polynomial coefficients in constant memory: the FP64 pipe takes them as c[bank][offset] operands, so they cost neither
+// registers nor the two moves per coefficient that an immediate needs (10 % of the drainage kernel's instructions were UMOV)
+__constant__ double VR_POW_LC[7] = VR_POW_L_INIT;
+__constant__ double VR_POW_EC[5] = VR_POW_E_INIT;
+// x^y for the hourly Brooks-Corey drainage (runoff.c:336): x = relative saturation, 0 <= x <= ~1 and finite, y = the
+// layer's exponent, y >= 1 (the caller checks).  Same arithmetic as pow_table_eval() -- identical results wherever that
+// one handles the argument -- without its range checks and special cases: x == 1 gives exactly 1 through the table
+// (r == 0, t == 0), x == 0 or subnormal has the biased exponent 0, hence t <= -1022 y, and everything with t <= -1021
+// returns 0 (x^y < 2^-1021: the result pow() gives there is below 2.3e-308).  No branch.  tb = shared-memory address of
+// vr_pow_tables.
+__device__ __forceinline__ double drain_pow(double x, double y, uint32_t tb)
+{
+  const int hi = __double2hiint(x);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const int i = ((hi & 0x000fffff) + 0x1000) >> 13;                    // 0..128
+  const int e = (hi >> 20) - 1023 + (i >= VR_POW_SPLIT ? 1 : 0);
+  double inv_c, l2c;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(inv_c), "=d"(l2c) : "r"(tb + 16u * (uint32_t)i));
+  const double r = fma(m, inv_c, -1.0);
+  const double r2 = r * r;
+  const double p01 = fma(VR_POW_LC[1], r, VR_POW_LC[0]), p23 = fma(VR_POW_LC[3], r, VR_POW_LC[2]), p45 = fma(VR_POW_LC[5], r, VR_POW_LC[4]);
+  const double q = fma(p23, r2, p01), u = fma(VR_POW_LC[6], r2, p45);
+  const double pl = fma(u, r2 * r2, q);
+  const double l2m = fma(r, pl, l2c);
+  const double t = fma(y, l2m, y * (double)e);                         // y * log2(x)
+  const double kd0 = fma(t, 64.0, 6755399441055744.0);
+  const int k = __double2loint(kd0);
+  const double kd = kd0 - 6755399441055744.0;
+  const double g = fma(kd, -0.015625, t);
+  double pe = fma(VR_POW_EC[4], g, VR_POW_EC[3]);
+  pe = fma(pe, g, VR_POW_EC[2]); pe = fma(pe, g, VR_POW_EC[1]); pe = fma(pe, g, VR_POW_EC[0]);
+  double T;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tb + (uint32_t)(2 * 129 * 8) + 8u * (uint32_t)(k & 63)));
+  const double res = fma(T * g, pe, T);
+  const double out = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+  return (t > -1021.0) ? out : 0.0;
+}
+#endif
 VR_HDN double m_exp(double x) { return exp(x); }
 VR_HDN double m_log(double x) { return log(x); }
 VR_HDN double m_log10(double x) { return log10(x); }
@@ -211,30 +251,36 @@ constexpr double MIN_SWQ_EB_THRES = 0.0010;
 constexpr double NEW_SNOW_ALB = 0.85;
 constexpr double SNOW_ALB_ACCUM_A = 0.94, SNOW_ALB_ACCUM_B = 0.58, SNOW_ALB_THAW_A = 0.82, SNOW_ALB_THAW_B = 0.46;
 constexpr double TraceSnow = 0.03;
-constexpr int MAXL = 3;
 
-// ---- per-cell constants, precomputed on the host (vicres_capi.cu: build_cell_consts) ----
-enum {  // index into the per-cell constant block  cc[k*C + c]
-  CC_LAT = 0, CC_ELEV, CC_HALF_ELEV_LAPSE, CC_B, CC_INV_B, CC_INV_B1, CC_ONE_PLUS_B, CC_EX, CC_TOP_MAX,
-  CC_TOP_MAX_INFIL, CC_ARNO_MAXM, CC_ARNO_MAX_INFIL, CC_DSMAX24, CC_BF_FRAC, CC_BF_NL, CC_WS, CC_ONE_M_WS,
-  CC_C, CC_AVG_T, CC_DP, CC_D1, CC_EXP_M, CC_EXP_P, CC_KB_BARE, CC_INV_ONE_M_WS,
-  CC_LAYER0,   // then per layer l: CC_LAYER0 + l*CL_N + field
-  CL_EXPT = 0, CL_KSAT24, CL_MAX_MOIST, CL_RESID, CL_QDEN, CL_WCR, CL_WPWP, CL_WCR_M_WPWP, CL_WET_DEN,
-  CL_DEPTH, CL_INV_QDEN, CL_KDRY, CL_KSAT_M_KDRY, CL_POROS, CL_SOILFR, CL_CS_SOLID, CL_N
+// ---- per-cell constants, precomputed on the host (vic_host_prep.h) ----
+// Rows of the constant block cc[k*C + c].  The rows the kernels before runoff() read (k_front, k_front_snow) come first:
+// those kernels stage exactly that prefix into shared memory (bulk copies), k_back reads its rows from global memory.
+// Per-layer fields are laid out for MAXL layers whatever NLAYER is.
+constexpr int MAXL = 3;
+enum {
+  // -- front block --
+  CC_LAT = 0, CC_ELEV, CC_HALF_ELEV_LAPSE, CC_B, CC_INV_B, CC_INV_B1, CC_ARNO_MAXM, CC_ARNO_MAX_INFIL, CC_AVG_T, CC_DP,
+  CC_D1, CC_EXP_M, CC_EXP_P, CC_KB_BARE,
+  CC_FL0,      // then per layer l: CC_FL0 + l*CLF_N + field
+  CLF_WCR = 0, CLF_WPWP, CLF_WCR_M_WPWP, CLF_RESID, CLF_DEPTH, CLF_KDRY, CLF_KSAT_M_KDRY, CLF_POROS, CLF_SOILFR,
+  CLF_CS_SOLID, CLF_N,
+  CC_FRONT_N = CC_FL0 + MAXL * CLF_N,
+  // -- back block --
+  CC_ONE_PLUS_B = CC_FRONT_N, CC_EX, CC_TOP_MAX, CC_TOP_MAX_INFIL, CC_DSMAX24, CC_BF_FRAC, CC_BF_NL, CC_WS, CC_ONE_M_WS,
+  CC_C, CC_INV_ONE_M_WS,
+  CC_BL0,      // then per layer l: CC_BL0 + l*CLB_N + field
+  CLB_EXPT = 0, CLB_KSAT24, CLB_MAX_MOIST, CLB_QDEN, CLB_INV_QDEN, CLB_WET_DEN, CLB_N,
+  CC_N = CC_BL0 + MAXL * CLB_N
 };
-#define VR_CC_N(nlayer) (::vr::CC_LAYER0 + (nlayer) * ::vr::CL_N)
+#define VR_CC_N(nlayer) (::vr::CC_N)
 // optional tail of the block: the zwtvmoist curves, (nlayer+2) curves x ZWT_NP points, zwt then moist
 constexpr int ZWT_NP = 11;      // MAX_ZWTVMOIST
 #define VR_CC_ZWT_N(nlayer) (2 * ((nlayer) + 2) * ::vr::ZWT_NP)
 
-struct CellC {   // read-only view of one cell's constants in the block cc[k*C + pos] (pos = sorted position)
-  const double *p;   // &cc[pos]
+struct CellC {   // read-only view of one cell's constants: row k at p[k*C] (global block, or the shared-memory stage)
+  const double *p;
   int64_t C;
-#if defined(__CUDA_ARCH__)
-  VR_HD double g(int k) const { return __ldg(p + (size_t)k * C); }
-#else
   VR_HD double g(int k) const { return p[(size_t)k * C]; }
-#endif
   VR_HD double lat() const { return g(CC_LAT); }
   VR_HD double elev() const { return g(CC_ELEV); }
   VR_HD double half_elev_lapse() const { return g(CC_HALF_ELEV_LAPSE); }
@@ -260,22 +306,22 @@ struct CellC {   // read-only view of one cell's constants in the block cc[k*C +
   VR_HD double exp_p() const { return g(CC_EXP_P); }
   VR_HD double kb_bare() const { return g(CC_KB_BARE); }
   VR_HD double inv_one_m_Ws() const { return g(CC_INV_ONE_M_WS); }
-  VR_HD double expt(int l) const { return g(CC_LAYER0 + l * CL_N + CL_EXPT); }
-  VR_HD double ksat24(int l) const { return g(CC_LAYER0 + l * CL_N + CL_KSAT24); }
-  VR_HD double max_moist(int l) const { return g(CC_LAYER0 + l * CL_N + CL_MAX_MOIST); }
-  VR_HD double resid(int l) const { return g(CC_LAYER0 + l * CL_N + CL_RESID); }
-  VR_HD double qden(int l) const { return g(CC_LAYER0 + l * CL_N + CL_QDEN); }
-  VR_HD double Wcr(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WCR); }
-  VR_HD double Wpwp(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WPWP); }
-  VR_HD double wcr_m_wpwp(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WCR_M_WPWP); }
-  VR_HD double wet_den(int l) const { return g(CC_LAYER0 + l * CL_N + CL_WET_DEN); }
-  VR_HD double depth(int l) const { return g(CC_LAYER0 + l * CL_N + CL_DEPTH); }
-  VR_HD double inv_qden(int l) const { return g(CC_LAYER0 + l * CL_N + CL_INV_QDEN); }
-  VR_HD double kdry(int l) const { return g(CC_LAYER0 + l * CL_N + CL_KDRY); }
-  VR_HD double ksat_m_kdry(int l) const { return g(CC_LAYER0 + l * CL_N + CL_KSAT_M_KDRY); }
-  VR_HD double poros(int l) const { return g(CC_LAYER0 + l * CL_N + CL_POROS); }
-  VR_HD double soilfr(int l) const { return g(CC_LAYER0 + l * CL_N + CL_SOILFR); }
-  VR_HD double cs_solid(int l) const { return g(CC_LAYER0 + l * CL_N + CL_CS_SOLID); }
+  VR_HD double expt(int l) const { return g(CC_BL0 + l * CLB_N + CLB_EXPT); }
+  VR_HD double ksat24(int l) const { return g(CC_BL0 + l * CLB_N + CLB_KSAT24); }
+  VR_HD double max_moist(int l) const { return g(CC_BL0 + l * CLB_N + CLB_MAX_MOIST); }
+  VR_HD double qden(int l) const { return g(CC_BL0 + l * CLB_N + CLB_QDEN); }
+  VR_HD double inv_qden(int l) const { return g(CC_BL0 + l * CLB_N + CLB_INV_QDEN); }
+  VR_HD double wet_den(int l) const { return g(CC_BL0 + l * CLB_N + CLB_WET_DEN); }
+  VR_HD double resid(int l) const { return g(CC_FL0 + l * CLF_N + CLF_RESID); }
+  VR_HD double Wcr(int l) const { return g(CC_FL0 + l * CLF_N + CLF_WCR); }
+  VR_HD double Wpwp(int l) const { return g(CC_FL0 + l * CLF_N + CLF_WPWP); }
+  VR_HD double wcr_m_wpwp(int l) const { return g(CC_FL0 + l * CLF_N + CLF_WCR_M_WPWP); }
+  VR_HD double depth(int l) const { return g(CC_FL0 + l * CLF_N + CLF_DEPTH); }
+  VR_HD double kdry(int l) const { return g(CC_FL0 + l * CLF_N + CLF_KDRY); }
+  VR_HD double ksat_m_kdry(int l) const { return g(CC_FL0 + l * CLF_N + CLF_KSAT_M_KDRY); }
+  VR_HD double poros(int l) const { return g(CC_FL0 + l * CLF_N + CLF_POROS); }
+  VR_HD double soilfr(int l) const { return g(CC_FL0 + l * CLF_N + CLF_SOILFR); }
+  VR_HD double cs_solid(int l) const { return g(CC_FL0 + l * CLF_N + CLF_CS_SOLID); }
   // zwtvmoist curve k, point i (only valid when the block carries the optional tail)
   VR_HD double zwt_z(int NL, int k, int i) const { return g(VR_CC_N(NL) + k * ZWT_NP + i); }
   VR_HD double zwt_m(int NL, int k, int i) const { return g(VR_CC_N(NL) + (NL + 2 + k) * ZWT_NP + i); }
@@ -412,12 +458,15 @@ VR_HDN double calc_rc(double rs, double net_short, double RGL, double tair, doub
   return rc;
 }
 
-VR_HDN double stability_correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0)
-{   // StabilityCorrection.c:44-81
+// StabilityCorrection.c:44-81.  lnz5 = log((Z - d) / Z0) + 5, which does not depend on the temperatures: the caller
+// evaluates it once per energy-balance solve instead of once per Brent evaluation (same value, same result).
+VR_HD double stability_lnz5(double Z, double d, double Z0) { return VR_LOG((Z - d) / Z0) + 5; }
+VR_HDN double stability_correction(double Zmd, double lnz5, double TSurf, double Tair, double Wind)
+{
   double Correction = 1.0;
   if (TSurf != Tair) {
-    double Ri = G_GRAV * (Tair - TSurf) * (Z - d) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * Wind * Wind);
-    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (VR_LOG((Z - d) / Z0) + 5));
+    double Ri = G_GRAV * (Tair - TSurf) * (Zmd) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * Wind * Wind);
+    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (lnz5));
     if (Ri > RiLimit) Ri = RiLimit;
     if (Ri > 0.0) Correction = (1 - Ri / 0.2) * (1 - Ri / 0.2);
     else {
@@ -494,7 +543,7 @@ struct Brent {
 // ---------------------------------------------------------------------------------------
 struct SnowPackEB {
   // inputs
-  double Dt, Ra, Z, Z0_2, AirDens, EactAir, LongSnowIn, Lv, Press, Rain, NetShortUnder, Vpd, Wind, OldTSurf,
+  double Dt, Ra, Z, lnz5, AirDens, EactAir, LongSnowIn, Lv, Press, Rain, NetShortUnder, Vpd, Wind, OldTSurf,
          SnowDepth, SnowDensity, SurfaceLiquidWater, SweSurfaceLayer, Tair, TGrnd;
   // outputs of the last evaluation
   double Ra_used0, AdvectedEnergy, DeltaColdContent, GroundFlux, LatentHeat, LatentHeatSub, NetLongUnder,
@@ -502,7 +551,7 @@ struct SnowPackEB {
   VR_HD double operator()(double TSurf)
   {
     double TMean = TSurf;
-    if (Wind > 0.0) Ra_used0 = Ra / stability_correction(Z, 0., TMean, Tair, Wind, Z0_2);
+    if (Wind > 0.0) Ra_used0 = Ra / stability_correction(Z - 0., lnz5, TMean, Tair, Wind);
     else Ra_used0 = HUGE_RESIST;
     double Tmp = TMean + KELVIN;
     NetLongUnder = LongSnowIn - STEFAN_B * Tmp * Tmp * Tmp * Tmp;
@@ -585,7 +634,7 @@ VR_HDN SnowMeltOut snow_melt(PackS s, double Le, double NetShortSnow, double Tca
   s.surf_water += RainFall;
 
   SnowPackEB x;
-  x.Dt = delta_t; x.Ra = aero_resist; x.Z = z2; x.Z0_2 = Z0_2; x.AirDens = density; x.EactAir = vp;
+  x.Dt = delta_t; x.Ra = aero_resist; x.Z = z2; x.lnz5 = (wind > 0.0) ? stability_lnz5(z2, 0., Z0_2) : 0.; x.AirDens = density; x.EactAir = vp;
   x.LongSnowIn = LongSnowIn; x.Lv = Le; x.Press = pressure; x.Rain = RainFall; x.NetShortUnder = NetShortSnow;
   x.Vpd = vpd; x.Wind = wind; x.OldTSurf = o.OldTSurf; x.SnowDepth = s.depth; x.SnowDensity = s.density;
   x.SurfaceLiquidWater = s.surf_water; x.SweSurfaceLayer = SurfaceSwq; x.Tair = Tcanopy; x.TGrnd = Tgrnd;
@@ -1353,17 +1402,28 @@ VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
     A = a.A; runoff_ = a.runoff;
   }
   const double tmp_dt_runoff = runoff_ / (double)dt, dt_inflow = ppt / (double)dt;
+#if defined(__CUDA_ARCH__) && !defined(VR_EXACT_LIBM) && !defined(VR_POW_CALL_IN_LOOP)
+  // branch-free power for the two drainage terms of an hour; legal for exponents >= 1 (Brooks-Corey: expt > 3)
+  const bool fastpow = ex0 >= 1.0 && (NL != 3 || ex1 >= 1.0);
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(&vr_pow_tables);
+#define VR_DRAIN_POW(x, y) (fastpow ? drain_pow((x), (y), tb) : m_pow((x), (y)))
+#else
+#define VR_DRAIN_POW(x, y) m_pow_inl((x), (y))
+#endif
 #pragma unroll 1
   for (int ts = 0; ts < dt; ts++) {
-    // Brooks-Corey drainage out of the upper layers (runoff.c:330-340)
+    // Brooks-Corey drainage out of the upper layers (runoff.c:330-340).  A layer at or below its residual moisture has
+    // t == r, i.e. the power of zero: the reference's `liq > resid ? ... : 0` needs no branch
     double t0 = liq0 - ev0;
     if (t0 < r0) t0 = r0;
-    double Q0 = (liq0 > r0) ? ks0 * m_pow_inl(VR_DIVC(t0 - r0, qd0, iq0), ex0) : 0.;
+    double Q0 = ks0 * VR_DRAIN_POW(VR_DIVC(t0 - r0, qd0, iq0), ex0);
+    if (!(liq0 > r0)) Q0 = 0.;
     double Q1 = 0.;
     if (NL == 3) {
       double t1 = liq1 - ev1;
       if (t1 < r1) t1 = r1;
-      Q1 = (liq1 > r1) ? ks1 * m_pow_inl(VR_DIVC(t1 - r1, qd1, iq1), ex1) : 0.;
+      Q1 = ks1 * VR_DRAIN_POW(VR_DIVC(t1 - r1, qd1, iq1), ex1);
+      if (!(liq1 > r1)) Q1 = 0.;
     }
     // top layer
     liq0 = liq0 + (dt_inflow - tmp_dt_runoff) - (Q0 + ev0);
@@ -1409,6 +1469,7 @@ VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
     baseflow += dt_baseflow;
     if (NL == 2) liq1 = liqB;
   }
+#undef VR_DRAIN_POW
   RunoffOut o;
   o.evap_bottom = evap.v[LB];
   if (baseflow < 0) {

@@ -6,7 +6,7 @@
 // runs as three small kernels (the cut is the call of runoff(), surface_fluxes.c:1130):
 //   k_front       surface_fluxes' pass WITHOUT the snow model for every unit that carries no snow and gets no snowfall
 //                 in this record; the others are appended to a list (warp ballot + one atomic per warp)
-//   k_front_snow  the pass WITH the snow model (solve_snow, Brent solves, sub-steps) for the listed units only: the
+//   k_snow  the pass WITH the snow model (solve_snow, Brent solves, sub-steps) for the listed units only: the
 //                 snow lanes are compacted into full warps instead of idling beside snow-free lanes
 //   k_back        runoff() -- the hourly drainage loop, 45 % of the step's instructions -- and the terms after it
 // and a chunk of records ends with
@@ -31,10 +31,10 @@
 // threads per block / blocks per SM the register allocation of each step kernel must allow (tuning knobs,
 // profiles/r2_tuning.md)
 #ifndef VR_FRONT_CTA
-#define VR_FRONT_CTA 256
+#define VR_FRONT_CTA 128
 #endif
 #ifndef VR_FRONT_MINB
-#define VR_FRONT_MINB 2
+#define VR_FRONT_MINB 3
 #endif
 #ifndef VR_SNOW_CTA
 #define VR_SNOW_CTA 128
@@ -43,10 +43,13 @@
 #define VR_SNOW_MINB 4
 #endif
 #ifndef VR_BACK_CTA
-#define VR_BACK_CTA 256
+#define VR_BACK_CTA 128
 #endif
 #ifndef VR_BACK_MINB
-#define VR_BACK_MINB 3
+#define VR_BACK_MINB 6
+#endif
+#ifndef VR_FRONT_STAGE
+#define VR_FRONT_STAGE 1     // k_front: constants staged in shared memory by bulk copies (0: read from global memory)
 #endif
 #define VR_CTA 256     // the set-up kernels
 
@@ -67,7 +70,9 @@ struct DevModel {
   double max_snow_temp, min_rain_temp;
   int64_t C, U, FC;                 // FC = number of forcing columns (== C unless a forcing map is set)
   const double *cc;                 // [ccn][C] per-cell constants by sorted position
-  const double *ccu;                // [ccn][U] the same per unit in slot order: what k_units reads (coalesced)
+  const double *ccu;                // [ccn][US] the same per unit in slot order: what the step kernels read (coalesced)
+  const double *tmu;                // [12][TM_N][US] the month's canopy terms per unit in slot order
+  int64_t US;                       // row stride of ccu / tmu: U rounded up to whole thread blocks (bulk copies read full rows)
   int ccn;
   const int64_t *cell_uptr, *fcol;
   const int64_t *order;             // sorted position -> caller's cell index
@@ -76,10 +81,11 @@ struct DevModel {
   const double *tl, *ap;            // potential-evaporation tables (valid when an OUT_PET_* is requested)
   const float *u_root;
   double *state;                    // [ST_N][U]
-  double *fo;                       // [FO_N][U] what k_front / k_front_snow hand to k_back (FrontOut)
+  double *fo;                       // [FO_N][U] what k_front / k_snow hand to k_back (FrontOut)
   int32_t *uflag;                   // [U] bit 0: the unit carries snow, bit 1: its stored snow flags need tidying
-  int32_t *snow_list;               // [U] slots of the units that run k_front_snow in the current record
-  int32_t *snow_cnt;                // [records per chunk] their number, per record of the chunk
+  int32_t *snow_list;               // [U] slots of the chunk's snow-class units (k_snow runs them)
+  int32_t *snow_cnt;                // [1] their number
+  unsigned long long *snow_total;   // diagnostic: unit-records that went through k_snow
   double *sv;                       // [SV_N][C]
   int32_t *cell_status;             // [C]
   int32_t out_vars[VR_MAX_OUT];
@@ -135,14 +141,17 @@ __device__ __forceinline__ void store_state(const DevModel &M, int64_t u, const 
 #undef S_
 }
 
-// per-unit copy of the per-cell constants in slot order: a warp of k_units reads 32 consecutive doubles per constant
-// instead of gathering 32 sectors (the units of a cell sit in different slots: slots are sorted by kind and climate)
-__global__ void k_unit_consts(DevModel M, double *ccu)
+// per-unit copies, in slot order, of the per-cell constants and of the per (tile, month) canopy terms: a warp reads 32
+// consecutive doubles per constant instead of gathering 32 sectors (the units of a cell sit in different slots: slots are
+// sorted by kind and climate), and a thread block's slice of a row is one contiguous bulk copy
+__global__ void k_unit_consts(DevModel M, double *ccu, double *tmu)
 {
   const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= M.U) return;
   const int64_t pos = M.u_pos[u];
-  for (int k = 0; k < M.ccn; k++) ccu[(size_t)k * M.U + u] = M.cc[(size_t)k * M.C + pos];
+  for (int k = 0; k < M.ccn; k++) ccu[(size_t)k * M.US + u] = M.cc[(size_t)k * M.C + pos];
+  const double *tm = M.tm + (size_t)M.u_tile[u] * 12 * TM_N;
+  for (int k = 0; k < 12 * TM_N; k++) tmu[(size_t)k * M.US + u] = tm[k];
 }
 
 // initialize_model_state() for every unit + its terms for put_data(rec = -nrecs)
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double 
   load_unit_consts(M, u, uc, cv, af);
   for (int l = 0; l < M.NL; l++) {
     im[l] = M.init_moist[(size_t)l * M.C + c];
-    mm[l] = M.cc[(size_t)(CC_LAYER0 + l * CL_N + CL_MAX_MOIST) * M.C + M.u_pos[u]];
+    mm[l] = M.cc[(size_t)(CC_BL0 + l * CLB_N + CLB_MAX_MOIST) * M.C + M.u_pos[u]];
   }
   const int64_t fc = M.fcol ? M.fcol[c] : c;
   unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
@@ -243,7 +252,7 @@ struct SnowIO {
 };
 
 // bits of M.uflag
-enum { UF_SNOWY = 1, UF_TIDY = 2 };
+enum { UF_SNOWY = 1, UF_TIDY = 2, UF_SCLASS = 4 };     // SCLASS: snow class in the current chunk (k_classify)
 
 // uflag from the state block (after vr_init_state / vr_set_state / a state file)
 __global__ void k_unit_flags(DevModel M)
@@ -255,6 +264,47 @@ __global__ void k_unit_flags(DevModel M)
   const bool snowy = st[ST_SWQ * U] > 0 || st[ST_SNOW_CANOPY * U] > 0 || st[ST_COVERAGE * U] != 0;
   const bool tidy = !snowy && ((int)st[ST_LAST_SNOW * U] != (int)MISSINGV || st[ST_MELTING * U] != 0. || st[ST_ALBEDO * U] != NEW_SNOW_ALB);
   M.uflag[u] = (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
+}
+
+// Classes of a chunk of records.  A unit belongs to the SNOW CLASS of the chunk when it carries snow at the start of the
+// chunk or any record of the chunk brings it snowfall (or, with a sub-stepped snow model, snowfall anywhere in its cell):
+// only then can solve_snow() have anything to do in the chunk.  The snow class is compacted into M.snow_list (one atomic
+// per warp, lanes keep their order: neighbours in the list are neighbours in kind and climate) and runs through k_snow on
+// its own stream; the others run k_front / k_back with the snow model compiled out.  The two classes never exchange
+// anything inside a chunk, so their kernel sequences overlap freely: the snow class is few warps with a long dependent
+// chain (two Brent solves per unit), the rest is many warps with short ones.
+__global__ void __launch_bounds__(256) k_classify(DevModel M, DevForcing F)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t u = k < M.U ? k : M.U - 1;
+  const int64_t c = M.u_cell[u];
+  const bool valid = k < M.U && M.cell_fail[c] == 0;
+  const int flags = M.uflag[u];
+  bool s = false;
+  if (valid) {
+    s = (flags & UF_SNOWY) != 0;
+    const int NS = M.NF > 1 ? M.NF + 1 : 1;
+    const double Tf = M.u_Tfactor[u], Pf = M.u_Pfactor[u];
+    for (int rec = 0; rec < F.nrec && !s; rec++) {
+      const double *q = F.slots + ((size_t)rec * NS + (NS - 1)) * VR_NFORCING * M.U + u;
+      Forc fr;
+      fr.air_temp = __ldg(q + (size_t)VR_F_AIR_TEMP * M.U); fr.prec = __ldg(q + (size_t)VR_F_PREC * M.U);
+      fr.snowflag = (M.NF > 1 && F.snowflag) ? (int)__ldg(F.snowflag + (size_t)rec * M.FC + (M.fcol ? M.fcol[c] : c)) : 0;
+      s = unit_needs_snow(fr, Tf, Pf, M.NF, M.max_snow_temp, M.min_rain_temp, false);
+    }
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, s);
+  if (ballot) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(M.snow_cnt, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (s) M.snow_list[base + __popc(ballot & ((1u << lane) - 1u))] = (int32_t)u;
+  }
+  if (valid) {
+    const int nf = (flags & ~UF_SCLASS) | (s ? UF_SCLASS : 0);
+    if (nf != flags) M.uflag[u] = nf;
+  }
 }
 
 // sub-record kk of record rec of the chunk for unit u, from the slot-ordered copy of k_forcing_slots
@@ -272,16 +322,49 @@ __device__ __forceinline__ Forc load_forcing(const DevModel &M, const DevForcing
   return f;
 }
 
-// surface_fluxes' passes of record `rec` of the chunk for unit u (everything before runoff()): hot state in, hot state
-// and the hand-off words out, terms to the term buffer column of the unit
-template <int EXTRAS, bool SUB, bool SNOW>
-__device__ __forceinline__ void front_unit(const DevModel &M, const DevForcing &F, int rec, int64_t u, int64_t c, int flags,
-                                           double *__restrict__ terms)
+// ---- staging of a thread block's constants in shared memory -------------------------------------------------------------
+// stage[row][thread]: rows 0 .. CC_FRONT_N-1 = the front block of the constants, then TM_N rows = the month's canopy terms.
+// k_front owns VR_FRONT_CTA consecutive slots, so each row is one contiguous slice of ccu / tmu: ONE thread issues the
+// rows as bulk asynchronous copies (TMA, cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier while all threads
+// classify their units; the physics then reads its constants from shared memory (~30 cycles) instead of stalling on one
+// L2 / HBM round trip per constant (k_front was 75 % long-scoreboard stalls, profiles/r2_k_units_ncu.md).  While a block
+// computes, the copies of the next blocks of the SM are in flight (4 resident blocks = a 4-deep ring of stages).
+constexpr int STAGE_ROWS = CC_FRONT_N + TM_N;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-  UnitC uc; CellC cc;
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+
+// surface_fluxes' passes of record `rec` of the chunk for unit u (everything before runoff()): hot state in, hot state
+// and the hand-off words out, terms to the term buffer column of the unit.  cc: the unit's staged constants,
+// tmrow: its staged canopy terms (row stride CTA)
+template <int EXTRAS, bool SUB, bool SNOW>
+__device__ __forceinline__ FrontOut front_unit(const DevModel &M, const DevForcing &F, int rec, int64_t u, int64_t c, int flags, int mon,
+                                               CellC cc, const double *tmrow, int64_t CTA, double *__restrict__ terms)
+{
+  UnitC uc;
   double cv, af;
   load_unit_consts(M, u, uc, cv, af);
-  load_cell_consts(M.ccu, M.U, u, M.NL, cc);
   SnowIO sio;
   sio.st = M.state + u;
   sio.U = (size_t)M.U;
@@ -293,82 +376,83 @@ __device__ __forceinline__ void front_unit(const DevModel &M, const DevForcing &
   h.Wdew = st[ST_WDEW * U]; h.T0 = st[ST_T0 * U]; h.T1 = st[ST_T1 * U]; h.LongUnderOut = st[ST_LONGUNDEROUT * U];
   h.Tfoliage = st[ST_TFOLIAGE * U];
   bool snowy = (flags & UF_SNOWY) != 0, tidy = (flags & UF_TIDY) != 0;
-  const int mon = __ldg(F.month + rec) - 1, doy = __ldg(F.doy + rec);
+  const int doy = __ldg(F.doy + rec);
   const int NS = M.NF > 1 ? M.NF + 1 : 1;
-  const double *tm = M.tm + ((size_t)M.u_tile[u] * 12 + mon) * TM_N;
+  CanopyM cm;
+  cm.vegcover = tmrow[TM_VEGCOVER * CTA]; cm.LAI = tmrow[TM_LAI * CTA]; cm.Wdmax = tmrow[TM_WDMAX * CTA];
+  cm.albedo = tmrow[TM_ALBEDO * CTA]; cm.surf_atten = tmrow[TM_SURF_ATTEN * CTA];
   const double *ae = M.ae + ((size_t)M.u_aero[u] * 12 + mon) * AE_N;
   const double *tl = (EXTRAS & EX_PET) ? M.tl + ((size_t)M.u_tile[u] * 12 + mon) * TL_N : nullptr;
   const double *ap = (EXTRAS & EX_PET) ? M.ap + ((size_t)M.u_aero[u] * 12 + mon) * AP_N : nullptr;
   auto forc = [&](int kk) { return load_forcing(M, F, rec, kk, NS, u, c, mon, doy); };
-  const FrontOut fo = unit_front<EXTRAS, SUB, SNOW>(cc, uc, tm, ae, forc, M.NF, M.NL, M.dt_hours, M.snow_step_hours, M.max_snow_temp,
+  const FrontOut fo = unit_front<EXTRAS, SUB, SNOW>(cc, uc, cm, ae, forc, M.NF, M.NL, M.dt_hours, M.snow_step_hours, M.max_snow_temp,
                                                     M.min_rain_temp, h, snowy, tidy, sio, cv, af, M.tmap,
                                                     terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true, false,
                                                     tl, ap);
   st[ST_WDEW * U] = h.Wdew; st[ST_T0 * U] = h.T0; st[ST_T1 * U] = h.T1; st[ST_LONGUNDEROUT * U] = h.LongUnderOut;
   st[ST_TFOLIAGE * U] = h.Tfoliage;
-  double *o = M.fo + u;
-  o[FO_PPT * U] = fo.ppt; o[FO_VAPOR * U] = fo.vapor; o[FO_CVAPOR * U] = fo.cvapor; o[FO_CANOPYEVAP * U] = fo.canopyevap;
-  o[FO_EVAP0 * U] = fo.evap.v[0]; o[FO_EVAP1 * U] = fo.evap.v[1]; o[FO_EVAP2 * U] = fo.evap.v[2];
-  o[FO_BEF0 * U] = fo.bef.v[0]; o[FO_BEF1 * U] = fo.bef.v[1]; o[FO_BEF2 * U] = fo.bef.v[2];
-  const int nf = (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
+  {     // hand-off to k_back
+    double *o = M.fo + u;
+    o[FO_PPT * U] = fo.ppt; o[FO_VAPOR * U] = fo.vapor; o[FO_CVAPOR * U] = fo.cvapor; o[FO_CANOPYEVAP * U] = fo.canopyevap;
+    o[FO_EVAP0 * U] = fo.evap.v[0]; o[FO_EVAP1 * U] = fo.evap.v[1]; o[FO_EVAP2 * U] = fo.evap.v[2];
+    o[FO_BEF0 * U] = fo.bef.v[0]; o[FO_BEF1 * U] = fo.bef.v[1]; o[FO_BEF2 * U] = fo.bef.v[2];
+  }
+  const int nf = (flags & UF_SCLASS) | (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
   if (nf != flags) M.uflag[u] = nf;
   if (fo.err) atomicCAS(M.cell_status + c, 0, F.rec_abs + rec + 1);     // first failing record + 1 (arno_evap.c:112-151)
+  return fo;
 }
 
-// Record `rec` of the chunk, units without snow: one thread per unit in slot order.  A unit that needs the snow model in
-// this record is appended to M.snow_list instead (one atomic per warp; the lanes keep their order, so neighbours in the
-// list are neighbours in kind and climate) and handled by k_front_snow.
+// Record `rec` of the chunk, everything before runoff() for the units outside the chunk's snow class: one thread per unit
+// in slot order (the lanes of snow-class units idle).
 template <int EXTRAS>
 __global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
 {
-  pow_tables_init();
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(128) double stage[];     // [STAGE_ROWS][VR_FRONT_CTA]
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  const int64_t u0 = (int64_t)blockIdx.x * VR_FRONT_CTA;
+  const int mon = __ldg(F.month + rec) - 1;
+  if (VR_FRONT_STAGE && tid == 0) mbar_init(&bar, 1);
+  pow_tables_init();                                   // (block barrier: the mbarrier is initialised for everyone)
+  if (VR_FRONT_STAGE && tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(STAGE_ROWS * VR_FRONT_CTA * sizeof(double)));
+    for (int k = 0; k < CC_FRONT_N; k++)
+      bulk_g2s(stage + k * VR_FRONT_CTA, M.ccu + (size_t)k * M.US + u0, VR_FRONT_CTA * sizeof(double), &bar);
+    for (int k = 0; k < TM_N; k++)
+      bulk_g2s(stage + (CC_FRONT_N + k) * VR_FRONT_CTA, M.tmu + ((size_t)mon * TM_N + k) * M.US + u0, VR_FRONT_CTA * sizeof(double), &bar);
+  }
+  const int64_t k = u0 + tid;
   const int64_t u = k < M.U ? k : M.U - 1;
   const int64_t c = M.u_cell[u];
-  const bool valid = k < M.U && M.cell_fail[c] == 0;
   const int flags = M.uflag[u];
-  bool general = false;
-  if (valid) {
-    const int NS = M.NF > 1 ? M.NF + 1 : 1;
-    const Forc fr = load_forcing(M, F, rec, NS - 1, NS, u, c, 0, 0);
-    general = unit_needs_snow(fr, M.u_Tfactor[u], M.u_Pfactor[u], M.NF, M.max_snow_temp, M.min_rain_temp, (flags & UF_SNOWY) != 0);
+  const bool mine = k < M.U && M.cell_fail[c] == 0 && !(flags & UF_SCLASS);
+  if (VR_FRONT_STAGE) mbar_wait(&bar, 0);     // every thread: the block's shared memory must not be released under a copy in flight
+  if (!mine) return;
+  CellC cc;
+  if (VR_FRONT_STAGE) {
+    cc.p = stage + tid; cc.C = VR_FRONT_CTA;
+    front_unit<EXTRAS, false, false>(M, F, rec, u, c, flags, mon, cc, stage + CC_FRONT_N * VR_FRONT_CTA + tid, VR_FRONT_CTA, terms);
   }
-  const unsigned ballot = __ballot_sync(0xffffffffu, general);
-  if (ballot) {
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(M.snow_cnt + rec, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (general) M.snow_list[base + __popc(ballot & ((1u << lane) - 1u))] = (int32_t)u;
-  }
-  if (!valid || general) return;
-  front_unit<EXTRAS, false, false>(M, F, rec, u, c, flags, terms);
-}
-
-// Record `rec` of the chunk, the listed units: solve_snow() and the rest of the pass, sub-stepped when SNOW_STEP <
-// TIME_STEP (SUB).  Grid-stride over the list (its length is only known on the device).
-template <int EXTRAS, bool SUB>
-__global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_front_snow(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
-{
-  pow_tables_init();
-  const int n = M.snow_cnt[rec];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t u = M.snow_list[i];
-    front_unit<EXTRAS, SUB, true>(M, F, rec, u, M.u_cell[u], M.uflag[u], terms);
+  else {
+    cc.p = M.ccu + u; cc.C = M.US;
+    front_unit<EXTRAS, false, false>(M, F, rec, u, c, flags, mon, cc, M.tmu + (size_t)mon * TM_N * M.US + u, M.US, terms);
   }
 }
 
-// Record `rec` of the chunk: runoff() and what follows it, one thread per unit in slot order.
+// Record `rec` of the chunk: runoff() and what follows it for unit u (k_back: the units outside the snow class, one
+// thread per unit in slot order; k_snow: the snow class).
 template <int EXTRAS>
-__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, int rec, double *__restrict__ terms)
+__device__ __forceinline__ void back_unit(const DevModel &M, int rec, int64_t u, double *__restrict__ terms)
 {
-  pow_tables_init();
-  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= M.U) return;
-  if (M.cell_fail[M.u_cell[u]] != 0) return;
   const size_t U = (size_t)M.U;
   CellC cc;
-  load_cell_consts(M.ccu, M.U, u, M.NL, cc);
+  cc.p = M.ccu + u; cc.C = M.US;
+  // the constants read after the hourly loop: on their way to L1 while the loop runs
+  for (int l = 0; l < M.NL; l++) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cc.p + (size_t)(CC_FL0 + l * CLF_N + CLF_WPWP) * cc.C));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cc.p + (size_t)(CC_BL0 + l * CLB_N + CLB_WET_DEN) * cc.C));
+  }
   const double *o = M.fo + u;
   FrontOut fo;
   fo.ppt = o[FO_PPT * U]; fo.vapor = o[FO_VAPOR * U]; fo.cvapor = o[FO_CVAPOR * U]; fo.canopyevap = o[FO_CANOPYEVAP * U];
@@ -382,6 +466,46 @@ __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, 
   unit_back<EXTRAS>(cc, (fl & 1) == 0, fl >> 8, M.NL, M.dt_hours, fo, moist, M.u_cv[u], M.u_af[u], M.tmap,
                     terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true);
   st[ST_MOIST0 * U] = moist.v[0]; st[ST_MOIST1 * U] = moist.v[1]; st[ST_MOIST2 * U] = moist.v[2];
+}
+
+template <int EXTRAS>
+__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, int rec, double *__restrict__ terms)
+{
+  pow_tables_init();
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= M.U) return;
+  if (M.cell_fail[M.u_cell[u]] != 0 || (M.uflag[u] & UF_SCLASS)) return;
+  back_unit<EXTRAS>(M, rec, u, terms);
+}
+
+// Record `rec` of the chunk for the snow class: solve_snow() and the rest of the pass (sub-stepped when SNOW_STEP <
+// TIME_STEP: SUB) for the listed units, then k_back_list = runoff() for the same units at its own (smaller) register
+// count.  Grid-stride over the list (its length is only known on the device).  Both run on the snow stream beside
+// k_front / k_back of the other units.  (One launch per record, not a loop over the chunk's records inside the kernel:
+// warps that drift apart in this large code thrash the instruction cache -- measured 495 us against 299 us per record,
+// profiles/r2_tuning.md.)
+template <int EXTRAS, bool SUB>
+__global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_snow(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
+{
+  pow_tables_init();
+  const int n = M.snow_cnt[0];
+  const int mon = __ldg(F.month + rec) - 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(M.snow_total, (unsigned long long)n);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = M.snow_list[i];
+    CellC cc;
+    cc.p = M.ccu + u; cc.C = M.US;
+    front_unit<EXTRAS, SUB, true>(M, F, rec, u, M.u_cell[u], M.uflag[u], mon, cc, M.tmu + (size_t)mon * TM_N * M.US + u, M.US, terms);
+  }
+}
+
+template <int EXTRAS>
+__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back_list(DevModel M, int rec, double *__restrict__ terms)
+{
+  pow_tables_init();
+  const int n = M.snow_cnt[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    back_unit<EXTRAS>(M, rec, M.snow_list[i], terms);
 }
 
 // put_data() for the same records: one thread per (cell in sorted order, record).  A cell's units are
@@ -500,13 +624,15 @@ struct vr_handle {
   } keep;
   std::vector<double> tair0_host;
   DevModel M;
-  DBuf<double> d_tl, d_ap, d_ccu, d_fslots;
+  DBuf<double> d_tl, d_ap, d_ccu, d_tmu, d_fslots;
   DBuf<double> d_cc, d_u_cv, d_u_af, d_u_Tf, d_u_Pf, d_u_rarc, d_u_rmin, d_u_RGL, d_tm, d_ae, d_init_moist, d_state, d_sv,
       d_forc, d_out, d_tair0, d_terms, d_sums;
   DBuf<float> d_u_root;
   DBuf<int64_t> d_cell_uptr, d_fcol, d_order;
   DBuf<int32_t> d_u_logical, d_u_cell, d_u_pos, d_u_tile, d_u_flags, d_u_aero, d_u_slot, d_cell_fail, d_cell_status, d_month, d_doy;
   cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_snow = nullptr;     // k_snow of the chunk's snow class runs here, beside k_front / k_back on the step stream
+  cudaEvent_t ev_cls = nullptr, ev_snow = nullptr;
   cudaStream_t s_cells = nullptr;    // k_cells of chunk k runs here, beside k_units of chunk k+1 on the step stream
   cudaEvent_t ev_fork = nullptr, ev_units[2] = {nullptr, nullptr}, ev_cells[2] = {nullptr, nullptr};
   int64_t pair_seq = 0;              // launch pairs so far: pair i uses term buffer i & 1
@@ -525,6 +651,12 @@ struct vr_handle {
   bool flags_dirty = true;           // M.uflag must be rebuilt from the state block before the next step
   DBuf<double> d_fo;
   DBuf<int32_t> d_uflag, d_snow_list, d_snow_cnt;
+  DBuf<unsigned long long> d_snow_total;
+  bool snow_stream = true;           // k_snow on its own stream (VICRES_SNOW_STREAM=0: on the step stream, for A/B timing)
+  bool detail = false;               // VICRES_TIME_KERNELS=1: CUDA events around every step kernel (vr_step_diag)
+  std::vector<cudaEvent_t> dev;      // 5 per record: around k_front and k_back on the step stream, around k_snow on the snow stream
+  size_t dev_used = 0;
+  int64_t diag_unit_records = 0;
   int chunk = 16;                    // records per launch of k_cells (and per pipelined copy of vr_step_block)
   int64_t launches = 0;
   bool timed = false;
@@ -541,18 +673,35 @@ static std::string g_create_error;
     }                                                                                                \
   } while (0)
 
+// the step kernels of record `rec` of a chunk: k_front, k_back on the step stream st, k_snow on the snow stream ss
 template <int EX>
-static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *terms, cudaStream_t st)
+static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *terms, cudaStream_t st, cudaStream_t ss)
 {
   const int64_t U = h->M.U;
   const unsigned gf = (unsigned)((U + VR_FRONT_CTA - 1) / VR_FRONT_CTA), gb = (unsigned)((U + VR_BACK_CTA - 1) / VR_BACK_CTA);
   int64_t gs = (U + VR_SNOW_CTA - 1) / VR_SNOW_CTA;
   const int64_t gs_max = (int64_t)h->sms * VR_SNOW_MINB * 4;     // grid-stride: a few waves at most
   if (gs > gs_max) gs = gs_max;
-  k_front<EX><<<gf, VR_FRONT_CTA, 0, st>>>(h->M, F, rec, terms);
-  if (h->M.NF > 1) k_front_snow<EX, true><<<(unsigned)gs, VR_SNOW_CTA, 0, st>>>(h->M, F, rec, terms);
-  else k_front_snow<EX, false><<<(unsigned)gs, VR_SNOW_CTA, 0, st>>>(h->M, F, rec, terms);
+  constexpr size_t smf = VR_FRONT_STAGE ? (size_t)STAGE_ROWS * VR_FRONT_CTA * sizeof(double) : 0;
+  cudaEvent_t *e = nullptr;
+  if (h->detail && h->dev_used + 5 <= 400000) {
+    while (h->dev.size() < h->dev_used + 5) { cudaEvent_t x; cudaEventCreate(&x); h->dev.push_back(x); }
+    e = &h->dev[h->dev_used];
+    h->dev_used += 5;
+  }
+  if (e) cudaEventRecord(e[0], st);
+  k_front<EX><<<gf, VR_FRONT_CTA, smf, st>>>(h->M, F, rec, terms);
+  if (e) cudaEventRecord(e[1], st);
   k_back<EX & EX_ZWT><<<gb, VR_BACK_CTA, 0, st>>>(h->M, rec, terms);
+  if (e) cudaEventRecord(e[2], st);
+  if (e) cudaEventRecord(e[3], ss);
+  if (h->M.NF > 1) k_snow<EX, true><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
+  else k_snow<EX, false><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
+  int64_t gl = gb;
+  if (gl > (int64_t)h->sms * VR_BACK_MINB * 4) gl = (int64_t)h->sms * VR_BACK_MINB * 4;
+  k_back_list<EX & EX_ZWT><<<(unsigned)gl, VR_BACK_CTA, 0, ss>>>(h->M, rec, terms);
+  if (e) cudaEventRecord(e[4], ss);
+  h->diag_unit_records += U;
 }
 
 extern "C" {
@@ -614,6 +763,9 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
             (e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) == cudaSuccess &&
             (e = cudaStreamCreateWithFlags(&h->s_cells, cudaStreamNonBlocking)) == cudaSuccess &&
+            (e = cudaStreamCreateWithFlags(&h->s_snow, cudaStreamNonBlocking)) == cudaSuccess &&
+            (e = cudaEventCreateWithFlags(&h->ev_cls, cudaEventDisableTiming)) == cudaSuccess &&
+            (e = cudaEventCreateWithFlags(&h->ev_snow, cudaEventDisableTiming)) == cudaSuccess &&
             (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) == cudaSuccess &&
             (e = cudaEventCreate(&h->ev0)) == cudaSuccess && (e = cudaEventCreate(&h->ev1)) == cudaSuccess;
   for (int b = 0; ok && b < vr_handle::NBUF; b++)
@@ -628,7 +780,16 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
     delete h;
     return VR_ERR_CUDA;
   }
+  {   // the stage of k_front exceeds the 48 kB default of dynamic shared memory
+    const int smf = (int)(STAGE_ROWS * VR_FRONT_CTA * sizeof(double));
+    cudaFuncSetAttribute(k_front<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    cudaFuncSetAttribute(k_front<EX_PET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    cudaFuncSetAttribute(k_front<EX_ZWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    cudaFuncSetAttribute(k_front<EX_PET | EX_ZWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+  }
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
+  { const char *d = getenv("VICRES_TIME_KERNELS"); h->detail = d && d[0] == '1'; }
+  { const char *d = getenv("VICRES_SNOW_STREAM"); h->snow_stream = !(d && d[0] == '0'); }
   *out = h;
   return VR_OK;
 }
@@ -645,11 +806,15 @@ void vr_destroy(vr_handle *h)
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
   h->d_order.release(); h->d_u_slot.release(); h->d_u_pos.release();
-  h->d_fo.release(); h->d_uflag.release(); h->d_snow_list.release(); h->d_snow_cnt.release();
+  h->d_tmu.release(); h->d_fo.release(); h->d_snow_total.release();
+  for (auto &x : h->dev) cudaEventDestroy(x); h->d_uflag.release(); h->d_snow_list.release(); h->d_snow_cnt.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto &t : h->evs) { cudaEventDestroy(t.u0); cudaEventDestroy(t.u1); cudaEventDestroy(t.c0); cudaEventDestroy(t.c1); }
   if (h->s_cells) cudaStreamDestroy(h->s_cells);
+  if (h->s_snow) cudaStreamDestroy(h->s_snow);
+  if (h->ev_cls) cudaEventDestroy(h->ev_cls);
+  if (h->ev_snow) cudaEventDestroy(h->ev_snow);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int b = 0; b < 2; b++) {
     if (h->ev_units[b]) cudaEventDestroy(h->ev_units[b]);
@@ -759,15 +924,19 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   M.state = h->d_state.p; M.sv = h->d_sv.p; M.cell_status = h->d_cell_status.p;
   M.order = h->d_order.p; M.u_slot = h->d_u_slot.p; M.u_logical = h->d_u_logical.p;
   M.ccn = P.ccn;
-  CK(h->d_ccu.reserve((size_t)P.ccn * (U ? U : 1)));
-  M.ccu = h->d_ccu.p;
+  M.US = ((U ? U : 1) + 255) / 256 * 256;
+  CK(h->d_ccu.reserve((size_t)P.ccn * M.US));
+  CK(h->d_tmu.reserve((size_t)12 * TM_N * M.US));
+  CK(cudaMemset(h->d_ccu.p, 0, (size_t)P.ccn * M.US * sizeof(double)));
+  CK(cudaMemset(h->d_tmu.p, 0, (size_t)12 * TM_N * M.US * sizeof(double)));
+  M.ccu = h->d_ccu.p; M.tmu = h->d_tmu.p;
   CK(h->d_fo.reserve((size_t)FO_N * (U ? U : 1)));
   CK(h->d_uflag.reserve(U ? U : 1));
   CK(h->d_snow_list.reserve(U ? U : 1));
   M.fo = h->d_fo.p; M.uflag = h->d_uflag.p; M.snow_list = h->d_snow_list.p;
   h->flags_dirty = true;
   if (U > 0) {
-    k_unit_consts<<<(unsigned)((U + 255) / 256), 256, 0, h->stream>>>(M, h->d_ccu.p);
+    k_unit_consts<<<(unsigned)((U + 255) / 256), 256, 0, h->stream>>>(M, h->d_ccu.p, h->d_tmu.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
   }
@@ -826,7 +995,7 @@ int vr_init_state(vr_handle *h, const double *tair0)
 }
 
 // One block of records = chunks of h->chunk records.  Per record of a chunk the step stream st runs k_front,
-// k_front_snow and k_back for all units; the chunk ends with k_cells on h->s_cells, so that the aggregation of chunk k
+// k_snow and k_back for all units; the chunk ends with k_cells on h->s_cells, so that the aggregation of chunk k
 // overlaps the step of chunk k+1 (two term buffers).  With join the step stream waits for the last aggregation, so
 // the caller sees ordinary stream semantics; the host pipeline of vr_step_block orders its copies on the events instead.
 static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cudaStream_t st, bool join)
@@ -838,8 +1007,13 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
   CK(h->d_sums.reserve((size_t)h->M.tmap.n * h->M.C * CH));
   const int NS = h->M.NF > 1 ? h->M.NF + 1 : 1;          // forcing sub-records per record (sub-steps + the record itself)
   CK(h->d_fslots.reserve((size_t)CH * NS * VR_NFORCING * U1));
-  CK(h->d_snow_cnt.reserve(CH));
+  CK(h->d_snow_cnt.reserve(1));
   h->M.snow_cnt = h->d_snow_cnt.p;
+  if (!h->d_snow_total.p) {
+    CK(h->d_snow_total.reserve(1));
+    CK(cudaMemset(h->d_snow_total.p, 0, sizeof(unsigned long long)));
+  }
+  h->M.snow_total = h->d_snow_total.p;
   cudaEventRecord(h->ev0, st);
   cudaEventRecord(h->ev_fork, st);                       // what the caller queued on st (forcing, free output buffer)
   cudaStreamWaitEvent(h->s_cells, h->ev_fork, 0);
@@ -873,19 +1047,25 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     if (h->pair_seq >= 2) cudaStreamWaitEvent(st, h->ev_cells[b], 0);     // chunk i-2 has been aggregated out of terms[b]
     if (t) cudaEventRecord(t->u0, st);
     if (h->M.U > 0) {
-      cudaMemsetAsync(h->d_snow_cnt.p, 0, (size_t)CH * sizeof(int32_t), st);
+      cudaStream_t ss = h->snow_stream ? h->s_snow : st;
+      cudaMemsetAsync(h->d_snow_cnt.p, 0, sizeof(int32_t), st);
       k_forcing_slots<<<dim3((unsigned)((h->M.U + 255) / 256), (unsigned)(F.nrec * NS)), 256, 0, st>>>(h->M, F, h->d_fslots.p);
       F.slots = h->d_fslots.p;
-      h->launches += 1;
+      k_classify<<<(unsigned)((h->M.U + 255) / 256), 256, 0, st>>>(h->M, F);
+      cudaEventRecord(h->ev_cls, st);
+      cudaStreamWaitEvent(ss, h->ev_cls, 0);           // the snow stream starts when the chunk's classes are known
+      h->launches += 2;
       for (int rec = 0; rec < F.nrec; rec++) {
         switch (h->extras) {      // one set of kernel instances per set of optional results
-          case 0: launch_record<0>(h, F, rec, terms, st); break;
-          case EX_PET: launch_record<EX_PET>(h, F, rec, terms, st); break;
-          case EX_ZWT: launch_record<EX_ZWT>(h, F, rec, terms, st); break;
-          default: launch_record<EX_PET | EX_ZWT>(h, F, rec, terms, st); break;
+          case 0: launch_record<0>(h, F, rec, terms, st, ss); break;
+          case EX_PET: launch_record<EX_PET>(h, F, rec, terms, st, ss); break;
+          case EX_ZWT: launch_record<EX_ZWT>(h, F, rec, terms, st, ss); break;
+          default: launch_record<EX_PET | EX_ZWT>(h, F, rec, terms, st, ss); break;
         }
-        h->launches += 3;
+        h->launches += 4;
       }
+      cudaEventRecord(h->ev_snow, ss);
+      cudaStreamWaitEvent(st, h->ev_snow, 0);          // both classes have finished the chunk
     }
     if (t) cudaEventRecord(t->u1, st);
     cudaEventRecord(h->ev_units[b], st);
@@ -1298,6 +1478,35 @@ int vr_kernel_times(vr_handle *h, double *units_ms, double *cells_ms, int64_t *l
     *units_ms += a; *cells_ms += b; *launch_pairs += 1; *records += t.nrec;
   }
   h->evs_used = 0;
+  return VR_OK;
+}
+
+// diagnostic: since the last call -- out[0..2] = summed durations (ms) of k_front, k_snow, k_back (only with
+// VICRES_TIME_KERNELS=1 in the environment at vr_create, else 0), out[3] = records timed, out[4] = unit-records that ran
+// the snow instance (k_snow), out[5] = unit-records in total
+int vr_step_diag(vr_handle *h, double *out)
+{
+  if (!h || !out) return VR_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < 6; i++) out[i] = 0;
+  for (size_t i = 0; i + 5 <= h->dev_used; i += 5) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, h->dev[i], h->dev[i + 1]);
+    cudaEventElapsedTime(&b, h->dev[i + 3], h->dev[i + 4]);
+    cudaEventElapsedTime(&c, h->dev[i + 1], h->dev[i + 2]);
+    out[0] += a; out[1] += b; out[2] += c; out[3] += 1;
+  }
+  h->dev_used = 0;
+  if (h->d_snow_total.p) {
+    unsigned long long n = 0;
+    CK(cudaMemcpy(&n, h->d_snow_total.p, sizeof n, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->d_snow_total.p, 0, sizeof n));
+    out[4] = (double)n;
+  }
+  out[5] = (double)h->diag_unit_records;
+  h->diag_unit_records = 0;
   return VR_OK;
 }
 

@@ -22,7 +22,7 @@ LIBPATH = os.environ.get("VICRES_LIB", os.path.join(HERE, "libvicres.so"))
 EXPORTS = ["vr_create", "vr_destroy", "vr_last_error", "vr_default_options", "vr_set_veglib",
            "vr_set_cells", "vr_set_forcing_map", "vr_init_state", "vr_step_block",
            "vr_step_block_device", "vr_synchronize", "vr_state_size", "vr_get_state", "vr_set_state",
-           "vr_write_state_file", "vr_read_state_file", "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts"]
+           "vr_write_state_file", "vr_read_state_file", "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts", "vr_step_diag"]
 
 _lib = None
 
@@ -73,6 +73,7 @@ def load_library(path=LIBPATH):
     L.vr_diag_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.vr_diag_pow.argtypes = [C.c_int, C.c_int64, vp, vp, vp]
     L.vr_fallback_counts.argtypes = [vp, vp]
+    L.vr_step_diag.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -195,6 +196,13 @@ class VicRes:
         a, b, n, r = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
         self._check(self.L.vr_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(r)))
         return float(a.value), float(b.value), int(n.value), int(r.value)
+
+    def step_diag(self):
+        """dict of the step-kernel diagnostics since the previous call (vr_step_diag); synchronises"""
+        a = np.zeros(6, dtype=np.float64)
+        self._check(self.L.vr_step_diag(self.h, a.ctypes.data))
+        return {"front_ms": a[0], "snow_ms": a[1], "back_ms": a[2], "records_timed": int(a[3]),
+                "snow_unit_records": int(a[4]), "unit_records": int(a[5])}
 
     def fallback_counts(self):
         a = np.zeros(2, dtype=np.int64)
