@@ -376,7 +376,7 @@ def run_ours(args):
                                  "fp64 object and DESIGN.md section 6"},
             "step_kernels": {"snow_unit_record_share": diag["snow_unit_records"] / max(diag["unit_records"], 1),
                              "us_per_record": None if not diag["records_timed"] else
-                             {k: 1e3 * diag[k + "_ms"] / diag["records_timed"] for k in ("front", "snow", "back")}},
+                             {k: 1e3 * diag[k + "_ms"] / diag["records_timed"] for k in ("front", "snow", "back", "back_list")}},
             "fp64": None if not (fp64_per and dfma_peak) else {
                 "fp64_thread_inst_per_cell_step": fp64_per,
                 "achieved_inst_per_s": fp64_per * C * recs_per_launch / (kernel_ms * 1e-3),

@@ -217,8 +217,8 @@ int  vr_kernel_times(vr_handle *h, double *units_ms, double *cells_ms, int64_t *
 int  vr_diag_fp64_peak(int device, double *dfma_per_s);
 /* diagnostic, since the last call: out[0..2] = summed durations (ms) of the step kernels k_front, k_snow, k_back
    (timed only when VICRES_TIME_KERNELS=1 was in the environment at vr_create), out[3] = records timed, out[4] =
-   unit-records that ran the snow instance, out[5] = unit-records in total */
-int  vr_step_diag(vr_handle *h, double *out6);
+   unit-records that ran the snow instance, out[5] = unit-records in total, out[6] = summed durations of k_back_list */
+int  vr_step_diag(vr_handle *h, double *out7);
 /* diagnostic: z[i] = the device's power function (vic_physics.cuh m_pow) of x[i], y[i]; host pointers */
 int  vr_diag_pow(int device, int64_t n, const double *x, const double *y, double *z);
 /* TFALLBACK counters summed over all units, as put_data.c:658-664 prints them:

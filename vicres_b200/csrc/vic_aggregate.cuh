@@ -341,14 +341,15 @@ VR_HD FrontOut unit_front(CellC cc, const UnitC &uc, CanopyM cm, const double *a
 }
 
 // runoff() of the record (surface_fluxes.c:1130-1150), full_energy.c:445-453, and the terms that depend on them
-template <int extras>
-VR_HD void unit_back(CellC cc, bool is_veg, int root0_mask, int NL, int dt_hours, FrontOut fo, M3 &moist, double cv, double af,
-                     const TermMap &tmap, double *col, int stride, bool write)
+// run(ppt, moist, evap) -> RunoffOut: runoff() with the loop constants where the caller keeps them
+template <int extras, class RunoffFn>
+VR_HD void unit_back_fn(CellC cc, bool is_veg, int root0_mask, int NL, FrontOut fo, M3 &moist, double cv, double af,
+                        const TermMap &tmap, double *col, int stride, bool write, RunoffFn run)
 {
   const double AF = cv * af * 1. * 1.;
 #define T_(k, expr) do { if (write && tmap.row[k] >= 0) VR_STREAM_ST(col + (size_t)tmap.row[k] * stride, (expr)); } while (0)
   // ---- runoff.c ----
-  const RunoffOut ro = runoff_step(cc, NL, dt_hours, fo.ppt, moist, fo.evap);
+  const RunoffOut ro = run(fo.ppt, moist, fo.evap);
   moist = ro.moist;
   M3 st_evap = fo.evap;
   if (NL == 3) st_evap.v[2] = ro.evap_bottom; else st_evap.v[1] = ro.evap_bottom;
@@ -390,6 +391,14 @@ VR_HD void unit_back(CellC cc, bool is_veg, int root0_mask, int NL, int dt_hours
     T_(TE_ZWTL, z.lumped * AF);
   }
 #undef T_
+}
+
+template <int extras>
+VR_HD void unit_back(CellC cc, bool is_veg, int root0_mask, int NL, int dt_hours, FrontOut fo, M3 &moist, double cv, double af,
+                     const TermMap &tmap, double *col, int stride, bool write)
+{
+  unit_back_fn<extras>(cc, is_veg, root0_mask, NL, fo, moist, cv, af, tmap, col, stride, write,
+                       [&](double ppt, M3 m, M3 e) { return runoff_step(cc, NL, dt_hours, ppt, m, e); });
 }
 
 // the two halves one after the other (host harness of the tests).  Returns 1 when the reference would have returned ERROR
@@ -491,6 +500,20 @@ VR_HD double cell_term_sum(const double *src, size_t sstride, int64_t u0, int nu
   double a = 0. + VR_STREAM_LD(p);
   for (int j = 1; j < nu; j++) a += VR_STREAM_LD(p + j);
   return a;
+}
+
+// ordered sum of term k over the cell's units, straight from the term buffer (rows of sstride doubles, the cell's units
+// in columns u0 .. u0+nu-1).  The three per-layer EVAP_BARE / TRANSP_VEG terms of a unit are added layer by layer into
+// ONE accumulator, exactly as collect_wb_terms does; they are asked for as TE_EB0 / TE_TV0.
+VR_HD double cell_sum(const double *src, size_t sstride, int64_t u0, int nu, const TermMap &tmap, int NL, int k)
+{
+  if (k == TE_EB0 || k == TE_TV0) {
+    double a = 0;
+    for (int j = 0; j < nu; j++)
+      for (int l = 0; l < NL; l++) a += VR_STREAM_LD(src + (size_t)tmap.row[k + l] * sstride + u0 + j);
+    return a;
+  }
+  return cell_term_sum(src, sstride, u0, nu, tmap.row[k]);
 }
 
 // One output variable of a cell-record from the summed terms (put_data.c:540-632).  S(k) reads sum k.

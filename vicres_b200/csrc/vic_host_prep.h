@@ -121,15 +121,17 @@ inline bool prepare(const vr_options &opt, const vr_veglib &lib, const vr_cells 
   const int64_t C = cells.ncell, T = cells.tile_ptr[C];
   P.NL = NL; P.NB = NB; P.C = C; P.T = T; P.cta_threads = cta_threads;
   if (NL < 2 || NL > VR_MAX_LAYERS || NB < 1 || NB > VR_MAX_BANDS) { P.error = "nlayer must be 2..3 and nbands 1..10"; return false; }
-  // Cells are processed in an internal order sorted by mean annual air temperature (soil_con.avg_temp,
-  // the QUICK_FLUX lower boundary), then latitude: neighbouring lanes/warps then share the snow /
-  // no-snow branch on most days.  Results are written back at the caller's cell index.
+  // The cells keep the caller's order (P.order is the identity; the indirection stays in the kernels): the per-cell
+  // aggregation then reads the forcing and writes the outputs coalesced.  What is sorted -- by kind and climate -- is the
+  // UNITS, into thread slots (below).  -DVR_SORT_CELLS restores round 1's climate-sorted cells.
   P.order.resize(C);
   for (int64_t c = 0; c < C; c++) P.order[c] = c;
+#if defined(VR_SORT_CELLS)
   std::stable_sort(P.order.begin(), P.order.end(), [&](int64_t a, int64_t b) {
     if (cells.avg_temp[a] != cells.avg_temp[b]) return cells.avg_temp[a] < cells.avg_temp[b];
     return cells.lat[a] > cells.lat[b];
   });
+#endif
   // per-cell constants, stored BY SORTED POSITION so that neighbouring lanes read neighbouring words
   bool want_pet_nat = false, want_zwt = false, want_pet = false;
   for (int v = 0; v < opt.n_out; v++) {

@@ -1370,18 +1370,94 @@ VR_HDN AsatOut runoff_and_asat(CellC cc, double top_moist, double inflow)
 // Layers are scalars (no dynamically indexed arrays -> no local memory in the hourly loop); the
 // reference's while-loops that push excess water upwards (runoff.c:362-391,448-475) are unrolled.
 struct RunoffOut { M3 moist; double evap_bottom, asat, runoff, baseflow; };
+
+// The per-cell constants of the hourly loop.  LoopRegs: values (read once from the constant block, live in registers);
+// LoopSmem (device): the same 18 words in a shared-memory column that the step kernel staged, re-read every hour, so
+// that the loop runs in few registers and the kernel fits all its warps on the SMs at once.
+enum { LK_R0 = 0, LK_R1, LK_RB, LK_M0, LK_M1, LK_MB, LK_KS0, LK_KS1, LK_EX0, LK_EX1, LK_IQ0, LK_IQ1, LK_IQB, LK_BF_FRAC, LK_BF_NL,
+       LK_WS, LK_INV_ONE_M_WS, LK_C, LK_N };
+// row of the constant block that holds loop constant k (NL layers)
+VR_HD int loop_const_row(int k, int NL)
+{
+  const int LB = NL - 1;
+  switch (k) {
+    case LK_R0: return CC_FL0 + 0 * CLF_N + CLF_RESID;
+    case LK_R1: return CC_FL0 + 1 * CLF_N + CLF_RESID;
+    case LK_RB: return CC_FL0 + LB * CLF_N + CLF_RESID;
+    case LK_M0: return CC_BL0 + 0 * CLB_N + CLB_MAX_MOIST;
+    case LK_M1: return CC_BL0 + 1 * CLB_N + CLB_MAX_MOIST;
+    case LK_MB: return CC_BL0 + LB * CLB_N + CLB_MAX_MOIST;
+    case LK_KS0: return CC_BL0 + 0 * CLB_N + CLB_KSAT24;
+    case LK_KS1: return CC_BL0 + 1 * CLB_N + CLB_KSAT24;
+    case LK_EX0: return CC_BL0 + 0 * CLB_N + CLB_EXPT;
+    case LK_EX1: return CC_BL0 + 1 * CLB_N + CLB_EXPT;
+    case LK_IQ0: return CC_BL0 + 0 * CLB_N + CLB_INV_QDEN;
+    case LK_IQ1: return CC_BL0 + 1 * CLB_N + CLB_INV_QDEN;
+    case LK_IQB: return CC_BL0 + LB * CLB_N + CLB_INV_QDEN;
+    case LK_BF_FRAC: return CC_BF_FRAC;
+    case LK_BF_NL: return CC_BF_NL;
+    case LK_WS: return CC_WS;
+    case LK_INV_ONE_M_WS: return CC_INV_ONE_M_WS;
+    default: return CC_C;
+  }
+}
+struct LoopRegs {
+  double v[LK_N], qd0, qd1, qdB, one_m_Ws;
+  VR_HD double k(int i) const { return v[i]; }
+};
 template <int NL>
-VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
+VR_HD LoopRegs loop_regs(CellC cc)
+{
+  constexpr int LB = NL - 1;
+  LoopRegs K;
+#pragma unroll
+  for (int i = 0; i < LK_N; i++) K.v[i] = cc.g(loop_const_row(i, NL));
+  K.qd0 = cc.qden(0); K.qd1 = cc.qden(1); K.qdB = cc.qden(LB); K.one_m_Ws = cc.one_m_Ws();
+  return K;
+}
+#if defined(__CUDACC__)
+struct LoopSmem {
+  uint32_t a;                   // shared-memory address of the thread's column of the stage
+  int S;                        // row stride in bytes
+  double qd0, qd1, qdB, one_m_Ws;     // unused on the device (divisions by constants are reciprocal multiplications)
+  __device__ __forceinline__ double k(int i) const
+  {
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a + (uint32_t)(i * S)));
+    return x;
+  }
+};
+#endif
+
+// moist: in/out (mm); evap: the layer evaporation of the step (mm), the bottom layer's may be reduced.
+// Layers are scalars (no dynamically indexed arrays -> no local memory in the hourly loop); the
+// reference's while-loops that push excess water upwards (runoff.c:362-391,448-475) are unrolled.
+template <int NL, class LoopK>
+VR_HD RunoffOut runoff_core(CellC cc, const LoopK &K, int dt, double ppt, M3 moist, M3 evap)
 {
   constexpr int LB = NL - 1;                      // bottom layer
-  const double r0 = cc.resid(0), r1 = cc.resid(1), rB = cc.resid(LB);
-  const double m0 = cc.max_moist(0), m1 = cc.max_moist(1), mB = cc.max_moist(LB);
-  const double ks0 = cc.ksat24(0), ks1 = cc.ksat24(1), ex0 = cc.expt(0), ex1 = cc.expt(1);
-  const double qd0 = cc.qden(0), qd1 = cc.qden(1), qdB = cc.qden(LB);
-  const double iq0 = cc.inv_qden(0), iq1 = cc.inv_qden(1), iqB = cc.inv_qden(LB);
-  const double bf_frac = cc.bf_frac(), bf_nl = cc.bf_nl(), Ws = cc.Ws(), one_m_Ws = cc.one_m_Ws(),
-               inv_one_m_Ws = cc.inv_one_m_Ws(), cexp = cc.c();
-  (void)qd0; (void)qd1; (void)qdB; (void)iq0; (void)iq1; (void)iqB; (void)one_m_Ws; (void)inv_one_m_Ws;
+#define r0 K.k(LK_R0)
+#define r1 K.k(LK_R1)
+#define rB K.k(LK_RB)
+#define m0 K.k(LK_M0)
+#define m1 K.k(LK_M1)
+#define mB K.k(LK_MB)
+#define ks0 K.k(LK_KS0)
+#define ks1 K.k(LK_KS1)
+#define ex0 K.k(LK_EX0)
+#define ex1 K.k(LK_EX1)
+#define iq0 K.k(LK_IQ0)
+#define iq1 K.k(LK_IQ1)
+#define iqB K.k(LK_IQB)
+#define bf_frac K.k(LK_BF_FRAC)
+#define bf_nl K.k(LK_BF_NL)
+#define Ws K.k(LK_WS)
+#define inv_one_m_Ws K.k(LK_INV_ONE_M_WS)
+#define cexp K.k(LK_C)
+#define qd0 K.qd0
+#define qd1 K.qd1
+#define qdB K.qdB
+#define one_m_Ws K.one_m_Ws
   double liq0 = moist.v[0], liq1 = moist.v[1], liqB = moist.v[LB];
   double ev[MAXL];
 #pragma unroll
@@ -1412,58 +1488,63 @@ VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
 #endif
 #pragma unroll 1
   for (int ts = 0; ts < dt; ts++) {
+    // the constants used more than once in an hour: one read each (LoopSmem re-reads shared memory on every K.k())
+    const double c_r0 = r0, c_m0 = m0, c_rB = rB, c_mB = mB;
+    const double c_r1 = (NL == 3) ? r1 : 0., c_m1 = (NL == 3) ? m1 : 0.;
     // Brooks-Corey drainage out of the upper layers (runoff.c:330-340).  A layer at or below its residual moisture has
     // t == r, i.e. the power of zero: the reference's `liq > resid ? ... : 0` needs no branch
     double t0 = liq0 - ev0;
-    if (t0 < r0) t0 = r0;
-    double Q0 = ks0 * VR_DRAIN_POW(VR_DIVC(t0 - r0, qd0, iq0), ex0);
-    if (!(liq0 > r0)) Q0 = 0.;
+    if (t0 < c_r0) t0 = c_r0;
+    double Q0 = ks0 * VR_DRAIN_POW(VR_DIVC(t0 - c_r0, qd0, iq0), ex0);
+    if (!(liq0 > c_r0)) Q0 = 0.;
     double Q1 = 0.;
     if (NL == 3) {
       double t1 = liq1 - ev1;
-      if (t1 < r1) t1 = r1;
-      Q1 = ks1 * VR_DRAIN_POW(VR_DIVC(t1 - r1, qd1, iq1), ex1);
-      if (!(liq1 > r1)) Q1 = 0.;
+      if (t1 < c_r1) t1 = c_r1;
+      Q1 = ks1 * VR_DRAIN_POW(VR_DIVC(t1 - c_r1, qd1, iq1), ex1);
+      if (!(liq1 > c_r1)) Q1 = 0.;
     }
     // top layer
     liq0 = liq0 + (dt_inflow - tmp_dt_runoff) - (Q0 + ev0);
-    if (liq0 > m0) { Q0 += liq0 - m0; liq0 = m0; }
+    if (liq0 > c_m0) { Q0 += liq0 - c_m0; liq0 = c_m0; }
     if (liq0 < 0) { Q0 += liq0; liq0 = 0; }
-    if (liq0 < r0) { Q0 += liq0 - r0; liq0 = r0; }
+    if (liq0 < c_r0) { Q0 += liq0 - c_r0; liq0 = c_r0; }
     double Qin = Q0;                       // what reaches the layer below
     if (NL == 3) {
       liq1 = liq1 + Qin - (Q1 + ev1);
-      if (liq1 > m1) {
-        double ex = liq1 - m1;
-        liq1 = m1;
+      if (liq1 > c_m1) {
+        double ex = liq1 - c_m1;
+        liq1 = c_m1;
         liq0 += ex;
-        if (liq0 > m0) { runoff_ += liq0 - m0; liq0 = m0; }
+        if (liq0 > c_m0) { runoff_ += liq0 - c_m0; liq0 = c_m0; }
       }
       if (liq1 < 0) { Q1 += liq1; liq1 = 0; }
-      if (liq1 < r1) { Q1 += liq1 - r1; liq1 = r1; }
+      if (liq1 < c_r1) { Q1 += liq1 - c_r1; liq1 = c_r1; }
       Qin = Q1;
     }
     // bottom layer: ARNO baseflow (runoff.c:420-435)
-    const double rel_moist = VR_DIVC(liqB - rB, qdB, iqB);
+    const double rel_moist = VR_DIVC(liqB - c_rB, qdB, iqB);
     double dt_baseflow = bf_frac * rel_moist;
-    if (rel_moist > Ws) {
-      const double frac = VR_DIVC(rel_moist - Ws, one_m_Ws, inv_one_m_Ws);
-      dt_baseflow += bf_nl * ((cexp == 2.0) ? frac * frac : VR_POW(frac, cexp));   // pow(x,2) == x*x
+    const double c_Ws = Ws;
+    if (rel_moist > c_Ws) {
+      const double frac = VR_DIVC(rel_moist - c_Ws, one_m_Ws, inv_one_m_Ws);
+      const double c_c = cexp;
+      dt_baseflow += bf_nl * ((c_c == 2.0) ? frac * frac : VR_POW(frac, c_c));   // pow(x,2) == x*x
     }
     if (dt_baseflow < 0) dt_baseflow = 0;
     liqB += Qin - (evB + dt_baseflow);
-    if (liqB < rB) { dt_baseflow += liqB - rB; liqB = rB; }
-    if (liqB > mB) {
-      double ex = liqB - mB;
-      liqB = mB;
+    if (liqB < c_rB) { dt_baseflow += liqB - c_rB; liqB = c_rB; }
+    if (liqB > c_mB) {
+      double ex = liqB - c_mB;
+      liqB = c_mB;
       if (NL == 3) {
         liq1 += ex;
-        if (liq1 > m1) { ex = liq1 - m1; liq1 = m1; }
+        if (liq1 > c_m1) { ex = liq1 - c_m1; liq1 = c_m1; }
         else ex = 0;
       }
       if (ex > 0) {
         liq0 += ex;
-        if (liq0 > m0) { runoff_ += liq0 - m0; liq0 = m0; }
+        if (liq0 > c_m0) { runoff_ += liq0 - c_m0; liq0 = c_m0; }
       }
     }
     baseflow += dt_baseflow;
@@ -1484,13 +1565,43 @@ VR_HD RunoffOut runoff_core(CellC cc, int dt, double ppt, M3 moist, M3 evap)
   o.runoff = runoff_;
   o.baseflow = baseflow;
   return o;
+#undef r0
+#undef r1
+#undef rB
+#undef m0
+#undef m1
+#undef mB
+#undef ks0
+#undef ks1
+#undef ex0
+#undef ex1
+#undef iq0
+#undef iq1
+#undef iqB
+#undef bf_frac
+#undef bf_nl
+#undef Ws
+#undef inv_one_m_Ws
+#undef cexp
+#undef qd0
+#undef qd1
+#undef qdB
+#undef one_m_Ws
 }
 
 VR_HDN RunoffOut runoff_step(CellC cc, int NL, int dt, double ppt, M3 moist, M3 evap)
 {
-  if (NL == 3) return runoff_core<3>(cc, dt, ppt, moist, evap);
-  return runoff_core<2>(cc, dt, ppt, moist, evap);
+  if (NL == 3) return runoff_core<3>(cc, loop_regs<3>(cc), dt, ppt, moist, evap);
+  return runoff_core<2>(cc, loop_regs<2>(cc), dt, ppt, moist, evap);
 }
+#if defined(__CUDACC__)
+// the same with the loop constants in the staged shared-memory column
+__device__ __noinline__ RunoffOut runoff_step_staged(CellC cc, LoopSmem K, int NL, int dt, double ppt, M3 moist, M3 evap)
+{
+  if (NL == 3) return runoff_core<3>(cc, K, dt, ppt, moist, evap);
+  return runoff_core<2>(cc, K, dt, ppt, moist, evap);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // one unit, one record

@@ -43,7 +43,7 @@
 #define VR_SNOW_MINB 4
 #endif
 #ifndef VR_BACK_CTA
-#define VR_BACK_CTA 128
+#define VR_BACK_CTA 192
 #endif
 #ifndef VR_BACK_MINB
 #define VR_BACK_MINB 6
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel 
 }
 
 // Record `rec` of the chunk: runoff() and what follows it for unit u (k_back: the units outside the snow class, one
-// thread per unit in slot order; k_snow: the snow class).
+// thread per unit in slot order; k_back_list: the snow class).  lk: the unit's staged loop constants.
 template <int EXTRAS>
-__device__ __forceinline__ void back_unit(const DevModel &M, int rec, int64_t u, double *__restrict__ terms)
+__device__ __forceinline__ void back_unit(const DevModel &M, int rec, int64_t u, LoopSmem lk, double *__restrict__ terms)
 {
   const size_t U = (size_t)M.U;
   CellC cc;
@@ -463,19 +463,39 @@ __device__ __forceinline__ void back_unit(const DevModel &M, int rec, int64_t u,
   M3 moist;
   moist.v[0] = st[ST_MOIST0 * U]; moist.v[1] = st[ST_MOIST1 * U]; moist.v[2] = st[ST_MOIST2 * U];
   const int fl = M.u_flags[u];
-  unit_back<EXTRAS>(cc, (fl & 1) == 0, fl >> 8, M.NL, M.dt_hours, fo, moist, M.u_cv[u], M.u_af[u], M.tmap,
-                    terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true);
+  const int NL = M.NL, dt = M.dt_hours;
+  unit_back_fn<EXTRAS>(cc, (fl & 1) == 0, fl >> 8, NL, fo, moist, M.u_cv[u], M.u_af[u], M.tmap,
+                       terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true,
+                       [&](double ppt, M3 m, M3 e) { return runoff_step_staged(cc, lk, NL, dt, ppt, m, e); });
   st[ST_MOIST0 * U] = moist.v[0]; st[ST_MOIST1 * U] = moist.v[1]; st[ST_MOIST2 * U] = moist.v[2];
 }
 
+// k_back owns VR_BACK_CTA consecutive slots: the 18 constants of the hourly loop are 18 contiguous row slices of ccu that
+// one thread fetches as bulk copies (TMA) into the stage [LK_N][VR_BACK_CTA]; the loop re-reads them from shared memory
+// every hour instead of holding 36 registers, which is what lets the kernel keep all its warps resident at once (one
+// wave instead of two half-empty ones, profiles/r2_tuning.md).
 template <int EXTRAS>
 __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, int rec, double *__restrict__ terms)
 {
+  __shared__ __align__(128) double stage[LK_N * VR_BACK_CTA];
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  const int64_t u0 = (int64_t)blockIdx.x * VR_BACK_CTA;
+  if (tid == 0) mbar_init(&bar, 1);
   pow_tables_init();
-  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= M.U) return;
-  if (M.cell_fail[M.u_cell[u]] != 0 || (M.uflag[u] & UF_SCLASS)) return;
-  back_unit<EXTRAS>(M, rec, u, terms);
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(LK_N * VR_BACK_CTA * sizeof(double)));
+    for (int k = 0; k < LK_N; k++)
+      bulk_g2s(stage + k * VR_BACK_CTA, M.ccu + (size_t)loop_const_row(k, M.NL) * M.US + u0, VR_BACK_CTA * sizeof(double), &bar);
+  }
+  const int64_t k = u0 + tid;
+  const int64_t u = k < M.U ? k : M.U - 1;
+  const bool mine = k < M.U && M.cell_fail[M.u_cell[u]] == 0 && !(M.uflag[u] & UF_SCLASS);
+  mbar_wait(&bar, 0);
+  if (!mine) return;
+  LoopSmem lk;
+  lk.a = smem_u32(stage + tid); lk.S = VR_BACK_CTA * (int)sizeof(double); lk.qd0 = lk.qd1 = lk.qdB = lk.one_m_Ws = 0;
+  back_unit<EXTRAS>(M, rec, u, lk, terms);
 }
 
 // Record `rec` of the chunk for the snow class: solve_snow() and the rest of the pass (sub-stepped when SNOW_STEP <
@@ -502,21 +522,31 @@ __global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_snow(DevModel M, 
 template <int EXTRAS>
 __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back_list(DevModel M, int rec, double *__restrict__ terms)
 {
+  __shared__ double stage[LK_N * VR_BACK_CTA];
   pow_tables_init();
   const int n = M.snow_cnt[0];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    back_unit<EXTRAS>(M, rec, M.snow_list[i], terms);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = M.snow_list[i];
+    double *col = stage + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < LK_N; k++) col[k * VR_BACK_CTA] = __ldg(M.ccu + (size_t)loop_const_row(k, M.NL) * M.US + u);
+    LoopSmem lk;
+    lk.a = smem_u32(col); lk.S = VR_BACK_CTA * (int)sizeof(double); lk.qd0 = lk.qd1 = lk.qdB = lk.one_m_Ws = 0;
+    back_unit<EXTRAS>(M, rec, u, lk, terms);
+  }
 }
 
-// put_data() for the same records: one thread per (cell in sorted order, record).  A cell's units are
-// contiguous columns of the term buffer, consecutive threads own consecutive cells, so the term reads are
-// coalesced; the ordered sums go to sums[rec][row][cell] and the outputs to the caller's cell index.  The
-// save_data words a record needs from its predecessor (storage deltas, closure error) are rebuilt from the
-// predecessor's terms, which makes the records of a chunk independent; record 0 uses the carried M.sv.
-// M.sv is double-buffered: the blocks of record 0 read buffer svb while the blocks of the last record write buffer
-// svb ^ 1 (blocks of one grid have no order), the host flips svb per launch.
-__global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const double *__restrict__ terms,
-                                               double *__restrict__ sums, double *__restrict__ out, int svb)
+// put_data() for the records of a chunk: one thread per (cell, record).  A cell's units are contiguous columns of the
+// term buffer and consecutive threads own consecutive cells, so the term reads, the forcing reads and the output
+// writes out[var][rec][cell] are all coalesced (the cells keep the caller's order; only the units are sorted into
+// slots).  Every requested output adds the terms it needs IN REFERENCE ORDER straight from the term buffer
+// (collect_wb_terms' summation order, so the fp64 sums round like the reference's); nothing is staged in memory.  The
+// save_data words a record needs from its predecessor (storage deltas, closure error) are rebuilt from the predecessor's
+// terms, which makes the records of a chunk independent; record 0 uses the carried M.sv.  M.sv is double-buffered: the
+// blocks of record 0 read buffer svb while the blocks of the last record write buffer svb ^ 1 (blocks of one grid have
+// no order), the host flips svb per launch.
+__global__ void __launch_bounds__(256) k_cells(DevModel M, DevForcing F, const double *__restrict__ terms,
+                                               double *__restrict__ out, int svb)
 {
   const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int rec = blockIdx.y;
@@ -526,12 +556,14 @@ __global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const d
   const int64_t fc = M.fcol ? M.fcol[c] : c;
   const bool ok = !M.cell_fail[c] && nu > 0;
   const int NL = M.NL;
-  const size_t rec_stride = (size_t)M.tmap.n * M.U, sum_stride = (size_t)M.tmap.n * M.C;
+  const size_t rec_stride = (size_t)M.tmap.n * M.U;
   const size_t orow = (size_t)(F.rec0 + rec) * M.C + c, ostride = (size_t)F.nrec_total * M.C;
   if (!ok) {
     for (int v = 0; v < M.n_out; v++) out[(size_t)v * ostride + orow] = 0.;
     return;
   }
+  const double *T = terms + rec * rec_stride;
+  auto S = [&](int k) { return cell_sum(T, (size_t)M.U, fu0, nu, M.tmap, NL, k); };
   double sv[SV_N];
   if (rec == 0)
     for (int k = 0; k < SV_N; k++) sv[k] = M.sv[((size_t)svb * SV_N + k) * M.C + c];
@@ -540,10 +572,6 @@ __global__ void __launch_bounds__(128) k_cells(DevModel M, DevForcing F, const d
     auto SP = [&](int k) { return cell_term_sum(P, (size_t)M.U, fu0, nu, M.tmap.row[k]); };
     cell_carry(SP, NL, sv);
   }
-  const double *T = terms + rec * rec_stride;
-  double *Sm = sums + rec * sum_stride;
-  cell_accumulate_to(T, (size_t)M.U, fu0, nu, M.tmap, NL, Sm, (size_t)M.C, cs);
-  auto S = [&](int k) { return Sm[(size_t)M.tmap.row[k] * M.C + cs]; };
   Forc f;
   const int NS = M.NF > 1 ? M.NF + 1 : 1;
   const size_t q = ((size_t)rec * NS + (NS - 1)) * M.FC + fc;        // the record's own values (atmos-><field>[NR])
@@ -654,7 +682,7 @@ struct vr_handle {
   DBuf<unsigned long long> d_snow_total;
   bool snow_stream = true;           // k_snow on its own stream (VICRES_SNOW_STREAM=0: on the step stream, for A/B timing)
   bool detail = false;               // VICRES_TIME_KERNELS=1: CUDA events around every step kernel (vr_step_diag)
-  std::vector<cudaEvent_t> dev;      // 5 per record: around k_front and k_back on the step stream, around k_snow on the snow stream
+  std::vector<cudaEvent_t> dev;      // 6 per record: around k_front and k_back on the step stream, around k_snow on the snow stream
   size_t dev_used = 0;
   int64_t diag_unit_records = 0;
   int chunk = 16;                    // records per launch of k_cells (and per pipelined copy of vr_step_block)
@@ -684,10 +712,10 @@ static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *te
   if (gs > gs_max) gs = gs_max;
   constexpr size_t smf = VR_FRONT_STAGE ? (size_t)STAGE_ROWS * VR_FRONT_CTA * sizeof(double) : 0;
   cudaEvent_t *e = nullptr;
-  if (h->detail && h->dev_used + 5 <= 400000) {
-    while (h->dev.size() < h->dev_used + 5) { cudaEvent_t x; cudaEventCreate(&x); h->dev.push_back(x); }
+  if (h->detail && h->dev_used + 6 <= 400000) {
+    while (h->dev.size() < h->dev_used + 6) { cudaEvent_t x; cudaEventCreate(&x); h->dev.push_back(x); }
     e = &h->dev[h->dev_used];
-    h->dev_used += 5;
+    h->dev_used += 6;
   }
   if (e) cudaEventRecord(e[0], st);
   k_front<EX><<<gf, VR_FRONT_CTA, smf, st>>>(h->M, F, rec, terms);
@@ -699,6 +727,7 @@ static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *te
   else k_snow<EX, false><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
   int64_t gl = gb;
   if (gl > (int64_t)h->sms * VR_BACK_MINB * 4) gl = (int64_t)h->sms * VR_BACK_MINB * 4;
+  if (e) cudaEventRecord(e[5], ss);
   k_back_list<EX & EX_ZWT><<<(unsigned)gl, VR_BACK_CTA, 0, ss>>>(h->M, rec, terms);
   if (e) cudaEventRecord(e[4], ss);
   h->diag_unit_records += U;
@@ -1071,7 +1100,7 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
     cudaEventRecord(h->ev_units[b], st);
     cudaStreamWaitEvent(h->s_cells, h->ev_units[b], 0);
     if (t) cudaEventRecord(t->c0, h->s_cells);
-    k_cells<<<dim3((unsigned)((h->M.C + 127) / 128), (unsigned)F.nrec), 128, 0, h->s_cells>>>(h->M, F, terms, h->d_sums.p, out_dev, h->svb);
+    k_cells<<<dim3((unsigned)((h->M.C + 255) / 256), (unsigned)F.nrec), 256, 0, h->s_cells>>>(h->M, F, terms, out_dev, h->svb);
     h->svb ^= 1;
     if (t) cudaEventRecord(t->c1, h->s_cells);
     cudaEventRecord(h->ev_cells[b], h->s_cells);
@@ -1483,20 +1512,21 @@ int vr_kernel_times(vr_handle *h, double *units_ms, double *cells_ms, int64_t *l
 
 // diagnostic: since the last call -- out[0..2] = summed durations (ms) of k_front, k_snow, k_back (only with
 // VICRES_TIME_KERNELS=1 in the environment at vr_create, else 0), out[3] = records timed, out[4] = unit-records that ran
-// the snow instance (k_snow), out[5] = unit-records in total
+// the snow instance (k_snow), out[5] = unit-records in total, out[6] = summed durations of k_back_list
 int vr_step_diag(vr_handle *h, double *out)
 {
   if (!h || !out) return VR_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaDeviceSynchronize());
-  for (int i = 0; i < 6; i++) out[i] = 0;
-  for (size_t i = 0; i + 5 <= h->dev_used; i += 5) {
-    float a = 0, b = 0, c = 0;
+  for (int i = 0; i < 7; i++) out[i] = 0;
+  for (size_t i = 0; i + 6 <= h->dev_used; i += 6) {
+    float a = 0, b = 0, c = 0, d = 0;
     cudaEventElapsedTime(&a, h->dev[i], h->dev[i + 1]);
-    cudaEventElapsedTime(&b, h->dev[i + 3], h->dev[i + 4]);
+    cudaEventElapsedTime(&b, h->dev[i + 3], h->dev[i + 5]);
     cudaEventElapsedTime(&c, h->dev[i + 1], h->dev[i + 2]);
-    out[0] += a; out[1] += b; out[2] += c; out[3] += 1;
+    cudaEventElapsedTime(&d, h->dev[i + 5], h->dev[i + 4]);
+    out[0] += a; out[1] += b; out[2] += c; out[3] += 1; out[6] += d;
   }
   h->dev_used = 0;
   if (h->d_snow_total.p) {

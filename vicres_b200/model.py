@@ -199,9 +199,9 @@ class VicRes:
 
     def step_diag(self):
         """dict of the step-kernel diagnostics since the previous call (vr_step_diag); synchronises"""
-        a = np.zeros(6, dtype=np.float64)
+        a = np.zeros(7, dtype=np.float64)
         self._check(self.L.vr_step_diag(self.h, a.ctypes.data))
-        return {"front_ms": a[0], "snow_ms": a[1], "back_ms": a[2], "records_timed": int(a[3]),
+        return {"front_ms": a[0], "snow_ms": a[1], "back_ms": a[2], "back_list_ms": a[6], "records_timed": int(a[3]),
                 "snow_unit_records": int(a[4]), "unit_records": int(a[5])}
 
     def fallback_counts(self):
