@@ -11,8 +11,9 @@ records) of every cell, so the default K=10 timed steps are the 10 years the con
   e2e     the same through the C-ABI host call vr_step_block(): pinned host forcing in, host outputs
           out, H2D + D2H copies inside the timed region
   roofline.achieved = 280 algorithmic bytes per cell-timestep (9 forcing + 26 output fp64 words,
-          SURVEY.md 8d) x cell-timesteps per launch / mean duration of the dominant kernel k_units
-          (CUDA events recorded by the library around every launch on the launching stream)
+          SURVEY.md 8d) x cells / mean duration of the step kernels of ONE record (k_front, k_back on the step
+          stream beside k_snow, k_back_list on the snow stream -- together "the cell step"; CUDA events recorded
+          by the library around every chunk of records on the launching stream)
   fp64    the same launches against the FP64 pipe: FP64 thread-instructions per cell-timestep (from
           the committed ncu capture, profiles/k_step_traffic.json) x rate / DFMA peak measured live
   cpu_baseline  the compiled reference (vic_ref_driver, step loop only) on a bounded sample on all
@@ -224,6 +225,14 @@ def run_ours(args):
         dist.barrier()
 
     C, R, K, W = args.cells, args.block, args.steps, max(args.warmup, 0)
+    if args.strong:            # the whole grid is args.cells: this rank takes its block of cells (vicres_b200/shard.py)
+        c0, c1 = shard.cell_block(args.cells, rank, world)
+        C = c1 - c0
+    if args.ensemble and world > 1:     # parameter sets shard over the ranks, every rank holds the basin's cells and forcing
+        p0, p1 = shard.cell_block(args.ensemble, rank, world)
+        args.ensemble_local = p1 - p0
+    else:
+        args.ensemble_local = args.ensemble
     lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=args.bands, seed=20261019 + rank,
                                       **({"lat_range": (35.0, 65.0), "overstory_frac": 0.3} if args.bands > 1 else {}))
     f_host, month, doy = synth_soa.make_forcing(cells, R, dt_hours=args.dt, seed=7 + rank, cold=args.cold)
@@ -233,7 +242,7 @@ def run_ours(args):
     n_out = opt.n_out
     fmap = None
     if args.ensemble:       # P copies of the basin's cells with perturbed calibration parameters, one forcing column per basin cell
-        P, N = args.ensemble, C
+        P, N = args.ensemble_local, C
         rng = np.random.default_rng(99 + rank)
         idx = np.tile(np.arange(N), P)
         ens = shard.slice_cells(cells, 0, N)            # (copy)
@@ -291,14 +300,18 @@ def run_ours(args):
     launches = m.num_launches - l0
     units_ms, cells_ms, pairs, krecs = m.kernel_times()      # every chunk of step kernels / k_cells launch of the timed region
     diag = m.step_diag()
-    kernel_ms = units_ms / max(pairs, 1)                     # mean k_units launch
-    recs_per_launch = krecs / max(pairs, 1)
+    kernel_ms = units_ms / max(krecs, 1)                     # the step kernels of one record (both streams)
+    recs_per_launch = 1.0
     finite = bool(torch.isfinite(out_dev).all().item())
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
-    value = world * C * R * K / (total_ms_max * 1e-3)
+    cells_job = torch.tensor([float(C)], dtype=torch.float64, device=dev)     # cells (x sets) of all ranks
+    if world > 1:
+        dist.all_reduce(cells_job, op=dist.ReduceOp.SUM)
+    cells_job = float(cells_job.item())
+    value = cells_job * R * K / (total_ms_max * 1e-3)
 
     # ---- e2e: host buffers through vr_step_block (H2D + D2H inside the timed region) ----
     f_pin = torch.from_numpy(f_host).pin_memory()
@@ -321,9 +334,27 @@ def run_ours(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * R * Ke / float(t.item())
+    e2e_value = cells_job * R * Ke / float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     finite = finite and bool(np.isfinite(out_np).all())
+    # the host-side ceiling of the end-to-end number: the same bytes (forcing in, outputs out) copied with no kernel at
+    # all, H2D and D2H on two streams, all ranks at once (they share the host's memory system and PCIe root complexes)
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        with torch.cuda.stream(s_h2d):
+            f_dev.copy_(f_pin, non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            out_pin.copy_(out_dev, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    copy_s = time.perf_counter() - t0
+    t = torch.tensor([copy_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_ms_per_step = 1e3 * float(t.item()) / Ke
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -331,7 +362,8 @@ def run_ours(args):
             peak, which = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = B_ALG * C * recs_per_launch / (kernel_ms * 1e-3) / 1e9
+        b_alg = 8 * n_out if args.ensemble else B_ALG       # ensemble: the sets share the forcing columns
+        achieved = b_alg * C * recs_per_launch / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k_step_traffic.json")
         if os.path.exists(tpath):
@@ -346,13 +378,15 @@ def run_ours(args):
             dfma_peak = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "strong" if (args.strong or args.ensemble) else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": ("synthetic 100k-cell grid, 3 soil layers, water-balance mode, daily step, "
                                     "10 years (one step = one simulated year of every cell)") if
                                    (C == 100000 and R == 365 and args.bands == 1 and args.dt == 24) else
-                                   (("ensemble of %d parameter sets x %d basin cells sharing %d forcing columns, outputs RUNOFF+BASEFLOW, "
-                                     % (args.ensemble, C // max(args.ensemble, 1), C // max(args.ensemble, 1)) if args.ensemble else "") +
+                                   (("ensemble of %d parameter sets (%d on this rank) x %d basin cells sharing %d forcing columns, outputs RUNOFF+BASEFLOW, "
+                                     % (args.ensemble, args.ensemble_local, C // max(args.ensemble_local, 1), C // max(args.ensemble_local, 1)) if args.ensemble else "") +
+                                    (("BASELINE configuration %d: " % args.config) if args.config else "") +
+                                    (("%d-cell grid sharded by cell blocks over %d rank(s), this rank " % (args.cells, world)) if args.strong else "") +
                                     "synthetic %d-cell grid, 3 soil layers, %d snow band(s), %d-hourly step, "
                                     "%d records per step" % (C, args.bands, args.dt, R)),
                        "cells_per_gpu": C, "records_per_step": R, "active_tile_band_units_per_gpu": m.num_units,
@@ -363,15 +397,19 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(f_host.nbytes),
                     "d2h_bytes_per_step": int(out_np.nbytes), "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
+                    "copies_only_ms_per_step": copy_ms_per_step,      # no kernels: what the host and PCIe allow, all ranks at once
+                    "copies_only_GBps_per_rank": (f_host.nbytes + out_np.nbytes) / 1e9 / (copy_ms_per_step * 1e-3),
                     "kernel_ms_in_last_step": e2e_kernel_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel": "k_units", "kernel_ms": kernel_ms,
-                         "launches_timed": pairs, "records_per_launch": recs_per_launch,
+                         "traffic": traffic, "peak_source": which,
+                         "kernel": "step kernels of one record: k_front + k_back (step stream) || k_snow + k_back_list (snow stream)",
+                         "kernel_ms": kernel_ms, "launches_timed": krecs, "records_per_launch": recs_per_launch,
+                         "traffic_source": "profiles/k_step_traffic.json (ncu --set full at 100 000 cells) x cells / 100 000",
                          "kernel_share_of_gpu_time": units_ms / max(units_ms + cells_ms, 1e-9),   # compare with the ncu launch list
                          "kernel_share_of_step": units_ms / max(sum(step_ms), 1e-9),            # k_cells overlaps the next k_units
                          "k_cells_share_of_step": cells_ms / max(sum(step_ms), 1e-9),
-                         "algorithmic_bytes_per_cell_step": B_ALG,
+                         "algorithmic_bytes_per_cell_step": b_alg,
                          "note": "the step is FP64 / dependent-issue bound, not HBM-bound (SURVEY.md 8d): see the "
                                  "fp64 object and DESIGN.md section 6"},
             "step_kernels": {"snow_unit_record_share": diag["snow_unit_records"] / max(diag["unit_records"], 1),
@@ -426,7 +464,18 @@ def main():
     ap.add_argument("--ensemble", type=int, default=0,
                     help="BASELINE config 4: P parameter sets x --cells basin cells sharing the basin's forcing columns "
                          "(outputs RUNOFF and BASEFLOW only)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4],
+                    help="BASELINE.json configuration preset: 2 = the default (100k cells, daily, 365 records per step, weak scaling); "
+                         "3 = 1M cells in total, 5 snow bands, 3-hourly, cold, 32 records per step, STRONG scaling over the ranks; "
+                         "4 = 4096 parameter sets x 64 basin cells, sets sharded over the ranks (config 5: tools/bench_pipeline.py)")
+    ap.add_argument("--strong", action="store_true", help="--cells is the whole grid, sharded by cell blocks over the ranks")
     args = ap.parse_args()
+    if args.config == 3:
+        args.cells, args.bands, args.dt, args.cold, args.block, args.strong = 1000000, 5, 3, 5.0, 32, True
+        args.forcing_prep = False
+    elif args.config == 4:
+        args.cells, args.ensemble, args.block = 64, 4096, 355
+        args.forcing_prep = False
     if args.impl == "reference":
         run_reference(args)
     else:

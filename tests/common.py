@@ -55,10 +55,57 @@ def load_fixture(name):
 # Parity is therefore asserted as: every value finite; at least MIN_FRAC of all (variable, record,
 # cell) values within RTOL = 1e-9 relative; and the rest either inside a tight envelope (fixtures
 # where no switch flips) or confined to at most MAX_BAD_CELLS of the cells (large seeded grids).
-MIN_FRAC = 0.99
+# The bounds are about twice what the round-2 build measures on B200 (profiles/parity_r2.json, written by these very
+# tests): share of values within 1e-9 >= 0.99659 on every fixture and one-year grid, 0.99533 over 10 years x 2 000
+# cells; cells with a value outside the envelope 0 on the fixtures, <= 0.017 on the one-year seeded grids, 0.026 after
+# 10 years (configuration 2), 0.042 on the 5-band 3-hourly configuration-3 grid.  tools/parity_probe.py shows where a
+# divergent cell starts: a 1e-8 .. 1e-7 difference in EVAP_CANOP (mechanism 1) that a later snow / regime switch amplifies.
+MIN_FRAC = 0.995
+MIN_FRAC_LONG = 0.99    # multi-year runs: the divergent cells stay divergent, so the share of mismatching values grows
 ENV_ABS = 1e-5      # mm or W/m2
 ENV_REL = 1e-5
-MAX_BAD_CELLS = 0.10   # the reference algorithm rebuilt with FMA contraction shows 0.02-0.06 on the same grids
+MAX_BAD_CELLS = 0.04   # one-year grids; the reference algorithm rebuilt with FMA contraction shows 0.02-0.06 on the same grids
+
+
+# Every check_outputs() call leaves its measured statistics in gpurun_out/parity_<tier>.json (tier "gpu" when the CUDA
+# path produced `out`, "cpu" for the host harness); the GPU tier's file of the round is kept as profiles/parity_r2.json.
+_PARITY_LOG = {}
+
+
+def _record_parity(what, st, names, out, ref):
+    import json
+    tier = "gpu" if "CUDA" in what or _cuda_available() else "cpu"
+    by_var = {}
+    for i, n in enumerate(names):
+        e = relerr(out[i], ref[i])
+        k = int((e > RTOL).sum())
+        if k:
+            by_var[n] = {"beyond_rtol": k, "max_rel": float(e.max())}
+    entry = dict(st)
+    entry["beyond_rtol_by_variable"] = by_var
+    _PARITY_LOG[what] = entry
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "parity_%s.json" % tier)
+        old = {}
+        if os.path.exists(path):
+            try:
+                old = json.load(open(path))
+            except Exception:
+                old = {}
+        old.update(_PARITY_LOG)
+        json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
 
 
 def parity_stats(out, ref):
@@ -72,7 +119,7 @@ def parity_stats(out, ref):
             "cells_all_within_rtol": float((e <= RTOL).all(axis=(0, 1)).mean())}
 
 
-def check_outputs(out, ref, names, rtol=RTOL, what="", mode="envelope"):
+def check_outputs(out, ref, names, rtol=RTOL, what="", mode="envelope", min_frac=MIN_FRAC, max_bad_cells=MAX_BAD_CELLS):
     """mode: 'strict' (everything within rtol), 'envelope' (small fixtures), 'cells' (large grids)"""
     assert np.all(np.isfinite(out)), "%s: non-finite output" % what
     st = parity_stats(out, ref)
@@ -87,13 +134,14 @@ def check_outputs(out, ref, names, rtol=RTOL, what="", mode="envelope"):
           "cells with a value outside the envelope: %.4f" % (what, st["frac_within_rtol"], st["n"], rtol,
                                                             st["cells_all_within_rtol"], st["max_rel"], st["max_abs"],
                                                             st["bad_cell_frac"]))
+    _record_parity(what, st, names, out, ref)
     if mode == "strict":
         assert not worst, what + " parity failures:\n" + "\n".join(worst)
-    assert st["frac_within_rtol"] >= MIN_FRAC, what + ": only %.4f within rtol\n" % st["frac_within_rtol"] + "\n".join(worst)
+    assert st["frac_within_rtol"] >= min_frac, what + ": only %.4f within rtol\n" % st["frac_within_rtol"] + "\n".join(worst)
     if mode == "envelope":
         assert st["all_in_envelope"], what + " values outside the ill-conditioning envelope:\n" + "\n".join(worst)
     if mode == "cells":
-        assert st["bad_cell_frac"] <= MAX_BAD_CELLS, what + ": %.4f of cells diverge\n" % st["bad_cell_frac"] + "\n".join(worst)
+        assert st["bad_cell_frac"] <= max_bad_cells, what + ": %.4f of cells diverge\n" % st["bad_cell_frac"] + "\n".join(worst)
     return st
 
 

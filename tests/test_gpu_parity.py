@@ -169,6 +169,48 @@ def test_closure_and_sampled_parity_at_scale(VicRes):
     m.close(); o.close()
 
 
+def _oracle_threads(opt, lib, cells, month, doy, f, nthreads=16):
+    """the oracle over all cells, on threads (cells are independent; the C call releases the GIL)"""
+    import threading
+    C = f.shape[2]
+    o = oracle_lib.Oracle(opt, lib, cells)
+    o.init_state(f[0, 0])
+    ref = np.zeros((opt.n_out, f.shape[1], C))
+    edges = np.linspace(0, C, min(nthreads, C) + 1).astype(int)
+    th = [threading.Thread(target=o.step_range, args=(month, doy, f, ref, int(a), int(b))) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    o.close()
+    return ref
+
+
+@pytest.mark.parametrize("config", ["cfg2", "cfg3"])
+def test_parity_at_baseline_shapes(VicRes, config):
+    """BASELINE.json configurations at their full record counts: 2 000 cells of configuration 2's distribution x 3 653
+    daily records (10 years), and 500 cells of configuration 3's (5 snow bands, 3-hourly, cold, 30 % overstory) x 2 920
+    records (1 year), every cell and record against the oracle."""
+    if config == "cfg2":
+        C, nrec, nb, dt, cold, kw = 2000, 3653, 1, 24, 0.0, {}
+    else:
+        C, nrec, nb, dt, cold, kw = 500, 2920, 5, 3, 5.0, {"lat_range": (35.0, 65.0), "overstory_frac": 0.3}
+    lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=nb, seed=20261019, **kw)
+    f, month, doy = synth_soa.make_forcing(cells, nrec, dt_hours=dt, seed=7, cold=cold)
+    names = abi.default_out_vars(3) + ["WATER_ERROR"]
+    opt = abi.default_options(3, nb, dt, out=names)
+    m = VicRes(opt, lib, cells)
+    m.init_state(f[0, 0])
+    out, status = m.step(month, doy, f)
+    assert not status.any()
+    ref = _oracle_threads(opt, lib, cells, month, doy, f)
+    from common import MIN_FRAC_LONG
+    check_outputs(out, ref, names, what="%s shape CUDA vs oracle (%d cells x %d records)" % (config, C, nrec), mode="cells",
+                  min_frac=MIN_FRAC_LONG if config == "cfg2" else 0.995, max_bad_cells=0.06 if config == "cfg2" else 0.09)
+    assert np.abs(out[names.index("WATER_ERROR")]).max() < 5e-11
+    m.close()
+
+
 def test_errors_are_reported_not_fatal(VicRes):
     fx = load_fixture("daily_warm")
     m = VicRes(fx["opt"], fx["lib"], fx["cells"])
@@ -176,6 +218,31 @@ def test_errors_are_reported_not_fatal(VicRes):
     with pytest.raises(VicResError) as e:
         m.step(fx["month"][:5], fx["doy"][:5], np.ascontiguousarray(fx["forcing"][:, :5]))   # before init_state
     assert e.value.code == abi.VR_ERR_STATE
+    m.close()
+
+
+def test_failing_cell_is_reported_and_isolated(VicRes):
+    """A cell whose top layer starts below zero moisture makes arno_evap return ERROR (arno_evap.c:112-151: ratio > 1).
+    The library keeps going for the other cells, reports VR_ERR_CELL through the status array -- cell_status = first
+    failing record + 1 -- and the neighbours' results are bit-identical to a run without the broken cell."""
+    lib, cells = synth_soa.make_cells(96, nbands=1, seed=21)
+    f, month, doy = synth_soa.make_forcing(cells, 12, seed=4)
+    opt = abi.default_options(3, 1, 24)
+    m = VicRes(opt, lib, cells)
+    m.init_state(f[0, 0])
+    good, st0 = m.step(month, doy, f)
+    assert not st0.any()
+    m.close()
+    bad = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in cells.items()}
+    bad["init_moist"][0, 17] = -5.0
+    m = VicRes(opt, lib, bad)
+    m.init_state(f[0, 0])
+    out, st = m.step(month, doy, f)
+    assert st[17] == 1, "first failing record + 1, got %d" % st[17]
+    assert not np.delete(st, 17).any()
+    keep = np.delete(np.arange(96), 17)
+    assert np.array_equal(out[:, :, keep], good[:, :, keep])
+    # the count continues over blocks: a second block of records reports record 12 + 1 .. for a cell failing later
     m.close()
 
 

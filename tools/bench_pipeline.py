@@ -26,6 +26,10 @@ def main():
     ap.add_argument("--reservoirs", type=int, default=200)
     ap.add_argument("--days", type=int, default=365)
     ap.add_argument("--sets", type=int, default=8)
+    ap.add_argument("--vic-cells", type=int, default=0,
+                    help="cells of the runoff grid (BASELINE config 5: 1 000 000); the first rows x cols of them are the routed "
+                         "network's cells, the others lie outside the basin.  0 = one VIC cell per grid node")
+    ap.add_argument("--block", type=int, default=73, help="records per vr_step_block_device call when --vic-cells is set")
     a = ap.parse_args()
     import torch
     from make_route_golden import random_tree
@@ -45,7 +49,8 @@ def main():
                 xmask=np.full((nrow, ncol), 12500.0, np.float32))
     box = np.zeros(12, np.float32); box[0] = 1.0
     hdr = {"xllcorner": "100.0", "yllcorner": "10.0", "cellsize": "0.125"}
-    C = nrow * ncol                                       # one VIC cell per grid node, file order
+    CR = nrow * ncol                                      # routed cells: one VIC cell per grid node, file order
+    C = max(a.vic_cells, CR)
     lib, cells = synth_soa.make_cells(C, nlayer=3, nbands=1, seed=11, lat_range=(10.0, 35.0))
     site = synth_soa.make_site(C, seed=12, lat_range=(10.0, 35.0))
     site["lat"], site["elevation"] = cells["lat"], cells["elevation"]
@@ -74,21 +79,42 @@ def main():
     m = model.VicRes(opt, lib, cells, device=0)
     m.init_state(f_dev[0, 0].cpu().numpy())
     T["model_setup_s"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    out_dev = torch.empty((opt.n_out, nd, C), dtype=torch.float64, device=dev)
     doy = (np.arange(nd) % 365 + 1).astype(np.int32)
     month = np.minimum((doy - 1) // 31 + 1, 12).astype(np.int32)
-    m.step_device(month, doy, [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], out_dev.data_ptr())
-    m.synchronize()
-    T["step_s"] = time.perf_counter() - t0
+    idx = np.full(C, -1, dtype=np.int64)                  # VIC cell -> routing grid node (-1: outside the basin)
+    idx[:CR] = np.arange(CR)
+    if C == CR:
+        t0 = time.perf_counter()
+        out_dev = torch.empty((opt.n_out, nd, C), dtype=torch.float64, device=dev)
+        m.step_device(month, doy, [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], out_dev.data_ptr())
+        m.synchronize()
+        T["step_s"] = time.perf_counter() - t0
+        # 3. hand-off on the device: the eight routing columns through the "%.4f" round trip the flux files impose,
+        #    transposed to [cell][day] float32 (vr_route_fluxes_from_step); one VIC cell per grid node, same order
+        t0 = time.perf_counter()
+        cols, present_dev = route.fluxes_from_step_device(out_dev, names, idx, CR)
+        torch.cuda.synchronize(dev)
+        T["handoff_s"] = time.perf_counter() - t0
+    else:
+        # the runoff grid is larger than the routed basin: records in blocks, the basin's columns handed off per block
+        T["step_s"], T["handoff_s"] = 0.0, 0.0
+        parts, present_dev = [], None
+        out_dev = torch.empty((opt.n_out, a.block, C), dtype=torch.float64, device=dev)
+        for r0 in range(0, nd, a.block):
+            nr = min(a.block, nd - r0)
+            t0 = time.perf_counter()
+            ob = out_dev[:, :nr] if nr == a.block else torch.empty((opt.n_out, nr, C), dtype=torch.float64, device=dev)
+            m.step_device(month[r0:r0 + nr], doy[r0:r0 + nr], [f_dev[f, r0:r0 + nr].data_ptr() for f in range(abi.VR_NFORCING)],
+                          ob.data_ptr())
+            m.synchronize()
+            T["step_s"] += time.perf_counter() - t0
+            t0 = time.perf_counter()
+            cb, present_dev = route.fluxes_from_step_device(ob, names, idx, CR)
+            parts.append(cb)
+            torch.cuda.synchronize(dev)
+            T["handoff_s"] += time.perf_counter() - t0
+        cols = {k: torch.cat([p[k] for p in parts], dim=1).contiguous() for k in parts[0]}
     T["step_cell_steps_per_s"] = C * nd / T["step_s"]
-
-    # 3. hand-off on the device: the eight routing columns through the "%.4f" round trip the flux files impose,
-    #    transposed to [cell][day] float32 (vr_route_fluxes_from_step); one VIC cell per grid node, same order
-    t0 = time.perf_counter()
-    cols, present_dev = route.fluxes_from_step_device(out_dev, names, np.arange(C, dtype=np.int64), C)
-    torch.cuda.synchronize(dev)
-    T["handoff_s"] = time.perf_counter() - t0
     m.close()
 
     # 4. routing: unit hydrographs, convolution, reservoirs
@@ -111,8 +137,8 @@ def main():
     routed = sum(len(r.node(n)[1]) for n in range(r.nnodes))
     r.close()
     T["total_s"] = time.perf_counter() - t_all
-    line = {"workload": "config 5 chain: %d VIC cells on a %dx%d D8 network (%d routed cells in the catchment lists), %d reservoirs "
-                        "x %d rule sets, %d days" % (C, nrow, ncol, routed, nres, a.sets, nd),
+    line = {"workload": "config 5 chain: %d VIC cells, the first %d of them on a %dx%d D8 network (%d routed cells in the catchment lists), %d reservoirs "
+                        "x %d rule sets, %d days" % (C, CR, nrow, ncol, routed, nres, a.sets, nd),
             "stages": T, "station_flow_finite": bool(np.isfinite(res["flow"]).all()),
             "mean_station_discharge_m3s": float(res["flow"].mean())}
     print(json.dumps(line))
