@@ -133,9 +133,9 @@ VR_HD double pow_table_eval(double x, double y, const double *logtab, const doub
 }
 
 #if defined(__CUDACC__)
-static __device__ const double VR_POW_LOGTAB_G[2 * 129] = VR_POW_LOGTAB_INIT;
-static __device__ const double VR_POW_EXPTAB_G[64] = VR_POW_EXPTAB_INIT;
-__shared__ PowTables vr_pow_tables;
+static __device__ __align__(16) const double VR_POW_LOGTAB_G[2 * 129] = VR_POW_LOGTAB_INIT;
+static __device__ __align__(16) const double VR_POW_EXPTAB_G[64] = VR_POW_EXPTAB_INIT;
+__shared__ __align__(16) PowTables vr_pow_tables;
 // every kernel that reaches m_pow() calls this first (all threads of the block)
 __device__ __forceinline__ void pow_tables_init()
 {

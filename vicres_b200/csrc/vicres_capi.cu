@@ -37,10 +37,10 @@
 #define VR_FRONT_MINB 3
 #endif
 #ifndef VR_SNOW_CTA
-#define VR_SNOW_CTA 128
+#define VR_SNOW_CTA 512
 #endif
 #ifndef VR_SNOW_MINB
-#define VR_SNOW_MINB 4
+#define VR_SNOW_MINB 1
 #endif
 #ifndef VR_BACK_CTA
 #define VR_BACK_CTA 192
@@ -50,6 +50,9 @@
 #endif
 #ifndef VR_FRONT_STAGE
 #define VR_FRONT_STAGE 1     // k_front: constants staged in shared memory by bulk copies (0: read from global memory)
+#endif
+#ifndef VR_SNOW_LOCKSTEP
+#define VR_SNOW_LOCKSTEP 1   // k_snow: phase barriers across the block (one 512-thread block per SM): +10 %, profiles/r2_tuning.md
 #endif
 #define VR_CTA 256     // the set-up kernels
 
@@ -252,7 +255,8 @@ struct SnowIO {
 };
 
 // bits of M.uflag
-enum { UF_SNOWY = 1, UF_TIDY = 2, UF_SCLASS = 4 };     // SCLASS: snow class in the current chunk (k_classify)
+enum { UF_SNOWY = 1, UF_TIDY = 2, UF_SCLASS = 4, UF_FAIL = 8 };     // SCLASS: snow class in the current chunk (k_classify);
+                                                                   // FAIL: the unit's cell failed at set-up (never stepped)
 
 // uflag from the state block (after vr_init_state / vr_set_state / a state file)
 __global__ void k_unit_flags(DevModel M)
@@ -263,7 +267,7 @@ __global__ void k_unit_flags(DevModel M)
   const size_t U = (size_t)M.U;
   const bool snowy = st[ST_SWQ * U] > 0 || st[ST_SNOW_CANOPY * U] > 0 || st[ST_COVERAGE * U] != 0;
   const bool tidy = !snowy && ((int)st[ST_LAST_SNOW * U] != (int)MISSINGV || st[ST_MELTING * U] != 0. || st[ST_ALBEDO * U] != NEW_SNOW_ALB);
-  M.uflag[u] = (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
+  M.uflag[u] = (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0) | (M.cell_fail[M.u_cell[u]] ? UF_FAIL : 0);
 }
 
 // Classes of a chunk of records.  A unit belongs to the SNOW CLASS of the chunk when it carries snow at the start of the
@@ -278,8 +282,8 @@ __global__ void __launch_bounds__(256) k_classify(DevModel M, DevForcing F)
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t u = k < M.U ? k : M.U - 1;
   const int64_t c = M.u_cell[u];
-  const bool valid = k < M.U && M.cell_fail[c] == 0;
   const int flags = M.uflag[u];
+  const bool valid = k < M.U && !(flags & UF_FAIL);
   bool s = false;
   if (valid) {
     s = (flags & UF_SNOWY) != 0;
@@ -346,6 +350,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the two tables of the device power function into vr_pow_tables, on the same mbarrier as the block's stage (instead of
+// pow_tables_init()'s loads and block barrier)
+constexpr uint32_t POW_TABLE_BYTES = (uint32_t)sizeof(PowTables);
+__device__ __forceinline__ void pow_tables_bulk(uint64_t *bar)
+{
+  bulk_g2s(vr_pow_tables.logtab, VR_POW_LOGTAB_G, (uint32_t)sizeof(vr_pow_tables.logtab), bar);
+  bulk_g2s(vr_pow_tables.exptab, VR_POW_EXPTAB_G, (uint32_t)sizeof(vr_pow_tables.exptab), bar);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 {
   uint32_t ok;
@@ -360,7 +372,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 // tmrow: its staged canopy terms (row stride CTA)
 template <int EXTRAS, bool SUB, bool SNOW>
 __device__ __forceinline__ FrontOut front_unit(const DevModel &M, const DevForcing &F, int rec, int64_t u, int64_t c, int flags, int mon,
-                                               CellC cc, const double *tmrow, int64_t CTA, double *__restrict__ terms)
+                                               CellC cc, const double *tmrow, int64_t CTA, double *__restrict__ terms,
+                                               bool wr = true, bool lockstep = false)
 {
   UnitC uc;
   double cv, af;
@@ -368,7 +381,7 @@ __device__ __forceinline__ FrontOut front_unit(const DevModel &M, const DevForci
   SnowIO sio;
   sio.st = M.state + u;
   sio.U = (size_t)M.U;
-  sio.wr = true;
+  sio.wr = wr;
   double *st = M.state + u;
   const size_t U = (size_t)M.U;
   HotS h;
@@ -387,8 +400,9 @@ __device__ __forceinline__ FrontOut front_unit(const DevModel &M, const DevForci
   auto forc = [&](int kk) { return load_forcing(M, F, rec, kk, NS, u, c, mon, doy); };
   const FrontOut fo = unit_front<EXTRAS, SUB, SNOW>(cc, uc, cm, ae, forc, M.NF, M.NL, M.dt_hours, M.snow_step_hours, M.max_snow_temp,
                                                     M.min_rain_temp, h, snowy, tidy, sio, cv, af, M.tmap,
-                                                    terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true, false,
+                                                    terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, wr, lockstep,
                                                     tl, ap);
+  if (!wr) return fo;      // a thread that only keeps its block's barriers company (k_snow in lock step)
   st[ST_WDEW * U] = h.Wdew; st[ST_T0 * U] = h.T0; st[ST_T1 * U] = h.T1; st[ST_LONGUNDEROUT * U] = h.LongUnderOut;
   st[ST_TFOLIAGE * U] = h.Tfoliage;
   {     // hand-off to k_back
@@ -397,7 +411,7 @@ __device__ __forceinline__ FrontOut front_unit(const DevModel &M, const DevForci
     o[FO_EVAP0 * U] = fo.evap.v[0]; o[FO_EVAP1 * U] = fo.evap.v[1]; o[FO_EVAP2 * U] = fo.evap.v[2];
     o[FO_BEF0 * U] = fo.bef.v[0]; o[FO_BEF1 * U] = fo.bef.v[1]; o[FO_BEF2 * U] = fo.bef.v[2];
   }
-  const int nf = (flags & UF_SCLASS) | (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
+  const int nf = (flags & (UF_SCLASS | UF_FAIL)) | (snowy ? UF_SNOWY : 0) | (tidy ? UF_TIDY : 0);
   if (nf != flags) M.uflag[u] = nf;
   if (fo.err) atomicCAS(M.cell_status + c, 0, F.rec_abs + rec + 1);     // first failing record + 1 (arno_evap.c:112-151)
   return fo;
@@ -414,9 +428,11 @@ __global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel 
   const int64_t u0 = (int64_t)blockIdx.x * VR_FRONT_CTA;
   const int mon = __ldg(F.month + rec) - 1;
   if (VR_FRONT_STAGE && tid == 0) mbar_init(&bar, 1);
-  pow_tables_init();                                   // (block barrier: the mbarrier is initialised for everyone)
+  if (VR_FRONT_STAGE) __syncthreads();                 // the mbarrier is initialised for everyone
+  else pow_tables_init();
   if (VR_FRONT_STAGE && tid == 0) {
-    mbar_expect_tx(&bar, (uint32_t)(STAGE_ROWS * VR_FRONT_CTA * sizeof(double)));
+    mbar_expect_tx(&bar, (uint32_t)(STAGE_ROWS * VR_FRONT_CTA * sizeof(double)) + POW_TABLE_BYTES);
+    pow_tables_bulk(&bar);
     for (int k = 0; k < CC_FRONT_N; k++)
       bulk_g2s(stage + k * VR_FRONT_CTA, M.ccu + (size_t)k * M.US + u0, VR_FRONT_CTA * sizeof(double), &bar);
     for (int k = 0; k < TM_N; k++)
@@ -426,7 +442,7 @@ __global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel 
   const int64_t u = k < M.U ? k : M.U - 1;
   const int64_t c = M.u_cell[u];
   const int flags = M.uflag[u];
-  const bool mine = k < M.U && M.cell_fail[c] == 0 && !(flags & UF_SCLASS);
+  const bool mine = k < M.U && !(flags & (UF_SCLASS | UF_FAIL));
   if (VR_FRONT_STAGE) mbar_wait(&bar, 0);     // every thread: the block's shared memory must not be released under a copy in flight
   if (!mine) return;
   CellC cc;
@@ -482,15 +498,16 @@ __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, 
   const int tid = threadIdx.x;
   const int64_t u0 = (int64_t)blockIdx.x * VR_BACK_CTA;
   if (tid == 0) mbar_init(&bar, 1);
-  pow_tables_init();
+  __syncthreads();                                     // the mbarrier is initialised for everyone
   if (tid == 0) {
-    mbar_expect_tx(&bar, (uint32_t)(LK_N * VR_BACK_CTA * sizeof(double)));
+    mbar_expect_tx(&bar, (uint32_t)(LK_N * VR_BACK_CTA * sizeof(double)) + POW_TABLE_BYTES);
+    pow_tables_bulk(&bar);
     for (int k = 0; k < LK_N; k++)
       bulk_g2s(stage + k * VR_BACK_CTA, M.ccu + (size_t)loop_const_row(k, M.NL) * M.US + u0, VR_BACK_CTA * sizeof(double), &bar);
   }
   const int64_t k = u0 + tid;
   const int64_t u = k < M.U ? k : M.U - 1;
-  const bool mine = k < M.U && M.cell_fail[M.u_cell[u]] == 0 && !(M.uflag[u] & UF_SCLASS);
+  const bool mine = k < M.U && !(M.uflag[u] & (UF_SCLASS | UF_FAIL));
   mbar_wait(&bar, 0);
   if (!mine) return;
   LoopSmem lk;
@@ -511,12 +528,27 @@ __global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_snow(DevModel M, 
   const int n = M.snow_cnt[0];
   const int mon = __ldg(F.month + rec) - 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(M.snow_total, (unsigned long long)n);
+#if VR_SNOW_LOCKSTEP
+  // one block per SM whose warps pass the phases of the pass together (block barriers in surface_pass): every
+  // instruction-cache line is fetched once for all of them.  Threads past the end of the list shadow its last unit
+  // without writing anything, so that all threads of a block reach the barriers.
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const bool wr = i < n;
+    const int64_t u = M.snow_list[wr ? i : n - 1];
+    CellC cc;
+    cc.p = M.ccu + u; cc.C = M.US;
+    front_unit<EXTRAS, SUB, true>(M, F, rec, u, M.u_cell[u], M.uflag[u], mon, cc, M.tmu + (size_t)mon * TM_N * M.US + u, M.US, terms,
+                                  wr, true);
+  }
+#else
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t u = M.snow_list[i];
     CellC cc;
     cc.p = M.ccu + u; cc.C = M.US;
     front_unit<EXTRAS, SUB, true>(M, F, rec, u, M.u_cell[u], M.uflag[u], mon, cc, M.tmu + (size_t)mon * TM_N * M.US + u, M.US, terms);
   }
+#endif
 }
 
 template <int EXTRAS>
