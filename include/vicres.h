@@ -208,9 +208,10 @@ int  vr_read_state_file(vr_handle *h, const char *path, int32_t binary, const do
 int64_t vr_num_units(const vr_handle *h);      /* active tile x band pairs */
 int64_t vr_num_launches(const vr_handle *h);   /* kernels launched by this handle so far */
 int  vr_last_kernel_ms(vr_handle *h, float *ms); /* CUDA-event time of all kernels of the last block of records */
-/* CUDA-event times, summed over every kernel pair launched since the previous call of this function (at most
- * 8192 pairs are kept): k_units = the step of all units, k_cells = put_data of all cells; launch_pairs and the
- * records they covered.  Synchronises with the launches; resets the sums. */
+/* CUDA-event times, summed over every chunk of records launched since the previous call of this function (at most
+ * 8192 chunks are kept): units_ms = the step kernels of the chunk (k_forcing_slots, k_classify, then per record
+ * k_front, k_back and -- on the snow stream -- k_snow, k_back_list), cells_ms = k_cells (put_data of all cells);
+ * launch_pairs = chunks, records = the records they covered.  Synchronises with the launches; resets the sums. */
 int  vr_kernel_times(vr_handle *h, double *units_ms, double *cells_ms, int64_t *launch_pairs, int64_t *records);
 /* diagnostic: measured FP64 fused-multiply-add thread-instructions per second of the device (independent
  * chains on every SM), the denominator of bench.py's FP64 roofline */

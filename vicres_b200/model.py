@@ -192,7 +192,7 @@ class VicRes:
         return float(ms.value)
 
     def kernel_times(self):
-        """(k_units ms, k_cells ms, launch pairs, records) summed since the previous call; synchronises"""
+        """(step-kernel ms, k_cells ms, chunks, records) summed since the previous call; synchronises"""
         a, b, n, r = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
         self._check(self.L.vr_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(r)))
         return float(a.value), float(b.value), int(n.value), int(r.value)
