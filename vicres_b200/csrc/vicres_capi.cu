@@ -54,6 +54,9 @@
 #ifndef VR_SNOW_LOCKSTEP
 #define VR_SNOW_LOCKSTEP 1   // k_snow: phase barriers across the block (one 512-thread block per SM): +10 %, profiles/r2_tuning.md
 #endif
+#ifndef VR_A_STREAMS
+#define VR_A_STREAMS 1       // slot ranges of the non-snow class on streams of their own (VICRES_A_STREAMS overrides)
+#endif
 #define VR_CTA 256     // the set-up kernels
 
 using namespace vr;
@@ -420,12 +423,13 @@ __device__ __forceinline__ FrontOut front_unit(const DevModel &M, const DevForci
 // Record `rec` of the chunk, everything before runoff() for the units outside the chunk's snow class: one thread per unit
 // in slot order (the lanes of snow-class units idle).
 template <int EXTRAS>
-__global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
+__global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel M, DevForcing F, int rec, double *__restrict__ terms,
+                                                                       int64_t ub, int64_t ue)
 {
   extern __shared__ __align__(128) double stage[];     // [STAGE_ROWS][VR_FRONT_CTA]
   __shared__ uint64_t bar;
   const int tid = threadIdx.x;
-  const int64_t u0 = (int64_t)blockIdx.x * VR_FRONT_CTA;
+  const int64_t u0 = ub + (int64_t)blockIdx.x * VR_FRONT_CTA;     // this launch covers slots [ub, ue)
   const int mon = __ldg(F.month + rec) - 1;
   if (VR_FRONT_STAGE && tid == 0) mbar_init(&bar, 1);
   if (VR_FRONT_STAGE) __syncthreads();                 // the mbarrier is initialised for everyone
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(VR_FRONT_CTA, VR_FRONT_MINB) k_front(DevModel 
   const int64_t u = k < M.U ? k : M.U - 1;
   const int64_t c = M.u_cell[u];
   const int flags = M.uflag[u];
-  const bool mine = k < M.U && !(flags & (UF_SCLASS | UF_FAIL));
+  const bool mine = k < ue && !(flags & (UF_SCLASS | UF_FAIL));
   if (VR_FRONT_STAGE) mbar_wait(&bar, 0);     // every thread: the block's shared memory must not be released under a copy in flight
   if (!mine) return;
   CellC cc;
@@ -491,12 +495,13 @@ __device__ __forceinline__ void back_unit(const DevModel &M, int rec, int64_t u,
 // every hour instead of holding 36 registers, which is what lets the kernel keep all its warps resident at once (one
 // wave instead of two half-empty ones, profiles/r2_tuning.md).
 template <int EXTRAS>
-__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, int rec, double *__restrict__ terms)
+__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, int rec, double *__restrict__ terms, int64_t ub,
+                                                                     int64_t ue)
 {
   __shared__ __align__(128) double stage[LK_N * VR_BACK_CTA];
   __shared__ uint64_t bar;
   const int tid = threadIdx.x;
-  const int64_t u0 = (int64_t)blockIdx.x * VR_BACK_CTA;
+  const int64_t u0 = ub + (int64_t)blockIdx.x * VR_BACK_CTA;      // this launch covers slots [ub, ue)
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();                                     // the mbarrier is initialised for everyone
   if (tid == 0) {
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, 
   }
   const int64_t k = u0 + tid;
   const int64_t u = k < M.U ? k : M.U - 1;
-  const bool mine = k < M.U && !(M.uflag[u] & (UF_SCLASS | UF_FAIL));
+  const bool mine = k < ue && !(M.uflag[u] & (UF_SCLASS | UF_FAIL));
   mbar_wait(&bar, 0);
   if (!mine) return;
   LoopSmem lk;
@@ -712,6 +717,9 @@ struct vr_handle {
   DBuf<double> d_fo;
   DBuf<int32_t> d_uflag, d_snow_list, d_snow_cnt;
   DBuf<unsigned long long> d_snow_total;
+  int na = 1;                        // slot ranges of the non-snow class that run side by side (VICRES_A_STREAMS, 1..4)
+  cudaStream_t s_a[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_a[3] = {nullptr, nullptr, nullptr};
   bool snow_stream = true;           // k_snow on its own stream (VICRES_SNOW_STREAM=0: on the step stream, for A/B timing)
   bool detail = false;               // VICRES_TIME_KERNELS=1: CUDA events around every step kernel (vr_step_diag)
   std::vector<cudaEvent_t> dev;      // 6 per record: around k_front and k_back on the step stream, around k_snow on the snow stream
@@ -750,10 +758,19 @@ static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *te
     h->dev_used += 6;
   }
   if (e) cudaEventRecord(e[0], st);
-  k_front<EX><<<gf, VR_FRONT_CTA, smf, st>>>(h->M, F, rec, terms);
-  if (e) cudaEventRecord(e[1], st);
-  k_back<EX & EX_ZWT><<<gb, VR_BACK_CTA, 0, st>>>(h->M, rec, terms);
+  // the units outside the snow class, in h->na slot ranges that run their k_front -> k_back sequences side by side
+  const int na = h->na;
+  const int64_t per = ((U + na - 1) / na + 383) / 384 * 384;      // multiple of both block sizes
+  for (int a = 0; a < na; a++) {
+    const int64_t ub = a * per, ue = (ub + per < U) ? ub + per : U;
+    if (ub >= U) break;
+    cudaStream_t sa = a == 0 ? st : h->s_a[a - 1];
+    k_front<EX><<<(unsigned)((ue - ub + VR_FRONT_CTA - 1) / VR_FRONT_CTA), VR_FRONT_CTA, smf, sa>>>(h->M, F, rec, terms, ub, ue);
+    if (e && a == 0) cudaEventRecord(e[1], st);
+    k_back<EX & EX_ZWT><<<(unsigned)((ue - ub + VR_BACK_CTA - 1) / VR_BACK_CTA), VR_BACK_CTA, 0, sa>>>(h->M, rec, terms, ub, ue);
+  }
   if (e) cudaEventRecord(e[2], st);
+  (void)gf;
   if (e) cudaEventRecord(e[3], ss);
   if (h->M.NF > 1) k_snow<EX, true><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
   else k_snow<EX, false><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
@@ -851,6 +868,11 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   { const char *d = getenv("VICRES_TIME_KERNELS"); h->detail = d && d[0] == '1'; }
   { const char *d = getenv("VICRES_SNOW_STREAM"); h->snow_stream = !(d && d[0] == '0'); }
+  { const char *d = getenv("VICRES_A_STREAMS"); h->na = (d && d[0] >= '1' && d[0] <= '4') ? d[0] - '0' : VR_A_STREAMS; }
+  for (int a = 0; a < 3; a++) {
+    cudaStreamCreateWithFlags(&h->s_a[a], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_a[a], cudaEventDisableTiming);
+  }
   *out = h;
   return VR_OK;
 }
@@ -874,6 +896,10 @@ void vr_destroy(vr_handle *h)
   for (auto &t : h->evs) { cudaEventDestroy(t.u0); cudaEventDestroy(t.u1); cudaEventDestroy(t.c0); cudaEventDestroy(t.c1); }
   if (h->s_cells) cudaStreamDestroy(h->s_cells);
   if (h->s_snow) cudaStreamDestroy(h->s_snow);
+  for (int a = 0; a < 3; a++) {
+    if (h->s_a[a]) cudaStreamDestroy(h->s_a[a]);
+    if (h->ev_a[a]) cudaEventDestroy(h->ev_a[a]);
+  }
   if (h->ev_cls) cudaEventDestroy(h->ev_cls);
   if (h->ev_snow) cudaEventDestroy(h->ev_snow);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1115,6 +1141,7 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
       k_classify<<<(unsigned)((h->M.U + 255) / 256), 256, 0, st>>>(h->M, F);
       cudaEventRecord(h->ev_cls, st);
       cudaStreamWaitEvent(ss, h->ev_cls, 0);           // the snow stream starts when the chunk's classes are known
+      for (int a = 1; a < h->na; a++) cudaStreamWaitEvent(h->s_a[a - 1], h->ev_cls, 0);
       h->launches += 2;
       for (int rec = 0; rec < F.nrec; rec++) {
         switch (h->extras) {      // one set of kernel instances per set of optional results
@@ -1127,6 +1154,10 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
       }
       cudaEventRecord(h->ev_snow, ss);
       cudaStreamWaitEvent(st, h->ev_snow, 0);          // both classes have finished the chunk
+      for (int a = 1; a < h->na; a++) {
+        cudaEventRecord(h->ev_a[a - 1], h->s_a[a - 1]);
+        cudaStreamWaitEvent(st, h->ev_a[a - 1], 0);
+      }
     }
     if (t) cudaEventRecord(t->u1, st);
     cudaEventRecord(h->ev_units[b], st);
