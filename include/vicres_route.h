@@ -160,6 +160,14 @@ int  vr_route_set_uh_r(vr_route *h, int32_t node, const float *uh_r);
 int  vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *natural, const vr_reservoir *res,
                          const vr_res_options *opt, float *flow, const vr_res_series *out);
 
+/* Days [day_begin, day_end) of the same day loop (0-based): the reference's STEPBYSTEP mode (reservoir.f:1142-1150,
+ * 1596-1675: one day per run of `rout`, VOL / FLOWOUT / RESFLOWS carried from run to run in files).  With day_begin > 0
+ * `out` carries the state IN as well: out->vol[.][day_begin] and out->flowout[.][0 .. day_begin) must hold what the
+ * previous call left (the other series of `out`, when given, are kept for the earlier days).  `flow` is valid for the
+ * days < day_end.  Calling it for [0, d), [d, ndays) gives bit for bit what vr_route_reservoirs gives for [0, ndays). */
+int  vr_route_reservoirs_range(vr_route *h, int32_t ndays, int32_t nsets, int32_t day_begin, int32_t day_end, const float *natural,
+                               const vr_reservoir *res, const vr_res_options *opt, float *flow, const vr_res_series *out);
+
 /* ---- calibration objectives (toolbox/calibration/basin_calibration_eNSGAII.py:86-175) ---------------------
  * out[set][4] = NSE, TRMSE (Box-Cox 0.3), MSDE, ROCE of sim[set][ndays] (station discharge of every parameter
  * set, e.g. the `flow` of vr_route_reservoirs) against obs[ndays]; handle_negatives = the toolbox's abs(). */

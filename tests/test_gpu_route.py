@@ -136,6 +136,44 @@ def test_cuda_reservoir_day_loop_bit_exact_vs_oracle(Route, legacy):
     r.close(); o.close()
 
 
+def test_step_by_step_equals_one_run(Route):
+    """The reference's STEPBYSTEP mode (reservoir.f:1142-1150, 1596-1675): the day loop run one day -- or one block of days --
+    per call with VOL / FLOWOUT carried over must give, bit for bit, what the whole period gives in one call: every
+    series of every reservoir (chained ones included: their inflow is the upstream releases routed through UH_R over up to
+    107 earlier days) and the station discharge."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_route_golden import random_tree
+    rng = np.random.default_rng(24)           # (a seed whose random tree covers the grid: 540 active cells)
+    nrow, ncol, ndays = 24, 30, 260
+    d, out = random_tree(nrow, ncol, rng, fill=0.75)
+    active = np.argwhere(d > 0)
+    reser = np.zeros_like(d)
+    for i, k in enumerate(rng.choice(len(active), 25, replace=False)):
+        reser[tuple(active[k])] = i + 1
+    grid = dict(dir=d, reser=reser, velo=np.full((nrow, ncol), 1.5, np.float32), diff=np.full((nrow, ncol), 800.0, np.float32),
+                xmask=np.full((nrow, ncol), 20000.0, np.float32))
+    box = rng.dirichlet(np.ones(12)).astype(np.float32)
+    r = Route(grid, int(out[1]) + 1, int(nrow - out[0]), box)
+    nres = r.nnodes - 1
+    natural = (rng.gamma(0.6, 30.0, (r.nnodes, ndays)) * (rng.uniform(size=(r.nnodes, ndays)) < 0.7)).astype(np.float32)
+    sets = [[random_reservoir(rng, int((n + s) % 7), ndays) for n in range(nres)] for s in range(3)]
+    whole = r.reservoirs(natural, sets, 2001, 2)
+    # blocks of days, then day by day
+    st = None
+    for d0, d1 in [(0, 1), (1, 2), (2, 120), (120, 121), (121, ndays)]:
+        st = r.reservoirs(natural, sets, 2001, 2, days=(d0, d1), state=st)
+    for k in whole:
+        assert np.array_equal(whole[k], st[k], equal_nan=True), k
+    st = None
+    for dd in range(40):
+        st = r.reservoirs(natural, sets, 2001, 2, days=(dd, dd + 1), state=st)
+    for k, ext in route_abi.RES_SERIES:
+        assert np.array_equal(whole[k][:, :, :40 + ext], st[k][:, :, :40 + ext], equal_nan=True), k
+    assert np.array_equal(whole["flow"][:, :40], st["flow"][:, :40], equal_nan=True)
+    r.close()
+
+
 def test_cuda_open_water_evaporation(Route, tmp_path):
     """reservoir-surface cells: device MAKE_CONVOLUTION incl. Penman table evaporation against the binary's
     NF1.txt (1e-5: device UH_S) and against the oracle (res_evaporation uses no UH: bit-exact)"""

@@ -8,7 +8,7 @@ from common import GOLDEN
 from vicres_b200 import rout, route_abi
 
 
-def write_case(work, z, layout):
+def write_case(work, z, layout, sbs=None):
     files_ = list(z.files)
     z = {k: z[k] for k in files_}              # an NpzFile decompresses an array on every access
     nrow, ncol = z["dir"].shape
@@ -65,8 +65,9 @@ def write_case(work, z, layout):
             "# RESERVOIR PARAMETERS", "../parameters/reservoirs/res_par/", "# NATURALIZED FLOW", ".false. ",
             "../parameters/naturalized_flow/ ", "# YEAR AND MONTH OF MODEL OUTPUT TO ROUTE & ROUTED OUTPUT TO WRITE         ",
             "2000 1 2000 5 ", "2000 1 2000 5 ", "# NAME OF UNIT HYDROGRAPH FILE         ", "../parameters/unit_hydrograph/",
-            "# Simulation Mode: True: Run Step-by-Step Mode; False: Run all Steps", ".false.",
-            "# Start Day and Current Simulation Day (for STEPBYSTEP Version)", "2000 1 1 2000 5 31", "# Coupler Iteration", "1",
+            "# Simulation Mode: True: Run Step-by-Step Mode; False: Run all Steps", ".true." if sbs else ".false.",
+            "# Start Day and Current Simulation Day (for STEPBYSTEP Version)",
+            "2000 1 1 %d %d %d" % (sbs if sbs else (2000, 5, 31)), "# Coupler Iteration", "1",
             "# Write Outputs", ".true."]
     path = os.path.join(par, "configuration.txt")
     with open(path, "w") as f:
@@ -130,3 +131,51 @@ def test_rout_command_line_reproduces_the_binary_outputs(name, tmp_path):
         assert err[:, 5:].max() < 1e-3, "reservoir %s flow/energy columns vs the binary: %.3e" % (k[7:], err[:, 5:].max())
         nres += 1
     print("ROUT %s: station discharge max rel %.2e vs the binary, %d reservoir files" % (name, err.max(), nres))
+    # WRITE_DATA's mm file and WRITE_MONTH's summaries (write_routines.f:64-70, 248-331) against the binary's
+    for ext, col in (("day_mm", 3), ("month", 2), ("month_mm", 2), ("year", 1), ("year_mm", 1)):
+        a = np.loadtxt(os.path.join(out, "OUTLT." + ext), ndmin=2)
+        b = z["station_" + ext]
+        if name == "route_toy" and ext != "day_mm":     # the binary's own monthly summaries of the toy basin are NaN /
+            continue                                     # uninitialised (its FIRST/LAST months lie outside the 5 months run)
+        # (the binary prints 9999 99 99 for the dates of its .day_mm: only the values are compared there)
+        assert a.shape == b.shape and (ext == "day_mm" or np.array_equal(a[:, :col], b[:, :col])), ext
+        e = np.abs(a[:, col] - b[:, col]) / np.maximum(np.abs(b[:, col]), 1e-2 * np.abs(b[:, col]).max() + 1e-30)
+        assert e.max() < 1e-4, "%s vs the binary: %.3e" % (ext, e.max())
+    assert os.path.exists(os.path.join(out, "OUTLT.end_of_month"))
+
+
+@pytest.mark.gpu
+def test_rout_step_by_step_mode_equals_all_steps(tmp_path):
+    """STEPBYSTEP (rout.f:255-317, reservoir.f:1142-1150, 1596-1675): one simulated day per run of the command line,
+    state in the reference's text files; the appended STEPBYSTEP/<station>.day must hold, line by line, what the
+    all-steps run writes for the same days (chained reservoirs: rand20x16 has four)."""
+    z = np.load(os.path.join(GOLDEN, "route_rand20x16.npz"))
+    work = str(tmp_path)
+    cfgp = write_case(work, z, "current")
+    model_dir = os.path.join(work, "model")
+    cwd = os.getcwd()
+    os.chdir(model_dir)
+    try:
+        assert rout.main(["../parameters/configuration.txt"]) == 0
+        whole = open(os.path.join(work, "output", "OUTLT.day")).read().splitlines()
+        whole_mm = open(os.path.join(work, "output", "OUTLT.day_mm")).read().splitlines()
+        days = [(2000, 1, d) for d in range(1, 32)] + [(2000, 2, d) for d in range(1, 10)]
+        for sim in days:
+            write_case(work, z, "current", sbs=sim)
+            assert rout.main(["../parameters/configuration.txt"]) == 0
+    finally:
+        os.chdir(cwd)
+    got = open(os.path.join(work, "output", "STEPBYSTEP", "OUTLT.day")).read().splitlines()
+    got_mm = open(os.path.join(work, "output", "STEPBYSTEP", "OUTLT.day_mm")).read().splitlines()
+    assert got == whole[:len(days)] and got_mm == whole_mm[:len(days)]
+    # the carried files: this step's and the next step's storage (the one before is deleted, reservoir.f:1660-1668)
+    left = sorted(os.listdir(os.path.join(work, "output", "stepbystep")))
+    assert left == ["RESERVOIR_VOL_STATION1_STEP%d.txt" % len(days), "RESERVOIR_VOL_STATION1_STEP%d.txt" % (len(days) + 1)]
+    # a step whose predecessor was not simulated is refused, as the reference does (label 9004)
+    os.chdir(model_dir)
+    try:
+        write_case(work, z, "current", sbs=(2000, 3, 15))
+        with pytest.raises(FileNotFoundError):
+            rout.main(["../parameters/configuration.txt"])
+    finally:
+        os.chdir(cwd)

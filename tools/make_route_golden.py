@@ -199,6 +199,12 @@ def collect(work, name, d, reser, station_rc, hdr, velo, diff, xmask, box, flux,
         arrays["restxt_%d" % rid] = np.array(open(os.path.join(work, "parameters", "reservoirs", "res_par", "res%d.txt" % rid)).read())
         arrays["resday_%d" % rid] = np.loadtxt(os.path.join(work, "output", "reservoir_%d_OUTLT.day" % rid), skiprows=1)[:, 3:].astype(np.float32)
     arrays["station_flow"] = np.loadtxt(os.path.join(work, "output", "OUTLT.day"))[:, 3].astype(np.float32)
+    # the summaries of WRITE_DATA / WRITE_MONTH (write_routines.f:64-70, 248-331): <station>.day_mm, .month, .month_mm,
+    # .year, .year_mm as the binary wrote them (all columns, float64 of the printed text)
+    for ext in ("day_mm", "month", "month_mm", "year", "year_mm"):
+        f = os.path.join(work, "output", "OUTLT." + ext)
+        if os.path.exists(f) and os.path.getsize(f) > 0:
+            arrays["station_" + ext] = np.loadtxt(f, ndmin=2)
     out = os.path.join(ROOT, "tests", "golden", "route_%s.npz" % name)
     np.savez_compressed(out, **arrays)
     print("%-12s grid %dx%d nodes %d  uh files %s  %.0f kB" % (name, nrow, ncol, nf.shape[0], sorted(uh), os.path.getsize(out) / 1e3))

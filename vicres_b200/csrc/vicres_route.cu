@@ -338,6 +338,8 @@ struct ResC {            // one reservoir of one parameter set, host-prepared
 
 struct ResArgs {
   int nnodes, ndays, start_year, start_month, legacy;
+  int day0, day1;                      // days [day0, day1] (1-based) are operated; earlier days only replay the routing of
+                                       // their releases from the series already in the buffers (STEPBYSTEP restart)
   const ResC *res;                     // [nsets][nres]
   const float *pool;                   // rule 4/6 and irrigation series
   const float *natural;                // [nnodes][ndays]
@@ -369,12 +371,12 @@ __global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
     RF[q] = (I >= 1 && I <= nd) ? a.natural[(size_t)n * nd + I - 1] : 0.0f;
   }
   __syncthreads();
-  for (int I = 1; I <= nd; I++) {
+  for (int I = 1; I <= a.day1; I++) {
     // ---- phase A: operate every reservoir on day I ----
-    for (int J = threadIdx.x; J < nres; J += blockDim.x) {
+    for (int J = threadIdx.x; I >= a.day0 && J < nres; J += blockDim.x) {
       const ResC &r = a.res[(size_t)set * nres + J];
       const size_t b1 = ((size_t)set * nres + J) * (nd + 1), b0 = ((size_t)set * nres + J) * nd;
-      float vol = (I == 1) ? r.vol1 : a.vol[b1 + I - 1];
+      float vol = (I == 1) ? r.vol1 : a.vol[b1 + I - 1];      // (a restart at day0 > 1 finds VOL(day0) in the buffer)
       float vnext = 0.0f, flowin, flowout = 0.0f, turb = 0.0f, energy = 0.0f, htk = 0.0f, hho0 = 0.0f, hho1 = 0.0f;
       const int year = a.start_year + I / 365;
       bool write_h1 = false;
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(1024) k_reservoirs(ResArgs a)
   //      One thread per day: the serial chain of up to (reservoirs x 107) fp32 adds runs for all days at once.
   {
     const int k = nres, u0 = a.up_ptr[k], u1 = a.up_ptr[k + 1];
-    for (int I = 1 + threadIdx.x; I <= nd; I += blockDim.x) {
+    for (int I = 1 + threadIdx.x; I <= a.day1; I += blockDim.x) {
       float acc = RF[(size_t)k * W + I];
       if (I >= 2)
         for (int u = u0; u < u1; u++) {
@@ -1092,7 +1094,20 @@ int vr_route_set_uh_r(vr_route *h, int32_t node, const float *uh_r)
 int vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *natural, const vr_reservoir *res,
                         const vr_res_options *opt, float *flow, const vr_res_series *out)
 {
+  return vr_route_reservoirs_range(h, ndays, nsets, 0, ndays, natural, res, opt, flow, out);
+}
+
+// Days [day_begin, day_end) of the day loop (0-based).  day_begin > 0 continues a run: `out` then carries the state IN as
+// well -- out->vol[.][day_begin] (VOL of the first day to operate) and out->flowout[.][0 .. day_begin) (the releases whose
+// routing through UH_R still reaches later days) must hold what the previous call left; all series of `out` that are
+// given are updated for the operated days, `flow` for every day < day_end.  This is the reference's STEPBYSTEP mode
+// (reservoir.f:1142-1150, 1596-1675: one day per run of `rout`, VOL / FLOWOUT / RESFLOWS carried in files).
+int vr_route_reservoirs_range(vr_route *h, int32_t ndays, int32_t nsets, int32_t day_begin, int32_t day_end, const float *natural,
+                              const vr_reservoir *res, const vr_res_options *opt, float *flow, const vr_res_series *out)
+{
   if (!h || !natural || !opt || !flow || ndays < 1 || nsets < 1) return VR_ERR_ARG;
+  if (day_begin < 0 || day_end > ndays || day_begin >= day_end) return VR_ERR_ARG;
+  if (day_begin > 0 && (!out || !out->vol || !out->flowout)) { h->err = "a continued day loop needs the vol and flowout series of the run so far"; return VR_ERR_ARG; }
   const int nnodes = (int)h->nodes.size(), nres = nnodes - 1;
   if (nres > 0 && !res) return VR_ERR_ARG;
   RK(cudaSetDevice(h->device));
@@ -1138,10 +1153,20 @@ int vr_route_reservoirs(vr_route *h, int32_t ndays, int32_t nsets, const float *
   RK(h->d_flowin.res(S * R * D)); RK(h->d_flowout.res(S * R * D)); RK(h->d_turb.res(S * R * D));
   RK(h->d_energy.res(S * R * D)); RK(h->d_htk.res(S * R * D)); RK(h->d_flow.res(S * D));
   RK(cudaMemset(h->d_hho.p, 0, S * R * (D + 1) * sizeof(float)));
+  if (day_begin > 0 && nres > 0) {       // the state of the run so far
+    RK(cudaMemcpy(h->d_vol.p, out->vol, S * R * (D + 1) * sizeof(float), cudaMemcpyHostToDevice));
+    RK(cudaMemcpy(h->d_flowout.p, out->flowout, S * R * D * sizeof(float), cudaMemcpyHostToDevice));
+    if (out->hho) RK(cudaMemcpy(h->d_hho.p, out->hho, S * R * (D + 1) * sizeof(float), cudaMemcpyHostToDevice));
+    if (out->flowin) RK(cudaMemcpy(h->d_flowin.p, out->flowin, S * R * D * sizeof(float), cudaMemcpyHostToDevice));
+    if (out->turbine) RK(cudaMemcpy(h->d_turb.p, out->turbine, S * R * D * sizeof(float), cudaMemcpyHostToDevice));
+    if (out->energy) RK(cudaMemcpy(h->d_energy.p, out->energy, S * R * D * sizeof(float), cudaMemcpyHostToDevice));
+    if (out->htk) RK(cudaMemcpy(h->d_htk.p, out->htk, S * R * D * sizeof(float), cudaMemcpyHostToDevice));
+  }
   std::vector<int> up0(nnodes + 1, 0);
   if (nres == 0) RK(h->d_up_ptr.put(up0.data(), up0.size()));
   ResArgs a;
   a.nnodes = nnodes; a.ndays = ndays; a.start_year = opt->start_year; a.start_month = opt->start_month;
+  a.day0 = day_begin + 1; a.day1 = day_end;
   a.legacy = opt->legacy_rule_curve; a.res = h->d_res.p; a.pool = h->d_pool.p; a.natural = h->d_natural.p;
   a.uh_r = h->d_uh_r.p; a.target = h->d_target.p; a.up_ptr = h->d_up_ptr.p; a.up_idx = h->d_up_idx.p;
   a.resflows = h->d_resflows.p; a.vol = h->d_vol.p; a.hho = h->d_hho.p; a.flowin = h->d_flowin.p;

@@ -12,7 +12,7 @@ from . import model, route_abi
 ROUTE_EXPORTS = ["vr_route_create", "vr_route_destroy", "vr_route_last_error", "vr_route_num_nodes",
                  "vr_route_node_info", "vr_route_node_cells", "vr_route_get_uh", "vr_route_convolve",
                  "vr_route_convolve_ex", "vr_route_convolve_in", "vr_route_last_kernel_ms", "vr_route_res_info", "vr_route_get_uh_r",
-                 "vr_route_set_uh_r", "vr_route_reservoirs", "vr_objectives", "vr_route_fluxes_from_step"]
+                 "vr_route_set_uh_r", "vr_route_reservoirs", "vr_route_reservoirs_range", "vr_objectives", "vr_route_fluxes_from_step"]
 
 
 def _lib():
@@ -36,6 +36,7 @@ def _lib():
         L.vr_route_get_uh_r.argtypes = [vp, C.c_int32, vp]
         L.vr_route_set_uh_r.argtypes = [vp, C.c_int32, vp]
         L.vr_route_reservoirs.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+        L.vr_route_reservoirs_range.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L.vr_objectives.argtypes = [C.c_int, C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]
         L.vr_route_fluxes_from_step.argtypes = [C.c_int, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, C.c_int64, vp, vp]
         L._route_ready = True
@@ -125,23 +126,28 @@ class Route:
         assert uh_r.size == route_abi.NS
         self._check(self.L.vr_route_set_uh_r(self.h, n, uh_r.ctypes.data))
 
-    def reservoirs(self, natural, sets, start_year, start_month, legacy=False):
+    def reservoirs(self, natural, sets, start_year, start_month, legacy=False, days=None, state=None):
         """MAKE_CONVOLUTIONRS for len(sets) parameter sets at once.  natural: [nnodes, ndays] from convolve();
         sets: list of lists of route_abi.reservoir dicts (node order).  Returns dict: flow [nsets, ndays] and
-        vol/hho [nsets, nres, ndays+1], flowin/flowout/turbine/energy/htk [nsets, nres, ndays]."""
+        vol/hho [nsets, nres, ndays+1], flowin/flowout/turbine/energy/htk [nsets, nres, ndays].
+        days = (d0, d1) operates only the days [d0, d1) (the reference's STEPBYSTEP mode, vr_route_reservoirs_range);
+        with d0 > 0 `state` is the dict a previous call returned (its series are continued in place)."""
         natural = np.ascontiguousarray(natural, dtype=np.float32)
         assert natural.shape[0] == self.nnodes
         ndays, nres, nsets = natural.shape[1], self.nnodes - 1, len(sets)
         arr, keep = route_abi.pack_reservoirs(sets) if nres else (None, None)
         opt = route_abi.vr_res_options(start_year, start_month, int(legacy))
-        out = {"flow": np.zeros((nsets, ndays), dtype=np.float32)}
+        d0, d1 = days if days is not None else (0, ndays)
+        out = state if (state is not None and d0 > 0) else {"flow": np.zeros((nsets, ndays), dtype=np.float32)}
         ser = route_abi.vr_res_series()
         for k, ext in route_abi.RES_SERIES:
-            out[k] = np.zeros((nsets, nres, ndays + ext), dtype=np.float32)
+            if k not in out:
+                out[k] = np.zeros((nsets, nres, ndays + ext), dtype=np.float32)
+            assert out[k].shape == (nsets, nres, ndays + ext) and out[k].dtype == np.float32 and out[k].flags.c_contiguous
             setattr(ser, k, out[k].ctypes.data_as(C.POINTER(C.c_float)))
-        self._check(self.L.vr_route_reservoirs(self.h, ndays, nsets, natural.ctypes.data,
-                                               C.cast(arr, C.c_void_p) if nres else None, C.cast(C.pointer(opt), C.c_void_p),
-                                               out["flow"].ctypes.data, C.cast(C.pointer(ser), C.c_void_p)))
+        self._check(self.L.vr_route_reservoirs_range(self.h, ndays, nsets, int(d0), int(d1), natural.ctypes.data,
+                                                     C.cast(arr, C.c_void_p) if nres else None, C.cast(C.pointer(opt), C.c_void_p),
+                                                     out["flow"].ctypes.data, C.cast(C.pointer(ser), C.c_void_p)))
         return out
 
     def last_kernel_ms(self):
