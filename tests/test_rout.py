@@ -179,3 +179,94 @@ def test_rout_step_by_step_mode_equals_all_steps(tmp_path):
             rout.main(["../parameters/configuration.txt"])
     finally:
         os.chdir(cwd)
+
+
+def _build_c_rout(tmp_path):
+    import subprocess
+    from common import ROOT
+    from vicres_b200 import build
+    build.build()
+    exe = str(tmp_path / "rout_gpu")
+    subprocess.run(["gcc", "-O2", "-Wall", "-Wno-format-truncation", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "host", "rout_gpu.c"), "-L", os.path.join(ROOT, "vicres_b200"), "-lvicres", "-lm",
+                    "-Wl,-rpath," + os.path.join(ROOT, "vicres_b200")], check=True)
+    return exe
+
+
+def test_c_rout_host_compiles_against_the_headers(tmp_path):
+    """CPU tier: host/rout_gpu.c is plain C over include/vicres_route.h; without a GPU it parses the case and stops at the
+    first device call with the library's message (no CPU path)."""
+    import subprocess
+    import torch
+    exe = _build_c_rout(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr
+    z = np.load(os.path.join(GOLDEN, "route_rand12x10.npz"))
+    write_case(str(tmp_path), z, "current")
+    r = subprocess.run([exe, "../parameters/configuration.txt"], capture_output=True, text=True, cwd=os.path.join(str(tmp_path), "model"))
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "vr_route_create" in r.stderr, r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,layout,legacy", [("route_rand20x16", "current", True), ("route_rand20x16", "binary", False),
+                                                ("route_toy", "current", True)])
+def test_c_rout_host_writes_the_same_files_as_the_python_command_line(name, layout, legacy, tmp_path):
+    """host/rout_gpu.c (plain C: configuration, grids, stations, UH.all, flux files, resN.txt, writers) against
+    python -m vicres_b200.rout on the same case: every file of the output directory, value for value (the two hosts do
+    the same fp32 arithmetic for FACTOR and the summaries; the routing itself is the same library calls)."""
+    import subprocess, shutil
+    exe = _build_c_rout(tmp_path)
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    work = str(tmp_path)
+    write_case(work, z, layout)
+    model_dir = os.path.join(work, "model")
+    cwd = os.getcwd()
+    os.chdir(model_dir)
+    try:
+        assert rout.main(["../parameters/configuration.txt"] + (["--legacy"] if legacy else [])) == 0
+    finally:
+        os.chdir(cwd)
+    out = os.path.join(work, "output")
+    shutil.move(out, os.path.join(work, "output_py"))
+    os.makedirs(out)
+    r = subprocess.run([exe, "../parameters/configuration.txt"] + (["--legacy"] if legacy else []), capture_output=True, text=True,
+                       cwd=model_dir)
+    assert r.returncode == 0, r.stderr[-2000:]
+    names = sorted(n for n in os.listdir(os.path.join(work, "output_py")) if os.path.isfile(os.path.join(work, "output_py", n)))
+    assert sorted(n for n in os.listdir(out) if os.path.isfile(os.path.join(out, n))) == names and len(names) >= 7
+    same = 0
+    for n in names:
+        ta, tb = open(os.path.join(out, n)).read(), open(os.path.join(work, "output_py", n)).read()
+        if ta == tb:
+            same += 1
+            continue
+        skip = 1 if n.startswith("reservoir_") else 0
+        a, b = np.loadtxt(os.path.join(out, n), skiprows=skip, ndmin=2), np.loadtxt(os.path.join(work, "output_py", n), skiprows=skip, ndmin=2)
+        assert a.shape == b.shape, n
+        # FACTOR holds |sin(lat - size/2) - sin(lat + size/2)| in fp32 (reservoir.f:357-364): a cancellation that turns the one
+        # ulp between numpy's float32 sin and libm's sinf into ~5e-6 relative; it scales the flows of the --legacy variant
+        # (FACTOR * 0.028) and the mm files.  Nothing else may differ.
+        # (releases are storage differences divided by 86.4: an fp32 ulp of a storage is up to 2e-4 of the release column's range)
+        bad = np.argwhere(~(np.abs(a - b) <= 2e-5 * np.abs(b) + 2e-4 * np.abs(b).max(axis=0, keepdims=True) * (1 if legacy else 0)))
+        assert len(bad) == 0, "%s: %d values differ, first at %s: %r vs %r" % (n, len(bad), bad[0], a[tuple(bad[0])], b[tuple(bad[0])])
+    print("ROUT_GPU (C host) %s %s: %d of %d files byte-identical to the Python command line's" % (name, layout, same, len(names)))
+    assert same >= 1
+
+
+@pytest.mark.gpu
+def test_c_rout_host_step_by_step(tmp_path):
+    """the C host in STEPBYSTEP mode: 12 consecutive one-day runs append the first 12 lines of its all-steps run"""
+    import subprocess
+    exe = _build_c_rout(tmp_path)
+    z = np.load(os.path.join(GOLDEN, "route_rand20x16.npz"))
+    work = str(tmp_path)
+    model_dir = os.path.join(work, "model")
+    write_case(work, z, "current")
+    assert subprocess.run([exe, "../parameters/configuration.txt"], cwd=model_dir).returncode == 0
+    whole = open(os.path.join(work, "output", "OUTLT.day")).read().splitlines()
+    for d in range(1, 13):
+        write_case(work, z, "current", sbs=(2000, 1, d))
+        assert subprocess.run([exe, "../parameters/configuration.txt"], cwd=model_dir).returncode == 0
+    got = open(os.path.join(work, "output", "STEPBYSTEP", "OUTLT.day")).read().splitlines()
+    assert got == whole[:12]
