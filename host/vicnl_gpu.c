@@ -8,7 +8,8 @@
  *   vr_global_read -> vr_params_read -> vr_read_forcing_file (per cell) -> vr_atmos_prepare
  *   -> vr_create / vr_set_veglib / vr_set_cells / vr_init_state | vr_read_state_file
  *   -> vr_step_block (in blocks of records; the state stays on the GPU) [-> vr_write_state_file]
- *   -> vr_write_results ("fluxes_<lat>_<lng>", "snow_<lat>_<lng>")
+ *   -> [vr_aggregate when OUT_STEP > TIME_STEP] -> vr_write_results_sel (the default "fluxes_<lat>_<lng>" / "snow_<lat>_<lng>"
+ *      or the files of the N_OUTFILES / OUTFILE / OUTVAR lines; ASCII or BINARY_OUTPUT)
  *
  * Build:  gcc -O2 -Iinclude -o host/vicnl_gpu host/vicnl_gpu.c -Lvicres_b200 -lvicres -Wl,-rpath,$PWD/vicres_b200
  * No numerics here: every number comes from the library, which has no CPU path.
@@ -116,6 +117,12 @@ int main(int argc, char **argv)
   /* the model */
   vr_options opt;
   vr_default_options(&opt, g.nlayer);
+  /* the output files and what the step has to compute for them (parse_output_info.c; put_data.c:686 inverts the aggregated
+   * conductance, so an aggregating run computes OUT_AERO_COND where a file asks for OUT_AERO_RESIST) */
+  static vr_outsel sel;
+  if (vr_outsel_read(gfile, g.nlayer, &sel) != VR_OK) die("output selection", vr_params_last_error());
+  const int ratio = g.out_step > 0 ? g.out_step / g.time_step : 1;
+  if (vr_outsel_step_vars(&sel, ratio > 1, opt.out_vars, &opt.n_out) != VR_OK) die("output selection", vr_params_last_error());
   opt.nbands = g.snow_band; opt.dt_hours = g.time_step; opt.snow_step_hours = g.snow_step;
   opt.max_snow_temp = g.max_snow_temp; opt.min_rain_temp = g.min_rain_temp; opt.wind_h = g.wind_h;
   vr_handle *h = NULL;
@@ -154,16 +161,45 @@ int main(int argc, char **argv)
     r0 += nr;
   }
 
-  /* write_data: the default fluxes / snow files (set_output_defaults.c:66-93) */
-  const int nflux = 20 + g.nlayer - 1;
-  int32_t cols[VR_MAX_OUT];
-  for (i = 0; i < nflux; i++) cols[i] = i;
-  if (vr_write_results(g.result_dir, "fluxes", g.grid_decimal, C, lat, lng, nrecs, year, month, day, g.time_step < 24 ? hour : NULL,
-                       nflux, cols, out) != VR_OK) die("fluxes files", vr_params_last_error());
-  for (i = 0; i < 4; i++) cols[i] = nflux + i;
-  if (vr_write_results(g.result_dir, "snow", g.grid_decimal, C, lat, lng, nrecs, year, month, day, g.time_step < 24 ? hour : NULL,
-                       4, cols, out) != VR_OK) die("snow files", vr_params_last_error());
-  fprintf(stderr, "vicnl_gpu: %lld cells x %d records written to %s\n", (long long)C, nrecs, g.result_dir);
+  /* put_data.c:665-688: one output record per `ratio` model records, dated by the interval's last record */
+  int32_t agg_vars[VR_MAX_OUT + 1], n_rows = n_out, want_resist = 0, want_cond = 0, fi, k;
+  for (fi = 0; fi < sel.nfiles; fi++)
+    for (k = 0; k < sel.ncols[fi]; k++) {
+      want_resist |= sel.var[fi][k] == VR_OUT_AERO_RESIST;
+      want_cond |= sel.var[fi][k] == VR_OUT_AERO_COND;
+    }
+  for (i = 0; i < n_out; i++) agg_vars[i] = opt.out_vars[i];
+  int nout = nrecs;
+  if (ratio > 1) {
+    nout = nrecs / ratio;
+    int cond_row = -1;
+    for (i = 0; i < n_out; i++) if (opt.out_vars[i] == VR_OUT_AERO_COND) cond_row = i;
+    if (want_resist && want_cond) n_rows = n_out + 1;      /* both columns come from the one conductance row */
+    double *src = malloc(sizeof(double) * (size_t)n_rows * nout * ratio * C), *agg = malloc(sizeof(double) * (size_t)n_rows * nout * C);
+    for (i = 0; i < n_rows; i++)
+      memcpy(src + (size_t)i * nout * ratio * C, out + (size_t)(i < n_out ? i : cond_row) * nrecs * C, sizeof(double) * (size_t)nout * ratio * C);
+    if (want_resist) agg_vars[want_cond ? n_out : cond_row] = VR_OUT_AERO_RESIST;
+    if (vr_aggregate(device, n_rows, agg_vars, 1, nout * ratio, ratio, C, src, agg) != VR_OK) die("vr_aggregate", vr_last_error(NULL));
+    free(src); free(out);
+    out = agg;
+    for (i = 0; i < nout; i++) {
+      year[i] = year[i * ratio + ratio - 1]; month[i] = month[i * ratio + ratio - 1];
+      day[i] = day[i * ratio + ratio - 1]; hour[i] = hour[i * ratio + ratio - 1];
+    }
+  }
+  /* write_data.c */
+  const int out_dt = g.out_step > 0 ? g.out_step : g.time_step;
+  for (fi = 0; fi < sel.nfiles; fi++) {
+    int32_t rows[VR_MAX_OUTCOLS];
+    for (k = 0; k < sel.ncols[fi]; k++) {
+      rows[k] = -1;
+      for (i = 0; i < n_rows; i++) if (agg_vars[i] == sel.var[fi][k]) rows[k] = i;
+      if (rows[k] < 0) die("output selection", "column without a computed row");
+    }
+    if (vr_write_results_sel(g.result_dir, &sel, fi, g.grid_decimal, C, lat, lng, nout, year, month, day, out_dt < 24 ? hour : NULL,
+                             g.binary_output, rows, out) != VR_OK) die(sel.prefix[fi], vr_params_last_error());
+  }
+  fprintf(stderr, "vicnl_gpu: %lld cells x %d output records written to %s\n", (long long)C, nout, g.result_dir);
   vr_destroy(h);
   vr_params_free(par);
   return 0;

@@ -51,6 +51,47 @@ int  vr_write_results(const char *result_dir, const char *prefix, int32_t grid_d
                       const int32_t *day, const int32_t *hour, int32_t n_cols, const int32_t *cols,
                       const double *out);
 
+/* ---- output selection, aggregation and the result writer in full (parse_output_info.c:55-125, set_output_defaults.c,
+ * put_data.c:665-790, write_data.c) ------------------------------------------------------------------------------ */
+#define VR_MAX_OUTFILES 8
+#define VR_MAX_OUTCOLS 64
+enum { VR_OUT_TYPE_DEFAULT = 0, VR_OUT_TYPE_CHAR, VR_OUT_TYPE_SINT, VR_OUT_TYPE_USINT, VR_OUT_TYPE_INT, VR_OUT_TYPE_FLOAT,
+       VR_OUT_TYPE_DOUBLE };                       /* vicNl_def.h: OUT_TYPE_* */
+/* The files a run writes and their columns.  A column is one ELEMENT of a reference variable (OUT_SOIL_LIQ is nlayer
+ * columns); format / type / mult belong to the variable as in the reference (out_data[varid]). */
+typedef struct vr_outsel {
+  int32_t nfiles;
+  char    prefix[VR_MAX_OUTFILES][64];
+  int32_t ncols[VR_MAX_OUTFILES];
+  int32_t var[VR_MAX_OUTFILES][VR_MAX_OUTCOLS];          /* VR_OUT_* id of the column                          */
+  char    format[VR_MAX_OUTFILES][VR_MAX_OUTCOLS][12];   /* printf format of the ASCII column ("%.4f")          */
+  int32_t type[VR_MAX_OUTFILES][VR_MAX_OUTCOLS];         /* binary type (OUT_TYPE_FLOAT unless the OUTVAR line says otherwise) */
+  double  mult[VR_MAX_OUTFILES][VR_MAX_OUTCOLS];         /* binary multiplier                                   */
+} vr_outsel;
+/* N_OUTFILES / OUTFILE / OUTVAR lines of a global parameter file; without them the default pair "fluxes" (20 variables,
+ * 20 + nlayer - 1 columns) and "snow" (4) of set_output_defaults.c:66-162.  An unknown variable name is an error, as in
+ * the reference (set_output_var). */
+int  vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *out);
+/* the VR_OUT_* ids the step must produce for a selection, each once, in order of first appearance: vars[VR_MAX_OUT].
+ * With aggregate != 0 (OUT_STEP > TIME_STEP) OUT_AERO_RESIST is produced as OUT_AERO_COND, because the reference
+ * aggregates the conductance and inverts the aggregate (put_data.c:686-688). */
+int  vr_outsel_step_vars(const vr_outsel *s, int32_t aggregate, int32_t *vars, int32_t *n);
+/* Temporal aggregation of put_data.c:665-685 on the device: in_dev [n][nrec][ncell] (device) -> out_dev [n][nrec/ratio][ncell]
+ * (device; may alias nothing), ratio = OUT_STEP / TIME_STEP records per output interval, vars[n] = the VR_OUT_* ids of the
+ * rows (a row that holds AERO_COND for a requested AERO_RESIST is passed as VR_OUT_AERO_RESIST with cond_for_resist != 0):
+ * fluxes are summed, storages take the interval's last record, the rest is averaged as sum of x / ratio, in record order. */
+int  vr_aggregate_device(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio,
+                         int64_t ncell, const double *in_dev, double *out_dev, void *cuda_stream);
+/* the same with host buffers (copies in, kernel, copies out) */
+int  vr_aggregate(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio, int64_t ncell,
+                  const double *in, double *out);
+/* File `file` of a selection for every cell: ASCII (write_data.c:196-226: date, then the columns in their formats separated by
+ * "\t ") or binary (write_data.c:103-193: 3 or 4 ints of date, then every column value * mult cast to its type).  hour == NULL
+ * when the output interval is a day or longer.  rows[c] = row of `out` ([.][nrec][ncell]) that holds column c of the file. */
+int  vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t file, int32_t grid_decimal, int64_t ncell,
+                          const float *lat, const float *lng, int32_t nrec, const int32_t *year, const int32_t *month,
+                          const int32_t *day, const int32_t *hour, int32_t binary, const int32_t *rows, const double *out);
+
 /* ---- global parameter file (get_global_param.c:210-727) and calendar (make_dmy.c) ---------------------- */
 #define VR_MAX_FORCE_TYPES 16
 typedef struct vr_global {

@@ -11,16 +11,153 @@ from vicres_b200 import files
 CASES = os.path.join(GOLDEN, "vicnl_case")
 
 
-def _stage(name, tmp_path):
+def _stage(name, tmp_path, variant=None):
     """copy the inputs, point the global file at the copy, drop the reference's results"""
     dst = tmp_path / name
     shutil.copytree(os.path.join(CASES, name), dst)
+    rdir = "results" if variant is None else "results_" + variant
     ref = tmp_path / (name + "_ref")
-    shutil.move(str(dst / "results"), ref)
-    os.makedirs(dst / "results")
-    g = dst / "global.txt"
+    shutil.move(str(dst / rdir), ref)
+    os.makedirs(dst / rdir)
+    g = dst / ("global.txt" if variant is None else "global_%s.txt" % variant)
     g.write_text(g.read_text().replace("@DIR@", str(dst)))
-    return str(g), str(dst / "results"), str(ref)
+    return str(g), str(dst / rdir), str(ref)
+
+
+# variants of the two cases: output interval, output selection, binary files (tools/make_vicnl_golden.py: VARIANTS)
+VARIANTS = [("sub3h", "out24"), ("sub3h", "out6sel"), ("daily", "selday"), ("sub3h", "bin"), ("sub3h", "bin24sel")]
+
+
+def _quantum(tok):
+    """one unit of the last printed digit of a number as the reference printed it"""
+    t = tok.lower()
+    if "e" in t:
+        m, e = t.split("e")
+        return 10.0 ** (int(e) - (len(m.split(".")[1]) if "." in m else 0))
+    return 10.0 ** -(len(t.split(".")[1]) if "." in t else 0)
+
+
+def _compare_ascii(res, ref, what):
+    """every token of every result file: identical text, or one unit of the last printed digit apart (cancellation
+    residues like OUT_WATER_ERROR ~ 1e-14 mm: both sides below 1e-9)"""
+    assert sorted(os.listdir(res)) == sorted(os.listdir(ref))
+    nbad = ntot = 0
+    for n in sorted(os.listdir(ref)):
+        la, lb = open(os.path.join(res, n)).read().split("\n"), open(os.path.join(ref, n)).read().split("\n")
+        assert len(la) == len(lb), n
+        for ra, rb in zip(la, lb):
+            ta, tb = ra.split("\t"), rb.split("\t")
+            assert len(ta) == len(tb), (n, ra, rb)
+            for xa, xb in zip(ta, tb):
+                ntot += 1
+                if xa == xb:
+                    continue
+                a, b = float(xa), float(xb)
+                nbad += int(max(abs(a), abs(b)) >= 1e-9)
+                assert abs(a - b) <= max(1.0001 * _quantum(xb.strip()) + 1e-5 * abs(b), 1e-9), (n, rb, xa, xb)
+    print("VICNL %s: %d of %d printed values differ from the reference's files (by one unit of the last digit)" % (what, nbad, ntot))
+    assert nbad <= 0.01 * ntot
+
+
+def _compare_binary(res, ref, gpath, nlayer, hourly, what):
+    """BINARY_OUTPUT files: same size, same dates; integer columns within one count (the cast truncates), floats within
+    fp32 rounding of the parity tolerance"""
+    sel = files.OutSel(gpath, nlayer)
+    assert sorted(os.listdir(res)) == sorted(os.listdir(ref))
+    nbad = ntot = 0
+    for prefix, cols in sel.files:
+        for n in sorted(x for x in os.listdir(ref) if x.startswith(prefix + "_")):
+            assert os.path.getsize(os.path.join(res, n)) == os.path.getsize(os.path.join(ref, n)), n
+            da, a = files.read_binary_results(os.path.join(res, n), cols, hourly)
+            db, b = files.read_binary_results(os.path.join(ref, n), cols, hourly)
+            assert np.array_equal(da, db), n
+            for k, c in enumerate(cols):
+                tol = 1.0001 / c[3] if c[2] in ("SINT", "USINT", "INT", "CHAR") else 1e-4 + 1e-5 * np.abs(b[k])
+                assert np.all(np.abs(a[k] - b[k]) <= tol), (n, c)
+                # doubles are written in full: "differs" = beyond the parity tolerance, for the other types any difference
+                nbad += int((np.abs(a[k] - b[k]) > 1e-9 * np.maximum(np.abs(b[k]), 1e-3)).sum() if c[2] == "DOUBLE" else (a[k] != b[k]).sum())
+            ntot += a.size
+    print("VICNL %s: %d of %d binary values differ from the reference's files" % (what, nbad, ntot))
+    assert nbad <= 0.01 * ntot
+
+
+def _compare_variant(case, variant, gpath, res, ref, what):
+    if variant.startswith("bin"):
+        _compare_binary(res, ref, gpath, 3, variant == "bin", what)
+    else:
+        _compare_ascii(res, ref, what)
+
+
+@pytest.mark.parametrize("case,variant", VARIANTS)
+def test_output_selection_of_the_variants_parses(case, variant, tmp_path):
+    """CPU tier: N_OUTFILES / OUTFILE / OUTVAR, OUT_STEP and BINARY_OUTPUT are read as parse_output_info.c reads them"""
+    gpath, _, ref = _stage(case, tmp_path, variant)
+    g = files.Global(gpath)
+    assert g.unsupported is None
+    sel = files.OutSel(gpath, g.nlayer)
+    fl = dict(sel.files)
+    assert sorted(set(n.split("_")[0] for n in os.listdir(ref))) == sorted(fl)
+    assert bool(g.binary_output) == variant.startswith("bin")
+    if variant in ("out24", "bin"):
+        assert [len(c) for c in fl.values()] == [22, 4] and g.out_step == (24 if variant == "out24" else 0)
+        assert sel.step_vars(aggregate=True)[15] == "AERO_COND" and sel.step_vars()[15] == "AERO_RESIST"
+    if variant == "out6sel":
+        assert g.out_step == 6
+        assert [c[0] for c in fl["wb"]] == ["PREC", "EVAP", "RUNOFF", "BASEFLOW", "SOIL_LIQ0", "SOIL_LIQ1", "SOIL_LIQ2", "DELSOILMOIST",
+                                            "DELSWE", "DELINTERCEPT", "WATER_ERROR"]
+        assert [c[1] for c in fl["wb"]][:4] == ["%.4f", "%.6f", "%.4f", "%.5e"] and fl["wb"][-1][1] == "%.3e"
+        names = sel.step_vars(aggregate=True)
+        assert names.count("AERO_COND") == 1 and "AERO_RESIST" not in names and sel.wants("AERO_RESIST") and sel.wants("AERO_COND")
+    if variant == "bin24sel":
+        assert [(c[0], c[2], c[3]) for c in fl["packed"]] == [
+            ("PREC", "USINT", 40.0), ("AIR_TEMP", "SINT", 100.0), ("SWE", "FLOAT", 1.0), ("SOIL_LIQ0", "DOUBLE", 1.0),
+            ("SOIL_LIQ1", "DOUBLE", 1.0), ("SOIL_LIQ2", "DOUBLE", 1.0), ("RUNOFF", "FLOAT", 1000.0), ("AERO_RESIST", "FLOAT", 1.0)]
+        # the reference's own file: 3 date ints + 2 + 2 + 4 + 24 + 4 + 4 bytes per daily record
+        n = os.listdir(ref)[0]
+        assert os.path.getsize(os.path.join(ref, n)) == (g.nrecs // 8) * (12 + 40)
+        d, v = files.read_binary_results(os.path.join(ref, n), fl["packed"], hourly=False)
+        assert tuple(d[0]) == (1986, 1, 1) and v.shape == (8, g.nrecs // 8)
+
+
+def test_unknown_output_variable_and_bad_out_step_are_refused(tmp_path):
+    gpath, _, _ = _stage("sub3h", tmp_path, "out6sel")
+    txt = open(gpath).read()
+    open(gpath, "w").write(txt + "OUTVAR OUT_LAKE_DEPTH\n")
+    with pytest.raises(Exception, match="OUT_LAKE_DEPTH"):
+        files.OutSel(gpath, 3)
+    open(gpath, "w").write(txt + "OUT_STEP 4\n")          # not a multiple of TIME_STEP 3 (get_global_param.c:754-760)
+    assert "OUT_STEP" in files.Global(gpath).unsupported
+    open(gpath, "w").write(txt.replace("N_OUTFILES 2", "N_OUTFILES 1"))
+    with pytest.raises(Exception, match="N_OUTFILES"):
+        files.OutSel(gpath, 3)
+
+
+@pytest.mark.gpu
+def test_aggregation_kernel_against_numpy():
+    """vr_aggregate: END / SUM / AVG / inverted conductance in record order (put_data.c:665-688)"""
+    rng = np.random.default_rng(5)
+    names = ["SWE", "RUNOFF", "SURF_TEMP", "AERO_RESIST", "SOIL_LIQ1", "AERO_COND"]
+    x = rng.uniform(0.1, 5.0, (len(names), 50, 301))
+    for ratio in (1, 2, 8):
+        got = files.aggregate(names, x, ratio)
+        nout = 50 // ratio
+        blk = x[:, :nout * ratio].reshape(len(names), nout, ratio, -1)
+        avg = np.zeros((len(names), nout, 301))
+        tot = np.zeros_like(avg)
+        for r in range(ratio):
+            avg += blk[:, :, r] / ratio
+            tot += blk[:, :, r]
+        want = np.stack([blk[0, :, -1], tot[1], avg[2], 1 / avg[3], blk[4, :, -1], avg[5]])
+        assert np.array_equal(got, want), ratio
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,variant", VARIANTS)
+def test_vicnl_output_variants_reproduce_the_reference_result_files(case, variant, tmp_path):
+    from vicres_b200 import vicnl
+    gpath, res, ref = _stage(case, tmp_path, variant)
+    assert vicnl.main(["-g", gpath]) == 0
+    _compare_variant(case, variant, gpath, res, ref, "%s/%s" % (case, variant))
 
 
 @pytest.mark.parametrize("name", ["daily", "sub3h"])
@@ -108,3 +245,14 @@ def test_c_host_driver_reproduces_the_reference_result_files(name, tmp_path):
         ntot += a.size
     print("VICNL_GPU (C host) %s: %d of %d printed values differ from the reference's files" % (name, nbad, ntot))
     assert nbad <= 0.01 * ntot
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,variant", VARIANTS)
+def test_c_host_driver_output_variants(case, variant, tmp_path):
+    import subprocess
+    exe = _build_c_driver(tmp_path)
+    gpath, res, ref = _stage(case, tmp_path, variant)
+    r = subprocess.run([exe, "-g", gpath, "--block", "64"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _compare_variant(case, variant, gpath, res, ref, "C host %s/%s" % (case, variant))

@@ -4,7 +4,9 @@ with the result files the UNMODIFIED reference writes for it (oracle/_ref/vicNl 
     python tools/make_vicnl_golden.py
 
 Two cases: `daily` (daily forcing, 2 snow bands, cells whose local time is not the forcing's) and `sub3h` (3-hourly
-AIR_TEMP forcing).  The global files are stored with @DIR@ in place of the case directory."""
+AIR_TEMP forcing).  Each case also holds VARIANTS of its global file (`global_<variant>.txt`, results in
+`results_<variant>/`): the output interval, the selection of output files / variables and the binary format.
+The global files are stored with @DIR@ in place of the case directory."""
 import os
 import shutil
 import subprocess
@@ -22,6 +24,25 @@ CASES = {
     "sub3h": dict(ncells=3, nlayer=3, nbands=1, ndays=60, dt=3, startyear=1986, cold=12.0, lat_range=(40, 62), seed=402),
 }
 
+# variant -> (case, lines appended to the case's global file; later lines win in get_global_param.c)
+VARIANTS = {
+    "out24": ("sub3h", ["OUT_STEP 24"]),
+    "out6sel": ("sub3h", ["OUT_STEP 6", "N_OUTFILES 2",
+                          "OUTFILE wb 9", "OUTVAR OUT_PREC", "OUTVAR OUT_EVAP %.6f", "OUTVAR OUT_RUNOFF", "OUTVAR OUT_BASEFLOW %.5e",
+                          "OUTVAR OUT_SOIL_MOIST", "OUTVAR OUT_DELSOILMOIST", "OUTVAR OUT_DELSWE", "OUTVAR OUT_DELINTERCEPT",
+                          "OUTVAR OUT_WATER_ERROR %.3e",
+                          "OUTFILE eb 8", "OUTVAR OUT_AERO_COND %.6f", "OUTVAR OUT_AERO_RESIST", "OUTVAR OUT_SURF_TEMP",
+                          "OUTVAR OUT_SNOW_MELT", "OUTVAR OUT_SWE %.3f", "OUTVAR OUT_PET_SHORT", "OUTVAR OUT_ROOTMOIST",
+                          "OUTVAR OUT_SHORTWAVE %.2f"]),
+    "selday": ("daily", ["N_OUTFILES 1", "OUTFILE cell 7", "OUTVAR OUT_RUNOFF", "OUTVAR OUT_BASEFLOW", "OUTVAR OUT_SWE %.5f",
+                         "OUTVAR OUT_AERO_RESIST", "OUTVAR OUT_SOIL_WET", "OUTVAR OUT_SNOW_COVER %.0f", "OUTVAR OUT_RAINF"]),
+    "bin": ("sub3h", ["BINARY_OUTPUT TRUE"]),
+    "bin24sel": ("sub3h", ["BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE packed 6",
+                           "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100",
+                           "OUTVAR OUT_SWE %.4f OUT_TYPE_FLOAT 1", "OUTVAR OUT_SOIL_LIQ %.4f OUT_TYPE_DOUBLE *",
+                           "OUTVAR OUT_RUNOFF %.4f OUT_TYPE_FLOAT 1000", "OUTVAR OUT_AERO_RESIST"]),
+}
+
 
 def main():
     if not os.path.exists(VICNL):
@@ -35,10 +56,25 @@ def main():
             r = subprocess.run([VICNL, "-g", g], capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(r.stderr[-2000:])
+            base = open(g).read()
+            gfiles = ["global.txt"]
+            for v, (case, lines) in VARIANTS.items():
+                if case != name:
+                    continue
+                os.makedirs(os.path.join(work, "results_" + v))
+                gv = os.path.join(work, "global_%s.txt" % v)
+                open(gv, "w").write(base.replace("RESULT_DIR %s/results/" % work, "RESULT_DIR %s/results_%s/" % (work, v)) +
+                                    "\n".join(lines) + "\n")
+                assert "results_" + v in open(gv).read()
+                r = subprocess.run([VICNL, "-g", gv], capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr[-2000:])
+                gfiles.append("global_%s.txt" % v)
             dst = os.path.join(dst_root, name)
             shutil.copytree(work, dst)
-            txt = open(os.path.join(dst, "global.txt")).read().replace(work, "@DIR@")
-            open(os.path.join(dst, "global.txt"), "w").write(txt)
+            for gf in gfiles:
+                txt = open(os.path.join(dst, gf)).read().replace(work, "@DIR@")
+                open(os.path.join(dst, gf), "w").write(txt)
             n = sum(len(fs) for _, _, fs in os.walk(dst))
             sz = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(dst) for f in fs)
             print("%s: %d files, %.0f kB" % (name, n, sz / 1e3))

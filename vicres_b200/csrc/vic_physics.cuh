@@ -177,8 +177,10 @@ VR_HD double m_pow_inl(double x, double y)
 #if defined(__CUDACC__)
 // polynomial coefficients in constant memory: the FP64 pipe takes them as c[bank][offset] operands, so they cost neither
 // registers nor the two moves per coefficient that an immediate needs (10 % of the drainage kernel's instructions were UMOV)
+#if !defined(VR_POW_IMMEDIATES)
 __constant__ double VR_POW_LC[7] = VR_POW_L_INIT;
 __constant__ double VR_POW_EC[5] = VR_POW_E_INIT;
+#endif
 // x^y for the hourly Brooks-Corey drainage (runoff.c:336): x = relative saturation, 0 <= x <= ~1 and finite, y = the
 // layer's exponent, y >= 1 (the caller checks).  Same arithmetic as pow_table_eval() -- identical results wherever that
 // one handles the argument -- without its range checks and special cases: x == 1 gives exactly 1 through the table
@@ -187,6 +189,10 @@ __constant__ double VR_POW_EC[5] = VR_POW_E_INIT;
 // vr_pow_tables.
 __device__ __forceinline__ double drain_pow(double x, double y, uint32_t tb)
 {
+#if defined(VR_POW_IMMEDIATES)       // A/B: coefficients as immediates (two moves each) instead of constant-bank loads
+  constexpr double VR_POW_LC[7] = VR_POW_L_INIT;
+  constexpr double VR_POW_EC[5] = VR_POW_E_INIT;
+#endif
   const int hi = __double2hiint(x);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
   const int i = ((hi & 0x000fffff) + 0x1000) >> 13;                    // 0..128

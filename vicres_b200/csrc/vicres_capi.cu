@@ -24,6 +24,7 @@
 #include <string>
 #include <vector>
 #include "../../include/vicres.h"
+#include "../../include/vicres_files.h"
 #include "vic_physics.cuh"
 #include "vic_aggregate.cuh"
 #include "vic_host_prep.h"
@@ -622,6 +623,25 @@ __global__ void __launch_bounds__(256) k_cells(DevModel M, DevForcing F, const d
     cell_carry(S, NL, sv);
     for (int k = 0; k < SV_N; k++) M.sv[((size_t)(svb ^ 1) * SV_N + k) * M.C + c] = sv[k];
   }
+}
+
+// Temporal aggregation of put_data.c:665-688: thread per (cell, output interval, variable).  kind: 0 = last record of the
+// interval (AGG_TYPE_END: storages), 1 = sum (AGG_TYPE_SUM: fluxes), 2 = sum of x / ratio (AGG_TYPE_AVG), 3 = the
+// conductance averaged like 2 and inverted (OUT_AERO_RESIST, :686), all in record order like the reference's += .
+__global__ void k_aggregate(int n, const int *__restrict__ kind, int nrec, int ratio, int64_t C, const double *__restrict__ in,
+                            double *__restrict__ out)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y, v = blockIdx.z, nout = nrec / ratio;
+  if (c >= C) return;
+  const double *p = in + ((size_t)v * nrec + (size_t)o * ratio) * C + c;
+  const int k = kind[v];
+  double a = 0.0;
+  if (k == 0) a = p[(size_t)(ratio - 1) * C];
+  else
+    for (int r = 0; r < ratio; r++) a += (k == 1) ? p[(size_t)r * C] : p[(size_t)r * C] / ratio;
+  if (k == 3) a = 1 / a;
+  out[((size_t)v * nout + o) * C + c] = a;
 }
 
 // diagnostic: the device power function on arbitrary arguments (tests/test_gpu_parity.py checks its error bound)
@@ -1601,6 +1621,59 @@ int vr_step_diag(vr_handle *h, double *out)
   out[5] = (double)h->diag_unit_records;
   h->diag_unit_records = 0;
   return VR_OK;
+}
+
+// aggregation type of a VR_OUT_* variable (output_list_utils.c:296-385): 0 END, 1 SUM, 2 AVG
+static int agg_kind(int var)
+{
+  switch (var) {
+    case VR_OUT_ASAT: case VR_OUT_ROOTMOIST: case VR_OUT_SNOW_CANOPY: case VR_OUT_SNOW_COVER: case VR_OUT_SNOW_DEPTH:
+    case VR_OUT_SOIL_LIQ0: case VR_OUT_SOIL_LIQ1: case VR_OUT_SOIL_LIQ2: case VR_OUT_SOIL_WET: case VR_OUT_SWE: case VR_OUT_WDEW:
+    case VR_OUT_ZWT: case VR_OUT_ZWT_LUMPED:
+      return 0;
+    case VR_OUT_BASEFLOW: case VR_OUT_DELINTERCEPT: case VR_OUT_DELSOILMOIST: case VR_OUT_DELSWE: case VR_OUT_EVAP:
+    case VR_OUT_EVAP_BARE: case VR_OUT_EVAP_CANOP: case VR_OUT_INFLOW: case VR_OUT_PET_SATSOIL: case VR_OUT_PET_H2OSURF:
+    case VR_OUT_PET_SHORT: case VR_OUT_PET_TALL: case VR_OUT_PET_NATVEG: case VR_OUT_PET_VEGNOCR: case VR_OUT_PREC: case VR_OUT_RAINF:
+    case VR_OUT_RUNOFF: case VR_OUT_SNOW_MELT: case VR_OUT_SNOWF: case VR_OUT_SUB_CANOP: case VR_OUT_SUB_SNOW: case VR_OUT_TRANSP_VEG:
+      return 1;
+    default:
+      return 2;
+  }
+}
+
+int vr_aggregate_device(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio, int64_t ncell,
+                        const double *in_dev, double *out_dev, void *cuda_stream)
+{
+  if (!vars || !in_dev || !out_dev || n < 1 || n > VR_MAX_OUT || ratio < 1 || nrec < ratio || nrec % ratio || ncell < 1) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  int kind[VR_MAX_OUT];
+  for (int v = 0; v < n; v++) kind[v] = (vars[v] == VR_OUT_AERO_RESIST && cond_for_resist) ? 3 : agg_kind(vars[v]);
+  int *d_kind = nullptr;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (cudaMalloc((void **)&d_kind, n * sizeof(int)) != cudaSuccess) return VR_ERR_CUDA;
+  cudaMemcpyAsync(d_kind, kind, n * sizeof(int), cudaMemcpyHostToDevice, st);
+  k_aggregate<<<dim3((unsigned)((ncell + 255) / 256), (unsigned)(nrec / ratio), (unsigned)n), 256, 0, st>>>(n, d_kind, nrec, ratio, ncell,
+                                                                                                     in_dev, out_dev);
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(st);
+  cudaFree(d_kind);
+  return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
+}
+
+int vr_aggregate(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio, int64_t ncell,
+                 const double *in, double *out)
+{
+  if (!in || !out || n < 1 || ratio < 1 || nrec < ratio || nrec % ratio || ncell < 1) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  double *d_in = nullptr, *d_out = nullptr;
+  const size_t ni = (size_t)n * nrec * ncell, no = (size_t)n * (nrec / ratio) * ncell;
+  if (cudaMalloc((void **)&d_in, ni * sizeof(double)) != cudaSuccess) return VR_ERR_CUDA;
+  if (cudaMalloc((void **)&d_out, no * sizeof(double)) != cudaSuccess) { cudaFree(d_in); return VR_ERR_CUDA; }
+  cudaMemcpy(d_in, in, ni * sizeof(double), cudaMemcpyHostToDevice);
+  const int rc = vr_aggregate_device(device, n, vars, cond_for_resist, nrec, ratio, ncell, d_in, d_out, nullptr);
+  if (rc == VR_OK) cudaMemcpy(out, d_out, no * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  return rc;
 }
 
 int vr_diag_fp64_peak(int device, double *dfma_per_s)

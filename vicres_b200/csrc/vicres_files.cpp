@@ -538,6 +538,189 @@ int vr_write_results(const char *result_dir, const char *prefix, int32_t grid_de
   return VR_OK;
 }
 
+// ---- output selection (parse_output_info.c, set_output_defaults.c) and the selection-aware writer (write_data.c) ----
+namespace {
+struct OutName { const char *name; int id; int per_layer; };
+// reference variable name -> first VR_OUT_* id; per_layer: the variable has nlayer elements (ids id .. id + nlayer - 1)
+const OutName OUT_TABLE[] = {
+  {"OUT_PREC", VR_OUT_PREC, 0}, {"OUT_EVAP", VR_OUT_EVAP, 0}, {"OUT_RUNOFF", VR_OUT_RUNOFF, 0}, {"OUT_BASEFLOW", VR_OUT_BASEFLOW, 0},
+  {"OUT_WDEW", VR_OUT_WDEW, 0}, {"OUT_SOIL_LIQ", VR_OUT_SOIL_LIQ0, 1}, {"OUT_SOIL_MOIST", VR_OUT_SOIL_LIQ0, 1},
+  {"OUT_NET_SHORT", VR_OUT_NET_SHORT, 0}, {"OUT_R_NET", VR_OUT_R_NET, 0}, {"OUT_EVAP_CANOP", VR_OUT_EVAP_CANOP, 0},
+  {"OUT_TRANSP_VEG", VR_OUT_TRANSP_VEG, 0}, {"OUT_EVAP_BARE", VR_OUT_EVAP_BARE, 0}, {"OUT_SUB_CANOP", VR_OUT_SUB_CANOP, 0},
+  {"OUT_SUB_SNOW", VR_OUT_SUB_SNOW, 0}, {"OUT_AERO_RESIST", VR_OUT_AERO_RESIST, 0}, {"OUT_SURF_TEMP", VR_OUT_SURF_TEMP, 0},
+  {"OUT_ALBEDO", VR_OUT_ALBEDO, 0}, {"OUT_REL_HUMID", VR_OUT_REL_HUMID, 0}, {"OUT_IN_LONG", VR_OUT_IN_LONG, 0},
+  {"OUT_AIR_TEMP", VR_OUT_AIR_TEMP, 0}, {"OUT_WIND", VR_OUT_WIND, 0}, {"OUT_SWE", VR_OUT_SWE, 0}, {"OUT_SNOW_DEPTH", VR_OUT_SNOW_DEPTH, 0},
+  {"OUT_SNOW_CANOPY", VR_OUT_SNOW_CANOPY, 0}, {"OUT_SNOW_COVER", VR_OUT_SNOW_COVER, 0}, {"OUT_WATER_ERROR", VR_OUT_WATER_ERROR, 0},
+  {"OUT_INFLOW", VR_OUT_INFLOW, 0}, {"OUT_SNOW_MELT", VR_OUT_SNOW_MELT, 0}, {"OUT_RAINF", VR_OUT_RAINF, 0}, {"OUT_SNOWF", VR_OUT_SNOWF, 0},
+  {"OUT_NET_LONG", VR_OUT_NET_LONG, 0}, {"OUT_ASAT", VR_OUT_ASAT, 0}, {"OUT_SOIL_WET", VR_OUT_SOIL_WET, 0}, {"OUT_ROOTMOIST", VR_OUT_ROOTMOIST, 0},
+  {"OUT_GRND_FLUX", VR_OUT_GRND_FLUX, 0}, {"OUT_DELTAH", VR_OUT_DELTAH, 0}, {"OUT_AERO_COND", VR_OUT_AERO_COND, 0},
+  {"OUT_SHORTWAVE", VR_OUT_SHORTWAVE, 0}, {"OUT_LONGWAVE", VR_OUT_LONGWAVE, 0}, {"OUT_DELSOILMOIST", VR_OUT_DELSOILMOIST, 0},
+  {"OUT_DELSWE", VR_OUT_DELSWE, 0}, {"OUT_DELINTERCEPT", VR_OUT_DELINTERCEPT, 0}, {"OUT_SNOW_SURF_TEMP", VR_OUT_SNOW_SURF_TEMP, 0},
+  {"OUT_SNOW_PACK_TEMP", VR_OUT_SNOW_PACK_TEMP, 0}, {"OUT_SALBEDO", VR_OUT_SALBEDO, 0}, {"OUT_PET_SATSOIL", VR_OUT_PET_SATSOIL, 0},
+  {"OUT_PET_H2OSURF", VR_OUT_PET_H2OSURF, 0}, {"OUT_PET_SHORT", VR_OUT_PET_SHORT, 0}, {"OUT_PET_TALL", VR_OUT_PET_TALL, 0},
+  {"OUT_PET_NATVEG", VR_OUT_PET_NATVEG, 0}, {"OUT_PET_VEGNOCR", VR_OUT_PET_VEGNOCR, 0}, {"OUT_ZWT", VR_OUT_ZWT, 0},
+  {"OUT_ZWT_LUMPED", VR_OUT_ZWT_LUMPED, 0},
+};
+const OutName *find_out(const char *name)
+{
+  for (const OutName &o : OUT_TABLE)
+    if (!strcmp(o.name, name)) return &o;
+  return nullptr;
+}
+bool outsel_add(vr_outsel *s, int f, const char *name, const char *format, int type, double mult, int nlayer)
+{
+  const OutName *o = find_out(name);
+  if (!o) {
+    g_err = std::string("set_output_var: \"") + name + "\" is not an output variable of the water-balance path of this library";
+    return false;
+  }
+  const int ne = o->per_layer ? nlayer : 1;
+  // format / type / mult belong to the VARIABLE (out_data[varid]): a later line for the same variable changes every column of it
+  for (int ff = 0; ff < s->nfiles; ff++)
+    for (int c = 0; c < s->ncols[ff]; c++)
+      if (s->var[ff][c] >= o->id && s->var[ff][c] < o->id + ne) {
+        if (strcmp(format, "*")) snprintf(s->format[ff][c], 12, "%s", format);
+        if (type) s->type[ff][c] = type;
+        if (mult != 0) s->mult[ff][c] = mult;
+      }
+  for (int e = 0; e < ne; e++) {
+    int &n = s->ncols[f];
+    if (n >= VR_MAX_OUTCOLS) { g_err = "too many output columns in one file"; return false; }
+    s->var[f][n] = o->id + e;
+    snprintf(s->format[f][n], 12, "%s", strcmp(format, "*") ? format : "%.4f");
+    s->type[f][n] = type ? type : VR_OUT_TYPE_FLOAT;
+    s->mult[f][n] = mult != 0 ? mult : 1.0;
+    n++;
+  }
+  return true;
+}
+}  // namespace
+
+int vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *s)
+{
+  if (!global_path || !s || nlayer < 1 || nlayer > 3) { g_err = "null or invalid argument"; return VR_ERR_ARG; }
+  memset(s, 0, sizeof *s);
+  FILE *gp = fopen(global_path, "r");
+  if (!gp) { g_err = std::string("cannot open ") + global_path; return VR_ERR_ARG; }
+  char line[4096], key[256], a1[256], a2[256], a3[256], a4[256];
+  int declared = 0, f = -1;
+  while (fgets(line, sizeof line, gp)) {
+    if (line[0] == '#' || line[0] == '\n' || line[0] == '\0') continue;
+    if (sscanf(line, "%255s", key) != 1) continue;
+    if (!strcasecmp(key, "N_OUTFILES")) {
+      if (sscanf(line, "%*s %d", &declared) != 1 || declared < 1 || declared > VR_MAX_OUTFILES) {
+        fclose(gp); g_err = "N_OUTFILES out of range (1..8)"; return VR_ERR_ARG;
+      }
+      memset(s, 0, sizeof *s);
+      f = -1;
+    }
+    else if (!strcasecmp(key, "OUTFILE")) {
+      if (!declared) { fclose(gp); g_err = "\"N_OUTFILES\" must be specified before you can specify \"OUTFILE\""; return VR_ERR_ARG; }
+      if (++f >= declared) { fclose(gp); g_err = "more OUTFILE lines than N_OUTFILES"; return VR_ERR_ARG; }
+      int nv = 0;
+      a1[0] = 0;
+      sscanf(line, "%*s %63s %d", a1, &nv);
+      snprintf(s->prefix[f], 64, "%s", a1);
+      s->nfiles = f + 1;
+    }
+    else if (!strcasecmp(key, "OUTVAR")) {
+      if (f < 0) { fclose(gp); g_err = "\"OUTFILE\" must be specified before you can specify \"OUTVAR\""; return VR_ERR_ARG; }
+      a1[0] = a2[0] = a3[0] = a4[0] = 0;
+      sscanf(line, "%*s %255s %255s %255s %255s", a1, a2, a3, a4);
+      int type = VR_OUT_TYPE_DEFAULT;
+      double mult = 0;
+      const char *fmt = "*";
+      if (a2[0]) {
+        fmt = a2;
+        if (!strcasecmp(a3, "OUT_TYPE_USINT")) type = VR_OUT_TYPE_USINT;
+        else if (!strcasecmp(a3, "OUT_TYPE_SINT")) type = VR_OUT_TYPE_SINT;
+        else if (!strcasecmp(a3, "OUT_TYPE_FLOAT")) type = VR_OUT_TYPE_FLOAT;
+        else if (!strcasecmp(a3, "OUT_TYPE_DOUBLE")) type = VR_OUT_TYPE_DOUBLE;
+        mult = !strcmp(a4, "*") ? 0 : (double)(float)atof(a4);
+      }
+      if (!outsel_add(s, f, a1, fmt, type, mult, nlayer)) { fclose(gp); return VR_ERR_ARG; }
+    }
+  }
+  fclose(gp);
+  if (!declared) {       // set_output_defaults.c:66-162, water-balance mode
+    s->nfiles = 2;
+    snprintf(s->prefix[0], 64, "fluxes");
+    snprintf(s->prefix[1], 64, "snow");
+    const char *flux[] = {"OUT_PREC", "OUT_EVAP", "OUT_RUNOFF", "OUT_BASEFLOW", "OUT_WDEW", "OUT_SOIL_LIQ", "OUT_NET_SHORT", "OUT_R_NET",
+                          "OUT_EVAP_CANOP", "OUT_TRANSP_VEG", "OUT_EVAP_BARE", "OUT_SUB_CANOP", "OUT_SUB_SNOW", "OUT_AERO_RESIST",
+                          "OUT_SURF_TEMP", "OUT_ALBEDO", "OUT_REL_HUMID", "OUT_IN_LONG", "OUT_AIR_TEMP", "OUT_WIND"};
+    const char *snow[] = {"OUT_SWE", "OUT_SNOW_DEPTH", "OUT_SNOW_CANOPY", "OUT_SNOW_COVER"};
+    for (const char *n : flux) outsel_add(s, 0, n, "%.4f", VR_OUT_TYPE_FLOAT, 1, nlayer);
+    for (const char *n : snow) outsel_add(s, 1, n, "%.4f", VR_OUT_TYPE_FLOAT, 1, nlayer);
+  }
+  else if (s->nfiles != declared) { g_err = "fewer OUTFILE lines than N_OUTFILES"; return VR_ERR_ARG; }
+  return VR_OK;
+}
+
+int vr_outsel_step_vars(const vr_outsel *s, int32_t aggregate, int32_t *vars, int32_t *n)
+{
+  if (!s || !vars || !n) { g_err = "null argument"; return VR_ERR_ARG; }
+  *n = 0;
+  for (int f = 0; f < s->nfiles; f++)
+    for (int c = 0; c < s->ncols[f]; c++) {
+      int v = s->var[f][c];
+      if (aggregate && v == VR_OUT_AERO_RESIST) v = VR_OUT_AERO_COND;
+      bool seen = false;
+      for (int k = 0; k < *n; k++) seen = seen || vars[k] == v;
+      if (seen) continue;
+      if (*n >= VR_MAX_OUT) { g_err = "more than VR_MAX_OUT distinct output columns"; return VR_ERR_ARG; }
+      vars[(*n)++] = v;
+    }
+  return VR_OK;
+}
+
+int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t file, int32_t grid_decimal, int64_t ncell,
+                         const float *lat, const float *lng, int32_t nrec, const int32_t *year, const int32_t *month,
+                         const int32_t *day, const int32_t *hour, int32_t binary, const int32_t *rows, const double *out)
+{
+  if (!result_dir || !s || !lat || !lng || !year || !month || !day || !rows || !out || file < 0 || file >= s->nfiles || ncell < 1 ||
+      nrec < 1) {
+    g_err = "null or empty argument";
+    return VR_ERR_ARG;
+  }
+  char fmt[64], name[4096];
+  snprintf(fmt, sizeof fmt, "%%s/%%s_%%.%df_%%.%df", grid_decimal, grid_decimal);      // make_in_and_outfiles.c:46-86
+  const int nc = s->ncols[file];
+  for (int64_t c = 0; c < ncell; c++) {
+    snprintf(name, sizeof name, fmt, result_dir, s->prefix[file], lat[c], lng[c]);
+    FILE *f = fopen(name, binary ? "wb" : "w");
+    if (!f) { g_err = std::string("cannot create ") + name; return VR_ERR_ARG; }
+    for (int r = 0; r < nrec; r++) {
+      if (binary) {       // write_data.c:103-193
+        const int date[4] = {year[r], month[r], day[r], hour ? hour[r] : 0};
+        fwrite(date, sizeof(int), hour ? 4 : 3, f);
+        for (int v = 0; v < nc; v++) {
+          const double x = out[((size_t)rows[v] * nrec + r) * ncell + c] * s->mult[file][v];      // put_data.c:766-772
+          switch (s->type[file][v]) {
+            case VR_OUT_TYPE_CHAR: { const char t = (char)x; fwrite(&t, sizeof t, 1, f); break; }
+            case VR_OUT_TYPE_SINT: { const short t = (short)x; fwrite(&t, sizeof t, 1, f); break; }
+            case VR_OUT_TYPE_USINT: { const unsigned short t = (unsigned short)x; fwrite(&t, sizeof t, 1, f); break; }
+            case VR_OUT_TYPE_INT: { const int t = (int)x; fwrite(&t, sizeof t, 1, f); break; }
+            case VR_OUT_TYPE_DOUBLE: fwrite(&x, sizeof x, 1, f); break;
+            default: { const float t = (float)x; fwrite(&t, sizeof t, 1, f); break; }
+          }
+        }
+      }
+      else {              // write_data.c:196-226
+        if (hour) fprintf(f, "%04i\t%02i\t%02i\t%02i\t", year[r], month[r], day[r], hour[r]);
+        else fprintf(f, "%04i\t%02i\t%02i\t", year[r], month[r], day[r]);
+        for (int v = 0; v < nc; v++) {
+          if (v) fprintf(f, "\t ");
+          fprintf(f, s->format[file][v], out[((size_t)rows[v] * nrec + r) * ncell + c]);
+        }
+        fprintf(f, "\n");
+      }
+    }
+    if (fclose(f) != 0) { g_err = std::string("write failed: ") + name; return VR_ERR_ARG; }
+  }
+  return VR_OK;
+}
+
 // ---- global parameter file (get_global_param.c) ----
 static bool leapyr(int y) { return ((y % 4 == 0) && (y % 100 != 0)) || (y % 400 == 0); }
 static void next_step(int &year, int &month, int &day, int &hr, int &jday, int dt)     // make_dmy.c:175-205
@@ -711,11 +894,10 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->snow_step != g->time_step) return "SNOW_STEP != TIME_STEP";
   if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
   if (g->forcing2) return "FORCING2 (a second forcing file)";
-  if (g->out_step != 0 && g->out_step != g->time_step) return "OUT_STEP != TIME_STEP (output aggregation)";
+  if (g->out_step > 0 && (g->out_step < g->time_step || g->out_step % g->time_step || g->out_step > 24))
+    return "OUT_STEP must be a multiple of TIME_STEP and at most 24 (get_global_param.c:754-760)";
   if (g->skipyear > 0) return "SKIPYEAR > 0";
-  if (g->binary_output) return "BINARY_OUTPUT TRUE";
   if (g->compress) return "COMPRESS TRUE";
-  if (g->n_outfile_lines > 0 || g->n_outvar_lines > 0) return "OUTFILE / OUTVAR (custom output selection)";
   return nullptr;
 }
 

@@ -214,3 +214,122 @@ class Global:
         if got < 0:
             raise VicResError(int(got), "vr_read_forcing_file: %s" % self.so.vr_params_last_error().decode())
         return {t: data[i, :got] for i, t in enumerate(self.force_types)}, int(got)
+
+
+# ---- output selection (N_OUTFILES / OUTFILE / OUTVAR), aggregation to OUT_STEP, ASCII / binary result files -----------
+VR_MAX_OUTFILES, VR_MAX_OUTCOLS = 8, 64
+OUT_TYPES = ["DEFAULT", "CHAR", "SINT", "USINT", "INT", "FLOAT", "DOUBLE"]
+OUT_TYPE_DTYPE = {"CHAR": "i1", "SINT": "<i2", "USINT": "<u2", "INT": "<i4", "FLOAT": "<f4", "DOUBLE": "<f8"}
+
+
+class OutSelC(C.Structure):
+    _fields_ = [("nfiles", C.c_int32), ("prefix", (C.c_char * 64) * VR_MAX_OUTFILES), ("ncols", C.c_int32 * VR_MAX_OUTFILES),
+                ("var", (C.c_int32 * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
+                ("format", ((C.c_char * 12) * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
+                ("type", (C.c_int32 * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
+                ("mult", (C.c_double * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES)]
+
+
+FILES_EXPORTS += ["vr_outsel_read", "vr_outsel_step_vars", "vr_aggregate_device", "vr_aggregate", "vr_write_results_sel"]
+
+
+def _bind_outsel(so):
+    i32, f32, pd = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    so.vr_outsel_read.argtypes = [C.c_char_p, C.c_int32, C.POINTER(OutSelC)]
+    so.vr_outsel_step_vars.argtypes = [C.POINTER(OutSelC), C.c_int32, i32, i32]
+    so.vr_aggregate_device.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    so.vr_aggregate.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, pd, pd]
+    so.vr_write_results_sel.argtypes = [C.c_char_p, C.POINTER(OutSelC), C.c_int32, C.c_int32, C.c_int64, f32, f32, C.c_int32,
+                                        i32, i32, i32, i32, C.c_int32, i32, pd]
+    return so
+
+
+class OutSel:
+    """the output files of a run and their columns (parse_output_info.c / set_output_defaults.c)"""
+
+    def __init__(self, global_path, nlayer=3, lib=None):
+        self.so = _bind_outsel(_bind(lib or load_library()))
+        self.c = OutSelC()
+        rc = self.so.vr_outsel_read(global_path.encode(), nlayer, C.byref(self.c))
+        if rc != 0:
+            raise VicResError(rc, "vr_outsel_read: %s" % self.so.vr_params_last_error().decode())
+
+    @property
+    def files(self):
+        """[(prefix, [(variable name, format, type name, multiplier)])]"""
+        out = []
+        for f in range(self.c.nfiles):
+            cols = [(abi.OUT_NAMES[self.c.var[f][k]], self.c.format[f][k].value.decode(), OUT_TYPES[self.c.type[f][k]],
+                     float(self.c.mult[f][k])) for k in range(self.c.ncols[f])]
+            out.append((self.c.prefix[f].value.decode(), cols))
+        return out
+
+    def step_vars(self, aggregate=False):
+        """names of the outputs the step has to produce (each once); AERO_RESIST becomes AERO_COND when aggregating"""
+        v = (C.c_int32 * abi.VR_MAX_OUT)()
+        n = C.c_int32()
+        rc = self.so.vr_outsel_step_vars(C.byref(self.c), int(aggregate), v, C.byref(n))
+        if rc != 0:
+            raise VicResError(rc, "vr_outsel_step_vars: %s" % self.so.vr_params_last_error().decode())
+        return [abi.OUT_NAMES[v[k]] for k in range(n.value)]
+
+    def rows(self, f, names):
+        """row of the output array (variables `names`) that holds each column of file f"""
+        return np.asarray([names.index(abi.OUT_NAMES[self.c.var[f][k]]) for k in range(self.c.ncols[f])], dtype=np.int32)
+
+    def wants(self, name):
+        return any(abi.OUT_NAMES[self.c.var[f][k]] == name for f in range(self.c.nfiles) for k in range(self.c.ncols[f]))
+
+    def write(self, f, result_dir, lat, lng, year, month, day, hour, out, rows, binary=False, grid_decimal=4):
+        out = np.ascontiguousarray(out, np.float64)
+        _, nrec, Cn = out.shape
+        lat, lng = np.ascontiguousarray(lat, np.float32), np.ascontiguousarray(lng, np.float32)
+        y, m, d = (np.ascontiguousarray(a, np.int32) for a in (year, month, day))
+        rows = np.ascontiguousarray(rows, np.int32)
+        f32, i32 = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        hp = None
+        if hour is not None:
+            hour = np.ascontiguousarray(hour, np.int32)
+            hp = hour.ctypes.data_as(i32)
+        rc = self.so.vr_write_results_sel(result_dir.encode(), C.byref(self.c), f, grid_decimal, Cn, lat.ctypes.data_as(f32),
+                                          lng.ctypes.data_as(f32), nrec, y.ctypes.data_as(i32), m.ctypes.data_as(i32),
+                                          d.ctypes.data_as(i32), hp, int(binary), rows.ctypes.data_as(i32),
+                                          out.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc != 0:
+            raise VicResError(rc, "vr_write_results_sel: %s" % self.so.vr_params_last_error().decode())
+
+
+def aggregate(names, data, ratio, device=0, lib=None):
+    """put_data.c:665-688 for host arrays: data [n, nrec, C] -> [n, nrec // ratio, C]; names: the variables of the rows, with
+    "AERO_RESIST" meaning "this row holds AERO_COND, give back the resistance"."""
+    so = _bind_outsel(_bind(lib or load_library()))
+    data = np.ascontiguousarray(data, np.float64)
+    n, nrec, Cn = data.shape
+    nout = nrec // ratio
+    data = np.ascontiguousarray(data[:, :nout * ratio])
+    out = np.empty((n, nout, Cn))
+    v = np.asarray([abi.OUT[x] for x in names], dtype=np.int32)
+    pd = C.POINTER(C.c_double)
+    rc = so.vr_aggregate(device, n, v.ctypes.data_as(C.POINTER(C.c_int32)), 1, nout * ratio, ratio, Cn, data.ctypes.data_as(pd),
+                         out.ctypes.data_as(pd))
+    if rc != 0:
+        raise VicResError(rc, "vr_aggregate")
+    return out
+
+
+def aggregate_device(names, in_ptr, out_ptr, nrec, ratio, ncell, device=0, stream=0, lib=None):
+    """the same on device buffers: in [n][nrec][ncell] -> out [n][nrec / ratio][ncell]; nrec must be a multiple of ratio"""
+    so = _bind_outsel(_bind(lib or load_library()))
+    v = np.asarray([abi.OUT[x] for x in names], dtype=np.int32)
+    rc = so.vr_aggregate_device(device, len(names), v.ctypes.data_as(C.POINTER(C.c_int32)), 1, nrec, ratio, ncell, in_ptr, out_ptr,
+                                stream or None)
+    if rc != 0:
+        raise VicResError(rc, "vr_aggregate_device")
+
+
+def read_binary_results(path, cols, hourly):
+    """a BINARY_OUTPUT result file -> (date [nrec, 3 or 4], values [ncol, nrec]); cols: [(name, format, type, mult)]"""
+    dt = [("date", "<i4", 4 if hourly else 3)] + [("c%d" % k, OUT_TYPE_DTYPE[c[2]]) for k, c in enumerate(cols)]
+    a = np.fromfile(path, dtype=np.dtype(dt))
+    return a["date"], np.stack([a["c%d" % k].astype(np.float64) / cols[k][3] for k in range(len(cols))])

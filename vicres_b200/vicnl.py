@@ -8,9 +8,11 @@ atmos[]), initialize_model_state, the record loop of full_energy + put_data, wri
 of the soil file at once:
 
     vr_global_read -> vr_params_read -> vr_read_forcing_file (per cell) -> vr_atmos_prepare_device
-    -> vr_create / vr_set_cells / vr_init_state -> vr_step_block_device -> vr_write_results
+    -> vr_create / vr_set_cells / vr_init_state -> vr_step_block_device -> [vr_aggregate_device] -> vr_write_results_sel
 
-and leaves the same `fluxes_<lat>_<lng>` / `snow_<lat>_<lng>` files in RESULT_DIR.  Marshalling only: every number
+and leaves the same result files in RESULT_DIR: `fluxes_<lat>_<lng>` / `snow_<lat>_<lng>` or the files and columns of the
+N_OUTFILES / OUTFILE / OUTVAR lines (parse_output_info.c), aggregated to OUT_STEP (put_data.c:665-688), ASCII or
+BINARY_OUTPUT (write_data.c).  Marshalling only: every number
 comes from the CUDA library; a global file with options outside the library's path is refused with the reason
 (vr_global_unsupported), never run differently.
 """
@@ -52,7 +54,12 @@ def run(global_path, device=0, write=True, records_per_block=0):
     atmos.prepare_device(ao, {k: ptr(v) for k, v in site_t.items()}, {k: ptr(v) for k, v in raw_t.items()},
                          [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["prec"].shape[0], device=device)
     torch.cuda.synchronize(dev)
-    opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, max_snow_temp=g.max_snow_temp,
+    # what to compute: the columns of the output files, each once (the conductance instead of the resistance when the
+    # output interval spans several records: put_data.c:686 inverts the aggregated conductance)
+    sel = files.OutSel(global_path, g.nlayer)
+    ratio = g.out_step // g.time_step if g.out_step > 0 else 1
+    names = sel.step_vars(aggregate=ratio > 1)
+    opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, out=names, max_snow_temp=g.max_snow_temp,
                               min_rain_temp=g.min_rain_temp, wind_h=g.wind_h)
     m = model.VicRes(opt, lib, cells, device=device)
     tair0 = f_dev[abi.FORCING_FIELDS.index("air_temp"), 0].cpu().numpy()
@@ -78,14 +85,29 @@ def run(global_path, device=0, write=True, records_per_block=0):
         if r1 - 1 == save_after:
             m.write_state_file("%s_%04d%02d%02d" % (g.statename, g.stateyear, g.statemonth, g.stateday), g.stateyear, g.statemonth,
                                g.stateday, meta["gridcel"], binary=bool(g.binary_state_file))
-    out = out_dev.cpu().numpy()
     m.close()
+    if ratio > 1:                           # OUT_STEP > TIME_STEP: one output record per `ratio` model records, dated by the last
+        nout = nrecs // ratio
+        want_resist = sel.wants("AERO_RESIST")
+        if want_resist and sel.wants("AERO_COND"):      # both columns from the one conductance row
+            k = names.index("AERO_COND")
+            out_dev = torch.cat([out_dev, out_dev[k:k + 1]])
+            names = names + ["AERO_RESIST"]
+        elif want_resist:
+            names = ["AERO_RESIST" if n == "AERO_COND" else n for n in names]
+        src = out_dev[:, :nout * ratio].contiguous()
+        agg = torch.empty((len(names), nout, Cn), dtype=torch.float64, device=dev)
+        files.aggregate_device(names, src.data_ptr(), agg.data_ptr(), nout * ratio, ratio, Cn, device=device)
+        out_dev = agg
+        dmy = dmy[ratio - 1::ratio][:nout]
+    out = out_dev.cpu().numpy()
     if write:
-        nflux = 20 + g.nlayer - 1               # set_output_defaults.c:66-93: fluxes = the first 20+L-1, snow = the last 4
-        hour = dmy[:, 3] if g.time_step < 24 else None
-        for prefix, sel in (("fluxes", np.arange(nflux)), ("snow", np.arange(nflux, nflux + 4))):
-            files.write_results(g.result_dir, prefix, meta["lat"], meta["lng"], dmy[:, 0], dmy[:, 1], dmy[:, 2], out,
-                                cols=sel, hour=hour, grid_decimal=g.grid_decimal)
+        out_dt = g.out_step if g.out_step > 0 else g.time_step
+        hour = dmy[:, 3] if out_dt < 24 else None
+        for f in range(len(sel.files)):
+            sel.write(f, g.result_dir, meta["lat"], meta["lng"], dmy[:, 0], dmy[:, 1], dmy[:, 2], hour, out, sel.rows(f, names),
+                      binary=bool(g.binary_output), grid_decimal=g.grid_decimal)
+    meta["out_names"] = names
     return out, meta, dmy
 
 
