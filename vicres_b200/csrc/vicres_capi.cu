@@ -727,14 +727,13 @@ struct vr_handle {
   struct EvTriple { cudaEvent_t u0, u1, c0, c1; int nrec; };
   std::vector<EvTriple> evs;         // around every k_units / k_cells launch since the last vr_kernel_times()
   size_t evs_used = 0;
-  static constexpr int NBUF = 4;     // copy buffers per direction of the host pipeline
+  static constexpr int NBUF = 16;    // at most this many copy buffers per direction of the host pipeline (vr_step_block picks)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[NBUF] = {}, ev_comp[NBUF] = {}, ev_out[NBUF] = {};
   int extras = 0;                    // EX_PET | EX_ZWT when such outputs are requested: selects the kernel instances
   int cta = VR_CTA;                  // threads per block of the set-up kernels
   int64_t ncta = 0;
   int sms = 148;
   bool flags_dirty = true;           // M.uflag must be rebuilt from the state block before the next step
-  DBuf<double> d_fo;
   DBuf<int32_t> d_uflag, d_snow_list, d_snow_cnt;
   DBuf<unsigned long long> d_snow_total;
   int na = 1;                        // slot ranges of the non-snow class that run side by side (VICRES_A_STREAMS, 1..4)
@@ -909,7 +908,7 @@ void vr_destroy(vr_handle *h)
   h->d_u_cell.release(); h->d_u_tile.release(); h->d_u_flags.release(); h->d_u_aero.release();
   h->d_cell_fail.release(); h->d_cell_status.release(); h->d_month.release(); h->d_doy.release();
   h->d_order.release(); h->d_u_slot.release(); h->d_u_pos.release();
-  h->d_tmu.release(); h->d_fo.release(); h->d_snow_total.release();
+  h->d_tmu.release(); h->d_snow_total.release();
   for (auto &x : h->dev) cudaEventDestroy(x); h->d_uflag.release(); h->d_snow_list.release(); h->d_snow_cnt.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1011,7 +1010,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   CK(h->d_tl.upload(P.tl)); CK(h->d_ap.upload(P.ap));
   CK(h->d_init_moist.upload(im));
   CK(h->d_order.upload(P.order)); CK(h->d_u_slot.upload(P.u_slot)); CK(h->d_u_logical.upload(P.u_logical));
-  CK(h->d_state.reserve((size_t)ST_N * (U ? U : 1)));
+  CK(h->d_state.reserve((size_t)(ST_N + FO_N) * (U ? U : 1)));     // state rows, then the FrontOut rows (one L2 window)
   CK(h->d_sv.reserve((size_t)2 * SV_N * C));
   CK(h->d_cell_status.reserve(C));
   CK(cudaMemset(h->d_state.p, 0, (size_t)ST_N * (U ? U : 1) * sizeof(double)));
@@ -1037,10 +1036,9 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   CK(cudaMemset(h->d_ccu.p, 0, (size_t)P.ccn * M.US * sizeof(double)));
   CK(cudaMemset(h->d_tmu.p, 0, (size_t)12 * TM_N * M.US * sizeof(double)));
   M.ccu = h->d_ccu.p; M.tmu = h->d_tmu.p;
-  CK(h->d_fo.reserve((size_t)FO_N * (U ? U : 1)));
   CK(h->d_uflag.reserve(U ? U : 1));
   CK(h->d_snow_list.reserve(U ? U : 1));
-  M.fo = h->d_fo.p; M.uflag = h->d_uflag.p; M.snow_list = h->d_snow_list.p;
+  M.fo = h->d_state.p + (size_t)ST_N * (U ? U : 1); M.uflag = h->d_uflag.p; M.snow_list = h->d_snow_list.p;
   h->flags_dirty = true;
   if (U > 0) {
     k_unit_consts<<<(unsigned)((U + 255) / 256), 256, 0, h->stream>>>(M, h->d_ccu.p, h->d_tmu.p);
@@ -1220,7 +1218,7 @@ int vr_step_block_device(vr_handle *h, const vr_forcing *f, double *out_dev, voi
 
 // Host-buffer entry point.  The block of records is cut into chunks of h->chunk records that flow
 // through four streams (copies in, k_units, k_cells, copies out): H2D of later chunks, the kernels of chunk k
-// and D2H of earlier chunks overlap (PCIe is full duplex), with NBUF device buffers per direction.  Forcing
+// and D2H of earlier chunks overlap (PCIe is full duplex), with a ring of device buffers per direction.  Forcing
 // [field][rec][col] and outputs
 // [var][rec][cell] are record-major, so a chunk is one contiguous copy per field / variable.
 int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *cell_status_host)
@@ -1234,7 +1232,22 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
   const size_t FC = (size_t)h->M.FC, C = (size_t)h->M.C;
   const size_t NS = h->M.NF > 1 ? h->M.NF + 1 : 1;               // forcing sub-records per record
   const size_t in_chunk = (size_t)CH * NS * FC * VR_NFORCING, out_chunk = (size_t)CH * C * n_out;
-  const int NB = vr_handle::NBUF;
+  // Depth of the buffer rings.  The kernels of a chunk take 4 .. 9 ms with the season (share of units under snow), the
+  // D2H of its outputs is constant, so a shallow ring makes every chunk cost max(kernels, copy); a deep one lets the
+  // kernels run ahead through the summer and the copies catch up in winter.  As deep as the block has chunks, NBUF, and
+  // a third of the free device memory allow (VICRES_PIPE_DEPTH overrides), at least 2.
+  int NB = (nrec + CH - 1) / CH;
+  if (NB > vr_handle::NBUF) NB = vr_handle::NBUF;
+  {
+    size_t free_b = 0, total_b = 0;
+    const size_t held = (h->d_forc.n + h->d_out.n) * sizeof(double), per = (in_chunk + out_chunk) * sizeof(double);
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t fit = ((free_b + held) / 3) / (per ? per : 1);
+      if ((size_t)NB > fit) NB = (int)fit;
+    }
+    if (const char *e = getenv("VICRES_PIPE_DEPTH")) NB = atoi(e) < vr_handle::NBUF ? atoi(e) : vr_handle::NBUF;
+    if (NB < 2) NB = 2;
+  }
   const bool flags = NS > 1 && f->snowflag;
   if (flags) {
     CK(h->d_snowflag.reserve((size_t)nrec * FC));
@@ -1245,6 +1258,14 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
   CK(h->d_month.reserve(nrec)); CK(h->d_doy.reserve(nrec));
   CK(cudaMemcpyAsync(h->d_month.p, f->month, nrec * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
   CK(cudaMemcpyAsync(h->d_doy.p, f->day_in_year, nrec * sizeof(int32_t), cudaMemcpyHostToDevice, h->s_in));
+  // VICRES_PIPE_TRACE=1: when each chunk's copy in, kernels and copy out ended, in ms after the call began (stderr)
+  const bool trace = getenv("VICRES_PIPE_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  if (trace) {
+    tev.resize(1 + 3 * (size_t)((nrec + CH - 1) / CH));
+    for (cudaEvent_t &e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[0], h->s_in);
+  }
   int k = 0;
   for (int r0 = 0; r0 < nrec; r0 += CH, k++) {
     const int nr = (nrec - r0 < CH) ? nrec - r0 : CH, b = k % NB;
@@ -1261,18 +1282,21 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
       F.field[i] = din + (size_t)i * nr * NS * FC;
     }
     CK(cudaEventRecord(h->ev_in[b], h->s_in));
+    if (trace) cudaEventRecord(tev[1 + 3 * k], h->s_in);
     CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
     if (k >= NB) CK(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));     // D2H of chunk k-NB has drained dout
-    // not joined: k_cells(k) trails behind k_units(k+1) on its own stream; four copy buffers per direction
+    // not joined: k_cells(k) trails behind k_units(k+1) on its own stream; the rings of copy buffers
     // keep H2D / kernels / D2H flowing although the outputs of a chunk leave one kernel later
     int rc = launch_step(h, F, dout, h->stream, false);
     if (rc != VR_OK) return rc;
     CK(cudaEventRecord(h->ev_comp[b], h->s_cells));                       // forcing consumed and outputs written
+    if (trace) cudaEventRecord(tev[2 + 3 * k], h->s_cells);
     CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
     for (int v = 0; v < n_out; v++)
       CK(cudaMemcpyAsync(out_host + ((size_t)v * nrec + r0) * C, dout + (size_t)v * nr * C, (size_t)nr * C * sizeof(double),
                          cudaMemcpyDeviceToHost, h->s_out));
     CK(cudaEventRecord(h->ev_out[b], h->s_out));
+    if (trace) cudaEventRecord(tev[3 + 3 * k], h->s_out);
   }
   if (cell_status_host) {
     CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[(k - 1) % NB], 0));
@@ -1283,6 +1307,16 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->s_cells));
   CK(cudaStreamSynchronize(h->s_out));
+  if (trace) {
+    fprintf(stderr, "vr_step_block pipeline (ring depth %d): chunk, copy in / kernels / copy out ended at (ms)\n", NB);
+    for (int i = 0; i < k; i++) {
+      float a = 0, b2 = 0, c2 = 0;
+      cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * i]); cudaEventElapsedTime(&b2, tev[0], tev[2 + 3 * i]);
+      cudaEventElapsedTime(&c2, tev[0], tev[3 + 3 * i]);
+      fprintf(stderr, "  %3d %9.3f %9.3f %9.3f\n", i, a, b2, c2);
+    }
+    for (cudaEvent_t &e : tev) cudaEventDestroy(e);
+  }
   if (cell_status_host)
     for (size_t c = 0; c < C; c++)
       if (cell_status_host[c]) return VR_ERR_CELL;
