@@ -187,6 +187,24 @@ int main(int argc, char **argv)
       day[i] = day[i * ratio + ratio - 1]; hour[i] = hour[i * ratio + ratio - 1];
     }
   }
+  /* SKIPYEAR: an output record is written when its last model record is past the skipped years (put_data.c:765) */
+  {
+    int32_t *year_all = malloc(sizeof(int32_t) * nrecs), *t1 = malloc(sizeof(int32_t) * nrecs), *t2 = malloc(sizeof(int32_t) * nrecs),
+            *t3 = malloc(sizeof(int32_t) * nrecs), *t4 = malloc(sizeof(int32_t) * nrecs);
+    vr_make_dmy(&g, year_all, t1, t2, t3, t4);
+    const int skip = vr_output_skip(&g, year_all);
+    int first = 0;
+    while (first < nout && first * ratio + ratio - 1 < skip) first++;
+    if (first > 0) {
+      for (i = 0; i < n_rows; i++)
+        memmove(out + (size_t)i * (nout - first) * C, out + ((size_t)i * nout + first) * C, sizeof(double) * (size_t)(nout - first) * C);
+      for (i = first; i < nout; i++) {
+        year[i - first] = year[i]; month[i - first] = month[i]; day[i - first] = day[i]; hour[i - first] = hour[i];
+      }
+      nout -= first;
+    }
+    free(year_all); free(t1); free(t2); free(t3); free(t4);
+  }
   /* write_data.c */
   const int out_dt = g.out_step > 0 ? g.out_step : g.time_step;
   for (fi = 0; fi < sel.nfiles; fi++) {
@@ -198,6 +216,13 @@ int main(int argc, char **argv)
     }
     if (vr_write_results_sel(g.result_dir, &sel, fi, g.grid_decimal, C, lat, lng, nout, year, month, day, out_dt < 24 ? hour : NULL,
                              g.binary_output, rows, out) != VR_OK) die(sel.prefix[fi], vr_params_last_error());
+    if (g.compress) {      /* close_files.c:51: gzip every result file (the forcing files are left alone) */
+      for (c = 0; c < C; c++) {
+        char cmd[1400];
+        snprintf(cmd, sizeof cmd, "gzip -f %s/%s_%.*f_%.*f", g.result_dir, sel.prefix[fi], g.grid_decimal, lat[c], g.grid_decimal, lng[c]);
+        if (system(cmd) != 0) die("gzip", cmd);
+      }
+    }
   }
   fprintf(stderr, "vicnl_gpu: %lld cells x %d output records written to %s\n", (long long)C, nout, g.result_dir);
   vr_destroy(h);

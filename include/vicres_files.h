@@ -135,6 +135,10 @@ const char *vr_global_unsupported(const vr_global *g);
 int  vr_make_dmy(const vr_global *g, int32_t *year, int32_t *month, int32_t *day, int32_t *hour, int32_t *day_in_year);
 /* records to skip at the head of the forcing file (make_dmy.c:122-150) */
 int32_t vr_force_skip(const vr_global *g);
+/* SKIPYEAR: the model records before the first one written (make_dmy.c:162-169: per skipped year the 365 or 366 days
+ * of the year the running offset has reached; year[] from vr_make_dmy).  put_data.c:765 writes an output interval only
+ * when its last record is >= this.  An offset beyond the run (which the reference reads past its array) counts 365 days. */
+int32_t vr_output_skip(const vr_global *g, const int32_t *year);
 /* one cell's forcing file "<forcing1><lat>_<lng>" (read_atmos_data.c:120-235): columns in FORCE_TYPE order, ASCII or
  * 2-byte scaled binary (with or without the 0xFFFF header); data: [n_force_types][nrec_forcing] (SKIP columns are
  * read and kept), nrec_forcing = nrecs * time_step / force_dt.  Returns the records read or a negative status. */

@@ -160,6 +160,23 @@ def test_vicnl_output_variants_reproduce_the_reference_result_files(case, varian
     _compare_variant(case, variant, gpath, res, ref, "%s/%s" % (case, variant))
 
 
+def test_skipyear_counts_records_like_make_dmy(tmp_path):
+    """CPU tier: SKIPYEAR -> records (make_dmy.c:162-169), per year the length of the year the offset has reached"""
+    gpath, _, ref = _stage("skip", tmp_path)
+    g = files.Global(gpath)
+    assert g.unsupported is None and g.skipyear == 1
+    dmy = g.dmy()
+    assert g.output_skip(dmy) == 366                        # 1984 is a leap year
+    assert len(open(os.path.join(ref, sorted(os.listdir(ref))[0])).readlines()) == g.nrecs - 366
+    txt = open(gpath).read()
+    open(gpath, "w").write(txt.replace("STARTYEAR 1984", "STARTYEAR 1985").replace("SKIPYEAR 1", "SKIPYEAR 1\nENDYEAR 1986"))
+    g = files.Global(gpath)
+    assert g.output_skip(g.dmy()) == 365
+    open(gpath, "w").write(txt.replace("SKIPYEAR 1", "SKIPYEAR 3"))      # beyond the run: nothing is written
+    g = files.Global(gpath)
+    assert g.output_skip(g.dmy()) == g.nrecs
+
+
 @pytest.mark.parametrize("name", ["daily", "sub3h"])
 def test_global_file_and_forcing_files_parse(name, tmp_path):
     """CPU tier: the host side of the driver up to the device hand-off."""
@@ -181,7 +198,7 @@ def test_global_file_and_forcing_files_parse(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["daily", "sub3h"])
+@pytest.mark.parametrize("name", ["daily", "sub3h", "skip"])
 def test_vicnl_command_line_reproduces_the_reference_result_files(name, tmp_path):
     from vicres_b200 import vicnl
     gpath, res, ref = _stage(name, tmp_path)
@@ -191,7 +208,7 @@ def test_vicnl_command_line_reproduces_the_reference_result_files(name, tmp_path
     for n in sorted(os.listdir(ref)):
         a, b = np.loadtxt(os.path.join(res, n)), np.loadtxt(os.path.join(ref, n))
         assert a.shape == b.shape, n
-        ncal = 3 if name == "daily" else 4
+        ncal = 4 if name == "sub3h" else 3
         assert np.array_equal(a[:, :ncal], b[:, :ncal]), n
         assert np.all(np.abs(a - b) <= 1.0001e-4 + 1e-5 * np.abs(b)), n     # one unit in the 4th decimal
         nbad += int((a != b).sum())
@@ -227,7 +244,7 @@ def test_c_host_driver_compiles_against_the_headers(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["daily", "sub3h"])
+@pytest.mark.parametrize("name", ["daily", "sub3h", "skip"])
 def test_c_host_driver_reproduces_the_reference_result_files(name, tmp_path):
     """the same command line from the plain C host program (host/vicnl_gpu.c), records in blocks of 50"""
     import subprocess
@@ -256,3 +273,30 @@ def test_c_host_driver_output_variants(case, variant, tmp_path):
     r = subprocess.run([exe, "-g", gpath, "--block", "64"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     _compare_variant(case, variant, gpath, res, ref, "C host %s/%s" % (case, variant))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", ["python", "c"])
+def test_compress_gzips_the_result_files_and_skipyear_beyond_the_run_leaves_them_empty(host, tmp_path):
+    """COMPRESS TRUE (close_files.c:51, compress_files.c): every result file becomes <name>.gz with the same content;
+    a SKIPYEAR past the end of the run leaves empty files like the reference's"""
+    import gzip
+    import subprocess
+    from vicres_b200 import vicnl
+    gpath, res, ref = _stage("skip", tmp_path)
+    txt = open(gpath).read()
+    run = (lambda: vicnl.main(["-g", gpath])) if host == "python" else \
+          (lambda exe=_build_c_driver(tmp_path): subprocess.run([exe, "-g", gpath]).returncode)
+    open(gpath, "w").write(txt.replace("COMPRESS FALSE", "COMPRESS TRUE"))
+    assert run() == 0
+    assert sorted(os.listdir(res)) == sorted(n + ".gz" for n in os.listdir(ref))
+    for n in os.listdir(ref):
+        a = np.loadtxt(gzip.open(os.path.join(res, n + ".gz"), "rt"))
+        b = np.loadtxt(os.path.join(ref, n))
+        assert a.shape == b.shape and np.all(np.abs(a - b) <= 1.0001e-4 + 1e-5 * np.abs(b)), n
+    for n in os.listdir(res):
+        os.remove(os.path.join(res, n))
+    open(gpath, "w").write(txt.replace("SKIPYEAR 1", "SKIPYEAR 2"))
+    assert run() == 0
+    assert sorted(os.listdir(res)) == sorted(os.listdir(ref))
+    assert all(os.path.getsize(os.path.join(res, n)) == 0 for n in os.listdir(res))

@@ -3,7 +3,7 @@ with the result files the UNMODIFIED reference writes for it (oracle/_ref/vicNl 
 
     python tools/make_vicnl_golden.py
 
-Two cases: `daily` (daily forcing, 2 snow bands, cells whose local time is not the forcing's) and `sub3h` (3-hourly
+Three cases: `skip` (SKIPYEAR 1 over a leap year), `daily` (daily forcing, 2 snow bands, cells whose local time is not the forcing's) and `sub3h` (3-hourly
 AIR_TEMP forcing).  Each case also holds VARIANTS of its global file (`global_<variant>.txt`, results in
 `results_<variant>/`): the output interval, the selection of output files / variables and the binary format.
 The global files are stored with @DIR@ in place of the case directory."""
@@ -22,6 +22,8 @@ CASES = {
     "daily": dict(ncells=4, nlayer=3, nbands=2, ndays=240, startyear=1984, cold=9.0, lat_range=(28, 58),
                   overstory_frac=0.5, off_gmt=1, seed=401),
     "sub3h": dict(ncells=3, nlayer=3, nbands=1, ndays=60, dt=3, startyear=1986, cold=12.0, lat_range=(40, 62), seed=402),
+    # SKIPYEAR 1 from 1984-01-01: the 366 days of the leap year are computed but not written
+    "skip": dict(ncells=2, nlayer=3, nbands=1, ndays=480, startyear=1984, cold=6.0, lat_range=(35, 55), seed=403, skip_output=True),
 }
 
 # variant -> (case, lines appended to the case's global file; later lines win in get_global_param.c)

@@ -679,7 +679,7 @@ int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t fil
                          const int32_t *day, const int32_t *hour, int32_t binary, const int32_t *rows, const double *out)
 {
   if (!result_dir || !s || !lat || !lng || !year || !month || !day || !rows || !out || file < 0 || file >= s->nfiles || ncell < 1 ||
-      nrec < 1) {
+      nrec < 0) {            // nrec == 0 (everything inside SKIPYEAR): the files are created empty, as the reference leaves them
     g_err = "null or empty argument";
     return VR_ERR_ARG;
   }
@@ -896,8 +896,6 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->forcing2) return "FORCING2 (a second forcing file)";
   if (g->out_step > 0 && (g->out_step < g->time_step || g->out_step % g->time_step || g->out_step > 24))
     return "OUT_STEP must be a multiple of TIME_STEP and at most 24 (get_global_param.c:754-760)";
-  if (g->skipyear > 0) return "SKIPYEAR > 0";
-  if (g->compress) return "COMPRESS TRUE";
   return nullptr;
 }
 
@@ -930,6 +928,18 @@ int32_t vr_force_skip(const vr_global *g)
     skip++;
   }
   return skip;
+}
+
+int32_t vr_output_skip(const vr_global *g, const int32_t *year)
+{
+  if (!g || !year || g->skipyear <= 0 || g->time_step <= 0) return 0;
+  int64_t skip = 0;
+  for (int i = 0; i < g->skipyear; i++) {
+    const bool leap = skip < g->nrecs && leapyr(year[skip]);
+    skip += (leap ? 366 : 365) * 24 / g->time_step;
+    if (skip > (int64_t)g->nrecs) { skip = g->nrecs; break; }
+  }
+  return (int32_t)skip;
 }
 
 int64_t vr_read_forcing_file(const vr_global *g, const char *path, int64_t nrec, double *data)

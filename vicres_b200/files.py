@@ -152,7 +152,7 @@ class GlobalC(C.Structure):
                                           "forcing2", "n_outfile_lines", "n_outvar_lines")])
 
 
-FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_read_forcing_file"]
+FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip", "vr_read_forcing_file"]
 
 
 def _bind_global(so):
@@ -161,6 +161,7 @@ def _bind_global(so):
     so.vr_global_unsupported.restype = C.c_char_p
     so.vr_make_dmy.argtypes = [C.POINTER(GlobalC)] + [C.POINTER(C.c_int32)] * 5
     so.vr_force_skip.argtypes = [C.POINTER(GlobalC)]
+    so.vr_output_skip.argtypes = [C.POINTER(GlobalC), C.POINTER(C.c_int32)]
     so.vr_read_forcing_file.argtypes = [C.POINTER(GlobalC), C.c_char_p, C.c_int64, C.POINTER(C.c_double)]
     so.vr_read_forcing_file.restype = C.c_int64
     return so
@@ -198,6 +199,11 @@ class Global:
         if rc != 0:
             raise VicResError(rc, "vr_make_dmy")
         return np.stack(a, axis=1)
+
+    def output_skip(self, dmy):
+        """SKIPYEAR as a count of model records (make_dmy.c:162-169); dmy from self.dmy()"""
+        y = np.ascontiguousarray(dmy[:, 0], np.int32)
+        return int(self.so.vr_output_skip(C.byref(self.c), y.ctypes.data_as(C.POINTER(C.c_int32))))
 
     def param_files(self):
         """keyword arguments for read_params()"""

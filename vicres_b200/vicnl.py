@@ -100,13 +100,25 @@ def run(global_path, device=0, write=True, records_per_block=0):
         files.aggregate_device(names, src.data_ptr(), agg.data_ptr(), nout * ratio, ratio, Cn, device=device)
         out_dev = agg
         dmy = dmy[ratio - 1::ratio][:nout]
-    out = out_dev.cpu().numpy()
+    # SKIPYEAR: an output record is written when its last model record is past the skipped years (put_data.c:765)
+    skip = g.output_skip(g.dmy())
+    first = 0
+    while first < out_dev.shape[1] and first * ratio + ratio - 1 < skip:
+        first += 1
+    out = out_dev[:, first:].cpu().numpy()
+    dmy = dmy[first:]
     if write:
         out_dt = g.out_step if g.out_step > 0 else g.time_step
         hour = dmy[:, 3] if out_dt < 24 else None
         for f in range(len(sel.files)):
             sel.write(f, g.result_dir, meta["lat"], meta["lng"], dmy[:, 0], dmy[:, 1], dmy[:, 2], hour, out, sel.rows(f, names),
                       binary=bool(g.binary_output), grid_decimal=g.grid_decimal)
+        if g.compress:                      # close_files.c:51: gzip every result file (the forcing files are left alone)
+            import subprocess
+            for prefix, _ in sel.files:
+                for c in range(Cn):
+                    subprocess.run(["gzip", "-f", "%s/%s_%.*f_%.*f" % (g.result_dir, prefix, g.grid_decimal, float(meta["lat"][c]),
+                                                                     g.grid_decimal, float(meta["lng"][c]))], check=True)
     meta["out_names"] = names
     return out, meta, dmy
 
