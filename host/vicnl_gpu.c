@@ -100,10 +100,14 @@ int main(int argc, char **argv)
   ao.has_wind = col_wind >= 0; ao.min_wind_speed = g.min_wind_speed; ao.vp_interp = g.vp_interp; ao.vp_iter = g.vp_iter;
   ao.mtclim_swe_corr = g.mtclim_swe_corr; ao.lw_type = g.lw_type; ao.lw_cloud = g.lw_cloud; ao.plapse = g.plapse;
   ao.sw_prec_thresh = g.sw_prec_thresh; ao.alma_input = g.alma_input;
+  ao.snow_step = g.snow_step != g.time_step ? g.snow_step : 0; ao.max_snow_temp = g.max_snow_temp;
+  /* SNOW_STEP < TIME_STEP: per record the NF windows' values, then the record's own (atmos-><field>[0..NF-1], [NR]) */
+  const int NF = g.time_step / g.snow_step, NS = NF > 1 ? NF + 1 : 1;
   vr_atmos_cells site;
   memset(&site, 0, sizeof site);
   site.ncell = C; site.lat = vr_params_site(par, 0); site.lng = vr_params_site(par, 1);
   site.time_zone_lng = vr_params_site(par, 2); site.elevation = vr_params_site(par, 3); site.annual_prec = vr_params_site(par, 4);
+  site.min_Tfactor = vr_params_site(par, 5);
   vr_atmos_raw rw;
   rw.nrec_forcing = nrf; rw.prec = raw + (size_t)col_prec * nrf * C; rw.t_a = raw + (size_t)col_ta * nrf * C;
   rw.t_b = col_tb >= 0 ? raw + (size_t)col_tb * nrf * C : NULL; rw.wind = col_wind >= 0 ? raw + (size_t)col_wind * nrf * C : NULL;
@@ -111,8 +115,9 @@ int main(int argc, char **argv)
   rw.vp = col_vp >= 0 ? raw + (size_t)col_vp * nrf * C : NULL;
   rw.pressure = col_pr >= 0 ? raw + (size_t)col_pr * nrf * C : NULL; rw.density = col_de >= 0 ? raw + (size_t)col_de * nrf * C : NULL;
   double *field[VR_NFORCING];
-  for (i = 0; i < VR_NFORCING; i++) field[i] = malloc(sizeof(double) * (size_t)nrecs * C);
-  if (vr_atmos_prepare(device, &ao, &site, &rw, field) != VR_OK) die("forcing preparation", vr_atmos_last_error());
+  for (i = 0; i < VR_NFORCING; i++) field[i] = malloc(sizeof(double) * (size_t)nrecs * NS * C);
+  int32_t *snowflag = malloc(sizeof(int32_t) * (size_t)nrecs * C);
+  if (vr_atmos_prepare_sub(device, &ao, &site, &rw, field, snowflag) != VR_OK) die("forcing preparation", vr_atmos_last_error());
 
   /* the model */
   vr_options opt;
@@ -128,7 +133,7 @@ int main(int argc, char **argv)
   vr_handle *h = NULL;
   if (vr_create(&opt, device, &h) != VR_OK) die("vr_create", vr_last_error(NULL));
   if (vr_set_veglib(h, vr_params_veglib(par)) != VR_OK || vr_set_cells(h, cells) != VR_OK) die("parameters", vr_last_error(h));
-  const double *tair0 = field[VR_F_AIR_TEMP];                 /* atmos[0].air_temp of every cell */
+  const double *tair0 = field[VR_F_AIR_TEMP] + (size_t)(NS - 1) * C;      /* atmos[0].air_temp[NR] of every cell */
   if (g.init_state) {
     if (vr_read_state_file(h, g.init_state_file, g.binary_state_file, tair0, gridcel) != VR_OK) die("INIT_STATE", vr_last_error(h));
   }
@@ -147,7 +152,8 @@ int main(int argc, char **argv)
     if (save_after >= r0 && save_after < r0 + nr) nr = save_after - r0 + 1;
     vr_forcing f;
     f.nrec = nr; f.month = month + r0; f.day_in_year = doy + r0;
-    for (i = 0; i < VR_NFORCING; i++) f.field[i] = field[i] + (size_t)r0 * C;
+    for (i = 0; i < VR_NFORCING; i++) f.field[i] = field[i] + (size_t)r0 * NS * C;
+    f.snowflag = NF > 1 ? snowflag + (size_t)r0 * C : NULL;
     int rc = vr_step_block(h, &f, blk, status);
     if (rc != VR_OK && rc != VR_ERR_CELL) die("vr_step_block", vr_last_error(h));
     for (v = 0; v < n_out; v++)

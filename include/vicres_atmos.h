@@ -18,7 +18,7 @@
  *   VR_ATMOS_DAILY_TMAX_TMIN    FORCE_DT 24, columns PREC TMAX TMIN [WIND]   (the bundled basin's format)
  *   VR_ATMOS_SUBDAILY_AIR_TEMP  FORCE_DT < 24, columns PREC AIR_TEMP [WIND]
  * each optionally with observed SHORTWAVE, LONGWAVE, VP, PRESSURE and DENSITY columns at the same FORCE_DT; SNOW_STEP == TIME_STEP
- * (NF == 1), no QAIR / REL_HUMID columns (nor the ALMA-only RAINF / SNOWF / WIND_E / WIND_N splits).  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
+ * (NF == 1) or, for daily steps, below it (vr_atmos_prepare_sub); no QAIR / REL_HUMID columns (nor the ALMA-only RAINF / SNOWF / WIND_E / WIND_N splits).  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
  */
 #ifndef VICRES_ATMOS_H
 #define VICRES_ATMOS_H
@@ -37,7 +37,7 @@ enum { VR_LW_CLOUD_BRAS = 0, VR_LW_CLOUD_DEARDORFF = 1 };
 /* The part of global_param_struct / option_struct / param_set_struct that initialize_atmos reads.
  * Defaults (vr_atmos_default_options) as initialize_global.c:146-211. */
 typedef struct vr_atmos_options {
-  int32_t time_step;        /* TIME_STEP, hours; SNOW_STEP is taken equal                        */
+  int32_t time_step;        /* TIME_STEP, hours                                                  */
   int32_t nrecs;            /* model records                                                     */
   int32_t startyear, startmonth, startday, starthour;
   int32_t layout;           /* VR_ATMOS_*                                                        */
@@ -55,6 +55,10 @@ typedef struct vr_atmos_options {
   double  sw_prec_thresh;   /* SW_PREC_THRESH   default 0 (mm; compared with MTCLIM's cm value as the reference does) */
   int32_t reserved[8];      /* [0] cells per batch (0 = 32768); [1] = 1: untiled daily-radiation kernel,
                              * [2] = 1: solar kernel in the caller's cell order instead of latitude order (tests) */
+  int32_t snow_step;        /* SNOW_STEP, hours: 0 = TIME_STEP.  Below TIME_STEP (daily runs only, get_global_param.c:761-765)
+                             * every record carries NF = TIME_STEP / SNOW_STEP windows plus its own values         */
+  int32_t pad_;
+  double  max_snow_temp;    /* MAX_SNOW_TEMP    default 0.5: atmos->snowflag (initialize_atmos.c:1736-1753)        */
 } vr_atmos_options;
 
 void vr_atmos_default_options(vr_atmos_options *o);
@@ -66,6 +70,8 @@ typedef struct vr_atmos_cells {
   int64_t ncell;
   const double *lat, *lng, *time_zone_lng, *elevation, *annual_prec;
   const double *slope, *aspect, *ehoriz, *whoriz;
+  const double *min_Tfactor;   /* the lowest Tfactor of the cell's snow bands (initialize_atmos.c:1737-1741), NULL = 0:
+                                * read only for the snow flags */
 } vr_atmos_cells;
 
 /* Raw forcing columns, record r of cell c at col[r*C + c], nrec_forcing = nrecs*time_step/force_dt records
@@ -92,6 +98,15 @@ int  vr_atmos_prepare(int device, const vr_atmos_options *o, const vr_atmos_cell
  * (NULL = default stream) and returns after the launches are queued */
 int  vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmos_cells *cells_dev,
                              const vr_atmos_raw *raw_dev, double *const out_dev[VR_NFORCING], void *cuda_stream);
+/* The same with SNOW_STEP < TIME_STEP (o->snow_step; NF = TIME_STEP / SNOW_STEP): out[f] is [nrecs][NF + 1][C] -- per record
+ * the NF windows' values, then the record's own (atmos-><field>[0..NF-1], [NR]) -- which is the layout vr_forcing takes for
+ * a sub-stepped snow model, and snowflag (may be NULL) [nrecs][C] = atmos->snowflag[NR].  With NF == 1 they are the calls
+ * above plus the flags. */
+int  vr_atmos_prepare_sub(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
+                          double *const out[VR_NFORCING], int32_t *snowflag);
+int  vr_atmos_prepare_sub_device(int device, const vr_atmos_options *o, const vr_atmos_cells *cells_dev,
+                                 const vr_atmos_raw *raw_dev, double *const out_dev[VR_NFORCING], int32_t *snowflag_dev,
+                                 void *cuda_stream);
 /* CUDA-event time of the kernels of the last vr_atmos_prepare* call on this thread: [0] solar geometry tables,
  * [1] MTCLIM daily pass, [2] sub-daily disaggregation; launches = kernels launched */
 int  vr_atmos_last_times(double ms[3], int64_t *launches);

@@ -37,7 +37,8 @@ const int32_t *vr_params_gridcel(const vr_params *p);     /* [C] cell numbers   
 const float   *vr_params_lat(const vr_params *p);         /* [C] as stored (float)       */
 const float   *vr_params_lng(const vr_params *p);
 /* [C] site values initialize_atmos reads, as soil_con holds them (floats widened): which = 0 lat, 1 lng,
- * 2 time_zone_lng (off_gmt*360/24, read_soilparam.c:934), 3 elevation, 4 annual_prec -> vr_atmos_cells */
+ * 2 time_zone_lng (off_gmt*360/24, read_soilparam.c:934), 3 elevation, 4 annual_prec, 5 the lowest Tfactor of the cell's
+ * snow bands -> vr_atmos_cells */
 const double  *vr_params_site(const vr_params *p, int32_t which);
 
 /* The reference's ASCII result files (write_data.c:196-226, names from make_in_and_outfiles.c:46-86):

@@ -154,8 +154,10 @@ def load_atmos_fixture(name):
     ov = {str(k): str(v) for k, v in zip(z["ov_keys"], z["ov_vals"]) if str(k)}
     for k, v in list(ov.items()):
         ov[k] = {"True": True, "False": False}.get(v, v)
-        if k == "sw_prec_thresh":
+        if k in ("sw_prec_thresh", "max_snow_temp"):
             ov[k] = float(v)
+        if k == "snow_step":
+            ov[k] = int(v)
     opt = atmos.options(time_step=dt, nrecs=nrecs, startyear=sy, startmonth=sm, startday=sd, starthour=sh, layout=layout,
                         force_dt=fdt, **ov)
     raw = z["raw"]
@@ -166,4 +168,4 @@ def load_atmos_fixture(name):
     rawd = {"prec": raw[0], "t_a": raw[1], "t_b": raw[2] if layout == 0 else None, "wind": raw[iw] if has_wind else None}
     for j, name in enumerate(extra):
         rawd[name.lower()] = raw[raw.shape[0] - len(extra) + j]
-    return {"opt": opt, "site": site, "raw": rawd, "ref": z["atmos"]}
+    return {"opt": opt, "site": site, "raw": rawd, "ref": z["atmos"], "snowflag": z["snowflag"] if "snowflag" in z.files else None}

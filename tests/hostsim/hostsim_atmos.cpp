@@ -7,7 +7,8 @@
 #include <vector>
 #include "../../vicres_b200/csrc/vic_atmos.cuh"
 
-extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw, double *const out[VR_NFORCING])
+extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw, double *const out[VR_NFORCING],
+                        int32_t *snowflag)
 {
   if (va::unsupported(*o)) return -2;
   va::Ctx x{};
@@ -33,6 +34,7 @@ extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, 
   x.tcon = tcon.data();
   x.tminh = hrs.data(); x.tmaxh = hrs.data() + (size_t)nd * C;
   for (int f = 0; f < VR_NFORCING; f++) x.out[f] = out[f];
+  x.min_tf = cells->min_Tfactor; x.snowflag = snowflag;
   for (int64_t c = 0; c < C; c++)
     for (int yd = 0; yd < va::NYD; yd++) va::solar_day(x, c, yd);
   for (int64_t c = 0; c < C; c++) va::daily_prep(x, c);

@@ -51,7 +51,7 @@ def test_exports_every_declared_routing_symbol(lib):
 def test_exports_every_declared_atmos_symbol(lib):
     from vicres_b200 import atmos
     syms = declared_symbols("vicres_atmos.h")
-    assert len(syms) == 8
+    assert len(syms) == 10
     for s in syms:
         assert hasattr(lib, s), "libvicres.so does not export %s" % s
     assert sorted(atmos.EXPORTS) == syms

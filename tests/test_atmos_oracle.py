@@ -8,7 +8,12 @@ from vicres_b200 import abi
 from common import ATMOS_FIXTURES, load_atmos_fixture
 
 
-@pytest.mark.parametrize("name", ATMOS_FIXTURES)
+# The restatement covers SNOW_STEP == TIME_STEP (NF == 1).  The sub-stepped fixtures (atmos_daily_snow*) pin the device code
+# directly to the reference's records: bit for bit in its host build (test_hostsim_atmos.py), within 1e-9 on the GPU.
+NF1_FIXTURES = [n for n in ATMOS_FIXTURES if "_snow" not in n]
+
+
+@pytest.mark.parametrize("name", NF1_FIXTURES)
 def test_restatement_is_bit_identical_to_the_reference(name):
     fx = load_atmos_fixture(name)
     out = atmos_lib.prepare(fx["opt"], fx["site"], fx["raw"])

@@ -251,7 +251,9 @@ def test_global_file_calendar_and_forcing_reader(tmp_path):
     assert files.Global(str(bad)).unsupported == "FULL_ENERGY TRUE"
     sub = tmp_path / "sub.txt"
     sub.write_text(g.read_text().replace("SNOW_STEP 24", "SNOW_STEP 3"))
-    assert files.Global(str(sub)).unsupported == "SNOW_STEP != TIME_STEP"
+    assert files.Global(str(sub)).unsupported is None                       # the snow model sub-stepped: NF = 8
+    sub.write_text(g.read_text().replace("SNOW_STEP 24", "SNOW_STEP 5"))
+    assert "divide TIME_STEP evenly" in files.Global(str(sub)).unsupported      # get_global_param.c:764-765
 
 
 @pytest.mark.skipif(not os.path.exists(DRIVER), reason="compiled reference (oracle/_ref) not built here")

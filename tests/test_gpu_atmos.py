@@ -44,7 +44,16 @@ def check(out, ref, what):
 @pytest.mark.parametrize("name", ATMOS_FIXTURES)
 def test_cuda_matches_reference_atmos(gpu, name):
     fx = load_atmos_fixture(name)
-    out = gpu.prepare(fx["opt"], fx["site"], fx["raw"])
+    if fx["snowflag"] is None:
+        out = gpu.prepare(fx["opt"], fx["site"], fx["raw"])
+    else:       # SNOW_STEP < TIME_STEP: [9, nrecs, NF + 1, C] (the windows, then the record) and atmos->snowflag[NR]
+        out, flag = gpu.prepare_sub(fx["opt"], fx["site"], fx["raw"])
+        assert out.shape == fx["ref"].shape and out.shape[2] == gpu.n_windows(fx["opt"]) + 1
+        nflag = int((flag != fx["snowflag"]).sum())
+        print("ATMOS PARITY %s: %d of %d snow flags differ" % (name, nflag, flag.size))
+        assert nflag <= 0.001 * flag.size      # a flag flips only where air_temp + Tfactor is within rounding of MAX_SNOW_TEMP
+        with pytest.raises(Exception, match="prepare_sub"):
+            gpu.prepare(fx["opt"], fx["site"], fx["raw"])
     check(out, fx["ref"], "%s CUDA vs reference" % name)
     ms = gpu.last_times()
     assert ms[3] >= 5 and ms[0] > 0

@@ -22,7 +22,7 @@ def hostsim():
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-std=c++17", "-Wno-unknown-pragmas",
                         "-o", HS_LIB, src[0], "-lm"], check=True)
     lib = C.CDLL(HS_LIB)
-    lib.hs_atmos.argtypes = [C.c_void_p] * 4
+    lib.hs_atmos.argtypes = [C.c_void_p] * 5
     return lib
 
 
@@ -33,7 +33,11 @@ def test_device_arithmetic_on_host_is_bit_identical(hostsim, name):
     out = np.zeros_like(fx["ref"])
     pd = C.POINTER(C.c_double)
     ptrs = (pd * abi.VR_NFORCING)(*[out[f].ctypes.data_as(pd) for f in range(abi.VR_NFORCING)])
-    assert hostsim.hs_atmos(C.byref(fx["opt"]), ps.ref(), pr.ref(), ptrs) == 0
+    flag = np.full(fx["ref"].shape[1:2] + fx["ref"].shape[-1:], -1, dtype=np.int32)
+    assert hostsim.hs_atmos(C.byref(fx["opt"]), ps.ref(), pr.ref(), ptrs, flag.ctypes.data) == 0
+    if fx["snowflag"] is not None:       # SNOW_STEP < TIME_STEP fixtures: [9, nrecs, NF + 1, C] and atmos->snowflag[NR]
+        assert out.ndim == 4 and out.shape[2] == atmos.n_windows(fx["opt"]) + 1
+        assert np.array_equal(flag, fx["snowflag"]), name
     for f, fname in enumerate(abi.FORCING_FIELDS):
         bad = np.argwhere(out[f] != fx["ref"][f])
         assert bad.size == 0, "%s: %s differs at %d values, first (rec, cell) %s: %r vs %r" % (

@@ -25,7 +25,8 @@ def _stage(name, tmp_path, variant=None):
 
 
 # variants of the two cases: output interval, output selection, binary files (tools/make_vicnl_golden.py: VARIANTS)
-VARIANTS = [("sub3h", "out24"), ("sub3h", "out6sel"), ("daily", "selday"), ("sub3h", "bin"), ("sub3h", "bin24sel")]
+VARIANTS = [("sub3h", "out24"), ("sub3h", "out6sel"), ("daily", "selday"), ("sub3h", "bin"), ("sub3h", "bin24sel"),
+            ("daily", "snow3"), ("skip", "snow1")]
 
 
 def _quantum(tok):
@@ -98,6 +99,8 @@ def test_output_selection_of_the_variants_parses(case, variant, tmp_path):
     fl = dict(sel.files)
     assert sorted(set(n.split("_")[0] for n in os.listdir(ref))) == sorted(fl)
     assert bool(g.binary_output) == variant.startswith("bin")
+    if variant.startswith("snow"):
+        assert g.snow_step == int(variant[4:]) and g.time_step == 24
     if variant in ("out24", "bin"):
         assert [len(c) for c in fl.values()] == [22, 4] and g.out_step == (24 if variant == "out24" else 0)
         assert sel.step_vars(aggregate=True)[15] == "AERO_COND" and sel.step_vars()[15] == "AERO_RESIST"

@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference and `make -C oracle ref`):
 
-    python tools/make_atmos_golden.py
+    python tools/make_atmos_golden.py [fixture names]
 
 Each case is a set of reference-format files written by vicres_b200/synth.py (or the reference's bundled
 Mekong cell); oracle/_ref/vic_ref_driver (the unmodified reference objects behind oracle/ref_driver.c) runs
@@ -68,6 +68,16 @@ CASES = {
                               extra_cols=("SHORTWAVE", "LONGWAVE")), dict(alma_input=True)),
     "atmos_daily_no_wind": (dict(ncells=3, ndays=120, startyear=1996, lat_range=(-35, 55), off_gmt=-2, no_wind=True, seed=310),
                             dict(has_wind=False)),
+    # SNOW_STEP < TIME_STEP (daily runs): every record carries NF windows + its own values, and the snow flags
+    "atmos_daily_snow3": (dict(ncells=4, ndays=400, startyear=1985, lat_range=(30, 66), cold=7.0, nbands=3, snow_step=3, off_gmt=1,
+                               seed=321), dict(snow_step=3)),
+    "atmos_daily_snow1_lowwind": (dict(ncells=3, ndays=120, startyear=1994, lat_range=(-45, 55), cold=4.0, snow_step=1, wind_zero_frac=0.3,
+                                       seed=322, extra_global="VP_INTERP FALSE\nMAX_SNOW_TEMP 1.5"),
+                                  dict(snow_step=1, vp_interp=False, max_snow_temp=1.5)),
+    "atmos_daily_snow6_obs": (dict(ncells=2, ndays=150, startyear=1996, lat_range=(35, 60), cold=5.0, nbands=2, snow_step=6, seed=323,
+                                   extra_cols=("LONGWAVE", "VP", "PRESSURE")), dict(snow_step=6)),
+    "atmos_daily_snow12_nowind": (dict(ncells=2, ndays=90, startyear=1997, lat_range=(40, 60), cold=6.0, snow_step=12, no_wind=True,
+                                       off_gmt=-5, seed=324, extra_cols=("DENSITY",)), dict(snow_step=12, has_wind=False)),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,
                                 extra_global="VP_ITER VP_ITER_NONE\nLW_TYPE LW_SATTERLUND"),
                            dict(vp_iter="VP_ITER_NONE", lw_type="LW_SATTERLUND")),
@@ -90,7 +100,11 @@ def save(name, gfile, dump, kw, ov, start=None):
     C = int(d["ncells"][0])
     sc = np.stack([d["c%d/soil_scalars" % c] for c in range(C)])
     site = {"lat": sc[:, 0], "lng": sc[:, 1], "elevation": sc[:, 2], "annual_prec": sc[:, 12], "time_zone_lng": sc[:, 17]}
-    atm = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2).transpose(1, 0, 2)   # [9, nrec, C]
+    NF = int(d["NF"][0])
+    if NF == 1:
+        atm = np.stack([d["c%d/atmos" % c][:, :, 0] for c in range(C)], axis=2).transpose(1, 0, 2)   # [9, nrec, C]
+    else:
+        atm = np.stack([d["c%d/atmos" % c] for c in range(C)], axis=3).transpose(1, 0, 2, 3)         # [9, nrec, NF + 1, C]
     dt = int(d["dt"][0])
     daily = dt == 24 or kw.get("force_daily", False)
     extra = list(kw.get("extra_cols", ()))
@@ -105,6 +119,9 @@ def save(name, gfile, dump, kw, ov, start=None):
                                dtype=np.int64),
               "ov_keys": np.array(list(ov.keys()) or [""]), "ov_vals": np.array([str(v) for v in ov.values()] or [""]),
               "extra_cols": np.array(extra or [""])}
+    if NF > 1:
+        arrays["snowflag"] = np.stack([d["c%d/snowflag" % c][:, NF] for c in range(C)], axis=1).astype(np.int32)   # [nrec, C], [NR]
+        site["min_Tfactor"] = np.array([d["c%d/Tfactor" % c].min() for c in range(C)])
     for k, v in site.items():
         arrays["site_" + k] = v
     out = os.path.join(ROOT, "tests", "golden", name + ".npz")
@@ -116,12 +133,17 @@ def main():
     if not os.path.exists(DRIVER):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
     with tempfile.TemporaryDirectory() as tmp:
+        only = sys.argv[1:]                         # optional: the names to (re)generate
         for name, (kw, ov) in CASES.items():
+            if only and name not in only:
+                continue
             work = os.path.join(tmp, name)
             g = synth.make_case(work, max_veg=1, **kw)
             dump = os.path.join(work, "dump.bin")
             make_golden.run_driver(g, dump)
             save(name, g, dump, kw, ov)
+        if only and "atmos_bundled_basin_cell" not in only:
+            return
         work = os.path.join(tmp, "bundled")
         os.makedirs(work)
         g = make_golden.bundled_case(work)

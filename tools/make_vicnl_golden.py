@@ -38,6 +38,9 @@ VARIANTS = {
                           "OUTVAR OUT_SHORTWAVE %.2f"]),
     "selday": ("daily", ["N_OUTFILES 1", "OUTFILE cell 7", "OUTVAR OUT_RUNOFF", "OUTVAR OUT_BASEFLOW", "OUTVAR OUT_SWE %.5f",
                          "OUTVAR OUT_AERO_RESIST", "OUTVAR OUT_SOIL_WET", "OUTVAR OUT_SNOW_COVER %.0f", "OUTVAR OUT_RAINF"]),
+    # the snow model sub-stepped (NF = 8 and NF = 24 passes per daily record): initialize_atmos's per-window values and snow flags
+    "snow3": ("daily", ["SNOW_STEP 3"]),
+    "snow1": ("skip", ["SNOW_STEP 1"]),
     "bin": ("sub3h", ["BINARY_OUTPUT TRUE"]),
     "bin24sel": ("sub3h", ["BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE packed 6",
                            "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100",

@@ -19,6 +19,7 @@ LW_TYPE = {"LW_TVA": 0, "LW_ANDERSON": 1, "LW_BRUTSAERT": 2, "LW_SATTERLUND": 3,
 LW_CLOUD = {"LW_CLOUD_BRAS": 0, "LW_CLOUD_DEARDORFF": 1}
 
 EXPORTS = ["vr_atmos_default_options", "vr_atmos_ndays", "vr_atmos_prepare", "vr_atmos_prepare_device",
+           "vr_atmos_prepare_sub", "vr_atmos_prepare_sub_device",
            "vr_atmos_last_times", "vr_atmos_last_error", "vr_atmos_diag_cr", "vr_atmos_diag_solar"]
 
 _pd = C.POINTER(C.c_double)
@@ -30,10 +31,10 @@ class vr_atmos_options(C.Structure):
                 ("has_wind", C.c_int32), ("vp_interp", C.c_int32), ("vp_iter", C.c_int32),
                 ("mtclim_swe_corr", C.c_int32), ("lw_type", C.c_int32), ("lw_cloud", C.c_int32), ("plapse", C.c_int32),
                 ("alma_input", C.c_int32), ("min_wind_speed", C.c_double), ("sw_prec_thresh", C.c_double),
-                ("reserved", C.c_int32 * 8)]
+                ("reserved", C.c_int32 * 8), ("snow_step", C.c_int32), ("pad_", C.c_int32), ("max_snow_temp", C.c_double)]
 
 
-SITE_FIELDS = ["lat", "lng", "time_zone_lng", "elevation", "annual_prec", "slope", "aspect", "ehoriz", "whoriz"]
+SITE_FIELDS = ["lat", "lng", "time_zone_lng", "elevation", "annual_prec", "slope", "aspect", "ehoriz", "whoriz", "min_Tfactor"]
 
 
 class vr_atmos_cells(C.Structure):
@@ -50,7 +51,8 @@ RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp", "pres
 
 def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, starthour=0, layout=None, force_dt=None,
             has_wind=True, vp_interp=True, vp_iter="VP_ITER_ALWAYS", mtclim_swe_corr=False, lw_type="LW_PRATA",
-            lw_cloud="LW_CLOUD_DEARDORFF", plapse=True, min_wind_speed=0.1, sw_prec_thresh=0.0, alma_input=False):
+            lw_cloud="LW_CLOUD_DEARDORFF", plapse=True, min_wind_speed=0.1, sw_prec_thresh=0.0, alma_input=False,
+            snow_step=0, max_snow_temp=0.5):
     """vr_atmos_options with the reference's defaults (initialize_global.c:146-211)."""
     o = vr_atmos_options()
     if force_dt is None:
@@ -63,7 +65,13 @@ def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, sta
     o.lw_type, o.lw_cloud, o.plapse = LW_TYPE.get(lw_type, lw_type), LW_CLOUD.get(lw_cloud, lw_cloud), int(plapse)
     o.min_wind_speed, o.sw_prec_thresh = min_wind_speed, sw_prec_thresh
     o.alma_input = int(alma_input)
+    o.snow_step, o.max_snow_temp = int(snow_step), float(max_snow_temp)
     return o
+
+
+def n_windows(opt):
+    """NF = TIME_STEP / SNOW_STEP"""
+    return opt.time_step // opt.snow_step if opt.snow_step > 0 else 1
 
 
 class Packed:
@@ -107,6 +115,8 @@ def _lib():
         L.vr_atmos_ndays.argtypes = [vp]
         L.vr_atmos_prepare.argtypes = [C.c_int, vp, vp, vp, vp]
         L.vr_atmos_prepare_device.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+        L.vr_atmos_prepare_sub.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+        L.vr_atmos_prepare_sub_device.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp]
         L.vr_atmos_last_times.argtypes = [vp, vp]
         L.vr_atmos_last_error.restype = C.c_char_p
         L.vr_atmos_diag_cr.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp]
@@ -131,9 +141,26 @@ def prepare(opt, site, raw, device=0):
     return out
 
 
-def prepare_device(opt, site_dev, raw_dev, out_dev, ncell, nrec_forcing, device=0, stream=None):
+def prepare_sub(opt, site, raw, device=0):
+    """initialize_atmos with the snow flags, and with the windows of a sub-stepped snow model when opt.snow_step <
+    opt.time_step: returns (fields, snowflag); fields [9, nrecs, C] for NF == 1, else [9, nrecs, NF + 1, C] (the NF
+    windows, then the record's own values: atmos-><field>[0..NF-1], [NR]); snowflag [nrecs, C] int32."""
+    L = _lib()
+    ps, pr = pack_site(site), pack_raw(raw)
+    Cn = ps.struct.ncell
+    NF = n_windows(opt)
+    shape = (abi.VR_NFORCING, opt.nrecs, Cn) if NF == 1 else (abi.VR_NFORCING, opt.nrecs, NF + 1, Cn)
+    out = np.zeros(shape)
+    flag = np.zeros((opt.nrecs, Cn), dtype=np.int32)
+    ptrs = (_pd * abi.VR_NFORCING)(*[out[f].ctypes.data_as(_pd) for f in range(abi.VR_NFORCING)])
+    _check(L, L.vr_atmos_prepare_sub(device, C.byref(opt), ps.ref(), pr.ref(), ptrs, flag.ctypes.data))
+    return out, flag
+
+
+def prepare_device(opt, site_dev, raw_dev, out_dev, ncell, nrec_forcing, device=0, stream=None, snowflag_dev=None):
     """Device-resident variant: site_dev / raw_dev map names to device pointers (ints), out_dev is a list of
-    nine device pointers, each [nrecs*C] doubles."""
+    nine device pointers, each [nrecs*C] doubles ([nrecs*(NF+1)*C] with opt.snow_step < opt.time_step); snowflag_dev:
+    device pointer to [nrecs*C] int32, or None."""
     L = _lib()
     s = vr_atmos_cells()
     s.ncell = ncell
@@ -146,7 +173,7 @@ def prepare_device(opt, site_dev, raw_dev, out_dev, ncell, nrec_forcing, device=
         if raw_dev.get(n):
             setattr(r, n, C.cast(raw_dev[n], _pd))
     ptrs = (_pd * abi.VR_NFORCING)(*[C.cast(p, _pd) for p in out_dev])
-    _check(L, L.vr_atmos_prepare_device(device, C.byref(opt), C.byref(s), C.byref(r), ptrs, stream))
+    _check(L, L.vr_atmos_prepare_sub_device(device, C.byref(opt), C.byref(s), C.byref(r), ptrs, snowflag_dev, stream))
 
 
 def last_times():
@@ -169,7 +196,8 @@ def options_from_global(g):
                    startday=g.startday, starthour=g.starthour, layout=layout, force_dt=g.force_dt,
                    has_wind="WIND" in types, min_wind_speed=g.min_wind_speed, vp_interp=g.vp_interp, vp_iter=g.vp_iter,
                    mtclim_swe_corr=g.mtclim_swe_corr, lw_type=g.lw_type, lw_cloud=g.lw_cloud, plapse=g.plapse,
-                   sw_prec_thresh=g.sw_prec_thresh, alma_input=g.alma_input)
+                   sw_prec_thresh=g.sw_prec_thresh, alma_input=g.alma_input,
+                   snow_step=g.snow_step if g.snow_step != g.time_step else 0, max_snow_temp=g.max_snow_temp)
 
 
 def raw_from_columns(cols, layout):

@@ -57,6 +57,8 @@ struct Ctx {
   int dt, nrecs, starthour, layout, fdt, has_wind, vp_interp, vp_iter, swe_corr, lw_type, lw_cloud, plapse, alma;
   double min_wind, sw_thresh;
   int Ndays, fsteps;
+  int NF;                      // TIME_STEP / SNOW_STEP: windows per record (1: the record itself)
+  double max_snow_temp;        // MAX_SNOW_TEMP, for atmos->snowflag (:1736-1753)
   const int16_t *cal;          // [Ndays+2] day_in_year of the days from one day BEFORE the start date on
   // cells
   int64_t C, c0, CB, nrf;
@@ -71,7 +73,9 @@ struct Ctx {
   double *tcon;                // [2][CB] Tmax, Tmin of the sub-daily layout
   int8_t *tminh, *tmaxh;       // [ndl][CB]
   const int32_t *perm;         // [CB] k_solar only: batch-local cell indices ordered by latitude (or null)
-  double *out[VR_NFORCING];
+  const double *min_tf;        // [C] the lowest band Tfactor of the cell (snowflag), or null = 0
+  double *out[VR_NFORCING];    // NF == 1: [nrecs][C]; NF > 1: [nrecs][NF + 1][C]
+  int32_t *snowflag;           // [nrecs][C] atmos->snowflag[NR], or null
 };
 
 struct Geo {                   // initialize_atmos.c:217-225, 271-292
@@ -841,44 +845,46 @@ VA_HD double hourly_vp(const Ctx &x, const Geo &g, int64_t lc, int idx)
   return v;
 }
 
-VA_HD void record_inl(const Ctx &x, int64_t c, int rec)
+// What initialize_atmos stores for one window of `len` hours starting at local hour `hour` -- a sub-step of SNOW_STEP hours,
+// which is the whole record when SNOW_STEP == TIME_STEP -- before the quantities derived from them: precipitation, wind,
+// air temperature, shortwave, vapour pressure, and the observed density / pressure / longwave columns when the file has
+// them.  nsub = windows per day (NF * stepspday), the divisor of a daily precipitation total (:601-606).
+struct Win { double prec, wind, ta, sw, vp, dens, p, lw; int dayi; };
+VA_HD Win window_vals(const Ctx &x, const Geo &g, int64_t c, int hour, int len, int nsub)
 {
-  const int64_t lc = c - x.c0, o = (int64_t)rec * x.C + c;
-  const Geo g = cell_geo(x, c);
-  const int dt = x.dt, stepspday = 24 / dt;
-  const int hour = rec * dt + x.starthour - g.hoi + g.shift;
-  const int dayi = (int)((float)hour / 24.0);
-  double prec, wind, ta;
+  const int64_t lc = c - x.c0;
+  Win w;
+  w.dayi = (int)((float)hour / 24.0);
+  const int dayi = w.dayi;
   if (x.fdt == 24) {                                       // :597-613, :641-659
-    prec = u_prec(x, local_daily(x.r_prec, x, g, c, dayi)) / (float)(1 * stepspday);
-    // the MIN_WIND_SPEED clamp at :654-657 addresses wind[NF], one past the record's value: no effect
-    wind = x.has_wind ? local_daily(x.r_wind, x, g, c, dayi) : 3.0;
+    w.prec = u_prec(x, local_daily(x.r_prec, x, g, c, dayi)) / (float)nsub;
+    w.wind = x.has_wind ? local_daily(x.r_wind, x, g, c, dayi) : 3.0;
     double s = 0;                                          // :1005-1019
     SplineSeg sg;
-    for (int idx = hour; idx < hour + dt; idx++) s += hourly_tair_cached(x, g, c, idx, sg);
-    ta = s / dt;
+    for (int idx = hour; idx < hour + len; idx++) s += hourly_tair_cached(x, g, c, idx, sg);
+    w.ta = s / len;
   }
   else {                                                   // :616-628, :662-678, :737-752
     double s = 0;
-    for (int idx = hour; idx < hour + dt; idx++) s += u_prec(x, local_hourly(x.r_prec, x, g, c, idx)) / x.fdt;
-    prec = s;
+    for (int idx = hour; idx < hour + len; idx++) s += u_prec(x, local_hourly(x.r_prec, x, g, c, idx)) / x.fdt;
+    w.prec = s;
     if (x.has_wind) {
       s = 0;
-      for (int idx = hour; idx < hour + dt; idx++) {
-        double w = local_hourly(x.r_wind, x, g, c, idx);
-        s += (w < x.min_wind) ? x.min_wind : w;
+      for (int idx = hour; idx < hour + len; idx++) {
+        double v = local_hourly(x.r_wind, x, g, c, idx);
+        s += (v < x.min_wind) ? x.min_wind : v;
       }
-      wind = s / dt;
+      w.wind = s / len;
     }
-    else wind = 3.0;
+    else w.wind = 3.0;
     s = 0;
-    for (int idx = hour; idx < hour + dt; idx++) s += u_temp(x, local_hourly(x.r_ta, x, g, c, idx));
-    ta = s / dt;
+    for (int idx = hour; idx < hour + len; idx++) s += u_temp(x, local_hourly(x.r_ta, x, g, c, idx));
+    w.ta = s / len;
   }
   double sw = 0, vp = 0;                                   // :974-987, :1278-1291
   int rad_day = -1, rad_ydi = 0;
   double tmp_rad = 0.;
-  for (int idx = hour; idx < hour + dt; idx++) {
+  for (int idx = hour; idx < hour + len; idx++) {
     const int d = idx / 24;
     if (x.r_sw) sw += hourly_rad(x, g, lc, d, idx - d * 24);
     else {
@@ -891,26 +897,43 @@ VA_HD void record_inl(const Ctx &x, int64_t c, int rec)
     }
     vp += hourly_vp(x, g, lc, idx);
   }
-  sw /= dt;
-  vp /= dt;
-  const double elevation = x.elev[c];
-  double p, dens = 0.;                                     // :1032-1170
+  w.sw = sw / len;
+  w.vp = vp / len;
+  w.dens = 0.; w.p = 0.; w.lw = 0.;                        // observed columns, :1032-1062, :1117-1145, :1389-1420
   if (x.r_de) {
-    if (x.fdt == 24) dens = local_daily(x.r_de, x, g, c, dayi);
-    else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_de, x, g, c, idx); dens = s / dt; }
+    if (x.fdt == 24) w.dens = local_daily(x.r_de, x, g, c, dayi);
+    else { double s = 0; for (int idx = hour; idx < hour + len; idx++) s += local_hourly(x.r_de, x, g, c, idx); w.dens = s / len; }
   }
   if (x.r_pr) {
-    if (x.fdt == 24) p = u_kpa(x, local_daily(x.r_pr, x, g, c, dayi));
-    else { double s = 0; for (int idx = hour; idx < hour + dt; idx++) s += u_kpa(x, local_hourly(x.r_pr, x, g, c, idx)); p = s / dt; }
+    if (x.fdt == 24) w.p = u_kpa(x, local_daily(x.r_pr, x, g, c, dayi));
+    else { double s = 0; for (int idx = hour; idx < hour + len; idx++) s += u_kpa(x, local_hourly(x.r_pr, x, g, c, idx)); w.p = s / len; }
   }
+  if (x.r_lw) {
+    if (x.fdt == 24) w.lw = local_daily(x.r_lw, x, g, c, dayi);
+    else { double s = 0; for (int idx = hour; idx < hour + len; idx++) s += local_hourly(x.r_lw, x, g, c, idx); w.lw = s / len; }
+  }
+  return w;
+}
+
+// pressure and density of a window or of the record from what is observed and its air temperature, :1070-1170
+VA_HD void pressure_density(const Ctx &x, double elevation, double ta, double &p, double &dens)
+{
+  if (x.r_pr) { }
   else if (x.r_de) p = x.plapse ? (KELVIN + ta) * dens * RD : (275.0 + ta) * dens / 0.003486;
   else if (x.plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
   else p = 95500.;
   if (!x.r_de) dens = x.plapse ? p / (RD * (KELVIN + ta)) : 0.003486 * p / (275.0 + ta);
-  double vpd = svp(ta) - vp;                               // :1336-1355
-  if (vpd < 0) { vpd = 0; vp = svp(ta); }
-  const double tf = x.tskc[(int64_t)dayi * x.CB + lc];      // :1188-1193, :1361-1388
-  const double tskc = (x.lw_cloud == VR_LW_CLOUD_DEARDORFF) ? (1. - tf) : sqrt((1. - tf) / 0.65);
+}
+
+VA_HD double cloud_tskc(const Ctx &x, int64_t lc, int dayi)     // :1188-1193, :1361-1388
+{
+  const double tf = x.tskc[(int64_t)dayi * x.CB + lc];
+  return (x.lw_cloud == VR_LW_CLOUD_DEARDORFF) ? (1. - tf) : sqrt((1. - tf) / 0.65);
+}
+
+VA_HD void store_fields(const Ctx &x, int64_t o, double ta, double prec, double wind, double vp, double vpd, double p, double dens,
+                        double sw, double lw)
+{
   x.out[VR_F_AIR_TEMP][o] = ta;
   x.out[VR_F_PREC][o] = prec;
   x.out[VR_F_WIND][o] = wind;
@@ -919,17 +942,61 @@ VA_HD void record_inl(const Ctx &x, int64_t c, int rec)
   x.out[VR_F_PRESSURE][o] = p;
   x.out[VR_F_DENSITY][o] = dens;
   x.out[VR_F_SHORTWAVE][o] = sw;
-  double lw;
-  if (x.r_lw) {                                            // :1389-1420
-    if (x.fdt == 24) lw = local_daily(x.r_lw, x, g, c, dayi);
-    else {
-      double s = 0;
-      for (int idx = hour; idx < hour + dt; idx++) s += local_hourly(x.r_lw, x, g, c, idx);
-      lw = s / dt;
-    }
-  }
-  else lw = longwave(x, tskc, ta, vp);
   x.out[VR_F_LONGWAVE][o] = lw;
+}
+
+// One record of one cell.  NF == 1 (SNOW_STEP == TIME_STEP): the record is its only window, stored at [rec][c].  NF > 1: the
+// NF windows of SNOW_STEP hours at [rec][0 .. NF-1][c], then the record's own values at [rec][NF][c] -- sums or means of
+// the windows' values in the reference's order, NOT means over the record's hours -- as atmos-><field>[0..NF-1], [NR].
+VA_HD void record_inl(const Ctx &x, int64_t c, int rec)
+{
+  const int64_t lc = c - x.c0;
+  const Geo g = cell_geo(x, c);
+  const int dt = x.dt, stepspday = 24 / dt, NF = x.NF;
+  const int hour = rec * dt + x.starthour - g.hoi + g.shift;
+  const double elevation = x.elev[c];
+  const double min_tf = x.min_tf ? x.min_tf[c] : 0.;
+  if (NF == 1) {
+    const int64_t o = (int64_t)rec * x.C + c;
+    Win w = window_vals(x, g, c, hour, dt, stepspday);
+    // the MIN_WIND_SPEED clamp at :654-657 addresses wind[NF], one past the record's value: no effect
+    double p = w.p, dens = w.dens, vp = w.vp;
+    pressure_density(x, elevation, w.ta, p, dens);
+    double vpd = svp(w.ta) - vp;                           // :1336-1355
+    if (vpd < 0) { vpd = 0; vp = svp(w.ta); }
+    const double lw = x.r_lw ? w.lw : longwave(x, cloud_tskc(x, lc, w.dayi), w.ta, vp);
+    store_fields(x, o, w.ta, w.prec, w.wind, vp, vpd, p, dens, w.sw, lw);
+    if (x.snowflag) x.snowflag[o] = ((w.ta + min_tf) < x.max_snow_temp && w.prec > 0) ? 1 : 0;      // :1736-1753
+    return;
+  }
+  const int ss = dt / NF;
+  const int64_t o0 = ((int64_t)rec * (NF + 1)) * x.C + c;
+  double s_prec = 0, s_wind = 0, s_ta = 0, s_sw = 0, s_vp0 = 0, s_dens = 0, s_p = 0, s_vpd = 0, s_vp = 0, s_lw = 0;
+  int flag = 0;
+  for (int i = 0; i < NF; i++) {
+    Win w = window_vals(x, g, c, hour + i * ss, ss, NF * stepspday);
+    double p = w.p, dens = w.dens, vp = w.vp;
+    pressure_density(x, elevation, w.ta, p, dens);
+    double vpd = svp(w.ta) - vp;
+    if (vpd < 0) { vpd = 0; vp = svp(w.ta); }
+    const double lw = x.r_lw ? w.lw : longwave(x, cloud_tskc(x, lc, w.dayi), w.ta, vp);
+    store_fields(x, o0 + (int64_t)i * x.C, w.ta, w.prec, w.wind, vp, vpd, p, dens, w.sw, lw);
+    s_prec += w.prec; s_wind += w.wind; s_ta += w.ta; s_sw += w.sw; s_vp0 += w.vp; s_dens += w.dens; s_p += w.p;
+    s_vpd += vpd; s_vp += vp; s_lw += lw;
+    if ((w.ta + min_tf) < x.max_snow_temp && w.prec > 0) flag = 1;
+  }
+  const float fNF = (float)NF;
+  const double ta = s_ta / fNF;
+  double wind = x.has_wind ? s_wind / fNF : 3.0;
+  // :654-657 clamps wind[j] with j == NF after the loop: with NF > 1 that IS the record's value (NR == NF)
+  if (x.has_wind && x.fdt == 24 && dt == 24 && wind < x.min_wind) wind = x.min_wind;
+  double p = s_p / fNF, dens = s_dens / fNF;               // observed columns: means of the windows (:1126, :1044)
+  pressure_density(x, elevation, ta, p, dens);
+  double vp, vpd;
+  if (x.r_vp || x.vp_interp) { vpd = s_vpd / fNF; vp = s_vp / fNF; }          // :1345-1349
+  else { vp = s_vp0 / fNF; vpd = svp(ta) - vp; }                              // :1350-1352 (no clamp)
+  store_fields(x, o0 + (int64_t)NF * x.C, ta, s_prec, wind, vp, vpd, p, dens, s_sw / fNF, s_lw / fNF);
+  if (x.snowflag) x.snowflag[(int64_t)rec * x.C + c] = flag;
 }
 
 VA_HDN void record(const Ctx &x, int64_t c, int rec) { record_inl(x, c, rec); }
@@ -979,6 +1046,10 @@ inline const char *unsupported(const vr_atmos_options &o)
 {
   if (o.time_step < 1 || o.time_step > 24 || 24 % o.time_step) return "TIME_STEP must divide 24";
   if (o.nrecs < 1) return "nrecs < 1";
+  if (o.snow_step != 0) {                                 // get_global_param.c:761-765
+    if (o.time_step < 24 && o.snow_step != o.time_step) return "If the model step is smaller than daily, the snow model should run at the same time step as the rest of the model.";
+    if (o.snow_step < 1 || o.snow_step > o.time_step || o.time_step % o.snow_step) return "SNOW_STEP should be <= TIME_STEP and divide TIME_STEP evenly";
+  }
   if (o.layout == VR_ATMOS_DAILY_TMAX_TMIN) { if (o.force_dt != 24) return "daily TMAX/TMIN layout needs FORCE_DT 24"; }
   else if (o.layout == VR_ATMOS_SUBDAILY_AIR_TEMP) {
     if (o.force_dt < 1 || o.force_dt >= 24 || 24 % o.force_dt) return "sub-daily AIR_TEMP layout needs FORCE_DT below 24 dividing 24";
@@ -991,8 +1062,10 @@ inline void fill_options(const vr_atmos_options &o, Ctx &x)
 {
   x.dt = o.time_step; x.nrecs = o.nrecs; x.starthour = o.starthour; x.layout = o.layout; x.fdt = o.force_dt;
   x.has_wind = o.has_wind; x.vp_interp = o.vp_interp; x.vp_iter = o.vp_iter; x.swe_corr = o.mtclim_swe_corr;
-  x.lw_type = o.lw_type; x.lw_cloud = o.lw_cloud; x.plapse = o.plapse; x.alma = o.alma_input; x.min_wind = o.min_wind_speed;
+  x.lw_type = o.lw_type; x.lw_cloud = o.lw_cloud; x.plapse = o.plapse; x.alma = o.alma_input;
+  x.min_wind = (double)(float)o.min_wind_speed;       // option_struct.MIN_WIND_SPEED is a float (vicNl_def.h)
   x.sw_thresh = o.sw_prec_thresh; x.Ndays = ndays_of(o); x.fsteps = 24 / o.force_dt;
+  x.NF = o.snow_step > 0 ? o.time_step / o.snow_step : 1; x.max_snow_temp = o.max_snow_temp;
 }
 
 }  // namespace va

@@ -144,6 +144,7 @@ void vr_atmos_default_options(vr_atmos_options *o)
   o->layout = VR_ATMOS_DAILY_TMAX_TMIN; o->force_dt = 24; o->has_wind = 1;
   o->vp_interp = 1; o->vp_iter = VR_VP_ITER_ALWAYS; o->mtclim_swe_corr = 0; o->lw_type = VR_LW_PRATA;
   o->lw_cloud = VR_LW_CLOUD_DEARDORFF; o->plapse = 1; o->min_wind_speed = 0.1; o->sw_prec_thresh = 0.;
+  o->snow_step = 0; o->max_snow_temp = 0.5;
 }
 
 int32_t vr_atmos_ndays(const vr_atmos_options *o) { return o ? va::ndays_of(*o) : 0; }
@@ -151,6 +152,14 @@ const char *vr_atmos_last_error(void) { return g_err.c_str(); }
 
 int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
                             double *const out[VR_NFORCING], void *cuda_stream)
+{
+  if (o && o->snow_step > 0 && o->snow_step != o->time_step)
+    return fail(VR_ERR_ARG, "SNOW_STEP < TIME_STEP: the output is [nrecs][NF + 1][C], use vr_atmos_prepare_sub_device");
+  return vr_atmos_prepare_sub_device(device, o, cells, raw, out, nullptr, cuda_stream);
+}
+
+int vr_atmos_prepare_sub_device(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
+                                double *const out[VR_NFORCING], int32_t *snowflag, void *cuda_stream)
 {
   if (!o || !cells || !raw || !out) return fail(VR_ERR_ARG, "null argument");
   if (const char *why = va::unsupported(*o)) return fail(VR_ERR_UNSUPPORTED, why);
@@ -181,6 +190,7 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
   x.r_prec = raw->prec; x.r_ta = raw->t_a; x.r_tb = raw->t_b; x.r_wind = raw->wind;
   x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp; x.r_pr = raw->pressure; x.r_de = raw->density;
   for (int f = 0; f < VR_NFORCING; f++) x.out[f] = out[f];
+  x.min_tf = cells->min_Tfactor; x.snowflag = snowflag;
 
   // scratch of one batch, one stream-ordered allocation
   const bool conv = o->vp_iter == VR_VP_ITER_CONVERGE;
@@ -256,6 +266,14 @@ int vr_atmos_prepare_device(int device, const vr_atmos_options *o, const vr_atmo
 int vr_atmos_prepare(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
                      double *const out[VR_NFORCING])
 {
+  if (o && o->snow_step > 0 && o->snow_step != o->time_step)
+    return fail(VR_ERR_ARG, "SNOW_STEP < TIME_STEP: the output is [nrecs][NF + 1][C], use vr_atmos_prepare_sub");
+  return vr_atmos_prepare_sub(device, o, cells, raw, out, nullptr);
+}
+
+int vr_atmos_prepare_sub(int device, const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw,
+                         double *const out[VR_NFORCING], int32_t *snowflag)
+{
   if (!o || !cells || !raw || !out) return fail(VR_ERR_ARG, "null argument");
   if (const char *why = va::unsupported(*o)) return fail(VR_ERR_UNSUPPORTED, why);
   int ndev = 0;
@@ -264,29 +282,34 @@ int vr_atmos_prepare(int device, const vr_atmos_options *o, const vr_atmos_cells
   CK(cudaSetDevice(device));
   const int64_t C = cells->ncell, nrf = raw->nrec_forcing;
   if (C < 1 || nrf < 1) return fail(VR_ERR_ARG, "empty input");
-  const double *site_h[9] = {cells->lat, cells->lng, cells->time_zone_lng, cells->elevation, cells->annual_prec,
-                             cells->slope, cells->aspect, cells->ehoriz, cells->whoriz};
+  const int NSITE = 10;
+  const double *site_h[NSITE] = {cells->lat, cells->lng, cells->time_zone_lng, cells->elevation, cells->annual_prec,
+                                 cells->slope, cells->aspect, cells->ehoriz, cells->whoriz, cells->min_Tfactor};
   const double *raw_h[9] = {raw->prec, raw->t_a, raw->t_b, raw->wind, raw->shortwave, raw->longwave, raw->vp, raw->pressure,
                             raw->density};
-  const size_t n_out = (size_t)o->nrecs * C;
+  const int NF = o->snow_step > 0 ? o->time_step / o->snow_step : 1;
+  const size_t n_flag = (size_t)o->nrecs * C, n_out = n_flag * (NF > 1 ? NF + 1 : 1);
   double *dev = nullptr;
-  CK(cudaMalloc((void **)&dev, ((size_t)9 * C + (size_t)9 * nrf * C + VR_NFORCING * n_out) * sizeof(double)));
-  const double *site_d[9] = {}, *raw_d[9] = {};
+  CK(cudaMalloc((void **)&dev, ((size_t)NSITE * C + (size_t)9 * nrf * C + VR_NFORCING * n_out) * sizeof(double) + n_flag * sizeof(int32_t)));
+  const double *site_d[NSITE] = {}, *raw_d[9] = {};
   double *p = dev;
   int rc = VR_OK;
-  for (int i = 0; i < 9 && rc == VR_OK; i++, p += C)
+  for (int i = 0; i < NSITE && rc == VR_OK; i++, p += C)
     if (site_h[i]) { site_d[i] = p; if (cudaMemcpy(p, site_h[i], C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
   for (int i = 0; i < 9 && rc == VR_OK; i++, p += (size_t)nrf * C)
     if (raw_h[i]) { raw_d[i] = p; if (cudaMemcpy(p, raw_h[i], (size_t)nrf * C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
   if (rc != VR_OK) { cudaFree(dev); return fail(rc, "host to device copy failed"); }
-  vr_atmos_cells cd{C, site_d[0], site_d[1], site_d[2], site_d[3], site_d[4], site_d[5], site_d[6], site_d[7], site_d[8]};
+  vr_atmos_cells cd{C, site_d[0], site_d[1], site_d[2], site_d[3], site_d[4], site_d[5], site_d[6], site_d[7], site_d[8], site_d[9]};
   vr_atmos_raw rd{nrf, raw_d[0], raw_d[1], raw_d[2], raw_d[3], raw_d[4], raw_d[5], raw_d[6], raw_d[7], raw_d[8]};
   double *out_d[VR_NFORCING];
   for (int f = 0; f < VR_NFORCING; f++) out_d[f] = p + (size_t)f * n_out;
-  rc = vr_atmos_prepare_device(device, o, &cd, &rd, out_d, nullptr);
+  int32_t *flag_d = (int32_t *)(p + (size_t)VR_NFORCING * n_out);
+  rc = vr_atmos_prepare_sub_device(device, o, &cd, &rd, out_d, snowflag ? flag_d : nullptr, nullptr);
   if (rc == VR_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(VR_ERR_CUDA, std::string("kernel: ") + cudaGetErrorString(cudaGetLastError()));
   for (int f = 0; f < VR_NFORCING && rc == VR_OK; f++)
     if (cudaMemcpy(out[f], out_d[f], n_out * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(VR_ERR_CUDA, "device to host copy failed");
+  if (rc == VR_OK && snowflag && cudaMemcpy(snowflag, flag_d, n_flag * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(VR_ERR_CUDA, "device to host copy failed");
   cudaFree(dev);
   return rc;
 }

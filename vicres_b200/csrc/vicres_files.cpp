@@ -58,6 +58,7 @@ struct vr_params {
   std::vector<int32_t> gridcel;
   std::vector<float> lat, lng;
   std::vector<double> site_lng, site_tz, site_annual_prec;   // what initialize_atmos reads from soil_con
+  std::vector<double> site_min_tf;                           // the lowest band Tfactor (initialize_atmos.c:1737-1741)
   // cells
   std::vector<double> c_lat, elevation, b_infilt, Ds, Dsmax, Ws, c_expt, avg_temp, dp, rough, snow_rough;
   std::vector<double> expt, Ksat, depth, max_moist, Wcr, Wpwp, resid_moist, init_moist, bulk_density, soil_density,
@@ -92,6 +93,7 @@ const double *vr_params_site(const vr_params *p, int32_t which)
     case 2: return p->site_tz.data();
     case 3: return p->cells.elevation;
     case 4: return p->site_annual_prec.data();
+    case 5: return p->site_min_tf.data();
     default: return nullptr;
   }
 }
@@ -502,6 +504,12 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
   cl.soil_density = P->soil_density.data(); cl.bulk_dens_min = P->bulk_dens_min.data(); cl.soil_dens_min = P->soil_dens_min.data();
   cl.quartz = P->quartz.data(); cl.organic = P->organic.data(); cl.porosity = P->porosity.data();
   cl.AreaFract = P->AreaFract.data(); cl.Tfactor = P->Tfactor.data(); cl.Pfactor = P->Pfactor.data();
+  P->site_min_tf.resize(C);
+  for (int64_t c = 0; c < C; c++) {
+    double m = P->Tfactor[c];
+    for (int b = 1; b < NB; b++) if (P->Tfactor[(size_t)b * C + c] < m) m = P->Tfactor[(size_t)b * C + c];
+    P->site_min_tf[c] = m;
+  }
   cl.tile_ptr = P->tile_ptr.data(); cl.tile_class = P->tile_class.data(); cl.tile_Cv = P->tile_Cv.data();
   cl.tile_root = P->tile_root.data(); cl.tile_LAI = P->tile_LAI.data(); cl.tile_albedo = P->tile_albedo.data();
   cl.tile_vegcover = P->tile_vegcover.data();
@@ -857,7 +865,6 @@ int vr_global_read(const char *path, vr_global *g)
   }
   fclose(f);
   if (g->time_step == -99999) { g_err = "TIME_STEP missing from the global parameter file"; return VR_ERR_ARG; }
-  if (g->snow_step == 1 && g->time_step != 1) { /* SNOW_STEP default 1 only matters in full-energy runs; keep what the file says */ }
   if (g->startyear <= 0 || g->startmonth < 1 || g->startmonth > 12 || g->startday < 1) { g_err = "simulation start date missing or invalid"; return VR_ERR_ARG; }
   if (g->nrecs == -99999) {            // make_dmy.c:52-90: count the steps up to the day after the end date
     if (endyear == -99999 || endmonth == -99999 || endday == -99999) { g_err = "neither NRECS nor ENDYEAR/ENDMONTH/ENDDAY given"; return VR_ERR_ARG; }
@@ -891,7 +898,10 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->compute_treeline) return "COMPUTE_TREELINE";
   if (g->dist_prcp) return "DIST_PRCP TRUE";
   if (g->organic_fract) return "ORGANIC_FRACT TRUE";
-  if (g->snow_step != g->time_step) return "SNOW_STEP != TIME_STEP";
+  if (g->time_step < 24 && g->snow_step != g->time_step)       // get_global_param.c:761-765
+    return "If the model step is smaller than daily, the snow model should run at the same time step as the rest of the model.";
+  if (g->snow_step < 1 || g->snow_step > g->time_step || g->time_step % g->snow_step)
+    return "SNOW_STEP should be <= TIME_STEP and divide TIME_STEP evenly";
   if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
   if (g->forcing2) return "FORCING2 (a second forcing file)";
   if (g->out_step > 0 && (g->out_step < g->time_step || g->out_step % g->time_step || g->out_step > 24))

@@ -87,7 +87,7 @@ def read_params(soil, veglib, vegparam, snowband=None, nlayer=3, nbands=1, root_
                 "lat": _arr(so.vr_params_lat(h), Cn, np.float32), "lng": _arr(so.vr_params_lng(h), Cn, np.float32),
                 # what initialize_atmos reads of soil_con: the vr_atmos_cells hand-off (vicres_b200/atmos.py)
                 "site": {n: _arr(so.vr_params_site(h, i), Cn, np.float64)
-                         for i, n in enumerate(["lat", "lng", "time_zone_lng", "elevation", "annual_prec"])}}
+                         for i, n in enumerate(["lat", "lng", "time_zone_lng", "elevation", "annual_prec", "min_Tfactor"])}}
     finally:
         so.vr_params_free(h)
     return libd, cells, meta

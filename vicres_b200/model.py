@@ -157,9 +157,10 @@ class VicRes:
                     allow=(abi.VR_ERR_CELL,))
         return out, status
 
-    def step_device(self, month, doy, forcing_ptrs, out_ptr, stream=None):
-        """forcing_ptrs: 9 device pointers (int) to [nrec, ncol] float64 arrays; out_ptr: device
-        pointer to [n_out, nrec, C].  Asynchronous on `stream` (int cudaStream_t) or the handle's."""
+    def step_device(self, month, doy, forcing_ptrs, out_ptr, stream=None, snowflag_ptr=None):
+        """forcing_ptrs: 9 device pointers (int) to [nrec, ncol] float64 arrays ([nrec * (NF + 1), ncol] with a sub-stepped
+        snow model, then with snowflag_ptr -> [nrec, ncol] int32 on the device); out_ptr: device pointer to
+        [n_out, nrec, C].  Asynchronous on `stream` (int cudaStream_t) or the handle's."""
         s = abi.vr_forcing()
         mon = np.ascontiguousarray(month, dtype=np.int32)
         dy = np.ascontiguousarray(doy, dtype=np.int32)
@@ -168,6 +169,8 @@ class VicRes:
         s.day_in_year = dy.ctypes.data_as(C.POINTER(C.c_int32))
         for i in range(abi.VR_NFORCING):
             s.field[i] = C.cast(C.c_void_p(int(forcing_ptrs[i])), C.POINTER(C.c_double))
+        if snowflag_ptr:
+            s.snowflag = C.cast(C.c_void_p(int(snowflag_ptr)), C.POINTER(C.c_int32))
         self._keep = (mon, dy, s)
         self._check(self.L.vr_step_block_device(self.h, C.byref(s), C.c_void_p(int(out_ptr)),
                                                 C.c_void_p(int(stream)) if stream else None))

@@ -49,10 +49,15 @@ def run(global_path, device=0, write=True, records_per_block=0):
     nrecs = g.nrecs
     site_t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in meta["site"].items()}
     raw_t = {k: (torch.from_numpy(np.ascontiguousarray(v)).to(dev) if v is not None else None) for k, v in raw.items()}
-    f_dev = torch.empty((abi.VR_NFORCING, nrecs, Cn), dtype=torch.float64, device=dev)
+    # SNOW_STEP < TIME_STEP (NF > 1): per record the NF windows' values, then the record's own, and the snow flags
+    NF = atmos.n_windows(ao)
+    NS = NF + 1 if NF > 1 else 1
+    f_dev = torch.empty((abi.VR_NFORCING, nrecs * NS, Cn), dtype=torch.float64, device=dev)
+    flag_dev = torch.empty((nrecs, Cn), dtype=torch.int32, device=dev)
     ptr = lambda t: t.data_ptr() if t is not None else 0
     atmos.prepare_device(ao, {k: ptr(v) for k, v in site_t.items()}, {k: ptr(v) for k, v in raw_t.items()},
-                         [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["prec"].shape[0], device=device)
+                         [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["prec"].shape[0], device=device,
+                         snowflag_dev=flag_dev.data_ptr())
     torch.cuda.synchronize(dev)
     # what to compute: the columns of the output files, each once (the conductance instead of the resistance when the
     # output interval spans several records: put_data.c:686 inverts the aggregated conductance)
@@ -60,9 +65,9 @@ def run(global_path, device=0, write=True, records_per_block=0):
     ratio = g.out_step // g.time_step if g.out_step > 0 else 1
     names = sel.step_vars(aggregate=ratio > 1)
     opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, out=names, max_snow_temp=g.max_snow_temp,
-                              min_rain_temp=g.min_rain_temp, wind_h=g.wind_h)
+                              min_rain_temp=g.min_rain_temp, wind_h=g.wind_h, snow_step_hours=g.snow_step)
     m = model.VicRes(opt, lib, cells, device=device)
-    tair0 = f_dev[abi.FORCING_FIELDS.index("air_temp"), 0].cpu().numpy()
+    tair0 = f_dev[abi.FORCING_FIELDS.index("air_temp"), NS - 1].cpu().numpy()       # atmos[0].air_temp[NR]
     if g.init_state:                     # INIT_STATE <file>: read_initial_model_state instead of the cold start
         m.read_state_file(g.init_state_file, tair0, meta["gridcel"], binary=bool(g.binary_state_file))
     else:
@@ -78,8 +83,9 @@ def run(global_path, device=0, write=True, records_per_block=0):
     cuts = sorted(set(list(range(0, nrecs, B)) + ([save_after + 1] if 0 <= save_after < nrecs - 1 else []) + [nrecs]))
     for r0, r1 in zip(cuts[:-1], cuts[1:]):
         blk = torch.empty((opt.n_out, r1 - r0, Cn), dtype=torch.float64, device=dev)
-        fb = f_dev[:, r0:r1].contiguous()
-        m.step_device(dmy[r0:r1, 1], dmy[r0:r1, 4], [fb[f].data_ptr() for f in range(abi.VR_NFORCING)], blk.data_ptr())
+        fb = f_dev[:, r0 * NS:r1 * NS].contiguous()
+        m.step_device(dmy[r0:r1, 1], dmy[r0:r1, 4], [fb[f].data_ptr() for f in range(abi.VR_NFORCING)], blk.data_ptr(),
+                      snowflag_ptr=flag_dev[r0:r1].data_ptr() if NF > 1 else None)
         m.synchronize()
         out_dev[:, r0:r1] = blk
         if r1 - 1 == save_after:
