@@ -466,10 +466,11 @@ def main():
     ap.add_argument("--ensemble", type=int, default=0,
                     help="BASELINE config 4: P parameter sets x --cells basin cells sharing the basin's forcing columns "
                          "(outputs RUNOFF and BASEFLOW only)")
-    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4],
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
                     help="BASELINE.json configuration preset: 2 = the default (100k cells, daily, 365 records per step, weak scaling); "
                          "3 = 1M cells in total, 5 snow bands, 3-hourly, cold, 32 records per step, STRONG scaling over the ranks; "
-                         "4 = 4096 parameter sets x 64 basin cells, sets sharded over the ranks (config 5: tools/bench_pipeline.py)")
+                         "4 = 4096 parameter sets x 64 basin cells, sets sharded over the ranks; 5 = the chain forcing preparation -> step -> "
+                         "hand-off -> routing with 200 reservoirs x 8 rule sets on 1M cells (tools/bench_pipeline.py), one GPU")
     ap.add_argument("--strong", action="store_true", help="--cells is the whole grid, sharded by cell blocks over the ranks")
     args = ap.parse_args()
     if args.config == 3:
@@ -478,10 +479,47 @@ def main():
     elif args.config == 4:
         args.cells, args.ensemble, args.block = 64, 4096, 355
         args.forcing_prep = False
+    if args.config == 5 and args.impl != "reference":
+        return run_chain(args)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+def run_chain(args):
+    """BASELINE configuration 5: the whole chain on ONE GPU (the routing network does not shard: replicas only; under
+    torchrun the other ranks leave).  A step is one pass of the chain over a simulated year; value = VIC cell-timesteps per
+    second of the chain's wall clock, host columns in and station discharge out (so `e2e` is the same number)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_pipeline
+    import torch
+    argv = ["--vic-cells", "1000000", "--rows", "200", "--cols", "250", "--reservoirs", "200", "--sets", "8", "--days", "365"]
+    K, W = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    for _ in range(W):
+        bench_pipeline.run(argv)
+    sampler = ClockSampler(0)
+    sampler.start()
+    lines = [bench_pipeline.run(argv) for _ in range(K)]
+    clocks = sampler.stop()
+    tot = sum(l["stages"]["total_s"] for l in lines)
+    C, nd = lines[-1]["cells"], lines[-1]["days"]
+    v = C * nd * K / tot
+    print(json.dumps({
+        "metric": "cell-timesteps/sec (water-balance, 3 layers)", "value": v, "unit": "cell-timesteps/s", "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * tot / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": "BASELINE configuration 5: " + lines[-1]["workload"],
+                                        "parallelism": "one GPU (the routed network does not shard: replicas only)",
+                                        "timing": "host wall clock around the public calls of the chain, model set-up included",
+                                        "l2": "inputs larger than L2"},
+        "clocks": clocks,
+        "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(4 * 8 * C * nd), "d2h_bytes_per_step": 0,
+                "note": "the chain starts from host forcing columns and ends with the station series on the host"},
+        "gpu_launches": K * (lines[-1]["stages"]["forcing_prep_launches"] + lines[-1]["stages"]["step_launches"] + 2),
+        "stages": lines[-1]["stages"], "station_flow_finite": lines[-1]["station_flow_finite"],
+        "step_cell_steps_per_s": lines[-1]["stages"]["step_cell_steps_per_s"]}))
 
 
 if __name__ == "__main__":

@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def main():
+def run(argv=None):
+    """runs the chain once; returns the line's dict"""
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=200)
     ap.add_argument("--cols", type=int, default=250)
@@ -30,7 +31,7 @@ def main():
                     help="cells of the runoff grid (BASELINE config 5: 1 000 000); the first rows x cols of them are the routed "
                          "network's cells, the others lie outside the basin.  0 = one VIC cell per grid node")
     ap.add_argument("--block", type=int, default=73, help="records per vr_step_block_device call when --vic-cells is set")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     import torch
     from make_route_golden import random_tree
     from test_gpu_route_helpers import random_reservoir
@@ -73,6 +74,7 @@ def main():
     torch.cuda.synchronize(dev)
     T["forcing_prep_s"] = time.perf_counter() - t0
     T["forcing_prep_kernel_ms"] = sum(atmos.last_times()[:3])
+    T["forcing_prep_launches"] = int(atmos.last_times()[3])
 
     # 2. cell step, device resident
     t0 = time.perf_counter()
@@ -115,6 +117,7 @@ def main():
             T["handoff_s"] += time.perf_counter() - t0
         cols = {k: torch.cat([p[k] for p in parts], dim=1).contiguous() for k in parts[0]}
     T["step_cell_steps_per_s"] = C * nd / T["step_s"]
+    T["step_launches"] = int(m.num_launches)
     m.close()
 
     # 4. routing: unit hydrographs, convolution, reservoirs
@@ -140,8 +143,13 @@ def main():
     line = {"workload": "config 5 chain: %d VIC cells, the first %d of them on a %dx%d D8 network (%d routed cells in the catchment lists), %d reservoirs "
                         "x %d rule sets, %d days" % (C, CR, nrow, ncol, routed, nres, a.sets, nd),
             "stages": T, "station_flow_finite": bool(np.isfinite(res["flow"]).all()),
-            "mean_station_discharge_m3s": float(res["flow"].mean())}
-    print(json.dumps(line))
+            "mean_station_discharge_m3s": float(res["flow"].mean()),
+            "cells": int(C), "days": int(nd)}
+    return line
+
+
+def main():
+    print(json.dumps(run()))
 
 
 if __name__ == "__main__":
