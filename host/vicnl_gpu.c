@@ -67,6 +67,7 @@ int main(int argc, char **argv)
   double *one = malloc(sizeof(double) * nt * nrf), *raw = calloc((size_t)nt * nrf * C, sizeof(double));
   int64_t c, r;
   int t, col_prec = -1, col_ta = -1, col_tb = -1, col_wind = -1, col_sw = -1, col_lw = -1, col_vp = -1, col_pr = -1, col_de = -1, subdaily = 0;
+  int col_q = -1, col_rh = -1, col_rf = -1, col_sf = -1, col_we = -1, col_wn = -1;
   for (t = 0; t < nt; t++) {
     if (!strcmp(g.force_type[t], "PREC")) col_prec = t;
     else if (!strcmp(g.force_type[t], "TMAX")) col_ta = t;
@@ -78,9 +79,16 @@ int main(int argc, char **argv)
     else if (!strcmp(g.force_type[t], "VP")) col_vp = t;
     else if (!strcmp(g.force_type[t], "PRESSURE")) col_pr = t;
     else if (!strcmp(g.force_type[t], "DENSITY")) col_de = t;
+    else if (!strcmp(g.force_type[t], "QAIR")) col_q = t;
+    else if (!strcmp(g.force_type[t], "REL_HUMID")) col_rh = t;
+    else if (!strcmp(g.force_type[t], "RAINF")) col_rf = t;
+    else if (!strcmp(g.force_type[t], "SNOWF")) col_sf = t;
+    else if (!strcmp(g.force_type[t], "WIND_E")) col_we = t;
+    else if (!strcmp(g.force_type[t], "WIND_N")) col_wn = t;
     else if (strcmp(g.force_type[t], "SKIP")) die("forcing column outside the supported layouts", g.force_type[t]);
   }
-  if (col_prec < 0 || col_ta < 0 || (!subdaily && col_tb < 0)) die("forcing file", "needs PREC and TMAX+TMIN or AIR_TEMP");
+  if ((col_prec < 0 && (col_rf < 0 || col_sf < 0)) || col_ta < 0 || (!subdaily && col_tb < 0))
+    die("forcing file", "needs PREC (or RAINF and SNOWF) and TMAX+TMIN or AIR_TEMP");
   for (c = 0; c < C; c++) {
     char path[1200];
     snprintf(path, sizeof path, "%s%.*f_%.*f", g.forcing1, g.grid_decimal, lat[c], g.grid_decimal, lng[c]);
@@ -97,7 +105,7 @@ int main(int argc, char **argv)
   ao.time_step = g.time_step; ao.nrecs = nrecs; ao.startyear = g.startyear; ao.startmonth = g.startmonth;
   ao.startday = g.startday; ao.starthour = g.starthour; ao.force_dt = g.force_dt;
   ao.layout = subdaily ? VR_ATMOS_SUBDAILY_AIR_TEMP : VR_ATMOS_DAILY_TMAX_TMIN;
-  ao.has_wind = col_wind >= 0; ao.min_wind_speed = g.min_wind_speed; ao.vp_interp = g.vp_interp; ao.vp_iter = g.vp_iter;
+  ao.has_wind = col_wind >= 0 || (col_we >= 0 && col_wn >= 0); ao.min_wind_speed = g.min_wind_speed; ao.vp_interp = g.vp_interp; ao.vp_iter = g.vp_iter;
   ao.mtclim_swe_corr = g.mtclim_swe_corr; ao.lw_type = g.lw_type; ao.lw_cloud = g.lw_cloud; ao.plapse = g.plapse;
   ao.sw_prec_thresh = g.sw_prec_thresh; ao.alma_input = g.alma_input;
   ao.snow_step = g.snow_step != g.time_step ? g.snow_step : 0; ao.max_snow_temp = g.max_snow_temp;
@@ -109,7 +117,11 @@ int main(int argc, char **argv)
   site.time_zone_lng = vr_params_site(par, 2); site.elevation = vr_params_site(par, 3); site.annual_prec = vr_params_site(par, 4);
   site.min_Tfactor = vr_params_site(par, 5);
   vr_atmos_raw rw;
-  rw.nrec_forcing = nrf; rw.prec = raw + (size_t)col_prec * nrf * C; rw.t_a = raw + (size_t)col_ta * nrf * C;
+  memset(&rw, 0, sizeof rw);
+#define COL(k) ((k) >= 0 ? raw + (size_t)(k) * nrf * C : NULL)
+  rw.qair = COL(col_q); rw.rel_humid = COL(col_rh); rw.rainf = COL(col_rf); rw.snowf = COL(col_sf); rw.wind_e = COL(col_we);
+  rw.wind_n = COL(col_wn);
+  rw.nrec_forcing = nrf; rw.prec = COL(col_prec); rw.t_a = raw + (size_t)col_ta * nrf * C;
   rw.t_b = col_tb >= 0 ? raw + (size_t)col_tb * nrf * C : NULL; rw.wind = col_wind >= 0 ? raw + (size_t)col_wind * nrf * C : NULL;
   rw.shortwave = col_sw >= 0 ? raw + (size_t)col_sw * nrf * C : NULL; rw.longwave = col_lw >= 0 ? raw + (size_t)col_lw * nrf * C : NULL;
   rw.vp = col_vp >= 0 ? raw + (size_t)col_vp * nrf * C : NULL;

@@ -187,6 +187,16 @@ int  vr_init_state(vr_handle *h, const double *tair0 /* [C] host */);
 int  vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *cell_status_host);
 int  vr_step_block_device(vr_handle *h, const vr_forcing *f_dev, double *out_dev, void *cuda_stream);
 int  vr_synchronize(vr_handle *h);
+/* Compatibility shim for record-by-record callers and single-cell tests: ONE record, the pair of calls of the reference's
+ * record loop, `full_energy(cellnum, rec, &atmos[rec], &all_vars, dmy, &global_param, &lake_con, &soil_con, veg_con, veg_hist);
+ * put_data(&all_vars, &atmos[rec], &soil_con, veg_con, &lake_con, out_data_files, out_data, &save_data, &dmy[rec], rec);`
+ * (vicNl.c:301-306), for every cell of the handle.  rec must be the next record of the run (records done so far:
+ * a skipped or repeated record is VR_ERR_STATE, where the reference would silently use stale storage terms).
+ * atmos: [VR_NFORCING][NF + 1 or 1][C] host values of this record in VR_F_* order (atmos-><field>[0..NF-1], [NR]);
+ * snowflag [C] or NULL; month 1..12 and day_in_year of dmy[rec]; out: [n_out][C]; cell_status [C] or NULL.
+ * Returns VR_OK, or VR_ERR_CELL as vr_step_block does (the reference's ERROR return of full_energy). */
+int  vr_full_energy_compat(vr_handle *h, int64_t rec, int32_t month, int32_t day_in_year, const double *atmos,
+                           const int32_t *snowflag, double *out, int32_t *cell_status);
 
 /* state hand-off (write_model_state / read_initial_model_state analogue): opaque flat blob */
 int64_t vr_state_size(const vr_handle *h);                 /* bytes */

@@ -18,7 +18,8 @@
  *   VR_ATMOS_DAILY_TMAX_TMIN    FORCE_DT 24, columns PREC TMAX TMIN [WIND]   (the bundled basin's format)
  *   VR_ATMOS_SUBDAILY_AIR_TEMP  FORCE_DT < 24, columns PREC AIR_TEMP [WIND]
  * each optionally with observed SHORTWAVE, LONGWAVE, VP, PRESSURE and DENSITY columns at the same FORCE_DT; SNOW_STEP == TIME_STEP
- * (NF == 1) or, for daily steps, below it (vr_atmos_prepare_sub); no QAIR / REL_HUMID columns (nor the ALMA-only RAINF / SNOWF / WIND_E / WIND_N splits).  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
+ * (NF == 1) or, for daily steps, below it (vr_atmos_prepare_sub); QAIR / REL_HUMID in place of VP and the split columns
+ * RAINF + SNOWF, WIND_E + WIND_N (vr_atmos_raw).  There is no CPU path: without a CUDA device the calls return VR_ERR_CUDA.
  */
 #ifndef VICRES_ATMOS_H
 #define VICRES_ATMOS_H
@@ -86,6 +87,15 @@ typedef struct vr_atmos_raw {
   /* optional observed PRESSURE (kPa as in the file) and DENSITY (kg/m3) columns (initialize_atmos.c:1032-1170): the one
    * that is missing is derived from the other and the air temperature, both missing = the PLAPSE estimate */
   const double *pressure, *density;
+  /* optional humidity columns, used when VP is absent (initialize_atmos.c:773-866, 1176-1215): QAIR (kg/kg) and REL_HUMID (%).
+   * With PRESSURE (QAIR) or in the AIR_TEMP layout (REL_HUMID) they become the observed VP before MTCLIM; in the daily
+   * TMAX/TMIN layout without those they replace MTCLIM's daily vapour pressure afterwards, from the record's own pressure
+   * or air temperature.  Sub-daily QAIR without PRESSURE is refused (the reference indexes atmos->pressure with a loop
+   * variable left over from an earlier loop, :1302). */
+  const double *qair, *rel_humid;
+  /* optional split columns that REPLACE prec / wind when both of a pair are given (:424-460): RAINF + SNOWF, and
+   * sqrt(WIND_E^2 + WIND_N^2) */
+  const double *rainf, *snowf, *wind_e, *wind_n;
 } vr_atmos_raw;
 
 /* Number of local days MTCLIM runs over for a cell with this integer hour offset (Ndays or Ndays+1). */

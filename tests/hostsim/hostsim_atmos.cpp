@@ -24,6 +24,28 @@ extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, 
   x.r_prec = raw->prec; x.r_ta = raw->t_a; x.r_tb = raw->t_b; x.r_wind = raw->wind;
   x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp; x.r_pr = raw->pressure; x.r_de = raw->density;
   if (va::unsupported_raw(*o, *raw)) return -2;
+  // derived columns, as vr_atmos_prepare_sub_device builds them with k_derive
+  const size_t n_col = (size_t)raw->nrec_forcing * C;
+  std::vector<double> d_prec, d_wind, d_vp;
+  if (raw->rainf && raw->snowf) {
+    d_prec.resize(n_col);
+    for (size_t i = 0; i < n_col; i++) d_prec[i] = va::derive_prec(x, raw->rainf[i], raw->snowf[i]);
+    x.r_prec = d_prec.data(); x.prec_native = 1;
+  }
+  if (raw->wind_e && raw->wind_n) {
+    d_wind.resize(n_col);
+    for (size_t i = 0; i < n_col; i++) d_wind[i] = va::derive_wind(raw->wind_e[i], raw->wind_n[i]);
+    x.r_wind = d_wind.data(); x.has_wind = 1;
+  }
+  const bool vp_q = !raw->vp && raw->qair && raw->pressure;
+  const bool vp_rh = !raw->vp && !vp_q && !raw->qair && raw->rel_humid && o->layout == VR_ATMOS_SUBDAILY_AIR_TEMP;
+  if (vp_q || vp_rh) {
+    d_vp.resize(n_col);
+    for (size_t i = 0; i < n_col; i++)
+      d_vp[i] = vp_q ? va::derive_vp_qair(x, raw->qair[i], raw->pressure[i]) : va::derive_vp_rh(x, raw->rel_humid[i], raw->t_a[i]);
+    x.r_vp = d_vp.data(); x.vp_native = 1;
+  }
+  else if (!raw->vp) { if (raw->qair) x.r_q = raw->qair; else if (raw->rel_humid) x.r_rh = raw->rel_humid; }
   std::vector<double> tab((size_t)va::NYD * 28 * C), dly((size_t)nd * 7 * C), tcon(2 * C);
   std::vector<int8_t> hrs((size_t)nd * 2 * C);
   x.ttmax0 = tab.data(); x.flat = x.ttmax0 + va::NYD * C; x.slp = x.flat + va::NYD * C; x.dayl = x.slp + va::NYD * C;
@@ -44,6 +66,8 @@ extern "C" int hs_atmos(const vr_atmos_options *o, const vr_atmos_cells *cells, 
     for (int64_t c = 0; c < C; c++) va::converge(x, c);
   for (int64_t c = 0; c < C; c++)
     for (int day = 0; day < nd; day++) va::minmax_hour(x, c, day);
+  for (int64_t c = 0; c < C; c++)
+    for (int day = 0; day < nd; day++) va::humid_day(x, c, day);
   for (int64_t c = 0; c < C; c++)
     for (int rec = 0; rec < x.nrecs; rec++) va::record(x, c, rec);
   return 0;

@@ -46,6 +46,29 @@ def test_block_split_is_bit_identical(VicRes):
     m.close()
 
 
+@pytest.mark.parametrize("name", ["daily_snow_bands", "daily_snowstep3"])
+def test_record_by_record_shim_equals_the_block_call(VicRes, name):
+    """vr_full_energy_compat: the reference's per-record `full_energy(); put_data();` pair, bit-identical to vr_step_block;
+    a record out of sequence is refused"""
+    from vicres_b200 import abi
+    fx = load_fixture(name)
+    n = 60
+    m = VicRes(fx["opt"], fx["lib"], fx["cells"])
+    m.init_state(fx["tair0"])
+    NS = fx["forcing"].shape[1] // len(fx["month"])
+    sf = fx["snowflag"]
+    whole, _ = m.step(fx["month"][:n], fx["doy"][:n], np.ascontiguousarray(fx["forcing"][:, :n * NS]),
+                      snowflag=None if sf is None else np.ascontiguousarray(sf[:n]))
+    m.init_state(fx["tair0"])
+    for r in range(n):
+        o, status = m.full_energy(r, fx["month"][r], fx["doy"][r], fx["forcing"][:, r * NS:(r + 1) * NS],
+                                  None if sf is None else sf[r])
+        assert not status.any() and np.array_equal(o, whole[:, r]), r
+    with pytest.raises(Exception, match="next record"):
+        m.full_energy(n + 3, 1, 1, fx["forcing"][:, :NS])
+    m.close()
+
+
 def test_state_roundtrip(VicRes):
     fx = load_fixture("sub3h_snow")
     m = VicRes(fx["opt"], fx["lib"], fx["cells"])

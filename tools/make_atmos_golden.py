@@ -78,6 +78,25 @@ CASES = {
                                    extra_cols=("LONGWAVE", "VP", "PRESSURE")), dict(snow_step=6)),
     "atmos_daily_snow12_nowind": (dict(ncells=2, ndays=90, startyear=1997, lat_range=(40, 60), cold=6.0, snow_step=12, no_wind=True,
                                        off_gmt=-5, seed=324, extra_cols=("DENSITY",)), dict(snow_step=12, has_wind=False)),
+    # humidity columns and the split precipitation / wind columns
+    "atmos_daily_qair_pressure": (dict(ncells=3, ndays=150, startyear=2004, lat_range=(5, 55), off_gmt=2, seed=325,
+                                       extra_cols=("QAIR", "PRESSURE")), {}),
+    "atmos_daily_qair": (dict(ncells=3, ndays=150, startyear=2005, lat_range=(-40, 55), off_gmt=-3, cold=3.0, seed=326,
+                              extra_cols=("QAIR",)), {}),
+    "atmos_daily_rh": (dict(ncells=3, ndays=200, startyear=2006, lat_range=(10, 60), seed=327, extra_cols=("REL_HUMID",),
+                            extra_global="VP_INTERP FALSE"), dict(vp_interp=False)),
+    "atmos_daily_rh_to_3h": (dict(ncells=2, ndays=80, dt=3, force_daily=True, startyear=2007, lat_range=(20, 50), off_gmt=4, seed=328,
+                                  extra_cols=("REL_HUMID",)), {}),
+    "atmos_daily_rh_snow6": (dict(ncells=2, ndays=100, startyear=2008, lat_range=(35, 60), cold=5.0, snow_step=6, nbands=2, seed=329,
+                                  extra_cols=("REL_HUMID",)), dict(snow_step=6)),
+    "atmos_sub3h_rh": (dict(ncells=2, ndays=60, dt=3, startyear=2009, lat_range=(30, 55), off_gmt=1, seed=330,
+                            extra_cols=("REL_HUMID",)), {}),
+    "atmos_sub3h_qair_pressure_alma": (dict(ncells=2, ndays=50, dt=3, startyear=2010, lat_range=(35, 60), seed=331, alma=True,
+                                            extra_cols=("QAIR", "PRESSURE")), dict(alma_input=True)),
+    "atmos_daily_split_alma": (dict(ncells=2, ndays=120, startyear=2011, lat_range=(25, 60), cold=2.0, off_gmt=-2, seed=332, alma=True,
+                                    extra_cols=("RAINF", "SNOWF", "WIND_E", "WIND_N")), dict(alma_input=True)),
+    "atmos_sub3h_split": (dict(ncells=2, ndays=40, dt=3, startyear=2012, lat_range=(30, 60), cold=3.0, seed=333,
+                               extra_cols=("RAINF", "SNOWF", "WIND_E", "WIND_N")), {}),
     "atmos_short_record": (dict(ncells=3, ndays=25, startyear=1995, seed=309,
                                 extra_global="VP_ITER VP_ITER_NONE\nLW_TYPE LW_SATTERLUND"),
                            dict(vp_iter="VP_ITER_NONE", lw_type="LW_SATTERLUND")),

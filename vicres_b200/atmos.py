@@ -43,10 +43,12 @@ class vr_atmos_cells(C.Structure):
 
 class vr_atmos_raw(C.Structure):
     _fields_ = [("nrec_forcing", C.c_int64), ("prec", _pd), ("t_a", _pd), ("t_b", _pd), ("wind", _pd),
-                ("shortwave", _pd), ("longwave", _pd), ("vp", _pd), ("pressure", _pd), ("density", _pd)]
+                ("shortwave", _pd), ("longwave", _pd), ("vp", _pd), ("pressure", _pd), ("density", _pd),
+                ("qair", _pd), ("rel_humid", _pd), ("rainf", _pd), ("snowf", _pd), ("wind_e", _pd), ("wind_n", _pd)]
 
 
-RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp", "pressure", "density")
+RAW_FIELDS = ("prec", "t_a", "t_b", "wind", "shortwave", "longwave", "vp", "pressure", "density", "qair", "rel_humid", "rainf",
+              "snowf", "wind_e", "wind_n")
 
 
 def options(time_step=24, nrecs=0, startyear=1981, startmonth=1, startday=1, starthour=0, layout=None, force_dt=None,
@@ -97,7 +99,7 @@ def pack_site(site):
 def pack_raw(raw):
     """raw: dict prec, t_a, t_b (or None), wind (or None) and optionally shortwave, longwave, vp (kPa), each [nrec_forcing, C]."""
     s, keep = vr_atmos_raw(), []
-    s.nrec_forcing = raw["prec"].shape[0]
+    s.nrec_forcing = raw["t_a"].shape[0]
     for n in RAW_FIELDS:
         if raw.get(n) is not None:
             a = np.ascontiguousarray(raw[n], dtype=np.float64)
@@ -188,13 +190,14 @@ def last_times():
 def options_from_global(g):
     """vr_atmos_options from a parsed global file (vicres_b200.files.Global)."""
     types = [t for t in g.force_types if t != "SKIP"]
-    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND", "SHORTWAVE", "LONGWAVE", "VP", "PRESSURE", "DENSITY")]
+    extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND", "SHORTWAVE", "LONGWAVE", "VP", "PRESSURE", "DENSITY",
+                                           "QAIR", "REL_HUMID", "RAINF", "SNOWF", "WIND_E", "WIND_N")]
     if extra:
         raise model.VicResError(abi.VR_ERR_UNSUPPORTED, "forcing column(s) %s are outside the supported layouts" % ", ".join(extra))
     layout = SUBDAILY_AIR_TEMP if "AIR_TEMP" in types else DAILY_TMAX_TMIN
     return options(time_step=g.time_step, nrecs=g.nrecs, startyear=g.startyear, startmonth=g.startmonth,
                    startday=g.startday, starthour=g.starthour, layout=layout, force_dt=g.force_dt,
-                   has_wind="WIND" in types, min_wind_speed=g.min_wind_speed, vp_interp=g.vp_interp, vp_iter=g.vp_iter,
+                   has_wind="WIND" in types or ("WIND_E" in types and "WIND_N" in types), min_wind_speed=g.min_wind_speed, vp_interp=g.vp_interp, vp_iter=g.vp_iter,
                    mtclim_swe_corr=g.mtclim_swe_corr, lw_type=g.lw_type, lw_cloud=g.lw_cloud, plapse=g.plapse,
                    sw_prec_thresh=g.sw_prec_thresh, alma_input=g.alma_input,
                    snow_step=g.snow_step if g.snow_step != g.time_step else 0, max_snow_temp=g.max_snow_temp)
@@ -202,10 +205,12 @@ def options_from_global(g):
 
 def raw_from_columns(cols, layout):
     """{FORCE_TYPE: [nrec, C]} -> the dict prepare() takes."""
-    return {"prec": cols["PREC"], "t_a": cols["TMAX" if layout == DAILY_TMAX_TMIN else "AIR_TEMP"],
+    return {"prec": cols.get("PREC"), "t_a": cols["TMAX" if layout == DAILY_TMAX_TMIN else "AIR_TEMP"],
             "t_b": cols.get("TMIN") if layout == DAILY_TMAX_TMIN else None, "wind": cols.get("WIND"),
             "shortwave": cols.get("SHORTWAVE"), "longwave": cols.get("LONGWAVE"), "vp": cols.get("VP"),
-            "pressure": cols.get("PRESSURE"), "density": cols.get("DENSITY")}
+            "pressure": cols.get("PRESSURE"), "density": cols.get("DENSITY"), "qair": cols.get("QAIR"),
+            "rel_humid": cols.get("REL_HUMID"), "rainf": cols.get("RAINF"), "snowf": cols.get("SNOWF"),
+            "wind_e": cols.get("WIND_E"), "wind_n": cols.get("WIND_N")}
 
 
 def diag_cr(x, y, device=0):

@@ -66,6 +66,8 @@ struct Ctx {
   const double *r_prec, *r_ta, *r_tb, *r_wind;
   const double *r_sw, *r_lw, *r_vp;   // optional observed SHORTWAVE, LONGWAVE, VP (kPa) columns, or null
   const double *r_pr, *r_de;          // optional observed PRESSURE (kPa), DENSITY columns, or null
+  const double *r_q, *r_rh;           // daily QAIR / REL_HUMID that replace MTCLIM's daily vapour pressure afterwards (:1176-1215), or null
+  int prec_native, vp_native;         // r_prec / r_vp are columns derived on the device, already in mm per step / Pa
   // scratch: solar tables [365][CB] and hourly fractions [365*24][CB]
   double *ttmax0, *flat, *slp, *dayl, *hf;
   // scratch: daily series [ndl][CB]
@@ -121,7 +123,8 @@ VA_HD double local_hourly(const double *col, const Ctx &x, const Geo &g, int64_t
 }
 // unit conversion of the columns as read (initialize_atmos.c:374-416): ALMA rates -> amounts per forcing step and K -> C,
 // else kPa -> Pa.  (x * 1.0 and x - 0.0 are exact, so the traditional units go through unchanged.)
-VA_HD double u_prec(const Ctx &x, double v) { return v * (x.alma ? (double)(x.fdt * 3600) : 1.0); }
+VA_HD double u_prec_raw(const Ctx &x, double v) { return v * (x.alma ? (double)(x.fdt * 3600) : 1.0); }
+VA_HD double u_prec(const Ctx &x, double v) { return x.prec_native ? v : u_prec_raw(x, v); }
 VA_HD double u_temp(const Ctx &x, double v) { return v - (x.alma ? KELVIN : 0.0); }
 VA_HD double u_kpa(const Ctx &x, double v) { return v * (x.alma ? 1.0 : 1000.); }
 
@@ -139,7 +142,11 @@ VA_HD double obs_hour(const double *col, const Ctx &x, const Geo &g, int64_t c, 
 {
   return x.fdt == 24 ? local_daily(col, x, g, c, idx / 24) : local_hourly(col, x, g, c, idx);
 }
-VA_HD double obs_vp_hour(const Ctx &x, const Geo &g, int64_t c, int idx) { return u_kpa(x, obs_hour(x.r_vp, x, g, c, idx)); }
+VA_HD double obs_vp_hour(const Ctx &x, const Geo &g, int64_t c, int idx)
+{
+  const double v = obs_hour(x.r_vp, x, g, c, idx);
+  return x.vp_native ? v : u_kpa(x, v);
+}
 
 #if defined(__CUDA_ARCH__)
 #define VA_POW15(x) ((x) * sqrt(x))
@@ -845,12 +852,19 @@ VA_HD double hourly_vp(const Ctx &x, const Geo &g, int64_t lc, int idx)
   return v;
 }
 
+// Columns the reference derives from others before anything else, element by element of the forcing file's records
+// (so in file time as well as in local time): :424-460 and :773-866.
+VA_HD double derive_prec(const Ctx &x, double rainf, double snowf) { return u_prec_raw(x, rainf) + u_prec_raw(x, snowf); }
+VA_HD double derive_wind(double e, double n) { return sqrt(e * e + n * n); }
+VA_HD double derive_vp_qair(const Ctx &x, double q, double p_file) { return q * u_kpa(x, p_file) / EPS_MW; }
+VA_HD double derive_vp_rh(const Ctx &x, double rh, double t_file) { return rh * svp(u_temp(x, t_file)) / 100; }
+
 // What initialize_atmos stores for one window of `len` hours starting at local hour `hour` -- a sub-step of SNOW_STEP hours,
 // which is the whole record when SNOW_STEP == TIME_STEP -- before the quantities derived from them: precipitation, wind,
 // air temperature, shortwave, vapour pressure, and the observed density / pressure / longwave columns when the file has
 // them.  nsub = windows per day (NF * stepspday), the divisor of a daily precipitation total (:601-606).
 struct Win { double prec, wind, ta, sw, vp, dens, p, lw; int dayi; };
-VA_HD Win window_vals(const Ctx &x, const Geo &g, int64_t c, int hour, int len, int nsub)
+VA_HD Win window_vals(const Ctx &x, const Geo &g, int64_t c, int hour, int len, int nsub, bool with_vp = true)
 {
   const int64_t lc = c - x.c0;
   Win w;
@@ -895,7 +909,7 @@ VA_HD Win window_vals(const Ctx &x, const Geo &g, int64_t c, int hour, int len, 
       }
       sw += x.hf[((int64_t)rad_ydi * 24 + (idx - d * 24)) * x.CB + lc] * tmp_rad;
     }
-    vp += hourly_vp(x, g, lc, idx);
+    if (with_vp) vp += hourly_vp(x, g, lc, idx);
   }
   w.sw = sw / len;
   w.vp = vp / len;
@@ -929,6 +943,34 @@ VA_HD double cloud_tskc(const Ctx &x, int64_t lc, int dayi)     // :1188-1193, :
 {
   const double tf = x.tskc[(int64_t)dayi * x.CB + lc];
   return (x.lw_cloud == VR_LW_CLOUD_DEARDORFF) ? (1. - tf) : sqrt((1. - tf) / 0.65);
+}
+
+// Daily QAIR or REL_HUMID without the pressure / air temperature to turn them into VP beforehand (:1176-1215): after MTCLIM
+// the reference walks the records and their windows in order and sets daily_vp[day of the window] = QAIR[day] *
+// pressure[window] / EPS (or REL_HUMID[day] * svp(air_temp[window]) / 100); the last window that starts in a day leaves
+// its value, days no record reaches keep MTCLIM's.  One (cell, local day).
+VA_HD void humid_day(const Ctx &x, int64_t c, int day)
+{
+  if (!x.r_q && !x.r_rh) return;
+  const Geo g = cell_geo(x, c);
+  if (day >= g.ndl) return;
+  const int NF = x.NF, ss = x.dt / NF, stepspday = 24 / x.dt;
+  const int base = x.starthour - g.hoi + g.shift;
+  const long last = (long)day * 24 + 23 - base;
+  if (last < 0) return;
+  long m = last / ss;
+  if (m >= (long)x.nrecs * NF) m = (long)x.nrecs * NF - 1;
+  const int hour = base + (int)m * ss;
+  if ((int)((float)hour / 24.0) != day) return;
+  const Win w = window_vals(x, g, c, hour, ss, NF * stepspday, false);
+  double v;
+  if (x.r_q) {
+    double p = w.p, dens = w.dens;
+    pressure_density(x, x.elev[c], w.ta, p, dens);
+    v = local_daily(x.r_q, x, g, c, day) * p / EPS_MW;
+  }
+  else v = local_daily(x.r_rh, x, g, c, day) * svp(w.ta) / 100;
+  x.pva[(int64_t)day * x.CB + (c - x.c0)] = v;
 }
 
 VA_HD void store_fields(const Ctx &x, int64_t o, double ta, double prec, double wind, double vp, double vpd, double p, double dens,
@@ -1039,7 +1081,12 @@ inline void build_calendar(const vr_atmos_options &o, int ndays, int16_t *cal /*
 }
 inline const char *unsupported_raw(const vr_atmos_options &o, const vr_atmos_raw &r)
 {
-  if (o.vp_iter == VR_VP_ITER_CONVERGE && (r.shortwave || r.vp)) return "VP_ITER_CONVERGE with observed SHORTWAVE or VP columns";
+  const bool vp_before = r.vp || (r.qair && r.pressure) || (!r.qair && r.rel_humid && o.layout == VR_ATMOS_SUBDAILY_AIR_TEMP);
+  if (o.vp_iter == VR_VP_ITER_CONVERGE && (r.shortwave || vp_before)) return "VP_ITER_CONVERGE with observed SHORTWAVE or VP columns";
+  if (!r.vp && r.qair && !r.pressure && o.force_dt < 24)
+    return "sub-daily QAIR without PRESSURE (the reference reads atmos->pressure at an index left over from an earlier loop, initialize_atmos.c:1302)";
+  if ((r.rainf != nullptr) != (r.snowf != nullptr)) return "RAINF and SNOWF are used together";
+  if ((r.wind_e != nullptr) != (r.wind_n != nullptr)) return "WIND_E and WIND_N are used together";
   return nullptr;
 }
 inline const char *unsupported(const vr_atmos_options &o)

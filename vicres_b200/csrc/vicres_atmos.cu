@@ -105,13 +105,27 @@ __global__ void __launch_bounds__(TPB) k_hours(const __grid_constant__ va::Ctx x
   int day; int64_t c;
   if (locate(x, cb, day, c)) va::minmax_hour(x, c, day);
 }
+__global__ void __launch_bounds__(TPB) k_humid(const __grid_constant__ va::Ctx x, int64_t cb)
+{
+  int day; int64_t c;
+  if (locate(x, cb, day, c)) va::humid_day(x, c, day);
+}
+// columns derived element by element from others (vic_atmos.cuh: derive_*): mode 0 RAINF + SNOWF, 1 |(WIND_E, WIND_N)|,
+// 2 QAIR * PRESSURE / EPS, 3 REL_HUMID * svp(AIR_TEMP) / 100
+__global__ void k_derive(const __grid_constant__ va::Ctx x, int mode, int64_t n, const double *a, const double *b, double *out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = mode == 0 ? va::derive_prec(x, a[i], b[i]) : mode == 1 ? va::derive_wind(a[i], b[i])
+         : mode == 2 ? va::derive_vp_qair(x, a[i], b[i]) : va::derive_vp_rh(x, a[i], b[i]);
+}
 __global__ void __launch_bounds__(TPB) k_rec(const __grid_constant__ va::Ctx x, int64_t cb)
 {
   int rec; int64_t c;
   if (!locate(x, cb, rec, c)) return;
   // the plain four-column layout in traditional units gets a copy of the body in which the observed-column branches
   // and the unit factors are compile-time dead (the fields are constants of the local copy)
-  if (!x.r_sw && !x.r_lw && !x.r_vp && !x.r_pr && !x.r_de && !x.alma) {
+  if (!x.r_sw && !x.r_lw && !x.r_vp && !x.r_pr && !x.r_de && !x.alma && !x.prec_native) {
     va::Ctx y = x;
     y.r_sw = nullptr; y.r_lw = nullptr; y.r_vp = nullptr; y.r_pr = nullptr; y.r_de = nullptr; y.alma = 0;
     va::record_inl(y, c, rec);
@@ -165,7 +179,9 @@ int vr_atmos_prepare_sub_device(int device, const vr_atmos_options *o, const vr_
   if (const char *why = va::unsupported(*o)) return fail(VR_ERR_UNSUPPORTED, why);
   if (cells->ncell < 1 || !cells->lat || !cells->lng || !cells->time_zone_lng || !cells->elevation)
     return fail(VR_ERR_ARG, "cells: lat, lng, time_zone_lng and elevation are required");
-  if (!raw->prec || !raw->t_a || (o->layout == VR_ATMOS_DAILY_TMAX_TMIN && !raw->t_b) || (o->has_wind && !raw->wind))
+  const bool split_prec = raw->rainf && raw->snowf, split_wind = raw->wind_e && raw->wind_n;
+  if ((!raw->prec && !split_prec) || !raw->t_a || (o->layout == VR_ATMOS_DAILY_TMAX_TMIN && !raw->t_b) ||
+      (o->has_wind && !raw->wind && !split_wind))
     return fail(VR_ERR_ARG, "raw: a forcing column of the declared layout is missing");
   if (raw->nrec_forcing < 1) return fail(VR_ERR_ARG, "raw: nrec_forcing < 1");
   if (const char *why = va::unsupported_raw(*o, *raw)) return fail(VR_ERR_UNSUPPORTED, why);
@@ -191,13 +207,23 @@ int vr_atmos_prepare_sub_device(int device, const vr_atmos_options *o, const vr_
   x.r_sw = raw->shortwave; x.r_lw = raw->longwave; x.r_vp = raw->vp; x.r_pr = raw->pressure; x.r_de = raw->density;
   for (int f = 0; f < VR_NFORCING; f++) x.out[f] = out[f];
   x.min_tf = cells->min_Tfactor; x.snowflag = snowflag;
+  // derived columns (initialize_atmos.c:424-460, 773-866): which, and from what
+  const bool vp_q = !raw->vp && raw->qair && raw->pressure;
+  const bool vp_rh = !raw->vp && !vp_q && !raw->qair && raw->rel_humid && o->layout == VR_ATMOS_SUBDAILY_AIR_TEMP;
+  if (!raw->vp && !vp_q && !vp_rh) {                 // the daily layout: after MTCLIM (humid_day)
+    if (raw->qair) x.r_q = raw->qair;
+    else if (raw->rel_humid) x.r_rh = raw->rel_humid;
+  }
+  if (split_wind) x.has_wind = 1;
+  const int nder = (split_prec ? 1 : 0) + (split_wind ? 1 : 0) + ((vp_q || vp_rh) ? 1 : 0);
+  const size_t n_col = (size_t)raw->nrec_forcing * (size_t)C;
 
   // scratch of one batch, one stream-ordered allocation
   const bool conv = o->vp_iter == VR_VP_ITER_CONVERGE;
   const int ndaily = 4 + (o->mtclim_swe_corr ? 1 : 0) + (conv ? 2 : 0);
   const size_t n_tab = (size_t)va::NYD * 28 * CB, n_day = (size_t)nd * CB;
   const size_t bytes = (n_tab + n_day * ndaily + 2 * (size_t)CB) * sizeof(double) + 2 * n_day + (size_t)(x.Ndays + 2) * sizeof(int16_t) + 64 +
-                       ((size_t)CB + LAT_BUCKETS) * sizeof(int32_t) + 16;
+                       ((size_t)CB + LAT_BUCKETS) * sizeof(int32_t) + 16 + (size_t)nder * n_col * sizeof(double) + 64;
   char *base = nullptr;
   {   // keep the scratch in the device's default pool between calls (the default threshold returns it at every sync)
     cudaMemPool_t pool;
@@ -223,6 +249,15 @@ int vr_atmos_prepare_sub_device(int device, const vr_atmos_options *o, const vr_
   int16_t *cal_dev = (int16_t *)(((uintptr_t)(x.tmaxh + n_day) + 15) & ~(uintptr_t)15);
   int32_t *perm_dev = (int32_t *)(((uintptr_t)(cal_dev + x.Ndays + 2) + 15) & ~(uintptr_t)15);
   int32_t *hist_dev = perm_dev + CB;
+  if (nder) {
+    double *dcol = (double *)(((uintptr_t)(hist_dev + LAT_BUCKETS) + 63) & ~(uintptr_t)63);
+    const unsigned nb = (unsigned)((n_col + 255) / 256);
+    if (split_prec) { k_derive<<<nb, 256, 0, st>>>(x, 0, (int64_t)n_col, raw->rainf, raw->snowf, dcol); x.r_prec = dcol; x.prec_native = 1; dcol += n_col; }
+    if (split_wind) { k_derive<<<nb, 256, 0, st>>>(x, 1, (int64_t)n_col, raw->wind_e, raw->wind_n, dcol); x.r_wind = dcol; dcol += n_col; }
+    if (vp_q) { k_derive<<<nb, 256, 0, st>>>(x, 2, (int64_t)n_col, raw->qair, raw->pressure, dcol); x.r_vp = dcol; x.vp_native = 1; }
+    if (vp_rh) { k_derive<<<nb, 256, 0, st>>>(x, 3, (int64_t)n_col, raw->rel_humid, raw->t_a, dcol); x.r_vp = dcol; x.vp_native = 1; }
+    g_t.launches += nder;
+  }
   std::vector<int16_t> cal(x.Ndays + 2);
   va::build_calendar(*o, x.Ndays, cal.data());
   CKF(cudaMemcpyAsync(cal_dev, cal.data(), cal.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
@@ -253,6 +288,7 @@ int vr_atmos_prepare_sub_device(int device, const vr_atmos_options *o, const vr_
     if (conv) { k_conv<<<(unsigned)nbc, TPB, 0, st>>>(x, cb); g_t.launches++; }
     mark();
     k_hours<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb);
+    if (x.r_q || x.r_rh) { k_humid<<<(unsigned)(nbc * nd), TPB, 0, st>>>(x, cb); g_t.launches++; }
     k_rec<<<(unsigned)(nbc * x.nrecs), TPB, 0, st>>>(x, cb);
     g_t.launches += 2;
     mark();
@@ -285,22 +321,30 @@ int vr_atmos_prepare_sub(int device, const vr_atmos_options *o, const vr_atmos_c
   const int NSITE = 10;
   const double *site_h[NSITE] = {cells->lat, cells->lng, cells->time_zone_lng, cells->elevation, cells->annual_prec,
                                  cells->slope, cells->aspect, cells->ehoriz, cells->whoriz, cells->min_Tfactor};
-  const double *raw_h[9] = {raw->prec, raw->t_a, raw->t_b, raw->wind, raw->shortwave, raw->longwave, raw->vp, raw->pressure,
-                            raw->density};
+  const int NRAW = 15;
+  const double *raw_h[NRAW] = {raw->prec, raw->t_a, raw->t_b, raw->wind, raw->shortwave, raw->longwave, raw->vp, raw->pressure,
+                               raw->density, raw->qair, raw->rel_humid, raw->rainf, raw->snowf, raw->wind_e, raw->wind_n};
+  int nraw = 0;
+  for (int i = 0; i < NRAW; i++) nraw += raw_h[i] ? 1 : 0;
   const int NF = o->snow_step > 0 ? o->time_step / o->snow_step : 1;
   const size_t n_flag = (size_t)o->nrecs * C, n_out = n_flag * (NF > 1 ? NF + 1 : 1);
   double *dev = nullptr;
-  CK(cudaMalloc((void **)&dev, ((size_t)NSITE * C + (size_t)9 * nrf * C + VR_NFORCING * n_out) * sizeof(double) + n_flag * sizeof(int32_t)));
-  const double *site_d[NSITE] = {}, *raw_d[9] = {};
+  CK(cudaMalloc((void **)&dev, ((size_t)NSITE * C + (size_t)nraw * nrf * C + VR_NFORCING * n_out) * sizeof(double) + n_flag * sizeof(int32_t)));
+  const double *site_d[NSITE] = {}, *raw_d[NRAW] = {};
   double *p = dev;
   int rc = VR_OK;
   for (int i = 0; i < NSITE && rc == VR_OK; i++, p += C)
     if (site_h[i]) { site_d[i] = p; if (cudaMemcpy(p, site_h[i], C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
-  for (int i = 0; i < 9 && rc == VR_OK; i++, p += (size_t)nrf * C)
-    if (raw_h[i]) { raw_d[i] = p; if (cudaMemcpy(p, raw_h[i], (size_t)nrf * C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA; }
+  for (int i = 0; i < NRAW && rc == VR_OK; i++)
+    if (raw_h[i]) {
+      raw_d[i] = p;
+      if (cudaMemcpy(p, raw_h[i], (size_t)nrf * C * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = VR_ERR_CUDA;
+      p += (size_t)nrf * C;
+    }
   if (rc != VR_OK) { cudaFree(dev); return fail(rc, "host to device copy failed"); }
   vr_atmos_cells cd{C, site_d[0], site_d[1], site_d[2], site_d[3], site_d[4], site_d[5], site_d[6], site_d[7], site_d[8], site_d[9]};
-  vr_atmos_raw rd{nrf, raw_d[0], raw_d[1], raw_d[2], raw_d[3], raw_d[4], raw_d[5], raw_d[6], raw_d[7], raw_d[8]};
+  vr_atmos_raw rd{nrf, raw_d[0], raw_d[1], raw_d[2], raw_d[3], raw_d[4], raw_d[5], raw_d[6], raw_d[7], raw_d[8], raw_d[9], raw_d[10],
+                  raw_d[11], raw_d[12], raw_d[13], raw_d[14]};
   double *out_d[VR_NFORCING];
   for (int f = 0; f < VR_NFORCING; f++) out_d[f] = p + (size_t)f * n_out;
   int32_t *flag_d = (int32_t *)(p + (size_t)VR_NFORCING * n_out);

@@ -1323,6 +1323,25 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
   return VR_OK;
 }
 
+int vr_full_energy_compat(vr_handle *h, int64_t rec, int32_t month, int32_t day_in_year, const double *atmos, const int32_t *snowflag,
+                          double *out, int32_t *cell_status)
+{
+  if (!h || !atmos || !out) return VR_ERR_ARG;
+  if (!h->initialised) { h->err = "vr_init_state (or vr_set_state) must precede vr_full_energy_compat"; return VR_ERR_STATE; }
+  if (rec != (int64_t)h->rec_done) {
+    h->err = "vr_full_energy_compat: record " + std::to_string(rec) + " is not the next record of the run (" +
+             std::to_string(h->rec_done) + ")";
+    return VR_ERR_STATE;
+  }
+  const size_t NS = h->M.NF > 1 ? h->M.NF + 1 : 1;
+  vr_forcing f;
+  memset(&f, 0, sizeof f);
+  f.nrec = 1; f.month = &month; f.day_in_year = &day_in_year;
+  for (int i = 0; i < VR_NFORCING; i++) f.field[i] = atmos + (size_t)i * NS * (size_t)h->M.FC;
+  f.snowflag = snowflag;
+  return vr_step_block(h, &f, out, cell_status);
+}
+
 int vr_synchronize(vr_handle *h)
 {
   if (!h) return VR_ERR_ARG;

@@ -22,7 +22,8 @@ LIBPATH = os.environ.get("VICRES_LIB", os.path.join(HERE, "libvicres.so"))
 EXPORTS = ["vr_create", "vr_destroy", "vr_last_error", "vr_default_options", "vr_set_veglib",
            "vr_set_cells", "vr_set_forcing_map", "vr_init_state", "vr_step_block",
            "vr_step_block_device", "vr_synchronize", "vr_state_size", "vr_get_state", "vr_set_state",
-           "vr_write_state_file", "vr_read_state_file", "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts", "vr_step_diag"]
+           "vr_write_state_file", "vr_read_state_file", "vr_num_units", "vr_num_launches", "vr_last_kernel_ms", "vr_kernel_times", "vr_diag_pow", "vr_diag_fp64_peak", "vr_fallback_counts", "vr_step_diag",
+           "vr_full_energy_compat"]
 
 _lib = None
 
@@ -74,6 +75,7 @@ def load_library(path=LIBPATH):
     L.vr_diag_pow.argtypes = [C.c_int, C.c_int64, vp, vp, vp]
     L.vr_fallback_counts.argtypes = [vp, vp]
     L.vr_step_diag.argtypes = [vp, vp]
+    L.vr_full_energy_compat.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -154,6 +156,18 @@ class VicRes:
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.n_out * nrec * self.ncell
         status = np.zeros(self.ncell, dtype=np.int32)
         self._check(self.L.vr_step_block(self.h, f.ref(), out.ctypes.data, status.ctypes.data),
+                    allow=(abi.VR_ERR_CELL,))
+        return out, status
+
+    def full_energy(self, rec, month, doy, atmos, snowflag=None):
+        """one record of every cell, the reference's `full_energy(...); put_data(...)` pair (vr_full_energy_compat):
+        atmos [9, C] (or [9, NF + 1, C]); returns (out [n_out, C], cell_status [C])"""
+        a = np.ascontiguousarray(atmos, dtype=np.float64)
+        out = np.empty((self.n_out, self.ncell), dtype=np.float64)
+        status = np.zeros(self.ncell, dtype=np.int32)
+        sf = None if snowflag is None else np.ascontiguousarray(snowflag, dtype=np.int32)
+        self._check(self.L.vr_full_energy_compat(self.h, int(rec), int(month), int(doy), a.ctypes.data,
+                                                 sf.ctypes.data if sf is not None else None, out.ctypes.data, status.ctypes.data),
                     allow=(abi.VR_ERR_CELL,))
         return out, status
 

@@ -185,7 +185,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         if wind_zero_frac > 0:
             wind = np.where(rng.uniform(size=ndays) < wind_zero_frac, 0.0, wind)
         # optional observed columns (values only need to be plausible)
-        if extra_cols:                  # drawn only when asked for: the random stream of the other cases stays as it was
+        if set(extra_cols) - {"RAINF", "SNOWF", "WIND_E", "WIND_N"}:   # drawn only when asked for: the random stream of the other cases stays as it was
             sw_day = np.clip(180.0 + 120.0 * np.cos(phase) * (1 if lat >= 0 else -1) + rng.normal(0, 40, ndays), 5.0, 420.0)
             lw_day = np.clip(300.0 + 2.5 * tmean + rng.normal(0, 15, ndays), 120.0, 480.0)
             vp_day = np.clip(0.6108 * np.exp(17.27 * tmin / (237.3 + tmin)) * rng.uniform(0.7, 1.0, ndays), 0.02, 4.0)
@@ -207,9 +207,22 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
                     out.append(1.25 * np.exp(-elev / 9000.0) - 0.003 * tmean[i] + (0.0 if k is None else 0.004 * np.cos(hrs[k] / 3.8)))
                 elif name == "VP":
                     out.append(vp_day[i] * (1.0 if k is None else 1.0 + 0.05 * np.cos(2.0 * np.pi * (hrs[k] - 15.0) / 24.0)))
+                elif name == "QAIR":                # kg/kg
+                    out.append(0.622 * vp_day[i] / (101.3 * np.exp(-elev / 8400.0)) * (1.0 if k is None else 1.0 + 0.04 * np.sin(hrs[k] / 3.0)))
+                elif name == "REL_HUMID":           # %
+                    out.append(float(np.clip(55.0 + 30.0 * np.sin(0.37 * i) + (0.0 if k is None else 8.0 * np.cos(2.0 * np.pi * (hrs[k] - 4.0) / 24.0)),
+                                             8.0, 100.0)))
+                elif name in ("RAINF", "SNOWF"):    # together they replace PREC (and differ from it: 90 % of it)
+                    sf = 1.0 if tmean[i] < -1.0 else (0.5 if tmean[i] < 1.0 else 0.0)
+                    amount = 0.9 * prec[i] * (sf if name == "SNOWF" else 1.0 - sf) / (1 if k is None else steps_per_day)
+                    out.append(amount / ((24 if k is None else dt) * 3600.0) if alma else amount)
+                elif name in ("WIND_E", "WIND_N"):  # together they replace WIND
+                    ang = 0.9 * i + (0.0 if k is None else 0.3 * k)
+                    out.append(1.1 * wind[i] * (np.cos(ang) if name == "WIND_E" else np.sin(ang)))
             if alma:
                 out = [x * 1000.0 if name in ("VP", "PRESSURE") else x for x, name in zip(out, extra_cols)]
-            return "".join(" %.4f" % x for x in out)
+            fmt = {"QAIR": " %.7f", "RAINF": " %.8e" if alma else " %.4f", "SNOWF": " %.8e" if alma else " %.4f"}
+            return "".join(fmt.get(name, " %.4f") % x for x, name in zip(out, extra_cols))
         hrs = (np.arange(steps_per_day) + 0.5) * dt if dt < 24 else None
         fn = os.path.join(forc_dir, "data_%.4f_%.4f" % (lat, lng))
         with open(fn, "w") as f:

@@ -56,7 +56,7 @@ def run(global_path, device=0, write=True, records_per_block=0):
     flag_dev = torch.empty((nrecs, Cn), dtype=torch.int32, device=dev)
     ptr = lambda t: t.data_ptr() if t is not None else 0
     atmos.prepare_device(ao, {k: ptr(v) for k, v in site_t.items()}, {k: ptr(v) for k, v in raw_t.items()},
-                         [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["prec"].shape[0], device=device,
+                         [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["t_a"].shape[0], device=device,
                          snowflag_dev=flag_dev.data_ptr())
     torch.cuda.synchronize(dev)
     # what to compute: the columns of the output files, each once (the conductance instead of the resistance when the
