@@ -744,7 +744,7 @@ struct vr_handle {
   std::vector<cudaEvent_t> dev;      // 6 per record: around k_front and k_back on the step stream, around k_snow on the snow stream
   size_t dev_used = 0;
   int64_t diag_unit_records = 0;
-  int chunk = 16;                    // records per launch of k_cells (and per pipelined copy of vr_step_block)
+  int chunk = 8;                     // records per launch of k_cells (and per pipelined copy of vr_step_block)
   int64_t launches = 0;
   bool timed = false;
 };
@@ -1048,9 +1048,10 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   for (int v = 0; v < h->opt.n_out; v++) M.out_vars[v] = h->opt.out_vars[v];
   build_term_map(h->opt.out_vars, h->opt.n_out, M.tmap);
   h->extras = term_extras(M.tmap);
-  {   // records per launch pair: the caller's hint or 16, capped so that the two term buffers stay below 24 GB
-      // (a 1M-cell, 5-band grid has 1.2e7 units: 16 records would need 80 GB of terms)
-    h->chunk = h->opt.cells_per_block_hint > 0 ? h->opt.cells_per_block_hint : 16;
+  {   // records per chunk: the caller's hint or 8 (the snow class of a chunk is every unit that needs the snow model in ANY
+      // of its records, so short chunks keep that class small; measured 2 .. 8 alike, 16 3 % slower: profiles/r2_tuning.md),
+      // capped so that the two term buffers stay below 24 GB (a 1M-cell, 5-band grid has 1.2e7 units)
+    h->chunk = h->opt.cells_per_block_hint > 0 ? h->opt.cells_per_block_hint : 8;
     const double per_rec = 2.0 * M.tmap.n * (double)(U ? U : 1) * sizeof(double);
     const int cap = (int)(24e9 / per_rec);
     if (h->chunk > cap) h->chunk = cap < 1 ? 1 : cap;
