@@ -318,7 +318,7 @@ def run_ours(args):
     out_pin = torch.empty((n_out, R, C), dtype=torch.float64).pin_memory()
     f_np, out_np = f_pin.numpy(), out_pin.numpy()
     Ke = max(1, min(K, args.e2e_steps))
-    for _ in range(min(W, 1)):
+    for _ in range(min(W, 2)):
         m.step(month, doy, f_np, out=out_np)
     torch.cuda.synchronize(dev)
     if world > 1:

@@ -1277,9 +1277,19 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     F.snowflag = flags ? h->d_snowflag.p + (size_t)r0 * FC : nullptr;
     F.rec_abs = (int)h->rec_done + r0;
     F.nrec = nr; F.rec0 = 0; F.nrec_total = nr; F.month = h->d_month.p + r0; F.doy = h->d_doy.p + r0;
+    // the nine fields of the chunk: one strided copy when the caller's fields are equally spaced in memory (one array
+    // [field][rec][col], the usual case), else one copy per field
+    const size_t row_in = (size_t)nr * NS * FC * sizeof(double);
+    const ptrdiff_t gap = (const char *)f->field[1] - (const char *)f->field[0];
+    const size_t MAX_PITCH = 2147483647;                 // cudaDeviceProp::memPitch: the widest pitch a strided copy takes
+    bool even = gap >= (ptrdiff_t)row_in && (size_t)gap <= MAX_PITCH;
+    for (int i = 2; even && i < VR_NFORCING; i++) even = ((const char *)f->field[i] - (const char *)f->field[i - 1]) == gap;
+    if (even)
+      CK(cudaMemcpy2DAsync(din, row_in, f->field[0] + (size_t)r0 * NS * FC, (size_t)gap, row_in, VR_NFORCING, cudaMemcpyHostToDevice,
+                           h->s_in));
     for (int i = 0; i < VR_NFORCING; i++) {
-      CK(cudaMemcpyAsync(din + (size_t)i * nr * NS * FC, f->field[i] + (size_t)r0 * NS * FC, (size_t)nr * NS * FC * sizeof(double),
-                         cudaMemcpyHostToDevice, h->s_in));
+      if (!even)
+        CK(cudaMemcpyAsync(din + (size_t)i * nr * NS * FC, f->field[i] + (size_t)r0 * NS * FC, row_in, cudaMemcpyHostToDevice, h->s_in));
       F.field[i] = din + (size_t)i * nr * NS * FC;
     }
     CK(cudaEventRecord(h->ev_in[b], h->s_in));
@@ -1293,9 +1303,14 @@ int vr_step_block(vr_handle *h, const vr_forcing *f, double *out_host, int32_t *
     CK(cudaEventRecord(h->ev_comp[b], h->s_cells));                       // forcing consumed and outputs written
     if (trace) cudaEventRecord(tev[2 + 3 * k], h->s_cells);
     CK(cudaStreamWaitEvent(h->s_out, h->ev_comp[b], 0));
-    for (int v = 0; v < n_out; v++)
-      CK(cudaMemcpyAsync(out_host + ((size_t)v * nrec + r0) * C, dout + (size_t)v * nr * C, (size_t)nr * C * sizeof(double),
-                         cudaMemcpyDeviceToHost, h->s_out));
+    // the chunk's records of every output variable: one strided copy (rows of nr * C values, nrec * C apart on the host)
+    if ((size_t)nrec * C * sizeof(double) <= MAX_PITCH)
+      CK(cudaMemcpy2DAsync(out_host + (size_t)r0 * C, (size_t)nrec * C * sizeof(double), dout, (size_t)nr * C * sizeof(double),
+                           (size_t)nr * C * sizeof(double), n_out, cudaMemcpyDeviceToHost, h->s_out));
+    else
+      for (int v = 0; v < n_out; v++)
+        CK(cudaMemcpyAsync(out_host + ((size_t)v * nrec + r0) * C, dout + (size_t)v * nr * C, (size_t)nr * C * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->s_out));
     CK(cudaEventRecord(h->ev_out[b], h->s_out));
     if (trace) cudaEventRecord(tev[3 + 3 * k], h->s_out);
   }
