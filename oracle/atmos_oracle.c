@@ -1,7 +1,9 @@
 /* atmos_oracle.c -- TEST INFRASTRUCTURE ONLY (oracle side).  Never linked into the product.
  *
  * Plain-C, one-cell-at-a-time restatement of the reference's forcing preparation for the two forcing
- * layouts of include/vicres_atmos.h (NF == 1):
+ * layouts of include/vicres_atmos.h, with or without the observed SHORTWAVE / LONGWAVE / VP / PRESSURE / DENSITY columns, QAIR /
+ * REL_HUMID, the split RAINF + SNOWF and WIND_E + WIND_N columns, and the NF = TIME_STEP / SNOW_STEP windows per record of a
+ * sub-stepped snow model with its snow flags:
  *   initialize_atmos            runoff/model/initialize_atmos.c:137-1818
  *   mtclim_wrapper/init/to_vic  runoff/model/mtclim_wrapper.c:69-278
  *   calc_tair, calc_prcp, snowpack, calc_srad_humidity_iterative, compute_srad_humidity_onetime,
@@ -420,11 +422,19 @@ int32_t ao_ndays(const vr_atmos_options *o)
 int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_lng, double elevation, double annual_prec,
             double slope, double aspect, double ehoriz, double whoriz, int64_t stride, int64_t nrec_forcing,
             const double *c_prec, const double *c_ta, const double *c_tb, const double *c_wind, const double *c_sw,
-            const double *c_lw, const double *c_vp, const double *c_pr, const double *c_de, double *const out[VR_NFORCING], double *dbg)
+            const double *c_lw, const double *c_vp, const double *c_pr, const double *c_de, const double *c_q, const double *c_rh,
+            const double *c_rainf, const double *c_snowf, const double *c_we, const double *c_wn, double min_Tfactor,
+            double *const out[VR_NFORCING], int32_t *snowflag, double *dbg)
 {
   static const int month_days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
   const int dt = o->time_step, nrecs = o->nrecs, fdt = o->force_dt, daily = (o->layout == VR_ATMOS_DAILY_TMAX_TMIN);
   const int stepspday = 24 / dt;
+  /* SNOW_STEP < TIME_STEP: NF windows of ss hours per record; a record's values follow its windows' (index NR = NF), and
+   * when NF == 1 the single window IS the record (NR = 0): get_global_param.c:761-770 */
+  const int NF = (o->snow_step > 0 && o->snow_step != dt) ? dt / o->snow_step : 1, ss = dt / NF, NS = NF > 1 ? NF + 1 : 1, NR = NF > 1 ? NF : 0;
+  const double min_wind = (double)(float)o->min_wind_speed;    /* option_struct.MIN_WIND_SPEED is a float */
+  double *l_q, *l_rh;
+  int have_wind = o->has_wind || (c_we && c_wn), vp_supplied;
   double hour_offset = (time_zone_lng - lng) * 24 / 360;       /* :217-225 */
   int hour_offset_int = (hour_offset < 0) ? (int)(hour_offset - 0.5) : (int)(hour_offset + 0.5);
   int Ndays = ao_ndays(o), Ndays_local, local_starthour, local_startday, local_startmonth, local_startyear;
@@ -436,6 +446,8 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   hour_offset -= hour_offset_int;
   Ndays_local = Ndays + (hour_offset_int != 0 ? 1 : 0);       /* :271-272 */
   if ((daily && fdt != 24) || (!daily && (fdt >= 24 || 24 % fdt)) || 24 % dt) return -1;
+  if (NF > 1 && (dt < 24 || dt % o->snow_step)) return -1;
+  if (!c_vp && c_q && !c_pr && fdt < 24) return -1;            /* the reference reads a stale index there (:1302) */
 
   local_starthour = o->starthour - hour_offset_int;            /* :274-292 */
   local_startday = o->startday; local_startmonth = o->startmonth; local_startyear = o->startyear;
@@ -474,6 +486,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
   l_vp = calloc(Ndays_local * 24, sizeof(double)); hourlyrad = calloc(Ndays_local * 24, sizeof(double));
   l_sw = calloc(Ndays_local * 24, sizeof(double)); l_lw = calloc(Ndays_local * 24, sizeof(double));
   l_pr = calloc(Ndays_local * 24, sizeof(double)); l_de = calloc(Ndays_local * 24, sizeof(double));
+  l_q = calloc(Ndays_local * 24, sizeof(double)); l_rh = calloc(Ndays_local * 24, sizeof(double));
   tair = calloc(Ndays_local * 24, sizeof(double));
   prec = calloc(Ndays_local, sizeof(double)); tmax = calloc(Ndays_local, sizeof(double));
   tmin = calloc(Ndays_local, sizeof(double)); tskc = calloc(Ndays_local, sizeof(double));
@@ -491,10 +504,15 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       if (hour_offset_int > 0) i--;
       if (i < 0) i = 0;
       if (i >= Ndays) i = Ndays - 1;
-      l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i) * pscale;
+      /* :424-460: RAINF + SNOWF replace PREC, |(WIND_E, WIND_N)| replaces WIND (element by element, before the local shift) */
+      l_prec[idx] = (c_rainf && c_snowf) ? fetch(c_rainf, stride, nrec_forcing, i) * pscale + fetch(c_snowf, stride, nrec_forcing, i) * pscale
+                                         : fetch(c_prec, stride, nrec_forcing, i) * pscale;
       l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i) - tshift;
       l_tb[idx] = fetch(c_tb, stride, nrec_forcing, i) - tshift;
-      l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
+      l_wind[idx] = (c_we && c_wn) ? sqrt(fetch(c_we, stride, nrec_forcing, i) * fetch(c_we, stride, nrec_forcing, i) +
+                                          fetch(c_wn, stride, nrec_forcing, i) * fetch(c_wn, stride, nrec_forcing, i))
+                                   : fetch(c_wind, stride, nrec_forcing, i);
+      l_q[idx] = fetch(c_q, stride, nrec_forcing, i); l_rh[idx] = fetch(c_rh, stride, nrec_forcing, i);
       l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
       l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * kpa;         /* kPa2Pa, :404-414 */
       l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * kpa; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
@@ -506,39 +524,57 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       i = (idx - o->starthour + hour_offset_int) / fdt;
       if (i < 0) i += fstepspday;
       if (i >= Ndays * fstepspday) i -= fstepspday;
-      l_prec[idx] = fetch(c_prec, stride, nrec_forcing, i) * pscale / fdt;
+      l_prec[idx] = ((c_rainf && c_snowf) ? fetch(c_rainf, stride, nrec_forcing, i) * pscale + fetch(c_snowf, stride, nrec_forcing, i) * pscale
+                                          : fetch(c_prec, stride, nrec_forcing, i) * pscale) / fdt;
       l_ta[idx] = fetch(c_ta, stride, nrec_forcing, i) - tshift;
-      l_wind[idx] = fetch(c_wind, stride, nrec_forcing, i);
+      l_wind[idx] = (c_we && c_wn) ? sqrt(fetch(c_we, stride, nrec_forcing, i) * fetch(c_we, stride, nrec_forcing, i) +
+                                          fetch(c_wn, stride, nrec_forcing, i) * fetch(c_wn, stride, nrec_forcing, i))
+                                   : fetch(c_wind, stride, nrec_forcing, i);
+      l_q[idx] = fetch(c_q, stride, nrec_forcing, i); l_rh[idx] = fetch(c_rh, stride, nrec_forcing, i);
       l_sw[idx] = fetch(c_sw, stride, nrec_forcing, i); l_lw[idx] = fetch(c_lw, stride, nrec_forcing, i);
       l_vp[idx] = fetch(c_vp, stride, nrec_forcing, i) * kpa;
       l_pr[idx] = fetch(c_pr, stride, nrec_forcing, i) * kpa; l_de[idx] = fetch(c_de, stride, nrec_forcing, i);
     }
   }
   shift = (o->starthour - hour_offset_int < 0) ? 24 : 0;
-#define REC_HOUR(rec) ((rec) * dt + o->starthour - hour_offset_int + shift)
+#define WIN_HOUR(rec, i) ((rec) * dt + (i) * ss + o->starthour - hour_offset_int + shift)
 #define DAY_OF(hour) ((int)((float)(hour) / 24.0))
+#define O(rec, i) ((size_t)((rec) * NS + (i)) * stride)
 
   /* precipitation :597-635, wind :641-689, sub-daily air temperature :737-752 */
   for (rec = 0; rec < nrecs; rec++) {
-    hour = REC_HOUR(rec);
-    if (fdt == 24) {
-      out[VR_F_PREC][rec * stride] = l_prec[DAY_OF(hour)] / (float)(1 * stepspday);
-      /* the clamp to MIN_WIND_SPEED at :654-657 addresses wind[NF], one past the record's value: no effect */
-      out[VR_F_WIND][rec * stride] = o->has_wind ? l_wind[DAY_OF(hour)] : 3.0;
-    }
-    else {
-      double s = 0;
-      for (idx = hour; idx < hour + dt; idx++) s += l_prec[idx];
-      out[VR_F_PREC][rec * stride] = s;
-      if (o->has_wind) {
-        s = 0;
-        for (idx = hour; idx < hour + dt; idx++) s += (l_wind[idx] < o->min_wind_speed) ? o->min_wind_speed : l_wind[idx];
-        out[VR_F_WIND][rec * stride] = s / dt;
+    double sp = 0, sw_ = 0, st = 0;
+    for (i = 0; i < NF; i++) {
+      hour = WIN_HOUR(rec, i);
+      if (fdt == 24) {
+        out[VR_F_PREC][O(rec, i)] = l_prec[DAY_OF(hour)] / (float)(NF * stepspday);
+        out[VR_F_WIND][O(rec, i)] = have_wind ? l_wind[DAY_OF(hour)] : 3.0;
       }
-      else out[VR_F_WIND][rec * stride] = 3.0;
-      s = 0;
-      for (idx = hour; idx < hour + dt; idx++) s += l_ta[idx];
-      out[VR_F_AIR_TEMP][rec * stride] = s / dt;
+      else {
+        double s = 0;
+        for (idx = hour; idx < hour + ss; idx++) s += l_prec[idx];
+        out[VR_F_PREC][O(rec, i)] = s;
+        if (have_wind) {
+          s = 0;
+          for (idx = hour; idx < hour + ss; idx++) s += (l_wind[idx] < min_wind) ? min_wind : l_wind[idx];
+          out[VR_F_WIND][O(rec, i)] = s / ss;
+        }
+        else out[VR_F_WIND][O(rec, i)] = 3.0;
+        s = 0;
+        for (idx = hour; idx < hour + ss; idx++) s += l_ta[idx];
+        out[VR_F_AIR_TEMP][O(rec, i)] = s / ss;
+        st += out[VR_F_AIR_TEMP][O(rec, i)];
+      }
+      sp += out[VR_F_PREC][O(rec, i)];
+      sw_ += out[VR_F_WIND][O(rec, i)];
+    }
+    if (NF > 1) {
+      out[VR_F_PREC][O(rec, NR)] = sp;
+      out[VR_F_WIND][O(rec, NR)] = have_wind ? sw_ / (float)NF : 3.0;
+      if (fdt < 24) out[VR_F_AIR_TEMP][O(rec, NR)] = st / (float)NF;
+      /* the clamp to MIN_WIND_SPEED at :654-657 addresses wind[j] with j == NF after the loop: with NF > 1 that is the
+       * record's value (NR == NF), with NF == 1 one past it (no effect) */
+      if (have_wind && fdt == 24 && dt == 24 && out[VR_F_WIND][O(rec, NR)] < min_wind) out[VR_F_WIND][O(rec, NR)] = min_wind;
     }
   }
   for (day = 0; day < Ndays_local; day++) {
@@ -555,8 +591,19 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     }
   }
 
-  /* vapour pressure, part 1 (:869-915) and shortwave, part 1 (:925-940) */
-  if (c_vp) {
+  /* vapour pressure, part 1: QAIR with PRESSURE, REL_HUMID with AIR_TEMP become the observed VP (:773-866; all columns share
+   * FORCE_DT here, so the daily / sub-daily cases are the same element-wise products) */
+  vp_supplied = c_vp != NULL;
+  if (!vp_supplied && c_q && c_pr) {
+    for (idx = 0; idx < Ndays_local * (fdt == 24 ? 1 : 24); idx++) l_vp[idx] = l_q[idx] * l_pr[idx] / 0.62196351;
+    vp_supplied = 1;
+  }
+  else if (!vp_supplied && !c_q && c_rh && !daily) {
+    for (idx = 0; idx < Ndays_local * 24; idx++) l_vp[idx] = l_rh[idx] * svp(l_ta[idx]) / 100;
+    vp_supplied = 1;
+  }
+  /* (:869-915) and shortwave, part 1 (:925-940) */
+  if (vp_supplied) {
     for (day = 0; day < Ndays_local; day++) {
       if (fdt == 24) daily_vp[day] = l_vp[day];
       else {
@@ -572,7 +619,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
 
   /* mtclim_wrapper.c:84-218: init, calc_tair (mtclim_vic.c:405-433), calc_prcp (:437-469), snowpack (:474-530) */
   d.ndays = Ndays_local;
-  d.insw = c_sw != NULL; d.invp = c_vp != NULL;
+  d.insw = c_sw != NULL; d.invp = vp_supplied;
   d.yday = yday;
   d.tmax = tmax; d.tmin = tmin;
   d.prcp = calloc(Ndays_local, sizeof(double)); d.s_tmax = calloc(Ndays_local, sizeof(double));
@@ -656,43 +703,75 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     for (i = 0; i < Ndays_local * 24; i++) hourlyrad[i] = l_sw[i];
   /* shortwave :974-987 */
   for (rec = 0; rec < nrecs; rec++) {
-    double s = 0;
-    hour = REC_HOUR(rec);
-    for (idx = hour; idx < hour + dt; idx++) s += hourlyrad[idx];
-    out[VR_F_SHORTWAVE][rec * stride] = s / dt;
+    double sum = 0;
+    for (i = 0; i < NF; i++) {
+      double s = 0;
+      hour = WIN_HOUR(rec, i);
+      for (idx = hour; idx < hour + ss; idx++) s += hourlyrad[idx];
+      out[VR_F_SHORTWAVE][O(rec, i)] = s / ss;
+      sum += out[VR_F_SHORTWAVE][O(rec, i)];
+    }
+    if (NF > 1) out[VR_F_SHORTWAVE][O(rec, NR)] = sum / (float)NF;
   }
   set_max_min_hour(hourlyrad, Ndays_local, tmaxhour, tminhour);   /* :998 */
   if (daily) {                                                      /* :1000-1021 */
     hourly_t(Ndays_local, tmaxhour, tmax, tminhour, tmin, tair);
     for (rec = 0; rec < nrecs; rec++) {
-      double s = 0;
-      hour = REC_HOUR(rec);
-      for (idx = hour; idx < hour + dt; idx++) s += tair[idx];
-      out[VR_F_AIR_TEMP][rec * stride] = s / dt;
+      double sum = 0;
+      for (i = 0; i < NF; i++) {
+        double s = 0;
+        hour = WIN_HOUR(rec, i);
+        for (idx = hour; idx < hour + ss; idx++) s += tair[idx];
+        out[VR_F_AIR_TEMP][O(rec, i)] = s / ss;
+        sum += out[VR_F_AIR_TEMP][O(rec, i)];
+      }
+      if (NF > 1) out[VR_F_AIR_TEMP][O(rec, NR)] = sum / (float)NF;
     }
   }
-  /* density :1032-1064, pressure :1070-1146, density from pressure :1152-1170 */
+  /* density :1032-1064, pressure :1070-1146, density from pressure :1152-1170: observed columns per window and their mean for
+   * the record; derived values from the window's or the record's own air temperature */
   for (rec = 0; rec < nrecs; rec++) {
-    double ta = out[VR_F_AIR_TEMP][rec * stride], p, de = 0.;
-    hour = REC_HOUR(rec);
-    if (c_de) {
-      if (fdt == 24) de = l_de[DAY_OF(hour)];
-      else { double s2 = 0; for (idx = hour; idx < hour + dt; idx++) s2 += l_de[idx]; de = s2 / dt; }
+    double sde = 0, spr = 0;
+    for (i = 0; i <= NF; i++) {
+      double ta, p = 0., de = 0.;
+      const int k = (i < NF) ? i : NR;
+      if (i == NF && NF == 1) break;
+      ta = out[VR_F_AIR_TEMP][O(rec, k)];
+      if (i < NF) {
+        hour = WIN_HOUR(rec, i);
+        if (c_de) {
+          if (fdt == 24) de = l_de[DAY_OF(hour)];
+          else { double s2 = 0; for (idx = hour; idx < hour + ss; idx++) s2 += l_de[idx]; de = s2 / ss; }
+          sde += de;
+        }
+        if (c_pr) {
+          if (fdt == 24) p = l_pr[DAY_OF(hour)];
+          else { double s2 = 0; for (idx = hour; idx < hour + ss; idx++) s2 += l_pr[idx]; p = s2 / ss; }
+          spr += p;
+        }
+      }
+      else { de = sde / (float)NF; p = spr / (float)NF; }
+      if (c_pr) { }
+      else if (c_de) p = o->plapse ? (KELVIN + ta) * de * RD : (275.0 + ta) * de / 0.003486;
+      else if (o->plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
+      else p = 95500.;
+      out[VR_F_PRESSURE][O(rec, k)] = p;
+      if (c_de) out[VR_F_DENSITY][O(rec, k)] = de;
+      else if (o->plapse) out[VR_F_DENSITY][O(rec, k)] = p / (RD * (KELVIN + ta));
+      else out[VR_F_DENSITY][O(rec, k)] = 0.003486 * p / (275.0 + ta);
     }
-    if (c_pr) {
-      if (fdt == 24) p = l_pr[DAY_OF(hour)];
-      else { double s2 = 0; for (idx = hour; idx < hour + dt; idx++) s2 += l_pr[idx]; p = s2 / dt; }
-    }
-    else if (c_de) p = o->plapse ? (KELVIN + ta) * de * RD : (275.0 + ta) * de / 0.003486;
-    else if (o->plapse) p = PS_PM * exp(-elevation * GRAV / (RD * (KELVIN + ta + 0.5 * elevation * T_LAPSE)));
-    else p = 95500.;
-    out[VR_F_PRESSURE][rec * stride] = p;
-    if (c_de) out[VR_F_DENSITY][rec * stride] = de;
-    else if (o->plapse) out[VR_F_DENSITY][rec * stride] = p / (RD * (KELVIN + ta));
-    else out[VR_F_DENSITY][rec * stride] = 0.003486 * p / (275.0 + ta);
   }
+  /* vapour pressure, part 2 (:1176-1215): daily QAIR / REL_HUMID that could not become VP before MTCLIM replace its daily
+   * value, window by window in record order (the last window of a day leaves its value) */
+  if (!vp_supplied && fdt == 24 && (c_q || c_rh))
+    for (rec = 0; rec < nrecs; rec++)
+      for (i = 0; i < NF; i++) {
+        idx = DAY_OF(WIN_HOUR(rec, i));
+        if (c_q) daily_vp[idx] = l_q[idx] * out[VR_F_PRESSURE][O(rec, i)] / 0.62196351;
+        else daily_vp[idx] = l_rh[idx] * svp(out[VR_F_AIR_TEMP][O(rec, i)]) / 100;
+      }
   /* vapour pressure :1220-1291 (skipped when sub-daily VP was supplied: l_vp holds the observations) */
-  if (c_vp && fdt < 24) { }
+  if (vp_supplied && fdt < 24) { }
   else if (o->vp_interp) {
     for (day = 0; day < Ndays_local; day++) {
       double delta_t_minus, delta_t_plus;
@@ -718,23 +797,44 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
     for (day = 0; day < Ndays_local; day++)
       for (hour = 0; hour < 24; hour++) l_vp[day * 24 + hour] = daily_vp[day];
   for (rec = 0; rec < nrecs; rec++) {
-    double s = 0, ta = out[VR_F_AIR_TEMP][rec * stride], vp, vpd;
-    hour = REC_HOUR(rec);
-    for (idx = hour; idx < hour + dt; idx++) s += l_vp[idx];
-    vp = s / dt;
-    vpd = svp(ta) - vp;                                             /* :1336-1355 */
-    if (vpd < 0) { vpd = 0; vp = svp(ta); }
-    out[VR_F_VP][rec * stride] = vp;
-    out[VR_F_VPD][rec * stride] = vpd;
-    if (c_lw) {                                        /* :1389-1420 */
-      if (fdt == 24) out[VR_F_LONGWAVE][rec * stride] = l_lw[DAY_OF(hour)];
-      else {
-        double sl = 0;
-        for (idx = hour; idx < hour + dt; idx++) sl += l_lw[idx];
-        out[VR_F_LONGWAVE][rec * stride] = sl / dt;
+    double s_vp0 = 0, s_vp = 0, s_vpd = 0, s_lw = 0;
+    int flag = 0;
+    for (i = 0; i < NF; i++) {
+      double s = 0, ta = out[VR_F_AIR_TEMP][O(rec, i)], vp, vpd, lw;
+      hour = WIN_HOUR(rec, i);
+      for (idx = hour; idx < hour + ss; idx++) s += l_vp[idx];            /* :1278-1291 */
+      vp = s / ss;
+      s_vp0 += vp;
+      vpd = svp(ta) - vp;                                             /* :1336-1355 */
+      if (vpd < 0) { vpd = 0; vp = svp(ta); }
+      out[VR_F_VP][O(rec, i)] = vp;
+      out[VR_F_VPD][O(rec, i)] = vpd;
+      s_vp += vp; s_vpd += vpd;
+      if (c_lw) {                                        /* :1389-1420 */
+        if (fdt == 24) lw = l_lw[DAY_OF(hour)];
+        else {
+          double sl = 0;
+          for (idx = hour; idx < hour + ss; idx++) sl += l_lw[idx];
+          lw = sl / ss;
+        }
       }
+      else lw = calc_longwave(o, tskc[DAY_OF(hour)], ta, vp);   /* :1361-1388 */
+      out[VR_F_LONGWAVE][O(rec, i)] = lw;
+      s_lw += lw;
+      if ((ta + min_Tfactor) < o->max_snow_temp && out[VR_F_PREC][O(rec, i)] > 0) flag = 1;      /* :1736-1753 */
     }
-    else out[VR_F_LONGWAVE][rec * stride] = calc_longwave(o, tskc[DAY_OF(hour)], ta, vp);   /* :1361-1388 */
+    if (NF > 1) {
+      if (vp_supplied || o->vp_interp) {                 /* :1345-1349 */
+        out[VR_F_VPD][O(rec, NR)] = s_vpd / (float)NF;
+        out[VR_F_VP][O(rec, NR)] = s_vp / (float)NF;
+      }
+      else {                                             /* :1350-1352: vp[NR] as transferred, no clamp */
+        out[VR_F_VP][O(rec, NR)] = s_vp0 / (float)NF;
+        out[VR_F_VPD][O(rec, NR)] = svp(out[VR_F_AIR_TEMP][O(rec, NR)]) - out[VR_F_VP][O(rec, NR)];
+      }
+      out[VR_F_LONGWAVE][O(rec, NR)] = s_lw / (float)NF;
+    }
+    if (snowflag) snowflag[(size_t)rec * stride] = flag;
   }
   if (dbg) {
     for (i = 0; i < Ndays_local; i++) {
@@ -743,7 +843,7 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
       dbg[4 * Ndays_local + i] = tminhour[i]; dbg[5 * Ndays_local + i] = tmaxhour[i];
     }
   }
-  free(l_sw); free(l_lw); free(l_pr); free(l_de);
+  free(l_sw); free(l_lw); free(l_pr); free(l_de); free(l_q); free(l_rh);
   free(yday); free(l_prec); free(l_ta); free(l_tb); free(l_wind); free(l_vp); free(hourlyrad); free(tair);
   free(prec); free(tmax); free(tmin); free(tskc); free(daily_vp); free(tmaxhour); free(tminhour); free(radfract);
   free(d.prcp); free(d.s_tmax); free(d.s_tmin); free(d.s_tday); free(d.s_prcp); free(d.s_hum); free(d.s_srad);
@@ -753,9 +853,10 @@ int ao_cell(const vr_atmos_options *o, double lat, double lng, double time_zone_
 
 /* all cells, serially (cells are independent); arrays as in include/vicres_atmos.h */
 int ao_prepare(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_atmos_raw *raw, double *const out[VR_NFORCING],
-               int64_t c_begin, int64_t c_end)
+               int32_t *snowflag, int64_t c_begin, int64_t c_end)
 {
   int64_t C = cells->ncell, c;
+#define COL(p) ((p) ? (p) + c : NULL)
   for (c = c_begin; c < c_end; c++) {
     double *oc[VR_NFORCING];
     int f, rc;
@@ -763,10 +864,12 @@ int ao_prepare(const vr_atmos_options *o, const vr_atmos_cells *cells, const vr_
     rc = ao_cell(o, cells->lat[c], cells->lng[c], cells->time_zone_lng[c], cells->elevation[c], cells->annual_prec[c],
                  cells->slope ? cells->slope[c] : 0., cells->aspect ? cells->aspect[c] : 0.,
                  cells->ehoriz ? cells->ehoriz[c] : 0., cells->whoriz ? cells->whoriz[c] : 0., C, raw->nrec_forcing,
-                 raw->prec + c, raw->t_a + c, raw->t_b ? raw->t_b + c : NULL, raw->wind ? raw->wind + c : NULL,
-                 raw->shortwave ? raw->shortwave + c : NULL, raw->longwave ? raw->longwave + c : NULL, raw->vp ? raw->vp + c : NULL,
-                 raw->pressure ? raw->pressure + c : NULL, raw->density ? raw->density + c : NULL, oc, NULL);
+                 COL(raw->prec), raw->t_a + c, COL(raw->t_b), COL(raw->wind), COL(raw->shortwave), COL(raw->longwave), COL(raw->vp),
+                 COL(raw->pressure), COL(raw->density), COL(raw->qair), COL(raw->rel_humid), COL(raw->rainf), COL(raw->snowf),
+                 COL(raw->wind_e), COL(raw->wind_n), cells->min_Tfactor ? cells->min_Tfactor[c] : 0., oc, snowflag ? snowflag + c : NULL,
+                 NULL);
     if (rc) return rc;
   }
+#undef COL
   return 0;
 }

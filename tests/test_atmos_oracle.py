@@ -8,22 +8,17 @@ from vicres_b200 import abi
 from common import ATMOS_FIXTURES, load_atmos_fixture
 
 
-# The restatement covers SNOW_STEP == TIME_STEP (NF == 1) and the PREC / TMAX / TMIN / AIR_TEMP / WIND / SHORTWAVE / LONGWAVE /
-# VP / PRESSURE / DENSITY columns.  The sub-stepped fixtures (atmos_daily_snow*, *_snow6) and the ones with QAIR, REL_HUMID
-# or the split RAINF + SNOWF / WIND_E + WIND_N columns pin the device code directly to the reference's records: bit for
-# bit in its host build (test_hostsim_atmos.py), within 1e-9 on the GPU (test_gpu_atmos.py).
-NF1_FIXTURES = [n for n in ATMOS_FIXTURES if not any(k in n for k in ("_snow", "qair", "_rh", "split"))]
-
-
-@pytest.mark.parametrize("name", NF1_FIXTURES)
+@pytest.mark.parametrize("name", ATMOS_FIXTURES)
 def test_restatement_is_bit_identical_to_the_reference(name):
     fx = load_atmos_fixture(name)
-    out = atmos_lib.prepare(fx["opt"], fx["site"], fx["raw"])
+    out, flag = atmos_lib.prepare_sub(fx["opt"], fx["site"], fx["raw"])
     assert out.shape == fx["ref"].shape
     for f, fname in enumerate(abi.FORCING_FIELDS):
         bad = np.argwhere(out[f] != fx["ref"][f])
-        assert bad.size == 0, "%s: %s differs at %d values, first (rec, cell) %s: %r vs %r" % (
+        assert bad.size == 0, "%s: %s differs at %d values, first index %s: %r vs %r" % (
             name, fname, len(bad), bad[0], out[f][tuple(bad[0])], fx["ref"][f][tuple(bad[0])])
+    if fx["snowflag"] is not None:           # SNOW_STEP < TIME_STEP fixtures carry atmos->snowflag[NR]
+        assert np.array_equal(flag, fx["snowflag"])
 
 
 def test_fixture_set_covers_the_branches():

@@ -82,6 +82,35 @@ def test_seeded_grid_matches_oracle_and_batches_are_bit_identical(gpu):
     assert np.array_equal(out, out4)
 
 
+def test_seeded_grid_with_sub_stepped_snow_and_humidity_columns_matches_oracle(gpu):
+    """2 000 cells x 300 days, SNOW_STEP 3 (NF = 8 windows per record + the record), daily REL_HUMID replacing MTCLIM's vapour
+    pressure after the fact, RAINF + SNOWF and WIND_E + WIND_N in place of PREC and WIND, three snow bands' lowest Tfactor:
+    a sample of cells against the oracle, snow flags included"""
+    C, nd = 2000, 300
+    site = synth_soa.make_site(C, seed=31, lat_range=(-50.0, 66.0))
+    raw = synth_soa.make_raw_forcing(site["lat"], site["elevation"], nd, seed=32, cold=6.0)
+    rng = np.random.default_rng(33)
+    cold = raw["t_a"] < 1.0
+    raw["rainf"], raw["snowf"] = np.where(cold, 0.0, raw["prec"]), np.where(cold, raw["prec"], 0.0)
+    ang = rng.uniform(0, 2 * np.pi, raw["wind"].shape)
+    raw["wind_e"], raw["wind_n"] = np.round(raw["wind"] * np.cos(ang), 4), np.round(raw["wind"] * np.sin(ang), 4)
+    raw["prec"] = raw["wind"] = None
+    raw["rel_humid"] = np.round(rng.uniform(15.0, 100.0, raw["t_a"].shape), 2)
+    site["min_Tfactor"] = -rng.uniform(0.0, 4.0, C)
+    opt = atmos.options(time_step=24, nrecs=nd, startyear=1987, snow_step=3, max_snow_temp=0.5)
+    out, flag = gpu.prepare_sub(opt, site, raw)
+    assert out.shape == (9, nd, 9, C) and flag.shape == (nd, C)
+    sample = np.arange(0, C, 53)
+    ssite = {k: v[sample] for k, v in site.items()}
+    sraw = {k: (np.ascontiguousarray(v[:, sample]) if v is not None else None) for k, v in raw.items()}
+    ref, rflag = atmos_lib.prepare_sub(opt, ssite, sraw)
+    o = out[:, :, :, sample]
+    check(o.reshape(9, nd * 9, -1), ref.reshape(9, nd * 9, -1), "seeded 2000 x 300, SNOW_STEP 3 + REL_HUMID + split columns CUDA vs oracle")
+    nflag = int((flag[:, sample] != rflag).sum())
+    print("ATMOS PARITY seeded sub-stepped grid: %d of %d snow flags differ; %.3f of the records flagged" % (nflag, rflag.size, rflag.mean()))
+    assert nflag <= 0.001 * rflag.size and 0.02 < rflag.mean() < 0.9
+
+
 def test_subdaily_grid_matches_oracle(gpu):
     C, nd = 600, 120
     site = synth_soa.make_site(C, seed=31, lat_range=(35.0, 65.0))
