@@ -583,7 +583,10 @@ __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back_list(DevMode
 // terms, which makes the records of a chunk independent; record 0 uses the carried M.sv.  M.sv is double-buffered: the
 // blocks of record 0 read buffer svb while the blocks of the last record write buffer svb ^ 1 (blocks of one grid have
 // no order), the host flips svb per launch.
-__global__ void __launch_bounds__(256) k_cells(DevModel M, DevForcing F, const double *__restrict__ terms,
+#ifndef VR_CELLS_MINB
+#define VR_CELLS_MINB 4     // resident blocks of k_cells the register allocation has to allow: 64 registers, no spill.  The
+#endif                      // kernel waits on its loads (26 % of HBM); 32 warps per SM instead of 8 have more of them in flight
+__global__ void __launch_bounds__(256, VR_CELLS_MINB) k_cells(DevModel M, DevForcing F, const double *__restrict__ terms,
                                                double *__restrict__ out, int svb)
 {
   const int64_t cs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
