@@ -527,28 +527,42 @@ __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back(DevModel M, 
 // k_front / k_back of the other units.  (One launch per record, not a loop over the chunk's records inside the kernel:
 // warps that drift apart in this large code thrash the instruction cache -- measured 495 us against 299 us per record,
 // profiles/r2_tuning.md.)
+// [lo, hi) of the snow list that part `part` of `nparts` handles (parts run on streams of their own so that the blocks
+// of one part's next record can start while another part's slow blocks still run); boundaries on block multiples
+__device__ __forceinline__ void list_part(int n, int part, int nparts, int align, int64_t &lo, int64_t &hi)
+{
+  const int64_t per = (((int64_t)n + nparts - 1) / nparts + align - 1) / align * align;
+  lo = (int64_t)part * per;
+  hi = lo + per;
+  if (lo > n) lo = n;
+  if (hi > n || part == nparts - 1) hi = n;
+}
+
 template <int EXTRAS, bool SUB>
-__global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_snow(DevModel M, DevForcing F, int rec, double *__restrict__ terms)
+__global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_snow(DevModel M, DevForcing F, int rec, double *__restrict__ terms,
+                                                                     int part, int nparts)
 {
   pow_tables_init();
   const int n = M.snow_cnt[0];
   const int mon = __ldg(F.month + rec) - 1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(M.snow_total, (unsigned long long)n);
+  if (part == 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(M.snow_total, (unsigned long long)n);
+  int64_t lo, hi;
+  list_part(n, part, nparts, VR_SNOW_CTA, lo, hi);
 #if VR_SNOW_LOCKSTEP
   // one block per SM whose warps pass the phases of the pass together (block barriers in surface_pass): every
   // instruction-cache line is fetched once for all of them.  Threads past the end of the list shadow its last unit
   // without writing anything, so that all threads of a block reach the barriers.
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t base = lo + (int64_t)blockIdx.x * blockDim.x; base < hi; base += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = base + threadIdx.x;
-    const bool wr = i < n;
-    const int64_t u = M.snow_list[wr ? i : n - 1];
+    const bool wr = i < hi;
+    const int64_t u = M.snow_list[wr ? i : hi - 1];
     CellC cc;
     cc.p = M.ccu + u; cc.C = M.US;
     front_unit<EXTRAS, SUB, true>(M, F, rec, u, M.u_cell[u], M.uflag[u], mon, cc, M.tmu + (size_t)mon * TM_N * M.US + u, M.US, terms,
                                   wr, true);
   }
 #else
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t u = M.snow_list[i];
     CellC cc;
     cc.p = M.ccu + u; cc.C = M.US;
@@ -558,12 +572,15 @@ __global__ void __launch_bounds__(VR_SNOW_CTA, VR_SNOW_MINB) k_snow(DevModel M, 
 }
 
 template <int EXTRAS>
-__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back_list(DevModel M, int rec, double *__restrict__ terms)
+__global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back_list(DevModel M, int rec, double *__restrict__ terms, int part,
+                                                                          int nparts)
 {
   __shared__ double stage[LK_N * VR_BACK_CTA];
   pow_tables_init();
   const int n = M.snow_cnt[0];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  int64_t lo, hi;
+  list_part(n, part, nparts, VR_SNOW_CTA, lo, hi);      // the same cut as k_snow's: a part's units stay on its stream
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t u = M.snow_list[i];
     double *col = stage + threadIdx.x;
 #pragma unroll
@@ -583,6 +600,9 @@ __global__ void __launch_bounds__(VR_BACK_CTA, VR_BACK_MINB) k_back_list(DevMode
 // terms, which makes the records of a chunk independent; record 0 uses the carried M.sv.  M.sv is double-buffered: the
 // blocks of record 0 read buffer svb while the blocks of the last record write buffer svb ^ 1 (blocks of one grid have
 // no order), the host flips svb per launch.
+#ifndef VR_SNOW_PARTS
+#define VR_SNOW_PARTS 1
+#endif
 #ifndef VR_CELLS_MINB
 #define VR_CELLS_MINB 4     // resident blocks of k_cells the register allocation has to allow: 64 registers, no spill.  The
 #endif                      // kernel waits on its loads (26 % of HBM); 32 warps per SM instead of 8 have more of them in flight
@@ -742,6 +762,9 @@ struct vr_handle {
   int na = 1;                        // slot ranges of the non-snow class that run side by side (VICRES_A_STREAMS, 1..4)
   cudaStream_t s_a[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_a[3] = {nullptr, nullptr, nullptr};
+  int snow_parts = 1;                // VICRES_SNOW_PARTS: the snow list in this many parts on streams of their own (<= 4)
+  cudaStream_t s_sp[3] = {};
+  cudaEvent_t ev_sp[3] = {};
   bool snow_stream = true;           // k_snow on its own stream (VICRES_SNOW_STREAM=0: on the step stream, for A/B timing)
   bool detail = false;               // VICRES_TIME_KERNELS=1: CUDA events around every step kernel (vr_step_diag)
   std::vector<cudaEvent_t> dev;      // 6 per record: around k_front and k_back on the step stream, around k_snow on the snow stream
@@ -794,12 +817,18 @@ static void launch_record(vr_handle *h, const DevForcing &F, int rec, double *te
   if (e) cudaEventRecord(e[2], st);
   (void)gf;
   if (e) cudaEventRecord(e[3], ss);
-  if (h->M.NF > 1) k_snow<EX, true><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
-  else k_snow<EX, false><<<(unsigned)gs, VR_SNOW_CTA, 0, ss>>>(h->M, F, rec, terms);
   int64_t gl = gb;
   if (gl > (int64_t)h->sms * VR_BACK_MINB * 4) gl = (int64_t)h->sms * VR_BACK_MINB * 4;
-  if (e) cudaEventRecord(e[5], ss);
-  k_back_list<EX & EX_ZWT><<<(unsigned)gl, VR_BACK_CTA, 0, ss>>>(h->M, rec, terms);
+  // the snow class in h->snow_parts parts of its list, each k_snow -> k_back_list sequence on a stream of its own
+  const int np = h->snow_parts;
+  const unsigned gsp = (unsigned)((gs + np - 1) / np), glp = (unsigned)((gl + np - 1) / np);
+  for (int p = 0; p < np; p++) {
+    cudaStream_t sp = p == 0 ? ss : h->s_sp[p - 1];
+    if (h->M.NF > 1) k_snow<EX, true><<<gsp, VR_SNOW_CTA, 0, sp>>>(h->M, F, rec, terms, p, np);
+    else k_snow<EX, false><<<gsp, VR_SNOW_CTA, 0, sp>>>(h->M, F, rec, terms, p, np);
+    if (e && p == 0) cudaEventRecord(e[5], ss);
+    k_back_list<EX & EX_ZWT><<<glp, VR_BACK_CTA, 0, sp>>>(h->M, rec, terms, p, np);
+  }
   if (e) cudaEventRecord(e[4], ss);
   h->diag_unit_records += U;
 }
@@ -890,6 +919,12 @@ int vr_create(const vr_options *opt, int device, vr_handle **out)
   if (opt->cells_per_block_hint > 0) h->chunk = opt->cells_per_block_hint;
   { const char *d = getenv("VICRES_TIME_KERNELS"); h->detail = d && d[0] == '1'; }
   { const char *d = getenv("VICRES_SNOW_STREAM"); h->snow_stream = !(d && d[0] == '0'); }
+  { const char *d = getenv("VICRES_SNOW_PARTS"); int n = d ? atoi(d) : VR_SNOW_PARTS; h->snow_parts = n < 1 ? 1 : (n > 4 ? 4 : n); }
+  if (!h->snow_stream) h->snow_parts = 1;
+  for (int p = 1; p < h->snow_parts; p++) {
+    cudaStreamCreateWithFlags(&h->s_sp[p - 1], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_sp[p - 1], cudaEventDisableTiming);
+  }
   { const char *d = getenv("VICRES_A_STREAMS"); h->na = (d && d[0] >= '1' && d[0] <= '4') ? d[0] - '0' : VR_A_STREAMS; }
   for (int a = 0; a < 3; a++) {
     cudaStreamCreateWithFlags(&h->s_a[a], cudaStreamNonBlocking);
@@ -918,6 +953,10 @@ void vr_destroy(vr_handle *h)
   for (auto &t : h->evs) { cudaEventDestroy(t.u0); cudaEventDestroy(t.u1); cudaEventDestroy(t.c0); cudaEventDestroy(t.c1); }
   if (h->s_cells) cudaStreamDestroy(h->s_cells);
   if (h->s_snow) cudaStreamDestroy(h->s_snow);
+  for (int p = 0; p < 3; p++) {
+    if (h->s_sp[p]) cudaStreamDestroy(h->s_sp[p]);
+    if (h->ev_sp[p]) cudaEventDestroy(h->ev_sp[p]);
+  }
   for (int a = 0; a < 3; a++) {
     if (h->s_a[a]) cudaStreamDestroy(h->s_a[a]);
     if (h->ev_a[a]) cudaEventDestroy(h->ev_a[a]);
@@ -1163,6 +1202,7 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
       k_classify<<<(unsigned)((h->M.U + 255) / 256), 256, 0, st>>>(h->M, F);
       cudaEventRecord(h->ev_cls, st);
       cudaStreamWaitEvent(ss, h->ev_cls, 0);           // the snow stream starts when the chunk's classes are known
+      for (int p = 1; p < h->snow_parts; p++) cudaStreamWaitEvent(h->s_sp[p - 1], h->ev_cls, 0);
       for (int a = 1; a < h->na; a++) cudaStreamWaitEvent(h->s_a[a - 1], h->ev_cls, 0);
       h->launches += 2;
       for (int rec = 0; rec < F.nrec; rec++) {
@@ -1172,10 +1212,14 @@ static int launch_step(vr_handle *h, const DevForcing &F0, double *out_dev, cuda
           case EX_ZWT: launch_record<EX_ZWT>(h, F, rec, terms, st, ss); break;
           default: launch_record<EX_PET | EX_ZWT>(h, F, rec, terms, st, ss); break;
         }
-        h->launches += 4;
+        h->launches += 2 + 2 * h->snow_parts;
       }
       cudaEventRecord(h->ev_snow, ss);
       cudaStreamWaitEvent(st, h->ev_snow, 0);          // both classes have finished the chunk
+      for (int p = 1; p < h->snow_parts; p++) {
+        cudaEventRecord(h->ev_sp[p - 1], h->s_sp[p - 1]);
+        cudaStreamWaitEvent(st, h->ev_sp[p - 1], 0);
+      }
       for (int a = 1; a < h->na; a++) {
         cudaEventRecord(h->ev_a[a - 1], h->s_a[a - 1]);
         cudaStreamWaitEvent(st, h->ev_a[a - 1], 0);
