@@ -745,6 +745,26 @@ static void next_step(int &year, int &month, int &day, int &hr, int &jday, int d
   }
 }
 
+// Options that change the results (physics or file contents) and of which this library implements the reference's default
+// only (initialize_global.c:146-211; parsed at get_global_param.c:230-720): key, the accepted values.
+static bool other_option_unsupported(const char *key, const char *val)
+{
+  static const struct { const char *key, *ok1, *ok2; } T[] = {
+    {"ALMA_OUTPUT", "FALSE", nullptr}, {"MOISTFRACT", "FALSE", nullptr}, {"PRT_HEADER", "FALSE", nullptr},
+    {"PRT_SNOW_BAND", "FALSE", nullptr}, {"OUTPUT_FORCE", "FALSE", nullptr}, {"BASEFLOW", "ARNO", nullptr},
+    {"ARC_SOIL", "FALSE", nullptr}, {"AERO_RESIST_CANSNOW", "AR_406_FULL", nullptr}, {"SNOW_ALBEDO", "USACE", nullptr},
+    {"SNOW_DENSITY", "DENS_BRAS", nullptr}, {"GRND_FLUX_TYPE", "GF_410", nullptr}, {"QUICK_FLUX", "TRUE", nullptr},
+    {"TFALLBACK", "TRUE", nullptr}, {"SPATIAL_SNOW", "FALSE", nullptr}, {"SPATIAL_FROST", "FALSE", nullptr},
+    {"RC_MODE", "RC_JARVIS", nullptr}, {"SHARE_LAYER_MOIST", "TRUE", nullptr}, {"VEGLIB_VEGCOVER", "FALSE", nullptr},
+    {"VEGLIB_PHOTO", "FALSE", nullptr}, {"VEGPARAM_ALB", "FALSE", nullptr}, {"VEGPARAM_VEGCOVER", "FALSE", nullptr},
+    {"ALB_SRC", "FROM_VEGLIB", "ALB_FROM_VEGLIB"}, {"VEGCOVER_SRC", "FROM_VEGLIB", "VEGCOVER_FROM_VEGLIB"},
+    {"CLOSE_ENERGY", "FALSE", nullptr}, {"LAKE_PROFILE", "FALSE", nullptr}, {"CONTINUEONERROR", "TRUE", nullptr},
+  };
+  for (const auto &e : T)
+    if (!strcasecmp(key, e.key)) return strcasecmp(val, e.ok1) != 0 && !(e.ok2 && strcasecmp(val, e.ok2) == 0);
+  return false;
+}
+
 int vr_global_read(const char *path, vr_global *g)
 {
   if (!path || !g) { g_err = "null argument"; return VR_ERR_ARG; }
@@ -838,6 +858,9 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
     else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
     else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }
+    else if (other_option_unsupported(k, t.size() > 1 ? t[1].c_str() : "")) {
+      if (!g->other_unsupported[0]) snprintf(g->other_unsupported, sizeof g->other_unsupported, "%s %s", k, t.size() > 1 ? t[1].c_str() : "");
+    }
     else if (!strcasecmp(k, "FORCING2")) {     // a second forcing file is not read by this library (vr_global_unsupported names it)
       file_num = 1;
       g->forcing2 = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0 && strcasecmp(t[1].c_str(), "MISSING") != 0);
@@ -904,6 +927,7 @@ const char *vr_global_unsupported(const vr_global *g)
     return "SNOW_STEP should be <= TIME_STEP and divide TIME_STEP evenly";
   if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
   if (g->forcing2) return "FORCING2 (a second forcing file)";
+  if (g->other_unsupported[0]) return g->other_unsupported;
   if (g->out_step > 0 && (g->out_step < g->time_step || g->out_step % g->time_step || g->out_step > 24))
     return "OUT_STEP must be a multiple of TIME_STEP and at most 24 (get_global_param.c:754-760)";
   return nullptr;

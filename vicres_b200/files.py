@@ -149,7 +149,8 @@ class GlobalC(C.Structure):
                                           "vp_interp", "vp_iter", "mtclim_swe_corr", "lw_type", "lw_cloud", "plapse")] +
                 [("sw_prec_thresh", C.c_double), ("init_state_file", C.c_char * 512), ("statename", C.c_char * 512)] +
                 [(n, C.c_int32) for n in ("stateyear", "statemonth", "stateday", "binary_state_file",
-                                          "forcing2", "n_outfile_lines", "n_outvar_lines")])
+                                          "forcing2", "n_outfile_lines", "n_outvar_lines")] +
+                [("other_unsupported", C.c_char * 96)])
 
 
 FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip", "vr_read_forcing_file"]
