@@ -139,7 +139,8 @@ int main(int argc, char **argv)
   static vr_outsel sel;
   if (vr_outsel_read(gfile, g.nlayer, &sel) != VR_OK) die("output selection", vr_params_last_error());
   const int ratio = g.out_step > 0 ? g.out_step / g.time_step : 1;
-  if (vr_outsel_step_vars(&sel, ratio > 1, opt.out_vars, &opt.n_out) != VR_OK) die("output selection", vr_params_last_error());
+  if (vr_outsel_step_vars(&sel, (ratio > 1 ? 1 : 0) | (g.alma_output ? 2 : 0), opt.out_vars, &opt.n_out) != VR_OK)
+    die("output selection", vr_params_last_error());
   opt.nbands = g.snow_band; opt.dt_hours = g.time_step; opt.snow_step_hours = g.snow_step;
   opt.max_snow_temp = g.max_snow_temp; opt.min_rain_temp = g.min_rain_temp; opt.wind_h = g.wind_h;
   vr_handle *h = NULL;
@@ -205,6 +206,17 @@ int main(int argc, char **argv)
       day[i] = day[i * ratio + ratio - 1]; hour[i] = hour[i * ratio + ratio - 1];
     }
   }
+  const int out_dt = g.out_step > 0 ? g.out_step : g.time_step;
+  if (g.alma_output && vr_alma_output(device, n_rows, agg_vars, nout, C, out_dt, out) != VR_OK)      /* put_data.c:697-760 */
+    die("vr_alma_output", vr_last_error(NULL));
+  if (g.prt_header) {      /* write_header.c: the run's record count and the date of the first MODEL record */
+    int32_t y0, m0, d0, h0, j0;
+    vr_global g1 = g;
+    g1.nrecs = 1;
+    vr_make_dmy(&g1, &y0, &m0, &d0, &h0, &j0);
+    sel.header = 1; sel.hdr_nrecs = nrecs; sel.hdr_out_dt = out_dt; sel.hdr_alma = g.alma_output;
+    sel.hdr_start[0] = y0; sel.hdr_start[1] = m0; sel.hdr_start[2] = d0; sel.hdr_start[3] = h0;
+  }
   /* SKIPYEAR: an output record is written when its last model record is past the skipped years (put_data.c:765) */
   {
     int32_t *year_all = malloc(sizeof(int32_t) * nrecs), *t1 = malloc(sizeof(int32_t) * nrecs), *t2 = malloc(sizeof(int32_t) * nrecs),
@@ -224,7 +236,6 @@ int main(int argc, char **argv)
     free(year_all); free(t1); free(t2); free(t3); free(t4);
   }
   /* write_data.c */
-  const int out_dt = g.out_step > 0 ? g.out_step : g.time_step;
   for (fi = 0; fi < sel.nfiles; fi++) {
     int32_t rows[VR_MAX_OUTCOLS];
     for (k = 0; k < sel.ncols[fi]; k++) {

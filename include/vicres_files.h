@@ -68,21 +68,36 @@ typedef struct vr_outsel {
   char    format[VR_MAX_OUTFILES][VR_MAX_OUTCOLS][12];   /* printf format of the ASCII column ("%.4f")          */
   int32_t type[VR_MAX_OUTFILES][VR_MAX_OUTCOLS];         /* binary type (OUT_TYPE_FLOAT unless the OUTVAR line says otherwise) */
   double  mult[VR_MAX_OUTFILES][VR_MAX_OUTCOLS];         /* binary multiplier                                   */
+  /* PRT_HEADER (write_header.c): the column's name as the header prints it (the reference's variable name, "_<element>"
+   * appended when the variable has several), the number of VARIABLES of the file, and what the caller fills in before
+   * vr_write_results_sel when the files are to carry the header: header != 0, the run's record count and OUT_STEP in hours,
+   * the date of the FIRST MODEL RECORD (year, month, day, hour), ALMA_OUTPUT */
+  char    name[VR_MAX_OUTFILES][VR_MAX_OUTCOLS][32];
+  int32_t nvars[VR_MAX_OUTFILES];
+  int32_t header, hdr_nrecs, hdr_out_dt, hdr_start[4], hdr_alma;
 } vr_outsel;
 /* N_OUTFILES / OUTFILE / OUTVAR lines of a global parameter file; without them the default pair "fluxes" (20 variables,
  * 20 + nlayer - 1 columns) and "snow" (4) of set_output_defaults.c:66-162.  An unknown variable name is an error, as in
  * the reference (set_output_var). */
 int  vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *out);
 /* the VR_OUT_* ids the step must produce for a selection, each once, in order of first appearance: vars[VR_MAX_OUT].
- * With aggregate != 0 (OUT_STEP > TIME_STEP) OUT_AERO_RESIST is produced as OUT_AERO_COND, because the reference
- * aggregates the conductance and inverts the aggregate (put_data.c:686-688). */
-int  vr_outsel_step_vars(const vr_outsel *s, int32_t aggregate, int32_t *vars, int32_t *n);
+ * mode bit 0 (OUT_STEP > TIME_STEP): OUT_AERO_RESIST is produced as OUT_AERO_COND, because the reference aggregates the
+ * conductance and inverts the aggregate (put_data.c:686-688); mode bit 1 (ALMA_OUTPUT): OUT_SUB_CANOP is produced whenever
+ * OUT_SUB_SNOW is asked for, because the ALMA value of the latter includes the former (put_data.c:742). */
+int  vr_outsel_step_vars(const vr_outsel *s, int32_t mode, int32_t *vars, int32_t *n);
 /* Temporal aggregation of put_data.c:665-685 on the device: in_dev [n][nrec][ncell] (device) -> out_dev [n][nrec/ratio][ncell]
  * (device; may alias nothing), ratio = OUT_STEP / TIME_STEP records per output interval, vars[n] = the VR_OUT_* ids of the
  * rows (a row that holds AERO_COND for a requested AERO_RESIST is passed as VR_OUT_AERO_RESIST with cond_for_resist != 0):
  * fluxes are summed, storages take the interval's last record, the rest is averaged as sum of x / ratio, in record order. */
 int  vr_aggregate_device(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio,
                          int64_t ncell, const double *in_dev, double *out_dev, void *cuda_stream);
+/* ALMA_OUTPUT (put_data.c:697-760), in place on [n][nrec][ncell] device values that are already aggregated to OUT_STEP =
+ * out_dt_hours: moisture fluxes become rates (/ seconds of the interval), temperatures Kelvin, OUT_DELTAH * seconds, and
+ * OUT_SUB_SNOW gets OUT_SUB_CANOP added (which therefore has to be one of the rows). */
+int  vr_alma_output_device(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours,
+                           double *data_dev, void *cuda_stream);
+/* the same on a host buffer (copy in, kernel, copy out) */
+int  vr_alma_output(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours, double *data);
 /* the same with host buffers (copies in, kernel, copies out) */
 int  vr_aggregate(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio, int64_t ncell,
                   const double *in, double *out);
@@ -127,9 +142,10 @@ typedef struct vr_global {
    * parse_output_info.c:62-118; counted here, parsed by vr_outsel_read) */
   int32_t forcing2, n_outfile_lines, n_outvar_lines;
   /* the first option of the file that changes the results and has a value this library does not implement ("KEY VALUE":
-   * ALMA_OUTPUT, MOISTFRACT, PRT_HEADER, PRT_SNOW_BAND, OUTPUT_FORCE, BASEFLOW NIJSSEN2001, SNOW_ALBEDO, SNOW_DENSITY,
+   * MOISTFRACT, PRT_SNOW_BAND, OUTPUT_FORCE, BASEFLOW NIJSSEN2001, SNOW_ALBEDO, SNOW_DENSITY,
    * AERO_RESIST_CANSNOW, GRND_FLUX_TYPE, SPATIAL_SNOW ...), or empty: named by vr_global_unsupported, never ignored */
   char    other_unsupported[96];
+  int32_t prt_header, alma_output;                 /* PRT_HEADER, ALMA_OUTPUT                                   */
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -26,7 +26,7 @@ def _stage(name, tmp_path, variant=None):
 
 # variants of the two cases: output interval, output selection, binary files (tools/make_vicnl_golden.py: VARIANTS)
 VARIANTS = [("sub3h", "out24"), ("sub3h", "out6sel"), ("daily", "selday"), ("sub3h", "bin"), ("sub3h", "bin24sel"),
-            ("daily", "snow3"), ("skip", "snow1")]
+            ("daily", "snow3"), ("skip", "snow1"), ("daily", "hdr"), ("sub3h", "hdrbin24"), ("sub3h", "alma6"), ("daily", "almadef")]
 
 
 def _quantum(tok):
@@ -60,7 +60,7 @@ def _compare_ascii(res, ref, what):
     assert nbad <= 0.01 * ntot
 
 
-def _compare_binary(res, ref, gpath, nlayer, hourly, what):
+def _compare_binary(res, ref, gpath, nlayer, hourly, what, header=False):
     """BINARY_OUTPUT files: same size, same dates; integer columns within one count (the cast truncates), floats within
     fp32 rounding of the parity tolerance"""
     sel = files.OutSel(gpath, nlayer)
@@ -69,8 +69,11 @@ def _compare_binary(res, ref, gpath, nlayer, hourly, what):
     for prefix, cols in sel.files:
         for n in sorted(x for x in os.listdir(ref) if x.startswith(prefix + "_")):
             assert os.path.getsize(os.path.join(res, n)) == os.path.getsize(os.path.join(ref, n)), n
-            da, a = files.read_binary_results(os.path.join(res, n), cols, hourly)
-            db, b = files.read_binary_results(os.path.join(ref, n), cols, hourly)
+            da, a = files.read_binary_results(os.path.join(res, n), cols, hourly, header)
+            db, b = files.read_binary_results(os.path.join(ref, n), cols, hourly, header)
+            if header:       # PRT_HEADER: the block before the records, byte for byte
+                nb = int(np.fromfile(os.path.join(ref, n), dtype="<u2", count=5)[4])
+                assert open(os.path.join(res, n), "rb").read(nb) == open(os.path.join(ref, n), "rb").read(nb), n
             assert np.array_equal(da, db), n
             for k, c in enumerate(cols):
                 tol = 1.0001 / c[3] if c[2] in ("SINT", "USINT", "INT", "CHAR") else 1e-4 + 1e-5 * np.abs(b[k])
@@ -83,8 +86,8 @@ def _compare_binary(res, ref, gpath, nlayer, hourly, what):
 
 
 def _compare_variant(case, variant, gpath, res, ref, what):
-    if variant.startswith("bin"):
-        _compare_binary(res, ref, gpath, 3, variant == "bin", what)
+    if "bin" in variant:
+        _compare_binary(res, ref, gpath, 3, variant == "bin", what, header=variant.startswith("hdr"))
     else:
         _compare_ascii(res, ref, what)
 
@@ -98,7 +101,11 @@ def test_output_selection_of_the_variants_parses(case, variant, tmp_path):
     sel = files.OutSel(gpath, g.nlayer)
     fl = dict(sel.files)
     assert sorted(set(n.split("_")[0] for n in os.listdir(ref))) == sorted(fl)
-    assert bool(g.binary_output) == variant.startswith("bin")
+    assert bool(g.binary_output) == ("bin" in variant)
+    assert bool(g.prt_header) == (variant in ("hdr", "hdrbin24", "alma6")) and bool(g.alma_output) == variant.startswith("alma")
+    if variant == "alma6":
+        assert "SUB_CANOP" not in sel.step_vars() and sel.step_vars(alma=True)[-1] == "SUB_CANOP"
+        assert [c[0] for c in fl["al"]][4] == "SUB_SNOW"
     if variant.startswith("snow"):
         assert g.snow_step == int(variant[4:]) and g.time_step == 24
     if variant in ("out24", "bin"):

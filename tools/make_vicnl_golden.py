@@ -41,6 +41,16 @@ VARIANTS = {
     # the snow model sub-stepped (NF = 8 and NF = 24 passes per daily record): initialize_atmos's per-window values and snow flags
     "snow3": ("daily", ["SNOW_STEP 3"]),
     "snow1": ("skip", ["SNOW_STEP 1"]),
+    # PRT_HEADER (write_header.c), ASCII and binary; ALMA_OUTPUT units (rates, Kelvin; OUT_SUB_SNOW includes OUT_SUB_CANOP)
+    "hdr": ("daily", ["PRT_HEADER TRUE"]),
+    "hdrbin24": ("sub3h", ["PRT_HEADER TRUE", "BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE hb 5",
+                           "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_SOIL_MOIST %.4f OUT_TYPE_FLOAT 1",
+                           "OUTVAR OUT_SWE %.4f OUT_TYPE_DOUBLE *", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100", "OUTVAR OUT_RUNOFF"]),
+    "alma6": ("sub3h", ["ALMA_OUTPUT TRUE", "PRT_HEADER TRUE", "OUT_STEP 6", "N_OUTFILES 1", "OUTFILE al 10",
+                        "OUTVAR OUT_PREC %.6e", "OUTVAR OUT_EVAP %.6e", "OUTVAR OUT_RUNOFF %.6e", "OUTVAR OUT_BASEFLOW %.6e",
+                        "OUTVAR OUT_SUB_SNOW %.6e", "OUTVAR OUT_SNOW_MELT %.6e", "OUTVAR OUT_SURF_TEMP", "OUTVAR OUT_AIR_TEMP",
+                        "OUTVAR OUT_DELTAH %.5e", "OUTVAR OUT_SWE"]),
+    "almadef": ("daily", ["ALMA_OUTPUT TRUE"]),
     "bin": ("sub3h", ["BINARY_OUTPUT TRUE"]),
     "bin24sel": ("sub3h", ["BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE packed 6",
                            "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100",

@@ -667,6 +667,30 @@ __global__ void k_aggregate(int n, const int *__restrict__ kind, int nrec, int r
   out[((size_t)v * nout + o) * C + c] = a;
 }
 
+// ALMA_OUTPUT (put_data.c:697-760) on aggregated values, in place: op 1 = / seconds, 2 = + KELVIN, 3 = * seconds; op 4
+// (OUT_SUB_SNOW: / seconds, then + the converted OUT_SUB_CANOP, :741-742) is left to k_alma_add, launched after this
+// kernel so that it reads the companion row converted.  Thread per (cell, record, variable).
+__global__ void k_alma(int n, const int *__restrict__ op, const int *__restrict__ aux, int nrec, int64_t C, double sec, double *__restrict__ d)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y, v = blockIdx.z;
+  if (c >= C) return;
+  const size_t i = ((size_t)v * nrec + r) * C + c;
+  const int k = op[v];
+  if (k == 1) d[i] = d[i] / sec;
+  else if (k == 2) d[i] = d[i] + 273.15;
+  else if (k == 3) d[i] = d[i] * sec;
+}
+__global__ void k_alma_add(int v, int aux, int nrec, int64_t C, double sec, double *__restrict__ d)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= C) return;
+  const size_t i = ((size_t)v * nrec + r) * C + c, j = ((size_t)aux * nrec + r) * C + c;
+  d[i] = d[i] / sec;
+  d[i] = d[i] + d[j];
+}
+
 // diagnostic: the device power function on arbitrary arguments (tests/test_gpu_parity.py checks its error bound)
 __global__ void k_diag_pow(int64_t n, const double *x, const double *y, double *z)
 {
@@ -1774,6 +1798,56 @@ int vr_aggregate_device(int device, int32_t n, const int32_t *vars, int32_t cond
   cudaStreamSynchronize(st);
   cudaFree(d_kind);
   return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
+}
+
+int vr_alma_output_device(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours, double *data_dev,
+                          void *cuda_stream)
+{
+  if (!vars || !data_dev || n < 1 || n > VR_MAX_OUT || nrec < 1 || ncell < 1 || out_dt_hours < 1) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  int op[VR_MAX_OUT], aux[VR_MAX_OUT], sub_snow = -1, sub_canop = -1;
+  for (int v = 0; v < n; v++) {
+    aux[v] = -1;
+    switch (vars[v]) {
+      case VR_OUT_BASEFLOW: case VR_OUT_EVAP: case VR_OUT_EVAP_BARE: case VR_OUT_EVAP_CANOP: case VR_OUT_INFLOW: case VR_OUT_PREC:
+      case VR_OUT_RAINF: case VR_OUT_RUNOFF: case VR_OUT_SNOW_MELT: case VR_OUT_SNOWF: case VR_OUT_SUB_CANOP: case VR_OUT_TRANSP_VEG:
+        op[v] = 1; break;
+      case VR_OUT_SNOW_PACK_TEMP: case VR_OUT_SNOW_SURF_TEMP: case VR_OUT_SURF_TEMP: case VR_OUT_AIR_TEMP: op[v] = 2; break;
+      case VR_OUT_DELTAH: op[v] = 3; break;
+      case VR_OUT_SUB_SNOW: op[v] = 4; sub_snow = v; break;
+      default: op[v] = 0;
+    }
+    if (vars[v] == VR_OUT_SUB_CANOP) sub_canop = v;
+  }
+  if (sub_snow >= 0 && sub_canop < 0) return VR_ERR_ARG;       // vr_outsel_step_vars(mode & 2) puts it there
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int *d_op = nullptr;
+  if (cudaMalloc((void **)&d_op, 2 * n * sizeof(int)) != cudaSuccess) return VR_ERR_CUDA;
+  cudaMemcpyAsync(d_op, op, n * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_op + n, aux, n * sizeof(int), cudaMemcpyHostToDevice, st);
+  const double sec = (double)(out_dt_hours * 3600);
+  const dim3 grid((unsigned)((ncell + 255) / 256), (unsigned)nrec, (unsigned)n);
+  k_alma<<<grid, 256, 0, st>>>(n, d_op, d_op + n, nrec, ncell, sec, data_dev);
+  if (sub_snow >= 0)
+    k_alma_add<<<dim3(grid.x, grid.y), 256, 0, st>>>(sub_snow, sub_canop, nrec, ncell, sec, data_dev);
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(st);
+  cudaFree(d_op);
+  return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
+}
+
+int vr_alma_output(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours, double *data)
+{
+  if (!data || n < 1 || nrec < 1 || ncell < 1) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  double *d = nullptr;
+  const size_t bytes = (size_t)n * nrec * ncell * sizeof(double);
+  if (cudaMalloc((void **)&d, bytes) != cudaSuccess) return VR_ERR_CUDA;
+  cudaMemcpy(d, data, bytes, cudaMemcpyHostToDevice);
+  const int rc = vr_alma_output_device(device, n, vars, nrec, ncell, out_dt_hours, d, nullptr);
+  if (rc == VR_OK) cudaMemcpy(data, d, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
 }
 
 int vr_aggregate(int device, int32_t n, const int32_t *vars, int32_t cond_for_resist, int32_t nrec, int32_t ratio, int64_t ncell,

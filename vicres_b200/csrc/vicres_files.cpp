@@ -591,9 +591,12 @@ bool outsel_add(vr_outsel *s, int f, const char *name, const char *format, int t
         if (type) s->type[ff][c] = type;
         if (mult != 0) s->mult[ff][c] = mult;
       }
+  s->nvars[f]++;
   for (int e = 0; e < ne; e++) {
     int &n = s->ncols[f];
     if (n >= VR_MAX_OUTCOLS) { g_err = "too many output columns in one file"; return false; }
+    if (ne > 1) snprintf(s->name[f][n], 32, "%s_%d", name, e);      // write_header.c:219-222
+    else snprintf(s->name[f][n], 32, "%s", name);
     s->var[f][n] = o->id + e;
     snprintf(s->format[f][n], 12, "%s", strcmp(format, "*") ? format : "%.4f");
     s->type[f][n] = type ? type : VR_OUT_TYPE_FLOAT;
@@ -665,9 +668,10 @@ int vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *s)
   return VR_OK;
 }
 
-int vr_outsel_step_vars(const vr_outsel *s, int32_t aggregate, int32_t *vars, int32_t *n)
+int vr_outsel_step_vars(const vr_outsel *s, int32_t mode, int32_t *vars, int32_t *n)
 {
   if (!s || !vars || !n) { g_err = "null argument"; return VR_ERR_ARG; }
+  const int aggregate = mode & 1, alma = mode & 2;
   *n = 0;
   for (int f = 0; f < s->nfiles; f++)
     for (int c = 0; c < s->ncols[f]; c++) {
@@ -679,6 +683,14 @@ int vr_outsel_step_vars(const vr_outsel *s, int32_t aggregate, int32_t *vars, in
       if (*n >= VR_MAX_OUT) { g_err = "more than VR_MAX_OUT distinct output columns"; return VR_ERR_ARG; }
       vars[(*n)++] = v;
     }
+  if (alma) {           // OUT_SUB_SNOW's ALMA value includes OUT_SUB_CANOP (put_data.c:742)
+    bool snow = false, canop = false;
+    for (int k = 0; k < *n; k++) { snow = snow || vars[k] == VR_OUT_SUB_SNOW; canop = canop || vars[k] == VR_OUT_SUB_CANOP; }
+    if (snow && !canop) {
+      if (*n >= VR_MAX_OUT) { g_err = "more than VR_MAX_OUT distinct output columns"; return VR_ERR_ARG; }
+      vars[(*n)++] = VR_OUT_SUB_CANOP;
+    }
+  }
   return VR_OK;
 }
 
@@ -698,6 +710,39 @@ int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t fil
     snprintf(name, sizeof name, fmt, result_dir, s->prefix[file], lat[c], lng[c]);
     FILE *f = fopen(name, binary ? "wb" : "w");
     if (!f) { g_err = std::string("cannot create ") + name; return VR_ERR_ARG; }
+    if (s->header) {      // PRT_HEADER, write_header.c:46-307
+      const int ndate = hour ? 4 : 3;
+      if (binary) {
+        static const char *DATE[4] = {"YEAR", "MONTH", "DAY", "HOUR"};
+        unsigned short id = 0xFFFF, nb1 = sizeof(unsigned short) + 6 * sizeof(int) + 2, nb2 = sizeof(unsigned short);
+        for (int k = 0; k < ndate; k++) nb2 += 1 + strlen(DATE[k]) + 1 + sizeof(float);
+        for (int v = 0; v < nc; v++) nb2 += 1 + strlen(s->name[file][v]) + 1 + sizeof(float);
+        const unsigned short nb = 4 * sizeof(unsigned short) + sizeof(unsigned short) + nb1 + nb2;
+        for (int k = 0; k < 4; k++) fwrite(&id, sizeof id, 1, f);
+        fwrite(&nb, sizeof nb, 1, f);
+        fwrite(&nb1, sizeof nb1, 1, f);
+        const int gl[6] = {s->hdr_nrecs, s->hdr_out_dt, s->hdr_start[0], s->hdr_start[1], s->hdr_start[2], s->hdr_start[3]};
+        fwrite(gl, sizeof(int), 6, f);
+        const char alma = s->hdr_alma ? 1 : 0, nvars = (char)(s->nvars[file] + ndate);
+        fwrite(&alma, 1, 1, f);
+        fwrite(&nvars, 1, 1, f);
+        fwrite(&nb2, sizeof nb2, 1, f);
+        auto var = [&](const char *nm, char type, float mult) {
+          const char len = (char)strlen(nm);
+          fwrite(&len, 1, 1, f); fwrite(nm, 1, len, f); fwrite(&type, 1, 1, f); fwrite(&mult, sizeof(float), 1, f);
+        };
+        for (int k = 0; k < ndate; k++) var(DATE[k], (char)VR_OUT_TYPE_INT, 1.f);
+        for (int v = 0; v < nc; v++) var(s->name[file][v], (char)s->type[file][v], (float)s->mult[file][v]);
+      }
+      else {
+        fprintf(f, "# NRECS: %d\n# DT: %d\n# STARTDATE: %04d-%02d-%02d %02d:00:00\n# ALMA_OUTPUT: %d\n# NVARS: %d\n# ", s->hdr_nrecs,
+                s->hdr_out_dt, s->hdr_start[0], s->hdr_start[1], s->hdr_start[2], s->hdr_start[3], s->hdr_alma ? 1 : 0,
+                s->nvars[file] + ndate);
+        fprintf(f, hour ? "YEAR\tMONTH\tDAY\tHOUR\t" : "YEAR\tMONTH\tDAY\t");
+        for (int v = 0; v < nc; v++) fprintf(f, "%s%s", v ? "\t " : "", s->name[file][v]);
+        fprintf(f, "\n");
+      }
+    }
     for (int r = 0; r < nrec; r++) {
       if (binary) {       // write_data.c:103-193
         const int date[4] = {year[r], month[r], day[r], hour ? hour[r] : 0};
@@ -750,7 +795,7 @@ static void next_step(int &year, int &month, int &day, int &hr, int &jday, int d
 static bool other_option_unsupported(const char *key, const char *val)
 {
   static const struct { const char *key, *ok1, *ok2; } T[] = {
-    {"ALMA_OUTPUT", "FALSE", nullptr}, {"MOISTFRACT", "FALSE", nullptr}, {"PRT_HEADER", "FALSE", nullptr},
+    {"MOISTFRACT", "FALSE", nullptr},
     {"PRT_SNOW_BAND", "FALSE", nullptr}, {"OUTPUT_FORCE", "FALSE", nullptr}, {"BASEFLOW", "ARNO", nullptr},
     {"ARC_SOIL", "FALSE", nullptr}, {"AERO_RESIST_CANSNOW", "AR_406_FULL", nullptr}, {"SNOW_ALBEDO", "USACE", nullptr},
     {"SNOW_DENSITY", "DENS_BRAS", nullptr}, {"GRND_FLUX_TYPE", "GF_410", nullptr}, {"QUICK_FLUX", "TRUE", nullptr},
@@ -855,6 +900,8 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "OUT_STEP")) g->out_step = I();
     else if (!strcasecmp(k, "BINARY_OUTPUT")) g->binary_output = flag(t);
     else if (!strcasecmp(k, "COMPRESS")) g->compress = flag(t);
+    else if (!strcasecmp(k, "PRT_HEADER")) g->prt_header = flag(t);
+    else if (!strcasecmp(k, "ALMA_OUTPUT")) g->alma_output = flag(t);
     else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
     else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
     else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }

@@ -150,7 +150,7 @@ class GlobalC(C.Structure):
                 [("sw_prec_thresh", C.c_double), ("init_state_file", C.c_char * 512), ("statename", C.c_char * 512)] +
                 [(n, C.c_int32) for n in ("stateyear", "statemonth", "stateday", "binary_state_file",
                                           "forcing2", "n_outfile_lines", "n_outvar_lines")] +
-                [("other_unsupported", C.c_char * 96)])
+                [("other_unsupported", C.c_char * 96), ("prt_header", C.c_int32), ("alma_output", C.c_int32)])
 
 
 FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip", "vr_read_forcing_file"]
@@ -234,10 +234,14 @@ class OutSelC(C.Structure):
                 ("var", (C.c_int32 * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
                 ("format", ((C.c_char * 12) * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
                 ("type", (C.c_int32 * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
-                ("mult", (C.c_double * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES)]
+                ("mult", (C.c_double * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
+                ("name", ((C.c_char * 32) * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES), ("nvars", C.c_int32 * VR_MAX_OUTFILES),
+                ("header", C.c_int32), ("hdr_nrecs", C.c_int32), ("hdr_out_dt", C.c_int32), ("hdr_start", C.c_int32 * 4),
+                ("hdr_alma", C.c_int32)]
 
 
-FILES_EXPORTS += ["vr_outsel_read", "vr_outsel_step_vars", "vr_aggregate_device", "vr_aggregate", "vr_write_results_sel"]
+FILES_EXPORTS += ["vr_outsel_read", "vr_outsel_step_vars", "vr_aggregate_device", "vr_aggregate", "vr_write_results_sel",
+                  "vr_alma_output_device", "vr_alma_output"]
 
 
 def _bind_outsel(so):
@@ -247,6 +251,7 @@ def _bind_outsel(so):
     so.vr_aggregate_device.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     so.vr_aggregate.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, pd, pd]
+    so.vr_alma_output_device.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     so.vr_write_results_sel.argtypes = [C.c_char_p, C.POINTER(OutSelC), C.c_int32, C.c_int32, C.c_int64, f32, f32, C.c_int32,
                                         i32, i32, i32, i32, C.c_int32, i32, pd]
     return so
@@ -272,11 +277,12 @@ class OutSel:
             out.append((self.c.prefix[f].value.decode(), cols))
         return out
 
-    def step_vars(self, aggregate=False):
-        """names of the outputs the step has to produce (each once); AERO_RESIST becomes AERO_COND when aggregating"""
+    def step_vars(self, aggregate=False, alma=False):
+        """names of the outputs the step has to produce (each once); AERO_RESIST becomes AERO_COND when aggregating, and
+        SUB_CANOP joins SUB_SNOW under ALMA_OUTPUT"""
         v = (C.c_int32 * abi.VR_MAX_OUT)()
         n = C.c_int32()
-        rc = self.so.vr_outsel_step_vars(C.byref(self.c), int(aggregate), v, C.byref(n))
+        rc = self.so.vr_outsel_step_vars(C.byref(self.c), int(bool(aggregate)) | (2 if alma else 0), v, C.byref(n))
         if rc != 0:
             raise VicResError(rc, "vr_outsel_step_vars: %s" % self.so.vr_params_last_error().decode())
         return [abi.OUT_NAMES[v[k]] for k in range(n.value)]
@@ -287,6 +293,12 @@ class OutSel:
 
     def wants(self, name):
         return any(abi.OUT_NAMES[self.c.var[f][k]] == name for f in range(self.c.nfiles) for k in range(self.c.ncols[f]))
+
+    def set_header(self, nrecs, out_dt, start, alma=False):
+        """PRT_HEADER: the run's record count, OUT_STEP (hours), the first model record's (year, month, day, hour)"""
+        self.c.header, self.c.hdr_nrecs, self.c.hdr_out_dt, self.c.hdr_alma = 1, int(nrecs), int(out_dt), int(alma)
+        for k in range(4):
+            self.c.hdr_start[k] = int(start[k])
 
     def write(self, f, result_dir, lat, lng, year, month, day, hour, out, rows, binary=False, grid_decimal=4):
         out = np.ascontiguousarray(out, np.float64)
@@ -335,8 +347,19 @@ def aggregate_device(names, in_ptr, out_ptr, nrec, ratio, ncell, device=0, strea
         raise VicResError(rc, "vr_aggregate_device")
 
 
-def read_binary_results(path, cols, hourly):
-    """a BINARY_OUTPUT result file -> (date [nrec, 3 or 4], values [ncol, nrec]); cols: [(name, format, type, mult)]"""
+def alma_output_device(names, data_ptr, nrec, ncell, out_dt, device=0, stream=0, lib=None):
+    """ALMA_OUTPUT units in place on device values [n][nrec][ncell] that are already at OUT_STEP = out_dt hours"""
+    so = _bind_outsel(_bind(lib or load_library()))
+    v = np.asarray([abi.OUT[x] for x in names], dtype=np.int32)
+    rc = so.vr_alma_output_device(device, len(names), v.ctypes.data_as(C.POINTER(C.c_int32)), nrec, ncell, out_dt, data_ptr, stream or None)
+    if rc != 0:
+        raise VicResError(rc, "vr_alma_output_device")
+
+
+def read_binary_results(path, cols, hourly, header=False):
+    """a BINARY_OUTPUT result file -> (date [nrec, 3 or 4], values [ncol, nrec]); cols: [(name, format, type, mult)];
+    header: the file starts with the PRT_HEADER block (its length is the fifth unsigned short)"""
     dt = [("date", "<i4", 4 if hourly else 3)] + [("c%d" % k, OUT_TYPE_DTYPE[c[2]]) for k, c in enumerate(cols)]
-    a = np.fromfile(path, dtype=np.dtype(dt))
+    off = int(np.fromfile(path, dtype="<u2", count=5)[4]) if header else 0
+    a = np.fromfile(path, dtype=np.dtype(dt), offset=off)
     return a["date"], np.stack([a["c%d" % k].astype(np.float64) / cols[k][3] for k in range(len(cols))])

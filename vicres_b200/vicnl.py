@@ -63,7 +63,7 @@ def run(global_path, device=0, write=True, records_per_block=0):
     # output interval spans several records: put_data.c:686 inverts the aggregated conductance)
     sel = files.OutSel(global_path, g.nlayer)
     ratio = g.out_step // g.time_step if g.out_step > 0 else 1
-    names = sel.step_vars(aggregate=ratio > 1)
+    names = sel.step_vars(aggregate=ratio > 1, alma=bool(g.alma_output))
     opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, out=names, max_snow_temp=g.max_snow_temp,
                               min_rain_temp=g.min_rain_temp, wind_h=g.wind_h, snow_step_hours=g.snow_step)
     m = model.VicRes(opt, lib, cells, device=device)
@@ -106,6 +106,13 @@ def run(global_path, device=0, write=True, records_per_block=0):
         files.aggregate_device(names, src.data_ptr(), agg.data_ptr(), nout * ratio, ratio, Cn, device=device)
         out_dev = agg
         dmy = dmy[ratio - 1::ratio][:nout]
+    out_dt = g.out_step if g.out_step > 0 else g.time_step
+    if g.alma_output:                       # put_data.c:697-760, after the aggregation
+        out_dev = out_dev.contiguous()
+        files.alma_output_device(names, out_dev.data_ptr(), out_dev.shape[1], Cn, out_dt, device=device)
+    if g.prt_header:                        # write_header.c: the run's record count and the first MODEL record's date
+        d0 = g.dmy()[0]
+        sel.set_header(nrecs, out_dt, (d0[0], d0[1], d0[2], d0[3]), alma=bool(g.alma_output))
     # SKIPYEAR: an output record is written when its last model record is past the skipped years (put_data.c:765)
     skip = g.output_skip(g.dmy())
     first = 0
@@ -114,7 +121,6 @@ def run(global_path, device=0, write=True, records_per_block=0):
     out = out_dev[:, first:].cpu().numpy()
     dmy = dmy[first:]
     if write:
-        out_dt = g.out_step if g.out_step > 0 else g.time_step
         hour = dmy[:, 3] if out_dt < 24 else None
         for f in range(len(sel.files)):
             sel.write(f, g.result_dir, meta["lat"], meta["lng"], dmy[:, 0], dmy[:, 1], dmy[:, 2], hour, out, sel.rows(f, names),
