@@ -81,6 +81,8 @@ enum {
   VR_OUT_PET_SATSOIL, VR_OUT_PET_H2OSURF, VR_OUT_PET_SHORT, VR_OUT_PET_TALL, VR_OUT_PET_NATVEG, VR_OUT_PET_VEGNOCR,
   /* water table position, cm (compute_zwt.c; needs vr_cells.zwt_zwt/zwt_moist) */
   VR_OUT_ZWT, VR_OUT_ZWT_LUMPED,
+  /* the record's own forcing values as put_data.c:271-292 passes them on: kg/m3, kPa, kPa, kPa, kg/kg */
+  VR_OUT_DENSITY, VR_OUT_PRESSURE, VR_OUT_VP, VR_OUT_VPD, VR_OUT_QAIR,
   VR_NOUTVAR
 };
 

@@ -93,6 +93,7 @@ REF_OUT = {
     "PET_SATSOIL": ("OUT_PET_SATSOIL", 0), "PET_H2OSURF": ("OUT_PET_H2OSURF", 0), "PET_SHORT": ("OUT_PET_SHORT", 0),
     "PET_TALL": ("OUT_PET_TALL", 0), "PET_NATVEG": ("OUT_PET_NATVEG", 0), "PET_VEGNOCR": ("OUT_PET_VEGNOCR", 0),
     "ZWT": ("OUT_ZWT", 0), "ZWT_LUMPED": ("OUT_ZWT_LUMPED", 0),
+    "DENSITY": ("OUT_DENSITY", 0), "PRESSURE": ("OUT_PRESSURE", 0), "VP": ("OUT_VP", 0), "VPD": ("OUT_VPD", 0), "QAIR": ("OUT_QAIR", 0),
 }
 
 

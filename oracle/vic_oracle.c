@@ -2648,6 +2648,11 @@ static void put_data(vo_model *m, int64_t c, const oatmos *atmos, double out_pre
   o[VR_OUT_PREC] = out_prec;
   o[VR_OUT_RAINF] = out_rain;
   o[VR_OUT_REL_HUMID] = 100. * atmos->vp / (atmos->vp + atmos->vpd);
+  o[VR_OUT_DENSITY] = atmos->density;                 /* put_data.c:275-291 */
+  o[VR_OUT_PRESSURE] = atmos->pressure / 1000.;
+  o[VR_OUT_VP] = atmos->vp / 1000.;
+  o[VR_OUT_VPD] = atmos->vpd / 1000.;
+  o[VR_OUT_QAIR] = 0.62196351 * atmos->vp / atmos->pressure;
   o[VR_OUT_SHORTWAVE] = atmos->shortwave;
   o[VR_OUT_SNOWF] = out_snow;
   o[VR_OUT_WIND] = atmos->wind;

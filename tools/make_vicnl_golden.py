@@ -51,6 +51,12 @@ VARIANTS = {
                         "OUTVAR OUT_SUB_SNOW %.6e", "OUTVAR OUT_SNOW_MELT %.6e", "OUTVAR OUT_SURF_TEMP", "OUTVAR OUT_AIR_TEMP",
                         "OUTVAR OUT_DELTAH %.5e", "OUTVAR OUT_SWE"]),
     "almadef": ("daily", ["ALMA_OUTPUT TRUE"]),
+    # the record's own forcing values as outputs (put_data.c:271-292), plain and in ALMA units (Pa)
+    "met6": ("sub3h", ["OUT_STEP 6", "N_OUTFILES 1", "OUTFILE met 8", "OUTVAR OUT_DENSITY %.6f", "OUTVAR OUT_PRESSURE %.5f",
+                       "OUTVAR OUT_VP %.6f", "OUTVAR OUT_VPD %.6f", "OUTVAR OUT_QAIR %.8f", "OUTVAR OUT_REL_HUMID",
+                       "OUTVAR OUT_SHORTWAVE", "OUTVAR OUT_LONGWAVE"]),
+    "metalma": ("daily", ["ALMA_OUTPUT TRUE", "N_OUTFILES 1", "OUTFILE met 5", "OUTVAR OUT_PRESSURE %.3f", "OUTVAR OUT_VP %.4f",
+                          "OUTVAR OUT_VPD %.4f", "OUTVAR OUT_QAIR %.8f", "OUTVAR OUT_AIR_TEMP"]),
     "bin": ("sub3h", ["BINARY_OUTPUT TRUE"]),
     "bin24sel": ("sub3h", ["BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE packed 6",
                            "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100",

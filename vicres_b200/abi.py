@@ -25,6 +25,7 @@ OUT_NAMES = [
     "ROOTMOIST", "GRND_FLUX", "DELTAH", "AERO_COND", "SHORTWAVE", "LONGWAVE", "DELSOILMOIST",
     "DELSWE", "DELINTERCEPT", "SNOW_SURF_TEMP", "SNOW_PACK_TEMP", "SALBEDO",
     "PET_SATSOIL", "PET_H2OSURF", "PET_SHORT", "PET_TALL", "PET_NATVEG", "PET_VEGNOCR", "ZWT", "ZWT_LUMPED",
+    "DENSITY", "PRESSURE", "VP", "VPD", "QAIR",
 ]
 OUT = {n: i for i, n in enumerate(OUT_NAMES)}
 VR_NOUTVAR = len(OUT_NAMES)

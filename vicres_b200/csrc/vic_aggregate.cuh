@@ -527,6 +527,11 @@ VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const
     case VR_OUT_SHORTWAVE: return f.shortwave;
     case VR_OUT_WIND: return f.wind;
     case VR_OUT_REL_HUMID: return 100. * f.vp / (f.vp + f.vpd);
+    case VR_OUT_DENSITY: return f.density;                       // put_data.c:275-291
+    case VR_OUT_PRESSURE: return f.pressure / 1000.;
+    case VR_OUT_VP: return f.vp / 1000.;
+    case VR_OUT_VPD: return f.vpd / 1000.;
+    case VR_OUT_QAIR: return 0.62196351 * f.vp / f.pressure;
     case VR_OUT_PREC: return S(TE_PREC);
     case VR_OUT_RAINF: return S(TE_RAIN);
     case VR_OUT_SNOWF: return S(TE_SNOWF);

@@ -639,7 +639,8 @@ __global__ void __launch_bounds__(256, VR_CELLS_MINB) k_cells(DevModel M, DevFor
   f.air_temp = __ldg(F.field[VR_F_AIR_TEMP] + q); f.wind = __ldg(F.field[VR_F_WIND] + q);
   f.vp = __ldg(F.field[VR_F_VP] + q); f.vpd = __ldg(F.field[VR_F_VPD] + q);
   f.shortwave = __ldg(F.field[VR_F_SHORTWAVE] + q); f.longwave = __ldg(F.field[VR_F_LONGWAVE] + q);
-  f.prec = 0; f.pressure = 0; f.density = 0; f.mon = 0; f.doy = 0; f.snowflag = 0;
+  f.pressure = __ldg(F.field[VR_F_PRESSURE] + q); f.density = __ldg(F.field[VR_F_DENSITY] + q);
+  f.prec = 0; f.mon = 0; f.doy = 0; f.snowflag = 0;
 #pragma unroll 1
   for (int v = 0; v < M.n_out; v++) VR_STREAM_ST(out + (size_t)v * ostride + orow, cell_output(M.out_vars[v], S, f, NL, false, sv));
   if (rec == F.nrec - 1) {
@@ -667,7 +668,7 @@ __global__ void k_aggregate(int n, const int *__restrict__ kind, int nrec, int r
   out[((size_t)v * nout + o) * C + c] = a;
 }
 
-// ALMA_OUTPUT (put_data.c:697-760) on aggregated values, in place: op 1 = / seconds, 2 = + KELVIN, 3 = * seconds; op 4
+// ALMA_OUTPUT (put_data.c:697-760) on aggregated values, in place: op 1 = / seconds, 2 = + KELVIN, 3 = * seconds, 5 = kPa -> Pa; op 4
 // (OUT_SUB_SNOW: / seconds, then + the converted OUT_SUB_CANOP, :741-742) is left to k_alma_add, launched after this
 // kernel so that it reads the companion row converted.  Thread per (cell, record, variable).
 __global__ void k_alma(int n, const int *__restrict__ op, const int *__restrict__ aux, int nrec, int64_t C, double sec, double *__restrict__ d)
@@ -680,6 +681,7 @@ __global__ void k_alma(int n, const int *__restrict__ op, const int *__restrict_
   if (k == 1) d[i] = d[i] / sec;
   else if (k == 2) d[i] = d[i] + 273.15;
   else if (k == 3) d[i] = d[i] * sec;
+  else if (k == 5) d[i] = d[i] * 1000;
 }
 __global__ void k_alma_add(int v, int aux, int nrec, int64_t C, double sec, double *__restrict__ d)
 {
@@ -1814,6 +1816,7 @@ int vr_alma_output_device(int device, int32_t n, const int32_t *vars, int32_t nr
         op[v] = 1; break;
       case VR_OUT_SNOW_PACK_TEMP: case VR_OUT_SNOW_SURF_TEMP: case VR_OUT_SURF_TEMP: case VR_OUT_AIR_TEMP: op[v] = 2; break;
       case VR_OUT_DELTAH: op[v] = 3; break;
+      case VR_OUT_PRESSURE: case VR_OUT_VP: case VR_OUT_VPD: op[v] = 5; break;
       case VR_OUT_SUB_SNOW: op[v] = 4; sub_snow = v; break;
       default: op[v] = 0;
     }

@@ -567,7 +567,8 @@ const OutName OUT_TABLE[] = {
   {"OUT_SNOW_PACK_TEMP", VR_OUT_SNOW_PACK_TEMP, 0}, {"OUT_SALBEDO", VR_OUT_SALBEDO, 0}, {"OUT_PET_SATSOIL", VR_OUT_PET_SATSOIL, 0},
   {"OUT_PET_H2OSURF", VR_OUT_PET_H2OSURF, 0}, {"OUT_PET_SHORT", VR_OUT_PET_SHORT, 0}, {"OUT_PET_TALL", VR_OUT_PET_TALL, 0},
   {"OUT_PET_NATVEG", VR_OUT_PET_NATVEG, 0}, {"OUT_PET_VEGNOCR", VR_OUT_PET_VEGNOCR, 0}, {"OUT_ZWT", VR_OUT_ZWT, 0},
-  {"OUT_ZWT_LUMPED", VR_OUT_ZWT_LUMPED, 0},
+  {"OUT_ZWT_LUMPED", VR_OUT_ZWT_LUMPED, 0}, {"OUT_DENSITY", VR_OUT_DENSITY, 0}, {"OUT_PRESSURE", VR_OUT_PRESSURE, 0},
+  {"OUT_VP", VR_OUT_VP, 0}, {"OUT_VPD", VR_OUT_VPD, 0}, {"OUT_QAIR", VR_OUT_QAIR, 0},
 };
 const OutName *find_out(const char *name)
 {
