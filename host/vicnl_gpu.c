@@ -48,6 +48,10 @@ int main(int argc, char **argv)
   pf.nlayer = g.nlayer; pf.nbands = g.snow_band; pf.root_zones = g.root_zones; pf.vegparam_lai = g.vegparam_lai;
   pf.lai_from_vegparam = g.lai_from_vegparam; pf.soil = g.soil; pf.veglib = g.veglib; pf.vegparam = g.vegparam;
   pf.snowband = g.snowband[0] ? g.snowband : NULL;
+  if (g.output_force) {      /* vicNl.c:226-234: read_snowband() is not called, so the cell keeps the soil file's elevation */
+    pf.snowband = NULL;      /* (read_snowband.c replaces it by the bands' mean elevation)                                   */
+    pf.nbands = 1;
+  }
   vr_params *par = NULL;
   if (vr_params_read(&pf, &par) != VR_OK) die("parameter files", vr_params_last_error());
   const vr_cells *cells = vr_params_cells(par);
@@ -130,6 +134,35 @@ int main(int argc, char **argv)
   for (i = 0; i < VR_NFORCING; i++) field[i] = malloc(sizeof(double) * (size_t)nrecs * NS * C);
   int32_t *snowflag = malloc(sizeof(int32_t) * (size_t)nrecs * C);
   if (vr_atmos_prepare_sub(device, &ao, &site, &rw, field, snowflag) != VR_OK) die("forcing preparation", vr_atmos_last_error());
+
+  if (g.output_force) {      /* OUTPUT_FORCE TRUE: write the forcing and stop (vicNl.c:226-234, write_forcing_file.c) */
+    static vr_outsel fs;
+    int32_t fvars[VR_MAX_OUT], nfv = 0, fi, k;
+    if (vr_outsel_read(gfile, g.nlayer, &fs) != VR_OK || vr_outsel_step_vars(&fs, 0, fvars, &nfv) != VR_OK)
+      die("output selection", vr_params_last_error());
+    const int nrows = nrecs * NF;
+    double *rows_h = malloc(sizeof(double) * (size_t)nfv * nrows * C);
+    if (vr_forcing_outputs(device, nfv, fvars, nrecs, NF, C, g.max_snow_temp, g.min_rain_temp, (const double *const *)field, rows_h) != VR_OK)
+      die("forcing outputs", "a variable of the output selection is not a forcing variable");
+    if (g.alma_output && vr_alma_output(device, nfv, fvars, nrows, C, g.time_step, rows_h) != VR_OK) die("vr_alma_output", "");
+    if (g.prt_header) {
+      fs.header = 1; fs.hdr_nrecs = nrecs; fs.hdr_out_dt = g.out_step > 0 ? g.out_step : g.time_step; fs.hdr_alma = g.alma_output;
+      fs.hdr_start[0] = year[0]; fs.hdr_start[1] = month[0]; fs.hdr_start[2] = day[0]; fs.hdr_start[3] = hour[0];
+    }
+    int32_t *zero = calloc(nrows, sizeof(int32_t));
+    for (fi = 0; fi < fs.nfiles; fi++) {
+      int32_t rws[VR_MAX_OUTCOLS];
+      for (k = 0; k < fs.ncols[fi]; k++) {
+        rws[k] = 0;
+        for (i = 0; i < nfv; i++) if (fvars[i] == fs.var[fi][k]) rws[k] = i;
+      }
+      if (vr_write_results_sel(g.result_dir, &fs, fi, g.grid_decimal, C, lat, lng, nrows, zero, zero, zero, NULL, g.binary_output, rws,
+                               rows_h) != VR_OK) die(fs.prefix[fi], vr_params_last_error());
+    }
+    fprintf(stderr, "vicnl_gpu: forcing of %lld cells x %d rows written to %s\n", (long long)C, nrows, g.result_dir);
+    vr_params_free(par);
+    return 0;
+  }
 
   /* the model */
   vr_options opt;

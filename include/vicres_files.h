@@ -75,6 +75,8 @@ typedef struct vr_outsel {
   char    name[VR_MAX_OUTFILES][VR_MAX_OUTCOLS][32];
   int32_t nvars[VR_MAX_OUTFILES];
   int32_t header, hdr_nrecs, hdr_out_dt, hdr_start[4], hdr_alma;
+  int32_t no_date;          /* OUTPUT_FORCE TRUE: the files hold the forcing, one row per snow step, without date columns
+                             * (write_data.c:118-131, 206-217); set by vr_outsel_read */
 } vr_outsel;
 /* N_OUTFILES / OUTFILE / OUTVAR lines of a global parameter file; without them the default pair "fluxes" (20 variables,
  * 20 + nlayer - 1 columns) and "snow" (4) of set_output_defaults.c:66-162.  An unknown variable name is an error, as in
@@ -96,6 +98,17 @@ int  vr_aggregate_device(int device, int32_t n, const int32_t *vars, int32_t con
  * OUT_SUB_SNOW gets OUT_SUB_CANOP added (which therefore has to be one of the rows). */
 int  vr_alma_output_device(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours,
                            double *data_dev, void *cuda_stream);
+/* OUTPUT_FORCE (write_forcing_file.c:46-85): the rows of the forcing files from the prepared forcing.  fields_dev: the nine
+ * VR_F_* arrays as vr_atmos_prepare_sub_device leaves them ([nrecs][NF + 1][C], or [nrecs][C] when nf == 1); out_dev:
+ * [n][nrecs * nf][C], row rec * nf + j = window j of record rec.  vars: VR_OUT_AIR_TEMP, DENSITY, LONGWAVE, PREC, PRESSURE,
+ * QAIR, REL_HUMID, SHORTWAVE, VP, VPD, WIND, RAINF, SNOWF (the rain / snow split by the two temperature thresholds);
+ * anything else is VR_ERR_UNSUPPORTED.  vr_alma_output_device with out_dt_hours = TIME_STEP does its ALMA units. */
+int  vr_forcing_outputs_device(int device, int32_t n, const int32_t *vars, int32_t nrecs, int32_t nf, int64_t ncell,
+                               double max_snow_temp, double min_rain_temp, const double *const fields_dev[9], double *out_dev,
+                               void *cuda_stream);
+/* the same with host buffers: fields [9] each [nrecs * (nf > 1 ? nf + 1 : 1) * ncell], out [n][nrecs * nf][ncell] */
+int  vr_forcing_outputs(int device, int32_t n, const int32_t *vars, int32_t nrecs, int32_t nf, int64_t ncell, double max_snow_temp,
+                        double min_rain_temp, const double *const fields[9], double *out);
 /* the same on a host buffer (copy in, kernel, copy out) */
 int  vr_alma_output(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours, double *data);
 /* the same with host buffers (copies in, kernel, copies out) */
@@ -145,7 +158,7 @@ typedef struct vr_global {
    * MOISTFRACT, PRT_SNOW_BAND, OUTPUT_FORCE, BASEFLOW NIJSSEN2001, SNOW_ALBEDO, SNOW_DENSITY,
    * AERO_RESIST_CANSNOW, GRND_FLUX_TYPE, SPATIAL_SNOW ...), or empty: named by vr_global_unsupported, never ignored */
   char    other_unsupported[96];
-  int32_t prt_header, alma_output;                 /* PRT_HEADER, ALMA_OUTPUT                                   */
+  int32_t prt_header, alma_output, output_force;   /* PRT_HEADER, ALMA_OUTPUT, OUTPUT_FORCE                     */
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -27,7 +27,7 @@ def _stage(name, tmp_path, variant=None):
 # variants of the two cases: output interval, output selection, binary files (tools/make_vicnl_golden.py: VARIANTS)
 VARIANTS = [("sub3h", "out24"), ("sub3h", "out6sel"), ("daily", "selday"), ("sub3h", "bin"), ("sub3h", "bin24sel"),
             ("daily", "snow3"), ("skip", "snow1"), ("daily", "hdr"), ("sub3h", "hdrbin24"), ("sub3h", "alma6"), ("daily", "almadef"),
-            ("sub3h", "met6"), ("daily", "metalma")]
+            ("sub3h", "met6"), ("daily", "metalma"), ("daily", "force"), ("sub3h", "forcebin"), ("daily", "force3")]
 
 
 def _quantum(tok):
@@ -61,7 +61,7 @@ def _compare_ascii(res, ref, what):
     assert nbad <= 0.01 * ntot
 
 
-def _compare_binary(res, ref, gpath, nlayer, hourly, what, header=False):
+def _compare_binary(res, ref, gpath, nlayer, hourly, what, header=False, no_date=False):
     """BINARY_OUTPUT files: same size, same dates; integer columns within one count (the cast truncates), floats within
     fp32 rounding of the parity tolerance"""
     sel = files.OutSel(gpath, nlayer)
@@ -70,8 +70,8 @@ def _compare_binary(res, ref, gpath, nlayer, hourly, what, header=False):
     for prefix, cols in sel.files:
         for n in sorted(x for x in os.listdir(ref) if x.startswith(prefix + "_")):
             assert os.path.getsize(os.path.join(res, n)) == os.path.getsize(os.path.join(ref, n)), n
-            da, a = files.read_binary_results(os.path.join(res, n), cols, hourly, header)
-            db, b = files.read_binary_results(os.path.join(ref, n), cols, hourly, header)
+            da, a = files.read_binary_results(os.path.join(res, n), cols, hourly, header, no_date)
+            db, b = files.read_binary_results(os.path.join(ref, n), cols, hourly, header, no_date)
             if header:       # PRT_HEADER: the block before the records, byte for byte
                 nb = int(np.fromfile(os.path.join(ref, n), dtype="<u2", count=5)[4])
                 assert open(os.path.join(res, n), "rb").read(nb) == open(os.path.join(ref, n), "rb").read(nb), n
@@ -88,7 +88,7 @@ def _compare_binary(res, ref, gpath, nlayer, hourly, what, header=False):
 
 def _compare_variant(case, variant, gpath, res, ref, what):
     if "bin" in variant:
-        _compare_binary(res, ref, gpath, 3, variant == "bin", what, header=variant.startswith("hdr"))
+        _compare_binary(res, ref, gpath, 3, variant == "bin", what, header=variant.startswith("hdr"), no_date=variant.startswith("force"))
     else:
         _compare_ascii(res, ref, what)
 
@@ -101,12 +101,19 @@ def test_output_selection_of_the_variants_parses(case, variant, tmp_path):
     assert g.unsupported is None
     sel = files.OutSel(gpath, g.nlayer)
     fl = dict(sel.files)
-    assert sorted(set(n.split("_")[0] for n in os.listdir(ref))) == sorted(fl)
+    assert sorted(set(n.rsplit("_", 2)[0] for n in os.listdir(ref))) == sorted(fl)       # <prefix>_<lat>_<lng>
     assert bool(g.binary_output) == ("bin" in variant)
-    assert bool(g.prt_header) == (variant in ("hdr", "hdrbin24", "alma6")) and bool(g.alma_output) == ("alma" in variant)
+    assert bool(g.prt_header) == (variant in ("hdr", "hdrbin24", "alma6", "force3"))
+    assert bool(g.alma_output) == ("alma" in variant or variant == "force3")
     if variant == "alma6":
         assert "SUB_CANOP" not in sel.step_vars() and sel.step_vars(alma=True)[-1] == "SUB_CANOP"
         assert [c[0] for c in fl["al"]][4] == "SUB_SNOW"
+    if variant.startswith("force"):
+        assert g.output_force == 1 and sel.c.no_date == 1
+        if variant != "force3":
+            assert list(fl) == ["full_data"] and [c[0] for c in fl["full_data"]] == ["PREC", "AIR_TEMP", "SHORTWAVE", "LONGWAVE", "DENSITY",
+                                                                                  "PRESSURE", "VP", "WIND"]
+            assert [(c[2], c[3]) for c in fl["full_data"]][:3] == [("USINT", 40.0), ("SINT", 100.0), ("USINT", 50.0)]
     if variant.startswith("snow"):
         assert g.snow_step == int(variant[4:]) and g.time_step == 24
     if variant in ("out24", "bin"):

@@ -57,6 +57,12 @@ VARIANTS = {
                        "OUTVAR OUT_SHORTWAVE", "OUTVAR OUT_LONGWAVE"]),
     "metalma": ("daily", ["ALMA_OUTPUT TRUE", "N_OUTFILES 1", "OUTFILE met 5", "OUTVAR OUT_PRESSURE %.3f", "OUTVAR OUT_VP %.4f",
                           "OUTVAR OUT_VPD %.4f", "OUTVAR OUT_QAIR %.8f", "OUTVAR OUT_AIR_TEMP"]),
+    # OUTPUT_FORCE: the disaggregated forcing written out, one row per snow step, no date columns (write_forcing_file.c)
+    "force": ("daily", ["OUTPUT_FORCE TRUE"]),
+    "forcebin": ("sub3h", ["OUTPUT_FORCE TRUE", "BINARY_OUTPUT TRUE"]),
+    "force3": ("daily", ["OUTPUT_FORCE TRUE", "SNOW_STEP 3", "PRT_HEADER TRUE", "ALMA_OUTPUT TRUE", "N_OUTFILES 1", "OUTFILE fd 8",
+                         "OUTVAR OUT_PREC %.6e", "OUTVAR OUT_RAINF %.6e", "OUTVAR OUT_SNOWF %.6e", "OUTVAR OUT_AIR_TEMP",
+                         "OUTVAR OUT_REL_HUMID %.2f", "OUTVAR OUT_QAIR %.8f", "OUTVAR OUT_PRESSURE %.2f", "OUTVAR OUT_LONGWAVE"]),
     "bin": ("sub3h", ["BINARY_OUTPUT TRUE"]),
     "bin24sel": ("sub3h", ["BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE packed 6",
                            "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100",

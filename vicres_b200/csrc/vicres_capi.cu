@@ -656,16 +656,18 @@ __global__ void k_aggregate(int n, const int *__restrict__ kind, int nrec, int r
                             double *__restrict__ out)
 {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int o = blockIdx.y, v = blockIdx.z, nout = nrec / ratio;
+  const int v = blockIdx.z, nout = nrec / ratio;
   if (c >= C) return;
-  const double *p = in + ((size_t)v * nrec + (size_t)o * ratio) * C + c;
   const int k = kind[v];
-  double a = 0.0;
-  if (k == 0) a = p[(size_t)(ratio - 1) * C];
-  else
-    for (int r = 0; r < ratio; r++) a += (k == 1) ? p[(size_t)r * C] : p[(size_t)r * C] / ratio;
-  if (k == 3) a = 1 / a;
-  out[((size_t)v * nout + o) * C + c] = a;
+  for (int o = blockIdx.y; o < nout; o += gridDim.y) {       // gridDim.y is capped at 65 535
+    const double *p = in + ((size_t)v * nrec + (size_t)o * ratio) * C + c;
+    double a = 0.0;
+    if (k == 0) a = p[(size_t)(ratio - 1) * C];
+    else
+      for (int r = 0; r < ratio; r++) a += (k == 1) ? p[(size_t)r * C] : p[(size_t)r * C] / ratio;
+    if (k == 3) a = 1 / a;
+    out[((size_t)v * nout + o) * C + c] = a;
+  }
 }
 
 // ALMA_OUTPUT (put_data.c:697-760) on aggregated values, in place: op 1 = / seconds, 2 = + KELVIN, 3 = * seconds, 5 = kPa -> Pa; op 4
@@ -674,23 +676,63 @@ __global__ void k_aggregate(int n, const int *__restrict__ kind, int nrec, int r
 __global__ void k_alma(int n, const int *__restrict__ op, const int *__restrict__ aux, int nrec, int64_t C, double sec, double *__restrict__ d)
 {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y, v = blockIdx.z;
+  const int v = blockIdx.z;
   if (c >= C) return;
-  const size_t i = ((size_t)v * nrec + r) * C + c;
   const int k = op[v];
-  if (k == 1) d[i] = d[i] / sec;
-  else if (k == 2) d[i] = d[i] + 273.15;
-  else if (k == 3) d[i] = d[i] * sec;
-  else if (k == 5) d[i] = d[i] * 1000;
+  for (int r = blockIdx.y; r < nrec; r += gridDim.y) {
+    const size_t i = ((size_t)v * nrec + r) * C + c;
+    if (k == 1) d[i] = d[i] / sec;
+    else if (k == 2) d[i] = d[i] + 273.15;
+    else if (k == 3) d[i] = d[i] * sec;
+    else if (k == 5) d[i] = d[i] * 1000;
+  }
 }
 __global__ void k_alma_add(int v, int aux, int nrec, int64_t C, double sec, double *__restrict__ d)
 {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
   if (c >= C) return;
-  const size_t i = ((size_t)v * nrec + r) * C + c, j = ((size_t)aux * nrec + r) * C + c;
-  d[i] = d[i] / sec;
-  d[i] = d[i] + d[j];
+  for (int r = blockIdx.y; r < nrec; r += gridDim.y) {
+    const size_t i = ((size_t)v * nrec + r) * C + c, j = ((size_t)aux * nrec + r) * C + c;
+    d[i] = d[i] / sec;
+    d[i] = d[i] + d[j];
+  }
+}
+
+// OUTPUT_FORCE (write_forcing_file.c:46-85): thread per (cell, row = rec * nf + window, variable) of the forcing files
+struct ForceFields { const double *f[VR_NFORCING]; };
+__global__ void k_forcing_outputs(int n, const int *__restrict__ vars, int nrows, int nf, int64_t C, double max_snow, double min_rain,
+                                  ForceFields F, double *__restrict__ out)
+{
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.z;
+  if (c >= C) return;
+  for (int row = blockIdx.y; row < nrows; row += gridDim.y) {
+  const int rec = row / nf, j = row - rec * nf, NS = nf > 1 ? nf + 1 : 1;
+  const size_t q = ((size_t)rec * NS + j) * C + c;
+  const double ta = F.f[VR_F_AIR_TEMP][q], prec = F.f[VR_F_PREC][q], vp = F.f[VR_F_VP][q], vpd = F.f[VR_F_VPD][q],
+               pr = F.f[VR_F_PRESSURE][q];
+  double rain;                                         // the split of :66-78
+  if (ta >= max_snow) rain = prec;
+  else if (ta <= min_rain) rain = 0;
+  else rain = ((ta - min_rain) / (max_snow - min_rain)) * prec;
+  double x = 0.;
+  switch (vars[v]) {
+    case VR_OUT_AIR_TEMP: x = ta; break;
+    case VR_OUT_DENSITY: x = F.f[VR_F_DENSITY][q]; break;
+    case VR_OUT_LONGWAVE: x = F.f[VR_F_LONGWAVE][q]; break;
+    case VR_OUT_PREC: x = prec; break;
+    case VR_OUT_PRESSURE: x = pr / 1000.; break;
+    case VR_OUT_QAIR: x = 0.62196351 * vp / pr; break;
+    case VR_OUT_REL_HUMID: x = 100. * vp / (vp + vpd); break;
+    case VR_OUT_SHORTWAVE: x = F.f[VR_F_SHORTWAVE][q]; break;
+    case VR_OUT_VP: x = vp / 1000.; break;
+    case VR_OUT_VPD: x = vpd / 1000.; break;
+    case VR_OUT_WIND: x = F.f[VR_F_WIND][q]; break;
+    case VR_OUT_RAINF: x = rain; break;
+    case VR_OUT_SNOWF: x = (ta >= max_snow) ? 0 : ((ta <= min_rain) ? prec : prec - rain); break;
+  }
+  out[((size_t)v * nrows + row) * C + c] = x;
+  }
 }
 
 // diagnostic: the device power function on arbitrary arguments (tests/test_gpu_parity.py checks its error bound)
@@ -1794,7 +1836,7 @@ int vr_aggregate_device(int device, int32_t n, const int32_t *vars, int32_t cond
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (cudaMalloc((void **)&d_kind, n * sizeof(int)) != cudaSuccess) return VR_ERR_CUDA;
   cudaMemcpyAsync(d_kind, kind, n * sizeof(int), cudaMemcpyHostToDevice, st);
-  k_aggregate<<<dim3((unsigned)((ncell + 255) / 256), (unsigned)(nrec / ratio), (unsigned)n), 256, 0, st>>>(n, d_kind, nrec, ratio, ncell,
+  k_aggregate<<<dim3((unsigned)((ncell + 255) / 256), (unsigned)(nrec / ratio < 65535 ? nrec / ratio : 65535), (unsigned)n), 256, 0, st>>>(n, d_kind, nrec, ratio, ncell,
                                                                                                      in_dev, out_dev);
   const cudaError_t e = cudaGetLastError();
   cudaStreamSynchronize(st);
@@ -1829,7 +1871,7 @@ int vr_alma_output_device(int device, int32_t n, const int32_t *vars, int32_t nr
   cudaMemcpyAsync(d_op, op, n * sizeof(int), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_op + n, aux, n * sizeof(int), cudaMemcpyHostToDevice, st);
   const double sec = (double)(out_dt_hours * 3600);
-  const dim3 grid((unsigned)((ncell + 255) / 256), (unsigned)nrec, (unsigned)n);
+  const dim3 grid((unsigned)((ncell + 255) / 256), (unsigned)(nrec < 65535 ? nrec : 65535), (unsigned)n);
   k_alma<<<grid, 256, 0, st>>>(n, d_op, d_op + n, nrec, ncell, sec, data_dev);
   if (sub_snow >= 0)
     k_alma_add<<<dim3(grid.x, grid.y), 256, 0, st>>>(sub_snow, sub_canop, nrec, ncell, sec, data_dev);
@@ -1837,6 +1879,54 @@ int vr_alma_output_device(int device, int32_t n, const int32_t *vars, int32_t nr
   cudaStreamSynchronize(st);
   cudaFree(d_op);
   return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
+}
+
+int vr_forcing_outputs_device(int device, int32_t n, const int32_t *vars, int32_t nrecs, int32_t nf, int64_t ncell, double max_snow_temp,
+                              double min_rain_temp, const double *const fields_dev[9], double *out_dev, void *cuda_stream)
+{
+  if (!vars || !fields_dev || !out_dev || n < 1 || n > VR_MAX_OUT || nrecs < 1 || nf < 1 || ncell < 1) return VR_ERR_ARG;
+  for (int v = 0; v < n; v++)
+    switch (vars[v]) {
+      case VR_OUT_AIR_TEMP: case VR_OUT_DENSITY: case VR_OUT_LONGWAVE: case VR_OUT_PREC: case VR_OUT_PRESSURE: case VR_OUT_QAIR:
+      case VR_OUT_REL_HUMID: case VR_OUT_SHORTWAVE: case VR_OUT_VP: case VR_OUT_VPD: case VR_OUT_WIND: case VR_OUT_RAINF:
+      case VR_OUT_SNOWF: break;
+      default: return VR_ERR_UNSUPPORTED;       // not a forcing variable (or OUT_CATM / COSZEN / FDIR / PAR / TSKC: not kept)
+    }
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  ForceFields F;
+  for (int i = 0; i < VR_NFORCING; i++) { if (!fields_dev[i]) return VR_ERR_ARG; F.f[i] = fields_dev[i]; }
+  int *d_vars = nullptr;
+  if (cudaMalloc((void **)&d_vars, n * sizeof(int)) != cudaSuccess) return VR_ERR_CUDA;
+  cudaMemcpyAsync(d_vars, vars, n * sizeof(int), cudaMemcpyHostToDevice, st);
+  const int nrows = nrecs * nf;
+  k_forcing_outputs<<<dim3((unsigned)((ncell + 255) / 256), (unsigned)(nrows < 65535 ? nrows : 65535), (unsigned)n), 256, 0, st>>>(n, d_vars, nrows, nf, ncell, max_snow_temp,
+                                                                                                 min_rain_temp, F, out_dev);
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(st);
+  cudaFree(d_vars);
+  return e == cudaSuccess ? VR_OK : VR_ERR_CUDA;
+}
+
+int vr_forcing_outputs(int device, int32_t n, const int32_t *vars, int32_t nrecs, int32_t nf, int64_t ncell, double max_snow_temp,
+                       double min_rain_temp, const double *const fields[9], double *out)
+{
+  if (!fields || !out || n < 1 || nrecs < 1 || nf < 1 || ncell < 1) return VR_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return VR_ERR_CUDA;
+  const size_t nin = (size_t)nrecs * (nf > 1 ? nf + 1 : 1) * ncell, nout = (size_t)n * nrecs * nf * ncell;
+  double *d = nullptr;
+  if (cudaMalloc((void **)&d, (VR_NFORCING * nin + nout) * sizeof(double)) != cudaSuccess) return VR_ERR_CUDA;
+  const double *fd[VR_NFORCING];
+  for (int i = 0; i < VR_NFORCING; i++) {
+    if (!fields[i]) { cudaFree(d); return VR_ERR_ARG; }
+    cudaMemcpy(d + (size_t)i * nin, fields[i], nin * sizeof(double), cudaMemcpyHostToDevice);
+    fd[i] = d + (size_t)i * nin;
+  }
+  double *dout = d + (size_t)VR_NFORCING * nin;
+  const int rc = vr_forcing_outputs_device(device, n, vars, nrecs, nf, ncell, max_snow_temp, min_rain_temp, fd, dout, nullptr);
+  if (rc == VR_OK) cudaMemcpy(out, dout, nout * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
 }
 
 int vr_alma_output(int device, int32_t n, const int32_t *vars, int32_t nrec, int64_t ncell, int32_t out_dt_hours, double *data)

@@ -615,11 +615,16 @@ int vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *s)
   FILE *gp = fopen(global_path, "r");
   if (!gp) { g_err = std::string("cannot open ") + global_path; return VR_ERR_ARG; }
   char line[4096], key[256], a1[256], a2[256], a3[256], a4[256];
-  int declared = 0, f = -1;
+  int declared = 0, f = -1, output_force = 0;
   while (fgets(line, sizeof line, gp)) {
     if (line[0] == '#' || line[0] == '\n' || line[0] == '\0') continue;
     if (sscanf(line, "%255s", key) != 1) continue;
-    if (!strcasecmp(key, "N_OUTFILES")) {
+    if (!strcasecmp(key, "OUTPUT_FORCE")) {
+      a1[0] = 0;
+      sscanf(line, "%*s %255s", a1);
+      output_force = !strcasecmp(a1, "TRUE");
+    }
+    else if (!strcasecmp(key, "N_OUTFILES")) {
       if (sscanf(line, "%*s %d", &declared) != 1 || declared < 1 || declared > VR_MAX_OUTFILES) {
         fclose(gp); g_err = "N_OUTFILES out of range (1..8)"; return VR_ERR_ARG;
       }
@@ -654,7 +659,16 @@ int vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *s)
     }
   }
   fclose(gp);
-  if (!declared) {       // set_output_defaults.c:66-162, water-balance mode
+  if (!declared && output_force) {       // set_output_defaults.c:40-62: the forcing file
+    s->nfiles = 1;
+    snprintf(s->prefix[0], 64, "full_data");
+    const struct { const char *n; int type; double mult; } fd[] = {
+      {"OUT_PREC", VR_OUT_TYPE_USINT, 40}, {"OUT_AIR_TEMP", VR_OUT_TYPE_SINT, 100}, {"OUT_SHORTWAVE", VR_OUT_TYPE_USINT, 50},
+      {"OUT_LONGWAVE", VR_OUT_TYPE_USINT, 80}, {"OUT_DENSITY", VR_OUT_TYPE_USINT, 100}, {"OUT_PRESSURE", VR_OUT_TYPE_USINT, 100},
+      {"OUT_VP", VR_OUT_TYPE_SINT, 100}, {"OUT_WIND", VR_OUT_TYPE_USINT, 100}};
+    for (const auto &v : fd) outsel_add(s, 0, v.n, "%.4f", v.type, v.mult, nlayer);
+  }
+  else if (!declared) {       // set_output_defaults.c:66-162, water-balance mode
     s->nfiles = 2;
     snprintf(s->prefix[0], 64, "fluxes");
     snprintf(s->prefix[1], 64, "snow");
@@ -666,6 +680,7 @@ int vr_outsel_read(const char *global_path, int32_t nlayer, vr_outsel *s)
     for (const char *n : snow) outsel_add(s, 1, n, "%.4f", VR_OUT_TYPE_FLOAT, 1, nlayer);
   }
   else if (s->nfiles != declared) { g_err = "fewer OUTFILE lines than N_OUTFILES"; return VR_ERR_ARG; }
+  s->no_date = output_force;
   return VR_OK;
 }
 
@@ -712,7 +727,7 @@ int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t fil
     FILE *f = fopen(name, binary ? "wb" : "w");
     if (!f) { g_err = std::string("cannot create ") + name; return VR_ERR_ARG; }
     if (s->header) {      // PRT_HEADER, write_header.c:46-307
-      const int ndate = hour ? 4 : 3;
+      const int ndate = s->no_date ? 0 : (hour ? 4 : 3);
       if (binary) {
         static const char *DATE[4] = {"YEAR", "MONTH", "DAY", "HOUR"};
         unsigned short id = 0xFFFF, nb1 = sizeof(unsigned short) + 6 * sizeof(int) + 2, nb2 = sizeof(unsigned short);
@@ -739,7 +754,7 @@ int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t fil
         fprintf(f, "# NRECS: %d\n# DT: %d\n# STARTDATE: %04d-%02d-%02d %02d:00:00\n# ALMA_OUTPUT: %d\n# NVARS: %d\n# ", s->hdr_nrecs,
                 s->hdr_out_dt, s->hdr_start[0], s->hdr_start[1], s->hdr_start[2], s->hdr_start[3], s->hdr_alma ? 1 : 0,
                 s->nvars[file] + ndate);
-        fprintf(f, hour ? "YEAR\tMONTH\tDAY\tHOUR\t" : "YEAR\tMONTH\tDAY\t");
+        if (!s->no_date) fprintf(f, hour ? "YEAR\tMONTH\tDAY\tHOUR\t" : "YEAR\tMONTH\tDAY\t");
         for (int v = 0; v < nc; v++) fprintf(f, "%s%s", v ? "\t " : "", s->name[file][v]);
         fprintf(f, "\n");
       }
@@ -747,7 +762,7 @@ int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t fil
     for (int r = 0; r < nrec; r++) {
       if (binary) {       // write_data.c:103-193
         const int date[4] = {year[r], month[r], day[r], hour ? hour[r] : 0};
-        fwrite(date, sizeof(int), hour ? 4 : 3, f);
+        if (!s->no_date) fwrite(date, sizeof(int), hour ? 4 : 3, f);
         for (int v = 0; v < nc; v++) {
           const double x = out[((size_t)rows[v] * nrec + r) * ncell + c] * s->mult[file][v];      // put_data.c:766-772
           switch (s->type[file][v]) {
@@ -761,7 +776,8 @@ int vr_write_results_sel(const char *result_dir, const vr_outsel *s, int32_t fil
         }
       }
       else {              // write_data.c:196-226
-        if (hour) fprintf(f, "%04i\t%02i\t%02i\t%02i\t", year[r], month[r], day[r], hour[r]);
+        if (s->no_date) { }
+        else if (hour) fprintf(f, "%04i\t%02i\t%02i\t%02i\t", year[r], month[r], day[r], hour[r]);
         else fprintf(f, "%04i\t%02i\t%02i\t", year[r], month[r], day[r]);
         for (int v = 0; v < nc; v++) {
           if (v) fprintf(f, "\t ");
@@ -797,7 +813,7 @@ static bool other_option_unsupported(const char *key, const char *val)
 {
   static const struct { const char *key, *ok1, *ok2; } T[] = {
     {"MOISTFRACT", "FALSE", nullptr},
-    {"PRT_SNOW_BAND", "FALSE", nullptr}, {"OUTPUT_FORCE", "FALSE", nullptr}, {"BASEFLOW", "ARNO", nullptr},
+    {"PRT_SNOW_BAND", "FALSE", nullptr}, {"BASEFLOW", "ARNO", nullptr},
     {"ARC_SOIL", "FALSE", nullptr}, {"AERO_RESIST_CANSNOW", "AR_406_FULL", nullptr}, {"SNOW_ALBEDO", "USACE", nullptr},
     {"SNOW_DENSITY", "DENS_BRAS", nullptr}, {"GRND_FLUX_TYPE", "GF_410", nullptr}, {"QUICK_FLUX", "TRUE", nullptr},
     {"TFALLBACK", "TRUE", nullptr}, {"SPATIAL_SNOW", "FALSE", nullptr}, {"SPATIAL_FROST", "FALSE", nullptr},
@@ -903,6 +919,7 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "COMPRESS")) g->compress = flag(t);
     else if (!strcasecmp(k, "PRT_HEADER")) g->prt_header = flag(t);
     else if (!strcasecmp(k, "ALMA_OUTPUT")) g->alma_output = flag(t);
+    else if (!strcasecmp(k, "OUTPUT_FORCE")) g->output_force = flag(t);
     else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
     else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
     else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }

@@ -150,7 +150,8 @@ class GlobalC(C.Structure):
                 [("sw_prec_thresh", C.c_double), ("init_state_file", C.c_char * 512), ("statename", C.c_char * 512)] +
                 [(n, C.c_int32) for n in ("stateyear", "statemonth", "stateday", "binary_state_file",
                                           "forcing2", "n_outfile_lines", "n_outvar_lines")] +
-                [("other_unsupported", C.c_char * 96), ("prt_header", C.c_int32), ("alma_output", C.c_int32)])
+                [("other_unsupported", C.c_char * 96), ("prt_header", C.c_int32), ("alma_output", C.c_int32),
+                 ("output_force", C.c_int32)])
 
 
 FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip", "vr_read_forcing_file"]
@@ -237,11 +238,11 @@ class OutSelC(C.Structure):
                 ("mult", (C.c_double * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES),
                 ("name", ((C.c_char * 32) * VR_MAX_OUTCOLS) * VR_MAX_OUTFILES), ("nvars", C.c_int32 * VR_MAX_OUTFILES),
                 ("header", C.c_int32), ("hdr_nrecs", C.c_int32), ("hdr_out_dt", C.c_int32), ("hdr_start", C.c_int32 * 4),
-                ("hdr_alma", C.c_int32)]
+                ("hdr_alma", C.c_int32), ("no_date", C.c_int32)]
 
 
 FILES_EXPORTS += ["vr_outsel_read", "vr_outsel_step_vars", "vr_aggregate_device", "vr_aggregate", "vr_write_results_sel",
-                  "vr_alma_output_device", "vr_alma_output"]
+                  "vr_alma_output_device", "vr_alma_output", "vr_forcing_outputs_device", "vr_forcing_outputs"]
 
 
 def _bind_outsel(so):
@@ -251,6 +252,8 @@ def _bind_outsel(so):
     so.vr_aggregate_device.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     so.vr_aggregate.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, pd, pd]
+    so.vr_forcing_outputs_device.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double,
+                                             C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     so.vr_alma_output_device.argtypes = [C.c_int, C.c_int32, i32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     so.vr_write_results_sel.argtypes = [C.c_char_p, C.POINTER(OutSelC), C.c_int32, C.c_int32, C.c_int64, f32, f32, C.c_int32,
                                         i32, i32, i32, i32, C.c_int32, i32, pd]
@@ -347,6 +350,18 @@ def aggregate_device(names, in_ptr, out_ptr, nrec, ratio, ncell, device=0, strea
         raise VicResError(rc, "vr_aggregate_device")
 
 
+def forcing_outputs_device(names, field_ptrs, out_ptr, nrecs, nf, ncell, max_snow_temp, min_rain_temp, device=0, stream=0, lib=None):
+    """OUTPUT_FORCE rows (write_forcing_file.c): field_ptrs = the nine prepared forcing arrays on the device, out [n][nrecs * nf][ncell]"""
+    so = _bind_outsel(_bind(lib or load_library()))
+    v = np.asarray([abi.OUT[x] for x in names], dtype=np.int32)
+    fp = (C.c_void_p * abi.VR_NFORCING)(*[int(p) for p in field_ptrs])
+    rc = so.vr_forcing_outputs_device(device, len(names), v.ctypes.data_as(C.POINTER(C.c_int32)), nrecs, nf, ncell, max_snow_temp,
+                                      min_rain_temp, fp, out_ptr, stream or None)
+    if rc != 0:
+        raise VicResError(rc, "vr_forcing_outputs_device: %s" % ("a variable that is not a forcing output" if rc == abi.VR_ERR_UNSUPPORTED
+                                                                 else "failed"))
+
+
 def alma_output_device(names, data_ptr, nrec, ncell, out_dt, device=0, stream=0, lib=None):
     """ALMA_OUTPUT units in place on device values [n][nrec][ncell] that are already at OUT_STEP = out_dt hours"""
     so = _bind_outsel(_bind(lib or load_library()))
@@ -356,10 +371,10 @@ def alma_output_device(names, data_ptr, nrec, ncell, out_dt, device=0, stream=0,
         raise VicResError(rc, "vr_alma_output_device")
 
 
-def read_binary_results(path, cols, hourly, header=False):
+def read_binary_results(path, cols, hourly, header=False, no_date=False):
     """a BINARY_OUTPUT result file -> (date [nrec, 3 or 4], values [ncol, nrec]); cols: [(name, format, type, mult)];
-    header: the file starts with the PRT_HEADER block (its length is the fifth unsigned short)"""
-    dt = [("date", "<i4", 4 if hourly else 3)] + [("c%d" % k, OUT_TYPE_DTYPE[c[2]]) for k, c in enumerate(cols)]
+    header: the file starts with the PRT_HEADER block (its length is the fifth unsigned short); no_date: an OUTPUT_FORCE file"""
+    dt = [("date", "<i4", 0 if no_date else (4 if hourly else 3))] + [("c%d" % k, OUT_TYPE_DTYPE[c[2]]) for k, c in enumerate(cols)]
     off = int(np.fromfile(path, dtype="<u2", count=5)[4]) if header else 0
     a = np.fromfile(path, dtype=np.dtype(dt), offset=off)
     return a["date"], np.stack([a["c%d" % k].astype(np.float64) / cols[k][3] for k in range(len(cols))])

@@ -29,7 +29,10 @@ def run(global_path, device=0, write=True, records_per_block=0):
     why = g.unsupported
     if why:
         raise model.VicResError(abi.VR_ERR_UNSUPPORTED, why)
-    lib, cells, meta = files.read_params(**g.param_files())
+    pf = g.param_files()
+    if g.output_force:                      # vicNl.c:226-234: read_snowband() is not called, so the cell keeps the soil file's
+        pf["snowband"], pf["nbands"] = None, 1          # elevation (read_snowband.c replaces it by the bands' mean elevation)
+    lib, cells, meta = files.read_params(**pf)
     Cn = len(meta["gridcel"])
     ao = atmos.options_from_global(g)
     # forcing files -> [type][record][cell] columns
@@ -59,6 +62,25 @@ def run(global_path, device=0, write=True, records_per_block=0):
                          [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], Cn, raw["t_a"].shape[0], device=device,
                          snowflag_dev=flag_dev.data_ptr())
     torch.cuda.synchronize(dev)
+    if g.output_force:                      # OUTPUT_FORCE TRUE: write the forcing and stop (vicNl.c:226-234, write_forcing_file.c)
+        sel = files.OutSel(global_path, g.nlayer)
+        names = sel.step_vars()
+        rows = torch.empty((len(names), nrecs * NF, Cn), dtype=torch.float64, device=dev)
+        files.forcing_outputs_device(names, [f_dev[f].data_ptr() for f in range(abi.VR_NFORCING)], rows.data_ptr(), nrecs, NF, Cn,
+                                     g.max_snow_temp, g.min_rain_temp, device=device)
+        if g.alma_output:
+            files.alma_output_device(names, rows.data_ptr(), nrecs * NF, Cn, g.time_step, device=device)
+        dmy = g.dmy()
+        if g.prt_header:
+            sel.set_header(nrecs, g.out_step if g.out_step > 0 else g.time_step, dmy[0, :4], alma=bool(g.alma_output))
+        out = rows.cpu().numpy()
+        if write:
+            z = np.zeros(nrecs * NF, dtype=np.int32)
+            for f in range(len(sel.files)):
+                sel.write(f, g.result_dir, meta["lat"], meta["lng"], z, z, z, None, out, sel.rows(f, names), binary=bool(g.binary_output),
+                          grid_decimal=g.grid_decimal)
+        meta["out_names"] = names
+        return out, meta, dmy
     # what to compute: the columns of the output files, each once (the conductance instead of the resistance when the
     # output interval spans several records: put_data.c:686 inverts the aggregated conductance)
     sel = files.OutSel(global_path, g.nlayer)
