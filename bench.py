@@ -168,7 +168,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", os.environ.get("VICRES_BENCH_SAMPLER_MS", "200")],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
