@@ -176,6 +176,7 @@ int main(int argc, char **argv)
     die("output selection", vr_params_last_error());
   opt.nbands = g.snow_band; opt.dt_hours = g.time_step; opt.snow_step_hours = g.snow_step;
   opt.max_snow_temp = g.max_snow_temp; opt.min_rain_temp = g.min_rain_temp; opt.wind_h = g.wind_h;
+  opt.moistfract = g.moistfract;
   vr_handle *h = NULL;
   if (vr_create(&opt, device, &h) != VR_OK) die("vr_create", vr_last_error(NULL));
   if (vr_set_veglib(h, vr_params_veglib(par)) != VR_OK || vr_set_cells(h, cells) != VR_OK) die("parameters", vr_last_error(h));

@@ -100,7 +100,9 @@ typedef struct vr_options {
   int32_t n_out;            /* number of output variables requested                     */
   int32_t out_vars[VR_MAX_OUT]; /* VR_OUT_* ids, in output order                        */
   int32_t cells_per_block_hint; /* records per pipelined H2D/compute/D2H chunk of vr_step_block; 0 = default (16) */
-  int32_t reserved[7];
+  int32_t moistfract;       /* options.MOISTFRACT: OUT_SOIL_LIQ / OUT_SOIL_MOIST as volume fractions (each tile's layer moisture
+                               divided by depth * 1000 before the area weighting, put_data.c:906-911)                  */
+  int32_t reserved[6];
 } vr_options;
 
 /* Vegetation library incl. nothing but real classes; the bare-soil pseudo class (index nclass) is

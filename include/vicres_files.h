@@ -155,10 +155,11 @@ typedef struct vr_global {
    * parse_output_info.c:62-118; counted here, parsed by vr_outsel_read) */
   int32_t forcing2, n_outfile_lines, n_outvar_lines;
   /* the first option of the file that changes the results and has a value this library does not implement ("KEY VALUE":
-   * MOISTFRACT, PRT_SNOW_BAND, OUTPUT_FORCE, BASEFLOW NIJSSEN2001, SNOW_ALBEDO, SNOW_DENSITY,
+   * PRT_SNOW_BAND, OUTPUT_FORCE, BASEFLOW NIJSSEN2001, SNOW_ALBEDO, SNOW_DENSITY,
    * AERO_RESIST_CANSNOW, GRND_FLUX_TYPE, SPATIAL_SNOW ...), or empty: named by vr_global_unsupported, never ignored */
   char    other_unsupported[96];
   int32_t prt_header, alma_output, output_force;   /* PRT_HEADER, ALMA_OUTPUT, OUTPUT_FORCE                     */
+  int32_t moistfract;                              /* MOISTFRACT -> vr_options.moistfract                       */
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -2705,6 +2705,7 @@ static void put_data(vo_model *m, int64_t c, const oatmos *atmos, double out_pre
         double tmp_moist = u->cell.layer[index].moist, tmp_ice = 0;
         tmp_ice += (0. * 1.);
         tmp_moist -= tmp_ice;
+        if (opt->moistfract) tmp_moist /= soil_con->depth[index] * 1000.;      /* put_data.c:906-909 */
         o[VR_OUT_SOIL_LIQ0 + index] += tmp_moist * AreaFactor;
       }
       o[VR_OUT_SOIL_WET] += u->cell.wetness * AreaFactor;
@@ -2761,7 +2762,10 @@ static void put_data(vo_model *m, int64_t c, const oatmos *atmos, double out_pre
   inflow = o[VR_OUT_PREC] + 0.;
   outflow = o[VR_OUT_EVAP] + o[VR_OUT_RUNOFF] + o[VR_OUT_BASEFLOW];
   storage = 0.;
-  for (index = 0; index < NLAYER; index++) storage += o[VR_OUT_SOIL_LIQ0 + index] + 0.;
+  for (index = 0; index < NLAYER; index++) {      /* put_data.c:624-630 */
+    if (opt->moistfract) storage += (o[VR_OUT_SOIL_LIQ0 + index] + 0.) * soil_con->depth[index] * 1000;
+    else storage += o[VR_OUT_SOIL_LIQ0 + index] + 0.;
+  }
   storage += o[VR_OUT_SWE] + o[VR_OUT_SNOW_CANOPY] + o[VR_OUT_WDEW] + 0.;
   /* calc_water_energy_balance_errors.c calc_water_balance_error */
   if (init) {

@@ -67,16 +67,19 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
     auto col_of = [&](int j) { return j; };
     auto S = [&](int k) { return buf[(size_t)tmap.row[k] * MAXU + 0]; };
     double *svc = &sv[(size_t)c * SV_N];
+    double depth_m[MAXL] = {0, 0, 0};                     // options.MOISTFRACT: the cell's layer depths
+    for (int l = 0; l < NL; l++) depth_m[l] = cc.depth(l);
+    const double *mfd = opt->moistfract ? depth_m : nullptr;
     {   // put_data(rec = -nrecs)
       UnitOut z;
       memset(&z, 0, sizeof z);
       for (int j = 0; j < nu; j++) {
         const int64_t u = P.u_slot[fu0 + j];       // per-unit arrays are in slot order
-        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S_[u], z, NL, tmap, &buf[j], MAXU);
+        unit_terms(UC[u], P.u_cv[u], P.u_af[u], S_[u], z, NL, tmap, &buf[j], MAXU, nullptr, mfd);
       }
       if (nu > 0) {
         cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);
-        cell_carry(S, NL, svc);
+        cell_carry(S, NL, svc, mfd);
       }
     }
     const int NF = opt->dt_hours / opt->snow_step_hours, NS = NF > 1 ? NF + 1 : 1;
@@ -108,7 +111,7 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
         bool snowy = s.swq > 0 || s.snow_canopy > 0 || s.coverage != 0;
         bool tidy = !snowy && (s.last_snow != (int)MISSINGV || s.MELTING != 0 || s.albedo != NEW_SNOW_ALB);
 #define HS_ARGS cc, UC[u], tm, ae, forc, NF, NL, opt->dt_hours, opt->snow_step_hours, opt->max_snow_temp, opt->min_rain_temp, h, snowy, \
-                tidy, sio, P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap
+                tidy, sio, P.u_cv[u], P.u_af[u], tmap, &buf[j], MAXU, true, tl, ap, opt->moistfract != 0
         // the instance the kernel would launch: the one without sums / averages when NF == 1
 #define HS_STEP(EX) do { if (NF > 1) unit_record<EX, true>(HS_ARGS); else unit_record<EX, false>(HS_ARGS); } while (0)
         switch (term_extras(tmap)) {
@@ -126,8 +129,8 @@ extern "C" int hs_run(const vr_options *opt, const vr_veglib *lib, const vr_cell
       if (nu > 0) {
         cell_accumulate_inplace(buf.data(), MAXU, tmap, nu, col_of, NL);
         for (int v = 0; v < opt->n_out; v++)
-          out[((size_t)v * nrec + rec) * C + c] = cell_output(opt->out_vars[v], S, fo, NL, false, svc);
-        cell_carry(S, NL, svc);
+          out[((size_t)v * nrec + rec) * C + c] = cell_output(opt->out_vars[v], S, fo, NL, false, svc, mfd);
+        cell_carry(S, NL, svc, mfd);
       }
     }
   }

@@ -250,15 +250,15 @@ def test_global_file_calendar_and_forcing_reader(tmp_path):
     bad.write_text(g.read_text().replace("FULL_ENERGY FALSE", "FULL_ENERGY TRUE"))
     assert files.Global(str(bad)).unsupported == "FULL_ENERGY TRUE"
     # options that change the results and have a value outside what the library implements are named, never ignored
-    for line, why in [("MOISTFRACT TRUE", "MOISTFRACT TRUE"), ("BASEFLOW NIJSSEN2001", "BASEFLOW NIJSSEN2001"),
+    for line, why in [("RC_MODE RC_PHOTO", "RC_MODE RC_PHOTO"), ("BASEFLOW NIJSSEN2001", "BASEFLOW NIJSSEN2001"),
                       ("SNOW_DENSITY DENS_SNTHRM", "SNOW_DENSITY DENS_SNTHRM"), ("PRT_SNOW_BAND TRUE", "PRT_SNOW_BAND TRUE"),
                       ("AERO_RESIST_CANSNOW AR_410", "AERO_RESIST_CANSNOW AR_410"), ("SPATIAL_SNOW TRUE", "SPATIAL_SNOW TRUE")]:
         bad.write_text(g.read_text() + line + "\n")
         assert files.Global(str(bad)).unsupported == why
     bad.write_text(g.read_text() + "SNOW_ALBEDO USACE\nGRND_FLUX_TYPE GF_410\nQUICK_FLUX TRUE\nEQUAL_AREA FALSE\nRESOLUTION 0.125\n"
-                   "PRT_HEADER TRUE\nALMA_OUTPUT TRUE\n")
+                   "PRT_HEADER TRUE\nALMA_OUTPUT TRUE\nMOISTFRACT TRUE\n")
     G3 = files.Global(str(bad))
-    assert G3.unsupported is None and G3.prt_header == 1 and G3.alma_output == 1
+    assert G3.unsupported is None and G3.prt_header == 1 and G3.alma_output == 1 and G3.moistfract == 1
     sub = tmp_path / "sub.txt"
     sub.write_text(g.read_text().replace("SNOW_STEP 24", "SNOW_STEP 3"))
     assert files.Global(str(sub)).unsupported is None                       # the snow model sub-stepped: NF = 8

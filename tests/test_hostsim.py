@@ -48,3 +48,39 @@ def test_pow_table_error_bound(tmp_path):
     n, norm, rel, unhandled = subprocess.run([exe, "2000000"], check=True, capture_output=True, text=True).stdout.split()
     assert int(unhandled) == 0
     assert float(norm) <= 2e-16 and float(rel) < 1e-13
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "vic_ref_driver")),
+                    reason="compiled reference (oracle/_ref) not built here")
+def test_moistfract_against_the_live_reference(hostsim, tmp_path):
+    """MOISTFRACT TRUE (soil moisture as volume fractions per tile before the area weighting, the water-balance storage back
+    in mm: put_data.c:624-630, 906-911): the oracle and the device code compiled for the host, bit for bit against the
+    compiled reference run on a seeded case"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib
+    import refdump
+    from vicres_b200 import synth
+    g = synth.make_case(str(tmp_path / "case"), ncells=3, nlayer=3, nbands=2, ndays=150, cold=8.0, lat_range=(30, 60),
+                        overstory_frac=0.5, seed=777, extra_global="MOISTFRACT TRUE")
+    dump = str(tmp_path / "dump.bin")
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "vic_ref_driver"), "-g", g, "-d", dump], check=True, capture_output=True)
+    d = refdump.read_dump(dump)
+    cs = refdump.case_from_dump(d)
+    names = abi.OUT_NAMES
+    opt = abi.default_options(cs["nlayer"], cs["nbands"], cs["dt"], out=names, max_snow_temp=cs["max_snow_temp"],
+                              min_rain_temp=cs["min_rain_temp"], moistfract=True)
+    ref = refdump.ref_outputs(d, names)
+    assert ref[names.index("SOIL_LIQ0")].max() < 1.0          # fractions, not mm
+    o = oracle_lib.Oracle(opt, cs["lib"], cs["cells"])
+    o.init_state(cs["tair0"])
+    rc, out, _ = o.step(cs["month"], cs["doy"], cs["forcing"])
+    o.close()
+    assert rc == 0 and np.array_equal(out, ref)
+    lib, cells = abi.pack_veglib(cs["lib"]), abi.pack_cells(cs["cells"])
+    f = abi.pack_forcing(cs["month"], cs["doy"], cs["forcing"], None)
+    hout = np.zeros_like(ref)
+    t0 = np.ascontiguousarray(cs["tair0"])
+    assert hostsim.hs_run(C.byref(opt), lib.ref(), cells.ref(), f.ref(), t0.ctypes.data, hout.ctypes.data) == 0
+    for i, n in enumerate(names):
+        assert np.array_equal(hout[i], ref[i]), "%s differs from the reference under MOISTFRACT" % n

@@ -27,7 +27,8 @@ def _stage(name, tmp_path, variant=None):
 # variants of the two cases: output interval, output selection, binary files (tools/make_vicnl_golden.py: VARIANTS)
 VARIANTS = [("sub3h", "out24"), ("sub3h", "out6sel"), ("daily", "selday"), ("sub3h", "bin"), ("sub3h", "bin24sel"),
             ("daily", "snow3"), ("skip", "snow1"), ("daily", "hdr"), ("sub3h", "hdrbin24"), ("sub3h", "alma6"), ("daily", "almadef"),
-            ("sub3h", "met6"), ("daily", "metalma"), ("daily", "force"), ("sub3h", "forcebin"), ("daily", "force3")]
+            ("sub3h", "met6"), ("daily", "metalma"), ("daily", "force"), ("sub3h", "forcebin"), ("daily", "force3"),
+            ("daily", "mfrac"), ("sub3h", "mfrac6")]
 
 
 def _quantum(tok):

@@ -63,6 +63,10 @@ VARIANTS = {
     "force3": ("daily", ["OUTPUT_FORCE TRUE", "SNOW_STEP 3", "PRT_HEADER TRUE", "ALMA_OUTPUT TRUE", "N_OUTFILES 1", "OUTFILE fd 8",
                          "OUTVAR OUT_PREC %.6e", "OUTVAR OUT_RAINF %.6e", "OUTVAR OUT_SNOWF %.6e", "OUTVAR OUT_AIR_TEMP",
                          "OUTVAR OUT_REL_HUMID %.2f", "OUTVAR OUT_QAIR %.8f", "OUTVAR OUT_PRESSURE %.2f", "OUTVAR OUT_LONGWAVE"]),
+    # MOISTFRACT: soil moisture as volume fractions (per tile, before the area weighting), the water-balance check back in mm
+    "mfrac": ("daily", ["MOISTFRACT TRUE"]),
+    "mfrac6": ("sub3h", ["MOISTFRACT TRUE", "OUT_STEP 6", "N_OUTFILES 1", "OUTFILE mf 5", "OUTVAR OUT_SOIL_MOIST %.8f",
+                         "OUTVAR OUT_SOIL_LIQ %.8f", "OUTVAR OUT_DELSOILMOIST %.8f", "OUTVAR OUT_WATER_ERROR %.3e", "OUTVAR OUT_ROOTMOIST"]),
     "bin": ("sub3h", ["BINARY_OUTPUT TRUE"]),
     "bin24sel": ("sub3h", ["BINARY_OUTPUT TRUE", "OUT_STEP 24", "N_OUTFILES 1", "OUTFILE packed 6",
                            "OUTVAR OUT_PREC %.4f OUT_TYPE_USINT 40", "OUTVAR OUT_AIR_TEMP %.4f OUT_TYPE_SINT 100",

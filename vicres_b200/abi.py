@@ -40,7 +40,7 @@ class vr_options(C.Structure):
                 ("snow_step_hours", C.c_int32), ("max_snow_temp", C.c_double),
                 ("min_rain_temp", C.c_double), ("wind_h", C.c_double), ("n_out", C.c_int32),
                 ("out_vars", C.c_int32 * VR_MAX_OUT), ("cells_per_block_hint", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("moistfract", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class vr_veglib(C.Structure):
@@ -79,12 +79,13 @@ def _ptr(a, ty):
 
 
 def default_options(nlayer=3, nbands=1, dt_hours=24, out=None, max_snow_temp=0.5, min_rain_temp=-0.5,
-                    wind_h=10.0, snow_step_hours=None):
+                    wind_h=10.0, snow_step_hours=None, moistfract=False):
     """Reference defaults (initialize_global.c:146-211) and the default fluxes+snow output set
     (set_output_defaults.c:78-162): 19 + nlayer flux columns, 4 snow columns."""
     o = vr_options()
     o.nlayer, o.nbands, o.dt_hours, o.snow_step_hours = nlayer, nbands, dt_hours, snow_step_hours or dt_hours
     o.max_snow_temp, o.min_rain_temp, o.wind_h = max_snow_temp, min_rain_temp, wind_h
+    o.moistfract = int(moistfract)
     if out is None:
         out = default_out_vars(nlayer)
     o.n_out = len(out)

@@ -95,8 +95,10 @@ inline void build_term_map(const int *out_vars, int n_out, TermMap &tmap)
 
 // One unit's area-weighted terms -> term buffer column `col` (rows of `stride` doubles).
 template <int extras = EX_PET | EX_ZWT>
+// mf_depth: options.MOISTFRACT -- the cell's layer depths (m): the layer moisture is stored as a volume fraction,
+// moist / (depth * 1000), before the area weighting (put_data.c:906-911); null = in mm.
 VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, const UnitOut &o, int NL,
-                       const TermMap &tmap, double *col, int stride, const UnitExtra *x = nullptr)
+                       const TermMap &tmap, double *col, int stride, const UnitExtra *x = nullptr, const double *mf_depth = nullptr)
 {
   const double AF = cv * af * 1. * 1.;
   const bool HasVeg = !uc.is_bare;
@@ -114,7 +116,7 @@ VR_HD void unit_terms(const UnitC &uc, double cv, double af, const UnitS &s, con
         T_(TE_EB0 + l, o.evap[l] * AF);
         T_(TE_TV0 + l, 0.);
       }
-      T_(TE_LIQ0 + l, s.moist[l] * AF);
+      T_(TE_LIQ0 + l, (mf_depth ? s.moist[l] / (mf_depth[l] * 1000.) : s.moist[l]) * AF);
     }
     else { T_(TE_EB0 + l, 0.); T_(TE_TV0 + l, 0.); T_(TE_LIQ0 + l, 0.); }
   }
@@ -344,7 +346,7 @@ VR_HD FrontOut unit_front(CellC cc, const UnitC &uc, CanopyM cm, const double *a
 // run(ppt, moist, evap) -> RunoffOut: runoff() with the loop constants where the caller keeps them
 template <int extras, class RunoffFn>
 VR_HD void unit_back_fn(CellC cc, bool is_veg, int root0_mask, int NL, FrontOut fo, M3 &moist, double cv, double af,
-                        const TermMap &tmap, double *col, int stride, bool write, RunoffFn run)
+                        const TermMap &tmap, double *col, int stride, bool write, RunoffFn run, bool moistfract = false)
 {
   const double AF = cv * af * 1. * 1.;
 #define T_(k, expr) do { if (write && tmap.row[k] >= 0) VR_STREAM_ST(col + (size_t)tmap.row[k] * stride, (expr)); } while (0)
@@ -369,7 +371,7 @@ VR_HD void unit_back_fn(CellC cc, bool is_veg, int root0_mask, int NL, FrontOut 
         T_(TE_EB0 + l, st_evap.v[l] * AF);
         T_(TE_TV0 + l, 0.);
       }
-      T_(TE_LIQ0 + l, moist.v[l] * AF);
+      T_(TE_LIQ0 + l, (moistfract ? moist.v[l] / (cc.depth(l) * 1000.) : moist.v[l]) * AF);
     }
     else { T_(TE_EB0 + l, 0.); T_(TE_TV0 + l, 0.); T_(TE_LIQ0 + l, 0.); }
   }
@@ -395,10 +397,10 @@ VR_HD void unit_back_fn(CellC cc, bool is_veg, int root0_mask, int NL, FrontOut 
 
 template <int extras>
 VR_HD void unit_back(CellC cc, bool is_veg, int root0_mask, int NL, int dt_hours, FrontOut fo, M3 &moist, double cv, double af,
-                     const TermMap &tmap, double *col, int stride, bool write)
+                     const TermMap &tmap, double *col, int stride, bool write, bool moistfract = false)
 {
   unit_back_fn<extras>(cc, is_veg, root0_mask, NL, fo, moist, cv, af, tmap, col, stride, write,
-                       [&](double ppt, M3 m, M3 e) { return runoff_step(cc, NL, dt_hours, ppt, m, e); });
+                       [&](double ppt, M3 m, M3 e) { return runoff_step(cc, NL, dt_hours, ppt, m, e); }, moistfract);
 }
 
 // the two halves one after the other (host harness of the tests).  Returns 1 when the reference would have returned ERROR
@@ -407,7 +409,7 @@ template <int extras, bool SUB, class ForcOf, class SnowIO>
 VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double *ae, ForcOf forc, int NF, int NL,
                       int dt_hours, int snow_step_hours, double max_snow_temp, double min_rain_temp, HotS &h, bool &snowy,
                       bool &tidy, SnowIO &sio, double cv, double af, const TermMap &tmap, double *col, int stride, bool write,
-                      const double *tl = nullptr, const double *ap = nullptr)
+                      const double *tl = nullptr, const double *ap = nullptr, bool moistfract = false)
 {
   const Forc fr = forc(NF > 1 ? NF : 0);
   const bool general = unit_needs_snow(fr, uc.Tfactor, uc.Pfactor, NF, max_snow_temp, min_rain_temp, snowy);
@@ -421,7 +423,7 @@ VR_HD int unit_record(CellC cc, const UnitC &uc, const double *tm, const double 
   else
     fo = unit_front<extras, false, false>(cc, uc, cm, ae, forc, NF, NL, dt_hours, snow_step_hours, max_snow_temp, min_rain_temp,
                                           h, snowy, tidy, sio, cv, af, tmap, col, stride, write, false, tl, ap);
-  unit_back<extras>(cc, !uc.is_bare, uc.root0_mask, NL, dt_hours, fo, h.moist, cv, af, tmap, col, stride, write);
+  unit_back<extras>(cc, !uc.is_bare, uc.root0_mask, NL, dt_hours, fo, h.moist, cv, af, tmap, col, stride, write, moistfract);
   return fo.err;
 }
 
@@ -518,8 +520,10 @@ VR_HD double cell_sum(const double *src, size_t sstride, int64_t u0, int nu, con
 
 // One output variable of a cell-record from the summed terms (put_data.c:540-632).  S(k) reads sum k.
 // water_error / deltas use the carried save_data words sv[] BEFORE cell_carry() updates them.
+// mfd: options.MOISTFRACT -- the cell's layer depths (m); the soil terms are volume fractions then, and the storage of the
+// water-balance check turns them back into mm (put_data.c:624-630); null = the terms are mm
 template <class Sum>
-VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const double *sv)
+VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const double *sv, const double *mfd = nullptr)
 {
   switch (var) {
     case VR_OUT_AIR_TEMP: return f.air_temp;
@@ -589,7 +593,7 @@ VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const
       const double inflow = S(TE_PREC) + 0.;
       const double outflow = S(TE_EVAP) + S(TE_RUNOFF) + S(TE_BASEFLOW);
       double storage = 0.;
-      for (int l = 0; l < NL; l++) storage += S(TE_LIQ0 + l) + 0.;
+      for (int l = 0; l < NL; l++) storage += mfd ? (S(TE_LIQ0 + l) + 0.) * mfd[l] * 1000 : S(TE_LIQ0 + l) + 0.;
       storage += S(TE_SWE) + S(TE_SCANOPY) + S(TE_WDEW) + 0.;
       return inflow - outflow - (storage - sv[SV_STORAGE]);
     }
@@ -599,11 +603,11 @@ VR_HD double cell_output(int var, Sum S, const Forc &f, int NL, bool init, const
 
 // carry the save_data words to the next record (put_data.c:612-620, calc_water_balance_error)
 template <class Sum>
-VR_HD void cell_carry(Sum S, int NL, double *sv)
+VR_HD void cell_carry(Sum S, int NL, double *sv, const double *mfd = nullptr)
 {
   double soil_tot = 0, storage = 0.;
   for (int l = 0; l < NL; l++) soil_tot += S(TE_LIQ0 + l) + 0.;
-  for (int l = 0; l < NL; l++) storage += S(TE_LIQ0 + l) + 0.;
+  for (int l = 0; l < NL; l++) storage += mfd ? (S(TE_LIQ0 + l) + 0.) * mfd[l] * 1000 : S(TE_LIQ0 + l) + 0.;
   storage += S(TE_SWE) + S(TE_SCANOPY) + S(TE_WDEW) + 0.;
   sv[SV_SOIL] = soil_tot;
   sv[SV_SWE] = S(TE_SWE) + S(TE_SCANOPY);

@@ -81,6 +81,7 @@ struct DevModel {
   const double *tmu;                // [12][TM_N][US] the month's canopy terms per unit in slot order
   int64_t US;                       // row stride of ccu / tmu: U rounded up to whole thread blocks (bulk copies read full rows)
   int ccn;
+  int moistfract;                   // options.MOISTFRACT
   const int64_t *cell_uptr, *fcol;
   const int64_t *order;             // sorted position -> caller's cell index
   const int32_t *u_cell, *u_pos, *u_tile, *u_flags, *u_aero, *u_slot, *u_logical, *cell_fail;
@@ -161,6 +162,14 @@ __global__ void k_unit_consts(DevModel M, double *ccu, double *tmu)
   for (int k = 0; k < 12 * TM_N; k++) tmu[(size_t)k * M.US + u] = tm[k];
 }
 
+// options.MOISTFRACT: the layer depths (m) of the cell at sorted position pos, or null when the option is off
+__device__ __forceinline__ const double *moistfract_depths(const DevModel &M, int64_t pos, double *d)
+{
+  if (!M.moistfract) return nullptr;
+  for (int l = 0; l < MAXL; l++) d[l] = l < M.NL ? M.cc[(size_t)(CC_FL0 + l * CLF_N + CLF_DEPTH) * M.C + pos] : 0.;
+  return d;
+}
+
 // initialize_model_state() for every unit + its terms for put_data(rec = -nrecs)
 __global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double *tair0 /* [FC] */, double *terms)
 {
@@ -178,7 +187,8 @@ __global__ void __launch_bounds__(VR_CTA) k_init_units(DevModel M, const double 
   unit_init(im, mm, M.NL, tair0[fc], uc.Tfactor, s);
   store_state(M, u, s);
   memset(&z, 0, sizeof z);
-  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U);
+  double dm[MAXL];
+  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U, nullptr, moistfract_depths(M, M.u_pos[u], dm));
 }
 
 // the terms of a state that is already in place (restart from a state file) for put_data(rec = -nrecs)
@@ -191,7 +201,8 @@ __global__ void __launch_bounds__(VR_CTA) k_restored_units(DevModel M, double *t
   load_unit_consts(M, u, uc, cv, af);
   load_state(M, u, s);
   memset(&z, 0, sizeof z);
-  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U);
+  double dm[MAXL];
+  unit_terms(uc, cv, af, s, z, M.NL, M.tmap, terms + M.u_logical[u], (int)M.U, nullptr, moistfract_depths(M, M.u_pos[u], dm));
 }
 
 __global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *terms, double *sums, int svb)
@@ -204,7 +215,8 @@ __global__ void __launch_bounds__(128) k_init_cells(DevModel M, const double *te
   if (nu > 0) {
     cell_accumulate_to(terms, (size_t)M.U, fu0, nu, M.tmap, M.NL, sums, (size_t)M.C, cs);
     auto S = [&](int k) { return sums[(size_t)M.tmap.row[k] * M.C + cs]; };
-    cell_carry(S, M.NL, sv);
+    double dm[MAXL];
+    cell_carry(S, M.NL, sv, moistfract_depths(M, cs, dm));
   }
   for (int k = 0; k < SV_N; k++) M.sv[((size_t)svb * SV_N + k) * M.C + c] = sv[k];
   M.cell_status[c] = M.cell_fail[c] ? 1 : 0;
@@ -487,7 +499,7 @@ __device__ __forceinline__ void back_unit(const DevModel &M, int rec, int64_t u,
   const int NL = M.NL, dt = M.dt_hours;
   unit_back_fn<EXTRAS>(cc, (fl & 1) == 0, fl >> 8, NL, fo, moist, M.u_cv[u], M.u_af[u], M.tmap,
                        terms + (size_t)rec * M.tmap.n * M.U + M.u_logical[u], (int)M.U, true,
-                       [&](double ppt, M3 m, M3 e) { return runoff_step_staged(cc, lk, NL, dt, ppt, m, e); });
+                       [&](double ppt, M3 m, M3 e) { return runoff_step_staged(cc, lk, NL, dt, ppt, m, e); }, M.moistfract != 0);
   st[ST_MOIST0 * U] = moist.v[0]; st[ST_MOIST1 * U] = moist.v[1]; st[ST_MOIST2 * U] = moist.v[2];
 }
 
@@ -625,13 +637,14 @@ __global__ void __launch_bounds__(256, VR_CELLS_MINB) k_cells(DevModel M, DevFor
   }
   const double *T = terms + rec * rec_stride;
   auto S = [&](int k) { return cell_sum(T, (size_t)M.U, fu0, nu, M.tmap, NL, k); };
-  double sv[SV_N];
+  double sv[SV_N], dm[MAXL];
+  const double *mfd = moistfract_depths(M, cs, dm);
   if (rec == 0)
     for (int k = 0; k < SV_N; k++) sv[k] = M.sv[((size_t)svb * SV_N + k) * M.C + c];
   else {
     const double *P = terms + (rec - 1) * rec_stride;
     auto SP = [&](int k) { return cell_term_sum(P, (size_t)M.U, fu0, nu, M.tmap.row[k]); };
-    cell_carry(SP, NL, sv);
+    cell_carry(SP, NL, sv, mfd);
   }
   Forc f;
   const int NS = M.NF > 1 ? M.NF + 1 : 1;
@@ -642,9 +655,9 @@ __global__ void __launch_bounds__(256, VR_CELLS_MINB) k_cells(DevModel M, DevFor
   f.pressure = __ldg(F.field[VR_F_PRESSURE] + q); f.density = __ldg(F.field[VR_F_DENSITY] + q);
   f.prec = 0; f.mon = 0; f.doy = 0; f.snowflag = 0;
 #pragma unroll 1
-  for (int v = 0; v < M.n_out; v++) VR_STREAM_ST(out + (size_t)v * ostride + orow, cell_output(M.out_vars[v], S, f, NL, false, sv));
+  for (int v = 0; v < M.n_out; v++) VR_STREAM_ST(out + (size_t)v * ostride + orow, cell_output(M.out_vars[v], S, f, NL, false, sv, mfd));
   if (rec == F.nrec - 1) {
-    cell_carry(S, NL, sv);
+    cell_carry(S, NL, sv, mfd);
     for (int k = 0; k < SV_N; k++) M.sv[((size_t)(svb ^ 1) * SV_N + k) * M.C + c] = sv[k];
   }
 }
@@ -1129,6 +1142,7 @@ int vr_set_cells(vr_handle *h, const vr_cells *cells)
   memset(&M, 0, sizeof M);
   M.NL = P.NL; M.NB = P.NB; M.dt_hours = h->opt.dt_hours; M.n_out = h->opt.n_out;
   M.snow_step_hours = h->opt.snow_step_hours; M.NF = h->opt.dt_hours / h->opt.snow_step_hours;
+  M.moistfract = h->opt.moistfract != 0;
   M.max_snow_temp = h->opt.max_snow_temp; M.min_rain_temp = h->opt.min_rain_temp;
   M.C = C; M.U = U; M.FC = C;
   M.cc = h->d_cc.p; M.cell_uptr = h->d_cell_uptr.p; M.fcol = nullptr;

@@ -812,7 +812,6 @@ static void next_step(int &year, int &month, int &day, int &hr, int &jday, int d
 static bool other_option_unsupported(const char *key, const char *val)
 {
   static const struct { const char *key, *ok1, *ok2; } T[] = {
-    {"MOISTFRACT", "FALSE", nullptr},
     {"PRT_SNOW_BAND", "FALSE", nullptr}, {"BASEFLOW", "ARNO", nullptr},
     {"ARC_SOIL", "FALSE", nullptr}, {"AERO_RESIST_CANSNOW", "AR_406_FULL", nullptr}, {"SNOW_ALBEDO", "USACE", nullptr},
     {"SNOW_DENSITY", "DENS_BRAS", nullptr}, {"GRND_FLUX_TYPE", "GF_410", nullptr}, {"QUICK_FLUX", "TRUE", nullptr},
@@ -920,6 +919,7 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "PRT_HEADER")) g->prt_header = flag(t);
     else if (!strcasecmp(k, "ALMA_OUTPUT")) g->alma_output = flag(t);
     else if (!strcasecmp(k, "OUTPUT_FORCE")) g->output_force = flag(t);
+    else if (!strcasecmp(k, "MOISTFRACT")) g->moistfract = flag(t);
     else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
     else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
     else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }

@@ -151,7 +151,7 @@ class GlobalC(C.Structure):
                 [(n, C.c_int32) for n in ("stateyear", "statemonth", "stateday", "binary_state_file",
                                           "forcing2", "n_outfile_lines", "n_outvar_lines")] +
                 [("other_unsupported", C.c_char * 96), ("prt_header", C.c_int32), ("alma_output", C.c_int32),
-                 ("output_force", C.c_int32)])
+                 ("output_force", C.c_int32), ("moistfract", C.c_int32)])
 
 
 FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip", "vr_read_forcing_file"]

@@ -87,7 +87,8 @@ def run(global_path, device=0, write=True, records_per_block=0):
     ratio = g.out_step // g.time_step if g.out_step > 0 else 1
     names = sel.step_vars(aggregate=ratio > 1, alma=bool(g.alma_output))
     opt = abi.default_options(g.nlayer, g.snow_band, g.time_step, out=names, max_snow_temp=g.max_snow_temp,
-                              min_rain_temp=g.min_rain_temp, wind_h=g.wind_h, snow_step_hours=g.snow_step)
+                              min_rain_temp=g.min_rain_temp, wind_h=g.wind_h, snow_step_hours=g.snow_step,
+                              moistfract=bool(g.moistfract))
     m = model.VicRes(opt, lib, cells, device=device)
     tair0 = f_dev[abi.FORCING_FIELDS.index("air_temp"), NS - 1].cpu().numpy()       # atmos[0].air_temp[NR]
     if g.init_state:                     # INIT_STATE <file>: read_initial_model_state instead of the cold start
