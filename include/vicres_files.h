@@ -24,6 +24,8 @@ typedef struct vr_param_files {
   int32_t lai_from_vegparam; /* LAI_SRC FROM_VEGPARAM */
   const char *soil, *veglib, *vegparam;
   const char *snowband;      /* may be NULL when nbands == 1 */
+  int32_t baseflow_nijssen;  /* BASEFLOW NIJSSEN2001: soil columns 5-8 are d1..d4 of Nijssen et al. (2001), converted to the ARNO
+                              * Ds, Dsmax, Ws as read_soilparam.c:719-726 does (c stays) */
 } vr_param_files;
 
 typedef struct vr_params vr_params;          /* owns every array the structs below point to */
@@ -155,11 +157,12 @@ typedef struct vr_global {
    * parse_output_info.c:62-118; counted here, parsed by vr_outsel_read) */
   int32_t forcing2, n_outfile_lines, n_outvar_lines;
   /* the first option of the file that changes the results and has a value this library does not implement ("KEY VALUE":
-   * PRT_SNOW_BAND, OUTPUT_FORCE, BASEFLOW NIJSSEN2001, SNOW_ALBEDO, SNOW_DENSITY,
+   * PRT_SNOW_BAND, SNOW_ALBEDO, SNOW_DENSITY,
    * AERO_RESIST_CANSNOW, GRND_FLUX_TYPE, SPATIAL_SNOW ...), or empty: named by vr_global_unsupported, never ignored */
   char    other_unsupported[96];
   int32_t prt_header, alma_output, output_force;   /* PRT_HEADER, ALMA_OUTPUT, OUTPUT_FORCE                     */
   int32_t moistfract;                              /* MOISTFRACT -> vr_options.moistfract                       */
+  int32_t baseflow_nijssen;                        /* BASEFLOW NIJSSEN2001 -> vr_param_files.baseflow_nijssen   */
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);

@@ -250,7 +250,7 @@ def test_global_file_calendar_and_forcing_reader(tmp_path):
     bad.write_text(g.read_text().replace("FULL_ENERGY FALSE", "FULL_ENERGY TRUE"))
     assert files.Global(str(bad)).unsupported == "FULL_ENERGY TRUE"
     # options that change the results and have a value outside what the library implements are named, never ignored
-    for line, why in [("RC_MODE RC_PHOTO", "RC_MODE RC_PHOTO"), ("BASEFLOW NIJSSEN2001", "BASEFLOW NIJSSEN2001"),
+    for line, why in [("RC_MODE RC_PHOTO", "RC_MODE RC_PHOTO"), ("ARC_SOIL TRUE", "ARC_SOIL TRUE"),
                       ("SNOW_DENSITY DENS_SNTHRM", "SNOW_DENSITY DENS_SNTHRM"), ("PRT_SNOW_BAND TRUE", "PRT_SNOW_BAND TRUE"),
                       ("AERO_RESIST_CANSNOW AR_410", "AERO_RESIST_CANSNOW AR_410"), ("SPATIAL_SNOW TRUE", "SPATIAL_SNOW TRUE")]:
         bad.write_text(g.read_text() + line + "\n")
@@ -293,3 +293,21 @@ def test_bundled_global_file():
     assert G.unsupported is None and (G.nlayer, G.time_step, G.root_zones) == (2, 24, 3)
     assert G.nrecs == 15340                                  # 1981-01-01 .. 2022-12-31
     assert G.force_types == ["PREC", "TMAX", "TMIN", "WIND"] and G.vegparam_lai == 1 and G.lai_from_vegparam == 1
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="compiled reference (oracle/_ref) not built here")
+def test_baseflow_nijssen2001_parameters_against_live_reference(tmp_path):
+    """BASEFLOW NIJSSEN2001: soil columns 5-8 converted to the ARNO Ds, Dsmax, Ws (read_soilparam.c:719-726), bit for bit
+    what the compiled reference holds in soil_con after reading the same file"""
+    work = str(tmp_path / "case")
+    g = synth.make_case(work, ncells=4, nlayer=3, nbands=1, ndays=30, startyear=1990, seed=91, extra_global="BASEFLOW NIJSSEN2001")
+    dump = str(tmp_path / "dump.bin")
+    subprocess.run([DRIVER, "-g", g, "-d", dump], check=True, capture_output=True)
+    ref = refdump.case_from_dump(refdump.read_dump(dump))["cells"]
+    G = files.Global(g)
+    assert G.unsupported is None and G.baseflow_nijssen == 1
+    _, cells, _ = files.read_params(**G.param_files())
+    _, plain, _ = files.read_params(**dict(G.param_files(), baseflow_nijssen=False))
+    for k in ("Ds", "Dsmax", "Ws", "c_expt", "b_infilt"):
+        assert np.array_equal(cells[k], ref[k]), k
+    assert not np.array_equal(cells["Dsmax"], plain["Dsmax"]) and np.array_equal(cells["c_expt"], plain["c_expt"])

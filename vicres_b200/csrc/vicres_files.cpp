@@ -225,6 +225,12 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
       P->porosity[k] = poros;
     }
     P->AreaFract[c] = 1.;                                       // band 0 (read_soilparam.c:478-486)
+    if (fo->baseflow_nijssen) {                                 // read_soilparam.c:719-726, statement for statement
+      const double mm = P->max_moist[(size_t)(L - 1) * C + c];
+      P->Dsmax[c] = P->Dsmax[c] * pow((double)(1. / (mm - P->Ws[c])), -P->c_expt[c]) + P->Ds[c] * mm;
+      P->Ds[c] = P->Ds[c] * P->Ws[c] / P->Dsmax[c];
+      P->Ws[c] = P->Ws[c] / mm;
+    }
   }
   // ---- soil moisture v water table curves (read_soilparam.c:822-921; arithmetic order kept) ----
   {
@@ -812,7 +818,7 @@ static void next_step(int &year, int &month, int &day, int &hr, int &jday, int d
 static bool other_option_unsupported(const char *key, const char *val)
 {
   static const struct { const char *key, *ok1, *ok2; } T[] = {
-    {"PRT_SNOW_BAND", "FALSE", nullptr}, {"BASEFLOW", "ARNO", nullptr},
+    {"PRT_SNOW_BAND", "FALSE", nullptr},
     {"ARC_SOIL", "FALSE", nullptr}, {"AERO_RESIST_CANSNOW", "AR_406_FULL", nullptr}, {"SNOW_ALBEDO", "USACE", nullptr},
     {"SNOW_DENSITY", "DENS_BRAS", nullptr}, {"GRND_FLUX_TYPE", "GF_410", nullptr}, {"QUICK_FLUX", "TRUE", nullptr},
     {"TFALLBACK", "TRUE", nullptr}, {"SPATIAL_SNOW", "FALSE", nullptr}, {"SPATIAL_FROST", "FALSE", nullptr},
@@ -920,6 +926,7 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "ALMA_OUTPUT")) g->alma_output = flag(t);
     else if (!strcasecmp(k, "OUTPUT_FORCE")) g->output_force = flag(t);
     else if (!strcasecmp(k, "MOISTFRACT")) g->moistfract = flag(t);
+    else if (!strcasecmp(k, "BASEFLOW")) g->baseflow_nijssen = (t.size() > 1 && !strcasecmp(t[1].c_str(), "NIJSSEN2001"));
     else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
     else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
     else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }
