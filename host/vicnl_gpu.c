@@ -48,7 +48,7 @@ int main(int argc, char **argv)
   pf.nlayer = g.nlayer; pf.nbands = g.snow_band; pf.root_zones = g.root_zones; pf.vegparam_lai = g.vegparam_lai;
   pf.lai_from_vegparam = g.lai_from_vegparam; pf.soil = g.soil; pf.veglib = g.veglib; pf.vegparam = g.vegparam;
   pf.snowband = g.snowband[0] ? g.snowband : NULL;
-  pf.baseflow_nijssen = g.baseflow_nijssen;
+  pf.baseflow_nijssen = g.baseflow_nijssen; pf.organic_fract = g.organic_fract;
   if (g.output_force) {      /* vicNl.c:226-234: read_snowband() is not called, so the cell keeps the soil file's elevation */
     pf.snowband = NULL;      /* (read_snowband.c replaces it by the bands' mean elevation)                                   */
     pf.nbands = 1;

@@ -26,6 +26,8 @@ typedef struct vr_param_files {
   const char *snowband;      /* may be NULL when nbands == 1 */
   int32_t baseflow_nijssen;  /* BASEFLOW NIJSSEN2001: soil columns 5-8 are d1..d4 of Nijssen et al. (2001), converted to the ARNO
                               * Ds, Dsmax, Ws as read_soilparam.c:719-726 does (c stays) */
+  int32_t organic_fract;     /* ORGANIC_FRACT TRUE: after the mineral soil densities the soil file holds, per layer, the organic
+                              * fraction and the organic bulk and soil densities (read_soilparam.c:444-506, 647-655) */
 } vr_param_files;
 
 typedef struct vr_params vr_params;          /* owns every array the structs below point to */

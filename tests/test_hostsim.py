@@ -84,3 +84,45 @@ def test_moistfract_against_the_live_reference(hostsim, tmp_path):
     assert hostsim.hs_run(C.byref(opt), lib.ref(), cells.ref(), f.ref(), t0.ctypes.data, hout.ctypes.data) == 0
     for i, n in enumerate(names):
         assert np.array_equal(hout[i], ref[i]), "%s differs from the reference under MOISTFRACT" % n
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "vic_ref_driver")),
+                    reason="compiled reference (oracle/_ref) not built here")
+def test_organic_fract_against_the_live_reference(hostsim, tmp_path):
+    """ORGANIC_FRACT TRUE: the soil file's organic fraction and organic densities (read_soilparam.c:444-506, 647-655) through
+    the parameter reader, and the step with organic soil layers (thermal conductivity and heat capacity of the solids,
+    porosity and maximum moisture) -- reader, oracle and host build of the device code bit for bit against the compiled
+    reference"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib
+    import refdump
+    from vicres_b200 import files, synth
+    g = synth.make_case(str(tmp_path / "case"), ncells=3, nlayer=3, nbands=2, ndays=150, cold=8.0, lat_range=(30, 60),
+                        overstory_frac=0.5, seed=778, organic=True)
+    dump = str(tmp_path / "dump.bin")
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "vic_ref_driver"), "-g", g, "-d", dump], check=True, capture_output=True)
+    d = refdump.read_dump(dump)
+    cs = refdump.case_from_dump(d)
+    G = files.Global(g)
+    assert G.unsupported is None and G.organic_fract == 1
+    _, cells, _ = files.read_params(**G.param_files())
+    assert cells["organic"][0].max() > 0.1
+    for k in ("organic", "bulk_density", "soil_density", "porosity", "max_moist", "Wcr", "Wpwp", "bulk_dens_min", "soil_dens_min"):
+        assert np.array_equal(cells[k], cs["cells"][k]), k
+    names = abi.OUT_NAMES
+    opt = abi.default_options(cs["nlayer"], cs["nbands"], cs["dt"], out=names, max_snow_temp=cs["max_snow_temp"],
+                              min_rain_temp=cs["min_rain_temp"])
+    ref = refdump.ref_outputs(d, names)
+    o = oracle_lib.Oracle(opt, cs["lib"], cs["cells"])
+    o.init_state(cs["tair0"])
+    rc, out, _ = o.step(cs["month"], cs["doy"], cs["forcing"])
+    o.close()
+    assert rc == 0 and np.array_equal(out, ref)
+    lib, pc = abi.pack_veglib(cs["lib"]), abi.pack_cells(cells)         # the cells as THIS library's reader delivers them
+    f = abi.pack_forcing(cs["month"], cs["doy"], cs["forcing"], None)
+    hout = np.zeros_like(ref)
+    t0 = np.ascontiguousarray(cs["tair0"])
+    assert hostsim.hs_run(C.byref(opt), lib.ref(), pc.ref(), f.ref(), t0.ctypes.data, hout.ctypes.data) == 0
+    for i, n in enumerate(names):
+        assert np.array_equal(hout[i], ref[i]), "%s differs from the reference under ORGANIC_FRACT" % n

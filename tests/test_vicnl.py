@@ -217,7 +217,7 @@ def test_global_file_and_forcing_files_parse(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["daily", "sub3h", "skip"])
+@pytest.mark.parametrize("name", ["daily", "sub3h", "skip", "organic"])
 def test_vicnl_command_line_reproduces_the_reference_result_files(name, tmp_path):
     from vicres_b200 import vicnl
     gpath, res, ref = _stage(name, tmp_path)
@@ -263,7 +263,7 @@ def test_c_host_driver_compiles_against_the_headers(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["daily", "sub3h", "skip"])
+@pytest.mark.parametrize("name", ["daily", "sub3h", "skip", "organic"])
 def test_c_host_driver_reproduces_the_reference_result_files(name, tmp_path):
     """the same command line from the plain C host program (host/vicnl_gpu.c), records in blocks of 50"""
     import subprocess

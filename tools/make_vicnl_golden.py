@@ -23,6 +23,9 @@ CASES = {
                   overstory_frac=0.5, off_gmt=1, seed=401),
     "sub3h": dict(ncells=3, nlayer=3, nbands=1, ndays=60, dt=3, startyear=1986, cold=12.0, lat_range=(40, 62), seed=402),
     # SKIPYEAR 1 from 1984-01-01: the 366 days of the leap year are computed but not written
+    # ORGANIC_FRACT TRUE (organic top layers) with BASEFLOW NIJSSEN2001-free ARNO columns
+    "organic": dict(ncells=2, nlayer=3, nbands=1, ndays=150, startyear=1988, cold=6.0, lat_range=(40, 60), overstory_frac=0.5, seed=404,
+                    organic=True),
     "skip": dict(ncells=2, nlayer=3, nbands=1, ndays=480, startyear=1984, cold=6.0, lat_range=(35, 55), seed=403, skip_output=True),
 }
 

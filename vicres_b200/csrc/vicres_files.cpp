@@ -146,6 +146,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
     int gridcel; float lat, lng, elevation; double off_gmt, annual_prec;
     double b, Ds, Dsmax, Ws, c, avg_temp, dp, rough, snow_rough;
     double expt[3], Ksat[3], init_moist[3], depth[3], quartz[3], bdm[3], sdm[3], wcr_fr[3], wpwp_fr[3], resid[3], bubble[3];
+    double org[3], bdo[3], sdo[3];
   };
   std::vector<Soil> soils;
   {
@@ -156,7 +157,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
       std::vector<std::string> t = tokens(line);
       if (t.empty()) continue;
       if (atoi(t[0].c_str()) == 0) continue;                  // RUN_MODEL flag
-      const size_t need = 9 + 4 * L + 1 + L + 2 + 4 * L + 1 + 2 * L + 3 + L + 1;
+      const size_t need = 9 + 4 * L + 1 + L + 2 + 4 * L + 1 + 2 * L + 3 + L + 1 + (fo->organic_fract ? 3 * L : 0);
       if (t.size() < need) { fclose(f); delete P; g_err = "soil file row has too few columns for NLAYER"; return VR_ERR_ARG; }
       Soil s;
       size_t k = 1;
@@ -183,6 +184,18 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
       for (int l = 0; l < L; l++) s.quartz[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.bdm[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.sdm[l] = strtod(t[k++].c_str(), nullptr);
+      for (int l = 0; l < L; l++) { s.org[l] = 0.0; s.bdo[l] = -9999; s.sdo[l] = -9999; }      // read_soilparam.c:501-506
+      if (fo->organic_fract) {                                                               // :444-499
+        for (int l = 0; l < L; l++) s.org[l] = strtod(t[k++].c_str(), nullptr);
+        for (int l = 0; l < L; l++) s.bdo[l] = strtod(t[k++].c_str(), nullptr);
+        for (int l = 0; l < L; l++) s.sdo[l] = strtod(t[k++].c_str(), nullptr);
+        for (int l = 0; l < L; l++) {
+          if (s.org[l] > 1. || s.org[l] < 0) { fclose(f); delete P; g_err = "Need valid volumetric organic soil fraction when options.ORGANIC_FRACT is set to TRUE."; return VR_ERR_ARG; }
+          if (s.bdo[l] <= 0 && s.org[l] > 0) s.bdo[l] = s.bdm[l];
+          if (s.sdo[l] <= 0 && s.org[l] > 0) s.sdo[l] = s.sdm[l];
+          if (s.org[l] > 0 && s.bdo[l] >= s.sdo[l]) { fclose(f); delete P; g_err = "organic bulk density must be less than organic soil density"; return VR_ERR_ARG; }
+        }
+      }
       s.off_gmt = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.wcr_fr[l] = strtod(t[k++].c_str(), nullptr);
       for (int l = 0; l < L; l++) s.wpwp_fr[l] = strtod(t[k++].c_str(), nullptr);
@@ -214,7 +227,7 @@ int vr_params_read(const vr_param_files *fo, vr_params **out)
     P->avg_temp[c] = s.avg_temp; P->dp[c] = s.dp; P->rough[c] = s.rough; P->snow_rough[c] = s.snow_rough;
     for (int l = 0; l < L; l++) {
       const size_t k = (size_t)l * C + c;
-      const double organic = 0.0, bdo = -9999, sdo = -9999;     // ORGANIC_FRACT FALSE (read_soilparam.c:268-274)
+      const double organic = s.org[l], bdo = s.bdo[l], sdo = s.sdo[l];      // read_soilparam.c:647-655
       const double bulk = (1 - organic) * s.bdm[l] + organic * bdo, sdens = (1 - organic) * s.sdm[l] + organic * sdo;
       const double poros = 1.0 - bulk / sdens, mm = s.depth[l] * poros * 1000.;
       P->expt[k] = s.expt[l]; P->Ksat[k] = s.Ksat[l]; P->depth[k] = s.depth[l]; P->max_moist[k] = mm;
@@ -992,7 +1005,6 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->corrprec) return "CORRPREC TRUE";
   if (g->compute_treeline) return "COMPUTE_TREELINE";
   if (g->dist_prcp) return "DIST_PRCP TRUE";
-  if (g->organic_fract) return "ORGANIC_FRACT TRUE";
   if (g->time_step < 24 && g->snow_step != g->time_step)       // get_global_param.c:761-765
     return "If the model step is smaller than daily, the snow model should run at the same time step as the rest of the model.";
   if (g->snow_step < 1 || g->snow_step > g->time_step || g->time_step % g->snow_step)

@@ -14,7 +14,7 @@ class ParamFilesC(C.Structure):
     _fields_ = [("nlayer", C.c_int32), ("nbands", C.c_int32), ("root_zones", C.c_int32),
                 ("vegparam_lai", C.c_int32), ("lai_from_vegparam", C.c_int32),
                 ("soil", C.c_char_p), ("veglib", C.c_char_p), ("vegparam", C.c_char_p),
-                ("snowband", C.c_char_p), ("baseflow_nijssen", C.c_int32)]
+                ("snowband", C.c_char_p), ("baseflow_nijssen", C.c_int32), ("organic_fract", C.c_int32)]
 
 
 FILES_EXPORTS = ["vr_params_read", "vr_params_free", "vr_params_last_error", "vr_params_cells",
@@ -51,12 +51,12 @@ def _arr(ptr, n, dtype):
 
 
 def read_params(soil, veglib, vegparam, snowband=None, nlayer=3, nbands=1, root_zones=3,
-                vegparam_lai=False, lai_from_vegparam=False, lib=None, baseflow_nijssen=False):
+                vegparam_lai=False, lai_from_vegparam=False, lib=None, baseflow_nijssen=False, organic_fract=False):
     """Parse the four parameter files; returns (lib_dict, cells_dict, meta) in the layout
     abi.pack_veglib / abi.pack_cells take.  meta: gridcel, lat, lng (float32 as the reference stores)."""
     so = _bind(lib or load_library())
     pf = ParamFilesC(nlayer, nbands, root_zones, int(vegparam_lai), int(lai_from_vegparam),
-                     soil.encode(), veglib.encode(), vegparam.encode(), snowband.encode() if snowband else None, int(baseflow_nijssen))
+                     soil.encode(), veglib.encode(), vegparam.encode(), snowband.encode() if snowband else None, int(baseflow_nijssen), int(organic_fract))
     h = C.c_void_p()
     rc = so.vr_params_read(C.byref(pf), C.byref(h))
     if rc != 0:
@@ -213,7 +213,7 @@ class Global:
         return dict(soil=self.soil, veglib=self.veglib, vegparam=self.vegparam, snowband=self.snowband or None,
                     nlayer=self.nlayer, nbands=self.snow_band, root_zones=self.root_zones,
                     vegparam_lai=bool(self.vegparam_lai), lai_from_vegparam=bool(self.lai_from_vegparam),
-                    baseflow_nijssen=bool(self.baseflow_nijssen))
+                    baseflow_nijssen=bool(self.baseflow_nijssen), organic_fract=bool(self.organic_fract))
 
     def read_forcing(self, lat, lng):
         """the columns of the cell's forcing file, {FORCE_TYPE: [nrec_forcing]} (no disaggregation)"""

@@ -56,7 +56,8 @@ def _fmt(x, nd=6):
 def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261019,
               startyear=1981, lat_range=(-40.0, 60.0), cold=0.0, overstory_frac=0.3,
               max_veg=3, extra_global="", result_dir=None, skip_output=False, snow_step=None,
-              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False, extra_cols=(), alma=False):
+              wind_zero_frac=0.0, coords=None, off_gmt=None, force_daily=False, no_wind=False, extra_cols=(), alma=False,
+              organic=False):
     """Write a complete reference-format case under `outdir`; return the global file path.
 
     dt == 24: daily PREC/TMAX/TMIN/WIND forcing (as the bundled basin); dt < 24: sub-daily
@@ -122,7 +123,12 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         cols += [_fmt(x, 4) for x in expt] + [_fmt(x, 3) for x in Ksat] + ["%.0f" % x for x in phi_s]
         cols += [_fmt(x, 4) for x in init_moist] + ["%.1f" % elev] + [_fmt(x, 4) for x in depth]
         cols += [_fmt(avg_T, 3), _fmt(dp, 1)] + [_fmt(x, 3) for x in bubble] + [_fmt(x, 4) for x in quartz]
-        cols += [_fmt(x, 2) for x in bulk] + [_fmt(x, 2) for x in sdens] + ["%g" % off_gmt_c]
+        cols += [_fmt(x, 2) for x in bulk] + [_fmt(x, 2) for x in sdens]
+        if organic:                      # ORGANIC_FRACT TRUE: organic fraction, organic bulk and soil densities per layer
+            org = np.round(np.linspace(0.35, 0.0, L) * rng.uniform(0.5, 1.0), 3)      # organic top layer, mineral bottom layer
+            cols += ["%.3f" % x for x in org] + ["%.1f" % x for x in rng.uniform(180.0, 320.0, L)]
+            cols += ["%.1f" % x for x in rng.uniform(1250.0, 1350.0, L)]
+        cols += ["%g" % off_gmt_c]
         cols += [_fmt(x, 4) for x in wcr_fr] + [_fmt(x, 4) for x in wpwp_fr]
         cols += [_fmt(rough, 4), _fmt(snow_rough, 4), _fmt(annual_prec, 1)] + [_fmt(x, 4) for x in resid] + ["0"]
         soil_lines.append("\t".join(cols))
@@ -267,7 +273,7 @@ def make_case(outdir, ncells=8, nlayer=3, nbands=1, ndays=365, dt=24, seed=20261
         g += ["N_TYPES %d" % len(types)] + ["FORCE_TYPE %s" % t for t in types] + ["FORCE_DT %d" % dt]
     g += ["FORCEYEAR %d" % startyear, "FORCEMONTH 1", "FORCEDAY 1", "FORCEHOUR 0", "GRID_DECIMAL 4",
           "WIND_H 10.0", "MEASURE_H 2.0", "ALMA_INPUT %s" % ("TRUE" if alma else "FALSE"),
-          "SOIL %s/soil.txt" % outdir, "BASEFLOW ARNO", "JULY_TAVG_SUPPLIED FALSE", "ORGANIC_FRACT FALSE",
+          "SOIL %s/soil.txt" % outdir, "BASEFLOW ARNO", "JULY_TAVG_SUPPLIED FALSE", "ORGANIC_FRACT %s" % ("TRUE" if organic else "FALSE"),
           "VEGLIB %s/veglib.txt" % outdir, "VEGPARAM %s/veg.txt" % outdir, "ROOT_ZONES 3",
           "VEGPARAM_LAI FALSE", "LAI_SRC FROM_VEGLIB"]
     if nbands > 1:
