@@ -66,42 +66,57 @@ int main(int argc, char **argv)
           *hour = malloc(sizeof(int32_t) * nrecs), *doy = malloc(sizeof(int32_t) * nrecs);
   if (vr_make_dmy(&g, year, month, day, hour, doy) != VR_OK) die("calendar", vr_params_last_error());
 
-  /* forcing files -> raw columns [type][record][cell] */
+  /* forcing files -> raw columns [type][record][cell]; FORCING2's columns follow FORCING1's, and a type in both is taken from
+   * the second file (the later entry wins below), as param_set.TYPE[].SUPPLIED ends up pointing at it */
   const int64_t nrf = (int64_t)nrecs * g.time_step / g.force_dt;
-  const int nt = g.n_force_types;
-  double *one = malloc(sizeof(double) * nt * nrf), *raw = calloc((size_t)nt * nrf * C, sizeof(double));
+  static vr_global g2;
+  const int nt1 = g.n_force_types;
+  int nt2 = 0;
+  if (g.forcing2) {
+    if (vr_global_read_forcing2(gfile, &g2) != VR_OK) die("global file (FORCING2)", vr_params_last_error());
+    if (g2.force_dt != g.force_dt) die("FORCING2", "a FORCE_DT other than FORCING1's is outside this library's forcing layouts");
+    nt2 = g2.n_force_types;
+  }
+  const int nt = nt1 + nt2;
+  double *one = malloc(sizeof(double) * (nt1 > nt2 ? nt1 : nt2) * nrf), *raw = calloc((size_t)nt * nrf * C, sizeof(double));
   int64_t c, r;
   int t, col_prec = -1, col_ta = -1, col_tb = -1, col_wind = -1, col_sw = -1, col_lw = -1, col_vp = -1, col_pr = -1, col_de = -1, subdaily = 0;
   int col_q = -1, col_rh = -1, col_rf = -1, col_sf = -1, col_we = -1, col_wn = -1;
   for (t = 0; t < nt; t++) {
-    if (!strcmp(g.force_type[t], "PREC")) col_prec = t;
-    else if (!strcmp(g.force_type[t], "TMAX")) col_ta = t;
-    else if (!strcmp(g.force_type[t], "TMIN")) col_tb = t;
-    else if (!strcmp(g.force_type[t], "AIR_TEMP")) { col_ta = t; subdaily = 1; }
-    else if (!strcmp(g.force_type[t], "WIND")) col_wind = t;
-    else if (!strcmp(g.force_type[t], "SHORTWAVE")) col_sw = t;
-    else if (!strcmp(g.force_type[t], "LONGWAVE")) col_lw = t;
-    else if (!strcmp(g.force_type[t], "VP")) col_vp = t;
-    else if (!strcmp(g.force_type[t], "PRESSURE")) col_pr = t;
-    else if (!strcmp(g.force_type[t], "DENSITY")) col_de = t;
-    else if (!strcmp(g.force_type[t], "QAIR")) col_q = t;
-    else if (!strcmp(g.force_type[t], "REL_HUMID")) col_rh = t;
-    else if (!strcmp(g.force_type[t], "RAINF")) col_rf = t;
-    else if (!strcmp(g.force_type[t], "SNOWF")) col_sf = t;
-    else if (!strcmp(g.force_type[t], "WIND_E")) col_we = t;
-    else if (!strcmp(g.force_type[t], "WIND_N")) col_wn = t;
-    else if (strcmp(g.force_type[t], "SKIP")) die("forcing column outside the supported layouts", g.force_type[t]);
+    const char *ft = t < nt1 ? g.force_type[t] : g2.force_type[t - nt1];
+    if (!strcmp(ft, "PREC")) col_prec = t;
+    else if (!strcmp(ft, "TMAX")) col_ta = t;
+    else if (!strcmp(ft, "TMIN")) col_tb = t;
+    else if (!strcmp(ft, "AIR_TEMP")) { col_ta = t; subdaily = 1; }
+    else if (!strcmp(ft, "WIND")) col_wind = t;
+    else if (!strcmp(ft, "SHORTWAVE")) col_sw = t;
+    else if (!strcmp(ft, "LONGWAVE")) col_lw = t;
+    else if (!strcmp(ft, "VP")) col_vp = t;
+    else if (!strcmp(ft, "PRESSURE")) col_pr = t;
+    else if (!strcmp(ft, "DENSITY")) col_de = t;
+    else if (!strcmp(ft, "QAIR")) col_q = t;
+    else if (!strcmp(ft, "REL_HUMID")) col_rh = t;
+    else if (!strcmp(ft, "RAINF")) col_rf = t;
+    else if (!strcmp(ft, "SNOWF")) col_sf = t;
+    else if (!strcmp(ft, "WIND_E")) col_we = t;
+    else if (!strcmp(ft, "WIND_N")) col_wn = t;
+    else if (strcmp(ft, "SKIP")) die("forcing column outside the supported layouts", ft);
   }
   if ((col_prec < 0 && (col_rf < 0 || col_sf < 0)) || col_ta < 0 || (!subdaily && col_tb < 0))
     die("forcing file", "needs PREC (or RAINF and SNOWF) and TMAX+TMIN or AIR_TEMP");
   for (c = 0; c < C; c++) {
-    char path[1200];
-    snprintf(path, sizeof path, "%s%.*f_%.*f", g.forcing1, g.grid_decimal, lat[c], g.grid_decimal, lng[c]);
-    int64_t got = vr_read_forcing_file(&g, path, nrf, one);
-    if (got < 0) die(path, vr_params_last_error());
-    if (got < nrf) die(path, "Not enough records in the forcing file");      /* read_atmos_data.c:178-182 */
-    for (t = 0; t < nt; t++)
-      for (r = 0; r < got; r++) raw[((size_t)t * nrf + r) * C + c] = one[(size_t)t * nrf + r];
+    int file;
+    for (file = 0; file < (g.forcing2 ? 2 : 1); file++) {
+      const vr_global *gf = file ? &g2 : &g;
+      const int ntf = file ? nt2 : nt1, t0 = file ? nt1 : 0;
+      char path[1200];
+      snprintf(path, sizeof path, "%s%.*f_%.*f", gf->forcing1, g.grid_decimal, lat[c], g.grid_decimal, lng[c]);
+      int64_t got = vr_read_forcing_file(gf, path, nrf, one);
+      if (got < 0) die(path, vr_params_last_error());
+      if (got < nrf) die(path, "Not enough records in the forcing file");      /* read_atmos_data.c:178-182 */
+      for (t = 0; t < ntf; t++)
+        for (r = 0; r < got; r++) raw[((size_t)(t0 + t) * nrf + r) * C + c] = one[(size_t)t * nrf + r];
+    }
   }
 
   /* initialize_atmos for all cells */

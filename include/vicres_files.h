@@ -155,7 +155,7 @@ typedef struct vr_global {
    * that day is "<prefix>_YYYYMMDD", get_global_param.c:961-964; BINARY_STATE_FILE) -> vr_read/write_state_file */
   char    init_state_file[512], statename[512];
   int32_t stateyear, statemonth, stateday, binary_state_file;
-  /* a second forcing file (FORCING2 <prefix>) and a custom output selection (N_OUTFILES / OUTFILE / OUTVAR lines,
+  /* a second forcing file (FORCING2 <prefix>: != 0, read through vr_global_read_forcing2) and a custom output selection (N_OUTFILES / OUTFILE / OUTVAR lines,
    * parse_output_info.c:62-118; counted here, parsed by vr_outsel_read) */
   int32_t forcing2, n_outfile_lines, n_outvar_lines;
   /* the first option of the file that changes the results and has a value this library does not implement ("KEY VALUE":
@@ -168,6 +168,11 @@ typedef struct vr_global {
 } vr_global;
 
 int  vr_global_read(const char *path, vr_global *out);
+/* FORCING2: the same global file read with the description of the SECOND forcing file in the forcing fields (forcing1 = its
+ * path prefix, force_type[], force_dt, format, FORCEYEAR ...), so that vr_force_skip / vr_read_forcing_file read that file;
+ * everything else equals what vr_global_read returns.  A type both files hold is taken from the second, as the reference's
+ * param_set.TYPE[].SUPPLIED ends up pointing at it.  Both files have to share FORCE_DT here (the hosts check). */
+int  vr_global_read_forcing2(const char *path, vr_global *out2);
 /* NULL when the water-balance path of this library covers the file's options, else a text naming the first
  * option it does not (FULL_ENERGY TRUE, FROZEN_SOIL TRUE, SNOW_STEP != TIME_STEP, ...) */
 const char *vr_global_unsupported(const vr_global *g);

@@ -34,7 +34,7 @@ def test_exports_every_declared_symbol(lib):
 def test_exports_every_declared_file_symbol(lib):
     from vicres_b200 import files
     syms = declared_symbols("vicres_files.h")
-    assert len(syms) == 26
+    assert len(syms) == 27
     for s in syms:
         assert hasattr(lib, s), "libvicres.so does not export %s" % s
     assert sorted(files.FILES_EXPORTS) == syms

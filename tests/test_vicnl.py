@@ -319,3 +319,67 @@ def test_compress_gzips_the_result_files_and_skipyear_beyond_the_run_leaves_them
     assert run() == 0
     assert sorted(os.listdir(res)) == sorted(os.listdir(ref))
     assert all(os.path.getsize(os.path.join(res, n)) == 0 for n in os.listdir(res))
+
+
+def _split_forcing(gpath, case_dir):
+    """the `daily` case with its four forcing columns in TWO files: PREC, TMAX (+ a WIND column of zeros that the second file
+    overrides) in FORCING1, TMIN, WIND in FORCING2 (get_global_param.c:441-470)"""
+    f1, f2 = os.path.join(case_dir, "forcing"), os.path.join(case_dir, "forcing2")
+    os.makedirs(f2)
+    for n in os.listdir(f1):
+        rows = [ln.split() for ln in open(os.path.join(f1, n)) if ln.strip()]
+        open(os.path.join(f1, n), "w").write("".join("%s %s 0.0000\n" % (r[0], r[1]) for r in rows))
+        open(os.path.join(f2, n), "w").write("".join("%s %s\n" % (r[2], r[3]) for r in rows))
+    txt = open(gpath).read()
+    i, j = txt.index("FORCING1"), txt.index("FORCEHOUR 0") + len("FORCEHOUR 0")
+    date = "FORCEYEAR 1984\nFORCEMONTH 1\nFORCEDAY 1\nFORCEHOUR 0"
+    desc = ("FORCING1 %s/data_\nFORCE_FORMAT ASCII\nFORCE_ENDIAN LITTLE\nN_TYPES 3\nFORCE_TYPE PREC\nFORCE_TYPE TMAX\nFORCE_TYPE WIND\n"
+            "FORCE_DT 24\n%s\nFORCING2 %s/data_\nFORCE_FORMAT ASCII\nFORCE_ENDIAN LITTLE\nN_TYPES 2\nFORCE_TYPE TMIN\nFORCE_TYPE WIND\n"
+            "FORCE_DT 24\n%s" % (f1, date, f2, date))
+    open(gpath, "w").write(txt[:i] + desc + txt[j:])
+
+
+def test_second_forcing_file_is_read_and_the_reference_agrees(tmp_path):
+    """CPU tier: FORCING2 -- both descriptions parse, the merged columns are the unsplit file's (WIND from the second file),
+    and the unmodified reference run on the split case writes the files of the unsplit golden case"""
+    import subprocess
+    from common import ROOT
+    gpath, res, ref = _stage("daily", tmp_path)
+    whole = {}
+    g = files.Global(gpath)
+    lib, cells, meta = files.read_params(**g.param_files())
+    for c in range(len(meta["lat"])):
+        whole[c] = g.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))[0]
+    _split_forcing(gpath, os.path.dirname(gpath))
+    g = files.Global(gpath)
+    assert g.unsupported is None and g.forcing2 == 1 and g.force_types == ["PREC", "TMAX", "WIND"]
+    g2 = g.second_forcing()
+    assert g2.force_types == ["TMIN", "WIND"] and g2.forcing1.endswith("forcing2/data_") and g2.nrecs == g.nrecs
+    for c in range(len(meta["lat"])):
+        d, got = g.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))
+        d2, got2 = g2.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))
+        assert got == got2 == g.nrecs and not d["WIND"].any()
+        d.update(d2)
+        for k in ("PREC", "TMAX", "TMIN", "WIND"):
+            assert np.array_equal(d[k], whole[c][k]), k
+    vicnl_ref = os.path.join(ROOT, "oracle", "_ref", "vicNl")
+    if os.path.exists(vicnl_ref):
+        r = subprocess.run([vicnl_ref, "-g", gpath], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        for n in sorted(os.listdir(ref)):
+            assert open(os.path.join(res, n)).read() == open(os.path.join(ref, n)).read(), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", ["python", "c"])
+def test_vicnl_with_a_second_forcing_file(host, tmp_path):
+    import subprocess
+    from vicres_b200 import vicnl
+    gpath, res, ref = _stage("daily", tmp_path)
+    _split_forcing(gpath, os.path.dirname(gpath))
+    if host == "python":
+        assert vicnl.main(["-g", gpath]) == 0
+    else:
+        r = subprocess.run([_build_c_driver(tmp_path), "-g", gpath], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+    _compare_ascii(res, ref, "daily with FORCING2 (%s host)" % host)

@@ -189,7 +189,8 @@ def last_times():
 
 def options_from_global(g):
     """vr_atmos_options from a parsed global file (vicres_b200.files.Global)."""
-    types = [t for t in g.force_types if t != "SKIP"]
+    g2 = g.second_forcing() if hasattr(g, "second_forcing") else None
+    types = [t for t in g.force_types + (g2.force_types if g2 is not None else []) if t != "SKIP"]
     extra = [t for t in types if t not in ("PREC", "TMAX", "TMIN", "AIR_TEMP", "WIND", "SHORTWAVE", "LONGWAVE", "VP", "PRESSURE", "DENSITY",
                                            "QAIR", "REL_HUMID", "RAINF", "SNOWF", "WIND_E", "WIND_N")]
     if extra:

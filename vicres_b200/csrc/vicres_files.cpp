@@ -845,7 +845,8 @@ static bool other_option_unsupported(const char *key, const char *val)
   return false;
 }
 
-int vr_global_read(const char *path, vr_global *g)
+// which: 0 = the description of FORCING1 is kept (vr_global_read), 1 = that of FORCING2, in the same fields (vr_global_read_forcing2)
+static int global_read_file(const char *path, vr_global *g, int which)
 {
   if (!path || !g) { g_err = "null argument"; return VR_ERR_ARG; }
   FILE *f = fopen(path, "r");
@@ -942,15 +943,19 @@ int vr_global_read(const char *path, vr_global *g)
     else if (!strcasecmp(k, "BASEFLOW")) g->baseflow_nijssen = (t.size() > 1 && !strcasecmp(t[1].c_str(), "NIJSSEN2001"));
     else if (!strcasecmp(k, "OUTFILE")) g->n_outfile_lines++;
     else if (!strcasecmp(k, "OUTVAR")) g->n_outvar_lines++;
-    else if (!strcasecmp(k, "FORCING1") && t.size() > 1) { copy(g->forcing1, t[1]); file_num = 0; field = -1; }
+    else if (!strcasecmp(k, "FORCING1") && t.size() > 1) {
+      file_num = 0;
+      if (which == 0) { copy(g->forcing1, t[1]); field = -1; }
+    }
     else if (other_option_unsupported(k, t.size() > 1 ? t[1].c_str() : "")) {
       if (!g->other_unsupported[0]) snprintf(g->other_unsupported, sizeof g->other_unsupported, "%s %s", k, t.size() > 1 ? t[1].c_str() : "");
     }
-    else if (!strcasecmp(k, "FORCING2")) {     // a second forcing file is not read by this library (vr_global_unsupported names it)
+    else if (!strcasecmp(k, "FORCING2")) {     // the second forcing file: its description follows (get_global_param.c:441-470)
       file_num = 1;
       g->forcing2 = (t.size() > 1 && strcasecmp(t[1].c_str(), "FALSE") != 0 && strcasecmp(t[1].c_str(), "MISSING") != 0);
+      if (which == 1 && g->forcing2) { copy(g->forcing1, t[1]); field = -1; }
     }
-    else if (file_num == 0) {          // description of FORCING1 (get_force_type.c)
+    else if (file_num == which) {      // description of the forcing file this call keeps (get_force_type.c)
       if (!strcasecmp(k, "FORCE_FORMAT")) g->force_ascii = (t.size() > 1 && !strcasecmp(t[1].c_str(), "ASCII"));
       else if (!strcasecmp(k, "FORCE_ENDIAN")) g->force_little_endian = !(t.size() > 1 && !strcasecmp(t[1].c_str(), "BIG"));
       else if (!strcasecmp(k, "N_TYPES")) g->n_force_types = I();
@@ -994,6 +999,15 @@ int vr_global_read(const char *path, vr_global *g)
   return VR_OK;
 }
 
+int vr_global_read(const char *path, vr_global *g) { return global_read_file(path, g, 0); }
+
+int vr_global_read_forcing2(const char *path, vr_global *g2)
+{
+  const int rc = global_read_file(path, g2, 1);
+  if (rc == VR_OK && !g2->forcing2) { g_err = "the global parameter file names no second forcing file"; return VR_ERR_ARG; }
+  return rc;
+}
+
 const char *vr_global_unsupported(const vr_global *g)
 {
   if (!g) return "null";
@@ -1010,7 +1024,6 @@ const char *vr_global_unsupported(const vr_global *g)
   if (g->snow_step < 1 || g->snow_step > g->time_step || g->time_step % g->snow_step)
     return "SNOW_STEP should be <= TIME_STEP and divide TIME_STEP evenly";
   if (g->nlayer < 2 || g->nlayer > VR_MAX_LAYERS) return "NLAYER outside 2..3";
-  if (g->forcing2) return "FORCING2 (a second forcing file)";
   if (g->other_unsupported[0]) return g->other_unsupported;
   if (g->out_step > 0 && (g->out_step < g->time_step || g->out_step % g->time_step || g->out_step > 24))
     return "OUT_STEP must be a multiple of TIME_STEP and at most 24 (get_global_param.c:754-760)";

@@ -155,11 +155,13 @@ class GlobalC(C.Structure):
                  ("baseflow_nijssen", C.c_int32)])
 
 
-FILES_EXPORTS += ["vr_global_read", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip", "vr_read_forcing_file"]
+FILES_EXPORTS += ["vr_global_read", "vr_global_read_forcing2", "vr_global_unsupported", "vr_make_dmy", "vr_force_skip", "vr_output_skip",
+                  "vr_read_forcing_file"]
 
 
 def _bind_global(so):
     so.vr_global_read.argtypes = [C.c_char_p, C.POINTER(GlobalC)]
+    so.vr_global_read_forcing2.argtypes = [C.c_char_p, C.POINTER(GlobalC)]
     so.vr_global_unsupported.argtypes = [C.POINTER(GlobalC)]
     so.vr_global_unsupported.restype = C.c_char_p
     so.vr_make_dmy.argtypes = [C.POINTER(GlobalC)] + [C.POINTER(C.c_int32)] * 5
@@ -173,12 +175,23 @@ def _bind_global(so):
 class Global:
     """a parsed global parameter file (get_global_param.c) with its calendar (make_dmy.c)"""
 
-    def __init__(self, path, lib=None):
+    def __init__(self, path, lib=None, second=False):
+        """second: the description of FORCING2 in the forcing fields (vr_global_read_forcing2)"""
         self.so = _bind_global(_bind(lib or load_library()))
         self.c = GlobalC()
-        rc = self.so.vr_global_read(path.encode(), C.byref(self.c))
+        self.path = path
+        rc = (self.so.vr_global_read_forcing2 if second else self.so.vr_global_read)(path.encode(), C.byref(self.c))
         if rc != 0:
             raise VicResError(rc, "vr_global_read: %s" % self.so.vr_params_last_error().decode())
+
+    def second_forcing(self):
+        """the same global file seen from its second forcing file, or None"""
+        if not self.c.forcing2:
+            return None
+        g2 = Global(self.path, second=True)
+        if g2.force_dt != self.force_dt:
+            raise VicResError(abi.VR_ERR_UNSUPPORTED, "FORCING2 with a FORCE_DT other than FORCING1's (%d, %d)" % (g2.force_dt, self.force_dt))
+        return g2
 
     def __getattr__(self, k):
         v = getattr(self.c, k)

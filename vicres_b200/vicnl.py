@@ -37,8 +37,13 @@ def run(global_path, device=0, write=True, records_per_block=0):
     ao = atmos.options_from_global(g)
     # forcing files -> [type][record][cell] columns
     cols = None
+    g2 = g.second_forcing()                 # FORCING2: its columns join (and, for a type in both, replace) those of FORCING1
     for c in range(Cn):
         d, got = g.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))
+        if g2 is not None:
+            d2, got2 = g2.read_forcing(float(meta["lat"][c]), float(meta["lng"][c]))
+            d.update(d2)
+            got = min(got, got2)
         need = g.nrecs * g.time_step // g.c.force_dt
         if got < need:                   # read_atmos_data.c:178-182, 258-262: "Not enough records in the forcing file"
             raise model.VicResError(abi.VR_ERR_ARG, "Not enough records in the forcing file of cell %d (%d < %d)"
